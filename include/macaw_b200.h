@@ -1,0 +1,277 @@
+/* macaw_b200.h -- C ABI of libmacaw_b200.so, the B200 (sm_100a) implementation of MaCaw's
+ * particle-history hot path.
+ *
+ * This is the drop-in boundary.  In the reference the path sits behind MOOSE objects
+ * (OpenMCStudy, CollisionKernel, OpenMCTally, OpenMCTallyAux) that call OpenMC C++ internals per ray
+ * segment.  In GPU mode those objects stay in the input file as configuration carriers; the study
+ * forwards their parameters through the calls below once, then calls mcw_run_generation() once per
+ * batch instead of looping rays through TraceRay::trace().  Every entry point cites the reference
+ * interface it replaces as  [file:line]  relative to the reference tree
+ * (MC = MaCaw src/, RT = moose/modules/ray_tracing, OMC = openmc/).
+ *
+ * Conventions (mirroring openmc/include/openmc/capi.h:37-190): every call returns int, 0 = success,
+ * negative = MCW_E_* and a message retrievable with mcw_last_error(); the caller owns all input
+ * arrays (they are copied during the call); the library owns all device memory; one handle per
+ * GPU / rank; calls on one handle come from one host thread.  No torch / C++ types cross the ABI.
+ */
+#ifndef MACAW_B200_H
+#define MACAW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (cf. OPENMC_E_* in OMC include/openmc/capi.h:180-190) ---- */
+#define MCW_OK 0
+#define MCW_E_INVALID_ARGUMENT (-1)
+#define MCW_E_NOT_READY (-2)   /* call order violated (e.g. run before mesh/library/materials set) */
+#define MCW_E_CUDA (-3)        /* CUDA runtime error or no sm_100-class device; never falls back to CPU */
+#define MCW_E_ALLOCATE (-4)
+#define MCW_E_PHYSICS (-5)     /* e.g. no fission sites banked (OMC eigenvalue.cpp:107-109) */
+#define MCW_E_UNSUPPORTED (-6)
+
+/* ---- element types (libMesh ElemType subset traced by MaCaw inputs; RT TraceRayTools.h:558-856) ---- */
+#define MCW_QUAD4 0
+#define MCW_TET4 1
+#define MCW_HEX8 2
+
+/* ---- boundary condition kinds (RT src/raybcs/ReflectRayBC.C:39-77, KillRayBC.C) ---- */
+#define MCW_BC_KILL 0
+#define MCW_BC_REFLECT 1
+
+/* ---- tally scores (OMC tally_scoring.cpp:557,581,726,760,1201), estimator fixed per tally ---- */
+#define MCW_SCORE_FLUX 0
+#define MCW_SCORE_TOTAL 1
+#define MCW_SCORE_FISSION 2
+#define MCW_SCORE_NU_FISSION 3
+#define MCW_SCORE_KAPPA_FISSION 4
+#define MCW_N_SCORES 5
+
+#define MCW_ESTIMATOR_COLLISION 0   /* MC OpenMCTally.C:89-90: the only estimator the reference accepts */
+#define MCW_ESTIMATOR_TRACKLENGTH 1 /* extension, spec OMC tally_scoring.cpp:2289-2352 */
+
+/* ---- tally granularity (MC OpenMCTallyAux.C:70-215 "granularity") ---- */
+#define MCW_FILTER_CELL 0     /* one bin per mesh element (cell filter, MC OpenMCTally.C:157-171) */
+#define MCW_FILTER_UNIVERSE 1 /* one bin per block index (universe filter, MC OpenMCTally.C:141-156) */
+#define MCW_FILTER_GLOBAL 2   /* a single spatial bin */
+
+#define MCW_MAX_DELAYED_GROUPS 8 /* OMC particle_data.h:26 */
+
+/* Source / fission-bank site.  Same 96-byte layout as openmc::SourceSite
+ * (OMC include/openmc/particle_data.h:43-53); the 4 padding bytes after `particle` carry the mesh
+ * element the site was born in (-1 = unknown, located on first use; MC relocates every batch with
+ * ClaimRays, RT ClaimRays.C:104-163). */
+typedef struct mcw_source_site
+{
+  double r[3];
+  double u[3];
+  double E;
+  double wgt;
+  int32_t delayed_group;
+  int32_t surf_id;
+  int32_t particle;
+  int32_t elem;
+  int64_t parent_id;
+  int64_t progeny_id;
+} mcw_source_site;
+
+/* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
+ * (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
+ * col = total, absorption, fission, nu-fission, photon-production.  Reactions present: elastic
+ * (MT 2, isotropic in CM, free-gas below 400 kT), optionally one level-inelastic (LevelInelastic,
+ * OMC distribution_energy.cpp:48-51, scatter in CM), radiative capture, optionally fission with
+ * polynomial total nu, constant delayed yields, Watt prompt spectrum and Maxwell delayed spectra. */
+typedef struct mcw_nuclide_desc
+{
+  int32_t n_grid;
+  int32_t fissionable;
+  double awr;
+  double kT;               /* temperature of the data set, eV (OMC nuclide.cpp kTs_) */
+  const double* energy;    /* [n_grid] strictly non-decreasing */
+  const double* xs;        /* [n_grid][5] row-major */
+  const double* elastic;   /* [n_grid] MT 2 */
+  int32_t n_inelastic;     /* 0 or 1 */
+  int32_t inel_threshold;  /* grid index of the reaction threshold (OMC reaction xs_.threshold) */
+  const double* inelastic; /* [n_grid - inel_threshold] */
+  double inel_threshold_energy; /* LevelInelastic threshold_ */
+  double inel_mass_ratio;       /* LevelInelastic mass_ratio_ */
+  double nu_poly[2];            /* total nu(E) = c0 + c1*E (OMC endf.cpp Polynomial) */
+  int32_t n_precursor;          /* delayed groups, <= MCW_MAX_DELAYED_GROUPS */
+  int32_t reserved0;
+  double delayed_yield[MCW_MAX_DELAYED_GROUPS]; /* constant yield per group */
+  double delayed_theta[MCW_MAX_DELAYED_GROUPS]; /* Maxwell temperature per group, eV */
+  double watt_a, watt_b;                        /* prompt Watt spectrum parameters */
+  double q_fission;                             /* fission Q value, eV (kappa-fission score) */
+} mcw_nuclide_desc;
+
+/* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm). */
+typedef struct mcw_material_desc
+{
+  int32_t n_nuclides;
+  int32_t reserved0;
+  const int32_t* nuclide;      /* indices into the library */
+  const double* atom_density;  /* [n_nuclides] */
+} mcw_material_desc;
+
+/* Run settings: the subset of openmc::settings MaCaw reads (OMC settings.cpp:41-116) plus the
+ * MaCaw/MOOSE parameters that change the numbers (MC CollisionKernel.C:38, RT RayTracingStudy.C). */
+typedef struct mcw_settings
+{
+  int64_t n_particles;     /* settings::n_particles (global, all ranks) */
+  int64_t master_seed;     /* OMC random_lcg.cpp:9, default 1 */
+  int32_t n_inactive;
+  int32_t n_log_bins;      /* settings::n_log_bins, default 8000 */
+  int32_t is_2d;           /* mesh dimension == 2 (MC CollisionKernel.C:47) */
+  int32_t seed_through_double; /* 1 = reproduce MaCaw's double-typed ray aux seeds */
+  double z_coord;          /* MC CollisionKernel.C:38 */
+  double source_box[6];    /* batch-1 box source lower-left / upper-right (OMC source.cpp:143-231) */
+  int32_t source_only_fissionable;
+  int32_t max_events;      /* safety cap on events per history (OMC constants.h:56 MAX_EVENTS) */
+  int32_t sort_xs_queue;   /* 1 = sort the cross-section queue by (material, energy bucket) */
+  int32_t record_traces;   /* 1 = keep per-history crossing hashes (parity output) */
+} mcw_settings;
+
+/* Per-generation result (MC OpenMCStudy.C:399-401 prints keff / keff_std / k_generation;
+ * counters follow RT PerProcessorRayTracingResultsVectorPostprocessor names). */
+typedef struct mcw_generation_result
+{
+  double k_generation;     /* OMC eigenvalue.cpp:49-69 (track-length based) */
+  double keff;             /* running mean over active generations, OMC eigenvalue.cpp:313-351 */
+  double keff_std;
+  double k_collision;      /* this generation's global tallies / total weight */
+  double k_absorption;
+  double k_tracklength;
+  double leakage;
+  double total_weight;
+  int64_t n_histories;
+  int64_t n_segments;      /* "intersections" */
+  int64_t n_collisions;
+  int64_t n_xs_lookups;    /* macroscopic lookups performed */
+  int64_t n_nuclide_lookups;
+  int64_t n_bank_sites;    /* fission sites banked before sampling */
+  int64_t n_vertex_edge_hits; /* exits through a vertex or edge (RT VERTEX_HITS + EDGE_HITS) */
+  int64_t n_moved_through_neighbors; /* RT MOVED_THROUGH_NEIGHBORS */
+  int64_t n_failed_traces;    /* RT FAILED_TRACES (tolerate_failure semantics: counted and killed) */
+  int64_t n_event_rounds;     /* event-loop iterations */
+  int64_t n_kernel_launches;  /* kernels of this library launched in the generation */
+  double ms_total;            /* device time of the generation (CUDA events) */
+  double ms_xs, ms_track, ms_collide, ms_bank; /* per-kernel-family device time */
+} mcw_generation_result;
+
+/* Per-history record for parity checks (device -> host on request). */
+typedef struct mcw_history_record
+{
+  uint64_t seed_tracking, seed_source, seed_urr; /* state at death */
+  double E;
+  double k_collision, k_absorption, k_tracklength;
+  int32_t n_segments, n_collisions, n_progeny;
+  int32_t last_elem;
+  int32_t fate;        /* 0 absorbed, 1 killed on boundary, 2 failed trace, 3 event cap */
+  int32_t n_xs;
+  uint64_t trace_hash; /* rolling hash of (element, exit side) for every segment */
+} mcw_history_record;
+
+typedef struct mcw_context* mcw_handle;
+
+/* Lifetime.  Replaces OpenMCStudy's ctor/dtor calls openmc_init / openmc_simulation_init /
+ * openmc_finalize [MC OpenMCStudy.C:129,147,213; OMC capi.h:37,56,105].  rank/nranks describe the
+ * particle sharding (OMC simulation.cpp:529-551 calculate_work). */
+int mcw_create(mcw_handle* h, int device_ordinal, int rank, int nranks);
+void mcw_destroy(mcw_handle h);
+const char* mcw_last_error(mcw_handle h); /* OMC error.cpp:32 openmc_err_msg */
+int mcw_version(void);
+
+/* Mesh.  Replaces libMesh access on the path: elem->point / neighbor_ptr / subdomain_id
+ * [RT TraceRayTools.C:404-407, TraceRay.C:1433, MC CollisionKernel.C:110] and boundary info
+ * [RT TraceRay.C:725-782].  conn is n_elem x (4 | 4 | 8) node ids in libMesh node order
+ * (SURVEY Appendix B).  neighbors may be NULL (computed by face matching); bc_kind is
+ * n_elem x n_sides with -1 on interior sides. */
+int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem,
+                 const int64_t* conn, const int32_t* block_id, const int64_t* neighbors,
+                 const int8_t* bc_kind);
+
+/* Nuclear data.  Replaces HDF5 loading in openmc_init + Nuclide::init_grid
+ * [OMC nuclide.cpp:50-302,446-476; simulation.cpp:553-619]. */
+int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
+
+/* Materials and the block -> material map of CollisionKernel's `blocks` / `materials` parameters
+ * [MC CollisionKernel.C:34-37,64-69,110]. */
+int mcw_set_materials(mcw_handle h, const mcw_material_desc* materials, int n,
+                      const int32_t* block_ids, const int32_t* block_material, int n_blocks);
+
+/* Coupled temperature variable of CollisionKernel, one value per element or one scalar (n = 1)
+ * [MC CollisionKernel.C:33,109]. */
+int mcw_set_temperature(mcw_handle h, const double* T, int64_t n);
+
+int mcw_set_settings(mcw_handle h, const mcw_settings* s);
+
+/* Tally definition.  Replaces OpenMCTally::initialize [MC OpenMCTally.C:103-225]. */
+int mcw_add_tally(mcw_handle h, int id, int estimator, int granularity, const int32_t* scores,
+                  int n_scores, const double* energy_bins, int n_energy_edges);
+
+/* Source bank.  mcw_sample_initial_source replaces initialize_source [OMC source.cpp:325-338];
+ * mcw_set_source_bank / mcw_get_source_bank replace openmc_source_bank [OMC bank.cpp:110-125].
+ * n is this rank's share (work_per_rank). */
+int mcw_sample_initial_source(mcw_handle h);
+int mcw_set_source_bank(mcw_handle h, const mcw_source_site* sites, int64_t n);
+int mcw_get_source_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n);
+
+/* One batch = one generation.  Replaces OpenMCStudy::execute -> generateRays / trace loop /
+ * postExecuteStudy on one rank [MC OpenMCStudy.C:218-402; RT TraceRay.C:999-1592;
+ * MC CollisionKernel.C:98-275].  Split in two so a multi-rank caller can exchange between them:
+ *   mcw_transport_generation : initialize_batch/generation, histories, local fission bank sorted by
+ *                              (parent_id, progeny_id) [OMC bank.cpp:60-104]
+ *   mcw_finalize_generation  : synchronize_bank sampling on this rank's slice of the global bank,
+ *                              k estimators, tally accumulation [OMC eigenvalue.cpp:49-351,
+ *                              simulation.cpp:334-449, tallies/tally.cpp:639-670,805-846]
+ * mcw_run_generation = both, for a single rank. */
+int mcw_transport_generation(mcw_handle h, int batch);
+int mcw_finalize_generation(mcw_handle h, int batch, mcw_generation_result* out);
+int mcw_run_generation(mcw_handle h, int batch, mcw_generation_result* out);
+
+/* Multi-rank plumbing: raw device views so the caller can run NCCL collectives in place
+ * (reference call sites: MC OpenMCStudy.C:467,477,548,559; OMC eigenvalue.cpp:60,233,279;
+ * tallies/tally.cpp:761-798).  Pointers stay valid until the next mcw_set_* / destroy call. */
+int mcw_bank_count(mcw_handle h, int64_t* n_local);               /* local fission sites */
+int mcw_bank_device_ptr(mcw_handle h, void** sites, int64_t* n);  /* sorted local fission bank */
+int mcw_set_bank_window(mcw_handle h, int64_t global_start, int64_t global_total); /* Exscan/Bcast result */
+int mcw_sampled_device_ptr(mcw_handle h, void** sites, int64_t* n); /* sites this rank sampled */
+int mcw_source_device_ptr(mcw_handle h, void** sites, int64_t capacity); /* where received sites go */
+int mcw_set_source_count(mcw_handle h, int64_t n);
+int mcw_reduction_device_ptr(mcw_handle h, void** doubles, int64_t* n); /* [tally VALUEs | k_col,k_abs,k_trk,leak | weight] */
+
+/* Tally read-back.  Replaces OpenMCTallyAux::computeValue [MC OpenMCTallyAux.C:70-215]:
+ * results layout = OpenMC results_(filter_bin, score, {VALUE,SUM,SUM_SQ}); filter_bin =
+ * spatial_bin * n_energy_bins + energy_bin (filters sorted universe, cell, energy;
+ * MC OpenMCTally.h:71-88). */
+int mcw_get_tally(mcw_handle h, int id, double* sum, double* sum_sq, int64_t n, int32_t* n_realizations);
+int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy, int32_t* n_scores);
+
+/* Parity / diagnostics output (RT TraceData.h:20-68 cached traces are the reference analogue). */
+int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n);
+int mcw_get_fission_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n);
+
+/* Stand-alone kernels of the path, exposed for unit parity and the XS-lookup bandwidth metric.
+ * mcw_xs_lookup: macroscopic cross sections for n (energy, material) pairs in HOST memory
+ * [OMC material.cpp:763-831 + nuclide.cpp:557-763]; out = n x 4 (total, absorption, fission,
+ * nu-fission).  mcw_xs_lookup_device: same on device pointers, returns device milliseconds. */
+int mcw_xs_lookup(mcw_handle h, int64_t n, const double* E, const int32_t* material, double* out);
+int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d_material,
+                         void* d_out, int sorted, int repeats, float* ms_per_launch);
+/* mcw_trace_rays: walk n rays through the mesh with no physics until a kill boundary (the RT
+ * `lots.i` tests' workload); out_distance[n], out_segments[n], out_hash[n]. */
+int mcw_trace_rays(mcw_handle h, int64_t n, const double* start, const double* dir,
+                   const int32_t* start_elem, double* out_distance, int32_t* out_segments,
+                   uint64_t* out_hash);
+/* mcw_locate_points: starting element by the ClaimRays rule [RT ClaimRays.C:104-139]. */
+int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem);
+
+/* Host-side helpers that need no GPU (work split and bank sampling plan; tested on CPU). */
+int mcw_calculate_work(int64_t n_particles, int nranks, int64_t* work_index /* nranks+1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACAW_B200_H */

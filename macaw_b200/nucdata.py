@@ -1,0 +1,245 @@
+"""Synthetic continuous-energy nuclide library of a named shape (n_nuclides x energy points).
+
+ENDF/B-VII.1 HDF5 files are not available offline, so runs use in-memory tables whose
+*structure* is what OpenMC builds in ``Nuclide::create_derived`` (openmc/src/nuclide.cpp:309-444):
+a per-nuclide strictly increasing energy grid on [1e-5, 2e7] eV clustered around resonances, and the
+derived 5-column table (total, absorption, fission, nu-fission, photon production) plus the partial
+elastic and level-inelastic cross sections the collision physics samples from.  All numbers come from
+``numpy.random.Generator(PCG64(seed))`` so every run, CPU or GPU, reads identical bytes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+E_MIN, E_MAX = 1.0e-5, 2.0e7
+KT_ROOM = 8.617333262e-5 * 293.6  # eV (OpenMC constants.h:90, temperature_default 293.6 K)
+MAX_DELAYED_GROUPS = 8
+
+
+@dataclass
+class Nuclide:
+    name: str
+    awr: float
+    energy: np.ndarray
+    xs: np.ndarray         # (G, 5)
+    elastic: np.ndarray    # (G,)
+    inelastic: np.ndarray  # (G - threshold,) or empty
+    inel_threshold: int = 0
+    inel_threshold_energy: float = 0.0
+    inel_mass_ratio: float = 0.0
+    fissionable: bool = False
+    nu_poly: tuple = (0.0, 0.0)
+    delayed_yield: np.ndarray = field(default_factory=lambda: np.zeros(MAX_DELAYED_GROUPS))
+    delayed_theta: np.ndarray = field(default_factory=lambda: np.zeros(MAX_DELAYED_GROUPS))
+    n_precursor: int = 0
+    watt_a: float = 0.988e6
+    watt_b: float = 2.249e-6
+    q_fission: float = 0.0
+    kT: float = KT_ROOM
+
+
+@dataclass
+class Material:
+    name: str
+    nuclides: list   # indices into the library
+    densities: list  # atom / b-cm
+
+
+@dataclass
+class Library:
+    nuclides: list
+    materials: list
+    n_log_bins: int = 8000
+
+    def total_points(self):
+        return int(sum(n.energy.size for n in self.nuclides))
+
+    def bytes(self):
+        return int(sum(n.energy.nbytes + n.xs.nbytes + n.elastic.nbytes + n.inelastic.nbytes for n in self.nuclides))
+
+
+def _grid(rng, G, res_E, res_G):
+    """Strictly increasing grid with `G` points: log-uniform background + clusters at resonances."""
+    n_res_pts = min(G // 2, 12 * len(res_E))
+    pts = [np.exp(rng.uniform(np.log(E_MIN), np.log(E_MAX), max(G - 2 - n_res_pts, 0)))]
+    if len(res_E) and n_res_pts:
+        k = rng.integers(0, len(res_E), n_res_pts)
+        pts.append(res_E[k] + res_G[k] * rng.standard_cauchy(n_res_pts) * 0.5)
+    e = np.concatenate(pts)
+    e = e[(e > E_MIN * 1.0001) & (e < E_MAX * 0.9999)]
+    e = np.unique(np.concatenate([[E_MIN, E_MAX], e]))
+    while e.size < G:  # top up (collisions / clipped points)
+        extra = np.exp(rng.uniform(np.log(E_MIN), np.log(E_MAX), G - e.size))
+        e = np.unique(np.concatenate([e, extra]))
+    if e.size > G:
+        keep = np.sort(rng.choice(np.arange(1, e.size - 1), G - 2, replace=False))
+        e = np.concatenate([[E_MIN], e[keep], [E_MAX]])
+    assert e.size == G and np.all(np.diff(e) > 0)
+    return e
+
+
+def make_nuclide(name, awr, G, rng, sig_el=5.0, cap0=0.1, fis0=0.0, fast_fis=0.0, n_res=0,
+                 res_scale=100.0, inel=0.0, inel_E=1.0e6, nu0=2.43, nu1=1.3e-7, q=193.0e6) -> Nuclide:
+    res_E = np.exp(rng.uniform(np.log(0.5), np.log(2.0e4), n_res)) if n_res else np.zeros(0)
+    res_G = res_E * rng.uniform(0.002, 0.03, n_res) if n_res else np.zeros(0)
+    res_H = res_scale * rng.uniform(0.2, 3.0, n_res) / np.sqrt(np.maximum(res_E, 1e-3)) if n_res else np.zeros(0)
+    e = _grid(rng, G, res_E, res_G)
+    inv_v = np.sqrt(0.0253 / e)
+    lor = np.zeros_like(e)
+    for E0, Gm, H in zip(res_E, res_G, res_H):
+        lor += H / (1.0 + ((e - E0) / (0.5 * Gm)) ** 2)
+    fast = 1.0 / (1.0 + (e / 3.0e6) ** 2)
+    elastic = sig_el * (0.25 + 0.75 * fast) + 0.3 * lor
+    capture = cap0 * inv_v + (0.6 if fis0 > 0 else 1.0) * lor * (cap0 > 0)
+    fission = np.zeros_like(e)
+    fissionable = fis0 > 0 or fast_fis > 0
+    if fissionable:
+        fission = fis0 * inv_v + 0.8 * lor * (fis0 > 0) + fast_fis / (1.0 + np.exp(-(e - 1.2e6) / 1.5e5))
+    thr = 0
+    inelastic = np.zeros(0)
+    mass_ratio = (awr / (awr + 1.0)) ** 2
+    thr_E = 0.0
+    if inel > 0:
+        thr = int(np.searchsorted(e, inel_E))
+        thr = min(max(thr, 1), G - 2)
+        thr_E = e[thr] * 0.999  # LevelInelastic threshold_: just below the first tabulated point
+        inelastic = inel * (1.0 - np.exp(-(e[thr:] - e[thr]) / (2.0 * inel_E)))
+    inel_full = np.zeros_like(e)
+    if inel > 0:
+        inel_full[thr:] = inelastic
+    # create_derived: total += xs per reaction in MT order (2, 18, 51, 102); absorption = fission + capture
+    total = elastic + fission + inel_full + capture
+    absorption = fission + capture
+    nu = nu1 * e + nu0
+    xs = np.zeros((G, 5))
+    xs[:, 0] = total
+    xs[:, 1] = absorption
+    xs[:, 2] = fission
+    xs[:, 3] = nu * fission if fissionable else 0.0
+    dy = np.zeros(MAX_DELAYED_GROUPS)
+    dth = np.zeros(MAX_DELAYED_GROUPS)
+    npre = 0
+    if fissionable:
+        npre = 6
+        dy[:6] = 0.0065 * nu0 * np.array([0.033, 0.219, 0.196, 0.395, 0.115, 0.042])
+        dth[:6] = np.array([0.25e6, 0.46e6, 0.41e6, 0.45e6, 0.41e6, 0.35e6])
+    return Nuclide(name, float(awr), e, xs, elastic, inelastic, thr, float(thr_E), float(mass_ratio),
+                   bool(fissionable), (float(nu0), float(nu1)), dy, dth, npre, 0.988e6, 2.249e-6,
+                   float(q if fissionable else 0.0))
+
+
+_BASE = [
+    # name, awr, kwargs
+    ("H1", 0.9992, dict(sig_el=20.4, cap0=0.332)),
+    ("O16", 15.858, dict(sig_el=3.9, cap0=1.9e-4, inel=0.4, inel_E=6.0e6)),
+    ("U235", 233.025, dict(sig_el=14.0, cap0=98.7, fis0=585.0, fast_fis=1.2, n_res=40, inel=1.5, inel_E=4.0e4)),
+    ("U238", 236.006, dict(sig_el=9.3, cap0=2.68, fast_fis=0.55, n_res=60, res_scale=600.0, inel=2.5, inel_E=5.0e4,
+                           nu0=2.49, nu1=1.4e-7)),
+    ("Pu239", 236.999, dict(sig_el=8.0, cap0=270.0, fis0=748.0, fast_fis=1.8, n_res=40, inel=1.2, inel_E=3.0e4,
+                            nu0=2.88, nu1=1.4e-7, q=198.0e6)),
+    ("Zr90", 89.132, dict(sig_el=6.2, cap0=0.011, n_res=10, res_scale=8.0, inel=1.0, inel_E=1.8e6)),
+    ("He4", 3.968, dict(sig_el=0.76, cap0=0.0)),
+    ("B10", 9.927, dict(sig_el=2.1, cap0=3840.0)),
+    ("B11", 10.915, dict(sig_el=4.8, cap0=0.0055)),
+]
+
+
+def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000) -> Library:
+    """First 9 nuclides are the named ones above; the rest are generic structural / fission-product
+    like nuclides so the BEAVRS shape (91 nuclides) can be reproduced."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nucs = []
+    for i in range(n_nuclides):
+        if i < len(_BASE):
+            name, awr, kw = _BASE[i]
+        else:
+            awr = float(rng.uniform(20, 240))
+            name = f"X{i}"
+            kw = dict(sig_el=float(rng.uniform(3, 12)), cap0=float(np.exp(rng.uniform(np.log(0.01), np.log(50)))),
+                      n_res=int(rng.integers(0, 30)), res_scale=float(rng.uniform(5, 200)),
+                      inel=float(rng.uniform(0, 2)), inel_E=float(np.exp(rng.uniform(np.log(5e4), np.log(3e6)))))
+        g = G if np.isscalar(G) else int(G[i])
+        nucs.append(make_nuclide(name, awr, g, rng, **kw))
+    mats = standard_materials(n_nuclides)
+    return Library(nucs, mats, n_log_bins)
+
+
+def standard_materials(n_nuclides) -> list:
+    """Material 0 fuel (UO2 3.1 %), 1 gap (He), 2 clad (Zr + generic alloying nuclides), 3 borated water.
+    Indices follow `_BASE`; nuclides beyond the named ones are spread over clad and fuel like the
+    25-nuclide Zircaloy / fission-product inventories of the BEAVRS materials.xml."""
+    H1, O16, U235, U238, Pu239, Zr90, He4, B10, B11 = range(9)
+    have = lambda i: i < n_nuclides
+    fuel = [(U235, 7.18e-4), (U238, 2.21e-2), (O16, 4.57e-2)]
+    gap = [(He4, 2.4e-5)] if have(He4) else [(O16, 1e-6)]
+    clad = [(Zr90, 4.3e-2)] if have(Zr90) else [(O16, 4.3e-2)]
+    water = [(H1, 6.6e-2), (O16, 3.3e-2)]
+    if have(B10):
+        water.append((B10, 1.0e-5))
+    if have(B11):
+        water.append((B11, 4.0e-5))
+    extra = list(range(9, n_nuclides))
+    for k, i in enumerate(extra):
+        (clad if k % 3 else fuel).append((i, 1.0e-4 / (1 + k % 7)))
+    mk = lambda name, lst: Material(name, [i for i, _ in lst if have(i)], [d for i, d in lst if have(i)])
+    return [mk("fuel", fuel), mk("gap", gap), mk("clad", clad), mk("water", water)]
+
+
+def infinite_medium_library(G=2000, seed=1) -> Library:
+    """C1: one homogeneous material with the six nuclides of examples/infinite_medium/run_openmc_csg.py:32-38."""
+    lib = make_library(6, G, seed)
+    H1, O16, U235, U238, Pu239, Zr90 = range(6)
+    mix = Material("mix", [H1, O16, U235, U238, Pu239, Zr90], [4.0e-2, 3.5e-2, 2.0e-4, 6.0e-3, 1.0e-5, 8.0e-3])
+    he = Material("moderator", [H1, O16], [6.6e-2, 3.3e-2])
+    lib.materials = [mix, he]
+    return lib
+
+
+# ---- ctypes mirror of include/macaw_b200.h ---------------------------------------------------------
+class NuclideDesc(C.Structure):
+    _fields_ = [("n_grid", C.c_int32), ("fissionable", C.c_int32), ("awr", C.c_double), ("kT", C.c_double),
+                ("energy", C.c_void_p), ("xs", C.c_void_p), ("elastic", C.c_void_p),
+                ("n_inelastic", C.c_int32), ("inel_threshold", C.c_int32), ("inelastic", C.c_void_p),
+                ("inel_threshold_energy", C.c_double), ("inel_mass_ratio", C.c_double),
+                ("nu_poly", C.c_double * 2), ("n_precursor", C.c_int32), ("reserved0", C.c_int32),
+                ("delayed_yield", C.c_double * MAX_DELAYED_GROUPS), ("delayed_theta", C.c_double * MAX_DELAYED_GROUPS),
+                ("watt_a", C.c_double), ("watt_b", C.c_double), ("q_fission", C.c_double)]
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [("n_nuclides", C.c_int32), ("reserved0", C.c_int32), ("nuclide", C.c_void_p),
+                ("atom_density", C.c_void_p)]
+
+
+def pack_library(lib: Library):
+    """Build the C descriptor arrays; returns (nuclide_descs, material_descs, keepalive)."""
+    keep = []
+    nd = (NuclideDesc * len(lib.nuclides))()
+    for d, n in zip(nd, lib.nuclides):
+        e = np.ascontiguousarray(n.energy, np.float64)
+        xs = np.ascontiguousarray(n.xs, np.float64)
+        el = np.ascontiguousarray(n.elastic, np.float64)
+        inel = np.ascontiguousarray(n.inelastic if n.inelastic.size else np.zeros(1), np.float64)
+        keep += [e, xs, el, inel]
+        d.n_grid, d.fissionable, d.awr, d.kT = e.size, int(n.fissionable), n.awr, n.kT
+        d.energy, d.xs, d.elastic = e.ctypes.data, xs.ctypes.data, el.ctypes.data
+        d.n_inelastic = int(n.inelastic.size > 0)
+        d.inel_threshold = n.inel_threshold
+        d.inelastic = inel.ctypes.data
+        d.inel_threshold_energy, d.inel_mass_ratio = n.inel_threshold_energy, n.inel_mass_ratio
+        d.nu_poly[0], d.nu_poly[1] = n.nu_poly
+        d.n_precursor = n.n_precursor
+        for g in range(MAX_DELAYED_GROUPS):
+            d.delayed_yield[g] = float(n.delayed_yield[g])
+            d.delayed_theta[g] = float(n.delayed_theta[g])
+        d.watt_a, d.watt_b, d.q_fission = n.watt_a, n.watt_b, n.q_fission
+    md = (MaterialDesc * len(lib.materials))()
+    for d, m in zip(md, lib.materials):
+        idx = np.ascontiguousarray(m.nuclides, np.int32)
+        den = np.ascontiguousarray(m.densities, np.float64)
+        keep += [idx, den]
+        d.n_nuclides, d.nuclide, d.atom_density = idx.size, idx.ctypes.data, den.ctypes.data
+    return nd, md, keep

@@ -1,0 +1,244 @@
+"""ctypes bridge to the CPU oracle (oracle/liboracle*.so).  TEST INFRASTRUCTURE: importable only from
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from macaw_b200 import meshgen, nucdata
+from macaw_b200.cstructs import (RECORD_DTYPE, SITE_DTYPE, GenerationResult, Settings)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(ref=True):
+    subprocess.run(["make", "-s", "-C", _HERE, "all"], check=True)
+    if ref:
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def _load(name):
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build(ref=False)
+    lib = C.CDLL(path)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    lib.orc_prn.restype = C.c_double
+    lib.orc_prn.argtypes = [u64p]
+    lib.orc_future_seed.restype = C.c_uint64
+    lib.orc_future_seed.argtypes = [C.c_uint64, C.c_uint64]
+    lib.orc_init_seed.restype = C.c_uint64
+    lib.orc_init_seed.argtypes = [C.c_int64, C.c_int, C.c_int64]
+    lib.orc_seed_via_double.restype = C.c_uint64
+    lib.orc_seed_via_double.argtypes = [C.c_uint64]
+    lib.orc_maxwell_spectrum.restype = C.c_double
+    lib.orc_maxwell_spectrum.argtypes = [C.c_double, u64p]
+    lib.orc_watt_spectrum.restype = C.c_double
+    lib.orc_watt_spectrum.argtypes = [C.c_double, C.c_double, u64p]
+    lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
+    lib.orc_isotropic_direction.argtypes = [f64p, u64p]
+    for f in ("orc_log", "orc_sin", "orc_cos"):
+        getattr(lib, f).restype = C.c_double
+        getattr(lib, f).argtypes = [C.c_double]
+    lib.orc_is_within_segment.argtypes = [f64p, f64p, f64p, C.c_double]
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_create.argtypes = [C.c_int, C.c_int]
+    lib.orc_destroy.argtypes = [C.c_void_p]
+    vp = C.c_void_p
+    lib.orc_set_mesh.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int64, vp, vp, C.c_int, vp, vp, C.c_int, vp]
+    lib.orc_set_library.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.orc_set_materials.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    lib.orc_set_settings.argtypes = [vp, C.POINTER(Settings)]
+    lib.orc_add_tally.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.orc_get_grid.argtypes = [vp, f64p, f64p, f64p]
+    lib.orc_get_grid_index.argtypes = [vp, C.c_int, vp]
+    lib.orc_xs_lookup.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.orc_trace_rays.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.orc_locate_points.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.orc_sample_initial_source.argtypes = [vp]
+    lib.orc_set_source_bank.argtypes = [vp, vp, C.c_int64]
+    for f in ("orc_get_source_bank", "orc_get_fission_bank", "orc_get_sampled", "orc_get_history_records"):
+        getattr(lib, f).restype = C.c_int64
+        getattr(lib, f).argtypes = [vp, vp, C.c_int64]
+    lib.orc_transport_generation.argtypes = [vp, C.c_int, C.c_int]
+    lib.orc_set_bank_window.argtypes = [vp, C.c_int64, C.c_int64]
+    lib.orc_sample_bank.restype = C.c_int64
+    lib.orc_sample_bank.argtypes = [vp, C.c_int]
+    lib.orc_finish_sampling.restype = C.c_int64
+    lib.orc_finish_sampling.argtypes = [vp, C.c_int64, C.c_int]
+    lib.orc_finalize_generation.argtypes = [vp, C.c_int, vp, C.POINTER(GenerationResult)]
+    lib.orc_run_generation.argtypes = [vp, C.c_int, C.c_int, C.POINTER(GenerationResult)]
+    lib.orc_get_tally.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int64]
+    lib.orc_tally_size.restype = C.c_int64
+    lib.orc_tally_size.argtypes = [vp, C.c_int]
+    lib.orc_set_keff.argtypes = [vp, C.c_double]
+    lib.orc_get_keff.restype = C.c_double
+    lib.orc_get_keff.argtypes = [vp]
+    lib.orc_calculate_work.argtypes = [C.c_int64, C.c_int, vp]
+    return lib
+
+
+_libs = {}
+
+
+def lib(libm=False):
+    key = "liboracle_libm.so" if libm else "liboracle.so"
+    if key not in _libs:
+        _libs[key] = _load(key)
+    return _libs[key]
+
+
+def ref_lib():
+    """The reference's own RNG / sampler sources compiled by oracle/Makefile (None if never built)."""
+    path = os.path.join(_HERE, "_ref", "libomc_ref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference/openmc/src"):
+            build(ref=True)
+        else:
+            return None
+    r = C.CDLL(path)
+    u64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    r.ref_prn.restype = C.c_double
+    r.ref_prn.argtypes = [u64p]
+    r.ref_future_prn.restype = C.c_double
+    r.ref_future_prn.argtypes = [C.c_int64, C.c_uint64]
+    r.ref_future_seed.restype = C.c_uint64
+    r.ref_future_seed.argtypes = [C.c_uint64, C.c_uint64]
+    r.ref_init_seed.restype = C.c_uint64
+    r.ref_init_seed.argtypes = [C.c_int64, C.c_int]
+    r.ref_init_particle_seeds.argtypes = [C.c_int64, u64p]
+    r.ref_set_master_seed.argtypes = [C.c_int64]
+    r.ref_maxwell_spectrum.restype = C.c_double
+    r.ref_maxwell_spectrum.argtypes = [C.c_double, u64p]
+    r.ref_watt_spectrum.restype = C.c_double
+    r.ref_watt_spectrum.argtypes = [C.c_double, C.c_double, u64p]
+    r.ref_uniform.restype = C.c_double
+    r.ref_uniform.argtypes = [C.c_double, C.c_double, u64p]
+    r.ref_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
+    return r
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Oracle:
+    """One oracle problem instance (mirrors the product's macaw_b200.Context call for call)."""
+
+    def __init__(self, libm=False, rank=0, nranks=1):
+        self.L = lib(libm)
+        self.h = self.L.orc_create(rank, nranks)
+        self._keep = []
+        self.mesh = None
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_mesh(self, m: meshgen.Mesh, block_ids=None):
+        self.mesh = m
+        ids = m.block_ids_sorted() if block_ids is None else np.asarray(block_ids, np.int32)
+        self.block_ids = ids
+        bi = np.ascontiguousarray(m.block_index(ids), np.int32)
+        xyz = np.ascontiguousarray(m.xyz, np.float64)
+        conn = np.ascontiguousarray(m.conn, np.int64)
+        nbr = np.ascontiguousarray(m.neighbors, np.int64)
+        sb = np.ascontiguousarray(m.side_bnd_id, np.int32)
+        bk = np.ascontiguousarray(m.bnd_kind, np.int32)
+        self.L.orc_set_mesh(self.h, m.elem_type, xyz.shape[0], _p(xyz), conn.shape[0], _p(conn), _p(bi), len(ids),
+                            _p(nbr), _p(sb), bk.size, _p(bk))
+
+    def set_library(self, libr: nucdata.Library, block_material):
+        nd, md, keep = nucdata.pack_library(libr)
+        self._keep.append((nd, md, keep))
+        self.L.orc_set_library(self.h, C.addressof(nd), len(libr.nuclides), libr.n_log_bins)
+        bm = np.ascontiguousarray(block_material, np.int32)
+        self.L.orc_set_materials(self.h, C.addressof(md), len(libr.materials), _p(bm), bm.size)
+
+    def set_settings(self, s: Settings):
+        self.settings = s
+        self.L.orc_set_settings(self.h, C.byref(s))
+
+    def add_tally(self, tid, estimator, granularity, scores, energy_bins=None):
+        sc = np.ascontiguousarray(scores, np.int32)
+        eb = np.ascontiguousarray(energy_bins if energy_bins is not None else [], np.float64)
+        self.L.orc_add_tally(self.h, tid, estimator, granularity, _p(sc), sc.size, _p(eb), eb.size)
+
+    def grid(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.L.orc_get_grid(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def grid_index(self, i_nuc, n_log_bins):
+        out = np.zeros(n_log_bins + 1, np.int32)
+        self.L.orc_get_grid_index(self.h, i_nuc, _p(out))
+        return out
+
+    def xs_lookup(self, E, mat):
+        E = np.ascontiguousarray(E, np.float64)
+        mat = np.ascontiguousarray(mat, np.int32)
+        out = np.zeros((E.size, 4))
+        self.L.orc_xs_lookup(self.h, E.size, _p(E), _p(mat), _p(out))
+        return out
+
+    def trace_rays(self, start, dirs, start_elem=None, start_side=None):
+        start = np.ascontiguousarray(start, np.float64)
+        dirs = np.ascontiguousarray(dirs, np.float64)
+        n = start.shape[0]
+        se = np.ascontiguousarray(start_elem if start_elem is not None else np.full(n, -1), np.int32)
+        ss = np.ascontiguousarray(start_side, np.int32) if start_side is not None else None
+        dist, seg, h, st = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(6, np.int64)
+        self.L.orc_trace_rays(self.h, n, _p(start), _p(dirs), _p(se), _p(ss), _p(dist), _p(seg), _p(h), _p(st))
+        return dist, seg, h, dict(zip(["segments", "vertex_edge_hits", "moved_through_neighbors", "failed",
+                                       "intersection_calls", "reflections"], st.tolist()))
+
+    def locate_points(self, xyz, ray_id=None):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        rid = np.ascontiguousarray(ray_id, np.int64) if ray_id is not None else None
+        out = np.zeros(xyz.shape[0], np.int32)
+        self.L.orc_locate_points(self.h, xyz.shape[0], _p(xyz), _p(rid), _p(out))
+        return out
+
+    def sample_initial_source(self):
+        self.L.orc_sample_initial_source(self.h)
+
+    def set_source_bank(self, sites):
+        sites = np.ascontiguousarray(sites, SITE_DTYPE)
+        self.L.orc_set_source_bank(self.h, _p(sites), sites.size)
+
+    def _get(self, fn, dtype):
+        n = fn(self.h, None, 0)
+        out = np.zeros(n, dtype)
+        fn(self.h, _p(out), n)
+        return out
+
+    def source_bank(self):
+        return self._get(self.L.orc_get_source_bank, SITE_DTYPE)
+
+    def fission_bank(self):
+        return self._get(self.L.orc_get_fission_bank, SITE_DTYPE)
+
+    def sampled(self):
+        return self._get(self.L.orc_get_sampled, SITE_DTYPE)
+
+    def history_records(self):
+        return self._get(self.L.orc_get_history_records, RECORD_DTYPE)
+
+    def run_generation(self, batch, n_threads=1):
+        res = GenerationResult()
+        rc = self.L.orc_run_generation(self.h, batch, n_threads, C.byref(res))
+        if rc:
+            raise RuntimeError(f"oracle run_generation failed rc={rc}")
+        return res
+
+    def transport_generation(self, batch, n_threads=1):
+        self.L.orc_transport_generation(self.h, batch, n_threads)
+
+    def get_tally(self, tid):
+        n = self.L.orc_tally_size(self.h, tid)
+        v, s, q = np.zeros(n), np.zeros(n), np.zeros(n)
+        nr = self.L.orc_get_tally(self.h, tid, _p(v), _p(s), _p(q), n)
+        return v, s, q, nr

@@ -1,0 +1,351 @@
+// orc_core.h -- CPU ORACLE (test infrastructure, NOT product code).
+//
+// A plain scalar C++ restatement of the reference algorithms on MaCaw's particle-history hot path
+// (SURVEY.md 8a).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may build, link or call anything under oracle/.  libmacaw_b200.so never does.
+//
+// Structure follows the reference on purpose: history-based, array-of-structs doubles, one scratch
+// particle per history, per-nuclide micro cross-section cache, std::lower_bound searches.
+// Every function cites the reference lines it restates (MC = MaCaw src/, RT =
+// moose/modules/ray_tracing, OMC = openmc/).
+//
+// Parity pinning (see tests/test_oracle_*.py and DESIGN.md):
+//   - RNG + samplers (prn, future_seed, init_seed, maxwell/watt spectrum, rotate_angle) are checked
+//     bit-exactly against the reference's own sources compiled into oracle/_ref/libomc_ref.so and
+//     against OpenMC's unit-test known answers (OMC tests/unit_tests/test_math.py:156-205);
+//   - seed bookkeeping (seed-through-double rounding, RN count per event, URR stream advance) is
+//     checked against the reference gold file test/tests/study/gold/openmc_study_rays.e through
+//     tests/golden/study_rays_*.npz;
+//   - the element walk is checked against RT's HEX8/QUAD4 `lots.i` total-distance gold CSVs;
+//   - cross-section VALUES and collision kinematics have no reference vectors offline (needs
+//     ENDF/B HDF5 + libMesh): "parity unpinned" for those, stated in DESIGN.md.
+//
+// Math library: by default log/sin/cos come from macaw_b200/csrc/mcw_detmath.h (the deterministic
+// libm replacement both sides use, so CPU and GPU histories are bit-identical); build with
+// -DMCW_ORACLE_LIBM to use glibc like the reference does.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/macaw_b200.h"
+#include "../macaw_b200/csrc/mcw_detmath.h"
+
+namespace orc
+{
+#ifdef MCW_ORACLE_LIBM
+inline double xlog(double x) { return std::log(x); }
+inline double xsin(double x) { return std::sin(x); }
+inline double xcos(double x) { return std::cos(x); }
+#else
+inline double xlog(double x) { return mcw_log(x); }
+inline double xsin(double x) { return mcw_sin(x); }
+inline double xcos(double x) { return mcw_cos(x); }
+#endif
+
+constexpr double PI = 3.1415926535897932384626433832795028841971693993751058209749445923078164062;
+constexpr double K_BOLTZMANN = 8.617333262e-5; // OMC constants.h:90
+constexpr double FREE_GAS_THRESHOLD = 400.0;    // OMC constants.h:42
+constexpr double TRACE_TOLERANCE = 1e-8;        // RT TraceRayTools.h:45
+constexpr double LOOSE_TRACE_TOLERANCE = 1e-5;  // RT TraceRayTools.h:47
+
+// ------------------------------------------------------------------ RNG (OMC random_lcg.cpp:12-114)
+constexpr uint64_t PRN_MULT = 6364136223846793005ULL;
+constexpr uint64_t PRN_ADD = 1442695040888963407ULL;
+constexpr uint64_t PRN_STRIDE = 152917ULL;
+enum
+{
+  STREAM_TRACKING = 0,
+  STREAM_SOURCE = 1,
+  STREAM_URR = 2
+};
+
+inline double prn(uint64_t* seed)
+{
+  *seed = PRN_MULT * (*seed) + PRN_ADD;
+  uint64_t word = ((*seed >> ((*seed >> 59u) + 5u)) ^ *seed) * 12605985483714917081ull;
+  uint64_t result = (word >> 43u) ^ word;
+  return (double)result * 5.42101086242752217003726400434970855712890625e-20; // ldexp(result,-64)
+}
+
+inline uint64_t future_seed(uint64_t n, uint64_t seed)
+{
+  uint64_t g = PRN_MULT, c = PRN_ADD, g_new = 1, c_new = 0;
+  while (n > 0)
+  {
+    if (n & 1)
+    {
+      g_new *= g;
+      c_new = c_new * g + c;
+    }
+    c *= (g + 1);
+    g *= g;
+    n >>= 1;
+  }
+  return g_new * seed + c_new;
+}
+
+inline uint64_t init_seed(int64_t id, int offset, int64_t master_seed)
+{
+  return future_seed((uint64_t)id * PRN_STRIDE, (uint64_t)(master_seed + offset));
+}
+
+// MaCaw keeps seeds in double-typed ray aux data (MC CollisionKernel.C:132-134,157-159,217-219,
+// OpenMCStudy.C:345-347): uint64 -> double (round to nearest even) -> uint64.
+inline uint64_t seed_via_double(uint64_t s)
+{
+  double d = (double)s;
+  if (d >= 18446744073709551616.0)
+    return 0; // x86 cvttsd2si wrap for 2^64; probability 2^-54 per conversion
+  return (uint64_t)d;
+}
+
+// ------------------------------------------------------------------ samplers
+inline double uniform_distribution(double a, double b, uint64_t* s) { return a + (b - a) * prn(s); }
+
+// OMC random_dist.cpp:15-27
+inline double maxwell_spectrum(double T, uint64_t* s)
+{
+  double r1 = prn(s), r2 = prn(s), r3 = prn(s);
+  double c = xcos(PI / 2. * r3);
+  return -T * (xlog(r1) + xlog(r2) * c * c);
+}
+
+// OMC random_dist.cpp:29-34
+inline double watt_spectrum(double a, double b, uint64_t* s)
+{
+  double w = maxwell_spectrum(a, s);
+  return w + 0.25 * a * a * b + uniform_distribution(-1., 1., s) * std::sqrt(a * a * b * w);
+}
+
+struct V3
+{
+  double x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline double norm(V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3 cross(V3 a, V3 b)
+{
+  return {a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x};
+}
+inline V3 unit(V3 a)
+{
+  double l = norm(a);
+  return {a.x / l, a.y / l, a.z / l};
+}
+
+// OMC math_functions.cpp:644-672 (phi sampled: 1 RN)
+inline V3 rotate_angle(V3 u, double mu, const double* phi, uint64_t* s)
+{
+  double phi_ = phi ? *phi : 2.0 * PI * prn(s);
+  double sinphi = xsin(phi_), cosphi = xcos(phi_);
+  double a = std::sqrt(std::fmax(0., 1. - mu * mu));
+  double b = std::sqrt(std::fmax(0., 1. - u.z * u.z));
+  if (b > 1e-10)
+  {
+    return {mu * u.x + a * (u.x * u.z * cosphi - u.y * sinphi) / b,
+            mu * u.y + a * (u.y * u.z * cosphi + u.x * sinphi) / b, mu * u.z - a * b * cosphi};
+  }
+  else
+  {
+    b = std::sqrt(1. - u.y * u.y);
+    return {mu * u.x + a * (-u.x * u.y * sinphi + u.z * cosphi) / b, mu * u.y + a * b * sinphi,
+            mu * u.z - a * (u.y * u.z * sinphi + u.x * cosphi) / b};
+  }
+}
+
+// OMC distribution_multi.cpp:73-79
+inline V3 isotropic_direction(uint64_t* s)
+{
+  double phi = uniform_distribution(0., 2.0 * PI, s);
+  double mu = uniform_distribution(-1., 1., s);
+  return {mu, std::sqrt(1.0 - mu * mu) * xcos(phi), std::sqrt(1.0 - mu * mu) * xsin(phi)};
+}
+
+// ------------------------------------------------------------------ nuclear data
+struct Nuclide
+{
+  int G = 0;
+  bool fissionable = false;
+  double awr = 1, kT = 0;
+  std::vector<double> energy, xs, elastic, inelastic;
+  int n_inel = 0, inel_thr = 0;
+  double inel_E = 0, inel_ratio = 0;
+  double nu_poly[2] = {0, 0};
+  int n_precursor = 0;
+  double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
+  double watt_a = 0, watt_b = 0, q = 0;
+  std::vector<int> grid_index;
+
+  // OMC endf.cpp:112-121 Polynomial (Horner, increasing powers) on nu_poly; nuclide.cpp:478-517
+  double nu_total(double E) const
+  {
+    double y = 0.0;
+    y = y * E + nu_poly[1];
+    y = y * E + nu_poly[0];
+    return y;
+  }
+  double nu_delayed(double) const
+  {
+    double nu = 0.0;
+    for (int g = 0; g < n_precursor; ++g)
+      nu += dyield[g];
+    return nu;
+  }
+};
+
+struct Material
+{
+  std::vector<int> nuc;
+  std::vector<double> dens;
+  bool fissionable = false;
+};
+
+struct Micro // subset of OMC particle_data.h:82-112 NuclideMicroXS
+{
+  double total, absorption, fission, nu_fission;
+  int i_grid;
+  double f;
+};
+
+struct Macro // OMC particle_data.h:134-146
+{
+  double total = 0, absorption = 0, fission = 0, nu_fission = 0;
+};
+
+struct Library
+{
+  std::vector<Nuclide> nuclides;
+  std::vector<Material> materials;
+  double E_min = 0, E_max = 0, log_spacing = 0;
+  int n_log_bins = 8000;
+
+  // OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
+  void finalize()
+  {
+    E_min = 0.0;
+    E_max = INFINITY;
+    for (auto& n : nuclides)
+    {
+      E_min = std::max(E_min, n.energy.front());
+      E_max = std::min(E_max, n.energy.back());
+    }
+    const int M = n_log_bins;
+    double spacing = xlog(E_max / E_min) / M;
+    for (auto& n : nuclides)
+    {
+      n.grid_index.assign(M + 1, 0);
+      int j = 0;
+      double step = (M * spacing - 0.0) / M; // xt::linspace(0, M*spacing, M+1)
+      for (int k = 0; k <= M; ++k)
+      {
+        double umesh = 0.0 + k * step;
+        while (xlog(n.energy[j + 1] / E_min) <= umesh)
+        {
+          if (j + 2 == n.G)
+            break;
+          ++j;
+        }
+        n.grid_index[k] = j;
+      }
+    }
+    log_spacing = xlog(E_max / E_min) / M;
+    for (auto& m : materials)
+    {
+      m.fissionable = false;
+      for (int i : m.nuc)
+        if (nuclides[i].fissionable)
+          m.fissionable = true;
+    }
+  }
+
+  // OMC search.h:14-20
+  static int lower_bound_index(const double* first, const double* last, double value)
+  {
+    if (*first == value)
+      return 0;
+    const double* it = std::lower_bound(first, last, value) - 1;
+    return (int)(it - first);
+  }
+
+  // OMC nuclide.cpp:557-763 (NEAREST temperature, single data set, no WMP / S(a,b) / URR)
+  Micro micro_xs(int i_nuc, double E, int i_log) const
+  {
+    const Nuclide& n = nuclides[i_nuc];
+    Micro m;
+    int i_grid;
+    if (E < n.energy.front())
+      i_grid = 0;
+    else if (E > n.energy.back())
+      i_grid = n.G - 2;
+    else
+    {
+      int i_low = n.grid_index[i_log];
+      int i_high = n.grid_index[i_log + 1] + 1;
+      i_grid = i_low + lower_bound_index(&n.energy[i_low], &n.energy[i_high], E);
+    }
+    if (n.energy[i_grid] == n.energy[i_grid + 1])
+      ++i_grid;
+    double f = (E - n.energy[i_grid]) / (n.energy[i_grid + 1] - n.energy[i_grid]);
+    m.i_grid = i_grid;
+    m.f = f;
+    const double* r0 = &n.xs[5 * (size_t)i_grid];
+    const double* r1 = r0 + 5;
+    m.total = (1.0 - f) * r0[0] + f * r1[0];
+    m.absorption = (1.0 - f) * r0[1] + f * r1[1];
+    if (n.fissionable)
+    {
+      m.fission = (1.0 - f) * r0[2] + f * r1[2];
+      m.nu_fission = (1.0 - f) * r0[3] + f * r1[3];
+    }
+    else
+    {
+      m.fission = 0.0;
+      m.nu_fission = 0.0;
+    }
+    return m;
+  }
+
+  int log_bin(double E) const
+  {
+    int i = (int)(xlog(E / E_min) / log_spacing); // OMC material.cpp:767-768
+    if (i < 0)
+      i = 0; // undefined in the reference (out-of-range read); clamp
+    if (i > n_log_bins - 1)
+      i = n_log_bins - 1;
+    return i;
+  }
+
+  // OMC material.cpp:748-831
+  Macro macro_xs(int i_mat, double E, Micro* cache /* [materials[i_mat].nuc.size()] or null */,
+                 int64_t* n_nuclide_lookups = nullptr) const
+  {
+    const Material& mat = materials[i_mat];
+    Macro M;
+    int i_log = log_bin(E);
+    for (size_t i = 0; i < mat.nuc.size(); ++i)
+    {
+      Micro m = micro_xs(mat.nuc[i], E, i_log);
+      if (cache)
+        cache[i] = m;
+      double d = mat.dens[i];
+      M.total += d * m.total;
+      M.absorption += d * m.absorption;
+      M.fission += d * m.fission;
+      M.nu_fission += d * m.nu_fission;
+    }
+    if (n_nuclide_lookups)
+      *n_nuclide_lookups += (int64_t)mat.nuc.size();
+    return M;
+  }
+};
+
+} // namespace orc

@@ -1,0 +1,1166 @@
+// orc_transport.cpp -- CPU ORACLE (test infrastructure, NOT product code): history-based transport,
+// eigenvalue bookkeeping and the ctypes-facing C entry points.  See orc_core.h for the rules on who
+// may use this and how it is pinned to the reference.
+#include <cstdio>
+#include <memory>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "orc_mesh.h"
+
+namespace orc
+{
+struct Tally
+{
+  int id, estimator, granularity;
+  std::vector<int> scores;
+  std::vector<double> ebins; // edges; empty = one bin
+  int64_t n_spatial = 1;
+  int n_energy = 1;
+  std::vector<double> value, sum, sum_sq;
+  int n_realizations = 0;
+  int64_t bins() const { return n_spatial * n_energy; }
+};
+
+struct Problem
+{
+  Mesh mesh;
+  Library lib;
+  mcw_settings set{};
+  std::vector<int32_t> block_material; // block index -> material index
+  int n_blocks = 0;
+  std::vector<double> temperature;
+  std::vector<Tally> tallies;
+  int rank = 0, nranks = 1;
+  std::vector<int64_t> work_index;
+
+  std::vector<mcw_source_site> source_bank, fission_bank, sampled;
+  std::vector<mcw_history_record> records;
+  int64_t bank_global_start = 0, bank_global_total = -1;
+
+  // eigenvalue state (OMC simulation.cpp:253-276)
+  double keff = 1.0, keff_std = 0.0;
+  std::vector<double> k_generation;
+  double k_sum[2] = {0, 0};
+  int n_realizations = 0;
+  double gt_value[4] = {0, 0, 0, 0}; // K_COLLISION, K_ABSORPTION, K_TRACKLENGTH, LEAKAGE
+  double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
+  double total_weight = 0;
+  TraceStats stats;
+  int64_t n_collisions = 0, n_xs = 0, n_nuc_lookups = 0;
+
+  // point location grid
+  int gx = 1, gy = 1, gz = 1;
+  std::vector<int64_t> cell_off, cell_elems;
+  std::string err;
+
+  void buildLocator()
+  {
+    const ElemTopo& t = mesh.T();
+    double n = std::max<double>(1.0, (double)mesh.n_elem);
+    V3 ext = mesh.bb_max - mesh.bb_min;
+    if (mesh.dim == 2)
+    {
+      int g = std::max(1, (int)std::sqrt(n));
+      gx = gy = g;
+      gz = 1;
+    }
+    else
+    {
+      int g = std::max(1, (int)std::cbrt(n));
+      gx = gy = gz = g;
+    }
+    auto cellRange = [&](double lo, double hi, double mn, double extent, int g, int& a, int& b) {
+      if (extent <= 0)
+      {
+        a = b = 0;
+        return;
+      }
+      a = (int)std::floor((lo - mn) / extent * g - 1e-9);
+      b = (int)std::floor((hi - mn) / extent * g + 1e-9);
+      a = std::min(std::max(a, 0), g - 1);
+      b = std::min(std::max(b, 0), g - 1);
+    };
+    std::vector<int64_t> cnt((size_t)gx * gy * gz + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+    {
+      for (int64_t e = 0; e < mesh.n_elem; ++e)
+      {
+        V3 lo = mesh.P(e, 0), hi = lo;
+        for (int v = 1; v < t.nv; ++v)
+        {
+          V3 p = mesh.P(e, v);
+          lo = {std::min(lo.x, p.x), std::min(lo.y, p.y), std::min(lo.z, p.z)};
+          hi = {std::max(hi.x, p.x), std::max(hi.y, p.y), std::max(hi.z, p.z)};
+        }
+        int ax, bx, ay, by, az, bz;
+        cellRange(lo.x, hi.x, mesh.bb_min.x, ext.x, gx, ax, bx);
+        cellRange(lo.y, hi.y, mesh.bb_min.y, ext.y, gy, ay, by);
+        cellRange(lo.z, hi.z, mesh.bb_min.z, ext.z, gz, az, bz);
+        for (int k = az; k <= bz; ++k)
+          for (int j = ay; j <= by; ++j)
+            for (int i = ax; i <= bx; ++i)
+            {
+              size_t c = ((size_t)k * gy + j) * gx + i;
+              if (pass == 0)
+                cnt[c + 1]++;
+              else
+                cell_elems[cnt[c]++] = e;
+            }
+      }
+      if (pass == 0)
+      {
+        for (size_t c = 0; c + 1 < cnt.size(); ++c)
+          cnt[c + 1] += cnt[c];
+        cell_off = cnt;
+        cell_elems.assign(cnt.back(), 0);
+        cnt.assign(cell_off.begin(), cell_off.end());
+      }
+    }
+  }
+
+  // Point locator + ClaimRays tie-break (RT ClaimRays.C:104-139): smallest containing element id
+  // for even ray ids, largest for odd.
+  int64_t locate(V3 p, int64_t ray_id) const
+  {
+    V3 ext = mesh.bb_max - mesh.bb_min;
+    auto cell = [&](double x, double mn, double extent, int g) {
+      if (extent <= 0)
+        return 0;
+      int c = (int)std::floor((x - mn) / extent * g);
+      return std::min(std::max(c, 0), g - 1);
+    };
+    int i = cell(p.x, mesh.bb_min.x, ext.x, gx), j = cell(p.y, mesh.bb_min.y, ext.y, gy),
+        k = mesh.dim == 3 ? cell(p.z, mesh.bb_min.z, ext.z, gz) : 0;
+    size_t c = ((size_t)k * gy + j) * gx + i;
+    const bool smallest = (ray_id % 2) == 0;
+    int64_t best = -1;
+    for (int64_t q = cell_off[c]; q < cell_off[c + 1]; ++q)
+    {
+      int64_t e = cell_elems[q];
+      if (!mesh.containsPoint(e, p))
+        continue;
+      if (best < 0 || (smallest && e < best) || (!smallest && e > best))
+        best = e;
+    }
+    return best;
+  }
+};
+
+// ------------------------------------------------------------------ collision physics
+struct Hist
+{
+  V3 r, u;
+  double E, wgt;
+  int64_t id;
+  int n_progeny = 0;
+  uint64_t seeds[3];
+  double k_col = 0, k_abs = 0, k_trk = 0;
+  int n_coll = 0, n_xs = 0;
+};
+
+// OMC physics.cpp:955-1004
+static V3 sample_cxs_target_velocity(double awr, double E, V3 u, double kT, uint64_t* seed)
+{
+  double beta_vn = std::sqrt(awr * E / kT);
+  double alpha = 1.0 / (1.0 + std::sqrt(PI) * beta_vn / 2.0);
+  double beta_vt_sq, mu;
+  while (true)
+  {
+    double r1 = prn(seed), r2 = prn(seed);
+    if (prn(seed) < alpha)
+      beta_vt_sq = -xlog(r1 * r2);
+    else
+    {
+      double c = xcos(PI / 2.0 * prn(seed));
+      beta_vt_sq = -xlog(r1) - xlog(r2) * c * c;
+    }
+    double beta_vt = std::sqrt(beta_vt_sq);
+    mu = uniform_distribution(-1., 1., seed);
+    double accept_prob =
+        std::sqrt(beta_vn * beta_vn + beta_vt_sq - 2 * beta_vn * beta_vt * mu) / (beta_vn + beta_vt);
+    if (prn(seed) < accept_prob)
+      break;
+  }
+  double vt = std::sqrt(beta_vt_sq * kT / awr);
+  return vt * rotate_angle(u, mu, nullptr, seed);
+}
+
+// OMC physics.cpp:721-786 (isotropic CM angular distribution: "assume isotropic" branch :750-752)
+static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
+{
+  double vel = std::sqrt(p.E);
+  double awr = nuc.awr;
+  V3 v_n = vel * p.u;
+  V3 v_t = {0, 0, 0};
+  // OMC physics.cpp:804-835 sample_target_velocity, non-resonant branch
+  if (!(p.E >= FREE_GAS_THRESHOLD * kT && awr > 1.0))
+    v_t = sample_cxs_target_velocity(awr, p.E, p.u, kT, &p.seeds[0]);
+  V3 v_cm = (v_n + awr * v_t) / (awr + 1.0);
+  v_n = v_n - v_cm;
+  vel = norm(v_n);
+  double mu_cm = uniform_distribution(-1., 1., &p.seeds[0]);
+  V3 u_cm = v_n / vel;
+  v_n = vel * rotate_angle(u_cm, mu_cm, nullptr, &p.seeds[0]);
+  v_n = v_n + v_cm;
+  p.E = dot(v_n, v_n);
+  vel = std::sqrt(p.E);
+  p.u = v_n / vel;
+}
+
+// OMC physics.cpp:1073-1120 with LevelInelastic (distribution_energy.cpp:48-51), isotropic CM
+// angle (secondary_uncorrelated.cpp:54-68), scatter_in_cm_ true, yield 1
+static void inelastic_scatter(const Nuclide& nuc, Hist& p)
+{
+  double E_in = p.E;
+  double mu = uniform_distribution(-1., 1., &p.seeds[0]);
+  double E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  double E_cm = E;
+  double A = nuc.awr;
+  E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
+  mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
+  if (std::fabs(mu) > 1.0)
+    mu = std::copysign(1.0, mu);
+  p.E = E;
+  p.u = rotate_angle(p.u, mu, nullptr, &p.seeds[0]);
+}
+
+// OMC physics.cpp:1006-1071
+static void sample_fission_neutron(const Nuclide& nuc, double E_in, double E_max,
+                                   mcw_source_site* site, uint64_t* seed)
+{
+  double nu_t = nuc.nu_total(E_in);
+  double nu_d = nuc.nu_delayed(E_in);
+  double beta = nu_d / nu_t;
+  if (prn(seed) < beta)
+  {
+    double xi = prn(seed) * nu_d;
+    double prob = 0.0;
+    int group;
+    for (group = 1; group < nuc.n_precursor; ++group)
+    {
+      prob += nuc.dyield[group - 1];
+      if (xi < prob)
+        break;
+    }
+    group = std::min(group, nuc.n_precursor);
+    site->delayed_group = group;
+  }
+  else
+    site->delayed_group = 0;
+  double mu;
+  while (true)
+  {
+    // OMC reaction_product.cpp:85-105 (single law) -> secondary_uncorrelated.cpp:54-68
+    mu = uniform_distribution(-1., 1., seed);
+    if (site->delayed_group == 0)
+      site->E = watt_spectrum(nuc.watt_a, nuc.watt_b, seed); // distribution_energy.cpp:342-356
+    else
+      site->E = maxwell_spectrum(nuc.dtheta[site->delayed_group - 1], seed); // :279-291
+    if (site->E < E_max)
+      break;
+  }
+  V3 u = rotate_angle({1., 0., 0.}, mu, nullptr, seed);
+  site->u[0] = u.x;
+  site->u[1] = u.y;
+  site->u[2] = u.z;
+}
+
+enum
+{
+  EV_SCATTER = 0,
+  EV_ABSORB = 1
+};
+
+struct CollisionOut
+{
+  int event;
+  double kappa_macro; // sum_i N_i q_i sigma_f,i (kappa-fission score, OMC tally_scoring.cpp:1240-1255)
+};
+
+// OMC particle.cpp:219-288 event_collide + physics.cpp:38-152, :154-247, :442-465, :592-625, :627-719
+static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, const Micro* micro,
+                            int elem, std::vector<mcw_source_site>& bank, int64_t bank_capacity)
+{
+  const Material& mat = P.lib.materials[i_mat];
+  CollisionOut out{EV_SCATTER, 0.0};
+  p.k_col += p.wgt * macro.nu_fission / macro.total;
+  ++p.n_coll;
+  for (size_t i = 0; i < mat.nuc.size(); ++i)
+  {
+    const Nuclide& n = P.lib.nuclides[mat.nuc[i]];
+    if (n.fissionable)
+      out.kappa_macro += n.q * micro[i].fission * mat.dens[i];
+  }
+  // sample_nuclide
+  double cutoff = prn(&p.seeds[0]) * macro.total;
+  double prob = 0.0;
+  size_t k = mat.nuc.size() - 1;
+  for (size_t i = 0; i < mat.nuc.size(); ++i)
+  {
+    prob += mat.dens[i] * micro[i].total;
+    if (prob >= cutoff)
+    {
+      k = i;
+      break;
+    }
+  }
+  const Nuclide& nuc = P.lib.nuclides[mat.nuc[k]];
+  const Micro& mx = micro[k];
+  const double E_last = p.E;
+  if (nuc.fissionable)
+  {
+    // create_fission_sites (eigenvalue mode, no UFS)
+    double nu_t = p.wgt / P.keff * 1.0 * mx.nu_fission / mx.total;
+    int nu = (int)nu_t;
+    if (prn(&p.seeds[0]) <= (nu_t - nu))
+      ++nu;
+    for (int i = 0; i < nu; ++i)
+    {
+      mcw_source_site site;
+      memset(&site, 0, sizeof(site));
+      site.r[0] = p.r.x;
+      site.r[1] = p.r.y;
+      site.r[2] = p.r.z;
+      site.particle = 0;
+      site.wgt = 1. / 1.0;
+      site.parent_id = p.id;
+      site.progeny_id = p.n_progeny++;
+      site.surf_id = 0;
+      site.elem = elem;
+      sample_fission_neutron(nuc, p.E, P.lib.E_max, &site, &p.seeds[0]);
+      bool full = false;
+#pragma omp critical(orc_bank)
+      {
+        if ((int64_t)bank.size() >= bank_capacity)
+          full = true; // OMC shared_array.h:71-89 returns -1
+        else
+          bank.push_back(site);
+      }
+      if (full)
+        break;
+    }
+  }
+  // absorption (analog)
+  if (mx.absorption > 0.0)
+  {
+    if (mx.absorption > prn(&p.seeds[0]) * mx.total)
+    {
+      p.k_abs += p.wgt * mx.nu_fission / mx.absorption;
+      out.event = EV_ABSORB;
+      return out;
+    }
+  }
+  // scatter
+  {
+    double cut = prn(&p.seeds[0]) * (mx.total - mx.absorption);
+    double f = mx.f;
+    int ig = mx.i_grid;
+    double elastic = (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
+    double pr = elastic;
+    bool can_inelastic = nuc.n_inel > 0 && ig >= nuc.inel_thr;
+    if (pr > cut || !can_inelastic)
+      elastic_scatter(nuc, nuc.kT, p);
+    else
+      inelastic_scatter(nuc, p);
+  }
+  // URR stream advance when the energy changed (OMC physics.cpp:140-144)
+  if (p.E != E_last)
+    p.seeds[STREAM_URR] = future_seed((uint64_t)P.lib.nuclides.size(), p.seeds[STREAM_URR]);
+  return out;
+}
+
+static void score_tally(Tally& t, int64_t spatial, double E, const double* score_by_kind)
+{
+  // OMC filter_energy.cpp:61-75 + tally_scoring.cpp:1453
+  int eb = 0;
+  if (!t.ebins.empty())
+  {
+    if (!(E >= t.ebins.front() && E <= t.ebins.back()))
+      return;
+    eb = Library::lower_bound_index(t.ebins.data(), t.ebins.data() + t.ebins.size(), E);
+    if (eb >= t.n_energy)
+      eb = t.n_energy - 1;
+  }
+  int64_t bin = spatial * t.n_energy + eb;
+  for (size_t s = 0; s < t.scores.size(); ++s)
+  {
+    double v = score_by_kind[t.scores[s]];
+#pragma omp atomic
+    t.value[bin * t.scores.size() + s] += v;
+  }
+}
+
+static int64_t spatialBin(const Problem& P, const Tally& t, int64_t elem)
+{
+  return t.granularity == MCW_FILTER_CELL ? elem
+                                          : (t.granularity == MCW_FILTER_UNIVERSE ? P.mesh.block[elem] : 0);
+}
+
+// One history = MC OpenMCStudy.C:317-363 (defineRays) + RT TraceRay::trace + MC
+// CollisionKernel::onSegment (CollisionKernel.C:98-275).
+static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_active,
+                        std::vector<mcw_source_site>& bank, int64_t bank_capacity, TraceStats& st,
+                        int64_t& n_coll, int64_t& n_xs, int64_t& n_nuc, mcw_history_record& rec)
+{
+  const mcw_source_site& src = P.source_bank[i_local];
+  const mcw_settings& S = P.set;
+  Hist p;
+  p.r = {src.r[0], src.r[1], src.r[2]};
+  V3 dir = {src.u[0], src.u[1], src.u[2]};
+  if (S.is_2d)
+    dir.z = 0;
+  dir = unit(dir); // Ray::setStartingDirection (RT Ray.C:291)
+  p.u = dir;
+  p.E = src.E;
+  p.wgt = src.wgt;
+  p.id = P.work_index[P.rank] + i_local + 1; // OMC simulation.cpp:469
+  // overall_generation() = batch (gen_per_batch 1, current_gen 1: MC OpenMCStudy.C:309-310)
+  int64_t particle_seed = (int64_t)(0 + batch - 1) * S.n_particles + p.id; // OMC simulation.cpp:477-480
+  for (int s = 0; s < 3; ++s)
+  {
+    p.seeds[s] = future_seed((uint64_t)particle_seed * PRN_STRIDE, (uint64_t)(S.master_seed + s));
+    if (S.seed_through_double)
+      p.seeds[s] = seed_via_double(p.seeds[s]);
+  }
+  int64_t ray_id = (int64_t)(batch - 1) * S.n_particles + (p.id - 1);
+  int64_t elem = src.elem;
+  if (elem < 0)
+    elem = P.locate(p.r, ray_id);
+  memset(&rec, 0, sizeof(rec));
+  if (elem < 0)
+  {
+    rec.fate = 2;
+    ++st.failed;
+    return;
+  }
+  int inc_side = startingIncomingSide(P.mesh, elem, p.r, dir);
+  std::vector<Micro> micro(32);
+  uint64_t hash = 0xcbf29ce484222325ull;
+  int64_t last_elem = elem;
+  TraceStats my;
+
+  auto onSegment = [&](const SegmentCtx& c, V3& nstart, V3& ndir) -> int {
+    int blk = P.mesh.block[c.elem];
+    int i_mat = P.block_material[blk];
+    const Material& mat = P.lib.materials[i_mat];
+    if (micro.size() < mat.nuc.size())
+      micro.resize(mat.nuc.size());
+    // event_calculate_xs: macro recomputed every segment
+    Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc);
+    ++p.n_xs;
+    // distance to collision: 1 RN per segment (MC CollisionKernel.C:150)
+    const double d = -xlog(prn(&p.seeds[0])) / macro.total;
+    p.k_trk += p.wgt * std::min(d, c.length) * macro.nu_fission; // :153
+    if (tallies_active)
+      for (auto& t : P.tallies)
+        if (t.estimator == MCW_ESTIMATOR_TRACKLENGTH)
+        {
+          // OMC tally_scoring.cpp:2289-2352: flux = wgt * distance
+          double flux = p.wgt * std::min(d, c.length);
+          double sc[MCW_N_SCORES] = {flux, macro.total * flux, macro.fission * flux,
+                                     macro.nu_fission * flux, 0.0};
+          if (macro.absorption == 0)
+            sc[2] = sc[3] = 0;
+          double kappa = 0;
+          for (size_t i = 0; i < mat.nuc.size(); ++i)
+            if (P.lib.nuclides[mat.nuc[i]].fissionable)
+              kappa += P.lib.nuclides[mat.nuc[i]].q * micro[i].fission * mat.dens[i] * flux;
+          sc[4] = macro.absorption == 0. ? 0.0 : kappa;
+          score_tally(t, spatialBin(P, t, c.elem), p.E, sc);
+        }
+    if (S.seed_through_double)
+      for (int s = 0; s < 3; ++s)
+        p.seeds[s] = seed_via_double(p.seeds[s]); // :157-159
+    if (d > c.length)
+      return 0;
+    // collision point computed backwards from the exit point (:173-175)
+    V3 pos = c.end - (c.length - d) * c.dir;
+    if (S.is_2d)
+      pos.z = S.z_coord;
+    p.r = pos;
+    p.u = c.dir;
+    const double E_last = p.E, wgt_last = p.wgt;
+    CollisionOut co = collide(P, p, i_mat, macro, micro.data(), (int)c.elem, bank, bank_capacity);
+    if (tallies_active)
+    {
+      // OMC tally_scoring.cpp:2354-2420 score_collision_tally, scores :557,:600,:752,:799,:1240-1255
+      double flux = wgt_last / macro.total;
+      double sc[MCW_N_SCORES];
+      sc[MCW_SCORE_FLUX] = flux;
+      sc[MCW_SCORE_TOTAL] = macro.total * flux;
+      sc[MCW_SCORE_FISSION] = macro.absorption == 0 ? 0.0 : macro.fission * flux;
+      sc[MCW_SCORE_NU_FISSION] = macro.absorption == 0 ? 0.0 : macro.nu_fission * flux;
+      sc[MCW_SCORE_KAPPA_FISSION] = macro.absorption == 0. ? 0.0 : co.kappa_macro * flux;
+      for (auto& t : P.tallies)
+        if (t.estimator == MCW_ESTIMATOR_COLLISION)
+          score_tally(t, spatialBin(P, t, c.elem), E_last, sc);
+    }
+    if (S.seed_through_double)
+      for (int s = 0; s < 3; ++s)
+        p.seeds[s] = seed_via_double(p.seeds[s]); // :217-219
+    if (co.event == EV_ABSORB)
+      return 1;
+    // changeRayStartDirection (RT RayKernelBase.C:62-97 -> Ray.C:216-226)
+    V3 nd = p.u;
+    if (S.is_2d)
+      nd.z = 0;
+    ndir = unit(nd);
+    nstart = pos;
+    return 2;
+  };
+
+  int max_seg = S.max_events > 0 ? S.max_events : 1000000;
+  int end = trace(P.mesh, elem, inc_side, p.r, dir, onSegment, my, &hash, nullptr, max_seg, &last_elem);
+  rec.seed_tracking = p.seeds[0];
+  rec.seed_source = p.seeds[1];
+  rec.seed_urr = p.seeds[2];
+  rec.E = p.E;
+  rec.k_collision = p.k_col;
+  rec.k_absorption = p.k_abs;
+  rec.k_tracklength = p.k_trk;
+  rec.n_segments = (int)my.segments;
+  rec.n_collisions = p.n_coll;
+  rec.n_progeny = p.n_progeny;
+  rec.last_elem = (int)last_elem;
+  rec.fate = end == END_KERNEL_KILL ? 0 : (end == END_BC_KILL ? 1 : (my.segments >= max_seg ? 3 : 2));
+  rec.n_xs = p.n_xs;
+  rec.trace_hash = hash;
+  st.segments += my.segments;
+  st.vertex_edge_hits += my.vertex_edge_hits;
+  st.moved_through_neighbors += my.moved_through_neighbors;
+  st.failed += my.failed;
+  st.intersection_calls += my.intersection_calls;
+  st.reflections += my.reflections;
+  n_coll += p.n_coll;
+  n_xs += p.n_xs;
+}
+
+static void calc_work(int64_t n_particles, int nranks, std::vector<int64_t>& wi)
+{
+  // OMC simulation.cpp:529-551
+  int64_t min_work = n_particles / nranks, rem = n_particles % nranks;
+  wi.assign(nranks + 1, 0);
+  for (int i = 0; i < nranks; ++i)
+    wi[i + 1] = wi[i] + (i < rem ? min_work + 1 : min_work);
+}
+
+} // namespace orc
+
+using namespace orc;
+
+extern "C" {
+
+// ------------------------------------------------------------------ unit-level entry points
+double orc_prn(uint64_t* seed) { return prn(seed); }
+uint64_t orc_future_seed(uint64_t n, uint64_t seed) { return future_seed(n, seed); }
+uint64_t orc_init_seed(int64_t id, int offset, int64_t master) { return init_seed(id, offset, master); }
+uint64_t orc_seed_via_double(uint64_t s) { return seed_via_double(s); }
+double orc_maxwell_spectrum(double T, uint64_t* seed) { return maxwell_spectrum(T, seed); }
+double orc_watt_spectrum(double a, double b, uint64_t* seed) { return watt_spectrum(a, b, seed); }
+void orc_rotate_angle(double* uvw, double mu, const double* phi, uint64_t* seed)
+{
+  V3 u = rotate_angle({uvw[0], uvw[1], uvw[2]}, mu, phi, seed);
+  uvw[0] = u.x;
+  uvw[1] = u.y;
+  uvw[2] = u.z;
+}
+void orc_isotropic_direction(double* uvw, uint64_t* seed)
+{
+  V3 u = isotropic_direction(seed);
+  uvw[0] = u.x;
+  uvw[1] = u.y;
+  uvw[2] = u.z;
+}
+double orc_log(double x) { return xlog(x); }
+double orc_sin(double x) { return xsin(x); }
+double orc_cos(double x) { return xcos(x); }
+int orc_is_within_segment(const double* s1, const double* s2, const double* p, double tol)
+{
+  return isWithinSegment({s1[0], s1[1], s1[2]}, {s2[0], s2[1], s2[2]}, {p[0], p[1], p[2]}, tol);
+}
+int orc_uses_libm(void)
+{
+#ifdef MCW_ORACLE_LIBM
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// ------------------------------------------------------------------ problem set-up
+void* orc_create(int rank, int nranks)
+{
+  Problem* P = new Problem();
+  P->rank = rank;
+  P->nranks = nranks;
+  return P;
+}
+void orc_destroy(void* h) { delete (Problem*)h; }
+
+int orc_set_mesh(void* h, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem,
+                 const int64_t* conn, const int32_t* block_index, int n_blocks,
+                 const int64_t* neighbors, const int32_t* side_bnd_id, int n_bnd,
+                 const int32_t* bnd_kind)
+{
+  Problem& P = *(Problem*)h;
+  Mesh& m = P.mesh;
+  m.type = elem_type;
+  const ElemTopo& t = m.T();
+  m.n_nodes = n_nodes;
+  m.n_elem = n_elem;
+  m.xyz.resize(n_nodes);
+  for (int64_t i = 0; i < n_nodes; ++i)
+    m.xyz[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  m.conn.assign(conn, conn + n_elem * t.nv);
+  m.block.assign(block_index, block_index + n_elem);
+  m.nbr.assign(neighbors, neighbors + n_elem * t.ns);
+  m.bnd.assign(side_bnd_id, side_bnd_id + n_elem * t.ns);
+  m.bnd_kind.assign(bnd_kind, bnd_kind + n_bnd);
+  P.n_blocks = n_blocks;
+  m.finalize(n_blocks);
+  P.buildLocator();
+  return 0;
+}
+
+int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
+{
+  Problem& P = *(Problem*)h;
+  P.lib.nuclides.clear();
+  for (int i = 0; i < n; ++i)
+  {
+    Nuclide N;
+    N.G = d[i].n_grid;
+    N.fissionable = d[i].fissionable != 0;
+    N.awr = d[i].awr;
+    N.kT = d[i].kT;
+    N.energy.assign(d[i].energy, d[i].energy + N.G);
+    N.xs.assign(d[i].xs, d[i].xs + 5 * (size_t)N.G);
+    N.elastic.assign(d[i].elastic, d[i].elastic + N.G);
+    N.n_inel = d[i].n_inelastic;
+    N.inel_thr = d[i].inel_threshold;
+    if (N.n_inel)
+    {
+      // stored over the full grid with zeros below threshold so indexing matches i_grid
+      N.inelastic.assign(N.G, 0.0);
+      for (int k = N.inel_thr; k < N.G; ++k)
+        N.inelastic[k] = d[i].inelastic[k - N.inel_thr];
+    }
+    N.inel_E = d[i].inel_threshold_energy;
+    N.inel_ratio = d[i].inel_mass_ratio;
+    N.nu_poly[0] = d[i].nu_poly[0];
+    N.nu_poly[1] = d[i].nu_poly[1];
+    N.n_precursor = d[i].n_precursor;
+    for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
+    {
+      N.dyield[g] = d[i].delayed_yield[g];
+      N.dtheta[g] = d[i].delayed_theta[g];
+    }
+    N.watt_a = d[i].watt_a;
+    N.watt_b = d[i].watt_b;
+    N.q = d[i].q_fission;
+    P.lib.nuclides.push_back(std::move(N));
+  }
+  P.lib.n_log_bins = n_log_bins;
+  return 0;
+}
+
+int orc_set_materials(void* h, const mcw_material_desc* m, int n, const int32_t* block_material,
+                      int n_blocks)
+{
+  Problem& P = *(Problem*)h;
+  P.lib.materials.clear();
+  for (int i = 0; i < n; ++i)
+  {
+    Material M;
+    M.nuc.assign(m[i].nuclide, m[i].nuclide + m[i].n_nuclides);
+    M.dens.assign(m[i].atom_density, m[i].atom_density + m[i].n_nuclides);
+    P.lib.materials.push_back(std::move(M));
+  }
+  P.block_material.assign(block_material, block_material + n_blocks);
+  P.lib.finalize();
+  return 0;
+}
+
+int orc_set_settings(void* h, const mcw_settings* s)
+{
+  Problem& P = *(Problem*)h;
+  P.set = *s;
+  calc_work(s->n_particles, P.nranks, P.work_index);
+  return 0;
+}
+
+int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t* scores,
+                  int n_scores, const double* ebins, int n_edges)
+{
+  Problem& P = *(Problem*)h;
+  Tally t;
+  t.id = id;
+  t.estimator = estimator;
+  t.granularity = granularity;
+  t.scores.assign(scores, scores + n_scores);
+  if (n_edges >= 2)
+  {
+    t.ebins.assign(ebins, ebins + n_edges);
+    t.n_energy = n_edges - 1;
+  }
+  t.n_spatial = granularity == MCW_FILTER_CELL
+                    ? P.mesh.n_elem
+                    : (granularity == MCW_FILTER_UNIVERSE ? P.n_blocks : 1);
+  size_t n = (size_t)t.bins() * n_scores;
+  t.value.assign(n, 0.0);
+  t.sum.assign(n, 0.0);
+  t.sum_sq.assign(n, 0.0);
+  P.tallies.push_back(std::move(t));
+  return 0;
+}
+
+void orc_get_grid(void* h, double* e_min, double* e_max, double* log_spacing)
+{
+  Problem& P = *(Problem*)h;
+  *e_min = P.lib.E_min;
+  *e_max = P.lib.E_max;
+  *log_spacing = P.lib.log_spacing;
+}
+int orc_get_grid_index(void* h, int i_nuc, int32_t* out)
+{
+  Problem& P = *(Problem*)h;
+  auto& g = P.lib.nuclides[i_nuc].grid_index;
+  for (size_t i = 0; i < g.size(); ++i)
+    out[i] = g[i];
+  return (int)g.size();
+}
+
+// macroscopic XS for n (E, material) pairs: out = n x 4
+int orc_xs_lookup(void* h, int64_t n, const double* E, const int32_t* mat, double* out)
+{
+  Problem& P = *(Problem*)h;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i)
+  {
+    Macro M = P.lib.macro_xs(mat[i], E[i], nullptr);
+    out[4 * i + 0] = M.total;
+    out[4 * i + 1] = M.absorption;
+    out[4 * i + 2] = M.fission;
+    out[4 * i + 3] = M.nu_fission;
+  }
+  return 0;
+}
+
+// geometry-only walk (the RT lots.i workload): no kernels, stop at the first kill boundary
+int orc_trace_rays(void* h, int64_t n, const double* start, const double* dirs,
+                   const int32_t* start_elem, const int32_t* start_side, double* out_distance,
+                   int32_t* out_segments, uint64_t* out_hash, int64_t* stats6)
+{
+  Problem& P = *(Problem*)h;
+  TraceStats total;
+  for (int64_t i = 0; i < n; ++i)
+  {
+    V3 p = {start[3 * i], start[3 * i + 1], start[3 * i + 2]};
+    V3 d = unit(V3{dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]});
+    int64_t e = start_elem[i];
+    if (e < 0)
+      e = P.locate(p, i);
+    int side = start_side ? start_side[i] : INVALID;
+    if (side == -2)
+      side = startingIncomingSide(P.mesh, e, p, d);
+    TraceStats st;
+    uint64_t hash = 0xcbf29ce484222325ull;
+    double dist = 0;
+    auto noop = [](const SegmentCtx&, V3&, V3&) { return 0; };
+    trace(P.mesh, e, side, p, d, noop, st, &hash, &dist, 10000000);
+    out_distance[i] = dist;
+    out_segments[i] = (int32_t)st.segments;
+    if (out_hash)
+      out_hash[i] = hash;
+    total.segments += st.segments;
+    total.vertex_edge_hits += st.vertex_edge_hits;
+    total.moved_through_neighbors += st.moved_through_neighbors;
+    total.failed += st.failed;
+    total.intersection_calls += st.intersection_calls;
+    total.reflections += st.reflections;
+  }
+  if (stats6)
+  {
+    stats6[0] = total.segments;
+    stats6[1] = total.vertex_edge_hits;
+    stats6[2] = total.moved_through_neighbors;
+    stats6[3] = total.failed;
+    stats6[4] = total.intersection_calls;
+    stats6[5] = total.reflections;
+  }
+  return 0;
+}
+
+int orc_locate_points(void* h, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem)
+{
+  Problem& P = *(Problem*)h;
+  for (int64_t i = 0; i < n; ++i)
+    elem[i] = (int32_t)P.locate({xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, ray_id ? ray_id[i] : i);
+  return 0;
+}
+
+// ------------------------------------------------------------------ source bank
+// OMC source.cpp:325-338 initialize_source + :143-231 IndependentSource::sample (box, isotropic,
+// Watt(0.988 MeV, 2.249 /MeV)); geometry rejection = "no mesh element contains the point".
+int orc_sample_initial_source(void* h)
+{
+  Problem& P = *(Problem*)h;
+  const mcw_settings& S = P.set;
+  int64_t n = P.work_index[P.rank + 1] - P.work_index[P.rank];
+  P.source_bank.assign(n, mcw_source_site{});
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = 0; i < n; ++i)
+  {
+    int64_t id = 0 * S.n_particles + P.work_index[P.rank] + i + 1;
+    uint64_t seed = init_seed(id, STREAM_SOURCE, S.master_seed);
+    mcw_source_site site;
+    memset(&site, 0, sizeof(site));
+    site.wgt = 1.0;
+    int64_t ray_id = P.work_index[P.rank] + i;
+    int64_t e = -1;
+    for (int tries = 0; tries < 1000000; ++tries)
+    {
+      double x1 = prn(&seed), x2 = prn(&seed), x3 = prn(&seed);
+      V3 r = {S.source_box[0] + x1 * (S.source_box[3] - S.source_box[0]),
+              S.source_box[1] + x2 * (S.source_box[4] - S.source_box[1]),
+              S.source_box[2] + x3 * (S.source_box[5] - S.source_box[2])};
+      e = P.locate(r, ray_id);
+      bool found = e >= 0;
+      if (found && S.source_only_fissionable)
+        found = P.lib.materials[P.block_material[P.mesh.block[e]]].fissionable;
+      if (found)
+      {
+        site.r[0] = r.x;
+        site.r[1] = r.y;
+        site.r[2] = r.z;
+        break;
+      }
+      e = -1;
+    }
+    V3 u = isotropic_direction(&seed);
+    site.u[0] = u.x;
+    site.u[1] = u.y;
+    site.u[2] = u.z;
+    while (true)
+    {
+      site.E = watt_spectrum(0.988e6, 2.249e-6, &seed);
+      if (site.E < P.lib.E_max && site.E > P.lib.E_min)
+        break;
+    }
+    site.elem = (int32_t)e;
+    site.parent_id = 0;
+    site.progeny_id = 0;
+    P.source_bank[i] = site;
+  }
+  return 0;
+}
+
+int orc_set_source_bank(void* h, const mcw_source_site* s, int64_t n)
+{
+  ((Problem*)h)->source_bank.assign(s, s + n);
+  return 0;
+}
+int64_t orc_get_source_bank(void* h, mcw_source_site* s, int64_t cap)
+{
+  Problem& P = *(Problem*)h;
+  int64_t n = std::min<int64_t>(cap, (int64_t)P.source_bank.size());
+  if (s)
+    memcpy(s, P.source_bank.data(), n * sizeof(mcw_source_site));
+  return (int64_t)P.source_bank.size();
+}
+int64_t orc_get_fission_bank(void* h, mcw_source_site* s, int64_t cap)
+{
+  Problem& P = *(Problem*)h;
+  int64_t n = std::min<int64_t>(cap, (int64_t)P.fission_bank.size());
+  if (s)
+    memcpy(s, P.fission_bank.data(), n * sizeof(mcw_source_site));
+  return (int64_t)P.fission_bank.size();
+}
+int64_t orc_get_sampled(void* h, mcw_source_site* s, int64_t cap)
+{
+  Problem& P = *(Problem*)h;
+  int64_t n = std::min<int64_t>(cap, (int64_t)P.sampled.size());
+  if (s)
+    memcpy(s, P.sampled.data(), n * sizeof(mcw_source_site));
+  return (int64_t)P.sampled.size();
+}
+int64_t orc_get_history_records(void* h, mcw_history_record* r, int64_t cap)
+{
+  Problem& P = *(Problem*)h;
+  int64_t n = std::min<int64_t>(cap, (int64_t)P.records.size());
+  if (r)
+    memcpy(r, P.records.data(), n * sizeof(mcw_history_record));
+  return (int64_t)P.records.size();
+}
+
+// ------------------------------------------------------------------ one generation
+// Transport half: OMC simulation.cpp:296-332,392-405 (initialize_batch / generation), all
+// histories, then bank.cpp:60-104 sort_fission_bank.
+int orc_transport_generation(void* h, int batch, int n_threads)
+{
+  Problem& P = *(Problem*)h;
+  const int64_t n = (int64_t)P.source_bank.size();
+  P.fission_bank.clear();
+  P.fission_bank.reserve(3 * n);
+  P.records.assign(n, mcw_history_record{});
+  P.total_weight = 0.0;
+  const bool tallies_active = batch > P.set.n_inactive;
+  TraceStats st;
+  int64_t n_coll = 0, n_xs = 0, n_nuc = 0;
+  (void)n_threads;
+#ifdef _OPENMP
+  if (n_threads > 0)
+    omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel
+  {
+    TraceStats my;
+    int64_t c = 0, x = 0, nn = 0;
+#pragma omp for schedule(dynamic, 20) // RT ParallelStudy.h:507-523
+    for (int64_t i = 0; i < n; ++i)
+      run_history(P, i, batch, tallies_active, P.fission_bank, 3 * n, my, c, x, nn, P.records[i]);
+#pragma omp critical(orc_stats)
+    {
+      st.segments += my.segments;
+      st.vertex_edge_hits += my.vertex_edge_hits;
+      st.moved_through_neighbors += my.moved_through_neighbors;
+      st.failed += my.failed;
+      st.intersection_calls += my.intersection_calls;
+      st.reflections += my.reflections;
+      n_coll += c;
+      n_xs += x;
+      n_nuc += nn;
+    }
+  }
+  P.stats = st;
+  P.n_collisions = n_coll;
+  P.n_xs = n_xs;
+  P.n_nuc_lookups = n_nuc;
+  // global tally accumulators in history order (OMC particle.cpp:331-345; simulation.cpp:409-425)
+  double kc = 0, ka = 0, kt = 0, w = 0;
+  for (int64_t i = 0; i < n; ++i)
+  {
+    kc += P.records[i].k_collision;
+    ka += P.records[i].k_absorption;
+    kt += P.records[i].k_tracklength;
+    w += P.source_bank[i].wgt;
+  }
+  P.gt_value[0] += kc;
+  P.gt_value[1] += ka;
+  P.gt_value[2] += kt;
+  P.total_weight = w;
+  // sort by (parent_id, progeny_id): equivalent to OMC bank.cpp:60-104
+  std::sort(P.fission_bank.begin(), P.fission_bank.end(),
+            [](const mcw_source_site& a, const mcw_source_site& b) {
+              return a.parent_id != b.parent_id ? a.parent_id < b.parent_id
+                                                : a.progeny_id < b.progeny_id;
+            });
+  P.bank_global_start = 0;
+  P.bank_global_total = (int64_t)P.fission_bank.size();
+  return 0;
+}
+
+int orc_set_bank_window(void* h, int64_t start, int64_t total)
+{
+  Problem& P = *(Problem*)h;
+  P.bank_global_start = start;
+  P.bank_global_total = total;
+  return 0;
+}
+
+// Sampling half of OMC eigenvalue.cpp:71-311 synchronize_bank on this rank's slice.  Returns the
+// number of sites sampled locally (before the last-rank trim/pad, which the caller applies through
+// orc_finish_sampling once it knows the global offsets).
+int64_t orc_sample_bank(void* h, int batch)
+{
+  Problem& P = *(Problem*)h;
+  const mcw_settings& S = P.set;
+  const int64_t total = P.bank_global_total, start = P.bank_global_start;
+  int64_t id = 0 + batch; // total_gen + overall_generation()
+  uint64_t seed = init_seed(id, STREAM_TRACKING, S.master_seed);
+  seed = future_seed((uint64_t)start, seed);
+  int64_t sites_needed = total < S.n_particles ? S.n_particles % total : S.n_particles;
+  double p_sample = (double)sites_needed / (double)total;
+  P.sampled.clear();
+  for (size_t i = 0; i < P.fission_bank.size(); ++i)
+  {
+    const auto& site = P.fission_bank[i];
+    if (total < S.n_particles)
+      for (int64_t j = 1; j <= S.n_particles / total; ++j)
+        P.sampled.push_back(site);
+    if (prn(&seed) < p_sample)
+      P.sampled.push_back(site);
+  }
+  return (int64_t)P.sampled.size();
+}
+
+// Last-rank adjustment (OMC eigenvalue.cpp:184-206): `start` = global offset of this rank's sampled
+// sites, is_last = this is the last rank.
+int64_t orc_finish_sampling(void* h, int64_t start, int is_last)
+{
+  Problem& P = *(Problem*)h;
+  const int64_t n = P.set.n_particles;
+  int64_t finish = start + (int64_t)P.sampled.size();
+  if (is_last)
+  {
+    if (finish > n)
+      P.sampled.resize(n - start);
+    else if (finish < n)
+    {
+      int64_t needed = n - finish;
+      for (int64_t i = 0; i < needed; ++i)
+      {
+        int64_t ib = (int64_t)P.fission_bank.size() - needed + i;
+        if (ib < 0)
+          ib = 0; // MC OpenMCStudy.C:584
+        P.sampled.push_back(P.fission_bank[ib]);
+      }
+    }
+  }
+  return (int64_t)P.sampled.size();
+}
+
+// k estimators + tally accumulation: OMC eigenvalue.cpp:49-69,313-351; tallies/tally.cpp:639-670,
+// 805-846; simulation.cpp:334-347.  `gt` = this generation's global [k_col,k_abs,k_trk,leak] and
+// total weight summed over ranks by the caller (or null = local values).
+int orc_finalize_generation(void* h, int batch, const double* reduced5, mcw_generation_result* out)
+{
+  Problem& P = *(Problem*)h;
+  const mcw_settings& S = P.set;
+  double g[4] = {P.gt_value[0], P.gt_value[1], P.gt_value[2], P.gt_value[3]};
+  double w = P.total_weight;
+  if (reduced5)
+  {
+    for (int i = 0; i < 4; ++i)
+      g[i] = reduced5[i];
+    w = reduced5[4];
+  }
+  double k_gen = g[2] / (double)S.n_particles;
+  P.k_generation.push_back(k_gen);
+  int n = batch > S.n_inactive ? P.n_realizations + 1 : 0; // gen_per_batch*n_realizations + current_gen
+  if (n <= 0)
+    P.keff = k_gen;
+  else
+  {
+    P.k_sum[0] += k_gen;
+    P.k_sum[1] += k_gen * k_gen;
+    P.keff = P.k_sum[0] / n;
+    if (n > 1)
+      P.keff_std = std::sqrt((P.k_sum[1] / n - P.keff * P.keff) / (n - 1));
+  }
+  // accumulate_tallies
+  P.n_realizations += 1;
+  for (int i = 0; i < 4; ++i)
+  {
+    double val = g[i] / w;
+    P.gt_sum[i] += val;
+    P.gt_sum_sq[i] += val * val;
+  }
+  if (out)
+  {
+    memset(out, 0, sizeof(*out));
+    out->k_generation = k_gen;
+    out->keff = P.keff;
+    out->keff_std = P.keff_std;
+    out->k_collision = g[0] / w;
+    out->k_absorption = g[1] / w;
+    out->k_tracklength = g[2] / w;
+    out->leakage = g[3] / w;
+    out->total_weight = w;
+    out->n_histories = (int64_t)P.source_bank.size();
+    out->n_segments = P.stats.segments;
+    out->n_collisions = P.n_collisions;
+    out->n_xs_lookups = P.n_xs;
+    out->n_nuclide_lookups = P.n_nuc_lookups;
+    out->n_bank_sites = (int64_t)P.fission_bank.size();
+    out->n_vertex_edge_hits = P.stats.vertex_edge_hits;
+    out->n_moved_through_neighbors = P.stats.moved_through_neighbors;
+    out->n_failed_traces = P.stats.failed;
+  }
+  for (int i = 0; i < 4; ++i)
+    P.gt_value[i] = 0.0;
+  if (batch > S.n_inactive)
+  {
+    double norm_ = 1.0 / ((double)S.n_particles * 1.0);
+    for (auto& t : P.tallies)
+    {
+      t.n_realizations += 1;
+      for (size_t i = 0; i < t.value.size(); ++i)
+      {
+        double val = t.value[i] * norm_;
+        t.value[i] = 0.0;
+        t.sum[i] += val;
+        t.sum_sq[i] += val * val;
+      }
+    }
+  }
+  else
+  {
+    for (int i = 0; i < 4; ++i)
+      P.gt_sum[i] = P.gt_sum_sq[i] = 0.0;
+    P.n_realizations = 0;
+  }
+  return 0;
+}
+
+// single-rank convenience: transport + sample + finalize; the sampled sites become the next source
+int orc_run_generation(void* h, int batch, int n_threads, mcw_generation_result* out)
+{
+  Problem& P = *(Problem*)h;
+  orc_transport_generation(h, batch, n_threads);
+  if (P.fission_bank.empty())
+    return MCW_E_PHYSICS;
+  orc_sample_bank(h, batch);
+  orc_finish_sampling(h, 0, 1);
+  orc_finalize_generation(h, batch, nullptr, out);
+  P.source_bank = P.sampled;
+  return 0;
+}
+
+int orc_get_tally(void* h, int id, double* value, double* sum, double* sum_sq, int64_t n)
+{
+  Problem& P = *(Problem*)h;
+  for (auto& t : P.tallies)
+    if (t.id == id)
+    {
+      int64_t m = std::min<int64_t>(n, (int64_t)t.sum.size());
+      if (value)
+        memcpy(value, t.value.data(), m * 8);
+      if (sum)
+        memcpy(sum, t.sum.data(), m * 8);
+      if (sum_sq)
+        memcpy(sum_sq, t.sum_sq.data(), m * 8);
+      return t.n_realizations;
+    }
+  return -1;
+}
+int64_t orc_tally_size(void* h, int id)
+{
+  Problem& P = *(Problem*)h;
+  for (auto& t : P.tallies)
+    if (t.id == id)
+      return (int64_t)t.sum.size();
+  return -1;
+}
+void orc_set_keff(void* h, double k) { ((Problem*)h)->keff = k; }
+double orc_get_keff(void* h) { return ((Problem*)h)->keff; }
+int orc_calculate_work(int64_t n, int nranks, int64_t* wi)
+{
+  std::vector<int64_t> v;
+  calc_work(n, nranks, v);
+  for (size_t i = 0; i < v.size(); ++i)
+    wi[i] = v[i];
+  return 0;
+}
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+} // extern "C"

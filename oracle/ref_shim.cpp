@@ -1,0 +1,26 @@
+// ref_shim.cpp -- extern "C" doorways into the REFERENCE's own compiled sources
+// (openmc/src/random_lcg.cpp, random_dist.cpp, math_functions.cpp), linked into
+// oracle/_ref/libomc_ref.so by oracle/Makefile.  Test infrastructure only: used to pin the oracle's
+// RNG and samplers bit-for-bit against the real reference code.  Nothing here restates an algorithm.
+#include <cstdint>
+
+#include "openmc/math_functions.h"
+#include "openmc/position.h"
+#include "openmc/random_dist.h"
+#include "openmc/random_lcg.h"
+
+extern "C" {
+double ref_prn(uint64_t* seed) { return openmc::prn(seed); }
+double ref_future_prn(int64_t n, uint64_t seed) { return openmc::future_prn(n, seed); }
+uint64_t ref_future_seed(uint64_t n, uint64_t seed) { return openmc::future_seed(n, seed); }
+uint64_t ref_init_seed(int64_t id, int offset) { return openmc::init_seed(id, offset); }
+void ref_init_particle_seeds(int64_t id, uint64_t* seeds) { openmc::init_particle_seeds(id, seeds); }
+void ref_set_master_seed(int64_t s) { openmc::openmc_set_seed(s); }
+double ref_maxwell_spectrum(double T, uint64_t* seed) { return openmc::maxwell_spectrum(T, seed); }
+double ref_watt_spectrum(double a, double b, uint64_t* seed) { return openmc::watt_spectrum(a, b, seed); }
+double ref_uniform(double a, double b, uint64_t* seed) { return openmc::uniform_distribution(a, b, seed); }
+void ref_rotate_angle(double* uvw, double mu, const double* phi, uint64_t* seed)
+{
+  openmc::rotate_angle_c(uvw, mu, phi, seed);
+}
+}
