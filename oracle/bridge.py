@@ -54,7 +54,7 @@ def _load(name):
     lib.orc_get_grid.argtypes = [vp, f64p, f64p, f64p]
     lib.orc_get_grid_index.argtypes = [vp, C.c_int, vp]
     lib.orc_xs_lookup.argtypes = [vp, C.c_int64, vp, vp, vp]
-    lib.orc_trace_rays.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.orc_trace_rays.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.orc_locate_points.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.orc_sample_initial_source.argtypes = [vp]
     lib.orc_set_source_bank.argtypes = [vp, vp, C.c_int64]
@@ -184,14 +184,16 @@ class Oracle:
         self.L.orc_xs_lookup(self.h, E.size, _p(E), _p(mat), _p(out))
         return out
 
-    def trace_rays(self, start, dirs, start_elem=None, start_side=None):
+    def trace_rays(self, start, dirs, start_elem=None, start_side=None, max_distance=None):
         start = np.ascontiguousarray(start, np.float64)
         dirs = np.ascontiguousarray(dirs, np.float64)
         n = start.shape[0]
         se = np.ascontiguousarray(start_elem if start_elem is not None else np.full(n, -1), np.int32)
         ss = np.ascontiguousarray(start_side, np.int32) if start_side is not None else None
         dist, seg, h, st = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.uint64), np.zeros(6, np.int64)
-        self.L.orc_trace_rays(self.h, n, _p(start), _p(dirs), _p(se), _p(ss), _p(dist), _p(seg), _p(h), _p(st))
+        md = np.ascontiguousarray(max_distance, np.float64) if max_distance is not None else None
+        self.L.orc_trace_rays(self.h, n, _p(start), _p(dirs), _p(se), _p(ss), _p(md), _p(dist), _p(seg), _p(h),
+                              _p(st))
         return dist, seg, h, dict(zip(["segments", "vertex_edge_hits", "moved_through_neighbors", "failed",
                                        "intersection_calls", "reflections"], st.tolist()))
 

@@ -597,8 +597,9 @@ enum TraceEnd
 template <typename OnSegment>
 inline int trace(const Mesh& m, int64_t elem, int incoming_side, V3 point, V3 dir, OnSegment&& seg,
                  TraceStats& st, uint64_t* hash, double* distance, int64_t max_segments,
-                 int64_t* last_elem_out = nullptr)
+                 int64_t* last_elem_out = nullptr, double max_distance = INFINITY)
 {
+  double travelled = 0;
   const ElemTopo& t = m.T();
   int64_t cur = elem, last = INVALID;
   int inc_side = incoming_side;
@@ -732,6 +733,22 @@ inline int trace(const Mesh& m, int64_t elem, int incoming_side, V3 point, V3 di
     if (ext.atExtrema())
       ++st.vertex_edge_hits;
     ++st.segments;
+    // RT TraceRay.C:1268-1315: stop at / move back to the ray's maximum distance
+    bool at_end = false;
+    if (max_distance == INFINITY)
+      at_end = false;
+    else if (std::fabs(travelled + idist - max_distance) <= 1e-10 * std::fmax(1.0, max_distance))
+      at_end = true;
+    else if (travelled + idist > max_distance)
+    {
+      double diff = travelled + idist - max_distance;
+      ipoint = ipoint - dir * diff;
+      idist -= diff;
+      iside = INVALID;
+      ext.invalidate();
+      at_end = true;
+    }
+    travelled += idist;
     if (distance)
       *distance += idist;
 
@@ -741,7 +758,7 @@ inline int trace(const Mesh& m, int64_t elem, int incoming_side, V3 point, V3 di
     int action = seg(ctx, nstart, ndir);
     if (hash)
       *hash = hashStep(*hash, cur, action == 0 ? iside : 15);
-    if (action == 1)
+    if (action == 1 || at_end)
     {
       if (last_elem_out)
         *last_elem_out = cur;
@@ -749,6 +766,7 @@ inline int trace(const Mesh& m, int64_t elem, int incoming_side, V3 point, V3 di
     }
     if (action == 2)
     {
+      travelled -= idist;
       if (distance)
         *distance -= idist; // RT TraceRay.C:1356-1358 (MOOSE bug F7: segment length zeroed)
       inc_point = nstart;

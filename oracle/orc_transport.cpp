@@ -750,8 +750,8 @@ int orc_xs_lookup(void* h, int64_t n, const double* E, const int32_t* mat, doubl
 
 // geometry-only walk (the RT lots.i workload): no kernels, stop at the first kill boundary
 int orc_trace_rays(void* h, int64_t n, const double* start, const double* dirs,
-                   const int32_t* start_elem, const int32_t* start_side, double* out_distance,
-                   int32_t* out_segments, uint64_t* out_hash, int64_t* stats6)
+                   const int32_t* start_elem, const int32_t* start_side, const double* max_distance,
+                   double* out_distance, int32_t* out_segments, uint64_t* out_hash, int64_t* stats6)
 {
   Problem& P = *(Problem*)h;
   TraceStats total;
@@ -769,7 +769,8 @@ int orc_trace_rays(void* h, int64_t n, const double* start, const double* dirs,
     uint64_t hash = 0xcbf29ce484222325ull;
     double dist = 0;
     auto noop = [](const SegmentCtx&, V3&, V3&) { return 0; };
-    trace(P.mesh, e, side, p, d, noop, st, &hash, &dist, 10000000);
+    trace(P.mesh, e, side, p, d, noop, st, &hash, &dist, 10000000, nullptr,
+          max_distance ? max_distance[i] : INFINITY);
     out_distance[i] = dist;
     out_segments[i] = (int32_t)st.segments;
     if (out_hash)

@@ -1,0 +1,215 @@
+"""Pins the CPU oracle to the reference: its own compiled RNG/sampler sources (oracle/_ref), OpenMC's
+unit-test known answers, the MOOSE ray-tracing lots.i gold distances, and MaCaw's gold ray file."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from macaw_b200 import cstructs, meshgen, nucdata
+from tests import lots_rays
+
+MULT, ADD, STRIDE = 6364136223846793005, 1442695040888963407, 152917
+M64 = (1 << 64) - 1
+
+
+def lcg(s):
+    return (MULT * s + ADD) & M64
+
+
+def test_rng_vs_reference_vectors(oracle_bridge, golden_dir):
+    """oracle prn/future_seed/init_particle_seeds == the reference's random_lcg.cpp, bit for bit
+    (vectors generated from oracle/_ref/libomc_ref.so by tests/golden/make_fixtures.py)."""
+    g = np.load(os.path.join(golden_dir, "ref_rng_vectors.npz"))
+    for libm in (False, True):
+        L = oracle_bridge.lib(libm)
+        s = C.c_uint64(1)
+        mine = np.array([L.orc_prn(C.byref(s)) for _ in range(1000)])
+        assert np.array_equal(mine, g["prn"])
+        fut = np.array([L.orc_future_seed(int(n), 12345) for n in g["future_n"]], np.uint64)
+        assert np.array_equal(fut, g["future_seed"])
+        for pid, ref in zip(g["ids"], g["particle_seeds"]):
+            for stream in range(4):
+                assert L.orc_init_seed(int(pid), stream, 1) == int(ref[stream])
+    # init_particle_seeds(1) and the first prn
+    assert [int(x) for x in g["particle_seeds"][0][:3]] == [3009189780765489792, 5497575982607593661,
+                                                             7985962184449697530]
+
+
+def test_samplers_libm_build_bit_exact_vs_reference(oracle_bridge, golden_dir):
+    """With glibc math the oracle's samplers reproduce the reference's compiled random_dist.cpp /
+    math_functions.cpp exactly; with the deterministic math header they agree to a few ulp."""
+    g = np.load(os.path.join(golden_dir, "ref_rng_vectors.npz"))
+    for libm, exact in ((True, True), (False, False)):
+        L = oracle_bridge.lib(libm)
+        s = C.c_uint64(7)
+        maxw = np.array([L.orc_maxwell_spectrum(1.3e6, C.byref(s)) for _ in range(200)])
+        s = C.c_uint64(7)
+        watt = np.array([L.orc_watt_spectrum(0.988e6, 2.249e-6, C.byref(s)) for _ in range(200)])
+        s = C.c_uint64(11)
+        rot = np.zeros((200, 3))
+        u = (C.c_double * 3)(0.6, 0.0, 0.8)
+        for i in range(200):
+            s.value = lcg(s.value)  # uniform_distribution(-1,1) consumed one RN in the reference run
+            word = (((s.value >> ((s.value >> 59) + 5)) ^ s.value) * 12605985483714917081) & M64
+            mu = -1.0 + 2.0 * (((word >> 43) ^ word) * 2.0 ** -64)
+            L.orc_rotate_angle(u, mu, None, C.byref(s))
+            rot[i] = list(u)
+        if exact:
+            assert np.array_equal(maxw, g["maxwell"]) and np.array_equal(watt, g["watt"])
+            assert np.array_equal(rot, g["rotate"])
+        else:
+            assert np.allclose(maxw, g["maxwell"], rtol=1e-13, atol=0)
+            assert np.allclose(watt, g["watt"], rtol=1e-13, atol=0)
+            assert np.allclose(rot, g["rotate"], rtol=0, atol=1e-9)  # 200 chained rotations accumulate ulps
+
+
+def test_live_reference_library_if_present(oracle_bridge):
+    r = oracle_bridge.ref_lib()
+    if r is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    L = oracle_bridge.lib(True)
+    rng = np.random.default_rng(3)
+    for seed0 in rng.integers(1, 2 ** 63, 50):
+        a, b = C.c_uint64(int(seed0)), C.c_uint64(int(seed0))
+        assert L.orc_prn(C.byref(a)) == r.ref_prn(C.byref(b)) and a.value == b.value
+        n = int(rng.integers(0, 2 ** 62))
+        assert L.orc_future_seed(n, int(seed0)) == r.ref_future_seed(n, int(seed0))
+        a, b = C.c_uint64(int(seed0)), C.c_uint64(int(seed0))
+        assert L.orc_watt_spectrum(0.9e6, 2.2e-6, C.byref(a)) == r.ref_watt_spectrum(0.9e6, 2.2e-6, C.byref(b))
+
+
+def test_openmc_math_known_answers(oracle_bridge, golden_dir):
+    kat = json.load(open(os.path.join(golden_dir, "omc_math_kat.json")))
+    L = oracle_bridge.lib(True)  # glibc build: exact equality like the reference's own test
+    s = C.c_uint64(kat["maxwell_spectrum"]["seed"])
+    assert L.orc_maxwell_spectrum(kat["maxwell_spectrum"]["T"], C.byref(s)) == kat["maxwell_spectrum"]["ref"]
+    s = C.c_uint64(kat["watt_spectrum"]["seed"])
+    w = kat["watt_spectrum"]
+    assert L.orc_watt_spectrum(w["a"], w["b"], C.byref(s)) == w["ref"]
+    r = kat["rotate_angle"]
+    for libm in (True, False):
+        L = oracle_bridge.lib(libm)
+        u = (C.c_double * 3)(*r["uvw0"])
+        phi = C.c_double(r["phi"])
+        L.orc_rotate_angle(u, r["mu"], C.byref(phi), None)
+        assert list(u) == r["ref_phi0"]
+        u = (C.c_double * 3)(*r["uvw0"])
+        L.orc_rotate_angle(u, 1.0, C.byref(phi), None)
+        assert list(u) == [1.0, 0.0, 0.0]
+        u = (C.c_double * 3)(*r["uvw0_random"])
+        s = C.c_uint64(r["seed"])
+        L.orc_rotate_angle(u, r["mu_random"], None, C.byref(s))
+        assert np.allclose(list(u), r["ref_random"], rtol=1e-12)
+    # deterministic-math build within 2 ulp of the known answers
+    L = oracle_bridge.lib(False)
+    s = C.c_uint64(1)
+    assert abs(L.orc_maxwell_spectrum(0.5, C.byref(s)) - 0.27767406743161277) < 1e-15
+
+
+def test_detmath_within_one_ulp_of_glibc(oracle_bridge):
+    L = oracle_bridge.lib(False)
+    rng = np.random.default_rng(0)
+    x = np.exp(rng.uniform(-40, 40, 20000))
+    u = rng.uniform(0, 1, 20000)
+    ph = 2 * np.pi * u
+    def ulps(a, b):
+        return np.abs(np.asarray(a).view(np.int64) - np.asarray(b).view(np.int64))
+    assert ulps(np.array([L.orc_log(v) for v in x]), np.log(x)).max() <= 1
+    assert ulps(np.array([L.orc_log(v) for v in u]), np.log(u)).max() <= 1
+    s, c = np.array([L.orc_sin(v) for v in ph]), np.array([L.orc_cos(v) for v in ph])
+    ok = np.abs(np.sin(ph)) > 1e-3
+    assert ulps(s[ok], np.sin(ph)[ok]).max() <= 1
+    ok = np.abs(np.cos(ph)) > 1e-3
+    assert ulps(c[ok], np.cos(ph)[ok]).max() <= 1
+    assert np.abs(s - np.sin(ph)).max() < 2e-16 and np.abs(c - np.cos(ph)).max() < 2e-16
+
+
+def test_is_within_segment_known_answers(oracle_bridge):
+    """RT unit/src/TraceRayToolsTest.C:269-274."""
+    L = oracle_bridge.lib(False)
+    def f(a, b, p):
+        A, B, Pt = [(C.c_double * 3)(*v) for v in (a, b, p)]
+        return bool(L.orc_is_within_segment(A, B, Pt, 1e-8))
+    assert f((0, 0, 0), (1, 1, 1), (0.5, 0.5, 0.5))
+    assert f((0, 0, 0), (1, 1, 1), (0, 0, 0)) and f((0, 0, 0), (1, 1, 1), (1, 1, 1))
+    assert not f((0, 0, 0), (1, 1, 1), (1.1, 1.1, 1.1))
+    assert not f((0, 0, 0), (1, 1, 1), (0.5, 0.5, 0.6))
+
+
+LOTS = [("hex8", "vtv", "ntn"), ("hex8", "ctv", "ctn"), ("hex8", "ete", "ete"), ("hex8", "ctc", "ctc"),
+        ("quad4", "vtv", "vtv"), ("quad4", "ctv", "ctv"), ("quad4", "ctc", "ctc")]
+
+
+@pytest.mark.parametrize("et,kind,gold_name", LOTS)
+def test_element_walk_reproduces_moose_lots_gold(oracle_bridge, golden_dir, et, kind, gold_name):
+    """The oracle's element walk (incl. vertex/edge fallbacks: these rays run through vertices and
+    along edges) reproduces the total traced distance of MOOSE's lots.i regression gold CSVs."""
+    gold = json.load(open(os.path.join(golden_dir, "rt_lots_gold.json")))[f"{et}/{gold_name}"]
+    if et == "hex8":
+        mesh = meshgen.hex_grid(5, 5, 5, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
+    else:
+        mesh = meshgen.quad_grid(5, 5, (0, 0), (5, 5), meshgen.BC_KILL)
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh)
+    start, dirs, elems, sides, maxd = lots_rays.lots(mesh, kind)
+    dist, seg, h, st = o.trace_rays(start, dirs, elems, sides, maxd if kind == "ctc" else None)
+    assert st["failed"] == 0
+    total = dist.sum()
+    assert abs(total - gold["total_distance"]) <= 1e-8 * gold["total_distance"], (total, gold)
+    if kind != "ctc":
+        exp = lots_rays.box_exit_distance(start, dirs, (0, 0, 0), (5, 5, 5), mesh.dim)
+        assert np.allclose(dist, exp, rtol=1e-9, atol=1e-9)
+        assert st["vertex_edge_hits"] > 0  # the fallbacks really ran
+
+
+def test_gold_ray_file_rng_facts(oracle_bridge, golden_dir):
+    """MaCaw's own gold file (test/tests/study/gold/openmc_study_rays.e): seeds live in doubles
+    (SURVEY F3), one tracking RN per segment, URR stream advanced by data::nuclides.size() = 9 per
+    energy-changing collision, initial seeds = future_seed(((batch-1)*n + id)*stride, master+stream)."""
+    g = np.load(os.path.join(golden_dir, "study_rays_gold.npz"))
+    L = oracle_bridge.lib(False)
+    E, pid = g["var_aux_energy"], g["var_aux_id"]
+    st, ss, su = g["var_aux_seed_tracking"], g["var_aux_seed_source"], g["var_aux_seed_URR"]
+    rid, npg = g["var_ray_id"], g["var_aux_n_progeny"]
+    assert E.size == 1796 and np.unique(rid).size == 30
+    assert np.all(g["var_aux_weight"] == 1.0) and np.all(g["var_aux_particle_type"] == 0)
+    # every stored seed is a double that holds an integer < 2^64 exactly representable in 53 bits
+    for arr in (st, ss, su):
+        assert np.all(arr == np.floor(arr)) and np.all(arr < 2.0 ** 64)
+        assert all(L.orc_seed_via_double(int(v)) == int(v) for v in arr[:200])
+    n_one_step = n_same = n_urr = n_urr_ok = 0
+    for r in np.unique(rid):
+        idx = np.nonzero(rid == r)[0]
+        # seed_source: constant per ray and equal to the rounded initial seed of stream 1
+        p = int(pid[idx[0]])
+        seed_id = ((3 - 1) * 30 + p) * STRIDE
+        assert np.all(ss[idx] == ss[idx[0]])
+        assert float(L.orc_seed_via_double(L.orc_future_seed(seed_id, 1 + 1))) == ss[idx[0]]
+        for a, b in zip(idx[:-1], idx[1:]):
+            if E[a] == E[b]:
+                n_same += 1
+                nxt = L.orc_seed_via_double(lcg(int(st[a])))
+                n_one_step += float(nxt) == st[b]
+                assert su[a] == su[b]  # URR stream untouched when the energy did not change
+            else:
+                # several collisions can happen between two recorded face crossings (collision points
+                # are not recorded): k rounds of (skip 9, round through double)
+                n_urr += 1
+                adv, ok = int(su[a]), False
+                for _ in range(40):
+                    adv = L.orc_seed_via_double(L.orc_future_seed(9, adv))
+                    if float(adv) == su[b]:
+                        ok = True
+                        break
+                n_urr_ok += ok
+    # 919 of the 939 same-energy transitions are exactly one LCG step from the double-rounded seed; the
+    # other 20 are final records of absorbed rays (several RNs consumed in the collision)
+    assert n_same == 939 and n_one_step == 919
+    assert n_urr > 800 and n_urr_ok == n_urr
+    # all recorded segment ends lie on faces of the 5x5x1 grid on [-5,5]^3
+    ends = g["coord"][g["conn"][:, 1]]
+    on_face = (np.isclose(np.abs(ends[:, 0]) % 2, 1, atol=1e-9) | np.isclose(np.abs(ends[:, 1]) % 2, 1, atol=1e-9)
+               | np.isclose(np.abs(ends[:, 2]), 5, atol=1e-9))
+    assert on_face.all()
