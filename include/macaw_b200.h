@@ -182,15 +182,25 @@ int mcw_create(mcw_handle* h, int device_ordinal, int rank, int nranks);
 void mcw_destroy(mcw_handle h);
 const char* mcw_last_error(mcw_handle h); /* OMC error.cpp:32 openmc_err_msg */
 int mcw_version(void);
+/* Run-time knobs that do not change results: "profile" (1 = per-kernel-family CUDA-event timing in
+ * mcw_generation_result, one host sync per event round), "sync_every" (event rounds between host
+ * reads of the queue counters), "fallback_blocks" (grid of the rare-path kernel). */
+int mcw_set_option(mcw_handle h, const char* name, int value);
+/* Builds all device state now (otherwise done lazily by the first call that needs it). */
+int mcw_prepare(mcw_handle h);
+int mcw_struct_sizes(int32_t* out, int n); /* sizeof of the six ABI structs, for binding self-checks */
 
 /* Mesh.  Replaces libMesh access on the path: elem->point / neighbor_ptr / subdomain_id
  * [RT TraceRayTools.C:404-407, TraceRay.C:1433, MC CollisionKernel.C:110] and boundary info
  * [RT TraceRay.C:725-782].  conn is n_elem x (4 | 4 | 8) node ids in libMesh node order
- * (SURVEY Appendix B).  neighbors may be NULL (computed by face matching); bc_kind is
- * n_elem x n_sides with -1 on interior sides. */
+ * (SURVEY Appendix B); block_id holds raw subdomain ids.  neighbors (n_elem x n_sides, -1 on the
+ * boundary) may be NULL (computed by face matching).  side_bnd_id is n_elem x n_sides with the
+ * boundary (sideset) id of every boundary side, -1 elsewhere; bnd_kind[n_bnd] gives the RayBC
+ * applied on each boundary id (MCW_BC_KILL / MCW_BC_REFLECT; RT TraceRay.C:2043-2146 looks the
+ * RayBCs up per boundary id the same way).  A boundary side without an id kills the ray. */
 int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem,
                  const int64_t* conn, const int32_t* block_id, const int64_t* neighbors,
-                 const int8_t* bc_kind);
+                 const int32_t* side_bnd_id, int n_bnd, const int32_t* bnd_kind);
 
 /* Nuclear data.  Replaces HDF5 loading in openmc_init + Nuclide::init_grid
  * [OMC nuclide.cpp:50-302,446-476; simulation.cpp:553-619]. */
@@ -237,8 +247,12 @@ int mcw_run_generation(mcw_handle h, int batch, mcw_generation_result* out);
 int mcw_bank_count(mcw_handle h, int64_t* n_local);               /* local fission sites */
 int mcw_bank_device_ptr(mcw_handle h, void** sites, int64_t* n);  /* sorted local fission bank */
 int mcw_set_bank_window(mcw_handle h, int64_t global_start, int64_t global_total); /* Exscan/Bcast result */
+/* synchronize_bank sampling on this rank's slice [OMC eigenvalue.cpp:112-160], then the last-rank
+ * trim / pad to exactly n_particles [OMC eigenvalue.cpp:184-206; MC OpenMCStudy.C:557-588]. */
+int mcw_sample_bank(mcw_handle h, int batch, int64_t* n_sampled);
+int mcw_finish_sampling(mcw_handle h, int64_t global_start_of_sampled, int is_last, int64_t* n_sampled);
 int mcw_sampled_device_ptr(mcw_handle h, void** sites, int64_t* n); /* sites this rank sampled */
-int mcw_source_device_ptr(mcw_handle h, void** sites, int64_t capacity); /* where received sites go */
+int mcw_source_device_ptr(mcw_handle h, void** sites, int64_t* capacity); /* where received sites go */
 int mcw_set_source_count(mcw_handle h, int64_t n);
 int mcw_reduction_device_ptr(mcw_handle h, void** doubles, int64_t* n); /* [tally VALUEs | k_col,k_abs,k_trk,leak | weight] */
 
@@ -252,6 +266,7 @@ int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy,
 /* Parity / diagnostics output (RT TraceData.h:20-68 cached traces are the reference analogue). */
 int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n);
 int mcw_get_fission_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n);
+int mcw_get_grid_index(mcw_handle h, int i_nuclide, int32_t* out, int n /* n_log_bins + 1 */);
 
 /* Stand-alone kernels of the path, exposed for unit parity and the XS-lookup bandwidth metric.
  * mcw_xs_lookup: macroscopic cross sections for n (energy, material) pairs in HOST memory
@@ -263,8 +278,9 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
 /* mcw_trace_rays: walk n rays through the mesh with no physics until a kill boundary (the RT
  * `lots.i` tests' workload); out_distance[n], out_segments[n], out_hash[n]. */
 int mcw_trace_rays(mcw_handle h, int64_t n, const double* start, const double* dir,
-                   const int32_t* start_elem, double* out_distance, int32_t* out_segments,
-                   uint64_t* out_hash);
+                   const int32_t* start_elem, const int32_t* start_side /* NULL, or -1 none / -2 find */,
+                   const double* max_distance /* NULL = unbounded */, double* out_distance,
+                   int32_t* out_segments, uint64_t* out_hash);
 /* mcw_locate_points: starting element by the ClaimRays rule [RT ClaimRays.C:104-139]. */
 int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem);
 

@@ -1,0 +1,1502 @@
+// mcw_api.cu -- host side of libmacaw_b200.so: context, set-up, the event loop, C ABI.
+// Declarations and the reference interfaces each entry point replaces are in include/macaw_b200.h.
+// There is no CPU execution path in this file: every compute call launches the sm_100a kernels of
+// mcw_kernels.cu and fails with MCW_E_CUDA if no Blackwell-class device is present.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "mcw_detmath.h"
+#include "mcw_kernels.h"
+
+namespace
+{
+struct HostTally
+{
+  int id, estimator, granularity, n_scores, n_energy;
+  int scores[MCW_N_SCORES];
+  std::vector<double> ebins;
+  int64_t n_spatial = 1, n_values = 0, offset = 0; // offset into the reduction buffer
+  double *d_sum = nullptr, *d_sum_sq = nullptr, *d_ebins = nullptr;
+  int n_realizations = 0;
+};
+
+struct HostNuclide
+{
+  McwNucParams prm;
+  std::vector<double> energy, xs5, elastic, inelastic_full;
+  std::vector<int32_t> grid_index;
+};
+
+template <int TYPE>
+struct Topo;
+template <>
+struct Topo<MCW_QUAD4>
+{
+  static constexpr int NV = 4, NS = 4, NPS = 2;
+  static const int (*side_nodes())[4]
+  {
+    static const int t[4][4] = {{0, 1, 0, 0}, {1, 2, 0, 0}, {2, 3, 0, 0}, {3, 0, 0, 0}};
+    return t;
+  }
+};
+template <>
+struct Topo<MCW_TET4>
+{
+  static constexpr int NV = 4, NS = 4, NPS = 3;
+  static const int (*side_nodes())[4]
+  {
+    static const int t[4][4] = {{0, 2, 1, 0}, {0, 1, 3, 0}, {1, 2, 3, 0}, {2, 0, 3, 0}};
+    return t;
+  }
+};
+template <>
+struct Topo<MCW_HEX8>
+{
+  static constexpr int NV = 8, NS = 6, NPS = 4;
+  static const int (*side_nodes())[4]
+  {
+    static const int t[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+    return t;
+  }
+};
+
+struct TopoRT
+{
+  int nv, ns, nps, cpv, stride;
+  const int (*sn)[4];
+};
+TopoRT topo_of(int type)
+{
+  if (type == MCW_QUAD4)
+    return {4, 4, 2, 2, McwElem<MCW_QUAD4>::STRIDE, Topo<MCW_QUAD4>::side_nodes()};
+  if (type == MCW_TET4)
+    return {4, 4, 3, 3, McwElem<MCW_TET4>::STRIDE, Topo<MCW_TET4>::side_nodes()};
+  return {8, 6, 4, 3, McwElem<MCW_HEX8>::STRIDE, Topo<MCW_HEX8>::side_nodes()};
+}
+} // namespace
+
+struct mcw_context
+{
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<void*> allocs;
+
+  // host-side problem description
+  int elem_type = -1;
+  int64_t n_nodes = 0, n_elem = 0;
+  std::vector<double> xyz;
+  std::vector<int64_t> conn, nbr;
+  std::vector<int32_t> block_raw, side_bnd, bnd_kind;
+  std::vector<HostNuclide> nuclides;
+  std::vector<std::vector<int32_t>> mat_nuc;
+  std::vector<std::vector<double>> mat_dens;
+  std::vector<int32_t> block_ids, block_material;
+  std::vector<double> temperature;
+  std::vector<HostTally> tallies;
+  mcw_settings set{};
+  bool have_mesh = false, have_lib = false, have_mats = false, have_set = false, prepared = false;
+  std::vector<int64_t> work_index;
+  int64_t n_local = 0;
+
+  // device state
+  McwParams P{};
+  McwCounters* h_counters = nullptr; // pinned
+  mcw_source_site *d_source = nullptr, *d_bank = nullptr, *d_sorted = nullptr, *d_sampled = nullptr;
+  int32_t *d_q_fly[2] = {nullptr, nullptr}, *d_q_collide = nullptr, *d_q_fallback = nullptr, *d_q_sorted = nullptr;
+  uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
+  int64_t *d_i64_a = nullptr, *d_i64_b = nullptr;
+  void* d_temp = nullptr;
+  size_t temp_bytes = 0;
+  double* d_reduce = nullptr; // [tally values | k_col k_abs k_trk leak | weight]
+  int64_t n_reduce = 0, n_tally_values = 0;
+  double* d_box = nullptr;
+  mcw_history_record* d_records = nullptr;
+  int64_t n_source = 0, n_bank = 0, n_sampled = 0, bank_capacity = 0, sampled_capacity = 0;
+  int64_t bank_global_start = 0, bank_global_total = -1;
+  bool records_valid = false;
+
+  // eigenvalue bookkeeping (OMC simulation.cpp:253-276)
+  double keff = 1.0, keff_std = 0.0, k_sum[2] = {0, 0};
+  int n_realizations = 0;
+  std::vector<double> k_generation;
+  double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
+
+  // options
+  int profile = 0, sync_every = 1, fallback_blocks = 8;
+  mcw_generation_result last{};
+  cudaEvent_t ev[8] = {};
+};
+
+#define CK(call)                                                                                               \
+  do                                                                                                           \
+  {                                                                                                            \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                     \
+    {                                                                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                             \
+      return MCW_E_CUDA;                                                                                       \
+    }                                                                                                          \
+  } while (0)
+
+static int fail(mcw_handle h, int code, const std::string& msg)
+{
+  if (h)
+    h->err = msg;
+  return code;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(mcw_handle h, T** p, size_t n)
+{
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e == cudaSuccess)
+  {
+    h->allocs.push_back(q);
+    *p = (T*)q;
+  }
+  return e;
+}
+
+template <typename T>
+static cudaError_t dev_upload(mcw_handle h, T** p, const std::vector<T>& v)
+{
+  cudaError_t e = dev_alloc(h, p, v.size());
+  if (e != cudaSuccess)
+    return e;
+  if (!v.empty())
+    e = cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+static void dev_free(mcw_handle h, void* p)
+{
+  if (!p)
+    return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+  if (it != h->allocs.end())
+    h->allocs.erase(it);
+  cudaFree(p);
+}
+
+extern "C" {
+
+int mcw_version(void) { return 100; }
+
+int mcw_create(mcw_handle* out, int device_ordinal, int rank, int nranks)
+{
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks)
+    return MCW_E_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+  {
+    cudaGetLastError();
+    return MCW_E_CUDA; // no GPU: there is deliberately no CPU fallback
+  }
+  if (device_ordinal < 0 || device_ordinal >= n_dev)
+    return MCW_E_INVALID_ARGUMENT;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess)
+    return MCW_E_CUDA;
+  if (prop.major != 10)
+    return MCW_E_CUDA; // kernels are built for sm_100a only
+  if (cudaSetDevice(device_ordinal) != cudaSuccess)
+    return MCW_E_CUDA;
+  mcw_handle h = new mcw_context();
+  h->device = device_ordinal;
+  h->rank = rank;
+  h->nranks = nranks;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_counters, sizeof(McwCounters)) != cudaSuccess)
+  {
+    delete h;
+    return MCW_E_CUDA;
+  }
+  for (auto& e : h->ev)
+    cudaEventCreate(&e);
+  *out = h;
+  return MCW_OK;
+}
+
+void mcw_destroy(mcw_handle h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs)
+    cudaFree(p);
+  if (h->h_counters)
+    cudaFreeHost(h->h_counters);
+  for (auto& e : h->ev)
+    if (e)
+      cudaEventDestroy(e);
+  if (h->stream)
+    cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* mcw_last_error(mcw_handle h) { return h ? h->err.c_str() : "invalid handle"; }
+
+int mcw_set_option(mcw_handle h, const char* name, int value)
+{
+  if (!h || !name)
+    return MCW_E_INVALID_ARGUMENT;
+  std::string n(name);
+  if (n == "profile")
+    h->profile = value;
+  else if (n == "sync_every")
+    h->sync_every = std::max(1, value);
+  else if (n == "fallback_blocks")
+    h->fallback_blocks = std::max(1, value);
+  else
+    return fail(h, MCW_E_INVALID_ARGUMENT, "unknown option " + n);
+  return MCW_OK;
+}
+
+int mcw_calculate_work(int64_t n_particles, int nranks, int64_t* work_index)
+{
+  // OMC simulation.cpp:529-551
+  if (nranks < 1 || !work_index || n_particles < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  int64_t min_work = n_particles / nranks, rem = n_particles % nranks;
+  work_index[0] = 0;
+  for (int i = 0; i < nranks; ++i)
+    work_index[i + 1] = work_index[i] + (i < rem ? min_work + 1 : min_work);
+  return MCW_OK;
+}
+
+int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem, const int64_t* conn,
+                 const int32_t* block_id, const int64_t* neighbors, const int32_t* side_bnd_id, int n_bnd,
+                 const int32_t* bnd_kind)
+{
+  if (!h)
+    return MCW_E_INVALID_ARGUMENT;
+  if (elem_type != MCW_QUAD4 && elem_type != MCW_TET4 && elem_type != MCW_HEX8)
+    return fail(h, MCW_E_UNSUPPORTED, "element type not supported (QUAD4, TET4, HEX8)");
+  if (!xyz || !conn || !block_id || n_nodes <= 0 || n_elem <= 0 || n_elem > 0x7fffffff)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_mesh: bad arguments");
+  TopoRT t = topo_of(elem_type);
+  h->elem_type = elem_type;
+  h->n_nodes = n_nodes;
+  h->n_elem = n_elem;
+  h->xyz.assign(xyz, xyz + 3 * n_nodes);
+  h->conn.assign(conn, conn + n_elem * t.nv);
+  h->block_raw.assign(block_id, block_id + n_elem);
+  for (int64_t i = 0; i < n_elem * t.nv; ++i)
+    if (conn[i] < 0 || conn[i] >= n_nodes)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_mesh: connectivity out of range");
+  if (neighbors)
+    h->nbr.assign(neighbors, neighbors + n_elem * t.ns);
+  else
+  {
+    // face matching (what libMesh find_neighbors provides as elem->neighbor_ptr, RT TraceRay.C:1433)
+    struct Face
+    {
+      int64_t k[4];
+      int64_t es;
+    };
+    std::vector<Face> faces((size_t)n_elem * t.ns);
+    for (int64_t e = 0; e < n_elem; ++e)
+      for (int s = 0; s < t.ns; ++s)
+      {
+        Face& f = faces[e * t.ns + s];
+        f.k[0] = f.k[1] = f.k[2] = f.k[3] = -1;
+        for (int i = 0; i < t.nps; ++i)
+          f.k[i] = conn[e * t.nv + t.sn[s][i]];
+        std::sort(f.k, f.k + t.nps);
+        f.es = e * t.ns + s;
+      }
+    std::sort(faces.begin(), faces.end(), [](const Face& a, const Face& b) {
+      for (int i = 0; i < 4; ++i)
+        if (a.k[i] != b.k[i])
+          return a.k[i] < b.k[i];
+      return a.es < b.es;
+    });
+    h->nbr.assign((size_t)n_elem * t.ns, -1);
+    for (size_t i = 0; i + 1 < faces.size(); ++i)
+      if (!memcmp(faces[i].k, faces[i + 1].k, sizeof(faces[i].k)))
+      {
+        h->nbr[faces[i].es] = faces[i + 1].es / t.ns;
+        h->nbr[faces[i + 1].es] = faces[i].es / t.ns;
+      }
+  }
+  if (side_bnd_id)
+    h->side_bnd.assign(side_bnd_id, side_bnd_id + n_elem * t.ns);
+  else
+    h->side_bnd.assign((size_t)n_elem * t.ns, -1);
+  h->bnd_kind.assign(bnd_kind, bnd_kind + (bnd_kind ? n_bnd : 0));
+  h->have_mesh = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
+{
+  if (!h || !d || n <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  h->nuclides.clear();
+  int64_t off = 0;
+  for (int i = 0; i < n; ++i)
+  {
+    if (d[i].n_grid < 2 || !d[i].energy || !d[i].xs || !d[i].elastic)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_library: nuclide table missing");
+    if (d[i].n_precursor < 0 || d[i].n_precursor > MCW_MAX_DELAYED_GROUPS)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_library: too many delayed groups");
+    HostNuclide N;
+    memset(&N.prm, 0, sizeof(N.prm));
+    const int G = d[i].n_grid;
+    N.prm.G = G;
+    N.prm.off = off;
+    off += G;
+    N.prm.fissionable = d[i].fissionable != 0;
+    N.prm.awr = d[i].awr;
+    N.prm.kT = d[i].kT;
+    N.prm.n_inel = d[i].n_inelastic;
+    N.prm.inel_thr = d[i].inel_threshold;
+    N.prm.inel_E = d[i].inel_threshold_energy;
+    N.prm.inel_ratio = d[i].inel_mass_ratio;
+    N.prm.nu_poly[0] = d[i].nu_poly[0];
+    N.prm.nu_poly[1] = d[i].nu_poly[1];
+    N.prm.n_precursor = d[i].n_precursor;
+    for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
+    {
+      N.prm.dyield[g] = d[i].delayed_yield[g];
+      N.prm.dtheta[g] = d[i].delayed_theta[g];
+    }
+    N.prm.watt_a = d[i].watt_a;
+    N.prm.watt_b = d[i].watt_b;
+    N.prm.q = d[i].q_fission;
+    N.energy.assign(d[i].energy, d[i].energy + G);
+    for (int k = 1; k < G; ++k)
+      if (N.energy[k] < N.energy[k - 1])
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_library: energy grid not sorted");
+    N.xs5.assign(d[i].xs, d[i].xs + 5 * (size_t)G);
+    N.elastic.assign(d[i].elastic, d[i].elastic + G);
+    N.inelastic_full.assign(G, 0.0);
+    if (N.prm.n_inel)
+    {
+      if (!d[i].inelastic || N.prm.inel_thr < 0 || N.prm.inel_thr >= G)
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_library: inelastic table missing");
+      for (int k = N.prm.inel_thr; k < G; ++k)
+        N.inelastic_full[k] = d[i].inelastic[k - N.prm.inel_thr];
+    }
+    h->nuclides.push_back(std::move(N));
+  }
+  h->have_lib = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_materials(mcw_handle h, const mcw_material_desc* m, int n, const int32_t* block_ids,
+                      const int32_t* block_material, int n_blocks)
+{
+  if (!h || !m || n <= 0 || !block_ids || !block_material || n_blocks <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  h->mat_nuc.clear();
+  h->mat_dens.clear();
+  for (int i = 0; i < n; ++i)
+  {
+    if (m[i].n_nuclides <= 0 || m[i].n_nuclides > MCW_MAX_NUC_PER_MAT)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_materials: bad nuclide count");
+    h->mat_nuc.emplace_back(m[i].nuclide, m[i].nuclide + m[i].n_nuclides);
+    h->mat_dens.emplace_back(m[i].atom_density, m[i].atom_density + m[i].n_nuclides);
+  }
+  h->block_ids.assign(block_ids, block_ids + n_blocks);
+  h->block_material.assign(block_material, block_material + n_blocks);
+  for (int b = 0; b < n_blocks; ++b)
+    if (block_material[b] < 0 || block_material[b] >= n)
+      // MC CollisionKernel.C:84-90 "Could not find material ... in OpenMC materials."
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_materials: block mapped to an unknown material");
+  h->have_mats = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_temperature(mcw_handle h, const double* T, int64_t n)
+{
+  if (!h || !T || n <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  // Single-temperature libraries: the coupled temperature only selects the (only) data set
+  // (OMC nuclide.cpp:614-626 NEAREST); kept so the CollisionKernel parameter has somewhere to go.
+  h->temperature.assign(T, T + n);
+  return MCW_OK;
+}
+
+int mcw_set_settings(mcw_handle h, const mcw_settings* s)
+{
+  if (!h || !s || s->n_particles <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  if (s->n_log_bins < 1)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "n_log_bins must be positive");
+  h->set = *s;
+  h->work_index.assign(h->nranks + 1, 0);
+  mcw_calculate_work(s->n_particles, h->nranks, h->work_index.data());
+  h->n_local = h->work_index[h->rank + 1] - h->work_index[h->rank];
+  h->have_set = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_add_tally(mcw_handle h, int id, int estimator, int granularity, const int32_t* scores, int n_scores,
+                  const double* energy_bins, int n_energy_edges)
+{
+  if (!h || !scores || n_scores <= 0 || n_scores > MCW_N_SCORES)
+    return MCW_E_INVALID_ARGUMENT;
+  if (estimator != MCW_ESTIMATOR_COLLISION && estimator != MCW_ESTIMATOR_TRACKLENGTH)
+    // MC OpenMCTally.C:89-90 "Only collision estimator currently supported" (+ track-length extension)
+    return fail(h, MCW_E_UNSUPPORTED, "estimator must be collision or tracklength");
+  if (granularity < 0 || granularity > MCW_FILTER_GLOBAL)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "unknown granularity");
+  if ((int)h->tallies.size() >= MCW_MAX_TALLIES)
+    return fail(h, MCW_E_UNSUPPORTED, "too many tallies");
+  for (auto& t : h->tallies)
+    if (t.id == id)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "duplicate tally id");
+  HostTally t;
+  t.id = id;
+  t.estimator = estimator;
+  t.granularity = granularity;
+  t.n_scores = n_scores;
+  for (int i = 0; i < n_scores; ++i)
+  {
+    if (scores[i] < 0 || scores[i] >= MCW_N_SCORES)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "unknown score");
+    t.scores[i] = scores[i];
+  }
+  t.n_energy = 1;
+  if (energy_bins && n_energy_edges >= 2)
+  {
+    t.ebins.assign(energy_bins, energy_bins + n_energy_edges);
+    t.n_energy = n_energy_edges - 1;
+  }
+  h->tallies.push_back(t);
+  h->prepared = false;
+  return MCW_OK;
+}
+
+// ------------------------------------------------------------------ prepare: build device state
+static int prepare(mcw_handle h)
+{
+  if (h->prepared)
+    return MCW_OK;
+  if (!h->have_mesh || !h->have_lib || !h->have_mats || !h->have_set)
+    return fail(h, MCW_E_NOT_READY, "mesh, library, materials and settings must be set first");
+  CK(cudaSetDevice(h->device));
+  for (void* p : h->allocs)
+    cudaFree(p);
+  h->allocs.clear();
+  McwParams& P = h->P;
+  memset(&P, 0, sizeof(P));
+  TopoRT t = topo_of(h->elem_type);
+  const int n_nuc = (int)h->nuclides.size(), n_mat = (int)h->mat_nuc.size();
+  for (auto& mn : h->mat_nuc)
+    for (int v : mn)
+      if (v < 0 || v >= n_nuc)
+        return fail(h, MCW_E_INVALID_ARGUMENT, "material refers to a nuclide outside the library");
+
+  // ---- library: OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
+  const int M = h->set.n_log_bins;
+  double E_min = 0.0, E_max = INFINITY;
+  for (auto& n : h->nuclides)
+  {
+    E_min = std::max(E_min, n.energy.front());
+    E_max = std::min(E_max, n.energy.back());
+  }
+  const double spacing = mcw_log(E_max / E_min) / M;
+  std::vector<double> energy, xs4, el_inel;
+  std::vector<int32_t> grid_index;
+  std::vector<McwNucParams> prm;
+  for (auto& n : h->nuclides)
+  {
+    const int G = n.prm.G;
+    energy.insert(energy.end(), n.energy.begin(), n.energy.end());
+    for (int k = 0; k < G; ++k)
+    {
+      for (int c = 0; c < 4; ++c)
+        xs4.push_back(n.xs5[5 * (size_t)k + c]);
+      el_inel.push_back(n.elastic[k]);
+      el_inel.push_back(n.inelastic_full[k]);
+    }
+    int j = 0;
+    const double step = (M * spacing - 0.0) / M;
+    for (int k = 0; k <= M; ++k)
+    {
+      double umesh = 0.0 + k * step;
+      while (mcw_log(n.energy[j + 1] / E_min) <= umesh)
+      {
+        if (j + 2 == G)
+          break;
+        ++j;
+      }
+      grid_index.push_back(j);
+    }
+    prm.push_back(n.prm);
+  }
+  std::vector<int32_t> mat_off(1, 0), mat_nuc, mat_fis;
+  std::vector<double> mat_dens;
+  for (int m = 0; m < n_mat; ++m)
+  {
+    bool fis = false;
+    for (size_t i = 0; i < h->mat_nuc[m].size(); ++i)
+    {
+      mat_nuc.push_back(h->mat_nuc[m][i]);
+      mat_dens.push_back(h->mat_dens[m][i]);
+      fis |= h->nuclides[h->mat_nuc[m][i]].prm.fissionable != 0;
+    }
+    mat_off.push_back((int32_t)mat_nuc.size());
+    mat_fis.push_back(fis);
+  }
+  double *d_energy, *d_xs4, *d_el, *d_dens;
+  int32_t *d_gi, *d_moff, *d_mnuc, *d_mfis;
+  McwNucParams* d_prm;
+  CK(dev_upload(h, &d_energy, energy));
+  CK(dev_upload(h, &d_xs4, xs4));
+  CK(dev_upload(h, &d_el, el_inel));
+  CK(dev_upload(h, &d_gi, grid_index));
+  CK(dev_upload(h, &d_prm, prm));
+  CK(dev_upload(h, &d_moff, mat_off));
+  CK(dev_upload(h, &d_mnuc, mat_nuc));
+  CK(dev_upload(h, &d_dens, mat_dens));
+  CK(dev_upload(h, &d_mfis, mat_fis));
+  P.lib.energy = d_energy;
+  P.lib.xs4 = d_xs4;
+  P.lib.el_inel = d_el;
+  P.lib.grid_index = d_gi;
+  P.lib.nuc = d_prm;
+  P.lib.mat_off = d_moff;
+  P.lib.mat_nuc = d_mnuc;
+  P.lib.mat_dens = d_dens;
+  P.lib.mat_fissionable = d_mfis;
+  P.lib.n_nuc = n_nuc;
+  P.lib.n_mat = n_mat;
+  P.lib.M = M;
+  P.lib.E_min = E_min;
+  P.lib.E_max = E_max;
+  P.lib.log_spacing = mcw_log(E_max / E_min) / M;
+
+  // ---- mesh: block index / material, subdomain hmax (RT RayTracingStudy.C:497-513), records
+  std::map<int32_t, int> block_index;
+  for (size_t b = 0; b < h->block_ids.size(); ++b)
+    block_index[h->block_ids[b]] = (int)b;
+  const int n_blocks = (int)h->block_ids.size();
+  std::vector<double> block_hmax(n_blocks, 0.0);
+  std::vector<int32_t> eblock(h->n_elem);
+  auto PX = [&](int64_t e, int v, int c) { return h->xyz[3 * h->conn[e * t.nv + v] + c]; };
+  for (int64_t e = 0; e < h->n_elem; ++e)
+  {
+    auto it = block_index.find(h->block_raw[e]);
+    if (it == block_index.end())
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mesh block " + std::to_string(h->block_raw[e]) + " has no material");
+    eblock[e] = it->second;
+    double h2 = 0;
+    for (int a = 0; a < t.nv; ++a)
+      for (int b = a + 1; b < t.nv; ++b)
+      {
+        double dx = PX(e, a, 0) - PX(e, b, 0), dy = PX(e, a, 1) - PX(e, b, 1), dz = PX(e, a, 2) - PX(e, b, 2);
+        h2 = std::max(h2, dx * dx + dy * dy + dz * dz);
+      }
+    block_hmax[eblock[e]] = std::max(block_hmax[eblock[e]], std::sqrt(h2));
+  }
+  const int n_bnd = (int)h->bnd_kind.size();
+  std::vector<unsigned char> rec((size_t)h->n_elem * t.stride, 0);
+  for (int64_t e = 0; e < h->n_elem; ++e)
+  {
+    unsigned char* r = rec.data() + (size_t)e * t.stride;
+    double* c = reinterpret_cast<double*>(r);
+    for (int v = 0; v < t.nv; ++v)
+      for (int k = 0; k < t.cpv; ++k)
+        c[v * t.cpv + k] = PX(e, v, k);
+    int32_t* nb = reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8);
+    for (int s = 0; s < t.ns; ++s)
+    {
+      int64_t n = h->nbr[e * t.ns + s];
+      if (n >= 0)
+        nb[s] = (int32_t)n;
+      else
+      {
+        int32_t id = h->side_bnd[e * t.ns + s];
+        if (id < 0 || id >= n_bnd)
+          id = n_bnd; // no boundary condition on this side: treated as kill (RT TraceRay.C:2100-2146 errors)
+        nb[s] = -1 - id;
+      }
+    }
+    *reinterpret_cast<double*>(r + t.nv * t.cpv * 8 + t.ns * 4) = block_hmax[eblock[e]];
+    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 8) = h->block_material[eblock[e]];
+    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 12) = eblock[e];
+  }
+  // node -> elements CSR
+  std::vector<int64_t> n2e_off(h->n_nodes + 1, 0);
+  for (int64_t i = 0; i < h->n_elem * t.nv; ++i)
+    n2e_off[h->conn[i] + 1]++;
+  for (int64_t i = 0; i < h->n_nodes; ++i)
+    n2e_off[i + 1] += n2e_off[i];
+  std::vector<int32_t> n2e(n2e_off.back());
+  {
+    std::vector<int64_t> fill(n2e_off.begin(), n2e_off.end() - 1);
+    for (int64_t e = 0; e < h->n_elem; ++e)
+      for (int v = 0; v < t.nv; ++v)
+        n2e[fill[h->conn[e * t.nv + v]]++] = (int32_t)e;
+  }
+  // bounding box, rectangular-domain flag, point-location grid
+  double bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = 0; i < h->n_nodes; ++i)
+    for (int c = 0; c < 3; ++c)
+    {
+      bmin[c] = std::min(bmin[c], h->xyz[3 * i + c]);
+      bmax[c] = std::max(bmax[c], h->xyz[3 * i + c]);
+    }
+  const int dim = h->elem_type == MCW_QUAD4 ? 2 : 3;
+  double diag = std::sqrt((bmax[0] - bmin[0]) * (bmax[0] - bmin[0]) + (bmax[1] - bmin[1]) * (bmax[1] - bmin[1]) +
+                          (bmax[2] - bmin[2]) * (bmax[2] - bmin[2]));
+  const double dml = 1.01 * diag; // RT RayTracingStudy.C:154
+  bool rectangular = true;
+  {
+    double tol = 1e-10 * dml;
+    for (int64_t e = 0; e < h->n_elem && rectangular; ++e)
+      for (int s = 0; s < t.ns && rectangular; ++s)
+        if (h->nbr[e * t.ns + s] < 0)
+        {
+          bool on_plane = false;
+          for (int d = 0; d < dim && !on_plane; ++d)
+          {
+            bool lo = true, hi = true;
+            for (int i = 0; i < t.nps; ++i)
+            {
+              double c = PX(e, t.sn[s][i], d);
+              lo = lo && std::fabs(c - bmin[d]) <= tol;
+              hi = hi && std::fabs(c - bmax[d]) <= tol;
+            }
+            on_plane = lo || hi;
+          }
+          if (!on_plane)
+            rectangular = false;
+        }
+  }
+  int gx, gy, gz;
+  {
+    double n = std::max<double>(1.0, (double)h->n_elem);
+    if (dim == 2)
+    {
+      gx = gy = std::max(1, (int)std::sqrt(n));
+      gz = 1;
+    }
+    else
+      gx = gy = gz = std::max(1, (int)std::cbrt(n));
+  }
+  std::vector<int64_t> cell_off((size_t)gx * gy * gz + 1, 0);
+  std::vector<int32_t> cell_elems;
+  {
+    double ext[3] = {bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]};
+    int g[3] = {gx, gy, gz};
+    auto range = [&](double lo, double hi, int d, int& a, int& b) {
+      if (ext[d] <= 0)
+      {
+        a = b = 0;
+        return;
+      }
+      a = (int)std::floor((lo - bmin[d]) / ext[d] * g[d] - 1e-9);
+      b = (int)std::floor((hi - bmin[d]) / ext[d] * g[d] + 1e-9);
+      a = std::min(std::max(a, 0), g[d] - 1);
+      b = std::min(std::max(b, 0), g[d] - 1);
+    };
+    std::vector<int64_t> cnt(cell_off.size(), 0);
+    for (int pass = 0; pass < 2; ++pass)
+    {
+      for (int64_t e = 0; e < h->n_elem; ++e)
+      {
+        double lo[3], hi[3];
+        for (int c = 0; c < 3; ++c)
+          lo[c] = hi[c] = PX(e, 0, c);
+        for (int v = 1; v < t.nv; ++v)
+          for (int c = 0; c < 3; ++c)
+          {
+            lo[c] = std::min(lo[c], PX(e, v, c));
+            hi[c] = std::max(hi[c], PX(e, v, c));
+          }
+        int a[3], b[3];
+        for (int c = 0; c < 3; ++c)
+          range(lo[c], hi[c], c, a[c], b[c]);
+        for (int k = a[2]; k <= b[2]; ++k)
+          for (int j = a[1]; j <= b[1]; ++j)
+            for (int i = a[0]; i <= b[0]; ++i)
+            {
+              size_t c = ((size_t)k * gy + j) * gx + i;
+              if (pass == 0)
+                cnt[c + 1]++;
+              else
+                cell_elems[cnt[c]++] = (int32_t)e;
+            }
+      }
+      if (pass == 0)
+      {
+        for (size_t c = 0; c + 1 < cnt.size(); ++c)
+          cnt[c + 1] += cnt[c];
+        cell_off = cnt;
+        cell_elems.assign(cnt.back(), 0);
+        cnt.assign(cell_off.begin(), cell_off.end());
+      }
+    }
+  }
+  unsigned char* d_rec;
+  int64_t *d_conn, *d_n2e_off, *d_cell_off;
+  int32_t *d_n2e, *d_bk, *d_cell_elems;
+  CK(dev_upload(h, &d_rec, rec));
+  CK(dev_upload(h, &d_conn, h->conn));
+  CK(dev_upload(h, &d_n2e_off, n2e_off));
+  CK(dev_upload(h, &d_n2e, n2e));
+  CK(dev_upload(h, &d_bk, h->bnd_kind));
+  CK(dev_upload(h, &d_cell_off, cell_off));
+  CK(dev_upload(h, &d_cell_elems, cell_elems));
+  P.mesh.rec = d_rec;
+  P.mesh.conn = d_conn;
+  P.mesh.n2e_off = d_n2e_off;
+  P.mesh.n2e = d_n2e;
+  P.mesh.bnd_kind = d_bk;
+  P.mesh.cell_off = d_cell_off;
+  P.mesh.cell_elems = d_cell_elems;
+  P.mesh.gx = gx;
+  P.mesh.gy = gy;
+  P.mesh.gz = gz;
+  P.mesh.type = h->elem_type;
+  P.mesh.n_bnd = n_bnd;
+  P.mesh.rectangular = rectangular;
+  P.mesh.n_elem = h->n_elem;
+  P.mesh.n_nodes = h->n_nodes;
+  for (int c = 0; c < 3; ++c)
+  {
+    P.mesh.bb_min[c] = bmin[c];
+    P.mesh.bb_max[c] = bmax[c];
+  }
+  P.mesh.domain_max_length = dml;
+
+  // ---- particles, queues, banks
+  const int64_t n = h->n_local;
+  McwParticlesDev& p = P.p;
+  double** dd[] = {&p.x, &p.y, &p.z, &p.ux, &p.uy, &p.uz, &p.E, &p.wgt, &p.sig_t, &p.sig_a, &p.sig_f, &p.sig_nf,
+                   &p.k_col, &p.k_abs, &p.k_trk};
+  for (auto q : dd)
+    CK(dev_alloc(h, q, n));
+  uint64_t** du[] = {&p.seed_trk, &p.seed_src, &p.seed_urr, &p.hash};
+  for (auto q : du)
+    CK(dev_alloc(h, q, n));
+  int32_t** di[] = {&p.elem, &p.last_elem, &p.xs_mat, &p.n_progeny, &p.n_seg, &p.n_coll, &p.n_xs};
+  for (auto q : di)
+    CK(dev_alloc(h, q, n));
+  int8_t** db[] = {&p.inc_side, &p.ext_first, &p.ext_second, &p.status, &p.fate};
+  for (auto q : db)
+    CK(dev_alloc(h, q, n));
+  h->bank_capacity = 3 * n; // OMC simulation.cpp:286
+  h->sampled_capacity = 3 * n + 16;
+  CK(dev_alloc(h, &h->d_source, h->sampled_capacity));
+  CK(dev_alloc(h, &h->d_bank, h->bank_capacity));
+  CK(dev_alloc(h, &h->d_sorted, h->bank_capacity));
+  CK(dev_alloc(h, &h->d_sampled, h->sampled_capacity));
+  CK(dev_alloc(h, &h->d_q_fly[0], n));
+  CK(dev_alloc(h, &h->d_q_fly[1], n));
+  CK(dev_alloc(h, &h->d_q_collide, n));
+  CK(dev_alloc(h, &h->d_q_fallback, n));
+  CK(dev_alloc(h, &h->d_q_sorted, n));
+  CK(dev_alloc(h, &h->d_keys, n));
+  CK(dev_alloc(h, &h->d_keys_out, n));
+  CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
+  CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
+  h->temp_bytes = mcwk_scan_temp_bytes(std::max(h->bank_capacity, n));
+  {
+    unsigned char* tmp;
+    CK(dev_alloc(h, &tmp, h->temp_bytes));
+    h->d_temp = tmp;
+  }
+  CK(dev_alloc(h, &P.counters, 1));
+  CK(cudaMemset(P.counters, 0, sizeof(McwCounters)));
+  CK(dev_alloc(h, &h->d_records, n));
+  CK(dev_alloc(h, &h->d_box, 6));
+  P.bank = h->d_bank;
+  P.bank_capacity = h->bank_capacity;
+
+  // ---- tallies: VALUE arrays live in one buffer followed by the 5 global doubles so a single
+  //      all-reduce covers everything (OMC tallies/tally.cpp:745-803 reduce_tally_results)
+  int64_t total_values = 0;
+  for (auto& tl : h->tallies)
+  {
+    tl.n_spatial =
+        tl.granularity == MCW_FILTER_CELL ? h->n_elem : (tl.granularity == MCW_FILTER_UNIVERSE ? n_blocks : 1);
+    tl.n_values = tl.n_spatial * tl.n_energy * tl.n_scores;
+    tl.offset = total_values;
+    total_values += tl.n_values;
+  }
+  h->n_tally_values = total_values;
+  h->n_reduce = total_values + 5;
+  CK(dev_alloc(h, &h->d_reduce, h->n_reduce));
+  CK(cudaMemset(h->d_reduce, 0, h->n_reduce * sizeof(double)));
+  P.n_tallies = (int)h->tallies.size();
+  P.any_tracklength = P.any_collision_tally = 0;
+  for (size_t i = 0; i < h->tallies.size(); ++i)
+  {
+    HostTally& tl = h->tallies[i];
+    CK(dev_alloc(h, &tl.d_sum, tl.n_values));
+    CK(dev_alloc(h, &tl.d_sum_sq, tl.n_values));
+    CK(cudaMemset(tl.d_sum, 0, tl.n_values * sizeof(double)));
+    CK(cudaMemset(tl.d_sum_sq, 0, tl.n_values * sizeof(double)));
+    CK(dev_upload(h, &tl.d_ebins, tl.ebins));
+    tl.n_realizations = 0;
+    McwTallyDev& d = P.tally[i];
+    d.value = h->d_reduce + tl.offset;
+    d.ebins = tl.d_ebins;
+    d.n_edges = (int)tl.ebins.size();
+    d.n_energy = tl.n_energy;
+    d.n_scores = tl.n_scores;
+    d.granularity = tl.granularity;
+    d.estimator = tl.estimator;
+    for (int s = 0; s < tl.n_scores; ++s)
+      d.scores[s] = tl.scores[s];
+    if (tl.estimator == MCW_ESTIMATOR_TRACKLENGTH)
+      P.any_tracklength = 1;
+    else
+      P.any_collision_tally = 1;
+  }
+  P.n_particles_global = h->set.n_particles;
+  P.work_offset = h->work_index[h->rank];
+  P.master_seed = h->set.master_seed;
+  P.is_2d = h->set.is_2d;
+  P.seed_through_double = h->set.seed_through_double;
+  P.max_events = h->set.max_events > 0 ? h->set.max_events : 1000000;
+  P.z_coord = h->set.z_coord;
+  h->keff = 1.0;
+  h->keff_std = 0.0;
+  h->k_sum[0] = h->k_sum[1] = 0.0;
+  h->n_realizations = 0;
+  h->k_generation.clear();
+  for (int i = 0; i < 4; ++i)
+    h->gt_sum[i] = h->gt_sum_sq[i] = 0.0;
+  h->n_source = 0;
+  h->prepared = true;
+  return MCW_OK;
+}
+
+int mcw_prepare(mcw_handle h)
+{
+  if (!h)
+    return MCW_E_INVALID_ARGUMENT;
+  return prepare(h);
+}
+
+// ------------------------------------------------------------------ source bank
+int mcw_sample_initial_source(mcw_handle h)
+{
+  if (!h)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_box, h->set.source_box, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->P.batch = 1;
+  mcwk_sample_source(h->P, h->d_source, h->n_local, h->d_box, h->set.source_only_fissionable, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_source = h->n_local;
+  return MCW_OK;
+}
+
+int mcw_set_source_bank(mcw_handle h, const mcw_source_site* sites, int64_t n)
+{
+  if (!h || !sites || n < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  if (n > h->n_local)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "source bank larger than this rank's share of n_particles");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_source, sites, n * sizeof(mcw_source_site), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_source = n;
+  return MCW_OK;
+}
+
+int mcw_get_source_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n)
+{
+  if (!h || !n)
+    return MCW_E_INVALID_ARGUMENT;
+  *n = h->n_source;
+  if (sites && capacity > 0)
+  {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(sites, h->d_source, std::min(capacity, h->n_source) * sizeof(mcw_source_site),
+                  cudaMemcpyDeviceToHost));
+  }
+  return MCW_OK;
+}
+
+// ------------------------------------------------------------------ the event loop
+int mcw_transport_generation(mcw_handle h, int batch)
+{
+  if (!h || batch < 1)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  if (h->n_source <= 0)
+    return fail(h, MCW_E_NOT_READY, "no source bank: call mcw_sample_initial_source or mcw_set_source_bank");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  McwParams& P = h->P;
+  const int64_t n = h->n_source;
+  P.batch = batch;
+  P.keff = h->keff;
+  P.tallies_active = batch > h->set.n_inactive; // OMC simulation.cpp:318-326
+  mcw_generation_result& R = h->last;
+  memset(&R, 0, sizeof(R));
+  CK(cudaEventRecord(h->ev[0], st));
+  CK(cudaMemsetAsync(P.counters, 0, sizeof(McwCounters), st));
+  CK(cudaMemsetAsync(h->d_reduce + h->n_tally_values, 0, 5 * sizeof(double), st));
+  mcwk_init_histories(P, h->d_source, n, h->d_q_fly[0], st);
+  R.n_kernel_launches += 1;
+  {
+    unsigned long long nn = (unsigned long long)n;
+    CK(cudaMemcpyAsync(&P.counters->n_fly[0], &nn, sizeof(nn), cudaMemcpyHostToDevice, st));
+  }
+  int cur = 0;
+  int64_t upper = n;
+  int64_t rounds = 0;
+  float ms;
+  const bool prof = h->profile != 0;
+  while (upper > 0)
+  {
+    int32_t* q = h->d_q_fly[cur];
+    unsigned long long* cnt_cur = &P.counters->n_fly[cur];
+    unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
+    if (prof)
+      cudaEventRecord(h->ev[1], st);
+    if (h->set.sort_xs_queue)
+    {
+      // particle-queue sort by (material, energy bucket): OpenMC's TODO at OMC event.cpp:76-82
+      int bits = 16 + 1;
+      for (int m = (int)h->mat_nuc.size(); m > 1; m >>= 1)
+        ++bits;
+      mcwk_xs_keys(P, q, cnt_cur, h->d_keys, upper, st);
+      mcwk_sort_queue(h->d_temp, h->temp_bytes, h->d_keys, h->d_keys_out, q, h->d_q_sorted, upper, 32, st);
+      (void)bits;
+      std::swap(h->d_q_fly[cur], h->d_q_sorted);
+      q = h->d_q_fly[cur];
+      R.n_kernel_launches += 4;
+    }
+    mcwk_xs_lookup(P, q, cnt_cur, upper, st);
+    if (prof)
+      cudaEventRecord(h->ev[2], st);
+    mcwk_track(P, q, cnt_cur, upper, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback, st);
+    if (prof)
+      cudaEventRecord(h->ev[3], st);
+    mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
+                  h->d_q_collide, st);
+    mcwk_collide(P, h->d_q_collide, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
+    if (prof)
+      cudaEventRecord(h->ev[4], st);
+    R.n_kernel_launches += 4;
+    ++rounds;
+    const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
+    if (sync_now || prof)
+    {
+      CK(cudaMemcpyAsync(h->h_counters, P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      upper = (int64_t)h->h_counters->n_fly[cur ^ 1];
+      if (prof)
+      {
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+        R.ms_xs += ms;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+        R.ms_track += ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+        R.ms_collide += ms;
+      }
+    }
+    // reset the consumed queues for the next round
+    CK(cudaMemsetAsync(cnt_cur, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(&P.counters->n_collide, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(&P.counters->n_fallback, 0, sizeof(unsigned long long), st));
+    cur ^= 1;
+    if (rounds > 100000000)
+      return fail(h, MCW_E_PHYSICS, "event loop did not terminate");
+  }
+  R.n_event_rounds = rounds;
+  if (prof)
+    cudaEventRecord(h->ev[5], st);
+  // ---- end of transport: counters, k accumulators, sorted bank
+  CK(cudaMemcpyAsync(h->h_counters, P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const McwCounters& C = *h->h_counters;
+  h->n_bank = std::min<int64_t>((int64_t)C.n_bank, h->bank_capacity);
+  double* g = h->d_reduce + h->n_tally_values;
+  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_col, g + 0, n, st);
+  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_abs, g + 1, n, st);
+  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_trk, g + 2, n, st);
+  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.wgt, g + 4, n, st);
+  mcwk_bank_sort(h->d_temp, h->temp_bytes, P.p, n, P.work_offset, h->d_bank, h->n_bank, h->d_i64_a, h->d_i64_b,
+                 h->d_sorted, st);
+  R.n_kernel_launches += 4 * 2 + 4;
+  CK(cudaEventRecord(h->ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+  R.ms_total = ms;
+  if (prof)
+  {
+    cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]);
+    R.ms_bank = ms;
+  }
+  R.n_histories = n;
+  R.n_segments = (int64_t)C.n_segments;
+  R.n_collisions = (int64_t)C.n_collisions;
+  R.n_bank_sites = h->n_bank;
+  R.n_vertex_edge_hits = (int64_t)C.n_vertex_edge;
+  R.n_moved_through_neighbors = (int64_t)C.n_moved;
+  R.n_failed_traces = (int64_t)C.n_failed;
+  h->bank_global_start = 0;
+  h->bank_global_total = h->n_bank;
+  h->records_valid = true;
+  h->n_sampled = 0;
+  return MCW_OK;
+}
+
+int mcw_bank_count(mcw_handle h, int64_t* n_local)
+{
+  if (!h || !n_local)
+    return MCW_E_INVALID_ARGUMENT;
+  *n_local = h->n_bank;
+  return MCW_OK;
+}
+
+int mcw_bank_device_ptr(mcw_handle h, void** sites, int64_t* n)
+{
+  if (!h || !sites || !n)
+    return MCW_E_INVALID_ARGUMENT;
+  *sites = h->d_sorted;
+  *n = h->n_bank;
+  return MCW_OK;
+}
+
+int mcw_set_bank_window(mcw_handle h, int64_t global_start, int64_t global_total)
+{
+  if (!h || global_start < 0 || global_total < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  h->bank_global_start = global_start;
+  h->bank_global_total = global_total;
+  return MCW_OK;
+}
+
+// OMC eigenvalue.cpp:112-160 on this rank's slice of the global fission bank
+int mcw_sample_bank(mcw_handle h, int batch, int64_t* n_sampled)
+{
+  if (!h || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  if (h->bank_global_total <= 0)
+    return fail(h, MCW_E_PHYSICS, "No fission sites banked"); // OMC eigenvalue.cpp:107-109
+  CK(cudaSetDevice(h->device));
+  const int64_t total = h->bank_global_total, np = h->set.n_particles;
+  uint64_t seed0 = mcwk_host_init_seed(0 + batch, 0 /*STREAM_TRACKING*/, h->set.master_seed);
+  if ((total < np ? np / total + 1 : 1) * h->n_bank > h->sampled_capacity)
+    return fail(h, MCW_E_ALLOCATE, "sampled-site buffer too small for this bank (too few fission sites)");
+  mcwk_sample_bank(h->d_temp, h->temp_bytes, h->d_sorted, h->n_bank, h->bank_global_start, total, np, seed0, h->d_i64_a,
+                   h->d_i64_b, h->d_sampled, h->sampled_capacity, h->stream);
+  int64_t last_off = 0, last_cnt = 0;
+  if (h->n_bank > 0)
+  {
+    CK(cudaMemcpyAsync(&last_off, h->d_i64_b + h->n_bank - 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&last_cnt, h->d_i64_a + h->n_bank - 1, 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->n_sampled = std::min(last_off + last_cnt, h->sampled_capacity);
+  h->last.n_kernel_launches += 3;
+  if (n_sampled)
+    *n_sampled = h->n_sampled;
+  return MCW_OK;
+}
+
+// OMC eigenvalue.cpp:184-206: only the last rank trims / pads to exactly n_particles
+int mcw_finish_sampling(mcw_handle h, int64_t global_start_of_sampled, int is_last, int64_t* n_sampled)
+{
+  if (!h || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  const int64_t np = h->set.n_particles;
+  int64_t finish = global_start_of_sampled + h->n_sampled;
+  if (is_last)
+  {
+    if (finish > np)
+      h->n_sampled = std::max<int64_t>(0, np - global_start_of_sampled);
+    else if (finish < np)
+    {
+      int64_t needed = np - finish;
+      if (h->n_sampled + needed > h->sampled_capacity)
+        return fail(h, MCW_E_ALLOCATE, "sampled-site buffer too small for padding");
+      mcwk_pad_from_bank_end(h->d_sorted, h->n_bank, h->d_sampled, h->n_sampled, needed, h->stream);
+      CK(cudaStreamSynchronize(h->stream));
+      h->n_sampled += needed;
+      h->last.n_kernel_launches += 1;
+    }
+  }
+  if (n_sampled)
+    *n_sampled = h->n_sampled;
+  return MCW_OK;
+}
+
+int mcw_sampled_device_ptr(mcw_handle h, void** sites, int64_t* n)
+{
+  if (!h || !sites || !n)
+    return MCW_E_INVALID_ARGUMENT;
+  *sites = h->d_sampled;
+  *n = h->n_sampled;
+  return MCW_OK;
+}
+
+int mcw_source_device_ptr(mcw_handle h, void** sites, int64_t* capacity)
+{
+  if (!h || !sites || !capacity)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  *sites = h->d_source;
+  *capacity = h->n_local;
+  return MCW_OK;
+}
+
+int mcw_set_source_count(mcw_handle h, int64_t n)
+{
+  if (!h || n < 0 || n > h->n_local)
+    return MCW_E_INVALID_ARGUMENT;
+  h->n_source = n;
+  return MCW_OK;
+}
+
+int mcw_reduction_device_ptr(mcw_handle h, void** doubles, int64_t* n)
+{
+  if (!h || !doubles || !n)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  *doubles = h->d_reduce;
+  *n = h->n_reduce;
+  return MCW_OK;
+}
+
+// OMC eigenvalue.cpp:49-69,313-351; tallies/tally.cpp:639-670,805-846; simulation.cpp:334-347
+int mcw_finalize_generation(mcw_handle h, int batch, mcw_generation_result* out)
+{
+  if (!h || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  double g[5];
+  CK(cudaMemcpyAsync(g, h->d_reduce + h->n_tally_values, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const mcw_settings& S = h->set;
+  const double w = g[4];
+  double k_gen = g[2] / (double)S.n_particles;
+  h->k_generation.push_back(k_gen);
+  int n = batch > S.n_inactive ? h->n_realizations + 1 : 0;
+  if (n <= 0)
+    h->keff = k_gen;
+  else
+  {
+    h->k_sum[0] += k_gen;
+    h->k_sum[1] += k_gen * k_gen;
+    h->keff = h->k_sum[0] / n;
+    if (n > 1)
+      h->keff_std = std::sqrt((h->k_sum[1] / n - h->keff * h->keff) / (n - 1));
+  }
+  h->n_realizations += 1;
+  for (int i = 0; i < 4; ++i)
+  {
+    double val = g[i] / w;
+    h->gt_sum[i] += val;
+    h->gt_sum_sq[i] += val * val;
+  }
+  mcw_generation_result& R = h->last;
+  R.k_generation = k_gen;
+  R.keff = h->keff;
+  R.keff_std = h->keff_std;
+  R.k_collision = g[0] / w;
+  R.k_absorption = g[1] / w;
+  R.k_tracklength = g[2] / w;
+  R.leakage = g[3] / w;
+  R.total_weight = w;
+  if (batch > S.n_inactive)
+  {
+    const double norm = 1.0 / ((double)S.n_particles * 1.0);
+    for (auto& t : h->tallies)
+    {
+      t.n_realizations += 1;
+      mcwk_tally_accumulate(h->d_reduce + t.offset, t.d_sum, t.d_sum_sq, t.n_values, norm, h->stream);
+      R.n_kernel_launches += 1;
+    }
+  }
+  else
+  {
+    for (int i = 0; i < 4; ++i)
+      h->gt_sum[i] = h->gt_sum_sq[i] = 0.0;
+    h->n_realizations = 0;
+    if (h->n_tally_values > 0)
+      CK(cudaMemsetAsync(h->d_reduce, 0, h->n_tally_values * sizeof(double), h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (out)
+    *out = R;
+  return MCW_OK;
+}
+
+int mcw_run_generation(mcw_handle h, int batch, mcw_generation_result* out)
+{
+  if (!h)
+    return MCW_E_INVALID_ARGUMENT;
+  if (h->nranks != 1)
+    return fail(h, MCW_E_UNSUPPORTED, "mcw_run_generation is single-rank; use the split calls with an exchange");
+  int rc = mcw_transport_generation(h, batch);
+  if (rc)
+    return rc;
+  rc = mcw_sample_bank(h, batch, nullptr);
+  if (rc)
+    return rc;
+  rc = mcw_finish_sampling(h, 0, 1, nullptr);
+  if (rc)
+    return rc;
+  std::swap(h->d_source, h->d_sampled);
+  h->n_source = std::min(h->n_sampled, h->n_local);
+  h->n_sampled = 0;
+  return mcw_finalize_generation(h, batch, out);
+}
+
+// ------------------------------------------------------------------ read-back
+int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy, int32_t* n_scores)
+{
+  if (!h)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  for (auto& t : h->tallies)
+    if (t.id == id)
+    {
+      if (n_spatial)
+        *n_spatial = t.n_spatial;
+      if (n_energy)
+        *n_energy = t.n_energy;
+      if (n_scores)
+        *n_scores = t.n_scores;
+      return MCW_OK;
+    }
+  return fail(h, MCW_E_INVALID_ARGUMENT, "unknown tally id");
+}
+
+int mcw_get_tally(mcw_handle h, int id, double* sum, double* sum_sq, int64_t n, int32_t* n_realizations)
+{
+  if (!h || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  for (auto& t : h->tallies)
+    if (t.id == id)
+    {
+      int64_t m = std::min(n, t.n_values);
+      if (sum)
+        CK(cudaMemcpy(sum, t.d_sum, m * sizeof(double), cudaMemcpyDeviceToHost));
+      if (sum_sq)
+        CK(cudaMemcpy(sum_sq, t.d_sum_sq, m * sizeof(double), cudaMemcpyDeviceToHost));
+      if (n_realizations)
+        *n_realizations = t.n_realizations;
+      return MCW_OK;
+    }
+  return fail(h, MCW_E_INVALID_ARGUMENT, "unknown tally id");
+}
+
+int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n)
+{
+  if (!h || !n || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  *n = h->records_valid ? h->last.n_histories : 0;
+  if (rec && capacity > 0 && *n > 0)
+  {
+    CK(cudaSetDevice(h->device));
+    mcwk_fill_records(h->P.p, *n, h->d_records, h->stream);
+    CK(cudaMemcpyAsync(rec, h->d_records, std::min(capacity, *n) * sizeof(mcw_history_record), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return MCW_OK;
+}
+
+int mcw_get_fission_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n)
+{
+  if (!h || !n || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  *n = h->n_bank;
+  if (sites && capacity > 0 && h->n_bank > 0)
+  {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(sites, h->d_sorted, std::min(capacity, h->n_bank) * sizeof(mcw_source_site),
+                  cudaMemcpyDeviceToHost));
+  }
+  return MCW_OK;
+}
+
+int mcw_get_grid_index(mcw_handle h, int i_nuc, int32_t* out, int n)
+{
+  if (!h || !out)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  if (i_nuc < 0 || i_nuc >= h->P.lib.n_nuc || n != h->P.lib.M + 1)
+    return MCW_E_INVALID_ARGUMENT;
+  CK(cudaMemcpy(out, h->P.lib.grid_index + (int64_t)i_nuc * (h->P.lib.M + 1), n * sizeof(int32_t),
+                cudaMemcpyDeviceToHost));
+  return MCW_OK;
+}
+
+// ------------------------------------------------------------------ stand-alone kernels
+int mcw_xs_lookup(mcw_handle h, int64_t n, const double* E, const int32_t* material, double* out)
+{
+  if (!h || !E || !material || !out || n < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  CK(cudaSetDevice(h->device));
+  for (int64_t i = 0; i < n; ++i)
+    if (material[i] < 0 || material[i] >= h->P.lib.n_mat)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "material index out of range");
+  double *dE = nullptr, *dO = nullptr;
+  int32_t* dM = nullptr;
+  CK(dev_alloc(h, &dE, n));
+  CK(dev_alloc(h, &dM, n));
+  CK(dev_alloc(h, &dO, 4 * n));
+  CK(cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dM, material, n * 4, cudaMemcpyHostToDevice, h->stream));
+  mcwk_xs_lookup_array(h->P.lib, n, dE, dM, dO, h->stream);
+  CK(cudaMemcpyAsync(out, dO, 4 * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  dev_free(h, dE);
+  dev_free(h, dM);
+  dev_free(h, dO);
+  return MCW_OK;
+}
+
+int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d_material, void* d_out, int sorted,
+                         int repeats, float* ms_per_launch)
+{
+  (void)sorted;
+  if (!h || !d_E || !d_material || !d_out || n < 0 || repeats < 1)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  for (int r = 0; r < repeats; ++r)
+    mcwk_xs_lookup_array(h->P.lib, n, (const double*)d_E, (const int32_t*)d_material, (double*)d_out, h->stream);
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  if (ms_per_launch)
+    *ms_per_launch = ms / repeats;
+  return MCW_OK;
+}
+
+int mcw_trace_rays(mcw_handle h, int64_t n, const double* start, const double* dir, const int32_t* start_elem,
+                   const int32_t* start_side, const double* max_distance, double* out_distance, int32_t* out_segments,
+                   uint64_t* out_hash)
+{
+  if (!h || !start || !dir || !start_elem || !out_distance || !out_segments || n < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  CK(cudaSetDevice(h->device));
+  double *dS, *dD, *dMx = nullptr, *dDist;
+  int32_t *dE, *dSd = nullptr, *dSeg, *dStat;
+  uint64_t* dH;
+  CK(dev_alloc(h, &dS, 3 * n));
+  CK(dev_alloc(h, &dD, 3 * n));
+  CK(dev_alloc(h, &dDist, n));
+  CK(dev_alloc(h, &dE, n));
+  CK(dev_alloc(h, &dSeg, n));
+  CK(dev_alloc(h, &dStat, n));
+  CK(dev_alloc(h, &dH, n));
+  CK(cudaMemcpy(dS, start, 3 * n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dD, dir, 3 * n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dE, start_elem, n * 4, cudaMemcpyHostToDevice));
+  if (start_side)
+  {
+    CK(dev_alloc(h, &dSd, n));
+    CK(cudaMemcpy(dSd, start_side, n * 4, cudaMemcpyHostToDevice));
+  }
+  if (max_distance)
+  {
+    CK(dev_alloc(h, &dMx, n));
+    CK(cudaMemcpy(dMx, max_distance, n * 8, cudaMemcpyHostToDevice));
+  }
+  mcwk_trace_rays(h->P, n, dS, dD, dE, dSd, dMx, dDist, dSeg, dH, dStat, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out_distance, dDist, n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_segments, dSeg, n * 4, cudaMemcpyDeviceToHost));
+  if (out_hash)
+    CK(cudaMemcpy(out_hash, dH, n * 8, cudaMemcpyDeviceToHost));
+  for (void* p : {(void*)dS, (void*)dD, (void*)dMx, (void*)dDist, (void*)dE, (void*)dSd, (void*)dSeg, (void*)dStat,
+                  (void*)dH})
+    dev_free(h, p);
+  return MCW_OK;
+}
+
+int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem)
+{
+  if (!h || !xyz || !elem || n < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  int rc = prepare(h);
+  if (rc)
+    return rc;
+  CK(cudaSetDevice(h->device));
+  double* dX;
+  int64_t* dR = nullptr;
+  int32_t* dE;
+  CK(dev_alloc(h, &dX, 3 * n));
+  CK(dev_alloc(h, &dE, n));
+  CK(cudaMemcpy(dX, xyz, 3 * n * 8, cudaMemcpyHostToDevice));
+  if (ray_id)
+  {
+    CK(dev_alloc(h, &dR, n));
+    CK(cudaMemcpy(dR, ray_id, n * 8, cudaMemcpyHostToDevice));
+  }
+  mcwk_locate_points(h->P, n, dX, dR, dE, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(elem, dE, n * 4, cudaMemcpyDeviceToHost));
+  dev_free(h, dX);
+  dev_free(h, dR);
+  dev_free(h, dE);
+  return MCW_OK;
+}
+
+int mcw_struct_sizes(int32_t* out, int n)
+{
+  const int32_t v[] = {(int32_t)sizeof(mcw_source_site), (int32_t)sizeof(mcw_nuclide_desc),
+                       (int32_t)sizeof(mcw_material_desc), (int32_t)sizeof(mcw_settings),
+                       (int32_t)sizeof(mcw_generation_result), (int32_t)sizeof(mcw_history_record)};
+  for (int i = 0; i < n && i < 6; ++i)
+    out[i] = v[i];
+  return 6;
+}
+
+} // extern "C"

@@ -1,0 +1,579 @@
+// mcw_device.cuh -- device functions of the particle-history path (sm_100a).
+//
+// Each function states the reference lines it implements (MC = MaCaw src/, RT =
+// moose/modules/ray_tracing, OMC = openmc/).  FP64 throughout; compiled with -fmad=false so every
+// +,-,*,/ rounds exactly as on the host, and log/sin/cos come from mcw_detmath.h, so a history is
+// bit-reproducible against the CPU oracle (tests/test_gpu_parity.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "mcw_detmath.h"
+#include "mcw_types.h"
+
+#define MCW_D __device__ __forceinline__
+#define MCW_PI 3.14159265358979323846264338327950288
+#define MCW_TRACE_TOL 1e-8        // RT TraceRayTools.h:45
+#define MCW_LOOSE_TRACE_TOL 1e-5  // RT TraceRayTools.h:47
+#define MCW_FREE_GAS_THRESHOLD 400.0 // OMC constants.h:42
+#define MCW_INVALID (-1)
+
+// ------------------------------------------------------------------ RNG: OMC random_lcg.cpp:12-114
+#define MCW_PRN_MULT 6364136223846793005ULL
+#define MCW_PRN_ADD 1442695040888963407ULL
+#define MCW_PRN_STRIDE 152917ULL
+
+MCW_D double mcw_prn(uint64_t& seed)
+{
+  seed = MCW_PRN_MULT * seed + MCW_PRN_ADD;
+  uint64_t word = ((seed >> ((seed >> 59u) + 5u)) ^ seed) * 12605985483714917081ull;
+  uint64_t result = (word >> 43u) ^ word;
+  return (double)result * 5.42101086242752217003726400434970855712890625e-20; // ldexp(result, -64)
+}
+
+MCW_D uint64_t mcw_future_seed(uint64_t n, uint64_t seed)
+{
+  uint64_t g = MCW_PRN_MULT, c = MCW_PRN_ADD, g_new = 1, c_new = 0;
+  while (n > 0)
+  {
+    if (n & 1)
+    {
+      g_new *= g;
+      c_new = c_new * g + c;
+    }
+    c *= (g + 1);
+    g *= g;
+    n >>= 1;
+  }
+  return g_new * seed + c_new;
+}
+
+// uint64 -> double -> uint64, the rounding MaCaw's double-typed ray aux data applies to every seed
+// at every segment boundary (MC CollisionKernel.C:132-134,157-159,217-219)
+MCW_D uint64_t mcw_seed_via_double(uint64_t s)
+{
+  double d = (double)s; // cvt.rn.f64.u64
+  if (d >= 18446744073709551616.0)
+    return 0;
+  return (uint64_t)d;
+}
+
+// ------------------------------------------------------------------ small vector type
+struct V3
+{
+  double x, y, z;
+};
+MCW_D V3 v3(double x, double y, double z)
+{
+  V3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+MCW_D V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MCW_D V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+MCW_D V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+MCW_D V3 operator*(V3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+MCW_D V3 operator/(V3 a, double s) { return v3(a.x / s, a.y / s, a.z / s); }
+MCW_D double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+MCW_D double norm(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+MCW_D V3 cross(V3 a, V3 b)
+{
+  return v3(a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x);
+}
+MCW_D V3 unit(V3 a)
+{
+  double l = norm(a);
+  return v3(a.x / l, a.y / l, a.z / l);
+}
+
+// ------------------------------------------------------------------ samplers
+MCW_D double mcw_uniform(double a, double b, uint64_t& s) { return a + (b - a) * mcw_prn(s); }
+
+MCW_D double mcw_maxwell_spectrum(double T, uint64_t& s) // OMC random_dist.cpp:15-27
+{
+  double r1 = mcw_prn(s), r2 = mcw_prn(s), r3 = mcw_prn(s);
+  double c = mcw_cos(MCW_PI / 2. * r3);
+  return -T * (mcw_log(r1) + mcw_log(r2) * c * c);
+}
+
+MCW_D double mcw_watt_spectrum(double a, double b, uint64_t& s) // OMC random_dist.cpp:29-34
+{
+  double w = mcw_maxwell_spectrum(a, s);
+  return w + 0.25 * a * a * b + mcw_uniform(-1., 1., s) * sqrt(a * a * b * w);
+}
+
+MCW_D V3 mcw_rotate_angle(V3 u, double mu, uint64_t& s) // OMC math_functions.cpp:644-672
+{
+  double phi = 2.0 * MCW_PI * mcw_prn(s);
+  double sinphi, cosphi;
+  mcw_sincos(phi, &sinphi, &cosphi);
+  double a = sqrt(fmax(0., 1. - mu * mu));
+  double b = sqrt(fmax(0., 1. - u.z * u.z));
+  if (b > 1e-10)
+  {
+    return v3(mu * u.x + a * (u.x * u.z * cosphi - u.y * sinphi) / b,
+              mu * u.y + a * (u.y * u.z * cosphi + u.x * sinphi) / b, mu * u.z - a * b * cosphi);
+  }
+  else
+  {
+    b = sqrt(1. - u.y * u.y);
+    return v3(mu * u.x + a * (-u.x * u.y * sinphi + u.z * cosphi) / b, mu * u.y + a * b * sinphi,
+              mu * u.z - a * (u.y * u.z * sinphi + u.x * cosphi) / b);
+  }
+}
+
+MCW_D V3 mcw_isotropic_direction(uint64_t& s) // OMC distribution_multi.cpp:73-79
+{
+  double phi = mcw_uniform(0., 2.0 * MCW_PI, s);
+  double mu = mcw_uniform(-1., 1., s);
+  double sp, cp;
+  mcw_sincos(phi, &sp, &cp);
+  return v3(mu, sqrt(1.0 - mu * mu) * cp, sqrt(1.0 - mu * mu) * sp);
+}
+
+// ------------------------------------------------------------------ cross sections
+struct Micro
+{
+  double total, absorption, fission, nu_fission;
+  int i_grid;
+  double f;
+};
+
+MCW_D int mcw_log_bin(const McwLibraryDev& L, double E) // OMC material.cpp:767-768
+{
+  int i = (int)(mcw_log(E / L.E_min) / L.log_spacing);
+  if (i < 0)
+    i = 0;
+  if (i > L.M - 1)
+    i = L.M - 1;
+  return i;
+}
+
+// OMC nuclide.cpp:557-763 (interpolation branch) + search.h:14-20.  Bounded binary search between
+// grid_index[i_log] and grid_index[i_log+1]+1, duplicate-point bump, lin-lin on two adjacent
+// 32-byte rows.
+MCW_D Micro mcw_micro_xs(const McwLibraryDev& L, int i_nuc, double E, int i_log)
+{
+  const McwNucParams& n = L.nuc[i_nuc];
+  const double* __restrict__ en = L.energy + n.off;
+  Micro m;
+  int i_grid;
+  if (E < en[0])
+    i_grid = 0;
+  else if (E > en[n.G - 1])
+    i_grid = n.G - 2;
+  else
+  {
+    const int32_t* gi = L.grid_index + (int64_t)i_nuc * (L.M + 1) + i_log;
+    int i_low = __ldg(gi);
+    int i_high = __ldg(gi + 1) + 1;
+    // lower_bound_index(&energy[i_low], &energy[i_high], E)
+    if (__ldg(en + i_low) == E)
+      i_grid = i_low;
+    else
+    {
+      int lo = i_low, hi = i_high; // first position in [lo, hi) with energy >= E
+      while (lo < hi)
+      {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(en + mid) < E)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      i_grid = lo - 1;
+    }
+  }
+  double e0 = __ldg(en + i_grid), e1 = __ldg(en + i_grid + 1);
+  if (e0 == e1)
+  {
+    ++i_grid;
+    e0 = e1;
+    e1 = __ldg(en + i_grid + 1);
+  }
+  double f = (E - e0) / (e1 - e0);
+  m.i_grid = i_grid;
+  m.f = f;
+  const double2* row = reinterpret_cast<const double2*>(L.xs4 + 4 * (n.off + i_grid));
+  double2 a0 = __ldg(row), a1 = __ldg(row + 1), b0 = __ldg(row + 2), b1 = __ldg(row + 3);
+  m.total = (1.0 - f) * a0.x + f * b0.x;
+  m.absorption = (1.0 - f) * a0.y + f * b0.y;
+  if (n.fissionable)
+  {
+    m.fission = (1.0 - f) * a1.x + f * b1.x;
+    m.nu_fission = (1.0 - f) * a1.y + f * b1.y;
+  }
+  else
+  {
+    m.fission = 0.0;
+    m.nu_fission = 0.0;
+  }
+  return m;
+}
+
+struct Macro
+{
+  double total, absorption, fission, nu_fission;
+};
+
+MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E) // OMC material.cpp:748-831
+{
+  Macro M;
+  M.total = M.absorption = M.fission = M.nu_fission = 0.0;
+  int i_log = mcw_log_bin(L, E);
+  int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
+  for (int i = b; i < e; ++i)
+  {
+    Micro m = mcw_micro_xs(L, L.mat_nuc[i], E, i_log);
+    double d = L.mat_dens[i];
+    M.total += d * m.total;
+    M.absorption += d * m.absorption;
+    M.fission += d * m.fission;
+    M.nu_fission += d * m.nu_fission;
+  }
+  return M;
+}
+
+// ------------------------------------------------------------------ element records
+template <int TYPE>
+struct ElemRec
+{
+  using T = McwElem<TYPE>;
+  const unsigned char* base;
+  MCW_D ElemRec(const McwMeshDev& m, int64_t e) : base(m.rec + (size_t)e * T::STRIDE) {}
+  MCW_D V3 P(int v) const
+  {
+    const double* c = reinterpret_cast<const double*>(base) + v * T::CPV;
+    if (T::CPV == 3)
+      return v3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
+    return v3(__ldg(c), __ldg(c + 1), 0.0);
+  }
+  MCW_D int nbr(int s) const
+  {
+    return __ldg(reinterpret_cast<const int32_t*>(base + T::NV * T::CPV * 8) + s);
+  }
+  MCW_D double hmax() const
+  {
+    return __ldg(reinterpret_cast<const double*>(base + T::NV * T::CPV * 8 + T::NS * 4));
+  }
+  MCW_D int material() const
+  {
+    return __ldg(reinterpret_cast<const int32_t*>(base + T::NV * T::CPV * 8 + T::NS * 4 + 8));
+  }
+  MCW_D int block() const
+  {
+    return __ldg(reinterpret_cast<const int32_t*>(base + T::NV * T::CPV * 8 + T::NS * 4 + 12));
+  }
+};
+
+template <int TYPE>
+MCW_D int side_node(int s, int i);
+template <>
+MCW_D int side_node<MCW_TET4>(int s, int i)
+{
+  // {0,2,1},{0,1,3},{1,2,3},{2,0,3}
+  const unsigned tbl = 0x0u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (3u << 10) | (1u << 12) |
+                       (2u << 14) | (3u << 16) | (2u << 18) | (0u << 20) | (3u << 22);
+  return (tbl >> (2 * (3 * s + i))) & 3u;
+}
+template <>
+MCW_D int side_node<MCW_HEX8>(int s, int i)
+{
+  // {0,3,2,1},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}; 3 bits each, 24 entries = 72 bits
+  const unsigned long long lo = 0ull | (3ull << 3) | (2ull << 6) | (1ull << 9) | (0ull << 12) | (1ull << 15) |
+                                (5ull << 18) | (4ull << 21) | (1ull << 24) | (2ull << 27) | (6ull << 30) |
+                                (5ull << 33) | (2ull << 36) | (3ull << 39) | (7ull << 42) | (6ull << 45);
+  const unsigned hi = 3u | (0u << 3) | (4u << 6) | (7u << 9) | (4u << 12) | (5u << 15) | (6u << 18) | (7u << 21);
+  int k = 4 * s + i;
+  return k < 16 ? (int)((lo >> (3 * k)) & 7ull) : (int)((hi >> (3 * (k - 16))) & 7u);
+}
+template <>
+MCW_D int side_node<MCW_QUAD4>(int s, int i)
+{
+  return (s + i) & 3; // {0,1},{1,2},{2,3},{3,0}
+}
+
+struct Extrema // RT include/raytracing/ElemExtrema.h
+{
+  int first, second;
+  MCW_D Extrema() : first(MCW_INVALID), second(MCW_INVALID) {}
+  MCW_D bool atVertex() const { return first != MCW_INVALID && second == MCW_INVALID; }
+  MCW_D bool atEdge() const { return first != MCW_INVALID && second != MCW_INVALID; }
+  MCW_D bool atExtrema() const { return first != MCW_INVALID; }
+  MCW_D void invalidate() { first = second = MCW_INVALID; }
+  MCW_D void setVertex(int v)
+  {
+    first = v;
+    second = MCW_INVALID;
+  }
+  MCW_D void setEdge(int a, int b)
+  {
+    first = a;
+    second = b;
+  }
+  MCW_D bool atEdgeOf(int a, int b) const
+  {
+    return atEdge() && ((first == a && second == b) || (first == b && second == a));
+  }
+};
+
+// RT TraceRayTools.C:371-478
+MCW_D bool mcw_intersect_triangle(V3 start, V3 dir, V3 p0, V3 p1, V3 p2, int v0, int v1, int v2,
+                                  double& dist, Extrema& ext, double hmax)
+{
+  const double inv_hmax = 1.0 / hmax;
+  V3 edge1 = (p1 - p0) * inv_hmax;
+  V3 edge2 = (p2 - p0) * inv_hmax;
+  V3 pvec = cross(dir, edge2);
+  double det = dot(edge1, pvec);
+  if (det < MCW_TRACE_TOL)
+    return false;
+  V3 tvec = (start - p0) * inv_hmax;
+  double u = dot(tvec, pvec);
+  if (u < -MCW_TRACE_TOL || u > det + MCW_TRACE_TOL)
+    return false;
+  V3 qvec = cross(tvec, edge1);
+  double v = dot(dir, qvec);
+  if (v < -MCW_TRACE_TOL || u + v > det + MCW_TRACE_TOL)
+    return false;
+  double possible = dot(edge2, qvec) / det;
+  if (possible <= MCW_TRACE_TOL)
+    return false;
+  dist = possible * hmax;
+  if (u < MCW_TRACE_TOL * det)
+  {
+    if (v < MCW_TRACE_TOL * det)
+      ext.setVertex(v0);
+    else if (v > (1.0 - MCW_TRACE_TOL) * det)
+      ext.setVertex(v2);
+    else
+      ext.setEdge(v0, v2);
+  }
+  else if (v < MCW_TRACE_TOL * det)
+  {
+    if (u > (1.0 - MCW_TRACE_TOL) * det)
+      ext.setVertex(v1);
+    else
+      ext.setEdge(v0, v1);
+  }
+  else if (u + v > (1.0 - MCW_TRACE_TOL) * det)
+    ext.setEdge(v1, v2);
+  return true;
+}
+
+// RT TraceRayTools.C:60-128
+MCW_D bool mcw_line_line_2d(V3 start, V3 dir, double length, V3 v0, V3 v1, V3& ipoint, double& idist,
+                            int& seg_v)
+{
+  V3 r = dir * length;
+  V3 s = v1 - v0;
+  double rxs = r.x * s.y - r.y * s.x;
+  if (fabs(rxs) < MCW_TRACE_TOL)
+    return false;
+  V3 v0mu0 = v0 - start;
+  double t = (v0mu0.x * s.y - v0mu0.y * s.x) / rxs;
+  if (0 >= t + MCW_TRACE_TOL || t - MCW_TRACE_TOL > 1.0)
+    return false;
+  double u = (v0mu0.x * r.y - v0mu0.y * r.x) / rxs;
+  if (0 < u + MCW_TRACE_TOL && u - MCW_TRACE_TOL <= 1.0)
+  {
+    ipoint = start + r * t;
+    idist = t * length;
+    if (u < MCW_TRACE_TOL)
+      seg_v = 0;
+    else if (u > 1.0 - MCW_TRACE_TOL)
+      seg_v = 1;
+    return true;
+  }
+  return false;
+}
+
+// RT TraceRayTools.h:558-856 sideIntersectedByLine<T>
+template <int TYPE>
+MCW_D bool mcw_side_hit(const McwMeshDev& mesh, const ElemRec<TYPE>& R, V3 start, V3 dir, int s,
+                        V3& ipoint, double& idist, Extrema& ext, double hmax)
+{
+  if (TYPE == MCW_QUAD4)
+  {
+    int seg_v = -1;
+    int a = side_node<TYPE>(s, 0), b = side_node<TYPE>(s, 1);
+    bool hit = mcw_line_line_2d(start, dir, mesh.domain_max_length, R.P(a), R.P(b), ipoint, idist, seg_v);
+    if (seg_v >= 0)
+      ext.setVertex(seg_v == 0 ? a : b);
+    return hit;
+  }
+  bool hit;
+  if (TYPE == MCW_TET4)
+  {
+    int a = side_node<TYPE>(s, 2), b = side_node<TYPE>(s, 1), c = side_node<TYPE>(s, 0);
+    hit = mcw_intersect_triangle(start, dir, R.P(a), R.P(b), R.P(c), a, b, c, idist, ext, hmax);
+  }
+  else
+  {
+    // RT TraceRayTools.C:480-553 intersectQuad(v00, v10, v11, v01)
+    int v00 = side_node<TYPE>(s, 3), v10 = side_node<TYPE>(s, 2), v11 = side_node<TYPE>(s, 1),
+        v01 = side_node<TYPE>(s, 0);
+    V3 p00 = R.P(v00), p11 = R.P(v11);
+    hit = mcw_intersect_triangle(start, dir, p00, R.P(v10), p11, v00, v10, v11, idist, ext, hmax);
+    if (!hit)
+      hit = mcw_intersect_triangle(start, dir, p11, R.P(v01), p00, v11, v01, v00, idist, ext, hmax);
+    if (hit && ext.atEdgeOf(v00, v11))
+      ext.invalidate();
+  }
+  if (hit)
+    ipoint = start + idist * dir;
+  return hit;
+}
+
+// RT TraceRay.C:292-493 exitsElem (no backface culling, planar sides)
+template <int TYPE>
+MCW_D bool mcw_exits_elem(const McwMeshDev& mesh, const ElemRec<TYPE>& R, int incoming_side, V3 start,
+                          V3 dir, V3& ipoint, int& iside, Extrema& iext, double& idist)
+{
+  const double hmax = R.hmax();
+  double best = MCW_TRACE_TOL * hmax;
+  iside = MCW_INVALID;
+#pragma unroll 1
+  for (int s = 0; s < McwElem<TYPE>::NS; ++s)
+  {
+    if (s == incoming_side)
+      continue;
+    V3 cp = v3(0, 0, 0);
+    double cd = 0;
+    Extrema ce;
+    if (mcw_side_hit<TYPE>(mesh, R, start, dir, s, cp, cd, ce, hmax) && cd > best)
+    {
+      iside = s;
+      idist = cd;
+      ipoint = cp;
+      iext = ce;
+      best = cd;
+    }
+  }
+  return iside != MCW_INVALID;
+}
+
+// Outward unit normal at the side centroid (libMesh FE face normal; oracle Mesh::sideNormal)
+template <int TYPE>
+MCW_D V3 mcw_side_normal(const ElemRec<TYPE>& R, int s)
+{
+  if (TYPE == MCW_QUAD4)
+  {
+    V3 a = R.P(side_node<TYPE>(s, 0)), b = R.P(side_node<TYPE>(s, 1));
+    return unit(v3(b.y - a.y, -(b.x - a.x), 0.0));
+  }
+  if (TYPE == MCW_TET4)
+  {
+    V3 a = R.P(side_node<TYPE>(s, 0)), b = R.P(side_node<TYPE>(s, 1)), c = R.P(side_node<TYPE>(s, 2));
+    return unit(cross(b - a, c - a));
+  }
+  V3 a = R.P(side_node<TYPE>(s, 0)), b = R.P(side_node<TYPE>(s, 1)), c = R.P(side_node<TYPE>(s, 2)),
+     d = R.P(side_node<TYPE>(s, 3));
+  V3 dxi = (b + c) - (a + d), deta = (c + d) - (a + b);
+  return unit(cross(dxi, deta));
+}
+
+template <int TYPE>
+MCW_D V3 mcw_side_centroid(const ElemRec<TYPE>& R, int s)
+{
+  V3 c = v3(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < McwElem<TYPE>::NPS; ++i)
+    c = c + R.P(side_node<TYPE>(s, i));
+  return c / (double)McwElem<TYPE>::NPS;
+}
+
+template <int TYPE>
+MCW_D bool mcw_contains_point(const ElemRec<TYPE>& R, V3 p)
+{
+  double tol = 1e-6 * R.hmax();
+  for (int s = 0; s < McwElem<TYPE>::NS; ++s)
+  {
+    V3 n = mcw_side_normal<TYPE>(R, s);
+    V3 d = p - mcw_side_centroid<TYPE>(R, s);
+    if (McwElem<TYPE>::DIM == 2)
+      d.z = 0;
+    if (dot(d, n) > tol)
+      return false;
+  }
+  return true;
+}
+
+template <int TYPE>
+MCW_D bool mcw_side_contains_point(const ElemRec<TYPE>& R, int s, V3 p)
+{
+  double tol = 1e-6 * R.hmax();
+  V3 d = p - mcw_side_centroid<TYPE>(R, s);
+  if (McwElem<TYPE>::DIM == 2)
+    d.z = 0;
+  return fabs(dot(d, mcw_side_normal<TYPE>(R, s))) <= tol && mcw_contains_point<TYPE>(R, p);
+}
+
+// Point locator + ClaimRays tie-break (RT ClaimRays.C:104-139)
+template <int TYPE>
+MCW_D int mcw_locate(const McwMeshDev& m, V3 p, int64_t ray_id)
+{
+  double ex = m.bb_max[0] - m.bb_min[0], ey = m.bb_max[1] - m.bb_min[1], ez = m.bb_max[2] - m.bb_min[2];
+  int i = 0, j = 0, k = 0;
+  if (ex > 0)
+  {
+    i = (int)floor((p.x - m.bb_min[0]) / ex * m.gx);
+    i = min(max(i, 0), m.gx - 1);
+  }
+  if (ey > 0)
+  {
+    j = (int)floor((p.y - m.bb_min[1]) / ey * m.gy);
+    j = min(max(j, 0), m.gy - 1);
+  }
+  if (McwElem<TYPE>::DIM == 3 && ez > 0)
+  {
+    k = (int)floor((p.z - m.bb_min[2]) / ez * m.gz);
+    k = min(max(k, 0), m.gz - 1);
+  }
+  size_t c = ((size_t)k * m.gy + j) * m.gx + i;
+  const bool smallest = (ray_id % 2) == 0;
+  int best = -1;
+  for (int64_t q = m.cell_off[c]; q < m.cell_off[c + 1]; ++q)
+  {
+    int e = m.cell_elems[q];
+    ElemRec<TYPE> R(m, e);
+    if (!mcw_contains_point<TYPE>(R, p))
+      continue;
+    if (best < 0 || (smallest && e < best) || (!smallest && e > best))
+      best = e;
+  }
+  return best;
+}
+
+template <int TYPE>
+MCW_D int mcw_starting_incoming_side(const ElemRec<TYPE>& R, V3 p, V3 dir) // RT ClaimRays.C:141-163
+{
+  for (int s = 0; s < McwElem<TYPE>::NS; ++s)
+    if (mcw_side_contains_point<TYPE>(R, s, p) && dot(mcw_side_normal<TYPE>(R, s), dir) < MCW_TRACE_TOL)
+      return s;
+  return MCW_INVALID;
+}
+
+MCW_D uint64_t mcw_hash_step(uint64_t h, int64_t elem, int side)
+{
+  uint64_t key = ((uint64_t)elem << 4) | (uint64_t)(side & 15);
+  return (h ^ key) * 0x100000001b3ull;
+}
+
+// ------------------------------------------------------------------ warp-aggregated helpers
+MCW_D unsigned long long mcw_warp_append(unsigned long long* counter, bool want)
+{
+  // one atomicAdd per warp: lanes that want a slot get consecutive indices
+  unsigned mask = __ballot_sync(__activemask(), want);
+  if (!want)
+    return 0;
+  int leader = __ffs(mask) - 1;
+  int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == leader)
+    base = atomicAdd(counter, (unsigned long long)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1));
+}

@@ -1,0 +1,959 @@
+// mcw_kernels.cu -- event-based sm_100a kernels of the particle-history path.
+//
+//   k_init_histories   source sites -> particle SoA            (MC OpenMCStudy.C:297-364, RT ClaimRays.C)
+//   k_sample_source    batch-1 box source with rejection        (OMC source.cpp:143-231,325-338)
+//   k_xs_lookup        macroscopic cross sections for a queue   (OMC material.cpp:763-831, nuclide.cpp:557-763)
+//   k_track            element walk until collision / material change / death
+//                                                               (RT TraceRay.C:292-493,999-1592; MC CollisionKernel.C:143-175)
+//   k_collide          event_collide + tallies + bank append    (OMC particle.cpp:219-288, physics.cpp:38-247,442-1120)
+//   k_fallback         general vertex/edge/neighbour step       (RT TraceRay.C:564-997,1134-1246)
+//   bank / tally / reduction helpers                            (OMC bank.cpp:60-104, eigenvalue.cpp:71-311, tally.cpp:639-670)
+//
+// One thread = one history slot; queues are index lists with warp-aggregated appends.
+#include <cub/cub.cuh>
+
+#include "mcw_kernels.h"
+#include "mcw_physics.cuh"
+
+#define MCW_BLOCK 128
+
+// ------------------------------------------------------------------ init
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n, int32_t* __restrict__ q_fly)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const mcw_source_site s = src[i];
+  V3 r = v3(s.r[0], s.r[1], s.r[2]);
+  V3 dir = v3(s.u[0], s.u[1], s.u[2]);
+  if (P.is_2d)
+    dir.z = 0;
+  dir = unit(dir); // Ray::setStartingDirection (RT Ray.C:291)
+  const int64_t id = P.work_offset + i + 1;                                      // OMC simulation.cpp:469
+  const int64_t particle_seed = (int64_t)(P.batch - 1) * P.n_particles_global + id; // :477-480
+  uint64_t seeds[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    seeds[k] = mcw_future_seed((uint64_t)particle_seed * MCW_PRN_STRIDE, (uint64_t)(P.master_seed + k));
+    if (P.seed_through_double)
+      seeds[k] = mcw_seed_via_double(seeds[k]); // MC OpenMCStudy.C:345-347
+  }
+  int elem = s.elem;
+  if (elem < 0)
+    elem = mcw_locate<TYPE>(P.mesh, r, (int64_t)(P.batch - 1) * P.n_particles_global + (id - 1));
+  McwParticlesDev& p = P.p;
+  p.x[i] = r.x;
+  p.y[i] = r.y;
+  p.z[i] = r.z;
+  p.ux[i] = dir.x;
+  p.uy[i] = dir.y;
+  p.uz[i] = dir.z;
+  p.E[i] = s.E;
+  p.wgt[i] = s.wgt;
+  p.seed_trk[i] = seeds[0];
+  p.seed_src[i] = seeds[1];
+  p.seed_urr[i] = seeds[2];
+  p.k_col[i] = 0.0;
+  p.k_abs[i] = 0.0;
+  p.k_trk[i] = 0.0;
+  p.n_progeny[i] = 0;
+  p.n_seg[i] = 0;
+  p.n_coll[i] = 0;
+  p.n_xs[i] = 0;
+  p.xs_mat[i] = -1;
+  p.last_elem[i] = -1;
+  p.ext_first[i] = -1;
+  p.ext_second[i] = -1;
+  p.hash[i] = 0xcbf29ce484222325ull;
+  q_fly[i] = (int32_t)i;
+  if (elem < 0)
+  {
+    p.elem[i] = -1;
+    p.inc_side[i] = -1;
+    p.status[i] = MCW_ST_DEAD;
+    p.fate[i] = 2;
+    atomicAdd(&P.counters->n_failed, 1ull);
+    return;
+  }
+  ElemRec<TYPE> R(P.mesh, elem);
+  p.elem[i] = elem;
+  p.inc_side[i] = (int8_t)mcw_starting_incoming_side<TYPE>(R, r, dir);
+  p.status[i] = MCW_ST_FLY;
+  p.fate[i] = -1;
+}
+
+// OMC source.cpp:325-338 + :143-231 (box, isotropic, Watt 0.988 MeV / 2.249 per MeV)
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_sample_source(McwParams P, mcw_source_site* __restrict__ out, int64_t n, const double* box, int only_fissionable)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int64_t id = 0 * P.n_particles_global + P.work_offset + i + 1;
+  uint64_t seed = mcw_future_seed((uint64_t)id * MCW_PRN_STRIDE, (uint64_t)(P.master_seed + 1));
+  mcw_source_site site;
+  site.wgt = 1.0;
+  site.delayed_group = 0;
+  site.surf_id = 0;
+  site.particle = 0;
+  site.parent_id = 0;
+  site.progeny_id = 0;
+  site.r[0] = site.r[1] = site.r[2] = 0.0;
+  int64_t ray_id = P.work_offset + i;
+  int e = -1;
+  for (int tries = 0; tries < 1000000; ++tries)
+  {
+    double x1 = mcw_prn(seed), x2 = mcw_prn(seed), x3 = mcw_prn(seed);
+    V3 r = v3(box[0] + x1 * (box[3] - box[0]), box[1] + x2 * (box[4] - box[1]), box[2] + x3 * (box[5] - box[2]));
+    e = mcw_locate<TYPE>(P.mesh, r, ray_id);
+    bool found = e >= 0;
+    if (found && only_fissionable)
+    {
+      ElemRec<TYPE> R(P.mesh, e);
+      found = P.lib.mat_fissionable[R.material()] != 0;
+    }
+    if (found)
+    {
+      site.r[0] = r.x;
+      site.r[1] = r.y;
+      site.r[2] = r.z;
+      break;
+    }
+    e = -1;
+  }
+  V3 u = mcw_isotropic_direction(seed);
+  site.u[0] = u.x;
+  site.u[1] = u.y;
+  site.u[2] = u.z;
+  while (true)
+  {
+    site.E = mcw_watt_spectrum(0.988e6, 2.249e-6, seed);
+    if (site.E < P.lib.E_max && site.E > P.lib.E_min)
+      break;
+  }
+  site.elem = e;
+  out[i] = site;
+}
+
+// ------------------------------------------------------------------ cross-section lookup
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_xs_lookup(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)*count)
+    return;
+  int i = queue[idx];
+  McwParticlesDev& p = P.p;
+  ElemRec<TYPE> R(P.mesh, p.elem[i]);
+  int mat = R.material();
+  if (p.xs_mat[i] == mat)
+    return; // still valid (same energy and material)
+  Macro M = mcw_macro_xs(P.lib, mat, p.E[i]);
+  p.sig_t[i] = M.total;
+  p.sig_a[i] = M.absorption;
+  p.sig_f[i] = M.fission;
+  p.sig_nf[i] = M.nu_fission;
+  p.xs_mat[i] = mat;
+  p.n_xs[i] += 1;
+}
+
+// stand-alone lookup for (E, material) arrays: the XS-lookup bandwidth metric and unit parity
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_xs_lookup_array(McwLibraryDev L, int64_t n, const double* __restrict__ E, const int32_t* __restrict__ mat,
+                  double* __restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  Macro M = mcw_macro_xs(L, mat[i], E[i]);
+  double2* o = reinterpret_cast<double2*>(out + 4 * i);
+  o[0] = make_double2(M.total, M.absorption);
+  o[1] = make_double2(M.fission, M.nu_fission);
+}
+
+// sort keys for the xs queue: (material << 16) | (energy log-bin >> 0)
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
+          uint32_t* __restrict__ keys, int64_t cap)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cap)
+    return;
+  if (idx >= (int64_t)*count)
+  {
+    keys[idx] = 0xffffffffu;
+    return;
+  }
+  int i = queue[idx];
+  ElemRec<TYPE> R(P.mesh, P.p.elem[i]);
+  keys[idx] = ((uint32_t)R.material() << 16) | (uint32_t)mcw_log_bin(P.lib, P.p.E[i]);
+}
+
+// ------------------------------------------------------------------ tracking
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
+        int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, int32_t* __restrict__ q_collide,
+        int32_t* __restrict__ q_fallback)
+{
+  using T = McwElem<TYPE>;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)*count)
+    return;
+  const int i = queue[idx];
+  McwParticlesDev& p = P.p;
+  if (p.status[i] != MCW_ST_FLY)
+    return;
+  V3 point = v3(p.x[i], p.y[i], p.z[i]);
+  V3 dir = v3(p.ux[i], p.uy[i], p.uz[i]);
+  int cur = p.elem[i];
+  int last = p.last_elem[i];
+  int inc_side = p.inc_side[i];
+  SegState s;
+  s.E = p.E[i];
+  s.wgt = p.wgt[i];
+  s.seed_trk = p.seed_trk[i];
+  s.seed_src = p.seed_src[i];
+  s.seed_urr = p.seed_urr[i];
+  s.sig_t = p.sig_t[i];
+  s.sig_a = p.sig_a[i];
+  s.sig_f = p.sig_f[i];
+  s.sig_nf = p.sig_nf[i];
+  s.k_trk = p.k_trk[i];
+  const int xs_mat = p.xs_mat[i];
+  int n_seg = p.n_seg[i];
+  uint64_t hash = p.hash[i];
+  int status = MCW_ST_FLY, fate = -1;
+  bool requeue = false;
+  unsigned long long segs = 0;
+  if (p.ext_first[i] != MCW_INVALID)
+    status = MCW_ST_FALLBACK; // last hit was a vertex/edge: general walk (RT TraceRay.C:1134)
+
+  while (status == MCW_ST_FLY)
+  {
+    if (n_seg >= P.max_events)
+    {
+      status = MCW_ST_DEAD;
+      fate = 3;
+      atomicAdd(&P.counters->n_failed, 1ull);
+      break;
+    }
+    ElemRec<TYPE> R(P.mesh, cur);
+    V3 ipoint;
+    int iside;
+    Extrema ext;
+    double idist;
+    if (!mcw_exits_elem<TYPE>(P.mesh, R, inc_side, point, dir, ipoint, iside, ext, idist) || ext.atExtrema())
+    {
+      status = MCW_ST_FALLBACK; // nothing modified: the general kernel redoes this step
+      break;
+    }
+    ++n_seg;
+    ++segs;
+    V3 pos;
+    const bool collided = mcw_segment(P, s, cur, R.block(), xs_mat, ipoint, dir, idist, pos);
+    hash = mcw_hash_step(hash, cur, collided ? 15 : iside);
+    if (collided)
+    {
+      point = pos;
+      status = MCW_ST_COLLIDE;
+      break;
+    }
+    // RT TraceRay.C:1420-1466 neighbour step
+    point = ipoint;
+    const int nb = R.nbr(iside);
+    if (nb >= 0)
+    {
+      ElemRec<TYPE> N(P.mesh, nb);
+      int s_in = MCW_INVALID;
+#pragma unroll
+      for (int k = T::NS - 1; k >= 0; --k)
+        if (N.nbr(k) == cur)
+          s_in = k;
+      inc_side = s_in;
+      last = cur;
+      cur = nb;
+      if (N.material() != xs_mat)
+      {
+        requeue = true; // new material: back through the cross-section kernel
+        break;
+      }
+    }
+    else
+    {
+      // RT TraceRay.C:725-782 external boundary, :2043 onBoundary
+      const int bid = -nb - 1;
+      const int kind = bid < P.mesh.n_bnd ? P.mesh.bnd_kind[bid] : MCW_BC_KILL;
+      if (kind == MCW_BC_KILL)
+      {
+        status = MCW_ST_DEAD;
+        fate = 1;
+        break;
+      }
+      // RT ReflectRayBC.C:68-76 + Ray::changeDirection (Ray.C:206-214)
+      V3 n = mcw_side_normal<TYPE>(R, iside);
+      double dn = dot(dir, n);
+      V3 r = dir - (2.0 * dn) * n;
+      r = r / norm(r);
+      dir = unit(r);
+      last = cur;
+      inc_side = iside;
+    }
+  }
+
+  p.x[i] = point.x;
+  p.y[i] = point.y;
+  p.z[i] = point.z;
+  p.ux[i] = dir.x;
+  p.uy[i] = dir.y;
+  p.uz[i] = dir.z;
+  p.elem[i] = cur;
+  p.last_elem[i] = last;
+  p.inc_side[i] = (int8_t)inc_side;
+  p.seed_trk[i] = s.seed_trk;
+  p.seed_src[i] = s.seed_src;
+  p.seed_urr[i] = s.seed_urr;
+  p.k_trk[i] = s.k_trk;
+  p.n_seg[i] = n_seg;
+  p.hash[i] = hash;
+  p.status[i] = (int8_t)(requeue ? MCW_ST_FLY : status);
+  if (fate >= 0)
+    p.fate[i] = (int8_t)fate;
+  // warp-aggregated queue appends and counters
+  {
+    unsigned long long k = mcw_warp_append(cnt_next, requeue);
+    if (requeue)
+      q_fly_next[k] = i;
+    k = mcw_warp_append(&P.counters->n_collide, status == MCW_ST_COLLIDE);
+    if (status == MCW_ST_COLLIDE)
+      q_collide[k] = i;
+    k = mcw_warp_append(&P.counters->n_fallback, status == MCW_ST_FALLBACK);
+    if (status == MCW_ST_FALLBACK)
+      q_fallback[k] = i;
+    unsigned mask = __activemask();
+    unsigned long long tot = segs;
+    for (int o = 16; o > 0; o >>= 1)
+      tot += __shfl_down_sync(mask, tot, o);
+    if ((threadIdx.x & 31) == (__ffs(mask) - 1))
+      atomicAdd(&P.counters->n_segments, tot);
+  }
+}
+
+// ------------------------------------------------------------------ collision
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
+          int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < (int64_t)*count;
+  // no early return: the bank append below is a full-warp aggregate
+  McwParticlesDev& p = P.p;
+  const McwLibraryDev& L = P.lib;
+  int i = active ? queue[idx] : -1;
+  bool valid = active && p.status[i] == MCW_ST_COLLIDE;
+
+  ColState c;
+  double sig_t = 1, sig_a = 0, sig_f = 0, sig_nf = 0, E_last = 0, wgt_last = 0, kappa = 0.0;
+  int i_mat = 0, elem = 0, block = 0, k_nuc = 0, nu = 0;
+  Micro mx;
+  mx.total = mx.absorption = mx.fission = mx.nu_fission = mx.f = 0;
+  mx.i_grid = 0;
+  double k_col = 0, k_abs = 0;
+  uint64_t seed_src = 0, seed_urr = 0;
+  if (valid)
+  {
+    c.r = v3(p.x[i], p.y[i], p.z[i]);
+    c.u = v3(p.ux[i], p.uy[i], p.uz[i]);
+    c.E = p.E[i];
+    c.wgt = p.wgt[i];
+    c.seed = p.seed_trk[i];
+    c.n_progeny = p.n_progeny[i];
+    seed_src = p.seed_src[i];
+    seed_urr = p.seed_urr[i];
+    sig_t = p.sig_t[i];
+    sig_a = p.sig_a[i];
+    sig_f = p.sig_f[i];
+    sig_nf = p.sig_nf[i];
+    i_mat = p.xs_mat[i];
+    elem = p.elem[i];
+    ElemRec<TYPE> R(P.mesh, elem);
+    block = R.block();
+    E_last = c.E;
+    wgt_last = c.wgt;
+    k_col = p.k_col[i] + c.wgt * sig_nf / sig_t; // OMC particle.cpp:223-226
+    k_abs = p.k_abs[i];
+    // kappa-fission needs every fissionable nuclide (OMC tally_scoring.cpp:1240-1255)
+    bool need_kappa = false;
+    if (P.tallies_active)
+      for (int t = 0; t < P.n_tallies; ++t)
+        if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
+          for (int q = 0; q < P.tally[t].n_scores; ++q)
+            need_kappa |= P.tally[t].scores[q] == MCW_SCORE_KAPPA_FISSION;
+    // sample_nuclide (OMC physics.cpp:442-465): re-evaluate the micro cross sections in material order
+    const int i_log = mcw_log_bin(L, c.E);
+    const double cutoff = mcw_prn(c.seed) * sig_t;
+    double prob = 0.0;
+    const int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
+    bool found = false;
+    k_nuc = L.mat_nuc[e - 1];
+    for (int q = b; q < e; ++q)
+    {
+      const int in = L.mat_nuc[q];
+      if (found && !(need_kappa && L.nuc[in].fissionable))
+        continue;
+      Micro m = mcw_micro_xs(L, in, c.E, i_log);
+      if (L.nuc[in].fissionable)
+        kappa += L.nuc[in].q * m.fission * L.mat_dens[q];
+      if (!found)
+      {
+        prob += L.mat_dens[q] * m.total;
+        if (prob >= cutoff || q == e - 1)
+        {
+          found = true;
+          k_nuc = in;
+          mx = m;
+        }
+      }
+      if (found && !need_kappa)
+        break;
+    }
+    // create_fission_sites: number of sites (OMC physics.cpp:154-170)
+    if (L.nuc[k_nuc].fissionable)
+    {
+      double nu_t = c.wgt / P.keff * 1.0 * mx.nu_fission / mx.total;
+      nu = (int)nu_t;
+      if (mcw_prn(c.seed) <= (nu_t - nu))
+        ++nu;
+    }
+  }
+  // warp-aggregated fission-bank append: one atomicAdd per warp for all sites of the warp
+  unsigned long long base = 0;
+  {
+    const unsigned full = 0xffffffffu;
+    int lane = threadIdx.x & 31;
+    int incl = nu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    int total = __shfl_sync(full, incl, 31);
+    unsigned long long wbase = 0;
+    if (lane == 0 && total > 0)
+      wbase = atomicAdd(&P.counters->n_bank, (unsigned long long)total);
+    wbase = __shfl_sync(full, wbase, 0);
+    base = wbase + (unsigned long long)(incl - nu);
+  }
+  if (!valid)
+    return;
+  const McwNucParams& nuc = L.nuc[k_nuc];
+  for (int k = 0; k < nu; ++k)
+  {
+    mcw_source_site site;
+    site.r[0] = c.r.x;
+    site.r[1] = c.r.y;
+    site.r[2] = c.r.z;
+    site.particle = 0;
+    site.wgt = 1. / 1.0;
+    site.parent_id = P.work_offset + i + 1;
+    site.progeny_id = c.n_progeny++;
+    site.surf_id = 0;
+    site.elem = elem;
+    mcw_sample_fission_neutron(nuc, c.E, L.E_max, site, c.seed);
+    unsigned long long slot = base + k;
+    if ((int64_t)slot < P.bank_capacity)
+      P.bank[slot] = site;
+    else
+      atomicAdd(&P.counters->n_bank_dropped, 1ull);
+  }
+  // absorption (analog, OMC physics.cpp:592-625)
+  bool absorbed = false;
+  if (mx.absorption > 0.0)
+  {
+    if (mx.absorption > mcw_prn(c.seed) * mx.total)
+    {
+      k_abs += c.wgt * mx.nu_fission / mx.absorption;
+      absorbed = true;
+    }
+  }
+  if (!absorbed)
+  {
+    // scatter (OMC physics.cpp:627-719)
+    double cut = mcw_prn(c.seed) * (mx.total - mx.absorption);
+    const double2* ei = reinterpret_cast<const double2*>(L.el_inel + 2 * (nuc.off + mx.i_grid));
+    double2 r0 = __ldg(ei), r1 = __ldg(ei + 1);
+    double elastic = (1.0 - mx.f) * r0.x + mx.f * r1.x;
+    bool can_inelastic = nuc.n_inel > 0 && mx.i_grid >= nuc.inel_thr;
+    if (elastic > cut || !can_inelastic)
+      mcw_elastic_scatter(nuc, c);
+    else
+      mcw_inelastic_scatter(nuc, c);
+    if (c.E != E_last) // OMC physics.cpp:140-144
+      seed_urr = mcw_future_seed((uint64_t)L.n_nuc, seed_urr);
+  }
+  // collision-estimator tallies (OMC tally_scoring.cpp:2354-2420)
+  if (P.tallies_active && P.any_collision_tally)
+  {
+    double flux = wgt_last / sig_t;
+    double sc[MCW_N_SCORES];
+    sc[MCW_SCORE_FLUX] = flux;
+    sc[MCW_SCORE_TOTAL] = sig_t * flux;
+    sc[MCW_SCORE_FISSION] = sig_a == 0 ? 0.0 : sig_f * flux;
+    sc[MCW_SCORE_NU_FISSION] = sig_a == 0 ? 0.0 : sig_nf * flux;
+    sc[MCW_SCORE_KAPPA_FISSION] = sig_a == 0. ? 0.0 : kappa * flux;
+    for (int t = 0; t < P.n_tallies; ++t)
+      if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
+        mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
+  }
+  uint64_t seed_trk = c.seed;
+  if (P.seed_through_double)
+  {
+    seed_trk = mcw_seed_via_double(seed_trk); // MC CollisionKernel.C:217-219
+    seed_src = mcw_seed_via_double(seed_src);
+    seed_urr = mcw_seed_via_double(seed_urr);
+  }
+  p.seed_trk[i] = seed_trk;
+  p.seed_src[i] = seed_src;
+  p.seed_urr[i] = seed_urr;
+  p.k_col[i] = k_col;
+  p.k_abs[i] = k_abs;
+  p.n_progeny[i] = c.n_progeny;
+  p.n_coll[i] += 1;
+  p.E[i] = c.E;
+  atomicAdd(&P.counters->n_collisions, 1ull);
+  if (absorbed)
+  {
+    p.status[i] = MCW_ST_DEAD;
+    p.fate[i] = 0;
+  }
+  else
+  {
+    // changeRayStartDirection (RT RayKernelBase.C:62-97 -> Ray.C:216-226); MC CollisionKernel.C:198-205
+    V3 nd = c.u;
+    if (P.is_2d)
+      nd.z = 0;
+    nd = unit(nd);
+    p.ux[i] = nd.x;
+    p.uy[i] = nd.y;
+    p.uz[i] = nd.z;
+    p.inc_side[i] = -1;
+    p.ext_first[i] = -1;
+    p.ext_second[i] = -1;
+    p.xs_mat[i] = -1; // energy changed: cross sections must be looked up again
+    p.status[i] = MCW_ST_FLY;
+  }
+  unsigned long long k = mcw_warp_append(cnt_next, !absorbed);
+  if (!absorbed)
+    q_fly_next[k] = i;
+}
+
+// ------------------------------------------------------------------ general (rare-path) step
+#include "mcw_fallback.cuh"
+
+// ------------------------------------------------------------------ bank helpers
+// OMC bank.cpp:60-104: position of a site in the sorted bank = exclusive_scan(progeny_per_particle)
+// [parent] + progeny_id
+__global__ void k_bank_scatter(const mcw_source_site* __restrict__ bank, int64_t n_bank,
+                               const int64_t* __restrict__ progeny_scan, int64_t work_offset,
+                               mcw_source_site* __restrict__ sorted)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bank)
+    return;
+  mcw_source_site s = bank[i];
+  int64_t off = s.parent_id - 1 - work_offset;
+  sorted[progeny_scan[off] + s.progeny_id] = s;
+}
+
+__global__ void k_progeny_to_i64(const int32_t* __restrict__ n_progeny, int64_t n, int64_t* __restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = n_progeny[i];
+}
+
+// OMC eigenvalue.cpp:112-160: how many copies of bank site i go to the next source
+__global__ void k_sample_counts(int64_t n_bank, int64_t global_start, int64_t total, int64_t n_particles,
+                                uint64_t seed0, int64_t* __restrict__ counts)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bank)
+    return;
+  int64_t sites_needed = total < n_particles ? n_particles % total : n_particles;
+  double p_sample = (double)sites_needed / (double)total;
+  uint64_t seed = mcw_future_seed((uint64_t)(global_start + i), seed0);
+  int64_t c = total < n_particles ? n_particles / total : 0;
+  if (mcw_prn(seed) < p_sample)
+    ++c;
+  counts[i] = c;
+}
+
+__global__ void k_sample_scatter(const mcw_source_site* __restrict__ sorted, int64_t n_bank,
+                                 const int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                 mcw_source_site* __restrict__ out, int64_t cap)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bank)
+    return;
+  int64_t c = counts[i], o = offsets[i];
+  if (c == 0)
+    return;
+  mcw_source_site s = sorted[i];
+  for (int64_t k = 0; k < c; ++k)
+    if (o + k < cap)
+      out[o + k] = s;
+}
+
+// OMC eigenvalue.cpp:195-203: repeat sites from the very end of the fission bank
+__global__ void k_pad_from_bank_end(const mcw_source_site* __restrict__ sorted, int64_t n_bank,
+                                    mcw_source_site* __restrict__ out, int64_t have, int64_t needed)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= needed)
+    return;
+  int64_t ib = n_bank - needed + i;
+  if (ib < 0)
+    ib = 0; // MC OpenMCStudy.C:584
+  out[have + i] = sorted[ib];
+}
+
+// OMC tallies/tally.cpp:639-670 Tally::accumulate
+__global__ void k_tally_accumulate(double* __restrict__ value, double* __restrict__ sum, double* __restrict__ sum_sq,
+                                   int64_t n, double norm)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double val = value[i] * norm;
+  value[i] = 0.0;
+  sum[i] += val;
+  sum_sq[i] += val * val;
+}
+
+__global__ void k_fill_records(McwParticlesDev p, int64_t n, mcw_history_record* __restrict__ rec)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  mcw_history_record r;
+  r.seed_tracking = p.seed_trk[i];
+  r.seed_source = p.seed_src[i];
+  r.seed_urr = p.seed_urr[i];
+  r.E = p.E[i];
+  r.k_collision = p.k_col[i];
+  r.k_absorption = p.k_abs[i];
+  r.k_tracklength = p.k_trk[i];
+  r.n_segments = p.n_seg[i];
+  r.n_collisions = p.n_coll[i];
+  r.n_progeny = p.n_progeny[i];
+  r.last_elem = p.elem[i];
+  r.fate = p.fate[i];
+  r.n_xs = p.n_xs[i];
+  r.trace_hash = p.hash[i];
+  rec[i] = r;
+}
+
+// geometry-only walk (RT lots.i workload)
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_trace_rays(McwParams P, int64_t n, const double* __restrict__ start, const double* __restrict__ dirs,
+             const int32_t* __restrict__ start_elem, const int32_t* __restrict__ start_side,
+             const double* __restrict__ max_distance, double* __restrict__ out_distance,
+             int32_t* __restrict__ out_segments, uint64_t* __restrict__ out_hash, int32_t* __restrict__ out_status)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  V3 p = v3(start[3 * i], start[3 * i + 1], start[3 * i + 2]);
+  V3 d = unit(v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+  int e = start_elem[i];
+  if (e < 0)
+    e = mcw_locate<TYPE>(P.mesh, p, i);
+  int side = start_side ? start_side[i] : MCW_INVALID;
+  if (e >= 0 && side == -2)
+  {
+    ElemRec<TYPE> R(P.mesh, e);
+    side = mcw_starting_incoming_side<TYPE>(R, p, d);
+  }
+  GeneralWalk<TYPE> W;
+  W.cur = e;
+  W.last = MCW_INVALID;
+  W.inc_side = side;
+  W.point = p;
+  W.dir = d;
+  W.ext.invalidate();
+  double maxd = max_distance ? max_distance[i] : INFINITY;
+  double travelled = 0;
+  int segs = 0;
+  uint64_t hash = 0xcbf29ce484222325ull;
+  int end = -1;
+  unsigned long long n_ve = 0, n_moved = 0;
+  while (end < 0 && e >= 0 && segs < 10000000)
+  {
+    StepResult st = W.step(P.mesh, n_ve, n_moved);
+    if (st.failed)
+    {
+      end = 2;
+      break;
+    }
+    ++segs;
+    // RT TraceRay.C:1268-1315
+    bool at_end = false;
+    if (maxd != INFINITY)
+    {
+      if (fabs(travelled + st.idist - maxd) <= 1e-10 * fmax(1.0, maxd))
+        at_end = true;
+      else if (travelled + st.idist > maxd)
+      {
+        st.idist -= travelled + st.idist - maxd;
+        st.iside = MCW_INVALID;
+        at_end = true;
+      }
+    }
+    travelled += st.idist;
+    hash = mcw_hash_step(hash, st.elem, st.iside);
+    if (at_end)
+    {
+      end = 0;
+      break;
+    }
+    int c = W.cross(P.mesh, st);
+    if (c == 1)
+      end = 1;
+    else if (c == 2)
+      end = 2;
+  }
+  out_distance[i] = travelled;
+  out_segments[i] = segs;
+  if (out_hash)
+    out_hash[i] = hash;
+  if (out_status)
+    out_status[i] = end;
+}
+
+__global__ void k_locate_points(McwParams P, int64_t n, const double* __restrict__ xyz, const int64_t* __restrict__ ray_id,
+                                int32_t* __restrict__ elem)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  V3 p = v3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  int64_t rid = ray_id ? ray_id[i] : i;
+  int e;
+  if (P.mesh.type == MCW_TET4)
+    e = mcw_locate<MCW_TET4>(P.mesh, p, rid);
+  else if (P.mesh.type == MCW_HEX8)
+    e = mcw_locate<MCW_HEX8>(P.mesh, p, rid);
+  else
+    e = mcw_locate<MCW_QUAD4>(P.mesh, p, rid);
+  elem[i] = e;
+}
+
+// ------------------------------------------------------------------ host launchers
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + MCW_BLOCK - 1) / MCW_BLOCK); }
+
+#define MCW_DISPATCH(type, CALL)                                                                               \
+  do                                                                                                           \
+  {                                                                                                            \
+    if ((type) == MCW_TET4)                                                                                    \
+    {                                                                                                          \
+      constexpr int TY = MCW_TET4;                                                                             \
+      CALL;                                                                                                    \
+    }                                                                                                          \
+    else if ((type) == MCW_HEX8)                                                                               \
+    {                                                                                                          \
+      constexpr int TY = MCW_HEX8;                                                                             \
+      CALL;                                                                                                    \
+    }                                                                                                          \
+    else                                                                                                       \
+    {                                                                                                          \
+      constexpr int TY = MCW_QUAD4;                                                                            \
+      CALL;                                                                                                    \
+    }                                                                                                          \
+  } while (0)
+
+void mcwk_init_histories(const McwParams& P, const mcw_source_site* src, int64_t n, int32_t* q_fly, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_init_histories<TY><<<grid_for(n), MCW_BLOCK, 0, st>>>(P, src, n, q_fly)));
+}
+
+void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, const double* d_box, int only_fissionable,
+                        cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_sample_source<TY><<<grid_for(n), MCW_BLOCK, 0, st>>>(P, out, n, d_box, only_fissionable)));
+}
+
+void mcwk_xs_lookup(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, cudaStream_t st)
+{
+  if (upper <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_xs_lookup<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count)));
+}
+
+void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
+                  cudaStream_t st)
+{
+  if (cap <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_xs_keys<TY><<<grid_for(cap), MCW_BLOCK, 0, st>>>(P, queue, count, keys, cap)));
+}
+
+void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
+                          cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_xs_lookup_array<<<grid_for(n), MCW_BLOCK, 0, st>>>(L, n, E, mat, out);
+}
+
+void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+                int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
+                cudaStream_t st)
+{
+  if (upper <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_track<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next,
+                                                                             q_collide, q_fallback)));
+}
+
+void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+                  int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st)
+{
+  if (upper <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type,
+               (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next)));
+}
+
+void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,
+                   int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, cudaStream_t st)
+{
+  if (n_blocks <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_fallback<TY><<<n_blocks, 64, 0, st>>>(P, queue, count, q_fly_next, cnt_next, q_collide)));
+}
+
+void mcwk_trace_rays(const McwParams& P, int64_t n, const double* start, const double* dirs, const int32_t* start_elem,
+                     const int32_t* start_side, const double* max_distance, double* out_distance, int32_t* out_segments,
+                     uint64_t* out_hash, int32_t* out_status, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  MCW_DISPATCH(P.mesh.type, (k_trace_rays<TY><<<grid_for(n), MCW_BLOCK, 0, st>>>(P, n, start, dirs, start_elem, start_side,
+                                                                                max_distance, out_distance, out_segments,
+                                                                                out_hash, out_status)));
+}
+
+void mcwk_locate_points(const McwParams& P, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem,
+                        cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_locate_points<<<grid_for(n), MCW_BLOCK, 0, st>>>(P, n, xyz, ray_id, elem);
+}
+
+void mcwk_fill_records(const McwParticlesDev& p, int64_t n, mcw_history_record* rec, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_fill_records<<<grid_for(n), MCW_BLOCK, 0, st>>>(p, n, rec);
+}
+
+void mcwk_tally_accumulate(double* value, double* sum, double* sum_sq, int64_t n, double norm, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_tally_accumulate<<<grid_for(n), MCW_BLOCK, 0, st>>>(value, sum, sum_sq, n, norm);
+}
+
+// ---- CUB-backed utilities (scan / reduce / sort are library calls; they are not on the hot path) ----
+size_t mcwk_scan_temp_bytes(int64_t n)
+{
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, a, (int64_t*)nullptr, (int64_t*)nullptr, n);
+  cub::DeviceReduce::Sum(nullptr, b, (double*)nullptr, (double*)nullptr, n);
+  cub::DeviceRadixSort::SortPairs(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
+                                  n);
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
+}
+
+void mcwk_exclusive_scan(void* temp, size_t temp_bytes, const int64_t* in, int64_t* out, int64_t n, cudaStream_t st)
+{
+  if (n > 0)
+    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, n, st);
+}
+
+void mcwk_reduce_sum(void* temp, size_t temp_bytes, const double* in, double* out, int64_t n, cudaStream_t st)
+{
+  cub::DeviceReduce::Sum(temp, temp_bytes, in, out, n, st);
+}
+
+void mcwk_sort_queue(void* temp, size_t temp_bytes, uint32_t* keys_in, uint32_t* keys_out, int32_t* q_in, int32_t* q_out,
+                     int64_t n, int end_bit, cudaStream_t st)
+{
+  if (n > 0)
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, q_in, q_out, n, 0, end_bit, st);
+}
+
+void mcwk_bank_sort(void* temp, size_t temp_bytes, const McwParticlesDev& p, int64_t n_particles, int64_t work_offset,
+                    const mcw_source_site* bank, int64_t n_bank, int64_t* scratch_counts, int64_t* scratch_scan,
+                    mcw_source_site* sorted, cudaStream_t st)
+{
+  if (n_particles <= 0)
+    return;
+  k_progeny_to_i64<<<grid_for(n_particles), MCW_BLOCK, 0, st>>>(p.n_progeny, n_particles, scratch_counts);
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, scratch_counts, scratch_scan, n_particles, st);
+  if (n_bank > 0)
+    k_bank_scatter<<<grid_for(n_bank), MCW_BLOCK, 0, st>>>(bank, n_bank, scratch_scan, work_offset, sorted);
+}
+
+void mcwk_sample_bank(void* temp, size_t temp_bytes, const mcw_source_site* sorted, int64_t n_bank, int64_t global_start,
+                      int64_t total, int64_t n_particles, uint64_t seed0, int64_t* counts, int64_t* offsets,
+                      mcw_source_site* out, int64_t cap, cudaStream_t st)
+{
+  if (n_bank <= 0)
+    return;
+  k_sample_counts<<<grid_for(n_bank), MCW_BLOCK, 0, st>>>(n_bank, global_start, total, n_particles, seed0, counts);
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, n_bank, st);
+  k_sample_scatter<<<grid_for(n_bank), MCW_BLOCK, 0, st>>>(sorted, n_bank, counts, offsets, out, cap);
+}
+
+void mcwk_pad_from_bank_end(const mcw_source_site* sorted, int64_t n_bank, mcw_source_site* out, int64_t have,
+                            int64_t needed, cudaStream_t st)
+{
+  if (needed > 0)
+    k_pad_from_bank_end<<<grid_for(needed), MCW_BLOCK, 0, st>>>(sorted, n_bank, out, have, needed);
+}
+
+uint64_t mcwk_host_init_seed(int64_t id, int offset, int64_t master_seed)
+{
+  // host copy of OMC random_lcg.cpp:58-61 (init_seed) for the bank-sampling stream
+  uint64_t n = (uint64_t)id * MCW_PRN_STRIDE, seed = (uint64_t)(master_seed + offset);
+  uint64_t g = MCW_PRN_MULT, c = MCW_PRN_ADD, g_new = 1, c_new = 0;
+  while (n > 0)
+  {
+    if (n & 1)
+    {
+      g_new *= g;
+      c_new = c_new * g + c;
+    }
+    c *= (g + 1);
+    g *= g;
+    n >>= 1;
+  }
+  return g_new * seed + c_new;
+}

@@ -1,0 +1,43 @@
+// mcw_kernels.h -- host-callable launchers of the kernels in mcw_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mcw_types.h"
+
+void mcwk_init_histories(const McwParams& P, const mcw_source_site* src, int64_t n, int32_t* q_fly, cudaStream_t st);
+void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, const double* d_box, int only_fissionable,
+                        cudaStream_t st);
+void mcwk_xs_lookup(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+                    cudaStream_t st);
+void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
+                  cudaStream_t st);
+void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
+                          cudaStream_t st);
+void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+                int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
+                cudaStream_t st);
+void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+                  int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st);
+void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,
+                   int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, cudaStream_t st);
+void mcwk_trace_rays(const McwParams& P, int64_t n, const double* start, const double* dirs, const int32_t* start_elem,
+                     const int32_t* start_side, const double* max_distance, double* out_distance, int32_t* out_segments,
+                     uint64_t* out_hash, int32_t* out_status, cudaStream_t st);
+void mcwk_locate_points(const McwParams& P, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem,
+                        cudaStream_t st);
+void mcwk_fill_records(const McwParticlesDev& p, int64_t n, mcw_history_record* rec, cudaStream_t st);
+void mcwk_tally_accumulate(double* value, double* sum, double* sum_sq, int64_t n, double norm, cudaStream_t st);
+size_t mcwk_scan_temp_bytes(int64_t n);
+void mcwk_exclusive_scan(void* temp, size_t temp_bytes, const int64_t* in, int64_t* out, int64_t n, cudaStream_t st);
+void mcwk_reduce_sum(void* temp, size_t temp_bytes, const double* in, double* out, int64_t n, cudaStream_t st);
+void mcwk_sort_queue(void* temp, size_t temp_bytes, uint32_t* keys_in, uint32_t* keys_out, int32_t* q_in, int32_t* q_out,
+                     int64_t n, int end_bit, cudaStream_t st);
+void mcwk_bank_sort(void* temp, size_t temp_bytes, const McwParticlesDev& p, int64_t n_particles, int64_t work_offset,
+                    const mcw_source_site* bank, int64_t n_bank, int64_t* scratch_counts, int64_t* scratch_scan,
+                    mcw_source_site* sorted, cudaStream_t st);
+void mcwk_sample_bank(void* temp, size_t temp_bytes, const mcw_source_site* sorted, int64_t n_bank, int64_t global_start,
+                      int64_t total, int64_t n_particles, uint64_t seed0, int64_t* counts, int64_t* offsets,
+                      mcw_source_site* out, int64_t cap, cudaStream_t st);
+void mcwk_pad_from_bank_end(const mcw_source_site* sorted, int64_t n_bank, mcw_source_site* out, int64_t have,
+                            int64_t needed, cudaStream_t st);
+uint64_t mcwk_host_init_seed(int64_t id, int offset, int64_t master_seed);

@@ -1,0 +1,141 @@
+// mcw_types.h -- device data layout of libmacaw_b200 (shared by kernels and the host API).
+//
+// HBM layout:
+//   * Library: all nuclides concatenated.  energy[sumG] (f64), xs4[sumG][4] (total, absorption,
+//     fission, nu-fission: one 32-byte sector per grid point, two adjacent rows = one 64-byte read),
+//     el_inel[sumG][2] (elastic, level-inelastic; collision kernel only), grid_index[n_nuc][M+1] (i32).
+//   * Mesh: one fixed-stride record per element (128 B for TET4/QUAD4 = one L2 line, 256 B for HEX8)
+//     holding the element's OWN copy of its vertex coordinates, its neighbour ids (boundary sides
+//     encode -(bnd_id)-2), the block's hmax, its material and block index.  One dependent load per
+//     element crossing instead of connectivity -> node-coordinate double indirection.
+//   * Particles: structure of arrays indexed by history slot.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/macaw_b200.h"
+
+#define MCW_MAX_NUC_PER_MAT 64
+
+struct McwNucParams
+{
+  double awr, kT;
+  double inel_E, inel_ratio;
+  double nu_poly[2];
+  double dyield[MCW_MAX_DELAYED_GROUPS];
+  double dtheta[MCW_MAX_DELAYED_GROUPS];
+  double watt_a, watt_b, q;
+  int64_t off;      // offset of this nuclide in the concatenated grids
+  int32_t G;
+  int32_t fissionable;
+  int32_t n_inel, inel_thr;
+  int32_t n_precursor;
+  int32_t pad;
+};
+
+struct McwLibraryDev
+{
+  const double* energy;      // [sumG]
+  const double* xs4;         // [sumG][4]
+  const double* el_inel;     // [sumG][2]
+  const int32_t* grid_index; // [n_nuc][M+1]
+  const McwNucParams* nuc;   // [n_nuc]
+  const int32_t* mat_off;    // [n_mat+1]
+  const int32_t* mat_nuc;    // concatenated nuclide indices
+  const double* mat_dens;
+  const int32_t* mat_fissionable;
+  int32_t n_nuc, n_mat, M;
+  double E_min, E_max, log_spacing;
+};
+
+// element record strides (bytes) and field offsets
+template <int TYPE>
+struct McwElem;
+template <>
+struct McwElem<MCW_TET4>
+{
+  static constexpr int NV = 4, NS = 4, NPS = 3, DIM = 3, NE = 6, CPV = 3, STRIDE = 128;
+};
+template <>
+struct McwElem<MCW_HEX8>
+{
+  static constexpr int NV = 8, NS = 6, NPS = 4, DIM = 3, NE = 12, CPV = 3, STRIDE = 256;
+};
+template <>
+struct McwElem<MCW_QUAD4>
+{
+  static constexpr int NV = 4, NS = 4, NPS = 2, DIM = 2, NE = 0, CPV = 2, STRIDE = 128;
+};
+
+struct McwMeshDev
+{
+  const unsigned char* rec; // element records
+  const int64_t* conn;      // [n_elem][NV] global node ids (rare path only)
+  const int64_t* n2e_off;   // node -> elements CSR (rare path only)
+  const int32_t* n2e;
+  const int32_t* bnd_kind;  // [n_bnd]
+  const int64_t* cell_off;  // point-location grid
+  const int32_t* cell_elems;
+  int32_t gx, gy, gz;
+  int32_t type, n_bnd, rectangular;
+  int64_t n_elem, n_nodes;
+  double bb_min[3], bb_max[3];
+  double domain_max_length;
+};
+
+// particle status between kernels
+enum
+{
+  MCW_ST_FLY = 0,      // needs (xs +) tracking
+  MCW_ST_COLLIDE = 1,  // stopped at a collision point, waiting for the collision kernel
+  MCW_ST_FALLBACK = 2, // next step needs the general (vertex/edge/neighbour) walk
+  MCW_ST_DEAD = 3
+};
+
+struct McwParticlesDev
+{
+  double *x, *y, *z, *ux, *uy, *uz, *E, *wgt;
+  uint64_t *seed_trk, *seed_src, *seed_urr;
+  double *sig_t, *sig_a, *sig_f, *sig_nf; // cached macroscopic xs for (E, xs_mat)
+  double *k_col, *k_abs, *k_trk;
+  int32_t *elem, *last_elem, *xs_mat;
+  int32_t *n_progeny, *n_seg, *n_coll, *n_xs;
+  int8_t *inc_side, *ext_first, *ext_second, *status, *fate;
+  uint64_t* hash;
+};
+
+struct McwTallyDev
+{
+  double* value; // [bins][n_scores]
+  const double* ebins;
+  int32_t n_edges, n_energy, n_scores, granularity, estimator;
+  int32_t scores[MCW_N_SCORES];
+};
+
+#define MCW_MAX_TALLIES 8
+
+struct McwCounters // device-side counters, one cache line each where contended
+{
+  unsigned long long n_fly[2], pad0[14]; // ping-pong counts of the two fly queues
+  unsigned long long n_collide, pad1[15];
+  unsigned long long n_fallback, pad2[15];
+  unsigned long long n_bank, pad3[15];
+  unsigned long long n_segments, n_collisions, n_xs, n_nuc_lookups, n_vertex_edge, n_moved, n_failed,
+      n_bank_dropped;
+};
+
+struct McwParams
+{
+  McwLibraryDev lib;
+  McwMeshDev mesh;
+  McwParticlesDev p;
+  McwTallyDev tally[MCW_MAX_TALLIES];
+  int32_t n_tallies, tallies_active;
+  int32_t any_tracklength, any_collision_tally;
+  mcw_source_site* bank;
+  int64_t bank_capacity;
+  McwCounters* counters;
+  int64_t n_particles_global, work_offset; // id = work_offset + slot + 1
+  int64_t master_seed;
+  int32_t batch, is_2d, seed_through_double, max_events;
+  double z_coord, keff;
+};

@@ -1,0 +1,73 @@
+"""Identical problem set-ups for the CPU oracle and the GPU library (same numpy arrays on both sides)."""
+import numpy as np
+
+from macaw_b200 import cstructs, meshgen, nucdata
+
+ALL_SCORES = [0, 1, 2, 3, 4]
+EBINS = [1e-5, 0.625, 1.0e5, 2.0e7]
+
+
+def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tally=False):
+    # block ids are 0..n_materials-1 in every synthetic mesh; pass them explicitly because a coarse mesh
+    # may not contain every block (e.g. no element centroid falls inside the thin gap)
+    block_ids = np.arange(len(block_material), dtype=np.int32)
+    if hasattr(obj, "L") and hasattr(obj.L, "orc_create"):
+        obj.set_mesh(mesh, block_ids)
+        obj.set_library(lib, block_material)
+    else:
+        obj.set_mesh(mesh)
+        obj.set_library(lib, block_material, block_ids)
+    obj.set_settings(settings)
+    if tallies:
+        obj.add_tally(1, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["cell"], ALL_SCORES, EBINS)
+        obj.add_tally(2, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["universe"], [0, 3])
+    if track_tally:
+        obj.add_tally(3, cstructs.ESTIMATOR["tracklength"], cstructs.GRANULARITY["cell"], [0, 3, 4], EBINS)
+    return obj
+
+
+def infinite_medium(n_particles=2000, G=400, n_inactive=1, **kw):
+    mesh = meshgen.infinite_medium(5)
+    lib = nucdata.infinite_medium_library(G=G)
+    s = cstructs.make_settings(n_particles, n_inactive=n_inactive, source_box=(-5, -5, -5, 5, 5, 5), **kw)
+    return mesh, lib, [0, 1], s
+
+
+def pin_cell_tet(n_particles=2000, G=400, n_xy=8, n_z=3, n_inactive=1, **kw):
+    mesh = meshgen.pin_cell_tet(n_xy, n_z)
+    lib = nucdata.make_library(9, G=G)
+    h = meshgen.PIN_PITCH / 2
+    s = cstructs.make_settings(n_particles, n_inactive=n_inactive, source_box=(-h, -h, -h, h, h, h), **kw)
+    return mesh, lib, [0, 1, 2, 3], s
+
+
+def pin_cell_hex(n_particles=2000, G=400, n_xy=10, n_z=2, n_inactive=1, **kw):
+    mesh = meshgen.pin_cell_hex(n_xy, n_z)
+    lib = nucdata.make_library(9, G=G)
+    h = meshgen.PIN_PITCH / 2
+    s = cstructs.make_settings(n_particles, n_inactive=n_inactive, source_box=(-h, -h, -h, h, h, h), **kw)
+    return mesh, lib, [0, 1, 2, 3], s
+
+
+def assembly_quad(n_particles=2000, G=400, n_pins=3, cells_per_pin=7, n_inactive=1, **kw):
+    mesh = meshgen.assembly_quad(n_pins, cells_per_pin)
+    lib = nucdata.make_library(9, G=G)
+    L = n_pins * meshgen.PIN_PITCH
+    s = cstructs.make_settings(n_particles, n_inactive=n_inactive, is_2d=True, z_coord=100.0,
+                               source_box=(0, 0, -1, L, L, 1), **kw)
+    return mesh, lib, [0, 1, 2, 3], s
+
+
+PROBLEMS = {"infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,
+            "assembly_quad": assembly_quad}
+
+
+def lookup_points(lib, n, seed=5):
+    rng = np.random.default_rng(seed)
+    E = np.exp(rng.uniform(np.log(1.1e-5), np.log(1.9e7), n))
+    # exact grid points, interval ends and duplicates exercise the search edge cases
+    g = lib.nuclides[min(3, len(lib.nuclides) - 1)].energy
+    E[: min(64, n)] = g[rng.integers(0, g.size, min(64, n))]
+    E[0], E[1] = 1e-5, 2e7 * (1 - 1e-16)
+    mat = rng.integers(0, len(lib.materials), n).astype(np.int32)
+    return E, mat

@@ -1,0 +1,141 @@
+"""GPU <-> oracle parity through the C ABI (run on the B200 box: pytest -m gpu).
+
+Bar: bit-exact for every integer / index / byte result (seeds, element sequences, bank contents are
+compared as raw bytes, which also makes the FP64 fields of histories and sites bit-exact); FP64
+sums that depend on atomic ordering (tallies, k totals) within rtol 1e-11."""
+import numpy as np
+import pytest
+
+from macaw_b200 import cstructs
+from tests import lots_rays, problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx_factory():
+    from macaw_b200.context import Context
+    made = []
+
+    def make():
+        c = Context(0)
+        made.append(c)
+        return c
+    yield make
+    for c in made:
+        c.close()
+
+
+def both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=False, **kw):
+    mesh, lib, bm, s = problems.PROBLEMS[name](**kw)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies, track_tally)
+    g = problems.configure(ctx_factory(), mesh, lib, bm, s, tallies, track_tally)
+    return o, g, mesh, lib, s
+
+
+@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad"])
+def test_xs_lookup_bit_exact(oracle_bridge, ctx_factory, name):
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
+    E, mat = problems.lookup_points(lib, 20000)
+    a, b = o.xs_lookup(E, mat), g.xs_lookup(E, mat)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    for i in range(len(lib.nuclides)):
+        assert np.array_equal(o.grid_index(i, lib.n_log_bins), g.grid_index(i, lib.n_log_bins))
+
+
+@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "pin_cell_hex", "assembly_quad"])
+def test_locate_and_source_bit_exact(oracle_bridge, ctx_factory, name):
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
+    rng = np.random.default_rng(2)
+    lo, hi = mesh.xyz.min(0), mesh.xyz.max(0)
+    pts = lo + rng.uniform(0, 1, (5000, 3)) * (hi - lo)
+    pts[:200] = mesh.xyz[rng.integers(0, mesh.xyz.shape[0], 200)]  # exactly on vertices: tie-break rule
+    rid = np.arange(5000, dtype=np.int64)
+    assert np.array_equal(o.locate_points(pts, rid), g.locate_points(pts, rid))
+    o.sample_initial_source()
+    g.sample_initial_source()
+    assert o.source_bank().tobytes() == g.source_bank().tobytes()
+
+
+@pytest.mark.parametrize("et,kind", [("hex8", "vtv"), ("hex8", "ctv"), ("hex8", "ete"), ("hex8", "ctc"),
+                                     ("quad4", "vtv"), ("quad4", "ctv"), ("quad4", "ctc"), ("tet4", "vtv"),
+                                     ("tet4", "ctv"), ("tet4", "ete")])
+def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, golden_dir, et, kind):
+    import json, os
+    from macaw_b200 import meshgen, nucdata
+    if et == "hex8":
+        mesh = meshgen.hex_grid(5, 5, 5, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
+    elif et == "quad4":
+        mesh = meshgen.quad_grid(5, 5, (0, 0), (5, 5), meshgen.BC_KILL)
+    else:
+        mesh = meshgen.tet_grid(4, 4, 4, (0, 0, 0), (4, 4, 4), meshgen.BC_KILL)
+    lib = nucdata.make_library(2, G=50)
+    s = cstructs.make_settings(100)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, [0], s, tallies=False)
+    g = problems.configure(ctx_factory(), mesh, lib, [0], s, tallies=False)
+    start, dirs, elems, sides, maxd = lots_rays.lots(mesh, kind)
+    md = maxd if kind == "ctc" else None
+    d0, s0, h0, st = o.trace_rays(start, dirs, elems, sides, md)
+    d1, s1, h1 = g.trace_rays(start, dirs, elems, sides, md)
+    assert st["failed"] == 0
+    assert np.array_equal(s0, s1) and np.array_equal(h0, h1)
+    assert np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+    gold_names = {"vtv": "ntn" if et == "hex8" else "vtv", "ctv": "ctn" if et == "hex8" else "ctv", "ete": "ete",
+                  "ctc": "ctc"}
+    if et != "tet4":
+        gold = json.load(open(os.path.join(golden_dir, "rt_lots_gold.json")))[f"{et}/{gold_names[kind]}"]
+        assert abs(d1.sum() - gold["total_distance"]) <= 1e-8 * gold["total_distance"]
+
+
+@pytest.mark.parametrize("name,kw", [("infinite_medium", {}), ("pin_cell_tet", {}), ("pin_cell_hex", {}),
+                                      ("assembly_quad", {}), ("pin_cell_tet", {"seed_through_double": False}),
+                                      ("infinite_medium", {"sort_xs_queue": 1})])
+def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw):
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
+    o.sample_initial_source()
+    g.sample_initial_source()
+    for batch in range(1, 4):
+        ro = o.run_generation(batch)
+        rg = g.run_generation(batch)
+        a, b = o.history_records(), g.history_records()
+        for f in ("seed_tracking", "seed_source", "seed_urr", "n_segments", "n_collisions", "n_progeny",
+                  "last_elem", "fate", "trace_hash"):
+            assert np.array_equal(a[f], b[f]), (batch, f, int((a[f] != b[f]).sum()))
+        for f in ("E", "k_collision", "k_absorption", "k_tracklength"):
+            assert np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)), (batch, f)
+        assert o.fission_bank().tobytes() == g.fission_bank().tobytes()
+        assert o.source_bank().tobytes() == g.source_bank().tobytes()  # sampled next-generation source
+        for f in ("n_segments", "n_collisions", "n_bank_sites", "n_failed_traces", "n_vertex_edge_hits"):
+            assert getattr(ro, f) == getattr(rg, f), f
+        for f in ("k_generation", "keff", "k_collision", "k_absorption", "k_tracklength", "total_weight"):
+            assert getattr(rg, f) == pytest.approx(getattr(ro, f), rel=1e-12), f
+        assert rg.n_failed_traces == 0
+    for tid in (1, 2, 3):
+        _, so, qo, nro = o.get_tally(tid)
+        sg, qg, nrg = g.get_tally(tid)
+        assert nro == nrg == 2
+        assert np.allclose(sg.ravel(), so, rtol=1e-11, atol=1e-300)
+        assert np.allclose(qg.ravel(), qo, rtol=1e-11, atol=1e-300)
+        assert so.sum() > 0
+
+
+def test_e2e_host_buffers_round_trip(oracle_bridge, ctx_factory):
+    """The reference-facing call sequence with HOST buffers: set_source_bank -> run -> get_source_bank."""
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, "pin_cell_tet")
+    o.sample_initial_source()
+    src = o.source_bank()
+    g.set_source_bank(src)
+    ro, rg = o.run_generation(1), g.run_generation(1)
+    assert o.source_bank().tobytes() == g.source_bank().tobytes()
+    assert rg.k_generation == pytest.approx(ro.k_generation, rel=1e-12)
+
+
+def test_error_paths(ctx_factory):
+    from macaw_b200.lib import McwError
+    c = ctx_factory()
+    with pytest.raises(McwError):
+        c.transport_generation(1)  # nothing configured: MCW_E_NOT_READY
+    mesh, lib, bm, s = problems.infinite_medium()
+    c.set_mesh(mesh)
+    with pytest.raises(McwError):
+        c.set_library(lib, [0, 7])  # block mapped to an unknown material (MC CollisionKernel.C:84-90)
