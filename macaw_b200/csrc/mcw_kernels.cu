@@ -337,11 +337,9 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
     if (status == MCW_ST_FALLBACK)
       q_fallback[k] = i;
     unsigned mask = __activemask();
-    unsigned long long tot = segs;
-    for (int o = 16; o > 0; o >>= 1)
-      tot += __shfl_down_sync(mask, tot, o);
+    unsigned tot = __reduce_add_sync(mask, (unsigned)segs);
     if ((threadIdx.x & 31) == (__ffs(mask) - 1))
-      atomicAdd(&P.counters->n_segments, tot);
+      atomicAdd(&P.counters->n_segments, (unsigned long long)tot);
   }
 }
 
