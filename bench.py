@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- neutron histories/sec over active batches (BASELINE.json metric).
+
+A "step" is one batch = one generation of the k-eigenvalue iteration over `particles` histories per
+GPU (weak scaling).  Workload at N=1: BASELINE.json configs[1], the UO2 pin cell on a ~100k-TET4
+mesh with a per-element collision-flux tally and the synthetic 9-nuclide library.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles P]
+
+Prints ONE JSON line (see the task contract): value = whole-job histories/s with the source bank
+resident in HBM; e2e = the same through the C ABI with HOST (pinned) source banks uploaded and the
+next-generation bank + k read back every step; roofline = the tracking kernel's algorithmic bytes
+(308 B per TET4 segment) over its CUDA-event time inside the timed region; cpu_baseline =
+the CPU oracle (history-based restatement of the reference algorithms) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEGMENT_BYTES = {"tet4": 308.0, "hex8": 412.0, "quad4": 280.0}  # SURVEY.md 8(d) / BASELINE.md section 2
+
+
+def build_problem(name, particles_total, n_inactive):
+    from macaw_b200 import cstructs, meshgen, nucdata
+    if name == "pin_cell_tet":
+        mesh = meshgen.pin_cell_tet(26, 25)  # 26*26*25*6 = 101 400 TET4
+        lib = nucdata.make_library(9, G=10000, seed=1)
+        h = meshgen.PIN_PITCH / 2
+        box = (-h, -h, -h, h, h, h)
+        et = "tet4"
+    elif name == "assembly_quad":
+        mesh = meshgen.assembly_quad(17, 9)
+        lib = nucdata.make_library(35, G=10000, seed=1)
+        L = 17 * meshgen.PIN_PITCH
+        box = (0, 0, -1, L, L, 1)
+        et = "quad4"
+    elif name == "infinite_medium":
+        mesh = meshgen.infinite_medium(5)
+        lib = nucdata.infinite_medium_library(G=10000)
+        box = (-5, -5, -5, 5, 5, 5)
+        et = "hex8"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    s = cstructs.make_settings(particles_total, n_inactive=n_inactive, is_2d=mesh.dim == 2, z_coord=100.0,
+                               source_box=box, record_traces=0)
+    n_mat = len(lib.materials)
+    blocks = list(range(n_mat)) if name != "infinite_medium" else [0, 1]
+    mats = [b + 1 for b in blocks]
+    return mesh, lib, blocks, mats, s, et
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch):
+    """Histories/s of the CPU oracle on a bounded sample of the same workload."""
+    from oracle import bridge
+    from macaw_b200 import cstructs
+    mesh, lib, blocks, mats, s, et = problem
+
+    def run(n):
+        o = bridge.Oracle()
+        o.set_mesh(mesh, np.asarray(blocks, np.int32))
+        o.set_library(lib, [m - 1 for m in mats])
+        s2 = cstructs.Settings.from_buffer_copy(bytes(s))
+        s2.n_particles = n
+        o.set_settings(s2)
+        o.add_tally(1, 0, 0, [0], None)
+        sub = source_sites[:n].copy()
+        o.set_source_bank(sub)
+        t0 = time.perf_counter()
+        o.transport_generation(batch, threads)
+        return time.perf_counter() - t0
+
+    n0 = min(len(source_sites), 200 * threads)
+    t = run(n0)
+    n = int(min(len(source_sites), max(n0, n0 * target_seconds / max(t, 1e-3))))
+    t = run(n)
+    return n / t, n, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithms (oracle restatement; the real MaCaw binary
+    cannot be built offline) on all host cores, same workload definition."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bridge
+    from macaw_b200 import cstructs
+    threads = os.cpu_count() or 1
+    bridge.build(ref=False)
+    probe = build_problem(args.workload, 1000, args.warmup)
+    mesh, lib, blocks, mats, s, et = probe
+    o = bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(lib, [m - 1 for m in mats])
+    # calibrate the per-step sample so K+W steps finish in a few minutes
+    s.n_particles = 100 * threads
+    o.set_settings(s)
+    o.sample_initial_source()
+    t0 = time.perf_counter()
+    o.run_generation(1, threads)
+    dt = time.perf_counter() - t0
+    budget = 150.0 / (args.steps + args.warmup)
+    n = int(max(100 * threads, min(2_000_000, s.n_particles * budget / max(dt, 1e-3))))
+    o = bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(lib, [m - 1 for m in mats])
+    s.n_particles = n
+    o.set_settings(s)
+    o.add_tally(1, 0, 0, [0], None)
+    o.sample_initial_source()
+    for b in range(1, args.warmup + 1):
+        o.run_generation(b, threads)
+    t0 = time.perf_counter()
+    for b in range(args.warmup + 1, args.warmup + args.steps + 1):
+        res = o.run_generation(b, threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} histories/step x {args.steps} steps of {args.workload} on {threads} host threads"
+    out = {"impl": "reference", "metric": "neutron histories/sec (active batches)", "value": value,
+           "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "mesh_elements": int(mesh.n_elem), "nuclides": len(lib.nuclides),
+                      "particles_per_step": n, "keff": res.keff},
+           "cpu_baseline": {"value": value, "unit": "histories/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pin_cell_tet")
+    ap.add_argument("--particles", type=int, default=1_000_000, help="histories per GPU per batch")
+    ap.add_argument("--sort-xs", type=int, default=0)
+    ap.add_argument("--sync-every", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from macaw_b200 import study as st
+    from macaw_b200.cstructs import SITE_DTYPE
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n_total = args.particles * world
+    problem = build_problem(args.workload, n_total, args.warmup)
+    mesh, lib, blocks, mats, s, et = problem
+    s.sort_xs_queue = args.sort_xs
+    kernel = st.CollisionKernel(blocks=blocks, materials=mats, temperature=293.6, z_coord=100.0 if mesh.dim == 2 else None)
+    tally = st.OpenMCTally(id=1, scores=["flux"], filters=["cell"], estimator="COLLISION")
+    study = st.OpenMCStudy(mesh, lib, kernel, s, [tally], device=local, group=group, rank=rank, nranks=world)
+    ctx = study.ctx
+    ctx.set_option("sync_every", args.sync_every)
+    ctx.set_option("profile", 1)
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ext):
+        for _ in range(args.warmup):
+            study.execute()
+        # ---- timed region: K active batches, inputs resident in HBM
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(ext)
+        acc = {"seg": 0, "col": 0, "launch": 0, "ms_track": 0.0, "ms_xs": 0.0, "ms_col": 0.0, "ms_bank": 0.0,
+               "rounds": 0, "ve": 0, "failed": 0}
+        for _ in range(args.steps):
+            res = study.execute()
+            acc["seg"] += res.n_segments
+            acc["col"] += res.n_collisions
+            acc["launch"] += res.n_kernel_launches
+            acc["ms_track"] += res.ms_track
+            acc["ms_xs"] += res.ms_xs
+            acc["ms_col"] += res.ms_collide
+            acc["ms_bank"] += res.ms_bank
+            acc["rounds"] += res.n_event_rounds
+            acc["ve"] += res.n_vertex_edge_hits
+            acc["failed"] += res.n_failed_traces
+        ev1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        ms_dev = ev0.elapsed_time(ev1)
+        del flush
+
+        # ---- e2e: same metric through the C ABI with HOST buffers, copies inside the timed region
+        n_loc = int(study.work_index[rank + 1] - study.work_index[rank])
+        pin_in = torch.empty(n_loc * 96, dtype=torch.uint8).pin_memory()
+        pin_out = torch.empty(n_loc * 96, dtype=torch.uint8).pin_memory()
+        host_in = pin_in.numpy().view(SITE_DTYPE)
+        host_out = pin_out.numpy().view(SITE_DTYPE)
+        host_in[:] = ctx.source_bank()
+        e2e_steps = max(1, min(args.steps, 5))
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.set_source_bank(host_in)          # H2D n*96 B
+            r2 = study.execute()
+            ctx.source_bank(out=host_out)         # D2H n*96 B (next generation's source) + result struct
+            k_host = r2.k_generation
+            host_in, host_out = host_out, host_in
+        barrier()
+        e2e_wall = time.perf_counter() - t1
+
+    times = torch.tensor([ms_dev, wall * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([acc["seg"], acc["col"], acc["launch"], acc["ve"], acc["failed"]], dtype=torch.float64,
+                        device="cuda")
+    if world > 1:
+        import torch.distributed as td
+        td.all_reduce(times, op=td.ReduceOp.MAX)
+        td.all_reduce(sums, op=td.ReduceOp.SUM)
+    ms_dev, wall_ms, e2e_ms = [float(x) for x in times.tolist()]
+    seg_all, col_all, launches_all, ve_all, failed_all = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        value = n_total * args.steps / (ms_dev * 1e-3)
+        e2e_value = n_total * e2e_steps / (e2e_ms * 1e-3)
+        peak, peak_src = peaks()
+        bytes_seg = SEGMENT_BYTES[et]
+        achieved = bytes_seg * acc["seg"] / (acc["ms_track"] * 1e-3) / 1e9 if acc["ms_track"] > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "track_kernel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                rate, n_s, t_s = cpu_oracle_rate(problem, ctx.source_bank(), 15.0, threads,
+                                                 args.warmup + args.steps + e2e_steps + 1)
+                cpu = {"value": rate, "unit": "histories/s", "cores": threads, "kind": "port",
+                       "sample": f"{n_s} histories of the same source bank, one generation, {t_s:.1f} s"}
+            except Exception as e:  # the oracle is only a reported baseline
+                cpu = {"value": None, "unit": "histories/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        out = {
+            "metric": "neutron histories/sec (active batches)", "value": value, "unit": "histories/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "mesh_elements": int(mesh.n_elem), "elem_type": et,
+                       "nuclides": len(lib.nuclides), "grid_points_per_nuclide": int(lib.nuclides[0].energy.size),
+                       "particles_per_gpu_per_batch": args.particles, "global_particles_per_batch": n_total,
+                       "parallelism": f"particle-sharded x{world}", "tally": "per-element collision flux",
+                       "seed_through_double": int(s.seed_through_double), "sort_xs_queue": args.sort_xs,
+                       "l2_policy": "inputs larger than L2 are not guaranteed; a 256 MiB buffer is written before "
+                                    "the timed region and every generation streams > L2 of particle state",
+                       "keff": res.keff, "keff_std": res.keff_std,
+                       "segments_per_history": seg_all / (n_total * args.steps),
+                       "collisions_per_history": col_all / (n_total * args.steps),
+                       "event_rounds_per_batch": acc["rounds"] / args.steps,
+                       "vertex_edge_hits": ve_all, "failed_traces": failed_all,
+                       "wall_ms_per_step": wall_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": n_total * 96,
+                    "d2h_bytes_per_step": n_total * 96 + 8 * world, "steps": e2e_steps, "k_read_back": k_host},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_track", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_segment": bytes_seg,
+                         "segments_per_launch": acc["seg"] / max(acc["rounds"], 1),
+                         "avg_launch_ms": acc["ms_track"] / max(acc["rounds"], 1),
+                         "kernel_share_of_step": acc["ms_track"] / ms_dev,
+                         "other_kernels_ms_per_step": {"xs_lookup": acc["ms_xs"] / args.steps,
+                                                       "collide+fallback": acc["ms_col"] / args.steps,
+                                                       "bank+reduce": acc["ms_bank"] / args.steps}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as td
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

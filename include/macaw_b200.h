@@ -188,6 +188,9 @@ int mcw_version(void);
 int mcw_set_option(mcw_handle h, const char* name, int value);
 /* Builds all device state now (otherwise done lazily by the first call that needs it). */
 int mcw_prepare(mcw_handle h);
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so a caller can time
+ * with its own events or enqueue collectives in order. */
+int mcw_stream(mcw_handle h, void** stream);
 int mcw_struct_sizes(int32_t* out, int n); /* sizeof of the six ABI structs, for binding self-checks */
 
 /* Mesh.  Replaces libMesh access on the path: elem->point / neighbor_ptr / subdomain_id

@@ -44,6 +44,11 @@ class Context:
     def prepare(self):
         self._ck(self.L.mcw_prepare(self.h))
 
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.L.mcw_stream(self.h, C.byref(p)))
+        return p.value
+
     def set_mesh(self, m: meshgen.Mesh, pass_neighbors=True):
         self.mesh = m
         xyz = np.ascontiguousarray(m.xyz, np.float64)

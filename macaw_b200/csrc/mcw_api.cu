@@ -131,6 +131,17 @@ struct mcw_context
   int profile = 0, sync_every = 1, fallback_blocks = 8;
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> pool; // per-round profiling events (5 per round), reused across generations
+  cudaEvent_t pool_event(size_t i)
+  {
+    while (pool.size() <= i)
+    {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[i];
+  }
 };
 
 #define CK(call)                                                                                               \
@@ -238,6 +249,8 @@ void mcw_destroy(mcw_handle h)
   for (auto& e : h->ev)
     if (e)
       cudaEventDestroy(e);
+  for (auto& e : h->pool)
+    cudaEventDestroy(e);
   if (h->stream)
     cudaStreamDestroy(h->stream);
   delete h;
@@ -258,6 +271,14 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->fallback_blocks = std::max(1, value);
   else
     return fail(h, MCW_E_INVALID_ARGUMENT, "unknown option " + n);
+  return MCW_OK;
+}
+
+int mcw_stream(mcw_handle h, void** stream)
+{
+  if (!h || !stream)
+    return MCW_E_INVALID_ARGUMENT;
+  *stream = (void*)h->stream;
   return MCW_OK;
 }
 
@@ -975,7 +996,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     unsigned long long* cnt_cur = &P.counters->n_fly[cur];
     unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
     if (prof)
-      cudaEventRecord(h->ev[1], st);
+      cudaEventRecord(h->pool_event(4 * rounds + 0), st);
     if (h->set.sort_xs_queue)
     {
       // particle-queue sort by (material, energy bucket): OpenMC's TODO at OMC event.cpp:76-82
@@ -991,32 +1012,23 @@ int mcw_transport_generation(mcw_handle h, int batch)
     }
     mcwk_xs_lookup(P, q, cnt_cur, upper, st);
     if (prof)
-      cudaEventRecord(h->ev[2], st);
+      cudaEventRecord(h->pool_event(4 * rounds + 1), st);
     mcwk_track(P, q, cnt_cur, upper, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback, st);
     if (prof)
-      cudaEventRecord(h->ev[3], st);
+      cudaEventRecord(h->pool_event(4 * rounds + 2), st);
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
                   h->d_q_collide, st);
     mcwk_collide(P, h->d_q_collide, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
     if (prof)
-      cudaEventRecord(h->ev[4], st);
+      cudaEventRecord(h->pool_event(4 * rounds + 3), st);
     R.n_kernel_launches += 4;
     ++rounds;
     const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
-    if (sync_now || prof)
+    if (sync_now)
     {
       CK(cudaMemcpyAsync(h->h_counters, P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       upper = (int64_t)h->h_counters->n_fly[cur ^ 1];
-      if (prof)
-      {
-        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
-        R.ms_xs += ms;
-        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
-        R.ms_track += ms;
-        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
-        R.ms_collide += ms;
-      }
     }
     // reset the consumed queues for the next round
     CK(cudaMemsetAsync(cnt_cur, 0, sizeof(unsigned long long), st));
@@ -1051,6 +1063,15 @@ int mcw_transport_generation(mcw_handle h, int batch)
   {
     cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]);
     R.ms_bank = ms;
+    for (int64_t r = 0; r < rounds; ++r)
+    {
+      cudaEventElapsedTime(&ms, h->pool[4 * r + 0], h->pool[4 * r + 1]);
+      R.ms_xs += ms;
+      cudaEventElapsedTime(&ms, h->pool[4 * r + 1], h->pool[4 * r + 2]);
+      R.ms_track += ms;
+      cudaEventElapsedTime(&ms, h->pool[4 * r + 2], h->pool[4 * r + 3]);
+      R.ms_collide += ms;
+    }
   }
   R.n_histories = n;
   R.n_segments = (int64_t)C.n_segments;
