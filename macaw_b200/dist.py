@@ -83,6 +83,37 @@ def exchange_sites(sampled_u8, source_u8, sampled_counts, work_index, group=None
             req.wait()
 
 
+def synchronize_banks(engine, batch, rank, nranks, work_index, group=None, device="cpu"):
+    """postExecuteStudy() for nranks > 1 (MaCaw OpenMCStudy.C:404-607, OpenMC eigenvalue.cpp:71-311):
+    bank offsets, the fused tally / k all-reduce, bank sampling on every rank's slice of the global bank,
+    last-rank trim / pad, redistribution of the sampled sites to their owners, finalize.
+
+    `engine` is the per-rank compute object (the GPU Context through study.DeviceEngine, or the CPU
+    oracle in the gloo tests).  It must offer bank_count(), set_bank_window(start, total),
+    reduction_tensor() -> float64 tensor reduced in place, sample_bank(batch) -> n,
+    finish_sampling(start, is_last) -> n, sampled_tensor(n) / source_tensor() -> uint8 tensors,
+    set_source_count(n), finalize_generation(batch)."""
+    import torch.distributed as td
+    counts = all_gather_int(engine.bank_count(), group, device)
+    if min(counts) == 0:
+        raise RuntimeError(f"No fission sites banked on rank {counts.index(0)}")  # eigenvalue.cpp:107-109
+    off = exclusive_offsets(counts)
+    engine.set_bank_window(int(off[rank]), int(off[-1]))
+    red = engine.reduction_tensor()
+    td.all_reduce(red, op=td.ReduceOp.SUM, group=group)
+    n_s = engine.sample_bank(batch)
+    scounts = all_gather_int(n_s, group, device)
+    soff = exclusive_offsets(scounts)
+    n_s = engine.finish_sampling(int(soff[rank]), rank == nranks - 1)
+    # only the last rank trims / pads (eigenvalue.cpp:184-206) and it always ends at exactly n_particles,
+    # so every rank can derive the final counts without a second all-gather
+    scounts[-1] = max(0, int(work_index[-1]) - int(soff[nranks - 1]))
+    assert rank != nranks - 1 or n_s == scounts[-1], (n_s, scounts)
+    exchange_sites(engine.sampled_tensor(max(scounts[rank], 0)), engine.source_tensor(), scounts, work_index, group)
+    engine.set_source_count(int(work_index[rank + 1] - work_index[rank]))
+    return engine.finalize_generation(batch)
+
+
 class DeviceBuffer:
     """Zero-copy torch view of a raw device pointer handed out by the C ABI."""
 

@@ -97,31 +97,37 @@ class OpenMCStudy:
 
     def _synchronize_banks_and_reduce(self, b):
         import torch
-        import torch.distributed as td
-        ctx = self.ctx
         dev = torch.device("cuda", torch.cuda.current_device())
-        counts = dist.all_gather_int(ctx.bank_count(), self.group, dev)
-        if min(counts) == 0:
-            raise RuntimeError(f"No fission sites banked on rank {counts.index(0)}")  # eigenvalue.cpp:107-109
-        off = dist.exclusive_offsets(counts)
-        ctx.set_bank_window(int(off[self.rank]), int(off[-1]))
-        rp, rn = ctx.reduction_device()
-        red = dist.device_tensor(rp, rn, "f8", dev)
-        td.all_reduce(red, op=td.ReduceOp.SUM, group=self.group)
-        n_s = ctx.sample_bank(b)
-        scounts = dist.all_gather_int(n_s, self.group, dev)
-        soff = dist.exclusive_offsets(scounts)
-        n_s = ctx.finish_sampling(int(soff[self.rank]), self.rank == self.nranks - 1)
-        scounts[self.rank] = n_s
-        scounts = dist.all_gather_int(n_s, self.group, dev)
-        sp, _ = ctx.sampled_device()
-        dp, cap = ctx.source_device()
-        sampled = dist.device_tensor(sp, max(n_s, 1) * dist.SITE_BYTES, "u8", dev)
-        source = dist.device_tensor(dp, cap * dist.SITE_BYTES, "u8", dev)
-        dist.exchange_sites(sampled, source, scounts, self.work_index, self.group)
-        torch.cuda.current_stream().synchronize()
-        ctx.set_source_count(int(self.work_index[self.rank + 1] - self.work_index[self.rank]))
-        return ctx.finalize_generation(b)
+        res = dist.synchronize_banks(DeviceEngine(self.ctx, dev), b, self.rank, self.nranks, self.work_index,
+                                     self.group, dev)
+        return res
+
+
+class DeviceEngine:
+    """dist.synchronize_banks hooks over the C ABI's raw device views (zero-copy torch tensors, so
+    NCCL reads and writes the library's own HBM buffers)."""
+
+    def __init__(self, ctx: Context, device):
+        self.ctx, self.device = ctx, device
+        for name in ("bank_count", "set_bank_window", "sample_bank", "finish_sampling", "set_source_count"):
+            setattr(self, name, getattr(ctx, name))
+
+    def reduction_tensor(self):
+        p, n = self.ctx.reduction_device()
+        return dist.device_tensor(p, n, "f8", self.device)
+
+    def sampled_tensor(self, n):
+        p, _ = self.ctx.sampled_device()
+        return dist.device_tensor(p, max(n, 1) * dist.SITE_BYTES, "u8", self.device)
+
+    def source_tensor(self):
+        p, cap = self.ctx.source_device()
+        return dist.device_tensor(p, cap * dist.SITE_BYTES, "u8", self.device)
+
+    def finalize_generation(self, batch):
+        import torch
+        torch.cuda.current_stream().synchronize()  # the exchange ran on torch's stream
+        return self.ctx.finalize_generation(batch)
 
 
 class OpenMCTallyAux:

@@ -1,0 +1,125 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), the work split / exchange plan arithmetic, and the world_size-2 bank
+synchronisation (gloo) driven through the same macaw_b200.dist code the GPU study runs over NCCL,
+with the CPU oracle as the per-rank engine."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "macaw_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcw_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from macaw_b200 import lib
+    L = lib.load()
+    names = _header_functions()
+    assert len(names) >= 39
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(lib.EXPORTS) == names  # the ctypes binding covers the whole header
+    assert L.mcw_version() >= 100
+
+
+def test_c_abi_struct_sizes_match_ctypes_mirror():
+    from macaw_b200 import cstructs, lib
+    L = lib.load()
+    out = (C.c_int32 * 6)()
+    assert L.mcw_struct_sizes(out, 6) == 6
+    assert out[0] == 96 == cstructs.SITE_DTYPE.itemsize  # openmc::SourceSite, particle_data.h:43-53
+    assert out[3] == C.sizeof(cstructs.Settings)
+    assert out[4] == C.sizeof(cstructs.GenerationResult)
+    assert out[5] == cstructs.RECORD_DTYPE.itemsize
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a CUDA device mcw_create must fail (MCW_E_CUDA); nothing routes to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from macaw_b200.context import Context
+    from macaw_b200.lib import McwError
+    with pytest.raises(McwError):
+        Context(0)
+
+
+@pytest.mark.parametrize("n,p", [(10, 1), (10, 3), (7, 8), (200000, 8), (1000003, 4)])
+def test_calculate_work_matches_openmc_rule(oracle_bridge, n, p):
+    from macaw_b200 import dist, lib
+    wi = dist.calculate_work(n, p)
+    assert wi[0] == 0 and wi[-1] == n
+    sizes = np.diff(wi)
+    assert sizes.max() - sizes.min() <= 1 and np.all(sizes[:-1] >= sizes[1:])  # first n%p ranks get +1
+    assert np.array_equal(wi, lib.calculate_work(n, p))
+    o = np.zeros(p + 1, np.int64)
+    oracle_bridge.lib().orc_calculate_work(n, p, o.ctypes.data)
+    assert np.array_equal(wi, o)
+
+
+def test_exchange_plan_conserves_and_orders_sites():
+    from macaw_b200 import dist
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        p = int(rng.integers(1, 9))
+        n = int(rng.integers(p, 5000))
+        wi = dist.calculate_work(n, p)
+        cuts = np.sort(rng.integers(0, n + 1, p - 1))
+        counts = np.diff(np.concatenate([[0], cuts, [n]]))
+        plan = dist.exchange_plan(counts, wi)
+        off = dist.exclusive_offsets(counts)
+        got = np.full(n, -1, np.int64)
+        for s, d, so, do, c in plan:
+            assert c > 0 and so + c <= counts[s] and do + c <= wi[d + 1] - wi[d]
+            got[wi[d] + do: wi[d] + do + c] = np.arange(off[s] + so, off[s] + so + c)
+        assert np.array_equal(got, np.arange(n))  # global order of the sampled bank is preserved
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bank_synchronisation_world_size_n_equals_single_rank(oracle_bridge, tmp_path, world):
+    """OpenMC's synchronize_bank is rank-count invariant: the next source bank and k_generation of an
+    N-rank run equal the 1-rank run's (OMC eigenvalue.cpp:71-311).  Runs N gloo processes."""
+    from tests import problems
+    n_particles, n_batches = 600, 3
+    port = _free_port()
+    out = str(tmp_path / "w")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world),
+                               str(port), out, str(n_particles), str(n_batches)], cwd=ROOT,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+
+    mesh, lib, bm, s = problems.pin_cell_tet(n_particles=n_particles)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, True, False)
+    o.sample_initial_source()
+    ks = []
+    for b in range(1, n_batches + 1):
+        r = o.run_generation(b)
+        ks.append([r.k_generation, r.keff, r.k_collision, r.k_absorption, r.k_tracklength])
+    ks = np.asarray(ks)
+    parts = [np.load(f"{out}.{r}.npz") for r in range(world)]
+    src = np.concatenate([p["source"] for p in parts])
+    assert src.size == n_particles
+    assert src.tobytes() == o.source_bank().tobytes()  # bit-identical next-generation source
+    for p in parts:
+        assert np.allclose(p["ks"], ks, rtol=1e-12, atol=0)  # summation order differs across ranks only
+    _, t_sum, _, _ = o.get_tally(1)
+    assert np.allclose(sum(p["tally_sum"] for p in parts), t_sum, rtol=1e-11, atol=1e-300)
