@@ -128,7 +128,7 @@ struct mcw_context
   double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
 
   // options
-  int profile = 0, sync_every = 1, fallback_blocks = 8;
+  int profile = 0, sync_every = 1, fallback_blocks = 8, xs_cache = 1, visit_cap = 1 << 30, track_max_blocks = 148;
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> pool; // per-round profiling events (5 per round), reused across generations
@@ -269,6 +269,16 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->sync_every = std::max(1, value);
   else if (n == "fallback_blocks")
     h->fallback_blocks = std::max(1, value);
+  else if (n == "xs_cache")
+  {
+    h->xs_cache = value != 0;
+    h->prepared = false;
+  }
+  else if (n == "visit_cap")
+  {
+    h->visit_cap = value > 0 ? value : (1 << 30);
+    h->P.visit_cap = h->visit_cap;
+  }
   else
     return fail(h, MCW_E_INVALID_ARGUMENT, "unknown option " + n);
   return MCW_OK;
@@ -814,6 +824,20 @@ static int prepare(mcw_handle h)
   int8_t** db[] = {&p.inc_side, &p.ext_first, &p.ext_second, &p.status, &p.fate};
   for (auto q : db)
     CK(dev_alloc(h, q, n));
+  // per-history macroscopic cross-section cache, one plane of 4 doubles per material
+  P.xs_slots = (h->xs_cache && n_mat <= MCW_XS_CACHE_MAX) ? n_mat : 0;
+  P.xs_stride = n;
+  P.visit_cap = h->visit_cap;
+  if (P.xs_slots)
+  {
+    CK(dev_alloc(h, &p.xs_cache, (size_t)P.xs_slots * 4 * (size_t)n));
+    CK(dev_alloc(h, &p.xs_valid, n));
+  }
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->track_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type)) * prop.multiProcessorCount;
+  }
   h->bank_capacity = 3 * n; // OMC simulation.cpp:286
   h->sampled_capacity = 3 * n + 16;
   CK(dev_alloc(h, &h->d_source, h->sampled_capacity));
@@ -1013,7 +1037,8 @@ int mcw_transport_generation(mcw_handle h, int batch)
     mcwk_xs_lookup(P, q, cnt_cur, upper, st);
     if (prof)
       cudaEventRecord(h->pool_event(4 * rounds + 1), st);
-    mcwk_track(P, q, cnt_cur, upper, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback, st);
+    mcwk_track(P, q, cnt_cur, upper, h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
+               st);
     if (prof)
       cudaEventRecord(h->pool_event(4 * rounds + 2), st);
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
@@ -1031,9 +1056,8 @@ int mcw_transport_generation(mcw_handle h, int batch)
       upper = (int64_t)h->h_counters->n_fly[cur ^ 1];
     }
     // reset the consumed queues for the next round
-    CK(cudaMemsetAsync(cnt_cur, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(&P.counters->n_collide, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(&P.counters->n_fallback, 0, sizeof(unsigned long long), st));
+    mcwk_round_reset(P.counters, cur, st);
+    R.n_kernel_launches += 1;
     cur ^= 1;
     if (rounds > 100000000)
       return fail(h, MCW_E_PHYSICS, "event loop did not terminate");

@@ -10,6 +10,7 @@
 //   bank / tally / reduction helpers                            (OMC bank.cpp:60-104, eigenvalue.cpp:71-311, tally.cpp:639-670)
 //
 // One thread = one history slot; queues are index lists with warp-aggregated appends.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "mcw_kernels.h"
@@ -64,6 +65,8 @@ k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n
   p.n_coll[i] = 0;
   p.n_xs[i] = 0;
   p.xs_mat[i] = -1;
+  if (P.xs_slots)
+    p.xs_valid[i] = 0u;
   p.last_elem[i] = -1;
   p.ext_first[i] = -1;
   p.ext_second[i] = -1;
@@ -144,22 +147,33 @@ template <int TYPE>
 __global__ void __launch_bounds__(MCW_BLOCK)
 k_xs_lookup(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count)
 {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)*count)
-    return;
-  int i = queue[idx];
+  const int64_t n_q = (int64_t)*count;
   McwParticlesDev& p = P.p;
-  ElemRec<TYPE> R(P.mesh, p.elem[i]);
-  int mat = R.material();
-  if (p.xs_mat[i] == mat)
-    return; // still valid (same energy and material)
-  Macro M = mcw_macro_xs(P.lib, mat, p.E[i]);
-  p.sig_t[i] = M.total;
-  p.sig_a[i] = M.absorption;
-  p.sig_f[i] = M.fission;
-  p.sig_nf[i] = M.nu_fission;
-  p.xs_mat[i] = mat;
-  p.n_xs[i] += 1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_q; idx += (int64_t)gridDim.x * blockDim.x)
+  {
+    int i = queue[idx];
+    ElemRec<TYPE> R(P.mesh, p.elem[i]);
+    int mat = R.material();
+    if (p.xs_mat[i] == mat)
+      continue; // still valid (same energy and material)
+    Macro M = mcw_macro_xs(P.lib, mat, p.E[i]);
+    p.sig_t[i] = M.total;
+    p.sig_a[i] = M.absorption;
+    p.sig_f[i] = M.fission;
+    p.sig_nf[i] = M.nu_fission;
+    p.xs_mat[i] = mat;
+    p.n_xs[i] += 1;
+    if (P.xs_slots)
+    {
+      // remember it: the tracking kernel re-enters this material without leaving (until the energy changes)
+      double* c = p.xs_cache + ((size_t)mat * 4) * (size_t)P.xs_stride + i;
+      c[0] = M.total;
+      c[(size_t)P.xs_stride] = M.absorption;
+      c[2 * (size_t)P.xs_stride] = M.fission;
+      c[3 * (size_t)P.xs_stride] = M.nu_fission;
+      p.xs_valid[i] |= 1u << mat;
+    }
+  }
 }
 
 // stand-alone lookup for (E, material) arrays: the XS-lookup bandwidth metric and unit parity
@@ -196,151 +210,15 @@ k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
 }
 
 // ------------------------------------------------------------------ tracking
-template <int TYPE>
-__global__ void __launch_bounds__(MCW_BLOCK)
-k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
-        int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, int32_t* __restrict__ q_collide,
-        int32_t* __restrict__ q_fallback)
+#include "mcw_track.cuh"
+
+// resets the per-round device counters (one launch instead of three memsets)
+__global__ void k_round_reset(McwCounters* c, int consumed)
 {
-  using T = McwElem<TYPE>;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)*count)
-    return;
-  const int i = queue[idx];
-  McwParticlesDev& p = P.p;
-  if (p.status[i] != MCW_ST_FLY)
-    return;
-  V3 point = v3(p.x[i], p.y[i], p.z[i]);
-  V3 dir = v3(p.ux[i], p.uy[i], p.uz[i]);
-  int cur = p.elem[i];
-  int last = p.last_elem[i];
-  int inc_side = p.inc_side[i];
-  SegState s;
-  s.E = p.E[i];
-  s.wgt = p.wgt[i];
-  s.seed_trk = p.seed_trk[i];
-  s.seed_src = p.seed_src[i];
-  s.seed_urr = p.seed_urr[i];
-  s.sig_t = p.sig_t[i];
-  s.sig_a = p.sig_a[i];
-  s.sig_f = p.sig_f[i];
-  s.sig_nf = p.sig_nf[i];
-  s.k_trk = p.k_trk[i];
-  const int xs_mat = p.xs_mat[i];
-  int n_seg = p.n_seg[i];
-  uint64_t hash = p.hash[i];
-  int status = MCW_ST_FLY, fate = -1;
-  bool requeue = false;
-  unsigned long long segs = 0;
-  if (p.ext_first[i] != MCW_INVALID)
-    status = MCW_ST_FALLBACK; // last hit was a vertex/edge: general walk (RT TraceRay.C:1134)
-
-  while (status == MCW_ST_FLY)
-  {
-    if (n_seg >= P.max_events)
-    {
-      status = MCW_ST_DEAD;
-      fate = 3;
-      atomicAdd(&P.counters->n_failed, 1ull);
-      break;
-    }
-    ElemRec<TYPE> R(P.mesh, cur);
-    V3 ipoint;
-    int iside;
-    Extrema ext;
-    double idist;
-    if (!mcw_exits_elem<TYPE>(P.mesh, R, inc_side, point, dir, ipoint, iside, ext, idist) || ext.atExtrema())
-    {
-      status = MCW_ST_FALLBACK; // nothing modified: the general kernel redoes this step
-      break;
-    }
-    ++n_seg;
-    ++segs;
-    V3 pos;
-    const bool collided = mcw_segment(P, s, cur, R.block(), xs_mat, ipoint, dir, idist, pos);
-    hash = mcw_hash_step(hash, cur, collided ? 15 : iside);
-    if (collided)
-    {
-      point = pos;
-      status = MCW_ST_COLLIDE;
-      break;
-    }
-    // RT TraceRay.C:1420-1466 neighbour step
-    point = ipoint;
-    const int nb = R.nbr(iside);
-    if (nb >= 0)
-    {
-      ElemRec<TYPE> N(P.mesh, nb);
-      int s_in = MCW_INVALID;
-#pragma unroll
-      for (int k = T::NS - 1; k >= 0; --k)
-        if (N.nbr(k) == cur)
-          s_in = k;
-      inc_side = s_in;
-      last = cur;
-      cur = nb;
-      if (N.material() != xs_mat)
-      {
-        requeue = true; // new material: back through the cross-section kernel
-        break;
-      }
-    }
-    else
-    {
-      // RT TraceRay.C:725-782 external boundary, :2043 onBoundary
-      const int bid = -nb - 1;
-      const int kind = bid < P.mesh.n_bnd ? P.mesh.bnd_kind[bid] : MCW_BC_KILL;
-      if (kind == MCW_BC_KILL)
-      {
-        status = MCW_ST_DEAD;
-        fate = 1;
-        break;
-      }
-      // RT ReflectRayBC.C:68-76 + Ray::changeDirection (Ray.C:206-214)
-      V3 n = mcw_side_normal<TYPE>(R, iside);
-      double dn = dot(dir, n);
-      V3 r = dir - (2.0 * dn) * n;
-      r = r / norm(r);
-      dir = unit(r);
-      last = cur;
-      inc_side = iside;
-    }
-  }
-
-  p.x[i] = point.x;
-  p.y[i] = point.y;
-  p.z[i] = point.z;
-  p.ux[i] = dir.x;
-  p.uy[i] = dir.y;
-  p.uz[i] = dir.z;
-  p.elem[i] = cur;
-  p.last_elem[i] = last;
-  p.inc_side[i] = (int8_t)inc_side;
-  p.seed_trk[i] = s.seed_trk;
-  p.seed_src[i] = s.seed_src;
-  p.seed_urr[i] = s.seed_urr;
-  p.k_trk[i] = s.k_trk;
-  p.n_seg[i] = n_seg;
-  p.hash[i] = hash;
-  p.status[i] = (int8_t)(requeue ? MCW_ST_FLY : status);
-  if (fate >= 0)
-    p.fate[i] = (int8_t)fate;
-  // warp-aggregated queue appends and counters
-  {
-    unsigned long long k = mcw_warp_append(cnt_next, requeue);
-    if (requeue)
-      q_fly_next[k] = i;
-    k = mcw_warp_append(&P.counters->n_collide, status == MCW_ST_COLLIDE);
-    if (status == MCW_ST_COLLIDE)
-      q_collide[k] = i;
-    k = mcw_warp_append(&P.counters->n_fallback, status == MCW_ST_FALLBACK);
-    if (status == MCW_ST_FALLBACK)
-      q_fallback[k] = i;
-    unsigned mask = __activemask();
-    unsigned tot = __reduce_add_sync(mask, (unsigned)segs);
-    if ((threadIdx.x & 31) == (__ffs(mask) - 1))
-      atomicAdd(&P.counters->n_segments, (unsigned long long)tot);
-  }
+  c->n_fly[consumed] = 0;
+  c->n_collide = 0;
+  c->n_fallback = 0;
+  c->head = 0;
 }
 
 // ------------------------------------------------------------------ collision
@@ -547,6 +425,8 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
     p.ext_first[i] = -1;
     p.ext_second[i] = -1;
     p.xs_mat[i] = -1; // energy changed: cross sections must be looked up again
+    if (P.xs_slots)
+      p.xs_valid[i] = 0u;
     p.status[i] = MCW_ST_FLY;
   }
   unsigned long long k = mcw_warp_append(cnt_next, !absorbed);
@@ -817,15 +697,26 @@ void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, co
   k_xs_lookup_array<<<grid_for(n), MCW_BLOCK, 0, st>>>(L, n, E, mat, out);
 }
 
-void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+int mcwk_track_blocks_per_sm(int type)
+{
+  int nb = 0;
+  MCW_DISPATCH(type, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_track<TY>, MCW_TRACK_BLOCK, 0)));
+  return nb;
+}
+
+void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
                 cudaStream_t st)
 {
   if (upper <= 0)
     return;
-  MCW_DISPATCH(P.mesh.type, (k_track<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next,
-                                                                             q_collide, q_fallback)));
+  // persistent grid: never more blocks than fit on the device at once, never more than the queue needs
+  unsigned g = (unsigned)std::min<int64_t>((upper + MCW_TRACK_BLOCK - 1) / MCW_TRACK_BLOCK, (int64_t)max_blocks);
+  MCW_DISPATCH(P.mesh.type, (k_track<TY><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
+                                                                       cnt_next, q_collide, q_fallback)));
 }
+
+void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st) { k_round_reset<<<1, 1, 0, st>>>(c, consumed); }
 
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
                   int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st)

@@ -13,7 +13,9 @@ void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long 
                   cudaStream_t st);
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st);
-void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
+int mcwk_track_blocks_per_sm(int type);
+void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
+void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
                 cudaStream_t st);
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,

@@ -15,6 +15,7 @@
 #include "../../include/macaw_b200.h"
 
 #define MCW_MAX_NUC_PER_MAT 64
+#define MCW_XS_CACHE_MAX 16
 
 struct McwNucParams
 {
@@ -101,6 +102,10 @@ struct McwParticlesDev
   int32_t *n_progeny, *n_seg, *n_coll, *n_xs;
   int8_t *inc_side, *ext_first, *ext_second, *status, *fate;
   uint64_t* hash;
+  // macroscopic cross sections of every material this history has looked up since its last
+  // collision: xs_cache[(material * 4 + k) * stride + slot], bit m of xs_valid = material m is cached
+  double* xs_cache;
+  uint32_t* xs_valid;
 };
 
 struct McwTallyDev
@@ -119,6 +124,7 @@ struct McwCounters // device-side counters, one cache line each where contended
   unsigned long long n_collide, pad1[15];
   unsigned long long n_fallback, pad2[15];
   unsigned long long n_bank, pad3[15];
+  unsigned long long head, pad4[15]; // next unclaimed entry of the queue the tracking kernel is draining
   unsigned long long n_segments, n_collisions, n_xs, n_nuc_lookups, n_vertex_edge, n_moved, n_failed,
       n_bank_dropped;
 };
@@ -137,5 +143,8 @@ struct McwParams
   int64_t n_particles_global, work_offset; // id = work_offset + slot + 1
   int64_t master_seed;
   int32_t batch, is_2d, seed_through_double, max_events;
+  int32_t xs_slots;  // > 0: the per-history cross-section cache is on (number of materials, <= MCW_XS_CACHE_MAX)
+  int32_t visit_cap; // segments one lane may walk per visit of the tracking kernel
+  int64_t xs_stride; // history slots per cache plane
   double z_coord, keff;
 };
