@@ -128,7 +128,9 @@ struct mcw_context
   double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
 
   // options
-  int profile = 0, sync_every = 1, fallback_blocks = 8, xs_cache = 1, visit_cap = 1 << 30, track_max_blocks = 148;
+  int profile = 0, sync_every = 1, fallback_blocks = 8, visit_cap = 1 << 30, track_max_blocks = 148;
+  int drain_lanes = 12;            // tracking warps below this many histories hand them to the next round ...
+  int64_t drain_min_queue = 65536; // ... when the round's queue is at least this long
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> pool; // per-round profiling events (5 per round), reused across generations
@@ -269,11 +271,10 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->sync_every = std::max(1, value);
   else if (n == "fallback_blocks")
     h->fallback_blocks = std::max(1, value);
-  else if (n == "xs_cache")
-  {
-    h->xs_cache = value != 0;
-    h->prepared = false;
-  }
+  else if (n == "drain_lanes")
+    h->drain_lanes = std::min(32, std::max(0, value));
+  else if (n == "drain_min_queue")
+    h->drain_min_queue = std::max(0, value);
   else if (n == "visit_cap")
   {
     h->visit_cap = value > 0 ? value : (1 << 30);
@@ -637,6 +638,25 @@ static int prepare(mcw_handle h)
     block_hmax[eblock[e]] = std::max(block_hmax[eblock[e]], std::sqrt(h2));
   }
   const int n_bnd = (int)h->bnd_kind.size();
+  if (h->n_elem > MCW_MAX_ELEMS)
+    return fail(h, MCW_E_UNSUPPORTED, "more than 2^28 elements: side codes hold neighbour << 3 | back side in 32 bits");
+  // cross-section slots: the materials the mesh actually uses, in material order
+  std::vector<int> slot_of(n_mat, -1);
+  {
+    std::vector<char> used(n_mat, 0);
+    for (int64_t e = 0; e < h->n_elem; ++e)
+      used[h->block_material[eblock[e]]] = 1;
+    int ns = 0;
+    for (int m = 0; m < n_mat; ++m)
+      if (used[m])
+      {
+        if (ns >= MCW_MAX_XS_SLOTS)
+          return fail(h, MCW_E_UNSUPPORTED, "the mesh uses more than " + std::to_string(MCW_MAX_XS_SLOTS) + " materials");
+        P.slot_mat[ns] = m;
+        slot_of[m] = ns++;
+      }
+    P.n_slots = ns;
+  }
   std::vector<unsigned char> rec((size_t)h->n_elem * t.stride, 0);
   for (int64_t e = 0; e < h->n_elem; ++e)
   {
@@ -650,7 +670,14 @@ static int prepare(mcw_handle h)
     {
       int64_t n = h->nbr[e * t.ns + s];
       if (n >= 0)
-        nb[s] = (int32_t)n;
+      {
+        // RT TraceRay.C:1456-1458: the first side of the neighbour whose neighbour is this element
+        int back = 0;
+        for (int k = t.ns - 1; k >= 0; --k)
+          if (h->nbr[n * t.ns + k] == e)
+            back = k;
+        nb[s] = (int32_t)((n << MCW_NBR_SHIFT) | back);
+      }
       else
       {
         int32_t id = h->side_bnd[e * t.ns + s];
@@ -660,7 +687,7 @@ static int prepare(mcw_handle h)
       }
     }
     *reinterpret_cast<double*>(r + t.nv * t.cpv * 8 + t.ns * 4) = block_hmax[eblock[e]];
-    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 8) = h->block_material[eblock[e]];
+    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 8) = slot_of[h->block_material[eblock[e]]];
     *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 12) = eblock[e];
   }
   // node -> elements CSR
@@ -811,28 +838,21 @@ static int prepare(mcw_handle h)
   // ---- particles, queues, banks
   const int64_t n = h->n_local;
   McwParticlesDev& p = P.p;
-  double** dd[] = {&p.x, &p.y, &p.z, &p.ux, &p.uy, &p.uz, &p.E, &p.wgt, &p.sig_t, &p.sig_a, &p.sig_f, &p.sig_nf,
-                   &p.k_col, &p.k_abs, &p.k_trk};
+  double** dd[] = {&p.x, &p.y, &p.z, &p.ux, &p.uy, &p.uz, &p.E, &p.wgt, &p.k_col, &p.k_abs, &p.k_trk};
   for (auto q : dd)
     CK(dev_alloc(h, q, n));
   uint64_t** du[] = {&p.seed_trk, &p.seed_src, &p.seed_urr, &p.hash};
   for (auto q : du)
     CK(dev_alloc(h, q, n));
-  int32_t** di[] = {&p.elem, &p.last_elem, &p.xs_mat, &p.n_progeny, &p.n_seg, &p.n_coll, &p.n_xs};
+  int32_t** di[] = {&p.elem, &p.last_elem, &p.n_progeny, &p.n_seg, &p.n_coll, &p.n_xs};
   for (auto q : di)
     CK(dev_alloc(h, q, n));
   int8_t** db[] = {&p.inc_side, &p.ext_first, &p.ext_second, &p.status, &p.fate};
   for (auto q : db)
     CK(dev_alloc(h, q, n));
-  // per-history macroscopic cross-section cache, one plane of 4 doubles per material
-  P.xs_slots = (h->xs_cache && n_mat <= MCW_XS_CACHE_MAX) ? n_mat : 0;
-  P.xs_stride = n;
+  // macroscopic cross sections of every material slot at each history's energy: 32 B per (history, slot)
   P.visit_cap = h->visit_cap;
-  if (P.xs_slots)
-  {
-    CK(dev_alloc(h, &p.xs_cache, (size_t)P.xs_slots * 4 * (size_t)n));
-    CK(dev_alloc(h, &p.xs_valid, n));
-  }
+  CK(dev_alloc(h, &p.xs, (size_t)P.n_slots * 4 * (size_t)n));
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -913,6 +933,7 @@ static int prepare(mcw_handle h)
   P.is_2d = h->set.is_2d;
   P.seed_through_double = h->set.seed_through_double;
   P.max_events = h->set.max_events > 0 ? h->set.max_events : 1000000;
+  P.record_traces = h->set.record_traces;
   P.z_coord = h->set.z_coord;
   h->keff = 1.0;
   h->keff_std = 0.0;
@@ -1014,39 +1035,39 @@ int mcw_transport_generation(mcw_handle h, int batch)
   int64_t rounds = 0;
   float ms;
   const bool prof = h->profile != 0;
+  if (prof)
+    cudaEventRecord(h->ev[4], st);
+  // One event round: every history in the fly queue walks elements until it collides or dies
+  // (k_track; rare vertex / edge steps go through k_fallback), then every collided history is
+  // processed by k_collide, which also refreshes its cross sections for all materials at the new
+  // energy and puts the survivors into the other fly queue.
   while (upper > 0)
   {
     int32_t* q = h->d_q_fly[cur];
     unsigned long long* cnt_cur = &P.counters->n_fly[cur];
     unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
     if (prof)
-      cudaEventRecord(h->pool_event(4 * rounds + 0), st);
-    if (h->set.sort_xs_queue)
-    {
-      // particle-queue sort by (material, energy bucket): OpenMC's TODO at OMC event.cpp:76-82
-      int bits = 16 + 1;
-      for (int m = (int)h->mat_nuc.size(); m > 1; m >>= 1)
-        ++bits;
-      mcwk_xs_keys(P, q, cnt_cur, h->d_keys, upper, st);
-      mcwk_sort_queue(h->d_temp, h->temp_bytes, h->d_keys, h->d_keys_out, q, h->d_q_sorted, upper, 32, st);
-      (void)bits;
-      std::swap(h->d_q_fly[cur], h->d_q_sorted);
-      q = h->d_q_fly[cur];
-      R.n_kernel_launches += 4;
-    }
-    mcwk_xs_lookup(P, q, cnt_cur, upper, st);
-    if (prof)
-      cudaEventRecord(h->pool_event(4 * rounds + 1), st);
+      cudaEventRecord(h->pool_event(3 * rounds + 0), st);
+    const int drain = upper >= h->drain_min_queue ? h->drain_lanes : 0;
     mcwk_track(P, q, cnt_cur, upper, h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
-               st);
+               drain, st);
     if (prof)
-      cudaEventRecord(h->pool_event(4 * rounds + 2), st);
+      cudaEventRecord(h->pool_event(3 * rounds + 1), st);
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
                   h->d_q_collide, st);
-    mcwk_collide(P, h->d_q_collide, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
+    int32_t* qc = h->d_q_collide;
+    if (h->set.sort_xs_queue)
+    {
+      // particle-queue sort by (material slot, energy bucket): OpenMC's TODO at OMC event.cpp:76-82
+      mcwk_xs_keys(P, qc, &P.counters->n_collide, h->d_keys, upper, st);
+      mcwk_sort_queue(h->d_temp, h->temp_bytes, h->d_keys, h->d_keys_out, qc, h->d_q_sorted, upper, 32, st);
+      qc = h->d_q_sorted;
+      R.n_kernel_launches += 4;
+    }
+    mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
     if (prof)
-      cudaEventRecord(h->pool_event(4 * rounds + 3), st);
-    R.n_kernel_launches += 4;
+      cudaEventRecord(h->pool_event(3 * rounds + 2), st);
+    R.n_kernel_launches += 3;
     ++rounds;
     const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
     if (sync_now)
@@ -1087,14 +1108,14 @@ int mcw_transport_generation(mcw_handle h, int batch)
   {
     cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]);
     R.ms_bank = ms;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[4]);
+    R.ms_xs = ms; // source initialisation including the first all-material cross-section lookup
     for (int64_t r = 0; r < rounds; ++r)
     {
-      cudaEventElapsedTime(&ms, h->pool[4 * r + 0], h->pool[4 * r + 1]);
-      R.ms_xs += ms;
-      cudaEventElapsedTime(&ms, h->pool[4 * r + 1], h->pool[4 * r + 2]);
+      cudaEventElapsedTime(&ms, h->pool[3 * r + 0], h->pool[3 * r + 1]);
       R.ms_track += ms;
-      cudaEventElapsedTime(&ms, h->pool[4 * r + 2], h->pool[4 * r + 3]);
-      R.ms_collide += ms;
+      cudaEventElapsedTime(&ms, h->pool[3 * r + 1], h->pool[3 * r + 2]);
+      R.ms_collide += ms; // general walk + (sort +) collision with the all-material lookup
     }
   }
   R.n_histories = n;

@@ -236,6 +236,33 @@ MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E) // OMC mat
   return M;
 }
 
+// Macroscopic cross sections of every material slot at energy E, written to the history's sectors
+// of McwParticlesDev::xs.  Called by the kernels that change a history's energy, so the tracking
+// kernel never has to stop for a lookup when it enters another material.
+MCW_D void mcw_lookup_all_slots(const McwParams& P, int64_t i, double E)
+{
+  double* xs_of_history = P.p.xs + (size_t)i * P.n_slots * 4;
+  for (int s = 0; s < P.n_slots; ++s)
+  {
+    const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], E);
+    double2* o = reinterpret_cast<double2*>(xs_of_history + 4 * s);
+    o[0] = make_double2(M.total, M.absorption);
+    o[1] = make_double2(M.fission, M.nu_fission);
+  }
+}
+
+MCW_D Macro mcw_load_xs(const double* __restrict__ xs, int n_slots, int64_t i, int slot)
+{
+  const double2* c = reinterpret_cast<const double2*>(xs + ((size_t)i * n_slots + slot) * 4);
+  const double2 a = c[0], b = c[1];
+  Macro M;
+  M.total = a.x;
+  M.absorption = a.y;
+  M.fission = b.x;
+  M.nu_fission = b.y;
+  return M;
+}
+
 // ------------------------------------------------------------------ element records
 template <int TYPE>
 struct ElemRec
@@ -250,15 +277,21 @@ struct ElemRec
       return v3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
     return v3(__ldg(c), __ldg(c + 1), 0.0);
   }
-  MCW_D int nbr(int s) const
+  MCW_D int nbr_code(int s) const
   {
     return __ldg(reinterpret_cast<const int32_t*>(base + T::NV * T::CPV * 8) + s);
+  }
+  // neighbour element id, or -(boundary id)-1 on the domain boundary
+  MCW_D int nbr(int s) const
+  {
+    const int c = nbr_code(s);
+    return c < 0 ? c : (c >> MCW_NBR_SHIFT);
   }
   MCW_D double hmax() const
   {
     return __ldg(reinterpret_cast<const double*>(base + T::NV * T::CPV * 8 + T::NS * 4));
   }
-  MCW_D int material() const
+  MCW_D int slot() const // cross-section slot of the element's material (McwParams::slot_mat)
   {
     return __ldg(reinterpret_cast<const int32_t*>(base + T::NV * T::CPV * 8 + T::NS * 4 + 8));
   }

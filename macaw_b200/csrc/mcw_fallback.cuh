@@ -522,21 +522,16 @@ k_fallback(McwParams P, const int32_t* __restrict__ queue, const unsigned long l
     s.seed_trk = p.seed_trk[i];
     s.seed_src = p.seed_src[i];
     s.seed_urr = p.seed_urr[i];
-    const int mat = R.material();
-    if (p.xs_mat[i] != mat)
+    const int slot = R.slot();
+    const int mat = P.slot_mat[slot];
     {
-      Macro M = mcw_macro_xs(P.lib, mat, s.E);
-      p.sig_t[i] = M.total;
-      p.sig_a[i] = M.absorption;
-      p.sig_f[i] = M.fission;
-      p.sig_nf[i] = M.nu_fission;
-      p.xs_mat[i] = mat;
-      p.n_xs[i] += 1;
+      // every material's cross sections at this energy are in the history's sectors (mcw_lookup_all_slots)
+      const Macro M = mcw_load_xs(p.xs, P.n_slots, i, slot);
+      s.sig_t = M.total;
+      s.sig_a = M.absorption;
+      s.sig_f = M.fission;
+      s.sig_nf = M.nu_fission;
     }
-    s.sig_t = p.sig_t[i];
-    s.sig_a = p.sig_a[i];
-    s.sig_f = p.sig_f[i];
-    s.sig_nf = p.sig_nf[i];
     s.k_trk = p.k_trk[i];
     p.n_seg[i] += 1;
     atomicAdd(&P.counters->n_segments, 1ull);

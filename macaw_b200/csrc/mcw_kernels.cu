@@ -2,8 +2,9 @@
 //
 //   k_init_histories   source sites -> particle SoA            (MC OpenMCStudy.C:297-364, RT ClaimRays.C)
 //   k_sample_source    batch-1 box source with rejection        (OMC source.cpp:143-231,325-338)
-//   k_xs_lookup        macroscopic cross sections for a queue   (OMC material.cpp:763-831, nuclide.cpp:557-763)
-//   k_track            element walk until collision / material change / death
+//   k_xs_lookup_array  macroscopic cross sections for (E, material) arrays
+//                                                               (OMC material.cpp:763-831, nuclide.cpp:557-763)
+//   k_track            element walk until collision / death
 //                                                               (RT TraceRay.C:292-493,999-1592; MC CollisionKernel.C:143-175)
 //   k_collide          event_collide + tallies + bank append    (OMC particle.cpp:219-288, physics.cpp:38-247,442-1120)
 //   k_fallback         general vertex/edge/neighbour step       (RT TraceRay.C:564-997,1134-1246)
@@ -64,9 +65,6 @@ k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n
   p.n_seg[i] = 0;
   p.n_coll[i] = 0;
   p.n_xs[i] = 0;
-  p.xs_mat[i] = -1;
-  if (P.xs_slots)
-    p.xs_valid[i] = 0u;
   p.last_elem[i] = -1;
   p.ext_first[i] = -1;
   p.ext_second[i] = -1;
@@ -86,6 +84,9 @@ k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n
   p.inc_side[i] = (int8_t)mcw_starting_incoming_side<TYPE>(R, r, dir);
   p.status[i] = MCW_ST_FLY;
   p.fate[i] = -1;
+  // Particle::event_calculate_xs for the birth energy, every material slot at once
+  mcw_lookup_all_slots(P, i, s.E);
+  p.n_xs[i] = P.n_slots;
 }
 
 // OMC source.cpp:325-338 + :143-231 (box, isotropic, Watt 0.988 MeV / 2.249 per MeV)
@@ -117,7 +118,7 @@ k_sample_source(McwParams P, mcw_source_site* __restrict__ out, int64_t n, const
     if (found && only_fissionable)
     {
       ElemRec<TYPE> R(P.mesh, e);
-      found = P.lib.mat_fissionable[R.material()] != 0;
+      found = P.lib.mat_fissionable[P.slot_mat[R.slot()]] != 0;
     }
     if (found)
     {
@@ -143,39 +144,6 @@ k_sample_source(McwParams P, mcw_source_site* __restrict__ out, int64_t n, const
 }
 
 // ------------------------------------------------------------------ cross-section lookup
-template <int TYPE>
-__global__ void __launch_bounds__(MCW_BLOCK)
-k_xs_lookup(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count)
-{
-  const int64_t n_q = (int64_t)*count;
-  McwParticlesDev& p = P.p;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_q; idx += (int64_t)gridDim.x * blockDim.x)
-  {
-    int i = queue[idx];
-    ElemRec<TYPE> R(P.mesh, p.elem[i]);
-    int mat = R.material();
-    if (p.xs_mat[i] == mat)
-      continue; // still valid (same energy and material)
-    Macro M = mcw_macro_xs(P.lib, mat, p.E[i]);
-    p.sig_t[i] = M.total;
-    p.sig_a[i] = M.absorption;
-    p.sig_f[i] = M.fission;
-    p.sig_nf[i] = M.nu_fission;
-    p.xs_mat[i] = mat;
-    p.n_xs[i] += 1;
-    if (P.xs_slots)
-    {
-      // remember it: the tracking kernel re-enters this material without leaving (until the energy changes)
-      double* c = p.xs_cache + ((size_t)mat * 4) * (size_t)P.xs_stride + i;
-      c[0] = M.total;
-      c[(size_t)P.xs_stride] = M.absorption;
-      c[2 * (size_t)P.xs_stride] = M.fission;
-      c[3 * (size_t)P.xs_stride] = M.nu_fission;
-      p.xs_valid[i] |= 1u << mat;
-    }
-  }
-}
-
 // stand-alone lookup for (E, material) arrays: the XS-lookup bandwidth metric and unit parity
 __global__ void __launch_bounds__(MCW_BLOCK)
 k_xs_lookup_array(McwLibraryDev L, int64_t n, const double* __restrict__ E, const int32_t* __restrict__ mat,
@@ -190,7 +158,8 @@ k_xs_lookup_array(McwLibraryDev L, int64_t n, const double* __restrict__ E, cons
   o[1] = make_double2(M.fission, M.nu_fission);
 }
 
-// sort keys for the xs queue: (material << 16) | (energy log-bin >> 0)
+// sort keys for the collision queue: (slot << 16) | energy log-bin, so neighbouring threads of
+// k_collide read neighbouring rows of the same nuclides (OpenMC's TODO at OMC event.cpp:76-82)
 template <int TYPE>
 __global__ void __launch_bounds__(MCW_BLOCK)
 k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
@@ -206,7 +175,7 @@ k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
   }
   int i = queue[idx];
   ElemRec<TYPE> R(P.mesh, P.p.elem[i]);
-  keys[idx] = ((uint32_t)R.material() << 16) | (uint32_t)mcw_log_bin(P.lib, P.p.E[i]);
+  keys[idx] = ((uint32_t)R.slot() << 16) | (uint32_t)mcw_log_bin(P.lib, P.p.E[i]);
 }
 
 // ------------------------------------------------------------------ tracking
@@ -253,14 +222,18 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
     c.n_progeny = p.n_progeny[i];
     seed_src = p.seed_src[i];
     seed_urr = p.seed_urr[i];
-    sig_t = p.sig_t[i];
-    sig_a = p.sig_a[i];
-    sig_f = p.sig_f[i];
-    sig_nf = p.sig_nf[i];
-    i_mat = p.xs_mat[i];
     elem = p.elem[i];
     ElemRec<TYPE> R(P.mesh, elem);
     block = R.block();
+    {
+      const int slot = R.slot();
+      const Macro M = mcw_load_xs(p.xs, P.n_slots, i, slot);
+      sig_t = M.total;
+      sig_a = M.absorption;
+      sig_f = M.fission;
+      sig_nf = M.nu_fission;
+      i_mat = P.slot_mat[slot];
+    }
     E_last = c.E;
     wgt_last = c.wgt;
     k_col = p.k_col[i] + c.wgt * sig_nf / sig_t; // OMC particle.cpp:223-226
@@ -424,10 +397,11 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
     p.inc_side[i] = -1;
     p.ext_first[i] = -1;
     p.ext_second[i] = -1;
-    p.xs_mat[i] = -1; // energy changed: cross sections must be looked up again
-    if (P.xs_slots)
-      p.xs_valid[i] = 0u;
     p.status[i] = MCW_ST_FLY;
+    // Particle::event_calculate_xs at the new energy, every material slot at once (if the
+    // collision kept the energy the sectors are rewritten with the same values)
+    mcw_lookup_all_slots(P, i, c.E);
+    p.n_xs[i] += P.n_slots;
   }
   unsigned long long k = mcw_warp_append(cnt_next, !absorbed);
   if (!absorbed)
@@ -674,13 +648,6 @@ void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, con
   MCW_DISPATCH(P.mesh.type, (k_sample_source<TY><<<grid_for(n), MCW_BLOCK, 0, st>>>(P, out, n, d_box, only_fissionable)));
 }
 
-void mcwk_xs_lookup(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, cudaStream_t st)
-{
-  if (upper <= 0)
-    return;
-  MCW_DISPATCH(P.mesh.type, (k_xs_lookup<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count)));
-}
-
 void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
                   cudaStream_t st)
 {
@@ -706,14 +673,14 @@ int mcwk_track_blocks_per_sm(int type)
 
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
-                cudaStream_t st)
+                int drain_lanes, cudaStream_t st)
 {
   if (upper <= 0)
     return;
   // persistent grid: never more blocks than fit on the device at once, never more than the queue needs
   unsigned g = (unsigned)std::min<int64_t>((upper + MCW_TRACK_BLOCK - 1) / MCW_TRACK_BLOCK, (int64_t)max_blocks);
   MCW_DISPATCH(P.mesh.type, (k_track<TY><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
-                                                                       cnt_next, q_collide, q_fallback)));
+                                                                       cnt_next, q_collide, q_fallback, drain_lanes)));
 }
 
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st) { k_round_reset<<<1, 1, 0, st>>>(c, consumed); }

@@ -7,8 +7,6 @@
 void mcwk_init_histories(const McwParams& P, const mcw_source_site* src, int64_t n, int32_t* q_fly, cudaStream_t st);
 void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, const double* d_box, int only_fissionable,
                         cudaStream_t st);
-void mcwk_xs_lookup(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
-                    cudaStream_t st);
 void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
                   cudaStream_t st);
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
@@ -17,7 +15,7 @@ int mcwk_track_blocks_per_sm(int type);
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
-                cudaStream_t st);
+                int drain_lanes, cudaStream_t st);
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
                   int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st);
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,

@@ -119,12 +119,11 @@ MCW_D bool mcw_segment(const McwParams& P, SegState& s, int elem, int block, int
         mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, sc);
       }
   }
+  // :157-159 store all three seeds as doubles.  The source and URR seeds did not change since they
+  // were last rounded (at initialisation or at the end of the last collision) and the rounding is
+  // idempotent, so only the tracking seed needs it here.
   if (P.seed_through_double)
-  {
-    s.seed_trk = mcw_seed_via_double(s.seed_trk); // :157-159
-    s.seed_src = mcw_seed_via_double(s.seed_src);
-    s.seed_urr = mcw_seed_via_double(s.seed_urr);
-  }
+    s.seed_trk = mcw_seed_via_double(s.seed_trk);
   if (d > L)
     return false;
   pos = end - (L - d) * dir;

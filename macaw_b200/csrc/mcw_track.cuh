@@ -1,26 +1,34 @@
 // mcw_track.cuh -- the tracking kernel: persistent warps with lane refill, a straight-line
-// exit-face search on register-resident element records, and a per-particle macroscopic
-// cross-section cache so a material change does not end the visit.
+// exit-face search on register-resident element records, parked reflections, and cross sections
+// for every material already waiting in the history's own sectors.
 //
 // Reference behaviour reproduced bit for bit (same IEEE operations in the same order, no FMA):
 //   RT TraceRay.C:292-493 exitsElem, RT TraceRayTools.C:371-553 intersectTriangle / intersectQuad,
 //   :60-128 lineLineIntersect2D, RT TraceRay.C:1420-1466 neighbour step, :725-782 + ReflectRayBC.C:68-76
 //   boundary conditions, MC CollisionKernel.C:143-175 the segment part of onSegment.
 //
-// Why it is shaped like this (profiles/track_r01a_baseline.md): with one thread per history and a
-// loop "until collision", lanes of a warp finish after wildly different segment counts and the
-// baseline kernel ran with 4.3 of 32 lanes active.  Here a warp keeps all lanes busy: a lane whose
-// history stops (collision, unknown cross section, boundary kill, rare-path hand-off) parks, and
-// when MCW_REFILL_MIN lanes are parked the warp pulls that many new histories from the queue with
-// one atomicAdd.  The exit search is split in two exact stages: stage 1 evaluates, for every side
-// at once and without divisions, the reference's own rejection tests (det, u, v) plus the sign of
-// the distance numerator; stage 2 runs the reference arithmetic (division, tolerance and
-// farthest-hit selection) only for the sides that survived -- normally one.
+// Why it is shaped like this (profiles/ncu_r01b_track.txt): the previous version issued ~1000
+// thread instructions per segment at 18.5 of 32 lanes and 41 % issue utilisation with 12 warps per SM.
+//   * A lane only ever leaves for a collision, a death or the rare general walk: the macroscopic
+//     cross sections of EVERY material at the history's energy were computed by the kernel that set
+//     that energy (mcw_lookup_all_slots), so entering another material is one 32-byte read.
+//   * Specular reflection (two square roots, six divisions) used to run inline with ~1.2 active
+//     lanes and cost 17 % of all issued instructions on the reflective pin cell; now the lane parks
+//     and the warp reflects all parked lanes together once MCW_REFLECT_MIN of them wait.
+//   * The neighbour code carries the side of the neighbour that faces back, so the incoming side
+//     needs no search; the source / URR seeds are not re-rounded (idempotent); the trace hash is
+//     only kept when asked for; one candidate face is kept instead of four evaluations.
+//   * Lanes refill from the queue as soon as MCW_REFILL_MIN are empty, and when the queue has run
+//     dry a warp that is down to a few lanes hands its stragglers to the next round instead of
+//     walking them at 1/8 efficiency.
 #pragma once
 #include "mcw_physics.cuh"
 
 #define MCW_TRACK_BLOCK 128
-#define MCW_REFILL_MIN 8
+#define MCW_TRACK_MIN_BLOCKS 4 // register budget 128 per thread -> 16 warps per SM
+#define MCW_REFILL_MIN 4
+#define MCW_REFLECT_MIN 4
+#define MCW_DRAIN_MIN_VISIT 32 // a straggler is only handed on after this many segments of progress
 #define MCW_FULL 0xffffffffu
 
 // ------------------------------------------------------------------ element record in registers
@@ -31,9 +39,9 @@ template <>
 struct ElemData<MCW_TET4>
 {
   V3 v[4];
-  int nbr[4];
+  int nbr[4]; // side codes (mcw_types.h)
   double hmax;
-  int material, block;
+  int slot, block;
   MCW_D void load(const McwMeshDev& m, int e)
   {
     const double2* q = reinterpret_cast<const double2*>(m.rec + (size_t)e * 128);
@@ -46,7 +54,7 @@ struct ElemData<MCW_TET4>
     v[3] = v3(f.y, g.x, g.y);
     nbr[0] = n.x, nbr[1] = n.y, nbr[2] = n.z, nbr[3] = n.w;
     hmax = __hiloint2double(t.y, t.x);
-    material = t.z;
+    slot = t.z;
     block = t.w;
   }
 };
@@ -57,7 +65,7 @@ struct ElemData<MCW_QUAD4>
   V3 v[4];
   int nbr[4];
   double hmax;
-  int material, block;
+  int slot, block;
   MCW_D void load(const McwMeshDev& m, int e)
   {
     const double2* q = reinterpret_cast<const double2*>(m.rec + (size_t)e * 128);
@@ -70,7 +78,7 @@ struct ElemData<MCW_QUAD4>
     v[3] = v3(d.x, d.y, 0.0);
     nbr[0] = n.x, nbr[1] = n.y, nbr[2] = n.z, nbr[3] = n.w;
     hmax = __hiloint2double(t.y, t.x);
-    material = t.z;
+    slot = t.z;
     block = t.w;
   }
 };
@@ -81,7 +89,7 @@ struct ElemData<MCW_HEX8>
   V3 v[8];
   int nbr[6];
   double hmax;
-  int material, block;
+  int slot, block;
   MCW_D void load(const McwMeshDev& m, int e)
   {
     const double2* q = reinterpret_cast<const double2*>(m.rec + (size_t)e * 256);
@@ -89,16 +97,16 @@ struct ElemData<MCW_HEX8>
 #pragma unroll
     for (int k = 0; k < 12; ++k)
       r[k] = __ldg(q + k);
-    int4 n = __ldg(reinterpret_cast<const int4*>(q + 12)); // bytes 192..207: nbr 0-3
-    int4 t = __ldg(reinterpret_cast<const int4*>(q + 13)); // 208..223: nbr 4,5, hmax
-    int2 w = __ldg(reinterpret_cast<const int2*>(q + 14)); // 224..231: material, block
+    int4 n = __ldg(reinterpret_cast<const int4*>(q + 12)); // bytes 192..207: side codes 0-3
+    int4 t = __ldg(reinterpret_cast<const int4*>(q + 13)); // 208..223: side codes 4,5, hmax
+    int2 w = __ldg(reinterpret_cast<const int2*>(q + 14)); // 224..231: slot, block
     const double* c = reinterpret_cast<const double*>(r);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       v[k] = v3(c[3 * k], c[3 * k + 1], c[3 * k + 2]);
     nbr[0] = n.x, nbr[1] = n.y, nbr[2] = n.z, nbr[3] = n.w, nbr[4] = t.x, nbr[5] = t.y;
     hmax = __hiloint2double(t.w, t.z);
-    material = w.x;
+    slot = w.x;
     block = w.y;
   }
 };
@@ -136,6 +144,14 @@ MCW_D bool mcw_tri_stage1(V3 start, V3 dir, V3 p0, V3 p1, V3 p2, double inv_hmax
   return !rej && t.num > 0.0;
 }
 
+// true when the hit is classified as a vertex or an edge (RT TraceRayTools.C:436-474); the general
+// kernel then redoes the step, so the fast path does not need to know which one
+MCW_D bool mcw_tri_at_extrema(const TriEval& t)
+{
+  const double lo = MCW_TRACE_TOL * t.det;
+  return (t.u < lo) | (t.v < lo) | (t.u + t.v > (1.0 - MCW_TRACE_TOL) * t.det);
+}
+
 // vertex / edge classification of a triangle hit (RT TraceRayTools.C:436-474)
 MCW_D void mcw_tri_classify(const TriEval& t, int v0, int v1, int v2, Extrema& ext)
 {
@@ -160,63 +176,63 @@ MCW_D void mcw_tri_classify(const TriEval& t, int v0, int v1, int v2, Extrema& e
     ext.setEdge(v1, v2);
 }
 
-// Exit search.  Same contract and same results as mcw_exits_elem<TYPE> (mcw_device.cuh), which stays
-// the definition: the rare multi-candidate hexahedron case calls it directly.
+// Exit search.  Returns true with (iside, idist, ipoint) when exactly the plain case applies: one
+// side is hit away from its vertices and edges.  Returns false when no side is hit or the hit is at
+// a vertex / edge -- the general kernel (mcw_fallback.cuh) then redoes the step from unchanged
+// state with mcw_exits_elem<TYPE> (mcw_device.cuh), which stays the definition of the search.
 template <int TYPE>
 MCW_D bool mcw_exit_fast(const McwMeshDev& mesh, const ElemData<TYPE>& D, int cur, int incoming_side, V3 start, V3 dir,
-                         V3& ipoint, int& iside, Extrema& iext, double& idist);
+                         V3& ipoint, int& iside, double& idist);
 
 template <>
 MCW_D bool mcw_exit_fast<MCW_TET4>(const McwMeshDev& mesh, const ElemData<MCW_TET4>& D, int cur, int incoming_side,
-                                   V3 start, V3 dir, V3& ipoint, int& iside, Extrema& iext, double& idist)
+                                   V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
   const double hmax = D.hmax;
   const double inv_hmax = 1.0 / hmax;
-  TriEval t[4];
-  unsigned surv = 0;
+  TriEval keep;
+  keep.det = 1.0;
+  keep.u = keep.v = keep.num = 0.0;
+  int n_cand = 0;
+  iside = MCW_INVALID;
 #pragma unroll
   for (int s = 0; s < 4; ++s)
   {
     const int a = side_node<MCW_TET4>(s, 2), b = side_node<MCW_TET4>(s, 1), c = side_node<MCW_TET4>(s, 0);
-    bool ok = mcw_tri_stage1(start, dir, D.v[a], D.v[b], D.v[c], inv_hmax, t[s]);
-    surv |= (ok && s != incoming_side) ? (1u << s) : 0u;
-  }
-  double best = MCW_TRACE_TOL * hmax;
-  iside = MCW_INVALID;
-  TriEval tb;
-  tb.det = tb.u = tb.v = tb.num = 0.0;
-  while (surv)
-  {
-    const int s = __ffs(surv) - 1;
-    surv &= surv - 1;
-    TriEval c = t[0];
-#pragma unroll
-    for (int j = 1; j < 4; ++j)
-      if (s == j)
-        c = t[j];
-    const double possible = c.num / c.det;
-    if (possible <= MCW_TRACE_TOL)
-      continue;
-    const double cd = possible * hmax;
-    if (cd > best)
+    TriEval t;
+    const bool ok = mcw_tri_stage1(start, dir, D.v[a], D.v[b], D.v[c], inv_hmax, t) && (s != incoming_side);
+    if (ok)
     {
+      keep = t;
       iside = s;
-      idist = cd;
-      best = cd;
-      tb = c;
+      ++n_cand;
     }
   }
-  if (iside == MCW_INVALID)
+  if (n_cand != 1)
+  {
+    if (n_cand == 0)
+      return false;
+    // two faces pass the rejection tests (the ray leaves through their common edge or vertex, or
+    // grazes a tolerance band): the reference routine decides, farthest hit wins
+    ElemRec<MCW_TET4> R(mesh, cur);
+    Extrema ext;
+    if (!mcw_exits_elem<MCW_TET4>(mesh, R, incoming_side, start, dir, ipoint, iside, ext, idist))
+      return false;
+    return !ext.atExtrema();
+  }
+  const double possible = keep.num / keep.det;
+  const double cd = possible * hmax;
+  // RT TraceRayTools.C:428 `possible <= tol` and RT TraceRay.C:435-444 `distance > 1e-8 * hmax`
+  if (possible <= MCW_TRACE_TOL || !(cd > MCW_TRACE_TOL * hmax))
     return false;
+  idist = cd;
   ipoint = start + idist * dir;
-  iext.invalidate();
-  mcw_tri_classify(tb, side_node<MCW_TET4>(iside, 2), side_node<MCW_TET4>(iside, 1), side_node<MCW_TET4>(iside, 0), iext);
-  return true;
+  return !mcw_tri_at_extrema(keep);
 }
 
 template <>
 MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HEX8>& D, int cur, int incoming_side,
-                                   V3 start, V3 dir, V3& ipoint, int& iside, Extrema& iext, double& idist)
+                                   V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
   // RT TraceRayTools.C:480-553 intersectQuad(v00, v10, v11, v01): triangle (v00, v10, v11) first,
   // then (v11, v01, v00) if the first did not hit.
@@ -224,7 +240,8 @@ MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HE
   const double inv_hmax = 1.0 / hmax;
   unsigned c1 = 0, c2 = 0;
   TriEval keep;
-  keep.det = keep.u = keep.v = keep.num = 0.0;
+  keep.det = 1.0;
+  keep.u = keep.v = keep.num = 0.0;
 #pragma unroll
   for (int s = 0; s < 6; ++s)
   {
@@ -247,11 +264,9 @@ MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HE
     }
   }
   const unsigned sides = c1 | c2;
+  iside = MCW_INVALID;
   if (sides == 0)
-  {
-    iside = MCW_INVALID;
     return false;
-  }
   if ((sides & (sides - 1)) == 0 && (c1 & c2) == 0)
   {
     // exactly one side and one triangle can hit: `keep` holds its evaluation
@@ -259,32 +274,32 @@ MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HE
     const double possible = keep.num / keep.det;
     const double cd = possible * hmax;
     if (possible <= MCW_TRACE_TOL || !(cd > MCW_TRACE_TOL * hmax))
-    {
-      iside = MCW_INVALID;
       return false;
-    }
     iside = s;
     idist = cd;
     ipoint = start + idist * dir;
     const int v00 = side_node<MCW_HEX8>(s, 3), v10 = side_node<MCW_HEX8>(s, 2), v11 = side_node<MCW_HEX8>(s, 1),
               v01 = side_node<MCW_HEX8>(s, 0);
-    iext.invalidate();
+    Extrema ext;
     if (c1)
-      mcw_tri_classify(keep, v00, v10, v11, iext);
+      mcw_tri_classify(keep, v00, v10, v11, ext);
     else
-      mcw_tri_classify(keep, v11, v01, v00, iext);
-    if (iext.atEdgeOf(v00, v11))
-      iext.invalidate();
-    return true;
+      mcw_tri_classify(keep, v11, v01, v00, ext);
+    if (ext.atEdgeOf(v00, v11))
+      ext.invalidate(); // the quad's diagonal is not an edge (RT TraceRayTools.C:545-550)
+    return !ext.atExtrema();
   }
   // several candidate sides, or both triangles of one side: the reference routine decides
   ElemRec<MCW_HEX8> R(mesh, cur);
-  return mcw_exits_elem<MCW_HEX8>(mesh, R, incoming_side, start, dir, ipoint, iside, iext, idist);
+  Extrema ext;
+  if (!mcw_exits_elem<MCW_HEX8>(mesh, R, incoming_side, start, dir, ipoint, iside, ext, idist))
+    return false;
+  return !ext.atExtrema();
 }
 
 template <>
 MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_QUAD4>& D, int cur, int incoming_side,
-                                    V3 start, V3 dir, V3& ipoint, int& iside, Extrema& iext, double& idist)
+                                    V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
   // RT TraceRayTools.C:60-128 lineLineIntersect2D per side.  Stage 1 rejects, without dividing, the
   // sides whose parameters t or u are outside their windows by more than twice the tolerance (the
@@ -313,6 +328,7 @@ MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_Q
   }
   double best = MCW_TRACE_TOL * D.hmax;
   iside = MCW_INVALID;
+  bool at_vertex = false;
   while (surv)
   {
     const int s = __ffs(surv) - 1;
@@ -335,59 +351,62 @@ MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_Q
       idist = cd;
       best = cd;
       ipoint = start + r * t;
-      iext.invalidate();
-      if (u < MCW_TRACE_TOL)
-        iext.setVertex(side_node<MCW_QUAD4>(s, 0));
-      else if (u > 1.0 - MCW_TRACE_TOL)
-        iext.setVertex(side_node<MCW_QUAD4>(s, 1));
+      at_vertex = (u < MCW_TRACE_TOL) | (u > 1.0 - MCW_TRACE_TOL);
     }
   }
-  return iside != MCW_INVALID;
+  return iside != MCW_INVALID && !at_vertex;
 }
 
 // ------------------------------------------------------------------ the kernel
 // One lane = one history in flight.  Lane state lives in registers between segments and is written
 // back only when the history leaves the kernel.
+enum
+{
+  MCW_LN_EMPTY = 0,  // no history: waits for a refill (or for the end of the launch)
+  MCW_LN_TRACK = 1,  // walks one element per iteration
+  MCW_LN_REFLECT = 2 // parked on a reflecting boundary side (inc_side = that side)
+};
+
 template <int TYPE>
-__global__ void __launch_bounds__(MCW_TRACK_BLOCK)
+__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 ? 2 : MCW_TRACK_MIN_BLOCKS))
 k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
         unsigned long long* __restrict__ head, int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next,
-        int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback)
+        int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback, int drain_lanes)
 {
-  using T = McwElem<TYPE>;
   const long long n_q = (long long)*count;
   const unsigned lane = threadIdx.x & 31u;
   McwParticlesDev& p = P.p;
+  const bool track_tally = P.tallies_active && P.any_tracklength;
+  const bool keep_hash = P.record_traces != 0;
 
-  bool active = false;
+  int state = MCW_LN_EMPTY;
   bool exhausted = n_q == 0;
   int i = -1;
   V3 point = v3(0, 0, 0), dir = v3(0, 0, 1);
-  int cur = 0, last = -1, inc_side = -1, xs_mat = -1, n_seg = 0, visit = 0;
-  bool need_inc = false;
-  unsigned valid = 0;
+  int cur = 0, last = -1, inc_side = -1, slot = -1, n_seg = 0, visit = 0;
   SegState s;
-  s.E = s.wgt = s.sig_t = s.sig_a = s.sig_f = s.sig_nf = s.k_trk = 0.0;
+  s.E = s.wgt = s.sig_a = s.sig_f = s.sig_nf = s.k_trk = 0.0;
+  s.sig_t = 1.0;
   s.seed_trk = s.seed_src = s.seed_urr = 0;
   uint64_t hash = 0;
-  unsigned long long segs = 0;
+  unsigned segs = 0;
 
   for (;;)
   {
-    const unsigned idle = __ballot_sync(MCW_FULL, !active);
-    if (idle == MCW_FULL && exhausted)
+    const unsigned m_empty = __ballot_sync(MCW_FULL, state == MCW_LN_EMPTY);
+    if (m_empty == MCW_FULL && exhausted)
       break;
-    if (!exhausted && __popc(idle) >= MCW_REFILL_MIN)
+    if (!exhausted && __popc(m_empty) >= MCW_REFILL_MIN)
     {
-      const int n_idle = __popc(idle);
+      const int n_idle = __popc(m_empty);
       unsigned long long base = 0;
       if (lane == 0)
         base = atomicAdd(head, (unsigned long long)n_idle);
       base = __shfl_sync(MCW_FULL, base, 0);
       if ((long long)base + n_idle >= n_q)
         exhausted = true;
-      const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
-      if (!active && mine < n_q)
+      const long long mine = (long long)base + __popc(m_empty & ((1u << lane) - 1u));
+      if (state == MCW_LN_EMPTY && mine < n_q)
       {
         i = queue[mine];
         const int st = p.status[i];
@@ -408,78 +427,78 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           s.E = p.E[i];
           s.wgt = p.wgt[i];
           s.seed_trk = p.seed_trk[i];
-          s.seed_src = p.seed_src[i];
-          s.seed_urr = p.seed_urr[i];
-          s.sig_t = p.sig_t[i];
-          s.sig_a = p.sig_a[i];
-          s.sig_f = p.sig_f[i];
-          s.sig_nf = p.sig_nf[i];
           s.k_trk = p.k_trk[i];
-          xs_mat = p.xs_mat[i];
-          valid = P.xs_slots ? p.xs_valid[i] : 0u;
           n_seg = p.n_seg[i];
-          hash = p.hash[i];
-          need_inc = false;
+          if (keep_hash)
+            hash = p.hash[i];
+          slot = -1;
           visit = 0;
-          active = true;
+          state = MCW_LN_TRACK;
         }
       }
     }
-    if (active)
+    // a warp that can no longer refill and is down to a few histories hands them to the next round
+    const bool drain = exhausted && (32 - __popc(__ballot_sync(MCW_FULL, state == MCW_LN_EMPTY))) < drain_lanes;
+
+    const unsigned m_refl = __ballot_sync(MCW_FULL, state == MCW_LN_REFLECT);
+    if (m_refl != 0u)
+    {
+      const unsigned m_track = __ballot_sync(MCW_FULL, state == MCW_LN_TRACK);
+      if (__popc(m_refl) >= MCW_REFLECT_MIN || m_track == 0u || drain)
+      {
+        if (state == MCW_LN_REFLECT)
+        {
+          // RT ReflectRayBC.C:68-76 + Ray::changeDirection (Ray.C:206-214); inc_side holds the side hit
+          ElemRec<TYPE> R(P.mesh, cur);
+          V3 n = mcw_side_normal<TYPE>(R, inc_side);
+          double dn = dot(dir, n);
+          V3 r = dir - (2.0 * dn) * n;
+          r = r / norm(r);
+          dir = unit(r);
+          last = cur;
+          state = MCW_LN_TRACK;
+        }
+      }
+    }
+
+    if (state == MCW_LN_TRACK)
     {
       int status = MCW_ST_FLY, fate = -1;
       bool leave = false, requeue = false;
       ElemData<TYPE> D;
       D.load(P.mesh, cur);
-      if (need_inc)
+      if (D.slot != slot)
       {
-        // RT TraceRay.C:1456-1458: the side of the new element that faces the one we came from
-        int s_in = MCW_INVALID;
-#pragma unroll
-        for (int k = T::NS - 1; k >= 0; --k)
-          if (D.nbr[k] == last)
-            s_in = k;
-        inc_side = s_in;
-        need_inc = false;
-      }
-      if (D.material != xs_mat)
-      {
-        // new material at the same energy: take the cached macroscopic cross sections if this
-        // history already looked them up since its last collision, else go back to the xs kernel
-        if (P.xs_slots && ((valid >> D.material) & 1u))
+        // another material at the same energy: its cross sections are already in this history's sector
+        slot = D.slot;
+        const double2* c = reinterpret_cast<const double2*>(p.xs + ((size_t)i * P.n_slots + slot) * 4);
+        const double2 a = c[0], b = c[1];
+        s.sig_t = a.x;
+        s.sig_nf = b.y;
+        if (track_tally)
         {
-          const double* c = p.xs_cache + ((size_t)D.material * 4) * (size_t)P.xs_stride + i;
-          s.sig_t = c[0];
-          s.sig_a = c[(size_t)P.xs_stride];
-          s.sig_f = c[2 * (size_t)P.xs_stride];
-          s.sig_nf = c[3 * (size_t)P.xs_stride];
-          xs_mat = D.material;
-        }
-        else
-        {
-          requeue = true;
-          leave = true;
+          s.sig_a = a.y;
+          s.sig_f = b.x;
         }
       }
-      if (!leave && (n_seg >= P.max_events))
+      if (n_seg >= P.max_events)
       {
         status = MCW_ST_DEAD;
         fate = 3;
         atomicAdd(&P.counters->n_failed, 1ull);
         leave = true;
       }
-      if (!leave && visit >= P.visit_cap)
+      else if (visit >= P.visit_cap || (drain && visit >= MCW_DRAIN_MIN_VISIT))
       {
-        requeue = true; // bound the time one lane can hold its warp after the queue ran dry
+        requeue = true;
         leave = true;
       }
-      if (!leave)
+      else
       {
         V3 ipoint;
         int iside;
-        Extrema ext;
         double idist;
-        if (!mcw_exit_fast<TYPE>(P.mesh, D, cur, inc_side, point, dir, ipoint, iside, ext, idist) || ext.atExtrema())
+        if (!mcw_exit_fast<TYPE>(P.mesh, D, cur, inc_side, point, dir, ipoint, iside, idist))
         {
           status = MCW_ST_FALLBACK; // nothing modified: the general kernel redoes this step
           leave = true;
@@ -490,8 +509,9 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           ++segs;
           ++visit;
           V3 pos;
-          const bool collided = mcw_segment(P, s, cur, D.block, xs_mat, ipoint, dir, idist, pos);
-          hash = mcw_hash_step(hash, cur, collided ? 15 : iside);
+          const bool collided = mcw_segment(P, s, cur, D.block, P.slot_mat[slot], ipoint, dir, idist, pos);
+          if (keep_hash)
+            hash = mcw_hash_step(hash, cur, collided ? 15 : iside);
           if (collided)
           {
             point = pos;
@@ -501,18 +521,20 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           else
           {
             point = ipoint;
-            const int nb = mcw_pick(D.nbr, iside);
-            if (nb >= 0)
+            const int code = mcw_pick(D.nbr, iside);
+            if (code >= 0)
             {
+              // RT TraceRay.C:1433-1458: neighbour and the side of it that faces back
               last = cur;
-              cur = nb;
-              need_inc = true;
+              cur = code >> MCW_NBR_SHIFT;
+              inc_side = code & ((1 << MCW_NBR_SHIFT) - 1);
             }
             else
             {
               // RT TraceRay.C:725-782 external boundary, :2043 onBoundary
-              const int bid = -nb - 1;
-              const int kind = bid < P.mesh.n_bnd ? P.mesh.bnd_kind[bid] : MCW_BC_KILL;
+              const int bid = -code - 1;
+              const int kind = bid < P.mesh.n_bnd ? __ldg(P.mesh.bnd_kind + bid) : MCW_BC_KILL;
+              inc_side = iside;
               if (kind == MCW_BC_KILL)
               {
                 status = MCW_ST_DEAD;
@@ -520,57 +542,28 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
                 leave = true;
               }
               else
-              {
-                // RT ReflectRayBC.C:68-76 + Ray::changeDirection (Ray.C:206-214)
-                ElemRec<TYPE> R(P.mesh, cur);
-                V3 n = mcw_side_normal<TYPE>(R, iside);
-                double dn = dot(dir, n);
-                V3 r = dir - (2.0 * dn) * n;
-                r = r / norm(r);
-                dir = unit(r);
-                last = cur;
-                inc_side = iside;
-              }
+                state = MCW_LN_REFLECT;
             }
           }
         }
       }
       if (leave)
       {
-        if (need_inc)
-        {
-          // cannot happen together with leave today (need_inc is consumed at the top), kept for safety
-          ElemData<TYPE> N;
-          N.load(P.mesh, cur);
-          int s_in = MCW_INVALID;
-#pragma unroll
-          for (int k = T::NS - 1; k >= 0; --k)
-            if (N.nbr[k] == last)
-              s_in = k;
-          inc_side = s_in;
-          need_inc = false;
-        }
         p.x[i] = point.x;
         p.y[i] = point.y;
         p.z[i] = point.z;
+        p.elem[i] = cur;
+        p.seed_trk[i] = s.seed_trk;
+        p.k_trk[i] = s.k_trk;
+        p.n_seg[i] = n_seg;
+        if (keep_hash)
+          p.hash[i] = hash;
+        p.status[i] = (int8_t)(requeue ? MCW_ST_FLY : status);
         p.ux[i] = dir.x;
         p.uy[i] = dir.y;
         p.uz[i] = dir.z;
-        p.elem[i] = cur;
         p.last_elem[i] = last;
         p.inc_side[i] = (int8_t)inc_side;
-        p.seed_trk[i] = s.seed_trk;
-        p.seed_src[i] = s.seed_src;
-        p.seed_urr[i] = s.seed_urr;
-        p.sig_t[i] = s.sig_t;
-        p.sig_a[i] = s.sig_a;
-        p.sig_f[i] = s.sig_f;
-        p.sig_nf[i] = s.sig_nf;
-        p.xs_mat[i] = xs_mat;
-        p.k_trk[i] = s.k_trk;
-        p.n_seg[i] = n_seg;
-        p.hash[i] = hash;
-        p.status[i] = (int8_t)(requeue ? MCW_ST_FLY : status);
         if (fate >= 0)
           p.fate[i] = (int8_t)fate;
         if (requeue)
@@ -579,17 +572,17 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           q_collide[mcw_warp_append(&P.counters->n_collide, true)] = i;
         else if (status == MCW_ST_FALLBACK)
           q_fallback[mcw_warp_append(&P.counters->n_fallback, true)] = i;
-        active = false;
+        state = MCW_LN_EMPTY;
       }
     }
   }
   // segment counter: one atomic per warp
   {
-    unsigned long long tot = segs;
+    unsigned tot = segs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
       tot += __shfl_xor_sync(MCW_FULL, tot, o);
     if (lane == 0 && tot)
-      atomicAdd(&P.counters->n_segments, tot);
+      atomicAdd(&P.counters->n_segments, (unsigned long long)tot);
   }
 }

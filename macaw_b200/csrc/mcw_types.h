@@ -5,9 +5,11 @@
 //     fission, nu-fission: one 32-byte sector per grid point, two adjacent rows = one 64-byte read),
 //     el_inel[sumG][2] (elastic, level-inelastic; collision kernel only), grid_index[n_nuc][M+1] (i32).
 //   * Mesh: one fixed-stride record per element (128 B for TET4/QUAD4 = one L2 line, 256 B for HEX8)
-//     holding the element's OWN copy of its vertex coordinates, its neighbour ids (boundary sides
-//     encode -(bnd_id)-2), the block's hmax, its material and block index.  One dependent load per
-//     element crossing instead of connectivity -> node-coordinate double indirection.
+//     holding the element's OWN copy of its vertex coordinates, one 32-bit code per side
+//     (interior: neighbour id << 3 | the neighbour's side that faces back, so the incoming side of
+//     the next element needs no second record; boundary: -(bnd_id)-1), the block's hmax, its
+//     cross-section slot (dense index over the materials the mesh uses) and block index.  One
+//     dependent load per element crossing instead of connectivity -> node-coordinate indirection.
 //   * Particles: structure of arrays indexed by history slot.
 #pragma once
 #include <stdint.h>
@@ -15,7 +17,9 @@
 #include "../../include/macaw_b200.h"
 
 #define MCW_MAX_NUC_PER_MAT 64
-#define MCW_XS_CACHE_MAX 16
+#define MCW_MAX_XS_SLOTS 32   // materials actually present in the mesh
+#define MCW_NBR_SHIFT 3       // side code = neighbour << 3 | back side
+#define MCW_MAX_ELEMS (1ll << 28)
 
 struct McwNucParams
 {
@@ -96,16 +100,16 @@ struct McwParticlesDev
 {
   double *x, *y, *z, *ux, *uy, *uz, *E, *wgt;
   uint64_t *seed_trk, *seed_src, *seed_urr;
-  double *sig_t, *sig_a, *sig_f, *sig_nf; // cached macroscopic xs for (E, xs_mat)
   double *k_col, *k_abs, *k_trk;
-  int32_t *elem, *last_elem, *xs_mat;
+  int32_t *elem, *last_elem;
   int32_t *n_progeny, *n_seg, *n_coll, *n_xs;
   int8_t *inc_side, *ext_first, *ext_second, *status, *fate;
   uint64_t* hash;
-  // macroscopic cross sections of every material this history has looked up since its last
-  // collision: xs_cache[(material * 4 + k) * stride + slot], bit m of xs_valid = material m is cached
-  double* xs_cache;
-  uint32_t* xs_valid;
+  // macroscopic cross sections at the history's current energy for EVERY material slot, refreshed
+  // by the kernel that changes the energy (source initialisation, collision):
+  // xs[(history * n_slots + slot) * 4 + {total, absorption, fission, nu-fission}] -- one 32-byte
+  // sector per (history, slot), so a material change in the tracking kernel is one sector read
+  double* xs;
 };
 
 struct McwTallyDev
@@ -143,8 +147,10 @@ struct McwParams
   int64_t n_particles_global, work_offset; // id = work_offset + slot + 1
   int64_t master_seed;
   int32_t batch, is_2d, seed_through_double, max_events;
-  int32_t xs_slots;  // > 0: the per-history cross-section cache is on (number of materials, <= MCW_XS_CACHE_MAX)
+  int32_t n_slots;   // cross-section slots = materials present in the mesh
   int32_t visit_cap; // segments one lane may walk per visit of the tracking kernel
-  int64_t xs_stride; // history slots per cache plane
+  int32_t record_traces; // keep the per-history crossing hash (parity output)
+  int32_t pad0;
+  int32_t slot_mat[MCW_MAX_XS_SLOTS]; // slot -> material index
   double z_coord, keff;
 };
