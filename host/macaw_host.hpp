@@ -1,0 +1,435 @@
+// macaw_host.hpp -- C++ host layer above the C ABI (include/macaw_b200.h).
+//
+// Mirrors, for the particle-history hot path only, the four MOOSE objects through which the
+// reference exposes that path (same parameter names, same error strings, same call order):
+//
+//   macaw::OpenMCStudy     <- MC src/userobjects/OpenMCStudy.C:48-76 validParams, :78-204 ctor, :366-402 execute
+//   macaw::CollisionKernel <- MC src/raykernels/CollisionKernel.C:24-70 (configuration carrier in GPU mode)
+//   macaw::OpenMCTally     <- MC src/userobjects/OpenMCTally.C:30-101 (filters / scores / estimator)
+//   macaw::OpenMCTallyAux  <- MC src/auxkernels/OpenMCTallyAux.C:26-215 (per-element read-back)
+//
+// MOOSE and libMesh are not in this image, so these are plain classes instead of
+// registerMooseObject'ed ones; INTEGRATION.md shows the thin MOOSE adapter that forwards
+// InputParameters into them.  Everything below is host plumbing: no physics, no geometry, and no CPU
+// fallback -- every number comes out of libmacaw_b200.so (CUDA, sm_100a).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/macaw_b200.h"
+
+namespace macaw
+{
+
+// mooseError / paramError analogue: the reference aborts through these; here they throw.
+struct Error : std::runtime_error
+{
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void mooseError(const std::string& m) { throw Error(MCW_E_INVALID_ARGUMENT, m); }
+inline void paramError(const std::string& param, const std::string& m) { throw Error(MCW_E_INVALID_ARGUMENT, param + ": " + m); }
+
+// What the study reads from libMesh on the path (RT TraceRayTools.C:404-407, TraceRay.C:1433,
+// MC CollisionKernel.C:110): node coordinates, connectivity in libMesh node order, subdomain ids,
+// neighbours (optional), boundary ids per side and the RayBC kind on every boundary id.
+struct Mesh
+{
+  int elem_type = MCW_HEX8;
+  std::vector<double> xyz;          // n_nodes x 3
+  std::vector<int64_t> conn;        // n_elem x nodes_per_elem
+  std::vector<int32_t> block_id;    // n_elem
+  std::vector<int64_t> neighbors;   // n_elem x n_sides or empty (library matches faces)
+  std::vector<int32_t> side_bnd_id; // n_elem x n_sides, -1 = interior
+  std::vector<int32_t> bnd_kind;    // per boundary id: MCW_BC_KILL / MCW_BC_REFLECT
+  int nodesPerElem() const { return elem_type == MCW_HEX8 ? 8 : 4; }
+  int sidesPerElem() const { return elem_type == MCW_HEX8 ? 6 : 4; }
+  int dimension() const { return elem_type == MCW_QUAD4 ? 2 : 3; }
+  int64_t nElem() const { return (int64_t)block_id.size(); }
+  int64_t nNodes() const { return (int64_t)xyz.size() / 3; }
+};
+
+struct Nuclide
+{
+  std::vector<double> energy, xs, elastic, inelastic;
+  mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
+};
+struct Material
+{
+  std::vector<int32_t> nuclide;
+  std::vector<double> atom_density;
+};
+struct Library
+{
+  std::vector<Nuclide> nuclides;
+  std::vector<Material> materials;
+  std::vector<mcw_nuclide_desc> nuclideDescs() const
+  {
+    std::vector<mcw_nuclide_desc> out;
+    static const double zero = 0.0;
+    for (const auto& n : nuclides)
+    {
+      mcw_nuclide_desc d = n.d;
+      d.n_grid = (int32_t)n.energy.size();
+      d.energy = n.energy.data();
+      d.xs = n.xs.data();
+      d.elastic = n.elastic.data();
+      d.n_inelastic = n.inelastic.empty() ? 0 : 1;
+      d.inelastic = n.inelastic.empty() ? &zero : n.inelastic.data();
+      out.push_back(d);
+    }
+    return out;
+  }
+  std::vector<mcw_material_desc> materialDescs() const
+  {
+    std::vector<mcw_material_desc> out;
+    for (const auto& m : materials)
+      out.push_back({(int32_t)m.nuclide.size(), 0, m.nuclide.data(), m.atom_density.data()});
+    return out;
+  }
+};
+
+// RAII over mcw_handle; check() turns the C convention (int + mcw_last_error, cf. OMC capi.h:180-190
+// + error.cpp:32) into the exception the MOOSE side would raise with mooseError.
+class Handle
+{
+public:
+  Handle(int device, int rank, int nranks)
+  {
+    if (int rc = mcw_create(&_h, device, rank, nranks))
+      throw Error(rc, "mcw_create failed: a CUDA device of compute capability 10.x (B200) is required; there is no CPU fallback");
+  }
+  ~Handle()
+  {
+    if (_h)
+      mcw_destroy(_h);
+  }
+  Handle(const Handle&) = delete;
+  Handle& operator=(const Handle&) = delete;
+  mcw_handle get() const { return _h; }
+  void check(int rc) const
+  {
+    if (rc)
+      throw Error(rc, mcw_last_error(_h));
+  }
+
+private:
+  mcw_handle _h = nullptr;
+};
+
+// Parameters: temperature, blocks, materials, z_coord, verbose (MC CollisionKernel.C:24-42).
+class CollisionKernel
+{
+public:
+  CollisionKernel(const Mesh& mesh, std::vector<unsigned> blocks, std::vector<unsigned> materials,
+                  std::vector<double> temperature, std::optional<double> z_coord = std::nullopt, bool verbose = false)
+    : _blocks(std::move(blocks)), _materials(std::move(materials)), _temperature(std::move(temperature)),
+      _is_2D(mesh.dimension() == 2), _z_coord(z_coord.value_or(0.0)), _verbose(verbose)
+  {
+    if (_is_2D && !z_coord)
+      mooseError("The z_coord parameter must be specified for 2D calculations"); // :60-61
+    if (_blocks.size() != _materials.size())
+      paramError("blocks", "The blocks parameter must be the same size as the materials parameter."); // :66-67
+    if (_temperature.size() != 1 && (int64_t)_temperature.size() != mesh.nElem())
+      paramError("temperature", "Only CONST MONOMIAL temperatures are supported."); // :52-57: one value per element
+  }
+  std::vector<int32_t> blockIds() const { return {_blocks.begin(), _blocks.end()}; }
+  // OpenMC material ids are 1-based; model::material_map resolves them to indices (:110)
+  std::vector<int32_t> materialIndices() const
+  {
+    std::vector<int32_t> out;
+    for (unsigned m : _materials)
+      out.push_back((int32_t)m - 1);
+    return out;
+  }
+  const std::vector<double>& temperature() const { return _temperature; }
+  bool is2D() const { return _is_2D; }
+  double zCoord() const { return _z_coord; }
+  bool verbose() const { return _verbose; }
+
+private:
+  std::vector<unsigned> _blocks, _materials;
+  std::vector<double> _temperature;
+  bool _is_2D;
+  double _z_coord;
+  bool _verbose;
+};
+
+// Parameters: id, particle_type, estimator, scores, filters, energy_bins (MC OpenMCTally.C:30-65).
+class OpenMCTally
+{
+public:
+  OpenMCTally(int id, std::vector<std::string> scores, std::vector<std::string> filters,
+              const std::string& estimator = "COLLISION", const std::string& particle_type = "neutron",
+              std::vector<double> energy_bins = {})
+    : _id(id), _score_names(std::move(scores)), _filters(std::move(filters)), _energy_bins(std::move(energy_bins))
+  {
+    if (particle_type != "neutron")
+      mooseError("Only neutrons are currently supported."); // :87-88
+    if (estimator == "COLLISION")
+      _estimator = MCW_ESTIMATOR_COLLISION;
+    else if (estimator == "TRACKLENGTH")
+      _estimator = MCW_ESTIMATOR_TRACKLENGTH; // extension: the reference rejects it (:89-90), north star names it
+    else
+      mooseError("Only collision estimator currently supported"); // :89-90
+    bool has_energy = false;
+    _granularity = MCW_FILTER_GLOBAL;
+    for (const auto& f : _filters)
+    {
+      if (f == "energy")
+        has_energy = true;
+      else if (f == "cell")
+        _granularity = MCW_FILTER_CELL;
+      else if (f == "universe")
+      {
+        if (_granularity != MCW_FILTER_CELL)
+          _granularity = MCW_FILTER_UNIVERSE;
+      }
+      else if (f != "particle")
+        mooseError("Unrecognized filter"); // :173-174
+    }
+    if (has_energy && _energy_bins.empty())
+      mooseError("The energy bins parameter should be supplied if an energy filter is requested.");
+    if (!has_energy)
+      _energy_bins.clear();
+    static const char* names[MCW_N_SCORES] = {"flux", "total", "fission", "nu-fission", "kappa-fission"};
+    for (const auto& s : _score_names)
+    {
+      int code = -1;
+      for (int k = 0; k < MCW_N_SCORES; ++k)
+        if (s == names[k])
+          code = k;
+      if (code < 0)
+        paramError("scores", "score '" + s + "' is not on the GPU path");
+      _scores.push_back(code);
+    }
+  }
+  int id() const { return _id; }
+  int estimator() const { return _estimator; }
+  int granularity() const { return _granularity; }
+  const std::vector<int32_t>& scores() const { return _scores; }
+  const std::vector<std::string>& scoreNames() const { return _score_names; }
+  const std::vector<double>& energyBins() const { return _energy_bins; }
+
+private:
+  int _id, _estimator = MCW_ESTIMATOR_COLLISION, _granularity;
+  std::vector<std::string> _score_names, _filters;
+  std::vector<int32_t> _scores;
+  std::vector<double> _energy_bins;
+};
+
+// Communication the study needs between transport and finalize when particles are sharded over
+// several GPUs (MC OpenMCStudy.C:454-607 synchronizeBanks; OMC eigenvalue.cpp:71-311).  The
+// single-rank study never calls it.  host/nccl_comm.hpp implements it over NCCL.
+struct Comm
+{
+  virtual ~Comm() = default;
+  virtual int rank() const = 0;
+  virtual int size() const = 0;
+  virtual std::vector<int64_t> allGather(int64_t v) = 0;                     // Exscan + Bcast of counts
+  virtual void allReduceSum(double* device_buf, int64_t n, void* stream) = 0; // tallies + k estimators
+  // grouped send/recv of byte ranges between device buffers
+  struct Range
+  {
+    int peer;
+    int64_t offset, bytes;
+  };
+  virtual void exchange(const char* send_base, const std::vector<Range>& sends, char* recv_base,
+                        const std::vector<Range>& recvs, void* stream) = 0;
+};
+
+// RayTracingStudy-derived transport study.  Construction = ctor + initialSetup of the reference
+// (openmc_init, material / cell set-up, openmc_simulation_init: MC OpenMCStudy.C:78-204);
+// execute() = one Transient time step = one batch = one generation (:366-402).
+class OpenMCStudy
+{
+public:
+  OpenMCStudy(const Mesh& mesh, const Library& library, const CollisionKernel& kernel, mcw_settings settings,
+              const std::vector<OpenMCTally>& tallies = {}, int device = 0, Comm* comm = nullptr, bool verbose = true)
+    : _comm(comm), _rank(comm ? comm->rank() : 0), _nranks(comm ? comm->size() : 1), _h(device, _rank, _nranks),
+      _verbose(verbose), _settings(settings)
+  {
+    _settings.is_2d = kernel.is2D();
+    if (kernel.is2D())
+      _settings.z_coord = kernel.zCoord();
+    const bool have_nbr = !mesh.neighbors.empty();
+    _h.check(mcw_set_mesh(_h.get(), mesh.elem_type, mesh.nNodes(), mesh.xyz.data(), mesh.nElem(), mesh.conn.data(),
+                          mesh.block_id.data(), have_nbr ? mesh.neighbors.data() : nullptr, mesh.side_bnd_id.data(),
+                          (int)mesh.bnd_kind.size(), mesh.bnd_kind.data()));
+    auto nd = library.nuclideDescs();
+    _h.check(mcw_set_library(_h.get(), nd.data(), (int)nd.size()));
+    auto md = library.materialDescs();
+    auto bid = kernel.blockIds();
+    auto bm = kernel.materialIndices();
+    _h.check(mcw_set_materials(_h.get(), md.data(), (int)md.size(), bid.data(), bm.data(), (int)bid.size()));
+    _h.check(mcw_set_temperature(_h.get(), kernel.temperature().data(), (int64_t)kernel.temperature().size()));
+    _h.check(mcw_set_settings(_h.get(), &_settings));
+    for (const auto& t : tallies)
+      _h.check(mcw_add_tally(_h.get(), t.id(), t.estimator(), t.granularity(), t.scores().data(), (int)t.scores().size(),
+                             t.energyBins().empty() ? nullptr : t.energyBins().data(), (int)t.energyBins().size()));
+    _work_index.resize(_nranks + 1);
+    _h.check(mcw_calculate_work(_settings.n_particles, _nranks, _work_index.data())); // OMC simulation.cpp:529-551
+    _h.check(mcw_prepare(_h.get()));
+    _h.check(mcw_sample_initial_source(_h.get())); // openmc_simulation_init -> initialize_source (:147)
+  }
+
+  // One batch.  Returns the generation result; prints the reference's line when verbose (:399-401).
+  mcw_generation_result execute()
+  {
+    ++_batch;
+    mcw_generation_result res{};
+    if (_nranks == 1)
+      _h.check(mcw_run_generation(_h.get(), _batch, &res));
+    else
+    {
+      _h.check(mcw_transport_generation(_h.get(), _batch)); // generateRays() + propagation
+      synchronizeBanks();                                    // postExecuteStudy()
+      _h.check(mcw_finalize_generation(_h.get(), _batch, &res));
+    }
+    _last = res;
+    if (_verbose && _rank == 0)
+      std::printf("Keff %.10f (%.10f) Generation: %.10f\n", res.keff, res.keff_std, res.k_generation);
+    return res;
+  }
+
+  int batch() const { return _batch; }
+  int rank() const { return _rank; }
+  const mcw_generation_result& last() const { return _last; }
+  const Handle& handle() const { return _h; }
+  int64_t localParticles() const { return _work_index[_rank + 1] - _work_index[_rank]; }
+
+  // openmc_source_bank analogue (OMC bank.cpp:110-125)
+  std::vector<mcw_source_site> sourceBank() const
+  {
+    int64_t n = 0;
+    _h.check(mcw_get_source_bank(_h.get(), nullptr, 0, &n));
+    std::vector<mcw_source_site> out((size_t)n);
+    _h.check(mcw_get_source_bank(_h.get(), out.data(), n, &n));
+    return out;
+  }
+  void setSourceBank(const std::vector<mcw_source_site>& sites)
+  {
+    _h.check(mcw_set_source_bank(_h.get(), sites.data(), (int64_t)sites.size()));
+  }
+
+private:
+  // MC OpenMCStudy.C:454-607 with its MPI calls mapped onto Comm (see macaw_b200/dist.py for the
+  // same sequence on torch.distributed): bank offsets, one fused all-reduce, sampling of this rank's
+  // slice of the global bank, last-rank trim / pad, redistribution to the owners.
+  void synchronizeBanks()
+  {
+    mcw_handle h = _h.get();
+    void* stream = nullptr;
+    _h.check(mcw_stream(h, &stream));
+    int64_t n_local = 0;
+    _h.check(mcw_bank_count(h, &n_local));
+    auto counts = _comm->allGather(n_local);
+    std::vector<int64_t> off(_nranks + 1, 0);
+    for (int r = 0; r < _nranks; ++r)
+    {
+      if (counts[r] == 0)
+        throw Error(MCW_E_PHYSICS, "No fission sites banked on rank " + std::to_string(r)); // OMC eigenvalue.cpp:107-109
+      off[r + 1] = off[r] + counts[r];
+    }
+    _h.check(mcw_set_bank_window(h, off[_rank], off[_nranks]));
+    void* red = nullptr;
+    int64_t n_red = 0;
+    _h.check(mcw_reduction_device_ptr(h, &red, &n_red));
+    _comm->allReduceSum(static_cast<double*>(red), n_red, stream);
+    int64_t n_s = 0;
+    _h.check(mcw_sample_bank(h, _batch, &n_s));
+    auto scounts = _comm->allGather(n_s);
+    std::vector<int64_t> soff(_nranks + 1, 0);
+    for (int r = 0; r < _nranks; ++r)
+      soff[r + 1] = soff[r] + scounts[r];
+    _h.check(mcw_finish_sampling(h, soff[_rank], _rank == _nranks - 1, &n_s));
+    // only the last rank trims / pads and it always ends at exactly n_particles (OMC eigenvalue.cpp:184-206)
+    scounts[_nranks - 1] = std::max<int64_t>(0, _work_index[_nranks] - soff[_nranks - 1]);
+    for (int r = 0; r < _nranks; ++r)
+      soff[r + 1] = soff[r] + scounts[r];
+    void *sampled = nullptr, *source = nullptr;
+    int64_t n_sampled = 0, cap = 0;
+    _h.check(mcw_sampled_device_ptr(h, &sampled, &n_sampled));
+    _h.check(mcw_source_device_ptr(h, &source, &cap));
+    const int64_t S = (int64_t)sizeof(mcw_source_site);
+    std::vector<Comm::Range> sends, recvs;
+    for (int d = 0; d < _nranks; ++d) // what I hold [soff[rank], soff[rank+1]) vs what d owns
+    {
+      const int64_t lo = std::max(soff[_rank], _work_index[d]), hi = std::min(soff[_rank + 1], _work_index[d + 1]);
+      if (hi > lo)
+        sends.push_back({d, (lo - soff[_rank]) * S, (hi - lo) * S});
+    }
+    for (int s = 0; s < _nranks; ++s)
+    {
+      const int64_t lo = std::max(soff[s], _work_index[_rank]), hi = std::min(soff[s + 1], _work_index[_rank + 1]);
+      if (hi > lo)
+        recvs.push_back({s, (lo - _work_index[_rank]) * S, (hi - lo) * S});
+    }
+    _comm->exchange(static_cast<const char*>(sampled), sends, static_cast<char*>(source), recvs, stream);
+    _h.check(mcw_set_source_count(h, localParticles()));
+  }
+
+  Comm* _comm;
+  int _rank, _nranks;
+  Handle _h;
+  bool _verbose;
+  mcw_settings _settings;
+  std::vector<int64_t> _work_index;
+  int _batch = 0;
+  mcw_generation_result _last{};
+};
+
+// Parameters: tally_id, granularity, score, estimator, particle_type, energy_bin (MC OpenMCTallyAux.C:26-50).
+// computeValue(elem) = results_(filter_index, score, SUM) summed over the energy bins unless
+// energy_bin is given -- the raw sum over batches, not the mean (:183,201).
+class OpenMCTallyAux
+{
+public:
+  OpenMCTallyAux(const OpenMCStudy& study, const OpenMCTally& tally, const std::string& granularity, const std::string& score,
+                 std::optional<int> energy_bin = std::nullopt)
+    : _study(study), _tally_id(tally.id()), _energy_bin(energy_bin)
+  {
+    if (granularity != "cell" && granularity != "universe")
+      mooseError("global granularity is not supported");
+    _score = -1;
+    for (size_t k = 0; k < tally.scoreNames().size(); ++k)
+      if (tally.scoreNames()[k] == score)
+        _score = (int)k;
+    if (_score < 0)
+      paramError("score", "score '" + score + "' is not part of tally " + std::to_string(_tally_id));
+  }
+  // fetches the tally once per step (the AuxKernel is evaluated once per element per step)
+  void timestepSetup()
+  {
+    const Handle& h = _study.handle();
+    h.check(mcw_tally_shape(h.get(), _tally_id, &_n_spatial, &_n_energy, &_n_scores));
+    _sum.assign((size_t)(_n_spatial * _n_energy * _n_scores), 0.0);
+    _sum_sq = _sum;
+    int32_t nr = 0;
+    h.check(mcw_get_tally(h.get(), _tally_id, _sum.data(), _sum_sq.data(), (int64_t)_sum.size(), &nr));
+  }
+  double computeValue(int64_t spatial_bin) const
+  {
+    double v = 0.0;
+    for (int e = 0; e < _n_energy; ++e)
+      if (!_energy_bin || *_energy_bin == e)
+        v += _sum[(size_t)((spatial_bin * _n_energy + e) * _n_scores + _score)];
+    return v;
+  }
+  int64_t nSpatial() const { return _n_spatial; }
+
+private:
+  const OpenMCStudy& _study;
+  int _tally_id, _score;
+  std::optional<int> _energy_bin;
+  int64_t _n_spatial = 0;
+  int32_t _n_energy = 0, _n_scores = 0;
+  std::vector<double> _sum, _sum_sq;
+};
+
+} // namespace macaw

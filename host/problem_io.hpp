@@ -1,0 +1,151 @@
+// problem_io.hpp -- reader of the problem files written by macaw_b200/problem_io.py
+// (magic "MCWPROB1", uint32 record count, records {char name[32]; u32 dtype; u32 reserved; u64 count; data}).
+// Stands in for what the MOOSE adapter gets from libMesh + the input file; set-up only, not hot path.
+#pragma once
+#include <cstring>
+#include <fstream>
+#include <map>
+
+#include "macaw_host.hpp"
+
+namespace macaw
+{
+
+struct Problem
+{
+  Mesh mesh;
+  Library library;
+  std::vector<unsigned> blocks, materials;
+  std::vector<double> temperature;
+  mcw_settings settings{};
+  struct TallyDef
+  {
+    int id, estimator, granularity;
+    std::vector<int32_t> scores;
+    std::vector<double> energy_bins;
+  };
+  std::vector<TallyDef> tallies;
+};
+
+class ProblemFile
+{
+public:
+  explicit ProblemFile(const std::string& path)
+  {
+    std::ifstream f(path, std::ios::binary);
+    if (!f)
+      mooseError("cannot open problem file " + path);
+    char magic[8];
+    f.read(magic, 8);
+    if (std::memcmp(magic, "MCWPROB1", 8) != 0)
+      mooseError(path + " is not a MCWPROB1 problem file");
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), 4);
+    for (uint32_t k = 0; k < n; ++k)
+    {
+      char name[33] = {0};
+      uint32_t dtype = 0, reserved = 0;
+      uint64_t count = 0;
+      f.read(name, 32);
+      f.read(reinterpret_cast<char*>(&dtype), 4);
+      f.read(reinterpret_cast<char*>(&reserved), 4);
+      f.read(reinterpret_cast<char*>(&count), 8);
+      const size_t item = dtype == 1 ? 4 : 8;
+      Rec r;
+      r.dtype = (int)dtype;
+      r.bytes.resize(count * item);
+      f.read(r.bytes.data(), (std::streamsize)r.bytes.size());
+      f.ignore((std::streamsize)((8 - r.bytes.size() % 8) % 8));
+      if (!f)
+        mooseError("truncated problem file " + path);
+      _recs[name] = std::move(r);
+    }
+  }
+  bool has(const std::string& n) const { return _recs.count(n) != 0; }
+  template <typename T>
+  std::vector<T> get(const std::string& n, int dtype) const
+  {
+    auto it = _recs.find(n);
+    if (it == _recs.end())
+      mooseError("problem file lacks record " + n);
+    if (it->second.dtype != dtype)
+      mooseError("record " + n + " has the wrong type");
+    std::vector<T> out(it->second.bytes.size() / sizeof(T));
+    std::memcpy(out.data(), it->second.bytes.data(), it->second.bytes.size());
+    return out;
+  }
+  std::vector<double> f64(const std::string& n) const { return get<double>(n, 0); }
+  std::vector<int32_t> i32(const std::string& n) const { return get<int32_t>(n, 1); }
+  std::vector<int64_t> i64(const std::string& n) const { return get<int64_t>(n, 2); }
+
+  Problem problem() const
+  {
+    Problem P;
+    P.mesh.elem_type = i32("mesh.elem_type")[0];
+    P.mesh.xyz = f64("mesh.xyz");
+    P.mesh.conn = i64("mesh.conn");
+    P.mesh.block_id = i32("mesh.block_id");
+    if (has("mesh.neighbors"))
+      P.mesh.neighbors = i64("mesh.neighbors");
+    P.mesh.side_bnd_id = i32("mesh.side_bnd_id");
+    P.mesh.bnd_kind = i32("mesh.bnd_kind");
+    const auto counts = i32("lib.counts");
+    for (int k = 0; k < counts[0]; ++k)
+    {
+      const std::string p = "nuc" + std::to_string(k) + ".";
+      Nuclide n;
+      const auto I = i32(p + "ints");
+      const auto S = f64(p + "scalars");
+      n.energy = f64(p + "energy");
+      n.xs = f64(p + "xs");
+      n.elastic = f64(p + "elastic");
+      n.inelastic = f64(p + "inelastic");
+      n.d.fissionable = I[1];
+      n.d.inel_threshold = I[3];
+      n.d.n_precursor = I[4];
+      n.d.awr = S[0], n.d.kT = S[1], n.d.inel_threshold_energy = S[2], n.d.inel_mass_ratio = S[3];
+      n.d.nu_poly[0] = S[4], n.d.nu_poly[1] = S[5], n.d.watt_a = S[6], n.d.watt_b = S[7], n.d.q_fission = S[8];
+      const auto dy = f64(p + "delayed_yield"), dt = f64(p + "delayed_theta");
+      for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
+        n.d.delayed_yield[g] = dy[g], n.d.delayed_theta[g] = dt[g];
+      P.library.nuclides.push_back(std::move(n));
+    }
+    for (int k = 0; k < counts[1]; ++k)
+    {
+      const std::string p = "mat" + std::to_string(k) + ".";
+      P.library.materials.push_back({i32(p + "nuclide"), f64(p + "density")});
+    }
+    for (int32_t b : i32("kernel.blocks"))
+      P.blocks.push_back((unsigned)b);
+    for (int32_t m : i32("kernel.materials"))
+      P.materials.push_back((unsigned)m);
+    P.temperature = f64("kernel.temperature");
+    const auto si = i64("settings.ints");
+    const auto sr = f64("settings.reals");
+    mcw_settings& s = P.settings;
+    s.n_particles = si[0], s.master_seed = si[1], s.n_inactive = (int32_t)si[2], s.n_log_bins = (int32_t)si[3];
+    s.is_2d = (int32_t)si[4], s.seed_through_double = (int32_t)si[5], s.source_only_fissionable = (int32_t)si[6];
+    s.max_events = (int32_t)si[7], s.sort_xs_queue = (int32_t)si[8], s.record_traces = (int32_t)si[9];
+    s.z_coord = sr[0];
+    for (int k = 0; k < 6; ++k)
+      s.source_box[k] = sr[1 + k];
+    const int nt = i32("tallies.count")[0];
+    for (int k = 0; k < nt; ++k)
+    {
+      const std::string p = "tally" + std::to_string(k) + ".";
+      const auto I = i32(p + "ints");
+      P.tallies.push_back({I[0], I[1], I[2], i32(p + "scores"), f64(p + "energy_bins")});
+    }
+    return P;
+  }
+
+private:
+  struct Rec
+  {
+    int dtype;
+    std::vector<char> bytes;
+  };
+  std::map<std::string, Rec> _recs;
+};
+
+} // namespace macaw

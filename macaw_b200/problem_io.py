@@ -1,0 +1,87 @@
+"""Problem files: one self-contained binary with mesh, nuclear data, block->material map, settings and
+tallies, so the C++ host (host/mcw_run) runs byte-identical inputs to the Python host and the oracle.
+
+Layout (little endian): 8-byte magic ``MCWPROB1``, uint32 record count, then records of
+``char name[32]; uint32 dtype (0 f64, 1 i32, 2 i64); uint32 reserved; uint64 count; data`` with the
+data padded to a multiple of 8 bytes.  host/problem_io.hpp is the reader."""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+MAGIC = b"MCWPROB1"
+_DT = {0: np.float64, 1: np.int32, 2: np.int64}
+_CODE = {np.dtype(np.float64): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2}
+
+
+def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
+    r = {}
+    r["mesh.elem_type"] = np.array([mesh.elem_type], np.int32)
+    r["mesh.xyz"] = np.ascontiguousarray(mesh.xyz, np.float64).ravel()
+    r["mesh.conn"] = np.ascontiguousarray(mesh.conn, np.int64).ravel()
+    r["mesh.block_id"] = np.ascontiguousarray(mesh.block_id, np.int32)
+    if mesh.neighbors is not None:
+        r["mesh.neighbors"] = np.ascontiguousarray(mesh.neighbors, np.int64).ravel()
+    r["mesh.side_bnd_id"] = np.ascontiguousarray(mesh.side_bnd_id, np.int32).ravel()
+    r["mesh.bnd_kind"] = np.ascontiguousarray(mesh.bnd_kind, np.int32)
+    r["lib.counts"] = np.array([len(lib.nuclides), len(lib.materials), lib.n_log_bins], np.int32)
+    for k, n in enumerate(lib.nuclides):
+        r[f"nuc{k}.ints"] = np.array([n.energy.size, int(n.fissionable), int(n.inelastic.size > 0), n.inel_threshold,
+                                      n.n_precursor], np.int32)
+        r[f"nuc{k}.scalars"] = np.array([n.awr, n.kT, n.inel_threshold_energy, n.inel_mass_ratio, n.nu_poly[0],
+                                         n.nu_poly[1], n.watt_a, n.watt_b, n.q_fission], np.float64)
+        r[f"nuc{k}.energy"] = np.ascontiguousarray(n.energy, np.float64)
+        r[f"nuc{k}.xs"] = np.ascontiguousarray(n.xs, np.float64).ravel()
+        r[f"nuc{k}.elastic"] = np.ascontiguousarray(n.elastic, np.float64)
+        r[f"nuc{k}.inelastic"] = np.ascontiguousarray(n.inelastic, np.float64)
+        r[f"nuc{k}.delayed_yield"] = np.ascontiguousarray(n.delayed_yield, np.float64)
+        r[f"nuc{k}.delayed_theta"] = np.ascontiguousarray(n.delayed_theta, np.float64)
+    for k, m in enumerate(lib.materials):
+        r[f"mat{k}.nuclide"] = np.ascontiguousarray(m.nuclides, np.int32)
+        r[f"mat{k}.density"] = np.ascontiguousarray(m.densities, np.float64)
+    r["kernel.blocks"] = np.ascontiguousarray(blocks, np.int32)
+    r["kernel.materials"] = np.ascontiguousarray(materials, np.int32)  # OpenMC material ids, 1-based
+    r["kernel.temperature"] = np.atleast_1d(np.asarray(temperature, np.float64))
+    s = settings
+    r["settings.ints"] = np.array([s.n_particles, s.master_seed, s.n_inactive, s.n_log_bins, s.is_2d,
+                                   s.seed_through_double, s.source_only_fissionable, s.max_events, s.sort_xs_queue,
+                                   s.record_traces], np.int64)
+    r["settings.reals"] = np.array([s.z_coord] + [s.source_box[i] for i in range(6)], np.float64)
+    r["tallies.count"] = np.array([len(tallies)], np.int32)
+    for k, (tid, estimator, granularity, scores, ebins) in enumerate(tallies):
+        r[f"tally{k}.ints"] = np.array([tid, estimator, granularity], np.int32)
+        r[f"tally{k}.scores"] = np.ascontiguousarray(scores, np.int32)
+        r[f"tally{k}.energy_bins"] = np.ascontiguousarray(ebins if ebins is not None else [], np.float64)
+    return r
+
+
+def write_problem(path, mesh, lib, blocks, materials, settings, tallies=(), temperature=293.6):
+    """tallies: iterable of (id, estimator, granularity, scores, energy_bins | None) in C-ABI codes."""
+    recs = _records(mesh, lib, blocks, materials, settings, list(tallies), temperature)
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<I", len(recs)))
+        for name, a in recs.items():
+            nb = name.encode()
+            assert len(nb) < 32
+            f.write(nb.ljust(32, b"\0"))
+            f.write(struct.pack("<IIQ", _CODE[a.dtype], 0, a.size))
+            b = a.tobytes()
+            f.write(b + b"\0" * (-len(b) % 8))
+
+
+def read_records(path):
+    """Inverse of write_problem at the record level (used by the CPU tests)."""
+    out = {}
+    with open(path, "rb") as f:
+        assert f.read(8) == MAGIC
+        (n,) = struct.unpack("<I", f.read(4))
+        for _ in range(n):
+            name = f.read(32).rstrip(b"\0").decode()
+            code, _, cnt = struct.unpack("<IIQ", f.read(16))
+            dt = np.dtype(_DT[code])
+            nbytes = cnt * dt.itemsize
+            out[name] = np.frombuffer(f.read(nbytes), dt).copy()
+            f.read(-nbytes % 8)
+    return out
