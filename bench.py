@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000, help="histories per GPU per batch")
     ap.add_argument("--sort-xs", type=int, default=0)
     ap.add_argument("--sync-every", type=int, default=4)
+    ap.add_argument("--tail-threshold", type=int, default=-1, help="histories in flight below which tracking runs fused")
+    ap.add_argument("--collide-min", type=int, default=-1, help="fused tracking: parked collisions per warp before they are processed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -229,6 +231,10 @@ def main():
     ctx = study.ctx
     ctx.set_option("sync_every", args.sync_every)
     ctx.set_option("profile", 1)
+    if args.collide_min >= 0:
+        ctx.set_option("collide_min", args.collide_min)
+    if args.tail_threshold >= 0:
+        ctx.set_option("tail_threshold", args.tail_threshold)
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
     def barrier():

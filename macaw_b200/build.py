@@ -59,5 +59,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines=()):
+    """Kernel A/B experiments: the same sources with extra -D flags into build/variants/<name>.so.
+    Selected at run time with MCW_LIB_PATH (macaw_b200/lib.py); never used by tests or the bench line."""
+    out_dir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(out_dir, name), exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, name, src.replace(".cu", ".o"))
+        cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        open(obj + ".log", "w").write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError((r.stdout + r.stderr)[-4000:])
+        objs.append(obj)
+    lib = os.path.join(out_dir, f"libmacaw_b200_{name}.so")
+    subprocess.run([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs,
+                   check=True)
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

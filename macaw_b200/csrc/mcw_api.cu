@@ -128,9 +128,13 @@ struct mcw_context
   double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
 
   // options
-  int profile = 0, sync_every = 1, fallback_blocks = 8, visit_cap = 1 << 30, track_max_blocks = 148;
+  int profile = 0, sync_every = 1, fallback_blocks = 8, visit_cap = 1 << 30, track_max_blocks = 148, fused_max_blocks = 148;
   int drain_lanes = 12;            // tracking warps below this many histories hand them to the next round ...
   int64_t drain_min_queue = 65536; // ... when the round's queue is at least this long
+  // below this many histories in flight the tracking kernel runs fused (collisions inline, no
+  // round per collision): rounds would last as long as the slowest flight with most lanes idle
+  int64_t tail_threshold = 65536;
+  int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> pool; // per-round profiling events (5 per round), reused across generations
@@ -275,6 +279,10 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->drain_lanes = std::min(32, std::max(0, value));
   else if (n == "drain_min_queue")
     h->drain_min_queue = std::max(0, value);
+  else if (n == "tail_threshold")
+    h->tail_threshold = std::max(0, value);
+  else if (n == "collide_min")
+    h->collide_min = std::min(32, std::max(1, value));
   else if (n == "visit_cap")
   {
     h->visit_cap = value > 0 ? value : (1 << 30);
@@ -856,7 +864,8 @@ static int prepare(mcw_handle h)
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
-    h->track_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type)) * prop.multiProcessorCount;
+    h->track_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, false)) * prop.multiProcessorCount;
+    h->fused_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, true)) * prop.multiProcessorCount;
   }
   h->bank_capacity = 3 * n; // OMC simulation.cpp:286
   h->sampled_capacity = 3 * n + 16;
@@ -1048,9 +1057,10 @@ int mcw_transport_generation(mcw_handle h, int batch)
     unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 0), st);
-    const int drain = upper >= h->drain_min_queue ? h->drain_lanes : 0;
-    mcwk_track(P, q, cnt_cur, upper, h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
-               drain, st);
+    const bool fused = upper < h->tail_threshold;
+    const int drain = (!fused && upper >= h->drain_min_queue) ? h->drain_lanes : 0;
+    mcwk_track(P, q, cnt_cur, upper, fused ? h->fused_max_blocks : h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
+               drain, fused, h->collide_min, st);
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 1), st);
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
@@ -1067,7 +1077,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 2), st);
-    R.n_kernel_launches += 3;
+    R.n_kernel_launches += 4; // k_track, k_fallback, k_collide, k_xs_all_slots
     ++rounds;
     const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
     if (sync_now)

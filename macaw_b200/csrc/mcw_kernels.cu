@@ -178,9 +178,6 @@ k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
   keys[idx] = ((uint32_t)R.slot() << 16) | (uint32_t)mcw_log_bin(P.lib, P.p.E[i]);
 }
 
-// ------------------------------------------------------------------ tracking
-#include "mcw_track.cuh"
-
 // resets the per-round device counters (one launch instead of three memsets)
 __global__ void k_round_reset(McwCounters* c, int consumed)
 {
@@ -191,18 +188,17 @@ __global__ void k_round_reset(McwCounters* c, int consumed)
 }
 
 // ------------------------------------------------------------------ collision
-template <int TYPE>
-__global__ void __launch_bounds__(MCW_BLOCK)
-k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
-          int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next)
+// event_collide for history i (OMC particle.cpp:219-288).  Called by ALL 32 lanes of a warp (the
+// fission-bank append is a full-warp aggregate); lanes with valid == false only take part in the
+// shuffles.  Returns true when the history survives (scattered, status MCW_ST_FLY, cross sections
+// of every material refreshed at the new energy).
+// LOOKUP = false leaves the all-material cross-section refresh to k_xs_all_slots (one thread per
+// (history, material) instead of one dependent chain of ~12 nuclide lookups per history).
+template <int TYPE, bool LOOKUP>
+MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
 {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = idx < (int64_t)*count;
-  // no early return: the bank append below is a full-warp aggregate
-  McwParticlesDev& p = P.p;
+  const McwParticlesDev& p = P.p;
   const McwLibraryDev& L = P.lib;
-  int i = active ? queue[idx] : -1;
-  bool valid = active && p.status[i] == MCW_ST_COLLIDE;
 
   ColState c;
   double sig_t = 1, sig_a = 0, sig_f = 0, sig_nf = 0, E_last = 0, wgt_last = 0, kappa = 0.0;
@@ -303,7 +299,7 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
     base = wbase + (unsigned long long)(incl - nu);
   }
   if (!valid)
-    return;
+    return false;
   const McwNucParams& nuc = L.nuc[k_nuc];
   for (int k = 0; k < nu; ++k)
   {
@@ -400,13 +396,52 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
     p.status[i] = MCW_ST_FLY;
     // Particle::event_calculate_xs at the new energy, every material slot at once (if the
     // collision kept the energy the sectors are rewritten with the same values)
-    mcw_lookup_all_slots(P, i, c.E);
+    if (LOOKUP)
+      mcw_lookup_all_slots(P, i, c.E);
     p.n_xs[i] += P.n_slots;
   }
-  unsigned long long k = mcw_warp_append(cnt_next, !absorbed);
-  if (!absorbed)
+  return !absorbed;
+}
+
+// Particle::event_calculate_xs for the survivors of k_collide (OMC particle.cpp:85-147,
+// material.cpp:763-831): thread (h, s) computes material slot s at the new energy of the h-th
+// history of the collision queue; the four slots of a history are neighbouring threads, so the
+// 32-byte results form one 128-byte store per history.
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_xs_all_slots(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t h = idx / P.n_slots;
+  const int s = (int)(idx - h * P.n_slots);
+  if (h >= (int64_t)*count)
+    return;
+  const int i = queue[h];
+  if (P.p.status[i] != MCW_ST_FLY)
+    return; // absorbed
+  const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], P.p.E[i]);
+  double2* o = reinterpret_cast<double2*>(P.p.xs + ((size_t)i * P.n_slots + s) * 4);
+  o[0] = make_double2(M.total, M.absorption);
+  o[1] = make_double2(M.fission, M.nu_fission);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(MCW_BLOCK)
+k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
+          int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < (int64_t)*count;
+  // no early return: the bank append and the queue append are full-warp aggregates
+  const int i = active ? queue[idx] : -1;
+  const bool valid = active && P.p.status[i] == MCW_ST_COLLIDE;
+  const bool survived = mcw_collide_history<TYPE, false>(P, i, valid);
+  unsigned long long k = mcw_warp_append(cnt_next, survived);
+  if (survived)
     q_fly_next[k] = i;
 }
+
+// ------------------------------------------------------------------ tracking (may collide inline: after mcw_collide_history)
+#include "mcw_track.cuh"
 
 // ------------------------------------------------------------------ general (rare-path) step
 #include "mcw_fallback.cuh"
@@ -664,23 +699,38 @@ void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, co
   k_xs_lookup_array<<<grid_for(n), MCW_BLOCK, 0, st>>>(L, n, E, mat, out);
 }
 
-int mcwk_track_blocks_per_sm(int type)
+int mcwk_track_blocks_per_sm(int type, bool fused)
 {
   int nb = 0;
-  MCW_DISPATCH(type, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_track<TY>, MCW_TRACK_BLOCK, 0)));
+  if (fused)
+  {
+    MCW_DISPATCH(type, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_track<TY, true>, MCW_TRACK_BLOCK, 0)));
+  }
+  else
+  {
+    MCW_DISPATCH(type, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_track<TY, false>, MCW_TRACK_BLOCK, 0)));
+  }
   return nb;
 }
 
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
-                int drain_lanes, cudaStream_t st)
+                int drain_lanes, bool fused, int collide_min, cudaStream_t st)
 {
   if (upper <= 0)
     return;
   // persistent grid: never more blocks than fit on the device at once, never more than the queue needs
   unsigned g = (unsigned)std::min<int64_t>((upper + MCW_TRACK_BLOCK - 1) / MCW_TRACK_BLOCK, (int64_t)max_blocks);
-  MCW_DISPATCH(P.mesh.type, (k_track<TY><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
-                                                                       cnt_next, q_collide, q_fallback, drain_lanes)));
+  if (fused)
+  {
+    MCW_DISPATCH(P.mesh.type, (k_track<TY, true><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
+                                                                               cnt_next, q_collide, q_fallback, 0, collide_min)));
+  }
+  else
+  {
+    MCW_DISPATCH(P.mesh.type, (k_track<TY, false><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
+                                                                                cnt_next, q_collide, q_fallback, drain_lanes, 32)));
+  }
 }
 
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st) { k_round_reset<<<1, 1, 0, st>>>(c, consumed); }
@@ -692,6 +742,7 @@ void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long 
     return;
   MCW_DISPATCH(P.mesh.type,
                (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next)));
+  k_xs_all_slots<<<grid_for(upper * P.n_slots), MCW_BLOCK, 0, st>>>(P, queue, count);
 }
 
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,

@@ -11,11 +11,11 @@ void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long 
                   cudaStream_t st);
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st);
-int mcwk_track_blocks_per_sm(int type);
+int mcwk_track_blocks_per_sm(int type, bool fused);
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
-                int drain_lanes, cudaStream_t st);
+                int drain_lanes, bool fused, int collide_min, cudaStream_t st);
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
                   int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st);
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,

@@ -92,10 +92,12 @@ struct SegState
   double k_trk;
 };
 
-MCW_D bool mcw_segment(const McwParams& P, SegState& s, int elem, int block, int i_mat, V3 end, V3 dir,
-                       double L, V3& pos)
+// `neg_log` = -log(prn(seed_trk)), with s.seed_trk already advanced by that draw (the caller may
+// compute it ahead of the geometry to overlap it with the element-record load).
+MCW_D bool mcw_segment_nl(const McwParams& P, SegState& s, double neg_log, int elem, int block, int i_mat, V3 end, V3 dir,
+                          double L, V3& pos)
 {
-  const double d = -mcw_log(mcw_prn(s.seed_trk)) / s.sig_t; // 1 RN per segment (:150)
+  const double d = neg_log / s.sig_t; // 1 RN per segment (:150): -log(prn) / Sigma_t
   const double dmin = (L < d) ? L : d;                       // std::min(d, L)
   s.k_trk += s.wgt * dmin * s.sig_nf;                        // :153
   if (P.tallies_active && P.any_tracklength)
@@ -130,6 +132,12 @@ MCW_D bool mcw_segment(const McwParams& P, SegState& s, int elem, int block, int
   if (P.is_2d)
     pos.z = P.z_coord;
   return true;
+}
+
+MCW_D bool mcw_segment(const McwParams& P, SegState& s, int elem, int block, int i_mat, V3 end, V3 dir, double L, V3& pos)
+{
+  const double neg_log = -mcw_log(mcw_prn(s.seed_trk));
+  return mcw_segment_nl(P, s, neg_log, elem, block, i_mat, end, dir, L, pos);
 }
 
 // ------------------------------------------------------------------ collision physics

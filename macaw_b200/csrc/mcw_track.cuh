@@ -25,7 +25,15 @@
 #include "mcw_physics.cuh"
 
 #define MCW_TRACK_BLOCK 128
+#ifndef MCW_TRACK_MIN_BLOCKS
 #define MCW_TRACK_MIN_BLOCKS 4 // register budget 128 per thread -> 16 warps per SM
+#endif
+#ifndef MCW_TRK_PIPELINE
+#define MCW_TRK_PIPELINE 0 // 1: the next element record is requested as soon as the exit side is known
+#endif
+#ifndef MCW_TRK_HOIST_LOG
+#define MCW_TRK_HOIST_LOG 1 // 1: the segment's random number and logarithm are computed ahead of the geometry
+#endif
 #define MCW_REFILL_MIN 4
 #define MCW_REFLECT_MIN 4
 #define MCW_DRAIN_MIN_VISIT 32 // a straggler is only handed on after this many segments of progress
@@ -181,15 +189,14 @@ MCW_D void mcw_tri_classify(const TriEval& t, int v0, int v1, int v2, Extrema& e
 // a vertex / edge -- the general kernel (mcw_fallback.cuh) then redoes the step from unchanged
 // state with mcw_exits_elem<TYPE> (mcw_device.cuh), which stays the definition of the search.
 template <int TYPE>
-MCW_D bool mcw_exit_fast(const McwMeshDev& mesh, const ElemData<TYPE>& D, int cur, int incoming_side, V3 start, V3 dir,
-                         V3& ipoint, int& iside, double& idist);
+MCW_D bool mcw_exit_fast(const McwMeshDev& mesh, const ElemData<TYPE>& D, double inv_hmax, int cur, int incoming_side,
+                         V3 start, V3 dir, V3& ipoint, int& iside, double& idist);
 
 template <>
-MCW_D bool mcw_exit_fast<MCW_TET4>(const McwMeshDev& mesh, const ElemData<MCW_TET4>& D, int cur, int incoming_side,
+MCW_D bool mcw_exit_fast<MCW_TET4>(const McwMeshDev& mesh, const ElemData<MCW_TET4>& D, double inv_hmax, int cur, int incoming_side,
                                    V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
-  const double hmax = D.hmax;
-  const double inv_hmax = 1.0 / hmax;
+  const double hmax = D.hmax; // inv_hmax = 1.0 / hmax, computed by the caller when hmax changes
   TriEval keep;
   keep.det = 1.0;
   keep.u = keep.v = keep.num = 0.0;
@@ -231,13 +238,12 @@ MCW_D bool mcw_exit_fast<MCW_TET4>(const McwMeshDev& mesh, const ElemData<MCW_TE
 }
 
 template <>
-MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HEX8>& D, int cur, int incoming_side,
+MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HEX8>& D, double inv_hmax, int cur, int incoming_side,
                                    V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
   // RT TraceRayTools.C:480-553 intersectQuad(v00, v10, v11, v01): triangle (v00, v10, v11) first,
   // then (v11, v01, v00) if the first did not hit.
   const double hmax = D.hmax;
-  const double inv_hmax = 1.0 / hmax;
   unsigned c1 = 0, c2 = 0;
   TriEval keep;
   keep.det = 1.0;
@@ -298,13 +304,14 @@ MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HE
 }
 
 template <>
-MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_QUAD4>& D, int cur, int incoming_side,
+MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_QUAD4>& D, double inv_hmax, int cur, int incoming_side,
                                     V3 start, V3 dir, V3& ipoint, int& iside, double& idist)
 {
   // RT TraceRayTools.C:60-128 lineLineIntersect2D per side.  Stage 1 rejects, without dividing, the
   // sides whose parameters t or u are outside their windows by more than twice the tolerance (the
   // quotients' rounding error is 1e-16 relative, the margin 1e-8 absolute); stage 2 is the
   // reference arithmetic on the survivors.
+  (void)inv_hmax;
   const double length = mesh.domain_max_length;
   const V3 r = dir * length;
   const double M = 2.0 * MCW_TRACE_TOL;
@@ -364,14 +371,21 @@ enum
 {
   MCW_LN_EMPTY = 0,  // no history: waits for a refill (or for the end of the launch)
   MCW_LN_TRACK = 1,  // walks one element per iteration
-  MCW_LN_REFLECT = 2 // parked on a reflecting boundary side (inc_side = that side)
+  MCW_LN_REFLECT = 2, // parked on a reflecting boundary side (inc_side = that side)
+  MCW_LN_COLLIDE = 3  // fused mode only: parked at a collision point, state written back to the SoA
 };
+// fused mode: parked collisions are processed together once `collide_min` of them wait (kernel argument)
 
-template <int TYPE>
-__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 ? 2 : MCW_TRACK_MIN_BLOCKS))
+// FUSED = false: the event-based kernel (a lane leaves at its collision; k_collide runs afterwards on
+// the whole queue).  FUSED = true: the tail of a generation, when fewer histories are left than the
+// device has lanes -- rounds would be as long as the slowest flight while most lanes idle, so each
+// lane keeps its history through its collisions (mcw_collide_history, batched per warp) until it
+// dies.  Only the rare vertex / edge steps still leave through the fallback queue.
+template <int TYPE, bool FUSED>
+__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 || FUSED ? 2 : MCW_TRACK_MIN_BLOCKS))
 k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
         unsigned long long* __restrict__ head, int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next,
-        int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback, int drain_lanes)
+        int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback, int drain_lanes, int collide_min)
 {
   const long long n_q = (long long)*count;
   const unsigned lane = threadIdx.x & 31u;
@@ -390,6 +404,28 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
   s.seed_trk = s.seed_src = s.seed_urr = 0;
   uint64_t hash = 0;
   unsigned segs = 0;
+  // The record of the element a lane stands in is lane state: it is loaded when the lane is
+  // (re)filled and, for the next element, as soon as the exit side is known -- before the
+  // logarithm / division chain of the segment physics, which then hides the L2 latency.
+  ElemData<TYPE> D;
+  D.load(P.mesh, 0);
+  double hmax_c = 0.0, inv_hmax = 0.0; // 1.0 / hmax, recomputed only when hmax (a block constant) changes
+
+  auto load_lane = [&]() {
+    point = v3(p.x[i], p.y[i], p.z[i]);
+    dir = v3(p.ux[i], p.uy[i], p.uz[i]);
+    cur = p.elem[i];
+    last = p.last_elem[i];
+    inc_side = p.inc_side[i];
+    s.E = p.E[i];
+    s.wgt = p.wgt[i];
+    s.seed_trk = p.seed_trk[i];
+    s.k_trk = p.k_trk[i];
+    n_seg = p.n_seg[i];
+    if (keep_hash)
+      hash = p.hash[i];
+    slot = -1; // the cross sections of the current material are (re)read from the history's sectors
+  };
 
   for (;;)
   {
@@ -419,21 +455,12 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
         }
         else if (st == MCW_ST_FLY)
         {
-          point = v3(p.x[i], p.y[i], p.z[i]);
-          dir = v3(p.ux[i], p.uy[i], p.uz[i]);
-          cur = p.elem[i];
-          last = p.last_elem[i];
-          inc_side = p.inc_side[i];
-          s.E = p.E[i];
-          s.wgt = p.wgt[i];
-          s.seed_trk = p.seed_trk[i];
-          s.k_trk = p.k_trk[i];
-          n_seg = p.n_seg[i];
-          if (keep_hash)
-            hash = p.hash[i];
-          slot = -1;
+          load_lane();
           visit = 0;
           state = MCW_LN_TRACK;
+#if MCW_TRK_PIPELINE
+          D.load(P.mesh, cur);
+#endif
         }
       }
     }
@@ -461,12 +488,47 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
       }
     }
 
+    if (FUSED)
+    {
+      const unsigned m_coll = __ballot_sync(MCW_FULL, state == MCW_LN_COLLIDE);
+      if (m_coll != 0u)
+      {
+        const unsigned m_track = __ballot_sync(MCW_FULL, state == MCW_LN_TRACK);
+        if (__popc(m_coll) >= collide_min || m_track == 0u)
+        {
+          // all 32 lanes enter (full-warp bank append); only the parked ones collide
+          const bool mine = state == MCW_LN_COLLIDE;
+          const bool survived = mcw_collide_history<TYPE, true>(P, mine ? i : 0, mine);
+          if (mine)
+          {
+            if (survived)
+            {
+              load_lane();
+              state = MCW_LN_TRACK;
+            }
+            else
+              state = MCW_LN_EMPTY;
+          }
+        }
+      }
+    }
+
     if (state == MCW_LN_TRACK)
     {
       int status = MCW_ST_FLY, fate = -1;
       bool leave = false, requeue = false;
-      ElemData<TYPE> D;
+#if !MCW_TRK_PIPELINE
       D.load(P.mesh, cur);
+#endif
+#if MCW_TRK_HOIST_LOG
+      uint64_t seed_next = s.seed_trk;
+      const double neg_log = -mcw_log(mcw_prn(seed_next));
+#endif
+      if (D.hmax != hmax_c)
+      {
+        hmax_c = D.hmax;
+        inv_hmax = 1.0 / hmax_c;
+      }
       if (D.slot != slot)
       {
         // another material at the same energy: its cross sections are already in this history's sector
@@ -498,7 +560,7 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
         V3 ipoint;
         int iside;
         double idist;
-        if (!mcw_exit_fast<TYPE>(P.mesh, D, cur, inc_side, point, dir, ipoint, iside, idist))
+        if (!mcw_exit_fast<TYPE>(P.mesh, D, inv_hmax, cur, inc_side, point, dir, ipoint, iside, idist))
         {
           status = MCW_ST_FALLBACK; // nothing modified: the general kernel redoes this step
           leave = true;
@@ -509,9 +571,21 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           ++segs;
           ++visit;
           V3 pos;
-          const bool collided = mcw_segment(P, s, cur, D.block, P.slot_mat[slot], ipoint, dir, idist, pos);
+          const int code = mcw_pick(D.nbr, iside);
+          const int block = D.block;
+          const int elem = cur;
+#if MCW_TRK_PIPELINE
+          if (code >= 0)
+            D.load(P.mesh, code >> MCW_NBR_SHIFT); // next record in flight during the physics below
+#endif
+#if MCW_TRK_HOIST_LOG
+          s.seed_trk = seed_next;
+          const bool collided = mcw_segment_nl(P, s, neg_log, elem, block, P.slot_mat[slot], ipoint, dir, idist, pos);
+#else
+          const bool collided = mcw_segment(P, s, elem, block, P.slot_mat[slot], ipoint, dir, idist, pos);
+#endif
           if (keep_hash)
-            hash = mcw_hash_step(hash, cur, collided ? 15 : iside);
+            hash = mcw_hash_step(hash, elem, collided ? 15 : iside);
           if (collided)
           {
             point = pos;
@@ -521,7 +595,6 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           else
           {
             point = ipoint;
-            const int code = mcw_pick(D.nbr, iside);
             if (code >= 0)
             {
               // RT TraceRay.C:1433-1458: neighbour and the side of it that faces back
@@ -569,10 +642,13 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
         if (requeue)
           q_fly_next[mcw_warp_append(cnt_next, true)] = i;
         else if (status == MCW_ST_COLLIDE)
-          q_collide[mcw_warp_append(&P.counters->n_collide, true)] = i;
+        {
+          if (!FUSED)
+            q_collide[mcw_warp_append(&P.counters->n_collide, true)] = i;
+        }
         else if (status == MCW_ST_FALLBACK)
           q_fallback[mcw_warp_append(&P.counters->n_fallback, true)] = i;
-        state = MCW_LN_EMPTY;
+        state = (FUSED && !requeue && status == MCW_ST_COLLIDE) ? MCW_LN_COLLIDE : MCW_LN_EMPTY;
       }
     }
   }

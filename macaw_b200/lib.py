@@ -22,7 +22,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("MCW_LIB_PATH") or _build.LIB  # MCW_LIB_PATH: an A/B build of the same CUDA library
     if not os.path.exists(path):
         _build.build()  # raises if nvcc is missing: no silent fallback
     L = C.CDLL(path)
