@@ -43,6 +43,19 @@ def build_problem(name, particles_total, n_inactive):
         L = 17 * meshgen.PIN_PITCH
         box = (0, 0, -1, L, L, 1)
         et = "quad4"
+    elif name == "assembly_hex":
+        mesh = meshgen.assembly_hex(17, 9, 4)  # 153*153*4 = 93 636 HEX8 (reference 3-D assembly: 95 504)
+        lib = nucdata.make_library(35, G=10000, seed=1)
+        L = 17 * meshgen.PIN_PITCH
+        box = (0, 0, 0, L, L, 4.0)
+        et = "hex8"
+    elif name.startswith("brick_tet_"):
+        n = int(name.split("_")[-1])  # C5 scaling sweep: 6 n^3 TET4, vacuum boundary
+        mesh = meshgen.brick_tet(n, bc=meshgen.BC_REFLECT)
+        lib = nucdata.make_library(9, G=10000, seed=1)
+        L = n * 0.05
+        box = (0, 0, 0, L, L, L)
+        et = "tet4"
     elif name == "infinite_medium":
         mesh = meshgen.infinite_medium(5)
         lib = nucdata.infinite_medium_library(G=10000)
@@ -138,6 +151,52 @@ def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch):
     return n / t, n, t
 
 
+def xs_lookup_leg(device, points=4 * 1024 * 1024, repeats=5):
+    """BASELINE.json's second metric: stand-alone macroscopic cross-section lookup on a BEAVRS-shaped
+    synthetic library (91 nuclides, ~3e6 grid points, 170 MB > L2), `points` random (E, material)
+    pairs resident in HBM.  GB/s are ALGORITHMIC bytes (100 B per (point, nuclide) + 44 B
+    per point) over CUDA-event time; the sorted variant's time includes key generation and the sort."""
+    import torch
+    from macaw_b200 import cstructs, meshgen, nucdata
+    from macaw_b200.context import Context
+    lib = nucdata.make_library(91, G=32768, seed=1)
+    ctx = Context(device)
+    ctx.set_mesh(meshgen.infinite_medium(5))
+    ctx.set_library(lib, [0, 1], [0, 1])
+    ctx.set_settings(cstructs.make_settings(1000, source_box=(-5, -5, -5, 5, 5, 5)))
+    ctx.prepare()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    lo, hi = np.log(1.1e-5), np.log(1.9e7)
+    E = torch.exp(torch.rand(points, generator=g, device="cuda", dtype=torch.float64) * (hi - lo) + lo)
+    mat = torch.randint(0, len(lib.materials), (points,), generator=g, device="cuda", dtype=torch.int32)
+    out = torch.empty(points * 4, device="cuda", dtype=torch.float64)
+    n_nuc = torch.tensor([len(m.nuclides) for m in lib.materials], device="cuda")[mat.long()].sum().item()
+    alg_bytes = 100.0 * n_nuc + 44.0 * points
+    peak, peak_src = peaks()
+    res = {"library": f"{len(lib.nuclides)} nuclides x 32768 points, {lib.bytes() / 1e6:.0f} MB", "points": points,
+           "nuclide_lookups": int(n_nuc), "algorithmic_bytes": alg_bytes, "peak": peak, "unit": "GB/s"}
+    ref = None
+    for name, mode in (("direct", 0), ("sort_plus_staged", 2)):
+        ctx.xs_lookup_device(points, E.data_ptr(), mat.data_ptr(), out.data_ptr(), 1, mode)  # warm-up
+        ms = ctx.xs_lookup_device(points, E.data_ptr(), mat.data_ptr(), out.data_ptr(), repeats, mode)
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "achieved": gbs, "frac": gbs / peak, "nuclide_lookups_per_s": n_nuc / (ms * 1e-3)}
+        if ref is None:
+            ref = out.clone()
+        else:
+            res["bit_identical"] = bool(torch.equal(ref.view(torch.int64), out.view(torch.int64)))
+    # the staged kernel alone, on arrays the caller already ordered by (material, energy)
+    key = mat.double() * 1e9 + E
+    order = torch.argsort(key)
+    Es, ms_ = E[order].contiguous(), mat[order].contiguous()
+    ctx.xs_lookup_device(points, Es.data_ptr(), ms_.data_ptr(), out.data_ptr(), 1, 1)
+    ms = ctx.xs_lookup_device(points, Es.data_ptr(), ms_.data_ptr(), out.data_ptr(), repeats, 1)
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    res["staged_presorted"] = {"ms": ms, "achieved": gbs, "frac": gbs / peak, "nuclide_lookups_per_s": n_nuc / (ms * 1e-3)}
+    ctx.close()
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithms (oracle restatement; the real MaCaw binary
     cannot be built offline) on all host cores, same workload definition."""
@@ -202,6 +261,7 @@ def main():
     ap.add_argument("--tail-threshold", type=int, default=-1, help="histories in flight below which tracking runs fused")
     ap.add_argument("--collide-min", type=int, default=-1, help="fused tracking: parked collisions per warp before they are processed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-xs-leg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -358,6 +418,11 @@ def main():
                                                        "bank+reduce": acc["ms_bank"] / args.steps}},
             "cpu_baseline": cpu,
         }
+        if not args.no_xs_leg:
+            try:
+                out["xs_lookup"] = xs_lookup_leg(local)
+            except Exception as e:
+                out["xs_lookup"] = {"failed": str(e)}
         print(json.dumps(out))
     if world > 1:
         import torch.distributed as td

@@ -274,7 +274,11 @@ int mcw_get_grid_index(mcw_handle h, int i_nuclide, int32_t* out, int n /* n_log
 /* Stand-alone kernels of the path, exposed for unit parity and the XS-lookup bandwidth metric.
  * mcw_xs_lookup: macroscopic cross sections for n (energy, material) pairs in HOST memory
  * [OMC material.cpp:763-831 + nuclide.cpp:557-763]; out = n x 4 (total, absorption, fission,
- * nu-fission).  mcw_xs_lookup_device: same on device pointers, returns device milliseconds. */
+ * nu-fission).  mcw_xs_lookup_device: same on device pointers, returns device milliseconds per
+ * launch; sorted = 0: one thread per point reading the tables directly; 1: the caller's arrays are
+ * already ordered by (material, energy), shared-memory-staged kernel; 2: the library orders the
+ * points itself (keys + 32-bit radix sort, inside the timed region) and runs the staged kernel,
+ * results in caller order.  All three are bit-identical. */
 int mcw_xs_lookup(mcw_handle h, int64_t n, const double* E, const int32_t* material, double* out);
 int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d_material,
                          void* d_out, int sorted, int repeats, float* ms_per_launch);

@@ -185,9 +185,9 @@ class Context:
         self._ck(self.L.mcw_xs_lookup(self.h, E.size, _p(E), _p(mat), _p(out)))
         return out
 
-    def xs_lookup_device(self, n, d_E, d_mat, d_out, repeats=1):
+    def xs_lookup_device(self, n, d_E, d_mat, d_out, repeats=1, sorted=0):
         ms = C.c_float()
-        self._ck(self.L.mcw_xs_lookup_device(self.h, n, d_E, d_mat, d_out, 0, repeats, C.byref(ms)))
+        self._ck(self.L.mcw_xs_lookup_device(self.h, n, d_E, d_mat, d_out, sorted, repeats, C.byref(ms)))
         return ms.value
 
     def grid_index(self, i_nuc, n_log_bins):

@@ -110,6 +110,8 @@ struct mcw_context
   mcw_source_site *d_source = nullptr, *d_bank = nullptr, *d_sorted = nullptr, *d_sampled = nullptr;
   int32_t *d_q_fly[2] = {nullptr, nullptr}, *d_q_collide = nullptr, *d_q_fallback = nullptr, *d_q_sorted = nullptr;
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
+  int32_t* d_q_hist = nullptr;
+  int64_t xs_sort_min = 32768; // event rounds with fewer collisions refresh cross sections without sorting
   int64_t *d_i64_a = nullptr, *d_i64_b = nullptr;
   void* d_temp = nullptr;
   size_t temp_bytes = 0;
@@ -281,6 +283,8 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->drain_min_queue = std::max(0, value);
   else if (n == "tail_threshold")
     h->tail_threshold = std::max(0, value);
+  else if (n == "xs_sort_min")
+    h->xs_sort_min = std::max(0, value);
   else if (n == "collide_min")
     h->collide_min = std::min(32, std::max(1, value));
   else if (n == "visit_cap")
@@ -395,7 +399,7 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
     const int G = d[i].n_grid;
     N.prm.G = G;
     N.prm.off = off;
-    off += G;
+    off += G + (G & 1); // every nuclide starts at an even grid point: 16-byte aligned windows (mcw_xs.cuh)
     N.prm.fissionable = d[i].fissionable != 0;
     N.prm.awr = d[i].awr;
     N.prm.kT = d[i].kT;
@@ -565,6 +569,13 @@ static int prepare(mcw_handle h)
       el_inel.push_back(n.elastic[k]);
       el_inel.push_back(n.inelastic_full[k]);
     }
+    if (G & 1)
+    {
+      // padding point so the next nuclide's offset is even (never indexed by a lookup)
+      energy.push_back(n.energy.back());
+      xs4.insert(xs4.end(), 4, 0.0);
+      el_inel.insert(el_inel.end(), 2, 0.0);
+    }
     int j = 0;
     const double step = (M * spacing - 0.0) / M;
     for (int k = 0; k <= M; ++k)
@@ -594,6 +605,8 @@ static int prepare(mcw_handle h)
     mat_off.push_back((int32_t)mat_nuc.size());
     mat_fis.push_back(fis);
   }
+  energy.insert(energy.end(), 2, energy.back()); // staged windows are copied in pairs: one pair of slack at the end
+  xs4.insert(xs4.end(), 8, 0.0);
   double *d_energy, *d_xs4, *d_el, *d_dens;
   int32_t *d_gi, *d_moff, *d_mnuc, *d_mfis;
   McwNucParams* d_prm;
@@ -880,6 +893,7 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_q_sorted, n));
   CK(dev_alloc(h, &h->d_keys, n));
   CK(dev_alloc(h, &h->d_keys_out, n));
+  CK(dev_alloc(h, &h->d_q_hist, n));
   CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
   CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
   h->temp_bytes = mcwk_scan_temp_bytes(std::max(h->bank_capacity, n));
@@ -1066,18 +1080,16 @@ int mcw_transport_generation(mcw_handle h, int batch)
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
                   h->d_q_collide, st);
     int32_t* qc = h->d_q_collide;
-    if (h->set.sort_xs_queue)
-    {
-      // particle-queue sort by (material slot, energy bucket): OpenMC's TODO at OMC event.cpp:76-82
-      mcwk_xs_keys(P, qc, &P.counters->n_collide, h->d_keys, upper, st);
-      mcwk_sort_queue(h->d_temp, h->temp_bytes, h->d_keys, h->d_keys_out, qc, h->d_q_sorted, upper, 32, st);
-      qc = h->d_q_sorted;
-      R.n_kernel_launches += 4;
-    }
     mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
+    // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
+    // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
+    // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
+    const bool staged = h->set.sort_xs_queue != 0 && upper >= h->xs_sort_min;
+    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->d_temp, h->temp_bytes, h->d_keys,
+                                           h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 2), st);
-    R.n_kernel_launches += 4; // k_track, k_fallback, k_collide, k_xs_all_slots
+    R.n_kernel_launches += 3; // k_track, k_fallback, k_collide
     ++rounds;
     const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
     if (sync_now)
@@ -1470,16 +1482,42 @@ int mcw_xs_lookup(mcw_handle h, int64_t n, const double* E, const int32_t* mater
 int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d_material, void* d_out, int sorted,
                          int repeats, float* ms_per_launch)
 {
-  (void)sorted;
-  if (!h || !d_E || !d_material || !d_out || n < 0 || repeats < 1)
+  if (!h || !d_E || !d_material || !d_out || n < 0 || repeats < 1 || sorted < 0 || sorted > 2)
     return MCW_E_INVALID_ARGUMENT;
   int rc = prepare(h);
   if (rc)
     return rc;
   CK(cudaSetDevice(h->device));
+  const double* E = (const double*)d_E;
+  const int32_t* mat = (const int32_t*)d_material;
+  uint32_t *keys = nullptr, *keys_out = nullptr;
+  int32_t *idx = nullptr, *idx_sorted = nullptr;
+  unsigned char* temp = nullptr;
+  size_t temp_bytes = 0;
+  if (sorted == 2 && n > 0)
+  {
+    if (n > INT32_MAX)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_xs_lookup_device: at most 2^31-1 points per call");
+    temp_bytes = mcwk_sort_temp_bytes(n);
+    CK(dev_alloc(h, &keys, n));
+    CK(dev_alloc(h, &keys_out, n));
+    CK(dev_alloc(h, &idx, n));
+    CK(dev_alloc(h, &idx_sorted, n));
+    CK(dev_alloc(h, &temp, temp_bytes));
+  }
   CK(cudaEventRecord(h->ev[0], h->stream));
   for (int r = 0; r < repeats; ++r)
-    mcwk_xs_lookup_array(h->P.lib, n, (const double*)d_E, (const int32_t*)d_material, (double*)d_out, h->stream);
+  {
+    if (sorted == 0)
+      mcwk_xs_lookup_array(h->P.lib, n, E, mat, (double*)d_out, h->stream);
+    else if (sorted == 1)
+      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, nullptr, (double*)d_out, h->stream);
+    else
+    {
+      mcwk_xs_sort(n, E, mat, temp, temp_bytes, keys, keys_out, idx, idx_sorted, h->stream);
+      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, idx_sorted, (double*)d_out, h->stream);
+    }
+  }
   CK(cudaEventRecord(h->ev[1], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1487,6 +1525,14 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
   if (ms_per_launch)
     *ms_per_launch = ms / repeats;
+  if (keys)
+  {
+    dev_free(h, keys);
+    dev_free(h, keys_out);
+    dev_free(h, idx);
+    dev_free(h, idx_sorted);
+    dev_free(h, temp);
+  }
   return MCW_OK;
 }
 

@@ -158,25 +158,7 @@ k_xs_lookup_array(McwLibraryDev L, int64_t n, const double* __restrict__ E, cons
   o[1] = make_double2(M.fission, M.nu_fission);
 }
 
-// sort keys for the collision queue: (slot << 16) | energy log-bin, so neighbouring threads of
-// k_collide read neighbouring rows of the same nuclides (OpenMC's TODO at OMC event.cpp:76-82)
-template <int TYPE>
-__global__ void __launch_bounds__(MCW_BLOCK)
-k_xs_keys(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
-          uint32_t* __restrict__ keys, int64_t cap)
-{
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cap)
-    return;
-  if (idx >= (int64_t)*count)
-  {
-    keys[idx] = 0xffffffffu;
-    return;
-  }
-  int i = queue[idx];
-  ElemRec<TYPE> R(P.mesh, P.p.elem[i]);
-  keys[idx] = ((uint32_t)R.slot() << 16) | (uint32_t)mcw_log_bin(P.lib, P.p.E[i]);
-}
+#include "mcw_xs.cuh"
 
 // resets the per-round device counters (one launch instead of three memsets)
 __global__ void k_round_reset(McwCounters* c, int consumed)
@@ -683,14 +665,6 @@ void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, con
   MCW_DISPATCH(P.mesh.type, (k_sample_source<TY><<<grid_for(n), MCW_BLOCK, 0, st>>>(P, out, n, d_box, only_fissionable)));
 }
 
-void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
-                  cudaStream_t st)
-{
-  if (cap <= 0)
-    return;
-  MCW_DISPATCH(P.mesh.type, (k_xs_keys<TY><<<grid_for(cap), MCW_BLOCK, 0, st>>>(P, queue, count, keys, cap)));
-}
-
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st)
 {
@@ -742,7 +716,51 @@ void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long 
     return;
   MCW_DISPATCH(P.mesh.type,
                (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next)));
-  k_xs_all_slots<<<grid_for(upper * P.n_slots), MCW_BLOCK, 0, st>>>(P, queue, count);
+}
+
+// Cross sections of every material slot at the new energy of the survivors of the collision queue.
+// sorted = false: one thread per (history, slot), direct table reads (2 launches fewer).
+// sorted = true : survivors ordered by energy (32-bit radix sort, 27 key bits), then the staged kernel.
+int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
+                    void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+                    cudaStream_t st)
+{
+  if (upper <= 0)
+    return 0;
+  if (!sorted)
+  {
+    k_xs_all_slots<<<grid_for(upper * P.n_slots), MCW_BLOCK, 0, st>>>(P, queue, count);
+    return 1;
+  }
+  k_refresh_keys<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(P, queue, count, upper, keys, hist);
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hist, hist_sorted, upper, 0, 27, st);
+  k_xs_all_slots_staged<<<(unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
+  return 5; // keys, 3 radix-sort kernels (histogram, onesweep x ...), staged lookup: counted as 5
+}
+
+// Stand-alone lookup of (E, material) arrays through the sort + staged kernel; out in caller order.
+void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, size_t temp_bytes, uint32_t* keys,
+                  uint32_t* keys_out, int32_t* idx, int32_t* idx_sorted, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_xs_sort_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, E, mat, keys, idx);
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, idx, idx_sorted, n, 0, 32, st);
+}
+
+void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
+                           double* out, cudaStream_t st)
+{
+  if (n <= 0)
+    return;
+  k_xs_lookup_staged<<<(unsigned)((n + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(L, n, E, mat, order, out);
+}
+
+size_t mcwk_sort_temp_bytes(int64_t n)
+{
+  size_t c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, n);
+  return c + 256;
 }
 
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,

@@ -7,10 +7,16 @@
 void mcwk_init_histories(const McwParams& P, const mcw_source_site* src, int64_t n, int32_t* q_fly, cudaStream_t st);
 void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, const double* d_box, int only_fissionable,
                         cudaStream_t st);
-void mcwk_xs_keys(const McwParams& P, const int32_t* queue, const unsigned long long* count, uint32_t* keys, int64_t cap,
-                  cudaStream_t st);
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st);
+int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
+                    void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+                    cudaStream_t st);
+void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, size_t temp_bytes, uint32_t* keys,
+                  uint32_t* keys_out, int32_t* idx, int32_t* idx_sorted, cudaStream_t st);
+void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
+                           double* out, cudaStream_t st);
+size_t mcwk_sort_temp_bytes(int64_t n);
 int mcwk_track_blocks_per_sm(int type, bool fused);
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,

@@ -43,6 +43,28 @@ def test_xs_lookup_bit_exact(oracle_bridge, ctx_factory, name):
         assert np.array_equal(o.grid_index(i, lib.n_log_bins), g.grid_index(i, lib.n_log_bins))
 
 
+@pytest.mark.parametrize("name,n", [("infinite_medium", 70001), ("pin_cell_tet", 300), ("assembly_quad", 200000)])
+def test_xs_lookup_sorted_staged_bit_exact(oracle_bridge, ctx_factory, name, n):
+    """The sorted, shared-memory-staged lookup (mcw_xs.cuh) against the oracle: library-sorted
+    (mode 2), caller-sorted (mode 1), and mode 1 fed UNSORTED arrays -- staging is an optimisation,
+    never a correctness assumption.  Ragged sizes: partial tiles, tiles that straddle materials."""
+    import torch
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
+    E, mat = problems.lookup_points(lib, n)
+    want = o.xs_lookup(E, mat).view(np.uint64)
+    dE, dm = torch.from_numpy(E).cuda(), torch.from_numpy(mat).cuda()
+    out = torch.zeros(n * 4, dtype=torch.float64, device="cuda")
+    for mode in (0, 2, 1):
+        out.zero_()
+        g.xs_lookup_device(n, dE.data_ptr(), dm.data_ptr(), out.data_ptr(), 1, mode)
+        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 4), want), mode
+    order = np.lexsort((E, mat))
+    dE, dm = torch.from_numpy(E[order].copy()).cuda(), torch.from_numpy(mat[order].copy()).cuda()
+    out.zero_()
+    g.xs_lookup_device(n, dE.data_ptr(), dm.data_ptr(), out.data_ptr(), 1, 1)
+    assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 4), want[order])
+
+
 @pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "pin_cell_hex", "assembly_quad"])
 def test_locate_and_source_bit_exact(oracle_bridge, ctx_factory, name):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
@@ -87,11 +109,26 @@ def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, 
         assert abs(d1.sum() - gold["total_distance"]) <= 1e-8 * gold["total_distance"]
 
 
-@pytest.mark.parametrize("name,kw", [("infinite_medium", {}), ("pin_cell_tet", {}), ("pin_cell_hex", {}),
-                                      ("assembly_quad", {}), ("pin_cell_tet", {"seed_through_double": False}),
-                                      ("infinite_medium", {"sort_xs_queue": 1})])
-def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw):
+# Event-loop regimes (mcw_set_option): EVENT = one round per collision throughout (tail_threshold 0),
+# FUSED = every history keeps its lane through its collisions (the default for these small banks),
+# MIXED = event rounds until fewer than 700 histories fly, then fused; SORTED = event rounds whose
+# cross-section refresh goes through the energy sort + staged kernel.
+EVENT = {"tail_threshold": 0}
+FUSED = {"tail_threshold": 1 << 30}
+MIXED = {"tail_threshold": 700, "collide_min": 3}
+SORTED = {"tail_threshold": 300, "xs_sort_min": 0}
+
+
+@pytest.mark.parametrize("name,kw,opts", [
+    ("infinite_medium", {}, EVENT), ("infinite_medium", {}, FUSED), ("infinite_medium", {"sort_xs_queue": 1}, SORTED),
+    ("pin_cell_tet", {}, EVENT), ("pin_cell_tet", {}, MIXED), ("pin_cell_tet", {"sort_xs_queue": 1}, SORTED),
+    ("pin_cell_hex", {}, EVENT), ("pin_cell_hex", {}, FUSED),
+    ("assembly_quad", {}, MIXED), ("assembly_quad", {"sort_xs_queue": 1}, SORTED),
+    ("pin_cell_tet", {"seed_through_double": False}, MIXED)])
+def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
+    for k, v in opts.items():
+        g.set_option(k, v)
     o.sample_initial_source()
     g.sample_initial_source()
     for batch in range(1, 4):
