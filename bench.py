@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its version / INFO lines to stdout when NCCL_DEBUG is set; stdout carries the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 SEGMENT_BYTES = {"tet4": 308.0, "hex8": 412.0, "quad4": 280.0}  # SURVEY.md 8(d) / BASELINE.md section 2
 
