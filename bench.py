@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--sync-every", type=int, default=4)
     ap.add_argument("--tail-threshold", type=int, default=-1, help="histories in flight below which tracking runs fused")
     ap.add_argument("--collide-min", type=int, default=-1, help="fused tracking: parked collisions per warp before they are processed")
+    ap.add_argument("--opt", action="append", default=[], help="mcw_set_option name=value (tuning knobs; results unchanged)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-xs-leg", action="store_true")
     args = ap.parse_args()
@@ -293,6 +294,9 @@ def main():
     ctx = study.ctx
     ctx.set_option("sync_every", args.sync_every)
     ctx.set_option("profile", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     if args.collide_min >= 0:
         ctx.set_option("collide_min", args.collide_min)
     if args.tail_threshold >= 0:

@@ -136,6 +136,7 @@ struct mcw_context
   // below this many histories in flight the tracking kernel runs fused (collisions inline, no
   // round per collision): rounds would last as long as the slowest flight with most lanes idle
   int64_t tail_threshold = 65536;
+  int ordered_queues = 1; // rebuild the collide / fly queues in history-index order every round
   int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
@@ -283,6 +284,8 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->drain_min_queue = std::max(0, value);
   else if (n == "tail_threshold")
     h->tail_threshold = std::max(0, value);
+  else if (n == "ordered_queues")
+    h->ordered_queues = value != 0;
   else if (n == "xs_sort_min")
     h->xs_sort_min = std::max(0, value);
   else if (n == "collide_min")
@@ -896,7 +899,7 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_q_hist, n));
   CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
   CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
-  h->temp_bytes = mcwk_scan_temp_bytes(std::max(h->bank_capacity, n));
+  h->temp_bytes = std::max(mcwk_scan_temp_bytes(std::max(h->bank_capacity, n)), mcwk_compact_temp_bytes(n));
   {
     unsigned char* tmp;
     CK(dev_alloc(h, &tmp, h->temp_bytes));
@@ -1042,6 +1045,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
   P.batch = batch;
   P.keff = h->keff;
   P.tallies_active = batch > h->set.n_inactive; // OMC simulation.cpp:318-326
+  P.ordered_queues = h->ordered_queues;
   mcw_generation_result& R = h->last;
   memset(&R, 0, sizeof(R));
   CK(cudaEventRecord(h->ev[0], st));
@@ -1080,6 +1084,11 @@ int mcw_transport_generation(mcw_handle h, int batch)
     mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
                   h->d_q_collide, st);
     int32_t* qc = h->d_q_collide;
+    if (P.ordered_queues)
+    {
+      mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_COLLIDE, qc, &P.counters->n_collide, st);
+      R.n_kernel_launches += 2;
+    }
     mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
     // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
@@ -1087,6 +1096,11 @@ int mcw_transport_generation(mcw_handle h, int batch)
     const bool staged = h->set.sort_xs_queue != 0 && upper >= h->xs_sort_min;
     R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->d_temp, h->temp_bytes, h->d_keys,
                                            h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
+    if (P.ordered_queues)
+    {
+      mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_FLY, h->d_q_fly[cur ^ 1], cnt_next, st);
+      R.n_kernel_launches += 2;
+    }
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 2), st);
     R.n_kernel_launches += 3; // k_track, k_fallback, k_collide

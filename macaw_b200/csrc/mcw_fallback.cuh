@@ -581,9 +581,12 @@ k_fallback(McwParams P, const int32_t* __restrict__ queue, const unsigned long l
     atomicAdd(&P.counters->n_vertex_edge, n_ve);
   if (n_moved)
     atomicAdd(&P.counters->n_moved, n_moved);
-  if (status == MCW_ST_FLY)
-    q_fly_next[atomicAdd(cnt_next, 1ull)] = i;
-  if (status == MCW_ST_COLLIDE)
-    q_collide[atomicAdd(&P.counters->n_collide, 1ull)] = i;
+  if (!P.ordered_queues)
+  {
+    if (status == MCW_ST_FLY)
+      q_fly_next[atomicAdd(cnt_next, 1ull)] = i;
+    if (status == MCW_ST_COLLIDE)
+      q_collide[atomicAdd(&P.counters->n_collide, 1ull)] = i;
+  }
   }
 }

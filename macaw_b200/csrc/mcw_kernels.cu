@@ -417,6 +417,8 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
   const int i = active ? queue[idx] : -1;
   const bool valid = active && P.p.status[i] == MCW_ST_COLLIDE;
   const bool survived = mcw_collide_history<TYPE, false>(P, i, valid);
+  if (P.ordered_queues)
+    return;
   unsigned long long k = mcw_warp_append(cnt_next, survived);
   if (survived)
     q_fly_next[k] = i;
@@ -754,6 +756,29 @@ void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, c
   if (n <= 0)
     return;
   k_xs_lookup_staged<<<(unsigned)((n + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(L, n, E, mat, order, out);
+}
+
+// queue = the histories whose status equals `want`, in history-index order; *count = how many
+struct McwStatusIs
+{
+  int8_t want;
+  __host__ __device__ bool operator()(int8_t s) const { return s == want; }
+};
+void mcwk_compact_status(void* temp, size_t temp_bytes, const int8_t* status, int64_t n, int want, int32_t* queue,
+                         unsigned long long* count, cudaStream_t st)
+{
+  cub::CountingInputIterator<int32_t> ids(0);
+  cub::TransformInputIterator<bool, McwStatusIs, const int8_t*> flags(status, McwStatusIs{(int8_t)want});
+  cub::DeviceSelect::Flagged(temp, temp_bytes, ids, flags, queue, count, (int)n, st);
+}
+
+size_t mcwk_compact_temp_bytes(int64_t n)
+{
+  size_t c = 0;
+  cub::CountingInputIterator<int32_t> ids(0);
+  cub::TransformInputIterator<bool, McwStatusIs, const int8_t*> flags(nullptr, McwStatusIs{0});
+  cub::DeviceSelect::Flagged(nullptr, c, ids, flags, (int32_t*)nullptr, (unsigned long long*)nullptr, (int)n);
+  return c + 256;
 }
 
 size_t mcwk_sort_temp_bytes(int64_t n)

@@ -17,6 +17,9 @@ void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, si
 void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
                            double* out, cudaStream_t st);
 size_t mcwk_sort_temp_bytes(int64_t n);
+void mcwk_compact_status(void* temp, size_t temp_bytes, const int8_t* status, int64_t n, int want, int32_t* queue,
+                         unsigned long long* count, cudaStream_t st);
+size_t mcwk_compact_temp_bytes(int64_t n);
 int mcwk_track_blocks_per_sm(int type, bool fused);
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,

@@ -640,10 +640,13 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
         if (fate >= 0)
           p.fate[i] = (int8_t)fate;
         if (requeue)
-          q_fly_next[mcw_warp_append(cnt_next, true)] = i;
+        {
+          if (!P.ordered_queues)
+            q_fly_next[mcw_warp_append(cnt_next, true)] = i;
+        }
         else if (status == MCW_ST_COLLIDE)
         {
-          if (!FUSED)
+          if (!FUSED && !P.ordered_queues)
             q_collide[mcw_warp_append(&P.counters->n_collide, true)] = i;
         }
         else if (status == MCW_ST_FALLBACK)

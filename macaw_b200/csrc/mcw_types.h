@@ -141,6 +141,9 @@ struct McwParams
   McwTallyDev tally[MCW_MAX_TALLIES];
   int32_t n_tallies, tallies_active;
   int32_t any_tracklength, any_collision_tally;
+  // 1: the collide / fly queues are rebuilt every round by compacting the status array (history-index
+  // order, so neighbouring threads touch neighbouring state); kernels then skip their queue appends
+  int32_t ordered_queues;
   mcw_source_site* bank;
   int64_t bank_capacity;
   McwCounters* counters;
