@@ -258,7 +258,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pin_cell_tet")
     ap.add_argument("--particles", type=int, default=1_000_000, help="histories per GPU per batch")
-    ap.add_argument("--sort-xs", type=int, default=0)
+    ap.add_argument("--sort-xs", type=int, default=-1,
+                    help="energy-sorted staged cross-section refresh: 1 on, 0 off, -1 when the materials hold > 16 nuclides")
     ap.add_argument("--sync-every", type=int, default=4)
     ap.add_argument("--tail-threshold", type=int, default=-1, help="histories in flight below which tracking runs fused")
     ap.add_argument("--collide-min", type=int, default=-1, help="fused tracking: parked collisions per warp before they are processed")
@@ -287,6 +288,8 @@ def main():
     n_total = args.particles * world
     problem = build_problem(args.workload, n_total, args.warmup)
     mesh, lib, blocks, mats, s, et = problem
+    if args.sort_xs < 0:
+        args.sort_xs = int(sum(len(lib.materials[m - 1].nuclides) for m in mats) > 16)
     s.sort_xs_queue = args.sort_xs
     kernel = st.CollisionKernel(blocks=blocks, materials=mats, temperature=293.6, z_coord=100.0 if mesh.dim == 2 else None)
     tally = st.OpenMCTally(id=1, scores=["flux"], filters=["cell"], estimator="COLLISION")

@@ -136,6 +136,7 @@ struct mcw_context
   // below this many histories in flight the tracking kernel runs fused (collisions inline, no
   // round per collision): rounds would last as long as the slowest flight with most lanes idle
   int64_t tail_threshold = 65536;
+  int xs_plan = 1; // sorted refresh: stage all (slot, nuclide) windows of a tile at once (k_xs_all_slots_plan)
   int ordered_queues = 1; // rebuild the collide / fly queues in history-index order every round
   int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
   mcw_generation_result last{};
@@ -284,6 +285,8 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->drain_min_queue = std::max(0, value);
   else if (n == "tail_threshold")
     h->tail_threshold = std::max(0, value);
+  else if (n == "xs_plan")
+    h->xs_plan = value != 0;
   else if (n == "ordered_queues")
     h->ordered_queues = value != 0;
   else if (n == "xs_sort_min")
@@ -680,6 +683,32 @@ static int prepare(mcw_handle h)
         slot_of[m] = ns++;
       }
     P.n_slots = ns;
+    std::vector<int32_t> pl_nuc, pl_slot;
+    std::vector<double> pl_dens, pl_e0, pl_e1;
+    bool every_slot = true;
+    for (int sl = 0; sl < ns; ++sl)
+    {
+      const int m = P.slot_mat[sl];
+      every_slot &= !h->mat_nuc[m].empty();
+      for (size_t q = 0; q < h->mat_nuc[m].size(); ++q)
+      {
+        const HostNuclide& N = h->nuclides[h->mat_nuc[m][q]];
+        pl_nuc.push_back(h->mat_nuc[m][q]);
+        pl_slot.push_back(sl);
+        pl_dens.push_back(h->mat_dens[m][q]);
+        pl_e0.push_back(N.energy.front());
+        pl_e1.push_back(N.energy.back());
+      }
+    }
+    P.n_plan = every_slot ? (int32_t)pl_nuc.size() : 0;
+    int32_t *d_pn, *d_ps;
+    double *d_pd, *d_p0, *d_p1;
+    CK(dev_upload(h, &d_pn, pl_nuc));
+    CK(dev_upload(h, &d_ps, pl_slot));
+    CK(dev_upload(h, &d_pd, pl_dens));
+    CK(dev_upload(h, &d_p0, pl_e0));
+    CK(dev_upload(h, &d_p1, pl_e1));
+    P.plan_nuc = d_pn, P.plan_slot = d_ps, P.plan_dens = d_pd, P.plan_e0 = d_p0, P.plan_e1 = d_p1;
   }
   std::vector<unsigned char> rec((size_t)h->n_elem * t.stride, 0);
   for (int64_t e = 0; e < h->n_elem; ++e)
@@ -1094,7 +1123,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
     const bool staged = h->set.sort_xs_queue != 0 && upper >= h->xs_sort_min;
-    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->d_temp, h->temp_bytes, h->d_keys,
+    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,
                                            h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
     if (P.ordered_queues)
     {

@@ -406,8 +406,11 @@ k_xs_all_slots(McwParams P, const int32_t* __restrict__ queue, const unsigned lo
   o[1] = make_double2(M.fission, M.nu_fission);
 }
 
+#ifndef MCW_COLLIDE_MIN_BLOCKS
+#define MCW_COLLIDE_MIN_BLOCKS 8 // 64 registers: the kernel waits on scattered loads, twice the warps beat the spills (A/B r01f)
+#endif
 template <int TYPE>
-__global__ void __launch_bounds__(MCW_BLOCK)
+__global__ void __launch_bounds__(MCW_BLOCK, MCW_COLLIDE_MIN_BLOCKS)
 k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
           int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next)
 {
@@ -724,7 +727,7 @@ void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long 
 // sorted = false: one thread per (history, slot), direct table reads (2 launches fewer).
 // sorted = true : survivors ordered by energy (32-bit radix sort, 27 key bits), then the staged kernel.
 int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
-                    void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+                    bool plan, void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
                     cudaStream_t st)
 {
   if (upper <= 0)
@@ -736,7 +739,11 @@ int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned lon
   }
   k_refresh_keys<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(P, queue, count, upper, keys, hist);
   cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hist, hist_sorted, upper, 0, 27, st);
-  k_xs_all_slots_staged<<<(unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
+  const unsigned tiles = (unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE);
+  if (plan && P.n_plan > 0)
+    k_xs_all_slots_plan<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
+  else
+    k_xs_all_slots_staged<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
   return 5; // keys, 3 radix-sort kernels (histogram, onesweep x ...), staged lookup: counted as 5
 }
 

@@ -10,7 +10,7 @@ void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, con
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st);
 int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
-                    void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+                    bool plan, void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
                     cudaStream_t st);
 void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, size_t temp_bytes, uint32_t* keys,
                   uint32_t* keys_out, int32_t* idx, int32_t* idx_sorted, cudaStream_t st);

@@ -155,5 +155,13 @@ struct McwParams
   int32_t record_traces; // keep the per-history crossing hash (parity output)
   int32_t pad0;
   int32_t slot_mat[MCW_MAX_XS_SLOTS]; // slot -> material index
+  // refresh plan: the (slot, nuclide) pairs of all slots, material order inside a slot (mcw_xs.cuh);
+  // n_plan = 0 when some slot's material has no nuclide (then the per-slot kernels are used)
+  const int32_t* plan_nuc;
+  const int32_t* plan_slot;
+  const double* plan_dens;
+  const double* plan_e0; // first / last grid energy of the entry's nuclide
+  const double* plan_e1;
+  int32_t n_plan, pad1;
   double z_coord, keff;
 };

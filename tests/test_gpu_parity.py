@@ -117,6 +117,7 @@ EVENT = {"tail_threshold": 0}
 FUSED = {"tail_threshold": 1 << 30}
 MIXED = {"tail_threshold": 700, "collide_min": 3}
 SORTED = {"tail_threshold": 300, "xs_sort_min": 0}
+SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 0, "xs_plan": 0}  # k_xs_all_slots_staged instead of _plan
 
 
 @pytest.mark.parametrize("name,kw,opts", [
@@ -124,6 +125,7 @@ SORTED = {"tail_threshold": 300, "xs_sort_min": 0}
     ("pin_cell_tet", {}, EVENT), ("pin_cell_tet", {}, MIXED), ("pin_cell_tet", {"sort_xs_queue": 1}, SORTED),
     ("pin_cell_hex", {}, EVENT), ("pin_cell_hex", {}, FUSED),
     ("assembly_quad", {}, MIXED), ("assembly_quad", {"sort_xs_queue": 1}, SORTED),
+    ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 0, "ordered_queues": 0}),
     ("pin_cell_tet", {"seed_through_double": False}, MIXED)])
 def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
