@@ -178,3 +178,61 @@ def test_error_paths(ctx_factory):
     c.set_mesh(mesh)
     with pytest.raises(McwError):
         c.set_library(lib, [0, 7])  # block mapped to an unknown material (MC CollisionKernel.C:84-90)
+
+
+def test_full_size_properties_pin_cell_1m():
+    """BASELINE.json configs[1] at bench size (101 400 TET4, 10^6 histories, 9 nuclides x 10 000
+    points): too big for the scalar oracle in a test, so size-independent properties of the path:
+    counter checksums, a checksum of checksums for the collision tally (sum of the `total` score =
+    number of collisions, because every history has weight 1), bank order, progeny bookkeeping,
+    exact bank resampling, agreement of the three k estimators, and run-to-run determinism of every
+    per-history quantity across event-loop regimes."""
+    from macaw_b200 import meshgen, nucdata
+    from macaw_b200.context import Context
+    mesh = meshgen.pin_cell_tet(26, 25)
+    lib = nucdata.make_library(9, G=10000, seed=1)
+    h = meshgen.PIN_PITCH / 2
+    n = 1_000_000
+
+    def run(opts, sort_xs=0):
+        s = cstructs.make_settings(n, n_inactive=1, source_box=(-h, -h, -h, h, h, h), record_traces=1, sort_xs_queue=sort_xs)
+        c = Context(0)
+        c.set_mesh(mesh)
+        c.set_library(lib, [0, 1, 2, 3], [0, 1, 2, 3])
+        c.set_settings(s)
+        c.add_tally(1, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["cell"], [0, 1], None)
+        for k, v in opts.items():
+            c.set_option(k, v)
+        c.sample_initial_source()
+        r1 = c.run_generation(1)
+        r2 = c.run_generation(2)
+        rec, bank, src = c.history_records(), c.fission_bank(), c.source_bank()
+        t, _, nr = c.get_tally(1)
+        c.close()
+        return r1, r2, rec, bank, src, t, nr
+
+    r1, r2, rec, bank, src, t, nr = run({})
+    assert r2.n_histories == n and rec.size == n and src.size == n
+    assert int(rec["n_segments"].sum()) == r2.n_segments and int(rec["n_collisions"].sum()) == r2.n_collisions
+    assert r2.n_segments > 1000 * n and r2.n_collisions > 10 * n  # fine mesh: segment dominated
+    assert set(np.unique(rec["fate"]).tolist()) <= {0, 2}  # reflective box: absorbed, or a counted failed trace
+    assert int((rec["fate"] == 2).sum()) == r2.n_failed_traces <= 2
+    # fission bank: sorted by (parent, progeny), progeny ids 0..n_progeny-1 of each parent (OMC bank.cpp:60-104)
+    key = bank["parent_id"].astype(np.int64) * 64 + bank["progeny_id"]
+    assert np.all(np.diff(key) > 0) and bank["progeny_id"].max() < 64
+    per_parent = np.bincount(bank["parent_id"] - 1, minlength=n)
+    assert np.array_equal(per_parent, rec["n_progeny"]) and bank.size == r2.n_bank_sites
+    # sites are born where fission happened: fuel elements only, inside the pin
+    assert np.all(mesh.block_id[src["elem"]] == 0) and np.all(np.hypot(src["r"][:, 0], src["r"][:, 1]) < meshgen.PIN_RADII[0] + 0.05)
+    # the three estimators of one generation agree statistically (sigma ~ 1e-3 at 1e6 histories)
+    assert abs(r2.k_collision - r2.k_tracklength) < 5e-3 and abs(r2.k_absorption - r2.k_tracklength) < 5e-3
+    assert abs(r2.k_generation - bank.size / n * r1.k_generation) < 5e-3 * r2.k_generation  # sites banked with 1/k weighting
+    # checksum of checksums: batch 2 is the only active batch; total score = sig_t * wgt / sig_t per collision
+    assert nr == 1 and t.shape == (mesh.n_elem, 1, 2)
+    # (Tally::accumulate normalises by the number of source particles, OMC tally.cpp:650-660)
+    assert abs(t[:, 0, 1].sum() * n - r2.n_collisions) <= 1e-9 * r2.n_collisions
+    assert np.all(t >= 0) and t[:, 0, 0].sum() > 0
+    # the same run through event rounds only, unordered queues, sorted refresh: every per-history result identical
+    r1b, r2b, recb, bankb, srcb, tb, _ = run({"tail_threshold": 0, "ordered_queues": 0, "xs_sort_min": 0}, sort_xs=1)
+    assert recb.tobytes() == rec.tobytes() and bankb.tobytes() == bank.tobytes() and srcb.tobytes() == src.tobytes()
+    assert np.allclose(tb, t, rtol=1e-11, atol=1e-300) and r2b.k_generation == pytest.approx(r2.k_generation, rel=1e-12)
