@@ -24,9 +24,14 @@
 #pragma once
 #include "mcw_physics.cuh"
 
+#ifndef MCW_TRACK_BLOCK
 #define MCW_TRACK_BLOCK 128
+#endif
 #ifndef MCW_TRACK_MIN_BLOCKS
 #define MCW_TRACK_MIN_BLOCKS 4 // register budget 128 per thread -> 16 warps per SM
+#endif
+#ifndef MCW_FUSED_MIN_BLOCKS
+#define MCW_FUSED_MIN_BLOCKS 2 // fused (tail) instantiation: 204 registers, 8 warps per SM
 #endif
 #ifndef MCW_TRK_PIPELINE
 #define MCW_TRK_PIPELINE 0 // 1: the next element record is requested as soon as the exit side is known
@@ -34,8 +39,12 @@
 #ifndef MCW_TRK_HOIST_LOG
 #define MCW_TRK_HOIST_LOG 1 // 1: the segment's random number and logarithm are computed ahead of the geometry
 #endif
+#ifndef MCW_REFILL_MIN
 #define MCW_REFILL_MIN 4
+#endif
+#ifndef MCW_REFLECT_MIN
 #define MCW_REFLECT_MIN 4
+#endif
 #define MCW_DRAIN_MIN_VISIT 32 // a straggler is only handed on after this many segments of progress
 #define MCW_FULL 0xffffffffu
 
@@ -382,7 +391,7 @@ enum
 // lane keeps its history through its collisions (mcw_collide_history, batched per warp) until it
 // dies.  Only the rare vertex / edge steps still leave through the fallback queue.
 template <int TYPE, bool FUSED>
-__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 || FUSED ? 2 : MCW_TRACK_MIN_BLOCKS))
+__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 ? 2 : (FUSED ? MCW_FUSED_MIN_BLOCKS : MCW_TRACK_MIN_BLOCKS)))
 k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
         unsigned long long* __restrict__ head, int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next,
         int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback, int drain_lanes, int collide_min)
