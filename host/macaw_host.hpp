@@ -63,6 +63,7 @@ struct Material
 {
   std::vector<int32_t> nuclide;
   std::vector<double> atom_density;
+  std::vector<int32_t> isotropic; // <isotropic> list of materials.xml as per-nuclide flags; empty = none
 };
 struct Library
 {
@@ -89,7 +90,8 @@ struct Library
   {
     std::vector<mcw_material_desc> out;
     for (const auto& m : materials)
-      out.push_back({(int32_t)m.nuclide.size(), 0, m.nuclide.data(), m.atom_density.data()});
+      out.push_back({(int32_t)m.nuclide.size(), 0, m.nuclide.data(), m.atom_density.data(),
+                     m.isotropic.size() == m.nuclide.size() ? m.isotropic.data() : nullptr});
     return out;
   }
 };

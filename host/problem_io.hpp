@@ -113,7 +113,7 @@ public:
     for (int k = 0; k < counts[1]; ++k)
     {
       const std::string p = "mat" + std::to_string(k) + ".";
-      P.library.materials.push_back({i32(p + "nuclide"), f64(p + "density")});
+      P.library.materials.push_back({i32(p + "nuclide"), f64(p + "density"), has(p + "isotropic") ? i32(p + "isotropic") : std::vector<int32_t>()});
     }
     for (int32_t b : i32("kernel.blocks"))
       P.blocks.push_back((unsigned)b);

@@ -106,13 +106,18 @@ typedef struct mcw_nuclide_desc
   double q_fission;                             /* fission Q value, eV (kappa-fission score) */
 } mcw_nuclide_desc;
 
-/* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm). */
+/* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab
+ * (may be NULL) flags the nuclides of the material's <isotropic> list: after a scatter off such a
+ * nuclide the outgoing direction is resampled isotropically in the laboratory frame
+ * [OMC material.cpp:255-270 p0_, physics.cpp:706-718]; MaCaw's own study test uses it for every
+ * nuclide (test/tests/study/materials.xml). */
 typedef struct mcw_material_desc
 {
   int32_t n_nuclides;
   int32_t reserved0;
-  const int32_t* nuclide;      /* indices into the library */
-  const double* atom_density;  /* [n_nuclides] */
+  const int32_t* nuclide;          /* indices into the library */
+  const double* atom_density;      /* [n_nuclides] */
+  const int32_t* isotropic_in_lab; /* [n_nuclides] 0 / 1, or NULL */
 } mcw_material_desc;
 
 /* Run settings: the subset of openmc::settings MaCaw reads (OMC settings.cpp:41-116) plus the

@@ -96,6 +96,7 @@ struct mcw_context
   std::vector<HostNuclide> nuclides;
   std::vector<std::vector<int32_t>> mat_nuc;
   std::vector<std::vector<double>> mat_dens;
+  std::vector<std::vector<int32_t>> mat_iso;
   std::vector<int32_t> block_ids, block_material;
   std::vector<double> temperature;
   std::vector<HostTally> tallies;
@@ -452,12 +453,17 @@ int mcw_set_materials(mcw_handle h, const mcw_material_desc* m, int n, const int
     return MCW_E_INVALID_ARGUMENT;
   h->mat_nuc.clear();
   h->mat_dens.clear();
+  h->mat_iso.clear();
   for (int i = 0; i < n; ++i)
   {
     if (m[i].n_nuclides <= 0 || m[i].n_nuclides > MCW_MAX_NUC_PER_MAT)
       return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_materials: bad nuclide count");
     h->mat_nuc.emplace_back(m[i].nuclide, m[i].nuclide + m[i].n_nuclides);
     h->mat_dens.emplace_back(m[i].atom_density, m[i].atom_density + m[i].n_nuclides);
+    if (m[i].isotropic_in_lab)
+      h->mat_iso.emplace_back(m[i].isotropic_in_lab, m[i].isotropic_in_lab + m[i].n_nuclides);
+    else
+      h->mat_iso.emplace_back((size_t)m[i].n_nuclides, 0);
   }
   h->block_ids.assign(block_ids, block_ids + n_blocks);
   h->block_material.assign(block_material, block_material + n_blocks);
@@ -597,7 +603,7 @@ static int prepare(mcw_handle h)
     }
     prm.push_back(n.prm);
   }
-  std::vector<int32_t> mat_off(1, 0), mat_nuc, mat_fis;
+  std::vector<int32_t> mat_off(1, 0), mat_nuc, mat_fis, mat_iso;
   std::vector<double> mat_dens;
   for (int m = 0; m < n_mat; ++m)
   {
@@ -606,6 +612,7 @@ static int prepare(mcw_handle h)
     {
       mat_nuc.push_back(h->mat_nuc[m][i]);
       mat_dens.push_back(h->mat_dens[m][i]);
+      mat_iso.push_back(h->mat_iso[m][i] != 0);
       fis |= h->nuclides[h->mat_nuc[m][i]].prm.fissionable != 0;
     }
     mat_off.push_back((int32_t)mat_nuc.size());
@@ -624,6 +631,9 @@ static int prepare(mcw_handle h)
   CK(dev_upload(h, &d_moff, mat_off));
   CK(dev_upload(h, &d_mnuc, mat_nuc));
   CK(dev_upload(h, &d_dens, mat_dens));
+  int32_t* d_miso;
+  CK(dev_upload(h, &d_miso, mat_iso));
+  P.lib.mat_iso = d_miso;
   CK(dev_upload(h, &d_mfis, mat_fis));
   P.lib.energy = d_energy;
   P.lib.xs4 = d_xs4;

@@ -184,7 +184,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
 
   ColState c;
   double sig_t = 1, sig_a = 0, sig_f = 0, sig_nf = 0, E_last = 0, wgt_last = 0, kappa = 0.0;
-  int i_mat = 0, elem = 0, block = 0, k_nuc = 0, nu = 0;
+  int i_mat = 0, elem = 0, block = 0, k_nuc = 0, q_nuc = 0, nu = 0;
   Micro mx;
   mx.total = mx.absorption = mx.fission = mx.nu_fission = mx.f = 0;
   mx.i_grid = 0;
@@ -230,6 +230,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     const int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
     bool found = false;
     k_nuc = L.mat_nuc[e - 1];
+    q_nuc = e - 1;
     for (int q = b; q < e; ++q)
     {
       const int in = L.mat_nuc[q];
@@ -245,6 +246,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
         {
           found = true;
           k_nuc = in;
+          q_nuc = q;
           mx = m;
         }
       }
@@ -324,6 +326,8 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       mcw_elastic_scatter(nuc, c);
     else
       mcw_inelastic_scatter(nuc, c);
+    if (L.mat_iso[q_nuc]) // isotropic-in-lab override (OMC physics.cpp:706-718): phi, then mu
+      c.u = mcw_isotropic_direction(c.seed);
     if (c.E != E_last) // OMC physics.cpp:140-144
       seed_urr = mcw_future_seed((uint64_t)L.n_nuc, seed_urr);
   }

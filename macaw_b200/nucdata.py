@@ -46,6 +46,7 @@ class Material:
     name: str
     nuclides: list   # indices into the library
     densities: list  # atom / b-cm
+    isotropic: list = None  # per-nuclide isotropic-in-lab flags (<isotropic> of materials.xml), None = none
 
 
 @dataclass
@@ -211,7 +212,7 @@ class NuclideDesc(C.Structure):
 
 class MaterialDesc(C.Structure):
     _fields_ = [("n_nuclides", C.c_int32), ("reserved0", C.c_int32), ("nuclide", C.c_void_p),
-                ("atom_density", C.c_void_p)]
+                ("atom_density", C.c_void_p), ("isotropic_in_lab", C.c_void_p)]
 
 
 def pack_library(lib: Library):
@@ -242,4 +243,9 @@ def pack_library(lib: Library):
         den = np.ascontiguousarray(m.densities, np.float64)
         keep += [idx, den]
         d.n_nuclides, d.nuclide, d.atom_density = idx.size, idx.ctypes.data, den.ctypes.data
+        if getattr(m, "isotropic", None) is not None:
+            iso = np.ascontiguousarray(m.isotropic, np.int32)
+            assert iso.size == idx.size
+            keep.append(iso)
+            d.isotropic_in_lab = iso.ctypes.data
     return nd, md, keep

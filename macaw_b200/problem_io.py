@@ -40,6 +40,8 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
     for k, m in enumerate(lib.materials):
         r[f"mat{k}.nuclide"] = np.ascontiguousarray(m.nuclides, np.int32)
         r[f"mat{k}.density"] = np.ascontiguousarray(m.densities, np.float64)
+        iso = getattr(m, "isotropic", None)
+        r[f"mat{k}.isotropic"] = np.ascontiguousarray(iso if iso is not None else np.zeros(len(m.nuclides)), np.int32)
     r["kernel.blocks"] = np.ascontiguousarray(blocks, np.int32)
     r["kernel.materials"] = np.ascontiguousarray(materials, np.int32)  # OpenMC material ids, 1-based
     r["kernel.temperature"] = np.atleast_1d(np.asarray(temperature, np.float64))

@@ -206,6 +206,7 @@ struct Material
 {
   std::vector<int> nuc;
   std::vector<double> dens;
+  std::vector<int> iso; // isotropic-in-lab flags (OMC material.cpp:255-270 p0_)
   bool fissionable = false;
 };
 

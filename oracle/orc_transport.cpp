@@ -364,6 +364,9 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
       elastic_scatter(nuc, nuc.kT, p);
     else
       inelastic_scatter(nuc, p);
+    // isotropic-in-lab override for nuclides of the material's <isotropic> list (OMC physics.cpp:706-718)
+    if (!mat.iso.empty() && mat.iso[k])
+      p.u = isotropic_direction(&p.seeds[0]);
   }
   // URR stream advance when the energy changed (OMC physics.cpp:140-144)
   if (p.E != E_last)
@@ -676,6 +679,8 @@ int orc_set_materials(void* h, const mcw_material_desc* m, int n, const int32_t*
     Material M;
     M.nuc.assign(m[i].nuclide, m[i].nuclide + m[i].n_nuclides);
     M.dens.assign(m[i].atom_density, m[i].atom_density + m[i].n_nuclides);
+    if (m[i].isotropic_in_lab)
+      M.iso.assign(m[i].isotropic_in_lab, m[i].isotropic_in_lab + m[i].n_nuclides);
     P.lib.materials.push_back(std::move(M));
   }
   P.block_material.assign(block_material, block_material + n_blocks);

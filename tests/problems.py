@@ -58,7 +58,24 @@ def assembly_quad(n_particles=2000, G=400, n_pins=3, cells_per_pin=7, n_inactive
     return mesh, lib, [0, 1, 2, 3], s
 
 
-PROBLEMS = {"infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,
+def infinite_medium_iso(**kw):
+    """Every nuclide isotropic-in-lab, as in the reference's own study test (test/tests/study/materials.xml)."""
+    mesh, lib, bm, s = infinite_medium(**kw)
+    for m in lib.materials:
+        m.isotropic = [1] * len(m.nuclides)
+    return mesh, lib, bm, s
+
+
+def pin_cell_tet_iso(**kw):
+    """Fuel and water nuclides isotropic-in-lab, gap and clad not (mixed flags)."""
+    mesh, lib, bm, s = pin_cell_tet(**kw)
+    for k, m in enumerate(lib.materials):
+        m.isotropic = [1 if (k in (0, 3) and j % 2 == 0) else 0 for j in range(len(m.nuclides))]
+    return mesh, lib, bm, s
+
+
+PROBLEMS = {"infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
+            "infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,
             "assembly_quad": assembly_quad}
 
 

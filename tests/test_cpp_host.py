@@ -56,7 +56,7 @@ def test_cpp_host_builds_and_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad"])
+@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad", "pin_cell_tet_iso"])
 def test_cpp_host_matches_oracle(oracle_bridge, tmp_path, name):
     exe = _build()
     path, (mesh, lib, bm, s) = _write(tmp_path, name, n_particles=3000)

@@ -213,3 +213,35 @@ def test_gold_ray_file_rng_facts(oracle_bridge, golden_dir):
     on_face = (np.isclose(np.abs(ends[:, 0]) % 2, 1, atol=1e-9) | np.isclose(np.abs(ends[:, 1]) % 2, 1, atol=1e-9)
                | np.isclose(np.abs(ends[:, 2]), 5, atol=1e-9))
     assert on_face.all()
+
+
+def test_isotropic_in_lab_direction_and_budget(oracle_bridge):
+    """OMC physics.cpp:706-718 + distribution_multi.cpp:73-79: a scatter off an <isotropic> nuclide draws
+    two numbers from the tracking stream -- phi = 2 pi xi_1 first, then mu = 2 xi_2 - 1 -- and the new
+    direction is (mu, sqrt(1 - mu^2) cos phi, sqrt(1 - mu^2) sin phi).  The oracle's sampler is checked
+    against that statement with the reference-pinned prn (libm build: bit for bit), and a run with every
+    nuclide flagged (as in test/tests/study/materials.xml) must differ from the unflagged one only
+    through the tracking stream."""
+    import math
+    from tests import problems
+    L = oracle_bridge.lib(True)
+    for seed0 in (1, 12345, 2 ** 61 + 7):
+        s, t = C.c_uint64(seed0), C.c_uint64(seed0)
+        uvw = np.zeros(3)
+        L.orc_isotropic_direction(uvw.ctypes.data_as(C.POINTER(C.c_double)), C.byref(s))
+        phi = 0.0 + (2.0 * math.pi - 0.0) * L.orc_prn(C.byref(t))
+        mu = -1.0 + (1.0 - -1.0) * L.orc_prn(C.byref(t))
+        assert s.value == t.value  # exactly two draws
+        want = np.array([mu, math.sqrt(1.0 - mu * mu) * math.cos(phi), math.sqrt(1.0 - mu * mu) * math.sin(phi)])
+        assert np.array_equal(uvw.view(np.uint64), want.view(np.uint64))
+    recs = {}
+    for name in ("infinite_medium", "infinite_medium_iso"):
+        mesh, lib, bm, st = problems.PROBLEMS[name](n_particles=300)
+        o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, st, tallies=False)
+        o.sample_initial_source()
+        o.run_generation(1)
+        recs[name] = o.history_records().copy()
+    a, b = recs["infinite_medium"], recs["infinite_medium_iso"]
+    assert np.array_equal(a["seed_source"], b["seed_source"])
+    assert not np.array_equal(a["seed_tracking"], b["seed_tracking"])
+    assert not np.array_equal(a["n_segments"], b["n_segments"])
