@@ -582,7 +582,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
       R.batches = std::stoi(ex->get("num_steps"));
   const XmlNode* src = st->child("source");
   const XmlNode* space = src ? src->child("space") : nullptr;
-  if (!space || space->value("type") != "box" && space->value("type") != "fission")
+  if (!space || (space->value("type") != "box" && space->value("type") != "fission"))
     mooseError("settings.xml: the source must be a box (or fission box) <space>");
   {
     const auto b = toReals(space->value("parameters"));

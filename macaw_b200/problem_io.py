@@ -87,3 +87,33 @@ def read_records(path):
             out[name] = np.frombuffer(f.read(nbytes), dt).copy()
             f.read(-nbytes % 8)
     return out
+
+
+def write_library(path, lib):
+    """Nuclide table file for the C++ input-file front end (host/input_file.hpp): the continuous-energy
+    tables by nuclide name, in place of cross_sections.xml + HDF5."""
+    from . import cstructs, meshgen
+    recs = {k: v for k, v in _records(meshgen.infinite_medium(1), lib, [0], [1], cstructs.make_settings(1), [], 0.0).items()
+            if k.startswith("nuc")}
+    recs["lib.names"] = np.frombuffer(";".join(n.name for n in lib.nuclides).encode(), np.uint8).astype(np.int32)
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<I", len(recs)))
+        for name, a in recs.items():
+            f.write(name.encode().ljust(32, b"\0"))
+            f.write(struct.pack("<IIQ", _CODE[a.dtype], 0, a.size))
+            b = a.tobytes()
+            f.write(b + b"\0" * (-len(b) % 8))
+
+
+if __name__ == "__main__":
+    import argparse
+    from . import nucdata
+    ap = argparse.ArgumentParser(description="write the synthetic nuclide table file read by host/mcw_run --tables")
+    ap.add_argument("--library", required=True)
+    ap.add_argument("--nuclides", type=int, default=9)
+    ap.add_argument("--grid-points", type=int, default=2000)
+    ap.add_argument("--seed", type=int, default=1)
+    a = ap.parse_args()
+    write_library(a.library, nucdata.make_library(a.nuclides, G=a.grid_points, seed=a.seed))
+    print(a.library)

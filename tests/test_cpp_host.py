@@ -78,3 +78,95 @@ def test_cpp_host_matches_oracle(oracle_bridge, tmp_path, name):
     assert t1["n_spatial"] == ns
     assert abs(t1["sum"] - flux.sum()) <= 1e-10 * abs(flux.sum())
     assert abs(t1["first"] - flux[0]) <= 1e-10 * max(abs(flux[0]), 1e-300)
+
+
+# ---- the input-file surface: MOOSE .i + OpenMC XML through host/input_file.hpp
+EXAMPLE = os.path.join(ROOT, "examples", "study_5x5")
+
+
+def _tables(tmp_path, G=400):
+    from macaw_b200 import nucdata
+    lib = nucdata.make_library(9, G=G)
+    path = str(tmp_path / "tables.bin")
+    problem_io.write_library(path, lib)
+    return path, lib
+
+
+def test_input_file_front_end_understands_the_example(tmp_path):
+    """mcw_run --input ... --check (no GPU): mesh, boundary kinds, block map, OpenMC density
+    normalisation (ao / wo / g/cm3 / atom/b-cm), <isotropic> lists and settings equal the Python
+    restatement that reads the same three files."""
+    from tests import input_problem
+    exe = _build()
+    tables, lib = _tables(tmp_path)
+    r = subprocess.run([exe, "--input", os.path.join(EXAMPLE, "study.i"), "--tables", tables, "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(
+        os.path.join(EXAMPLE, "study.i"), EXAMPLE, lib)
+    assert d["n_elem"] == mesh.n_elem == 25 and d["elem_type"] == mesh.elem_type
+    assert np.array_equal(np.array(d["xyz"]).reshape(-1, 3), mesh.xyz)
+    assert np.array_equal(np.array(d["conn"]).reshape(mesh.conn.shape), mesh.conn)
+    assert d["block_id"] == mesh.block_id.tolist() and sum(d["block_id"]) == 1
+    assert np.array_equal(np.array(d["side_bnd_id"]).reshape(mesh.side_bnd_id.shape), mesh.side_bnd_id)
+    assert d["bnd_kind"] == mesh.bnd_kind.tolist() == [1] * 6
+    assert d["blocks"] == blocks and [m - 1 for m in d["materials"]] == mat_index
+    assert d["batches"] == batches == 4 and d["n_particles"] == s.n_particles and d["n_inactive"] == s.n_inactive
+    assert d["temperature"] == T0 and d["source_box"] == [s.source_box[i] for i in range(6)]
+    assert len(d["library_materials"]) == len(library.materials) == 4 and d["n_library_nuclides"] == len(library.nuclides)
+    for a, b in zip(d["library_materials"], library.materials):
+        assert a["nuclide"] == b.nuclides
+        assert a["atom_density"] == b.densities  # same IEEE operations in the same order: exact
+        assert a["isotropic"] == (b.isotropic or [])
+    assert d["tallies"] == len(tallies) == 1 and d["aux"] == len(aux) == 1
+
+
+def test_input_file_front_end_rejects_what_the_reference_rejects(tmp_path):
+    exe = _build()
+    tables, _ = _tables(tmp_path)
+    text = open(os.path.join(EXAMPLE, "study.i")).read()
+    cases = [(text.replace('materials = "4 1"', 'materials = "4 9"'), "is not in materials.xml"),
+             (text.replace("type = CollisionKernel", "type = SomethingElse"), "no CollisionKernel"),
+             (text.replace("dim = 3", "dim = 2"), "z_coord parameter must be specified for 2D"),
+             (text.replace("GeneratedMeshGenerator", "FileMeshGenerator"), "Exodus meshes need libMesh")]
+    for k, (bad, msg) in enumerate(cases):
+        d = tmp_path / f"case{k}"
+        d.mkdir()
+        (d / "study.i").write_text(bad)
+        for f in ("settings.xml", "materials.xml"):
+            (d / f).write_text(open(os.path.join(EXAMPLE, f)).read())
+        r = subprocess.run([exe, "--input", str(d / "study.i"), "--tables", tables, "--check"], capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (msg, r.stderr)
+
+
+@pytest.mark.gpu
+def test_input_file_run_matches_oracle(oracle_bridge, tmp_path):
+    """The example input through the C++ host on the GPU == the oracle on the Python restatement of
+    the same files: k per batch, counters, and the OpenMCTallyAux values of every element."""
+    from tests import input_problem
+    exe = _build()
+    tables, lib = _tables(tmp_path)
+    r = subprocess.run([exe, "--input", os.path.join(EXAMPLE, "study.i"), "--tables", tables], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.splitlines()]
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(
+        os.path.join(EXAMPLE, "study.i"), EXAMPLE, lib)
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(library, mat_index)
+    o.set_settings(s)
+    for t in tallies:
+        o.add_tally(*t)
+    o.sample_initial_source()
+    for b in range(1, batches + 1):
+        ro, rc = o.run_generation(b), lines[b - 1]
+        assert rc["n_segments"] == ro.n_segments and rc["n_collisions"] == ro.n_collisions
+        for f in ("k_generation", "keff", "k_collision", "k_absorption", "k_tracklength"):
+            assert abs(rc[f] - getattr(ro, f)) <= 1e-11 * abs(getattr(ro, f)), f
+    _, so, _, nr = o.get_tally(7)
+    want = so.reshape(mesh.n_elem, 2, 2)[:, 0, 0]  # energy_bin = 0 (thermal), score flux
+    got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
+    assert nr == batches - s.n_inactive and got.shape == want.shape
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-300) and want.sum() > 0
