@@ -187,9 +187,16 @@ int mcw_create(mcw_handle* h, int device_ordinal, int rank, int nranks);
 void mcw_destroy(mcw_handle h);
 const char* mcw_last_error(mcw_handle h); /* OMC error.cpp:32 openmc_err_msg */
 int mcw_version(void);
-/* Run-time knobs that do not change results: "profile" (1 = per-kernel-family CUDA-event timing in
- * mcw_generation_result, one host sync per event round), "sync_every" (event rounds between host
- * reads of the queue counters), "fallback_blocks" (grid of the rare-path kernel). */
+/* Run-time knobs that do not change any per-history result (tally / k sums move by FP64 addition
+ * order only):
+ *   "profile"          1 = per-kernel-family CUDA-event timing in mcw_generation_result
+ *   "sync_every"       event rounds between host reads of the queue counters (default 4)
+ *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (65536)
+ *   "collide_min"      fused mode: parked collisions per warp before they are processed (8)
+ *   "ordered_queues"   1 = collide / fly queues rebuilt in history-index order every round (1)
+ *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort (32768)
+ *   "xs_plan"          sorted refresh stages all (slot, nuclide) windows of a tile at once (1)
+ *   "drain_lanes", "drain_min_queue", "visit_cap", "fallback_blocks"   tracking / rare-path launch shape */
 int mcw_set_option(mcw_handle h, const char* name, int value);
 /* Builds all device state now (otherwise done lazily by the first call that needs it). */
 int mcw_prepare(mcw_handle h);

@@ -932,10 +932,10 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_q_fly[1], n));
   CK(dev_alloc(h, &h->d_q_collide, n));
   CK(dev_alloc(h, &h->d_q_fallback, n));
-  CK(dev_alloc(h, &h->d_q_sorted, n));
-  CK(dev_alloc(h, &h->d_keys, n));
-  CK(dev_alloc(h, &h->d_keys_out, n));
-  CK(dev_alloc(h, &h->d_q_hist, n));
+  CK(dev_alloc(h, &h->d_q_sorted, n + 256)); // k_collide writes keys / hist for whole blocks of its grid
+  CK(dev_alloc(h, &h->d_keys, n + 256));
+  CK(dev_alloc(h, &h->d_keys_out, n + 256));
+  CK(dev_alloc(h, &h->d_q_hist, n + 256));
   CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
   CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
   h->temp_bytes = std::max(mcwk_scan_temp_bytes(std::max(h->bank_capacity, n)), mcwk_compact_temp_bytes(n));
@@ -1128,11 +1128,12 @@ int mcw_transport_generation(mcw_handle h, int batch)
       mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_COLLIDE, qc, &P.counters->n_collide, st);
       R.n_kernel_launches += 2;
     }
-    mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, st);
     // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
     const bool staged = h->set.sort_xs_queue != 0 && upper >= h->xs_sort_min;
+    mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
+                 staged ? h->d_q_sorted : nullptr, st);
     R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,
                                            h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
     if (P.ordered_queues)

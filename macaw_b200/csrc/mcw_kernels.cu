@@ -416,7 +416,8 @@ k_xs_all_slots(McwParams P, const int32_t* __restrict__ queue, const unsigned lo
 template <int TYPE>
 __global__ void __launch_bounds__(MCW_BLOCK, MCW_COLLIDE_MIN_BLOCKS)
 k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
-          int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next)
+          int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, uint32_t* __restrict__ keys,
+          int32_t* __restrict__ hist)
 {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = idx < (int64_t)*count;
@@ -424,6 +425,13 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
   const int i = active ? queue[idx] : -1;
   const bool valid = active && P.p.status[i] == MCW_ST_COLLIDE;
   const bool survived = mcw_collide_history<TYPE, false>(P, i, valid);
+  if (keys)
+  {
+    // sort keys of the energy-ordered cross-section refresh (mcw_xs.cuh): 15-bit energy image, or the
+    // dead flag for absorbed histories and the padding beyond the device-side count
+    keys[idx] = survived ? (mcw_energy_key(P.p.E[i]) >> (26 - MCW_REFRESH_KEY_BITS)) : (1u << MCW_REFRESH_KEY_BITS);
+    hist[idx] = survived ? i : -1;
+  }
   if (P.ordered_queues)
     return;
   unsigned long long k = mcw_warp_append(cnt_next, survived);
@@ -719,12 +727,13 @@ void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long lo
 void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st) { k_round_reset<<<1, 1, 0, st>>>(c, consumed); }
 
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
-                  int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st)
+                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, cudaStream_t st)
 {
   if (upper <= 0)
     return;
+  // the grid covers whole blocks: keys / hist hold grid_for(upper) * MCW_BLOCK entries
   MCW_DISPATCH(P.mesh.type,
-               (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next)));
+               (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next, keys, hist)));
 }
 
 // Cross sections of every material slot at the new energy of the survivors of the collision queue.
@@ -741,14 +750,14 @@ int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned lon
     k_xs_all_slots<<<grid_for(upper * P.n_slots), MCW_BLOCK, 0, st>>>(P, queue, count);
     return 1;
   }
-  k_refresh_keys<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(P, queue, count, upper, keys, hist);
-  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hist, hist_sorted, upper, 0, 27, st);
+  // keys and hist were written by k_collide; 16 key bits = two radix passes
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hist, hist_sorted, upper, 0, MCW_REFRESH_KEY_BITS + 1, st);
   const unsigned tiles = (unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE);
   if (plan && P.n_plan > 0)
     k_xs_all_slots_plan<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
   else
     k_xs_all_slots_staged<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
-  return 5; // keys, 3 radix-sort kernels (histogram, onesweep x ...), staged lookup: counted as 5
+  return 5; // radix sort (histogram, scan, two onesweep passes) + staged lookup
 }
 
 // Stand-alone lookup of (E, material) arrays through the sort + staged kernel; out in caller order.
@@ -758,7 +767,7 @@ void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, si
   if (n <= 0)
     return;
   k_xs_sort_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, E, mat, keys, idx);
-  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, idx, idx_sorted, n, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, idx, idx_sorted, n, 0, 24, st);
 }
 
 void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,

@@ -26,7 +26,7 @@ void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long lo
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
                 int drain_lanes, bool fused, int collide_min, cudaStream_t st);
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
-                  int32_t* q_fly_next, unsigned long long* cnt_next, cudaStream_t st);
+                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, cudaStream_t st);
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,
                    int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, cudaStream_t st);
 void mcwk_trace_rays(const McwParams& P, int64_t n, const double* start, const double* dirs, const int32_t* start_elem,
