@@ -25,11 +25,14 @@ g.set_library(lib, [m - 1 for m in mats], blocks)
 g.set_settings(s)
 g.sample_initial_source()
 bridge.build(ref=False)
+keff = 1.0  # the k the fission-site yield is divided by in the coming batch (OMC physics.cpp:165)
 for b in range(1, nb + 1):
     src = g.source_bank().copy()
+    k_used = keff
     r = g.run_generation(b)
+    keff = r.keff
     print(f"batch {b}: k {r.k_generation:.5f} failed {r.n_failed_traces} vertex/edge {r.n_vertex_edge_hits}", flush=True)
-    if r.n_failed_traces == 0:
+    if r.n_failed_traces == 0 and b != nb:
         continue
     rec = g.history_records()
     bad = np.nonzero(rec["fate"] == 2)[0]
@@ -40,6 +43,7 @@ for b in range(1, nb + 1):
     o.set_library(lib, [m - 1 for m in mats])
     o.set_settings(s)
     o.set_source_bank(src)
+    o.L.orc_set_keff(o.h, k_used)
     t0 = time.time()
     o.transport_generation(b, os.cpu_count() or 1)
     ro = o.history_records()

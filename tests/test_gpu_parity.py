@@ -237,3 +237,41 @@ def test_full_size_properties_pin_cell_1m():
     r1b, r2b, recb, bankb, srcb, tb, _ = run({"tail_threshold": 0, "ordered_queues": 0, "xs_sort_min": 0}, sort_xs=1)
     assert recb.tobytes() == rec.tobytes() and bankb.tobytes() == bank.tobytes() and srcb.tobytes() == src.tobytes()
     assert np.allclose(tb, t, rtol=1e-11, atol=1e-300) and r2b.k_generation == pytest.approx(r2.k_generation, rel=1e-12)
+
+
+def test_full_size_oracle_parity_pin_cell_1m(oracle_bridge):
+    """The bench workload at bench size against the oracle on all host threads (~20 s of CPU): one
+    generation of 10^6 histories, ~1.5e9 element crossings.  Every history's crossing hash, seeds,
+    counters, fate and final energy, and the whole fission bank, must be bit-identical."""
+    import os
+    from macaw_b200 import meshgen, nucdata
+    from macaw_b200.context import Context
+    mesh = meshgen.pin_cell_tet(26, 25)
+    lib = nucdata.make_library(9, G=10000, seed=1)
+    h = meshgen.PIN_PITCH / 2
+    n = 1_000_000
+    s = cstructs.make_settings(n, n_inactive=1, source_box=(-h, -h, -h, h, h, h), record_traces=1)
+    g = Context(0)
+    g.set_mesh(mesh)
+    g.set_library(lib, [0, 1, 2, 3], [0, 1, 2, 3])
+    g.set_settings(s)
+    g.sample_initial_source()
+    src = g.source_bank().copy()
+    rg = g.run_generation(1)
+    rec, bank = g.history_records(), g.fission_bank()
+    g.close()
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh, np.arange(4, dtype=np.int32))
+    o.set_library(lib, [0, 1, 2, 3])
+    o.set_settings(s)
+    o.set_source_bank(src)
+    o.transport_generation(1, os.cpu_count() or 1)
+    ro = o.history_records()
+    for f in ("trace_hash", "seed_tracking", "seed_source", "seed_urr", "n_segments", "n_collisions", "n_progeny",
+              "last_elem", "fate"):
+        assert np.array_equal(rec[f], ro[f]), (f, int((rec[f] != ro[f]).sum()))
+    for f in ("E", "k_collision", "k_absorption", "k_tracklength"):
+        assert np.array_equal(rec[f].view(np.uint64), ro[f].view(np.uint64)), f
+    assert int(ro["n_segments"].sum()) == rg.n_segments > 1_000_000_000
+    ob = o.fission_bank()
+    assert ob.tobytes() == bank.tobytes()
