@@ -872,13 +872,6 @@ void mcwk_reduce_sum(void* temp, size_t temp_bytes, const double* in, double* ou
   cub::DeviceReduce::Sum(temp, temp_bytes, in, out, n, st);
 }
 
-void mcwk_sort_queue(void* temp, size_t temp_bytes, uint32_t* keys_in, uint32_t* keys_out, int32_t* q_in, int32_t* q_out,
-                     int64_t n, int end_bit, cudaStream_t st)
-{
-  if (n > 0)
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, q_in, q_out, n, 0, end_bit, st);
-}
-
 void mcwk_bank_sort(void* temp, size_t temp_bytes, const McwParticlesDev& p, int64_t n_particles, int64_t work_offset,
                     const mcw_source_site* bank, int64_t n_bank, int64_t* scratch_counts, int64_t* scratch_scan,
                     mcw_source_site* sorted, cudaStream_t st)

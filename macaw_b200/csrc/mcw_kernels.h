@@ -39,8 +39,6 @@ void mcwk_tally_accumulate(double* value, double* sum, double* sum_sq, int64_t n
 size_t mcwk_scan_temp_bytes(int64_t n);
 void mcwk_exclusive_scan(void* temp, size_t temp_bytes, const int64_t* in, int64_t* out, int64_t n, cudaStream_t st);
 void mcwk_reduce_sum(void* temp, size_t temp_bytes, const double* in, double* out, int64_t n, cudaStream_t st);
-void mcwk_sort_queue(void* temp, size_t temp_bytes, uint32_t* keys_in, uint32_t* keys_out, int32_t* q_in, int32_t* q_out,
-                     int64_t n, int end_bit, cudaStream_t st);
 void mcwk_bank_sort(void* temp, size_t temp_bytes, const McwParticlesDev& p, int64_t n_particles, int64_t work_offset,
                     const mcw_source_site* bank, int64_t n_bank, int64_t* scratch_counts, int64_t* scratch_scan,
                     mcw_source_site* sorted, cudaStream_t st);

@@ -30,6 +30,9 @@
 #ifndef MCW_TRACK_MIN_BLOCKS
 #define MCW_TRACK_MIN_BLOCKS 4 // register budget 128 per thread -> 16 warps per SM
 #endif
+#ifndef MCW_HEX_MIN_BLOCKS
+#define MCW_HEX_MIN_BLOCKS 3 // HEX8: 24 vertex coordinates and twelve triangles per element; 168 registers
+#endif
 #ifndef MCW_FUSED_MIN_BLOCKS
 #define MCW_FUSED_MIN_BLOCKS 2 // fused (tail) instantiation: 204 registers, 8 warps per SM
 #endif
@@ -161,6 +164,40 @@ MCW_D bool mcw_tri_stage1(V3 start, V3 dir, V3 p0, V3 p1, V3 p2, double inv_hmax
   return !rej && t.num > 0.0;
 }
 
+// Both triangles of a quadrilateral side, intersectQuad's (v00, v10, v11) and (v11, v01, v00)
+// (RT TraceRayTools.C:514-550), with the second one reusing what is an exact negation of the first:
+// its edge2 = (v00 - v11) / hmax = -edge2 of the first, hence pvec' = -pvec, det' = -(edge1' . pvec),
+// u' = -(tvec' . pvec), num' = -(edge2 . qvec').  IEEE subtraction, multiplication and the
+// left-to-right sums of dot / cross are sign-symmetric under round-to-nearest, so every value is
+// bit-identical to evaluating the second triangle from scratch (41 instead of 64 FP64 operations).
+MCW_D void mcw_quad_stage1(V3 start, V3 dir, V3 v00, V3 v10, V3 v11, V3 v01, double inv_hmax, TriEval& t1, bool& ok1,
+                           TriEval& t2, bool& ok2)
+{
+  const V3 edge1 = (v10 - v00) * inv_hmax;
+  const V3 edge2 = (v11 - v00) * inv_hmax;
+  const V3 pvec = cross(dir, edge2);
+  t1.det = dot(edge1, pvec);
+  const V3 tvec = (start - v00) * inv_hmax;
+  t1.u = dot(tvec, pvec);
+  const V3 qvec = cross(tvec, edge1);
+  t1.v = dot(dir, qvec);
+  t1.num = dot(edge2, qvec);
+  const bool rej1 = (t1.det < MCW_TRACE_TOL) | (t1.u < -MCW_TRACE_TOL) | (t1.u > t1.det + MCW_TRACE_TOL) |
+                    (t1.v < -MCW_TRACE_TOL) | (t1.u + t1.v > t1.det + MCW_TRACE_TOL);
+  ok1 = !rej1 && t1.num > 0.0;
+
+  const V3 edge1b = (v01 - v11) * inv_hmax;
+  t2.det = -dot(edge1b, pvec);
+  const V3 tvecb = (start - v11) * inv_hmax;
+  t2.u = -dot(tvecb, pvec);
+  const V3 qvecb = cross(tvecb, edge1b);
+  t2.v = dot(dir, qvecb);
+  t2.num = -dot(edge2, qvecb);
+  const bool rej2 = (t2.det < MCW_TRACE_TOL) | (t2.u < -MCW_TRACE_TOL) | (t2.u > t2.det + MCW_TRACE_TOL) |
+                    (t2.v < -MCW_TRACE_TOL) | (t2.u + t2.v > t2.det + MCW_TRACE_TOL);
+  ok2 = !rej2 && t2.num > 0.0;
+}
+
 // true when the hit is classified as a vertex or an edge (RT TraceRayTools.C:436-474); the general
 // kernel then redoes the step, so the fast path does not need to know which one
 MCW_D bool mcw_tri_at_extrema(const TriEval& t)
@@ -263,8 +300,8 @@ MCW_D bool mcw_exit_fast<MCW_HEX8>(const McwMeshDev& mesh, const ElemData<MCW_HE
     const int v00 = side_node<MCW_HEX8>(s, 3), v10 = side_node<MCW_HEX8>(s, 2), v11 = side_node<MCW_HEX8>(s, 1),
               v01 = side_node<MCW_HEX8>(s, 0);
     TriEval t1, t2;
-    bool ok1 = mcw_tri_stage1(start, dir, D.v[v00], D.v[v10], D.v[v11], inv_hmax, t1);
-    bool ok2 = mcw_tri_stage1(start, dir, D.v[v11], D.v[v01], D.v[v00], inv_hmax, t2);
+    bool ok1, ok2;
+    mcw_quad_stage1(start, dir, D.v[v00], D.v[v10], D.v[v11], D.v[v01], inv_hmax, t1, ok1, t2, ok2);
     const bool live = s != incoming_side;
     if (ok1 && live)
     {
@@ -391,7 +428,7 @@ enum
 // lane keeps its history through its collisions (mcw_collide_history, batched per warp) until it
 // dies.  Only the rare vertex / edge steps still leave through the fallback queue.
 template <int TYPE, bool FUSED>
-__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (TYPE == MCW_HEX8 ? 2 : (FUSED ? MCW_FUSED_MIN_BLOCKS : MCW_TRACK_MIN_BLOCKS)))
+__global__ void __launch_bounds__(MCW_TRACK_BLOCK, (FUSED ? MCW_FUSED_MIN_BLOCKS : (TYPE == MCW_HEX8 ? MCW_HEX_MIN_BLOCKS : MCW_TRACK_MIN_BLOCKS)))
 k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
         unsigned long long* __restrict__ head, int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next,
         int32_t* __restrict__ q_collide, int32_t* __restrict__ q_fallback, int drain_lanes, int collide_min)
