@@ -191,7 +191,7 @@ int mcw_version(void);
  * order only):
  *   "profile"          1 = per-kernel-family CUDA-event timing in mcw_generation_result
  *   "sync_every"       event rounds between host reads of the queue counters (default 4)
- *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (65536)
+ *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (49152)
  *   "collide_min"      fused mode: parked collisions per warp before they are processed (8)
  *   "ordered_queues"   1 = collide / fly queues rebuilt in history-index order every round (1)
  *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort (32768)

@@ -132,11 +132,11 @@ struct mcw_context
 
   // options
   int profile = 0, sync_every = 1, fallback_blocks = 8, visit_cap = 1 << 30, track_max_blocks = 148, fused_max_blocks = 148;
-  int drain_lanes = 12;            // tracking warps below this many histories hand them to the next round ...
-  int64_t drain_min_queue = 65536; // ... when the round's queue is at least this long
+  int drain_lanes = 28;        // exhausted tracking warps below this many histories hand them to the next round ...
+  int64_t drain_min_queue = 0; // ... when the round's queue is at least this long (sweeps: profiles/ab_r01g_drain.txt)
   // below this many histories in flight the tracking kernel runs fused (collisions inline, no
   // round per collision): rounds would last as long as the slowest flight with most lanes idle
-  int64_t tail_threshold = 65536;
+  int64_t tail_threshold = 49152;
   int xs_plan = 1; // sorted refresh: stage all (slot, nuclide) windows of a tile at once (k_xs_all_slots_plan)
   int ordered_queues = 1; // rebuild the collide / fly queues in history-index order every round
   int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
