@@ -196,6 +196,7 @@ int mcw_version(void);
  *   "ordered_queues"   1 = collide / fly queues rebuilt in history-index order every round (1)
  *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort (32768)
  *   "xs_plan"          sorted refresh stages all (slot, nuclide) windows of a tile at once (1)
+ *   "fallback_every_round"  1 = serve the general-walk queue in every round instead of after host syncs (0)
  *   "drain_lanes", "drain_min_queue", "visit_cap", "fallback_blocks"   tracking / rare-path launch shape */
 int mcw_set_option(mcw_handle h, const char* name, int value);
 /* Builds all device state now (otherwise done lazily by the first call that needs it). */

@@ -137,6 +137,7 @@ struct mcw_context
   // below this many histories in flight the tracking kernel runs fused (collisions inline, no
   // round per collision): rounds would last as long as the slowest flight with most lanes idle
   int64_t tail_threshold = 49152;
+  int fallback_every_round = 0; // 1: serve the general-walk queue in every round (A/B, tests)
   int xs_plan = 1; // sorted refresh: stage all (slot, nuclide) windows of a tile at once (k_xs_all_slots_plan)
   int ordered_queues = 1; // rebuild the collide / fly queues in history-index order every round
   int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
@@ -286,6 +287,8 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->drain_min_queue = std::max(0, value);
   else if (n == "tail_threshold")
     h->tail_threshold = std::max(0, value);
+  else if (n == "fallback_every_round")
+    h->fallback_every_round = value != 0;
   else if (n == "xs_plan")
     h->xs_plan = value != 0;
   else if (n == "ordered_queues")
@@ -1107,7 +1110,13 @@ int mcw_transport_generation(mcw_handle h, int batch)
   // (k_track; rare vertex / edge steps go through k_fallback), then every collided history is
   // processed by k_collide, which also refreshes its cross sections for all materials at the new
   // energy and puts the survivors into the other fly queue.
-  while (upper > 0)
+  // The general walk is a long single-thread step (~60 us for a TET4 vertex hit) for a handful of
+  // histories per round, so its queue is only served in the round after a host sync (every round
+  // once few histories are left, and in fused rounds); until then those histories wait in
+  // MCW_ST_FALLBACK.  fb_pending is exact at every sync, so the loop cannot end with work waiting.
+  int64_t fb_pending = 0;
+  bool fb_round = true;
+  while (upper > 0 || fb_pending > 0)
   {
     int32_t* q = h->d_q_fly[cur];
     unsigned long long* cnt_cur = &P.counters->n_fly[cur];
@@ -1120,8 +1129,15 @@ int mcw_transport_generation(mcw_handle h, int batch)
                drain, fused, h->collide_min, st);
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 1), st);
-    mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
-                  h->d_q_collide, st);
+    const bool fb_now = fb_round || fused || h->fallback_every_round;
+    // collisions of this round: at most every flight plus every general step served now
+    const int64_t upper_c = upper + (fb_now ? fb_pending : 0);
+    if (fb_now)
+    {
+      mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
+                    h->d_q_collide, st);
+      R.n_kernel_launches += 1;
+    }
     int32_t* qc = h->d_q_collide;
     if (P.ordered_queues)
     {
@@ -1131,10 +1147,10 @@ int mcw_transport_generation(mcw_handle h, int batch)
     // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
-    const bool staged = h->set.sort_xs_queue != 0 && upper >= h->xs_sort_min;
-    mcwk_collide(P, qc, &P.counters->n_collide, upper, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
+    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= h->xs_sort_min;
+    mcwk_collide(P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
                  staged ? h->d_q_sorted : nullptr, st);
-    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,
+    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper_c, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,
                                            h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
     if (P.ordered_queues)
     {
@@ -1143,17 +1159,22 @@ int mcw_transport_generation(mcw_handle h, int batch)
     }
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 2), st);
-    R.n_kernel_launches += 3; // k_track, k_fallback, k_collide
+    R.n_kernel_launches += 2; // k_track, k_collide
     ++rounds;
     const bool sync_now = (rounds % h->sync_every) == 0 || upper < 4096;
+    if (fb_now)
+      fb_pending = 0; // k_fallback ran after k_track: nothing waits
     if (sync_now)
     {
       CK(cudaMemcpyAsync(h->h_counters, P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       upper = (int64_t)h->h_counters->n_fly[cur ^ 1];
+      if (!fb_now)
+        fb_pending = (int64_t)h->h_counters->n_fallback;
     }
-    // reset the consumed queues for the next round
-    mcwk_round_reset(P.counters, cur, st);
+    // reset the consumed queues for the next round (the fallback queue only when it was served)
+    mcwk_round_reset(P.counters, cur, fb_now, st);
+    fb_round = sync_now;
     R.n_kernel_launches += 1;
     cur ^= 1;
     if (rounds > 100000000)

@@ -161,11 +161,12 @@ k_xs_lookup_array(McwLibraryDev L, int64_t n, const double* __restrict__ E, cons
 #include "mcw_xs.cuh"
 
 // resets the per-round device counters (one launch instead of three memsets)
-__global__ void k_round_reset(McwCounters* c, int consumed)
+__global__ void k_round_reset(McwCounters* c, int consumed, bool fallback_served)
 {
   c->n_fly[consumed] = 0;
   c->n_collide = 0;
-  c->n_fallback = 0;
+  if (fallback_served)
+    c->n_fallback = 0;
   c->head = 0;
 }
 
@@ -724,7 +725,10 @@ void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long lo
   }
 }
 
-void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st) { k_round_reset<<<1, 1, 0, st>>>(c, consumed); }
+void mcwk_round_reset(McwCounters* c, int consumed, bool fallback_served, cudaStream_t st)
+{
+  k_round_reset<<<1, 1, 0, st>>>(c, consumed, fallback_served);
+}
 
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
                   int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, cudaStream_t st)

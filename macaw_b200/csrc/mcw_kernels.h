@@ -21,7 +21,7 @@ void mcwk_compact_status(void* temp, size_t temp_bytes, const int8_t* status, in
                          unsigned long long* count, cudaStream_t st);
 size_t mcwk_compact_temp_bytes(int64_t n);
 int mcwk_track_blocks_per_sm(int type, bool fused);
-void mcwk_round_reset(McwCounters* c, int consumed, cudaStream_t st);
+void mcwk_round_reset(McwCounters* c, int consumed, bool fallback_served, cudaStream_t st);
 void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, int max_blocks,
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
                 int drain_lanes, bool fused, int collide_min, cudaStream_t st);

@@ -127,7 +127,11 @@ SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 0, "xs_plan": 0}  # k_x
     ("assembly_quad", {}, MIXED), ("assembly_quad", {"sort_xs_queue": 1}, SORTED),
     ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 0, "ordered_queues": 0}),
     ("pin_cell_tet", {"seed_through_double": False}, MIXED),
-    ("infinite_medium_iso", {}, EVENT), ("pin_cell_tet_iso", {}, MIXED)])
+    ("infinite_medium_iso", {}, EVENT), ("pin_cell_tet_iso", {}, MIXED),
+    # 20 000 histories: host syncs every 4th round, so the general-walk queue is served only after syncs
+    ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000, "fallback_every_round": 1}),
+    ("pin_cell_hex", {"n_particles": 20000}, {"tail_threshold": 0, "sync_every": 7})])
 def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
     for k, v in opts.items():
