@@ -386,7 +386,7 @@ def main():
         except Exception:
             pass
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
             try:
                 threads = os.cpu_count() or 1
                 rate, n_s, t_s = cpu_oracle_rate(problem, ctx.source_bank(), 15.0, threads,
@@ -427,7 +427,7 @@ def main():
                                                        "bank+reduce": acc["ms_bank"] / args.steps}},
             "cpu_baseline": cpu,
         }
-        if not args.no_xs_leg:
+        if not args.no_xs_leg and world == 1:
             try:
                 out["xs_lookup"] = xs_lookup_leg(local)
             except Exception as e:
