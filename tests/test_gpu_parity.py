@@ -185,6 +185,49 @@ def test_error_paths(ctx_factory):
         c.set_library(lib, [0, 7])  # block mapped to an unknown material (MC CollisionKernel.C:84-90)
 
 
+@pytest.mark.parametrize("n", [1, 7, 33])
+def test_ragged_banks_bit_exact(oracle_bridge, ctx_factory, n):
+    """Banks smaller than a warp / not a multiple of 32: partial warps in every kernel, a fission bank
+    that can be empty (MCW_E_PHYSICS like OpenMC's "No fission sites banked", OMC eigenvalue.cpp:107-109)."""
+    from macaw_b200.lib import McwError
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, "pin_cell_tet", tallies=True, n_particles=n)
+    o.sample_initial_source()
+    g.sample_initial_source()
+    assert o.source_bank().tobytes() == g.source_bank().tobytes()
+    for batch in (1, 2):
+        try:
+            ro = o.run_generation(batch)
+        except RuntimeError:  # the oracle banked no fission site
+            with pytest.raises(McwError):
+                g.run_generation(batch)
+            return
+        rg = g.run_generation(batch)
+        a, b = o.history_records(), g.history_records()
+        assert a.size == b.size == n
+        for f in ("seed_tracking", "seed_urr", "n_segments", "n_collisions", "n_progeny", "last_elem", "fate", "trace_hash"):
+            assert np.array_equal(a[f], b[f]), (batch, f)
+        assert o.fission_bank().tobytes() == g.fission_bank().tobytes()
+        assert o.source_bank().tobytes() == g.source_bank().tobytes() and g.source_bank().size == n
+        assert rg.k_generation == pytest.approx(ro.k_generation, rel=1e-12)
+
+
+def test_empty_inputs(ctx_factory):
+    """Zero-length calls are no-ops, not errors or crashes (the reference's containers are simply empty)."""
+    import torch
+    c = ctx_factory()
+    mesh, lib, bm, s = problems.infinite_medium()
+    problems.configure(c, mesh, lib, bm, s, tallies=False)
+    assert c.xs_lookup(np.zeros(0), np.zeros(0, np.int32)).shape == (0, 4)
+    d, seg, hsh = c.trace_rays(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert d.size == seg.size == hsh.size == 0
+    assert c.locate_points(np.zeros((0, 3))).size == 0
+    buf = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for mode in (0, 1, 2):
+        c.xs_lookup_device(0, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 1, mode)
+    one = c.xs_lookup(np.array([1.0e3]), np.array([0], np.int32))
+    assert one.shape == (1, 4) and one[0, 0] > 0
+
+
 def test_full_size_properties_pin_cell_1m():
     """BASELINE.json configs[1] at bench size (101 400 TET4, 10^6 histories, 9 nuclides x 10 000
     points): too big for the scalar oracle in a test, so size-independent properties of the path:
