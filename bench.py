@@ -258,8 +258,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pin_cell_tet")
     ap.add_argument("--particles", type=int, default=1_000_000, help="histories per GPU per batch")
-    ap.add_argument("--sort-xs", type=int, default=-1,
-                    help="energy-sorted staged cross-section refresh: 1 on, 0 off, -1 when the materials hold > 16 nuclides")
+    ap.add_argument("--sort-xs", type=int, default=1,
+                    help="energy-sorted staged cross-section refresh (settings.sort_xs_queue): the library sorts "
+                         "the rounds that are large enough for their nuclide count")
     ap.add_argument("--sync-every", type=int, default=4)
     ap.add_argument("--tail-threshold", type=int, default=-1, help="histories in flight below which tracking runs fused")
     ap.add_argument("--collide-min", type=int, default=-1, help="fused tracking: parked collisions per warp before they are processed")
@@ -288,8 +289,6 @@ def main():
     n_total = args.particles * world
     problem = build_problem(args.workload, n_total, args.warmup)
     mesh, lib, blocks, mats, s, et = problem
-    if args.sort_xs < 0:
-        args.sort_xs = int(sum(len(lib.materials[m - 1].nuclides) for m in mats) > 16)
     s.sort_xs_queue = args.sort_xs
     kernel = st.CollisionKernel(blocks=blocks, materials=mats, temperature=293.6, z_coord=100.0 if mesh.dim == 2 else None)
     tally = st.OpenMCTally(id=1, scores=["flux"], filters=["cell"], estimator="COLLISION")
@@ -320,7 +319,8 @@ def main():
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
         sampler = ClockSampler(local)
         barrier()
-        sampler.start()
+        if rank == 0:  # one nvidia-smi poller per job: eight of them stall each other's driver calls
+            sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record(ext)
@@ -341,7 +341,7 @@ def main():
         ev1.record(ext)
         barrier()
         wall = time.perf_counter() - t0
-        clocks = sampler.stop()
+        clocks = sampler.stop() if rank == 0 else None
         ms_dev = ev0.elapsed_time(ev1)
         del flush
 

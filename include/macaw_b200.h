@@ -194,7 +194,8 @@ int mcw_version(void);
  *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (49152)
  *   "collide_min"      fused mode: parked collisions per warp before they are processed (8)
  *   "ordered_queues"   1 = collide / fly queues rebuilt in history-index order every round (1)
- *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort (32768)
+ *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort
+ *                      (default: max(32768, 2.4e6 / number of (material, nuclide) pairs in use))
  *   "xs_plan"          sorted refresh stages all (slot, nuclide) windows of a tile at once (1)
  *   "fallback_every_round"  1 = serve the general-walk queue in every round instead of after host syncs (0)
  *   "drain_lanes", "drain_min_queue", "visit_cap", "fallback_blocks"   tracking / rare-path launch shape */

@@ -112,7 +112,10 @@ struct mcw_context
   int32_t *d_q_fly[2] = {nullptr, nullptr}, *d_q_collide = nullptr, *d_q_fallback = nullptr, *d_q_sorted = nullptr;
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
   int32_t* d_q_hist = nullptr;
-  int64_t xs_sort_min = 32768; // event rounds with fewer collisions refresh cross sections without sorting
+  // event rounds with fewer collisions refresh cross sections without sorting; 0 = chosen from the
+  // number of (slot, nuclide) plan entries: the sort pays off sooner the more lookups it serves
+  // (A/B: 39 entries from ~32k collisions, 12 entries from ~200k; profiles/ab_r01h_sort_threshold.txt)
+  int64_t xs_sort_min = 0;
   int64_t *d_i64_a = nullptr, *d_i64_b = nullptr;
   void* d_temp = nullptr;
   size_t temp_bytes = 0;
@@ -294,7 +297,7 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
   else if (n == "ordered_queues")
     h->ordered_queues = value != 0;
   else if (n == "xs_sort_min")
-    h->xs_sort_min = std::max(0, value);
+    h->xs_sort_min = std::max(1, value);
   else if (n == "collide_min")
     h->collide_min = std::min(32, std::max(1, value));
   else if (n == "visit_cap")
@@ -1147,7 +1150,8 @@ int mcw_transport_generation(mcw_handle h, int batch)
     // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
-    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= h->xs_sort_min;
+    const int64_t sort_min = h->xs_sort_min > 0 ? h->xs_sort_min : std::max<int64_t>(32768, 2400000 / std::max(1, P.n_plan));
+    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min;
     mcwk_collide(P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
                  staged ? h->d_q_sorted : nullptr, st);
     R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper_c, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,

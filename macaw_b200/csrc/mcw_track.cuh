@@ -36,12 +36,6 @@
 #ifndef MCW_FUSED_MIN_BLOCKS
 #define MCW_FUSED_MIN_BLOCKS 2 // fused (tail) instantiation: 204 registers, 8 warps per SM
 #endif
-#ifndef MCW_TRK_PIPELINE
-#define MCW_TRK_PIPELINE 0 // 1: the next element record is requested as soon as the exit side is known
-#endif
-#ifndef MCW_TRK_HOIST_LOG
-#define MCW_TRK_HOIST_LOG 1 // 1: the segment's random number and logarithm are computed ahead of the geometry
-#endif
 #ifndef MCW_REFILL_MIN
 #define MCW_REFILL_MIN 4
 #endif
@@ -450,11 +444,6 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
   s.seed_trk = s.seed_src = s.seed_urr = 0;
   uint64_t hash = 0;
   unsigned segs = 0;
-  // The record of the element a lane stands in is lane state: it is loaded when the lane is
-  // (re)filled and, for the next element, as soon as the exit side is known -- before the
-  // logarithm / division chain of the segment physics, which then hides the L2 latency.
-  ElemData<TYPE> D;
-  D.load(P.mesh, 0);
   double hmax_c = 0.0, inv_hmax = 0.0; // 1.0 / hmax, recomputed only when hmax (a block constant) changes
 
   auto load_lane = [&]() {
@@ -504,9 +493,6 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           load_lane();
           visit = 0;
           state = MCW_LN_TRACK;
-#if MCW_TRK_PIPELINE
-          D.load(P.mesh, cur);
-#endif
         }
       }
     }
@@ -563,13 +549,12 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
     {
       int status = MCW_ST_FLY, fate = -1;
       bool leave = false, requeue = false;
-#if !MCW_TRK_PIPELINE
+      ElemData<TYPE> D;
       D.load(P.mesh, cur);
-#endif
-#if MCW_TRK_HOIST_LOG
+      // the segment's random number and logarithm, ahead of the exit search (independent work while
+      // the record arrives); the seed is committed only if the segment is taken
       uint64_t seed_next = s.seed_trk;
       const double neg_log = -mcw_log(mcw_prn(seed_next));
-#endif
       if (D.hmax != hmax_c)
       {
         hmax_c = D.hmax;
@@ -620,16 +605,8 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
           const int code = mcw_pick(D.nbr, iside);
           const int block = D.block;
           const int elem = cur;
-#if MCW_TRK_PIPELINE
-          if (code >= 0)
-            D.load(P.mesh, code >> MCW_NBR_SHIFT); // next record in flight during the physics below
-#endif
-#if MCW_TRK_HOIST_LOG
           s.seed_trk = seed_next;
           const bool collided = mcw_segment_nl(P, s, neg_log, elem, block, P.slot_mat[slot], ipoint, dir, idist, pos);
-#else
-          const bool collided = mcw_segment(P, s, elem, block, P.slot_mat[slot], ipoint, dir, idist, pos);
-#endif
           if (keep_hash)
             hash = mcw_hash_step(hash, elem, collided ? 15 : iside);
           if (collided)

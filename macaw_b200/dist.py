@@ -65,6 +65,29 @@ def all_gather_int(value: int, group=None, device="cpu"):
     return [int(x.item()) for x in out]
 
 
+def warm_up(group=None, device="cpu"):
+    """Open every point-to-point channel and the collective rings once, outside any timed region: NCCL
+    connects a pair of ranks lazily on their first send / recv, and which pairs exchange sites depends
+    on the generation (at 8 ranks new pairs kept appearing for dozens of generations, ~100 ms each)."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    if ws == 1:
+        return
+    send = torch.zeros(ws, 96, dtype=torch.uint8, device=device)
+    recv = torch.zeros(ws, 96, dtype=torch.uint8, device=device)
+    ops = []
+    for peer in range(ws):
+        if peer != rank:
+            ops.append(dist.P2POp(dist.isend, send[peer], peer, group))
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    t = torch.zeros(8, dtype=torch.float64, device=device)
+    dist.all_reduce(t, group=group)
+    all_gather_int(0, group, device)
+
+
 def exchange_sites(sampled_u8, source_u8, sampled_counts, work_index, group=None):
     """Move sampled sites to their owners.  sampled_u8 / source_u8 are flat uint8 tensors over this
     rank's sampled-site and source-bank buffers (device or CPU)."""

@@ -82,6 +82,9 @@ class OpenMCStudy:
         self.ctx.prepare()
         self.ctx.sample_initial_source()  # openmc_simulation_init -> initialize_source (OpenMCStudy.C:147)
         self._views = None
+        if nranks > 1:
+            import torch
+            dist.warm_up(group, torch.device("cuda", torch.cuda.current_device()))
 
     # -- one Transient time step (OpenMCStudy.C:366-402)
     def execute(self):

@@ -73,6 +73,7 @@ def main():
     from oracle import bridge
     from tests import problems
     td.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dist.warm_up(None, "cpu")  # the channel warm-up the GPU study does at construction
     mesh, lib, bm, s = problems.pin_cell_tet(n_particles=n_particles)
     o = problems.configure(bridge.Oracle(rank=rank, nranks=world), mesh, lib, bm, s, True, False)
     wi = dist.calculate_work(n_particles, world)

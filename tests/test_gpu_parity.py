@@ -116,8 +116,8 @@ def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, 
 EVENT = {"tail_threshold": 0}
 FUSED = {"tail_threshold": 1 << 30}
 MIXED = {"tail_threshold": 700, "collide_min": 3}
-SORTED = {"tail_threshold": 300, "xs_sort_min": 0}
-SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 0, "xs_plan": 0}  # k_xs_all_slots_staged instead of _plan
+SORTED = {"tail_threshold": 300, "xs_sort_min": 1}
+SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 1, "xs_plan": 0}  # k_xs_all_slots_staged instead of _plan
 
 
 @pytest.mark.parametrize("name,kw,opts", [
@@ -125,7 +125,7 @@ SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 0, "xs_plan": 0}  # k_x
     ("pin_cell_tet", {}, EVENT), ("pin_cell_tet", {}, MIXED), ("pin_cell_tet", {"sort_xs_queue": 1}, SORTED),
     ("pin_cell_hex", {}, EVENT), ("pin_cell_hex", {}, FUSED),
     ("assembly_quad", {}, MIXED), ("assembly_quad", {"sort_xs_queue": 1}, SORTED),
-    ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 0, "ordered_queues": 0}),
+    ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 1, "ordered_queues": 0}),
     ("pin_cell_tet", {"seed_through_double": False}, MIXED),
     ("infinite_medium_iso", {}, EVENT), ("pin_cell_tet_iso", {}, MIXED),
     # 20 000 histories: host syncs every 4th round, so the general-walk queue is served only after syncs
@@ -281,7 +281,7 @@ def test_full_size_properties_pin_cell_1m():
     assert abs(t[:, 0, 1].sum() * n - r2.n_collisions) <= 1e-9 * r2.n_collisions
     assert np.all(t >= 0) and t[:, 0, 0].sum() > 0
     # the same run through event rounds only, unordered queues, sorted refresh: every per-history result identical
-    r1b, r2b, recb, bankb, srcb, tb, _ = run({"tail_threshold": 0, "ordered_queues": 0, "xs_sort_min": 0}, sort_xs=1)
+    r1b, r2b, recb, bankb, srcb, tb, _ = run({"tail_threshold": 0, "ordered_queues": 0, "xs_sort_min": 1}, sort_xs=1)
     assert recb.tobytes() == rec.tobytes() and bankb.tobytes() == bank.tobytes() and srcb.tobytes() == src.tobytes()
     assert np.allclose(tb, t, rtol=1e-11, atol=1e-300) and r2b.k_generation == pytest.approx(r2.k_generation, rel=1e-12)
 
