@@ -176,7 +176,10 @@ def xs_lookup_leg(device, points=4 * 1024 * 1024, repeats=5):
     alg_bytes = 100.0 * n_nuc + 44.0 * points
     peak, peak_src = peaks()
     res = {"library": f"{len(lib.nuclides)} nuclides x 32768 points, {lib.bytes() / 1e6:.0f} MB", "points": points,
-           "nuclide_lookups": int(n_nuc), "algorithmic_bytes": alg_bytes, "peak": peak, "unit": "GB/s"}
+           "nuclide_lookups": int(n_nuc), "algorithmic_bytes": alg_bytes, "peak": peak, "unit": "GB/s",
+           "note": "achieved = ALGORITHMIC bytes (SURVEY 8d: 100 B per (point, nuclide) + 44 B per point) / time; the sorted "
+                   "kernels stage each grid window once per 256-point tile, so their DRAM traffic is ~18x below that figure "
+                   "(profiles/ncu_r01h_xs_lookup.txt) and frac can exceed 1; the direct kernel reads every bracket itself"}
     ref = None
     for name, mode in (("direct", 0), ("sort_plus_staged", 2)):
         ctx.xs_lookup_device(points, E.data_ptr(), mat.data_ptr(), out.data_ptr(), 1, mode)  # warm-up

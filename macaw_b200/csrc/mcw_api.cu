@@ -610,7 +610,7 @@ static int prepare(mcw_handle h)
     prm.push_back(n.prm);
   }
   std::vector<int32_t> mat_off(1, 0), mat_nuc, mat_fis, mat_iso;
-  std::vector<double> mat_dens;
+  std::vector<double> mat_dens, mat_e0, mat_e1;
   for (int m = 0; m < n_mat; ++m)
   {
     bool fis = false;
@@ -619,6 +619,8 @@ static int prepare(mcw_handle h)
       mat_nuc.push_back(h->mat_nuc[m][i]);
       mat_dens.push_back(h->mat_dens[m][i]);
       mat_iso.push_back(h->mat_iso[m][i] != 0);
+      mat_e0.push_back(h->nuclides[h->mat_nuc[m][i]].energy.front());
+      mat_e1.push_back(h->nuclides[h->mat_nuc[m][i]].energy.back());
       fis |= h->nuclides[h->mat_nuc[m][i]].prm.fissionable != 0;
     }
     mat_off.push_back((int32_t)mat_nuc.size());
@@ -640,6 +642,11 @@ static int prepare(mcw_handle h)
   int32_t* d_miso;
   CK(dev_upload(h, &d_miso, mat_iso));
   P.lib.mat_iso = d_miso;
+  double *d_me0, *d_me1;
+  CK(dev_upload(h, &d_me0, mat_e0));
+  CK(dev_upload(h, &d_me1, mat_e1));
+  P.lib.mat_e0 = d_me0;
+  P.lib.mat_e1 = d_me1;
   CK(dev_upload(h, &d_mfis, mat_fis));
   P.lib.energy = d_energy;
   P.lib.xs4 = d_xs4;
@@ -1590,11 +1597,11 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
     if (sorted == 0)
       mcwk_xs_lookup_array(h->P.lib, n, E, mat, (double*)d_out, h->stream);
     else if (sorted == 1)
-      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, nullptr, (double*)d_out, h->stream);
+      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, nullptr, (double*)d_out, h->xs_plan != 0, h->stream);
     else
     {
       mcwk_xs_sort(n, E, mat, temp, temp_bytes, keys, keys_out, idx, idx_sorted, h->stream);
-      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, idx_sorted, (double*)d_out, h->stream);
+      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, idx_sorted, (double*)d_out, h->xs_plan != 0, h->stream);
     }
   }
   CK(cudaEventRecord(h->ev[1], h->stream));

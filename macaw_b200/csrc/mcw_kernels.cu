@@ -775,11 +775,15 @@ void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, si
 }
 
 void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
-                           double* out, cudaStream_t st)
+                           double* out, bool plan, cudaStream_t st)
 {
   if (n <= 0)
     return;
-  k_xs_lookup_staged<<<(unsigned)((n + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(L, n, E, mat, order, out);
+  const unsigned tiles = (unsigned)((n + MCW_XS_TILE - 1) / MCW_XS_TILE);
+  if (plan)
+    k_xs_lookup_plan<<<tiles, MCW_XS_TILE, 0, st>>>(L, n, E, mat, order, out);
+  else
+    k_xs_lookup_staged<<<tiles, MCW_XS_TILE, 0, st>>>(L, n, E, mat, order, out);
 }
 
 // queue = the histories whose status equals `want`, in history-index order; *count = how many

@@ -15,7 +15,7 @@ int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned lon
 void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, size_t temp_bytes, uint32_t* keys,
                   uint32_t* keys_out, int32_t* idx, int32_t* idx_sorted, cudaStream_t st);
 void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
-                           double* out, cudaStream_t st);
+                           double* out, bool plan, cudaStream_t st);
 size_t mcwk_sort_temp_bytes(int64_t n);
 void mcwk_compact_status(void* temp, size_t temp_bytes, const int8_t* status, int64_t n, int want, int32_t* queue,
                          unsigned long long* count, cudaStream_t st);

@@ -48,6 +48,8 @@ struct McwLibraryDev
   const int32_t* mat_nuc;    // concatenated nuclide indices
   const double* mat_dens;
   const int32_t* mat_iso;    // isotropic-in-lab flag per material entry (OMC material.cpp p0_)
+  const double* mat_e0;      // first / last grid energy of the entry's nuclide (staged lookup)
+  const double* mat_e1;
   const int32_t* mat_fissionable;
   int32_t n_nuc, n_mat, M;
   double E_min, E_max, log_spacing;

@@ -54,10 +54,12 @@ def test_xs_lookup_sorted_staged_bit_exact(oracle_bridge, ctx_factory, name, n):
     want = o.xs_lookup(E, mat).view(np.uint64)
     dE, dm = torch.from_numpy(E).cuda(), torch.from_numpy(mat).cuda()
     out = torch.zeros(n * 4, dtype=torch.float64, device="cuda")
-    for mode in (0, 2, 1):
-        out.zero_()
-        g.xs_lookup_device(n, dE.data_ptr(), dm.data_ptr(), out.data_ptr(), 1, mode)
-        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 4), want), mode
+    for plan in (1, 0):  # k_xs_lookup_plan (all windows of a pass staged at once) / k_xs_lookup_staged (per nuclide)
+        g.set_option("xs_plan", plan)
+        for mode in (0, 2, 1):
+            out.zero_()
+            g.xs_lookup_device(n, dE.data_ptr(), dm.data_ptr(), out.data_ptr(), 1, mode)
+            assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 4), want), (plan, mode)
     order = np.lexsort((E, mat))
     dE, dm = torch.from_numpy(E[order].copy()).cuda(), torch.from_numpy(mat[order].copy()).cuda()
     out.zero_()
