@@ -1,7 +1,7 @@
 """Hunt for failed traces (fate 2: counted and killed, RT FAILED_TRACES with tolerate_failure) on the
 bench workload at 2M histories per batch and check each one against the CPU oracle: same source
 bank, same batch -> the oracle must report the same fate, segment count and last element for that
-history.  Run on the GPU box:  python profiles/failed_trace_check.py [n_particles] [n_batches]"""
+history.  Run on the GPU box:  python tests/failed_trace_check.py [n_particles] [n_batches]"""
 import os
 import sys
 import time
