@@ -45,6 +45,12 @@ def build_problem(name, particles_total, n_inactive):
         L = 17 * meshgen.PIN_PITCH
         box = (0, 0, -1, L, L, 1)
         et = "quad4"
+    elif name == "beavrs_assembly":
+        # the reference's own mesh (31enr_16_in.e via tests/golden/make_beavrs_mesh.py), 35 synthetic nuclides
+        mesh = meshgen.beavrs_assembly_file(os.path.join(ROOT, "tests", "golden", "beavrs_assembly_mesh.npz"))
+        lib = nucdata.make_library(35, G=10000, seed=1)
+        box = (-0.6, -20.7, -1, 20.7, 0.6, 1)  # examples/beavrs_assembly/settings.xml source box
+        et = "quad4"
     elif name == "assembly_hex":
         mesh = meshgen.assembly_hex(17, 9, 4)  # 153*153*4 = 93 636 HEX8 (reference 3-D assembly: 95 504)
         lib = nucdata.make_library(35, G=10000, seed=1)
@@ -70,6 +76,10 @@ def build_problem(name, particles_total, n_inactive):
     n_mat = len(lib.materials)
     blocks = list(range(n_mat)) if name != "infinite_medium" else [0, 1]
     mats = [b + 1 for b in blocks]
+    if name == "beavrs_assembly":
+        role = {"fuel": 1, "gap": 2, "clad": 3, "water": 4}  # OpenMC ids of the synthetic library's four materials
+        blocks = sorted(meshgen.BEAVRS_BLOCK_ROLE)
+        mats = [role[meshgen.BEAVRS_BLOCK_ROLE[b]] for b in blocks]
     return mesh, lib, blocks, mats, s, et
 
 

@@ -1,0 +1,63 @@
+"""Reader for Exodus-II meshes stored as classic NetCDF (what MaCaw's FileMeshGenerator inputs are, e.g.
+examples/beavrs_assembly/31enr_16_in.e): coordinates, element blocks (QUAD4 / TET4 / HEX8), block ids
+and side sets -> meshgen.Mesh.  scipy's netcdf_file reads the container; no libMesh / netCDF4 needed.
+Host-side set-up code; the hot path never sees it.
+
+Exodus numbers nodes, elements and sides from 1; its QUAD4 / HEX8 / TET4 node and side orders are the
+libMesh ones (libMesh's ExodusII_IO conversion tables are the identity for these three types)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import meshgen
+
+_TYPES = {"QUAD4": meshgen.QUAD4, "QUAD": meshgen.QUAD4, "TETRA4": meshgen.TET4, "TETRA": meshgen.TET4,
+          "TET4": meshgen.TET4, "HEX8": meshgen.HEX8, "HEX": meshgen.HEX8}
+
+
+def read_exodus(path, reflect=(), kill=()) -> meshgen.Mesh:
+    """`reflect` / `kill`: side-set ids carrying ReflectRayBC / KillRayBC (boundary ids of the input's
+    [RayBCs] block); boundary sides in no listed set get no id (the ray is killed there)."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    dim = f.dimensions["num_dim"]
+    xyz = np.zeros((f.dimensions["num_nodes"], 3))
+    if "coord" in v:
+        xyz[:, :dim] = np.asarray(v["coord"][:]).T
+    else:
+        for d, name in enumerate(("coordx", "coordy", "coordz")[:dim]):
+            xyz[:, d] = v[name][:]
+    conns, blocks, etype = [], [], None
+    ids = np.asarray(v["eb_prop1"][:])
+    for b in range(f.dimensions["num_el_blk"]):
+        c = v[f"connect{b + 1}"]
+        t = _TYPES.get(c.elem_type.decode().strip().upper())
+        if t is None:
+            raise ValueError(f"element type {c.elem_type!r} is not traced by this path (QUAD4, TET4, HEX8)")
+        if etype is not None and t != etype:
+            raise ValueError("mixed element types in one mesh")
+        etype = t
+        conns.append(np.asarray(c[:], np.int64) - 1)
+        blocks.append(np.full(c.shape[0], ids[b], np.int32))
+    conn, block_id = np.concatenate(conns), np.concatenate(blocks)
+    m = meshgen.Mesh(etype, xyz, conn, block_id, name=str(path))
+    m.neighbors = meshgen.compute_neighbors(etype, conn)
+    sb = np.full(m.neighbors.shape, -1, np.int32)
+    ss_ids = np.asarray(v["ss_prop1"][:]) if "ss_prop1" in v else np.zeros(0, int)
+    wanted = {int(i): meshgen.BC_REFLECT for i in reflect}
+    wanted.update({int(i): meshgen.BC_KILL for i in kill})
+    for k, sid in enumerate(ss_ids):
+        if int(sid) not in wanted:
+            continue
+        e = np.asarray(v[f"elem_ss{k + 1}"][:], np.int64) - 1
+        s = np.asarray(v[f"side_ss{k + 1}"][:], np.int64) - 1
+        on_boundary = m.neighbors[e, s] < 0
+        sb[e[on_boundary], s[on_boundary]] = int(sid)
+    m.side_bnd_id = sb
+    n_bnd = (max(wanted) + 1) if wanted else 0
+    m.bnd_kind = np.zeros(n_bnd, np.int32)
+    for sid, kind in wanted.items():
+        m.bnd_kind[sid] = kind
+    f.close()
+    return m

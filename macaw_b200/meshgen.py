@@ -250,3 +250,21 @@ def brick_tet(n, bc=BC_KILL, checker=4) -> Mesh:
         q = np.floor(c / (L / checker)).astype(int)
         return np.where((q.sum(axis=1) % 2) == 0, 0, 3).astype(np.int32)
     return tet_grid(n, n, n, (0, 0, 0), (L, L, L), bc, blocks, f"brick_tet_{n}")
+
+
+# BEAVRS assembly blocks -> role (examples/beavrs_assembly/run_assembly.i:39-44 with materials.xml):
+# 10004 helium gap, 10006 and 11006 Zircaloy-4 (cladding, guide tubes), 10010 fuel 3.1 %, 10014 borated water
+BEAVRS_BLOCK_ROLE = {10004: "gap", 10006: "clad", 10010: "fuel", 10014: "water", 11006: "clad"}
+
+
+def beavrs_assembly_file(path) -> Mesh:
+    """C3 on the reference's own mesh: the .npz written by tests/golden/make_beavrs_mesh.py from
+    31enr_16_in.e (23 876 QUAD4, reflecting side sets 1-4)."""
+    z = np.load(path)
+    xyz = np.zeros((z["xy"].shape[0], 3))
+    xyz[:, :2] = z["xy"]
+    m = Mesh(QUAD4, xyz, z["conn"].astype(np.int64), z["block_id"].astype(np.int32), name="beavrs_assembly")
+    m.neighbors = compute_neighbors(QUAD4, m.conn)
+    m.side_bnd_id = z["side_bnd_id"].astype(np.int32)
+    m.bnd_kind = z["bnd_kind"].astype(np.int32)
+    return m

@@ -11,6 +11,9 @@ def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tall
     # block ids are 0..n_materials-1 in every synthetic mesh; pass them explicitly because a coarse mesh
     # may not contain every block (e.g. no element centroid falls inside the thin gap)
     block_ids = np.arange(len(block_material), dtype=np.int32)
+    if int(mesh.block_id.max()) >= len(block_material):  # raw Exodus subdomain ids (BEAVRS: 10004 ... 11006)
+        block_ids = mesh.block_ids_sorted()
+        assert block_ids.size == len(block_material)
     if hasattr(obj, "L") and hasattr(obj.L, "orc_create"):
         obj.set_mesh(mesh, block_ids)
         obj.set_library(lib, block_material)
@@ -74,7 +77,20 @@ def pin_cell_tet_iso(**kw):
     return mesh, lib, bm, s
 
 
-PROBLEMS = {"infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
+def beavrs_assembly(n_particles=3000, G=400, n_inactive=1, **kw):
+    """BASELINE.json configs[2] on the reference's own mesh (tests/golden/beavrs_assembly_mesh.npz, 23 876 QUAD4
+    from examples/beavrs_assembly/31enr_16_in.e) with the settings.xml source box; 35 synthetic nuclides."""
+    import os
+    mesh = meshgen.beavrs_assembly_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                     "beavrs_assembly_mesh.npz"))
+    lib = nucdata.make_library(35, G=G)
+    s = cstructs.make_settings(n_particles, n_inactive=n_inactive, is_2d=True, z_coord=100.0,
+                               source_box=(-0.6, -20.7, -1, 20.7, 0.6, 1), **kw)
+    role = {"fuel": 0, "gap": 1, "clad": 2, "water": 3}
+    return mesh, lib, [role[meshgen.BEAVRS_BLOCK_ROLE[b]] for b in sorted(meshgen.BEAVRS_BLOCK_ROLE)], s
+
+
+PROBLEMS = {"beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
             "infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,
             "assembly_quad": assembly_quad}
 

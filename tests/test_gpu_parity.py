@@ -130,6 +130,8 @@ SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 1, "xs_plan": 0}  # k_x
     ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 1, "ordered_queues": 0}),
     ("pin_cell_tet", {"seed_through_double": False}, MIXED),
     ("infinite_medium_iso", {}, EVENT), ("pin_cell_tet_iso", {}, MIXED),
+    # the reference's own BEAVRS assembly mesh (31enr_16_in.e, raw block ids 10004 ... 11006), 35 nuclides
+    ("beavrs_assembly", {}, MIXED), ("beavrs_assembly", {"sort_xs_queue": 1}, SORTED),
     # 20 000 histories: host syncs every 4th round, so the general-walk queue is served only after syncs
     ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000}),
     ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000, "fallback_every_round": 1}),

@@ -123,3 +123,31 @@ def test_bank_synchronisation_world_size_n_equals_single_rank(oracle_bridge, tmp
         assert np.allclose(p["ks"], ks, rtol=1e-12, atol=0)  # summation order differs across ranks only
     _, t_sum, _, _ = o.get_tally(1)
     assert np.allclose(sum(p["tally_sum"] for p in parts), t_sum, rtol=1e-11, atol=1e-300)
+
+
+def test_exodus_reader_and_beavrs_mesh_fixture(golden_dir):
+    """macaw_b200/exodus.py on the reference's BEAVRS assembly mesh (when the reference tree is here) must
+    reproduce the committed fixture; the fixture itself must be a closed, positively oriented QUAD4 mesh
+    of the published size with every boundary side in one of the reflecting side sets 1-4."""
+    import numpy as np
+    from macaw_b200 import exodus, meshgen
+    path = os.path.join(golden_dir, "beavrs_assembly_mesh.npz")
+    m = meshgen.beavrs_assembly_file(path)
+    assert m.n_elem == 23876 and m.xyz.shape[0] == 24081  # SURVEY section 8: C3
+    ids, counts = np.unique(m.block_id, return_counts=True)
+    assert ids.tolist() == [10004, 10006, 10010, 10014, 11006] and counts.tolist() == [4224, 4224, 8448, 6580, 400]
+    p = m.xyz[m.conn]
+    area = 0.5 * ((p[:, 1, 0] - p[:, 3, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 3, 1]))
+    assert area.min() > 0 and abs(area.sum() - (17 * 1.25984) ** 2) < 1e-6
+    boundary = m.neighbors < 0
+    assert boundary.sum() == 408 and set(np.unique(m.side_bnd_id[boundary]).tolist()) == {1, 2, 3, 4}
+    assert (m.side_bnd_id[~boundary] == -1).all() and m.bnd_kind.tolist() == [0, 1, 1, 1, 1]
+    # neighbour symmetry: the neighbour of my side s has me as a neighbour
+    e, s = np.nonzero(~boundary)
+    nb = m.neighbors[e, s]
+    assert (m.neighbors[nb] == e[:, None]).any(axis=1).all()
+    ref = "/root/reference/examples/beavrs_assembly/31enr_16_in.e"
+    if os.path.exists(ref):
+        r = exodus.read_exodus(ref, reflect=(1, 2, 3, 4))
+        assert np.array_equal(r.xyz, m.xyz) and np.array_equal(r.conn, m.conn) and np.array_equal(r.block_id, m.block_id)
+        assert np.array_equal(r.side_bnd_id, m.side_bnd_id) and np.array_equal(r.bnd_kind, m.bnd_kind)
