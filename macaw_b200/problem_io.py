@@ -108,12 +108,32 @@ def write_library(path, lib):
 
 if __name__ == "__main__":
     import argparse
-    from . import nucdata
-    ap = argparse.ArgumentParser(description="write the synthetic nuclide table file read by host/mcw_run --tables")
-    ap.add_argument("--library", required=True)
+    from . import cstructs, exodus, nucdata
+    ap = argparse.ArgumentParser(description="nuclide table files (--library) and problem files (--problem) for host/mcw_run")
+    ap.add_argument("--library", help="write the synthetic nuclide table file read by mcw_run --tables")
+    ap.add_argument("--problem", help="write a problem file from an Exodus mesh (FileMeshGenerator inputs)")
+    ap.add_argument("--exodus", help="Exodus-II mesh (classic NetCDF), e.g. examples/beavrs_assembly/31enr_16_in.e")
+    ap.add_argument("--reflect", type=int, nargs="*", default=[], help="side-set ids with ReflectRayBC")
+    ap.add_argument("--kill", type=int, nargs="*", default=[], help="side-set ids with KillRayBC")
+    ap.add_argument("--blocks", type=int, nargs="*", help="CollisionKernel blocks")
+    ap.add_argument("--materials", type=int, nargs="*", help="CollisionKernel materials (1-based ids into the library's materials)")
+    ap.add_argument("--particles", type=int, default=100000)
+    ap.add_argument("--inactive", type=int, default=0)
+    ap.add_argument("--box", type=float, nargs=6, help="source box: x0 y0 z0 x1 y1 z1")
+    ap.add_argument("--z-coord", type=float, default=0.0)
     ap.add_argument("--nuclides", type=int, default=9)
     ap.add_argument("--grid-points", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
-    write_library(a.library, nucdata.make_library(a.nuclides, G=a.grid_points, seed=a.seed))
-    print(a.library)
+    lib = nucdata.make_library(a.nuclides, G=a.grid_points, seed=a.seed)
+    if a.library:
+        write_library(a.library, lib)
+        print(a.library)
+    if a.problem:
+        if not (a.exodus and a.blocks and a.materials and a.box):
+            ap.error("--problem needs --exodus, --blocks, --materials and --box")
+        mesh = exodus.read_exodus(a.exodus, reflect=a.reflect, kill=a.kill)
+        s = cstructs.make_settings(a.particles, n_inactive=a.inactive, is_2d=mesh.dim == 2, z_coord=a.z_coord,
+                                   source_box=a.box, record_traces=0)
+        write_problem(a.problem, mesh, lib, a.blocks, a.materials, s, [(1, 0, 0, [0], None)])
+        print(a.problem, mesh.n_elem, "elements")
