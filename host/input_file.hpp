@@ -3,6 +3,8 @@
 //   * a MOOSE input file (hit syntax: [Block] / [./sub] [../] / [A/B] paths, key = value, quoted lists,
 //     # comments) with the blocks MaCaw's examples use for the path:
 //       [Mesh]        GeneratedMeshGenerator (+ SubdomainBoundingBoxGenerator)   examples/infinite_medium/infinite_medium.i:1-22
+//                     FileMeshGenerator (Exodus-II, host/exodus_reader.hpp) + TransformGenerator TRANSLATE
+//                                                                               examples/beavrs_assembly/run_assembly.i:5-16
 //       [Variables/temperature] initial_condition                               :30-34
 //       [RayKernels]  CollisionKernel: temperature, blocks, materials, z_coord  MC raykernels/CollisionKernel.C:24-42
 //       [RayBCs]      ReflectRayBC / KillRayBC: boundary                         RT raybcs/ReflectRayBC.C, KillRayBC.C
@@ -14,8 +16,6 @@
 //   * a nuclide table file in place of cross_sections.xml + HDF5 (written by
 //     `python -m macaw_b200.problem_io --library`): the synthetic continuous-energy tables by name.
 //
-// Exodus meshes (FileMeshGenerator) need libMesh / netCDF and are not read here: such a problem goes
-// through macaw_b200/problem_io.py (scipy reads the classic-NetCDF Exodus file) into a problem file.
 // Blocks and parameters outside the list above are parsed and ignored, like MOOSE objects that are
 // not on the path (Postprocessors, Outputs, ...).  Set-up code only; nothing here is on the hot path.
 #pragma once
@@ -25,6 +25,7 @@
 #include <map>
 #include <sstream>
 
+#include "exodus_reader.hpp"
 #include "problem_io.hpp"
 
 namespace macaw
@@ -437,12 +438,26 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
   Problem& P = R.problem;
   const HitNode in = parseHit(readFile(input_path));
 
+  // ---- [RayBCs] (read first: a file mesh needs the side-set ids that carry a boundary condition)
+  std::vector<std::pair<int, std::vector<std::string>>> ray_bcs; // (kind, boundary names or ids)
+  if (const HitNode* bc = in.child("RayBCs"))
+    for (const auto& b : bc->children)
+    {
+      const std::string type = b.get("type");
+      const int kind = type == "ReflectRayBC" ? MCW_BC_REFLECT : type == "KillRayBC" ? MCW_BC_KILL : -1;
+      if (kind < 0)
+        mooseError("RayBC '" + type + "' is not on this path");
+      ray_bcs.emplace_back(kind, splitWords(b.get("boundary")));
+    }
+
   // ---- [Mesh]
   const HitNode* mesh = in.child("Mesh");
   if (!mesh)
     mooseError("the input has no [Mesh] block");
-  bool have_mesh = false;
+  bool have_mesh = false, file_mesh = false;
   int dim = 3;
+  const size_t slash = input_path.find_last_of('/');
+  const std::string input_dir = slash == std::string::npos ? "." : input_path.substr(0, slash);
   std::vector<const HitNode*> generators;
   for (const auto& g : mesh->children)
     generators.push_back(&g);
@@ -458,6 +473,44 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
       const double hi[3] = {std::stod(g->get("xmax", "1")), std::stod(g->get("ymax", "1")), std::stod(g->get("zmax", "1"))};
       P.mesh = generatedMesh(dim, std::stoi(g->get("nx", "1")), std::stoi(g->get("ny", "1")), std::stoi(g->get("nz", "1")), lo, hi);
       have_mesh = true;
+    }
+    else if (type == "FileMeshGenerator" || type == "FileMesh")
+    {
+      std::vector<int> reflect, kill;
+      for (const auto& bc : ray_bcs)
+        for (const auto& n : bc.second)
+        {
+          int id = -1;
+          try
+          {
+            id = std::stoi(n);
+          }
+          catch (...)
+          {
+            mooseError("boundary '" + n + "': a file mesh's side sets are addressed by id here");
+          }
+          (bc.first == MCW_BC_REFLECT ? reflect : kill).push_back(id);
+        }
+      std::string file = g->get("file");
+      if (!file.empty() && file[0] != '/')
+        file = input_dir + "/" + file;
+      P.mesh = readExodus(file, reflect, kill);
+      dim = P.mesh.dimension();
+      have_mesh = file_mesh = true;
+    }
+    else if (type == "TransformGenerator")
+    {
+      if (!have_mesh)
+        mooseError("TransformGenerator before its input mesh");
+      if (g->get("transform") != "TRANSLATE")
+        mooseError("TransformGenerator: only TRANSLATE is supported by this front end");
+      const auto v = toReals(g->get("vector_value"));
+      if (v.size() != 3)
+        mooseError("TransformGenerator: vector_value needs three components");
+      // a 2-D mesh stays in its plane: the z shift of examples/beavrs_assembly only matters through z_coord
+      for (size_t i = 0; i < P.mesh.xyz.size() / 3; ++i)
+        for (int d = 0; d < dim; ++d)
+          P.mesh.xyz[3 * i + d] += v[d];
     }
     else if (type == "SubdomainBoundingBoxGenerator")
     {
@@ -479,19 +532,18 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
           P.mesh.block_id[e] = id;
       }
     }
-    else if (type == "FileMeshGenerator" || type == "FileMesh")
-      mooseError("Exodus meshes need libMesh: convert the problem with macaw_b200/problem_io.py");
     else if (!type.empty())
       mooseError("mesh generator '" + type + "' is not supported by this front end");
   }
   if (!have_mesh)
-    mooseError("[Mesh] holds no GeneratedMeshGenerator");
+    mooseError("[Mesh] holds no GeneratedMeshGenerator or FileMeshGenerator");
 
   // ---- [Variables/temperature]
   double T0 = 0.0; // MOOSE default initial condition (the study test runs with T = 0)
-  if (const HitNode* v = in.child("Variables"))
-    if (const HitNode* t = v->child("temperature"))
-      T0 = std::stod(t->get("initial_condition", "0"));
+  for (const char* blk : {"Variables", "AuxVariables"}) // the examples declare it either way
+    if (const HitNode* v = in.child(blk))
+      if (const HitNode* t = v->child("temperature"))
+        T0 = std::stod(t->get("initial_condition", "0"));
 
   // ---- [RayKernels]: the CollisionKernel
   const HitNode* ck = nullptr;
@@ -511,22 +563,16 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
     mooseError("The z_coord parameter must be specified for 2D calculations"); // MC CollisionKernel.C:60-61
   // blocks named by the kernel but absent from the mesh are legal (examples list "0 1 2" for a 2-block mesh)
 
-  // ---- [RayBCs]
-  if (const HitNode* bc = in.child("RayBCs"))
-    for (const auto& b : bc->children)
-    {
-      const std::string type = b.get("type");
-      const int kind = type == "ReflectRayBC" ? MCW_BC_REFLECT : type == "KillRayBC" ? MCW_BC_KILL : -1;
-      if (kind < 0)
-        mooseError("RayBC '" + type + "' is not on this path");
-      for (const auto& n : splitWords(b.get("boundary")))
+  // ---- [RayBCs] on a generated mesh: boundaries by name or id (a file mesh got them in readExodus)
+  if (!file_mesh)
+    for (const auto& bc : ray_bcs)
+      for (const auto& n : bc.second)
       {
         const int id = boundaryIdByName(dim, n);
         if (id < 0 || id >= (int)P.mesh.bnd_kind.size())
           mooseError("boundary '" + n + "' does not exist on the mesh");
-        P.mesh.bnd_kind[id] = kind;
+        P.mesh.bnd_kind[id] = bc.first;
       }
-    }
 
   // ---- [UserObjects]: OpenMCStudy (present), OpenMCTally
   bool have_study = false;
@@ -663,6 +709,9 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
     }
     for (double f : frac)
       M.atom_density.push_back(f * density);
+    if (const XmlNode* sab = m.child("sab"))
+      std::fprintf(stderr, "note: material %s: S(alpha,beta) table %s ignored (thermal scattering data are not on this path yet)\n",
+                   m.value("id").c_str(), sab->value("name").c_str());
     if (const XmlNode* iso = m.child("isotropic"))
     {
       const auto list = splitWords(iso->text);

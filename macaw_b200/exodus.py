@@ -61,3 +61,54 @@ def read_exodus(path, reflect=(), kill=()) -> meshgen.Mesh:
         m.bnd_kind[sid] = kind
     f.close()
     return m
+
+
+def write_exodus(path, m: meshgen.Mesh, block_names=None):
+    """Minimal Exodus-II writer (classic NetCDF, 64-bit offsets): coordinates, one element block per
+    subdomain id, one side set per boundary id present on the mesh.  Enough for read_exodus, the C++
+    reader (host/exodus_reader.hpp) and libMesh's ExodusII_IO; used to hand generated meshes to the
+    FileMeshGenerator path."""
+    from scipy.io import netcdf_file
+    names = {meshgen.QUAD4: "QUAD4", meshgen.TET4: "TETRA4", meshgen.HEX8: "HEX8"}
+    ids = m.block_ids_sorted()
+    bnd = np.unique(m.side_bnd_id[m.side_bnd_id >= 0])
+    f = netcdf_file(path, "w", version=2)
+    f.title = "macaw_b200 mesh export"
+    f.createDimension("len_string", 33)
+    f.createDimension("num_dim", m.dim)
+    f.createDimension("num_nodes", m.xyz.shape[0])
+    f.createDimension("num_elem", m.n_elem)
+    f.createDimension("num_el_blk", ids.size)
+    if bnd.size:
+        f.createDimension("num_side_sets", bnd.size)
+    for d, name in enumerate(("coordx", "coordy", "coordz")[:m.dim]):
+        v = f.createVariable(name, ">f8", ("num_nodes",))
+        v[:] = m.xyz[:, d]
+    v = f.createVariable("eb_prop1", ">i4", ("num_el_blk",))
+    v[:] = ids
+    v.name = "ID"
+    order = []
+    for b, bid in enumerate(ids):
+        elems = np.nonzero(m.block_id == bid)[0]
+        order.append(elems)
+        f.createDimension(f"num_el_in_blk{b + 1}", elems.size)
+        f.createDimension(f"num_nod_per_el{b + 1}", m.conn.shape[1])
+        v = f.createVariable(f"connect{b + 1}", ">i4", (f"num_el_in_blk{b + 1}", f"num_nod_per_el{b + 1}"))
+        v[:] = m.conn[elems] + 1
+        v.elem_type = names[m.elem_type]
+    # Exodus numbers elements block by block
+    new_id = np.empty(m.n_elem, np.int64)
+    new_id[np.concatenate(order)] = np.arange(m.n_elem)
+    if bnd.size:
+        v = f.createVariable("ss_prop1", ">i4", ("num_side_sets",))
+        v[:] = bnd
+        v.name = "ID"
+        for k, sid in enumerate(bnd):
+            e, sd = np.nonzero(m.side_bnd_id == sid)
+            f.createDimension(f"num_side_ss{k + 1}", e.size)
+            ve = f.createVariable(f"elem_ss{k + 1}", ">i4", (f"num_side_ss{k + 1}",))
+            ve[:] = new_id[e] + 1
+            vs = f.createVariable(f"side_ss{k + 1}", ">i4", (f"num_side_ss{k + 1}",))
+            vs[:] = sd + 1
+    f.close()
+    return np.concatenate(order)  # old element index of every element in file order

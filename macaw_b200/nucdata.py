@@ -168,6 +168,36 @@ def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000) -> Library:
     return Library(nucs, mats, n_log_bins)
 
 
+def library_for_names(names, G=2000, seed=1, n_log_bins=8000) -> Library:
+    """One synthetic nuclide per name (e.g. every nuclide of a materials.xml), so an unmodified OpenMC
+    deck can run without ENDF/B data: the named base nuclides keep their parameters, any other name gets
+    parameters drawn from a stream seeded by the name (mass number from its digits, fissile / fertile
+    actinides by element).  The shapes are plausible, the values are NOT evaluated nuclear data."""
+    import re
+    import zlib
+    base = {b[0]: b for b in _BASE}
+    nucs = []
+    for name in names:
+        rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
+        if name in base:
+            _, awr, kw = base[name]
+        else:
+            m = re.match(r"([A-Za-z]+)(\d+)", name)
+            a = int(m.group(2)) if m else 100
+            el = m.group(1) if m else name
+            awr = 0.9914 * a if a > 1 else 0.9992
+            kw = dict(sig_el=float(rng.uniform(3, 12)), cap0=float(np.exp(rng.uniform(np.log(0.01), np.log(50)))),
+                      n_res=int(rng.integers(0, 30)) if a > 20 else 0, res_scale=float(rng.uniform(5, 200)),
+                      inel=float(rng.uniform(0, 2)) if a > 10 else 0.0,
+                      inel_E=float(np.exp(rng.uniform(np.log(5e4), np.log(3e6)))))
+            if el in ("U", "Pu", "Th", "Np", "Am", "Cm"):
+                fissile = a % 2 == 1
+                kw.update(fis0=float(rng.uniform(300, 800)) if fissile else 0.0, fast_fis=float(rng.uniform(0.4, 2.0)),
+                          n_res=40, nu0=float(rng.uniform(2.3, 2.9)))
+        nucs.append(make_nuclide(name, awr, G, rng, **kw))
+    return Library(nucs, [], n_log_bins)
+
+
 def standard_materials(n_nuclides) -> list:
     """Material 0 fuel (UO2 3.1 %), 1 gap (He), 2 clad (Zr + generic alloying nuclides), 3 borated water.
     Indices follow `_BASE`; nuclides beyond the named ones are spread over clad and fuel like the

@@ -111,6 +111,7 @@ if __name__ == "__main__":
     from . import cstructs, exodus, nucdata
     ap = argparse.ArgumentParser(description="nuclide table files (--library) and problem files (--problem) for host/mcw_run")
     ap.add_argument("--library", help="write the synthetic nuclide table file read by mcw_run --tables")
+    ap.add_argument("--names-from", help="materials.xml: one synthetic nuclide per nuclide name found there")
     ap.add_argument("--problem", help="write a problem file from an Exodus mesh (FileMeshGenerator inputs)")
     ap.add_argument("--exodus", help="Exodus-II mesh (classic NetCDF), e.g. examples/beavrs_assembly/31enr_16_in.e")
     ap.add_argument("--reflect", type=int, nargs="*", default=[], help="side-set ids with ReflectRayBC")
@@ -126,6 +127,13 @@ if __name__ == "__main__":
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
     lib = nucdata.make_library(a.nuclides, G=a.grid_points, seed=a.seed)
+    if a.names_from:
+        import xml.etree.ElementTree as ET
+        names = []
+        for n in ET.parse(a.names_from).getroot().iter("nuclide"):
+            if n.get("name") not in names:
+                names.append(n.get("name"))
+        lib = nucdata.library_for_names(names, G=a.grid_points, seed=a.seed)
     if a.library:
         write_library(a.library, lib)
         print(a.library)

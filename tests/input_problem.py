@@ -35,7 +35,19 @@ def parse_hit(text):
 
 def read_input(input_path, xml_dir, lib):
     """-> mesh, library (nuclides in order of first use), blocks, material indices, settings, batches, tallies, aux."""
+    import os
+    from macaw_b200 import exodus
     hit = parse_hit(open(input_path).read())
+    bcs = [(v["type"], v["boundary"].split()) for k, v in hit.items() if k.startswith("RayBCs/")]
+    fm = [v for v in hit.values() if v.get("type") == "FileMeshGenerator"]
+    if fm:
+        path = os.path.join(os.path.dirname(input_path), fm[0]["file"])
+        mesh = exodus.read_exodus(path, reflect=[int(b) for t, bl in bcs if t == "ReflectRayBC" for b in bl],
+                                  kill=[int(b) for t, bl in bcs if t == "KillRayBC" for b in bl])
+        for v in hit.values():
+            if v.get("type") == "TransformGenerator":
+                mesh.xyz[:, :mesh.dim] += np.array(v["vector_value"].split(), float)[:mesh.dim]
+        return _finish_input(hit, mesh, mesh.dim, xml_dir, lib)
     g = next(v for k, v in hit.items() if v.get("type") == "GeneratedMeshGenerator")
     dim = int(g["dim"])
     lo = [float(g.get(a, 0)) for a in ("xmin", "ymin", "zmin")]
@@ -61,8 +73,12 @@ def read_input(input_path, xml_dir, lib):
             for b in v["boundary"].split():
                 kinds[names.index(b)] = meshgen.BC_REFLECT if v["type"] == "ReflectRayBC" else meshgen.BC_KILL
     mesh.bnd_kind = kinds
+    return _finish_input(hit, mesh, dim, xml_dir, lib)
+
+
+def _finish_input(hit, mesh, dim, xml_dir, lib):
     ck = next(v for v in hit.values() if v.get("type") == "CollisionKernel")
-    T0 = float(hit.get("Variables/temperature", {}).get("initial_condition", 0))
+    T0 = float(hit.get("Variables/temperature", hit.get("AuxVariables/temperature", {})).get("initial_condition", 0))
 
     st = ET.parse(f"{xml_dir}/settings.xml").getroot()
     box = [float(x) for x in st.find("source/space/parameters").text.split()]
@@ -88,7 +104,7 @@ def read_input(input_path, xml_dir, lib):
             total += f
         d = m.find("density")
         units = d.get("units")
-        density = total if units == "sum" else float(d.get("value")) * (1 if units == "atom/b-cm" else -1)
+        density = total if units == "sum" else float(d.get("value")) * (1 if units == "atom/b-cm" else -1)  # g/cm3 | g/cc
         frac = frac / total
         if density < 0:
             sp = 0.0

@@ -129,7 +129,9 @@ def test_input_file_front_end_rejects_what_the_reference_rejects(tmp_path):
     cases = [(text.replace('materials = "4 1"', 'materials = "4 9"'), "is not in materials.xml"),
              (text.replace("type = CollisionKernel", "type = SomethingElse"), "no CollisionKernel"),
              (text.replace("dim = 3", "dim = 2"), "z_coord parameter must be specified for 2D"),
-             (text.replace("GeneratedMeshGenerator", "FileMeshGenerator"), "Exodus meshes need libMesh")]
+             (text.replace("GeneratedMeshGenerator", "FileMeshGenerator"), "a file mesh's side sets are addressed by id"),
+             (text.replace("GeneratedMeshGenerator", "FileMeshGenerator\n    file = nowhere.e").replace(
+                 "'back front top right left bottom'", "'1 2'"), "cannot open mesh file")]
     for k, (bad, msg) in enumerate(cases):
         d = tmp_path / f"case{k}"
         d.mkdir()
@@ -170,3 +172,102 @@ def test_input_file_run_matches_oracle(oracle_bridge, tmp_path):
     got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
     assert nr == batches - s.n_inactive and got.shape == want.shape
     assert np.allclose(got, want, rtol=1e-10, atol=1e-300) and want.sum() > 0
+
+
+# ---- FileMeshGenerator decks: Exodus mesh through host/exodus_reader.hpp
+def _file_mesh_deck(tmp_path):
+    """examples/assembly_file with its mesh written from the committed fixture of the reference's mesh."""
+    import shutil
+    from macaw_b200 import exodus, meshgen
+    d = tmp_path / "assembly_file"
+    shutil.copytree(os.path.join(ROOT, "examples", "assembly_file"), d, ignore=shutil.ignore_patterns("*.e"))
+    exodus.write_exodus(str(d / "assembly.e"),
+                        meshgen.beavrs_assembly_file(os.path.join(ROOT, "tests", "golden", "beavrs_assembly_mesh.npz")))
+    return str(d)
+
+
+def _check_against_restatement(d, mesh, library, blocks, mat_index, s, T0, batches):
+    assert d["n_elem"] == mesh.n_elem and d["elem_type"] == mesh.elem_type and d["n_nodes"] == mesh.xyz.shape[0]
+    assert np.array_equal(np.array(d["xyz"]).reshape(-1, 3), mesh.xyz)
+    assert np.array_equal(np.array(d["conn"]).reshape(mesh.conn.shape), mesh.conn)
+    assert d["block_id"] == mesh.block_id.tolist()
+    assert np.array_equal(np.array(d["side_bnd_id"]).reshape(mesh.side_bnd_id.shape), mesh.side_bnd_id)
+    assert d["bnd_kind"] == mesh.bnd_kind.tolist()
+    assert d["blocks"] == blocks and [m - 1 for m in d["materials"]] == mat_index
+    assert d["batches"] == batches and d["n_particles"] == s.n_particles and d["n_inactive"] == s.n_inactive
+    assert d["temperature"] == T0 and d["source_box"] == [s.source_box[i] for i in range(6)]
+    assert d["only_fissionable"] == s.source_only_fissionable
+    assert len(d["library_materials"]) == len(library.materials) and d["n_library_nuclides"] == len(library.nuclides)
+    for a, b in zip(d["library_materials"], library.materials):
+        assert a["nuclide"] == b.nuclides and a["atom_density"] == b.densities and a["isotropic"] == (b.isotropic or [])
+
+
+def test_file_mesh_deck_front_end(tmp_path):
+    """FileMeshGenerator + TransformGenerator + numeric side-set boundaries + [AuxVariables] temperature +
+    g/cc densities + <sab> note: the C++ front end (own NetCDF reader) equals the Python restatement
+    (scipy's reader) on the same deck -- every coordinate, side, block and atom density."""
+    from tests import input_problem
+    exe = _build()
+    tables, lib = _tables(tmp_path)
+    deck = _file_mesh_deck(tmp_path)
+    r = subprocess.run([exe, "--input", os.path.join(deck, "run.i"), "--tables", tables, "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "S(alpha,beta) table c_H_in_H2O ignored" in r.stderr
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(os.path.join(deck, "run.i"), deck, lib)
+    _check_against_restatement(json.loads(r.stdout), mesh, library, blocks, mat_index, s, T0, batches)
+    assert mesh.n_elem == 23876 and batches == 3 and T0 == 300.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/beavrs_assembly"), reason="reference tree not present")
+def test_reference_beavrs_deck_is_understood_unmodified(tmp_path):
+    """MaCaw's own examples/beavrs_assembly (run_assembly.i, settings.xml, materials.xml with 91 nuclides in 17
+    materials, 31enr_16_in.e) read in place, unmodified; nuclear data = one synthetic table per nuclide name."""
+    import xml.etree.ElementTree as ET
+    from macaw_b200 import nucdata
+    from tests import input_problem
+    exe = _build()
+    deck = "/root/reference/examples/beavrs_assembly"
+    names = []
+    for n in ET.parse(os.path.join(deck, "materials.xml")).getroot().iter("nuclide"):
+        if n.get("name") not in names:
+            names.append(n.get("name"))
+    lib = nucdata.library_for_names(names, G=200)
+    tables = str(tmp_path / "beavrs_tables.bin")
+    problem_io.write_library(tables, lib)
+    r = subprocess.run([exe, "--input", os.path.join(deck, "run_assembly.i"), "--tables", tables, "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(
+        os.path.join(deck, "run_assembly.i"), deck, lib)
+    d = json.loads(r.stdout)
+    _check_against_restatement(d, mesh, library, blocks, mat_index, s, T0, batches)
+    assert d["n_elem"] == 23876 and d["n_particles"] == 200000 and d["batches"] == 5 and len(names) == 91
+    assert len(library.materials) == 17 and blocks == [10000, 10001, 10004, 10006, 10008, 10009, 10010, 10013, 10014, 11006]
+
+
+@pytest.mark.gpu
+def test_file_mesh_deck_run_matches_oracle(oracle_bridge, tmp_path):
+    from tests import input_problem
+    exe = _build()
+    tables, lib = _tables(tmp_path)
+    deck = _file_mesh_deck(tmp_path)
+    r = subprocess.run([exe, "--input", os.path.join(deck, "run.i"), "--tables", tables], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.splitlines()]
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(os.path.join(deck, "run.i"), deck, lib)
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(library, mat_index)
+    o.set_settings(s)
+    for t in tallies:
+        o.add_tally(*t)
+    o.sample_initial_source()
+    for b in range(1, batches + 1):
+        ro, rc = o.run_generation(b), lines[b - 1]
+        assert rc["n_segments"] == ro.n_segments and rc["n_collisions"] == ro.n_collisions
+        for f in ("k_generation", "keff", "k_collision", "k_absorption", "k_tracklength"):
+            assert abs(rc[f] - getattr(ro, f)) <= 1e-11 * abs(getattr(ro, f)), f
+    _, so, _, nr = o.get_tally(1)
+    got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
+    assert nr == batches and got.shape == so.shape
+    assert np.allclose(got, so, rtol=1e-10, atol=1e-300) and so.sum() > 0
