@@ -271,3 +271,31 @@ def test_file_mesh_deck_run_matches_oracle(oracle_bridge, tmp_path):
     got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
     assert nr == batches and got.shape == so.shape
     assert np.allclose(got, so, rtol=1e-10, atol=1e-300) and so.sum() > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/tests/study"), reason="reference tree not present")
+def test_reference_study_test_deck_is_understood_unmodified(tmp_path):
+    """MaCaw's own regression input test/tests/study/openmc_study.i with its settings.xml / materials.xml
+    (30 particles, 3 batches, every nuclide <isotropic>), read in place."""
+    import xml.etree.ElementTree as ET
+    from macaw_b200 import nucdata
+    from tests import input_problem
+    exe = _build()
+    deck = "/root/reference/test/tests/study"
+    names = []
+    for n in ET.parse(os.path.join(deck, "materials.xml")).getroot().iter("nuclide"):
+        if n.get("name") not in names:
+            names.append(n.get("name"))
+    lib = nucdata.library_for_names(names, G=200)
+    tables = str(tmp_path / "study_tables.bin")
+    problem_io.write_library(tables, lib)
+    r = subprocess.run([exe, "--input", os.path.join(deck, "openmc_study.i"), "--tables", tables, "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(
+        os.path.join(deck, "openmc_study.i"), deck, lib)
+    d = json.loads(r.stdout)
+    _check_against_restatement(d, mesh, library, blocks, mat_index, s, T0, batches)
+    assert d["n_elem"] == 25 and d["n_particles"] == 30 and d["batches"] == 3 and d["n_inactive"] == 1
+    assert sum(d["block_id"]) == 1 and d["block_id"][12] == 1  # the centre element of the 5 x 5 x 1 grid
+    assert all(all(m["isotropic"]) for m in d["library_materials"])  # every nuclide isotropic-in-lab
