@@ -5,6 +5,7 @@
 //       [Mesh]        GeneratedMeshGenerator (+ SubdomainBoundingBoxGenerator)   examples/infinite_medium/infinite_medium.i:1-22
 //                     FileMeshGenerator (Exodus-II, host/exodus_reader.hpp) + TransformGenerator TRANSLATE
 //                                                                               examples/beavrs_assembly/run_assembly.i:5-16
+//                     FancyExtruderGenerator (QUAD4 -> HEX8)                     examples/beavrs_assembly/run_assembly_3d.i:16-31
 //       [Variables/temperature] initial_condition                               :30-34
 //       [RayKernels]  CollisionKernel: temperature, blocks, materials, z_coord  MC raykernels/CollisionKernel.C:24-42
 //       [RayBCs]      ReflectRayBC / KillRayBC: boundary                         RT raybcs/ReflectRayBC.C, KillRayBC.C
@@ -66,6 +67,9 @@ struct HitNode
   }
 };
 
+// MOOSE's `active = '...'` / `inactive = '...'` lists on a block select which sub-blocks exist
+inline bool blockIsActive(const HitNode& parent, const std::string& child);
+
 inline std::string trim(const std::string& s)
 {
   const size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
@@ -79,6 +83,23 @@ inline std::vector<std::string> splitWords(const std::string& s)
   for (std::string w; is >> w;)
     out.push_back(w);
   return out;
+}
+
+inline bool blockIsActive(const HitNode& parent, const std::string& child)
+{
+  if (const std::string* a = parent.find("active"))
+  {
+    const auto l = splitWords(*a);
+    if (std::find(l.begin(), l.end(), child) == l.end())
+      return false;
+  }
+  if (const std::string* a = parent.find("inactive"))
+  {
+    const auto l = splitWords(*a);
+    if (std::find(l.begin(), l.end(), child) != l.end())
+      return false;
+  }
+  return true;
 }
 
 inline std::vector<double> toReals(const std::string& s)
@@ -348,6 +369,58 @@ inline Mesh generatedMesh(int dim, int nx, int ny, int nz, const double lo[3], c
   return m;
 }
 
+// QUAD4 -> HEX8 extrusion with the numbering of MOOSE's FancyExtruderGenerator
+// (moose/framework/src/meshgenerators/FancyExtruderGenerator.C:255-285, 444-462, 551, 604-646): node id =
+// node + plane * n_nodes; element id = elem + layer * n_elem; Hex8 nodes = the quad's nodes on the lower plane,
+// then on the upper one; quad side s -> hex side s + 1 with its boundary id; hex side 0 of the first layer and
+// side 5 of the last one get the bottom / top boundary ids.  Plane positions accumulate height / num_layers.
+inline Mesh extrudeQuads(const Mesh& q, const std::vector<int>& num_layers, const std::vector<double>& heights, const double dir[3],
+                         int bottom_boundary, int top_boundary)
+{
+  if (q.elem_type != MCW_QUAD4)
+    mooseError("FancyExtruderGenerator: only QUAD4 input meshes are extruded by this front end");
+  if (num_layers.size() != heights.size() || num_layers.empty())
+    mooseError("FancyExtruderGenerator: num_layers and heights must have the same, non-zero, length");
+  std::vector<double> px{0.0}, py{0.0}, pz{0.0};
+  for (size_t e = 0; e < num_layers.size(); ++e)
+    for (int k = 0; k < num_layers[e]; ++k)
+    {
+      const double step = heights[e] / (double)num_layers[e];
+      px.push_back(px.back() + dir[0] * step);
+      py.push_back(py.back() + dir[1] * step);
+      pz.push_back(pz.back() + dir[2] * step);
+    }
+  const int64_t L = (int64_t)px.size() - 1, nn = q.nNodes(), ne = q.nElem();
+  Mesh h;
+  h.elem_type = MCW_HEX8;
+  for (int64_t k = 0; k <= L; ++k)
+    for (int64_t i = 0; i < nn; ++i)
+    {
+      h.xyz.push_back(q.xyz[3 * i] + px[k]);
+      h.xyz.push_back(q.xyz[3 * i + 1] + py[k]);
+      h.xyz.push_back(q.xyz[3 * i + 2] + pz[k]);
+    }
+  int n_bnd = (int)q.bnd_kind.size();
+  for (int64_t k = 0; k < L; ++k)
+    for (int64_t e = 0; e < ne; ++e)
+    {
+      for (int up = 0; up < 2; ++up)
+        for (int v = 0; v < 4; ++v)
+          h.conn.push_back(q.conn[4 * e + v] + (k + up) * nn);
+      h.block_id.push_back(q.block_id[e]);
+      int32_t sb[6] = {-1, q.side_bnd_id[4 * e], q.side_bnd_id[4 * e + 1], q.side_bnd_id[4 * e + 2], q.side_bnd_id[4 * e + 3], -1};
+      if (k == 0 && bottom_boundary >= 0)
+        sb[0] = bottom_boundary;
+      if (k == L - 1 && top_boundary >= 0)
+        sb[5] = top_boundary;
+      h.side_bnd_id.insert(h.side_bnd_id.end(), sb, sb + 6);
+    }
+  n_bnd = std::max(n_bnd, std::max(bottom_boundary, top_boundary) + 1);
+  h.bnd_kind.assign((size_t)n_bnd, MCW_BC_KILL);
+  std::copy(q.bnd_kind.begin(), q.bnd_kind.end(), h.bnd_kind.begin());
+  return h;
+}
+
 inline int boundaryIdByName(int dim, const std::string& n)
 {
   static const char* n3[6] = {"back", "bottom", "right", "top", "left", "front"};
@@ -443,6 +516,8 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
   if (const HitNode* bc = in.child("RayBCs"))
     for (const auto& b : bc->children)
     {
+      if (!blockIsActive(*bc, b.name))
+        continue;
       const std::string type = b.get("type");
       const int kind = type == "ReflectRayBC" ? MCW_BC_REFLECT : type == "KillRayBC" ? MCW_BC_KILL : -1;
       if (kind < 0)
@@ -507,10 +582,34 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
       const auto v = toReals(g->get("vector_value"));
       if (v.size() != 3)
         mooseError("TransformGenerator: vector_value needs three components");
-      // a 2-D mesh stays in its plane: the z shift of examples/beavrs_assembly only matters through z_coord
+      // (a 2-D run ignores z: the shift of examples/beavrs_assembly only matters through z_coord or an extrusion)
       for (size_t i = 0; i < P.mesh.xyz.size() / 3; ++i)
-        for (int d = 0; d < dim; ++d)
+        for (int d = 0; d < 3; ++d)
           P.mesh.xyz[3 * i + d] += v[d];
+    }
+    else if (type == "FancyExtruderGenerator" || type == "AdvancedExtruderGenerator")
+    {
+      if (!have_mesh)
+        mooseError("FancyExtruderGenerator before its input mesh");
+      std::vector<int> nl;
+      for (const auto& w : splitWords(g->get("num_layers")))
+        nl.push_back(std::stoi(w));
+      const auto dirv = toReals(g->get("direction"));
+      if (dirv.size() != 3)
+        mooseError("FancyExtruderGenerator: direction needs three components");
+      const double d3[3] = {dirv[0], dirv[1], dirv[2]};
+      const std::vector<int32_t> kinds = P.mesh.bnd_kind;
+      P.mesh = extrudeQuads(P.mesh, nl, toReals(g->get("heights")), d3, g->find("bottom_boundary") ? std::stoi(g->get("bottom_boundary")) : -1,
+                            g->find("top_boundary") ? std::stoi(g->get("top_boundary")) : -1);
+      dim = 3;
+      // boundary ids the extruder created may carry RayBCs too
+      for (const auto& bc : ray_bcs)
+        for (const auto& n : bc.second)
+        {
+          const int id = std::stoi(n);
+          if (id >= 0 && id < (int)P.mesh.bnd_kind.size())
+            P.mesh.bnd_kind[id] = bc.first;
+        }
     }
     else if (type == "SubdomainBoundingBoxGenerator")
     {
@@ -549,7 +648,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
   const HitNode* ck = nullptr;
   if (const HitNode* rk = in.child("RayKernels"))
     for (const auto& k : rk->children)
-      if (k.get("type") == "CollisionKernel")
+      if (k.get("type") == "CollisionKernel" && blockIsActive(*rk, k.name))
         ck = &k;
   if (!ck)
     mooseError("the input has no CollisionKernel in [RayKernels]");
@@ -557,6 +656,14 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
     P.blocks.push_back((unsigned)std::stoul(w));
   for (const auto& w : splitWords(ck->get("materials")))
     P.materials.push_back((unsigned)std::stoul(w));
+  {
+    // `temperature` is a coupled variable name, or a constant (examples/beavrs_assembly/run_assembly_3d.i:62)
+    const std::string t = ck->get("temperature");
+    char* end = nullptr;
+    const double c = std::strtod(t.c_str(), &end);
+    if (!t.empty() && end && *end == '\0')
+      T0 = c;
+  }
   P.temperature.assign(1, T0);
   P.settings.z_coord = std::stod(ck->get("z_coord", "0"));
   if (dim == 2 && !ck->find("z_coord"))
@@ -579,6 +686,8 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
   if (const HitNode* uo = in.child("UserObjects"))
     for (const auto& u : uo->children)
     {
+      if (!blockIsActive(*uo, u.name))
+        continue;
       const std::string type = u.get("type");
       if (type == "OpenMCStudy")
         have_study = true;
@@ -601,7 +710,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
   // ---- [AuxKernels]: OpenMCTallyAux
   if (const HitNode* ak = in.child("AuxKernels"))
     for (const auto& a : ak->children)
-      if (a.get("type") == "OpenMCTallyAux")
+      if (a.get("type") == "OpenMCTallyAux" && blockIsActive(*ak, a.name))
         R.aux.push_back({a.name, a.get("granularity"), a.get("score"), std::stoi(a.get("tally_id", "-1")),
                          a.find("energy_bin") ? std::stoi(a.get("energy_bin")) : -1});
 

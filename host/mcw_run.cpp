@@ -214,5 +214,10 @@ int main(int argc, char** argv)
     std::fprintf(stderr, "*** ERROR *** (%d) %s\n", e.code, e.what());
     return 1;
   }
+  catch (const std::exception& e) // e.g. a malformed number in an input file
+  {
+    std::fprintf(stderr, "*** ERROR *** %s\n", e.what());
+    return 1;
+  }
   return 0;
 }

@@ -268,3 +268,37 @@ def beavrs_assembly_file(path) -> Mesh:
     m.side_bnd_id = z["side_bnd_id"].astype(np.int32)
     m.bnd_kind = z["bnd_kind"].astype(np.int32)
     return m
+
+
+def extrude_quads(m: Mesh, num_layers, heights, direction=(0, 0, 1), bottom_boundary=None, top_boundary=None) -> Mesh:
+    """QUAD4 -> HEX8 extrusion with the numbering of MOOSE's FancyExtruderGenerator
+    (moose/framework/src/meshgenerators/FancyExtruderGenerator.C:255-285 nodes, :444-462 Hex8 nodes, :551 element
+    ids, :604-646 sides): node id = node + plane * n_nodes, element id = elem + layer * n_elem, quad side s becomes
+    hex side s + 1 with its boundary id, hex side 0 of the first layer / side 5 of the last layer get the
+    bottom / top boundary ids.  Plane positions accumulate height / num_layers like the generator does."""
+    assert m.elem_type == QUAD4
+    d = np.asarray(direction, float)
+    planes = [np.zeros(3)]
+    for nl, h in zip(num_layers, heights):
+        for _ in range(int(nl)):
+            planes.append(planes[-1] + d * (float(h) / float(nl)))
+    L = len(planes) - 1
+    nn, ne = m.xyz.shape[0], m.n_elem
+    xyz = np.concatenate([m.xyz + p for p in planes])
+    conn = np.concatenate([np.concatenate([m.conn + k * nn, m.conn + (k + 1) * nn], axis=1) for k in range(L)])
+    out = Mesh(HEX8, xyz, conn.astype(np.int64), np.tile(m.block_id, L), name=m.name + "_extruded")
+    out.neighbors = compute_neighbors(HEX8, out.conn)
+    sb = np.full((L * ne, 6), -1, np.int32)
+    for k in range(L):
+        sb[k * ne:(k + 1) * ne, 1:5] = m.side_bnd_id
+    n_bnd = m.bnd_kind.size
+    if bottom_boundary is not None:
+        sb[:ne, 0] = bottom_boundary
+        n_bnd = max(n_bnd, bottom_boundary + 1)
+    if top_boundary is not None:
+        sb[(L - 1) * ne:, 5] = top_boundary
+        n_bnd = max(n_bnd, top_boundary + 1)
+    out.side_bnd_id = sb
+    out.bnd_kind = np.zeros(n_bnd, np.int32)
+    out.bnd_kind[:m.bnd_kind.size] = m.bnd_kind
+    return out

@@ -44,9 +44,21 @@ def read_input(input_path, xml_dir, lib):
         path = os.path.join(os.path.dirname(input_path), fm[0]["file"])
         mesh = exodus.read_exodus(path, reflect=[int(b) for t, bl in bcs if t == "ReflectRayBC" for b in bl],
                                   kill=[int(b) for t, bl in bcs if t == "KillRayBC" for b in bl])
-        for v in hit.values():
+        for v in hit.values():  # generators in file order
             if v.get("type") == "TransformGenerator":
-                mesh.xyz[:, :mesh.dim] += np.array(v["vector_value"].split(), float)[:mesh.dim]
+                mesh.xyz += np.array(v["vector_value"].split(), float)
+            elif v.get("type") == "FancyExtruderGenerator":
+                kinds = mesh.bnd_kind
+                mesh = meshgen.extrude_quads(mesh, [int(x) for x in v["num_layers"].split()],
+                                             [float(x) for x in v["heights"].split()],
+                                             [float(x) for x in v["direction"].split()],
+                                             int(v["bottom_boundary"]) if "bottom_boundary" in v else None,
+                                             int(v["top_boundary"]) if "top_boundary" in v else None)
+                mesh.bnd_kind[:kinds.size] = kinds
+                for t, bl in bcs:  # ids created by the extruder
+                    for b in bl:
+                        if int(b) < mesh.bnd_kind.size:
+                            mesh.bnd_kind[int(b)] = meshgen.BC_REFLECT if t == "ReflectRayBC" else meshgen.BC_KILL
         return _finish_input(hit, mesh, mesh.dim, xml_dir, lib)
     g = next(v for k, v in hit.items() if v.get("type") == "GeneratedMeshGenerator")
     dim = int(g["dim"])
@@ -79,6 +91,10 @@ def read_input(input_path, xml_dir, lib):
 def _finish_input(hit, mesh, dim, xml_dir, lib):
     ck = next(v for v in hit.values() if v.get("type") == "CollisionKernel")
     T0 = float(hit.get("Variables/temperature", hit.get("AuxVariables/temperature", {})).get("initial_condition", 0))
+    try:
+        T0 = float(ck.get("temperature"))  # a constant instead of a coupled variable (run_assembly_3d.i:62)
+    except (TypeError, ValueError):
+        pass
 
     st = ET.parse(f"{xml_dir}/settings.xml").getroot()
     box = [float(x) for x in st.find("source/space/parameters").text.split()]
@@ -118,13 +134,19 @@ def _finish_input(hit, mesh, dim, xml_dir, lib):
     library = nucdata.Library([by_name[n] for n in order], mats, lib.n_log_bins)
     blocks = [int(b) for b in ck["blocks"].split()]
     mat_index = [index_of_id[int(i)] for i in ck["materials"].split()]
+    def active(path):
+        parent, _, child = path.rpartition("/")
+        p = hit.get(parent, {})
+        if "active" in p and child not in p["active"].split():
+            return False
+        return child not in p.get("inactive", "").split()
     tallies = []
-    for v in hit.values():
-        if v.get("type") == "OpenMCTally":
+    for k, v in hit.items():
+        if v.get("type") == "OpenMCTally" and active(k):
             filters = v["filters"].split()
             gran = "cell" if "cell" in filters else "universe" if "universe" in filters else "global"
             tallies.append((int(v["id"]), cstructs.ESTIMATOR[v.get("estimator", "COLLISION").lower()],
                             cstructs.GRANULARITY[gran], [cstructs.SCORE[x] for x in v["scores"].split()],
                             [float(x) for x in v["energy_bins"].split()] if "energy" in filters else None))
-    aux = [v for v in hit.values() if v.get("type") == "OpenMCTallyAux"]
+    aux = [v for k, v in hit.items() if v.get("type") == "OpenMCTallyAux" and active(k)]
     return mesh, library, blocks, mat_index, s, T0, batches, tallies, aux

@@ -299,3 +299,42 @@ def test_reference_study_test_deck_is_understood_unmodified(tmp_path):
     assert d["n_elem"] == 25 and d["n_particles"] == 30 and d["batches"] == 3 and d["n_inactive"] == 1
     assert sum(d["block_id"]) == 1 and d["block_id"][12] == 1  # the centre element of the 5 x 5 x 1 grid
     assert all(all(m["isotropic"]) for m in d["library_materials"])  # every nuclide isotropic-in-lab
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/beavrs_assembly"), reason="reference tree not present")
+def test_reference_beavrs_3d_deck_is_understood_unmodified(oracle_bridge, tmp_path):
+    """run_assembly_3d.i: the same Exodus mesh translated and extruded by FancyExtruderGenerator into the
+    95 504 HEX8 of SURVEY section 8 (C3 3-D), side sets 1-4 plus the extruder's 8 / 9 reflecting, a constant
+    temperature, `inactive` tallies.  The C++ front end equals the Python restatement, and the oracle walks
+    the extruded mesh without a failed trace."""
+    import xml.etree.ElementTree as ET
+    from macaw_b200 import nucdata
+    from tests import input_problem
+    exe = _build()
+    deck = "/root/reference/examples/beavrs_assembly"
+    names = []
+    for n in ET.parse(os.path.join(deck, "materials.xml")).getroot().iter("nuclide"):
+        if n.get("name") not in names:
+            names.append(n.get("name"))
+    lib = nucdata.library_for_names(names, G=200)
+    tables = str(tmp_path / "beavrs_tables.bin")
+    problem_io.write_library(tables, lib)
+    r = subprocess.run([exe, "--input", os.path.join(deck, "run_assembly_3d.i"), "--tables", tables, "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(
+        os.path.join(deck, "run_assembly_3d.i"), deck, lib)
+    d = json.loads(r.stdout)
+    _check_against_restatement(d, mesh, library, blocks, mat_index, s, T0, batches)
+    assert d["n_elem"] == 95504 and d["elem_type"] == 2 and d["bnd_kind"] == [0, 1, 1, 1, 1, 0, 0, 0, 1, 1]
+    assert d["tallies"] == len(tallies) == 1 and d["aux"] == len(aux) == 1 and T0 == 300.0
+    z = np.unique(mesh.xyz[:, 2])
+    assert z.tolist() == [-100.0, 0.0, 100.0, 200.0, 300.0]
+    s.n_particles = 400
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(library, mat_index)
+    o.set_settings(s)
+    o.sample_initial_source()
+    res = o.run_generation(1, 4)
+    assert res.n_failed_traces == 0 and res.n_segments > 100 * 400 and 0.1 < res.k_generation < 2.0
