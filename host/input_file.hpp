@@ -129,9 +129,12 @@ inline HitNode parseHit(const std::string& text)
     ++lineno;
     if (open_quote) // continuation of a multi-line quoted value
     {
-      pending_val += " " + line;
-      if (line.find(open_quote) != std::string::npos)
+      const size_t close = line.find(open_quote);
+      if (close == std::string::npos)
+        pending_val += " " + line;
+      else
       {
+        pending_val += " " + line.substr(0, close + 1); // whatever follows the closing quote is a comment
         store(pending_key, pending_val);
         open_quote = 0;
       }

@@ -338,3 +338,26 @@ def test_reference_beavrs_3d_deck_is_understood_unmodified(oracle_bridge, tmp_pa
     o.sample_initial_source()
     res = o.run_generation(1, 4)
     assert res.n_failed_traces == 0 and res.n_segments > 100 * 400 and 0.1 < res.k_generation < 2.0
+
+
+def test_hit_syntax_variants(tmp_path):
+    """The older MOOSE block syntax ([./name] ... [../]), a value quoted over several lines, comments after
+    values and a block given twice (MOOSE merges them) parse to the same problem as the plain deck."""
+    exe = _build()
+    tables, _ = _tables(tmp_path)
+    text = open(os.path.join(EXAMPLE, "study.i")).read()
+    alt = text.replace("  [add_subdomain]", "  [./add_subdomain]").replace("    block_name = 'center'\n  []", "    block_name = 'center'\n  [../]")
+    alt = alt.replace("boundary = 'back front top right left bottom'", "boundary = 'back front top\n                right left bottom'  # split over two lines")
+    alt = alt.replace("[Executioner]\n  type = Transient\n  num_steps = 4\n[]", "[Executioner]\n  type = Transient\n[]\n[Executioner]\n  num_steps = 4 # merged\n[]")
+    assert alt != text and "[../]" in alt
+    outs = []
+    for k, t in enumerate((text, alt)):
+        d = tmp_path / f"variant{k}"
+        d.mkdir()
+        (d / "study.i").write_text(t)
+        for f in ("settings.xml", "materials.xml"):
+            (d / f).write_text(open(os.path.join(EXAMPLE, f)).read())
+        r = subprocess.run([exe, "--input", str(d / "study.i"), "--tables", tables, "--check"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(json.loads(r.stdout))
+    assert outs[0] == outs[1] and outs[0]["batches"] == 4 and outs[0]["bnd_kind"] == [1] * 6
