@@ -1,12 +1,18 @@
-"""Python restatement of what host/input_file.hpp understands (MOOSE input + OpenMC settings.xml /
-materials.xml), used to check the C++ front end: same files in, same mesh / materials / settings out,
-and the same problem for the oracle."""
+"""The reference's input-file surface for the Python host: a MOOSE input (hit syntax) next to OpenMC's
+settings.xml / materials.xml -> mesh, library, CollisionKernel map, settings, tallies.  The same decks
+are read by the C++ front end (host/input_file.hpp); tests/test_cpp_host.py checks the two against each
+other field by field (exact coordinates, sides and atom densities), so each is the other's restatement.
+
+  python -m macaw_b200.inputs --input examples/study_5x5/study.i [--grid-points G]    # runs the deck on cuda:0
+
+Mesh generators: GeneratedMeshGenerator + SubdomainBoundingBoxGenerator, FileMeshGenerator (Exodus-II via
+macaw_b200/exodus.py) + TransformGenerator TRANSLATE + FancyExtruderGenerator.  Set-up code only."""
 import re
 import xml.etree.ElementTree as ET
 
 import numpy as np
 
-from macaw_b200 import cstructs, meshgen, nucdata
+from . import cstructs, meshgen, nucdata
 
 N_AVOGADRO, MASS_NEUTRON = 0.602214076, 1.00866491595  # OMC constants.h:81,89
 
@@ -36,7 +42,7 @@ def parse_hit(text):
 def read_input(input_path, xml_dir, lib):
     """-> mesh, library (nuclides in order of first use), blocks, material indices, settings, batches, tallies, aux."""
     import os
-    from macaw_b200 import exodus
+    from . import exodus
     hit = parse_hit(open(input_path).read())
     bcs = [(v["type"], v["boundary"].split()) for k, v in hit.items() if k.startswith("RayBCs/")]
     fm = [v for v in hit.values() if v.get("type") == "FileMeshGenerator"]
@@ -150,3 +156,49 @@ def _finish_input(hit, mesh, dim, xml_dir, lib):
                             [float(x) for x in v["energy_bins"].split()] if "energy" in filters else None))
     aux = [v for k, v in hit.items() if v.get("type") == "OpenMCTallyAux" and active(k)]
     return mesh, library, blocks, mat_index, s, T0, batches, tallies, aux
+
+
+def nuclide_names(materials_xml):
+    names = []
+    for n in ET.parse(materials_xml).getroot().iter("nuclide"):
+        if n.get("name") not in names:
+            names.append(n.get("name"))
+    return names
+
+
+def run_deck(input_path, xml_dir=None, grid_points=2000, device=0, batches=None, verbose=True, lib=None):
+    """Run a deck on the GPU through the Python host objects (study.py); nuclear data = one synthetic table
+    per nuclide name of materials.xml (nucdata.library_for_names).  Returns the per-batch results."""
+    import os
+    from . import study as st
+    xml_dir = xml_dir or os.path.dirname(os.path.abspath(input_path))
+    if lib is None:
+        lib = nucdata.library_for_names(nuclide_names(os.path.join(xml_dir, "materials.xml")), G=grid_points)
+    mesh, library, blocks, mat_index, s, T0, n_batches, tallies, aux = read_input(input_path, xml_dir, lib)
+    kernel = st.CollisionKernel(blocks=blocks, materials=[m + 1 for m in mat_index], temperature=T0,
+                                z_coord=s.z_coord if mesh.dim == 2 else None)
+    inv_score = {v: k for k, v in cstructs.SCORE.items()}
+    tl = []
+    for tid, est, gran, scores, ebins in tallies:
+        filters = [{0: "cell", 1: "universe"}[gran]] if gran in (0, 1) else []
+        tl.append(st.OpenMCTally(id=tid, scores=[inv_score[x] for x in scores], filters=filters + (["energy"] if ebins else []),
+                                 estimator="COLLISION" if est == 0 else "TRACKLENGTH", energy_bins=ebins))
+    study = st.OpenMCStudy(mesh, library, kernel, s, tl, device=device)
+    out = []
+    for _ in range(batches or n_batches):
+        r = study.execute()
+        out.append(r)
+        if verbose:
+            print(f"Keff {r.keff} ({r.keff_std}) Generation: {r.k_generation}")  # MC OpenMCStudy.C:399-401
+    return study, out
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="run a MOOSE / OpenMC deck on cuda:0 with synthetic nuclear data")
+    ap.add_argument("--input", required=True)
+    ap.add_argument("--xml-dir")
+    ap.add_argument("--grid-points", type=int, default=2000)
+    ap.add_argument("--batches", type=int)
+    a = ap.parse_args()
+    run_deck(a.input, a.xml_dir, a.grid_points, batches=a.batches)

@@ -96,7 +96,7 @@ def test_input_file_front_end_understands_the_example(tmp_path):
     """mcw_run --input ... --check (no GPU): mesh, boundary kinds, block map, OpenMC density
     normalisation (ao / wo / g/cm3 / atom/b-cm), <isotropic> lists and settings equal the Python
     restatement that reads the same three files."""
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     tables, lib = _tables(tmp_path)
     r = subprocess.run([exe, "--input", os.path.join(EXAMPLE, "study.i"), "--tables", tables, "--check"],
@@ -146,7 +146,7 @@ def test_input_file_front_end_rejects_what_the_reference_rejects(tmp_path):
 def test_input_file_run_matches_oracle(oracle_bridge, tmp_path):
     """The example input through the C++ host on the GPU == the oracle on the Python restatement of
     the same files: k per batch, counters, and the OpenMCTallyAux values of every element."""
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     tables, lib = _tables(tmp_path)
     r = subprocess.run([exe, "--input", os.path.join(EXAMPLE, "study.i"), "--tables", tables], capture_output=True, text=True,
@@ -206,7 +206,7 @@ def test_file_mesh_deck_front_end(tmp_path):
     """FileMeshGenerator + TransformGenerator + numeric side-set boundaries + [AuxVariables] temperature +
     g/cc densities + <sab> note: the C++ front end (own NetCDF reader) equals the Python restatement
     (scipy's reader) on the same deck -- every coordinate, side, block and atom density."""
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     tables, lib = _tables(tmp_path)
     deck = _file_mesh_deck(tmp_path)
@@ -224,7 +224,7 @@ def test_reference_beavrs_deck_is_understood_unmodified(tmp_path):
     materials, 31enr_16_in.e) read in place, unmodified; nuclear data = one synthetic table per nuclide name."""
     import xml.etree.ElementTree as ET
     from macaw_b200 import nucdata
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     deck = "/root/reference/examples/beavrs_assembly"
     names = []
@@ -247,7 +247,7 @@ def test_reference_beavrs_deck_is_understood_unmodified(tmp_path):
 
 @pytest.mark.gpu
 def test_file_mesh_deck_run_matches_oracle(oracle_bridge, tmp_path):
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     tables, lib = _tables(tmp_path)
     deck = _file_mesh_deck(tmp_path)
@@ -279,7 +279,7 @@ def test_reference_study_test_deck_is_understood_unmodified(tmp_path):
     (30 particles, 3 batches, every nuclide <isotropic>), read in place."""
     import xml.etree.ElementTree as ET
     from macaw_b200 import nucdata
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     deck = "/root/reference/test/tests/study"
     names = []
@@ -309,7 +309,7 @@ def test_reference_beavrs_3d_deck_is_understood_unmodified(oracle_bridge, tmp_pa
     the extruded mesh without a failed trace."""
     import xml.etree.ElementTree as ET
     from macaw_b200 import nucdata
-    from tests import input_problem
+    from macaw_b200 import inputs as input_problem
     exe = _build()
     deck = "/root/reference/examples/beavrs_assembly"
     names = []
@@ -361,3 +361,28 @@ def test_hit_syntax_variants(tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(json.loads(r.stdout))
     assert outs[0] == outs[1] and outs[0]["batches"] == 4 and outs[0]["bnd_kind"] == [1] * 6
+
+
+@pytest.mark.gpu
+def test_python_and_cpp_hosts_agree_on_a_deck(tmp_path):
+    """examples/study_5x5 through macaw_b200.inputs.run_deck (ctypes host) and through host/mcw_run (C++ host):
+    same counters, k within the FP64 addition-order tolerance, same per-element tally read-back."""
+    from macaw_b200 import inputs
+    exe = _build()
+    tables, lib = _tables(tmp_path)
+    deck = os.path.join(EXAMPLE, "study.i")
+    r = subprocess.run([exe, "--input", deck, "--tables", tables], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.splitlines()]
+    study, res = inputs.run_deck(deck, lib=lib, verbose=False)
+    assert len(res) == 4
+    for b, rp in enumerate(res):
+        rc = lines[b]
+        assert rc["n_segments"] == rp.n_segments and rc["n_collisions"] == rp.n_collisions
+        assert rc["n_bank_sites"] == rp.n_bank_sites
+        for f in ("k_generation", "keff", "k_collision", "k_absorption", "k_tracklength"):
+            assert abs(rc[f] - getattr(rp, f)) <= 1e-11 * abs(getattr(rp, f)), f
+    t, _, nr = study.ctx.get_tally(7)
+    got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
+    assert nr == 3 and np.allclose(got, t[:, 0, 0], rtol=1e-10, atol=1e-300)
+    study.ctx.close()
