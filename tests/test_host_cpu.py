@@ -151,3 +151,22 @@ def test_exodus_reader_and_beavrs_mesh_fixture(golden_dir):
         r = exodus.read_exodus(ref, reflect=(1, 2, 3, 4))
         assert np.array_equal(r.xyz, m.xyz) and np.array_equal(r.conn, m.conn) and np.array_equal(r.block_id, m.block_id)
         assert np.array_equal(r.side_bnd_id, m.side_bnd_id) and np.array_equal(r.bnd_kind, m.bnd_kind)
+
+
+def test_extrusion_reproduces_generated_hex_mesh():
+    """meshgen.extrude_quads (MOOSE FancyExtruderGenerator numbering, FancyExtruderGenerator.C:255-285,444-462,551,
+    604-646) of a generated QUAD4 grid is the generated HEX8 grid: same connectivity, neighbours and lateral
+    boundary ids shifted by one side, bottom / top ids on hex sides 0 / 5."""
+    import numpy as np
+    from macaw_b200 import meshgen
+    q = meshgen.quad_grid(3, 2, (0, 0), (3, 2))
+    h = meshgen.extrude_quads(q, [2, 1], [1.0, 0.5], (0, 0, 1), 8, 9)
+    g = meshgen.hex_grid(3, 2, 3, (0, 0, 0), (3, 2, 1.5))
+    assert np.array_equal(h.conn, g.conn) and np.array_equal(h.neighbors, g.neighbors)
+    assert np.allclose(h.xyz, g.xyz) and np.array_equal(h.block_id, g.block_id)
+    assert np.array_equal(h.side_bnd_id[:, 1:5], np.tile(q.side_bnd_id, (3, 1)))
+    assert (h.side_bnd_id[:6, 0] == 8).all() and (h.side_bnd_id[12:, 5] == 9).all()
+    assert (h.side_bnd_id[6:, 0] == -1).all() and (h.side_bnd_id[:12, 5] == -1).all()
+    # lateral ids: quad bottom / right / top / left = 0 / 1 / 2 / 3 sit where the hex grid has bottom / right / top / left = 1 / 2 / 3 / 4
+    lat = g.side_bnd_id[:, 1:5]
+    assert np.array_equal(np.where(lat >= 0, lat - 1, -1), h.side_bnd_id[:, 1:5])
