@@ -1,15 +1,36 @@
 // ref_shim.cpp -- extern "C" doorways into the REFERENCE's own compiled sources
-// (openmc/src/random_lcg.cpp, random_dist.cpp, math_functions.cpp), linked into
+// (openmc/src/random_lcg.cpp, random_dist.cpp, math_functions.cpp, distribution.cpp, distribution_multi.cpp,
+// position.cpp, xml_interface.cpp, string_utils.cpp + vendored pugixml), linked into
 // oracle/_ref/libomc_ref.so by oracle/Makefile.  Test infrastructure only: used to pin the oracle's
 // RNG and samplers bit-for-bit against the real reference code.  Nothing here restates an algorithm.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 
+#include "openmc/distribution_multi.h"
 #include "openmc/math_functions.h"
 #include "openmc/position.h"
 #include "openmc/random_dist.h"
 #include "openmc/random_lcg.h"
 
+// error.cpp needs MPI / HDF5-tainted headers; the samplers only reach fatal_error on malformed XML
+namespace openmc
+{
+void fatal_error(const std::string& message, int err)
+{
+  std::fprintf(stderr, "reference fatal_error: %s\n", message.c_str());
+  std::exit(err ? err : 1);
+}
+}
+
 extern "C" {
+// OMC distribution_multi.cpp:73-79 (used by isotropic-in-lab scattering, physics.cpp:715, and the source)
+void ref_isotropic_direction(double* uvw, uint64_t* seed)
+{
+  const openmc::Direction u = openmc::isotropic_direction(seed);
+  uvw[0] = u.x, uvw[1] = u.y, uvw[2] = u.z;
+}
 double ref_prn(uint64_t* seed) { return openmc::prn(seed); }
 double ref_future_prn(int64_t n, uint64_t seed) { return openmc::future_prn(n, seed); }
 uint64_t ref_future_seed(uint64_t n, uint64_t seed) { return openmc::future_seed(n, seed); }

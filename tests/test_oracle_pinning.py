@@ -78,6 +78,13 @@ def test_live_reference_library_if_present(oracle_bridge):
         assert L.orc_future_seed(n, int(seed0)) == r.ref_future_seed(n, int(seed0))
         a, b = C.c_uint64(int(seed0)), C.c_uint64(int(seed0))
         assert L.orc_watt_spectrum(0.9e6, 2.2e-6, C.byref(a)) == r.ref_watt_spectrum(0.9e6, 2.2e-6, C.byref(b))
+        # isotropic_direction: the reference's own distribution_multi.cpp:73-79 (isotropic-in-lab scattering, source angle)
+        if hasattr(r, "ref_isotropic_direction"):
+            a, b = C.c_uint64(int(seed0)), C.c_uint64(int(seed0))
+            ua, ub = np.zeros(3), np.zeros(3)
+            L.orc_isotropic_direction(ua.ctypes.data_as(C.POINTER(C.c_double)), C.byref(a))
+            r.ref_isotropic_direction(ub.ctypes.data_as(C.POINTER(C.c_double)), C.byref(b))
+            assert a.value == b.value and np.array_equal(ua.view(np.uint64), ub.view(np.uint64))
 
 
 def test_openmc_math_known_answers(oracle_bridge, golden_dir):
