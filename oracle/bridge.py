@@ -110,6 +110,8 @@ def ref_lib():
     r.ref_init_particle_seeds.argtypes = [C.c_int64, u64p]
     if hasattr(r, "ref_isotropic_direction"):
         r.ref_isotropic_direction.argtypes = [f64p, u64p]
+    if hasattr(r, "ref_box_sample"):
+        r.ref_box_sample.argtypes = [f64p, u64p, f64p]
     r.ref_set_master_seed.argtypes = [C.c_int64]
     r.ref_maxwell_spectrum.restype = C.c_double
     r.ref_maxwell_spectrum.argtypes = [C.c_double, u64p]

@@ -9,6 +9,8 @@
 #include <string>
 
 #include "openmc/distribution_multi.h"
+#include "openmc/distribution_spatial.h"
+#include "pugixml.hpp"
 #include "openmc/math_functions.h"
 #include "openmc/position.h"
 #include "openmc/random_dist.h"
@@ -25,6 +27,19 @@ void fatal_error(const std::string& message, int err)
 }
 
 extern "C" {
+// OMC distribution_spatial.cpp SpatialBox (the <space type="box"> of settings.xml), built the way
+// OpenMC builds it: from an XML node
+void ref_box_sample(const double* box6, uint64_t* seed, double* xyz)
+{
+  char xml[512];
+  std::snprintf(xml, sizeof(xml), "<space type=\"box\"><parameters>%.17g %.17g %.17g %.17g %.17g %.17g</parameters></space>", box6[0],
+                box6[1], box6[2], box6[3], box6[4], box6[5]);
+  pugi::xml_document doc;
+  doc.load_string(xml);
+  const openmc::SpatialBox box(doc.child("space"));
+  const openmc::Position r = box.sample(seed);
+  xyz[0] = r.x, xyz[1] = r.y, xyz[2] = r.z;
+}
 // OMC distribution_multi.cpp:73-79 (used by isotropic-in-lab scattering, physics.cpp:715, and the source)
 void ref_isotropic_direction(double* uvw, uint64_t* seed)
 {

@@ -252,3 +252,43 @@ def test_isotropic_in_lab_direction_and_budget(oracle_bridge):
     assert np.array_equal(a["seed_source"], b["seed_source"])
     assert not np.array_equal(a["seed_tracking"], b["seed_tracking"])
     assert not np.array_equal(a["n_segments"], b["n_segments"])
+
+
+def test_initial_source_sites_from_reference_components(oracle_bridge):
+    """Batch-1 source (OMC source.cpp:325-338,143-221): site i uses the stream init_seed(i + 1, STREAM_SOURCE) and
+    draws SpatialBox::sample (3 numbers, x then y then z), isotropic_direction (2) and the Watt spectrum
+    (0.988 MeV, 2.249e-6 /eV; resampled outside the data's energy range).  Composed here from the REFERENCE's own
+    compiled SpatialBox, isotropic_direction and watt_spectrum, every site of the oracle's bank must match bit
+    for bit (libm build; no rejection: the box lies inside the mesh and non-fissionable regions are accepted)."""
+    from macaw_b200 import cstructs, meshgen, nucdata
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_box_sample"):
+        pytest.skip("oracle/_ref not built with the distribution sources (no /root/reference on this box)")
+    mesh = meshgen.infinite_medium(5)
+    lib = nucdata.infinite_medium_library(G=300)
+    box = (-4.5, -3.0, -2.0, 4.0, 3.5, 1.0)
+    n = 500
+    s = cstructs.make_settings(n, source_box=box, only_fissionable=False)
+    o = oracle_bridge.Oracle(libm=True)
+    o.set_mesh(mesh, np.array([0, 1], np.int32))
+    o.set_library(lib, [0, 1])
+    o.set_settings(s)
+    o.sample_initial_source()
+    bank = o.source_bank()
+    e_min = max(nuc.energy[0] for nuc in lib.nuclides)
+    e_max = min(nuc.energy[-1] for nuc in lib.nuclides)
+    b6 = np.array(box)
+    f64p = C.POINTER(C.c_double)
+    r.ref_set_master_seed(1)
+    for i in range(n):
+        seed = C.c_uint64(r.ref_init_seed(i + 1, 1))  # STREAM_SOURCE = 1 (OMC random_lcg.h)
+        xyz, u = np.zeros(3), np.zeros(3)
+        r.ref_box_sample(b6.ctypes.data_as(f64p), C.byref(seed), xyz.ctypes.data_as(f64p))
+        r.ref_isotropic_direction(u.ctypes.data_as(f64p), C.byref(seed))
+        while True:
+            E = r.ref_watt_spectrum(0.988e6, 2.249e-6, C.byref(seed))
+            if e_min < E < e_max:
+                break
+        assert np.array_equal(bank["r"][i].view(np.uint64), xyz.view(np.uint64)), i
+        assert np.array_equal(bank["u"][i].view(np.uint64), u.view(np.uint64)), i
+        assert bank["E"][i] == E and bank["wgt"][i] == 1.0
