@@ -110,6 +110,9 @@ def ref_lib():
     r.ref_init_particle_seeds.argtypes = [C.c_int64, u64p]
     if hasattr(r, "ref_isotropic_direction"):
         r.ref_isotropic_direction.argtypes = [f64p, u64p]
+    if hasattr(r, "ref_lower_bound_index"):
+        r.ref_lower_bound_index.restype = C.c_int64
+        r.ref_lower_bound_index.argtypes = [f64p, C.c_int64, C.c_double]
     if hasattr(r, "ref_box_sample"):
         r.ref_box_sample.argtypes = [f64p, u64p, f64p]
     r.ref_set_master_seed.argtypes = [C.c_int64]

@@ -10,6 +10,7 @@
 
 #include "openmc/distribution_multi.h"
 #include "openmc/distribution_spatial.h"
+#include "openmc/search.h"
 #include "pugixml.hpp"
 #include "openmc/math_functions.h"
 #include "openmc/position.h"
@@ -27,6 +28,11 @@ void fatal_error(const std::string& message, int err)
 }
 
 extern "C" {
+// OMC search.h:14-20, the primitive of Nuclide::calculate_xs' energy-grid search (nuclide.cpp:596-611)
+int64_t ref_lower_bound_index(const double* first, int64_t n, double value)
+{
+  return (int64_t)openmc::lower_bound_index(first, first + n, value);
+}
 // OMC distribution_spatial.cpp SpatialBox (the <space type="box"> of settings.xml), built the way
 // OpenMC builds it: from an XML node
 void ref_box_sample(const double* box6, uint64_t* seed, double* xyz)

@@ -292,3 +292,68 @@ def test_initial_source_sites_from_reference_components(oracle_bridge):
         assert np.array_equal(bank["r"][i].view(np.uint64), xyz.view(np.uint64)), i
         assert np.array_equal(bank["u"][i].view(np.uint64), u.view(np.uint64)), i
         assert bank["E"][i] == E and bank["wgt"][i] == 1.0
+
+
+def test_xs_lookup_against_reference_search_primitive(oracle_bridge):
+    """Macroscopic lookup of the oracle (libm build) against a direct transcription of OMC nuclide.cpp:446-476
+    (init_grid) and :646-691 (calculate_xs) whose energy-grid search is the REFERENCE's own compiled
+    lower_bound_index (search.h:14-20), summed like material.cpp:790-829: bit for bit, including exact grid
+    points, duplicated grid points and energies outside a nuclide's grid."""
+    import math
+    from macaw_b200 import cstructs, meshgen, nucdata
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_lower_bound_index"):
+        pytest.skip("oracle/_ref not built with search.h (no /root/reference on this box)")
+    lib = nucdata.make_library(9, G=300)
+    dup = lib.nuclides[3]
+    dup.energy[101] = dup.energy[100]  # the "rare case where two energy points are the same" (nuclide.cpp:662)
+    lib.nuclides[5].energy[-1] *= 0.5  # a grid that ends early: E > energy.back() for the others' top range
+    lib.nuclides[5].energy[:] = np.sort(lib.nuclides[5].energy)
+    M = lib.n_log_bins
+    o = oracle_bridge.Oracle(libm=True)
+    o.set_mesh(meshgen.pin_cell_tet(4, 2), np.arange(4, dtype=np.int32))
+    o.set_library(lib, [0, 1, 2, 3])
+    o.set_settings(cstructs.make_settings(10))
+    E_min = max(n.energy[0] for n in lib.nuclides)
+    E_max = min(n.energy[-1] for n in lib.nuclides)
+    spacing = math.log(E_max / E_min) / M
+    step = (M * spacing - 0.0) / M  # xt::linspace(0.0, M*spacing, M+1)
+    f64p = C.POINTER(C.c_double)
+    grid_index = []
+    for k, n in enumerate(lib.nuclides):
+        gi, j = np.zeros(M + 1, np.int32), 0
+        for b in range(M + 1):
+            while math.log(n.energy[j + 1] / E_min) <= 0.0 + b * step:
+                if j + 2 == n.energy.size:
+                    break
+                j += 1
+            gi[b] = j
+        assert np.array_equal(gi, o.grid_index(k, M)), k
+        grid_index.append(gi)
+    E, mat = problems.lookup_points(lib, 1500)
+    E[2:6] = [dup.energy[100], dup.energy[99], dup.energy[102], lib.nuclides[5].energy[-1] * 1.5]
+    got = o.xs_lookup(E, mat)
+    for p in range(E.size):
+        e = float(E[p])
+        i_log = min(max(int(math.log(e / E_min) / spacing), 0), M - 1)
+        tot = [0.0, 0.0, 0.0, 0.0]
+        m = lib.materials[mat[p]]
+        for i_nuc, dens in zip(m.nuclides, m.densities):
+            n = lib.nuclides[i_nuc]
+            en = np.ascontiguousarray(n.energy)
+            if e < en[0]:
+                ig = 0
+            elif e > en[-1]:
+                ig = en.size - 2
+            else:
+                lo, hi = int(grid_index[i_nuc][i_log]), int(grid_index[i_nuc][i_log + 1]) + 1
+                ig = lo + r.ref_lower_bound_index(en[lo:].ctypes.data_as(f64p), hi - lo, e)
+            if en[ig] == en[ig + 1]:
+                ig += 1
+            f = (e - float(en[ig])) / (float(en[ig + 1]) - float(en[ig]))
+            cols = 4 if n.fissionable else 2
+            for c in range(cols):
+                micro = (1.0 - f) * float(n.xs[ig, c]) + f * float(n.xs[ig + 1, c])
+                tot[c] += dens * micro
+        assert np.array_equal(np.array(tot).view(np.uint64), got[p].view(np.uint64)), (p, e, mat[p])
