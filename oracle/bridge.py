@@ -38,6 +38,7 @@ def _load(name):
     lib.orc_watt_spectrum.argtypes = [C.c_double, C.c_double, u64p]
     lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
+    lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     for f in ("orc_log", "orc_sin", "orc_cos"):
         getattr(lib, f).restype = C.c_double
         getattr(lib, f).argtypes = [C.c_double]
@@ -110,6 +111,8 @@ def ref_lib():
     r.ref_init_particle_seeds.argtypes = [C.c_int64, u64p]
     if hasattr(r, "ref_isotropic_direction"):
         r.ref_isotropic_direction.argtypes = [f64p, u64p]
+    if hasattr(r, "ref_sample_cxs_target_velocity"):
+        r.ref_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     if hasattr(r, "ref_lower_bound_index"):
         r.ref_lower_bound_index.restype = C.c_int64
         r.ref_lower_bound_index.argtypes = [f64p, C.c_int64, C.c_double]

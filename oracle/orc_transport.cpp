@@ -569,6 +569,11 @@ void orc_rotate_angle(double* uvw, double mu, const double* phi, uint64_t* seed)
   uvw[1] = u.y;
   uvw[2] = u.z;
 }
+void orc_sample_cxs_target_velocity(double awr, double E, const double* u, double kT, uint64_t* seed, double* v)
+{
+  V3 r = sample_cxs_target_velocity(awr, E, V3{u[0], u[1], u[2]}, kT, seed);
+  v[0] = r.x, v[1] = r.y, v[2] = r.z;
+}
 void orc_isotropic_direction(double* uvw, uint64_t* seed)
 {
   V3 u = isotropic_direction(seed);

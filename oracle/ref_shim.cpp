@@ -10,6 +10,7 @@
 
 #include "openmc/distribution_multi.h"
 #include "openmc/distribution_spatial.h"
+#include "openmc/physics.h"
 #include "openmc/search.h"
 #include "pugixml.hpp"
 #include "openmc/math_functions.h"
@@ -28,6 +29,12 @@ void fatal_error(const std::string& message, int err)
 }
 
 extern "C" {
+// OMC physics.cpp:955-1004, linked out of the reference's physics.cpp (see oracle/fake_hdf5/hdf5.h)
+void ref_sample_cxs_target_velocity(double awr, double E, const double* u, double kT, uint64_t* seed, double* v)
+{
+  const openmc::Direction d = openmc::sample_cxs_target_velocity(awr, E, {u[0], u[1], u[2]}, kT, seed);
+  v[0] = d.x, v[1] = d.y, v[2] = d.z;
+}
 // OMC search.h:14-20, the primitive of Nuclide::calculate_xs' energy-grid search (nuclide.cpp:596-611)
 int64_t ref_lower_bound_index(const double* first, int64_t n, double value)
 {

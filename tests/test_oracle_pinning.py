@@ -357,3 +357,35 @@ def test_xs_lookup_against_reference_search_primitive(oracle_bridge):
                 micro = (1.0 - f) * float(n.xs[ig, c]) + f * float(n.xs[ig + 1, c])
                 tot[c] += dens * micro
         assert np.array_equal(np.array(tot).view(np.uint64), got[p].view(np.uint64)), (p, e, mat[p])
+
+
+def test_free_gas_target_velocity_against_reference_physics_cpp(oracle_bridge):
+    """sample_cxs_target_velocity (OMC physics.cpp:955-1004: the constant-cross-section free-gas target sampler
+    with its rejection loop, 5+ random numbers per try, then rotate_angle) -- the REFERENCE's own function, linked
+    out of its physics.cpp (oracle/Makefile: stub hdf5.h + --gc-sections), against the oracle (libm build): same
+    velocity bits and the same stream position for light and heavy targets, thermal to 10 eV."""
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_sample_cxs_target_velocity"):
+        pytest.skip("oracle/_ref not built with physics.cpp (no /root/reference on this box)")
+    L = oracle_bridge.lib(True)
+    rng = np.random.default_rng(11)
+    f64p = C.POINTER(C.c_double)
+    kT = 8.617333262e-5 * 293.6
+    n_draws = []
+    for k in range(400):
+        awr = float(rng.choice([0.9992, 15.858, 89.132, 236.006]))
+        E = float(np.exp(rng.uniform(np.log(1e-4), np.log(10.0))))
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        seed0 = int(rng.integers(1, 2 ** 63))
+        a, b = C.c_uint64(seed0), C.c_uint64(seed0)
+        va, vb = np.zeros(3), np.zeros(3)
+        L.orc_sample_cxs_target_velocity(awr, E, u.ctypes.data_as(f64p), kT, C.byref(a), va.ctypes.data_as(f64p))
+        r.ref_sample_cxs_target_velocity(awr, E, u.ctypes.data_as(f64p), kT, C.byref(b), vb.ctypes.data_as(f64p))
+        assert a.value == b.value, k
+        assert np.array_equal(va.view(np.uint64), vb.view(np.uint64)), (k, va, vb)
+        s, n = seed0, 0
+        while s != a.value and n < 400:
+            s, n = lcg(s), n + 1
+        n_draws.append(n)
+    assert min(n_draws) >= 6 and max(n_draws) > 6  # at least one try (5 or 6 draws) + the azimuth; rejections occur
