@@ -111,6 +111,10 @@ def ref_lib():
     r.ref_init_particle_seeds.argtypes = [C.c_int64, u64p]
     if hasattr(r, "ref_isotropic_direction"):
         r.ref_isotropic_direction.argtypes = [f64p, u64p]
+    if hasattr(r, "ref_sort_and_synchronize_bank"):
+        r.ref_sort_and_synchronize_bank.restype = C.c_int64
+        r.ref_sort_and_synchronize_bank.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                                    C.c_int, C.c_void_p, C.c_void_p]
     if hasattr(r, "ref_sample_cxs_target_velocity"):
         r.ref_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     if hasattr(r, "ref_lower_bound_index"):

@@ -8,7 +8,14 @@
 #include <cstdlib>
 #include <string>
 
+#include <cstring>
+
+#include "openmc/bank.h"
 #include "openmc/distribution_multi.h"
+#include "openmc/eigenvalue.h"
+#include "openmc/message_passing.h"
+#include "openmc/settings.h"
+#include "openmc/simulation.h"
 #include "openmc/distribution_spatial.h"
 #include "openmc/physics.h"
 #include "openmc/search.h"
@@ -29,6 +36,36 @@ void fatal_error(const std::string& message, int err)
 }
 
 extern "C" {
+// OMC bank.cpp:60-104 sort_fission_bank + eigenvalue.cpp:71-311 synchronize_bank (single process), the
+// reference's own functions on the reference's own globals: fission bank in, sorted bank and next source bank out
+int64_t ref_sort_and_synchronize_bank(const void* fission_sites, int64_t n_sites, const int64_t* progeny_per_particle,
+                                      int64_t n_particles, int total_gen, int current_batch, int current_gen,
+                                      int gen_per_batch, void* sorted_out, void* source_out)
+{
+  using namespace openmc;
+  static_assert(sizeof(SourceSite) == 96, "SourceSite layout (particle_data.h:43-53)");
+  settings::n_particles = n_particles;
+  settings::gen_per_batch = gen_per_batch;
+  simulation::total_gen = total_gen;
+  simulation::current_batch = current_batch;
+  simulation::current_gen = current_gen;
+  mpi::n_procs = 1;
+  mpi::rank = 0;
+  simulation::work_index = {0, n_particles};
+  simulation::work_per_rank = n_particles;
+  simulation::fission_bank.reserve(3 * n_particles);
+  simulation::fission_bank.resize(0);
+  const SourceSite* in = static_cast<const SourceSite*>(fission_sites);
+  for (int64_t i = 0; i < n_sites; ++i)
+    simulation::fission_bank.thread_safe_append(in[i]);
+  simulation::progeny_per_particle.assign(progeny_per_particle, progeny_per_particle + n_particles);
+  simulation::source_bank.resize(n_particles);
+  sort_fission_bank();
+  std::memcpy(sorted_out, simulation::fission_bank.data(), sizeof(SourceSite) * n_sites);
+  synchronize_bank();
+  std::memcpy(source_out, simulation::source_bank.data(), sizeof(SourceSite) * n_particles);
+  return (int64_t)simulation::source_bank.size();
+}
 // OMC physics.cpp:955-1004, linked out of the reference's physics.cpp (see oracle/fake_hdf5/hdf5.h)
 void ref_sample_cxs_target_velocity(double awr, double E, const double* u, double kT, uint64_t* seed, double* v)
 {

@@ -389,3 +389,42 @@ def test_free_gas_target_velocity_against_reference_physics_cpp(oracle_bridge):
             s, n = lcg(s), n + 1
         n_draws.append(n)
     assert min(n_draws) >= 6 and max(n_draws) > 6  # at least one try (5 or 6 draws) + the azimuth; rejections occur
+
+
+def test_bank_sort_and_synchronize_against_reference_eigenvalue_cpp(oracle_bridge):
+    """sort_fission_bank (OMC bank.cpp:60-104) and synchronize_bank (eigenvalue.cpp:71-311, single process) -- the
+    REFERENCE's own functions working on the reference's own globals, linked out of bank.cpp / eigenvalue.cpp /
+    simulation.cpp / settings.cpp (oracle/Makefile) -- fed the oracle's fission bank in shuffled order: the sorted
+    bank and the sampled next-generation source bank must equal the oracle's byte for byte, in a generation that
+    banks fewer sites than n_particles (padding / duplication branch) and in one that banks more (sampling)."""
+    from macaw_b200.cstructs import SITE_DTYPE
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_sort_and_synchronize_bank"):
+        pytest.skip("oracle/_ref not built with eigenvalue.cpp (no /root/reference on this box)")
+    n = 3000
+    mesh, lib, bm, s = problems.pin_cell_tet(n_particles=n)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    o.sample_initial_source()
+    r.ref_set_master_seed(1)
+    rng = np.random.default_rng(5)
+    ratios = []
+    for batch in (1, 2, 3):
+        o.transport_generation(batch, 4)
+        bank = o.fission_bank().copy()  # sorted by (parent, progeny)
+        progeny = o.history_records()["n_progeny"].astype(np.int64)
+        assert progeny.sum() == bank.size
+        shuffled = bank[rng.permutation(bank.size)].copy()
+        sorted_out = np.zeros(bank.size, SITE_DTYPE)
+        source_out = np.zeros(n, SITE_DTYPE)
+        got = r.ref_sort_and_synchronize_bank(shuffled.ctypes.data, bank.size, progeny.ctypes.data, n, 0, batch, 1, 1,
+                                              sorted_out.ctypes.data, source_out.ctypes.data)
+        assert got == n and sorted_out.tobytes() == bank.tobytes()
+        o.L.orc_sample_bank(o.h, batch)
+        o.L.orc_finish_sampling(o.h, 0, 1)
+        mine = o.sampled()
+        assert mine.size == n and mine.tobytes() == source_out.tobytes(), batch
+        ratios.append(bank.size / n)
+        o.set_source_bank(mine)
+        o.L.orc_set_keff(o.h, 0.3 if batch == 1 else 1.0)  # sites ~ 1 / keff: batch 2 banks more than n, batch 3 fewer
+    assert min(ratios) < 1.0 < max(ratios), ratios  # both branches of synchronize_bank were exercised
