@@ -16,6 +16,7 @@
 #include "openmc/message_passing.h"
 #include "openmc/settings.h"
 #include "openmc/simulation.h"
+#include "openmc/tallies/tally.h"
 #include "openmc/distribution_spatial.h"
 #include "openmc/physics.h"
 #include "openmc/search.h"
@@ -32,6 +33,15 @@ void fatal_error(const std::string& message, int err)
 {
   std::fprintf(stderr, "reference fatal_error: %s\n", message.c_str());
   std::exit(err ? err : 1);
+}
+}
+
+// simulation::n_realizations is defined in tallies/tally.cpp, whose other contents are not needed here
+namespace openmc
+{
+namespace simulation
+{
+extern "C" int32_t n_realizations {0};
 }
 }
 
@@ -65,6 +75,30 @@ int64_t ref_sort_and_synchronize_bank(const void* fission_sites, int64_t n_sites
   synchronize_bank();
   std::memcpy(source_out, simulation::source_bank.data(), sizeof(SourceSite) * n_particles);
   return (int64_t)simulation::source_bank.size();
+}
+// OMC eigenvalue.cpp:313-351 calculate_average_keff on the reference's own globals: the running mean and the
+// standard deviation of the mean over active generations, one call per batch (gen_per_batch = 1)
+void ref_keff_statistics(const double* k_generation, int n_batches, int n_inactive, double* keff, double* keff_std)
+{
+  using namespace openmc;
+  settings::gen_per_batch = 1;
+  settings::n_inactive = n_inactive;
+  settings::confidence_intervals = false;
+  simulation::total_gen = 0;
+  simulation::k_generation.clear();
+  simulation::k_sum = {0.0, 0.0};
+  simulation::keff = 1.0;
+  simulation::keff_std = 0.0;
+  for (int b = 1; b <= n_batches; ++b)
+  {
+    simulation::current_batch = b;
+    simulation::current_gen = 1;
+    simulation::n_realizations = b > n_inactive ? b - n_inactive - 1 : 0; // finalize_batch increments it afterwards
+    simulation::k_generation.push_back(k_generation[b - 1]);
+    calculate_average_keff();
+    keff[b - 1] = simulation::keff;
+    keff_std[b - 1] = simulation::keff_std;
+  }
 }
 // OMC physics.cpp:955-1004, linked out of the reference's physics.cpp (see oracle/fake_hdf5/hdf5.h)
 void ref_sample_cxs_target_velocity(double awr, double E, const double* u, double kT, uint64_t* seed, double* v)

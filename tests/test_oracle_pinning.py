@@ -428,3 +428,24 @@ def test_bank_sort_and_synchronize_against_reference_eigenvalue_cpp(oracle_bridg
         o.set_source_bank(mine)
         o.L.orc_set_keff(o.h, 0.3 if batch == 1 else 1.0)  # sites ~ 1 / keff: batch 2 banks more than n, batch 3 fewer
     assert min(ratios) < 1.0 < max(ratios), ratios  # both branches of synchronize_bank were exercised
+
+
+def test_keff_statistics_against_reference_eigenvalue_cpp(oracle_bridge):
+    """calculate_average_keff (OMC eigenvalue.cpp:313-351), the reference's own function on its own globals, fed the
+    oracle's k_generation sequence: keff and keff_std of every batch (inactive: last generation's k; active: running
+    mean and standard deviation of the mean) equal the oracle's bit for bit."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_keff_statistics"):
+        pytest.skip("oracle/_ref not built with eigenvalue.cpp (no /root/reference on this box)")
+    mesh, lib, bm, s = problems.infinite_medium(n_particles=1500, n_inactive=2)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    o.sample_initial_source()
+    res = [o.run_generation(b, 4) for b in range(1, 8)]
+    kg = np.array([x.k_generation for x in res])
+    keff, std = np.zeros(kg.size), np.zeros(kg.size)
+    f64p = C.POINTER(C.c_double)
+    r.ref_keff_statistics(kg.ctypes.data_as(f64p), kg.size, 2, keff.ctypes.data_as(f64p), std.ctypes.data_as(f64p))
+    assert np.array_equal(keff.view(np.uint64), np.array([x.keff for x in res]).view(np.uint64))
+    assert np.array_equal(std.view(np.uint64), np.array([x.keff_std for x in res]).view(np.uint64))
+    assert keff[0] == kg[0] and keff[1] == kg[1] and std[2] == 0.0 and std[3] > 0.0
