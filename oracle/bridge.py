@@ -115,6 +115,8 @@ def ref_lib():
         r.ref_sort_and_synchronize_bank.restype = C.c_int64
         r.ref_sort_and_synchronize_bank.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                     C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(r, "ref_tally_accumulate"):
+        r.ref_tally_accumulate.argtypes = [f64p, C.c_int, C.c_int, C.c_int64, f64p, f64p]
     if hasattr(r, "ref_keff_statistics"):
         r.ref_keff_statistics.argtypes = [f64p, C.c_int, C.c_int, f64p, f64p]
     if hasattr(r, "ref_sample_cxs_target_velocity"):

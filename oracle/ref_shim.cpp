@@ -36,15 +36,6 @@ void fatal_error(const std::string& message, int err)
 }
 }
 
-// simulation::n_realizations is defined in tallies/tally.cpp, whose other contents are not needed here
-namespace openmc
-{
-namespace simulation
-{
-extern "C" int32_t n_realizations {0};
-}
-}
-
 extern "C" {
 // OMC bank.cpp:60-104 sort_fission_bank + eigenvalue.cpp:71-311 synchronize_bank (single process), the
 // reference's own functions on the reference's own globals: fission bank in, sorted bank and next source bank out
@@ -75,6 +66,32 @@ int64_t ref_sort_and_synchronize_bank(const void* fission_sites, int64_t n_sites
   synchronize_bank();
   std::memcpy(source_out, simulation::source_bank.data(), sizeof(SourceSite) * n_particles);
   return (int64_t)simulation::source_bank.size();
+}
+// OMC tallies/tally.cpp:639-670 Tally::accumulate on a reference Tally object: `values` = n_batches x n_entries
+// VALUE arrays scored in successive batches; returns SUM and SUM_SQ per entry and the number of realisations
+int ref_tally_accumulate(const double* values, int n_batches, int n_entries, int64_t n_particles, double* sum, double* sum_sq)
+{
+  using namespace openmc;
+  settings::n_particles = n_particles;
+  settings::gen_per_batch = 1;
+  settings::reduce_tallies = true;
+  settings::run_mode = RunMode::EIGENVALUE;
+  mpi::master = true;
+  mpi::n_procs = 1;
+  Tally t(987654);
+  t.results_ = xt::zeros<double>({(size_t)n_entries, (size_t)1, (size_t)3});
+  for (int b = 0; b < n_batches; ++b)
+  {
+    for (int i = 0; i < n_entries; ++i)
+      t.results_(i, 0, static_cast<int>(TallyResult::VALUE)) = values[(size_t)b * n_entries + i];
+    t.accumulate();
+  }
+  for (int i = 0; i < n_entries; ++i)
+  {
+    sum[i] = t.results_(i, 0, static_cast<int>(TallyResult::SUM));
+    sum_sq[i] = t.results_(i, 0, static_cast<int>(TallyResult::SUM_SQ));
+  }
+  return t.n_realizations_;
 }
 // OMC eigenvalue.cpp:313-351 calculate_average_keff on the reference's own globals: the running mean and the
 // standard deviation of the mean over active generations, one call per batch (gen_per_batch = 1)

@@ -449,3 +449,38 @@ def test_keff_statistics_against_reference_eigenvalue_cpp(oracle_bridge):
     assert np.array_equal(keff.view(np.uint64), np.array([x.keff for x in res]).view(np.uint64))
     assert np.array_equal(std.view(np.uint64), np.array([x.keff_std for x in res]).view(np.uint64))
     assert keff[0] == kg[0] and keff[1] == kg[1] and std[2] == 0.0 and std[3] > 0.0
+
+
+def test_tally_accumulate_against_reference_tally_cpp(oracle_bridge):
+    """Tally::accumulate (OMC tallies/tally.cpp:639-670) on a reference Tally object, fed the VALUE arrays the oracle
+    scored in three active batches: SUM, SUM_SQ (normalised by n_particles) and the realisation count equal the
+    oracle's bit for bit."""
+    from macaw_b200.cstructs import GenerationResult
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_tally_accumulate"):
+        pytest.skip("oracle/_ref not built with tally.cpp (no /root/reference on this box)")
+    n = 1500
+    mesh, lib, bm, s = problems.infinite_medium(n_particles=n, n_inactive=1)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=True)
+    o.sample_initial_source()
+    values = []
+    for b in range(1, 5):
+        o.transport_generation(b, 4)
+        v, _, _, _ = o.get_tally(1)
+        if b > 1:  # batch 1 is inactive: nothing is scored
+            values.append(v.copy())
+            assert v.sum() > 0
+        o.L.orc_sample_bank(o.h, b)
+        o.L.orc_finish_sampling(o.h, 0, 1)
+        res = GenerationResult()
+        o.L.orc_finalize_generation(o.h, b, None, C.byref(res))
+        o.set_source_bank(o.sampled())
+    v_after, sm, sq, nr = o.get_tally(1)
+    assert nr == 3 and not v_after.any()
+    vals = np.ascontiguousarray(np.stack(values))
+    f64p = C.POINTER(C.c_double)
+    ref_sum, ref_sq = np.zeros(sm.size), np.zeros(sm.size)
+    got = r.ref_tally_accumulate(vals.ctypes.data_as(f64p), 3, sm.size, n, ref_sum.ctypes.data_as(f64p), ref_sq.ctypes.data_as(f64p))
+    assert got == 3
+    assert np.array_equal(ref_sum.view(np.uint64), sm.view(np.uint64)) and np.array_equal(ref_sq.view(np.uint64), sq.view(np.uint64))
