@@ -63,7 +63,7 @@ def read_exodus(path, reflect=(), kill=()) -> meshgen.Mesh:
     return m
 
 
-def write_exodus(path, m: meshgen.Mesh, block_names=None):
+def write_exodus(path, m: meshgen.Mesh, version=2):
     """Minimal Exodus-II writer (classic NetCDF, 64-bit offsets): coordinates, one element block per
     subdomain id, one side set per boundary id present on the mesh.  Enough for read_exodus, the C++
     reader (host/exodus_reader.hpp) and libMesh's ExodusII_IO; used to hand generated meshes to the
@@ -72,7 +72,7 @@ def write_exodus(path, m: meshgen.Mesh, block_names=None):
     names = {meshgen.QUAD4: "QUAD4", meshgen.TET4: "TETRA4", meshgen.HEX8: "HEX8"}
     ids = m.block_ids_sorted()
     bnd = np.unique(m.side_bnd_id[m.side_bnd_id >= 0])
-    f = netcdf_file(path, "w", version=2)
+    f = netcdf_file(path, "w", version=version)  # 1 = classic (32-bit offsets), 2 = 64-bit offsets
     f.title = "macaw_b200 mesh export"
     f.createDimension("len_string", 33)
     f.createDimension("num_dim", m.dim)

@@ -175,14 +175,15 @@ def test_input_file_run_matches_oracle(oracle_bridge, tmp_path):
 
 
 # ---- FileMeshGenerator decks: Exodus mesh through host/exodus_reader.hpp
-def _file_mesh_deck(tmp_path):
+def _file_mesh_deck(tmp_path, version=2, name="assembly_file"):
     """examples/assembly_file with its mesh written from the committed fixture of the reference's mesh."""
     import shutil
     from macaw_b200 import exodus, meshgen
-    d = tmp_path / "assembly_file"
+    d = tmp_path / name
     shutil.copytree(os.path.join(ROOT, "examples", "assembly_file"), d, ignore=shutil.ignore_patterns("*.e"))
     exodus.write_exodus(str(d / "assembly.e"),
-                        meshgen.beavrs_assembly_file(os.path.join(ROOT, "tests", "golden", "beavrs_assembly_mesh.npz")))
+                        meshgen.beavrs_assembly_file(os.path.join(ROOT, "tests", "golden", "beavrs_assembly_mesh.npz")),
+                        version=version)
     return str(d)
 
 
@@ -216,6 +217,12 @@ def test_file_mesh_deck_front_end(tmp_path):
     mesh, library, blocks, mat_index, s, T0, batches, tallies, aux = input_problem.read_input(os.path.join(deck, "run.i"), deck, lib)
     _check_against_restatement(json.loads(r.stdout), mesh, library, blocks, mat_index, s, T0, batches)
     assert mesh.n_elem == 23876 and batches == 3 and T0 == 300.0
+    # the same mesh as a CDF-1 file (32-bit offsets): the C++ reader handles both header variants
+    deck1 = _file_mesh_deck(tmp_path, version=1, name="assembly_file_cdf1")
+    assert open(os.path.join(deck1, "assembly.e"), "rb").read(4) == b"CDF\x01"
+    r1 = subprocess.run([exe, "--input", os.path.join(deck1, "run.i"), "--tables", tables, "--check"], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr
+    assert json.loads(r1.stdout) == json.loads(r.stdout)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples/beavrs_assembly"), reason="reference tree not present")
