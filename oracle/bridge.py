@@ -115,6 +115,9 @@ def ref_lib():
         r.ref_sort_and_synchronize_bank.restype = C.c_int64
         r.ref_sort_and_synchronize_bank.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                     C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(r, "ref_calculate_work"):
+        r.ref_calculate_work.restype = C.c_int64
+        r.ref_calculate_work.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p]
     if hasattr(r, "ref_tally_accumulate"):
         r.ref_tally_accumulate.argtypes = [f64p, C.c_int, C.c_int, C.c_int64, f64p, f64p]
     if hasattr(r, "ref_keff_statistics"):

@@ -67,6 +67,18 @@ int64_t ref_sort_and_synchronize_bank(const void* fission_sites, int64_t n_sites
   std::memcpy(source_out, simulation::source_bank.data(), sizeof(SourceSite) * n_particles);
   return (int64_t)simulation::source_bank.size();
 }
+// OMC simulation.cpp:529-551 calculate_work: the particle split over ranks (work_index has n_procs + 1 entries)
+int64_t ref_calculate_work(int64_t n_particles, int n_procs, int rank, int64_t* work_index)
+{
+  using namespace openmc;
+  settings::n_particles = n_particles;
+  mpi::n_procs = n_procs;
+  mpi::rank = rank;
+  calculate_work();
+  for (int i = 0; i <= n_procs; ++i)
+    work_index[i] = simulation::work_index[i];
+  return simulation::work_per_rank;
+}
 // OMC tallies/tally.cpp:639-670 Tally::accumulate on a reference Tally object: `values` = n_batches x n_entries
 // VALUE arrays scored in successive batches; returns SUM and SUM_SQ per entry and the number of realisations
 int ref_tally_accumulate(const double* values, int n_batches, int n_entries, int64_t n_particles, double* sum, double* sum_sq)

@@ -484,3 +484,21 @@ def test_tally_accumulate_against_reference_tally_cpp(oracle_bridge):
     got = r.ref_tally_accumulate(vals.ctypes.data_as(f64p), 3, sm.size, n, ref_sum.ctypes.data_as(f64p), ref_sq.ctypes.data_as(f64p))
     assert got == 3
     assert np.array_equal(ref_sum.view(np.uint64), sm.view(np.uint64)) and np.array_equal(ref_sq.view(np.uint64), sq.view(np.uint64))
+
+
+def test_work_split_against_reference_simulation_cpp(oracle_bridge):
+    """calculate_work (OMC simulation.cpp:529-551), the reference's own function: the particle split used by the
+    C ABI (mcw_calculate_work), by macaw_b200.dist and by the oracle for every rank count the study supports."""
+    from macaw_b200 import dist, lib
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_calculate_work"):
+        pytest.skip("oracle/_ref not built with simulation.cpp (no /root/reference on this box)")
+    L = lib.load()
+    for n in (1, 7, 30, 1000, 200000, 10 ** 8 + 3):
+        for P in (1, 2, 3, 4, 8, 13):
+            want = np.zeros(P + 1, np.int64)
+            per_rank = [r.ref_calculate_work(n, P, k, want.ctypes.data) for k in range(P)]
+            mine = np.zeros(P + 1, np.int64)
+            assert L.mcw_calculate_work(n, P, mine.ctypes.data) == 0
+            assert np.array_equal(mine, want) and np.array_equal(dist.calculate_work(n, P), want)
+            assert per_rank == np.diff(want).tolist() and want[-1] == n
