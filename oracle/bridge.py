@@ -39,6 +39,9 @@ def _load(name):
     lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
+    lib.orc_score_events.restype = C.c_int64
+    lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
+                                     f64p, f64p]
     for f in ("orc_log", "orc_sin", "orc_cos"):
         getattr(lib, f).restype = C.c_double
         getattr(lib, f).argtypes = [C.c_double]
@@ -118,6 +121,11 @@ def ref_lib():
     if hasattr(r, "ref_calculate_work"):
         r.ref_calculate_work.restype = C.c_int64
         r.ref_calculate_work.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p]
+    if hasattr(r, "ref_score_collision_events"):
+        r.ref_score_collision_events.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                                 C.c_int64, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p]
+        r.ref_score_tracklength_events.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                                   C.c_int64, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p, f64p]
     if hasattr(r, "ref_tally_accumulate"):
         r.ref_tally_accumulate.argtypes = [f64p, C.c_int, C.c_int, C.c_int64, f64p, f64p]
     if hasattr(r, "ref_keff_statistics"):

@@ -395,6 +395,32 @@ static void score_tally(Tally& t, int64_t spatial, double E, const double* score
   }
 }
 
+// collision-estimator scores of one collision (OMC tally_scoring.cpp:2354-2365 flux, :557, :600, :752, :799, :1240-1255)
+static void collision_scores(double wgt_last, double total, double absorption, double fission, double nu_fission,
+                             double kappa_macro, double* sc)
+{
+  const double flux = wgt_last / total;
+  sc[MCW_SCORE_FLUX] = flux;
+  sc[MCW_SCORE_TOTAL] = total * flux;
+  sc[MCW_SCORE_FISSION] = absorption == 0 ? 0.0 : fission * flux;
+  sc[MCW_SCORE_NU_FISSION] = absorption == 0 ? 0.0 : nu_fission * flux;
+  sc[MCW_SCORE_KAPPA_FISSION] = absorption == 0. ? 0.0 : kappa_macro * flux;
+}
+
+// track-length-estimator scores of one segment (OMC tally_scoring.cpp:2289-2300 flux = wgt * distance; same score cases);
+// returns the flux, kappa-fission is filled in by the caller
+static double tracklength_scores(double wgt, double distance, double total, double absorption, double fission,
+                                 double nu_fission, double* sc)
+{
+  const double flux = wgt * distance;
+  sc[MCW_SCORE_FLUX] = flux;
+  sc[MCW_SCORE_TOTAL] = total * flux;
+  sc[MCW_SCORE_FISSION] = absorption == 0 ? 0.0 : fission * flux;
+  sc[MCW_SCORE_NU_FISSION] = absorption == 0 ? 0.0 : nu_fission * flux;
+  sc[MCW_SCORE_KAPPA_FISSION] = 0.0;
+  return flux;
+}
+
 static int64_t spatialBin(const Problem& P, const Tally& t, int64_t elem)
 {
   return t.granularity == MCW_FILTER_CELL ? elem
@@ -461,11 +487,9 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
         if (t.estimator == MCW_ESTIMATOR_TRACKLENGTH)
         {
           // OMC tally_scoring.cpp:2289-2352: flux = wgt * distance
-          double flux = p.wgt * std::min(d, c.length);
-          double sc[MCW_N_SCORES] = {flux, macro.total * flux, macro.fission * flux,
-                                     macro.nu_fission * flux, 0.0};
-          if (macro.absorption == 0)
-            sc[2] = sc[3] = 0;
+          double sc[MCW_N_SCORES];
+          const double flux = tracklength_scores(p.wgt, std::min(d, c.length), macro.total, macro.absorption, macro.fission,
+                                                 macro.nu_fission, sc);
           double kappa = 0;
           for (size_t i = 0; i < mat.nuc.size(); ++i)
             if (P.lib.nuclides[mat.nuc[i]].fissionable)
@@ -489,13 +513,8 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
     if (tallies_active)
     {
       // OMC tally_scoring.cpp:2354-2420 score_collision_tally, scores :557,:600,:752,:799,:1240-1255
-      double flux = wgt_last / macro.total;
       double sc[MCW_N_SCORES];
-      sc[MCW_SCORE_FLUX] = flux;
-      sc[MCW_SCORE_TOTAL] = macro.total * flux;
-      sc[MCW_SCORE_FISSION] = macro.absorption == 0 ? 0.0 : macro.fission * flux;
-      sc[MCW_SCORE_NU_FISSION] = macro.absorption == 0 ? 0.0 : macro.nu_fission * flux;
-      sc[MCW_SCORE_KAPPA_FISSION] = macro.absorption == 0. ? 0.0 : co.kappa_macro * flux;
+      collision_scores(wgt_last, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_macro, sc);
       for (auto& t : P.tallies)
         if (t.estimator == MCW_ESTIMATOR_COLLISION)
           score_tally(t, spatialBin(P, t, c.elem), E_last, sc);
@@ -724,6 +743,38 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
   t.sum_sq.assign(n, 0.0);
   P.tallies.push_back(std::move(t));
   return 0;
+}
+
+// Replays collision events through the scoring + binning used by the transport loop above (collision_scores +
+// score_tally); exists so tests can hold it against the reference's own score_collision_tally /
+// score_tracklength_tally (oracle/_ref ref_score_collision_events, ref_score_tracklength_events).  macro4 = (total, absorption, fission, nu_fission) per event; value_out is
+// [n_spatial][n_energy][n_scores].
+// distance == nullptr: collision estimator; else track-length estimator with (E, wgt) the particle's current values.
+int64_t orc_score_events(int64_t n_spatial, const double* ebins, int n_edges, const int32_t* scores, int n_scores,
+                         int64_t n_events, const int32_t* spatial, const double* E_last, const double* wgt_last,
+                         const double* distance, const double* macro4, double* value_out)
+{
+  Tally t;
+  t.id = 1, t.estimator = distance ? MCW_ESTIMATOR_TRACKLENGTH : MCW_ESTIMATOR_COLLISION, t.granularity = MCW_FILTER_CELL;
+  t.scores.assign(scores, scores + n_scores);
+  if (n_edges >= 2)
+  {
+    t.ebins.assign(ebins, ebins + n_edges);
+    t.n_energy = n_edges - 1;
+  }
+  t.n_spatial = n_spatial;
+  t.value.assign((size_t)t.bins() * n_scores, 0.0);
+  for (int64_t k = 0; k < n_events; ++k)
+  {
+    double sc[MCW_N_SCORES];
+    if (distance)
+      tracklength_scores(wgt_last[k], distance[k], macro4[4 * k], macro4[4 * k + 1], macro4[4 * k + 2], macro4[4 * k + 3], sc);
+    else
+      collision_scores(wgt_last[k], macro4[4 * k], macro4[4 * k + 1], macro4[4 * k + 2], macro4[4 * k + 3], 0.0, sc);
+    score_tally(t, spatial[k], E_last[k], sc);
+  }
+  std::copy(t.value.begin(), t.value.end(), value_out);
+  return (int64_t)t.value.size();
 }
 
 void orc_get_grid(void* h, double* e_min, double* e_max, double* log_spacing)

@@ -486,6 +486,61 @@ def test_tally_accumulate_against_reference_tally_cpp(oracle_bridge):
     assert np.array_equal(ref_sum.view(np.uint64), sm.view(np.uint64)) and np.array_equal(ref_sq.view(np.uint64), sq.view(np.uint64))
 
 
+@pytest.mark.parametrize("use_universe", [0, 1])
+@pytest.mark.parametrize("with_energy", [1, 0])
+@pytest.mark.parametrize("tracklength", [0, 1])
+def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe, with_energy, tracklength):
+    """score_collision_tally -> score_general_ce (OMC tallies/tally_scoring.cpp:2354-2420, :516) with the reference's own
+    CellFilter / UniverseFilter / EnergyFilter doing the binning and its Tally holding the results -- what MaCaw's
+    CollisionKernel.C:185 event_collide() runs (particle.cpp:247) -- replayed over the same collision events as the oracle's scoring + binning: every
+    (filter bin, score) VALUE equal bit for bit.  Events sit on energy-bin edges, outside the filter's range, and on the
+    zero-absorption branch of the fission scores.  tracklength=1: score_tracklength_tally (:2289-2352) over (E, wgt,
+    segment length) events instead (OpenMC's estimator; MaCaw's kernel leaves it as a TODO, CollisionKernel.C:147)."""
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_score_collision_events"):
+        pytest.skip("oracle/_ref not built with tally_scoring.cpp (no /root/reference on this box)")
+    L = oracle_bridge.lib(False)
+    rng = np.random.default_rng(20 + 4 * tracklength + 2 * use_universe + with_energy)
+    n_cells, n_uni, n = 37, 5, 6000
+    edges = np.array([1e-5, 0.0253, 0.625, 1e3, 1e5, 2e7])
+    cell = rng.integers(0, n_cells, n).astype(np.int32)
+    uni = rng.integers(0, n_uni, n).astype(np.int32)
+    E = np.exp(rng.uniform(np.log(2e-6), np.log(6e7), n))
+    E[:6] = edges                          # on every edge, first and last included
+    E[6], E[7] = np.nextafter(edges[0], 0), np.nextafter(edges[-1], 1e9)   # just outside
+    w = rng.uniform(0.2, 1.7, n)
+    macro = rng.uniform(0.05, 3.0, (n, 4))
+    macro[::17, 1] = 0.0                   # no absorption: fission / nu-fission are skipped
+    macro[::23, 2:] = 0.0                  # non-fissile material
+    names = [b"flux", b"total", b"fission", b"nu-fission"]
+    score_ids = np.array([0, 1, 2, 3], np.int32)   # MCW_SCORE_FLUX .. MCW_SCORE_NU_FISSION
+    n_spatial = n_uni if use_universe else n_cells
+    n_e = edges.size - 1 if with_energy else 1
+    f64p = C.POINTER(C.c_double)
+    ref = np.zeros(n_spatial * n_e * 4)
+    dist = rng.uniform(1e-4, 3.0, n)
+    head = (n_cells, n_uni, edges.ctypes.data_as(f64p), edges.size if with_energy else 0, use_universe,
+            (C.c_char_p * 4)(*names), 4, n, cell.ctypes.data, uni.ctypes.data, E.ctypes.data_as(f64p), w.ctypes.data_as(f64p))
+    tail = (macro.ctypes.data_as(f64p), ref.ctypes.data_as(f64p))
+    if tracklength:
+        got_n = r.ref_score_tracklength_events(*head, dist.ctypes.data_as(f64p), *tail)
+    else:
+        got_n = r.ref_score_collision_events(*head, *tail)
+    assert got_n == ref.size
+    mine = np.zeros_like(ref)
+    spatial = uni if use_universe else cell
+    assert L.orc_score_events(n_spatial, edges.ctypes.data_as(f64p), edges.size if with_energy else 0, score_ids.ctypes.data, 4,
+                              n, spatial.ctypes.data, E.ctypes.data_as(f64p), w.ctypes.data_as(f64p),
+                              dist.ctypes.data_as(f64p) if tracklength else None, macro.ctypes.data_as(f64p),
+                              mine.ctypes.data_as(f64p)) == ref.size
+    assert np.array_equal(mine.view(np.uint64), ref.view(np.uint64))
+    v = ref.reshape(n_spatial, n_e, 4)
+    inside = (E >= edges[0]) & (E <= edges[-1]) if with_energy else np.ones(n, bool)
+    flux = w * dist if tracklength else w / macro[:, 0]
+    assert abs(v[..., 0].sum() - flux[inside].sum()) < 1e-9 * v[..., 0].sum()
+    assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
+
+
 def test_work_split_against_reference_simulation_cpp(oracle_bridge):
     """calculate_work (OMC simulation.cpp:529-551), the reference's own function: the particle split used by the
     C ABI (mcw_calculate_work), by macaw_b200.dist and by the oracle for every rank count the study supports."""
