@@ -39,6 +39,9 @@ def _load(name):
     lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
+    lib.orc_collide_events.restype = C.c_int64
+    lib.orc_collide_events.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, f64p, f64p,
+                                       u64p, C.c_void_p, C.c_int64, f64p]
     lib.orc_score_events.restype = C.c_int64
     lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
                                      f64p, f64p]
@@ -121,6 +124,16 @@ def ref_lib():
     if hasattr(r, "ref_calculate_work"):
         r.ref_calculate_work.restype = C.c_int64
         r.ref_calculate_work.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p]
+    if hasattr(r, "ref_collide_events"):
+        r.ref_library_reset.argtypes = []
+        r.ref_add_nuclide.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int, f64p, f64p, f64p, f64p, C.c_int, C.c_int,
+                                      f64p, C.c_double, C.c_double, f64p, C.c_int, f64p, f64p, C.c_double, C.c_double]
+        r.ref_finish_library.argtypes = [C.c_int]
+        r.ref_nuclide_tables.argtypes = [C.c_int, f64p, C.c_void_p, C.c_void_p, C.c_void_p]
+        r.ref_add_material.argtypes = [C.c_int, C.c_void_p, f64p, C.c_void_p]
+        r.ref_collide_events.restype = C.c_int64
+        r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,
+                                         u64p, C.c_void_p, C.c_int64, f64p]
     if hasattr(r, "ref_score_collision_events"):
         r.ref_score_collision_events.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
                                                  C.c_int64, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p]
@@ -150,6 +163,38 @@ def ref_lib():
 
 def _p(a):
     return a.ctypes.data if a is not None else None
+
+
+def ref_load_library(r, libr: nucdata.Library):
+    """Hands a synthetic library to the REFERENCE's own constructors (oracle/ref_shim_physics.cpp: Nuclide, Reaction,
+    ReactionProduct, distributions, Material, init_grid) and returns, per nuclide, the reference's derived tables
+    (xs_[0] as [G][5], fissionable_, n_precursor_, grid_index).  Capture is handed over as absorption - fission."""
+    f64p = C.POINTER(C.c_double)
+
+    def dp(a):
+        return a.ctypes.data_as(f64p)
+    r.ref_library_reset()
+    for n in libr.nuclides:
+        e, el = np.ascontiguousarray(n.energy, np.float64), np.ascontiguousarray(n.elastic, np.float64)
+        fis = np.ascontiguousarray(n.xs[:, 2])
+        cap = np.ascontiguousarray(n.xs[:, 1] - n.xs[:, 2])
+        inel = np.ascontiguousarray(n.inelastic if n.inelastic.size else np.zeros(1), np.float64)
+        nu, dy, dth = np.array(n.nu_poly, np.float64), np.ascontiguousarray(n.delayed_yield), np.ascontiguousarray(n.delayed_theta)
+        r.ref_add_nuclide(n.name.encode(), n.awr, n.kT, e.size, dp(e), dp(el), dp(cap), dp(fis) if n.fissionable else None,
+                          int(n.inelastic.size), n.inel_threshold, dp(inel), n.inel_threshold_energy, n.inel_mass_ratio,
+                          dp(nu), n.n_precursor, dp(dy), dp(dth), n.watt_a, n.watt_b)
+    r.ref_finish_library(libr.n_log_bins)
+    out = []
+    for i, n in enumerate(libr.nuclides):
+        xs5, gi = np.zeros((n.energy.size, 5)), np.zeros(libr.n_log_bins + 1, np.int32)
+        fz, npre = C.c_int32(), C.c_int32()
+        r.ref_nuclide_tables(i, dp(xs5), C.byref(fz), C.byref(npre), gi.ctypes.data)
+        out.append((xs5, bool(fz.value), npre.value, gi))
+    for m in libr.materials:
+        nn, dd = np.ascontiguousarray(m.nuclides, np.int32), np.ascontiguousarray(m.densities, np.float64)
+        iso = np.ascontiguousarray(m.isotropic, np.int32) if m.isotropic is not None else None
+        r.ref_add_material(nn.size, nn.ctypes.data, dp(dd), iso.ctypes.data if iso is not None else None)
+    return out
 
 
 class Oracle:

@@ -17,8 +17,12 @@
 //     checked against the reference gold file test/tests/study/gold/openmc_study_rays.e through
 //     tests/golden/study_rays_*.npz;
 //   - the element walk is checked against RT's HEX8/QUAD4 `lots.i` total-distance gold CSVs;
-//   - cross-section VALUES and collision kinematics have no reference vectors offline (needs
-//     ENDF/B HDF5 + libMesh): "parity unpinned" for those, stated in DESIGN.md.
+//   - cross-section lookup, collision physics and tally scoring are checked bit for bit against the reference's own
+//     compiled Material::calculate_xs / Particle::event_collide / score_collision_tally running on Nuclide / Material /
+//     Tally objects built by its own constructors from an in-memory nuclide file of the synthetic library
+//     (oracle/ref_shim_physics.cpp, ref_shim_tally.cpp, ref_hdf5_mem.*);
+//   - "parity unpinned" remains only for physics the synthetic library does not carry (S(a,b), URR tables, tabulated
+//     secondaries: needs ENDF/B HDF5) and for libMesh itself, stated in DESIGN.md.
 //
 // Math library: by default log/sin/cos come from macaw_b200/csrc/mcw_detmath.h (the deterministic
 // libm replacement both sides use, so CPU and GPU histories are bit-identical); build with

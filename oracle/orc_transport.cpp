@@ -276,7 +276,8 @@ enum
 struct CollisionOut
 {
   int event;
-  double kappa_macro; // sum_i N_i q_i sigma_f,i (kappa-fission score, OMC tally_scoring.cpp:1240-1255)
+  int nuclide = -1; // library index of the sampled nuclide
+  double kappa_macro = 0.0; // sum_i N_i q_i sigma_f,i (kappa-fission score, OMC tally_scoring.cpp:1240-1255)
 };
 
 // OMC particle.cpp:219-288 event_collide + physics.cpp:38-152, :154-247, :442-465, :592-625, :627-719
@@ -284,7 +285,8 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
                             int elem, std::vector<mcw_source_site>& bank, int64_t bank_capacity)
 {
   const Material& mat = P.lib.materials[i_mat];
-  CollisionOut out{EV_SCATTER, 0.0};
+  CollisionOut out;
+  out.event = EV_SCATTER;
   p.k_col += p.wgt * macro.nu_fission / macro.total;
   ++p.n_coll;
   for (size_t i = 0; i < mat.nuc.size(); ++i)
@@ -308,6 +310,7 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
   }
   const Nuclide& nuc = P.lib.nuclides[mat.nuc[k]];
   const Micro& mx = micro[k];
+  out.nuclide = mat.nuc[k];
   const double E_last = p.E;
   if (nuc.fissionable)
   {
@@ -743,6 +746,52 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
   t.sum_sq.assign(n, 0.0);
   P.tallies.push_back(std::move(t));
   return 0;
+}
+
+// Replays n independent collision events in material i_mat through the lookup + collision of the transport loop above
+// (Library::macro_xs, collide); exists so tests can hold them against the reference's own Material::calculate_xs and
+// Particle::event_collide (oracle/_ref ref_collide_events, same argument layout: macro4 = total, absorption, fission,
+// nu_fission; state8 = E, u, alive, k_collision, k_absorption, sampled nuclide; site7 = E, u, delayed_group, parent_id,
+// progeny_id).  seeds are 4 per event like the reference's streams; the oracle keeps the first 3.
+int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const double* E, const double* u3, const uint64_t* seeds4,
+                           const int64_t* id, double* macro4, double* state8, uint64_t* seeds_out, int32_t* n_sites,
+                           int64_t bank_capacity, double* site7)
+{
+  Problem& P = *(Problem*)h;
+  const double keff_saved = P.keff;
+  P.keff = keff;
+  std::vector<mcw_source_site> bank;
+  std::vector<Micro> micro(P.lib.materials[i_mat].nuc.size());
+  for (int64_t k = 0; k < n; ++k)
+  {
+    Hist p;
+    p.r = {0.25 * k, -0.5, 1.0};
+    p.u = {u3[3 * k], u3[3 * k + 1], u3[3 * k + 2]};
+    p.E = E[k], p.wgt = 1.0, p.id = id[k];
+    for (int s = 0; s < 3; ++s)
+      p.seeds[s] = seeds4[4 * k + s];
+    int64_t n_nuc = 0;
+    const Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc);
+    macro4[4 * k] = macro.total, macro4[4 * k + 1] = macro.absorption;
+    macro4[4 * k + 2] = macro.fission, macro4[4 * k + 3] = macro.nu_fission;
+    const size_t before = bank.size();
+    const CollisionOut co = collide(P, p, i_mat, macro, micro.data(), 0, bank, bank_capacity);
+    double* st = state8 + 8 * k;
+    st[0] = p.E, st[1] = p.u.x, st[2] = p.u.y, st[3] = p.u.z, st[4] = co.event == EV_ABSORB ? 0.0 : 1.0;
+    st[5] = p.k_col, st[6] = p.k_abs, st[7] = co.nuclide;
+    for (int s = 0; s < 3; ++s)
+      seeds_out[4 * k + s] = p.seeds[s];
+    seeds_out[4 * k + 3] = seeds4[4 * k + 3];
+    n_sites[k] = (int32_t)(bank.size() - before);
+  }
+  for (size_t j = 0; j < bank.size(); ++j)
+  {
+    double* o = site7 + 7 * j;
+    o[0] = bank[j].E, o[1] = bank[j].u[0], o[2] = bank[j].u[1], o[3] = bank[j].u[2], o[4] = bank[j].delayed_group;
+    o[5] = (double)bank[j].parent_id, o[6] = (double)bank[j].progeny_id;
+  }
+  P.keff = keff_saved;
+  return (int64_t)bank.size();
 }
 
 // Replays collision events through the scoring + binning used by the transport loop above (collision_scores +

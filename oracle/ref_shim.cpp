@@ -26,16 +26,6 @@
 #include "openmc/random_dist.h"
 #include "openmc/random_lcg.h"
 
-// error.cpp needs MPI / HDF5-tainted headers; the samplers only reach fatal_error on malformed XML
-namespace openmc
-{
-void fatal_error(const std::string& message, int err)
-{
-  std::fprintf(stderr, "reference fatal_error: %s\n", message.c_str());
-  std::exit(err ? err : 1);
-}
-}
-
 extern "C" {
 // OMC bank.cpp:60-104 sort_fission_bank + eigenvalue.cpp:71-311 synchronize_bank (single process), the
 // reference's own functions on the reference's own globals: fission bank in, sorted bank and next source bank out

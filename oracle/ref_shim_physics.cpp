@@ -1,0 +1,262 @@
+// ref_shim_physics.cpp -- extern "C" doorways into the REFERENCE's own cross-section lookup and collision physics:
+// Nuclide / Reaction / ReactionProduct / distribution objects built by their own constructors (openmc/src/nuclide.cpp:51,
+// reaction.cpp:22, reaction_product.cpp:24, secondary_uncorrelated.cpp:17, distribution_energy.cpp:42,271,328,
+// endf.cpp:80-151) from an in-memory tree (ref_hdf5_mem.*) laid out like an OpenMC HDF5 nuclide file; Nuclide::init_grid
+// (nuclide.cpp:446); Material::calculate_xs (material.cpp:773-829) -> Nuclide::calculate_xs (nuclide.cpp:550-750); and
+// Particle::event_collide (particle.cpp:219-288) -> collision (physics.cpp:38) -> sample_neutron_reaction (:86) with
+// everything below it (sample_nuclide, sample_fission, create_fission_sites, absorption, scatter, elastic / inelastic
+// scatter, sample_fission_neutron).  That is the chain MaCaw's CollisionKernel.C:143,185 runs.  Linked into
+// oracle/_ref/libomc_ref.so by oracle/Makefile; test infrastructure only.  Nothing here restates an algorithm: the shim
+// only lays arrays out as the data file would and sets / reads particle state.
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "openmc/bank.h"
+#include "openmc/geometry.h"
+#include "openmc/tallies/tally.h"
+#include "openmc/constants.h"
+#include "openmc/material.h"
+#include "openmc/nuclide.h"
+#include "openmc/particle.h"
+#include "openmc/settings.h"
+#include "openmc/simulation.h"
+#include "ref_hdf5_mem.h"
+
+namespace
+{
+std::unique_ptr<memh5::Node> g_root;
+
+void constant_function(memh5::Node* parent, const char* name, double v, double e0, double e1)
+{
+  // Tabulated1D, one lin-lin region, two points of equal value
+  memh5::Node* d = parent->dataset(name, {e0, e1, v, v}, {2, 2});
+  d->attr("type", "Tabulated1D");
+  d->attr("breakpoints", std::vector<int>{2});
+  d->attr("interpolation", std::vector<int>{2});
+}
+void polynomial(memh5::Node* parent, const char* name, const std::vector<double>& coef)
+{
+  memh5::Node* d = parent->dataset(name, coef);
+  d->attr("type", "Polynomial");
+}
+memh5::Node* reaction(memh5::Node* rxs, int mt, double q, bool cm, const std::string& temp, const double* xs, int n, int threshold)
+{
+  char nm[32];
+  std::snprintf(nm, sizeof(nm), "reaction_%03d", mt);
+  memh5::Node* r = rxs->group(nm);
+  r->attr("Q_value", q);
+  r->attr("mt", mt);
+  r->attr("center_of_mass", cm ? 1 : 0);
+  r->attr("redundant", 0);
+  memh5::Node* d = r->group(temp)->dataset("xs", std::vector<double>(xs, xs + n));
+  d->attr("threshold_idx", threshold);
+  return r;
+}
+memh5::Node* neutron_product(memh5::Node* rx, int k, const char* mode, const std::vector<double>& yield_coef)
+{
+  memh5::Node* p = rx->group("product_" + std::to_string(k));
+  p->attr("particle", "neutron");
+  p->attr("emission_mode", mode);
+  p->attr("n_distribution", 1);
+  polynomial(p, "yield", yield_coef);
+  memh5::Node* d = p->group("distribution_0");
+  d->attr("type", "uncorrelated"); // no "angle" group: isotropic (secondary_uncorrelated.cpp:60-63)
+  return d;
+}
+} // namespace
+
+extern "C" {
+#define REF_API __attribute__((visibility("default")))
+
+REF_API void ref_library_reset()
+{
+  using namespace openmc;
+  model::materials.clear();
+  data::nuclides.clear();
+  data::nuclide_map.clear();
+  g_root.reset(new memh5::Node);
+  settings::run_CE = true;
+  settings::run_mode = RunMode::EIGENVALUE;
+  settings::survival_biasing = false;
+  settings::ufs_on = false;
+  settings::photon_transport = false;
+  settings::res_scat_on = false;
+  settings::urr_ptables_on = true;
+  settings::temperature_method = TemperatureMethod::NEAREST;
+  model::n_coord_levels = 1;
+  model::active_collision_tallies.clear();
+  model::active_analog_tallies.clear();
+  model::active_tallies.clear();
+  model::active_surface_tallies.clear();
+  model::active_meshsurf_tallies.clear();
+}
+
+// One synthetic nuclide of macaw_b200/nucdata.py as a nuclide file: MT 2 elastic (isotropic in the centre of mass),
+// optionally MT 51 (one level, isotropic CM), MT 102 capture, optionally MT 18 fission with a polynomial total nu, a Watt
+// prompt spectrum and n_precursor Maxwell delayed groups of constant yield.  Returns the nuclide's index.
+REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, const double* energy, const double* elastic,
+                            const double* capture, const double* fission, int n_inel, int inel_thr, const double* inel,
+                            double inel_E, double inel_ratio, const double* nu_poly, int n_precursor, const double* dyield,
+                            const double* dtheta, double watt_a, double watt_b)
+{
+  using namespace openmc;
+  memh5::Node* g = g_root->group(name);
+  g->attr("Z", 1);
+  g->attr("A", 1);
+  g->attr("metastable", 0);
+  g->attr("atomic_weight_ratio", awr);
+  const int T = (int)std::round(kT / K_BOLTZMANN);
+  const std::string temp = std::to_string(T) + "K";
+  g->group("kTs")->dataset(temp, {kT}, {})->data.shape.clear();
+  g->group("energy")->dataset(temp, std::vector<double>(energy, energy + G));
+  memh5::Node* rxs = g->group("reactions");
+  neutron_product(reaction(rxs, 2, 0.0, true, temp, elastic, G, 0), 0, "prompt", {1.0});
+  if (n_inel > 0)
+  {
+    memh5::Node* e = neutron_product(reaction(rxs, 51, -inel_E, true, temp, inel, n_inel, inel_thr), 0, "prompt", {1.0})->group("energy");
+    e->attr("type", "level");
+    e->attr("threshold", inel_E);
+    e->attr("mass_ratio", inel_ratio);
+  }
+  reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
+  if (fission)
+  {
+    memh5::Node* f = reaction(rxs, 18, 0.0, false, temp, fission, G, 0);
+    const double e0 = energy[0], e1 = energy[G - 1];
+    double nu_d = 0.0;
+    for (int k = 0; k < n_precursor; ++k)
+      nu_d += dyield[k];
+    memh5::Node* pe = neutron_product(f, 0, "prompt", {nu_poly[0] - nu_d, nu_poly[1]})->group("energy");
+    pe->attr("type", "watt");
+    pe->attr("u", -2.0e7);
+    constant_function(pe, "a", watt_a, e0, e1);
+    constant_function(pe, "b", watt_b, e0, e1);
+    for (int k = 0; k < n_precursor; ++k)
+    {
+      memh5::Node* dp = neutron_product(f, k + 1, "delayed", {dyield[k]});
+      memh5::Node* de = dp->group("energy");
+      de->attr("type", "maxwell");
+      de->attr("u", -2.0e7);
+      constant_function(de, "theta", dtheta[k], e0, e1);
+    }
+    for (int k = 0; k < n_precursor; ++k)
+      f->children.at("product_" + std::to_string(k + 1))->attr("decay_rate", 1.0);
+    polynomial(g->group("total_nu"), "yield", {nu_poly[0], nu_poly[1]});
+  }
+  data::nuclides.push_back(std::make_unique<Nuclide>(memh5::id_of(g), std::vector<double>{(double)T}));
+  return (int)data::nuclides.size() - 1;
+}
+
+// energy limits of the library, then every nuclide's logarithmic grid index (what read_ce_cross_sections does after loading)
+REF_API void ref_finish_library(int n_log_bins)
+{
+  using namespace openmc;
+  const int neutron = static_cast<int>(ParticleType::neutron);
+  data::energy_min[neutron] = 0.0;
+  data::energy_max[neutron] = INFTY;
+  for (const auto& nuc : data::nuclides)
+  {
+    data::energy_min[neutron] = std::max(data::energy_min[neutron], nuc->grid_[0].energy.front());
+    data::energy_max[neutron] = std::min(data::energy_max[neutron], nuc->grid_[0].energy.back());
+  }
+  settings::n_log_bins = n_log_bins;
+  simulation::log_spacing = std::log(data::energy_max[neutron] / data::energy_min[neutron]) / settings::n_log_bins;
+  for (auto& nuc : data::nuclides)
+    nuc->init_grid();
+}
+
+// derived tables of nuclide i (create_derived, nuclide.cpp:317-390): xs_[0] as [G][5], and its flags
+REF_API void ref_nuclide_tables(int i, double* xs5, int32_t* fissionable, int32_t* n_precursor, int32_t* grid_index)
+{
+  const auto& nuc = *openmc::data::nuclides[i];
+  const auto& xs = nuc.xs_[0];
+  for (size_t k = 0; k < xs.shape()[0]; ++k)
+    for (int c = 0; c < 5; ++c)
+      xs5[5 * k + c] = xs(k, c);
+  *fissionable = nuc.fissionable_;
+  *n_precursor = nuc.n_precursor_;
+  if (grid_index)
+    for (size_t k = 0; k < nuc.grid_[0].grid_index.size(); ++k)
+      grid_index[k] = nuc.grid_[0].grid_index[k];
+}
+
+// isotropic: per-nuclide <isotropic> flags (material.cpp:255-270 p0_) or null
+REF_API int ref_add_material(int n, const int32_t* nuc, const double* dens, const int32_t* isotropic)
+{
+  using namespace openmc;
+  model::materials.push_back(std::make_unique<Material>());
+  Material& m = *model::materials.back();
+  m.nuclide_.assign(nuc, nuc + n);
+  m.atom_density_ = xt::zeros<double>({(size_t)n});
+  for (int k = 0; k < n; ++k)
+    m.atom_density_(k) = dens[k];
+  if (isotropic)
+  {
+    m.p0_.resize(n);
+    for (int k = 0; k < n; ++k)
+      m.p0_[k] = isotropic[k] != 0;
+  }
+  m.init_nuclide_index();
+  return (int)model::materials.size() - 1;
+}
+
+// Replays n independent collision events in material i_mat: each starts from (E, u, seeds[4], id, wgt 1), gets the macroscopic
+// cross sections from Material::calculate_xs and collides through Particle::event_collide.  Outputs per event: macro4 =
+// (total, absorption, fission, nu_fission); state8 = (E, ux, uy, uz, alive, keff_tally_collision, keff_tally_absorption,
+// sampled nuclide); seeds_out[4]; n_sites.  Fission sites of all events in order: site7 = (E, ux, uy, uz, delayed_group,
+// parent_id, progeny_id).  Returns the number of banked sites.
+REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const double* E, const double* u3, const uint64_t* seeds4,
+                                   const int64_t* id, double sqrtkT, double* macro4, double* state8, uint64_t* seeds_out,
+                                   int32_t* n_sites, int64_t bank_capacity, double* site7)
+{
+  using namespace openmc;
+  simulation::keff = keff;
+  simulation::fission_bank.clear();
+  simulation::fission_bank.reserve(bank_capacity);
+  for (int64_t k = 0; k < n; ++k)
+  {
+    Particle p;
+    p.type() = ParticleType::neutron;
+    p.n_coord() = 1;
+    p.material() = i_mat;
+    p.sqrtkT() = sqrtkT;
+    p.wgt() = 1.0;
+    p.id() = id[k];
+    p.E() = E[k];
+    p.u() = {u3[3 * k], u3[3 * k + 1], u3[3 * k + 2]};
+    p.r() = {0.25 * k, -0.5, 1.0};
+    for (int s = 0; s < N_STREAMS; ++s)
+      p.seeds(s) = seeds4[4 * k + s];
+    p.stream() = STREAM_TRACKING;
+    // event_calculate_xs (particle.cpp:86-135) minus the cell search: remember the pre-collision state, look up
+    p.E_last() = p.E();
+    p.u_last() = p.u();
+    p.r_last() = p.r();
+    p.wgt_last() = p.wgt();
+    model::materials[i_mat]->calculate_xs(p);
+    macro4[4 * k] = p.macro_xs().total;
+    macro4[4 * k + 1] = p.macro_xs().absorption;
+    macro4[4 * k + 2] = p.macro_xs().fission;
+    macro4[4 * k + 3] = p.macro_xs().nu_fission;
+    const int64_t before = simulation::fission_bank.size();
+    p.event_collide();
+    double* st = state8 + 8 * k;
+    st[0] = p.E(), st[1] = p.u().x, st[2] = p.u().y, st[3] = p.u().z, st[4] = p.alive();
+    st[5] = p.keff_tally_collision(), st[6] = p.keff_tally_absorption(), st[7] = p.event_nuclide();
+    for (int s = 0; s < N_STREAMS; ++s)
+      seeds_out[4 * k + s] = p.seeds(s);
+    n_sites[k] = (int32_t)(simulation::fission_bank.size() - before);
+  }
+  const int64_t nb = simulation::fission_bank.size();
+  for (int64_t j = 0; j < nb; ++j)
+  {
+    const auto& s = simulation::fission_bank[j];
+    double* o = site7 + 7 * j;
+    o[0] = s.E, o[1] = s.u.x, o[2] = s.u.y, o[3] = s.u.z, o[4] = s.delayed_group, o[5] = (double)s.parent_id, o[6] = (double)s.progeny_id;
+  }
+  return nb;
+}
+}

@@ -541,6 +541,106 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
     assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
 
 
+def _reference_library(oracle_bridge, r, n_log_bins=500, G=600):
+    """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
+    tables, so both sides hold the same numbers.  One material is given <isotropic> flags."""
+    from macaw_b200 import nucdata
+    lib = nucdata.make_library(n_nuclides=9, G=G, seed=3, n_log_bins=n_log_bins)
+    lib.materials[3].isotropic = [1] + [0] * (len(lib.materials[3].nuclides) - 1)
+    generator = [n.xs.copy() for n in lib.nuclides]
+    tables = oracle_bridge.ref_load_library(r, lib)
+    for n, (xs5, fissionable, n_precursor, _) in zip(lib.nuclides, tables):
+        assert fissionable == n.fissionable and n_precursor == n.n_precursor
+        n.xs = xs5.copy()
+    return lib, generator, tables
+
+
+def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_bridge):
+    """The reference's own Nuclide constructor + create_derived (OMC nuclide.cpp:51-315, :317-390) and init_grid
+    (:446-476), run on an in-memory image of a nuclide file (oracle/ref_hdf5_mem.*): the total / absorption / fission /
+    nu-fission tables it derives from the reactions equal the ones macaw_b200.nucdata generates bit for bit (non-fissionable
+    nuclides; for fissionable ones capture is handed over as absorption - fission, so only to rounding), and its
+    logarithmic grid index equals the oracle's for every nuclide."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_collide_events"):
+        pytest.skip("oracle/_ref not built with nuclide.cpp (no /root/reference on this box)")
+    lib, generator, tables = _reference_library(oracle_bridge, r)
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    n_exact = 0
+    for i, (n, gen, (xs5, _, _, gi)) in enumerate(zip(lib.nuclides, generator, tables)):
+        if not n.fissionable:
+            assert np.array_equal(xs5[:, :4].view(np.uint64), gen[:, :4].view(np.uint64)), n.name
+            n_exact += 1
+        else:
+            assert np.allclose(xs5[:, :4], gen[:, :4], rtol=1e-12, atol=0) and xs5[:, 3].max() > 0
+        assert np.array_equal(o.grid_index(i, lib.n_log_bins), gi), n.name
+    assert n_exact >= 5
+
+
+@pytest.mark.parametrize("libm", [True, False])
+def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm):
+    """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
+    Material::calculate_xs -> Nuclide::calculate_xs (OMC material.cpp:773-829, nuclide.cpp:550-750) and
+    Particle::event_collide -> collision -> sample_neutron_reaction with sample_nuclide, sample_fission,
+    create_fission_sites, absorption, scatter, elastic_scatter (free-gas target), inelastic_scatter (LevelInelastic),
+    sample_fission_neutron (Watt prompt / Maxwell delayed), isotropic-in-lab override and the URR stream advance
+    (particle.cpp:219-288, physics.cpp:38-1120), replayed over 20 000 independent collisions in each of the four
+    materials and held against the oracle's macro_xs + collide on the same states.  libm=True (the oracle built on
+    glibc's log / sin / cos like the reference): macroscopic cross sections, outgoing energy and direction, alive flag,
+    keff collision / absorption scores, sampled nuclide, all stream seeds, fission-site counts and every site equal BIT
+    FOR BIT.  libm=False (the deterministic-math build the GPU is compared with): seeds, site counts, sampled nuclides,
+    fates and the cross sections still equal exactly (same random-number consumption, same branches); energies and
+    directions agree to 1e-12 (last-bit differences of the transcendental functions)."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_collide_events"):
+        pytest.skip("oracle/_ref not built with physics.cpp + particle.cpp (no /root/reference on this box)")
+    lib, _, _ = _reference_library(oracle_bridge, r)
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
+    f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    n, keff = 20000, 1.02
+    seen = {"absorbed": 0, "sites": 0, "delayed": 0, "inelastic": 0, "upscatter": 0}
+    for i_mat, m in enumerate(lib.materials):
+        rng = np.random.default_rng(5 + i_mat)
+        E = np.exp(rng.uniform(np.log(1.2e-5), np.log(1.9e7), n))
+        E[:8] = lib.nuclides[m.nuclides[0]].energy[[3, 4, 50, 51, 200, 300, 400, 500]]   # exactly on grid points
+        u = rng.normal(size=(n, 3))
+        u /= np.linalg.norm(u, axis=1)[:, None]
+        seeds = rng.integers(1, 2 ** 63, (n, 4), dtype=np.uint64)
+        ids = np.arange(1, n + 1, dtype=np.int64)
+
+        def run(f, *head, extra=()):
+            macro, st, so = np.zeros((n, 4)), np.zeros((n, 8)), np.zeros((n, 4), np.uint64)
+            ns, cap = np.zeros(n, np.int32), 3 * n
+            sites = np.zeros((cap, 7))
+            nb = f(*head, n, E.ctypes.data_as(f64p), u.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p), ids.ctypes.data, *extra,
+                   macro.ctypes.data_as(f64p), st.ctypes.data_as(f64p), so.ctypes.data_as(u64p), ns.ctypes.data, cap,
+                   sites.ctypes.data_as(f64p))
+            return macro, st, so, ns, sites[:nb]
+        ref = run(r.ref_collide_events, i_mat, keff, extra=(float(np.sqrt(lib.nuclides[0].kT)),))
+        mine = run(o.L.orc_collide_events, o.h, i_mat, keff)
+        assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
+        assert np.array_equal(mine[2], ref[2]) and np.array_equal(mine[3], ref[3])       # seeds, site counts
+        assert mine[4].shape == ref[4].shape
+        if libm:
+            assert np.array_equal(mine[1].view(np.uint64), ref[1].view(np.uint64))
+            assert np.array_equal(mine[4].view(np.uint64), ref[4].view(np.uint64))
+        else:
+            assert np.array_equal(mine[1][:, [4, 7]], ref[1][:, [4, 7]]) and np.array_equal(mine[4][:, 4:], ref[4][:, 4:])
+            assert np.allclose(mine[1], ref[1], rtol=1e-12, atol=1e-14) and np.allclose(mine[4], ref[4], rtol=1e-12, atol=1e-14)
+        st, sites = ref[1], ref[4]
+        assert np.allclose(np.linalg.norm(st[:, 1:4], axis=1), 1.0)
+        seen["absorbed"] += int((st[:, 4] == 0).sum())
+        seen["sites"] += len(sites)
+        seen["delayed"] += int((sites[:, 4] > 0).sum())
+        seen["upscatter"] += int(((st[:, 0] > E) & (st[:, 4] == 1)).sum())
+        seen["inelastic"] += int(((st[:, 0] < 0.5 * E) & (E > 1e6) & (st[:, 4] == 1)).sum())
+    assert all(v > 0 for v in seen.values()), seen
+
+
 def test_work_split_against_reference_simulation_cpp(oracle_bridge):
     """calculate_work (OMC simulation.cpp:529-551), the reference's own function: the particle split used by the
     C ABI (mcw_calculate_work), by macaw_b200.dist and by the oracle for every rank count the study supports."""
