@@ -41,7 +41,7 @@ def _load(name):
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     lib.orc_collide_events.restype = C.c_int64
     lib.orc_collide_events.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, f64p, f64p,
-                                       u64p, C.c_void_p, C.c_int64, f64p]
+                                       u64p, C.c_void_p, C.c_int64, f64p, f64p]
     lib.orc_score_events.restype = C.c_int64
     lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
                                      f64p, f64p]
@@ -127,13 +127,13 @@ def ref_lib():
     if hasattr(r, "ref_collide_events"):
         r.ref_library_reset.argtypes = []
         r.ref_add_nuclide.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int, f64p, f64p, f64p, f64p, C.c_int, C.c_int,
-                                      f64p, C.c_double, C.c_double, f64p, C.c_int, f64p, f64p, C.c_double, C.c_double]
+                                      f64p, C.c_double, C.c_double, f64p, C.c_int, f64p, f64p, C.c_double, C.c_double, C.c_double]
         r.ref_finish_library.argtypes = [C.c_int]
         r.ref_nuclide_tables.argtypes = [C.c_int, f64p, C.c_void_p, C.c_void_p, C.c_void_p]
         r.ref_add_material.argtypes = [C.c_int, C.c_void_p, f64p, C.c_void_p]
         r.ref_collide_events.restype = C.c_int64
         r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,
-                                         u64p, C.c_void_p, C.c_int64, f64p]
+                                         u64p, C.c_void_p, C.c_int64, f64p, f64p]
     if hasattr(r, "ref_score_collision_events"):
         r.ref_score_collision_events.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
                                                  C.c_int64, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p]
@@ -182,7 +182,7 @@ def ref_load_library(r, libr: nucdata.Library):
         nu, dy, dth = np.array(n.nu_poly, np.float64), np.ascontiguousarray(n.delayed_yield), np.ascontiguousarray(n.delayed_theta)
         r.ref_add_nuclide(n.name.encode(), n.awr, n.kT, e.size, dp(e), dp(el), dp(cap), dp(fis) if n.fissionable else None,
                           int(n.inelastic.size), n.inel_threshold, dp(inel), n.inel_threshold_energy, n.inel_mass_ratio,
-                          dp(nu), n.n_precursor, dp(dy), dp(dth), n.watt_a, n.watt_b)
+                          dp(nu), n.n_precursor, dp(dy), dp(dth), n.watt_a, n.watt_b, n.q_fission)
     r.ref_finish_library(libr.n_log_bins)
     out = []
     for i, n in enumerate(libr.nuclides):

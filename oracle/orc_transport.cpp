@@ -755,7 +755,7 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
 // progeny_id).  seeds are 4 per event like the reference's streams; the oracle keeps the first 3.
 int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const double* E, const double* u3, const uint64_t* seeds4,
                            const int64_t* id, double* macro4, double* state8, uint64_t* seeds_out, int32_t* n_sites,
-                           int64_t bank_capacity, double* site7)
+                           int64_t bank_capacity, double* site7, double* kappa)
 {
   Problem& P = *(Problem*)h;
   const double keff_saved = P.keff;
@@ -779,6 +779,12 @@ int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const dou
     double* st = state8 + 8 * k;
     st[0] = p.E, st[1] = p.u.x, st[2] = p.u.y, st[3] = p.u.z, st[4] = co.event == EV_ABSORB ? 0.0 : 1.0;
     st[5] = p.k_col, st[6] = p.k_abs, st[7] = co.nuclide;
+    if (kappa)
+    {
+      double sc[MCW_N_SCORES];
+      collision_scores(1.0, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_macro, sc);
+      kappa[k] = sc[MCW_SCORE_KAPPA_FISSION];
+    }
     for (int s = 0; s < 3; ++s)
       seeds_out[4 * k + s] = p.seeds[s];
     seeds_out[4 * k + 3] = seeds4[4 * k + 3];

@@ -100,7 +100,7 @@ REF_API void ref_library_reset()
 REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, const double* energy, const double* elastic,
                             const double* capture, const double* fission, int n_inel, int inel_thr, const double* inel,
                             double inel_E, double inel_ratio, const double* nu_poly, int n_precursor, const double* dyield,
-                            const double* dtheta, double watt_a, double watt_b)
+                            const double* dtheta, double watt_a, double watt_b, double q_fission)
 {
   using namespace openmc;
   memh5::Node* g = g_root->group(name);
@@ -124,7 +124,7 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
   reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
   if (fission)
   {
-    memh5::Node* f = reaction(rxs, 18, 0.0, false, temp, fission, G, 0);
+    memh5::Node* f = reaction(rxs, 18, q_fission, false, temp, fission, G, 0);
     const double e0 = energy[0], e1 = energy[G - 1];
     double nu_d = 0.0;
     for (int k = 0; k < n_precursor; ++k)
@@ -207,12 +207,28 @@ REF_API int ref_add_material(int n, const int32_t* nuc, const double* dens, cons
 // cross sections from Material::calculate_xs and collides through Particle::event_collide.  Outputs per event: macro4 =
 // (total, absorption, fission, nu_fission); state8 = (E, ux, uy, uz, alive, keff_tally_collision, keff_tally_absorption,
 // sampled nuclide); seeds_out[4]; n_sites.  Fission sites of all events in order: site7 = (E, ux, uy, uz, delayed_group,
-// parent_id, progeny_id).  Returns the number of banked sites.
+// parent_id, progeny_id).  kappa (or null): per event, what score_collision_tally (called by event_collide, particle.cpp:247)
+// adds to a filterless collision-estimator tally with the kappa-fission score (tally_scoring.cpp:1216-1258).  Returns the
+// number of banked sites.
 REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const double* E, const double* u3, const uint64_t* seeds4,
                                    const int64_t* id, double sqrtkT, double* macro4, double* state8, uint64_t* seeds_out,
-                                   int32_t* n_sites, int64_t bank_capacity, double* site7)
+                                   int32_t* n_sites, int64_t bank_capacity, double* site7, double* kappa)
 {
   using namespace openmc;
+  Tally* tally = nullptr;
+  model::tallies.clear();
+  model::tally_map.clear();
+  model::tally_filters.clear();
+  model::filter_map.clear();
+  if (kappa)
+  {
+    tally = Tally::create(1);
+    tally->set_scores(std::vector<std::string>{"kappa-fission"});
+    tally->estimator_ = TallyEstimator::COLLISION;
+    tally->set_active(true);
+    tally->init_results();
+  }
+  setup_active_tallies();
   simulation::keff = keff;
   simulation::fission_bank.clear();
   simulation::fission_bank.reserve(bank_capacity);
@@ -242,7 +258,11 @@ REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const doub
     macro4[4 * k + 2] = p.macro_xs().fission;
     macro4[4 * k + 3] = p.macro_xs().nu_fission;
     const int64_t before = simulation::fission_bank.size();
+    if (tally)
+      tally->reset();
     p.event_collide();
+    if (tally)
+      kappa[k] = tally->results_(0, 0, static_cast<int>(TallyResult::VALUE));
     double* st = state8 + 8 * k;
     st[0] = p.E(), st[1] = p.u().x, st[2] = p.u().y, st[3] = p.u().z, st[4] = p.alive();
     st[5] = p.keff_tally_collision(), st[6] = p.keff_tally_absorption(), st[7] = p.event_nuclide();
@@ -257,6 +277,9 @@ REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const doub
     double* o = site7 + 7 * j;
     o[0] = s.E, o[1] = s.u.x, o[2] = s.u.y, o[3] = s.u.z, o[4] = s.delayed_group, o[5] = (double)s.parent_id, o[6] = (double)s.progeny_id;
   }
+  model::tallies.clear();
+  model::tally_map.clear();
+  setup_active_tallies();
   return nb;
 }
 }

@@ -615,11 +615,11 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
         def run(f, *head, extra=()):
             macro, st, so = np.zeros((n, 4)), np.zeros((n, 8)), np.zeros((n, 4), np.uint64)
             ns, cap = np.zeros(n, np.int32), 3 * n
-            sites = np.zeros((cap, 7))
+            sites, kappa = np.zeros((cap, 7)), np.zeros(n)
             nb = f(*head, n, E.ctypes.data_as(f64p), u.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p), ids.ctypes.data, *extra,
                    macro.ctypes.data_as(f64p), st.ctypes.data_as(f64p), so.ctypes.data_as(u64p), ns.ctypes.data, cap,
-                   sites.ctypes.data_as(f64p))
-            return macro, st, so, ns, sites[:nb]
+                   sites.ctypes.data_as(f64p), kappa.ctypes.data_as(f64p))
+            return macro, st, so, ns, sites[:nb], kappa
         ref = run(r.ref_collide_events, i_mat, keff, extra=(float(np.sqrt(lib.nuclides[0].kT)),))
         mine = run(o.L.orc_collide_events, o.h, i_mat, keff)
         assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
@@ -631,6 +631,12 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
         else:
             assert np.array_equal(mine[1][:, [4, 7]], ref[1][:, [4, 7]]) and np.array_equal(mine[4][:, 4:], ref[4][:, 4:])
             assert np.allclose(mine[1], ref[1], rtol=1e-12, atol=1e-14) and np.allclose(mine[4], ref[4], rtol=1e-12, atol=1e-14)
+        # kappa-fission, collision estimator: the reference sums q * sigma_f * N * flux per nuclide (tally_scoring.cpp:
+        # 1246-1255); the oracle and the GPU sum q * sigma_f * N and multiply by the flux once -- same value to rounding
+        # (a known last-bits deviation), identical zero pattern
+        assert np.array_equal(mine[5] == 0, ref[5] == 0)
+        assert np.allclose(mine[5], ref[5], rtol=1e-15 * 4, atol=0)
+        seen["kappa"] = seen.get("kappa", 0) + int((ref[5] > 0).sum())
         st, sites = ref[1], ref[4]
         assert np.allclose(np.linalg.norm(st[:, 1:4], axis=1), 1.0)
         seen["absorbed"] += int((st[:, 4] == 0).sum())
