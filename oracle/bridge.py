@@ -39,6 +39,7 @@ def _load(name):
     lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
+    lib.orc_history_identity.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), u64p]
     lib.orc_collide_events.restype = C.c_int64
     lib.orc_collide_events.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, f64p, f64p,
                                        u64p, C.c_void_p, C.c_int64, f64p, f64p]
@@ -121,6 +122,9 @@ def ref_lib():
         r.ref_sort_and_synchronize_bank.restype = C.c_int64
         r.ref_sort_and_synchronize_bank.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                     C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(r, "ref_initialize_history"):
+        r.ref_initialize_history.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, f64p,
+                                             C.POINTER(C.c_int64), u64p, f64p]
     if hasattr(r, "ref_calculate_work"):
         r.ref_calculate_work.restype = C.c_int64
         r.ref_calculate_work.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p]

@@ -430,6 +430,21 @@ static int64_t spatialBin(const Problem& P, const Tally& t, int64_t elem)
                                           : (t.granularity == MCW_FILTER_UNIVERSE ? P.mesh.block[elem] : 0);
 }
 
+// id and stream seeds of the i_local-th history of this rank in `batch` (OMC simulation.cpp:466-481 initialize_history)
+static void history_identity(const Problem& P, int64_t i_local, int batch, Hist& p)
+{
+  const mcw_settings& S = P.set;
+  p.id = P.work_index[P.rank] + i_local + 1; // OMC simulation.cpp:469
+  // overall_generation() = batch (gen_per_batch 1, current_gen 1: MC OpenMCStudy.C:309-310)
+  int64_t particle_seed = (int64_t)(0 + batch - 1) * S.n_particles + p.id; // OMC simulation.cpp:477-480
+  for (int s = 0; s < 3; ++s)
+  {
+    p.seeds[s] = future_seed((uint64_t)particle_seed * PRN_STRIDE, (uint64_t)(S.master_seed + s));
+    if (S.seed_through_double)
+      p.seeds[s] = seed_via_double(p.seeds[s]);
+  }
+}
+
 // One history = MC OpenMCStudy.C:317-363 (defineRays) + RT TraceRay::trace + MC
 // CollisionKernel::onSegment (CollisionKernel.C:98-275).
 static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_active,
@@ -447,15 +462,7 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
   p.u = dir;
   p.E = src.E;
   p.wgt = src.wgt;
-  p.id = P.work_index[P.rank] + i_local + 1; // OMC simulation.cpp:469
-  // overall_generation() = batch (gen_per_batch 1, current_gen 1: MC OpenMCStudy.C:309-310)
-  int64_t particle_seed = (int64_t)(0 + batch - 1) * S.n_particles + p.id; // OMC simulation.cpp:477-480
-  for (int s = 0; s < 3; ++s)
-  {
-    p.seeds[s] = future_seed((uint64_t)particle_seed * PRN_STRIDE, (uint64_t)(S.master_seed + s));
-    if (S.seed_through_double)
-      p.seeds[s] = seed_via_double(p.seeds[s]);
-  }
+  history_identity(P, i_local, batch, p);
   int64_t ray_id = (int64_t)(batch - 1) * S.n_particles + (p.id - 1);
   int64_t elem = src.elem;
   if (elem < 0)
@@ -746,6 +753,16 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
   t.sum_sq.assign(n, 0.0);
   P.tallies.push_back(std::move(t));
   return 0;
+}
+
+// history_identity for tests (held against the reference's own initialize_history, oracle/_ref ref_initialize_history)
+void orc_history_identity(void* h, int64_t i_local, int batch, int64_t* id, uint64_t* seeds3)
+{
+  Hist p;
+  history_identity(*(Problem*)h, i_local, batch, p);
+  *id = p.id;
+  for (int s = 0; s < 3; ++s)
+    seeds3[s] = p.seeds[s];
 }
 
 // Replays n independent collision events in material i_mat through the lookup + collision of the transport loop above

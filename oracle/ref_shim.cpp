@@ -18,6 +18,7 @@
 #include "openmc/simulation.h"
 #include "openmc/tallies/tally.h"
 #include "openmc/distribution_spatial.h"
+#include "openmc/particle.h"
 #include "openmc/physics.h"
 #include "openmc/search.h"
 #include "pugixml.hpp"
@@ -68,6 +69,41 @@ int64_t ref_calculate_work(int64_t n_particles, int n_procs, int rank, int64_t* 
   for (int i = 0; i <= n_procs; ++i)
     work_index[i] = simulation::work_index[i];
   return simulation::work_per_rank;
+}
+// OMC simulation.cpp:451-481 initialize_history (MC OpenMCStudy.C:326, CollisionKernel.C:75) for the index_source-th site of
+// this rank's source bank in batch `batch` (gen_per_batch 1): the particle's id, its four stream seeds and what from_source
+// copied (E, wgt, r, u)
+void ref_initialize_history(int64_t n_particles, int n_procs, int rank, int64_t master_seed, int batch, int64_t index_source,
+                            const double* site_r_u_E_wgt, int64_t* id, uint64_t* seeds4, double* state8)
+{
+  using namespace openmc;
+  settings::run_mode = RunMode::EIGENVALUE;
+  settings::n_particles = n_particles;
+  settings::gen_per_batch = 1;
+  settings::write_all_tracks = false;
+  settings::track_identifiers.clear();
+  mpi::n_procs = n_procs;
+  mpi::rank = rank;
+  calculate_work();
+  openmc_set_seed(master_seed);
+  simulation::total_gen = 0;
+  simulation::current_batch = batch;
+  simulation::current_gen = 1;
+  simulation::source_bank.assign(index_source, SourceSite{});
+  SourceSite& s = simulation::source_bank[index_source - 1];
+  s.r = {site_r_u_E_wgt[0], site_r_u_E_wgt[1], site_r_u_E_wgt[2]};
+  s.u = {site_r_u_E_wgt[3], site_r_u_E_wgt[4], site_r_u_E_wgt[5]};
+  s.E = site_r_u_E_wgt[6];
+  s.wgt = site_r_u_E_wgt[7];
+  s.particle = ParticleType::neutron;
+  Particle p;
+  initialize_history(p, index_source);
+  *id = p.id();
+  for (int k = 0; k < N_STREAMS; ++k)
+    seeds4[k] = p.seeds(k);
+  state8[0] = p.r().x, state8[1] = p.r().y, state8[2] = p.r().z;
+  state8[3] = p.u().x, state8[4] = p.u().y, state8[5] = p.u().z;
+  state8[6] = p.E(), state8[7] = p.wgt();
 }
 // OMC tallies/tally.cpp:639-670 Tally::accumulate on a reference Tally object: `values` = n_batches x n_entries
 // VALUE arrays scored in successive batches; returns SUM and SUM_SQ per entry and the number of realisations

@@ -647,6 +647,34 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
     assert all(v > 0 for v in seen.values()), seen
 
 
+def test_history_identity_against_reference_initialize_history(oracle_bridge):
+    """initialize_history (OMC simulation.cpp:451-481; MC OpenMCStudy.C:326), the reference's own function on its own
+    Particle: id = work_index[rank] + index_source, seeds = init_particle_seeds((batch - 1) * n_particles + id) with the
+    master seed of settings.xml, and from_source copying the site -- equal to the oracle's history_identity for 1 / 3 / 8
+    ranks, several batches and sites (seed_through_double off: the rounding through aux data is MaCaw's)."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_initialize_history"):
+        pytest.skip("oracle/_ref not built with particle.cpp (no /root/reference on this box)")
+    f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    n = 1000
+    for master_seed in (1, 7919):
+        mesh, lib, bm, s = problems.infinite_medium(n_particles=n, seed=master_seed, seed_through_double=False)
+        for nranks, rank in ((1, 0), (3, 1), (8, 7)):
+            o = problems.configure(oracle_bridge.Oracle(rank=rank, nranks=nranks), mesh, lib, bm, s, tallies=False)
+            for batch in (1, 2, 9):
+                for i_local in (0, 1, 57, n // nranks - 1):
+                    site = np.array([0.1, -0.2, 0.3, 0.0, 0.6, 0.8, 2.0e6 + i_local, 1.0])
+                    rid, rseeds, state = C.c_int64(), np.zeros(4, np.uint64), np.zeros(8)
+                    r.ref_initialize_history(n, nranks, rank, master_seed, batch, i_local + 1, site.ctypes.data_as(f64p),
+                                             C.byref(rid), rseeds.ctypes.data_as(u64p), state.ctypes.data_as(f64p))
+                    oid, oseeds = C.c_int64(), np.zeros(3, np.uint64)
+                    o.L.orc_history_identity(o.h, i_local, batch, C.byref(oid), oseeds.ctypes.data_as(u64p))
+                    assert oid.value == rid.value and np.array_equal(oseeds, rseeds[:3])
+                    assert np.array_equal(state, site)
+    r.ref_set_master_seed(1)
+
+
 def test_work_split_against_reference_simulation_cpp(oracle_bridge):
     """calculate_work (OMC simulation.cpp:529-551), the reference's own function: the particle split used by the
     C ABI (mcw_calculate_work), by macaw_b200.dist and by the oracle for every rank count the study supports."""
