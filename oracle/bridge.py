@@ -39,6 +39,7 @@ def _load(name):
     lib.orc_rotate_angle.argtypes = [f64p, C.c_double, f64p, u64p]
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
+    lib.orc_tracklength_kappa.argtypes = [C.c_void_p, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
     lib.orc_history_identity.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), u64p]
     lib.orc_collide_events.restype = C.c_int64
     lib.orc_collide_events.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, f64p, f64p,
@@ -135,6 +136,7 @@ def ref_lib():
         r.ref_finish_library.argtypes = [C.c_int]
         r.ref_nuclide_tables.argtypes = [C.c_int, f64p, C.c_void_p, C.c_void_p, C.c_void_p]
         r.ref_add_material.argtypes = [C.c_int, C.c_void_p, f64p, C.c_void_p]
+        r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
         r.ref_collide_events.restype = C.c_int64
         r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,
                                          u64p, C.c_void_p, C.c_int64, f64p, f64p]

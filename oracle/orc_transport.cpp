@@ -398,6 +398,16 @@ static void score_tally(Tally& t, int64_t spatial, double E, const double* score
   }
 }
 
+// kappa-fission of one segment: q * sigma_f * N * flux nuclide by nuclide (OMC tally_scoring.cpp:1246-1255)
+static double tracklength_kappa(const Problem& P, const Material& mat, const Micro* micro, double flux)
+{
+  double kappa = 0;
+  for (size_t i = 0; i < mat.nuc.size(); ++i)
+    if (P.lib.nuclides[mat.nuc[i]].fissionable)
+      kappa += P.lib.nuclides[mat.nuc[i]].q * micro[i].fission * mat.dens[i] * flux;
+  return kappa;
+}
+
 // collision-estimator scores of one collision (OMC tally_scoring.cpp:2354-2365 flux, :557, :600, :752, :799, :1240-1255)
 static void collision_scores(double wgt_last, double total, double absorption, double fission, double nu_fission,
                              double kappa_macro, double* sc)
@@ -500,11 +510,7 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
           double sc[MCW_N_SCORES];
           const double flux = tracklength_scores(p.wgt, std::min(d, c.length), macro.total, macro.absorption, macro.fission,
                                                  macro.nu_fission, sc);
-          double kappa = 0;
-          for (size_t i = 0; i < mat.nuc.size(); ++i)
-            if (P.lib.nuclides[mat.nuc[i]].fissionable)
-              kappa += P.lib.nuclides[mat.nuc[i]].q * micro[i].fission * mat.dens[i] * flux;
-          sc[4] = macro.absorption == 0. ? 0.0 : kappa;
+          sc[MCW_SCORE_KAPPA_FISSION] = macro.absorption == 0. ? 0.0 : tracklength_kappa(P, mat, micro.data(), flux);
           score_tally(t, spatialBin(P, t, c.elem), p.E, sc);
         }
     if (S.seed_through_double)
@@ -753,6 +759,21 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
   t.sum_sq.assign(n, 0.0);
   P.tallies.push_back(std::move(t));
   return 0;
+}
+
+// kappa-fission track-length score of n segments (E, wgt, length) in material i_mat, through macro_xs + tracklength_kappa;
+// held against the reference's score_tracklength_tally on its own objects (oracle/_ref ref_tracklength_kappa)
+void orc_tracklength_kappa(void* h, int i_mat, int64_t n, const double* E, const double* wgt, const double* distance, double* out)
+{
+  Problem& P = *(Problem*)h;
+  const Material& mat = P.lib.materials[i_mat];
+  std::vector<Micro> micro(mat.nuc.size());
+  for (int64_t k = 0; k < n; ++k)
+  {
+    int64_t n_nuc = 0;
+    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc);
+    out[k] = macro.absorption == 0. ? 0.0 : tracklength_kappa(P, mat, micro.data(), wgt[k] * distance[k]);
+  }
 }
 
 // history_identity for tests (held against the reference's own initialize_history, oracle/_ref ref_initialize_history)

@@ -17,6 +17,7 @@
 #include "openmc/bank.h"
 #include "openmc/geometry.h"
 #include "openmc/tallies/tally.h"
+#include "openmc/tallies/tally_scoring.h"
 #include "openmc/constants.h"
 #include "openmc/material.h"
 #include "openmc/nuclide.h"
@@ -281,5 +282,40 @@ REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const doub
   model::tally_map.clear();
   setup_active_tallies();
   return nb;
+}
+
+// kappa-fission track-length score of n segments: Material::calculate_xs, then score_tracklength_tally (tally_scoring.cpp:
+// 2289-2352 -> :1216-1258) on a filterless track-length tally, per segment
+REF_API void ref_tracklength_kappa(int i_mat, int64_t n, const double* E, const double* wgt, const double* distance,
+                                   double sqrtkT, double* out)
+{
+  using namespace openmc;
+  model::tallies.clear();
+  model::tally_map.clear();
+  model::tally_filters.clear();
+  model::filter_map.clear();
+  Tally* tally = Tally::create(1);
+  tally->set_scores(std::vector<std::string>{"kappa-fission"});
+  tally->estimator_ = TallyEstimator::TRACKLENGTH;
+  tally->set_active(true);
+  tally->init_results();
+  setup_active_tallies();
+  Particle p;
+  p.type() = ParticleType::neutron;
+  p.n_coord() = 1;
+  p.material() = i_mat;
+  p.sqrtkT() = sqrtkT;
+  for (int64_t k = 0; k < n; ++k)
+  {
+    p.E() = p.E_last() = E[k];
+    p.wgt() = wgt[k];
+    model::materials[i_mat]->calculate_xs(p);
+    tally->reset();
+    score_tracklength_tally(p, distance[k]);
+    out[k] = tally->results_(0, 0, static_cast<int>(TallyResult::VALUE));
+  }
+  model::tallies.clear();
+  model::tally_map.clear();
+  setup_active_tallies();
 }
 }

@@ -647,6 +647,33 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
     assert all(v > 0 for v in seen.values()), seen
 
 
+def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
+    """kappa-fission on the track-length estimator (OMC tally_scoring.cpp:2289-2352 -> :1216-1258) through the reference's
+    own Material::calculate_xs and score_tracklength_tally on its own Nuclide / Material / Tally objects: per segment equal
+    to the oracle's macro_xs + tracklength_kappa BIT FOR BIT (same per-nuclide q * sigma_f * N * flux summation)."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_tracklength_kappa"):
+        pytest.skip("oracle/_ref not built with tally_scoring.cpp + nuclide.cpp (no /root/reference on this box)")
+    lib, _, _ = _reference_library(oracle_bridge, r)
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    f64p = C.POINTER(C.c_double)
+    n, n_pos = 20000, 0
+    for i_mat in range(len(lib.materials)):
+        rng = np.random.default_rng(40 + i_mat)
+        E = np.exp(rng.uniform(np.log(1.2e-5), np.log(1.9e7), n))
+        w, d = rng.uniform(0.3, 1.5, n), rng.uniform(1e-4, 4.0, n)
+        ref, mine = np.zeros(n), np.zeros(n)
+        r.ref_tracklength_kappa(i_mat, n, E.ctypes.data_as(f64p), w.ctypes.data_as(f64p), d.ctypes.data_as(f64p),
+                                float(np.sqrt(lib.nuclides[0].kT)), ref.ctypes.data_as(f64p))
+        o.L.orc_tracklength_kappa(o.h, i_mat, n, E.ctypes.data_as(f64p), w.ctypes.data_as(f64p), d.ctypes.data_as(f64p),
+                                  mine.ctypes.data_as(f64p))
+        assert np.array_equal(mine.view(np.uint64), ref.view(np.uint64))
+        n_pos += int((ref > 0).sum())
+    assert n_pos >= n   # the fuel material scores on every segment, the others never
+
+
 def test_history_identity_against_reference_initialize_history(oracle_bridge):
     """initialize_history (OMC simulation.cpp:451-481; MC OpenMCStudy.C:326), the reference's own function on its own
     Particle: id = work_index[rank] + index_source, seeds = init_particle_seeds((batch - 1) * n_particles + id) with the
