@@ -326,3 +326,29 @@ def test_full_size_oracle_parity_pin_cell_1m(oracle_bridge):
     assert int(ro["n_segments"].sum()) == rg.n_segments > 1_000_000_000
     ob = o.fission_bank()
     assert ob.tobytes() == bank.tobytes()
+
+
+def test_xs_lookup_against_reference_objects_fixture(ctx_factory, golden_dir):
+    """GPU against the REFERENCE's own outputs, no oracle in between: tests/golden/ref_collisions.npz holds what the
+    reference's compiled Material::calculate_xs (OMC material.cpp:773-829 -> nuclide.cpp:550-750) and Nuclide::init_grid
+    (:446-476) gave on Nuclide / Material objects built by its own constructors (tests/golden/make_ref_collisions.py).
+    mcw_xs_lookup returns the same macroscopic total / absorption / fission / nu-fission bit for bit for all 4 x 1000
+    energies (grid points included), and the library's logarithmic grid index equals the reference's for every nuclide."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_ref_collisions", os.path.join(golden_dir, "make_ref_collisions.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ref = np.load(os.path.join(golden_dir, "ref_collisions.npz"))
+    lib = gen.library()
+    for i, n in enumerate(lib.nuclides):
+        if n.fissionable:
+            n.xs = ref[f"xs_{i}"].copy()
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100, n_log_bins=lib.n_log_bins)
+    g = problems.configure(ctx_factory(), mesh, lib, bm, s, False)
+    for i_mat in range(len(lib.materials)):
+        E, _, _, _ = gen.events(i_mat, lib)
+        got = g.xs_lookup(E, np.full(E.size, i_mat, np.int32))
+        assert np.array_equal(got.view(np.uint64), ref[f"m{i_mat}_macro"].view(np.uint64)), i_mat
+    for i in range(len(lib.nuclides)):
+        assert np.array_equal(g.grid_index(i, lib.n_log_bins), ref[f"grid_index_{i}"]), i

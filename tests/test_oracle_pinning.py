@@ -647,6 +647,46 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
     assert all(v > 0 for v in seen.values()), seen
 
 
+@pytest.mark.parametrize("libm", [True, False])
+def test_collision_fixture_from_reference_objects(oracle_bridge, libm):
+    """tests/golden/ref_collisions.npz (made by tests/golden/make_ref_collisions.py where the reference tree exists):
+    4 x 1000 collisions through the reference's own Material::calculate_xs + Particle::event_collide.  Needs neither
+    /root/reference nor oracle/_ref, so it also holds on the GPU box and on a fresh clone: the oracle reproduces the
+    reference's outputs bit for bit on glibc math, and to 1e-12 with identical seeds / counts / fates on its
+    deterministic math."""
+    import importlib.util
+    import os
+    from tests import problems
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_ref_collisions", os.path.join(here, "make_ref_collisions.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "ref_collisions.npz"))
+    lib = gen.library()
+    for i, n in enumerate(lib.nuclides):
+        if n.fissionable:
+            n.xs = g[f"xs_{i}"].copy()
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
+    for i in range(len(lib.nuclides)):
+        assert np.array_equal(o.grid_index(i, lib.n_log_bins), g[f"grid_index_{i}"])
+    for i_mat in range(len(lib.materials)):
+        E, u, seeds, ids = gen.events(i_mat, lib)
+        mine = gen.run_events(o.L.orc_collide_events, (o.h, i_mat, gen.KEFF), E, u, seeds, ids)
+        ref = {k: g[f"m{i_mat}_{k}"] for k in mine}
+        assert np.array_equal(mine["macro"].view(np.uint64), ref["macro"].view(np.uint64))
+        assert np.array_equal(mine["seeds_out"], ref["seeds_out"]) and np.array_equal(mine["n_sites"], ref["n_sites"])
+        assert mine["sites"].shape == ref["sites"].shape
+        if libm:
+            assert np.array_equal(mine["state"].view(np.uint64), ref["state"].view(np.uint64))
+            assert np.array_equal(mine["sites"].view(np.uint64), ref["sites"].view(np.uint64))
+        else:
+            assert np.array_equal(mine["state"][:, [4, 7]], ref["state"][:, [4, 7]])
+            assert np.allclose(mine["state"], ref["state"], rtol=1e-12, atol=1e-14)
+            assert np.allclose(mine["sites"], ref["sites"], rtol=1e-12, atol=1e-14)
+        assert np.allclose(mine["kappa"], ref["kappa"], rtol=4e-15, atol=0)   # summation order, DESIGN.md section 2
+
+
 def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
     """kappa-fission on the track-length estimator (OMC tally_scoring.cpp:2289-2352 -> :1216-1258) through the reference's
     own Material::calculate_xs and score_tracklength_tally on its own Nuclide / Material / Tally objects: per segment equal
