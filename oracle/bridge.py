@@ -123,6 +123,8 @@ def ref_lib():
         r.ref_sort_and_synchronize_bank.restype = C.c_int64
         r.ref_sort_and_synchronize_bank.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                     C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(r, "ref_generation_bookkeeping"):
+        r.ref_generation_bookkeeping.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, f64p, f64p, f64p, f64p, f64p]
     if hasattr(r, "ref_initialize_history"):
         r.ref_initialize_history.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, f64p,
                                              C.POINTER(C.c_int64), u64p, f64p]

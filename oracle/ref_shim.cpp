@@ -22,6 +22,7 @@
 #include "openmc/physics.h"
 #include "openmc/search.h"
 #include "pugixml.hpp"
+#include "xtensor/xview.hpp"
 #include "openmc/math_functions.h"
 #include "openmc/position.h"
 #include "openmc/random_dist.h"
@@ -153,6 +154,77 @@ void ref_keff_statistics(const double* k_generation, int n_batches, int n_inacti
     calculate_average_keff();
     keff[b - 1] = simulation::keff;
     keff_std[b - 1] = simulation::keff_std;
+  }
+}
+// End-of-generation bookkeeping on the reference's own Particle and globals: every history's k scores go through
+// Particle::event_death (OMC particle.cpp:319-352: atomic adds into global_tally_*, in history order here), then the
+// global-tally update MaCaw does (MC OpenMCStudy.C:411-428 = OMC simulation.cpp:409-425), calculate_generation_keff
+// (eigenvalue.cpp:49-69) and calculate_average_keff (:313-351).  k3 = [n_generations][n_histories][collision, absorption,
+// tracklength]; outputs per generation: the three global-tally VALUEs, k_generation, keff, keff_std.
+void ref_generation_bookkeeping(int64_t n_particles, int n_inactive, int n_generations, int64_t n_histories, const double* k3,
+                                double* gt3, double* k_generation, double* keff, double* keff_std)
+{
+  using namespace openmc;
+  settings::run_mode = RunMode::EIGENVALUE;
+  settings::n_particles = n_particles;
+  settings::gen_per_batch = 1;
+  settings::n_inactive = n_inactive;
+  settings::confidence_intervals = false;
+  mpi::n_procs = 1;
+  mpi::rank = 0;
+  simulation::work_index = {0, n_particles};
+  simulation::progeny_per_particle.assign(n_particles, 0);
+  simulation::total_gen = 0;
+  simulation::k_generation.clear();
+  simulation::k_sum = {0.0, 0.0};
+  simulation::keff = 1.0;
+  simulation::keff_std = 0.0;
+  simulation::keff_generation = 0.0;
+  simulation::n_realizations = 0;
+  settings::reduce_tallies = true;
+  model::tallies.clear();
+  simulation::global_tallies = xt::zeros<double>({N_GLOBAL_TALLIES, 3});
+  global_tally_collision = global_tally_absorption = global_tally_tracklength = global_tally_leakage = 0.0;
+  auto& gt = simulation::global_tallies;
+  for (int b = 1; b <= n_generations; ++b)
+  {
+    simulation::current_batch = b;
+    simulation::current_gen = 1;
+    // initialize_generation (simulation.cpp:401-403; MC OpenMCStudy.C:305) remembers the starting track-length VALUE; not
+    // called itself because its ufs branch would drag mesh.cpp into the link
+    simulation::keff_generation = gt(GlobalTally::K_TRACKLENGTH, TallyResult::VALUE);
+    const double* k = k3 + (size_t)(b - 1) * n_histories * 3;
+    Particle p;
+    for (int64_t i = 0; i < n_histories; ++i)
+    {
+      p.id() = i + 1;
+      p.n_progeny() = 0;
+      p.keff_tally_collision() = k[3 * i];
+      p.keff_tally_absorption() = k[3 * i + 1];
+      p.keff_tally_tracklength() = k[3 * i + 2];
+      p.event_death();
+    }
+    gt(GlobalTally::K_COLLISION, TallyResult::VALUE) += global_tally_collision;
+    gt(GlobalTally::K_ABSORPTION, TallyResult::VALUE) += global_tally_absorption;
+    gt(GlobalTally::K_TRACKLENGTH, TallyResult::VALUE) += global_tally_tracklength;
+    global_tally_collision = global_tally_absorption = global_tally_tracklength = 0.0;
+    gt3[3 * (b - 1)] = gt(GlobalTally::K_COLLISION, TallyResult::VALUE);
+    gt3[3 * (b - 1) + 1] = gt(GlobalTally::K_ABSORPTION, TallyResult::VALUE);
+    gt3[3 * (b - 1) + 2] = gt(GlobalTally::K_TRACKLENGTH, TallyResult::VALUE);
+    calculate_generation_keff();
+    calculate_average_keff();
+    k_generation[b - 1] = simulation::k_generation.back();
+    keff[b - 1] = simulation::keff;
+    keff_std[b - 1] = simulation::keff_std;
+    // finalize_batch (simulation.cpp:334-345): accumulate_tallies moves VALUE / total_weight into SUM, SUM_SQ and counts
+    // the realisation; inactive batches are wiped
+    simulation::total_weight = (double)n_histories;
+    accumulate_tallies();
+    if (b <= n_inactive)
+    {
+      xt::view(gt, xt::all()) = 0.0;
+      simulation::n_realizations = 0;
+    }
   }
 }
 // OMC physics.cpp:955-1004, linked out of the reference's physics.cpp (see oracle/fake_hdf5/hdf5.h)

@@ -451,6 +451,45 @@ def test_keff_statistics_against_reference_eigenvalue_cpp(oracle_bridge):
     assert keff[0] == kg[0] and keff[1] == kg[1] and std[2] == 0.0 and std[3] > 0.0
 
 
+def test_generation_bookkeeping_against_reference_particle_and_eigenvalue_cpp(oracle_bridge):
+    """End of generation on the reference's own Particle and globals: Particle::event_death (OMC particle.cpp:319-352) fed
+    every history's k scores from the oracle's records in history order, the global-tally update MaCaw does (MC
+    OpenMCStudy.C:411-428), initialize_generation, calculate_generation_keff, calculate_average_keff and accumulate_tallies
+    (eigenvalue.cpp:49-69,313-351; tallies/tally.cpp) -- against the oracle's own generation results over 2 inactive + 4
+    active batches: the three k sums, k_generation, keff and keff_std bit for bit."""
+    from macaw_b200.cstructs import GenerationResult
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_generation_bookkeeping"):
+        pytest.skip("oracle/_ref not built with particle.cpp (no /root/reference on this box)")
+    n, n_inactive, n_gen = 1200, 2, 6
+    mesh, lib, bm, s = problems.infinite_medium(n_particles=n, n_inactive=n_inactive)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    o.sample_initial_source()
+    k3, results = np.zeros((n_gen, n, 3)), []
+    for b in range(1, n_gen + 1):
+        o.transport_generation(b, 4)
+        rec = o.history_records()
+        k3[b - 1] = np.stack([rec["k_collision"], rec["k_absorption"], rec["k_tracklength"]], axis=1)
+        o.L.orc_sample_bank(o.h, b)
+        o.L.orc_finish_sampling(o.h, 0, 1)
+        res = GenerationResult()
+        o.L.orc_finalize_generation(o.h, b, None, C.byref(res))
+        results.append((res.k_collision, res.k_absorption, res.k_tracklength, res.k_generation, res.keff, res.keff_std,
+                        res.total_weight))
+        o.set_source_bank(o.sampled())
+    f64p = C.POINTER(C.c_double)
+    gt3, kg, keff, std = np.zeros((n_gen, 3)), np.zeros(n_gen), np.zeros(n_gen), np.zeros(n_gen)
+    r.ref_generation_bookkeeping(n, n_inactive, n_gen, n, k3.ctypes.data_as(f64p), gt3.ctypes.data_as(f64p),
+                                 kg.ctypes.data_as(f64p), keff.ctypes.data_as(f64p), std.ctypes.data_as(f64p))
+    mine = np.array(results)
+    assert np.all(mine[:, 6] == n)
+    assert np.array_equal((gt3 / float(n)).view(np.uint64), np.ascontiguousarray(mine[:, :3]).view(np.uint64))
+    for col, ref in ((3, kg), (4, keff), (5, std)):
+        assert np.array_equal(np.ascontiguousarray(mine[:, col]).view(np.uint64), ref.view(np.uint64)), col
+    assert std[n_inactive] == 0.0 and std[-1] > 0.0 and 0.1 < keff[-1] < 2.0
+
+
 def test_tally_accumulate_against_reference_tally_cpp(oracle_bridge):
     """Tally::accumulate (OMC tallies/tally.cpp:639-670) on a reference Tally object, fed the VALUE arrays the oracle
     scored in three active batches: SUM, SUM_SQ (normalised by n_particles) and the realisation count equal the
