@@ -1,8 +1,10 @@
-// ref_shim.cpp -- extern "C" doorways into the REFERENCE's own compiled sources
-// (openmc/src/random_lcg.cpp, random_dist.cpp, math_functions.cpp, distribution.cpp, distribution_multi.cpp,
-// position.cpp, xml_interface.cpp, string_utils.cpp + vendored pugixml), linked into
-// oracle/_ref/libomc_ref.so by oracle/Makefile.  Test infrastructure only: used to pin the oracle's
-// RNG and samplers bit-for-bit against the real reference code.  Nothing here restates an algorithm.
+// ref_shim.cpp -- extern "C" doorways into the REFERENCE's own compiled sources (openmc/src: random_lcg, random_dist,
+// math_functions, distribution*, position, bank, eigenvalue, simulation, settings, particle, tallies/tally, physics, ... --
+// the REF_SRCS list of oracle/Makefile -- + vendored pugixml / Faddeeva), linked into oracle/_ref/libomc_ref.so.
+// Test infrastructure only: used to pin the oracle's RNG, samplers, bank / keff / tally bookkeeping and history
+// initialisation bit for bit against the real reference code (ref_shim_tally.cpp and ref_shim_physics.cpp do the same for
+// tally scoring and for lookup + collision physics).  Nothing here restates an algorithm; where a few lines of glue from
+// a function that cannot be linked are repeated, the comment at that spot says which and why.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
