@@ -82,6 +82,7 @@ def _load(name):
     lib.orc_tally_size.restype = C.c_int64
     lib.orc_tally_size.argtypes = [vp, C.c_int]
     lib.orc_set_keff.argtypes = [vp, C.c_double]
+    lib.orc_set_renormalise_direction.argtypes = [vp, C.c_int]
     lib.orc_get_keff.restype = C.c_double
     lib.orc_get_keff.argtypes = [vp]
     lib.orc_calculate_work.argtypes = [C.c_int64, C.c_int, vp]
@@ -138,6 +139,10 @@ def ref_lib():
         r.ref_finish_library.argtypes = [C.c_int]
         r.ref_nuclide_tables.argtypes = [C.c_int, f64p, C.c_void_p, C.c_void_p, C.c_void_p]
         r.ref_add_material.argtypes = [C.c_int, C.c_void_p, f64p, C.c_void_p]
+        if hasattr(r, "ref_transport_histories"):
+            r.ref_transport_histories.restype = C.c_int64
+            r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
+                                                  u64p, C.c_int64, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
         r.ref_collide_events.restype = C.c_int64
         r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,

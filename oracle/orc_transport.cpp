@@ -41,6 +41,7 @@ struct Problem
 
   // eigenvalue state (OMC simulation.cpp:253-276)
   double keff = 1.0, keff_std = 0.0;
+  bool renormalise_direction = true; // MaCaw / MOOSE re-normalise every new direction; off only to compare with plain OpenMC
   std::vector<double> k_generation;
   double k_sum[2] = {0, 0};
   int n_realizations = 0;
@@ -468,7 +469,8 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
   V3 dir = {src.u[0], src.u[1], src.u[2]};
   if (S.is_2d)
     dir.z = 0;
-  dir = unit(dir); // Ray::setStartingDirection (RT Ray.C:291)
+  if (P.renormalise_direction)
+    dir = unit(dir); // Ray::setStartingDirection (RT Ray.C:291)
   p.u = dir;
   p.E = src.E;
   p.wgt = src.wgt;
@@ -544,7 +546,7 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
     V3 nd = p.u;
     if (S.is_2d)
       nd.z = 0;
-    ndir = unit(nd);
+    ndir = P.renormalise_direction ? unit(nd) : nd;
     nstart = pos;
     return 2;
   };
@@ -1300,6 +1302,8 @@ int64_t orc_tally_size(void* h, int id)
   return -1;
 }
 void orc_set_keff(void* h, double k) { ((Problem*)h)->keff = k; }
+// test hook: 0 = keep directions as the collision physics returns them (plain OpenMC), 1 = MaCaw's Point::unit() (default)
+void orc_set_renormalise_direction(void* h, int on) { ((Problem*)h)->renormalise_direction = on != 0; }
 double orc_get_keff(void* h) { return ((Problem*)h)->keff; }
 int orc_calculate_work(int64_t n, int nranks, int64_t* wi)
 {

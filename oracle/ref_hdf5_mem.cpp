@@ -120,6 +120,11 @@ void write_dataset_lowlevel(hid_t, int, const hsize_t*, const char*, hid_t, hid_
 }
 void write_string(hid_t, const char*, const std::string&, bool) { die("write_string: the tree is read-only"); }
 void write_attr(hid_t, int, const hsize_t*, const char*, hid_t, const void*) { die("write_attr: the tree is read-only"); }
+hid_t create_group(hid_t, const std::string& name)
+{
+  die("create_group(" + name + "): the tree is read-only");
+  return -1;
+}
 hid_t file_open(const std::string& filename, char, bool)
 {
   die("file_open(" + filename + "): there are no files here");

@@ -15,6 +15,9 @@
 #include <vector>
 
 #include "openmc/bank.h"
+#include "openmc/cell.h"
+#include "openmc/message_passing.h"
+#include "openmc/random_lcg.h"
 #include "openmc/geometry.h"
 #include "openmc/tallies/tally.h"
 #include "openmc/tallies/tally_scoring.h"
@@ -317,5 +320,92 @@ REF_API void ref_tracklength_kappa(int i_mat, int64_t n, const double* E, const 
   model::tallies.clear();
   model::tally_map.clear();
   setup_active_tallies();
+}
+
+// Whole histories in an infinite medium of material i_mat through the reference's own history loop:
+// initialize_history (simulation.cpp:451) + transport_history_based_single_particle (:662-677: event_calculate_xs,
+// event_advance, event_collide, event_revive_from_secondary, event_death) in a one-cell, no-surface CSG geometry built here
+// (cell 0 fills universe 0 with the material; every flight ends in a collision).  site8 = (r, u, E, wgt) per history.
+// Outputs per history: state8 = (final E, n_collision, n_progeny, k_collision, k_absorption, k_tracklength, alive, n_event),
+// seeds_out[4]; fission sites of all histories: site7 as in ref_collide_events.  Returns the number of banked sites.
+REF_API int64_t ref_transport_histories(int i_mat, double keff, int64_t master_seed, int batch, int64_t n, const double* site8,
+                                        double sqrtkT, double* state8, uint64_t* seeds_out, int64_t bank_capacity,
+                                        double* site7)
+{
+  using namespace openmc;
+  model::cells.clear();
+  model::cell_map.clear();
+  model::universes.clear();
+  model::universe_map.clear();
+  auto cell = std::make_unique<CSGCell>();
+  cell->id_ = 1;
+  cell->type_ = Fill::MATERIAL;
+  cell->universe_ = 0;
+  cell->material_ = {i_mat};
+  cell->sqrtkT_ = {sqrtkT};
+  cell->simple_ = true; // empty region: contains() is true everywhere, no surface to hit
+  model::cells.push_back(std::move(cell));
+  model::cell_map[1] = 0;
+  model::universes.push_back(std::make_unique<Universe>());
+  model::universes[0]->id_ = 0;
+  model::universes[0]->cells_ = {0};
+  model::universe_map[0] = 0;
+  model::root_universe = 0;
+  model::n_coord_levels = 1;
+  model::tallies.clear();
+  model::tally_map.clear();
+  model::tally_filters.clear();
+  model::filter_map.clear();
+  setup_active_tallies();
+  settings::check_overlaps = false;
+  settings::n_particles = n;
+  settings::gen_per_batch = 1;
+  settings::write_all_tracks = false;
+  settings::track_identifiers.clear();
+  mpi::n_procs = 1;
+  mpi::rank = 0;
+  simulation::work_index = {0, n};
+  simulation::work_per_rank = n;
+  simulation::progeny_per_particle.assign(n, 0);
+  openmc_set_seed(master_seed);
+  simulation::total_gen = 0;
+  simulation::current_batch = batch;
+  simulation::current_gen = 1;
+  simulation::keff = keff;
+  simulation::fission_bank.clear();
+  simulation::fission_bank.reserve(bank_capacity);
+  simulation::source_bank.assign(n, SourceSite{});
+  for (int64_t k = 0; k < n; ++k)
+  {
+    SourceSite& s = simulation::source_bank[k];
+    const double* v = site8 + 8 * k;
+    s.r = {v[0], v[1], v[2]};
+    s.u = {v[3], v[4], v[5]};
+    s.E = v[6];
+    s.wgt = v[7];
+    s.particle = ParticleType::neutron;
+  }
+  for (int64_t k = 0; k < n; ++k)
+  {
+    Particle p;
+    initialize_history(p, k + 1);
+    global_tally_collision = global_tally_absorption = global_tally_tracklength = global_tally_leakage = 0.0;
+    transport_history_based_single_particle(p);
+    double* st = state8 + 8 * k;
+    st[0] = p.E(), st[1] = p.n_collision(), st[2] = (double)p.n_progeny();
+    st[3] = global_tally_collision, st[4] = global_tally_absorption, st[5] = global_tally_tracklength;
+    st[6] = p.alive(), st[7] = p.n_event();
+    for (int q = 0; q < N_STREAMS; ++q)
+      seeds_out[4 * k + q] = p.seeds(q);
+  }
+  global_tally_collision = global_tally_absorption = global_tally_tracklength = global_tally_leakage = 0.0;
+  const int64_t nb = simulation::fission_bank.size();
+  for (int64_t j = 0; j < nb; ++j)
+  {
+    const auto& s = simulation::fission_bank[j];
+    double* o = site7 + 7 * j;
+    o[0] = s.E, o[1] = s.u.x, o[2] = s.u.y, o[3] = s.u.z, o[4] = s.delayed_group, o[5] = (double)s.parent_id, o[6] = (double)s.progeny_id;
+  }
+  return nb;
 }
 }

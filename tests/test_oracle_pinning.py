@@ -726,6 +726,76 @@ def test_collision_fixture_from_reference_objects(oracle_bridge, libm):
         assert np.allclose(mine["kappa"], ref["kappa"], rtol=4e-15, atol=0)   # summation order, DESIGN.md section 2
 
 
+@pytest.mark.parametrize("renormalise", [0, 1])
+@pytest.mark.parametrize("i_mat", [0, 3])
+def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, renormalise):
+    """Whole histories, all carried state: the reference's own initialize_history + transport_history_based_single_particle
+    (OMC simulation.cpp:451,662-677: event_calculate_xs, event_advance, event_collide, event_revive_from_secondary,
+    event_death) in a one-cell, no-surface geometry of one material, against the oracle's PRODUCTION history loop
+    (run_history: locate, exit search, distance sample, collide) on a single 2e9-cm HEX8 element that no flight leaves, so
+    that MaCaw's one-random-number-per-segment rule coincides with OpenMC's one-per-flight.  Oracle on glibc
+    math, seed-through-double off (MaCaw's aux-data rounding, F3).  Per history: final energy, collision and progeny
+    counts, all stream seeds and the three k scores bit for bit; the fission bank site by site (energy, direction,
+    delayed group, parent / progeny ids; positions are the oracle's backward-from-exit points in a huge element and are
+    not compared).  Material 0 is the fuel (fission, delayed neutrons); material 3 carries an <isotropic> nuclide.
+    renormalise=0 switches off the one thing MaCaw does to the physics state that plain OpenMC does not -- Point::unit() on
+    every new direction (RT Ray.C:216-226) -- and then everything is BIT-IDENTICAL.  renormalise=1 (the
+    oracle's and the GPU's default, MaCaw's behaviour): the last-bit direction differences reach the energies (<= 1e-12
+    relative; k scores 1e-10), while seeds, collision and progeny counts, bank size and ids stay identical."""
+    from macaw_b200 import cstructs, meshgen
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_transport_histories"):
+        pytest.skip("oracle/_ref not built with the history loop (no /root/reference on this box)")
+    lib, _, _ = _reference_library(oracle_bridge, r)
+    n, batch, keff, master_seed, L = 1500, 3, 0.97, 11, 1.0e9
+    mesh = meshgen.hex_grid(1, 1, 1, (-L, -L, -L), (L, L, L), meshgen.BC_REFLECT, None, "one_element")
+    s = cstructs.make_settings(n, n_inactive=0, source_box=(-1, -1, -1, 1, 1, 1), seed=master_seed,
+                               n_log_bins=lib.n_log_bins, seed_through_double=False)
+    o = problems.configure(oracle_bridge.Oracle(libm=True), mesh, lib, [i_mat], s, tallies=False)
+    rng = np.random.default_rng(77 + i_mat)
+    sites = np.zeros(n, cstructs.SITE_DTYPE)
+    sites["r"] = rng.uniform(-1, 1, (n, 3))
+    u = rng.normal(size=(n, 3))
+    sites["u"] = u / np.linalg.norm(u, axis=1)[:, None]
+    sites["E"] = np.exp(rng.uniform(np.log(1e-2), np.log(1.0e7), n))
+    sites["wgt"], sites["elem"] = 1.0, -1
+    o.set_source_bank(sites)
+    o.L.orc_set_keff(o.h, keff)
+    o.L.orc_set_renormalise_direction(o.h, renormalise)
+    o.transport_generation(batch, 1)
+    rec, bank = o.history_records(), o.fission_bank()
+    assert int((rec["fate"] != 0).sum()) == 0 and int(rec["n_segments"].max()) > 20   # every history ends by absorption
+    f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    site8 = np.ascontiguousarray(np.concatenate([sites["r"], sites["u"], sites["E"][:, None], sites["wgt"][:, None]], axis=1))
+    state, seeds, cap = np.zeros((n, 8)), np.zeros((n, 4), np.uint64), 4 * n
+    site7 = np.zeros((cap, 7))
+    nb = r.ref_transport_histories(i_mat, keff, master_seed, batch, n, site8.ctypes.data_as(f64p),
+                                   float(np.sqrt(lib.nuclides[0].kT)), state.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p),
+                                   cap, site7.ctypes.data_as(f64p))
+    r.ref_set_master_seed(1)
+    assert np.all(state[:, 6] == 0)
+
+    def same(a, b):
+        a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+        return np.array_equal(a.view(np.uint64), b.view(np.uint64)) if not renormalise else np.allclose(a, b, rtol=1e-10, atol=1e-13)
+    assert same(state[:, 0], rec["E"])
+    assert np.array_equal(state[:, 1].astype(np.int64), rec["n_collisions"]) and np.array_equal(state[:, 1].astype(np.int64), rec["n_segments"])
+    assert np.array_equal(state[:, 2].astype(np.int64), rec["n_progeny"])
+    for col, f in ((0, "seed_tracking"), (1, "seed_source"), (2, "seed_urr")):
+        assert np.array_equal(seeds[:, col], rec[f]), f
+    for col, f in ((3, "k_collision"), (4, "k_absorption"), (5, "k_tracklength")):
+        assert same(state[:, col], rec[f]), f
+    # the oracle returns its bank sorted by (parent, progeny); the reference's is in creation order = the same order here
+    assert nb == bank.size
+    ref_sites = site7[:nb]
+    assert np.array_equal(ref_sites[:, 5].astype(np.int64), bank["parent_id"]) and np.array_equal(ref_sites[:, 6].astype(np.int64), bank["progeny_id"])
+    assert same(ref_sites[:, 0], bank["E"]) and same(ref_sites[:, 1:4], bank["u"])
+    assert np.array_equal(ref_sites[:, 4].astype(np.int32), bank["delayed_group"])
+    if i_mat == 0:
+        assert nb > n // 2 and int((ref_sites[:, 4] > 0).sum()) > 0
+
+
 def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
     """kappa-fission on the track-length estimator (OMC tally_scoring.cpp:2289-2352 -> :1216-1258) through the reference's
     own Material::calculate_xs and score_tracklength_tally on its own Nuclide / Material / Tally objects: per segment equal
