@@ -726,9 +726,9 @@ def test_collision_fixture_from_reference_objects(oracle_bridge, libm):
         assert np.allclose(mine["kappa"], ref["kappa"], rtol=4e-15, atol=0)   # summation order, DESIGN.md section 2
 
 
-@pytest.mark.parametrize("renormalise", [0, 1])
+@pytest.mark.parametrize("renormalise,libm", [(0, True), (1, True), (1, False)])
 @pytest.mark.parametrize("i_mat", [0, 3])
-def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, renormalise):
+def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, renormalise, libm):
     """Whole histories, all carried state: the reference's own initialize_history + transport_history_based_single_particle
     (OMC simulation.cpp:451,662-677: event_calculate_xs, event_advance, event_collide, event_revive_from_secondary,
     event_death) in a one-cell, no-surface geometry of one material, against the oracle's PRODUCTION history loop
@@ -741,7 +741,10 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     renormalise=0 switches off the one thing MaCaw does to the physics state that plain OpenMC does not -- Point::unit() on
     every new direction (RT Ray.C:216-226) -- and then everything is BIT-IDENTICAL.  renormalise=1 (the
     oracle's and the GPU's default, MaCaw's behaviour): the last-bit direction differences reach the energies (<= 1e-12
-    relative; k scores 1e-10), while seeds, collision and progeny counts, bank size and ids stay identical."""
+    relative; k scores 1e-10), while seeds, collision and progeny counts, bank size and ids stay identical.  libm=False:
+    the deterministic-math build, i.e. exactly the configuration the GPU is bit-compared with -- LCG streams, counts and
+    bank ids of whole histories still identical to the reference's (the north star's stream-parity bar, by transitivity
+    GPU == oracle == OpenMC)."""
     from macaw_b200 import cstructs, meshgen
     from tests import problems
     r = oracle_bridge.ref_lib()
@@ -752,7 +755,7 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     mesh = meshgen.hex_grid(1, 1, 1, (-L, -L, -L), (L, L, L), meshgen.BC_REFLECT, None, "one_element")
     s = cstructs.make_settings(n, n_inactive=0, source_box=(-1, -1, -1, 1, 1, 1), seed=master_seed,
                                n_log_bins=lib.n_log_bins, seed_through_double=False)
-    o = problems.configure(oracle_bridge.Oracle(libm=True), mesh, lib, [i_mat], s, tallies=False)
+    o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, [i_mat], s, tallies=False)
     rng = np.random.default_rng(77 + i_mat)
     sites = np.zeros(n, cstructs.SITE_DTYPE)
     sites["r"] = rng.uniform(-1, 1, (n, 3))
