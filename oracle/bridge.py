@@ -142,7 +142,7 @@ def ref_lib():
         if hasattr(r, "ref_transport_histories"):
             r.ref_transport_histories.restype = C.c_int64
             r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
-                                                  u64p, C.c_int64, f64p]
+                                                  u64p, C.c_int64, f64p, f64p, C.c_int, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
         r.ref_collide_events.restype = C.c_int64
         r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,

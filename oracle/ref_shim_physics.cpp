@@ -19,6 +19,8 @@
 #include "openmc/message_passing.h"
 #include "openmc/random_lcg.h"
 #include "openmc/geometry.h"
+#include "openmc/tallies/filter.h"
+#include "openmc/tallies/filter_energy.h"
 #include "openmc/tallies/tally.h"
 #include "openmc/tallies/tally_scoring.h"
 #include "openmc/constants.h"
@@ -328,9 +330,12 @@ REF_API void ref_tracklength_kappa(int i_mat, int64_t n, const double* E, const 
 // (cell 0 fills universe 0 with the material; every flight ends in a collision).  site8 = (r, u, E, wgt) per history.
 // Outputs per history: state8 = (final E, n_collision, n_progeny, k_collision, k_absorption, k_tracklength, alive, n_event),
 // seeds_out[4]; fission sites of all histories: site7 as in ref_collide_events.  Returns the number of banked sites.
+// tallies4 (or null): VALUEs of two tallies scored by the loop itself (event_advance -> score_tracklength_tally,
+// event_collide -> score_collision_tally), each EnergyFilter(ebins) x (flux, total, fission, nu-fission):
+// [collision | tracklength][n_edges - 1][4].
 REF_API int64_t ref_transport_histories(int i_mat, double keff, int64_t master_seed, int batch, int64_t n, const double* site8,
                                         double sqrtkT, double* state8, uint64_t* seeds_out, int64_t bank_capacity,
-                                        double* site7)
+                                        double* site7, const double* ebins, int n_edges, double* tallies4)
 {
   using namespace openmc;
   model::cells.clear();
@@ -356,6 +361,23 @@ REF_API int64_t ref_transport_histories(int i_mat, double keff, int64_t master_s
   model::tally_map.clear();
   model::tally_filters.clear();
   model::filter_map.clear();
+  Tally* tally[2] = {nullptr, nullptr};
+  if (tallies4)
+  {
+    auto* ef = Filter::create<EnergyFilter>();
+    ef->set_bins({ebins, (size_t)n_edges});
+    std::vector<Filter*> filters{ef};
+    for (int t = 0; t < 2; ++t)
+    {
+      tally[t] = Tally::create(t + 1);
+      tally[t]->set_filters(filters);
+      tally[t]->set_scores(std::vector<std::string>{"flux", "total", "fission", "nu-fission"});
+      tally[t]->estimator_ = t == 0 ? TallyEstimator::COLLISION : TallyEstimator::TRACKLENGTH;
+      tally[t]->set_active(true);
+      tally[t]->init_results();
+      tally[t]->reset();
+    }
+  }
   setup_active_tallies();
   settings::check_overlaps = false;
   settings::n_particles = n;
@@ -399,6 +421,19 @@ REF_API int64_t ref_transport_histories(int i_mat, double keff, int64_t master_s
       seeds_out[4 * k + q] = p.seeds(q);
   }
   global_tally_collision = global_tally_absorption = global_tally_tracklength = global_tally_leakage = 0.0;
+  if (tallies4)
+  {
+    size_t o = 0;
+    for (int t = 0; t < 2; ++t)
+      for (size_t i = 0; i < tally[t]->results_.shape()[0]; ++i)
+        for (size_t j = 0; j < tally[t]->results_.shape()[1]; ++j)
+          tallies4[o++] = tally[t]->results_(i, j, static_cast<int>(TallyResult::VALUE));
+    model::tallies.clear();
+    model::tally_map.clear();
+    model::tally_filters.clear();
+    model::filter_map.clear();
+    setup_active_tallies();
+  }
   const int64_t nb = simulation::fission_bank.size();
   for (int64_t j = 0; j < nb; ++j)
   {

@@ -756,6 +756,9 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     s = cstructs.make_settings(n, n_inactive=0, source_box=(-1, -1, -1, 1, 1, 1), seed=master_seed,
                                n_log_bins=lib.n_log_bins, seed_through_double=False)
     o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, [i_mat], s, tallies=False)
+    edges = np.array([1e-5, 0.0253, 0.625, 1e3, 1e5, 2e7])
+    o.add_tally(1, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["cell"], [0, 1, 2, 3], edges)
+    o.add_tally(2, cstructs.ESTIMATOR["tracklength"], cstructs.GRANULARITY["cell"], [0, 1, 2, 3], edges)
     rng = np.random.default_rng(77 + i_mat)
     sites = np.zeros(n, cstructs.SITE_DTYPE)
     sites["r"] = rng.uniform(-1, 1, (n, 3))
@@ -772,10 +775,11 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
     site8 = np.ascontiguousarray(np.concatenate([sites["r"], sites["u"], sites["E"][:, None], sites["wgt"][:, None]], axis=1))
     state, seeds, cap = np.zeros((n, 8)), np.zeros((n, 4), np.uint64), 4 * n
-    site7 = np.zeros((cap, 7))
+    site7, ref_tallies = np.zeros((cap, 7)), np.zeros((2, edges.size - 1, 4))
     nb = r.ref_transport_histories(i_mat, keff, master_seed, batch, n, site8.ctypes.data_as(f64p),
                                    float(np.sqrt(lib.nuclides[0].kT)), state.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p),
-                                   cap, site7.ctypes.data_as(f64p))
+                                   cap, site7.ctypes.data_as(f64p), edges.ctypes.data_as(f64p), edges.size,
+                                   ref_tallies.ctypes.data_as(f64p))
     r.ref_set_master_seed(1)
     assert np.all(state[:, 6] == 0)
 
@@ -797,6 +801,12 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     assert np.array_equal(ref_sites[:, 4].astype(np.int32), bank["delayed_group"])
     if i_mat == 0:
         assert nb > n // 2 and int((ref_sites[:, 4] > 0).sum()) > 0
+    # tallies scored by the loops themselves, accumulated in history order on both sides (one oracle thread): collision
+    # and track-length estimators x energy bins x (flux, total, fission, nu-fission)
+    for t, tid in enumerate((1, 2)):
+        v, _, _, _ = o.get_tally(tid)
+        assert v.size == ref_tallies[t].size and ref_tallies[t][:, 0].sum() > 0
+        assert same(v, ref_tallies[t].ravel()), tid
 
 
 def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
