@@ -163,6 +163,9 @@ typedef struct mcw_generation_result
   int64_t n_kernel_launches;  /* kernels of this library launched in the generation */
   double ms_total;            /* device time of the generation (CUDA events) */
   double ms_xs, ms_track, ms_collide, ms_bank; /* per-kernel-family device time */
+  int64_t n_bank_dropped;     /* fission sites not banked because the bank (3 x this rank's histories, OMC
+                               * simulation.cpp:286) was full: OMC physics.cpp:203-209 warns "The shared fission
+                               * bank is full"; here the count is returned and mcw_last_error carries the warning */
 } mcw_generation_result;
 
 /* Per-history record for parity checks (device -> host on request). */

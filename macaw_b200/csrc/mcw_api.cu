@@ -110,7 +110,7 @@ struct mcw_context
   McwCounters* h_counters = nullptr; // pinned
   mcw_source_site *d_source = nullptr, *d_bank = nullptr, *d_sorted = nullptr, *d_sampled = nullptr;
   int32_t *d_q_fly[2] = {nullptr, nullptr}, *d_q_collide = nullptr, *d_q_fallback = nullptr, *d_q_sorted = nullptr;
-  uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
+  uint32_t *d_keys = nullptr, *d_bins = nullptr, *d_bin_offsets = nullptr; // energy binning of the refresh queue (mcw_xs.cuh)
   int32_t* d_q_hist = nullptr;
   // event rounds with fewer collisions refresh cross sections without sorting; 0 = chosen from the
   // number of (slot, nuclide) plan entries: the sort pays off sooner the more lookups it serves
@@ -723,7 +723,15 @@ static int prepare(mcw_handle h)
         pl_e1.push_back(N.energy.back());
       }
     }
-    P.n_plan = every_slot ? (int32_t)pl_nuc.size() : 0;
+    (void)every_slot; // mcw_set_materials rejects empty materials
+    P.n_plan = (int32_t)pl_nuc.size();
+    P.n_plan_pad = (P.n_plan + 3) & ~3;
+    for (int sl = 0, q = 0; sl <= ns; ++sl)
+    {
+      P.slot_plan_off[sl] = q;
+      if (sl < ns)
+        q += (int)h->mat_nuc[P.slot_mat[sl]].size();
+    }
     int32_t *d_pn, *d_ps;
     double *d_pd, *d_p0, *d_p1;
     CK(dev_upload(h, &d_pn, pl_nuc));
@@ -929,6 +937,7 @@ static int prepare(mcw_handle h)
   // macroscopic cross sections of every material slot at each history's energy: 32 B per (history, slot)
   P.visit_cap = h->visit_cap;
   CK(dev_alloc(h, &p.xs, (size_t)P.n_slots * 4 * (size_t)n));
+  CK(dev_alloc(h, &p.xs_prefix, (size_t)P.n_plan_pad * (size_t)n)); // 8 B per (history, plan entry)
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -945,10 +954,12 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_q_fly[1], n));
   CK(dev_alloc(h, &h->d_q_collide, n));
   CK(dev_alloc(h, &h->d_q_fallback, n));
-  CK(dev_alloc(h, &h->d_q_sorted, n + 256)); // k_collide writes keys / hist for whole blocks of its grid
+  CK(dev_alloc(h, &h->d_q_sorted, n + 256));
   CK(dev_alloc(h, &h->d_keys, n + 256));
-  CK(dev_alloc(h, &h->d_keys_out, n + 256));
   CK(dev_alloc(h, &h->d_q_hist, n + 256));
+  CK(dev_alloc(h, &h->d_bins, mcwk_refresh_bins()));
+  CK(dev_alloc(h, &h->d_bin_offsets, mcwk_refresh_bins()));
+  CK(cudaMemset(h->d_bins, 0, mcwk_refresh_bins() * sizeof(uint32_t)));
   CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
   CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
   h->temp_bytes = std::max(mcwk_scan_temp_bytes(std::max(h->bank_capacity, n)), mcwk_compact_temp_bytes(n));
@@ -980,7 +991,7 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_reduce, h->n_reduce));
   CK(cudaMemset(h->d_reduce, 0, h->n_reduce * sizeof(double)));
   P.n_tallies = (int)h->tallies.size();
-  P.any_tracklength = P.any_collision_tally = 0;
+  P.any_tracklength = P.any_collision_tally = P.collision_kappa = 0;
   for (size_t i = 0; i < h->tallies.size(); ++i)
   {
     HostTally& tl = h->tallies[i];
@@ -1003,7 +1014,12 @@ static int prepare(mcw_handle h)
     if (tl.estimator == MCW_ESTIMATOR_TRACKLENGTH)
       P.any_tracklength = 1;
     else
+    {
       P.any_collision_tally = 1;
+      for (int s = 0; s < tl.n_scores; ++s)
+        if (tl.scores[s] == MCW_SCORE_KAPPA_FISSION)
+          P.collision_kappa = 1;
+    }
   }
   P.n_particles_global = h->set.n_particles;
   P.work_offset = h->work_index[h->rank];
@@ -1160,9 +1176,9 @@ int mcw_transport_generation(mcw_handle h, int batch)
     const int64_t sort_min = h->xs_sort_min > 0 ? h->xs_sort_min : std::max<int64_t>(32768, 2400000 / std::max(1, P.n_plan));
     const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min;
     mcwk_collide(P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
-                 staged ? h->d_q_sorted : nullptr, st);
-    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper_c, staged, h->xs_plan != 0, h->d_temp, h->temp_bytes, h->d_keys,
-                                           h->d_keys_out, h->d_q_sorted, h->d_q_hist, st);
+                 staged ? h->d_q_hist : nullptr, h->d_bins, st);
+    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper_c, staged, h->d_keys, h->d_q_hist, h->d_bins,
+                                           h->d_bin_offsets, h->d_q_sorted, st);
     if (P.ordered_queues)
     {
       mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_FLY, h->d_q_fly[cur ^ 1], cnt_next, st);
@@ -1233,6 +1249,11 @@ int mcw_transport_generation(mcw_handle h, int batch)
   R.n_vertex_edge_hits = (int64_t)C.n_vertex_edge;
   R.n_moved_through_neighbors = (int64_t)C.n_moved;
   R.n_failed_traces = (int64_t)C.n_failed;
+  R.n_bank_dropped = (int64_t)C.n_bank_dropped;
+  if (C.n_bank_dropped)
+    // OMC physics.cpp:203-209: a warning, not an error -- the generation goes on with the sites that fit
+    h->err = "The shared fission bank is full. " + std::to_string(C.n_bank_dropped) +
+             " fission sites created in this generation were not banked.";
   h->bank_global_start = 0;
   h->bank_global_total = h->n_bank;
   h->records_valid = true;

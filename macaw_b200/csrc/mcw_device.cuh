@@ -218,7 +218,9 @@ struct Macro
   double total, absorption, fission, nu_fission;
 };
 
-MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E) // OMC material.cpp:748-831
+// OMC material.cpp:748-831.  prefix (may be null) receives the running total after every nuclide: the
+// partial sums sample_nuclide (OMC physics.cpp:442-465) forms at the next collision at this energy.
+MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E, double* __restrict__ prefix = nullptr)
 {
   Macro M;
   M.total = M.absorption = M.fission = M.nu_fission = 0.0;
@@ -232,6 +234,8 @@ MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E) // OMC mat
     M.absorption += d * m.absorption;
     M.fission += d * m.fission;
     M.nu_fission += d * m.nu_fission;
+    if (prefix)
+      prefix[i - b] = M.total;
   }
   return M;
 }
@@ -242,9 +246,10 @@ MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E) // OMC mat
 MCW_D void mcw_lookup_all_slots(const McwParams& P, int64_t i, double E)
 {
   double* xs_of_history = P.p.xs + (size_t)i * P.n_slots * 4;
+  double* prefix = P.p.xs_prefix + (size_t)i * P.n_plan_pad;
   for (int s = 0; s < P.n_slots; ++s)
   {
-    const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], E);
+    const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], E, prefix + P.slot_plan_off[s]);
     double2* o = reinterpret_cast<double2*>(xs_of_history + 4 * s);
     o[0] = make_double2(M.total, M.absorption);
     o[1] = make_double2(M.fission, M.nu_fission);

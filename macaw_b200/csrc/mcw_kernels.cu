@@ -204,8 +204,8 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     elem = p.elem[i];
     ElemRec<TYPE> R(P.mesh, elem);
     block = R.block();
+    const int slot = R.slot();
     {
-      const int slot = R.slot();
       const Macro M = mcw_load_xs(p.xs, P.n_slots, i, slot);
       sig_t = M.total;
       sig_a = M.absorption;
@@ -217,42 +217,43 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     wgt_last = c.wgt;
     k_col = p.k_col[i] + c.wgt * sig_nf / sig_t; // OMC particle.cpp:223-226
     k_abs = p.k_abs[i];
-    // kappa-fission needs every fissionable nuclide (OMC tally_scoring.cpp:1240-1255)
-    bool need_kappa = false;
-    if (P.tallies_active)
-      for (int t = 0; t < P.n_tallies; ++t)
-        if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
-          for (int q = 0; q < P.tally[t].n_scores; ++q)
-            need_kappa |= P.tally[t].scores[q] == MCW_SCORE_KAPPA_FISSION;
-    // sample_nuclide (OMC physics.cpp:442-465): re-evaluate the micro cross sections in material order
-    const int i_log = mcw_log_bin(L, c.E);
+    // sample_nuclide (OMC physics.cpp:442-465).  Its partial sums `prob` are the running totals the last
+    // cross-section refresh stored for this energy (McwParticlesDev::xs_prefix), so the material's nuclides
+    // are not looked up a second time: scan the stored sums, four independent loads at a time.
     const double cutoff = mcw_prn(c.seed) * sig_t;
-    double prob = 0.0;
-    const int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
-    bool found = false;
-    k_nuc = L.mat_nuc[e - 1];
-    q_nuc = e - 1;
-    for (int q = b; q < e; ++q)
+    const int pb = P.slot_plan_off[slot], pe = P.slot_plan_off[slot + 1];
     {
-      const int in = L.mat_nuc[q];
-      if (found && !(need_kappa && L.nuc[in].fissionable))
-        continue;
-      Micro m = mcw_micro_xs(L, in, c.E, i_log);
-      if (L.nuc[in].fissionable)
-        kappa += L.nuc[in].q * m.fission * L.mat_dens[q];
-      if (!found)
+      const double* pf = p.xs_prefix + (size_t)i * P.n_plan_pad; // plain loads: the fused kernel writes these rows itself
+      int k = pe - 1; // `q == e - 1`: the last nuclide takes what rounding leaves over
+      for (int q0 = pb; q0 < pe; q0 += 4)
       {
-        prob += L.mat_dens[q] * m.total;
-        if (prob >= cutoff || q == e - 1)
+        const double v0 = pf[q0], v1 = pf[min(q0 + 1, pe - 1)], v2 = pf[min(q0 + 2, pe - 1)], v3 = pf[min(q0 + 3, pe - 1)];
+        const int hit = v0 >= cutoff ? 0 : (v1 >= cutoff ? 1 : (v2 >= cutoff ? 2 : (v3 >= cutoff ? 3 : 4)));
+        if (hit < 4)
         {
-          found = true;
-          k_nuc = in;
-          q_nuc = q;
-          mx = m;
+          k = min(q0 + hit, pe - 1);
+          break;
         }
       }
-      if (found && !need_kappa)
-        break;
+      k_nuc = P.plan_nuc[k];
+      q_nuc = L.mat_off[i_mat] + (k - pb);
+    }
+    const int i_log = mcw_log_bin(L, c.E);
+    mx = mcw_micro_xs(L, k_nuc, c.E, i_log);
+    // kappa-fission, only when a collision tally asks for it: q * sigma_f * N * flux summed nuclide by
+    // nuclide over the fissionable nuclides of the material (OMC tally_scoring.cpp:1246-1255)
+    if (P.tallies_active && P.collision_kappa && sig_a != 0.)
+    {
+      const double flux = c.wgt / sig_t;
+      for (int q = pb; q < pe; ++q)
+      {
+        const int in = P.plan_nuc[q];
+        if (L.nuc[in].fissionable)
+        {
+          const Micro m = (in == k_nuc) ? mx : mcw_micro_xs(L, in, c.E, i_log);
+          kappa += L.nuc[in].q * m.fission * P.plan_dens[q] * flux;
+        }
+      }
     }
     // create_fission_sites: number of sites (OMC physics.cpp:154-170)
     if (L.nuc[k_nuc].fissionable)
@@ -299,11 +300,18 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     site.surf_id = 0;
     site.elem = elem;
     mcw_sample_fission_neutron(nuc, c.E, L.E_max, site, c.seed);
-    unsigned long long slot = base + k;
-    if ((int64_t)slot < P.bank_capacity)
-      P.bank[slot] = site;
+    const unsigned long long bank_slot = base + k;
+    if ((int64_t)bank_slot < P.bank_capacity)
+      P.bank[bank_slot] = site;
     else
-      atomicAdd(&P.counters->n_bank_dropped, 1ull);
+    {
+      // "The shared fission bank is full" (OMC physics.cpp:203-209): this site is not banked and no further
+      // ones are sampled.  The id it took is handed back, so n_progeny counts banked sites only and the bank
+      // sort's offsets (exclusive scan of n_progeny) stay inside the bank; the host reports the count.
+      --c.n_progeny;
+      atomicAdd(&P.counters->n_bank_dropped, (unsigned long long)(nu - k));
+      break;
+    }
   }
   // absorption (analog, OMC physics.cpp:592-625)
   bool absorbed = false;
@@ -341,7 +349,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     sc[MCW_SCORE_TOTAL] = sig_t * flux;
     sc[MCW_SCORE_FISSION] = sig_a == 0 ? 0.0 : sig_f * flux;
     sc[MCW_SCORE_NU_FISSION] = sig_a == 0 ? 0.0 : sig_nf * flux;
-    sc[MCW_SCORE_KAPPA_FISSION] = sig_a == 0. ? 0.0 : kappa * flux;
+    sc[MCW_SCORE_KAPPA_FISSION] = kappa; // 0 when the material absorbs nothing or no collision tally scores it
     for (int t = 0; t < P.n_tallies; ++t)
       if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
         mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
@@ -405,10 +413,80 @@ k_xs_all_slots(McwParams P, const int32_t* __restrict__ queue, const unsigned lo
   const int i = queue[h];
   if (P.p.status[i] != MCW_ST_FLY)
     return; // absorbed
-  const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], P.p.E[i]);
+  const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], P.p.E[i], P.p.xs_prefix + (size_t)i * P.n_plan_pad + P.slot_plan_off[s]);
   double2* o = reinterpret_cast<double2*>(P.p.xs + ((size_t)i * P.n_slots + s) * 4);
   o[0] = make_double2(M.total, M.absorption);
   o[1] = make_double2(M.fission, M.nu_fission);
+}
+
+// Particle::event_calculate_xs for the histories of `m_need` (lanes of this warp; lane l holds history
+// i and its new energy E), done by the whole warp: the (slot, nuclide) entries of the refresh plan are
+// dealt to the 32 lanes, each lane looks its nuclides up, and the products N_i * sigma_i are then added
+// in plan order -- the order of Material::calculate_xs (OMC material.cpp:790-829) -- so the sums are
+// bit-identical to one thread walking the material.  Used by the fused tracking kernel, where one lane
+// doing ~40 dependent nuclide lookups would hold its whole warp for the length of that chain.
+// Called by all 32 lanes.
+MCW_D void mcw_warp_lookup_all_slots(const McwParams& P, unsigned m_need, int i, double E)
+{
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  while (m_need)
+  {
+    const int src = __ffs(m_need) - 1;
+    m_need &= m_need - 1;
+    const int hi = __shfl_sync(full, i, src);
+    const double he = __shfl_sync(full, E, src);
+    const int i_log = mcw_log_bin(P.lib, he);
+    double* xs_rows = P.p.xs + (size_t)hi * P.n_slots * 4;
+    double* prefix = P.p.xs_prefix + (size_t)hi * P.n_plan_pad;
+    double Mt = 0.0, Ma = 0.0, Mf = 0.0, Mn = 0.0;
+    int cur_slot = 0;
+    for (int base = 0; base < P.n_plan; base += 32)
+    {
+      const int q = base + lane;
+      double t = 0.0, a = 0.0, f = 0.0, nf = 0.0, mine = 0.0;
+      if (q < P.n_plan)
+      {
+        const Micro m = mcw_micro_xs(P.lib, P.plan_nuc[q], he, i_log);
+        const double d = P.plan_dens[q];
+        t = d * m.total;
+        a = d * m.absorption;
+        f = d * m.fission;
+        nf = d * m.nu_fission;
+      }
+      const int n_here = min(32, P.n_plan - base);
+      for (int k = 0; k < n_here; ++k)
+      {
+        const int sk = P.plan_slot[base + k];
+        if (sk != cur_slot)
+        {
+          if (lane == 0)
+          {
+            double2* o = reinterpret_cast<double2*>(xs_rows + 4 * cur_slot);
+            o[0] = make_double2(Mt, Ma);
+            o[1] = make_double2(Mf, Mn);
+          }
+          Mt = Ma = Mf = Mn = 0.0;
+          cur_slot = sk;
+        }
+        Mt += __shfl_sync(full, t, k);
+        Ma += __shfl_sync(full, a, k);
+        Mf += __shfl_sync(full, f, k);
+        Mn += __shfl_sync(full, nf, k);
+        if (lane == k)
+          mine = Mt;
+      }
+      if (q < P.n_plan)
+        prefix[q] = mine; // sample_nuclide's partial sum after this entry
+    }
+    if (lane == 0)
+    {
+      double2* o = reinterpret_cast<double2*>(xs_rows + 4 * cur_slot);
+      o[0] = make_double2(Mt, Ma);
+      o[1] = make_double2(Mf, Mn);
+    }
+  }
+  __syncwarp(); // rows written by other lanes are read by the history's own lane next
 }
 
 #ifndef MCW_COLLIDE_MIN_BLOCKS
@@ -418,20 +496,24 @@ template <int TYPE>
 __global__ void __launch_bounds__(MCW_BLOCK, MCW_COLLIDE_MIN_BLOCKS)
 k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
           int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, uint32_t* __restrict__ keys,
-          int32_t* __restrict__ hist)
+          int32_t* __restrict__ hist, uint32_t* __restrict__ bins)
 {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = idx < (int64_t)*count;
-  // no early return: the bank append and the queue append are full-warp aggregates
+  if (!__any_sync(0xffffffffu, active))
+    return; // grids are sized from the host's last known queue length
+  // no early return inside a warp: the bank append and the queue append are full-warp aggregates
   const int i = active ? queue[idx] : -1;
   const bool valid = active && P.p.status[i] == MCW_ST_COLLIDE;
   const bool survived = mcw_collide_history<TYPE, false>(P, i, valid);
-  if (keys)
+  if (keys && active)
   {
-    // sort keys of the energy-ordered cross-section refresh (mcw_xs.cuh): 15-bit energy image, or the
-    // dead flag for absorbed histories and the padding beyond the device-side count
-    keys[idx] = survived ? (mcw_energy_key(P.p.E[i]) >> (26 - MCW_REFRESH_KEY_BITS)) : (1u << MCW_REFRESH_KEY_BITS);
-    hist[idx] = survived ? i : -1;
+    // energy bucket of the survivor for the binned cross-section refresh (mcw_xs.cuh), counted here
+    const uint32_t k = survived ? mcw_refresh_key(P.p.E[i]) : MCW_KEY_DEAD;
+    keys[idx] = k;
+    hist[idx] = i;
+    if (survived)
+      atomicAdd(bins + k, 1u);
   }
   if (P.ordered_queues)
     return;
@@ -458,7 +540,9 @@ __global__ void k_bank_scatter(const mcw_source_site* __restrict__ bank, int64_t
     return;
   mcw_source_site s = bank[i];
   int64_t off = s.parent_id - 1 - work_offset;
-  sorted[progeny_scan[off] + s.progeny_id] = s;
+  const int64_t dst = progeny_scan[off] + s.progeny_id;
+  if (dst >= 0 && dst < n_bank) // n_progeny counts banked sites only, so this always holds; never write outside the bank
+    sorted[dst] = s;
 }
 
 __global__ void k_progeny_to_i64(const int32_t* __restrict__ n_progeny, int64_t n, int64_t* __restrict__ out)
@@ -731,37 +815,37 @@ void mcwk_round_reset(McwCounters* c, int consumed, bool fallback_served, cudaSt
 }
 
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
-                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, cudaStream_t st)
+                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, uint32_t* bins,
+                  cudaStream_t st)
 {
   if (upper <= 0)
     return;
-  // the grid covers whole blocks: keys / hist hold grid_for(upper) * MCW_BLOCK entries
   MCW_DISPATCH(P.mesh.type,
-               (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next, keys, hist)));
+               (k_collide<TY><<<grid_for(upper), MCW_BLOCK, 0, st>>>(P, queue, count, q_fly_next, cnt_next, keys, hist, bins)));
 }
 
-// Cross sections of every material slot at the new energy of the survivors of the collision queue.
-// sorted = false: one thread per (history, slot), direct table reads (2 launches fewer).
-// sorted = true : survivors ordered by energy (32-bit radix sort, 27 key bits), then the staged kernel.
-int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
-                    bool plan, void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+// Cross sections of every material slot (and sample_nuclide's partial sums) at the new energy of the
+// survivors of the collision queue.
+// binned = false: one thread per (history, slot), direct table reads.
+// binned = true : k_collide counted the survivors per energy bucket; scan + scatter place them (the
+//                 event loop's particle-queue sort, mcw_xs.cuh), then the tile kernel serves each
+//                 256 neighbouring energies from shared-memory windows.
+int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool binned,
+                    const uint32_t* keys, const int32_t* hist, uint32_t* bins, uint32_t* bin_offsets, int32_t* hist_binned,
                     cudaStream_t st)
 {
   if (upper <= 0)
     return 0;
-  if (!sorted)
+  if (!binned)
   {
     k_xs_all_slots<<<grid_for(upper * P.n_slots), MCW_BLOCK, 0, st>>>(P, queue, count);
     return 1;
   }
-  // keys and hist were written by k_collide; 16 key bits = two radix passes
-  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hist, hist_sorted, upper, 0, MCW_REFRESH_KEY_BITS + 1, st);
-  const unsigned tiles = (unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE);
-  if (plan && P.n_plan > 0)
-    k_xs_all_slots_plan<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
-  else
-    k_xs_all_slots_staged<<<tiles, MCW_XS_TILE, 0, st>>>(P, hist_sorted, upper);
-  return 5; // radix sort (histogram, scan, two onesweep passes) + staged lookup
+  k_bin_scan<<<1, 1024, 0, st>>>(bins, bin_offsets, &P.counters->n_refresh);
+  k_bin_scatter<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(keys, hist, count, bin_offsets, hist_binned);
+  k_xs_refresh_tile<<<(unsigned)((upper + MCW_XS_TILE - 1) / MCW_XS_TILE), MCW_XS_TILE, 0, st>>>(P, hist_binned,
+                                                                                                 &P.counters->n_refresh);
+  return 3;
 }
 
 // Stand-alone lookup of (E, material) arrays through the sort + staged kernel; out in caller order.
@@ -808,6 +892,8 @@ size_t mcwk_compact_temp_bytes(int64_t n)
   cub::DeviceSelect::Flagged(nullptr, c, ids, flags, (int32_t*)nullptr, (unsigned long long*)nullptr, (int)n);
   return c + 256;
 }
+
+int mcwk_refresh_bins(void) { return MCW_REFRESH_BINS; }
 
 size_t mcwk_sort_temp_bytes(int64_t n)
 {

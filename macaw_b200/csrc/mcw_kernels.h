@@ -9,9 +9,10 @@ void mcwk_sample_source(const McwParams& P, mcw_source_site* out, int64_t n, con
                         cudaStream_t st);
 void mcwk_xs_lookup_array(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, double* out,
                           cudaStream_t st);
-int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool sorted,
-                    bool plan, void* temp, size_t temp_bytes, uint32_t* keys, uint32_t* keys_out, int32_t* hist, int32_t* hist_sorted,
+int mcwk_xs_refresh(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper, bool binned,
+                    const uint32_t* keys, const int32_t* hist, uint32_t* bins, uint32_t* bin_offsets, int32_t* hist_binned,
                     cudaStream_t st);
+int mcwk_refresh_bins(void); // number of energy buckets of the binned refresh
 void mcwk_xs_sort(int64_t n, const double* E, const int32_t* mat, void* temp, size_t temp_bytes, uint32_t* keys,
                   uint32_t* keys_out, int32_t* idx, int32_t* idx_sorted, cudaStream_t st);
 void mcwk_xs_lookup_staged(const McwLibraryDev& L, int64_t n, const double* E, const int32_t* mat, const int32_t* order,
@@ -26,7 +27,8 @@ void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long lo
                 int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, int32_t* q_fallback,
                 int drain_lanes, bool fused, int collide_min, cudaStream_t st);
 void mcwk_collide(const McwParams& P, const int32_t* queue, const unsigned long long* count, int64_t upper,
-                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, cudaStream_t st);
+                  int32_t* q_fly_next, unsigned long long* cnt_next, uint32_t* keys, int32_t* hist, uint32_t* bins,
+                  cudaStream_t st);
 void mcwk_fallback(const McwParams& P, const int32_t* queue, const unsigned long long* count, int n_blocks,
                    int32_t* q_fly_next, unsigned long long* cnt_next, int32_t* q_collide, cudaStream_t st);
 void mcwk_trace_rays(const McwParams& P, int64_t n, const double* start, const double* dirs, const int32_t* start_elem,

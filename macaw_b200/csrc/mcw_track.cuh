@@ -530,7 +530,9 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
         {
           // all 32 lanes enter (full-warp bank append); only the parked ones collide
           const bool mine = state == MCW_LN_COLLIDE;
-          const bool survived = mcw_collide_history<TYPE, true>(P, mine ? i : 0, mine);
+          const bool survived = mcw_collide_history<TYPE, false>(P, mine ? i : 0, mine) && mine;
+          // cross sections at the survivors' new energies: the warp shares each history's nuclide lookups
+          mcw_warp_lookup_all_slots(P, __ballot_sync(MCW_FULL, survived), i, survived ? p.E[i] : 0.0);
           if (mine)
           {
             if (survived)

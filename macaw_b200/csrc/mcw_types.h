@@ -113,6 +113,12 @@ struct McwParticlesDev
   // xs[(history * n_slots + slot) * 4 + {total, absorption, fission, nu-fission}] -- one 32-byte
   // sector per (history, slot), so a material change in the tracking kernel is one sector read
   double* xs;
+  // Running sums of N_i * sigma_t,i over the refresh plan (McwParams::plan_*), restarting at every slot:
+  // xs_prefix[history * n_plan_pad + entry].  They are the partial sums `prob` of sample_nuclide
+  // (OMC physics.cpp:442-465) -- the same additions, in the same order, that form the material's total in
+  // Material::calculate_xs (OMC material.cpp:790-829) -- so the collision kernel picks the nuclide by scanning
+  // them instead of looking every nuclide of the material up a second time.
+  double* xs_prefix;
 };
 
 struct McwTallyDev
@@ -134,6 +140,7 @@ struct McwCounters // device-side counters, one cache line each where contended
   unsigned long long head, pad4[15]; // next unclaimed entry of the queue the tracking kernel is draining
   unsigned long long n_segments, n_collisions, n_xs, n_nuc_lookups, n_vertex_edge, n_moved, n_failed,
       n_bank_dropped;
+  unsigned long long n_refresh, pad5[7]; // survivors of the round's collisions = entries of the energy-binned refresh queue
 };
 
 struct McwParams
@@ -156,7 +163,7 @@ struct McwParams
   int32_t n_slots;   // cross-section slots = materials present in the mesh
   int32_t visit_cap; // segments one lane may walk per visit of the tracking kernel
   int32_t record_traces; // keep the per-history crossing hash (parity output)
-  int32_t pad0;
+  int32_t collision_kappa; // some collision-estimator tally scores kappa-fission (needs every fissionable nuclide)
   int32_t slot_mat[MCW_MAX_XS_SLOTS]; // slot -> material index
   // refresh plan: the (slot, nuclide) pairs of all slots, material order inside a slot (mcw_xs.cuh);
   // n_plan = 0 when some slot's material has no nuclide (then the per-slot kernels are used)
@@ -165,6 +172,9 @@ struct McwParams
   const double* plan_dens;
   const double* plan_e0; // first / last grid energy of the entry's nuclide
   const double* plan_e1;
-  int32_t n_plan, pad1;
+  int32_t n_plan;
+  int32_t n_plan_pad;                           // row stride of xs_prefix (n_plan rounded up to 4 doubles = 32 bytes)
+  int32_t slot_plan_off[MCW_MAX_XS_SLOTS + 1]; // plan entries of slot s: [slot_plan_off[s], slot_plan_off[s + 1])
+  int32_t pad1;
   double z_coord, keff;
 };

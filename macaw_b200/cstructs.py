@@ -33,7 +33,7 @@ class GenerationResult(C.Structure):
                 ("n_vertex_edge_hits", C.c_int64), ("n_moved_through_neighbors", C.c_int64),
                 ("n_failed_traces", C.c_int64), ("n_event_rounds", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("ms_total", C.c_double), ("ms_xs", C.c_double), ("ms_track", C.c_double),
-                ("ms_collide", C.c_double), ("ms_bank", C.c_double)]
+                ("ms_collide", C.c_double), ("ms_bank", C.c_double), ("n_bank_dropped", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

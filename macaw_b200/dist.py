@@ -56,13 +56,20 @@ def exchange_plan(sampled_counts, work_index):
 
 
 def all_gather_int(value: int, group=None, device="cpu"):
+    """One int64 per rank -> list on every rank: one collective into one tensor and ONE device -> host copy
+    (the per-rank `.item()` reads of a tensor list cost a stream synchronisation each)."""
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size(group)
     t = torch.tensor([int(value)], dtype=torch.int64, device=device)
-    out = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(ws)]
-    dist.all_gather(out, t, group=group)
-    return [int(x.item()) for x in out]
+    out = torch.empty(ws, dtype=torch.int64, device=device)
+    try:
+        dist.all_gather_into_tensor(out, t, group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the flat variant
+        parts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(ws)]
+        dist.all_gather(parts, t, group=group)
+        out = torch.cat(parts)
+    return [int(x) for x in out.cpu().tolist()]
 
 
 def warm_up(group=None, device="cpu"):
@@ -115,15 +122,21 @@ def synchronize_banks(engine, batch, rank, nranks, work_index, group=None, devic
     oracle in the gloo tests).  It must offer bank_count(), set_bank_window(start, total),
     reduction_tensor() -> float64 tensor reduced in place, sample_bank(batch) -> n,
     finish_sampling(start, is_last) -> n, sampled_tensor(n) / source_tensor() -> uint8 tensors,
-    set_source_count(n), finalize_generation(batch)."""
+    set_source_count(n), finalize_generation(batch).
+
+    On a GPU the caller runs this with the library's stream as torch's current stream.  The all-reduce is
+    issued first and asynchronously: NCCL runs it beside the bank-sampling kernels and the site exchange, and
+    the stream only waits for it before finalize_generation reads the reduced k sums -- nothing here blocks
+    the host except the two count all-gathers, which the exchange plan needs as host integers."""
     import torch.distributed as td
+    red = engine.reduction_tensor()
+    red_work = td.all_reduce(red, op=td.ReduceOp.SUM, group=group, async_op=True)
     counts = all_gather_int(engine.bank_count(), group, device)
     if min(counts) == 0:
+        red_work.wait()
         raise RuntimeError(f"No fission sites banked on rank {counts.index(0)}")  # eigenvalue.cpp:107-109
     off = exclusive_offsets(counts)
     engine.set_bank_window(int(off[rank]), int(off[-1]))
-    red = engine.reduction_tensor()
-    td.all_reduce(red, op=td.ReduceOp.SUM, group=group)
     n_s = engine.sample_bank(batch)
     scounts = all_gather_int(n_s, group, device)
     soff = exclusive_offsets(scounts)
@@ -134,6 +147,7 @@ def synchronize_banks(engine, batch, rank, nranks, work_index, group=None, devic
     assert rank != nranks - 1 or n_s == scounts[-1], (n_s, scounts)
     exchange_sites(engine.sampled_tensor(max(scounts[rank], 0)), engine.source_tensor(), scounts, work_index, group)
     engine.set_source_count(int(work_index[rank + 1] - work_index[rank]))
+    red_work.wait()  # a stream-level wait on a GPU
     return engine.finalize_generation(batch)
 
 

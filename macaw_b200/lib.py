@@ -10,6 +10,7 @@ from . import build as _build
 from .cstructs import GenerationResult, Settings
 
 _LIB = None
+_PATH = None
 
 
 class McwError(RuntimeError):
@@ -19,7 +20,7 @@ class McwError(RuntimeError):
 
 
 def load():
-    global _LIB
+    global _LIB, _PATH
     if _LIB is not None:
         return _LIB
     path = os.environ.get("MCW_LIB_PATH") or _build.LIB  # MCW_LIB_PATH: an A/B build of the same CUDA library
@@ -75,8 +76,15 @@ def load():
     L.mcw_last_error.argtypes = [vp]
     L.mcw_last_error.restype = C.c_char_p
     L.mcw_version.restype = C.c_int
-    _LIB = L
+    _LIB, _PATH = L, os.path.relpath(os.path.abspath(path), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     return L
+
+
+def loaded_path():
+    """Path (relative to the repo root) of the CUDA library this process bound: bench.py prints it so an
+    MCW_LIB_PATH override can never hide behind a bench line."""
+    load()
+    return _PATH
 
 
 EXPORTS = ["mcw_create", "mcw_destroy", "mcw_last_error", "mcw_version", "mcw_set_option", "mcw_prepare", "mcw_stream",

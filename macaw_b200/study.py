@@ -82,6 +82,7 @@ class OpenMCStudy:
         self.ctx.prepare()
         self.ctx.sample_initial_source()  # openmc_simulation_init -> initialize_source (OpenMCStudy.C:147)
         self._views = None
+        self._ext_stream = None
         if nranks > 1:
             import torch
             dist.warm_up(group, torch.device("cuda", torch.cuda.current_device()))
@@ -101,9 +102,13 @@ class OpenMCStudy:
     def _synchronize_banks_and_reduce(self, b):
         import torch
         dev = torch.device("cuda", torch.cuda.current_device())
-        res = dist.synchronize_banks(DeviceEngine(self.ctx, dev), b, self.rank, self.nranks, self.work_index,
-                                     self.group, dev)
-        return res
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream(), device=dev)
+        # collectives and copies are issued with the library's stream as torch's current stream, so they are
+        # ordered with its kernels by the stream itself and no full-stream host synchronisation is needed
+        with torch.cuda.stream(self._ext_stream):
+            return dist.synchronize_banks(DeviceEngine(self.ctx, dev), b, self.rank, self.nranks, self.work_index,
+                                          self.group, dev)
 
 
 class DeviceEngine:
@@ -128,8 +133,7 @@ class DeviceEngine:
         return dist.device_tensor(p, cap * dist.SITE_BYTES, "u8", self.device)
 
     def finalize_generation(self, batch):
-        import torch
-        torch.cuda.current_stream().synchronize()  # the exchange ran on torch's stream
+        # the exchange and the all-reduce were issued on (or waited for by) the library's own stream
         return self.ctx.finalize_generation(batch)
 
 

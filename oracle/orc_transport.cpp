@@ -278,7 +278,7 @@ struct CollisionOut
 {
   int event;
   int nuclide = -1; // library index of the sampled nuclide
-  double kappa_macro = 0.0; // sum_i N_i q_i sigma_f,i (kappa-fission score, OMC tally_scoring.cpp:1240-1255)
+  double kappa_score = 0.0; // sum_i q_i sigma_f,i N_i flux, nuclide by nuclide (kappa-fission, OMC tally_scoring.cpp:1246-1255)
 };
 
 // OMC particle.cpp:219-288 event_collide + physics.cpp:38-152, :154-247, :442-465, :592-625, :627-719
@@ -290,11 +290,15 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
   out.event = EV_SCATTER;
   p.k_col += p.wgt * macro.nu_fission / macro.total;
   ++p.n_coll;
-  for (size_t i = 0; i < mat.nuc.size(); ++i)
   {
-    const Nuclide& n = P.lib.nuclides[mat.nuc[i]];
-    if (n.fissionable)
-      out.kappa_macro += n.q * micro[i].fission * mat.dens[i];
+    // collision-estimator flux of this event (OMC tally_scoring.cpp:2354-2365): wgt_last / Sigma_t
+    const double flux = p.wgt / macro.total;
+    for (size_t i = 0; i < mat.nuc.size(); ++i)
+    {
+      const Nuclide& n = P.lib.nuclides[mat.nuc[i]];
+      if (n.fissionable)
+        out.kappa_score += n.q * micro[i].fission * mat.dens[i] * flux;
+    }
   }
   // sample_nuclide
   double cutoff = prn(&p.seeds[0]) * macro.total;
@@ -343,7 +347,12 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
           bank.push_back(site);
       }
       if (full)
+      {
+        // OMC physics.cpp:203-209: the site is not banked and no further ones are sampled.  The id it took is handed
+        // back so that progeny_per_particle counts banked sites only and sort_fission_bank's offsets stay inside the bank.
+        --p.n_progeny;
         break;
+      }
     }
   }
   // absorption (analog)
@@ -411,14 +420,14 @@ static double tracklength_kappa(const Problem& P, const Material& mat, const Mic
 
 // collision-estimator scores of one collision (OMC tally_scoring.cpp:2354-2365 flux, :557, :600, :752, :799, :1240-1255)
 static void collision_scores(double wgt_last, double total, double absorption, double fission, double nu_fission,
-                             double kappa_macro, double* sc)
+                             double kappa_score, double* sc)
 {
   const double flux = wgt_last / total;
   sc[MCW_SCORE_FLUX] = flux;
   sc[MCW_SCORE_TOTAL] = total * flux;
   sc[MCW_SCORE_FISSION] = absorption == 0 ? 0.0 : fission * flux;
   sc[MCW_SCORE_NU_FISSION] = absorption == 0 ? 0.0 : nu_fission * flux;
-  sc[MCW_SCORE_KAPPA_FISSION] = absorption == 0. ? 0.0 : kappa_macro * flux;
+  sc[MCW_SCORE_KAPPA_FISSION] = absorption == 0. ? 0.0 : kappa_score;
 }
 
 // track-length-estimator scores of one segment (OMC tally_scoring.cpp:2289-2300 flux = wgt * distance; same score cases);
@@ -532,7 +541,7 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
     {
       // OMC tally_scoring.cpp:2354-2420 score_collision_tally, scores :557,:600,:752,:799,:1240-1255
       double sc[MCW_N_SCORES];
-      collision_scores(wgt_last, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_macro, sc);
+      collision_scores(wgt_last, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_score, sc);
       for (auto& t : P.tallies)
         if (t.estimator == MCW_ESTIMATOR_COLLISION)
           score_tally(t, spatialBin(P, t, c.elem), E_last, sc);
@@ -822,7 +831,7 @@ int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const dou
     if (kappa)
     {
       double sc[MCW_N_SCORES];
-      collision_scores(1.0, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_macro, sc);
+      collision_scores(1.0, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_score, sc);
       kappa[k] = sc[MCW_SCORE_KAPPA_FISSION];
     }
     for (int s = 0; s < 3; ++s)

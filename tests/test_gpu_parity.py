@@ -114,12 +114,11 @@ def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, 
 # Event-loop regimes (mcw_set_option): EVENT = one round per collision throughout (tail_threshold 0),
 # FUSED = every history keeps its lane through its collisions (the default for these small banks),
 # MIXED = event rounds until fewer than 700 histories fly, then fused; SORTED = event rounds whose
-# cross-section refresh goes through the energy sort + staged kernel.
+# cross-section refresh goes through the energy binning + tile kernel (mcw_xs.cuh).
 EVENT = {"tail_threshold": 0}
 FUSED = {"tail_threshold": 1 << 30}
 MIXED = {"tail_threshold": 700, "collide_min": 3}
 SORTED = {"tail_threshold": 300, "xs_sort_min": 1}
-SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 1, "xs_plan": 0}  # k_xs_all_slots_staged instead of _plan
 
 
 @pytest.mark.parametrize("name,kw,opts", [
@@ -127,7 +126,7 @@ SORTED_PER_SLOT = {"tail_threshold": 300, "xs_sort_min": 1, "xs_plan": 0}  # k_x
     ("pin_cell_tet", {}, EVENT), ("pin_cell_tet", {}, MIXED), ("pin_cell_tet", {"sort_xs_queue": 1}, SORTED),
     ("pin_cell_hex", {}, EVENT), ("pin_cell_hex", {}, FUSED),
     ("assembly_quad", {}, MIXED), ("assembly_quad", {"sort_xs_queue": 1}, SORTED),
-    ("assembly_quad", {"sort_xs_queue": 1}, SORTED_PER_SLOT), ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 1, "ordered_queues": 0}),
+    ("pin_cell_tet", {"sort_xs_queue": 1}, {"tail_threshold": 0, "xs_sort_min": 1, "ordered_queues": 0}),
     ("pin_cell_tet", {"seed_through_double": False}, MIXED),
     ("infinite_medium_iso", {}, EVENT), ("pin_cell_tet_iso", {}, MIXED),
     # the reference's own BEAVRS assembly mesh (31enr_16_in.e, raw block ids 10004 ... 11006), 35 nuclides

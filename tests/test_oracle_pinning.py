@@ -670,11 +670,9 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
         else:
             assert np.array_equal(mine[1][:, [4, 7]], ref[1][:, [4, 7]]) and np.array_equal(mine[4][:, 4:], ref[4][:, 4:])
             assert np.allclose(mine[1], ref[1], rtol=1e-12, atol=1e-14) and np.allclose(mine[4], ref[4], rtol=1e-12, atol=1e-14)
-        # kappa-fission, collision estimator: the reference sums q * sigma_f * N * flux per nuclide (tally_scoring.cpp:
-        # 1246-1255); the oracle and the GPU sum q * sigma_f * N and multiply by the flux once -- same value to rounding
-        # (a known last-bits deviation), identical zero pattern
-        assert np.array_equal(mine[5] == 0, ref[5] == 0)
-        assert np.allclose(mine[5], ref[5], rtol=1e-15 * 4, atol=0)
+        # kappa-fission, collision estimator: q * sigma_f * N * flux summed nuclide by nuclide like the reference
+        # (tally_scoring.cpp:1246-1255) -- bit for bit (the cross sections are bit-equal in both math builds)
+        assert np.array_equal(mine[5].view(np.uint64), ref[5].view(np.uint64))
         seen["kappa"] = seen.get("kappa", 0) + int((ref[5] > 0).sum())
         st, sites = ref[1], ref[4]
         assert np.allclose(np.linalg.norm(st[:, 1:4], axis=1), 1.0)
@@ -723,7 +721,7 @@ def test_collision_fixture_from_reference_objects(oracle_bridge, libm):
             assert np.array_equal(mine["state"][:, [4, 7]], ref["state"][:, [4, 7]])
             assert np.allclose(mine["state"], ref["state"], rtol=1e-12, atol=1e-14)
             assert np.allclose(mine["sites"], ref["sites"], rtol=1e-12, atol=1e-14)
-        assert np.allclose(mine["kappa"], ref["kappa"], rtol=4e-15, atol=0)   # summation order, DESIGN.md section 2
+        assert np.array_equal(mine["kappa"].view(np.uint64), ref["kappa"].view(np.uint64))  # per-nuclide summation order
 
 
 @pytest.mark.parametrize("renormalise,libm", [(0, True), (1, True), (1, False)])
