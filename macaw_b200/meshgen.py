@@ -190,6 +190,47 @@ def tet_grid(nx, ny, nz, lo=(0, 0, 0), hi=(1, 1, 1), bc=BC_REFLECT, block_fn=Non
     return _finish(m, _box_bnd_ids(m, lo, hi), 6, bc)
 
 
+def tet_grid_24(nx, ny, nz, lo=(0, 0, 0), hi=(1, 1, 1), bc=BC_REFLECT, name="tet_grid_24") -> Mesh:
+    """GeneratedMeshGenerator with elem_type = TET4 as libMesh builds it (MeshTools::Generation::build_cube):
+    a HEX27 grid whose every hex is split into 24 tetrahedra -- for each of the six hex sides, four tets
+    (side corner k, side centre, side corner k + 1, hex centre); the mid-edge nodes are dropped.  This is the mesh
+    of the reference's TET4 trace tests (moose/modules/ray_tracing/test/tests/traceray/tet4/tests: 3 x 3 x 3
+    on [0, 5]^3), whose gold total distances tests/test_oracle_pinning.py reproduces on it."""
+    xs = np.linspace(lo[0], hi[0], nx + 1)
+    ys = np.linspace(lo[1], hi[1], ny + 1)
+    zs = np.linspace(lo[2], hi[2], nz + 1)
+    pts, index = [], {}
+
+    def node(p):
+        key = (round(p[0], 12), round(p[1], 12), round(p[2], 12))
+        if key not in index:
+            index[key] = len(pts)
+            pts.append(p)
+        return index[key]
+
+    conn = []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                c = [(xs[i], ys[j], zs[k]), (xs[i + 1], ys[j], zs[k]), (xs[i + 1], ys[j + 1], zs[k]), (xs[i], ys[j + 1], zs[k]),
+                     (xs[i], ys[j], zs[k + 1]), (xs[i + 1], ys[j], zs[k + 1]), (xs[i + 1], ys[j + 1], zs[k + 1]),
+                     (xs[i], ys[j + 1], zs[k + 1])]
+                c = [np.array(q, float) for q in c]
+                apex = node(sum(c) / 8.0)
+                for side in SIDE_NODES[HEX8]:
+                    sc = node(sum(c[v] for v in side) / 4.0)
+                    for t in range(4):
+                        conn.append([node(c[side[t]]), sc, node(c[side[(t + 1) % 4]]), apex])
+    xyz = np.array(pts, float)
+    conn = np.array(conn, np.int64)
+    p = xyz[conn]
+    vol = np.einsum("ij,ij->i", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0])
+    flip = vol < 0
+    conn[flip, 1], conn[flip, 2] = conn[flip, 2].copy(), conn[flip, 1].copy()
+    m = Mesh(TET4, xyz, conn, np.zeros(conn.shape[0], np.int32), name=name)
+    return _finish(m, _box_bnd_ids(m, lo, hi), 6, bc)
+
+
 # ---- BASELINE.json configs -------------------------------------------------------------------------
 PIN_PITCH = 1.25984  # cm, reference test/tests/study/geometry.xml:8-16
 PIN_RADII = (0.39218, 0.40005, 0.45720)  # fuel / gap / clad outer radii

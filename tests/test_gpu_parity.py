@@ -83,7 +83,8 @@ def test_locate_and_source_bit_exact(oracle_bridge, ctx_factory, name):
 
 @pytest.mark.parametrize("et,kind", [("hex8", "vtv"), ("hex8", "ctv"), ("hex8", "ete"), ("hex8", "ctc"),
                                      ("quad4", "vtv"), ("quad4", "ctv"), ("quad4", "ctc"), ("tet4", "vtv"),
-                                     ("tet4", "ctv"), ("tet4", "ete")])
+                                     ("tet4", "ctv"), ("tet4", "ete"), ("tet4", "ctc"), ("tet4k", "vtv"),
+                                     ("tet4k", "ctv"), ("tet4k", "ete")])
 def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, golden_dir, et, kind):
     import json, os
     from macaw_b200 import meshgen, nucdata
@@ -91,8 +92,11 @@ def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, 
         mesh = meshgen.hex_grid(5, 5, 5, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
     elif et == "quad4":
         mesh = meshgen.quad_grid(5, 5, (0, 0), (5, 5), meshgen.BC_KILL)
+    elif et == "tet4":
+        # libMesh's own TET4 GeneratedMesh (24 tets per hex): the mesh of the reference's tet4 trace tests
+        mesh = meshgen.tet_grid_24(3, 3, 3, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
     else:
-        mesh = meshgen.tet_grid(4, 4, 4, (0, 0, 0), (4, 4, 4), meshgen.BC_KILL)
+        mesh = meshgen.tet_grid(4, 4, 4, (0, 0, 0), (4, 4, 4), meshgen.BC_KILL)  # Kuhn split (the bench meshes)
     lib = nucdata.make_library(2, G=50)
     s = cstructs.make_settings(100)
     o = problems.configure(oracle_bridge.Oracle(), mesh, lib, [0], s, tallies=False)
@@ -106,9 +110,14 @@ def test_general_walk_matches_oracle_and_moose_gold(oracle_bridge, ctx_factory, 
     assert np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
     gold_names = {"vtv": "ntn" if et == "hex8" else "vtv", "ctv": "ctn" if et == "hex8" else "ctv", "ete": "ete",
                   "ctc": "ctc"}
-    if et != "tet4":
-        gold = json.load(open(os.path.join(golden_dir, "rt_lots_gold.json")))[f"{et}/{gold_names[kind]}"]
+    if et != "tet4k":  # every element type has the reference's own gold total distance (TET4 on libMesh's 24-split)
+        name = gold_names[kind] if et == "hex8" else kind
+        gold = json.load(open(os.path.join(golden_dir, "rt_lots_gold.json")))[f"{et}/{name}"]
         assert abs(d1.sum() - gold["total_distance"]) <= 1e-8 * gold["total_distance"]
+    if kind != "ctc":  # the reference's analytic check (LotsOfRaysRayStudy.C:117-256): distance to the bounding box
+        lo, hi = mesh.xyz.min(0), mesh.xyz.max(0)
+        exp = lots_rays.box_exit_distance(start, dirs, lo, hi, mesh.dim)
+        assert np.allclose(d1, exp, rtol=1e-9, atol=1e-9)
 
 
 # Event-loop regimes (mcw_set_option): EVENT = one round per collision throughout (tail_threshold 0),

@@ -146,7 +146,10 @@ def test_is_within_segment_known_answers(oracle_bridge):
 
 
 LOTS = [("hex8", "vtv", "ntn"), ("hex8", "ctv", "ctn"), ("hex8", "ete", "ete"), ("hex8", "ctc", "ctc"),
-        ("quad4", "vtv", "vtv"), ("quad4", "ctv", "ctv"), ("quad4", "ctc", "ctc")]
+        ("quad4", "vtv", "vtv"), ("quad4", "ctv", "ctv"), ("quad4", "ctc", "ctc"),
+        # TET4 (the headline bench's element type): libMesh's 24-tets-per-hex GeneratedMesh, 3 x 3 x 3 on [0, 5]^3
+        # (moose/modules/ray_tracing/test/tests/traceray/tet4/tests)
+        ("tet4", "vtv", "vtv"), ("tet4", "ctv", "ctv"), ("tet4", "ete", "ete"), ("tet4", "ctc", "ctc")]
 
 
 @pytest.mark.parametrize("et,kind,gold_name", LOTS)
@@ -156,6 +159,8 @@ def test_element_walk_reproduces_moose_lots_gold(oracle_bridge, golden_dir, et, 
     gold = json.load(open(os.path.join(golden_dir, "rt_lots_gold.json")))[f"{et}/{gold_name}"]
     if et == "hex8":
         mesh = meshgen.hex_grid(5, 5, 5, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
+    elif et == "tet4":
+        mesh = meshgen.tet_grid_24(3, 3, 3, (0, 0, 0), (5, 5, 5), meshgen.BC_KILL)
     else:
         mesh = meshgen.quad_grid(5, 5, (0, 0), (5, 5), meshgen.BC_KILL)
     o = oracle_bridge.Oracle()
