@@ -194,12 +194,16 @@ int mcw_version(void);
  * order only):
  *   "profile"          1 = per-kernel-family CUDA-event timing in mcw_generation_result
  *   "sync_every"       event rounds between host reads of the queue counters (default 4)
- *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (49152)
+ *   "tail_threshold"   histories in flight below which k_track runs fused, collisions inline (16384)
+ *   "pump_threshold"   histories in flight below which the REST of the generation runs in the persistent kernel
+ *                      k_pump (tracking / collision / general-walk warps connected by device-side rings, one
+ *                      launch, no host round trip); 0 = off (default).  "pump_track_warps" (1-3 of a CTA's 4 warps
+ *                      track, default 2), "pump_patience" (polls a collision warp waits for a full batch, default 4)
  *   "collide_min"      fused mode: parked collisions per warp before they are processed (8)
  *   "ordered_queues"   1 = collide / fly queues rebuilt in history-index order every round (1)
  *   "xs_sort_min"      with settings.sort_xs_queue: smallest collision queue worth an energy sort
  *                      (default: max(32768, 2.4e6 / number of (material, nuclide) pairs in use))
- *   "xs_plan"          sorted refresh stages all (slot, nuclide) windows of a tile at once (1)
+ *   "xs_plan"          stand-alone sorted lookup: 1 = tile kernel (all windows of a pass staged at once), 0 = per nuclide
  *   "fallback_every_round"  1 = serve the general-walk queue in every round instead of after host syncs (0)
  *   "drain_lanes", "drain_min_queue", "visit_cap", "fallback_blocks"   tracking / rare-path launch shape */
 int mcw_set_option(mcw_handle h, const char* name, int value);
@@ -307,6 +311,12 @@ int mcw_trace_rays(mcw_handle h, int64_t n, const double* start, const double* d
                    int32_t* out_segments, uint64_t* out_hash);
 /* mcw_locate_points: starting element by the ClaimRays rule [RT ClaimRays.C:104-139]. */
 int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t* ray_id, int32_t* elem);
+
+/* Diagnostics: the FP64 division the tile lookup inlines (the compiler's own expansion of a / b written out so that
+ * several divisions overlap) next to the plain operator, for n host operand pairs; ok[i] = the expansion's range
+ * checks held, i.e. q_fast[i] is used as is -- it must then equal q_plain[i] bit for bit. */
+int mcw_test_division(mcw_handle h, int64_t n, const double* a, const double* b, double* q_fast, double* q_plain,
+                      int32_t* ok);
 
 /* Host-side helpers that need no GPU (work split and bank sampling plan; tested on CPU). */
 int mcw_calculate_work(int64_t n_particles, int nranks, int64_t* work_index /* nranks+1 */);

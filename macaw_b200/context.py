@@ -190,6 +190,12 @@ class Context:
         self._ck(self.L.mcw_xs_lookup_device(self.h, n, d_E, d_mat, d_out, sorted, repeats, C.byref(ms)))
         return ms.value
 
+    def test_division(self, a, b):
+        a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+        qf, qp, ok = np.zeros(a.size), np.zeros(a.size), np.zeros(a.size, np.int32)
+        self._ck(self.L.mcw_test_division(self.h, a.size, _p(a), _p(b), _p(qf), _p(qp), _p(ok)))
+        return qf, qp, ok
+
     def grid_index(self, i_nuc, n_log_bins):
         out = np.zeros(n_log_bins + 1, np.int32)
         self._ck(self.L.mcw_get_grid_index(self.h, i_nuc, _p(out), out.size))

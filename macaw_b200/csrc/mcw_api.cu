@@ -139,11 +139,18 @@ struct mcw_context
   int64_t drain_min_queue = 0; // ... when the round's queue is at least this long (sweeps: profiles/ab_r01g_drain.txt)
   // below this many histories in flight the tracking kernel runs fused (collisions inline, no
   // round per collision): rounds would last as long as the slowest flight with most lanes idle
-  int64_t tail_threshold = 49152;
+  int64_t tail_threshold = 16384; // sweeps: profiles/sweep_r02_tail_threshold.txt (49152 before the warp-shared refresh)
   int fallback_every_round = 0; // 1: serve the general-walk queue in every round (A/B, tests)
   int xs_plan = 1; // sorted refresh: stage all (slot, nuclide) windows of a tile at once (k_xs_all_slots_plan)
   int ordered_queues = 1; // rebuild the collide / fly queues in history-index order every round
   int collide_min = 8; // fused mode: a warp processes its parked collisions once this many wait
+  // below this many histories in flight the rest of the generation runs in the persistent kernel (mcw_pump.cuh);
+  // 0 = never (event rounds, then the fused tracking kernel below tail_threshold)
+  int64_t pump_threshold = 0;
+  int pump_track_warps = 2, pump_patience = 4, pump_blocks = 0;
+  McwPump Q{};
+  void* d_pump_ctl = nullptr;
+  size_t pump_ctl_bytes = 0;
   mcw_generation_result last{};
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> pool; // per-round profiling events (5 per round), reused across generations
@@ -300,6 +307,12 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->xs_sort_min = std::max(1, value);
   else if (n == "collide_min")
     h->collide_min = std::min(32, std::max(1, value));
+  else if (n == "pump_threshold")
+    h->pump_threshold = std::max(0, value);
+  else if (n == "pump_track_warps")
+    h->pump_track_warps = std::min(3, std::max(1, value));
+  else if (n == "pump_patience")
+    h->pump_patience = std::max(1, value);
   else if (n == "visit_cap")
   {
     h->visit_cap = value > 0 ? value : (1 << 30);
@@ -582,8 +595,11 @@ static int prepare(mcw_handle h)
     energy.insert(energy.end(), n.energy.begin(), n.energy.end());
     for (int k = 0; k < G; ++k)
     {
+      // a non-fissionable nuclide contributes no fission / nu-fission whatever its table holds (OMC
+      // nuclide.cpp:680-689 `if (fissionable_)`): the device rows carry zeros there, so kernels may interpolate
+      // all four columns unconditionally
       for (int c = 0; c < 4; ++c)
-        xs4.push_back(n.xs5[5 * (size_t)k + c]);
+        xs4.push_back((c >= 2 && !n.prm.fissionable) ? 0.0 : n.xs5[5 * (size_t)k + c]);
       el_inel.push_back(n.elastic[k]);
       el_inel.push_back(n.inelastic_full[k]);
     }
@@ -943,6 +959,7 @@ static int prepare(mcw_handle h)
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->track_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, false)) * prop.multiProcessorCount;
     h->fused_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, true)) * prop.multiProcessorCount;
+    h->pump_blocks = std::max(1, mcwk_pump_blocks_per_sm(h->elem_type)) * prop.multiProcessorCount;
   }
   h->bank_capacity = 3 * n; // OMC simulation.cpp:286
   h->sampled_capacity = 3 * n + 16;
@@ -970,6 +987,29 @@ static int prepare(mcw_handle h)
   }
   CK(dev_alloc(h, &P.counters, 1));
   CK(cudaMemset(P.counters, 0, sizeof(McwCounters)));
+  {
+    // rings of the persistent generation kernel: every history is in at most one ring at a time and every
+    // consumer lane holds at most one ticket, so 2 n + 2^18 slots never wrap onto a live entry
+    uint64_t cap = 1;
+    while (cap < 2 * (uint64_t)n + (1u << 18))
+      cap <<= 1;
+    McwPump& Q = h->Q;
+    CK(dev_alloc(h, &Q.q_fly, cap));
+    CK(dev_alloc(h, &Q.q_collide, cap));
+    CK(dev_alloc(h, &Q.q_fallback, cap));
+    CK(cudaMemset(Q.q_fly, 0xff, cap * 4));
+    CK(cudaMemset(Q.q_collide, 0xff, cap * 4));
+    CK(cudaMemset(Q.q_fallback, 0xff, cap * 4));
+    unsigned long long* ctl;
+    h->pump_ctl_bytes = 7 * 16 * sizeof(unsigned long long);
+    CK(dev_alloc(h, &ctl, 7 * 16));
+    h->d_pump_ctl = ctl;
+    CK(cudaMemset(ctl, 0, h->pump_ctl_bytes));
+    Q.fly_head = ctl, Q.fly_tail = ctl + 16, Q.collide_head = ctl + 32, Q.collide_tail = ctl + 48;
+    Q.fallback_head = ctl + 64, Q.fallback_tail = ctl + 80;
+    Q.alive = reinterpret_cast<long long*>(ctl + 96);
+    Q.mask = (uint32_t)(cap - 1);
+  }
   CK(dev_alloc(h, &h->d_records, n));
   CK(dev_alloc(h, &h->d_box, 6));
   P.bank = h->d_bank;
@@ -1149,6 +1189,23 @@ int mcw_transport_generation(mcw_handle h, int batch)
     unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 0), st);
+    if (upper + fb_pending < h->pump_threshold)
+    {
+      // the rest of the generation in one persistent launch: tracking, collision and general-walk warps
+      // connected by device-side rings (mcw_pump.cuh)
+      mcwk_pump(P, h->Q, h->d_pump_ctl, h->pump_ctl_bytes, q, cnt_cur, h->d_q_fallback, &P.counters->n_fallback, h->pump_blocks,
+                h->pump_track_warps, h->pump_patience, st);
+      R.n_kernel_launches += 2;
+      if (prof)
+      {
+        cudaEventRecord(h->pool_event(3 * rounds + 1), st);
+        cudaEventRecord(h->pool_event(3 * rounds + 2), st);
+      }
+      ++rounds;
+      mcwk_round_reset(P.counters, cur, true, st);
+      R.n_kernel_launches += 1;
+      break;
+    }
     const bool fused = upper < h->tail_threshold;
     const int drain = (!fused && upper >= h->drain_min_queue) ? h->drain_lanes : 0;
     mcwk_track(P, q, cnt_cur, upper, fused ? h->fused_max_blocks : h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
@@ -1214,6 +1271,14 @@ int mcw_transport_generation(mcw_handle h, int batch)
   CK(cudaMemcpyAsync(h->h_counters, P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const McwCounters& C = *h->h_counters;
+  if (h->pump_threshold > 0)
+  {
+    long long alive = 0;
+    CK(cudaMemcpy(&alive, h->Q.alive, sizeof(alive), cudaMemcpyDeviceToHost));
+    if (alive != 0)
+      return fail(h, MCW_E_CUDA, "persistent generation kernel stopped with histories unfinished (alive = " +
+                                     std::to_string(alive) + ")");
+  }
   h->n_bank = std::min<int64_t>((int64_t)C.n_bank, h->bank_capacity);
   double* g = h->d_reduce + h->n_tally_values;
   mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_col, g + 0, n, st);
@@ -1715,6 +1780,31 @@ int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t*
   dev_free(h, dX);
   dev_free(h, dR);
   dev_free(h, dE);
+  return MCW_OK;
+}
+
+int mcw_test_division(mcw_handle h, int64_t n, const double* a, const double* b, double* q_fast, double* q_plain, int32_t* ok)
+{
+  if (!h || !a || !b || !q_fast || !q_plain || !ok || n < 0)
+    return MCW_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  double *da, *db, *df, *dp;
+  int32_t* dk;
+  CK(dev_alloc(h, &da, n));
+  CK(dev_alloc(h, &db, n));
+  CK(dev_alloc(h, &df, n));
+  CK(dev_alloc(h, &dp, n));
+  CK(dev_alloc(h, &dk, n));
+  CK(cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
+  mcwk_test_division(n, da, db, df, dp, dk, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(q_fast, df, n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q_plain, dp, n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ok, dk, n * 4, cudaMemcpyDeviceToHost));
+  for (void* p : {(void*)da, (void*)db, (void*)df, (void*)dp, (void*)dk})
+    dev_free(h, p);
   return MCW_OK;
 }
 

@@ -482,20 +482,12 @@ struct GeneralWalk
   }
 };
 
-// One general step for every particle in the fallback queue, including the segment physics.
+// One general step of history i (status MCW_ST_FALLBACK), including the segment physics: the rare path of
+// RT TraceRay.C:564-997,1134-1246 for exits through a vertex or an edge.  Returns the new status.
 template <int TYPE>
-__global__ void __launch_bounds__(64)
-k_fallback(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
-           int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, int32_t* __restrict__ q_collide)
+MCW_D int mcw_fallback_history(const McwParams& P, int i)
 {
-  // grid-stride: a small fixed grid serves whatever the (device-side) count turns out to be
-  McwParticlesDev& p = P.p;
-  const int64_t n_q = (int64_t)*count;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_q; idx += (int64_t)gridDim.x * blockDim.x)
-  {
-  const int i = queue[idx];
-  if (p.status[i] != MCW_ST_FALLBACK)
-    continue;
+  const McwParticlesDev& p = P.p;
   GeneralWalk<TYPE> W;
   W.cur = p.elem[i];
   W.last = p.last_elem[i];
@@ -581,12 +573,29 @@ k_fallback(McwParams P, const int32_t* __restrict__ queue, const unsigned long l
     atomicAdd(&P.counters->n_vertex_edge, n_ve);
   if (n_moved)
     atomicAdd(&P.counters->n_moved, n_moved);
-  if (!P.ordered_queues)
+  return status;
+}
+
+// One general step for every particle in the fallback queue.
+template <int TYPE>
+__global__ void __launch_bounds__(64)
+k_fallback(McwParams P, const int32_t* __restrict__ queue, const unsigned long long* __restrict__ count,
+           int32_t* __restrict__ q_fly_next, unsigned long long* __restrict__ cnt_next, int32_t* __restrict__ q_collide)
+{
+  // grid-stride: a small fixed grid serves whatever the (device-side) count turns out to be
+  const int64_t n_q = (int64_t)*count;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_q; idx += (int64_t)gridDim.x * blockDim.x)
   {
-    if (status == MCW_ST_FLY)
-      q_fly_next[atomicAdd(cnt_next, 1ull)] = i;
-    if (status == MCW_ST_COLLIDE)
-      q_collide[atomicAdd(&P.counters->n_collide, 1ull)] = i;
-  }
+    const int i = queue[idx];
+    if (P.p.status[i] != MCW_ST_FALLBACK)
+      continue;
+    const int status = mcw_fallback_history<TYPE>(P, i);
+    if (!P.ordered_queues)
+    {
+      if (status == MCW_ST_FLY)
+        q_fly_next[atomicAdd(cnt_next, 1ull)] = i;
+      if (status == MCW_ST_COLLIDE)
+        q_collide[atomicAdd(&P.counters->n_collide, 1ull)] = i;
+    }
   }
 }

@@ -528,6 +528,9 @@ k_collide(McwParams P, const int32_t* __restrict__ queue, const unsigned long lo
 // ------------------------------------------------------------------ general (rare-path) step
 #include "mcw_fallback.cuh"
 
+// ------------------------------------------------------------------ persistent generation kernel
+#include "mcw_pump.cuh"
+
 // ------------------------------------------------------------------ bank helpers
 // OMC bank.cpp:60-104: position of a site in the sorted bank = exclusive_scan(progeny_per_particle)
 // [parent] + progeny_id
@@ -729,6 +732,25 @@ __global__ void k_locate_points(McwParams P, int64_t n, const double* __restrict
   elem[i] = e;
 }
 
+// diagnostics: the division the tile lookup inlines (mcw_div_fast) next to the compiler's own a / b
+__global__ void k_test_division(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ q_fast,
+                                double* __restrict__ q_plain, int32_t* __restrict__ ok)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  bool good;
+  q_fast[i] = mcw_div_fast(a[i], b[i], good);
+  q_plain[i] = a[i] / b[i];
+  ok[i] = good;
+}
+
+void mcwk_test_division(int64_t n, const double* a, const double* b, double* q_fast, double* q_plain, int32_t* ok, cudaStream_t st)
+{
+  if (n > 0)
+    k_test_division<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, b, q_fast, q_plain, ok);
+}
+
 // ------------------------------------------------------------------ host launchers
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + MCW_BLOCK - 1) / MCW_BLOCK); }
 
@@ -807,6 +829,23 @@ void mcwk_track(const McwParams& P, const int32_t* queue, const unsigned long lo
     MCW_DISPATCH(P.mesh.type, (k_track<TY, false><<<g, MCW_TRACK_BLOCK, 0, st>>>(P, queue, count, &P.counters->head, q_fly_next,
                                                                                 cnt_next, q_collide, q_fallback, drain_lanes, 32)));
   }
+}
+
+int mcwk_pump_blocks_per_sm(int type)
+{
+  int nb = 0;
+  MCW_DISPATCH(type, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pump<TY>, MCW_TRACK_BLOCK, 0)));
+  return nb;
+}
+
+// Everything that is still alive, from here to the end of the generation, in one launch (mcw_pump.cuh).
+void mcwk_pump(const McwParams& P, const McwPump& Q, void* ctl, size_t ctl_bytes, const int32_t* q_fly,
+               const unsigned long long* n_fly, const int32_t* q_fallback, const unsigned long long* n_fallback, int blocks,
+               int n_track_warps, int patience, cudaStream_t st)
+{
+  cudaMemsetAsync(ctl, 0, ctl_bytes, st);
+  k_pump_fill<<<592, 256, 0, st>>>(Q, P.p.status, q_fly, n_fly, q_fallback, n_fallback);
+  MCW_DISPATCH(P.mesh.type, (k_pump<TY><<<blocks, MCW_TRACK_BLOCK, 0, st>>>(P, Q, n_track_warps, patience)));
 }
 
 void mcwk_round_reset(McwCounters* c, int consumed, bool fallback_served, cudaStream_t st)

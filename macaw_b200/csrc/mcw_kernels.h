@@ -50,3 +50,8 @@ void mcwk_sample_bank(void* temp, size_t temp_bytes, const mcw_source_site* sort
 void mcwk_pad_from_bank_end(const mcw_source_site* sorted, int64_t n_bank, mcw_source_site* out, int64_t have,
                             int64_t needed, cudaStream_t st);
 uint64_t mcwk_host_init_seed(int64_t id, int offset, int64_t master_seed);
+void mcwk_test_division(int64_t n, const double* a, const double* b, double* q_fast, double* q_plain, int32_t* ok, cudaStream_t st);
+int mcwk_pump_blocks_per_sm(int type);
+void mcwk_pump(const McwParams& P, const McwPump& Q, void* ctl, size_t ctl_bytes, const int32_t* q_fly,
+               const unsigned long long* n_fly, const int32_t* q_fallback, const unsigned long long* n_fallback, int blocks,
+               int n_track_warps, int patience, cudaStream_t st);

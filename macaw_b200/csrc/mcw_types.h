@@ -143,6 +143,16 @@ struct McwCounters // device-side counters, one cache line each where contended
   unsigned long long n_refresh, pad5[7]; // survivors of the round's collisions = entries of the energy-binned refresh queue
 };
 
+// Device-side queues of the persistent generation kernel (mcw_pump.cuh): three rings of history indices
+// (-1 = empty slot) with ticket counters one cache line apart, and the count of histories still alive.
+struct McwPump
+{
+  int32_t *q_fly, *q_collide, *q_fallback;
+  unsigned long long *fly_head, *fly_tail, *collide_head, *collide_tail, *fallback_head, *fallback_tail;
+  long long* alive;
+  uint32_t mask; // ring capacity - 1 (power of two, > 2 x histories + every lane of the device)
+};
+
 struct McwParams
 {
   McwLibraryDev lib;

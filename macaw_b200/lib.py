@@ -66,6 +66,7 @@ def load():
         "mcw_trace_rays": [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
         "mcw_locate_points": [vp, i64, vp, vp, vp],
         "mcw_calculate_work": [i64, C.c_int, vp],
+        "mcw_test_division": [vp, i64, vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -95,7 +96,7 @@ EXPORTS = ["mcw_create", "mcw_destroy", "mcw_last_error", "mcw_version", "mcw_se
            "mcw_sampled_device_ptr", "mcw_source_device_ptr", "mcw_set_source_count", "mcw_reduction_device_ptr",
            "mcw_get_tally", "mcw_tally_shape", "mcw_get_history_records", "mcw_get_fission_bank",
            "mcw_get_grid_index", "mcw_xs_lookup", "mcw_xs_lookup_device", "mcw_trace_rays", "mcw_locate_points",
-           "mcw_calculate_work"]
+           "mcw_calculate_work", "mcw_test_division"]
 
 
 def calculate_work(n_particles, nranks):

@@ -128,7 +128,17 @@ def hex_grid(nx, ny, nz, lo=(0, 0, 0), hi=(1, 1, 1), bc=BC_REFLECT, block_fn=Non
     m = Mesh(HEX8, xyz, conn, np.zeros(conn.shape[0], np.int32), name=name)
     if block_fn is not None:
         m.block_id = np.asarray(block_fn(m.centroids()), np.int32)
-    return _finish(m, _box_bnd_ids(m, lo, hi), 6, bc)
+    # structured grid: neighbours and boundary ids follow from (i, j, k) -- side s faces (k-1, j-1, i+1, j+1, i-1, k+1)
+    # with boundary ids back=0 bottom=1 right=2 top=3 left=4 front=5; face matching
+    # (compute_neighbors) gives the same tables and is what the unstructured meshes use
+    eid = i + nx * (j + ny * k)
+    nbr = np.stack([np.where(k > 0, eid - nx * ny, -1), np.where(j > 0, eid - nx, -1), np.where(i < nx - 1, eid + 1, -1),
+                    np.where(j < ny - 1, eid + nx, -1), np.where(i > 0, eid - 1, -1), np.where(k < nz - 1, eid + nx * ny, -1)],
+                   axis=1).astype(np.int64)
+    m.neighbors = nbr
+    m.side_bnd_id = np.where(nbr < 0, np.arange(6, dtype=np.int32)[None, :], -1).astype(np.int32)
+    m.bnd_kind = np.full(6, bc, np.int32) if np.isscalar(bc) else np.asarray(bc, np.int32)
+    return m
 
 
 def quad_grid(nx, ny, lo=(0, 0), hi=(1, 1), bc=BC_REFLECT, block_fn=None, name="quad_grid") -> Mesh:
@@ -282,6 +292,17 @@ def assembly_hex(n_pins=17, cells_per_pin=9, n_z=4, height=4.0) -> Mesh:
     L = n_pins * PIN_PITCH
     n = n_pins * cells_per_pin
     return hex_grid(n, n, n_z, (0, 0, 0), (L, L, height), BC_REFLECT, assembly_blocks(n_pins), "assembly_hex")
+
+
+def core_hex(n_asm=15, cells_per_pin=3, n_layers=17, layer_height=2.0) -> Mesh:
+    """C4: a BEAVRS-core-sized synthetic (reference examples/beavrs_core/run_3d_core_cycle1.i: 3-D full core whose
+    mesh files are not in the tree, vacuum boundary): n_asm x n_asm assemblies of 17 x 17 pin cells, `cells_per_pin`
+    HEX8 cells per pin pitch, `n_layers` axial layers, every outer face killing the ray.
+    15 x 15 assemblies x 3 cells x 17 layers = 9 948 825 HEX8."""
+    n = n_asm * 17 * cells_per_pin
+    L = n_asm * 17 * PIN_PITCH
+    return hex_grid(n, n, n_layers, (0, 0, 0), (L, L, n_layers * layer_height), BC_KILL, assembly_blocks(n_asm * 17),
+                    f"core_hex_{n_asm}_{cells_per_pin}_{n_layers}")
 
 
 def brick_tet(n, bc=BC_KILL, checker=4) -> Mesh:

@@ -67,6 +67,29 @@ def test_xs_lookup_sorted_staged_bit_exact(oracle_bridge, ctx_factory, name, n):
     assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 4), want[order])
 
 
+def test_inlined_division_equals_the_operator(ctx_factory):
+    """mcw_div_fast (the compiler's expansion of a / b, written out for instruction-level parallelism in the tile
+    lookup) against the plain operator and against IEEE division on the host: wherever its range checks hold the
+    quotient is used as is and must be the correctly rounded one; elsewhere the kernels fall back to the operator."""
+    g = ctx_factory()
+    rng = np.random.default_rng(11)
+    n = 400000
+    a = np.concatenate([rng.uniform(0, 1, n // 2) * 10.0 ** rng.uniform(-12, 8, n // 2), rng.standard_normal(n // 4),
+                        np.ldexp(rng.uniform(0.5, 1, n // 4), rng.integers(-1070, 1020, n // 4))])
+    b = np.concatenate([rng.uniform(0, 1, n // 2) * 10.0 ** rng.uniform(-12, 8, n // 2) + 1e-300, rng.standard_normal(n // 4),
+                        np.ldexp(rng.uniform(0.5, 1, n // 4), rng.integers(-1070, 1020, n // 4))])
+    a[:8] = [0.0, 1.0, -1.0, 5e-324, 1e308, np.inf, np.nan, 3.0]
+    b[:8] = [1.0, 0.0, 3.0, 2.0, 1e-308, 2.0, 1.0, 3.0]
+    qf, qp, ok = g.test_division(a, b)
+    with np.errstate(all="ignore"):
+        want = a / b
+    same = (qp.view(np.uint64) == want.view(np.uint64)) | (np.isnan(qp) & np.isnan(want))
+    assert same.all()  # the device operator is IEEE division
+    used = ok != 0
+    assert used.mean() > 0.7  # the energy-grid operands of the lookup are all in this class
+    assert np.array_equal(qf[used].view(np.uint64), qp[used].view(np.uint64))
+
+
 @pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "pin_cell_hex", "assembly_quad"])
 def test_locate_and_source_bit_exact(oracle_bridge, ctx_factory, name):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
@@ -128,6 +151,10 @@ EVENT = {"tail_threshold": 0}
 FUSED = {"tail_threshold": 1 << 30}
 MIXED = {"tail_threshold": 700, "collide_min": 3}
 SORTED = {"tail_threshold": 300, "xs_sort_min": 1}
+# PUMP = the whole generation in the persistent kernel (mcw_pump.cuh: tracking / collision / general-walk warps
+# connected by device-side rings); PUMP_TAIL = event rounds until fewer than 700 histories fly, then the pump
+PUMP = {"pump_threshold": 1 << 30}
+PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
 
 
 @pytest.mark.parametrize("name,kw,opts", [
@@ -143,7 +170,12 @@ SORTED = {"tail_threshold": 300, "xs_sort_min": 1}
     # 20 000 histories: host syncs every 4th round, so the general-walk queue is served only after syncs
     ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000}),
     ("pin_cell_tet", {"n_particles": 20000}, {"tail_threshold": 3000, "fallback_every_round": 1}),
-    ("pin_cell_hex", {"n_particles": 20000}, {"tail_threshold": 0, "sync_every": 7})])
+    ("pin_cell_hex", {"n_particles": 20000}, {"tail_threshold": 0, "sync_every": 7}),
+    ("infinite_medium", {}, PUMP), ("pin_cell_tet", {}, PUMP), ("pin_cell_hex", {}, PUMP), ("assembly_quad", {}, PUMP_TAIL),
+    ("beavrs_assembly", {}, PUMP), ("pin_cell_tet_iso", {}, PUMP_TAIL),
+    ("pin_cell_tet", {"n_particles": 20000}, PUMP), ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 5000}),
+    ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 1 << 30, "pump_track_warps": 1, "pump_patience": 1}),
+    ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 1 << 30, "pump_track_warps": 3, "pump_patience": 64})])
 def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
     for k, v in opts.items():
@@ -360,3 +392,47 @@ def test_xs_lookup_against_reference_objects_fixture(ctx_factory, golden_dir):
         assert np.array_equal(got.view(np.uint64), ref[f"m{i_mat}_macro"].view(np.uint64)), i_mat
     for i in range(len(lib.nuclides)):
         assert np.array_equal(g.grid_index(i, lib.n_log_bins), ref[f"grid_index_{i}"]), i
+
+
+@pytest.mark.parametrize("name,world", [("pin_cell_tet", 2), ("beavrs_assembly", 2)])
+def test_two_gpus_equal_one_gpu(ctx_factory, tmp_path, name, world):
+    """Rank-count invariance ON THE GPUS over NCCL (OMC eigenvalue.cpp:71-311 synchronize_bank): the next source
+    bank of an N-GPU run, concatenated in rank order, equals the 1-GPU run's byte for byte; k per generation to
+    1e-12 (summation order across ranks), tallies to 1e-11.  Skipped on a box with fewer GPUs."""
+    import os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n_particles, n_batches = 40000, 3
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "g")
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "dist_gpu_worker.py"), str(r), str(world),
+                               str(port), out, name, str(n_particles), str(n_batches)], cwd=root,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    from macaw_b200 import study as st
+    mesh, lib, bm, s = problems.PROBLEMS[name](n_particles=n_particles)
+    blocks = list(range(len(bm))) if int(mesh.block_id.max()) < len(bm) else [int(b) for b in mesh.block_ids_sorted()]
+    kernel = st.CollisionKernel(blocks=blocks, materials=[m + 1 for m in bm], z_coord=100.0 if mesh.dim == 2 else None)
+    tally = st.OpenMCTally(id=1, scores=["flux", "nu-fission"], filters=["cell"], estimator="COLLISION")
+    one = st.OpenMCStudy(mesh, lib, kernel, s, [tally], device=0)
+    ks = []
+    for _ in range(n_batches):
+        r = one.execute()
+        ks.append([r.k_generation, r.keff, r.k_collision, r.k_absorption, r.k_tracklength])
+    parts = [np.load(f"{out}.{r}.npz") for r in range(world)]
+    src = np.concatenate([p["source"] for p in parts])
+    assert src.tobytes() == one.ctx.source_bank().tobytes()
+    rec = np.concatenate([p["records"] for p in parts])
+    assert rec.tobytes() == one.ctx.history_records().tobytes()  # every history of the last generation, bit for bit
+    for p in parts:
+        assert np.allclose(p["ks"], np.asarray(ks), rtol=1e-12, atol=0)
+    t_sum, _, _ = one.ctx.get_tally(1)
+    for p in parts:  # the VALUE arrays are all-reduced in place: every rank accumulates the global tally
+        assert np.allclose(p["tally_sum"], t_sum, rtol=1e-11, atol=1e-300)
+    one.ctx.close()
