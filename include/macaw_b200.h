@@ -135,7 +135,7 @@ typedef struct mcw_settings
   int32_t source_only_fissionable;
   int32_t max_events;      /* safety cap on events per history (OMC constants.h:56 MAX_EVENTS) */
   int32_t sort_xs_queue;   /* 1 = sort the cross-section queue by (material, energy bucket) */
-  int32_t record_traces;   /* 1 = keep per-history crossing hashes (parity output) */
+  int32_t record_traces;   /* 1 = keep per-history crossing hashes (parity output); 2 = also cache trace points */
 } mcw_settings;
 
 /* Per-generation result (MC OpenMCStudy.C:399-401 prints keff / keff_std / k_generation;
@@ -180,6 +180,21 @@ typedef struct mcw_history_record
   int32_t n_xs;
   uint64_t trace_hash; /* rolling hash of (element, exit side) for every segment */
 } mcw_history_record;
+
+/* One cached trace point (RT include/raytracing/TraceData.h:15-29 TracePointData + the ray's aux data): what
+ * RayTracingStudy caches per completed segment when `segments_on_cache_traces` / `aux_data_on_cache_traces` are on
+ * and RayTracingExodus writes as one EDGE2 element per segment (RT src/outputs/RayTracingMeshOutput.C:252-445,
+ * 447-580).  A segment in which the history scatters is restarted from the collision point and caches nothing
+ * (SURVEY F7): every cached point lies on an element side.  Kept when settings.record_traces == 2. */
+typedef struct mcw_trace_point
+{
+  int64_t ray_id;  /* RT ray id of the history: (batch - 1) * n_particles + (id - 1) [SURVEY A13] */
+  int32_t seq;     /* segments the history had walked when the point was cached (orders a ray's points) */
+  int32_t kind;    /* 0 start point, 1 end of a completed segment (an element side), 3 absorbed in the element (last point) */
+  double point[3];
+  double aux[8];   /* energy, weight, n_progeny, id, seed_tracking, seed_source, seed_URR, particle_type
+                    * (registration order of MC OpenMCStudy.C:190-197), as after the segment */
+} mcw_trace_point;
 
 typedef struct mcw_context* mcw_handle;
 
@@ -289,6 +304,9 @@ int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy,
 
 /* Parity / diagnostics output (RT TraceData.h:20-68 cached traces are the reference analogue). */
 int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n);
+/* Cached trace points of the last generation, ordered by (ray_id, seq); *n = how many were cached (may exceed
+ * capacity; the device buffer holds 256 points per history of this rank, at most 2^24). */
+int mcw_get_traces(mcw_handle h, mcw_trace_point* out, int64_t capacity, int64_t* n);
 int mcw_get_fission_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n);
 int mcw_get_grid_index(mcw_handle h, int i_nuclide, int32_t* out, int n /* n_log_bins + 1 */);
 

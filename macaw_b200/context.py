@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import meshgen, nucdata
-from .cstructs import RECORD_DTYPE, SITE_DTYPE, GenerationResult, Settings
+from .cstructs import RECORD_DTYPE, SITE_DTYPE, TRACE_DTYPE, GenerationResult, Settings
 from .lib import McwError, load
 
 
@@ -110,6 +110,14 @@ class Context:
         self._ck(self.L.mcw_get_history_records(self.h, None, 0, C.byref(n)))
         out = np.zeros(n.value, RECORD_DTYPE)
         self._ck(self.L.mcw_get_history_records(self.h, _p(out), out.size, C.byref(n)))
+        return out
+
+    def traces(self):
+        """Cached trace points of the last generation (settings.record_traces = 2), ordered by (ray_id, seq)."""
+        n = C.c_int64()
+        self._ck(self.L.mcw_get_traces(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, TRACE_DTYPE)
+        self._ck(self.L.mcw_get_traces(self.h, _p(out), out.size, C.byref(n)))
         return out
 
     # ---- generations

@@ -954,6 +954,15 @@ static int prepare(mcw_handle h)
   P.visit_cap = h->visit_cap;
   CK(dev_alloc(h, &p.xs, (size_t)P.n_slots * 4 * (size_t)n));
   CK(dev_alloc(h, &p.xs_prefix, (size_t)P.n_plan_pad * (size_t)n)); // 8 B per (history, plan entry)
+  if (h->set.record_traces == 2)
+  {
+    // cached trace points (RT TraceData.h): parity / RayTracingExodus-style output, not a production mode
+    double** dt[] = {&p.tx, &p.ty, &p.tz};
+    for (auto q : dt)
+      CK(dev_alloc(h, q, n));
+    P.trace_capacity = std::min<int64_t>(256 * n, (int64_t)1 << 24);
+    CK(dev_alloc(h, &P.trace, P.trace_capacity));
+  }
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -1590,6 +1599,27 @@ int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capac
     CK(cudaMemcpyAsync(rec, h->d_records, std::min(capacity, *n) * sizeof(mcw_history_record), cudaMemcpyDeviceToHost,
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
+  }
+  return MCW_OK;
+}
+
+int mcw_get_traces(mcw_handle h, mcw_trace_point* out, int64_t capacity, int64_t* n)
+{
+  if (!h || !n || !h->prepared)
+    return MCW_E_INVALID_ARGUMENT;
+  if (!h->P.trace)
+    return fail(h, MCW_E_NOT_READY, "trace points are cached only with settings.record_traces = 2");
+  CK(cudaSetDevice(h->device));
+  *n = (int64_t)h->h_counters->n_trace; // counters of the last generation (copied at the end of transport)
+  const int64_t have = std::min<int64_t>(*n, h->P.trace_capacity);
+  if (out && capacity > 0 && have > 0)
+  {
+    std::vector<mcw_trace_point> all((size_t)have);
+    CK(cudaMemcpy(all.data(), h->P.trace, have * sizeof(mcw_trace_point), cudaMemcpyDeviceToHost));
+    std::sort(all.begin(), all.end(), [](const mcw_trace_point& a, const mcw_trace_point& b) {
+      return a.ray_id != b.ray_id ? a.ray_id < b.ray_id : (a.seq != b.seq ? a.seq < b.seq : a.kind < b.kind);
+    });
+    memcpy(out, all.data(), std::min(capacity, have) * sizeof(mcw_trace_point));
   }
   return MCW_OK;
 }

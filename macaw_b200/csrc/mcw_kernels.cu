@@ -84,6 +84,8 @@ k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n
   p.inc_side[i] = (int8_t)mcw_starting_incoming_side<TYPE>(R, r, dir);
   p.status[i] = MCW_ST_FLY;
   p.fate[i] = -1;
+  if (P.trace)
+    mcw_trace_emit(P, (int)i, 0, 0, r, s.E, s.wgt, 0, seeds[0], seeds[1], seeds[2]);
   // Particle::event_calculate_xs for the birth energy, every material slot at once
   mcw_lookup_all_slots(P, i, s.E);
   p.n_xs[i] = P.n_slots;
@@ -374,6 +376,8 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
   {
     p.status[i] = MCW_ST_DEAD;
     p.fate[i] = 0;
+    if (P.trace) // the last cached point of the ray: the end of the segment it was absorbed in
+      mcw_trace_emit(P, i, p.n_seg[i], 3, v3(p.tx[i], p.ty[i], p.tz[i]), c.E, c.wgt, c.n_progeny, seed_trk, seed_src, seed_urr);
   }
   else
   {

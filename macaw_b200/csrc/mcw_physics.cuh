@@ -81,6 +81,26 @@ MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E)
   return kappa;
 }
 
+// ------------------------------------------------------------------ cached trace points
+// RT TraceData.h:15-29 / RayTracingStudy's cached traces with aux data (what RayTracingExodus writes).  Off the hot
+// path: only when settings.record_traces == 2.
+MCW_D void mcw_trace_emit(const McwParams& P, int i, int seq, int kind, V3 pt, double E, double wgt, int n_progeny,
+                          uint64_t seed_trk, uint64_t seed_src, uint64_t seed_urr)
+{
+  const unsigned long long k = atomicAdd(&P.counters->n_trace, 1ull);
+  if ((int64_t)k >= P.trace_capacity)
+    return;
+  mcw_trace_point r;
+  const int64_t id = P.work_offset + i + 1;
+  r.ray_id = (int64_t)(P.batch - 1) * P.n_particles_global + (id - 1);
+  r.seq = seq;
+  r.kind = kind;
+  r.point[0] = pt.x, r.point[1] = pt.y, r.point[2] = pt.z;
+  r.aux[0] = E, r.aux[1] = wgt, r.aux[2] = (double)n_progeny, r.aux[3] = (double)id;
+  r.aux[4] = (double)seed_trk, r.aux[5] = (double)seed_src, r.aux[6] = (double)seed_urr, r.aux[7] = 0.0;
+  P.trace[k] = r;
+}
+
 // ------------------------------------------------------------------ segment part of onSegment
 // MC CollisionKernel.C:143-175.  Returns true if a collision happens inside the segment, and then
 // `pos` is the collision point (computed backwards from the exit point, :173-175).

@@ -119,6 +119,9 @@ struct McwParticlesDev
   // Material::calculate_xs (OMC material.cpp:790-829) -- so the collision kernel picks the nuclide by scanning
   // them instead of looking every nuclide of the material up a second time.
   double* xs_prefix;
+  // settings.record_traces == 2 only: exit point of the segment a collision interrupted (the point the reference
+  // caches when the history is absorbed there, RT TraceRay caches the untruncated segment end)
+  double *tx, *ty, *tz;
 };
 
 struct McwTallyDev
@@ -140,7 +143,7 @@ struct McwCounters // device-side counters, one cache line each where contended
   unsigned long long head, pad4[15]; // next unclaimed entry of the queue the tracking kernel is draining
   unsigned long long n_segments, n_collisions, n_xs, n_nuc_lookups, n_vertex_edge, n_moved, n_failed,
       n_bank_dropped;
-  unsigned long long n_refresh, pad5[7]; // survivors of the round's collisions = entries of the energy-binned refresh queue
+  unsigned long long n_refresh, n_trace, pad5[6]; // survivors of the round's collisions = entries of the energy-binned refresh queue
 };
 
 // Device-side queues of the persistent generation kernel (mcw_pump.cuh): three rings of history indices
@@ -174,6 +177,8 @@ struct McwParams
   int32_t visit_cap; // segments one lane may walk per visit of the tracking kernel
   int32_t record_traces; // keep the per-history crossing hash (parity output)
   int32_t collision_kappa; // some collision-estimator tally scores kappa-fission (needs every fissionable nuclide)
+  mcw_trace_point* trace;  // cached trace points (null unless settings.record_traces == 2)
+  int64_t trace_capacity;
   int32_t slot_mat[MCW_MAX_XS_SLOTS]; // slot -> material index
   // refresh plan: the (slot, nuclide) pairs of all slots, material order inside a slot (mcw_xs.cuh);
   // n_plan = 0 when some slot's material has no nuclide (then the per-slot kernels are used)

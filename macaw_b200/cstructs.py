@@ -45,6 +45,10 @@ RECORD_DTYPE = np.dtype([("seed_tracking", "u8"), ("seed_source", "u8"), ("seed_
                          ("fate", "i4"), ("n_xs", "i4"), ("trace_hash", "u8")])
 assert RECORD_DTYPE.itemsize == 88
 
+TRACE_DTYPE = np.dtype([("ray_id", "i8"), ("seq", "i4"), ("kind", "i4"), ("point", "f8", 3), ("aux", "f8", 8)])
+assert TRACE_DTYPE.itemsize == 104
+TRACE_AUX_NAMES = ("energy", "weight", "n_progeny", "id", "seed_tracking", "seed_source", "seed_URR", "particle_type")
+
 SCORE = {"flux": 0, "total": 1, "fission": 2, "nu-fission": 3, "kappa-fission": 4}
 ESTIMATOR = {"collision": 0, "tracklength": 1}
 GRANULARITY = {"cell": 0, "universe": 1, "global": 2}

@@ -112,3 +112,79 @@ def write_exodus(path, m: meshgen.Mesh, version=2):
             vs[:] = sd + 1
     f.close()
     return np.concatenate(order)  # old element index of every element in file order
+
+
+RAY_VAR_ORDER = ("aux_energy", "aux_id", "aux_n_progeny", "aux_particle_type", "aux_seed_URR", "aux_seed_source",
+                 "aux_seed_tracking", "aux_weight", "intersections", "ray_id")
+
+
+def ray_segments(traces):
+    """Cached trace points (Context.traces(): ordered by ray and sequence) -> the segment mesh RayTracingExodus
+    builds (RT src/outputs/RayTracingMeshOutput.C:252-445): one node per cached point, one EDGE2 element between
+    consecutive points of a ray, and per element the ray id, the running intersection count and the ray's aux data
+    as after that segment (:447-580).  Returns (coord, conn, {var name: values per element})."""
+    from .cstructs import TRACE_AUX_NAMES
+    t = traces
+    coord = np.ascontiguousarray(t["point"], np.float64)
+    same_ray = t["ray_id"][1:] == t["ray_id"][:-1]
+    a = np.nonzero(same_ray)[0]
+    conn = np.stack([a, a + 1], axis=1).astype(np.int64)
+    end = t[a + 1]
+    first_of_ray = np.concatenate([[0], np.nonzero(~same_ray)[0] + 1])
+    ray_start = np.repeat(first_of_ray, np.diff(np.concatenate([first_of_ray, [len(t)]])))
+    data = {"ray_id": end["ray_id"].astype(np.float64), "intersections": (a - ray_start[a]).astype(np.float64)}
+    for k, name in enumerate(TRACE_AUX_NAMES):
+        data["aux_" + name] = np.ascontiguousarray(end["aux"][:, k])
+    return coord, conn, data
+
+
+def write_ray_exodus(path, traces, version=2):
+    """The `rays` output of the reference's study test (test/tests/study/openmc_study.i:77-83: RayTracingExodus with
+    output_aux_data): EDGE2 segments with element variables, one time step.  Readable by read_ray_exodus and laid
+    out like test/tests/study/gold/openmc_study_rays.e (variable names in the gold file's order)."""
+    from scipy.io import netcdf_file
+    coord, conn, data = ray_segments(traces)
+    f = netcdf_file(path, "w", version=version)
+    f.title = "macaw_b200 ray trace export"
+    f.createDimension("len_string", 33)
+    f.createDimension("len_name", 33)
+    f.createDimension("time_step", 1)
+    f.createDimension("num_dim", 3)
+    f.createDimension("num_nodes", coord.shape[0])
+    f.createDimension("num_elem", conn.shape[0])
+    f.createDimension("num_el_blk", 1)
+    f.createDimension("num_el_in_blk1", conn.shape[0])
+    f.createDimension("num_nod_per_el1", 2)
+    f.createDimension("num_elem_var", len(RAY_VAR_ORDER))
+    for d, name in enumerate(("coordx", "coordy", "coordz")):
+        v = f.createVariable(name, ">f8", ("num_nodes",))
+        v[:] = coord[:, d]
+    v = f.createVariable("eb_prop1", ">i4", ("num_el_blk",))
+    v[:] = [0]
+    v.name = "ID"
+    v = f.createVariable("connect1", ">i4", ("num_el_in_blk1", "num_nod_per_el1"))
+    v[:] = conn + 1
+    v.elem_type = "EDGE2"
+    v = f.createVariable("time_whole", ">f8", ("time_step",))
+    v[:] = [1.0]
+    v = f.createVariable("name_elem_var", "c", ("num_elem_var", "len_name"))
+    for i, nm in enumerate(RAY_VAR_ORDER):
+        v[i] = list(nm.ljust(33, "\0"))
+    for i, nm in enumerate(RAY_VAR_ORDER):
+        v = f.createVariable(f"vals_elem_var{i + 1}eb1", ">f8", ("time_step", "num_el_in_blk1"))
+        v[0, :] = data[nm]
+    f.close()
+
+
+def read_ray_exodus(path):
+    """(coord, conn, {name: element values of the last time step}) of a RayTracingExodus file -- the reference's gold
+    file or one written by write_ray_exodus."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    names = ["".join(c.decode() for c in row).strip("\x00 ").strip() for row in v["name_elem_var"][:]]
+    coord = np.stack([np.array(v["coordx"][:]), np.array(v["coordy"][:]), np.array(v["coordz"][:])], axis=1)
+    conn = np.array(v["connect1"][:], np.int64) - 1
+    data = {nm: np.array(v[f"vals_elem_var{i + 1}eb1"][:][-1], np.float64) for i, nm in enumerate(names)}
+    f.close()
+    return coord, conn, data

@@ -166,7 +166,8 @@ def nuclide_names(materials_xml):
     return names
 
 
-def run_deck(input_path, xml_dir=None, grid_points=2000, device=0, batches=None, verbose=True, lib=None):
+def run_deck(input_path, xml_dir=None, grid_points=2000, device=0, batches=None, verbose=True, lib=None, rays=None,
+             particles=None):
     """Run a deck on the GPU through the Python host objects (study.py); nuclear data = one synthetic table
     per nuclide name of materials.xml (nucdata.library_for_names).  Returns the per-batch results."""
     import os
@@ -175,6 +176,10 @@ def run_deck(input_path, xml_dir=None, grid_points=2000, device=0, batches=None,
     if lib is None:
         lib = nucdata.library_for_names(nuclide_names(os.path.join(xml_dir, "materials.xml")), G=grid_points)
     mesh, library, blocks, mat_index, s, T0, n_batches, tallies, aux = read_input(input_path, xml_dir, lib)
+    if particles:
+        s.n_particles = int(particles)
+    if rays:
+        s.record_traces = 2  # [Outputs] RayTracingExodus with output_aux_data (test/tests/study/openmc_study.i:77-83)
     kernel = st.CollisionKernel(blocks=blocks, materials=[m + 1 for m in mat_index], temperature=T0,
                                 z_coord=s.z_coord if mesh.dim == 2 else None)
     inv_score = {v: k for k, v in cstructs.SCORE.items()}
@@ -190,6 +195,9 @@ def run_deck(input_path, xml_dir=None, grid_points=2000, device=0, batches=None,
         out.append(r)
         if verbose:
             print(f"Keff {r.keff} ({r.keff_std}) Generation: {r.k_generation}")  # MC OpenMCStudy.C:399-401
+    if rays:  # execute_on = final: the cached traces of the last batch
+        from . import exodus
+        exodus.write_ray_exodus(rays, study.ctx.traces())
     return study, out
 
 
@@ -200,5 +208,7 @@ if __name__ == "__main__":
     ap.add_argument("--xml-dir")
     ap.add_argument("--grid-points", type=int, default=2000)
     ap.add_argument("--batches", type=int)
+    ap.add_argument("--particles", type=int)
+    ap.add_argument("--rays", help="write the last batch's ray traces as an Exodus EDGE2 file (RayTracingExodus layout)")
     a = ap.parse_args()
-    run_deck(a.input, a.xml_dir, a.grid_points, batches=a.batches)
+    run_deck(a.input, a.xml_dir, a.grid_points, batches=a.batches, rays=a.rays, particles=a.particles)

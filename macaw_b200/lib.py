@@ -60,6 +60,7 @@ def load():
         "mcw_tally_shape": [vp, C.c_int, P(i64), P(i32), P(i32)],
         "mcw_get_history_records": [vp, vp, i64, P(i64)],
         "mcw_get_fission_bank": [vp, vp, i64, P(i64)],
+        "mcw_get_traces": [vp, vp, i64, P(i64)],
         "mcw_get_grid_index": [vp, C.c_int, vp, C.c_int],
         "mcw_xs_lookup": [vp, i64, vp, vp, vp],
         "mcw_xs_lookup_device": [vp, i64, vp, vp, vp, C.c_int, C.c_int, P(C.c_float)],
@@ -94,7 +95,7 @@ EXPORTS = ["mcw_create", "mcw_destroy", "mcw_last_error", "mcw_version", "mcw_se
            "mcw_get_source_bank", "mcw_transport_generation", "mcw_finalize_generation", "mcw_run_generation",
            "mcw_bank_count", "mcw_bank_device_ptr", "mcw_set_bank_window", "mcw_sample_bank", "mcw_finish_sampling",
            "mcw_sampled_device_ptr", "mcw_source_device_ptr", "mcw_set_source_count", "mcw_reduction_device_ptr",
-           "mcw_get_tally", "mcw_tally_shape", "mcw_get_history_records", "mcw_get_fission_bank",
+           "mcw_get_tally", "mcw_tally_shape", "mcw_get_history_records", "mcw_get_fission_bank", "mcw_get_traces",
            "mcw_get_grid_index", "mcw_xs_lookup", "mcw_xs_lookup_device", "mcw_trace_rays", "mcw_locate_points",
            "mcw_calculate_work", "mcw_test_division"]
 

@@ -67,7 +67,7 @@ def _load(name):
     lib.orc_locate_points.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.orc_sample_initial_source.argtypes = [vp]
     lib.orc_set_source_bank.argtypes = [vp, vp, C.c_int64]
-    for f in ("orc_get_source_bank", "orc_get_fission_bank", "orc_get_sampled", "orc_get_history_records"):
+    for f in ("orc_get_source_bank", "orc_get_fission_bank", "orc_get_sampled", "orc_get_history_records", "orc_get_traces"):
         getattr(lib, f).restype = C.c_int64
         getattr(lib, f).argtypes = [vp, vp, C.c_int64]
     lib.orc_transport_generation.argtypes = [vp, C.c_int, C.c_int]
@@ -315,6 +315,10 @@ class Oracle:
 
     def history_records(self):
         return self._get(self.L.orc_get_history_records, RECORD_DTYPE)
+
+    def traces(self):
+        from macaw_b200.cstructs import TRACE_DTYPE
+        return self._get(self.L.orc_get_traces, TRACE_DTYPE)
 
     def run_generation(self, batch, n_threads=1):
         res = GenerationResult()

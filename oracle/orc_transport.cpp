@@ -37,6 +37,7 @@ struct Problem
 
   std::vector<mcw_source_site> source_bank, fission_bank, sampled;
   std::vector<mcw_history_record> records;
+  std::vector<mcw_trace_point> traces; // cached trace points of the last generation (settings.record_traces == 2)
   int64_t bank_global_start = 0, bank_global_total = -1;
 
   // eigenvalue state (OMC simulation.cpp:253-276)
@@ -500,6 +501,21 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
   uint64_t hash = 0xcbf29ce484222325ull;
   int64_t last_elem = elem;
   TraceStats my;
+  // RT TraceData.h:15-29: the point and the ray's aux data (MC OpenMCStudy.C:190-197 order) cached per completed segment
+  auto cache_point = [&](int kind, V3 pt) {
+    if (S.record_traces != 2)
+      return;
+    mcw_trace_point r;
+    r.ray_id = ray_id;
+    r.seq = (int32_t)my.segments;
+    r.kind = kind;
+    r.point[0] = pt.x, r.point[1] = pt.y, r.point[2] = pt.z;
+    r.aux[0] = p.E, r.aux[1] = p.wgt, r.aux[2] = (double)p.n_progeny, r.aux[3] = (double)p.id;
+    r.aux[4] = (double)p.seeds[0], r.aux[5] = (double)p.seeds[1], r.aux[6] = (double)p.seeds[2], r.aux[7] = 0.0;
+#pragma omp critical(orc_traces)
+    P.traces.push_back(r);
+  };
+  cache_point(0, p.r);
 
   auto onSegment = [&](const SegmentCtx& c, V3& nstart, V3& ndir) -> int {
     int blk = P.mesh.block[c.elem];
@@ -528,7 +544,10 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
       for (int s = 0; s < 3; ++s)
         p.seeds[s] = seed_via_double(p.seeds[s]); // :157-159
     if (d > c.length)
+    {
+      cache_point(1, c.end);
       return 0;
+    }
     // collision point computed backwards from the exit point (:173-175)
     V3 pos = c.end - (c.length - d) * c.dir;
     if (S.is_2d)
@@ -550,7 +569,10 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
       for (int s = 0; s < 3; ++s)
         p.seeds[s] = seed_via_double(p.seeds[s]); // :217-219
     if (co.event == EV_ABSORB)
+    {
+      cache_point(3, c.end); // the killed ray still caches the end of this segment (RT TraceRay.C:1318-1364)
       return 1;
+    }
     // changeRayStartDirection (RT RayKernelBase.C:62-97 -> Ray.C:216-226)
     V3 nd = p.u;
     if (S.is_2d)
@@ -1052,6 +1074,17 @@ int64_t orc_get_sampled(void* h, mcw_source_site* s, int64_t cap)
     memcpy(s, P.sampled.data(), n * sizeof(mcw_source_site));
   return (int64_t)P.sampled.size();
 }
+int64_t orc_get_traces(void* h, mcw_trace_point* r, int64_t cap)
+{
+  Problem& P = *(Problem*)h;
+  std::sort(P.traces.begin(), P.traces.end(), [](const mcw_trace_point& a, const mcw_trace_point& b) {
+    return a.ray_id != b.ray_id ? a.ray_id < b.ray_id : (a.seq != b.seq ? a.seq < b.seq : a.kind < b.kind);
+  });
+  int64_t n = std::min<int64_t>(cap, (int64_t)P.traces.size());
+  if (r)
+    memcpy(r, P.traces.data(), n * sizeof(mcw_trace_point));
+  return (int64_t)P.traces.size();
+}
 int64_t orc_get_history_records(void* h, mcw_history_record* r, int64_t cap)
 {
   Problem& P = *(Problem*)h;
@@ -1069,6 +1102,7 @@ int orc_transport_generation(void* h, int batch, int n_threads)
   Problem& P = *(Problem*)h;
   const int64_t n = (int64_t)P.source_bank.size();
   P.fission_bank.clear();
+  P.traces.clear();
   P.fission_bank.reserve(3 * n);
   P.records.assign(n, mcw_history_record{});
   P.total_weight = 0.0;

@@ -207,6 +207,32 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
         assert so.sum() > 0
 
 
+@pytest.mark.parametrize("name,opts", [("infinite_medium_iso", EVENT), ("pin_cell_tet", MIXED), ("pin_cell_hex", FUSED),
+                                       ("assembly_quad", PUMP), ("beavrs_assembly", EVENT)])
+def test_cached_trace_points_bit_exact(oracle_bridge, ctx_factory, tmp_path, name, opts):
+    """mcw_get_traces (RT TraceData.h:15-29: the point and the ray's aux data cached per completed segment, what
+    RayTracingExodus writes) against the oracle: every record of every ray, byte for byte -- positions on element
+    sides, energies, the three stream seeds as doubles, progeny counts -- in event rounds, the fused tail and the
+    persistent kernel; then through the Exodus EDGE2 writer and back."""
+    from macaw_b200 import exodus
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, n_particles=300, record_traces=2)
+    for k, v in opts.items():
+        g.set_option(k, v)
+    o.sample_initial_source()
+    g.sample_initial_source()
+    for batch in (1, 2):
+        o.run_generation(batch)
+        g.run_generation(batch)
+        a, b = o.traces(), g.traces()
+        assert a.size == b.size and a.size > 300
+        assert a.tobytes() == b.tobytes()
+    path = str(tmp_path / "rays.e")
+    exodus.write_ray_exodus(path, b)
+    coord, conn, d = exodus.read_ray_exodus(path)
+    assert coord.shape[0] == b.size and conn.shape[0] == b.size - 300
+    assert np.array_equal(d["aux_energy"], b["aux"][:, 0][b["kind"] != 0])
+
+
 def test_e2e_host_buffers_round_trip(oracle_bridge, ctx_factory):
     """The reference-facing call sequence with HOST buffers: set_source_bank -> run -> get_source_bank."""
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, "pin_cell_tet")

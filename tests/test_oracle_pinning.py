@@ -227,6 +227,40 @@ def test_gold_ray_file_rng_facts(oracle_bridge, golden_dir):
     assert on_face.all()
 
 
+def test_ray_trace_output_has_the_structure_of_the_reference_gold(oracle_bridge, golden_dir, tmp_path):
+    """The `rays` output (RayTracingExodus, EDGE2 segments + aux data; RT RayTracingMeshOutput.C:252-580) of
+    examples/study_5x5 -- the shape of the reference's own study test -- written by macaw_b200/exodus.py from the
+    oracle's cached trace points, read back, and held to the same nuclear-data-free facts as the reference's gold
+    file: one polyline per particle with the reference's ray ids, every cached point on an element side, sources
+    interior, per-ray constant rounded source seed, exactly one tracking-stream step per same-energy record pair
+    except a ray's last (absorbed) record."""
+    from macaw_b200 import exodus, inputs, nucdata
+    from tests import ray_facts
+    L = oracle_bridge.lib(False)
+    g = np.load(os.path.join(golden_dir, "study_rays_gold.npz"))
+    gold = ray_facts.check(g["coord"], g["conn"], {k[4:]: g[k] for k in g.files if k.startswith("var_")}, 30, 3, L)
+    assert gold == {"segments": 1796, "rays": 30, "same_energy": 939, "one_step": 919, "final_other": 20}
+
+    deck = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "study_5x5")
+    lib = nucdata.library_for_names(inputs.nuclide_names(os.path.join(deck, "materials.xml")), G=400)
+    mesh, library, blocks, mat_index, s, T0, n_batches, tallies, aux = inputs.read_input(os.path.join(deck, "study.i"), deck, lib)
+    s.n_particles, s.record_traces = 30, 2
+    o = oracle_bridge.Oracle()
+    o.set_mesh(mesh, np.asarray(blocks, np.int32))
+    o.set_library(library, mat_index)
+    o.set_settings(s)
+    o.sample_initial_source()
+    for b in (1, 2, 3):
+        o.run_generation(b)
+    path = str(tmp_path / "rays.e")
+    exodus.write_ray_exodus(path, o.traces())
+    coord, conn, d = exodus.read_ray_exodus(path)
+    assert list(d) == list(exodus.RAY_VAR_ORDER) == [str(n) for n in g["names"]]  # same variables, same order
+    mine = ray_facts.check(coord, conn, d, 30, 3, L)
+    assert mine["rays"] == 30 and mine["segments"] > 300 and mine["same_energy"] > 100
+    assert mine["one_step"] + mine["final_other"] == mine["same_energy"]
+
+
 def test_isotropic_in_lab_direction_and_budget(oracle_bridge):
     """OMC physics.cpp:706-718 + distribution_multi.cpp:73-79: a scatter off an <isotropic> nuclide draws
     two numbers from the tracking stream -- phi = 2 pi xi_1 first, then mu = 2 xi_2 - 1 -- and the new
