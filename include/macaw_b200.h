@@ -77,6 +77,28 @@ typedef struct mcw_source_site
   int64_t progeny_id;
 } mcw_source_site;
 
+/* Distributions tabulated on a grid of incoming energies, the layout OpenMC's HDF5 files use for angular
+ * distributions ("angle": `energy` + `mu` (3, N) with `offsets` / `interpolation`, OMC distribution_angle.cpp:20-63)
+ * and for continuous tabular outgoing-energy laws ("continuous": `energy` + `distribution` (3, N) with `offsets` /
+ * `interpolation` / `n_discrete_lines`, OMC distribution_energy.cpp:56-148): distribution k holds the points
+ * [offset[k], offset[k + 1]) of x (mu or E_out), pdf and cdf.  The cdf is used as tabulated (as the reference does to
+ * match ACE data) and must end at exactly 1.  n_energy = 0: no table. */
+typedef struct mcw_tabular2d
+{
+  int32_t n_energy;
+  int32_t histogram_in_energy;  /* continuous tabular only: the one incoming-energy interpolation region is histogram */
+  const double* energy;         /* [n_energy] incoming energies, increasing */
+  const int32_t* offset;        /* [n_energy + 1] */
+  const int32_t* interpolation; /* [n_energy] 1 = histogram, 2 = linear-linear */
+  const int32_t* n_discrete;    /* [n_energy] discrete lines leading each distribution (continuous tabular), or NULL */
+  const double* x;
+  const double* pdf;
+  const double* cdf;
+} mcw_tabular2d;
+
+#define MCW_LAW_LEVEL 0              /* LevelInelastic, OMC distribution_energy.cpp:42-51 */
+#define MCW_LAW_CONTINUOUS_TABULAR 1 /* ContinuousTabular, OMC distribution_energy.cpp:150-275 */
+
 /* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
  * (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
  * col = total, absorption, fission, nu-fission, photon-production.  Reactions present: elastic
@@ -104,6 +126,15 @@ typedef struct mcw_nuclide_desc
   double delayed_theta[MCW_MAX_DELAYED_GROUPS]; /* Maxwell temperature per group, eV */
   double watt_a, watt_b;                        /* prompt Watt spectrum parameters */
   double q_fission;                             /* fission Q value, eV (kappa-fission score) */
+  /* Secondary distributions beyond "isotropic in the centre of mass" (all optional, zero = absent):
+   * tabular angular distributions of the elastic and of the inelastic reaction (AngleDistribution::sample, OMC
+   * distribution_angle.cpp:65-95, used by elastic_scatter physics.cpp:749-757 and UncorrelatedAngleEnergy::sample
+   * secondary_uncorrelated.cpp:54-68), and the outgoing-energy law of the inelastic reaction. */
+  mcw_tabular2d elastic_angle;
+  mcw_tabular2d inelastic_angle;
+  int32_t inelastic_law;                        /* MCW_LAW_LEVEL (default) or MCW_LAW_CONTINUOUS_TABULAR */
+  int32_t inelastic_in_cm;                      /* scatter_in_cm_ of the inelastic reaction (level: always 1) */
+  mcw_tabular2d inelastic_energy;               /* the table of MCW_LAW_CONTINUOUS_TABULAR */
 } mcw_nuclide_desc;
 
 /* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab
@@ -305,7 +336,8 @@ int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy,
 /* Parity / diagnostics output (RT TraceData.h:20-68 cached traces are the reference analogue). */
 int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n);
 /* Cached trace points of the last generation, ordered by (ray_id, seq); *n = how many were cached (may exceed
- * capacity; the device buffer holds 256 points per history of this rank, at most 2^24). */
+ * capacity).  The device buffer holds 2048 points per history of this rank, at most 2^23; a generation that
+ * caches more fails with MCW_E_ALLOCATE -- tracing is a parity / visualisation output for small runs. */
 int mcw_get_traces(mcw_handle h, mcw_trace_point* out, int64_t capacity, int64_t* n);
 int mcw_get_fission_bank(mcw_handle h, mcw_source_site* sites, int64_t capacity, int64_t* n);
 int mcw_get_grid_index(mcw_handle h, int i_nuclide, int32_t* out, int n /* n_log_bins + 1 */);

@@ -25,12 +25,56 @@ struct HostTally
   int n_realizations = 0;
 };
 
+struct HostTable // one mcw_tabular2d, copied
+{
+  std::vector<double> energy, x, p, c;
+  std::vector<int32_t> off, interp, ndisc;
+  int hist = 0;
+};
+
 struct HostNuclide
 {
   McwNucParams prm;
   std::vector<double> energy, xs5, elastic, inelastic_full;
   std::vector<int32_t> grid_index;
+  HostTable el_angle, inel_angle, inel_energy;
 };
+
+// copies and checks one table of the descriptor; returns an error text or nullptr
+static const char* take_table(const mcw_tabular2d& t, HostTable& out, bool continuous)
+{
+  out = HostTable();
+  if (t.n_energy == 0)
+    return nullptr;
+  if (t.n_energy < 2 || !t.energy || !t.offset || !t.interpolation || !t.x || !t.pdf || !t.cdf)
+    return "tabulated distribution incomplete (needs >= 2 incoming energies and all arrays)";
+  const int n = t.n_energy;
+  out.energy.assign(t.energy, t.energy + n);
+  out.off.assign(t.offset, t.offset + n + 1);
+  out.interp.assign(t.interpolation, t.interpolation + n);
+  out.ndisc.assign(n, 0);
+  if (continuous && t.n_discrete)
+    out.ndisc.assign(t.n_discrete, t.n_discrete + n);
+  out.hist = continuous ? (t.histogram_in_energy != 0) : 0;
+  for (int k = 0; k < n; ++k)
+  {
+    if (k && !(out.energy[k] > out.energy[k - 1]))
+      return "tabulated distribution: incoming energies must increase";
+    const int m = out.off[k + 1] - out.off[k];
+    if (out.off[k] < 0 || m < 2 || out.ndisc[k] < 0 || out.ndisc[k] > m - 2)
+      return "tabulated distribution: every distribution needs at least two continuous points";
+    if (out.interp[k] != 1 && out.interp[k] != 2)
+      // OMC distribution.cpp:201-205 "Only histogram and linear-linear interpolation ..."
+      return "Only histogram and linear-linear interpolation for tabular distribution is supported.";
+    if (t.cdf[out.off[k + 1] - 1] != 1.0)
+      return "tabulated distribution: the cdf must end at exactly 1";
+  }
+  const int total = out.off[n];
+  out.x.assign(t.x, t.x + total);
+  out.p.assign(t.pdf, t.pdf + total);
+  out.c.assign(t.cdf, t.cdf + total);
+  return nullptr;
+}
 
 template <int TYPE>
 struct Topo;
@@ -458,6 +502,20 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
       for (int k = N.prm.inel_thr; k < G; ++k)
         N.inelastic_full[k] = d[i].inelastic[k - N.prm.inel_thr];
     }
+    N.prm.inel_law = d[i].inelastic_law;
+    N.prm.inel_in_cm = N.prm.inel_law == MCW_LAW_LEVEL ? 1 : (d[i].inelastic_in_cm != 0);
+    if (N.prm.inel_law != MCW_LAW_LEVEL && N.prm.inel_law != MCW_LAW_CONTINUOUS_TABULAR)
+      // OMC secondary_uncorrelated.cpp:47 "Energy distribution type '...' not implemented."
+      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_library: inelastic energy law not implemented (level, continuous tabular)");
+    const char* bad = take_table(d[i].elastic_angle, N.el_angle, false);
+    if (!bad)
+      bad = take_table(d[i].inelastic_angle, N.inel_angle, false);
+    if (!bad)
+      bad = take_table(d[i].inelastic_energy, N.inel_energy, true);
+    if (!bad && N.prm.n_inel && N.prm.inel_law == MCW_LAW_CONTINUOUS_TABULAR && N.inel_energy.energy.empty())
+      bad = "continuous tabular law without its table";
+    if (bad)
+      return fail(h, MCW_E_INVALID_ARGUMENT, std::string("mcw_set_library: ") + bad);
     h->nuclides.push_back(std::move(N));
   }
   h->have_lib = true;
@@ -589,8 +647,30 @@ static int prepare(mcw_handle h)
   std::vector<double> energy, xs4, el_inel;
   std::vector<int32_t> grid_index;
   std::vector<McwNucParams> prm;
+  std::vector<double> tab_energy, tab_x, tab_p, tab_c;
+  std::vector<int32_t> tab_off, tab_end, tab_interp, tab_ndisc;
+  auto add_table = [&](const HostTable& t, int32_t& first, int32_t& count) {
+    first = (int32_t)tab_energy.size();
+    count = (int32_t)t.energy.size();
+    const int32_t base = (int32_t)tab_x.size();
+    for (size_t k = 0; k < t.energy.size(); ++k)
+    {
+      tab_energy.push_back(t.energy[k]);
+      tab_off.push_back(base + t.off[k]);
+      tab_end.push_back(base + t.off[k + 1]);
+      tab_interp.push_back(t.interp[k]);
+      tab_ndisc.push_back(t.ndisc[k]);
+    }
+    tab_x.insert(tab_x.end(), t.x.begin(), t.x.end());
+    tab_p.insert(tab_p.end(), t.p.begin(), t.p.end());
+    tab_c.insert(tab_c.end(), t.c.begin(), t.c.end());
+  };
   for (auto& n : h->nuclides)
   {
+    add_table(n.el_angle, n.prm.el_ang_first, n.prm.el_ang_n);
+    add_table(n.inel_angle, n.prm.inel_ang_first, n.prm.inel_ang_n);
+    add_table(n.inel_energy, n.prm.inel_en_first, n.prm.inel_en_n);
+    n.prm.inel_en_hist = n.inel_energy.hist;
     const int G = n.prm.G;
     energy.insert(energy.end(), n.energy.begin(), n.energy.end());
     for (int k = 0; k < G; ++k)
@@ -664,6 +744,20 @@ static int prepare(mcw_handle h)
   P.lib.mat_e0 = d_me0;
   P.lib.mat_e1 = d_me1;
   CK(dev_upload(h, &d_mfis, mat_fis));
+  {
+    double *d_te, *d_tx, *d_tp, *d_tc;
+    int32_t *d_to, *d_tn, *d_ti, *d_td;
+    CK(dev_upload(h, &d_te, tab_energy));
+    CK(dev_upload(h, &d_tx, tab_x));
+    CK(dev_upload(h, &d_tp, tab_p));
+    CK(dev_upload(h, &d_tc, tab_c));
+    CK(dev_upload(h, &d_to, tab_off));
+    CK(dev_upload(h, &d_tn, tab_end));
+    CK(dev_upload(h, &d_ti, tab_interp));
+    CK(dev_upload(h, &d_td, tab_ndisc));
+    P.lib.tab_energy = d_te, P.lib.tab_x = d_tx, P.lib.tab_p = d_tp, P.lib.tab_c = d_tc;
+    P.lib.tab_off = d_to, P.lib.tab_end = d_tn, P.lib.tab_interp = d_ti, P.lib.tab_ndisc = d_td;
+  }
   P.lib.energy = d_energy;
   P.lib.xs4 = d_xs4;
   P.lib.el_inel = d_el;
@@ -960,7 +1054,7 @@ static int prepare(mcw_handle h)
     double** dt[] = {&p.tx, &p.ty, &p.tz};
     for (auto q : dt)
       CK(dev_alloc(h, q, n));
-    P.trace_capacity = std::min<int64_t>(256 * n, (int64_t)1 << 24);
+    P.trace_capacity = std::min<int64_t>(2048 * n, (int64_t)1 << 23); // 104 B each: at most 0.9 GB
     CK(dev_alloc(h, &P.trace, P.trace_capacity));
   }
   {
@@ -1611,7 +1705,10 @@ int mcw_get_traces(mcw_handle h, mcw_trace_point* out, int64_t capacity, int64_t
     return fail(h, MCW_E_NOT_READY, "trace points are cached only with settings.record_traces = 2");
   CK(cudaSetDevice(h->device));
   *n = (int64_t)h->h_counters->n_trace; // counters of the last generation (copied at the end of transport)
-  const int64_t have = std::min<int64_t>(*n, h->P.trace_capacity);
+  if (*n > h->P.trace_capacity)
+    return fail(h, MCW_E_ALLOCATE, "the generation cached " + std::to_string(*n) + " trace points, the buffer holds " +
+                                       std::to_string(h->P.trace_capacity) + " (2048 per history, at most 2^23): trace fewer histories");
+  const int64_t have = *n;
   if (out && capacity > 0 && have > 0)
   {
     std::vector<mcw_trace_point> all((size_t)have);

@@ -334,9 +334,9 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     double elastic = (1.0 - mx.f) * r0.x + mx.f * r1.x;
     bool can_inelastic = nuc.n_inel > 0 && mx.i_grid >= nuc.inel_thr;
     if (elastic > cut || !can_inelastic)
-      mcw_elastic_scatter(nuc, c);
+      mcw_elastic_scatter(L, nuc, c);
     else
-      mcw_inelastic_scatter(nuc, c);
+      mcw_inelastic_scatter(L, nuc, c);
     if (L.mat_iso[q_nuc]) // isotropic-in-lab override (OMC physics.cpp:706-718): phi, then mu
       c.u = mcw_isotropic_direction(c.seed);
     if (c.E != E_last) // OMC physics.cpp:140-144

@@ -196,8 +196,174 @@ MCW_D V3 mcw_sample_cxs_target_velocity(double awr, double E, V3 u, double kT, u
   return vt * mcw_rotate_angle(u, mu, seed);
 }
 
-// OMC physics.cpp:721-786, isotropic-in-CM elastic, free gas below 400 kT (:804-835)
-MCW_D void mcw_elastic_scatter(const McwNucParams& nuc, ColState& p)
+// ------------------------------------------------------------------ tabulated secondary distributions
+// lower_bound_index (OMC search.h:14-20) on the incoming-energy grid of one table
+MCW_D int mcw_tab_energy_bin(const double* __restrict__ en, int n, double E)
+{
+  if (__ldg(en) == E)
+    return 0;
+  int lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(en + mid) < E)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo - 1;
+}
+
+// Tabular::sample (OMC distribution.cpp:223-266) of distribution `e` of the pools
+MCW_D double mcw_tabular_sample(const McwLibraryDev& L, int e, uint64_t& seed)
+{
+  const int b = __ldg(L.tab_off + e), n = __ldg(L.tab_end + e) - b;
+  const double* __restrict__ x = L.tab_x + b;
+  const double* __restrict__ pd = L.tab_p + b;
+  const double* __restrict__ cd = L.tab_c + b;
+  const double c = mcw_prn(seed);
+  double c_i = __ldg(cd);
+  int i;
+  for (i = 0; i < n - 1; ++i)
+  {
+    const double c1 = __ldg(cd + i + 1);
+    if (c <= c1)
+      break;
+    c_i = c1;
+  }
+  const double x_i = __ldg(x + i), p_i = __ldg(pd + i);
+  if (__ldg(L.tab_interp + e) == 1)
+    return p_i > 0.0 ? x_i + (c - c_i) / p_i : x_i;
+  const double x_i1 = __ldg(x + i + 1), p_i1 = __ldg(pd + i + 1);
+  const double m = (p_i1 - p_i) / (x_i1 - x_i);
+  if (m == 0.0)
+    return x_i + (c - c_i) / p_i;
+  return x_i + (sqrt(fmax(0.0, p_i * p_i + 2 * m * (c - c_i))) - p_i) / m;
+}
+
+// AngleDistribution::sample (OMC distribution_angle.cpp:65-95)
+MCW_D double mcw_angle_sample(const McwLibraryDev& L, int first, int n, double E, uint64_t& seed)
+{
+  const double* __restrict__ en = L.tab_energy + first;
+  int i;
+  double r;
+  if (E < __ldg(en))
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E > __ldg(en + n - 1))
+  {
+    i = n - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = mcw_tab_energy_bin(en, n, E);
+    r = (E - __ldg(en + i)) / (__ldg(en + i + 1) - __ldg(en + i));
+  }
+  if (r > mcw_prn(seed))
+    ++i;
+  double mu = mcw_tabular_sample(L, first + i, seed);
+  if (fabs(mu) > 1.0)
+    mu = copysign(1.0, mu);
+  return mu;
+}
+
+// ContinuousTabular::sample (OMC distribution_energy.cpp:150-275)
+MCW_D double mcw_continuous_tabular_sample(const McwLibraryDev& L, int first, int n_in, bool histogram_interp, double E,
+                                           uint64_t& seed)
+{
+  const double* __restrict__ en = L.tab_energy + first;
+  int i;
+  double r;
+  if (E < __ldg(en))
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E > __ldg(en + n_in - 1))
+  {
+    i = n_in - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = mcw_tab_energy_bin(en, n_in, E);
+    r = (E - __ldg(en + i)) / (__ldg(en + i + 1) - __ldg(en + i));
+  }
+  int l;
+  if (histogram_interp)
+    l = i;
+  else
+    l = r > mcw_prn(seed) ? i + 1 : i;
+  // interpolation for energy E1 and EK
+  const int b_i = __ldg(L.tab_off + first + i), e_i = __ldg(L.tab_end + first + i);
+  const int b_i1 = __ldg(L.tab_off + first + i + 1), e_i1 = __ldg(L.tab_end + first + i + 1);
+  const double E_i_1 = __ldg(L.tab_x + b_i + __ldg(L.tab_ndisc + first + i)), E_i_K = __ldg(L.tab_x + e_i - 1);
+  const double E_i1_1 = __ldg(L.tab_x + b_i1 + __ldg(L.tab_ndisc + first + i + 1)), E_i1_K = __ldg(L.tab_x + e_i1 - 1);
+  const double E_1 = E_i_1 + r * (E_i1_1 - E_i_1);
+  const double E_K = E_i_K + r * (E_i1_K - E_i_K);
+  // outgoing energy bin of distribution l
+  const int b = __ldg(L.tab_off + first + l), n_energy_out = __ldg(L.tab_end + first + l) - b;
+  const int n_discrete = __ldg(L.tab_ndisc + first + l);
+  const double* __restrict__ eo = L.tab_x + b;
+  const double* __restrict__ pd = L.tab_p + b;
+  const double* __restrict__ cd = L.tab_c + b;
+  const double r1 = mcw_prn(seed);
+  double c_k = __ldg(cd);
+  int k = 0, end = n_energy_out - 2;
+  for (int j = 0; j < n_discrete; ++j) // discrete portion
+  {
+    k = j;
+    c_k = __ldg(cd + k);
+    if (r1 < c_k)
+    {
+      end = j;
+      break;
+    }
+  }
+  for (int j = n_discrete; j < end; ++j) // continuous portion
+  {
+    k = j;
+    const double c_k1 = __ldg(cd + k + 1);
+    if (r1 < c_k1)
+      break;
+    k = j + 1;
+    c_k = c_k1;
+  }
+  const double E_l_k = __ldg(eo + k), p_l_k = __ldg(pd + k);
+  double E_out = E_l_k;
+  if (__ldg(L.tab_interp + first + l) == 1)
+  {
+    if (p_l_k > 0.0 && k >= n_discrete)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+  }
+  else
+  {
+    const double E_l_k1 = __ldg(eo + k + 1), p_l_k1 = __ldg(pd + k + 1);
+    if (E_l_k != E_l_k1)
+    {
+      const double frac = (p_l_k1 - p_l_k) / (E_l_k1 - E_l_k);
+      if (frac == 0.0)
+        E_out = E_l_k + (r1 - c_k) / p_l_k;
+      else
+        E_out = E_l_k + (sqrt(fmax(0.0, p_l_k * p_l_k + 2.0 * frac * (r1 - c_k))) - p_l_k) / frac;
+    }
+  }
+  // interpolate between incident energy bins i and i + 1
+  if (!histogram_interp && n_energy_out > 1 && k >= n_discrete)
+  {
+    if (l == i)
+      return E_1 + (E_out - E_i_1) * (E_K - E_1) / (E_i_K - E_i_1);
+    return E_1 + (E_out - E_i1_1) * (E_K - E_1) / (E_i1_K - E_i1_1);
+  }
+  return E_out;
+}
+
+// OMC physics.cpp:721-786: elastic scattering, angle from the nuclide's tabular distribution when it has one
+// (:749-757) else isotropic in CM; free gas below 400 kT (:804-835)
+MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p)
 {
   double vel = sqrt(p.E);
   double awr = nuc.awr;
@@ -208,7 +374,11 @@ MCW_D void mcw_elastic_scatter(const McwNucParams& nuc, ColState& p)
   V3 v_cm = (v_n + awr * v_t) / (awr + 1.0);
   v_n = v_n - v_cm;
   vel = norm(v_n);
-  double mu_cm = mcw_uniform(-1., 1., p.seed);
+  double mu_cm;
+  if (nuc.el_ang_n > 0)
+    mu_cm = mcw_angle_sample(L, nuc.el_ang_first, nuc.el_ang_n, p.E, p.seed);
+  else
+    mu_cm = mcw_uniform(-1., 1., p.seed);
   V3 u_cm = v_n / vel;
   v_n = vel * mcw_rotate_angle(u_cm, mu_cm, p.seed);
   v_n = v_n + v_cm;
@@ -217,16 +387,29 @@ MCW_D void mcw_elastic_scatter(const McwNucParams& nuc, ColState& p)
   p.u = v_n / vel;
 }
 
-// OMC physics.cpp:1073-1120 with LevelInelastic (distribution_energy.cpp:48-51), CM system
-MCW_D void mcw_inelastic_scatter(const McwNucParams& nuc, ColState& p)
+// OMC physics.cpp:1073-1120 inelastic_scatter over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68):
+// cosine from the reaction's tabular angle distribution or uniform, outgoing energy from LevelInelastic
+// (distribution_energy.cpp:48-51) or ContinuousTabular (:150-275), then CM -> LAB if the reaction scatters in CM
+MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p)
 {
   double E_in = p.E;
-  double mu = mcw_uniform(-1., 1., p.seed);
-  double E = nuc.inel_ratio * (E_in - nuc.inel_E);
-  double E_cm = E;
-  double A = nuc.awr;
-  E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
-  mu = mu * sqrt(E_cm / E) + 1.0 / (A + 1.0) * sqrt(E_in / E);
+  double mu;
+  if (nuc.inel_ang_n > 0)
+    mu = mcw_angle_sample(L, nuc.inel_ang_first, nuc.inel_ang_n, E_in, p.seed);
+  else
+    mu = mcw_uniform(-1., 1., p.seed);
+  double E;
+  if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+    E = mcw_continuous_tabular_sample(L, nuc.inel_en_first, nuc.inel_en_n, nuc.inel_en_hist != 0, E_in, p.seed);
+  else
+    E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  if (nuc.inel_in_cm)
+  {
+    double E_cm = E;
+    double A = nuc.awr;
+    E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
+    mu = mu * sqrt(E_cm / E) + 1.0 / (A + 1.0) * sqrt(E_in / E);
+  }
   if (fabs(mu) > 1.0)
     mu = copysign(1.0, mu);
   p.E = E;

@@ -34,7 +34,12 @@ struct McwNucParams
   int32_t fissionable;
   int32_t n_inel, inel_thr;
   int32_t n_precursor;
-  int32_t pad;
+  int32_t inel_law;            // MCW_LAW_LEVEL / MCW_LAW_CONTINUOUS_TABULAR
+  // tabulated secondary distributions: first incoming energy in McwLibraryDev::tab_* and how many (0 = absent)
+  int32_t el_ang_first, el_ang_n;
+  int32_t inel_ang_first, inel_ang_n;
+  int32_t inel_en_first, inel_en_n;
+  int32_t inel_en_hist, inel_in_cm; // ContinuousTabular: histogram interpolation in incoming energy; scatter_in_cm_
 };
 
 struct McwLibraryDev
@@ -51,6 +56,15 @@ struct McwLibraryDev
   const double* mat_e0;      // first / last grid energy of the entry's nuclide (staged lookup)
   const double* mat_e1;
   const int32_t* mat_fissionable;
+  // pools of the tabulated secondary distributions of all nuclides (mcw_tabular2d): per incoming energy its
+  // value, the ABSOLUTE first / one-past-last point in tab_x / tab_p / tab_c, the interpolation and the number
+  // of leading discrete lines
+  const double* tab_energy;
+  const int32_t* tab_off; // [n_tab_energy + 1 per table, tables back to back: entry e -> points [tab_off[e], tab_end[e])]
+  const int32_t* tab_end;
+  const int32_t* tab_interp;
+  const int32_t* tab_ndisc;
+  const double *tab_x, *tab_p, *tab_c;
   int32_t n_nuc, n_mat, M;
   double E_min, E_max, log_spacing;
 };

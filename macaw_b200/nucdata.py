@@ -39,6 +39,74 @@ class Nuclide:
     watt_b: float = 2.249e-6
     q_fission: float = 0.0
     kT: float = KT_ROOM
+    # optional tabulated secondary distributions (Tabular2D below); None = isotropic in CM / level law
+    elastic_angle: object = None
+    inelastic_angle: object = None
+    inelastic_energy: object = None  # ContinuousTabular law of the inelastic reaction (then inelastic_in_cm as given)
+    inelastic_in_cm: bool = True
+
+
+@dataclass
+class Tabular2D:
+    """Distributions on a grid of incoming energies (mcw_tabular2d): OpenMC's "angle" / "continuous" layouts."""
+    energy: np.ndarray
+    offset: np.ndarray         # (n_energy + 1,)
+    interpolation: np.ndarray  # (n_energy,) 1 histogram, 2 lin-lin
+    x: np.ndarray
+    pdf: np.ndarray
+    cdf: np.ndarray
+    n_discrete: np.ndarray = None
+    histogram_in_energy: bool = False
+
+
+def _tabulated_pdf(rng, x, interp):
+    """A positive pdf on the points x with the cdf the reference's Tabular / CTTable would rebuild from it,
+    normalised so that cdf[-1] == 1.0 exactly (its own normalisation is then the identity)."""
+    p = rng.uniform(0.2, 1.0, x.size)
+    c = np.zeros(x.size)
+    for i in range(1, x.size):
+        c[i] = c[i - 1] + (p[i - 1] if interp == 1 else 0.5 * (p[i - 1] + p[i])) * (x[i] - x[i - 1])
+    p, c = p / c[-1], c / c[-1]
+    c[-1] = 1.0
+    return p, c
+
+
+def make_angle_table(rng, e_lo, e_hi, n_energy=5) -> Tabular2D:
+    """Anisotropy growing with energy, alternating histogram / lin-lin distributions, 4-17 cosines each."""
+    energy = np.exp(np.linspace(np.log(e_lo), np.log(e_hi), n_energy))
+    xs, ps, cs, off, interp = [], [], [], [0], []
+    for k in range(n_energy):
+        n = int(rng.integers(4, 18))
+        mu = np.sort(np.concatenate([[-1.0, 1.0], rng.uniform(-1, 1, n - 2)]))
+        it = 1 if k % 2 else 2
+        p, c = _tabulated_pdf(rng, mu, it)
+        xs.append(mu); ps.append(p); cs.append(c); interp.append(it); off.append(off[-1] + n)
+    return Tabular2D(energy, np.array(off, np.int32), np.array(interp, np.int32), np.concatenate(xs), np.concatenate(ps),
+                     np.concatenate(cs))
+
+
+def make_continuous_table(rng, e_thr, e_hi, n_energy=4, discrete=True) -> Tabular2D:
+    """Outgoing energies up to ~0.8 (E_in - threshold) + a little; the first distributions carry discrete lines."""
+    energy = np.exp(np.linspace(np.log(e_thr), np.log(e_hi), n_energy))
+    xs, ps, cs, off, interp, nd = [], [], [], [0], [], []
+    for k in range(n_energy):
+        n_d = int(rng.integers(0, 3)) if (discrete and k < n_energy - 1) else 0
+        n_c = int(rng.integers(3, 12))
+        top = 0.8 * (energy[k] - 0.5 * e_thr) + 1.0e3
+        e_c = np.sort(np.concatenate([[1.0e-2 * top, top], rng.uniform(1.0e-2 * top, top, n_c - 2)]))
+        it = 1 if k % 2 == 0 else 2
+        p_c, c_c = _tabulated_pdf(rng, e_c, it)
+        w_d = rng.uniform(0.02, 0.1, n_d)  # probability of each discrete line
+        e_d = np.sort(rng.uniform(0.05 * top, 0.5 * top, n_d))
+        scale = 1.0 - w_d.sum()
+        p = np.concatenate([w_d, p_c * scale])
+        # CTTable cdf (OMC distribution_energy.cpp:115-141): running sum over the lines, then the continuous part
+        c = np.concatenate([np.cumsum(w_d), w_d.sum() + c_c * scale])
+        c[-1] = 1.0
+        xs.append(np.concatenate([e_d, e_c])); ps.append(p); cs.append(c); interp.append(it); nd.append(n_d)
+        off.append(off[-1] + n_d + n_c)
+    return Tabular2D(energy, np.array(off, np.int32), np.array(interp, np.int32), np.concatenate(xs), np.concatenate(ps),
+                     np.concatenate(cs), np.array(nd, np.int32), False)
 
 
 @dataclass
@@ -148,9 +216,13 @@ _BASE = [
 ]
 
 
-def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000) -> Library:
+def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000, tabular=False) -> Library:
     """First 9 nuclides are the named ones above; the rest are generic structural / fission-product
-    like nuclides so the BEAVRS shape (91 nuclides) can be reproduced."""
+    like nuclides so the BEAVRS shape (91 nuclides) can be reproduced.  tabular = True gives the nuclides
+    tabulated secondary distributions (drawn from a separate stream, so the cross sections are the same):
+    angular distributions of the elastic reaction for every second nuclide and of the inelastic one for every
+    third, and a ContinuousTabular law (alternately in the CM and the LAB system) instead of the level law for
+    every second nuclide that has an inelastic reaction."""
     rng = np.random.Generator(np.random.PCG64(seed))
     nucs = []
     for i in range(n_nuclides):
@@ -164,6 +236,19 @@ def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000) -> Library:
                       inel=float(rng.uniform(0, 2)), inel_E=float(np.exp(rng.uniform(np.log(5e4), np.log(3e6)))))
         g = G if np.isscalar(G) else int(G[i])
         nucs.append(make_nuclide(name, awr, g, rng, **kw))
+    if tabular:
+        trng = np.random.Generator(np.random.PCG64([seed, 77]))
+        k_inel = 0
+        for i, n in enumerate(nucs):
+            if i % 2 == 0:
+                n.elastic_angle = make_angle_table(trng, 1.0e2 * (1 + i), 1.5e7)
+            if n.inelastic.size:
+                if i % 3 == 0:
+                    n.inelastic_angle = make_angle_table(trng, n.inel_threshold_energy, 1.8e7, 4)
+                if k_inel % 2 == 0:
+                    n.inelastic_energy = make_continuous_table(trng, n.inel_threshold_energy, 1.9e7, discrete=k_inel % 4 == 0)
+                    n.inelastic_in_cm = k_inel % 4 != 0
+                k_inel += 1
     mats = standard_materials(n_nuclides)
     return Library(nucs, mats, n_log_bins)
 
@@ -230,6 +315,27 @@ def infinite_medium_library(G=2000, seed=1) -> Library:
 
 
 # ---- ctypes mirror of include/macaw_b200.h ---------------------------------------------------------
+class Tabular2DDesc(C.Structure):
+    _fields_ = [("n_energy", C.c_int32), ("histogram_in_energy", C.c_int32), ("energy", C.c_void_p), ("offset", C.c_void_p),
+                ("interpolation", C.c_void_p), ("n_discrete", C.c_void_p), ("x", C.c_void_p), ("pdf", C.c_void_p),
+                ("cdf", C.c_void_p)]
+
+
+def _pack_table(d: Tabular2DDesc, t, keep):
+    if t is None:
+        return
+    arrs = [np.ascontiguousarray(t.energy, np.float64), np.ascontiguousarray(t.offset, np.int32),
+            np.ascontiguousarray(t.interpolation, np.int32), np.ascontiguousarray(t.x, np.float64),
+            np.ascontiguousarray(t.pdf, np.float64), np.ascontiguousarray(t.cdf, np.float64)]
+    keep += arrs
+    d.n_energy, d.histogram_in_energy = arrs[0].size, int(t.histogram_in_energy)
+    d.energy, d.offset, d.interpolation, d.x, d.pdf, d.cdf = [a.ctypes.data for a in arrs]
+    if t.n_discrete is not None:
+        nd = np.ascontiguousarray(t.n_discrete, np.int32)
+        keep.append(nd)
+        d.n_discrete = nd.ctypes.data
+
+
 class NuclideDesc(C.Structure):
     _fields_ = [("n_grid", C.c_int32), ("fissionable", C.c_int32), ("awr", C.c_double), ("kT", C.c_double),
                 ("energy", C.c_void_p), ("xs", C.c_void_p), ("elastic", C.c_void_p),
@@ -237,7 +343,9 @@ class NuclideDesc(C.Structure):
                 ("inel_threshold_energy", C.c_double), ("inel_mass_ratio", C.c_double),
                 ("nu_poly", C.c_double * 2), ("n_precursor", C.c_int32), ("reserved0", C.c_int32),
                 ("delayed_yield", C.c_double * MAX_DELAYED_GROUPS), ("delayed_theta", C.c_double * MAX_DELAYED_GROUPS),
-                ("watt_a", C.c_double), ("watt_b", C.c_double), ("q_fission", C.c_double)]
+                ("watt_a", C.c_double), ("watt_b", C.c_double), ("q_fission", C.c_double),
+                ("elastic_angle", Tabular2DDesc), ("inelastic_angle", Tabular2DDesc), ("inelastic_law", C.c_int32),
+                ("inelastic_in_cm", C.c_int32), ("inelastic_energy", Tabular2DDesc)]
 
 
 class MaterialDesc(C.Structure):
@@ -267,6 +375,11 @@ def pack_library(lib: Library):
             d.delayed_yield[g] = float(n.delayed_yield[g])
             d.delayed_theta[g] = float(n.delayed_theta[g])
         d.watt_a, d.watt_b, d.q_fission = n.watt_a, n.watt_b, n.q_fission
+        _pack_table(d.elastic_angle, getattr(n, "elastic_angle", None), keep)
+        _pack_table(d.inelastic_angle, getattr(n, "inelastic_angle", None), keep)
+        _pack_table(d.inelastic_energy, getattr(n, "inelastic_energy", None), keep)
+        d.inelastic_law = 1 if getattr(n, "inelastic_energy", None) is not None else 0
+        d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
     md = (MaterialDesc * len(lib.materials))()
     for d, m in zip(md, lib.materials):
         idx = np.ascontiguousarray(m.nuclides, np.int32)
