@@ -136,6 +136,8 @@ def ref_lib():
         r.ref_library_reset.argtypes = []
         r.ref_add_nuclide.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int, f64p, f64p, f64p, f64p, C.c_int, C.c_int,
                                       f64p, C.c_double, C.c_double, f64p, C.c_int, f64p, f64p, C.c_double, C.c_double, C.c_double]
+        if hasattr(r, "ref_stage_tables"):
+            r.ref_stage_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         r.ref_finish_library.argtypes = [C.c_int]
         r.ref_nuclide_tables.argtypes = [C.c_int, f64p, C.c_void_p, C.c_void_p, C.c_void_p]
         r.ref_add_material.argtypes = [C.c_int, C.c_void_p, f64p, C.c_void_p]
@@ -193,6 +195,14 @@ def ref_load_library(r, libr: nucdata.Library):
         cap = np.ascontiguousarray(n.xs[:, 1] - n.xs[:, 2])
         inel = np.ascontiguousarray(n.inelastic if n.inelastic.size else np.zeros(1), np.float64)
         nu, dy, dth = np.array(n.nu_poly, np.float64), np.ascontiguousarray(n.delayed_yield), np.ascontiguousarray(n.delayed_theta)
+        if any(getattr(n, a, None) is not None for a in ("elastic_angle", "inelastic_angle", "inelastic_energy")):
+            from macaw_b200 import nucdata as _nd
+            descs, keep = [], []
+            for a in ("elastic_angle", "inelastic_angle", "inelastic_energy"):
+                d = _nd.Tabular2DDesc()
+                _nd._pack_table(d, getattr(n, a, None), keep)
+                descs.append(d)
+            r.ref_stage_tables(C.addressof(descs[0]), C.addressof(descs[1]), C.addressof(descs[2]), int(n.inelastic_in_cm))
         r.ref_add_nuclide(n.name.encode(), n.awr, n.kT, e.size, dp(e), dp(el), dp(cap), dp(fis) if n.fissionable else None,
                           int(n.inelastic.size), n.inel_threshold, dp(inel), n.inel_threshold_energy, n.inel_mass_ratio,
                           dp(nu), n.n_precursor, dp(dy), dp(dth), n.watt_a, n.watt_b, n.q_fission)

@@ -175,6 +175,33 @@ inline V3 isotropic_direction(uint64_t* s)
 }
 
 // ------------------------------------------------------------------ nuclear data
+// Distributions tabulated on a grid of incoming energies (mcw_tabular2d; the layouts OMC distribution_angle.cpp:20-63
+// and distribution_energy.cpp:56-148 read)
+struct Tabular2D
+{
+  std::vector<double> energy, x, p, c;
+  std::vector<int> off, interp, ndisc;
+  bool hist_in_energy = false;
+  bool empty() const { return energy.empty(); }
+  void take(const mcw_tabular2d& t, bool continuous)
+  {
+    *this = Tabular2D();
+    if (t.n_energy == 0)
+      return;
+    const int n = t.n_energy;
+    energy.assign(t.energy, t.energy + n);
+    off.assign(t.offset, t.offset + n + 1);
+    interp.assign(t.interpolation, t.interpolation + n);
+    ndisc.assign(n, 0);
+    if (continuous && t.n_discrete)
+      ndisc.assign(t.n_discrete, t.n_discrete + n);
+    hist_in_energy = continuous && t.histogram_in_energy != 0;
+    x.assign(t.x, t.x + off[n]);
+    p.assign(t.pdf, t.pdf + off[n]);
+    c.assign(t.cdf, t.cdf + off[n]);
+  }
+};
+
 struct Nuclide
 {
   int G = 0;
@@ -188,6 +215,9 @@ struct Nuclide
   double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
   double watt_a = 0, watt_b = 0, q = 0;
   std::vector<int> grid_index;
+  Tabular2D el_angle, inel_angle, inel_energy; // optional tabulated secondary distributions
+  int inel_law = MCW_LAW_LEVEL;
+  bool inel_in_cm = true;
 
   // OMC endf.cpp:112-121 Polynomial (Horner, increasing powers) on nu_poly; nuclide.cpp:478-517
   double nu_total(double E) const

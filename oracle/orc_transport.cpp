@@ -189,7 +189,160 @@ static V3 sample_cxs_target_velocity(double awr, double E, V3 u, double kT, uint
   return vt * rotate_angle(u, mu, nullptr, seed);
 }
 
-// OMC physics.cpp:721-786 (isotropic CM angular distribution: "assume isotropic" branch :750-752)
+// lower_bound_index (OMC search.h:14-20)
+static int lower_bound_index(const std::vector<double>& v, double x)
+{
+  if (v.front() == x)
+    return 0;
+  return (int)(std::lower_bound(v.begin(), v.end(), x) - v.begin()) - 1;
+}
+
+// Tabular::sample (OMC distribution.cpp:223-266) of distribution k of a table
+static double tabular_sample(const Tabular2D& t, int k, uint64_t* seed)
+{
+  const int b = t.off[k], n = t.off[k + 1] - b;
+  const double* x = &t.x[b];
+  const double* pd = &t.p[b];
+  const double* cd = &t.c[b];
+  double c = prn(seed);
+  double c_i = cd[0];
+  int i;
+  for (i = 0; i < n - 1; ++i)
+  {
+    if (c <= cd[i + 1])
+      break;
+    c_i = cd[i + 1];
+  }
+  double x_i = x[i], p_i = pd[i];
+  if (t.interp[k] == 1)
+  {
+    if (p_i > 0.0)
+      return x_i + (c - c_i) / p_i;
+    return x_i;
+  }
+  double x_i1 = x[i + 1], p_i1 = pd[i + 1];
+  double m = (p_i1 - p_i) / (x_i1 - x_i);
+  if (m == 0.0)
+    return x_i + (c - c_i) / p_i;
+  return x_i + (std::sqrt(std::max(0.0, p_i * p_i + 2 * m * (c - c_i))) - p_i) / m;
+}
+
+// AngleDistribution::sample (OMC distribution_angle.cpp:65-95)
+static double angle_sample(const Tabular2D& t, double E, uint64_t* seed)
+{
+  const int n = (int)t.energy.size();
+  int i;
+  double r;
+  if (E < t.energy[0])
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E > t.energy[n - 1])
+  {
+    i = n - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = lower_bound_index(t.energy, E);
+    r = (E - t.energy[i]) / (t.energy[i + 1] - t.energy[i]);
+  }
+  if (r > prn(seed))
+    ++i;
+  double mu = tabular_sample(t, i, seed);
+  if (std::fabs(mu) > 1.0)
+    mu = std::copysign(1.0, mu);
+  return mu;
+}
+
+// ContinuousTabular::sample (OMC distribution_energy.cpp:150-275)
+static double continuous_tabular_sample(const Tabular2D& t, double E, uint64_t* seed)
+{
+  const bool histogram_interp = t.hist_in_energy;
+  const int n_energy_in = (int)t.energy.size();
+  int i;
+  double r;
+  if (E < t.energy[0])
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E > t.energy[n_energy_in - 1])
+  {
+    i = n_energy_in - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = lower_bound_index(t.energy, E);
+    r = (E - t.energy[i]) / (t.energy[i + 1] - t.energy[i]);
+  }
+  int l;
+  if (histogram_interp)
+    l = i;
+  else
+    l = r > prn(seed) ? i + 1 : i;
+  double E_i_1 = t.x[t.off[i] + t.ndisc[i]], E_i_K = t.x[t.off[i + 1] - 1];
+  double E_i1_1 = t.x[t.off[i + 1] + t.ndisc[i + 1]], E_i1_K = t.x[t.off[i + 2] - 1];
+  double E_1 = E_i_1 + r * (E_i1_1 - E_i_1);
+  double E_K = E_i_K + r * (E_i1_K - E_i_K);
+  const int b = t.off[l], n_energy_out = t.off[l + 1] - b, n_discrete = t.ndisc[l];
+  const double* eo = &t.x[b];
+  const double* pd = &t.p[b];
+  const double* cd = &t.c[b];
+  double r1 = prn(seed);
+  double c_k = cd[0];
+  int k = 0, end = n_energy_out - 2;
+  for (int j = 0; j < n_discrete; ++j)
+  {
+    k = j;
+    c_k = cd[k];
+    if (r1 < c_k)
+    {
+      end = j;
+      break;
+    }
+  }
+  double c_k1;
+  for (int j = n_discrete; j < end; ++j)
+  {
+    k = j;
+    c_k1 = cd[k + 1];
+    if (r1 < c_k1)
+      break;
+    k = j + 1;
+    c_k = c_k1;
+  }
+  double E_l_k = eo[k], p_l_k = pd[k];
+  double E_out = E_l_k;
+  if (t.interp[l] == 1)
+  {
+    if (p_l_k > 0.0 && k >= n_discrete)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+  }
+  else
+  {
+    double E_l_k1 = eo[k + 1], p_l_k1 = pd[k + 1];
+    if (E_l_k != E_l_k1)
+    {
+      double frac = (p_l_k1 - p_l_k) / (E_l_k1 - E_l_k);
+      if (frac == 0.0)
+        E_out = E_l_k + (r1 - c_k) / p_l_k;
+      else
+        E_out = E_l_k + (std::sqrt(std::max(0.0, p_l_k * p_l_k + 2.0 * frac * (r1 - c_k))) - p_l_k) / frac;
+    }
+  }
+  if (!histogram_interp && n_energy_out > 1 && k >= n_discrete)
+  {
+    if (l == i)
+      return E_1 + (E_out - E_i_1) * (E_K - E_1) / (E_i_K - E_i_1);
+    return E_1 + (E_out - E_i1_1) * (E_K - E_1) / (E_i1_K - E_i1_1);
+  }
+  return E_out;
+}
+
+// OMC physics.cpp:721-786 (tabular angular distribution :749-757, else "assume isotropic")
 static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
 {
   double vel = std::sqrt(p.E);
@@ -202,7 +355,11 @@ static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
   V3 v_cm = (v_n + awr * v_t) / (awr + 1.0);
   v_n = v_n - v_cm;
   vel = norm(v_n);
-  double mu_cm = uniform_distribution(-1., 1., &p.seeds[0]);
+  double mu_cm;
+  if (!nuc.el_angle.empty())
+    mu_cm = angle_sample(nuc.el_angle, p.E, &p.seeds[0]);
+  else
+    mu_cm = uniform_distribution(-1., 1., &p.seeds[0]);
   V3 u_cm = v_n / vel;
   v_n = vel * rotate_angle(u_cm, mu_cm, nullptr, &p.seeds[0]);
   v_n = v_n + v_cm;
@@ -211,17 +368,29 @@ static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
   p.u = v_n / vel;
 }
 
-// OMC physics.cpp:1073-1120 with LevelInelastic (distribution_energy.cpp:48-51), isotropic CM
-// angle (secondary_uncorrelated.cpp:54-68), scatter_in_cm_ true, yield 1
+// OMC physics.cpp:1073-1120 over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68): cosine from the
+// reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
+// (:150-275), CM -> LAB when scatter_in_cm_, yield 1
 static void inelastic_scatter(const Nuclide& nuc, Hist& p)
 {
   double E_in = p.E;
-  double mu = uniform_distribution(-1., 1., &p.seeds[0]);
-  double E = nuc.inel_ratio * (E_in - nuc.inel_E);
-  double E_cm = E;
-  double A = nuc.awr;
-  E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
-  mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
+  double mu;
+  if (!nuc.inel_angle.empty())
+    mu = angle_sample(nuc.inel_angle, E_in, &p.seeds[0]);
+  else
+    mu = uniform_distribution(-1., 1., &p.seeds[0]);
+  double E;
+  if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+    E = continuous_tabular_sample(nuc.inel_energy, E_in, &p.seeds[0]);
+  else
+    E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  if (nuc.inel_in_cm)
+  {
+    double E_cm = E;
+    double A = nuc.awr;
+    E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
+    mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
+  }
   if (std::fabs(mu) > 1.0)
     mu = std::copysign(1.0, mu);
   p.E = E;
@@ -736,6 +905,11 @@ int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
     N.watt_a = d[i].watt_a;
     N.watt_b = d[i].watt_b;
     N.q = d[i].q_fission;
+    N.el_angle.take(d[i].elastic_angle, false);
+    N.inel_angle.take(d[i].inelastic_angle, false);
+    N.inel_energy.take(d[i].inelastic_energy, true);
+    N.inel_law = d[i].inelastic_law;
+    N.inel_in_cm = N.inel_law == MCW_LAW_LEVEL ? true : d[i].inelastic_in_cm != 0;
     P.lib.nuclides.push_back(std::move(N));
   }
   P.lib.n_log_bins = n_log_bins;

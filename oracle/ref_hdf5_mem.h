@@ -56,6 +56,12 @@ struct Node
     a.integer.assign(v.begin(), v.end());
     attrs[name] = a;
   }
+  void attr(const std::string& name, const std::vector<int>& v, std::vector<unsigned long long> shape)
+  {
+    Array a{Array::INT, shape, {}, {}, {}};
+    a.integer.assign(v.begin(), v.end());
+    attrs[name] = a;
+  }
   void attr(const std::string& name, const char* v) { attrs[name] = Array{Array::TEXT, {}, {}, {}, v}; }
 };
 

@@ -30,10 +30,38 @@
 #include "openmc/settings.h"
 #include "openmc/simulation.h"
 #include "ref_hdf5_mem.h"
+#include "../include/macaw_b200.h" // mcw_tabular2d: the tables arrive in the product's own descriptor layout
 
 namespace
 {
 std::unique_ptr<memh5::Node> g_root;
+// tables staged by ref_stage_tables for the next ref_add_nuclide (null = none)
+const mcw_tabular2d *g_el_angle = nullptr, *g_inel_angle = nullptr, *g_inel_energy = nullptr;
+int g_inel_in_cm = 1;
+
+// (3, N) dataset x / pdf / cdf with `offsets` and `interpolation` attributes: the layout of an angular distribution's `mu`
+// (OMC distribution_angle.cpp:26-33) and of a continuous law's `distribution` (distribution_energy.cpp:80-92)
+memh5::Node* table_dataset(memh5::Node* parent, const char* name, const mcw_tabular2d& t)
+{
+  const int n = t.n_energy, total = t.offset[n];
+  std::vector<double> flat(3 * (size_t)total);
+  for (int k = 0; k < total; ++k)
+  {
+    flat[k] = t.x[k];
+    flat[total + k] = t.pdf[k];
+    flat[2 * (size_t)total + k] = t.cdf[k];
+  }
+  memh5::Node* d = parent->dataset(name, flat, {3, (unsigned long long)total});
+  d->attr("offsets", std::vector<int>(t.offset, t.offset + n));
+  d->attr("interpolation", std::vector<int>(t.interpolation, t.interpolation + n));
+  return d;
+}
+void angle_group(memh5::Node* distribution, const mcw_tabular2d& t)
+{
+  memh5::Node* a = distribution->group("angle");
+  a->dataset("energy", std::vector<double>(t.energy, t.energy + t.n_energy));
+  table_dataset(a, "mu", t);
+}
 
 void constant_function(memh5::Node* parent, const char* name, double v, double e0, double e1)
 {
@@ -100,6 +128,18 @@ REF_API void ref_library_reset()
   model::active_meshsurf_tallies.clear();
 }
 
+// Tabulated secondary distributions of the NEXT nuclide added (null = none): angular distributions of the elastic and
+// the inelastic reaction (read by AngleDistribution's own constructor), a continuous tabular energy law instead of the
+// level law (read by ContinuousTabular's own constructor) and that reaction's centre-of-mass flag.
+REF_API void ref_stage_tables(const mcw_tabular2d* elastic_angle, const mcw_tabular2d* inelastic_angle,
+                              const mcw_tabular2d* inelastic_energy, int inelastic_in_cm)
+{
+  g_el_angle = elastic_angle && elastic_angle->n_energy ? elastic_angle : nullptr;
+  g_inel_angle = inelastic_angle && inelastic_angle->n_energy ? inelastic_angle : nullptr;
+  g_inel_energy = inelastic_energy && inelastic_energy->n_energy ? inelastic_energy : nullptr;
+  g_inel_in_cm = inelastic_in_cm;
+}
+
 // One synthetic nuclide of macaw_b200/nucdata.py as a nuclide file: MT 2 elastic (isotropic in the centre of mass),
 // optionally MT 51 (one level, isotropic CM), MT 102 capture, optionally MT 18 fission with a polynomial total nu, a Watt
 // prompt spectrum and n_precursor Maxwell delayed groups of constant yield.  Returns the nuclide's index.
@@ -119,14 +159,37 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
   g->group("kTs")->dataset(temp, {kT}, {})->data.shape.clear();
   g->group("energy")->dataset(temp, std::vector<double>(energy, energy + G));
   memh5::Node* rxs = g->group("reactions");
-  neutron_product(reaction(rxs, 2, 0.0, true, temp, elastic, G, 0), 0, "prompt", {1.0});
+  memh5::Node* del = neutron_product(reaction(rxs, 2, 0.0, true, temp, elastic, G, 0), 0, "prompt", {1.0});
+  if (g_el_angle)
+    angle_group(del, *g_el_angle);
   if (n_inel > 0)
   {
-    memh5::Node* e = neutron_product(reaction(rxs, 51, -inel_E, true, temp, inel, n_inel, inel_thr), 0, "prompt", {1.0})->group("energy");
-    e->attr("type", "level");
-    e->attr("threshold", inel_E);
-    e->attr("mass_ratio", inel_ratio);
+    memh5::Node* dist = neutron_product(reaction(rxs, 51, -inel_E, g_inel_energy ? g_inel_in_cm != 0 : true, temp, inel, n_inel, inel_thr),
+                                        0, "prompt", {1.0});
+    if (g_inel_angle)
+      angle_group(dist, *g_inel_angle);
+    memh5::Node* e = dist->group("energy");
+    if (g_inel_energy)
+    {
+      // ContinuousTabular (OMC distribution_energy.cpp:56-148): `energy` with one incoming-energy interpolation region
+      const mcw_tabular2d& t = *g_inel_energy;
+      e->attr("type", "continuous");
+      memh5::Node* en = e->dataset("energy", std::vector<double>(t.energy, t.energy + t.n_energy));
+      en->attr("interpolation", std::vector<int>{t.n_energy, t.histogram_in_energy ? 1 : 2}, {2, 1});
+      memh5::Node* d = table_dataset(e, "distribution", t);
+      std::vector<int> nd(t.n_energy, 0);
+      if (t.n_discrete)
+        nd.assign(t.n_discrete, t.n_discrete + t.n_energy);
+      d->attr("n_discrete_lines", nd);
+    }
+    else
+    {
+      e->attr("type", "level");
+      e->attr("threshold", inel_E);
+      e->attr("mass_ratio", inel_ratio);
+    }
   }
+  g_el_angle = g_inel_angle = g_inel_energy = nullptr;
   reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
   if (fission)
   {

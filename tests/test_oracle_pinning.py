@@ -619,11 +619,13 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
     assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
 
 
-def _reference_library(oracle_bridge, r, n_log_bins=500, G=600):
+def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False):
     """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
-    tables, so both sides hold the same numbers.  One material is given <isotropic> flags."""
+    tables, so both sides hold the same numbers.  One material is given <isotropic> flags.  tabular: the nuclides carry
+    tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
+    ContinuousTabular constructors from the in-memory nuclide file."""
     from macaw_b200 import nucdata
-    lib = nucdata.make_library(n_nuclides=9, G=G, seed=3, n_log_bins=n_log_bins)
+    lib = nucdata.make_library(n_nuclides=9, G=G, seed=3, n_log_bins=n_log_bins, tabular=tabular)
     lib.materials[3].isotropic = [1] + [0] * (len(lib.materials[3].nuclides) - 1)
     generator = [n.xs.copy() for n in lib.nuclides]
     tables = oracle_bridge.ref_load_library(r, lib)
@@ -657,8 +659,9 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
+@pytest.mark.parametrize("tabular", [False, True])
 @pytest.mark.parametrize("libm", [True, False])
-def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm):
+def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
     Material::calculate_xs -> Nuclide::calculate_xs (OMC material.cpp:773-829, nuclide.cpp:550-750) and
     Particle::event_collide -> collision -> sample_neutron_reaction with sample_nuclide, sample_fission,
@@ -670,12 +673,17 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm)
     keff collision / absorption scores, sampled nuclide, all stream seeds, fission-site counts and every site equal BIT
     FOR BIT.  libm=False (the deterministic-math build the GPU is compared with): seeds, site counts, sampled nuclides,
     fates and the cross sections still equal exactly (same random-number consumption, same branches); energies and
-    directions agree to 1e-12 (last-bit differences of the transcendental functions)."""
+    directions agree to 1e-12 (last-bit differences of the transcendental functions).
+    tabular=True: the same with tabulated secondary distributions in the data -- AngleDistribution::sample (OMC
+    distribution_angle.cpp:65-95) -> Tabular::sample (distribution.cpp:223-266) for the elastic and the inelastic
+    reaction, ContinuousTabular::sample (distribution_energy.cpp:150-275; histogram and lin-lin, with and without
+    discrete lines) in the centre-of-mass and in the laboratory system -- the reference's own objects built by its own
+    constructors from the in-memory nuclide file, against the oracle's restatement."""
     from tests import problems
     r = oracle_bridge.ref_lib()
-    if r is None or not hasattr(r, "ref_collide_events"):
+    if r is None or not hasattr(r, "ref_collide_events") or (tabular and not hasattr(r, "ref_stage_tables")):
         pytest.skip("oracle/_ref not built with physics.cpp + particle.cpp (no /root/reference on this box)")
-    lib, _, _ = _reference_library(oracle_bridge, r)
+    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
     o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
     f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
