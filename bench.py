@@ -104,7 +104,7 @@ def declared_config(args, mesh, lib, et, world, particles_per_gpu, n_total):
     return {"workload": args.workload, "mesh_elements": int(mesh.n_elem), "elem_type": et,
             "nuclides": len(lib.nuclides), "grid_points_per_nuclide": int(lib.nuclides[0].energy.size),
             "particles_per_gpu_per_batch": int(particles_per_gpu), "global_particles_per_batch": int(n_total),
-            "parallelism": f"particle-sharded x{world}", "tally": "per-element collision flux",
+            "parallelism": f"particle-sharded x{world}", "tally": f"per-element {args.tally.lower()} flux",
             "seed_through_double": 1, "scaling": args.scaling,
             "parity": "GPU == CPU oracle bit for bit on the deterministic-math build (streams, crossing sequences, banks); "
                       "oracle == reference OpenMC code: seeds / counts / bank ids exactly, energies to 1e-12 (DESIGN.md 2)",
@@ -175,7 +175,7 @@ def ncu_counters(workload):
         return None
 
 
-def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch):
+def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch, estimator=0):
     """Histories/s of the CPU oracle on a bounded sample of the same workload."""
     from oracle import bridge
     from macaw_b200 import cstructs
@@ -188,7 +188,7 @@ def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch):
         s2 = cstructs.Settings.from_buffer_copy(bytes(s))
         s2.n_particles = n
         o.set_settings(s2)
-        o.add_tally(1, 0, 0, [0], None)
+        o.add_tally(1, estimator, 0, [0], None)
         sub = source_sites[:n].copy()
         o.set_source_bank(sub)
         t0 = time.perf_counter()
@@ -281,7 +281,7 @@ def run_reference(args):
         o.set_library(lib, [m - 1 for m in mats])
         s.n_particles = n
         o.set_settings(s)
-        o.add_tally(1, 0, 0, [0], None)
+        o.add_tally(1, int(args.tally == "TRACKLENGTH"), 0, [0], None)
         o.sample_initial_source()
         return o
 
@@ -328,7 +328,7 @@ class Runner:
         s.sort_xs_queue = args.sort_xs
         kernel = st.CollisionKernel(blocks=blocks, materials=mats, temperature=293.6,
                                     z_coord=100.0 if mesh.dim == 2 else None)
-        tally = st.OpenMCTally(id=1, scores=["flux"], filters=["cell"], estimator="COLLISION")
+        tally = st.OpenMCTally(id=1, scores=["flux"], filters=["cell"], estimator=args.tally)
         self.study = st.OpenMCStudy(mesh, lib, kernel, s, [tally], device=local, group=group, rank=rank, nranks=world)
         self.ctx = self.study.ctx
         self.ctx.set_option("sync_every", args.sync_every)
@@ -426,6 +426,8 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000,
                     help="histories per batch: per GPU with --scaling weak, in total with --scaling strong")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--tally", default="COLLISION", choices=["COLLISION", "TRACKLENGTH"],
+                    help="estimator of the per-element flux tally (TRACKLENGTH scores every segment: the atomic-throughput case)")
     ap.add_argument("--sort-xs", type=int, default=1,
                     help="energy-binned tile refresh of the cross sections (settings.sort_xs_queue): the library bins "
                          "the rounds that are large enough for their nuclide count")
@@ -517,7 +519,7 @@ def main():
         if src_bank is not None:  # reported on rank 0 at N = 1 only
             try:
                 threads = os.cpu_count() or 1
-                rate, n_s, t_s = cpu_oracle_rate(R.problem, src_bank, 15.0, threads, next_batch)
+                rate, n_s, t_s = cpu_oracle_rate(R.problem, src_bank, 15.0, threads, next_batch, int(args.tally == "TRACKLENGTH"))
                 cpu = {"value": rate, "unit": "histories/s", "cores": threads, "kind": "port",
                        "sample": f"{n_s} histories of the same source bank, one generation, {t_s:.1f} s, "
                                  f"{threads} host threads (os.cpu_count)"}

@@ -502,10 +502,12 @@ struct InputProblem
     std::string name, granularity, score;
     int tally_id;
     int energy_bin; // -1 = all
+    std::string nuclide = "all"; // OpenMCTallyAux.C:44,61-62
   };
   std::vector<AuxDef> aux;
   std::vector<std::vector<std::string>> tally_scores, tally_filters; // as written, parallel to problem.tallies
   std::vector<std::string> tally_estimators;
+  std::vector<std::vector<std::string>> tally_nuclides; // OpenMCTally `nuclides` (default "total")
 };
 
 inline InputProblem readInput(const std::string& input_path, const std::string& xml_dir, const std::string& tables_path)
@@ -704,6 +706,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
         R.tally_scores.push_back(splitWords(u.get("scores")));
         R.tally_filters.push_back(splitWords(u.get("filters")));
         R.tally_estimators.push_back(u.get("estimator", "COLLISION"));
+        R.tally_nuclides.push_back(splitWords(u.get("nuclides", "total")));
         P.tallies.back().energy_bins = toReals(u.get("energy_bins"));
       }
     }
@@ -715,7 +718,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
     for (const auto& a : ak->children)
       if (a.get("type") == "OpenMCTallyAux" && blockIsActive(*ak, a.name))
         R.aux.push_back({a.name, a.get("granularity"), a.get("score"), std::stoi(a.get("tally_id", "-1")),
-                         a.find("energy_bin") ? std::stoi(a.get("energy_bin")) : -1});
+                         a.find("energy_bin") ? std::stoi(a.get("energy_bin")) : -1, a.get("nuclide", "all")});
 
   // ---- settings.xml (OMC settings.cpp:230-420)
   const XmlNode sx = parseXml(readFile(xml_dir + "/settings.xml"));
@@ -778,6 +781,7 @@ inline InputProblem readInput(const std::string& input_path, const std::string& 
         {
           lib_index[name] = (int)P.library.nuclides.size();
           P.library.nuclides.push_back(T.nuclides[t]);
+          P.library.nuclides.back().name = name;
         }
         M.nuclide.push_back(lib_index[name]);
         names.push_back(name);

@@ -56,6 +56,7 @@ struct Mesh
 
 struct Nuclide
 {
+  std::string name; // as in materials.xml (OMC data::nuclide_map); may be empty for generated libraries
   std::vector<double> energy, xs, elastic, inelastic;
   mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
 };
@@ -162,15 +163,18 @@ private:
   bool _verbose;
 };
 
-// Parameters: id, particle_type, estimator, scores, filters, energy_bins (MC OpenMCTally.C:30-65).
+// Parameters: id, particle_type, estimator, scores, filters, nuclides, energy_bins (MC OpenMCTally.C:30-65).
 class OpenMCTally
 {
 public:
   OpenMCTally(int id, std::vector<std::string> scores, std::vector<std::string> filters,
               const std::string& estimator = "COLLISION", const std::string& particle_type = "neutron",
-              std::vector<double> energy_bins = {})
-    : _id(id), _score_names(std::move(scores)), _filters(std::move(filters)), _energy_bins(std::move(energy_bins))
+              std::vector<double> energy_bins = {}, std::vector<std::string> nuclides = {"total"})
+    : _id(id), _score_names(std::move(scores)), _filters(std::move(filters)), _energy_bins(std::move(energy_bins)),
+      _nuclides(std::move(nuclides))
   {
+    if (_nuclides.empty())
+      _nuclides = {"total"};
     if (particle_type != "neutron")
       mooseError("Only neutrons are currently supported."); // :87-88
     if (estimator == "COLLISION")
@@ -218,11 +222,53 @@ public:
   const std::vector<std::string>& scoreNames() const { return _score_names; }
   const std::vector<double>& energyBins() const { return _energy_bins; }
 
+  // MC OpenMCTally.C:188-204 against the study's library.  Fills what every nuclide bin of results_ scores (library index,
+  // -1 = total, -2 = allocated but never scored) and the reference's own nuclides_ vector (what OpenMCTallyAux.C:93-106
+  // inspects).  `all` appends every nuclide and -1 to the tally's default {-1} without clearing it, so results_ has
+  // n + 2 nuclide bins: score_all_nuclides (OMC tally_scoring.cpp:2142-2175) fills bin i for nuclide i and bin n for the
+  // total.  A list of names gets "total" appended (:198-202); unknown names fail like OMC tally.cpp:552-554.
+  void resolveNuclides(const Library& library) const
+  {
+    const int n = (int)library.nuclides.size();
+    _bins.clear();
+    _ref_nuclides.clear();
+    if (_nuclides[0] == "all")
+    {
+      _ref_nuclides.push_back(-1);
+      for (int i = 0; i < n; ++i)
+        _bins.push_back(i), _ref_nuclides.push_back(i);
+      _bins.push_back(-1), _bins.push_back(-2);
+      _ref_nuclides.push_back(-1);
+      return;
+    }
+    if (_nuclides[0] == "total")
+    {
+      _bins = _ref_nuclides = {-1};
+      return;
+    }
+    for (const auto& name : _nuclides)
+    {
+      int found = name == "total" ? -1 : -3;
+      for (int i = 0; i < n && found == -3; ++i)
+        if (library.nuclides[i].name == name)
+          found = i;
+      if (found == -3)
+        mooseError("Could not find the nuclide " + name + " specified in tally " + std::to_string(_id) + " in any material");
+      _bins.push_back(found);
+    }
+    _bins.push_back(-1);
+    _ref_nuclides = _bins;
+  }
+  const std::vector<int32_t>& nuclideBins() const { return _bins; }
+  const std::vector<int32_t>& referenceNuclides() const { return _ref_nuclides; }
+
 private:
   int _id, _estimator = MCW_ESTIMATOR_COLLISION, _granularity;
   std::vector<std::string> _score_names, _filters;
   std::vector<int32_t> _scores;
   std::vector<double> _energy_bins;
+  std::vector<std::string> _nuclides;
+  mutable std::vector<int32_t> _bins = {-1}, _ref_nuclides = {-1};
 };
 
 // Communication the study needs between transport and finalize when particles are sharded over
@@ -272,8 +318,13 @@ public:
     _h.check(mcw_set_temperature(_h.get(), kernel.temperature().data(), (int64_t)kernel.temperature().size()));
     _h.check(mcw_set_settings(_h.get(), &_settings));
     for (const auto& t : tallies)
+    {
       _h.check(mcw_add_tally(_h.get(), t.id(), t.estimator(), t.granularity(), t.scores().data(), (int)t.scores().size(),
                              t.energyBins().empty() ? nullptr : t.energyBins().data(), (int)t.energyBins().size()));
+      t.resolveNuclides(library);
+      if (t.nuclideBins().size() != 1 || t.nuclideBins()[0] != -1)
+        _h.check(mcw_set_tally_nuclides(_h.get(), t.id(), t.nuclideBins().data(), (int)t.nuclideBins().size()));
+    }
     _work_index.resize(_nranks + 1);
     _h.check(mcw_calculate_work(_settings.n_particles, _nranks, _work_index.data())); // OMC simulation.cpp:529-551
     _h.check(mcw_prepare(_h.get()));
@@ -393,7 +444,8 @@ class OpenMCTallyAux
 {
 public:
   OpenMCTallyAux(const OpenMCStudy& study, const OpenMCTally& tally, const std::string& granularity, const std::string& score,
-                 std::optional<int> energy_bin = std::nullopt)
+                 std::optional<int> energy_bin = std::nullopt, const std::string& nuclide = "all",
+                 const Library* library = nullptr)
     : _study(study), _tally_id(tally.id()), _energy_bin(energy_bin)
   {
     if (granularity != "cell" && granularity != "universe")
@@ -404,12 +456,35 @@ public:
         _score = (int)k;
     if (_score < 0)
       paramError("score", "score '" + score + "' is not part of tally " + std::to_string(_tally_id));
+    // MC OpenMCTallyAux.C:93-119: the nuclide bin and the score index.  The reference combines them as
+    // score_bin * nuclides_.size() + nuc_bin although OpenMC stores nuclide_bin * n_scores + score_bin
+    // (OMC tally_scoring.cpp:2400); the two agree when either count is 1.  Kept as the reference has it and flagged here.
+    const auto& ref = tally.referenceNuclides();
+    int nuc_bin = 0;
+    if (ref[0] != -1)
+    {
+      if (nuclide == "all")
+        nuc_bin = (int)ref.size() - 1;
+      else
+      {
+        int idx = -1;
+        if (library)
+          for (size_t i = 0; i < library->nuclides.size(); ++i)
+            if (library->nuclides[i].name == nuclide)
+              idx = (int)i;
+        nuc_bin = (int)(std::find(ref.begin(), ref.end(), idx) - ref.begin());
+      }
+    }
+    _score = _score * (int)ref.size() + nuc_bin;
   }
   // fetches the tally once per step (the AuxKernel is evaluated once per element per step)
   void timestepSetup()
   {
     const Handle& h = _study.handle();
     h.check(mcw_tally_shape(h.get(), _tally_id, &_n_spatial, &_n_energy, &_n_scores));
+    int32_t n_bins = 1;
+    h.check(mcw_tally_nuclide_bins(h.get(), _tally_id, &n_bins));
+    _n_scores *= n_bins; // OpenMC's score_index dimension: nuclide bins x scores
     _sum.assign((size_t)(_n_spatial * _n_energy * _n_scores), 0.0);
     _sum_sq = _sum;
     int32_t nr = 0;

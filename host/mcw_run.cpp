@@ -139,7 +139,7 @@ int main(int argc, char** argv)
     std::vector<OpenMCTally> tallies;
     for (size_t k = 0; k < in.tally_scores.size(); ++k) // --input: the strings as written, validated by OpenMCTally
       tallies.emplace_back(P.tallies[k].id, in.tally_scores[k], in.tally_filters[k], in.tally_estimators[k], "neutron",
-                           P.tallies[k].energy_bins);
+                           P.tallies[k].energy_bins, in.tally_nuclides[k]);
     for (const auto& t : P.tallies)
     {
       if (!in.tally_scores.empty())
@@ -180,7 +180,8 @@ int main(int argc, char** argv)
             t = &c;
         if (!t)
           mooseError("OpenMCTallyAux " + a.name + ": no OpenMCTally with id " + std::to_string(a.tally_id));
-        OpenMCTallyAux aux(study, *t, a.granularity, a.score, a.energy_bin >= 0 ? std::optional<int>(a.energy_bin) : std::nullopt);
+        OpenMCTallyAux aux(study, *t, a.granularity, a.score, a.energy_bin >= 0 ? std::optional<int>(a.energy_bin) : std::nullopt,
+                           a.nuclide, &P.library);
         aux.timestepSetup();
         std::printf("%s{\"name\": \"%s\", \"tally_id\": %d, \"score\": \"%s\", \"values\": [", k ? ", " : "", a.name.c_str(),
                     a.tally_id, a.score.c_str());

@@ -291,6 +291,18 @@ int mcw_set_settings(mcw_handle h, const mcw_settings* s);
 int mcw_add_tally(mcw_handle h, int id, int estimator, int granularity, const int32_t* scores,
                   int n_scores, const double* energy_bins, int n_energy_edges);
 
+/* Nuclide bins of a tally: the `nuclides` parameter of OpenMCTally [MC OpenMCTally.C:56-58,188-204 ->
+ * OMC tallies/tally.cpp:543-558 Tally::set_nuclides].  nuclides[j] = index of a library nuclide, or -1 for the
+ * material total ("total"), or -2 for a bin that is allocated but never scored.  The caller spells the reference's
+ * conventions out: a list of names = the list followed by -1 (OpenMCTally.C:198-202); "all" = 0 .. n_nuclides-1, -1, -2:
+ * OpenMCTally.C:190-197 appends every nuclide and -1 to the tally's default {-1} WITHOUT clearing it (OpenMC's own
+ * reader clears first, OMC tally.cpp:517-533), so results_ has n_nuclides + 2 nuclide bins of which
+ * score_all_nuclides (OMC tally_scoring.cpp:2142-2175) fills bin i for nuclide i and bin n_nuclides for the total.  A bin whose nuclide is not in the material of the event scores nothing
+ * (OMC tally_scoring.cpp:2391-2396); the others score micro * atom_density * flux (tally_scoring.cpp:516-1260).
+ * Results gain a nuclide dimension: score_index = nuclide_bin * n_scores + score, as in OpenMC's results_.  Without
+ * this call a tally has the single bin "total". */
+int mcw_set_tally_nuclides(mcw_handle h, int id, const int32_t* nuclides, int n);
+
 /* Source bank.  mcw_sample_initial_source replaces initialize_source [OMC source.cpp:325-338];
  * mcw_set_source_bank / mcw_get_source_bank replace openmc_source_bank [OMC bank.cpp:110-125].
  * n is this rank's share (work_per_rank). */
@@ -332,6 +344,8 @@ int mcw_reduction_device_ptr(mcw_handle h, void** doubles, int64_t* n); /* [tall
  * MC OpenMCTally.h:71-88). */
 int mcw_get_tally(mcw_handle h, int id, double* sum, double* sum_sq, int64_t n, int32_t* n_realizations);
 int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy, int32_t* n_scores);
+/* number of nuclide bins (1 unless mcw_set_tally_nuclides was called): values per filter bin = bins * n_scores */
+int mcw_tally_nuclide_bins(mcw_handle h, int id, int32_t* n_nuclide_bins);
 
 /* Parity / diagnostics output (RT TraceData.h:20-68 cached traces are the reference analogue). */
 int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capacity, int64_t* n);

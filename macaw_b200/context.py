@@ -82,6 +82,11 @@ class Context:
         eb = np.ascontiguousarray(energy_bins if energy_bins is not None else [], np.float64)
         self._ck(self.L.mcw_add_tally(self.h, tid, estimator, granularity, _p(sc), sc.size, _p(eb), eb.size))
 
+    def set_tally_nuclides(self, tid, nuclides):
+        """nuclide bins of a tally: library indices, -1 = total (OpenMCTally.C:188-204)"""
+        nn = np.ascontiguousarray(nuclides, np.int32)
+        self._ck(self.L.mcw_set_tally_nuclides(self.h, tid, _p(nn), nn.size))
+
     # ---- source / banks
     def sample_initial_source(self):
         self._ck(self.L.mcw_sample_initial_source(self.h))
@@ -178,8 +183,15 @@ class Context:
         self._ck(self.L.mcw_tally_shape(self.h, tid, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def tally_nuclide_bins(self, tid):
+        a = C.c_int32()
+        self._ck(self.L.mcw_tally_nuclide_bins(self.h, tid, C.byref(a)))
+        return a.value
+
     def get_tally(self, tid):
+        """SUM, SUM_SQ as [spatial][energy][score_index], score_index = nuclide_bin * n_scores + score (OpenMC's results_)"""
         ns, ne, nc = self.tally_shape(tid)
+        nc *= self.tally_nuclide_bins(tid)
         n = ns * ne * nc
         s, q, nr = np.zeros(n), np.zeros(n), C.c_int32()
         self._ck(self.L.mcw_get_tally(self.h, tid, _p(s), _p(q), n, C.byref(nr)))

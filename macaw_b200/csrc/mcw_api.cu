@@ -20,6 +20,9 @@ struct HostTally
   int id, estimator, granularity, n_scores, n_energy;
   int scores[MCW_N_SCORES];
   std::vector<double> ebins;
+  std::vector<int32_t> nuclides; // nuclide bins (empty = the single bin "total")
+  int32_t* d_nuclides = nullptr;
+  int n_nuc_bins() const { return nuclides.empty() ? 1 : (int)nuclides.size(); }
   int64_t n_spatial = 1, n_values = 0, offset = 0; // offset into the reduction buffer
   double *d_sum = nullptr, *d_sum_sq = nullptr, *d_ebins = nullptr;
   int n_realizations = 0;
@@ -615,6 +618,25 @@ int mcw_add_tally(mcw_handle h, int id, int estimator, int granularity, const in
   return MCW_OK;
 }
 
+int mcw_set_tally_nuclides(mcw_handle h, int id, const int32_t* nuclides, int n)
+{
+  if (!h || !nuclides || n <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  for (auto& t : h->tallies)
+    if (t.id == id)
+    {
+      for (int j = 0; j < n; ++j)
+        if (nuclides[j] < -2 || nuclides[j] >= (int)h->nuclides.size())
+          // OMC tally.cpp:552-554 "Could not find the nuclide ... specified in tally ... in any material"
+          return fail(h, MCW_E_INVALID_ARGUMENT, "Could not find the nuclide with index " + std::to_string(nuclides[j]) +
+                                                     " specified in tally " + std::to_string(id) + " in the library");
+      t.nuclides.assign(nuclides, nuclides + n);
+      h->prepared = false;
+      return MCW_OK;
+    }
+  return fail(h, MCW_E_INVALID_ARGUMENT, "unknown tally id");
+}
+
 // ------------------------------------------------------------------ prepare: build device state
 static int prepare(mcw_handle h)
 {
@@ -1125,7 +1147,7 @@ static int prepare(mcw_handle h)
   {
     tl.n_spatial =
         tl.granularity == MCW_FILTER_CELL ? h->n_elem : (tl.granularity == MCW_FILTER_UNIVERSE ? n_blocks : 1);
-    tl.n_values = tl.n_spatial * tl.n_energy * tl.n_scores;
+    tl.n_values = tl.n_spatial * tl.n_energy * tl.n_nuc_bins() * tl.n_scores;
     tl.offset = total_values;
     total_values += tl.n_values;
   }
@@ -1143,10 +1165,15 @@ static int prepare(mcw_handle h)
     CK(cudaMemset(tl.d_sum, 0, tl.n_values * sizeof(double)));
     CK(cudaMemset(tl.d_sum_sq, 0, tl.n_values * sizeof(double)));
     CK(dev_upload(h, &tl.d_ebins, tl.ebins));
+    tl.d_nuclides = nullptr;
+    if (!tl.nuclides.empty())
+      CK(dev_upload(h, &tl.d_nuclides, tl.nuclides));
     tl.n_realizations = 0;
     McwTallyDev& d = P.tally[i];
     d.value = h->d_reduce + tl.offset;
     d.ebins = tl.d_ebins;
+    d.nuclides = tl.d_nuclides;
+    d.n_nuc_bins = tl.n_nuc_bins();
     d.n_edges = (int)tl.ebins.size();
     d.n_energy = tl.n_energy;
     d.n_scores = tl.n_scores;
@@ -1656,6 +1683,19 @@ int mcw_tally_shape(mcw_handle h, int id, int64_t* n_spatial, int32_t* n_energy,
         *n_energy = t.n_energy;
       if (n_scores)
         *n_scores = t.n_scores;
+      return MCW_OK;
+    }
+  return fail(h, MCW_E_INVALID_ARGUMENT, "unknown tally id");
+}
+
+int mcw_tally_nuclide_bins(mcw_handle h, int id, int32_t* n_nuclide_bins)
+{
+  if (!h || !n_nuclide_bins)
+    return MCW_E_INVALID_ARGUMENT;
+  for (auto& t : h->tallies)
+    if (t.id == id)
+    {
+      *n_nuclide_bins = t.n_nuc_bins();
       return MCW_OK;
     }
   return fail(h, MCW_E_INVALID_ARGUMENT, "unknown tally id");

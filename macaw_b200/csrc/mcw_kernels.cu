@@ -354,7 +354,12 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     sc[MCW_SCORE_KAPPA_FISSION] = kappa; // 0 when the material absorbs nothing or no collision tally scores it
     for (int t = 0; t < P.n_tallies; ++t)
       if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
-        mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
+      {
+        if (P.tally[t].nuclides)
+          mcw_score_tally_nuclides(L, P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, i_mat, flux, sig_a, sc);
+        else
+          mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
+      }
   }
   uint64_t seed_trk = c.seed;
   if (P.seed_through_double)

@@ -8,16 +8,16 @@
 // OMC filter_energy.cpp:61-75 energy bin + tally_scoring.cpp:1453 atomic update.  Lanes of a warp
 // that hit the same bin are pre-reduced with __match_any_sync so each distinct bin gets one FP64
 // atomic per warp.
-MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, const double* sc)
+// energy bin of a tally (OMC filter_energy.cpp:61-75); -1 = outside the filter's range
+MCW_D int mcw_tally_energy_bin(const McwTallyDev& t, double E)
 {
   int eb = 0;
-  bool ok = true;
   if (t.n_edges >= 2)
   {
     const double* b = t.ebins;
     if (!(E >= b[0] && E <= b[t.n_edges - 1]))
-      ok = false;
-    else if (b[0] == E)
+      return -1;
+    if (b[0] == E)
       eb = 0;
     else
     {
@@ -35,7 +35,13 @@ MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, cons
     if (eb >= t.n_energy)
       eb = t.n_energy - 1;
   }
-  long long bin = ok ? (long long)(spatial * t.n_energy + eb) : -1ll;
+  return eb;
+}
+
+MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, const double* sc)
+{
+  const int eb = mcw_tally_energy_bin(t, E);
+  long long bin = eb >= 0 ? (long long)(spatial * t.n_energy + eb) : -1ll;
   unsigned active = __activemask();
   unsigned peers = __match_any_sync(active, bin);
   int lane = threadIdx.x & 31;
@@ -58,14 +64,79 @@ MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, cons
   }
 }
 
+// A tally with nuclide bins (MC OpenMCTally.C:188-204; OMC tally_scoring.cpp:2381-2407 and score_all_nuclides
+// :2142-2175): bin j scores micro * atom_density * flux of its nuclide when the event's material holds it
+// (score_general_ce, i_nuclide >= 0: :600-606 total, :746-750 fission, :805-809 nu-fission, :1238-1244 kappa-fission)
+// and nothing otherwise (:2391-2394); the bin -1 scores the material totals `sc`.  score_index = j * n_scores + s.
+// Rarely asked for, so out of line (the collision kernel's code stays compact) and with plain atomics.
+__device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev& L, const McwTallyDev& t, int64_t spatial, double E,
+                                                      int i_mat, double flux, double sig_a, const double* sc)
+{
+  const int eb = mcw_tally_energy_bin(t, E);
+  if (eb < 0)
+    return;
+  const long long base = (long long)(spatial * t.n_energy + eb) * t.n_nuc_bins;
+  const int i_log = mcw_log_bin(L, E);
+  for (int j = 0; j < t.n_nuc_bins; ++j)
+  {
+    double* out = t.value + (base + j) * t.n_scores;
+    const int in = t.nuclides[j];
+    if (in == -2)
+      continue; // a bin the reference allocates but never scores (mcw_set_tally_nuclides)
+    if (in < 0)
+    {
+      for (int s = 0; s < t.n_scores; ++s)
+        atomicAdd(out + s, sc[t.scores[s]]);
+      continue;
+    }
+    int q = L.mat_off[i_mat];
+    const int qe = L.mat_off[i_mat + 1];
+    while (q < qe && L.mat_nuc[q] != in)
+      ++q;
+    if (q == qe)
+      continue; // mat_nuclide_index_ == C_NONE
+    const double dens = L.mat_dens[q];
+    const Micro m = mcw_micro_xs(L, in, E, i_log);
+    for (int s = 0; s < t.n_scores; ++s)
+    {
+      double v;
+      switch (t.scores[s])
+      {
+        case MCW_SCORE_FLUX:
+          v = flux;
+          break;
+        case MCW_SCORE_TOTAL:
+          v = m.total * dens * flux;
+          break;
+        case MCW_SCORE_FISSION:
+          if (sig_a == 0)
+            continue;
+          v = m.fission * dens * flux;
+          break;
+        case MCW_SCORE_NU_FISSION:
+          if (sig_a == 0)
+            continue;
+          v = m.nu_fission * dens * flux;
+          break;
+        default: // MCW_SCORE_KAPPA_FISSION
+          if (sig_a == 0.)
+            continue;
+          v = L.nuc[in].fissionable ? L.nuc[in].q * m.fission * dens * flux : 0.0;
+          break;
+      }
+      atomicAdd(out + s, v);
+    }
+  }
+}
+
 MCW_D int64_t mcw_spatial_bin(const McwTallyDev& t, int elem, int block)
 {
   return t.granularity == MCW_FILTER_CELL ? (int64_t)elem
                                           : (t.granularity == MCW_FILTER_UNIVERSE ? (int64_t)block : 0);
 }
 
-// kappa-fission macro: sum_i N_i q_i sigma_f,i (OMC tally_scoring.cpp:1240-1255)
-MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E)
+// kappa-fission of a material: q_i * sigma_f,i * N_i * flux summed nuclide by nuclide (OMC tally_scoring.cpp:1246-1255)
+MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E, double flux)
 {
   int i_log = mcw_log_bin(L, E);
   double kappa = 0.0;
@@ -75,7 +146,7 @@ MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E)
     if (L.nuc[in].fissionable)
     {
       Micro m = mcw_micro_xs(L, in, E, i_log);
-      kappa += L.nuc[in].q * m.fission * L.mat_dens[i];
+      kappa += L.nuc[in].q * m.fission * L.mat_dens[i] * flux;
     }
   }
   return kappa;
@@ -137,8 +208,11 @@ MCW_D bool mcw_segment_nl(const McwParams& P, SegState& s, double neg_log, int e
         for (int q = 0; q < P.tally[t].n_scores; ++q)
           need_kappa |= P.tally[t].scores[q] == MCW_SCORE_KAPPA_FISSION;
         if (need_kappa)
-          sc[MCW_SCORE_KAPPA_FISSION] = s.sig_a == 0. ? 0.0 : mcw_kappa_macro(P.lib, i_mat, s.E) * flux;
-        mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, sc);
+          sc[MCW_SCORE_KAPPA_FISSION] = s.sig_a == 0. ? 0.0 : mcw_kappa_macro(P.lib, i_mat, s.E, flux);
+        if (P.tally[t].nuclides)
+          mcw_score_tally_nuclides(P.lib, P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, i_mat, flux, s.sig_a, sc);
+        else
+          mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, sc);
       }
   }
   // :157-159 store all three seeds as doubles.  The source and URR seeds did not change since they

@@ -404,6 +404,11 @@ MCW_D bool mcw_exit_fast<MCW_QUAD4>(const McwMeshDev& mesh, const ElemData<MCW_Q
   return iside != MCW_INVALID && !at_vertex;
 }
 
+#ifndef MCW_FUSED_PREFETCH
+#define MCW_FUSED_PREFETCH 0
+#endif
+MCW_D void mcw_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------ the kernel
 // One lane = one history in flight.  Lane state lives in registers between segments and is written
 // back only when the history leaves the kernel.
@@ -460,6 +465,10 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
     if (keep_hash)
       hash = p.hash[i];
     slot = -1; // the cross sections of the current material are (re)read from the history's sectors
+#if MCW_FUSED_PREFETCH > 1
+    if (FUSED)
+      mcw_prefetch_l1(p.xs + (size_t)i * P.n_slots * 4);
+#endif
   };
 
   for (;;)
@@ -553,6 +562,18 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
       bool leave = false, requeue = false;
       ElemData<TYPE> D;
       D.load(P.mesh, cur);
+#if MCW_FUSED_PREFETCH
+      if (FUSED)
+      {
+        // the tail is bound by the latency of single histories (few live lanes per warp, DRAM and L2 nearly idle):
+        // pull the records of all neighbours into L1 while the exit search runs, so the next element's record
+        // is an L1 hit instead of an L2 round trip on the history's critical path
+#pragma unroll
+        for (int sd = 0; sd < (int)(sizeof(D.nbr) / sizeof(int)); ++sd)
+          if (D.nbr[sd] >= 0 && sd != inc_side)
+            mcw_prefetch_l1(P.mesh.rec + (size_t)(D.nbr[sd] >> MCW_NBR_SHIFT) * (TYPE == MCW_HEX8 ? 256 : 128));
+      }
+#endif
       // the segment's random number and logarithm, ahead of the exit search (independent work while
       // the record arrives); the seed is committed only if the segment is taken
       uint64_t seed_next = s.seed_trk;

@@ -140,8 +140,10 @@ struct McwParticlesDev
 
 struct McwTallyDev
 {
-  double* value; // [bins][n_scores]
+  double* value; // [bins][n_nuc_bins][n_scores]
   const double* ebins;
+  const int32_t* nuclides; // nuclide bins (library index, -1 = material total); null = the single bin "total"
+  int32_t n_nuc_bins;
   int32_t n_edges, n_energy, n_scores, granularity, estimator;
   int32_t scores[MCW_N_SCORES];
 };

@@ -41,6 +41,8 @@ def load():
         "mcw_set_temperature": [vp, vp, i64],
         "mcw_set_settings": [vp, P(Settings)],
         "mcw_add_tally": [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int],
+        "mcw_set_tally_nuclides": [vp, C.c_int, vp, C.c_int],
+        "mcw_tally_nuclide_bins": [vp, C.c_int, P(i32)],
         "mcw_sample_initial_source": [vp],
         "mcw_set_source_bank": [vp, vp, i64],
         "mcw_get_source_bank": [vp, vp, i64, P(i64)],
@@ -91,7 +93,8 @@ def loaded_path():
 
 EXPORTS = ["mcw_create", "mcw_destroy", "mcw_last_error", "mcw_version", "mcw_set_option", "mcw_prepare", "mcw_stream",
            "mcw_struct_sizes", "mcw_set_mesh", "mcw_set_library", "mcw_set_materials", "mcw_set_temperature",
-           "mcw_set_settings", "mcw_add_tally", "mcw_sample_initial_source", "mcw_set_source_bank",
+           "mcw_set_settings", "mcw_add_tally", "mcw_set_tally_nuclides", "mcw_tally_nuclide_bins",
+           "mcw_sample_initial_source", "mcw_set_source_bank",
            "mcw_get_source_bank", "mcw_transport_generation", "mcw_finalize_generation", "mcw_run_generation",
            "mcw_bank_count", "mcw_bank_device_ptr", "mcw_set_bank_window", "mcw_sample_bank", "mcw_finish_sampling",
            "mcw_sampled_device_ptr", "mcw_source_device_ptr", "mcw_set_source_count", "mcw_reduction_device_ptr",

@@ -47,13 +47,38 @@ class OpenMCTally:
         for f in filters:
             if f not in ("universe", "cell", "energy", "particle"):
                 raise ValueError("Unrecognized filter")  # :173-174
-        if tuple(nuclides) != ("total",):
-            raise NotImplementedError("per-nuclide tally bins are not on the GPU path yet")
+        self.nuclides = [str(x) for x in nuclides]  # "total" | "all" | names (OpenMCTally.C:56-58)
         self.id, self.scores, self.filters = int(id), list(scores), list(filters)
         self.estimator = cstructs.ESTIMATOR[est.lower()]
         self.energy_bins = list(energy_bins) if energy_bins is not None else None
         self.granularity = (cstructs.GRANULARITY["cell"] if "cell" in filters else
                             cstructs.GRANULARITY["universe"] if "universe" in filters else cstructs.GRANULARITY["global"])
+
+
+    def nuclide_indices(self, library):
+        """What each nuclide bin of results_ scores (OpenMCTally.C:188-204): a list of names -> the list, then total (-1);
+        "total" -> the single total bin; "all" -> bin i = nuclide i, bin n = total and one more bin that is never scored
+        (-2): the reference appends to the default nuclides_ = {-1} without clearing it, so its results_ has n + 2
+        nuclide bins.  self.ref_nuclides is the reference's nuclides_ vector itself (what OpenMCTallyAux.C:93-106 looks
+        at).  Unknown names raise like OMC tally.cpp:552-554."""
+        if self.nuclides[0] == "all":
+            n = len(library.nuclides)
+            self.ref_nuclides = [-1] + list(range(n)) + [-1]
+            return list(range(n)) + [-1, -2]
+        self.ref_nuclides = [-1]
+        if self.nuclides[0] == "total":
+            return [-1]
+        index = {n.name: i for i, n in enumerate(library.nuclides)}
+        out = []
+        for name in self.nuclides:
+            if name == "total":
+                out.append(-1)
+            elif name in index:
+                out.append(index[name])
+            else:
+                raise ValueError(f"Could not find the nuclide {name} specified in tally {self.id} in any material")
+        self.ref_nuclides = out + [-1]
+        return out + [-1]
 
 
 class OpenMCStudy:
@@ -76,7 +101,11 @@ class OpenMCStudy:
         for t in tallies:
             sc = [cstructs.SCORE[s] for s in t.scores]
             self.ctx.add_tally(t.id, t.estimator, t.granularity, sc, t.energy_bins if "energy" in t.filters else None)
+            t.nuclide_bins = t.nuclide_indices(library)
+            if t.nuclide_bins != [-1]:
+                self.ctx.set_tally_nuclides(t.id, t.nuclide_bins)
         self.settings = settings
+        self.library = library
         self.work_index = dist.calculate_work(settings.n_particles, nranks)
         self.batch = 0
         self.ctx.prepare()
@@ -141,17 +170,34 @@ class OpenMCTallyAux:
     """AuxKernel read-back (OpenMCTallyAux.C:70-215): per element, results_(filter_index, score, SUM)
     summed over the energy bins -- the raw sum over batches, not the mean."""
 
-    def __init__(self, study: OpenMCStudy, tally_id, score, tally: OpenMCTally = None, granularity="cell"):
+    def __init__(self, study: OpenMCStudy, tally_id, score, tally: OpenMCTally = None, granularity="cell", nuclide=None):
         if granularity == "global":
             raise ValueError("global granularity is not supported")  # OpenMCTallyAux.C errors
         self.study, self.tally_id, self.score, self.granularity = study, tally_id, score, granularity
         self._tally = tally
+        self.nuclide = nuclide if nuclide is not None else "all"  # OpenMCTallyAux.C:61-62
+
+    def score_index(self):
+        """OpenMCTallyAux.C:93-119.  The tally's total bin for nuclide "all" (the last bin), else the named nuclide's bin.
+        The reference combines the two as score_bin * n_nuclide_bins + nuclide_bin although OpenMC stores
+        nuclide_bin * n_scores + score_bin (tally_scoring.cpp:2400); the two agree when either count is 1.  Kept as the
+        reference has it (drop-in), flagged here."""
+        scores = self._tally.scores if self._tally is not None else None
+        score_bin = scores.index(self.score) if scores else 0
+        bins = getattr(self._tally, "ref_nuclides", [-1]) if self._tally is not None else [-1]
+        if bins[0] != -1:
+            if self.nuclide == "all":
+                nuc_bin = len(bins) - 1
+            else:
+                names = [n.name for n in self.study.library.nuclides]
+                nuc_bin = bins.index(names.index(self.nuclide))
+        else:
+            nuc_bin = 0  # also what a `nuclides = all` tally gets: its nuclides_ starts with the default -1
+        return score_bin * len(bins) + nuc_bin
 
     def compute(self):
         s, _, _ = self.study.ctx.get_tally(self.tally_id)
-        scores = self._tally.scores if self._tally is not None else None
-        j = scores.index(self.score) if scores else 0
-        return s[:, :, j].sum(axis=1)
+        return s[:, :, self.score_index()].sum(axis=1)
 
     def compute_value(self, elem):
         return float(self.compute()[elem])

@@ -40,6 +40,9 @@ def _load(name):
     lib.orc_isotropic_direction.argtypes = [f64p, u64p]
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     lib.orc_tracklength_kappa.argtypes = [C.c_void_p, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
+    lib.orc_set_tally_nuclides.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.orc_score_nuclide_bins.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, f64p, f64p,
+                                           f64p, f64p]
     lib.orc_history_identity.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), u64p]
     lib.orc_collide_events.restype = C.c_int64
     lib.orc_collide_events.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, f64p, f64p,
@@ -146,6 +149,9 @@ def ref_lib():
             r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
                                                   u64p, C.c_int64, f64p, f64p, C.c_int, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
+        if hasattr(r, "ref_score_nuclide_bins"):
+            r.ref_score_nuclide_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int64,
+                                                 f64p, f64p, f64p, C.c_double, f64p]
         r.ref_collide_events.restype = C.c_int64
         r.ref_collide_events.argtypes = [C.c_int, C.c_double, C.c_int64, f64p, f64p, u64p, C.c_void_p, C.c_double, f64p, f64p,
                                          u64p, C.c_void_p, C.c_int64, f64p, f64p]
@@ -263,6 +269,11 @@ class Oracle:
         sc = np.ascontiguousarray(scores, np.int32)
         eb = np.ascontiguousarray(energy_bins if energy_bins is not None else [], np.float64)
         self.L.orc_add_tally(self.h, tid, estimator, granularity, _p(sc), sc.size, _p(eb), eb.size)
+
+    def set_tally_nuclides(self, tid, nuclides):
+        nn = np.ascontiguousarray(nuclides, np.int32)
+        if self.L.orc_set_tally_nuclides(self.h, tid, _p(nn), nn.size):
+            raise RuntimeError("unknown tally id")
 
     def grid(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -16,11 +16,13 @@ struct Tally
   int id, estimator, granularity;
   std::vector<int> scores;
   std::vector<double> ebins; // edges; empty = one bin
+  std::vector<int> nuclides; // nuclide bins (library index, -1 = total); empty = the single bin "total"
   int64_t n_spatial = 1;
   int n_energy = 1;
   std::vector<double> value, sum, sum_sq;
   int n_realizations = 0;
-  int64_t bins() const { return n_spatial * n_energy; }
+  int n_nuc_bins() const { return nuclides.empty() ? 1 : (int)nuclides.size(); }
+  int64_t bins() const { return n_spatial * n_energy * n_nuc_bins(); }
 };
 
 struct Problem
@@ -578,6 +580,81 @@ static void score_tally(Tally& t, int64_t spatial, double E, const double* score
   }
 }
 
+// Tally with nuclide bins (MC OpenMCTally.C:188-204): the loop over nuclide bins of score_collision_tally /
+// score_tracklength_tally (OMC tally_scoring.cpp:2381-2407, :2310-2336; "all" = score_all_nuclides :2142-2175) around
+// score_general_ce with i_nuclide >= 0 (:600-606 total, :746-750 fission, :805-809 nu-fission, :1238-1244
+// kappa-fission): micro * atom_density * flux; a nuclide the material does not hold scores nothing (:2391-2394).
+// `micro` holds the material's nuclides in material order (what p.neutron_xs(i) holds after calculate_xs).
+static void score_tally_nuclides(const Problem& P, Tally& t, int64_t spatial, double E, const Material& mat, const Micro* micro,
+                                 double flux, double macro_absorption, const double* score_total)
+{
+  int eb = 0;
+  if (!t.ebins.empty())
+  {
+    if (!(E >= t.ebins.front() && E <= t.ebins.back()))
+      return;
+    eb = Library::lower_bound_index(t.ebins.data(), t.ebins.data() + t.ebins.size(), E);
+    if (eb >= t.n_energy)
+      eb = t.n_energy - 1;
+  }
+  const size_t ns = t.scores.size();
+  const int64_t base = (spatial * t.n_energy + eb) * t.n_nuc_bins();
+  for (int j = 0; j < t.n_nuc_bins(); ++j)
+  {
+    double* out = &t.value[(size_t)(base + j) * ns];
+    const int in = t.nuclides[j];
+    if (in == -2)
+      continue; // allocated, never scored (MaCaw's `nuclides = all`, see mcw_set_tally_nuclides)
+    if (in < 0)
+    {
+      for (size_t s = 0; s < ns; ++s)
+      {
+#pragma omp atomic
+        out[s] += score_total[t.scores[s]];
+      }
+      continue;
+    }
+    size_t q = 0;
+    while (q < mat.nuc.size() && mat.nuc[q] != in)
+      ++q;
+    if (q == mat.nuc.size())
+      continue;
+    const Micro& m = micro[q];
+    const double dens = mat.dens[q];
+    const Nuclide& nuc = P.lib.nuclides[in];
+    for (size_t s = 0; s < ns; ++s)
+    {
+      double v;
+      switch (t.scores[s])
+      {
+        case MCW_SCORE_FLUX:
+          v = flux;
+          break;
+        case MCW_SCORE_TOTAL:
+          v = m.total * dens * flux;
+          break;
+        case MCW_SCORE_FISSION:
+          if (macro_absorption == 0)
+            continue;
+          v = m.fission * dens * flux;
+          break;
+        case MCW_SCORE_NU_FISSION:
+          if (macro_absorption == 0)
+            continue;
+          v = m.nu_fission * dens * flux;
+          break;
+        default:
+          if (macro_absorption == 0.)
+            continue;
+          v = nuc.fissionable ? nuc.q * m.fission * dens * flux : 0.0;
+          break;
+      }
+#pragma omp atomic
+      out[s] += v;
+    }
+  }
+}
+
 // kappa-fission of one segment: q * sigma_f * N * flux nuclide by nuclide (OMC tally_scoring.cpp:1246-1255)
 static double tracklength_kappa(const Problem& P, const Material& mat, const Micro* micro, double flux)
 {
@@ -707,7 +784,10 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
           const double flux = tracklength_scores(p.wgt, std::min(d, c.length), macro.total, macro.absorption, macro.fission,
                                                  macro.nu_fission, sc);
           sc[MCW_SCORE_KAPPA_FISSION] = macro.absorption == 0. ? 0.0 : tracklength_kappa(P, mat, micro.data(), flux);
-          score_tally(t, spatialBin(P, t, c.elem), p.E, sc);
+          if (!t.nuclides.empty())
+            score_tally_nuclides(P, t, spatialBin(P, t, c.elem), p.E, mat, micro.data(), flux, macro.absorption, sc);
+          else
+            score_tally(t, spatialBin(P, t, c.elem), p.E, sc);
         }
     if (S.seed_through_double)
       for (int s = 0; s < 3; ++s)
@@ -732,7 +812,14 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
       collision_scores(wgt_last, macro.total, macro.absorption, macro.fission, macro.nu_fission, co.kappa_score, sc);
       for (auto& t : P.tallies)
         if (t.estimator == MCW_ESTIMATOR_COLLISION)
-          score_tally(t, spatialBin(P, t, c.elem), E_last, sc);
+        {
+          if (!t.nuclides.empty())
+            // `micro` still holds the pre-collision cross sections of the material's nuclides (p.neutron_xs at E_last)
+            score_tally_nuclides(P, t, spatialBin(P, t, c.elem), E_last, mat, micro.data(), wgt_last / macro.total,
+                                 macro.absorption, sc);
+          else
+            score_tally(t, spatialBin(P, t, c.elem), E_last, sc);
+        }
     }
     if (S.seed_through_double)
       for (int s = 0; s < 3; ++s)
@@ -966,6 +1053,60 @@ int orc_add_tally(void* h, int id, int estimator, int granularity, const int32_t
   t.sum_sq.assign(n, 0.0);
   P.tallies.push_back(std::move(t));
   return 0;
+}
+
+// MC OpenMCTally.C:188-204 / OMC tally.cpp:543-558: nuclide bins of tally `id` (-1 = total)
+int orc_set_tally_nuclides(void* h, int id, const int32_t* nuclides, int n)
+{
+  Problem& P = *(Problem*)h;
+  for (auto& t : P.tallies)
+    if (t.id == id)
+    {
+      t.nuclides.assign(nuclides, nuclides + n);
+      size_t m = (size_t)t.bins() * t.scores.size();
+      t.value.assign(m, 0.0);
+      t.sum.assign(m, 0.0);
+      t.sum_sq.assign(m, 0.0);
+      return 0;
+    }
+  return -1;
+}
+
+// n independent scoring events in material i_mat on a filterless tally with nuclide bins: macro_xs, then the collision
+// (distance == nullptr: flux = wgt / total) or track-length (flux = wgt * distance) scores of every nuclide bin; out is
+// [event][nuclide bin][score].  Held against the reference's score_collision_tally / score_tracklength_tally on its own
+// Tally (nuclides_ / all_nuclides_), Material and Nuclide objects (oracle/_ref ref_score_nuclide_bins).
+void orc_score_nuclide_bins(void* h, int i_mat, const int32_t* nuclides, int n_bins, const int32_t* scores, int n_scores, int64_t n,
+                            const double* E, const double* wgt, const double* distance, double* out)
+{
+  Problem& P = *(Problem*)h;
+  const Material& mat = P.lib.materials[i_mat];
+  std::vector<Micro> micro(mat.nuc.size());
+  Tally t;
+  t.id = 1, t.estimator = distance ? MCW_ESTIMATOR_TRACKLENGTH : MCW_ESTIMATOR_COLLISION, t.granularity = MCW_FILTER_GLOBAL;
+  t.scores.assign(scores, scores + n_scores);
+  t.nuclides.assign(nuclides, nuclides + n_bins);
+  for (int64_t k = 0; k < n; ++k)
+  {
+    int64_t n_nuc = 0;
+    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc);
+    double sc[MCW_N_SCORES];
+    double flux;
+    if (distance)
+    {
+      flux = tracklength_scores(wgt[k], distance[k], macro.total, macro.absorption, macro.fission, macro.nu_fission, sc);
+      sc[MCW_SCORE_KAPPA_FISSION] = macro.absorption == 0. ? 0.0 : tracklength_kappa(P, mat, micro.data(), flux);
+    }
+    else
+    {
+      flux = wgt[k] / macro.total;
+      collision_scores(wgt[k], macro.total, macro.absorption, macro.fission, macro.nu_fission,
+                       tracklength_kappa(P, mat, micro.data(), flux), sc);
+    }
+    t.value.assign((size_t)n_bins * n_scores, 0.0);
+    score_tally_nuclides(P, t, 0, E[k], mat, micro.data(), flux, macro.absorption, sc);
+    memcpy(out + (size_t)k * n_bins * n_scores, t.value.data(), sizeof(double) * n_bins * n_scores);
+  }
 }
 
 // kappa-fission track-length score of n segments (E, wgt, length) in material i_mat, through macro_xs + tracklength_kappa;

@@ -387,6 +387,63 @@ REF_API void ref_tracklength_kappa(int i_mat, int64_t n, const double* E, const 
   setup_active_tallies();
 }
 
+// n independent scoring events in material i_mat on a filterless tally with NUCLIDE BINS, built the way MaCaw's
+// OpenMCTally::initialize builds it (OpenMCTally.C:188-204): all != 0 -> every nuclide and -1 APPENDED to the default
+// nuclides_ = {-1} (no clear: n + 2 bins) and all_nuclides_ (scored by score_all_nuclides, tally_scoring.cpp:2142-2175); else nuclides_ = the given list (library indices, -1 =
+// total; scored by the bin loop :2381-2407 / :2310-2336).  Material::calculate_xs, then score_collision_tally
+// (distance == nullptr, wgt = wgt_last) or score_tracklength_tally.  out = [event][nuclide bin][score] VALUEs.
+REF_API void ref_score_nuclide_bins(int i_mat, int all, const int32_t* nuclides, int n_bins, const char* const* score_names,
+                                    int n_scores, int64_t n, const double* E, const double* wgt, const double* distance,
+                                    double sqrtkT, double* out)
+{
+  using namespace openmc;
+  model::tallies.clear();
+  model::tally_map.clear();
+  model::tally_filters.clear();
+  model::filter_map.clear();
+  Tally* tally = Tally::create(1);
+  tally->set_scores(std::vector<std::string>(score_names, score_names + n_scores));
+  if (all)
+  {
+    for (size_t i = 0; i < data::nuclides.size(); ++i)
+      tally->nuclides_.push_back((int)i);
+    tally->nuclides_.push_back(-1);
+    tally->all_nuclides_ = true;
+  }
+  else
+  {
+    tally->nuclides_.clear();
+    for (int j = 0; j < n_bins; ++j)
+      tally->nuclides_.push_back(nuclides[j]);
+  }
+  tally->estimator_ = distance ? TallyEstimator::TRACKLENGTH : TallyEstimator::COLLISION;
+  tally->set_active(true);
+  tally->init_results();
+  setup_active_tallies();
+  const int nb = (int)tally->nuclides_.size();
+  Particle p;
+  p.type() = ParticleType::neutron;
+  p.n_coord() = 1;
+  p.material() = i_mat;
+  p.sqrtkT() = sqrtkT;
+  for (int64_t k = 0; k < n; ++k)
+  {
+    p.E() = p.E_last() = E[k];
+    p.wgt() = p.wgt_last() = wgt[k];
+    model::materials[i_mat]->calculate_xs(p);
+    tally->reset();
+    if (distance)
+      score_tracklength_tally(p, distance[k]);
+    else
+      score_collision_tally(p);
+    for (int j = 0; j < nb * n_scores; ++j)
+      out[(size_t)k * nb * n_scores + j] = tally->results_(0, j, static_cast<int>(TallyResult::VALUE));
+  }
+  model::tallies.clear();
+  model::tally_map.clear();
+  setup_active_tallies();
+}
+
 // Whole histories in an infinite medium of material i_mat through the reference's own history loop:
 // initialize_history (simulation.cpp:451) + transport_history_based_single_particle (:662-677: event_calculate_xs,
 // event_advance, event_collide, event_revive_from_secondary, event_death) in a one-cell, no-surface CSG geometry built here

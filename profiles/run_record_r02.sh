@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 record run on one B200 (under gpurun): GPU parity tests, the default bench line, the reference arm,
+# a launch list and ncu --set full captures of the tracking kernel (collision / track-length tally) and the lookup leg.
+O=gpurun_out/${1:-r2k}
+mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1
+( time python bench.py ) > $O/bench.json 2> $O/bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > $O/ref.json 2> $O/ref.err
+python bench.py --tally TRACKLENGTH --no-extra --no-xs-leg --no-cpu-baseline --steps 5 --warmup 3 > $O/bench_tracklength.json 2> $O/bench_tracklength.err
+Q="--no-extra --no-xs-leg --no-cpu-baseline"
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 $Q > $O/launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_track -s 3 -c 2 -o $O/track python bench.py --steps 1 --warmup 0 $Q > $O/ncu_track.log 2>&1
+RED=l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_requests_op_red.sum,l1tex__t_requests_pipe_lsu_mem_global_op_red.sum,smsp__inst_executed_op_global_red.sum
+ncu --set full --metrics $RED --clock-control none --import-source on -k regex:k_track -s 3 -c 2 -o $O/track_tl python bench.py --tally TRACKLENGTH --steps 1 --warmup 0 $Q > $O/ncu_track_tl.log 2>&1
+ncu --set full --clock-control none -k regex:k_xs_lookup -c 6 -o $O/xs python bench.py --steps 1 --warmup 1 --no-extra --no-cpu-baseline > $O/ncu_xs.log 2>&1

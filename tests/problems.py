@@ -7,7 +7,7 @@ ALL_SCORES = [0, 1, 2, 3, 4]
 EBINS = [1e-5, 0.625, 1.0e5, 2.0e7]
 
 
-def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tally=False):
+def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tally=False, nuclide_tallies=False):
     # block ids are 0..n_materials-1 in every synthetic mesh; pass them explicitly because a coarse mesh
     # may not contain every block (e.g. no element centroid falls inside the thin gap)
     block_ids = np.arange(len(block_material), dtype=np.int32)
@@ -26,6 +26,13 @@ def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tall
         obj.add_tally(2, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["universe"], [0, 3])
     if track_tally:
         obj.add_tally(3, cstructs.ESTIMATOR["tracklength"], cstructs.GRANULARITY["cell"], [0, 3, 4], EBINS)
+    if nuclide_tallies:
+        # OpenMCTally `nuclides` (OpenMCTally.C:188-204): a list (+ total) on a collision tally, `all` on a track-length one
+        n = len(lib.nuclides)
+        obj.add_tally(4, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["universe"], ALL_SCORES, EBINS)
+        obj.set_tally_nuclides(4, [min(2, n - 1), 0, n - 1, -1])
+        obj.add_tally(5, cstructs.ESTIMATOR["tracklength"], cstructs.GRANULARITY["global"], [1, 2, 4, 0])
+        obj.set_tally_nuclides(5, list(range(n)) + [-1, -2])
     return obj
 
 

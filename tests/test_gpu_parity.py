@@ -26,10 +26,10 @@ def ctx_factory():
         c.close()
 
 
-def both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=False, **kw):
+def both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=False, nuclide_tallies=False, **kw):
     mesh, lib, bm, s = problems.PROBLEMS[name](**kw)
-    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies, track_tally)
-    g = problems.configure(ctx_factory(), mesh, lib, bm, s, tallies, track_tally)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies, track_tally, nuclide_tallies)
+    g = problems.configure(ctx_factory(), mesh, lib, bm, s, tallies, track_tally, nuclide_tallies)
     return o, g, mesh, lib, s
 
 
@@ -205,6 +205,39 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
         assert np.allclose(sg.ravel(), so, rtol=1e-11, atol=1e-300)
         assert np.allclose(qg.ravel(), qo, rtol=1e-11, atol=1e-300)
         assert so.sum() > 0
+
+
+@pytest.mark.parametrize("name,opts", [("pin_cell_tet", MIXED), ("beavrs_assembly", EVENT), ("infinite_medium", FUSED),
+                                       ("assembly_quad", PUMP)])
+def test_nuclide_bin_tallies(oracle_bridge, ctx_factory, name, opts):
+    """Tallies with nuclide bins (mcw_set_tally_nuclides; MC OpenMCTally.C:188-204 `nuclides = all | list`) on both
+    estimators against the oracle, whose per-bin scoring equals the reference's own score_all_nuclides / nuclide-bin loop
+    bit for bit (tests/test_oracle_pinning.py::test_nuclide_bins_against_reference_tally_objects).  Sums over histories are
+    atomic-order dependent: 1e-11 like the other tallies.  Bins of nuclides a material does not hold and the never-scored
+    bin of `all` stay exactly zero; the per-nuclide totals add up to the total bin."""
+    o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, nuclide_tallies=True)
+    for k, v in opts.items():
+        g.set_option(k, v)
+    o.sample_initial_source()
+    g.sample_initial_source()
+    for batch in range(1, 4):
+        o.run_generation(batch)
+        g.run_generation(batch)
+    assert o.source_bank().tobytes() == g.source_bank().tobytes()
+    n = len(lib.nuclides)
+    for tid, n_bins, n_sc in ((4, 4, 5), (5, n + 2, 4), (1, 1, 5)):
+        assert g.tally_nuclide_bins(tid) == n_bins
+        _, so, qo, nro = o.get_tally(tid)
+        sg, qg, nrg = g.get_tally(tid)
+        assert nro == nrg == 2 and sg.shape[2] == n_bins * n_sc and sg.size == so.size
+        assert np.allclose(sg.ravel(), so, rtol=1e-11, atol=1e-300)
+        assert np.allclose(qg.ravel(), qo, rtol=1e-11, atol=1e-300)
+        assert np.array_equal(sg.ravel() == 0, so == 0)
+        assert so.sum() > 0
+    s5 = g.get_tally(5)[0].reshape(n + 2, 4)
+    assert not s5[n + 1].any()                                     # allocated, never scored
+    assert np.allclose(s5[:n, 0].sum(), s5[n, 0], rtol=1e-10)      # total: sum over nuclides == material total
+
 
 
 @pytest.mark.parametrize("name,opts", [("infinite_medium_iso", EVENT), ("pin_cell_tet", MIXED), ("pin_cell_hex", FUSED),

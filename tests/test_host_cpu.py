@@ -170,3 +170,28 @@ def test_extrusion_reproduces_generated_hex_mesh():
     # lateral ids: quad bottom / right / top / left = 0 / 1 / 2 / 3 sit where the hex grid has bottom / right / top / left = 1 / 2 / 3 / 4
     lat = g.side_bnd_id[:, 1:5]
     assert np.array_equal(np.where(lat >= 0, lat - 1, -1), h.side_bnd_id[:, 1:5])
+
+
+def test_tally_nuclide_bins_follow_the_reference():
+    """OpenMCTally `nuclides` (MC OpenMCTally.C:188-204) and OpenMCTallyAux's score index (OpenMCTallyAux.C:93-119),
+    host logic only: a list gets the total appended; `all` keeps the reference's n + 2 bins (its nuclides_ starts with the
+    default -1, which it never clears), of which the last is never scored; unknown names fail with OpenMC's message."""
+    from macaw_b200 import nucdata, study
+    lib = nucdata.make_library(9, G=50)
+    names = [n.name for n in lib.nuclides]
+    t = study.OpenMCTally(1, ["flux", "total"], ["cell"], nuclides=[names[3], names[0]])
+    assert t.nuclide_indices(lib) == [3, 0, -1] and t.ref_nuclides == [3, 0, -1]
+    t = study.OpenMCTally(2, ["flux"], ["cell"], nuclides=["all"])
+    assert t.nuclide_indices(lib) == list(range(9)) + [-1, -2] and t.ref_nuclides == [-1] + list(range(9)) + [-1]
+    t = study.OpenMCTally(3, ["flux"], ["cell"])
+    assert t.nuclide_indices(lib) == [-1]
+    with pytest.raises(ValueError, match="Could not find the nuclide Unobtainium"):
+        study.OpenMCTally(4, ["flux"], ["cell"], nuclides=["Unobtainium"]).nuclide_indices(lib)
+
+    class FakeStudy:
+        library = lib
+    t = study.OpenMCTally(1, ["flux", "total"], ["cell"], nuclides=[names[3], names[0]])
+    t.nuclide_bins = t.nuclide_indices(lib)
+    aux = study.OpenMCTallyAux(FakeStudy(), 1, "total", tally=t, nuclide=names[0])
+    assert aux.score_index() == 1 * 3 + 1      # score_bin * n_nuclide_bins + nuclide_bin, as the reference computes it
+    assert study.OpenMCTallyAux(FakeStudy(), 1, "flux", tally=t).score_index() == 2   # "all" -> the total bin

@@ -927,6 +927,55 @@ def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
     assert n_pos >= n   # the fuel material scores on every segment, the others never
 
 
+@pytest.mark.parametrize("estimator", ["collision", "tracklength"])
+@pytest.mark.parametrize("mode", ["all", "list"])
+def test_nuclide_bins_against_reference_tally_objects(oracle_bridge, estimator, mode):
+    """Tallies with nuclide bins (MC OpenMCTally.C:188-204 `nuclides = all | list`): the reference's own Tally built the way
+    OpenMCTally::initialize builds it (nuclides_ + all_nuclides_, or the list followed by total), scored by its own
+    score_collision_tally / score_tracklength_tally -> score_all_nuclides / the nuclide-bin loop -> score_general_ce
+    (OMC tally_scoring.cpp:2142-2175, :2381-2407, :516-1260) on its own Material / Nuclide objects, against the oracle's
+    score_tally_nuclides: every (nuclide bin, score) VALUE of every event BIT FOR BIT -- flux, total, fission, nu-fission
+    and kappa-fission; bins whose nuclide is not in the material stay zero on both sides."""
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_score_nuclide_bins"):
+        pytest.skip("oracle/_ref not built with the nuclide-bin doorway (no /root/reference on this box)")
+    lib, _, _ = _reference_library(oracle_bridge, r)
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    f64p = C.POINTER(C.c_double)
+    names = [b"flux", b"total", b"fission", b"nu-fission", b"kappa-fission"]
+    scores = np.arange(5, dtype=np.int32)
+    n_nuc = len(lib.nuclides)
+    # "all": MaCaw appends to the default {-1} without clearing (OpenMCTally.C:190-197): n + 2 bins, the last never scored
+    bins = list(range(n_nuc)) + [-1, -2] if mode == "all" else [4, 0, 7, 2, -1]  # list: no particular order, then total
+    nb = np.asarray(bins, np.int32)
+    n, n_pos = 4000, 0
+    for i_mat in range(len(lib.materials)):
+        rng = np.random.default_rng(70 + i_mat)
+        E = np.exp(rng.uniform(np.log(1.2e-5), np.log(1.9e7), n))
+        w, d = rng.uniform(0.3, 1.5, n), rng.uniform(1e-4, 4.0, n)
+        dp = d.ctypes.data_as(f64p) if estimator == "tracklength" else None
+        ref, mine = np.zeros((n, nb.size, 5)), np.zeros((n, nb.size, 5))
+        r.ref_score_nuclide_bins(i_mat, int(mode == "all"), nb.ctypes.data, nb.size, (C.c_char_p * 5)(*names), 5, n,
+                                 E.ctypes.data_as(f64p), w.ctypes.data_as(f64p), dp, float(np.sqrt(lib.nuclides[0].kT)),
+                                 ref.ctypes.data_as(f64p))
+        o.L.orc_score_nuclide_bins(o.h, i_mat, nb.ctypes.data, nb.size, scores.ctypes.data, 5, n, E.ctypes.data_as(f64p),
+                                   w.ctypes.data_as(f64p), dp, mine.ctypes.data_as(f64p))
+        assert np.array_equal(mine.view(np.uint64), ref.view(np.uint64))
+        held = set(lib.materials[i_mat].nuclides)
+        for j, b in enumerate(bins):
+            if b == -2 or (b >= 0 and b not in held):
+                assert not ref[:, j].any()
+            else:
+                assert (ref[:, j, 0] > 0).all()  # flux scores in every bin the material feeds
+        # the per-nuclide totals add up to the material total (to rounding)
+        if mode == "all":
+            assert np.allclose(ref[:, :-2, 1].sum(1), ref[:, -2, 1], rtol=1e-13)
+        n_pos += int((ref[..., 4] > 0).sum())
+    assert n_pos > 0
+
+
 def test_history_identity_against_reference_initialize_history(oracle_bridge):
     """initialize_history (OMC simulation.cpp:451-481; MC OpenMCStudy.C:326), the reference's own function on its own
     Particle: id = work_index[rank] + index_source, seeds = init_particle_seeds((batch - 1) * n_particles + id) with the
