@@ -69,13 +69,17 @@ def build_problem(name, particles_total, n_inactive):
         # n x n assemblies of 17 x 17 pins, `cells` QUAD cells per pin pitch, extruded to `layers` HEX8 layers
         _, _, n_asm, cells, layers = name.split("_")
         mesh = meshgen.core_hex(int(n_asm), int(cells), int(layers))
+        if os.environ.get("MCW_BENCH_MORTON"):
+            mesh = meshgen.renumber_elements(mesh)
         lib = nucdata.make_library(35, G=10000, seed=1)
         L = int(n_asm) * 17 * meshgen.PIN_PITCH
         box = (0, 0, 0, L, L, mesh.xyz[:, 2].max())
         et = "hex8"
     elif name.startswith("brick_tet_"):
-        n = int(name.split("_")[-1])  # C5 scaling sweep: 6 n^3 TET4
+        n = int(name.split("_")[2])  # C5 scaling sweep: 6 n^3 TET4; brick_tet_<n>_morton = elements in Morton order
         mesh = meshgen.brick_tet(n, bc=meshgen.BC_REFLECT)
+        if name.endswith("_morton"):
+            mesh = meshgen.renumber_elements(mesh)
         lib = nucdata.make_library(9, G=10000, seed=1)
         L = n * 0.05
         box = (0, 0, 0, L, L, L)

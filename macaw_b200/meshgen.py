@@ -314,6 +314,43 @@ def brick_tet(n, bc=BC_KILL, checker=4) -> Mesh:
     return tet_grid(n, n, n, (0, 0, 0), (L, L, L), bc, blocks, f"brick_tet_{n}")
 
 
+def _spread3(v):
+    """bits of v (< 2^21) spread to every third position"""
+    v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def renumber_elements(m: Mesh, order="morton") -> Mesh:
+    """The same mesh with its elements renumbered along a space-filling curve (Morton order of the centroids): what a
+    host hands over when the element records do not fit in L2, so that a history's successive crossings stay within a
+    few DRAM pages.  Element ids are labels (libMesh renumbers too): tallies, banks and traces are in the new numbering,
+    `m.renumbering[new] = old` maps back.  Physics is unchanged -- every history visits the same elements in the same
+    order (tests/test_host_cpu.py)."""
+    if order != "morton":
+        raise ValueError("order must be 'morton'")
+    cent = m.xyz[m.conn].mean(axis=1)
+    lo, hi = cent.min(0), cent.max(0)
+    q = ((cent - lo) / np.maximum(hi - lo, 1e-300) * (2 ** 21 - 1)).astype(np.uint64)
+    code = _spread3(q[:, 0]) | (_spread3(q[:, 1]) << np.uint64(1)) | (_spread3(q[:, 2]) << np.uint64(2))
+    perm = np.argsort(code, kind="stable")          # new -> old
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)                # old -> new
+    out = Mesh(m.elem_type, m.xyz, m.conn[perm], m.block_id[perm], name=m.name + "_morton")
+    if m.neighbors is not None:
+        nb = m.neighbors[perm]
+        out.neighbors = np.where(nb >= 0, inv[np.maximum(nb, 0)], -1).astype(np.int64)
+    if m.side_bnd_id is not None:
+        out.side_bnd_id = m.side_bnd_id[perm]
+    out.bnd_kind = m.bnd_kind
+    out.renumbering = perm
+    return out
+
+
 # BEAVRS assembly blocks -> role (examples/beavrs_assembly/run_assembly.i:39-44 with materials.xml):
 # 10004 helium gap, 10006 and 11006 Zircaloy-4 (cladding, guide tubes), 10010 fuel 3.1 %, 10014 borated water
 BEAVRS_BLOCK_ROLE = {10004: "gap", 10006: "clad", 10010: "fuel", 10014: "water", 11006: "clad"}
