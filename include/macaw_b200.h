@@ -151,6 +151,47 @@ typedef struct mcw_material_desc
   const int32_t* isotropic_in_lab; /* [n_nuclides] 0 / 1, or NULL */
 } mcw_material_desc;
 
+/* Thermal scattering S(alpha, beta) table at one temperature: openmc::ThermalScattering / ThermalData (OMC thermal.cpp:
+ * 38-282) with the angle-energy distributions of secondary_thermal.cpp.  Bound-atom cross sections replace the free-atom
+ * elastic one below energy_max (Nuclide::calculate_sab_xs, OMC nuclide.cpp:763-791; Material::calculate_neutron_xs,
+ * material.cpp:778-806) and sab_scatter (physics.cpp:788-802) samples the outgoing energy and cosine.
+ * Inelastic: Tabulated1D cross section (lin-lin, endf.cpp:153-212) with IncoherentInelasticAE (continuous outgoing
+ * energies with n_mu equiprobable cosines each, secondary_thermal.cpp:190-332) or IncoherentInelasticAEDiscrete
+ * (:128-188: equiprobable or skewed outgoing energies on the cross section's own energy grid).
+ * Elastic (optional): CoherentElasticXS (Bragg edges and partial sums of structure factors, endf.cpp:214-239) with
+ * CoherentElasticAE (secondary_thermal.cpp:27-58), or a Tabulated1D cross section with IncoherentElasticAEDiscrete
+ * (:88-126).  The Debye-Waller form (IncoherentElasticXS / IncoherentElasticAE) is not carried. */
+#define MCW_SAB_INELASTIC_CONTINUOUS 0
+#define MCW_SAB_INELASTIC_DISCRETE 1
+#define MCW_SAB_ELASTIC_NONE 0
+#define MCW_SAB_ELASTIC_COHERENT 1
+#define MCW_SAB_ELASTIC_INCOHERENT_DISCRETE 2
+typedef struct mcw_thermal_desc
+{
+  double energy_max;                /* energy_max_: the table is not used above it */
+  int32_t inelastic_type;           /* MCW_SAB_INELASTIC_* */
+  int32_t elastic_type;             /* MCW_SAB_ELASTIC_* */
+  int32_t n_inelastic_xs;           /* inelastic cross section: points of the Tabulated1D */
+  int32_t n_inelastic_energy;       /* CONTINUOUS: incident energies of the distribution */
+  const double* inelastic_xs_energy;
+  const double* inelastic_xs;
+  const double* inelastic_energy;   /* CONTINUOUS: [n_inelastic_energy] */
+  const int32_t* inelastic_offset;  /* CONTINUOUS: [n_inelastic_energy + 1]; distribution l = points [offset[l], offset[l+1]) */
+  const double* inelastic_e_out;    /* CONTINUOUS: per point.  DISCRETE: [n_inelastic_xs][n_e_out] */
+  const double* inelastic_pdf;      /* CONTINUOUS */
+  const double* inelastic_cdf;      /* CONTINUOUS, used as tabulated */
+  const double* inelastic_mu;       /* CONTINUOUS: [point][n_mu].  DISCRETE: [n_inelastic_xs][n_e_out][n_mu] */
+  int32_t n_mu;
+  int32_t n_e_out;                  /* DISCRETE */
+  int32_t skewed;                   /* DISCRETE */
+  int32_t n_elastic;                /* elastic: Bragg edges (COHERENT) or points of the Tabulated1D */
+  const double* elastic_x;
+  const double* elastic_y;          /* COHERENT: partial sums of structure factors; else the cross section */
+  const double* elastic_mu;         /* INCOHERENT_DISCRETE: [n_elastic][n_elastic_mu] */
+  int32_t n_elastic_mu;
+  int32_t reserved0;
+} mcw_thermal_desc;
+
 /* Run settings: the subset of openmc::settings MaCaw reads (OMC settings.cpp:41-116) plus the
  * MaCaw/MOOSE parameters that change the numbers (MC CollisionKernel.C:38, RT RayTracingStudy.C). */
 typedef struct mcw_settings
@@ -280,6 +321,14 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
  * [MC CollisionKernel.C:34-37,64-69,110]. */
 int mcw_set_materials(mcw_handle h, const mcw_material_desc* materials, int n,
                       const int32_t* block_ids, const int32_t* block_material, int n_blocks);
+
+/* Thermal scattering tables of the library (data::thermal_scatt, OMC thermal.cpp:30-32) and their assignment to the
+ * nuclides of a material: `<sab name= fraction=>` of materials.xml -> Material::thermal_tables_ (index_table,
+ * index_nuclide, fraction; OMC material.cpp:140-160,317-360).  nuclide_position indexes the material's own nuclide
+ * list.  Call after mcw_set_library / mcw_set_materials. */
+int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* tables, int n);
+int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* nuclide_position, const int32_t* table,
+                             const double* fraction);
 
 /* Coupled temperature variable of CollisionKernel, one value per element or one scalar (n = 1)
  * [MC CollisionKernel.C:33,109]. */

@@ -17,7 +17,10 @@ LIB = os.path.join(HERE, "libmacaw_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v"]
-SOURCES = ["mcw_kernels.cu", "mcw_api.cu"]
+# (source, object, extra flags): the kernels are compiled twice, without and with the rarely used branches
+# (csrc/mcw_kernels.h: namespaces mcw_r0 / mcw_r1)
+SOURCES = [("mcw_kernels.cu", "mcw_kernels_r0.o", ["-DMCW_RARE=0"]), ("mcw_kernels.cu", "mcw_kernels.o", ["-DMCW_RARE=1"]),
+           ("mcw_api.cu", "mcw_api.o", [])]
 
 
 def _newest(paths):
@@ -37,9 +40,10 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     objs = []
 
-    def compile_one(src):
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(item):
+        src, oname, extra = item
+        obj = os.path.join(HERE, "build", oname)
+        cmd = [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
@@ -64,15 +68,18 @@ def build_variant(name, defines=()):
     Selected at run time with MCW_LIB_PATH (macaw_b200/lib.py); never used by tests or the bench line."""
     out_dir = os.path.join(HERE, "variants")
     os.makedirs(os.path.join(out_dir, name), exist_ok=True)
-    objs = []
-    for src in SOURCES:
-        obj = os.path.join(out_dir, name, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(item):
+        src, oname, extra = item
+        obj = os.path.join(out_dir, name, oname)
+        cmd = [NVCC] + FLAGS + extra + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         open(obj + ".log", "w").write(r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError((r.stdout + r.stderr)[-4000:])
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
     lib = os.path.join(out_dir, f"libmacaw_b200_{name}.so")
     subprocess.run([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs,
                    check=True)

@@ -68,6 +68,16 @@ class Context:
         bm = np.ascontiguousarray(block_material, np.int32)
         assert ids.size == bm.size
         self._ck(self.L.mcw_set_materials(self.h, C.addressof(md), len(libr.materials), _p(ids), _p(bm), bm.size))
+        if getattr(libr, "thermal_tables", None):  # S(a,b): data::thermal_scatt + the materials' <sab> entries
+            td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
+            self._keep.append((td, keep2))
+            self._ck(self.L.mcw_set_thermal_tables(self.h, C.addressof(td), len(libr.thermal_tables)))
+            for im, m in enumerate(libr.materials):
+                if getattr(m, "sab", None):
+                    pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)
+                    tab = np.ascontiguousarray([a[1] for a in m.sab], np.int32)
+                    fr = np.ascontiguousarray([a[2] for a in m.sab], np.float64)
+                    self._ck(self.L.mcw_set_material_thermal(self.h, im, pos.size, _p(pos), _p(tab), _p(fr)))
 
     def set_temperature(self, T):
         T = np.ascontiguousarray(np.atleast_1d(T), np.float64)

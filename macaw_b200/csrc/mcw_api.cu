@@ -13,6 +13,9 @@
 #include "mcw_detmath.h"
 #include "mcw_kernels.h"
 
+// launcher of the kernel build this problem needs (mcw_kernels.h): `h` must be in scope
+#define MCWK(fn, ...) (h->rare ? mcw_r1::fn(__VA_ARGS__) : mcw_r0::fn(__VA_ARGS__))
+
 namespace
 {
 struct HostTally
@@ -26,6 +29,14 @@ struct HostTally
   int64_t n_spatial = 1, n_values = 0, offset = 0; // offset into the reduction buffer
   double *d_sum = nullptr, *d_sum_sq = nullptr, *d_ebins = nullptr;
   int n_realizations = 0;
+};
+
+struct HostThermal // one mcw_thermal_desc, copied
+{
+  double energy_max = 0;
+  int inel_type = 0, el_type = 0, n_mu = 0, n_e_out = 0, skewed = 0, n_el_mu = 0;
+  std::vector<double> ixs_e, ixs, ien, eout, pdf, cdf, mu, el_x, el_y, el_mu;
+  std::vector<int32_t> ioff;
 };
 
 struct HostTable // one mcw_tabular2d, copied
@@ -144,6 +155,9 @@ struct mcw_context
   std::vector<std::vector<int32_t>> mat_nuc;
   std::vector<std::vector<double>> mat_dens;
   std::vector<std::vector<int32_t>> mat_iso;
+  std::vector<HostThermal> thermal;                // S(a,b) tables (data::thermal_scatt)
+  std::vector<std::vector<int32_t>> mat_sab;       // per material, per nuclide position: table or -1 (empty = none)
+  std::vector<std::vector<double>> mat_sab_frac;
   std::vector<int32_t> block_ids, block_material;
   std::vector<double> temperature;
   std::vector<HostTally> tallies;
@@ -179,6 +193,11 @@ struct mcw_context
   int n_realizations = 0;
   std::vector<double> k_generation;
   double gt_sum[4] = {0, 0, 0, 0}, gt_sum_sq[4] = {0, 0, 0, 0};
+
+  // which build of the kernels runs this problem (mcw_kernels.h): 1 when it has S(a,b) tables, tallies with nuclide
+  // bins, cached trace points or tabulated secondary distributions; "force_rare" option for tests
+  bool rare = false;
+  int force_rare = -1;
 
   // options
   int profile = 0, sync_every = 1, fallback_blocks = 8, visit_cap = 1 << 30, track_max_blocks = 148, fused_max_blocks = 148;
@@ -354,6 +373,11 @@ int mcw_set_option(mcw_handle h, const char* name, int value)
     h->xs_sort_min = std::max(1, value);
   else if (n == "collide_min")
     h->collide_min = std::min(32, std::max(1, value));
+  else if (n == "force_rare")
+  {
+    h->force_rare = value;
+    h->prepared = false;
+  }
   else if (n == "pump_threshold")
     h->pump_threshold = std::max(0, value);
   else if (n == "pump_track_warps")
@@ -534,6 +558,8 @@ int mcw_set_materials(mcw_handle h, const mcw_material_desc* m, int n, const int
   h->mat_nuc.clear();
   h->mat_dens.clear();
   h->mat_iso.clear();
+  h->mat_sab.clear(); // S(a,b) assignments belong to the materials they were made for
+  h->mat_sab_frac.clear();
   for (int i = 0; i < n; ++i)
   {
     if (m[i].n_nuclides <= 0 || m[i].n_nuclides > MCW_MAX_NUC_PER_MAT)
@@ -552,6 +578,99 @@ int mcw_set_materials(mcw_handle h, const mcw_material_desc* m, int n, const int
       // MC CollisionKernel.C:84-90 "Could not find material ... in OpenMC materials."
       return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_materials: block mapped to an unknown material");
   h->have_mats = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* d, int n)
+{
+  if (!h || n < 0 || (n > 0 && !d))
+    return MCW_E_INVALID_ARGUMENT;
+  std::vector<HostThermal> out;
+  for (int k = 0; k < n; ++k)
+  {
+    const mcw_thermal_desc& s = d[k];
+    const std::string at = " (thermal table " + std::to_string(k) + ")";
+    if (s.n_inelastic_xs < 2 || !s.inelastic_xs_energy || !s.inelastic_xs || s.n_mu < 1 || !s.inelastic_e_out || !s.inelastic_mu)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: inelastic data missing" + at);
+    HostThermal t;
+    t.energy_max = s.energy_max;
+    t.inel_type = s.inelastic_type;
+    t.el_type = s.elastic_type;
+    t.n_mu = s.n_mu;
+    t.n_e_out = s.n_e_out;
+    t.skewed = s.skewed;
+    t.n_el_mu = s.n_elastic_mu;
+    t.ixs_e.assign(s.inelastic_xs_energy, s.inelastic_xs_energy + s.n_inelastic_xs);
+    t.ixs.assign(s.inelastic_xs, s.inelastic_xs + s.n_inelastic_xs);
+    if (s.inelastic_type == MCW_SAB_INELASTIC_CONTINUOUS)
+    {
+      if (s.n_inelastic_energy < 2 || !s.inelastic_energy || !s.inelastic_offset || !s.inelastic_pdf || !s.inelastic_cdf)
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: continuous inelastic distribution missing" + at);
+      t.ien.assign(s.inelastic_energy, s.inelastic_energy + s.n_inelastic_energy);
+      t.ioff.assign(s.inelastic_offset, s.inelastic_offset + s.n_inelastic_energy + 1);
+      for (int l = 0; l < s.n_inelastic_energy; ++l)
+        if (t.ioff[l + 1] - t.ioff[l] < 2)
+          return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: a distribution needs at least two outgoing energies" + at);
+      const size_t np = (size_t)t.ioff.back();
+      t.eout.assign(s.inelastic_e_out, s.inelastic_e_out + np);
+      t.pdf.assign(s.inelastic_pdf, s.inelastic_pdf + np);
+      t.cdf.assign(s.inelastic_cdf, s.inelastic_cdf + np);
+      t.mu.assign(s.inelastic_mu, s.inelastic_mu + np * s.n_mu);
+    }
+    else if (s.inelastic_type == MCW_SAB_INELASTIC_DISCRETE)
+    {
+      if (s.n_e_out < (s.skewed ? 5 : 1))
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: too few discrete outgoing energies" + at);
+      const size_t np = (size_t)s.n_inelastic_xs * s.n_e_out;
+      t.eout.assign(s.inelastic_e_out, s.inelastic_e_out + np);
+      t.mu.assign(s.inelastic_mu, s.inelastic_mu + np * s.n_mu);
+    }
+    else
+      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_thermal_tables: unknown inelastic type" + at);
+    if (s.elastic_type == MCW_SAB_ELASTIC_COHERENT || s.elastic_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+    {
+      if (s.n_elastic < 2 || !s.elastic_x || !s.elastic_y)
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: elastic data missing" + at);
+      t.el_x.assign(s.elastic_x, s.elastic_x + s.n_elastic);
+      t.el_y.assign(s.elastic_y, s.elastic_y + s.n_elastic);
+      if (s.elastic_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+      {
+        if (!s.elastic_mu || s.n_elastic_mu < 1)
+          return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: elastic cosines missing" + at);
+        t.el_mu.assign(s.elastic_mu, s.elastic_mu + (size_t)s.n_elastic * s.n_elastic_mu);
+      }
+    }
+    else if (s.elastic_type != MCW_SAB_ELASTIC_NONE)
+      // IncoherentElasticXS / IncoherentElasticAE (Debye-Waller form, OMC endf.cpp:245-258) is not carried
+      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_thermal_tables: unsupported elastic type" + at);
+    out.push_back(std::move(t));
+  }
+  h->thermal = std::move(out);
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* position, const int32_t* table,
+                             const double* fraction)
+{
+  if (!h || n < 0 || (n > 0 && (!position || !table || !fraction)))
+    return MCW_E_INVALID_ARGUMENT;
+  if (!h->have_mats || material < 0 || material >= (int)h->mat_nuc.size())
+    return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_material_thermal: unknown material (call mcw_set_materials first)");
+  h->mat_sab.resize(h->mat_nuc.size());
+  h->mat_sab_frac.resize(h->mat_nuc.size());
+  std::vector<int32_t> tab(h->mat_nuc[material].size(), -1);
+  std::vector<double> frac(h->mat_nuc[material].size(), 0.0);
+  for (int k = 0; k < n; ++k)
+  {
+    if (position[k] < 0 || position[k] >= (int)tab.size() || table[k] < 0 || table[k] >= (int)h->thermal.size())
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_material_thermal: nuclide position or table out of range");
+    tab[position[k]] = table[k];
+    frac[position[k]] = fraction[k];
+  }
+  h->mat_sab[material] = std::move(tab);
+  h->mat_sab_frac[material] = std::move(frac);
   h->prepared = false;
   return MCW_OK;
 }
@@ -656,6 +775,18 @@ static int prepare(mcw_handle h)
     for (int v : mn)
       if (v < 0 || v >= n_nuc)
         return fail(h, MCW_E_INVALID_ARGUMENT, "material refers to a nuclide outside the library");
+  {
+    // which build of the kernels this problem needs (mcw_kernels.h)
+    bool rare = h->set.record_traces == 2;
+    for (size_t m = 0; m < h->mat_sab.size(); ++m)
+      for (int32_t ts : h->mat_sab[m])
+        rare |= ts >= 0;
+    for (const auto& tl : h->tallies)
+      rare |= !tl.nuclides.empty();
+    for (const auto& n : h->nuclides)
+      rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty();
+    h->rare = rare || h->force_rare > 0;
+  }
 
   // ---- library: OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
   const int M = h->set.n_log_bins;
@@ -780,6 +911,60 @@ static int prepare(mcw_handle h)
     P.lib.tab_energy = d_te, P.lib.tab_x = d_tx, P.lib.tab_p = d_tp, P.lib.tab_c = d_tc;
     P.lib.tab_off = d_to, P.lib.tab_end = d_tn, P.lib.tab_interp = d_ti, P.lib.tab_ndisc = d_td;
   }
+  {
+    // thermal scattering: tables into one pool, per material entry its table and bound fraction
+    std::vector<McwSabDev> sab;
+    std::vector<double> pool;
+    std::vector<int32_t> ipool, mat_sab;
+    std::vector<double> mat_sab_frac;
+    auto put = [&](const std::vector<double>& v) {
+      const int32_t at = (int32_t)pool.size();
+      pool.insert(pool.end(), v.begin(), v.end());
+      return at;
+    };
+    for (const HostThermal& t : h->thermal)
+    {
+      McwSabDev d{};
+      d.energy_max = t.energy_max;
+      d.inel_type = t.inel_type, d.el_type = t.el_type;
+      d.n_ixs = (int32_t)t.ixs_e.size(), d.n_ien = (int32_t)t.ien.size();
+      d.n_mu = t.n_mu, d.n_e_out = t.n_e_out, d.skewed = t.skewed;
+      d.n_el = (int32_t)t.el_x.size(), d.n_el_mu = t.n_el_mu;
+      d.ioff = (int32_t)ipool.size();
+      ipool.insert(ipool.end(), t.ioff.begin(), t.ioff.end());
+      d.ixs_e = put(t.ixs_e), d.ixs = put(t.ixs), d.ien = put(t.ien), d.eout = put(t.eout), d.pdf = put(t.pdf);
+      d.cdf = put(t.cdf), d.mu = put(t.mu), d.el_x = put(t.el_x), d.el_y = put(t.el_y), d.el_mu = put(t.el_mu);
+      sab.push_back(d);
+    }
+    bool any = false;
+    for (int m = 0; m < n_mat; ++m)
+      for (size_t i = 0; i < h->mat_nuc[m].size(); ++i)
+      {
+        const bool have = (size_t)m < h->mat_sab.size() && h->mat_sab[m].size() == h->mat_nuc[m].size();
+        mat_sab.push_back(have ? h->mat_sab[m][i] : -1);
+        mat_sab_frac.push_back(have ? h->mat_sab_frac[m][i] : 0.0);
+        if (mat_sab.back() >= (int32_t)sab.size())
+          return fail(h, MCW_E_INVALID_ARGUMENT, "a material names a thermal table that is not set");
+        any |= mat_sab.back() >= 0;
+      }
+    McwSabDev* d_sab = nullptr;
+    double *d_pool = nullptr, *d_frac = nullptr;
+    int32_t *d_ipool = nullptr, *d_msab = nullptr;
+    if (any)
+    {
+      pool.push_back(0.0);
+      ipool.push_back(0);
+      CK(dev_upload(h, &d_sab, sab));
+      CK(dev_upload(h, &d_pool, pool));
+      CK(dev_upload(h, &d_ipool, ipool));
+      CK(dev_upload(h, &d_msab, mat_sab));
+      CK(dev_upload(h, &d_frac, mat_sab_frac));
+    }
+    P.lib.sab = d_sab, P.lib.sab_pool = d_pool, P.lib.sab_ipool = d_ipool;
+    P.lib.mat_sab = d_msab, P.lib.mat_sab_frac = d_frac;
+    P.lib.n_sab = any ? (int32_t)sab.size() : 0; // 0 switches every S(a,b) branch of the kernels off
+    P.lib.pad_sab = 0;
+  }
   P.lib.energy = d_energy;
   P.lib.xs4 = d_xs4;
   P.lib.el_inel = d_el;
@@ -795,6 +980,13 @@ static int prepare(mcw_handle h)
   P.lib.E_min = E_min;
   P.lib.E_max = E_max;
   P.lib.log_spacing = mcw_log(E_max / E_min) / M;
+  {
+    // the library descriptor once more in global memory, for out-of-line device paths (McwLibraryDev::self_dev)
+    McwLibraryDev* d_lib = nullptr;
+    CK(dev_alloc(h, &d_lib, 1));
+    P.lib.self_dev = d_lib;
+    CK(cudaMemcpy(d_lib, &P.lib, sizeof(McwLibraryDev), cudaMemcpyHostToDevice));
+  }
 
   // ---- mesh: block index / material, subdomain hmax (RT RayTracingStudy.C:497-513), records
   std::map<int32_t, int> block_index;
@@ -1082,9 +1274,9 @@ static int prepare(mcw_handle h)
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
-    h->track_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, false)) * prop.multiProcessorCount;
-    h->fused_max_blocks = std::max(1, mcwk_track_blocks_per_sm(h->elem_type, true)) * prop.multiProcessorCount;
-    h->pump_blocks = std::max(1, mcwk_pump_blocks_per_sm(h->elem_type)) * prop.multiProcessorCount;
+    h->track_max_blocks = std::max(1, MCWK(mcwk_track_blocks_per_sm, h->elem_type, false)) * prop.multiProcessorCount;
+    h->fused_max_blocks = std::max(1, MCWK(mcwk_track_blocks_per_sm, h->elem_type, true)) * prop.multiProcessorCount;
+    h->pump_blocks = std::max(1, MCWK(mcwk_pump_blocks_per_sm, h->elem_type)) * prop.multiProcessorCount;
   }
   h->bank_capacity = 3 * n; // OMC simulation.cpp:286
   h->sampled_capacity = 3 * n + 16;
@@ -1099,12 +1291,12 @@ static int prepare(mcw_handle h)
   CK(dev_alloc(h, &h->d_q_sorted, n + 256));
   CK(dev_alloc(h, &h->d_keys, n + 256));
   CK(dev_alloc(h, &h->d_q_hist, n + 256));
-  CK(dev_alloc(h, &h->d_bins, mcwk_refresh_bins()));
-  CK(dev_alloc(h, &h->d_bin_offsets, mcwk_refresh_bins()));
-  CK(cudaMemset(h->d_bins, 0, mcwk_refresh_bins() * sizeof(uint32_t)));
+  CK(dev_alloc(h, &h->d_bins, MCWK(mcwk_refresh_bins, )));
+  CK(dev_alloc(h, &h->d_bin_offsets, MCWK(mcwk_refresh_bins, )));
+  CK(cudaMemset(h->d_bins, 0, MCWK(mcwk_refresh_bins, ) * sizeof(uint32_t)));
   CK(dev_alloc(h, &h->d_i64_a, std::max(h->bank_capacity, n)));
   CK(dev_alloc(h, &h->d_i64_b, std::max(h->bank_capacity, n)));
-  h->temp_bytes = std::max(mcwk_scan_temp_bytes(std::max(h->bank_capacity, n)), mcwk_compact_temp_bytes(n));
+  h->temp_bytes = std::max(MCWK(mcwk_scan_temp_bytes, std::max(h->bank_capacity, n)), MCWK(mcwk_compact_temp_bytes, n));
   {
     unsigned char* tmp;
     CK(dev_alloc(h, &tmp, h->temp_bytes));
@@ -1191,6 +1383,12 @@ static int prepare(mcw_handle h)
           P.collision_kappa = 1;
     }
   }
+  {
+    McwTallyDev* d_tallies = nullptr;
+    CK(dev_alloc(h, &d_tallies, MCW_MAX_TALLIES));
+    CK(cudaMemcpy(d_tallies, P.tally, sizeof(P.tally), cudaMemcpyHostToDevice));
+    P.tally_dev = d_tallies;
+  }
   P.n_particles_global = h->set.n_particles;
   P.work_offset = h->work_index[h->rank];
   P.master_seed = h->set.master_seed;
@@ -1229,7 +1427,7 @@ int mcw_sample_initial_source(mcw_handle h)
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->d_box, h->set.source_box, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->P.batch = 1;
-  mcwk_sample_source(h->P, h->d_source, h->n_local, h->d_box, h->set.source_only_fissionable, h->stream);
+  MCWK(mcwk_sample_source, h->P, h->d_source, h->n_local, h->d_box, h->set.source_only_fissionable, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   h->n_source = h->n_local;
@@ -1289,7 +1487,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
   CK(cudaEventRecord(h->ev[0], st));
   CK(cudaMemsetAsync(P.counters, 0, sizeof(McwCounters), st));
   CK(cudaMemsetAsync(h->d_reduce + h->n_tally_values, 0, 5 * sizeof(double), st));
-  mcwk_init_histories(P, h->d_source, n, h->d_q_fly[0], st);
+  MCWK(mcwk_init_histories, P, h->d_source, n, h->d_q_fly[0], st);
   R.n_kernel_launches += 1;
   {
     unsigned long long nn = (unsigned long long)n;
@@ -1323,7 +1521,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     {
       // the rest of the generation in one persistent launch: tracking, collision and general-walk warps
       // connected by device-side rings (mcw_pump.cuh)
-      mcwk_pump(P, h->Q, h->d_pump_ctl, h->pump_ctl_bytes, q, cnt_cur, h->d_q_fallback, &P.counters->n_fallback, h->pump_blocks,
+      MCWK(mcwk_pump, P, h->Q, h->d_pump_ctl, h->pump_ctl_bytes, q, cnt_cur, h->d_q_fallback, &P.counters->n_fallback, h->pump_blocks,
                 h->pump_track_warps, h->pump_patience, st);
       R.n_kernel_launches += 2;
       if (prof)
@@ -1332,13 +1530,13 @@ int mcw_transport_generation(mcw_handle h, int batch)
         cudaEventRecord(h->pool_event(3 * rounds + 2), st);
       }
       ++rounds;
-      mcwk_round_reset(P.counters, cur, true, st);
+      MCWK(mcwk_round_reset, P.counters, cur, true, st);
       R.n_kernel_launches += 1;
       break;
     }
     const bool fused = upper < h->tail_threshold;
     const int drain = (!fused && upper >= h->drain_min_queue) ? h->drain_lanes : 0;
-    mcwk_track(P, q, cnt_cur, upper, fused ? h->fused_max_blocks : h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
+    MCWK(mcwk_track, P, q, cnt_cur, upper, fused ? h->fused_max_blocks : h->track_max_blocks, h->d_q_fly[cur ^ 1], cnt_next, h->d_q_collide, h->d_q_fallback,
                drain, fused, h->collide_min, st);
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 1), st);
@@ -1347,28 +1545,29 @@ int mcw_transport_generation(mcw_handle h, int batch)
     const int64_t upper_c = upper + (fb_now ? fb_pending : 0);
     if (fb_now)
     {
-      mcwk_fallback(P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
+      MCWK(mcwk_fallback, P, h->d_q_fallback, &P.counters->n_fallback, h->fallback_blocks, h->d_q_fly[cur ^ 1], cnt_next,
                     h->d_q_collide, st);
       R.n_kernel_launches += 1;
     }
     int32_t* qc = h->d_q_collide;
     if (P.ordered_queues)
     {
-      mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_COLLIDE, qc, &P.counters->n_collide, st);
+      MCWK(mcwk_compact_status, h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_COLLIDE, qc, &P.counters->n_collide, st);
       R.n_kernel_launches += 2;
     }
     // Particle::event_calculate_xs at the survivors' new energies, all material slots.  With
     // sort_xs_queue the survivors are first ordered by energy (OpenMC's TODO at OMC event.cpp:76-82)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
     const int64_t sort_min = h->xs_sort_min > 0 ? h->xs_sort_min : std::max<int64_t>(32768, 2400000 / std::max(1, P.n_plan));
-    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min;
-    mcwk_collide(P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
+    // the tile kernels stage free-atom tables only: libraries with S(a,b) tables refresh through the direct kernel
+    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min && P.lib.n_sab == 0;
+    MCWK(mcwk_collide, P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
                  staged ? h->d_q_hist : nullptr, h->d_bins, st);
-    R.n_kernel_launches += mcwk_xs_refresh(P, qc, &P.counters->n_collide, upper_c, staged, h->d_keys, h->d_q_hist, h->d_bins,
+    R.n_kernel_launches += MCWK(mcwk_xs_refresh, P, qc, &P.counters->n_collide, upper_c, staged, h->d_keys, h->d_q_hist, h->d_bins,
                                            h->d_bin_offsets, h->d_q_sorted, st);
     if (P.ordered_queues)
     {
-      mcwk_compact_status(h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_FLY, h->d_q_fly[cur ^ 1], cnt_next, st);
+      MCWK(mcwk_compact_status, h->d_temp, h->temp_bytes, P.p.status, n, MCW_ST_FLY, h->d_q_fly[cur ^ 1], cnt_next, st);
       R.n_kernel_launches += 2;
     }
     if (prof)
@@ -1387,7 +1586,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
         fb_pending = (int64_t)h->h_counters->n_fallback;
     }
     // reset the consumed queues for the next round (the fallback queue only when it was served)
-    mcwk_round_reset(P.counters, cur, fb_now, st);
+    MCWK(mcwk_round_reset, P.counters, cur, fb_now, st);
     fb_round = sync_now;
     R.n_kernel_launches += 1;
     cur ^= 1;
@@ -1411,11 +1610,11 @@ int mcw_transport_generation(mcw_handle h, int batch)
   }
   h->n_bank = std::min<int64_t>((int64_t)C.n_bank, h->bank_capacity);
   double* g = h->d_reduce + h->n_tally_values;
-  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_col, g + 0, n, st);
-  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_abs, g + 1, n, st);
-  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.k_trk, g + 2, n, st);
-  mcwk_reduce_sum(h->d_temp, h->temp_bytes, P.p.wgt, g + 4, n, st);
-  mcwk_bank_sort(h->d_temp, h->temp_bytes, P.p, n, P.work_offset, h->d_bank, h->n_bank, h->d_i64_a, h->d_i64_b,
+  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_col, g + 0, n, st);
+  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_abs, g + 1, n, st);
+  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_trk, g + 2, n, st);
+  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.wgt, g + 4, n, st);
+  MCWK(mcwk_bank_sort, h->d_temp, h->temp_bytes, P.p, n, P.work_offset, h->d_bank, h->n_bank, h->d_i64_a, h->d_i64_b,
                  h->d_sorted, st);
   R.n_kernel_launches += 4 * 2 + 4;
   CK(cudaEventRecord(h->ev[6], st));
@@ -1491,10 +1690,10 @@ int mcw_sample_bank(mcw_handle h, int batch, int64_t* n_sampled)
     return fail(h, MCW_E_PHYSICS, "No fission sites banked"); // OMC eigenvalue.cpp:107-109
   CK(cudaSetDevice(h->device));
   const int64_t total = h->bank_global_total, np = h->set.n_particles;
-  uint64_t seed0 = mcwk_host_init_seed(0 + batch, 0 /*STREAM_TRACKING*/, h->set.master_seed);
+  uint64_t seed0 = MCWK(mcwk_host_init_seed, 0 + batch, 0 /*STREAM_TRACKING*/, h->set.master_seed);
   if ((total < np ? np / total + 1 : 1) * h->n_bank > h->sampled_capacity)
     return fail(h, MCW_E_ALLOCATE, "sampled-site buffer too small for this bank (too few fission sites)");
-  mcwk_sample_bank(h->d_temp, h->temp_bytes, h->d_sorted, h->n_bank, h->bank_global_start, total, np, seed0, h->d_i64_a,
+  MCWK(mcwk_sample_bank, h->d_temp, h->temp_bytes, h->d_sorted, h->n_bank, h->bank_global_start, total, np, seed0, h->d_i64_a,
                    h->d_i64_b, h->d_sampled, h->sampled_capacity, h->stream);
   int64_t last_off = 0, last_cnt = 0;
   if (h->n_bank > 0)
@@ -1528,7 +1727,7 @@ int mcw_finish_sampling(mcw_handle h, int64_t global_start_of_sampled, int is_la
       int64_t needed = np - finish;
       if (h->n_sampled + needed > h->sampled_capacity)
         return fail(h, MCW_E_ALLOCATE, "sampled-site buffer too small for padding");
-      mcwk_pad_from_bank_end(h->d_sorted, h->n_bank, h->d_sampled, h->n_sampled, needed, h->stream);
+      MCWK(mcwk_pad_from_bank_end, h->d_sorted, h->n_bank, h->d_sampled, h->n_sampled, needed, h->stream);
       CK(cudaStreamSynchronize(h->stream));
       h->n_sampled += needed;
       h->last.n_kernel_launches += 1;
@@ -1626,7 +1825,7 @@ int mcw_finalize_generation(mcw_handle h, int batch, mcw_generation_result* out)
     for (auto& t : h->tallies)
     {
       t.n_realizations += 1;
-      mcwk_tally_accumulate(h->d_reduce + t.offset, t.d_sum, t.d_sum_sq, t.n_values, norm, h->stream);
+      MCWK(mcwk_tally_accumulate, h->d_reduce + t.offset, t.d_sum, t.d_sum_sq, t.n_values, norm, h->stream);
       R.n_kernel_launches += 1;
     }
   }
@@ -1729,7 +1928,7 @@ int mcw_get_history_records(mcw_handle h, mcw_history_record* rec, int64_t capac
   if (rec && capacity > 0 && *n > 0)
   {
     CK(cudaSetDevice(h->device));
-    mcwk_fill_records(h->P.p, *n, h->d_records, h->stream);
+    MCWK(mcwk_fill_records, h->P.p, *n, h->d_records, h->stream);
     CK(cudaMemcpyAsync(rec, h->d_records, std::min(capacity, *n) * sizeof(mcw_history_record), cudaMemcpyDeviceToHost,
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1808,7 +2007,7 @@ int mcw_xs_lookup(mcw_handle h, int64_t n, const double* E, const int32_t* mater
   CK(dev_alloc(h, &dO, 4 * n));
   CK(cudaMemcpyAsync(dE, E, n * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dM, material, n * 4, cudaMemcpyHostToDevice, h->stream));
-  mcwk_xs_lookup_array(h->P.lib, n, dE, dM, dO, h->stream);
+  MCWK(mcwk_xs_lookup_array, h->P.lib, n, dE, dM, dO, h->stream);
   CK(cudaMemcpyAsync(out, dO, 4 * n * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1837,7 +2036,7 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
   {
     if (n > INT32_MAX)
       return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_xs_lookup_device: at most 2^31-1 points per call");
-    temp_bytes = mcwk_sort_temp_bytes(n);
+    temp_bytes = MCWK(mcwk_sort_temp_bytes, n);
     CK(dev_alloc(h, &keys, n));
     CK(dev_alloc(h, &keys_out, n));
     CK(dev_alloc(h, &idx, n));
@@ -1845,16 +2044,18 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
     CK(dev_alloc(h, &temp, temp_bytes));
   }
   CK(cudaEventRecord(h->ev[0], h->stream));
+  if (h->P.lib.n_sab)
+    sorted = 0; // the staged kernels hold free-atom tables only
   for (int r = 0; r < repeats; ++r)
   {
     if (sorted == 0)
-      mcwk_xs_lookup_array(h->P.lib, n, E, mat, (double*)d_out, h->stream);
+      MCWK(mcwk_xs_lookup_array, h->P.lib, n, E, mat, (double*)d_out, h->stream);
     else if (sorted == 1)
-      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, nullptr, (double*)d_out, h->xs_plan != 0, h->stream);
+      MCWK(mcwk_xs_lookup_staged, h->P.lib, n, E, mat, nullptr, (double*)d_out, h->xs_plan != 0, h->stream);
     else
     {
-      mcwk_xs_sort(n, E, mat, temp, temp_bytes, keys, keys_out, idx, idx_sorted, h->stream);
-      mcwk_xs_lookup_staged(h->P.lib, n, E, mat, idx_sorted, (double*)d_out, h->xs_plan != 0, h->stream);
+      MCWK(mcwk_xs_sort, n, E, mat, temp, temp_bytes, keys, keys_out, idx, idx_sorted, h->stream);
+      MCWK(mcwk_xs_lookup_staged, h->P.lib, n, E, mat, idx_sorted, (double*)d_out, h->xs_plan != 0, h->stream);
     }
   }
   CK(cudaEventRecord(h->ev[1], h->stream));
@@ -1908,7 +2109,7 @@ int mcw_trace_rays(mcw_handle h, int64_t n, const double* start, const double* d
     CK(dev_alloc(h, &dMx, n));
     CK(cudaMemcpy(dMx, max_distance, n * 8, cudaMemcpyHostToDevice));
   }
-  mcwk_trace_rays(h->P, n, dS, dD, dE, dSd, dMx, dDist, dSeg, dH, dStat, h->stream);
+  MCWK(mcwk_trace_rays, h->P, n, dS, dD, dE, dSd, dMx, dDist, dSeg, dH, dStat, h->stream);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   CK(cudaMemcpy(out_distance, dDist, n * 8, cudaMemcpyDeviceToHost));
@@ -1940,7 +2141,7 @@ int mcw_locate_points(mcw_handle h, int64_t n, const double* xyz, const int64_t*
     CK(dev_alloc(h, &dR, n));
     CK(cudaMemcpy(dR, ray_id, n * 8, cudaMemcpyHostToDevice));
   }
-  mcwk_locate_points(h->P, n, dX, dR, dE, h->stream);
+  MCWK(mcwk_locate_points, h->P, n, dX, dR, dE, h->stream);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   CK(cudaMemcpy(elem, dE, n * 4, cudaMemcpyDeviceToHost));
@@ -1964,7 +2165,7 @@ int mcw_test_division(mcw_handle h, int64_t n, const double* a, const double* b,
   CK(dev_alloc(h, &dk, n));
   CK(cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
-  mcwk_test_division(n, da, db, df, dp, dk, h->stream);
+  MCWK(mcwk_test_division, n, da, db, df, dp, dk, h->stream);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   CK(cudaMemcpy(q_fast, df, n * 8, cudaMemcpyDeviceToHost));

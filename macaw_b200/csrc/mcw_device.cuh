@@ -213,6 +213,103 @@ MCW_D Micro mcw_micro_xs(const McwLibraryDev& L, int i_nuc, double E, int i_log)
   return m;
 }
 
+// ---- thermal scattering cross sections (OMC thermal.cpp:229-243, endf.cpp:153-239, nuclide.cpp:763-791)
+// lower_bound_index (OMC search.h:14-20) on x[0 .. n)
+MCW_D int mcw_lower_bound_index(const double* __restrict__ x, int n, double v)
+{
+  if (x[0] == v)
+    return 0;
+  int lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const int mid = (lo + hi) >> 1;
+    if (x[mid] < v)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo - 1;
+}
+
+// Tabulated1D::operator() with one lin-lin region
+MCW_D double mcw_tabulated1d(const double* __restrict__ x, const double* __restrict__ y, int n, double v)
+{
+  if (v < x[0])
+    return y[0];
+  if (v > x[n - 1])
+    return y[n - 1];
+  const int i = mcw_lower_bound_index(x, n, v);
+  const double r = (v - x[i]) / (x[i + 1] - x[i]);
+  return y[i] + r * (y[i + 1] - y[i]);
+}
+
+// S(a,b) table of material entry q at energy E, or -1 (OMC material.cpp:778-806: none assigned, or E above the table)
+MCW_D int mcw_sab_of_entry(const McwLibraryDev& L, int q, double E)
+{
+  if (!MCW_RARE || L.n_sab == 0)
+    return -1;
+  const int t = L.mat_sab[q];
+  if (t < 0 || E > L.sab[t].energy_max)
+    return -1;
+  return t;
+}
+
+// ThermalData::calculate_xs
+MCW_D void mcw_sab_xs(const McwLibraryDev& L, const McwSabDev& t, double E, double& elastic, double& inelastic)
+{
+  const double* P = L.sab_pool;
+  if (t.el_type == MCW_SAB_ELASTIC_COHERENT)
+    elastic = E < P[t.el_x] ? 0.0 : P[t.el_y + mcw_lower_bound_index(P + t.el_x, t.n_el, E)] / E;
+  else if (t.el_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+    elastic = mcw_tabulated1d(P + t.el_x, P + t.el_y, t.n_el, E);
+  else
+    elastic = 0.0;
+  inelastic = mcw_tabulated1d(P + t.ixs_e, P + t.ixs, t.n_ixs, E);
+}
+
+// Nuclide::calculate_sab_xs on a freshly interpolated micro of material entry q (table i_sab >= 0): corrects
+// m.total; returns thermal, thermal_elastic and the corrected micro.elastic.  Kept out of line: only libraries
+// with S(a,b) tables come here, and the callers' hot paths should not carry its registers.
+__device__ __noinline__ void mcw_sab_apply_ool(const McwLibraryDev* Lg, int q, int i_sab, double E, int i_grid, double f,
+                                               double* out4)
+{
+  const McwLibraryDev& L = *Lg; // the global-memory copy (McwLibraryDev::self_dev)
+  const double sab_frac = L.mat_sab_frac[q];
+  double el, inel;
+  mcw_sab_xs(L, L.sab[i_sab], E, el, inel);
+  const double thermal = sab_frac * (el + inel);
+  const McwNucParams& n = L.nuc[L.mat_nuc[q]];
+  const double* ei = L.el_inel + 2 * (n.off + i_grid);
+  const double free_elastic = (1.0 - f) * ei[0] + f * ei[2]; // Nuclide::calculate_elastic_xs (nuclide.cpp:517-529)
+  out4[0] = thermal;
+  out4[1] = sab_frac * el;                               // thermal_elastic
+  out4[2] = sab_frac * free_elastic;                     // what the total loses
+  out4[3] = thermal + (1.0 - sab_frac) * free_elastic;   // corrected micro.elastic
+}
+MCW_D void mcw_sab_apply(const McwLibraryDev& L, int q, int i_sab, double E, Micro& m, double& thermal, double& thermal_elastic,
+                         double& elastic)
+{
+  double o[4];
+  mcw_sab_apply_ool(L.self_dev, q, i_sab, E, m.i_grid, m.f, o);
+  thermal = o[0];
+  thermal_elastic = o[1];
+  m.total = m.total + thermal - o[2];
+  elastic = o[3];
+}
+
+// micro cross sections of material entry q (its nuclide, with the S(a,b) correction of the total where a table applies)
+MCW_D Micro mcw_micro_xs_entry(const McwLibraryDev& L, int q, double E, int i_log)
+{
+  Micro m = mcw_micro_xs(L, L.mat_nuc[q], E, i_log);
+  const int i_sab = mcw_sab_of_entry(L, q, E);
+  if (i_sab >= 0)
+  {
+    double th, the, el;
+    mcw_sab_apply(L, q, i_sab, E, m, th, the, el);
+  }
+  return m;
+}
+
 struct Macro
 {
   double total, absorption, fission, nu_fission;
@@ -228,7 +325,7 @@ MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E, double* __
   int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
   for (int i = b; i < e; ++i)
   {
-    Micro m = mcw_micro_xs(L, L.mat_nuc[i], E, i_log);
+    Micro m = mcw_micro_xs_entry(L, i, E, i_log);
     double d = L.mat_dens[i];
     M.total += d * m.total;
     M.absorption += d * m.absorption;

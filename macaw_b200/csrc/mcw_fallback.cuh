@@ -538,13 +538,13 @@ MCW_D int mcw_fallback_history(const McwParams& P, int i)
     {
       W.point = pos;
       status = MCW_ST_COLLIDE;
-      if (P.trace)
+      if (MCW_RARE && P.trace)
         p.tx[i] = st.ipoint.x, p.ty[i] = st.ipoint.y, p.tz[i] = st.ipoint.z;
     }
     else
     {
       int c = W.cross(P.mesh, st);
-      if (P.trace)
+      if (MCW_RARE && P.trace)
         mcw_trace_emit(P, i, p.n_seg[i], 1, st.ipoint, s.E, s.wgt, p.n_progeny[i], s.seed_trk, s.seed_src, s.seed_urr);
       if (c == 1)
       {

@@ -13,8 +13,25 @@
 // One thread = one history slot; queues are index lists with warp-aggregated appends.
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <math.h>
 
+#include "mcw_detmath.h"
 #include "mcw_kernels.h"
+
+// MCW_RARE: 1 = with the rarely used branches (S(a,b), nuclide tally bins, cached trace points, tabulated secondary
+// distributions), 0 = without them; one namespace each (mcw_kernels.h)
+#ifndef MCW_RARE
+#define MCW_RARE 1
+#endif
+#if MCW_RARE
+#define MCW_NS mcw_r1
+#else
+#define MCW_NS mcw_r0
+#endif
+
+namespace MCW_NS
+{
 #include "mcw_physics.cuh"
 
 #define MCW_BLOCK 128
@@ -84,7 +101,7 @@ k_init_histories(McwParams P, const mcw_source_site* __restrict__ src, int64_t n
   p.inc_side[i] = (int8_t)mcw_starting_incoming_side<TYPE>(R, r, dir);
   p.status[i] = MCW_ST_FLY;
   p.fate[i] = -1;
-  if (P.trace)
+  if (MCW_RARE && P.trace)
     mcw_trace_emit(P, (int)i, 0, 0, r, s.E, s.wgt, 0, seeds[0], seeds[1], seeds[2]);
   // Particle::event_calculate_xs for the birth energy, every material slot at once
   mcw_lookup_all_slots(P, i, s.E);
@@ -241,7 +258,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       q_nuc = L.mat_off[i_mat] + (k - pb);
     }
     const int i_log = mcw_log_bin(L, c.E);
-    mx = mcw_micro_xs(L, k_nuc, c.E, i_log);
+    mx = mcw_micro_xs_entry(L, q_nuc, c.E, i_log); // with the S(a,b) correction of the total where a table applies
     // kappa-fission, only when a collision tally asks for it: q * sigma_f * N * flux summed nuclide by
     // nuclide over the fissionable nuclides of the material (OMC tally_scoring.cpp:1246-1255)
     if (P.tallies_active && P.collision_kappa && sig_a != 0.)
@@ -333,10 +350,23 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     double2 r0 = __ldg(ei), r1 = __ldg(ei + 1);
     double elastic = (1.0 - mx.f) * r0.x + mx.f * r1.x;
     bool can_inelastic = nuc.n_inel > 0 && mx.i_grid >= nuc.inel_thr;
-    if (elastic > cut || !can_inelastic)
-      mcw_elastic_scatter(L, nuc, c);
-    else
+    // S(a,b): micro.elastic as corrected by calculate_sab_xs, micro.thermal and micro.thermal_elastic, re-derived here
+    // from the same grid index and interpolation factor instead of being carried through the absorption / fission code
+    double thermal = 0.0, thermal_el = 0.0;
+    const int i_sab = mcw_sab_of_entry(L, q_nuc, E_last);
+    if (i_sab >= 0)
+    {
+      Micro scratch = mx;
+      mcw_sab_apply(L, q_nuc, i_sab, E_last, scratch, thermal, thermal_el, elastic);
+    }
+    if (elastic - thermal > cut)
+      mcw_elastic_scatter(L, nuc, c); // non-S(a,b) elastic (OMC physics.cpp:649-661)
+    else if (i_sab >= 0 && elastic > cut)
+      mcw_sab_scatter(L.self_dev, i_sab, thermal, thermal_el, c); // :663-672
+    else if (can_inelastic)
       mcw_inelastic_scatter(L, nuc, c);
+    else
+      mcw_elastic_scatter(L, nuc, c);
     if (L.mat_iso[q_nuc]) // isotropic-in-lab override (OMC physics.cpp:706-718): phi, then mu
       c.u = mcw_isotropic_direction(c.seed);
     if (c.E != E_last) // OMC physics.cpp:140-144
@@ -355,8 +385,9 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     for (int t = 0; t < P.n_tallies; ++t)
       if (P.tally[t].estimator == MCW_ESTIMATOR_COLLISION)
       {
-        if (P.tally[t].nuclides)
-          mcw_score_tally_nuclides(L, P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, i_mat, flux, sig_a, sc);
+        if (MCW_RARE && P.tally[t].nuclides)
+          mcw_score_tally_nuclides(L.self_dev, P.tally_dev + t, mcw_spatial_bin(P.tally[t], elem, block), E_last, i_mat, flux,
+                                   sig_a, sc);
         else
           mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
       }
@@ -381,7 +412,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
   {
     p.status[i] = MCW_ST_DEAD;
     p.fate[i] = 0;
-    if (P.trace) // the last cached point of the ray: the end of the segment it was absorbed in
+    if (MCW_RARE && P.trace) // the last cached point of the ray: the end of the segment it was absorbed in
       mcw_trace_emit(P, i, p.n_seg[i], 3, v3(p.tx[i], p.ty[i], p.tz[i]), c.E, c.wgt, c.n_progeny, seed_trk, seed_src, seed_urr);
   }
   else
@@ -456,7 +487,19 @@ MCW_D void mcw_warp_lookup_all_slots(const McwParams& P, unsigned m_need, int i,
       double t = 0.0, a = 0.0, f = 0.0, nf = 0.0, mine = 0.0;
       if (q < P.n_plan)
       {
-        const Micro m = mcw_micro_xs(P.lib, P.plan_nuc[q], he, i_log);
+        Micro m = mcw_micro_xs(P.lib, P.plan_nuc[q], he, i_log);
+        if (MCW_RARE && P.lib.n_sab)
+        {
+          // the plan entry's position in its material, for the S(a,b) correction of the total
+          const int sl = P.plan_slot[q];
+          const int ent = P.lib.mat_off[P.slot_mat[sl]] + q - P.slot_plan_off[sl];
+          const int i_sab = mcw_sab_of_entry(P.lib, ent, he);
+          if (i_sab >= 0)
+          {
+            double th, the, el;
+            mcw_sab_apply(P.lib, ent, i_sab, he, m, th, the, el);
+          }
+        }
         const double d = P.plan_dens[q];
         t = d * m.total;
         a = d * m.absorption;
@@ -1062,3 +1105,4 @@ uint64_t mcwk_host_init_seed(int64_t id, int offset, int64_t master_seed)
   }
   return g_new * seed + c_new;
 }
+} // namespace MCW_NS

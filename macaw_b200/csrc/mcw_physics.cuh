@@ -69,9 +69,11 @@ MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, cons
 // (score_general_ce, i_nuclide >= 0: :600-606 total, :746-750 fission, :805-809 nu-fission, :1238-1244 kappa-fission)
 // and nothing otherwise (:2391-2394); the bin -1 scores the material totals `sc`.  score_index = j * n_scores + s.
 // Rarely asked for, so out of line (the collision kernel's code stays compact) and with plain atomics.
-__device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev& L, const McwTallyDev& t, int64_t spatial, double E,
+__device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev* Lg, const McwTallyDev* tg, int64_t spatial, double E,
                                                       int i_mat, double flux, double sig_a, const double* sc)
 {
+  const McwLibraryDev& L = *Lg; // global-memory copies: see McwLibraryDev::self_dev
+  const McwTallyDev& t = *tg;
   const int eb = mcw_tally_energy_bin(t, E);
   if (eb < 0)
     return;
@@ -96,7 +98,7 @@ __device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev& L, co
     if (q == qe)
       continue; // mat_nuclide_index_ == C_NONE
     const double dens = L.mat_dens[q];
-    const Micro m = mcw_micro_xs(L, in, E, i_log);
+    const Micro m = mcw_micro_xs_entry(L, q, E, i_log);
     for (int s = 0; s < t.n_scores; ++s)
     {
       double v;
@@ -209,8 +211,9 @@ MCW_D bool mcw_segment_nl(const McwParams& P, SegState& s, double neg_log, int e
           need_kappa |= P.tally[t].scores[q] == MCW_SCORE_KAPPA_FISSION;
         if (need_kappa)
           sc[MCW_SCORE_KAPPA_FISSION] = s.sig_a == 0. ? 0.0 : mcw_kappa_macro(P.lib, i_mat, s.E, flux);
-        if (P.tally[t].nuclides)
-          mcw_score_tally_nuclides(P.lib, P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, i_mat, flux, s.sig_a, sc);
+        if (MCW_RARE && P.tally[t].nuclides)
+          mcw_score_tally_nuclides(P.lib.self_dev, P.tally_dev + t, mcw_spatial_bin(P.tally[t], elem, block), s.E, i_mat, flux,
+                                   s.sig_a, sc);
         else
           mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, sc);
       }
@@ -242,6 +245,137 @@ struct ColState
   uint64_t seed; // tracking stream
   int n_progeny;
 };
+
+// ---- thermal scattering S(a,b): OMC secondary_thermal.cpp; all tables live in McwLibraryDev::sab_pool
+// get_energy_index (:14-25)
+MCW_D void mcw_sab_energy_index(const double* __restrict__ e, int n, double E, int& i, double& f)
+{
+  i = 0;
+  f = 0.0;
+  if (E >= e[0])
+  {
+    i = mcw_lower_bound_index(e, n, E);
+    f = (E - e[i]) / (e[i + 1] - e[i]);
+  }
+}
+
+// sab_scatter (OMC physics.cpp:788-802) over ThermalData::sample (thermal.cpp:245-262): CoherentElasticAE (:36-58),
+// IncoherentElasticAEDiscrete (:96-126), IncoherentInelasticAEDiscrete (:138-188), IncoherentInelasticAE (:236-332).
+// Out of line: only libraries with S(a,b) tables come here.
+__device__ __noinline__ void mcw_sab_scatter(const McwLibraryDev* Lg, int i_sab, double thermal, double thermal_elastic,
+                                             ColState& p)
+{
+  const McwLibraryDev& L = *Lg; // the global-memory copy (McwLibraryDev::self_dev)
+  const McwSabDev& t = L.sab[i_sab];
+  const double* P = L.sab_pool;
+  const double E_in = p.E;
+  double E_out, mu, f;
+  int i;
+  if (mcw_prn(p.seed) < thermal_elastic / thermal)
+  {
+    if (t.el_type == MCW_SAB_ELASTIC_COHERENT)
+    {
+      const double* edges = P + t.el_x;
+      const double* factors = P + t.el_y;
+      mcw_sab_energy_index(edges, t.n_el, E_in, i, f);
+      const double prob = mcw_prn(p.seed) * factors[i + 1];
+      int k = 0;
+      if (prob >= factors[0])
+        k = mcw_lower_bound_index(factors, i + 1, prob);
+      mu = 1.0 - 2.0 * edges[k] / E_in;
+    }
+    else
+    {
+      mcw_sab_energy_index(P + t.el_x, t.n_el, E_in, i, f);
+      const int n_mu = t.n_el_mu;
+      const int k = (int)(mcw_prn(p.seed) * n_mu);
+      const double* m0 = P + t.el_mu + (size_t)i * n_mu;
+      const double* m1 = m0 + n_mu;
+      mu = m0[k] + f * (m1[k] - m0[k]);
+      const double mu_left = (k == 0) ? -1.0 - (mu + 1.0) : m0[k - 1] + f * (m1[k - 1] - m0[k - 1]);
+      const double mu_right = (k == n_mu - 1) ? 1.0 + (1.0 - mu) : m0[k + 1] + f * (m1[k + 1] - m0[k + 1]);
+      mu += fmin(mu - mu_left, mu_right - mu) * (mcw_prn(p.seed) - 0.5);
+    }
+    E_out = E_in;
+  }
+  else if (t.inel_type == MCW_SAB_INELASTIC_DISCRETE)
+  {
+    mcw_sab_energy_index(P + t.ixs_e, t.n_ixs, E_in, i, f);
+    int j;
+    const int n = t.n_e_out;
+    if (!t.skewed)
+      j = (int)(mcw_prn(p.seed) * n);
+    else
+    {
+      const double r = mcw_prn(p.seed) * (n - 3);
+      if (r > 1.0)
+        j = (int)(r + 1);
+      else if (r > 0.6)
+        j = n - 2;
+      else if (r > 0.5)
+        j = n - 1;
+      else if (r > 0.1)
+        j = 1;
+      else
+        j = 0;
+    }
+    const double E_ij = P[t.eout + (size_t)i * n + j];
+    const double E_i1j = P[t.eout + (size_t)(i + 1) * n + j];
+    E_out = (1 - f) * E_ij + f * E_i1j;
+    const int m = t.n_mu;
+    const int k = (int)(mcw_prn(p.seed) * m);
+    const double mu_ijk = P[t.mu + ((size_t)i * n + j) * m + k];
+    const double mu_i1jk = P[t.mu + ((size_t)(i + 1) * n + j) * m + k];
+    mu = (1 - f) * mu_ijk + f * mu_i1jk;
+  }
+  else
+  {
+    const double* ien = P + t.ien;
+    mcw_sab_energy_index(ien, t.n_ien, E_in, i, f);
+    const int l = f > 0.5 ? i + 1 : i;
+    const int b = L.sab_ipool[t.ioff + l];
+    const int n = L.sab_ipool[t.ioff + l + 1] - b;
+    const double* e_out = P + t.eout + b;
+    const double* pdf = P + t.pdf + b;
+    const double* cdf = P + t.cdf + b;
+    const double r1 = mcw_prn(p.seed);
+    double c_j = cdf[0], c_j1 = 0.0;
+    int j;
+    for (j = 0; j < n - 1; ++j)
+    {
+      c_j1 = cdf[j + 1];
+      if (r1 < c_j1)
+        break;
+      c_j = c_j1;
+    }
+    j = min(j, n - 2);
+    const double E_l_j = e_out[j], p_l_j = pdf[j];
+    const double E_l_j1 = e_out[j + 1], p_l_j1 = pdf[j + 1];
+    const double frac = (p_l_j1 - p_l_j) / (E_l_j1 - E_l_j);
+    if (frac == 0.0)
+      E_out = E_l_j + (r1 - c_j) / p_l_j;
+    else
+      E_out = E_l_j + (sqrt(fmax(0.0, p_l_j * p_l_j + 2.0 * frac * (r1 - c_j))) - p_l_j) / frac;
+    const double E_l = ien[l];
+    if (E_out < 0.5 * E_l)
+      E_out *= 2.0 * E_in / E_l - 1.0;
+    else
+      E_out += E_in - E_l;
+    const int n_mu = t.n_mu;
+    const int k = (int)(mcw_prn(p.seed) * n_mu);
+    const double* mu_j = P + t.mu + ((size_t)b + j) * n_mu;
+    const double* mu_j1 = mu_j + n_mu;
+    f = (r1 - c_j) / (c_j1 - c_j);
+    mu = mu_j[k] + f * (mu_j1[k] - mu_j[k]);
+    const double mu_left = (k == 0) ? -1.0 - (mu + 1.0) : mu_j[k - 1] + f * (mu_j1[k - 1] - mu_j[k - 1]);
+    const double mu_right = (k == n_mu - 1) ? 1.0 + (1.0 - mu) : mu_j[k + 1] + f * (mu_j1[k + 1] - mu_j[k + 1]);
+    mu += fmin(mu - mu_left, mu_right - mu) * (mcw_prn(p.seed) - 0.5);
+  }
+  if (fabs(mu) > 1.0)
+    mu = copysign(1.0, mu);
+  p.E = E_out;
+  p.u = mcw_rotate_angle(p.u, mu, p.seed);
+}
 
 // OMC physics.cpp:955-1004
 MCW_D V3 mcw_sample_cxs_target_velocity(double awr, double E, V3 u, double kT, uint64_t& seed)
@@ -449,7 +583,7 @@ MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, 
   v_n = v_n - v_cm;
   vel = norm(v_n);
   double mu_cm;
-  if (nuc.el_ang_n > 0)
+  if (MCW_RARE && nuc.el_ang_n > 0)
     mu_cm = mcw_angle_sample(L, nuc.el_ang_first, nuc.el_ang_n, p.E, p.seed);
   else
     mu_cm = mcw_uniform(-1., 1., p.seed);
@@ -468,16 +602,16 @@ MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc
 {
   double E_in = p.E;
   double mu;
-  if (nuc.inel_ang_n > 0)
+  if (MCW_RARE && nuc.inel_ang_n > 0)
     mu = mcw_angle_sample(L, nuc.inel_ang_first, nuc.inel_ang_n, E_in, p.seed);
   else
     mu = mcw_uniform(-1., 1., p.seed);
   double E;
-  if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+  if (MCW_RARE && nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
     E = mcw_continuous_tabular_sample(L, nuc.inel_en_first, nuc.inel_en_n, nuc.inel_en_hist != 0, E_in, p.seed);
   else
     E = nuc.inel_ratio * (E_in - nuc.inel_E);
-  if (nuc.inel_in_cm)
+  if (!MCW_RARE || nuc.inel_in_cm) // the level law always scatters in the centre of mass
   {
     double E_cm = E;
     double A = nuc.awr;

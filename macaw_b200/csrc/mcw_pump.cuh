@@ -257,7 +257,7 @@ MCW_D void mcw_pump_track(const McwParams& P, const McwPump& Q)
             point = pos;
             status = MCW_ST_COLLIDE;
             leave = true;
-            if (P.trace)
+            if (MCW_RARE && P.trace)
               p.tx[i] = ipoint.x, p.ty[i] = ipoint.y, p.tz[i] = ipoint.z;
           }
           else
@@ -283,7 +283,7 @@ MCW_D void mcw_pump_track(const McwParams& P, const McwPump& Q)
               else
                 state = LN_REFLECT;
             }
-            if (P.trace)
+            if (MCW_RARE && P.trace)
               mcw_trace_emit(P, i, n_seg, 1, ipoint, s.E, s.wgt, p.n_progeny[i], s.seed_trk, p.seed_src[i],
                              p.seed_urr[i]);
           }

@@ -637,7 +637,7 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
             point = pos;
             status = MCW_ST_COLLIDE;
             leave = true;
-            if (P.trace)
+            if (MCW_RARE && P.trace)
               p.tx[i] = ipoint.x, p.ty[i] = ipoint.y, p.tz[i] = ipoint.z;
           }
           else
@@ -665,7 +665,7 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
               else
                 state = MCW_LN_REFLECT;
             }
-            if (P.trace)
+            if (MCW_RARE && P.trace)
               mcw_trace_emit(P, i, n_seg, 1, ipoint, s.E, s.wgt, p.n_progeny[i], s.seed_trk, p.seed_src[i],
                              p.seed_urr[i]);
           }

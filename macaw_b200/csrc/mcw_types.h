@@ -42,6 +42,15 @@ struct McwNucParams
   int32_t inel_en_hist, inel_in_cm; // ContinuousTabular: histogram interpolation in incoming energy; scatter_in_cm_
 };
 
+// One temperature of an S(alpha, beta) table (mcw_thermal_desc): offsets into McwLibraryDev::sab_pool (doubles) /
+// sab_ipool (the continuous law's distribution offsets)
+struct McwSabDev
+{
+  double energy_max;
+  int32_t inel_type, el_type, n_ixs, n_ien, n_mu, n_e_out, skewed, n_el, n_el_mu, ioff;
+  int32_t ixs_e, ixs, ien, eout, pdf, cdf, mu, el_x, el_y, el_mu;
+};
+
 struct McwLibraryDev
 {
   const double* energy;      // [sumG]
@@ -65,6 +74,17 @@ struct McwLibraryDev
   const int32_t* tab_interp;
   const int32_t* tab_ndisc;
   const double *tab_x, *tab_p, *tab_c;
+  // thermal scattering: tables, their pools, and per material entry the table (-1 = none) and the bound fraction
+  const McwSabDev* sab;
+  const double* sab_pool;
+  const int32_t* sab_ipool;
+  const int32_t* mat_sab;
+  const double* mat_sab_frac;
+  int32_t n_sab, pad_sab;
+  // This struct again, in global memory.  The kernels get McwParams by value (parameter space); an out-of-line device
+  // function that took `lib` by reference would force a private copy of the whole parameter block into every thread's
+  // local memory, so the rare out-of-line paths (S(a,b), nuclide tally bins) are handed this pointer instead.
+  const McwLibraryDev* self_dev;
   int32_t n_nuc, n_mat, M;
   double E_min, E_max, log_spacing;
 };
@@ -178,6 +198,7 @@ struct McwParams
   McwMeshDev mesh;
   McwParticlesDev p;
   McwTallyDev tally[MCW_MAX_TALLIES];
+  const McwTallyDev* tally_dev; // the same array in global memory, for out-of-line scoring paths (see McwLibraryDev::self_dev)
   int32_t n_tallies, tallies_active;
   int32_t any_tracklength, any_collision_tally;
   // 1: the collide / fly queues are rebuilt every round by compacting the status array (history-index

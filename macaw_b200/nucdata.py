@@ -115,6 +115,97 @@ class Material:
     nuclides: list   # indices into the library
     densities: list  # atom / b-cm
     isotropic: list = None  # per-nuclide isotropic-in-lab flags (<isotropic> of materials.xml), None = none
+    sab: list = None        # S(a,b) tables: (position in `nuclides`, table index, fraction), sorted by position
+
+
+@dataclass
+class ThermalTable:
+    """One temperature of an S(alpha, beta) table (mcw_thermal_desc; OMC thermal.cpp ThermalData)."""
+    name: str
+    energy_max: float
+    inelastic_type: int            # 0 continuous (IncoherentInelasticAE), 1 discrete (IncoherentInelasticAEDiscrete)
+    inelastic_xs_energy: np.ndarray
+    inelastic_xs: np.ndarray
+    n_mu: int
+    # continuous
+    inelastic_energy: np.ndarray = None
+    inelastic_offset: np.ndarray = None
+    inelastic_e_out: np.ndarray = None   # continuous: per point; discrete: (n_xs, n_e_out)
+    inelastic_pdf: np.ndarray = None
+    inelastic_cdf: np.ndarray = None
+    inelastic_mu: np.ndarray = None      # continuous: (points, n_mu); discrete: (n_xs, n_e_out, n_mu)
+    n_e_out: int = 0
+    skewed: bool = False
+    elastic_type: int = 0          # 0 none, 1 coherent (Bragg edges), 2 incoherent discrete
+    elastic_x: np.ndarray = None
+    elastic_y: np.ndarray = None
+    elastic_mu: np.ndarray = None  # (n_elastic, n_elastic_mu)
+
+
+def make_thermal_table(rng, name, kind="continuous", elastic="none", energy_max=4.0, n_mu=8) -> ThermalTable:
+    """A synthetic S(a,b) table of the shape the ENDF/B thermal files have: an inelastic cross section that falls from
+    the bound to the free value over [1e-5, energy_max] eV, and either continuous outgoing-energy distributions with
+    n_mu equiprobable cosines per outgoing energy or equiprobable discrete (energy, cosine) bins; optionally Bragg edges
+    (coherent elastic) or a tabulated elastic cross section with discrete cosines."""
+    n_xs = 24
+    ex = np.exp(np.linspace(np.log(1.0e-5), np.log(energy_max), n_xs))
+    ixs = 20.0 + 60.0 / (1.0 + (ex / 0.05) ** 0.8) * rng.uniform(0.9, 1.1, n_xs)
+    t = ThermalTable(name, float(energy_max), 0 if kind == "continuous" else 1, ex, ixs, n_mu)
+
+    def cosines(n):
+        m = np.sort(rng.uniform(-1.0, 1.0, (n, n_mu)), axis=1)
+        return m
+    if kind == "continuous":
+        n_in = 9
+        ein = np.exp(np.linspace(np.log(1.0e-5), np.log(energy_max), n_in))
+        off, eo, pd, cd = [0], [], [], []
+        for l in range(n_in):
+            n = int(rng.integers(5, 14))
+            top = ein[l] + 0.25 * rng.uniform(0.5, 1.5)   # up-scatter by about kT-ish amounts
+            e = np.sort(np.concatenate([[1.0e-6 * top, top], rng.uniform(1.0e-6 * top, top, n - 2)]))
+            p, c = _tabulated_pdf(rng, e, 2)
+            eo.append(e); pd.append(p); cd.append(c); off.append(off[-1] + n)
+        t.inelastic_energy = ein
+        t.inelastic_offset = np.array(off, np.int32)
+        t.inelastic_e_out, t.inelastic_pdf, t.inelastic_cdf = np.concatenate(eo), np.concatenate(pd), np.concatenate(cd)
+        t.inelastic_mu = cosines(off[-1])
+    else:
+        t.n_e_out = 12
+        t.skewed = kind == "discrete_skewed"
+        t.inelastic_e_out = np.sort(ex[:, None] * rng.uniform(0.05, 1.6, (n_xs, t.n_e_out)) + 1.0e-4, axis=1)
+        t.inelastic_mu = cosines(n_xs * t.n_e_out).reshape(n_xs, t.n_e_out, n_mu)
+    if elastic == "coherent":
+        t.elastic_type = 1
+        t.elastic_x = np.sort(np.exp(rng.uniform(np.log(1.8e-3), np.log(0.9 * energy_max), 14)))
+        t.elastic_y = np.cumsum(rng.uniform(0.002, 0.02, 14))
+    elif elastic == "incoherent_discrete":
+        t.elastic_type = 2
+        t.elastic_x = np.exp(np.linspace(np.log(1.0e-5), np.log(energy_max), 11))
+        t.elastic_y = 5.0 / (1.0 + t.elastic_x / 0.02) + 0.01
+        t.elastic_mu = np.sort(rng.uniform(-1.0, 1.0, (11, 6)), axis=1)
+    return t
+
+
+def add_thermal_scattering(lib: "Library", seed=5):
+    """Gives a library S(a,b) tables the way the BEAVRS deck has them (materials.xml <sab name="c_H_in_H2O"/>): hydrogen
+    in every material that holds H1 is bound (continuous inelastic, no elastic); a second nuclide, where a material has
+    one with A > 10, gets a table with coherent elastic + discrete inelastic at fraction 0.75 (the partial-binding
+    branch of calculate_sab_xs), a third one incoherent-discrete elastic + skewed discrete inelastic."""
+    rng = np.random.Generator(np.random.PCG64([seed, 4242]))
+    lib.thermal_tables = [make_thermal_table(rng, "c_H_in_H2O", "continuous", "none", 4.0),
+                          make_thermal_table(rng, "c_Graphite_like", "discrete", "coherent", 2.5),
+                          make_thermal_table(rng, "c_ZrH_like", "discrete_skewed", "incoherent_discrete", 1.9)]
+    for m in lib.materials:
+        sab, used = [], 1
+        for pos, i in enumerate(m.nuclides):
+            n = lib.nuclides[i]
+            if n.name == "H1":
+                sab.append((pos, 0, 1.0))
+            elif n.awr > 10 and not n.fissionable and used < 3:
+                sab.append((pos, used, 0.75 if used == 1 else 1.0))
+                used += 1
+        m.sab = sorted(sab) if sab else None
+    return lib
 
 
 @dataclass
@@ -122,6 +213,7 @@ class Library:
     nuclides: list
     materials: list
     n_log_bins: int = 8000
+    thermal_tables: list = None
 
     def total_points(self):
         return int(sum(n.energy.size for n in self.nuclides))
@@ -346,6 +438,42 @@ class NuclideDesc(C.Structure):
                 ("watt_a", C.c_double), ("watt_b", C.c_double), ("q_fission", C.c_double),
                 ("elastic_angle", Tabular2DDesc), ("inelastic_angle", Tabular2DDesc), ("inelastic_law", C.c_int32),
                 ("inelastic_in_cm", C.c_int32), ("inelastic_energy", Tabular2DDesc)]
+
+
+class ThermalDesc(C.Structure):
+    _fields_ = [("energy_max", C.c_double), ("inelastic_type", C.c_int32), ("elastic_type", C.c_int32),
+                ("n_inelastic_xs", C.c_int32), ("n_inelastic_energy", C.c_int32), ("inelastic_xs_energy", C.c_void_p),
+                ("inelastic_xs", C.c_void_p), ("inelastic_energy", C.c_void_p), ("inelastic_offset", C.c_void_p),
+                ("inelastic_e_out", C.c_void_p), ("inelastic_pdf", C.c_void_p), ("inelastic_cdf", C.c_void_p),
+                ("inelastic_mu", C.c_void_p), ("n_mu", C.c_int32), ("n_e_out", C.c_int32), ("skewed", C.c_int32),
+                ("n_elastic", C.c_int32), ("elastic_x", C.c_void_p), ("elastic_y", C.c_void_p), ("elastic_mu", C.c_void_p),
+                ("n_elastic_mu", C.c_int32), ("reserved0", C.c_int32)]
+
+
+def pack_thermal(tables):
+    """mcw_thermal_desc array of a list of ThermalTable; returns (descs, keepalive)."""
+    keep = []
+    td = (ThermalDesc * max(len(tables), 1))()
+
+    def ptr(a, dt=np.float64):
+        if a is None:
+            return None
+        b = np.ascontiguousarray(a, dt)
+        keep.append(b)
+        return b.ctypes.data
+    for d, t in zip(td, tables):
+        d.energy_max, d.inelastic_type, d.elastic_type = t.energy_max, t.inelastic_type, t.elastic_type
+        d.n_inelastic_xs = int(np.size(t.inelastic_xs_energy))
+        d.inelastic_xs_energy, d.inelastic_xs = ptr(t.inelastic_xs_energy), ptr(t.inelastic_xs)
+        d.n_inelastic_energy = int(np.size(t.inelastic_energy)) if t.inelastic_energy is not None else 0
+        d.inelastic_energy, d.inelastic_offset = ptr(t.inelastic_energy), ptr(t.inelastic_offset, np.int32)
+        d.inelastic_e_out, d.inelastic_pdf, d.inelastic_cdf = ptr(t.inelastic_e_out), ptr(t.inelastic_pdf), ptr(t.inelastic_cdf)
+        d.inelastic_mu = ptr(t.inelastic_mu)
+        d.n_mu, d.n_e_out, d.skewed = t.n_mu, t.n_e_out, int(t.skewed)
+        d.n_elastic = int(np.size(t.elastic_x)) if t.elastic_x is not None else 0
+        d.elastic_x, d.elastic_y, d.elastic_mu = ptr(t.elastic_x), ptr(t.elastic_y), ptr(t.elastic_mu)
+        d.n_elastic_mu = int(t.elastic_mu.shape[1]) if t.elastic_mu is not None else 0
+    return td, keep
 
 
 class MaterialDesc(C.Structure):

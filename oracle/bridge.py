@@ -41,6 +41,8 @@ def _load(name):
     lib.orc_sample_cxs_target_velocity.argtypes = [C.c_double, C.c_double, f64p, C.c_double, u64p, f64p]
     lib.orc_tracklength_kappa.argtypes = [C.c_void_p, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
     lib.orc_set_tally_nuclides.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.orc_set_thermal_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.orc_set_material_thermal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.orc_score_nuclide_bins.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, f64p, f64p,
                                            f64p, f64p]
     lib.orc_history_identity.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), u64p]
@@ -149,6 +151,9 @@ def ref_lib():
             r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
                                                   u64p, C.c_int64, f64p, f64p, C.c_int, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
+        if hasattr(r, "ref_add_thermal_table"):
+            r.ref_add_thermal_table.argtypes = [C.c_char_p, C.c_void_p, C.c_double]
+            r.ref_set_material_thermal.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, f64p]
         if hasattr(r, "ref_score_nuclide_bins"):
             r.ref_score_nuclide_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int64,
                                                  f64p, f64p, f64p, C.c_double, f64p]
@@ -223,6 +228,17 @@ def ref_load_library(r, libr: nucdata.Library):
         nn, dd = np.ascontiguousarray(m.nuclides, np.int32), np.ascontiguousarray(m.densities, np.float64)
         iso = np.ascontiguousarray(m.isotropic, np.int32) if m.isotropic is not None else None
         r.ref_add_material(nn.size, nn.ctypes.data, dp(dd), iso.ctypes.data if iso is not None else None)
+    if getattr(libr, "thermal_tables", None):
+        from macaw_b200 import nucdata as _nd
+        td, keep = _nd.pack_thermal(libr.thermal_tables)
+        for k, t in enumerate(libr.thermal_tables):
+            r.ref_add_thermal_table(t.name.encode(), C.addressof(td[k]), libr.nuclides[0].kT)
+        for im, m in enumerate(libr.materials):
+            if getattr(m, "sab", None):
+                pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)
+                tab = np.ascontiguousarray([a[1] for a in m.sab], np.int32)
+                fr = np.ascontiguousarray([a[2] for a in m.sab], np.float64)
+                r.ref_set_material_thermal(im, pos.size, pos.ctypes.data, tab.ctypes.data, dp(fr))
     return out
 
 
@@ -260,6 +276,17 @@ class Oracle:
         self.L.orc_set_library(self.h, C.addressof(nd), len(libr.nuclides), libr.n_log_bins)
         bm = np.ascontiguousarray(block_material, np.int32)
         self.L.orc_set_materials(self.h, C.addressof(md), len(libr.materials), _p(bm), bm.size)
+        if getattr(libr, "thermal_tables", None):
+            td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
+            self._keep.append((td, keep2))
+            self.L.orc_set_thermal_tables(self.h, C.addressof(td), len(libr.thermal_tables))
+            for im, m in enumerate(libr.materials):
+                if getattr(m, "sab", None):
+                    pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)
+                    tab = np.ascontiguousarray([a[1] for a in m.sab], np.int32)
+                    fr = np.ascontiguousarray([a[2] for a in m.sab], np.float64)
+                    if self.L.orc_set_material_thermal(self.h, im, pos.size, _p(pos), _p(tab), _p(fr)):
+                        raise RuntimeError("orc_set_material_thermal failed")
 
     def set_settings(self, s: Settings):
         self.settings = s

@@ -241,6 +241,8 @@ struct Material
   std::vector<int> nuc;
   std::vector<double> dens;
   std::vector<int> iso; // isotropic-in-lab flags (OMC material.cpp:255-270 p0_)
+  std::vector<int> sab_table;   // per nuclide position: S(a,b) table index or -1 (OMC material.cpp thermal_tables_); empty = none
+  std::vector<double> sab_frac; // per nuclide position: fraction bound
   bool fissionable = false;
 };
 
@@ -249,6 +251,19 @@ struct Micro // subset of OMC particle_data.h:82-112 NuclideMicroXS
   double total, absorption, fission, nu_fission;
   int i_grid;
   double f;
+  // S(a,b) treatment (OMC nuclide.cpp:740-791): index_sab, thermal = sab_frac * (elastic + inelastic), thermal_elastic,
+  // and the corrected micro.elastic; i_sab < 0 = free-atom scattering (elastic is then evaluated on demand)
+  int i_sab = -1;
+  double thermal = 0.0, thermal_elastic = 0.0, elastic = 0.0;
+};
+
+// One temperature of a thermal scattering table (mcw_thermal_desc; OMC thermal.cpp ThermalData + secondary_thermal.cpp)
+struct ThermalTable
+{
+  double energy_max = 0;
+  int inel_type = 0, el_type = 0, n_mu = 0, n_e_out = 0, skewed = 0, n_el_mu = 0;
+  std::vector<double> ixs_e, ixs, ien, eout, pdf, cdf, mu, el_x, el_y, el_mu;
+  std::vector<int> ioff;
 };
 
 struct Macro // OMC particle_data.h:134-146
@@ -260,6 +275,7 @@ struct Library
 {
   std::vector<Nuclide> nuclides;
   std::vector<Material> materials;
+  std::vector<ThermalTable> thermal;
   double E_min = 0, E_max = 0, log_spacing = 0;
   int n_log_bins = 8000;
 
@@ -359,6 +375,50 @@ struct Library
     return i;
   }
 
+  // Tabulated1D::operator() with one lin-lin region (OMC endf.cpp:153-212)
+  static double tabulated1d(const std::vector<double>& x, const std::vector<double>& y, double v)
+  {
+    const int n = (int)x.size();
+    if (v < x[0])
+      return y[0];
+    if (v > x[n - 1])
+      return y[n - 1];
+    const int i = lower_bound_index(x.data(), x.data() + n, v);
+    const double r = (v - x[i]) / (x[i + 1] - x[i]);
+    return y[i] + r * (y[i + 1] - y[i]);
+  }
+
+  // ThermalData::calculate_xs (OMC thermal.cpp:229-243) with CoherentElasticXS::operator() (endf.cpp:229-239)
+  void thermal_xs(const ThermalTable& t, double E, double& elastic, double& inelastic) const
+  {
+    if (t.el_type == MCW_SAB_ELASTIC_COHERENT)
+    {
+      if (E < t.el_x[0])
+        elastic = 0.0;
+      else
+        elastic = t.el_y[lower_bound_index(t.el_x.data(), t.el_x.data() + t.el_x.size(), E)] / E;
+    }
+    else if (t.el_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+      elastic = tabulated1d(t.el_x, t.el_y, E);
+    else
+      elastic = 0.0;
+    inelastic = tabulated1d(t.ixs_e, t.ixs, E);
+  }
+
+  // Nuclide::calculate_sab_xs (OMC nuclide.cpp:763-791) on a freshly interpolated micro; the free-atom elastic cross
+  // section is Nuclide::calculate_elastic_xs (:517-529)
+  void apply_sab(const Nuclide& n, int i_sab, double sab_frac, double E, Micro& m) const
+  {
+    m.i_sab = i_sab;
+    double elastic, inelastic;
+    thermal_xs(thermal[i_sab], E, elastic, inelastic);
+    m.thermal = sab_frac * (elastic + inelastic);
+    m.thermal_elastic = sab_frac * elastic;
+    const double free_elastic = (1.0 - m.f) * n.elastic[m.i_grid] + m.f * n.elastic[m.i_grid + 1];
+    m.total = m.total + m.thermal - sab_frac * free_elastic;
+    m.elastic = m.thermal + (1.0 - sab_frac) * free_elastic;
+  }
+
   // OMC material.cpp:748-831
   Macro macro_xs(int i_mat, double E, Micro* cache /* [materials[i_mat].nuc.size()] or null */,
                  int64_t* n_nuclide_lookups = nullptr) const
@@ -369,6 +429,9 @@ struct Library
     for (size_t i = 0; i < mat.nuc.size(); ++i)
     {
       Micro m = micro_xs(mat.nuc[i], E, i_log);
+      // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)
+      if (!mat.sab_table.empty() && mat.sab_table[i] >= 0 && !(E > thermal[mat.sab_table[i]].energy_max))
+        apply_sab(nuclides[mat.nuc[i]], mat.sab_table[i], mat.sab_frac[i], E, m);
       if (cache)
         cache[i] = m;
       double d = mat.dens[i];

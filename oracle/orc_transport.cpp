@@ -344,6 +344,153 @@ static double continuous_tabular_sample(const Tabular2D& t, double E, uint64_t* 
   return E_out;
 }
 
+// ---- thermal scattering S(a,b): OMC secondary_thermal.cpp
+// get_energy_index (:14-25)
+static void get_energy_index(const double* e, int n, double E, int& i, double& f)
+{
+  i = 0;
+  f = 0.0;
+  if (E >= e[0])
+  {
+    i = Library::lower_bound_index(e, e + n, E);
+    f = (E - e[i]) / (e[i + 1] - e[i]);
+  }
+}
+
+// CoherentElasticAE::sample (:36-58)
+static void sab_coherent_elastic(const ThermalTable& t, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  int i;
+  double f;
+  const int n = (int)t.el_x.size();
+  get_energy_index(t.el_x.data(), n, E_in, i, f);
+  const double prob = prn(seed) * t.el_y[i + 1];
+  int k = 0;
+  if (prob >= t.el_y[0])
+    k = Library::lower_bound_index(t.el_y.data(), t.el_y.data() + (i + 1), prob);
+  mu = 1.0 - 2.0 * t.el_x[k] / E_in;
+  E_out = E_in;
+}
+
+// IncoherentElasticAEDiscrete::sample (:96-126)
+static void sab_incoherent_elastic_discrete(const ThermalTable& t, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  int i;
+  double f;
+  get_energy_index(t.el_x.data(), (int)t.el_x.size(), E_in, i, f);
+  const int n_mu = t.n_el_mu;
+  const int k = (int)(prn(seed) * n_mu);
+  const double* m0 = &t.el_mu[(size_t)i * n_mu];
+  const double* m1 = m0 + n_mu;
+  mu = m0[k] + f * (m1[k] - m0[k]);
+  const double mu_left = (k == 0) ? -1.0 - (mu + 1.0) : m0[k - 1] + f * (m1[k - 1] - m0[k - 1]);
+  const double mu_right = (k == n_mu - 1) ? 1.0 + (1.0 - mu) : m0[k + 1] + f * (m1[k + 1] - m0[k + 1]);
+  mu += std::min(mu - mu_left, mu_right - mu) * (prn(seed) - 0.5);
+  E_out = E_in;
+}
+
+// IncoherentInelasticAEDiscrete::sample (:138-188)
+static void sab_inelastic_discrete(const ThermalTable& t, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  int i;
+  double f;
+  get_energy_index(t.ixs_e.data(), (int)t.ixs_e.size(), E_in, i, f);
+  int j;
+  const int n = t.n_e_out;
+  if (!t.skewed)
+    j = (int)(prn(seed) * n);
+  else
+  {
+    const double r = prn(seed) * (n - 3);
+    if (r > 1.0)
+      j = (int)(r + 1);
+    else if (r > 0.6)
+      j = n - 2;
+    else if (r > 0.5)
+      j = n - 1;
+    else if (r > 0.1)
+      j = 1;
+    else
+      j = 0;
+  }
+  const double E_ij = t.eout[(size_t)i * n + j];
+  const double E_i1j = t.eout[(size_t)(i + 1) * n + j];
+  E_out = (1 - f) * E_ij + f * E_i1j;
+  const int m = t.n_mu;
+  const int k = (int)(prn(seed) * m);
+  const double mu_ijk = t.mu[((size_t)i * n + j) * m + k];
+  const double mu_i1jk = t.mu[((size_t)(i + 1) * n + j) * m + k];
+  mu = (1 - f) * mu_ijk + f * mu_i1jk;
+}
+
+// IncoherentInelasticAE::sample (:236-332)
+static void sab_inelastic_continuous(const ThermalTable& t, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  int i;
+  double f;
+  get_energy_index(t.ien.data(), (int)t.ien.size(), E_in, i, f);
+  const int l = f > 0.5 ? i + 1 : i;
+  const int b = t.ioff[l];
+  const size_t n = (size_t)(t.ioff[l + 1] - b);
+  const double* e_out = &t.eout[b];
+  const double* pdf = &t.pdf[b];
+  const double* cdf = &t.cdf[b];
+  const double r1 = prn(seed);
+  double c_j = cdf[0];
+  double c_j1 = 0.0; // the reference leaves it uninitialised; it is always assigned when n >= 2
+  size_t j;
+  for (j = 0; j < n - 1; ++j)
+  {
+    c_j1 = cdf[j + 1];
+    if (r1 < c_j1)
+      break;
+    c_j = c_j1;
+  }
+  j = std::min(j, n - 2);
+  const double E_l_j = e_out[j], p_l_j = pdf[j];
+  const double E_l_j1 = e_out[j + 1], p_l_j1 = pdf[j + 1];
+  const double frac = (p_l_j1 - p_l_j) / (E_l_j1 - E_l_j);
+  if (frac == 0.0)
+    E_out = E_l_j + (r1 - c_j) / p_l_j;
+  else
+    E_out = E_l_j + (std::sqrt(std::max(0.0, p_l_j * p_l_j + 2.0 * frac * (r1 - c_j))) - p_l_j) / frac;
+  const double E_l = t.ien[l];
+  if (E_out < 0.5 * E_l)
+    E_out *= 2.0 * E_in / E_l - 1.0;
+  else
+    E_out += E_in - E_l;
+  const int n_mu = t.n_mu;
+  const size_t k = (size_t)(prn(seed) * n_mu);
+  const double* mu_j = &t.mu[((size_t)b + j) * n_mu];
+  const double* mu_j1 = mu_j + n_mu;
+  f = (r1 - c_j) / (c_j1 - c_j);
+  mu = mu_j[k] + f * (mu_j1[k] - mu_j[k]);
+  const double mu_left = (k == 0) ? -1.0 - (mu + 1.0) : mu_j[k - 1] + f * (mu_j1[k - 1] - mu_j[k - 1]);
+  const double mu_right = (k == (size_t)n_mu - 1) ? 1.0 + (1.0 - mu) : mu_j[k + 1] + f * (mu_j1[k + 1] - mu_j[k + 1]);
+  mu += std::min(mu - mu_left, mu_right - mu) * (prn(seed) - 0.5);
+}
+
+// sab_scatter (OMC physics.cpp:788-802) over ThermalData::sample (thermal.cpp:245-262)
+static void sab_scatter(const ThermalTable& t, const Micro& micro, Hist& p)
+{
+  double E_out, mu;
+  if (prn(&p.seeds[0]) < micro.thermal_elastic / micro.thermal)
+  {
+    if (t.el_type == MCW_SAB_ELASTIC_COHERENT)
+      sab_coherent_elastic(t, p.E, E_out, mu, &p.seeds[0]);
+    else
+      sab_incoherent_elastic_discrete(t, p.E, E_out, mu, &p.seeds[0]);
+  }
+  else if (t.inel_type == MCW_SAB_INELASTIC_CONTINUOUS)
+    sab_inelastic_continuous(t, p.E, E_out, mu, &p.seeds[0]);
+  else
+    sab_inelastic_discrete(t, p.E, E_out, mu, &p.seeds[0]);
+  if (std::fabs(mu) > 1.0)
+    mu = std::copysign(1.0, mu);
+  p.E = E_out;
+  p.u = rotate_angle(p.u, mu, nullptr, &p.seeds[0]);
+}
+
 // OMC physics.cpp:721-786 (tabular angular distribution :749-757, else "assume isotropic")
 static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
 {
@@ -542,13 +689,17 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
     double cut = prn(&p.seeds[0]) * (mx.total - mx.absorption);
     double f = mx.f;
     int ig = mx.i_grid;
-    double elastic = (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
-    double pr = elastic;
+    // micro.elastic: corrected by calculate_sab_xs when a table applies, else evaluated now (physics.cpp:644-647)
+    double elastic = mx.i_sab >= 0 ? mx.elastic : (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
     bool can_inelastic = nuc.n_inel > 0 && ig >= nuc.inel_thr;
-    if (pr > cut || !can_inelastic)
-      elastic_scatter(nuc, nuc.kT, p);
-    else
+    if (elastic - mx.thermal > cut)
+      elastic_scatter(nuc, nuc.kT, p); // non-S(a,b) elastic (:649-661)
+    else if (elastic > cut && mx.i_sab >= 0)
+      sab_scatter(P.lib.thermal[mx.i_sab], mx, p); // :663-672
+    else if (can_inelastic)
       inelastic_scatter(nuc, p);
+    else
+      elastic_scatter(nuc, nuc.kT, p);
     // isotropic-in-lab override for nuclides of the material's <isotropic> list (OMC physics.cpp:706-718)
     if (!mat.iso.empty() && mat.iso[k])
       p.u = isotropic_direction(&p.seeds[0]);
@@ -1019,6 +1170,73 @@ int orc_set_materials(void* h, const mcw_material_desc* m, int n, const int32_t*
   }
   P.block_material.assign(block_material, block_material + n_blocks);
   P.lib.finalize();
+  return 0;
+}
+
+// data::thermal_scatt (OMC thermal.cpp:30-32), one temperature each
+int orc_set_thermal_tables(void* h, const mcw_thermal_desc* d, int n)
+{
+  Problem& P = *(Problem*)h;
+  P.lib.thermal.clear();
+  for (int k = 0; k < n; ++k)
+  {
+    const mcw_thermal_desc& s = d[k];
+    ThermalTable t;
+    t.energy_max = s.energy_max;
+    t.inel_type = s.inelastic_type;
+    t.el_type = s.elastic_type;
+    t.n_mu = s.n_mu;
+    t.n_e_out = s.n_e_out;
+    t.skewed = s.skewed;
+    t.n_el_mu = s.n_elastic_mu;
+    t.ixs_e.assign(s.inelastic_xs_energy, s.inelastic_xs_energy + s.n_inelastic_xs);
+    t.ixs.assign(s.inelastic_xs, s.inelastic_xs + s.n_inelastic_xs);
+    if (s.inelastic_type == MCW_SAB_INELASTIC_CONTINUOUS)
+    {
+      t.ien.assign(s.inelastic_energy, s.inelastic_energy + s.n_inelastic_energy);
+      t.ioff.assign(s.inelastic_offset, s.inelastic_offset + s.n_inelastic_energy + 1);
+      const int np = t.ioff.back();
+      t.eout.assign(s.inelastic_e_out, s.inelastic_e_out + np);
+      t.pdf.assign(s.inelastic_pdf, s.inelastic_pdf + np);
+      t.cdf.assign(s.inelastic_cdf, s.inelastic_cdf + np);
+      t.mu.assign(s.inelastic_mu, s.inelastic_mu + (size_t)np * s.n_mu);
+    }
+    else
+    {
+      const size_t np = (size_t)s.n_inelastic_xs * s.n_e_out;
+      t.eout.assign(s.inelastic_e_out, s.inelastic_e_out + np);
+      t.mu.assign(s.inelastic_mu, s.inelastic_mu + np * s.n_mu);
+    }
+    if (s.elastic_type != MCW_SAB_ELASTIC_NONE)
+    {
+      t.el_x.assign(s.elastic_x, s.elastic_x + s.n_elastic);
+      t.el_y.assign(s.elastic_y, s.elastic_y + s.n_elastic);
+      if (s.elastic_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+        t.el_mu.assign(s.elastic_mu, s.elastic_mu + (size_t)s.n_elastic * s.n_elastic_mu);
+    }
+    P.lib.thermal.push_back(std::move(t));
+  }
+  return 0;
+}
+
+// Material::thermal_tables_ (OMC material.cpp:140-160,317-360)
+int orc_set_material_thermal(void* h, int material, int n, const int32_t* position, const int32_t* table, const double* fraction)
+{
+  Problem& P = *(Problem*)h;
+  if (material < 0 || material >= (int)P.lib.materials.size())
+    return -1;
+  Material& M = P.lib.materials[material];
+  M.sab_table.assign(M.nuc.size(), -1);
+  M.sab_frac.assign(M.nuc.size(), 0.0);
+  for (int k = 0; k < n; ++k)
+  {
+    if (position[k] < 0 || position[k] >= (int)M.nuc.size() || table[k] < 0 || table[k] >= (int)P.lib.thermal.size())
+      return -1;
+    M.sab_table[position[k]] = table[k];
+    M.sab_frac[position[k]] = fraction[k];
+  }
+  if (n == 0)
+    M.sab_table.clear(), M.sab_frac.clear();
   return 0;
 }
 

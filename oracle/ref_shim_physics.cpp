@@ -29,6 +29,7 @@
 #include "openmc/particle.h"
 #include "openmc/settings.h"
 #include "openmc/simulation.h"
+#include "openmc/thermal.h"
 #include "ref_hdf5_mem.h"
 #include "../include/macaw_b200.h" // mcw_tabular2d: the tables arrive in the product's own descriptor layout
 
@@ -111,6 +112,8 @@ REF_API void ref_library_reset()
   model::materials.clear();
   data::nuclides.clear();
   data::nuclide_map.clear();
+  data::thermal_scatt.clear();
+  data::thermal_scatt_map.clear();
   g_root.reset(new memh5::Node);
   settings::run_CE = true;
   settings::run_mode = RunMode::EIGENVALUE;
@@ -217,6 +220,109 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
   }
   data::nuclides.push_back(std::make_unique<Nuclide>(memh5::id_of(g), std::vector<double>{(double)T}));
   return (int)data::nuclides.size() - 1;
+}
+
+// One S(a,b) table at the temperature of kT as a thermal-scattering file image, read by the reference's own
+// ThermalScattering / ThermalData constructors (thermal.cpp:38-227) -- and through them Tabulated1D, CoherentElasticXS,
+// CorrelatedAngleEnergy -> IncoherentInelasticAE, IncoherentInelasticAEDiscrete, CoherentElasticAE,
+// IncoherentElasticAEDiscrete.  Returns its index in data::thermal_scatt.
+REF_API int ref_add_thermal_table(const char* name, const mcw_thermal_desc* t, double kT)
+{
+  using namespace openmc;
+  auto tabulated = [](memh5::Node* parent, const double* x, const double* y, int n) {
+    std::vector<double> flat(2 * (size_t)n);
+    for (int k = 0; k < n; ++k)
+      flat[k] = x[k], flat[n + k] = y[k];
+    memh5::Node* d = parent->dataset("xs", flat, {2, (unsigned long long)n});
+    d->attr("type", "Tabulated1D");
+    d->attr("breakpoints", std::vector<int>{n});
+    d->attr("interpolation", std::vector<int>{2});
+    return d;
+  };
+  memh5::Node* g = g_root->group(name);
+  g->attr("atomic_weight_ratio", 0.999167);
+  g->attr("energy_max", t->energy_max);
+  g->attrs["nuclides"] = memh5::Array{memh5::Array::TEXT, {1}, {}, {}, "H1"};
+  const int T = (int)std::round(kT / K_BOLTZMANN);
+  const std::string temp = std::to_string(T) + "K";
+  g->group("kTs")->dataset(temp, {kT}, {})->data.shape.clear();
+  memh5::Node* tg = g->group(temp);
+  // ---- inelastic
+  memh5::Node* in = tg->group("inelastic");
+  tabulated(in, t->inelastic_xs_energy, t->inelastic_xs, t->n_inelastic_xs);
+  memh5::Node* d = in->group("distribution");
+  if (t->inelastic_type == MCW_SAB_INELASTIC_CONTINUOUS)
+  {
+    // the correlated angle-energy layout (secondary_correlated.cpp:22-150): energy_out rows = E_out, pdf, cdf, cosine
+    // interpolation (0 = discrete cosines), offset into mu; mu rows = cosine, pdf, cdf
+    d->attr("type", "incoherent_inelastic");
+    const int n_in = t->n_inelastic_energy, np = t->inelastic_offset[n_in], n_mu = t->n_mu;
+    memh5::Node* en = d->dataset("energy", std::vector<double>(t->inelastic_energy, t->inelastic_energy + n_in));
+    en->attr("interpolation", std::vector<int>{n_in, 2}, {2, 1});
+    std::vector<double> eo(5 * (size_t)np), mu(3 * (size_t)np * n_mu);
+    for (int k = 0; k < np; ++k)
+    {
+      eo[k] = t->inelastic_e_out[k];
+      eo[np + k] = t->inelastic_pdf[k];
+      eo[2 * (size_t)np + k] = t->inelastic_cdf[k];
+      eo[3 * (size_t)np + k] = 0.0;
+      eo[4 * (size_t)np + k] = (double)k * n_mu;
+      for (int m = 0; m < n_mu; ++m)
+      {
+        const size_t c = (size_t)k * n_mu + m, M = (size_t)np * n_mu;
+        mu[c] = t->inelastic_mu[c];
+        mu[M + c] = 1.0 / n_mu;
+        mu[2 * M + c] = (m + 1.0) / n_mu;
+      }
+    }
+    memh5::Node* eod = d->dataset("energy_out", eo, {5, (unsigned long long)np});
+    eod->attr("offsets", std::vector<int>(t->inelastic_offset, t->inelastic_offset + n_in));
+    eod->attr("interpolation", std::vector<int>(n_in, 2));
+    eod->attr("n_discrete_lines", std::vector<int>(n_in, 0));
+    d->dataset("mu", mu, {3, (unsigned long long)np * n_mu});
+  }
+  else
+  {
+    d->attr("type", "incoherent_inelastic_discrete");
+    const unsigned long long n_in = t->n_inelastic_xs, n_out = t->n_e_out, n_mu = t->n_mu;
+    d->dataset("energy_out", std::vector<double>(t->inelastic_e_out, t->inelastic_e_out + n_in * n_out), {n_in, n_out});
+    d->dataset("mu_out", std::vector<double>(t->inelastic_mu, t->inelastic_mu + n_in * n_out * n_mu), {n_in, n_out, n_mu});
+    d->dataset("skewed", {(double)(t->skewed != 0)}, {})->data.shape.clear();
+  }
+  // ---- elastic
+  if (t->elastic_type != MCW_SAB_ELASTIC_NONE)
+  {
+    memh5::Node* el = tg->group("elastic");
+    memh5::Node* ed = el->group("distribution");
+    const int n = t->n_elastic;
+    if (t->elastic_type == MCW_SAB_ELASTIC_COHERENT)
+    {
+      std::vector<double> flat(2 * (size_t)n);
+      for (int k = 0; k < n; ++k)
+        flat[k] = t->elastic_x[k], flat[n + k] = t->elastic_y[k];
+      el->dataset("xs", flat, {2, (unsigned long long)n})->attr("type", "CoherentElastic");
+      ed->attr("type", "coherent_elastic");
+    }
+    else
+    {
+      tabulated(el, t->elastic_x, t->elastic_y, n);
+      ed->attr("type", "incoherent_elastic_discrete");
+      ed->dataset("mu_out", std::vector<double>(t->elastic_mu, t->elastic_mu + (size_t)n * t->n_elastic_mu),
+                  {(unsigned long long)n, (unsigned long long)t->n_elastic_mu});
+    }
+  }
+  data::thermal_scatt.push_back(std::make_unique<ThermalScattering>(memh5::id_of(g), std::vector<double>{(double)T}));
+  return (int)data::thermal_scatt.size() - 1;
+}
+
+// <sab> entries of a material (Material::thermal_tables_, material.cpp:317-360): sorted by nuclide position
+REF_API void ref_set_material_thermal(int i_mat, int n, const int32_t* position, const int32_t* table, const double* fraction)
+{
+  using namespace openmc;
+  std::vector<Material::ThermalTable> tables;
+  for (int k = 0; k < n; ++k)
+    tables.push_back({table[k], position[k], fraction[k]});
+  model::materials[i_mat]->thermal_tables_ = tables;
 }
 
 // energy limits of the library, then every nuclide's logarithmic grid index (what read_ce_cross_sections does after loading)

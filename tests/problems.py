@@ -97,7 +97,35 @@ def beavrs_assembly(n_particles=3000, G=400, n_inactive=1, **kw):
     return mesh, lib, [role[meshgen.BEAVRS_BLOCK_ROLE[b]] for b in sorted(meshgen.BEAVRS_BLOCK_ROLE)], s
 
 
-PROBLEMS = {"beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
+def pin_cell_tet_tabular(**kw):
+    """Tabulated secondary distributions in the data: angular distributions of elastic / inelastic reactions,
+    ContinuousTabular laws in the CM and the LAB system (OMC distribution_angle.cpp, distribution_energy.cpp)."""
+    mesh, lib, bm, s = pin_cell_tet(**kw)
+    lib2 = nucdata.make_library(9, G=lib.nuclides[0].energy.size, tabular=True)
+    return mesh, lib2, bm, s
+
+
+def pin_cell_tet_sab(**kw):
+    """S(alpha, beta) tables on hydrogen (continuous inelastic), on a second nuclide per material (coherent elastic +
+    discrete inelastic, fraction 0.75) and a third (incoherent-discrete elastic + skewed discrete inelastic)."""
+    mesh, lib, bm, s = pin_cell_tet(**kw)
+    return mesh, nucdata.add_thermal_scattering(lib), bm, s
+
+
+def beavrs_assembly_sab(**kw):
+    """The BEAVRS assembly with bound hydrogen in the water, as its materials.xml has it (<sab name="c_H_in_H2O"/>)."""
+    mesh, lib, bm, s = beavrs_assembly(**kw)
+    return mesh, nucdata.add_thermal_scattering(lib), bm, s
+
+
+def infinite_medium_sab(**kw):
+    mesh, lib, bm, s = infinite_medium(**kw)
+    return mesh, nucdata.add_thermal_scattering(lib), bm, s
+
+
+PROBLEMS = {"pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
+            "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
+            "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
             "infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,
             "assembly_quad": assembly_quad}
 

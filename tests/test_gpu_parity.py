@@ -33,7 +33,7 @@ def both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=False, nucl
     return o, g, mesh, lib, s
 
 
-@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad"])
+@pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad", "pin_cell_tet_sab", "beavrs_assembly_sab"])
 def test_xs_lookup_bit_exact(oracle_bridge, ctx_factory, name):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=False)
     E, mat = problems.lookup_points(lib, 20000)
@@ -175,7 +175,19 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     ("beavrs_assembly", {}, PUMP), ("pin_cell_tet_iso", {}, PUMP_TAIL),
     ("pin_cell_tet", {"n_particles": 20000}, PUMP), ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 5000}),
     ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 1 << 30, "pump_track_warps": 1, "pump_patience": 1}),
-    ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 1 << 30, "pump_track_warps": 3, "pump_patience": 64})])
+    ("pin_cell_tet", {"n_particles": 20000}, {"pump_threshold": 1 << 30, "pump_track_warps": 3, "pump_patience": 64}),
+    # the kernel build with the rarely used branches compiled in (csrc/mcw_kernels.h) on problems that do not need it:
+    # same results as the common build
+    ("pin_cell_tet", {}, {**MIXED, "force_rare": 1}), ("beavrs_assembly", {"sort_xs_queue": 1}, {**SORTED, "force_rare": 1}),
+    ("pin_cell_hex", {}, {**EVENT, "force_rare": 1}), ("assembly_quad", {}, {**PUMP_TAIL, "force_rare": 1}),
+    # tabulated secondary distributions (AngleDistribution, ContinuousTabular in CM and LAB)
+    ("pin_cell_tet_tabular", {}, EVENT), ("pin_cell_tet_tabular", {}, FUSED), ("pin_cell_tet_tabular", {}, PUMP),
+    ("pin_cell_tet_tabular", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # thermal scattering S(a,b): bound cross sections below energy_max, sab_scatter (continuous / discrete inelastic,
+    # coherent / incoherent-discrete elastic, partial binding)
+    ("infinite_medium_sab", {}, EVENT), ("pin_cell_tet_sab", {}, EVENT), ("pin_cell_tet_sab", {}, FUSED),
+    ("pin_cell_tet_sab", {"sort_xs_queue": 1}, SORTED), ("pin_cell_tet_sab", {}, PUMP),
+    ("beavrs_assembly_sab", {"sort_xs_queue": 1}, MIXED), ("pin_cell_tet_sab", {"n_particles": 20000}, {"tail_threshold": 3000})])
 def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
     for k, v in opts.items():
