@@ -8,7 +8,9 @@
 #pragma once
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <thread>
+#include <unistd.h>
 
 #include <cuda_runtime_api.h>
 #include <nccl.h>
@@ -25,12 +27,23 @@ public:
   {
     cuda(cudaSetDevice(device), "cudaSetDevice");
     ncclUniqueId id;
+    // The id file carries a launch nonce next to the id (MCW_LAUNCH_NONCE if set, else the launcher's pid, which the
+    // ranks of one torchrun / mpirun-style launch share), so a file left behind by an earlier or crashed run is never
+    // mistaken for this launch's; rank 0 also removes any old file first and deletes its own once every rank is in.
+    unsigned long long nonce = (unsigned long long)getppid();
+    if (const char* env = std::getenv("MCW_LAUNCH_NONCE"))
+    {
+      nonce = 1469598103934665603ull;
+      for (const char* c = env; *c; ++c)
+        nonce = (nonce ^ (unsigned char)*c) * 1099511628211ull;
+    }
     if (rank == 0)
     {
+      std::remove(id_file.c_str());
       nccl(ncclGetUniqueId(&id), "ncclGetUniqueId");
       const std::string tmp = id_file + ".tmp";
       FILE* f = std::fopen(tmp.c_str(), "wb");
-      if (!f || std::fwrite(&id, sizeof(id), 1, f) != 1)
+      if (!f || std::fwrite(&nonce, sizeof(nonce), 1, f) != 1 || std::fwrite(&id, sizeof(id), 1, f) != 1)
         mooseError("cannot write " + tmp);
       std::fclose(f);
       if (std::rename(tmp.c_str(), id_file.c_str()) != 0)
@@ -38,14 +51,24 @@ public:
     }
     else
     {
-      FILE* f = nullptr;
-      for (int tries = 0; tries < 6000 && !(f = std::fopen(id_file.c_str(), "rb")); ++tries)
-        std::this_thread::sleep_for(std::chrono::milliseconds(10));
-      if (!f || std::fread(&id, sizeof(id), 1, f) != 1)
-        mooseError("rank " + std::to_string(rank) + " never saw the NCCL id file " + id_file);
-      std::fclose(f);
+      bool ok = false;
+      for (int tries = 0; tries < 6000 && !ok; ++tries)
+      {
+        unsigned long long seen = 0;
+        if (FILE* f = std::fopen(id_file.c_str(), "rb"))
+        {
+          ok = std::fread(&seen, sizeof(seen), 1, f) == 1 && seen == nonce && std::fread(&id, sizeof(id), 1, f) == 1;
+          std::fclose(f);
+        }
+        if (!ok)
+          std::this_thread::sleep_for(std::chrono::milliseconds(10));
+      }
+      if (!ok)
+        mooseError("rank " + std::to_string(rank) + " never saw this launch's NCCL id in " + id_file);
     }
-    nccl(ncclCommInitRank(&_comm, nranks, id, rank), "ncclCommInitRank");
+    nccl(ncclCommInitRank(&_comm, nranks, id, rank), "ncclCommInitRank"); // returns once every rank has joined
+    if (rank == 0)
+      std::remove(id_file.c_str());
     cuda(cudaMalloc(&_d_counts, sizeof(int64_t) * (size_t)(nranks + 1)), "cudaMalloc");
     cuda(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   }

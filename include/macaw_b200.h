@@ -192,6 +192,26 @@ typedef struct mcw_thermal_desc
   int32_t reserved0;
 } mcw_thermal_desc;
 
+/* Unresolved-resonance probability tables of one nuclide at its temperature: openmc::UrrData (OMC urr.cpp:7-33), used by
+ * Nuclide::calculate_urr_xs (nuclide.cpp:795-924) when the energy lies strictly inside the table's range.  The band is
+ * picked with one random number of the history's URR stream, future_prn(nuclide index, seed) -- the stream MaCaw carries
+ * as ray aux data and advances by n_nuclides after every collision that changes the energy (OMC physics.cpp:140-144) --
+ * so the cross sections of a history depend on its URR seed.  Elastic scattering off a nuclide in its unresolved range
+ * takes the target at rest (physics.cpp:735-738).  Linear-linear tables only (interpolation = 2). */
+typedef struct mcw_urr_desc
+{
+  int32_t nuclide;          /* library index */
+  int32_t interpolation;    /* 2 = lin-lin; log-log (5) is not carried */
+  int32_t inelastic_flag;   /* -1 = none (C_NONE), else the MT of the competing inelastic reaction (the nuclide's own: 51) */
+  int32_t absorption_flag;  /* read by the reference, not used in the cross-section calculation */
+  int32_t multiply_smooth;  /* 1: the table holds factors on the smooth cross sections */
+  int32_t n_energy;
+  int32_t n_band;
+  int32_t reserved0;
+  const double* energy;     /* [n_energy] */
+  const double* table;      /* [n_energy][6][n_band]: cumulative probability, total, elastic, fission, (n,gamma), heating */
+} mcw_urr_desc;
+
 /* Run settings: the subset of openmc::settings MaCaw reads (OMC settings.cpp:41-116) plus the
  * MaCaw/MOOSE parameters that change the numbers (MC CollisionKernel.C:38, RT RayTracingStudy.C). */
 typedef struct mcw_settings
@@ -220,7 +240,8 @@ typedef struct mcw_generation_result
   double k_collision;      /* this generation's global tallies / total weight */
   double k_absorption;
   double k_tracklength;
-  double leakage;
+  double leakage;          /* always 0: MaCaw's kill boundary ends the ray without scoring OpenMC's leakage global tally
+                            * (that happens in Particle::cross_vacuum_bc, which the MOOSE path never calls) */
   double total_weight;
   int64_t n_histories;
   int64_t n_segments;      /* "intersections" */
@@ -329,6 +350,11 @@ int mcw_set_materials(mcw_handle h, const mcw_material_desc* materials, int n,
 int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* tables, int n);
 int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* nuclide_position, const int32_t* table,
                              const double* fraction);
+
+/* Probability tables of the nuclides that have them (`urr/<T>K` of a nuclide file, OMC nuclide.cpp:225-270).  Call after
+ * mcw_set_library.  The stand-alone lookups mcw_xs_lookup / mcw_xs_lookup_device have no history and therefore no URR
+ * stream: they return the smooth cross sections. */
+int mcw_set_urr_tables(mcw_handle h, const mcw_urr_desc* tables, int n);
 
 /* Coupled temperature variable of CollisionKernel, one value per element or one scalar (n = 1)
  * [MC CollisionKernel.C:33,109]. */

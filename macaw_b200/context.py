@@ -68,6 +68,10 @@ class Context:
         bm = np.ascontiguousarray(block_material, np.int32)
         assert ids.size == bm.size
         self._ck(self.L.mcw_set_materials(self.h, C.addressof(md), len(libr.materials), _p(ids), _p(bm), bm.size))
+        if getattr(libr, "urr_tables", None):  # unresolved-resonance probability tables
+            ud, keep3 = nucdata.pack_urr(libr.urr_tables)
+            self._keep.append((ud, keep3))
+            self._ck(self.L.mcw_set_urr_tables(self.h, C.addressof(ud), len(libr.urr_tables)))
         if getattr(libr, "thermal_tables", None):  # S(a,b): data::thermal_scatt + the materials' <sab> entries
             td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
             self._keep.append((td, keep2))

@@ -46,8 +46,15 @@ struct HostTable // one mcw_tabular2d, copied
   int hist = 0;
 };
 
+struct HostUrr // one mcw_urr_desc, copied
+{
+  std::vector<double> energy, table;
+  int n_band = 0, inel_flag = -1, multiply_smooth = 0;
+};
+
 struct HostNuclide
 {
+  HostUrr urr;
   McwNucParams prm;
   std::vector<double> energy, xs5, elastic, inelastic_full;
   std::vector<int32_t> grid_index;
@@ -651,6 +658,39 @@ int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* d, int n)
   return MCW_OK;
 }
 
+int mcw_set_urr_tables(mcw_handle h, const mcw_urr_desc* d, int n)
+{
+  if (!h || n < 0 || (n > 0 && !d))
+    return MCW_E_INVALID_ARGUMENT;
+  if (!h->have_lib)
+    return fail(h, MCW_E_NOT_READY, "mcw_set_urr_tables: call mcw_set_library first");
+  for (auto& nuc : h->nuclides)
+    nuc.urr = HostUrr();
+  for (int k = 0; k < n; ++k)
+  {
+    const mcw_urr_desc& u = d[k];
+    if (u.nuclide < 0 || u.nuclide >= (int)h->nuclides.size() || u.n_energy < 2 || u.n_band < 1 || !u.energy || !u.table)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_urr_tables: bad table " + std::to_string(k));
+    if (u.interpolation != 2)
+      // log-log tables (OMC nuclide.cpp:846-884) need exp / log of the table values: not carried
+      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_urr_tables: only linear-linear probability tables are supported");
+    HostNuclide& nuc = h->nuclides[u.nuclide];
+    if (u.inelastic_flag > 0 && nuc.prm.n_inel == 0)
+      // OMC nuclide.cpp:266-270
+      return fail(h, MCW_E_INVALID_ARGUMENT, "Could no find inelastic reaction specified on unresolved resonance probability table.");
+    for (int e = 0; e < u.n_energy; ++e)
+      if (!(u.table[((size_t)e * 6 + 0) * u.n_band + u.n_band - 1] >= 1.0))
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_urr_tables: a cumulative probability does not reach 1");
+    nuc.urr.energy.assign(u.energy, u.energy + u.n_energy);
+    nuc.urr.table.assign(u.table, u.table + (size_t)u.n_energy * 6 * u.n_band);
+    nuc.urr.n_band = u.n_band;
+    nuc.urr.inel_flag = u.inelastic_flag > 0 ? u.inelastic_flag : -1;
+    nuc.urr.multiply_smooth = u.multiply_smooth != 0;
+  }
+  h->prepared = false;
+  return MCW_OK;
+}
+
 int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* position, const int32_t* table,
                              const double* fraction)
 {
@@ -784,7 +824,7 @@ static int prepare(mcw_handle h)
     for (const auto& tl : h->tallies)
       rare |= !tl.nuclides.empty();
     for (const auto& n : h->nuclides)
-      rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty();
+      rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty();
     h->rare = rare || h->force_rare > 0;
   }
 
@@ -818,6 +858,21 @@ static int prepare(mcw_handle h)
     tab_p.insert(tab_p.end(), t.p.begin(), t.p.end());
     tab_c.insert(tab_c.end(), t.c.begin(), t.c.end());
   };
+  std::vector<double> urr_pool;
+  int n_urr = 0;
+  for (auto& n : h->nuclides)
+  {
+    // probability tables: energies, then the table
+    n.prm.urr_first = (int32_t)urr_pool.size();
+    n.prm.urr_n = (int32_t)n.urr.energy.size();
+    n.prm.urr_bands = n.urr.n_band;
+    n.prm.urr_inel_flag = n.urr.inel_flag;
+    n.prm.urr_multiply_smooth = n.urr.multiply_smooth;
+    n.prm.urr_pad = 0;
+    urr_pool.insert(urr_pool.end(), n.urr.energy.begin(), n.urr.energy.end());
+    urr_pool.insert(urr_pool.end(), n.urr.table.begin(), n.urr.table.end());
+    n_urr += n.prm.urr_n > 0;
+  }
   for (auto& n : h->nuclides)
   {
     add_table(n.el_angle, n.prm.el_ang_first, n.prm.el_ang_n);
@@ -963,7 +1018,14 @@ static int prepare(mcw_handle h)
     P.lib.sab = d_sab, P.lib.sab_pool = d_pool, P.lib.sab_ipool = d_ipool;
     P.lib.mat_sab = d_msab, P.lib.mat_sab_frac = d_frac;
     P.lib.n_sab = any ? (int32_t)sab.size() : 0; // 0 switches every S(a,b) branch of the kernels off
-    P.lib.pad_sab = 0;
+  }
+  {
+    double* d_urr = nullptr;
+    urr_pool.push_back(0.0);
+    if (n_urr)
+      CK(dev_upload(h, &d_urr, urr_pool));
+    P.lib.urr_pool = d_urr;
+    P.lib.n_urr = n_urr;
   }
   P.lib.energy = d_energy;
   P.lib.xs4 = d_xs4;
@@ -1427,9 +1489,19 @@ int mcw_sample_initial_source(mcw_handle h)
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->d_box, h->set.source_box, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->P.batch = 1;
+  CK(cudaMemsetAsync(h->P.counters, 0, sizeof(McwCounters), h->stream));
   MCWK(mcwk_sample_source, h->P, h->d_source, h->n_local, h->d_box, h->set.source_only_fissionable, h->stream);
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_counters, h->P.counters, sizeof(McwCounters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->h_counters->n_failed)
+    // OMC source.cpp:218-226 (EXTSRC_REJECT_THRESHOLD / _FRACTION): a box that misses the mesh or the fissionable
+    // region is a fatal error in the reference, not a silently biased first generation
+    return fail(h, MCW_E_PHYSICS,
+                "More than 95% of external source sites sampled were rejected. Please check your external source's spatial "
+                "definition. (" + std::to_string(h->h_counters->n_failed) + " of " + std::to_string(h->n_local) +
+                    " sites found no position in the mesh" + (h->set.source_only_fissionable ? " in fissionable material" : "") +
+                    " within 10^6 tries)");
   h->n_source = h->n_local;
   return MCW_OK;
 }
@@ -1517,7 +1589,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     unsigned long long* cnt_next = &P.counters->n_fly[cur ^ 1];
     if (prof)
       cudaEventRecord(h->pool_event(3 * rounds + 0), st);
-    if (upper + fb_pending < h->pump_threshold)
+    if (upper + fb_pending < h->pump_threshold && P.lib.n_urr == 0) // the pump's lanes do not carry the URR stream
     {
       // the rest of the generation in one persistent launch: tracking, collision and general-walk warps
       // connected by device-side rings (mcw_pump.cuh)
@@ -1560,7 +1632,7 @@ int mcw_transport_generation(mcw_handle h, int batch)
     // and the lookup runs from shared-memory windows (mcw_xs.cuh); small queues are not worth a sort.
     const int64_t sort_min = h->xs_sort_min > 0 ? h->xs_sort_min : std::max<int64_t>(32768, 2400000 / std::max(1, P.n_plan));
     // the tile kernels stage free-atom tables only: libraries with S(a,b) tables refresh through the direct kernel
-    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min && P.lib.n_sab == 0;
+    const bool staged = h->set.sort_xs_queue != 0 && upper_c >= sort_min && P.lib.n_sab == 0 && P.lib.n_urr == 0;
     MCWK(mcwk_collide, P, qc, &P.counters->n_collide, upper_c, h->d_q_fly[cur ^ 1], cnt_next, staged ? h->d_keys : nullptr,
                  staged ? h->d_q_hist : nullptr, h->d_bins, st);
     R.n_kernel_launches += MCWK(mcwk_xs_refresh, P, qc, &P.counters->n_collide, upper_c, staged, h->d_keys, h->d_q_hist, h->d_bins,
@@ -2045,7 +2117,7 @@ int mcw_xs_lookup_device(mcw_handle h, int64_t n, const void* d_E, const void* d
   }
   CK(cudaEventRecord(h->ev[0], h->stream));
   if (h->P.lib.n_sab)
-    sorted = 0; // the staged kernels hold free-atom tables only
+    sorted = 0; // the staged kernels hold free-atom tables only (no history here: probability tables never apply)
   for (int r = 0; r < repeats; ++r)
   {
     if (sorted == 0)

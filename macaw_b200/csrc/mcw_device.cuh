@@ -88,14 +88,42 @@ MCW_D V3 unit(V3 a)
   return v3(a.x / l, a.y / l, a.z / l);
 }
 
+// The collision physics calls the software log / sin / cos (mcw_detmath.h, a few hundred instructions each) from many
+// places; inlined everywhere they make the collision code several times larger than its own arithmetic, and the tail of
+// a generation (one or two warps per scheduler) stalls on instruction fetch.  MCW_COLLISION_MATH_OOL = 1 calls them out
+// of line from the collision samplers; the tracking loop and the cross-section lookups keep the inline versions.
+#ifndef MCW_COLLISION_MATH_OOL
+#define MCW_COLLISION_MATH_OOL 0
+#endif
+#if MCW_COLLISION_MATH_OOL
+__device__ __noinline__ double mcw_log_c(double x) { return mcw_log(x); }
+__device__ __noinline__ double mcw_cos_c(double x) { return mcw_cos(x); }
+__device__ __noinline__ double2 mcw_sincos_c2(double x)
+{
+  double s, c;
+  mcw_sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+MCW_D void mcw_sincos_c(double x, double* s, double* c)
+{
+  const double2 r = mcw_sincos_c2(x);
+  *s = r.x;
+  *c = r.y;
+}
+#else
+#define mcw_log_c mcw_log
+#define mcw_cos_c mcw_cos
+#define mcw_sincos_c mcw_sincos
+#endif
+
 // ------------------------------------------------------------------ samplers
 MCW_D double mcw_uniform(double a, double b, uint64_t& s) { return a + (b - a) * mcw_prn(s); }
 
 MCW_D double mcw_maxwell_spectrum(double T, uint64_t& s) // OMC random_dist.cpp:15-27
 {
   double r1 = mcw_prn(s), r2 = mcw_prn(s), r3 = mcw_prn(s);
-  double c = mcw_cos(MCW_PI / 2. * r3);
-  return -T * (mcw_log(r1) + mcw_log(r2) * c * c);
+  double c = mcw_cos_c(MCW_PI / 2. * r3);
+  return -T * (mcw_log_c(r1) + mcw_log_c(r2) * c * c);
 }
 
 MCW_D double mcw_watt_spectrum(double a, double b, uint64_t& s) // OMC random_dist.cpp:29-34
@@ -108,7 +136,7 @@ MCW_D V3 mcw_rotate_angle(V3 u, double mu, uint64_t& s) // OMC math_functions.cp
 {
   double phi = 2.0 * MCW_PI * mcw_prn(s);
   double sinphi, cosphi;
-  mcw_sincos(phi, &sinphi, &cosphi);
+  mcw_sincos_c(phi, &sinphi, &cosphi);
   double a = sqrt(fmax(0., 1. - mu * mu));
   double b = sqrt(fmax(0., 1. - u.z * u.z));
   if (b > 1e-10)
@@ -129,7 +157,7 @@ MCW_D V3 mcw_isotropic_direction(uint64_t& s) // OMC distribution_multi.cpp:73-7
   double phi = mcw_uniform(0., 2.0 * MCW_PI, s);
   double mu = mcw_uniform(-1., 1., s);
   double sp, cp;
-  mcw_sincos(phi, &sp, &cp);
+  mcw_sincos_c(phi, &sp, &cp);
   return v3(mu, sqrt(1.0 - mu * mu) * cp, sqrt(1.0 - mu * mu) * sp);
 }
 
@@ -297,15 +325,101 @@ MCW_D void mcw_sab_apply(const McwLibraryDev& L, int q, int i_sab, double E, Mic
   elastic = o[3];
 }
 
-// micro cross sections of material entry q (its nuclide, with the S(a,b) correction of the total where a table applies)
-MCW_D Micro mcw_micro_xs_entry(const McwLibraryDev& L, int q, double E, int i_log)
+// ---- unresolved-resonance probability tables (OMC nuclide.cpp:753-759, 795-924)
+// true when nuclide i_nuc has tables and E lies strictly inside their range
+MCW_D bool mcw_urr_in_range(const McwLibraryDev& L, int i_nuc, double E)
 {
-  Micro m = mcw_micro_xs(L, L.mat_nuc[q], E, i_log);
+  if (!MCW_RARE || L.n_urr == 0)
+    return false;
+  const McwNucParams& n = L.nuc[i_nuc];
+  if (n.urr_n == 0)
+    return false;
+  const double* e = L.urr_pool + n.urr_first;
+  return E > e[0] && E < e[n.urr_n - 1];
+}
+
+// Nuclide::calculate_urr_xs, lin-lin tables, on the smooth values (i_grid, f, absorption, fission) of nuclide i_nuc;
+// seed = the history's URR stream.  out5 = total, absorption, fission, nu_fission, elastic.  Out of line, on the
+// global-memory copy of the library (McwLibraryDev::self_dev).
+__device__ __noinline__ void mcw_urr_apply_ool(const McwLibraryDev* Lg, int i_nuc, double E, uint64_t seed, int i_grid, double f_grid,
+                                               double absorption, double fission_smooth, double* out5)
+{
+  const McwLibraryDev& L = *Lg;
+  const McwNucParams& n = L.nuc[i_nuc];
+  const double* en = L.urr_pool + n.urr_first;
+  const double* tab = en + n.urr_n;
+  const int nb = n.urr_bands;
+  int i_energy = 0;
+  while (E >= en[i_energy + 1])
+    ++i_energy;
+  uint64_t fseed = mcw_future_seed((uint64_t)i_nuc, seed); // future_prn (OMC random_lcg.cpp:49-53)
+  const double r = mcw_prn(fseed);
+  const double* t0 = tab + (size_t)i_energy * 6 * nb;
+  const double* t1 = t0 + 6 * nb;
+  int i_low = 0;
+  while (t0[i_low] <= r)
+    ++i_low;
+  int i_up = 0;
+  while (t1[i_up] <= r)
+    ++i_up;
+  double f = (E - en[i_energy]) / (en[i_energy + 1] - en[i_energy]);
+  double elastic = (1. - f) * t0[2 * nb + i_low] + f * t1[2 * nb + i_up];
+  double fission = (1. - f) * t0[3 * nb + i_low] + f * t1[3 * nb + i_up];
+  double capture = (1. - f) * t0[4 * nb + i_low] + f * t1[4 * nb + i_up];
+  const double* ei = L.el_inel + 2 * (n.off + i_grid); // (elastic, inelastic) per grid point
+  double inelastic = 0.;
+  if (n.urr_inel_flag != -1 && i_grid - n.inel_thr >= 0)
+    inelastic = (1. - f_grid) * ei[1] + f_grid * ei[3];
+  if (n.urr_multiply_smooth)
+  {
+    const double free_elastic = (1.0 - f_grid) * ei[0] + f_grid * ei[2];
+    elastic *= free_elastic;
+    capture *= (absorption - fission_smooth);
+    fission *= fission_smooth;
+  }
+  if (elastic < 0.)
+    elastic = 0.;
+  if (fission < 0.)
+    fission = 0.;
+  if (capture < 0.)
+    capture = 0.;
+  out5[0] = elastic + inelastic + capture + fission;
+  out5[1] = capture + fission;
+  out5[2] = fission;
+  double nu = 0.0; // Polynomial (OMC endf.cpp:112-121): Horner, increasing powers
+  nu = nu * E + n.nu_poly[1];
+  nu = nu * E + n.nu_poly[0];
+  out5[3] = nu * fission;
+  out5[4] = elastic;
+}
+MCW_D void mcw_urr_apply(const McwLibraryDev& L, int i_nuc, double E, uint64_t seed, Micro& m, double& elastic)
+{
+  double o[5];
+  mcw_urr_apply_ool(L.self_dev, i_nuc, E, seed, m.i_grid, m.f, m.absorption, m.fission, o);
+  m.total = o[0];
+  m.absorption = o[1];
+  m.fission = o[2];
+  if (L.nuc[i_nuc].fissionable)
+    m.nu_fission = o[3];
+  elastic = o[4];
+}
+
+// micro cross sections of material entry q: its nuclide, with the S(a,b) correction of the total where a table applies
+// and, when the history's URR stream seed is given, the probability tables of a nuclide in its unresolved range
+MCW_D Micro mcw_micro_xs_entry(const McwLibraryDev& L, int q, double E, int i_log, const uint64_t* seed_urr = nullptr)
+{
+  const int i_nuc = L.mat_nuc[q];
+  Micro m = mcw_micro_xs(L, i_nuc, E, i_log);
   const int i_sab = mcw_sab_of_entry(L, q, E);
   if (i_sab >= 0)
   {
     double th, the, el;
     mcw_sab_apply(L, q, i_sab, E, m, th, the, el);
+  }
+  if (seed_urr && mcw_urr_in_range(L, i_nuc, E))
+  {
+    double el;
+    mcw_urr_apply(L, i_nuc, E, *seed_urr, m, el);
   }
   return m;
 }
@@ -317,7 +431,8 @@ struct Macro
 
 // OMC material.cpp:748-831.  prefix (may be null) receives the running total after every nuclide: the
 // partial sums sample_nuclide (OMC physics.cpp:442-465) forms at the next collision at this energy.
-MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E, double* __restrict__ prefix = nullptr)
+MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E, double* __restrict__ prefix = nullptr,
+                         const uint64_t* seed_urr = nullptr)
 {
   Macro M;
   M.total = M.absorption = M.fission = M.nu_fission = 0.0;
@@ -325,7 +440,7 @@ MCW_D Macro mcw_macro_xs(const McwLibraryDev& L, int i_mat, double E, double* __
   int b = L.mat_off[i_mat], e = L.mat_off[i_mat + 1];
   for (int i = b; i < e; ++i)
   {
-    Micro m = mcw_micro_xs_entry(L, i, E, i_log);
+    Micro m = mcw_micro_xs_entry(L, i, E, i_log, seed_urr);
     double d = L.mat_dens[i];
     M.total += d * m.total;
     M.absorption += d * m.absorption;
@@ -344,9 +459,13 @@ MCW_D void mcw_lookup_all_slots(const McwParams& P, int64_t i, double E)
 {
   double* xs_of_history = P.p.xs + (size_t)i * P.n_slots * 4;
   double* prefix = P.p.xs_prefix + (size_t)i * P.n_plan_pad;
+  uint64_t seed_urr = 0;
+  const bool urr = MCW_RARE && P.lib.n_urr != 0;
+  if (urr)
+    seed_urr = P.p.seed_urr[i]; // the history's URR stream picks the probability-table band
   for (int s = 0; s < P.n_slots; ++s)
   {
-    const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], E, prefix + P.slot_plan_off[s]);
+    const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], E, prefix + P.slot_plan_off[s], urr ? &seed_urr : nullptr);
     double2* o = reinterpret_cast<double2*>(xs_of_history + 4 * s);
     o[0] = make_double2(M.total, M.absorption);
     o[1] = make_double2(M.fission, M.nu_fission);

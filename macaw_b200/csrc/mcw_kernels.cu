@@ -148,6 +148,8 @@ k_sample_source(McwParams P, mcw_source_site* __restrict__ out, int64_t n, const
     }
     e = -1;
   }
+  if (e < 0)
+    atomicAdd(&P.counters->n_failed, 1ull); // no position accepted: the host turns this into the reference's fatal error
   V3 u = mcw_isotropic_direction(seed);
   site.u[0] = u.x;
   site.u[1] = u.y;
@@ -209,7 +211,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
   mx.total = mx.absorption = mx.fission = mx.nu_fission = mx.f = 0;
   mx.i_grid = 0;
   double k_col = 0, k_abs = 0;
-  uint64_t seed_src = 0, seed_urr = 0;
+  uint64_t seed_src = 0, seed_urr = 0, seed_urr_pre = 0; // _pre: the URR seed the pre-collision cross sections were made with
   if (valid)
   {
     c.r = v3(p.x[i], p.y[i], p.z[i]);
@@ -220,6 +222,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     c.n_progeny = p.n_progeny[i];
     seed_src = p.seed_src[i];
     seed_urr = p.seed_urr[i];
+    seed_urr_pre = seed_urr;
     elem = p.elem[i];
     ElemRec<TYPE> R(P.mesh, elem);
     block = R.block();
@@ -258,7 +261,8 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       q_nuc = L.mat_off[i_mat] + (k - pb);
     }
     const int i_log = mcw_log_bin(L, c.E);
-    mx = mcw_micro_xs_entry(L, q_nuc, c.E, i_log); // with the S(a,b) correction of the total where a table applies
+    // with the S(a,b) correction of the total and the probability tables where they apply
+    mx = mcw_micro_xs_entry(L, q_nuc, c.E, i_log, (MCW_RARE && L.n_urr) ? &seed_urr : nullptr);
     // kappa-fission, only when a collision tally asks for it: q * sigma_f * N * flux summed nuclide by
     // nuclide over the fissionable nuclides of the material (OMC tally_scoring.cpp:1246-1255)
     if (P.tallies_active && P.collision_kappa && sig_a != 0.)
@@ -269,7 +273,9 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
         const int in = P.plan_nuc[q];
         if (L.nuc[in].fissionable)
         {
-          const Micro m = (in == k_nuc) ? mx : mcw_micro_xs(L, in, c.E, i_log);
+          const Micro m = (in == k_nuc) ? mx
+                                        : mcw_micro_xs_entry(L, L.mat_off[i_mat] + (q - pb), c.E, i_log,
+                                                             (MCW_RARE && L.n_urr) ? &seed_urr : nullptr);
           kappa += L.nuc[in].q * m.fission * P.plan_dens[q] * flux;
         }
       }
@@ -359,14 +365,22 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       Micro scratch = mx;
       mcw_sab_apply(L, q_nuc, i_sab, E_last, scratch, thermal, thermal_el, elastic);
     }
+    // probability tables: micro.elastic is the table's value and the target is taken at rest (physics.cpp:735-738);
+    // re-derived from the smooth values at the pre-collision energy and URR seed (seed_urr advances only below)
+    const bool use_ptable = mcw_urr_in_range(L, k_nuc, E_last);
+    if (use_ptable)
+    {
+      Micro smooth = mcw_micro_xs(L, k_nuc, E_last, mcw_log_bin(L, E_last));
+      mcw_urr_apply(L, k_nuc, E_last, seed_urr, smooth, elastic);
+    }
     if (elastic - thermal > cut)
-      mcw_elastic_scatter(L, nuc, c); // non-S(a,b) elastic (OMC physics.cpp:649-661)
+      mcw_elastic_scatter(L, nuc, c, use_ptable); // non-S(a,b) elastic (OMC physics.cpp:649-661)
     else if (i_sab >= 0 && elastic > cut)
       mcw_sab_scatter(L.self_dev, i_sab, thermal, thermal_el, c); // :663-672
     else if (can_inelastic)
       mcw_inelastic_scatter(L, nuc, c);
     else
-      mcw_elastic_scatter(L, nuc, c);
+      mcw_elastic_scatter(L, nuc, c, use_ptable);
     if (L.mat_iso[q_nuc]) // isotropic-in-lab override (OMC physics.cpp:706-718): phi, then mu
       c.u = mcw_isotropic_direction(c.seed);
     if (c.E != E_last) // OMC physics.cpp:140-144
@@ -387,7 +401,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       {
         if (MCW_RARE && P.tally[t].nuclides)
           mcw_score_tally_nuclides(L.self_dev, P.tally_dev + t, mcw_spatial_bin(P.tally[t], elem, block), E_last, i_mat, flux,
-                                   sig_a, sc);
+                                   sig_a, sc, seed_urr_pre);
         else
           mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), E_last, sc);
       }
@@ -453,7 +467,12 @@ k_xs_all_slots(McwParams P, const int32_t* __restrict__ queue, const unsigned lo
   const int i = queue[h];
   if (P.p.status[i] != MCW_ST_FLY)
     return; // absorbed
-  const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], P.p.E[i], P.p.xs_prefix + (size_t)i * P.n_plan_pad + P.slot_plan_off[s]);
+  uint64_t seed_urr = 0;
+  const bool urr = MCW_RARE && P.lib.n_urr != 0; // the history's URR stream picks the probability-table band
+  if (urr)
+    seed_urr = P.p.seed_urr[i];
+  const Macro M = mcw_macro_xs(P.lib, P.slot_mat[s], P.p.E[i], P.p.xs_prefix + (size_t)i * P.n_plan_pad + P.slot_plan_off[s],
+                               urr ? &seed_urr : nullptr);
   double2* o = reinterpret_cast<double2*>(P.p.xs + ((size_t)i * P.n_slots + s) * 4);
   o[0] = make_double2(M.total, M.absorption);
   o[1] = make_double2(M.fission, M.nu_fission);
@@ -487,19 +506,17 @@ MCW_D void mcw_warp_lookup_all_slots(const McwParams& P, unsigned m_need, int i,
       double t = 0.0, a = 0.0, f = 0.0, nf = 0.0, mine = 0.0;
       if (q < P.n_plan)
       {
-        Micro m = mcw_micro_xs(P.lib, P.plan_nuc[q], he, i_log);
-        if (MCW_RARE && P.lib.n_sab)
+        Micro m;
+        if (MCW_RARE && (P.lib.n_sab | P.lib.n_urr))
         {
-          // the plan entry's position in its material, for the S(a,b) correction of the total
+          // the plan entry's position in its material: S(a,b) correction of the total, probability tables
           const int sl = P.plan_slot[q];
           const int ent = P.lib.mat_off[P.slot_mat[sl]] + q - P.slot_plan_off[sl];
-          const int i_sab = mcw_sab_of_entry(P.lib, ent, he);
-          if (i_sab >= 0)
-          {
-            double th, the, el;
-            mcw_sab_apply(P.lib, ent, i_sab, he, m, th, the, el);
-          }
+          const uint64_t hs = P.p.seed_urr[hi];
+          m = mcw_micro_xs_entry(P.lib, ent, he, i_log, P.lib.n_urr ? &hs : nullptr);
         }
+        else
+          m = mcw_micro_xs(P.lib, P.plan_nuc[q], he, i_log);
         const double d = P.plan_dens[q];
         t = d * m.total;
         a = d * m.absorption;

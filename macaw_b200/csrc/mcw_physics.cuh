@@ -70,7 +70,7 @@ MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, cons
 // and nothing otherwise (:2391-2394); the bin -1 scores the material totals `sc`.  score_index = j * n_scores + s.
 // Rarely asked for, so out of line (the collision kernel's code stays compact) and with plain atomics.
 __device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev* Lg, const McwTallyDev* tg, int64_t spatial, double E,
-                                                      int i_mat, double flux, double sig_a, const double* sc)
+                                                      int i_mat, double flux, double sig_a, const double* sc, uint64_t seed_urr)
 {
   const McwLibraryDev& L = *Lg; // global-memory copies: see McwLibraryDev::self_dev
   const McwTallyDev& t = *tg;
@@ -98,7 +98,7 @@ __device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev* Lg, c
     if (q == qe)
       continue; // mat_nuclide_index_ == C_NONE
     const double dens = L.mat_dens[q];
-    const Micro m = mcw_micro_xs_entry(L, q, E, i_log);
+    const Micro m = mcw_micro_xs_entry(L, q, E, i_log, L.n_urr ? &seed_urr : nullptr);
     for (int s = 0; s < t.n_scores; ++s)
     {
       double v;
@@ -138,7 +138,7 @@ MCW_D int64_t mcw_spatial_bin(const McwTallyDev& t, int elem, int block)
 }
 
 // kappa-fission of a material: q_i * sigma_f,i * N_i * flux summed nuclide by nuclide (OMC tally_scoring.cpp:1246-1255)
-MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E, double flux)
+MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E, double flux, uint64_t seed_urr)
 {
   int i_log = mcw_log_bin(L, E);
   double kappa = 0.0;
@@ -147,7 +147,7 @@ MCW_D double mcw_kappa_macro(const McwLibraryDev& L, int i_mat, double E, double
     int in = L.mat_nuc[i];
     if (L.nuc[in].fissionable)
     {
-      Micro m = mcw_micro_xs(L, in, E, i_log);
+      Micro m = mcw_micro_xs_entry(L, i, E, i_log, (MCW_RARE && L.n_urr) ? &seed_urr : nullptr);
       kappa += L.nuc[in].q * m.fission * L.mat_dens[i] * flux;
     }
   }
@@ -210,10 +210,10 @@ MCW_D bool mcw_segment_nl(const McwParams& P, SegState& s, double neg_log, int e
         for (int q = 0; q < P.tally[t].n_scores; ++q)
           need_kappa |= P.tally[t].scores[q] == MCW_SCORE_KAPPA_FISSION;
         if (need_kappa)
-          sc[MCW_SCORE_KAPPA_FISSION] = s.sig_a == 0. ? 0.0 : mcw_kappa_macro(P.lib, i_mat, s.E, flux);
+          sc[MCW_SCORE_KAPPA_FISSION] = s.sig_a == 0. ? 0.0 : mcw_kappa_macro(P.lib, i_mat, s.E, flux, s.seed_urr);
         if (MCW_RARE && P.tally[t].nuclides)
           mcw_score_tally_nuclides(P.lib.self_dev, P.tally_dev + t, mcw_spatial_bin(P.tally[t], elem, block), s.E, i_mat, flux,
-                                   s.sig_a, sc);
+                                   s.sig_a, sc, s.seed_urr);
         else
           mcw_score_tally(P.tally[t], mcw_spatial_bin(P.tally[t], elem, block), s.E, sc);
       }
@@ -387,11 +387,11 @@ MCW_D V3 mcw_sample_cxs_target_velocity(double awr, double E, V3 u, double kT, u
   {
     double r1 = mcw_prn(seed), r2 = mcw_prn(seed);
     if (mcw_prn(seed) < alpha)
-      beta_vt_sq = -mcw_log(r1 * r2);
+      beta_vt_sq = -mcw_log_c(r1 * r2);
     else
     {
-      double c = mcw_cos(MCW_PI / 2.0 * mcw_prn(seed));
-      beta_vt_sq = -mcw_log(r1) - mcw_log(r2) * c * c;
+      double c = mcw_cos_c(MCW_PI / 2.0 * mcw_prn(seed));
+      beta_vt_sq = -mcw_log_c(r1) - mcw_log_c(r2) * c * c;
     }
     double beta_vt = sqrt(beta_vt_sq);
     mu = mcw_uniform(-1., 1., seed);
@@ -571,13 +571,13 @@ MCW_D double mcw_continuous_tabular_sample(const McwLibraryDev& L, int first, in
 
 // OMC physics.cpp:721-786: elastic scattering, angle from the nuclide's tabular distribution when it has one
 // (:749-757) else isotropic in CM; free gas below 400 kT (:804-835)
-MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p)
+MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p, bool use_ptable = false)
 {
   double vel = sqrt(p.E);
   double awr = nuc.awr;
   V3 v_n = vel * p.u;
   V3 v_t = v3(0, 0, 0);
-  if (!(p.E >= MCW_FREE_GAS_THRESHOLD * nuc.kT && awr > 1.0))
+  if (!use_ptable && !(p.E >= MCW_FREE_GAS_THRESHOLD * nuc.kT && awr > 1.0))
     v_t = mcw_sample_cxs_target_velocity(awr, p.E, p.u, nuc.kT, p.seed);
   V3 v_cm = (v_n + awr * v_t) / (awr + 1.0);
   v_n = v_n - v_cm;

@@ -460,6 +460,8 @@ k_track(McwParams P, const int32_t* __restrict__ queue, const unsigned long long
     s.E = p.E[i];
     s.wgt = p.wgt[i];
     s.seed_trk = p.seed_trk[i];
+    if (MCW_RARE && P.lib.n_urr)
+      s.seed_urr = p.seed_urr[i]; // track-length scores of a nuclide in its unresolved range need the band
     s.k_trk = p.k_trk[i];
     n_seg = p.n_seg[i];
     if (keep_hash)

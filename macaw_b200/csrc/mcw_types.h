@@ -40,6 +40,9 @@ struct McwNucParams
   int32_t inel_ang_first, inel_ang_n;
   int32_t inel_en_first, inel_en_n;
   int32_t inel_en_hist, inel_in_cm; // ContinuousTabular: histogram interpolation in incoming energy; scatter_in_cm_
+  // unresolved-resonance probability tables (mcw_urr_desc): energies at McwLibraryDev::urr_pool[urr_first ..], then the
+  // table [n_energy][6][n_band]; urr_n = 0: none
+  int32_t urr_first, urr_n, urr_bands, urr_inel_flag, urr_multiply_smooth, urr_pad;
 };
 
 // One temperature of an S(alpha, beta) table (mcw_thermal_desc): offsets into McwLibraryDev::sab_pool (doubles) /
@@ -80,7 +83,8 @@ struct McwLibraryDev
   const int32_t* sab_ipool;
   const int32_t* mat_sab;
   const double* mat_sab_frac;
-  int32_t n_sab, pad_sab;
+  int32_t n_sab, n_urr; // number of S(a,b) tables in use / of nuclides with probability tables (0: branches off)
+  const double* urr_pool;
   // This struct again, in global memory.  The kernels get McwParams by value (parameter space); an out-of-line device
   // function that took `lib` by reference would force a private copy of the whole parameter block into every thread's
   // local memory, so the rare out-of-line paths (S(a,b), nuclide tally bins) are handed this pointer instead.

@@ -186,6 +186,49 @@ def make_thermal_table(rng, name, kind="continuous", elastic="none", energy_max=
     return t
 
 
+@dataclass
+class UrrTable:
+    """Unresolved-resonance probability tables of one nuclide (mcw_urr_desc; OMC urr.cpp UrrData)."""
+    nuclide: int
+    energy: np.ndarray          # (n_energy,)
+    table: np.ndarray           # (n_energy, 6, n_band): cum. probability, total, elastic, fission, (n,gamma), heating
+    inelastic_flag: int = -1
+    absorption_flag: int = -1
+    multiply_smooth: bool = False
+    interpolation: int = 2
+
+
+def add_urr_tables(lib: "Library", seed=9, e_lo=2.0e3, e_hi=1.5e5):
+    """Probability tables for every nuclide heavier than A = 80 (the resonance absorbers and structural nuclides):
+    16 bands on 8-13 energies in [e_lo, e_hi], alternately as absolute cross sections and as factors on the smooth
+    ones (multiply_smooth), with inelastic competition where the nuclide has an inelastic reaction."""
+    rng = np.random.Generator(np.random.PCG64([seed, 909]))
+    lib.urr_tables = []
+    for i, n in enumerate(lib.nuclides):
+        if n.awr < 80:
+            continue
+        n_e, n_b = int(rng.integers(8, 14)), 16
+        lo = e_lo * rng.uniform(0.8, 1.5)
+        energy = np.exp(np.linspace(np.log(lo), np.log(e_hi * rng.uniform(0.7, 1.3)), n_e))
+        t = np.zeros((n_e, 6, n_b))
+        smooth = len(lib.urr_tables) % 2 == 1
+        for k in range(n_e):
+            w = rng.uniform(0.2, 1.0, n_b)
+            c = np.cumsum(w / w.sum())
+            c[-1] = 1.0
+            t[k, 0] = c
+            if smooth:
+                t[k, 2], t[k, 3], t[k, 4] = rng.lognormal(0, 0.3, n_b), rng.lognormal(0, 0.5, n_b), rng.lognormal(0, 0.8, n_b)
+            else:
+                t[k, 2] = 9.0 * rng.lognormal(0, 0.3, n_b)
+                t[k, 3] = (2.0 * rng.lognormal(0, 0.5, n_b)) if n.fissionable else 0.0
+                t[k, 4] = 0.8 * rng.lognormal(0, 0.8, n_b)
+            t[k, 1] = t[k, 2] + t[k, 3] + t[k, 4]
+            t[k, 5] = 1.0
+        lib.urr_tables.append(UrrTable(i, energy, t, 51 if n.inelastic.size else -1, -1, smooth))
+    return lib
+
+
 def add_thermal_scattering(lib: "Library", seed=5):
     """Gives a library S(a,b) tables the way the BEAVRS deck has them (materials.xml <sab name="c_H_in_H2O"/>): hydrogen
     in every material that holds H1 is bound (continuous inelastic, no elastic); a second nuclide, where a material has
@@ -214,6 +257,7 @@ class Library:
     materials: list
     n_log_bins: int = 8000
     thermal_tables: list = None
+    urr_tables: list = None
 
     def total_points(self):
         return int(sum(n.energy.size for n in self.nuclides))
@@ -448,6 +492,24 @@ class ThermalDesc(C.Structure):
                 ("inelastic_mu", C.c_void_p), ("n_mu", C.c_int32), ("n_e_out", C.c_int32), ("skewed", C.c_int32),
                 ("n_elastic", C.c_int32), ("elastic_x", C.c_void_p), ("elastic_y", C.c_void_p), ("elastic_mu", C.c_void_p),
                 ("n_elastic_mu", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class UrrDesc(C.Structure):
+    _fields_ = [("nuclide", C.c_int32), ("interpolation", C.c_int32), ("inelastic_flag", C.c_int32),
+                ("absorption_flag", C.c_int32), ("multiply_smooth", C.c_int32), ("n_energy", C.c_int32),
+                ("n_band", C.c_int32), ("reserved0", C.c_int32), ("energy", C.c_void_p), ("table", C.c_void_p)]
+
+
+def pack_urr(tables):
+    keep = []
+    ud = (UrrDesc * max(len(tables), 1))()
+    for d, t in zip(ud, tables):
+        e, tb = np.ascontiguousarray(t.energy, np.float64), np.ascontiguousarray(t.table, np.float64)
+        keep += [e, tb]
+        d.nuclide, d.interpolation, d.inelastic_flag, d.absorption_flag = t.nuclide, t.interpolation, t.inelastic_flag, t.absorption_flag
+        d.multiply_smooth, d.n_energy, d.n_band = int(t.multiply_smooth), e.size, tb.shape[2]
+        d.energy, d.table = e.ctypes.data, tb.ctypes.data
+    return ud, keep
 
 
 def pack_thermal(tables):

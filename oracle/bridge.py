@@ -42,6 +42,7 @@ def _load(name):
     lib.orc_tracklength_kappa.argtypes = [C.c_void_p, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
     lib.orc_set_tally_nuclides.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.orc_set_thermal_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.orc_set_urr_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.orc_set_material_thermal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.orc_score_nuclide_bins.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, f64p, f64p,
                                            f64p, f64p]
@@ -151,6 +152,8 @@ def ref_lib():
             r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
                                                   u64p, C.c_int64, f64p, f64p, C.c_int, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
+        if hasattr(r, "ref_stage_urr"):
+            r.ref_stage_urr.argtypes = [C.c_void_p]
         if hasattr(r, "ref_add_thermal_table"):
             r.ref_add_thermal_table.argtypes = [C.c_char_p, C.c_void_p, C.c_double]
             r.ref_set_material_thermal.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, f64p]
@@ -214,6 +217,11 @@ def ref_load_library(r, libr: nucdata.Library):
                 _nd._pack_table(d, getattr(n, a, None), keep)
                 descs.append(d)
             r.ref_stage_tables(C.addressof(descs[0]), C.addressof(descs[1]), C.addressof(descs[2]), int(n.inelastic_in_cm))
+        urr = [t for t in (getattr(libr, "urr_tables", None) or []) if libr.nuclides[t.nuclide] is n]
+        if urr:
+            from macaw_b200 import nucdata as _nd
+            ud, keep_u = _nd.pack_urr(urr)
+            r.ref_stage_urr(C.addressof(ud))
         r.ref_add_nuclide(n.name.encode(), n.awr, n.kT, e.size, dp(e), dp(el), dp(cap), dp(fis) if n.fissionable else None,
                           int(n.inelastic.size), n.inel_threshold, dp(inel), n.inel_threshold_energy, n.inel_mass_ratio,
                           dp(nu), n.n_precursor, dp(dy), dp(dth), n.watt_a, n.watt_b, n.q_fission)
@@ -276,6 +284,11 @@ class Oracle:
         self.L.orc_set_library(self.h, C.addressof(nd), len(libr.nuclides), libr.n_log_bins)
         bm = np.ascontiguousarray(block_material, np.int32)
         self.L.orc_set_materials(self.h, C.addressof(md), len(libr.materials), _p(bm), bm.size)
+        if getattr(libr, "urr_tables", None):
+            ud, keep3 = nucdata.pack_urr(libr.urr_tables)
+            self._keep.append((ud, keep3))
+            if self.L.orc_set_urr_tables(self.h, C.addressof(ud), len(libr.urr_tables)):
+                raise RuntimeError("orc_set_urr_tables failed")
         if getattr(libr, "thermal_tables", None):
             td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
             self._keep.append((td, keep2))

@@ -218,6 +218,10 @@ struct Nuclide
   Tabular2D el_angle, inel_angle, inel_energy; // optional tabulated secondary distributions
   int inel_law = MCW_LAW_LEVEL;
   bool inel_in_cm = true;
+  // unresolved-resonance probability tables (mcw_urr_desc; OMC urr.cpp UrrData); urr_energy empty = none
+  std::vector<double> urr_energy, urr_table; // table[n_energy][6][n_band]
+  int urr_bands = 0, urr_inel_flag = -1, urr_multiply_smooth = 0;
+  double urr_prob(int i_energy, int param, int band) const { return urr_table[((size_t)i_energy * 6 + param) * urr_bands + band]; }
 
   // OMC endf.cpp:112-121 Polynomial (Horner, increasing powers) on nu_poly; nuclide.cpp:478-517
   double nu_total(double E) const
@@ -255,6 +259,7 @@ struct Micro // subset of OMC particle_data.h:82-112 NuclideMicroXS
   // and the corrected micro.elastic; i_sab < 0 = free-atom scattering (elastic is then evaluated on demand)
   int i_sab = -1;
   double thermal = 0.0, thermal_elastic = 0.0, elastic = 0.0;
+  bool use_ptable = false; // URR probability table used: `elastic` holds the table's value (OMC nuclide.cpp:795-924)
 };
 
 // One temperature of a thermal scattering table (mcw_thermal_desc; OMC thermal.cpp ThermalData + secondary_thermal.cpp)
@@ -419,9 +424,57 @@ struct Library
     m.elastic = m.thermal + (1.0 - sab_frac) * free_elastic;
   }
 
-  // OMC material.cpp:748-831
+  // Nuclide::calculate_urr_xs (OMC nuclide.cpp:795-924), lin-lin tables; seed = the history's URR stream
+  void apply_urr(const Nuclide& n, int i_nuc, double E, uint64_t seed, Micro& m) const
+  {
+    m.use_ptable = true;
+    int i_energy = 0;
+    while (E >= n.urr_energy[i_energy + 1])
+      ++i_energy;
+    uint64_t fseed = future_seed((uint64_t)i_nuc, seed); // future_prn (random_lcg.cpp:49-53)
+    const double r = prn(&fseed);
+    int i_low = 0;
+    while (n.urr_prob(i_energy, 0, i_low) <= r)
+      ++i_low;
+    int i_up = 0;
+    while (n.urr_prob(i_energy + 1, 0, i_up) <= r)
+      ++i_up;
+    double f = (E - n.urr_energy[i_energy]) / (n.urr_energy[i_energy + 1] - n.urr_energy[i_energy]);
+    double elastic = (1. - f) * n.urr_prob(i_energy, 2, i_low) + f * n.urr_prob(i_energy + 1, 2, i_up);
+    double fission = (1. - f) * n.urr_prob(i_energy, 3, i_low) + f * n.urr_prob(i_energy + 1, 3, i_up);
+    double capture = (1. - f) * n.urr_prob(i_energy, 4, i_low) + f * n.urr_prob(i_energy + 1, 4, i_up);
+    double inelastic = 0.;
+    if (n.urr_inel_flag != -1)
+    {
+      f = m.f;
+      const int xs_index = m.i_grid - n.inel_thr;
+      if (xs_index >= 0)
+        inelastic = (1. - f) * n.inelastic[m.i_grid] + f * n.inelastic[m.i_grid + 1]; // stored on the full grid here
+    }
+    if (n.urr_multiply_smooth)
+    {
+      const double free_elastic = (1.0 - m.f) * n.elastic[m.i_grid] + m.f * n.elastic[m.i_grid + 1];
+      elastic *= free_elastic;
+      capture *= (m.absorption - m.fission);
+      fission *= m.fission;
+    }
+    if (elastic < 0.)
+      elastic = 0.;
+    if (fission < 0.)
+      fission = 0.;
+    if (capture < 0.)
+      capture = 0.;
+    m.elastic = elastic;
+    m.absorption = capture + fission;
+    m.fission = fission;
+    m.total = elastic + inelastic + capture + fission;
+    if (n.fissionable)
+      m.nu_fission = n.nu_total(E) * m.fission;
+  }
+
+  // OMC material.cpp:748-831.  seed_urr: the history's URR stream seed (null: no history, smooth cross sections)
   Macro macro_xs(int i_mat, double E, Micro* cache /* [materials[i_mat].nuc.size()] or null */,
-                 int64_t* n_nuclide_lookups = nullptr) const
+                 int64_t* n_nuclide_lookups = nullptr, const uint64_t* seed_urr = nullptr) const
   {
     const Material& mat = materials[i_mat];
     Macro M;
@@ -432,6 +485,12 @@ struct Library
       // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)
       if (!mat.sab_table.empty() && mat.sab_table[i] >= 0 && !(E > thermal[mat.sab_table[i]].energy_max))
         apply_sab(nuclides[mat.nuc[i]], mat.sab_table[i], mat.sab_frac[i], E, m);
+      {
+        // probability tables, strictly inside their energy range (nuclide.cpp:753-759)
+        const Nuclide& n = nuclides[mat.nuc[i]];
+        if (seed_urr && !n.urr_energy.empty() && E > n.urr_energy.front() && E < n.urr_energy.back())
+          apply_urr(n, mat.nuc[i], E, *seed_urr, m);
+      }
       if (cache)
         cache[i] = m;
       double d = mat.dens[i];

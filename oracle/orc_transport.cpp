@@ -492,14 +492,15 @@ static void sab_scatter(const ThermalTable& t, const Micro& micro, Hist& p)
 }
 
 // OMC physics.cpp:721-786 (tabular angular distribution :749-757, else "assume isotropic")
-static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p)
+static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p, bool use_ptable = false)
 {
   double vel = std::sqrt(p.E);
   double awr = nuc.awr;
   V3 v_n = vel * p.u;
   V3 v_t = {0, 0, 0};
-  // OMC physics.cpp:804-835 sample_target_velocity, non-resonant branch
-  if (!(p.E >= FREE_GAS_THRESHOLD * kT && awr > 1.0))
+  // OMC physics.cpp:804-835 sample_target_velocity, non-resonant branch; a nuclide in its unresolved range is taken
+  // at rest (:735-738)
+  if (!use_ptable && !(p.E >= FREE_GAS_THRESHOLD * kT && awr > 1.0))
     v_t = sample_cxs_target_velocity(awr, p.E, p.u, kT, &p.seeds[0]);
   V3 v_cm = (v_n + awr * v_t) / (awr + 1.0);
   v_n = v_n - v_cm;
@@ -690,16 +691,16 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
     double f = mx.f;
     int ig = mx.i_grid;
     // micro.elastic: corrected by calculate_sab_xs when a table applies, else evaluated now (physics.cpp:644-647)
-    double elastic = mx.i_sab >= 0 ? mx.elastic : (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
+    double elastic = (mx.i_sab >= 0 || mx.use_ptable) ? mx.elastic : (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
     bool can_inelastic = nuc.n_inel > 0 && ig >= nuc.inel_thr;
     if (elastic - mx.thermal > cut)
-      elastic_scatter(nuc, nuc.kT, p); // non-S(a,b) elastic (:649-661)
+      elastic_scatter(nuc, nuc.kT, p, mx.use_ptable); // non-S(a,b) elastic (:649-661)
     else if (elastic > cut && mx.i_sab >= 0)
       sab_scatter(P.lib.thermal[mx.i_sab], mx, p); // :663-672
     else if (can_inelastic)
       inelastic_scatter(nuc, p);
     else
-      elastic_scatter(nuc, nuc.kT, p);
+      elastic_scatter(nuc, nuc.kT, p, mx.use_ptable);
     // isotropic-in-lab override for nuclides of the material's <isotropic> list (OMC physics.cpp:706-718)
     if (!mat.iso.empty() && mat.iso[k])
       p.u = isotropic_direction(&p.seeds[0]);
@@ -921,7 +922,7 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
     if (micro.size() < mat.nuc.size())
       micro.resize(mat.nuc.size());
     // event_calculate_xs: macro recomputed every segment
-    Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc);
+    Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR]);
     ++p.n_xs;
     // distance to collision: 1 RN per segment (MC CollisionKernel.C:150)
     const double d = -xlog(prn(&p.seeds[0])) / macro.total;
@@ -1219,6 +1220,26 @@ int orc_set_thermal_tables(void* h, const mcw_thermal_desc* d, int n)
   return 0;
 }
 
+// urr_data_ of the nuclides that have probability tables (OMC nuclide.cpp:225-270, urr.cpp:7-33)
+int orc_set_urr_tables(void* h, const mcw_urr_desc* d, int n)
+{
+  Problem& P = *(Problem*)h;
+  for (auto& nuc : P.lib.nuclides)
+    nuc.urr_energy.clear(), nuc.urr_table.clear();
+  for (int k = 0; k < n; ++k)
+  {
+    if (d[k].nuclide < 0 || d[k].nuclide >= (int)P.lib.nuclides.size() || d[k].interpolation != 2)
+      return -1;
+    Nuclide& nuc = P.lib.nuclides[d[k].nuclide];
+    nuc.urr_energy.assign(d[k].energy, d[k].energy + d[k].n_energy);
+    nuc.urr_table.assign(d[k].table, d[k].table + (size_t)d[k].n_energy * 6 * d[k].n_band);
+    nuc.urr_bands = d[k].n_band;
+    nuc.urr_inel_flag = d[k].inelastic_flag;
+    nuc.urr_multiply_smooth = d[k].multiply_smooth;
+  }
+  return 0;
+}
+
 // Material::thermal_tables_ (OMC material.cpp:140-160,317-360)
 int orc_set_material_thermal(void* h, int material, int n, const int32_t* position, const int32_t* table, const double* fraction)
 {
@@ -1375,7 +1396,7 @@ int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const dou
     for (int s = 0; s < 3; ++s)
       p.seeds[s] = seeds4[4 * k + s];
     int64_t n_nuc = 0;
-    const Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc);
+    const Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR]);
     macro4[4 * k] = macro.total, macro4[4 * k + 1] = macro.absorption;
     macro4[4 * k + 2] = macro.fission, macro4[4 * k + 3] = macro.nu_fission;
     const size_t before = bank.size();

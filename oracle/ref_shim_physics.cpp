@@ -39,6 +39,7 @@ std::unique_ptr<memh5::Node> g_root;
 // tables staged by ref_stage_tables for the next ref_add_nuclide (null = none)
 const mcw_tabular2d *g_el_angle = nullptr, *g_inel_angle = nullptr, *g_inel_energy = nullptr;
 int g_inel_in_cm = 1;
+const mcw_urr_desc* g_urr = nullptr; // probability tables staged for the next ref_add_nuclide
 
 // (3, N) dataset x / pdf / cdf with `offsets` and `interpolation` attributes: the layout of an angular distribution's `mu`
 // (OMC distribution_angle.cpp:26-33) and of a continuous law's `distribution` (distribution_energy.cpp:80-92)
@@ -143,6 +144,10 @@ REF_API void ref_stage_tables(const mcw_tabular2d* elastic_angle, const mcw_tabu
   g_inel_in_cm = inelastic_in_cm;
 }
 
+// Probability tables of the NEXT nuclide added: written as the `urr/<T>K` group UrrData's own constructor reads
+// (urr.cpp:7-33: attributes interpolation / inelastic / absorption / multiply_smooth, datasets energy and table)
+REF_API void ref_stage_urr(const mcw_urr_desc* urr) { g_urr = urr; }
+
 // One synthetic nuclide of macaw_b200/nucdata.py as a nuclide file: MT 2 elastic (isotropic in the centre of mass),
 // optionally MT 51 (one level, isotropic CM), MT 102 capture, optionally MT 18 fission with a polynomial total nu, a Watt
 // prompt spectrum and n_precursor Maxwell delayed groups of constant yield.  Returns the nuclide's index.
@@ -193,6 +198,18 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     }
   }
   g_el_angle = g_inel_angle = g_inel_energy = nullptr;
+  if (g_urr)
+  {
+    memh5::Node* u = g->group("urr")->group(temp);
+    u->attr("interpolation", g_urr->interpolation);
+    u->attr("inelastic", g_urr->inelastic_flag);
+    u->attr("absorption", g_urr->absorption_flag);
+    u->attr("multiply_smooth", g_urr->multiply_smooth);
+    const unsigned long long ne = g_urr->n_energy, nb = g_urr->n_band;
+    u->dataset("energy", std::vector<double>(g_urr->energy, g_urr->energy + ne));
+    u->dataset("table", std::vector<double>(g_urr->table, g_urr->table + ne * 6 * nb), {ne, 6, nb});
+    g_urr = nullptr;
+  }
   reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
   if (fission)
   {

@@ -23,10 +23,10 @@ ncu --set full --metrics $RED --clock-control none --import-source on -k regex:k
 export_rep track_tl
 ncu --set full --clock-control none -k regex:k_xs_lookup -c 6 -o $O/xs python bench.py --steps 1 --warmup 1 --no-extra --no-cpu-baseline > $O/ncu_xs.log 2>&1
 export_rep xs
-# fused-tail L1 prefetch A/B
-bash profiles/ab_variants.sh $O/ab_prefetch.txt "" default pf1 pf2 > /dev/null 2>&1
-bash profiles/ab_variants.sh $O/ab_prefetch.txt "--particles 200000" default pf1 pf2 > /dev/null 2>&1
-bash profiles/ab_variants.sh $O/ab_prefetch.txt "--workload pin_cell_tet" default pf1 pf2 > /dev/null 2>&1
+# A/B of build variants: fused-tail L1 prefetch (pf1, pf2), out-of-line collision math (ool), both (oolpf2)
+for fl in "" "--particles 200000" "--workload pin_cell_tet"; do
+  bash profiles/ab_variants.sh $O/ab_variants.txt "$fl" default pf1 pf2 ool oolpf2 default > /dev/null 2>&1
+done
 # meshes larger than L2: lexicographic vs Morton element numbering
 for w in brick_tet_100 brick_tet_100_morton brick_tet_160 brick_tet_160_morton; do
   python bench.py --workload $w --particles 2000000 --steps 3 --warmup 3 $Q > $O/bench_$w.json 2> $O/bench_$w.err

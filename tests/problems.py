@@ -118,12 +118,29 @@ def beavrs_assembly_sab(**kw):
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
 
 
+def pin_cell_tet_urr(**kw):
+    """Unresolved-resonance probability tables on every nuclide heavier than A = 80 (absolute and multiply_smooth
+    tables, inelastic competition); the band of a history follows its URR stream."""
+    mesh, lib, bm, s = pin_cell_tet(**kw)
+    return mesh, nucdata.add_urr_tables(lib), bm, s
+
+
+def beavrs_assembly_full(**kw):
+    """BEAVRS assembly with everything a real library brings: S(a,b) on hydrogen, probability tables on the heavy
+    nuclides, tabulated secondary distributions."""
+    import os
+    mesh, lib, bm, s = beavrs_assembly(**kw)
+    lib2 = nucdata.make_library(35, G=lib.nuclides[0].energy.size, tabular=True)
+    return mesh, nucdata.add_urr_tables(nucdata.add_thermal_scattering(lib2)), bm, s
+
+
 def infinite_medium_sab(**kw):
     mesh, lib, bm, s = infinite_medium(**kw)
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
 
 
-PROBLEMS = {"pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
+PROBLEMS = {"pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+            "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,
             "infinite_medium": infinite_medium, "pin_cell_tet": pin_cell_tet, "pin_cell_hex": pin_cell_hex,

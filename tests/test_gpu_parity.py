@@ -187,7 +187,13 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     # coherent / incoherent-discrete elastic, partial binding)
     ("infinite_medium_sab", {}, EVENT), ("pin_cell_tet_sab", {}, EVENT), ("pin_cell_tet_sab", {}, FUSED),
     ("pin_cell_tet_sab", {"sort_xs_queue": 1}, SORTED), ("pin_cell_tet_sab", {}, PUMP),
-    ("beavrs_assembly_sab", {"sort_xs_queue": 1}, MIXED), ("pin_cell_tet_sab", {"n_particles": 20000}, {"tail_threshold": 3000})])
+    ("beavrs_assembly_sab", {"sort_xs_queue": 1}, MIXED), ("pin_cell_tet_sab", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # unresolved-resonance probability tables: cross sections that depend on the history's URR stream, targets at rest
+    ("pin_cell_tet_urr", {}, EVENT), ("pin_cell_tet_urr", {}, FUSED), ("pin_cell_tet_urr", {"sort_xs_queue": 1}, SORTED),
+    ("pin_cell_tet_urr", {}, PUMP), ("pin_cell_tet_urr", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    ("pin_cell_tet_urr", {"seed_through_double": False}, MIXED),
+    # all of it at once on the reference's BEAVRS mesh
+    ("beavrs_assembly_full", {"sort_xs_queue": 1}, MIXED), ("beavrs_assembly_full", {}, EVENT)])
 def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     o, g, mesh, lib, s = both(oracle_bridge, ctx_factory, name, tallies=True, track_tally=True, **kw)
     for k, v in opts.items():

@@ -619,7 +619,7 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
     assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
 
 
-def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False):
+def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False):
     """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
     tables, so both sides hold the same numbers.  One material is given <isotropic> flags.  tabular: the nuclides carry
     tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
@@ -630,6 +630,8 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
     if thermal:  # S(a,b) tables, read by the reference's own ThermalScattering / ThermalData constructors
         nucdata.add_thermal_scattering(lib)
         lib.materials[3].isotropic = None
+    if urr:      # probability tables, read by the reference's own UrrData constructor
+        nucdata.add_urr_tables(lib)
     generator = [n.xs.copy() for n in lib.nuclides]
     tables = oracle_bridge.ref_load_library(r, lib)
     for n, (xs5, fissionable, n_precursor, _) in zip(lib.nuclides, tables):
@@ -662,7 +664,7 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -687,8 +689,10 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     if r is None or not hasattr(r, "ref_collide_events") or (tabular and not hasattr(r, "ref_stage_tables")) or \
             (tabular == "thermal" and not hasattr(r, "ref_add_thermal_table")):
         pytest.skip("oracle/_ref not built with physics.cpp + particle.cpp (no /root/reference on this box)")
-    thermal = tabular == "thermal"
-    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular is True, thermal=thermal)
+    thermal, urr = tabular == "thermal", tabular == "urr"
+    if urr and not hasattr(r, "ref_stage_urr"):
+        pytest.skip("oracle/_ref built without the probability-table doorway")
+    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular is True, thermal=thermal, urr=urr)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
     o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
     f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
