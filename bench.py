@@ -179,6 +179,17 @@ def ncu_counters(workload):
         return None
 
 
+def tally_atomics(estimator):
+    """ncu-measured FP64 RED traffic of the tracking kernel with the track-length tally on (profiles/); None for the
+    collision estimator, whose scores are one RED per collision inside k_collide."""
+    if estimator != "TRACKLENGTH":
+        return None
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "tracklength_atomics.json")))
+    except Exception:
+        return None
+
+
 def cpu_oracle_rate(problem, source_sites, target_seconds, threads, batch, estimator=0):
     """Histories/s of the CPU oracle on a bounded sample of the same workload."""
     from oracle import bridge
@@ -563,6 +574,7 @@ def main():
                                                        "collide+fallback": acc["ms_col"] / args.steps,
                                                        "bank+reduce": acc["ms_bank"] / args.steps}},
             "cpu_baseline": cpu,
+            "tally_atomics": tally_atomics(args.tally),
             "reference_size": ref_size,
             "extra": extra,
         }

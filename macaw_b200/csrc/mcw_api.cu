@@ -641,6 +641,10 @@ int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* d, int n)
         return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: elastic data missing" + at);
       t.el_x.assign(s.elastic_x, s.elastic_x + s.n_elastic);
       t.el_y.assign(s.elastic_y, s.elastic_y + s.n_elastic);
+      // the samplers interpolate between the grid point below and the one ABOVE the incident energy (OMC
+      // secondary_thermal.cpp:14-25,46-48): the grid has to reach energy_max or they would read past its end
+      if (!(t.el_x.back() >= s.energy_max) || (s.elastic_type == MCW_SAB_ELASTIC_COHERENT && !(t.el_x.back() > s.energy_max)))
+        return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: the elastic grid ends below energy_max" + at);
       if (s.elastic_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
       {
         if (!s.elastic_mu || s.n_elastic_mu < 1)
@@ -651,6 +655,8 @@ int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* d, int n)
     else if (s.elastic_type != MCW_SAB_ELASTIC_NONE)
       // IncoherentElasticXS / IncoherentElasticAE (Debye-Waller form, OMC endf.cpp:245-258) is not carried
       return fail(h, MCW_E_UNSUPPORTED, "mcw_set_thermal_tables: unsupported elastic type" + at);
+    if (!((t.inel_type == MCW_SAB_INELASTIC_CONTINUOUS ? t.ien.back() : t.ixs_e.back()) >= s.energy_max))
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_tables: the inelastic grid ends below energy_max" + at);
     out.push_back(std::move(t));
   }
   h->thermal = std::move(out);

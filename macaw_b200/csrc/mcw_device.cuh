@@ -93,7 +93,7 @@ MCW_D V3 unit(V3 a)
 // a generation (one or two warps per scheduler) stalls on instruction fetch.  MCW_COLLISION_MATH_OOL = 1 calls them out
 // of line from the collision samplers; the tracking loop and the cross-section lookups keep the inline versions.
 #ifndef MCW_COLLISION_MATH_OOL
-#define MCW_COLLISION_MATH_OOL 0
+#define MCW_COLLISION_MATH_OOL 1
 #endif
 #if MCW_COLLISION_MATH_OOL
 __device__ __noinline__ double mcw_log_c(double x) { return mcw_log(x); }

@@ -5,9 +5,7 @@
 #include "mcw_device.cuh"
 
 // ------------------------------------------------------------------ tallies
-// OMC filter_energy.cpp:61-75 energy bin + tally_scoring.cpp:1453 atomic update.  Lanes of a warp
-// that hit the same bin are pre-reduced with __match_any_sync so each distinct bin gets one FP64
-// atomic per warp.
+// OMC filter_energy.cpp:61-75 energy bin + tally_scoring.cpp:1453 atomic update.
 // energy bin of a tally (OMC filter_energy.cpp:61-75); -1 = outside the filter's range
 MCW_D int mcw_tally_energy_bin(const McwTallyDev& t, double E)
 {
@@ -42,6 +40,18 @@ MCW_D void mcw_score_tally(const McwTallyDev& t, int64_t spatial, double E, cons
 {
   const int eb = mcw_tally_energy_bin(t, E);
   long long bin = eb >= 0 ? (long long)(spatial * t.n_energy + eb) : -1ll;
+  if (t.granularity == MCW_FILTER_CELL)
+  {
+    // one bin per element: the lanes of a warp sit in different elements (measured: 26.1 distinct bins per 26.3 active
+    // lanes, profiles/ncu_r02m_track_tl.txt), so looking for equal bins first costs more than it saves -- and the
+    // L2's RED units run at 4 % of their peak.  One FP64 RED per lane and score.
+    if (bin >= 0)
+      for (int s = 0; s < t.n_scores; ++s)
+        atomicAdd(&t.value[bin * t.n_scores + s], sc[t.scores[s]]);
+    return;
+  }
+  // few bins (one per block, or one): lanes that hit the same bin are pre-reduced with __match_any_sync so that each
+  // distinct bin gets one FP64 atomic per warp
   unsigned active = __activemask();
   unsigned peers = __match_any_sync(active, bin);
   int lane = threadIdx.x & 31;

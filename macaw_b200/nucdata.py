@@ -176,7 +176,10 @@ def make_thermal_table(rng, name, kind="continuous", elastic="none", energy_max=
         t.inelastic_mu = cosines(n_xs * t.n_e_out).reshape(n_xs, t.n_e_out, n_mu)
     if elastic == "coherent":
         t.elastic_type = 1
-        t.elastic_x = np.sort(np.exp(rng.uniform(np.log(1.8e-3), np.log(0.9 * energy_max), 14)))
+        # Bragg edges reach beyond energy_max, as in the evaluated files: CoherentElasticAE::sample reads the structure
+        # factor of the edge ABOVE the incident energy (secondary_thermal.cpp:46-48)
+        t.elastic_x = np.concatenate([np.sort(np.exp(rng.uniform(np.log(1.8e-3), np.log(0.9 * energy_max), 13))),
+                                      [1.5 * energy_max]])
         t.elastic_y = np.cumsum(rng.uniform(0.002, 0.02, 14))
     elif elastic == "incoherent_discrete":
         t.elastic_type = 2

@@ -206,7 +206,8 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
         a, b = o.history_records(), g.history_records()
         for f in ("seed_tracking", "seed_source", "seed_urr", "n_segments", "n_collisions", "n_progeny",
                   "last_elem", "fate", "trace_hash"):
-            assert np.array_equal(a[f], b[f]), (batch, f, int((a[f] != b[f]).sum()))
+            bad = np.flatnonzero(a[f] != b[f])
+            assert bad.size == 0, (batch, f, bad.size, bad[:4].tolist(), [str(a[k]) for k in bad[:2]], [str(b[k]) for k in bad[:2]])
         for f in ("E", "k_collision", "k_absorption", "k_tracklength"):
             assert np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)), (batch, f)
         assert o.fission_bank().tobytes() == g.fission_bank().tobytes()
