@@ -54,10 +54,31 @@ struct Mesh
   int64_t nNodes() const { return (int64_t)xyz.size() / 3; }
 };
 
+// Distributions on a grid of incoming energies (mcw_tabular2d): AngleDistribution / ContinuousTabular data
+struct Tabular2D
+{
+  std::vector<double> energy, x, pdf, cdf;
+  std::vector<int32_t> offset, interpolation, n_discrete;
+  int histogram_in_energy = 0;
+  mcw_tabular2d desc() const
+  {
+    mcw_tabular2d t{};
+    t.n_energy = (int32_t)energy.size();
+    if (t.n_energy == 0)
+      return t;
+    t.histogram_in_energy = histogram_in_energy;
+    t.energy = energy.data(), t.offset = offset.data(), t.interpolation = interpolation.data();
+    t.n_discrete = n_discrete.empty() ? nullptr : n_discrete.data();
+    t.x = x.data(), t.pdf = pdf.data(), t.cdf = cdf.data();
+    return t;
+  }
+};
 struct Nuclide
 {
   std::string name; // as in materials.xml (OMC data::nuclide_map); may be empty for generated libraries
   std::vector<double> energy, xs, elastic, inelastic;
+  Tabular2D elastic_angle, inelastic_angle, inelastic_energy; // optional tabulated secondary distributions
+  int inelastic_in_cm = 1;
   mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
 };
 struct Material
@@ -65,11 +86,48 @@ struct Material
   std::vector<int32_t> nuclide;
   std::vector<double> atom_density;
   std::vector<int32_t> isotropic; // <isotropic> list of materials.xml as per-nuclide flags; empty = none
+  // <sab> entries (OMC Material::thermal_tables_): position in `nuclide`, table index, fraction
+  std::vector<int32_t> sab_position, sab_table;
+  std::vector<double> sab_fraction;
+};
+// One temperature of an S(alpha, beta) table (mcw_thermal_desc; OMC ThermalData)
+struct ThermalTable
+{
+  double energy_max = 0;
+  int inelastic_type = 0, elastic_type = 0, n_mu = 0, n_e_out = 0, skewed = 0, n_elastic_mu = 0;
+  std::vector<double> i_xs_energy, i_xs, i_energy, i_e_out, i_pdf, i_cdf, i_mu, e_x, e_y, e_mu;
+  std::vector<int32_t> i_offset;
+  mcw_thermal_desc desc() const
+  {
+    mcw_thermal_desc t{};
+    t.energy_max = energy_max, t.inelastic_type = inelastic_type, t.elastic_type = elastic_type;
+    t.n_inelastic_xs = (int32_t)i_xs_energy.size(), t.n_inelastic_energy = (int32_t)i_energy.size();
+    t.inelastic_xs_energy = i_xs_energy.data(), t.inelastic_xs = i_xs.data(), t.inelastic_energy = i_energy.data();
+    t.inelastic_offset = i_offset.data(), t.inelastic_e_out = i_e_out.data(), t.inelastic_pdf = i_pdf.data();
+    t.inelastic_cdf = i_cdf.data(), t.inelastic_mu = i_mu.data();
+    t.n_mu = n_mu, t.n_e_out = n_e_out, t.skewed = skewed;
+    t.n_elastic = (int32_t)e_x.size(), t.elastic_x = e_x.data(), t.elastic_y = e_y.data(), t.elastic_mu = e_mu.data();
+    t.n_elastic_mu = n_elastic_mu;
+    return t;
+  }
+};
+// Probability tables of one nuclide (mcw_urr_desc; OMC UrrData)
+struct UrrTable
+{
+  int nuclide = 0, interpolation = 2, inelastic_flag = -1, absorption_flag = -1, multiply_smooth = 0, n_band = 0;
+  std::vector<double> energy, table;
+  mcw_urr_desc desc() const
+  {
+    return {nuclide, interpolation, inelastic_flag, absorption_flag, multiply_smooth, (int32_t)energy.size(), n_band, 0,
+            energy.data(), table.data()};
+  }
 };
 struct Library
 {
   std::vector<Nuclide> nuclides;
   std::vector<Material> materials;
+  std::vector<ThermalTable> thermal; // data::thermal_scatt
+  std::vector<UrrTable> urr;         // urr_data_ of the nuclides that have it
   std::vector<mcw_nuclide_desc> nuclideDescs() const
   {
     std::vector<mcw_nuclide_desc> out;
@@ -83,6 +141,11 @@ struct Library
       d.elastic = n.elastic.data();
       d.n_inelastic = n.inelastic.empty() ? 0 : 1;
       d.inelastic = n.inelastic.empty() ? &zero : n.inelastic.data();
+      d.elastic_angle = n.elastic_angle.desc();
+      d.inelastic_angle = n.inelastic_angle.desc();
+      d.inelastic_energy = n.inelastic_energy.desc();
+      d.inelastic_law = n.inelastic_energy.energy.empty() ? MCW_LAW_LEVEL : MCW_LAW_CONTINUOUS_TABULAR;
+      d.inelastic_in_cm = n.inelastic_in_cm;
       out.push_back(d);
     }
     return out;
@@ -227,8 +290,17 @@ public:
   // inspects).  `all` appends every nuclide and -1 to the tally's default {-1} without clearing it, so results_ has
   // n + 2 nuclide bins: score_all_nuclides (OMC tally_scoring.cpp:2142-2175) fills bin i for nuclide i and bin n for the
   // total.  A list of names gets "total" appended (:198-202); unknown names fail like OMC tally.cpp:552-554.
+  // nuclide bins given as library indices (problem files); resolveNuclides then leaves them alone
+  void setNuclideBins(std::vector<int32_t> bins)
+  {
+    _bins = std::move(bins);
+    _ref_nuclides = _bins;
+    _bins_given = true;
+  }
   void resolveNuclides(const Library& library) const
   {
+    if (_bins_given)
+      return;
     const int n = (int)library.nuclides.size();
     _bins.clear();
     _ref_nuclides.clear();
@@ -269,6 +341,7 @@ private:
   std::vector<double> _energy_bins;
   std::vector<std::string> _nuclides;
   mutable std::vector<int32_t> _bins = {-1}, _ref_nuclides = {-1};
+  bool _bins_given = false;
 };
 
 // Communication the study needs between transport and finalize when particles are sharded over
@@ -315,6 +388,27 @@ public:
     auto bid = kernel.blockIds();
     auto bm = kernel.materialIndices();
     _h.check(mcw_set_materials(_h.get(), md.data(), (int)md.size(), bid.data(), bm.data(), (int)bid.size()));
+    if (!library.urr.empty())
+    {
+      std::vector<mcw_urr_desc> ud;
+      for (const auto& u : library.urr)
+        ud.push_back(u.desc());
+      _h.check(mcw_set_urr_tables(_h.get(), ud.data(), (int)ud.size()));
+    }
+    if (!library.thermal.empty())
+    {
+      std::vector<mcw_thermal_desc> td;
+      for (const auto& t : library.thermal)
+        td.push_back(t.desc());
+      _h.check(mcw_set_thermal_tables(_h.get(), td.data(), (int)td.size()));
+      for (size_t m = 0; m < library.materials.size(); ++m)
+      {
+        const Material& M = library.materials[m];
+        if (!M.sab_position.empty())
+          _h.check(mcw_set_material_thermal(_h.get(), (int)m, (int)M.sab_position.size(), M.sab_position.data(),
+                                            M.sab_table.data(), M.sab_fraction.data()));
+      }
+    }
     _h.check(mcw_set_temperature(_h.get(), kernel.temperature().data(), (int64_t)kernel.temperature().size()));
     _h.check(mcw_set_settings(_h.get(), &_settings));
     for (const auto& t : tallies)

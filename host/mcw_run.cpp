@@ -155,6 +155,8 @@ int main(int argc, char** argv)
         filters.push_back("energy");
       tallies.emplace_back(t.id, scores, filters, t.estimator == MCW_ESTIMATOR_TRACKLENGTH ? "TRACKLENGTH" : "COLLISION",
                            "neutron", t.energy_bins);
+      if (!t.nuclides.empty())
+        tallies.back().setNuclideBins(t.nuclides);
     }
     OpenMCStudy study(P.mesh, P.library, kernel, P.settings, tallies, device, comm.get(), /*verbose=*/false);
     for (int b = 1; b <= batches; ++b)

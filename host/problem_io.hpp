@@ -23,6 +23,7 @@ struct Problem
     int id, estimator, granularity;
     std::vector<int32_t> scores;
     std::vector<double> energy_bins;
+    std::vector<int32_t> nuclides; // nuclide bins already as library indices (-1 total, -2 never scored); empty = total
   };
   std::vector<TallyDef> tallies;
 };
@@ -108,12 +109,67 @@ public:
       const auto dy = f64(p + "delayed_yield"), dt = f64(p + "delayed_theta");
       for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
         n.d.delayed_yield[g] = dy[g], n.d.delayed_theta[g] = dt[g];
+      auto table = [&](const std::string& key, Tabular2D& t) {
+        if (!has(p + key + ".e"))
+          return;
+        t.energy = f64(p + key + ".e");
+        const size_t ne = t.energy.size();
+        const auto ti = i32(p + key + ".i"); // histogram flag, in_cm flag, offsets[ne + 1], interpolation[ne], n_discrete[ne]
+        t.histogram_in_energy = ti[0];
+        if (key == "inel_energy")
+          n.inelastic_in_cm = ti[1];
+        t.offset.assign(ti.begin() + 2, ti.begin() + 2 + ne + 1);
+        t.interpolation.assign(ti.begin() + 3 + ne, ti.begin() + 3 + 2 * ne);
+        t.n_discrete.assign(ti.begin() + 3 + 2 * ne, ti.begin() + 3 + 3 * ne);
+        const auto xpc = f64(p + key + ".xpc");
+        const size_t np = xpc.size() / 3;
+        t.x.assign(xpc.begin(), xpc.begin() + np);
+        t.pdf.assign(xpc.begin() + np, xpc.begin() + 2 * np);
+        t.cdf.assign(xpc.begin() + 2 * np, xpc.end());
+      };
+      table("el_angle", n.elastic_angle);
+      table("inel_angle", n.inelastic_angle);
+      table("inel_energy", n.inelastic_energy);
       P.library.nuclides.push_back(std::move(n));
     }
     for (int k = 0; k < counts[1]; ++k)
     {
       const std::string p = "mat" + std::to_string(k) + ".";
-      P.library.materials.push_back({i32(p + "nuclide"), f64(p + "density"), has(p + "isotropic") ? i32(p + "isotropic") : std::vector<int32_t>()});
+      Material M{i32(p + "nuclide"), f64(p + "density"), has(p + "isotropic") ? i32(p + "isotropic") : std::vector<int32_t>(), {}, {}, {}};
+      if (has(p + "sab_i"))
+      {
+        const auto si = i32(p + "sab_i");
+        for (size_t a = 0; a + 1 < si.size(); a += 2)
+          M.sab_position.push_back(si[a]), M.sab_table.push_back(si[a + 1]);
+        M.sab_fraction = f64(p + "sab_f");
+      }
+      P.library.materials.push_back(std::move(M));
+    }
+    const int n_thermal = has("lib.n_thermal") ? i32("lib.n_thermal")[0] : 0;
+    for (int k = 0; k < n_thermal; ++k)
+    {
+      const std::string p = "sab" + std::to_string(k) + ".";
+      ThermalTable t;
+      const auto I = i32(p + "ints");
+      t.inelastic_type = I[0], t.elastic_type = I[1], t.n_mu = I[2], t.n_e_out = I[3], t.skewed = I[4], t.n_elastic_mu = I[5];
+      t.energy_max = f64(p + "emax")[0];
+      t.i_xs_energy = f64(p + "i_xs_energy"), t.i_xs = f64(p + "i_xs"), t.i_energy = f64(p + "i_energy");
+      t.i_e_out = f64(p + "i_e_out"), t.i_pdf = f64(p + "i_pdf"), t.i_cdf = f64(p + "i_cdf"), t.i_mu = f64(p + "i_mu");
+      t.e_x = f64(p + "e_x"), t.e_y = f64(p + "e_y"), t.e_mu = f64(p + "e_mu");
+      t.i_offset = i32(p + "i_offset");
+      P.library.thermal.push_back(std::move(t));
+    }
+    const int n_urr = has("lib.n_urr") ? i32("lib.n_urr")[0] : 0;
+    for (int k = 0; k < n_urr; ++k)
+    {
+      const std::string p = "urr" + std::to_string(k) + ".";
+      const auto I = i32(p + "ints");
+      UrrTable u;
+      u.nuclide = I[0], u.interpolation = I[1], u.inelastic_flag = I[2], u.absorption_flag = I[3], u.multiply_smooth = I[4];
+      u.n_band = I[6];
+      u.energy = f64(p + "energy");
+      u.table = f64(p + "table");
+      P.library.urr.push_back(std::move(u));
     }
     for (int32_t b : i32("kernel.blocks"))
       P.blocks.push_back((unsigned)b);
@@ -134,7 +190,8 @@ public:
     {
       const std::string p = "tally" + std::to_string(k) + ".";
       const auto I = i32(p + "ints");
-      P.tallies.push_back({I[0], I[1], I[2], i32(p + "scores"), f64(p + "energy_bins")});
+      P.tallies.push_back({I[0], I[1], I[2], i32(p + "scores"), f64(p + "energy_bins"),
+                           has(p + "nuclides") ? i32(p + "nuclides") : std::vector<int32_t>()});
     }
     return P;
   }

@@ -37,11 +37,45 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
         r[f"nuc{k}.inelastic"] = np.ascontiguousarray(n.inelastic, np.float64)
         r[f"nuc{k}.delayed_yield"] = np.ascontiguousarray(n.delayed_yield, np.float64)
         r[f"nuc{k}.delayed_theta"] = np.ascontiguousarray(n.delayed_theta, np.float64)
+        # tabulated secondary distributions (mcw_tabular2d), when the nuclide has them
+        for key, t in (("el_angle", getattr(n, "elastic_angle", None)), ("inel_angle", getattr(n, "inelastic_angle", None)),
+                       ("inel_energy", getattr(n, "inelastic_energy", None))):
+            if t is None:
+                continue
+            nd = t.n_discrete if t.n_discrete is not None else np.zeros(len(t.energy), np.int32)
+            r[f"nuc{k}.{key}.i"] = np.concatenate([[int(t.histogram_in_energy), int(getattr(n, "inelastic_in_cm", True))],
+                                                   t.offset, t.interpolation, nd]).astype(np.int32)
+            r[f"nuc{k}.{key}.e"] = np.ascontiguousarray(t.energy, np.float64)
+            r[f"nuc{k}.{key}.xpc"] = np.concatenate([t.x, t.pdf, t.cdf]).astype(np.float64)
     for k, m in enumerate(lib.materials):
         r[f"mat{k}.nuclide"] = np.ascontiguousarray(m.nuclides, np.int32)
         r[f"mat{k}.density"] = np.ascontiguousarray(m.densities, np.float64)
         iso = getattr(m, "isotropic", None)
         r[f"mat{k}.isotropic"] = np.ascontiguousarray(iso if iso is not None else np.zeros(len(m.nuclides)), np.int32)
+        if getattr(m, "sab", None):  # (position, table, fraction)
+            r[f"mat{k}.sab_i"] = np.array([[a[0], a[1]] for a in m.sab], np.int32).ravel()
+            r[f"mat{k}.sab_f"] = np.array([a[2] for a in m.sab], np.float64)
+    # thermal scattering tables (mcw_thermal_desc) and probability tables (mcw_urr_desc)
+    th = getattr(lib, "thermal_tables", None) or []
+    r["lib.n_thermal"] = np.array([len(th)], np.int32)
+    for k, t in enumerate(th):
+        zero = np.zeros(0)
+        r[f"sab{k}.ints"] = np.array([t.inelastic_type, t.elastic_type, t.n_mu, t.n_e_out, int(t.skewed),
+                                      0 if t.elastic_mu is None else t.elastic_mu.shape[1]], np.int32)
+        r[f"sab{k}.emax"] = np.array([t.energy_max], np.float64)
+        for key in ("inelastic_xs_energy", "inelastic_xs", "inelastic_energy", "inelastic_e_out", "inelastic_pdf",
+                    "inelastic_cdf", "inelastic_mu", "elastic_x", "elastic_y", "elastic_mu"):
+            a = getattr(t, key)
+            r[f"sab{k}.{key.replace('inelastic_', 'i_').replace('elastic_', 'e_')}"] = \
+                np.ascontiguousarray(a if a is not None else zero, np.float64).ravel()
+        r[f"sab{k}.i_offset"] = np.ascontiguousarray(t.inelastic_offset if t.inelastic_offset is not None else [], np.int32)
+    ur = getattr(lib, "urr_tables", None) or []
+    r["lib.n_urr"] = np.array([len(ur)], np.int32)
+    for k, t in enumerate(ur):
+        r[f"urr{k}.ints"] = np.array([t.nuclide, t.interpolation, t.inelastic_flag, t.absorption_flag, int(t.multiply_smooth),
+                                      t.energy.size, t.table.shape[2]], np.int32)
+        r[f"urr{k}.energy"] = np.ascontiguousarray(t.energy, np.float64)
+        r[f"urr{k}.table"] = np.ascontiguousarray(t.table, np.float64).ravel()
     r["kernel.blocks"] = np.ascontiguousarray(blocks, np.int32)
     r["kernel.materials"] = np.ascontiguousarray(materials, np.int32)  # OpenMC material ids, 1-based
     r["kernel.temperature"] = np.atleast_1d(np.asarray(temperature, np.float64))
@@ -51,15 +85,18 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
                                    s.record_traces], np.int64)
     r["settings.reals"] = np.array([s.z_coord] + [s.source_box[i] for i in range(6)], np.float64)
     r["tallies.count"] = np.array([len(tallies)], np.int32)
-    for k, (tid, estimator, granularity, scores, ebins) in enumerate(tallies):
+    for k, tl in enumerate(tallies):
+        tid, estimator, granularity, scores, ebins = tl[:5]
         r[f"tally{k}.ints"] = np.array([tid, estimator, granularity], np.int32)
         r[f"tally{k}.scores"] = np.ascontiguousarray(scores, np.int32)
         r[f"tally{k}.energy_bins"] = np.ascontiguousarray(ebins if ebins is not None else [], np.float64)
+        if len(tl) > 5 and tl[5] is not None:  # nuclide bins (library indices, -1 total, -2 never scored)
+            r[f"tally{k}.nuclides"] = np.ascontiguousarray(tl[5], np.int32)
     return r
 
 
 def write_problem(path, mesh, lib, blocks, materials, settings, tallies=(), temperature=293.6):
-    """tallies: iterable of (id, estimator, granularity, scores, energy_bins | None) in C-ABI codes."""
+    """tallies: iterable of (id, estimator, granularity, scores, energy_bins | None[, nuclide bins]) in C-ABI codes."""
     recs = _records(mesh, lib, blocks, materials, settings, list(tallies), temperature)
     with open(path, "wb") as f:
         f.write(MAGIC)

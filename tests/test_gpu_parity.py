@@ -305,6 +305,34 @@ def test_error_paths(ctx_factory):
     c.set_mesh(mesh)
     with pytest.raises(McwError):
         c.set_library(lib, [0, 7])  # block mapped to an unknown material (MC CollisionKernel.C:84-90)
+    # data the library does not carry is refused, never dropped: Debye-Waller incoherent elastic, log-log probability
+    # tables, thermal grids that end below energy_max (the samplers would read past them), unknown tally nuclides
+    from macaw_b200 import nucdata
+    c = ctx_factory()
+    mesh, lib, bm, s = problems.pin_cell_tet()
+    nucdata.add_thermal_scattering(lib)
+    lib.thermal_tables[1].elastic_type = 3
+    c.set_mesh(mesh)
+    with pytest.raises(McwError, match="unsupported elastic type"):
+        c.set_library(lib, bm, np.arange(4, dtype=np.int32))
+    lib.thermal_tables[1].elastic_type = 1
+    lib.thermal_tables[1].elastic_x = lib.thermal_tables[1].elastic_x * 0.1
+    with pytest.raises(McwError, match="ends below energy_max"):
+        c.set_library(lib, bm, np.arange(4, dtype=np.int32))
+    mesh, lib, bm, s = problems.pin_cell_tet()
+    nucdata.add_urr_tables(lib)
+    lib.urr_tables[0].interpolation = 5
+    with pytest.raises(McwError, match="linear-linear"):
+        c.set_library(lib, bm, np.arange(4, dtype=np.int32))
+    c = problems.configure(ctx_factory(), *problems.pin_cell_tet()[:3], problems.pin_cell_tet()[3], tallies=True)
+    with pytest.raises(McwError, match="Could not find the nuclide"):
+        c.set_tally_nuclides(1, [0, 99, -1])
+    # a source box that misses the mesh is the reference's fatal error, not an empty first generation
+    mesh, lib, bm, s = problems.pin_cell_tet(n_particles=64)
+    s.source_box[0], s.source_box[3] = 50.0, 51.0
+    c = problems.configure(ctx_factory(), mesh, lib, bm, s, tallies=False)
+    with pytest.raises(McwError, match="external source sites sampled were rejected"):
+        c.sample_initial_source()
 
 
 @pytest.mark.parametrize("n", [1, 7, 33])
