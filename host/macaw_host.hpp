@@ -79,6 +79,12 @@ struct Nuclide
   std::vector<double> energy, xs, elastic, inelastic;
   Tabular2D elastic_angle, inelastic_angle, inelastic_energy; // optional tabulated secondary distributions
   int inelastic_in_cm = 1;
+  // -1: level, or continuous tabular when inelastic_energy is set; else MCW_LAW_CORRELATED / KALBACH_MANN / NBODY with
+  // the angular distribution per point of inelastic_energy (correlated), r / a per point (Kalbach-Mann), or
+  // d.nbody_n / nbody_mass_ratio / nbody_q (N-body)
+  int inelastic_law = -1;
+  std::vector<int32_t> corr_offset, corr_interp;
+  std::vector<double> corr_mu, corr_pdf, corr_cdf, km_r, km_a;
   mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
 };
 struct Material
@@ -144,8 +150,12 @@ struct Library
       d.elastic_angle = n.elastic_angle.desc();
       d.inelastic_angle = n.inelastic_angle.desc();
       d.inelastic_energy = n.inelastic_energy.desc();
-      d.inelastic_law = n.inelastic_energy.energy.empty() ? MCW_LAW_LEVEL : MCW_LAW_CONTINUOUS_TABULAR;
+      d.inelastic_law = n.inelastic_law >= 0 ? n.inelastic_law
+                                             : (n.inelastic_energy.energy.empty() ? MCW_LAW_LEVEL : MCW_LAW_CONTINUOUS_TABULAR);
       d.inelastic_in_cm = n.inelastic_in_cm;
+      d.corr_offset = n.corr_offset.data(), d.corr_interp = n.corr_interp.data();
+      d.corr_mu = n.corr_mu.data(), d.corr_pdf = n.corr_pdf.data(), d.corr_cdf = n.corr_cdf.data();
+      d.km_r = n.km_r.data(), d.km_a = n.km_a.data();
       out.push_back(d);
     }
     return out;

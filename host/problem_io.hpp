@@ -130,6 +130,31 @@ public:
       table("el_angle", n.elastic_angle);
       table("inel_angle", n.inelastic_angle);
       table("inel_energy", n.inelastic_energy);
+      if (has(p + "law.i"))
+      {
+        // law, in_cm, n_particles [, offsets[np + 1], interpolation[np]]; total_mass, q_value [, mu / pdf / cdf | r / a]
+        const auto li = i32(p + "law.i");
+        const auto lf = f64(p + "law.f");
+        n.inelastic_law = li[0];
+        n.inelastic_in_cm = li[1];
+        n.d.nbody_n = li[2];
+        n.d.nbody_mass_ratio = lf[0], n.d.nbody_q = lf[1];
+        const size_t np = n.inelastic_energy.offset.empty() ? 0 : (size_t)n.inelastic_energy.offset.back();
+        if (n.inelastic_law == MCW_LAW_CORRELATED)
+        {
+          n.corr_offset.assign(li.begin() + 3, li.begin() + 3 + np + 1);
+          n.corr_interp.assign(li.begin() + 4 + np, li.begin() + 4 + 2 * np);
+          const size_t nm = (size_t)n.corr_offset.back();
+          n.corr_mu.assign(lf.begin() + 2, lf.begin() + 2 + nm);
+          n.corr_pdf.assign(lf.begin() + 2 + nm, lf.begin() + 2 + 2 * nm);
+          n.corr_cdf.assign(lf.begin() + 2 + 2 * nm, lf.begin() + 2 + 3 * nm);
+        }
+        else if (n.inelastic_law == MCW_LAW_KALBACH_MANN)
+        {
+          n.km_r.assign(lf.begin() + 2, lf.begin() + 2 + np);
+          n.km_a.assign(lf.begin() + 2 + np, lf.begin() + 2 + 2 * np);
+        }
+      }
       P.library.nuclides.push_back(std::move(n));
     }
     for (int k = 0; k < counts[1]; ++k)

@@ -98,6 +98,9 @@ typedef struct mcw_tabular2d
 
 #define MCW_LAW_LEVEL 0              /* LevelInelastic, OMC distribution_energy.cpp:42-51 */
 #define MCW_LAW_CONTINUOUS_TABULAR 1 /* ContinuousTabular, OMC distribution_energy.cpp:150-275 */
+#define MCW_LAW_CORRELATED 2         /* CorrelatedAngleEnergy, OMC secondary_correlated.cpp:156-262 */
+#define MCW_LAW_KALBACH_MANN 3       /* KalbachMann, OMC secondary_kalbach.cpp:117-235 */
+#define MCW_LAW_NBODY 4              /* NBodyPhaseSpace, OMC secondary_nbody.cpp:25-68 */
 
 /* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
  * (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
@@ -132,9 +135,25 @@ typedef struct mcw_nuclide_desc
    * secondary_uncorrelated.cpp:54-68), and the outgoing-energy law of the inelastic reaction. */
   mcw_tabular2d elastic_angle;
   mcw_tabular2d inelastic_angle;
-  int32_t inelastic_law;                        /* MCW_LAW_LEVEL (default) or MCW_LAW_CONTINUOUS_TABULAR */
+  int32_t inelastic_law;                        /* MCW_LAW_* (default MCW_LAW_LEVEL) */
   int32_t inelastic_in_cm;                      /* scatter_in_cm_ of the inelastic reaction (level: always 1) */
-  mcw_tabular2d inelastic_energy;               /* the table of MCW_LAW_CONTINUOUS_TABULAR */
+  mcw_tabular2d inelastic_energy;               /* outgoing-energy table of CONTINUOUS_TABULAR, CORRELATED, KALBACH_MANN */
+  /* MCW_LAW_CORRELATED (product distribution "correlated"; replaces the angle table): one angular Tabular per POINT
+   * of inelastic_energy -- point j holds the cosines [corr_offset[j], corr_offset[j + 1]) of corr_mu / corr_pdf /
+   * corr_cdf, interpolation corr_interp[j] (1 histogram, 2 lin-lin). */
+  const int32_t* corr_offset;
+  const int32_t* corr_interp;
+  const double* corr_mu;
+  const double* corr_pdf;
+  const double* corr_cdf;
+  /* MCW_LAW_KALBACH_MANN ("kalbach-mann"): precompound fraction r and angular slope a per point of inelastic_energy */
+  const double* km_r;
+  const double* km_a;
+  /* MCW_LAW_NBODY ("nbody"): n_particles (3, 4 or 5), total_mass and q_value; A is the nuclide's awr */
+  int32_t nbody_n;
+  int32_t reserved1;
+  double nbody_mass_ratio;
+  double nbody_q;
 } mcw_nuclide_desc;
 
 /* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab

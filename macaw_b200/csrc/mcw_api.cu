@@ -59,6 +59,7 @@ struct HostNuclide
   std::vector<double> energy, xs5, elastic, inelastic_full;
   std::vector<int32_t> grid_index;
   HostTable el_angle, inel_angle, inel_energy;
+  HostTable law; // correlated: one angular distribution per point of inel_energy; Kalbach-Mann: one entry, x = r, p = a
 };
 
 // copies and checks one table of the descriptor; returns an error text or nullptr
@@ -538,16 +539,68 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
     }
     N.prm.inel_law = d[i].inelastic_law;
     N.prm.inel_in_cm = N.prm.inel_law == MCW_LAW_LEVEL ? 1 : (d[i].inelastic_in_cm != 0);
-    if (N.prm.inel_law != MCW_LAW_LEVEL && N.prm.inel_law != MCW_LAW_CONTINUOUS_TABULAR)
+    if (N.prm.inel_law < MCW_LAW_LEVEL || N.prm.inel_law > MCW_LAW_NBODY)
       // OMC secondary_uncorrelated.cpp:47 "Energy distribution type '...' not implemented."
-      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_library: inelastic energy law not implemented (level, continuous tabular)");
+      return fail(h, MCW_E_UNSUPPORTED, "mcw_set_library: inelastic law not implemented (level, continuous tabular, "
+                                        "correlated, Kalbach-Mann, N-body)");
     const char* bad = take_table(d[i].elastic_angle, N.el_angle, false);
     if (!bad)
       bad = take_table(d[i].inelastic_angle, N.inel_angle, false);
     if (!bad)
       bad = take_table(d[i].inelastic_energy, N.inel_energy, true);
-    if (!bad && N.prm.n_inel && N.prm.inel_law == MCW_LAW_CONTINUOUS_TABULAR && N.inel_energy.energy.empty())
-      bad = "continuous tabular law without its table";
+    const int law = N.prm.inel_law;
+    if (!bad && N.prm.n_inel && (law == MCW_LAW_CONTINUOUS_TABULAR || law == MCW_LAW_CORRELATED || law == MCW_LAW_KALBACH_MANN) &&
+        N.inel_energy.energy.empty())
+      bad = "tabulated inelastic law without its outgoing-energy table";
+    if (!bad && N.prm.n_inel && law == MCW_LAW_CORRELATED)
+    {
+      // one angular Tabular per point of the outgoing-energy table (OMC secondary_correlated.cpp:100-147)
+      const int np = N.inel_energy.off.back();
+      if (!d[i].corr_offset || !d[i].corr_interp || !d[i].corr_mu || !d[i].corr_pdf || !d[i].corr_cdf)
+        bad = "correlated law without its angular distributions";
+      else
+      {
+        HostTable& t = N.law;
+        t.energy.assign(np, 0.0);
+        t.off.assign(d[i].corr_offset, d[i].corr_offset + np + 1);
+        t.interp.assign(d[i].corr_interp, d[i].corr_interp + np);
+        t.ndisc.assign(np, 0);
+        for (int k = 0; k < np && !bad; ++k)
+          if (t.off[k + 1] - t.off[k] < 2 || (t.interp[k] != 1 && t.interp[k] != 2))
+            bad = "correlated law: every angular distribution needs >= 2 points, histogram or lin-lin";
+        if (!bad)
+        {
+          t.x.assign(d[i].corr_mu, d[i].corr_mu + t.off[np]);
+          t.p.assign(d[i].corr_pdf, d[i].corr_pdf + t.off[np]);
+          t.c.assign(d[i].corr_cdf, d[i].corr_cdf + t.off[np]);
+        }
+      }
+    }
+    if (!bad && N.prm.n_inel && law == MCW_LAW_KALBACH_MANN)
+    {
+      const int np = N.inel_energy.off.back();
+      if (!d[i].km_r || !d[i].km_a)
+        bad = "Kalbach-Mann law without r / a";
+      else
+      {
+        HostTable& t = N.law;
+        t.energy.assign(1, 0.0);
+        t.off = {0, np};
+        t.interp.assign(1, 2);
+        t.ndisc.assign(1, 0);
+        t.x.assign(d[i].km_r, d[i].km_r + np);
+        t.p.assign(d[i].km_a, d[i].km_a + np);
+        t.c.assign(np, 0.0);
+      }
+    }
+    if (!bad && N.prm.n_inel && law == MCW_LAW_NBODY && (d[i].nbody_n < 3 || d[i].nbody_n > 5))
+      // OMC secondary_nbody.cpp:57 "N-body phase space with >5 bodies."
+      bad = "N-body phase space needs 3, 4 or 5 bodies";
+    N.prm.nbody_n = d[i].nbody_n;
+    N.prm.nbody_mass_ratio = d[i].nbody_mass_ratio;
+    N.prm.nbody_q = d[i].nbody_q;
+    if (law >= MCW_LAW_CORRELATED)
+      N.inel_angle = HostTable(); // the product distribution gives the cosine itself
     if (bad)
       return fail(h, MCW_E_INVALID_ARGUMENT, std::string("mcw_set_library: ") + bad);
     h->nuclides.push_back(std::move(N));
@@ -830,7 +883,8 @@ static int prepare(mcw_handle h)
     for (const auto& tl : h->tallies)
       rare |= !tl.nuclides.empty();
     for (const auto& n : h->nuclides)
-      rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty();
+      rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty() ||
+              (n.prm.n_inel && n.prm.inel_law >= MCW_LAW_CORRELATED);
     h->rare = rare || h->force_rare > 0;
   }
 
@@ -885,6 +939,10 @@ static int prepare(mcw_handle h)
     add_table(n.inel_angle, n.prm.inel_ang_first, n.prm.inel_ang_n);
     add_table(n.inel_energy, n.prm.inel_en_first, n.prm.inel_en_n);
     n.prm.inel_en_hist = n.inel_energy.hist;
+    {
+      int32_t count;
+      add_table(n.law, n.prm.law_first, count);
+    }
     const int G = n.prm.G;
     energy.insert(energy.end(), n.energy.begin(), n.energy.end());
     for (int k = 0; k < G; ++k)

@@ -605,22 +605,203 @@ MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, 
   p.u = v_n / vel;
 }
 
+// The outgoing-energy part CorrelatedAngleEnergy::sample (OMC secondary_correlated.cpp:156-245) and KalbachMann::sample
+// (secondary_kalbach.cpp:117-222) share: ContinuousTabular without the histogram-in-incoming-energy case and without its
+// E_l_k != E_l_k1 guard.  Returns what the angular parts need.
+struct McwEnergyPick
+{
+  double E_out, E_unscaled, r1, c_k, c_k1, E_l_k, E_l_k1;
+  int point; // index of the chosen point within the table (distribution l, point k)
+  bool lin_lin;
+};
+MCW_D McwEnergyPick mcw_correlated_energy_sample(const McwLibraryDev& L, int first, int n_in, double E, uint64_t& seed)
+{
+  McwEnergyPick o;
+  const double* __restrict__ en = L.tab_energy + first;
+  int i;
+  double r;
+  if (E < __ldg(en))
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E > __ldg(en + n_in - 1))
+  {
+    i = n_in - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = mcw_tab_energy_bin(en, n_in, E);
+    r = (E - __ldg(en + i)) / (__ldg(en + i + 1) - __ldg(en + i));
+  }
+  const int l = r > mcw_prn(seed) ? i + 1 : i;
+  const int b_i = __ldg(L.tab_off + first + i), e_i = __ldg(L.tab_end + first + i);
+  const int b_i1 = __ldg(L.tab_off + first + i + 1), e_i1 = __ldg(L.tab_end + first + i + 1);
+  const double E_i_1 = __ldg(L.tab_x + b_i + __ldg(L.tab_ndisc + first + i)), E_i_K = __ldg(L.tab_x + e_i - 1);
+  const double E_i1_1 = __ldg(L.tab_x + b_i1 + __ldg(L.tab_ndisc + first + i + 1)), E_i1_K = __ldg(L.tab_x + e_i1 - 1);
+  const double E_1 = E_i_1 + r * (E_i1_1 - E_i_1);
+  const double E_K = E_i_K + r * (E_i1_K - E_i_K);
+  const int b = __ldg(L.tab_off + first + l), n_energy_out = __ldg(L.tab_end + first + l) - b;
+  const int n_discrete = __ldg(L.tab_ndisc + first + l);
+  const double* __restrict__ eo = L.tab_x + b;
+  const double* __restrict__ pd = L.tab_p + b;
+  const double* __restrict__ cd = L.tab_c + b;
+  const double r1 = mcw_prn(seed);
+  double c_k = __ldg(cd);
+  int k = 0, end = n_energy_out - 2;
+  for (int j = 0; j < n_discrete; ++j)
+  {
+    k = j;
+    c_k = __ldg(cd + k);
+    if (r1 < c_k)
+    {
+      end = j;
+      break;
+    }
+  }
+  double c_k1 = 0.0;
+  for (int j = n_discrete; j < end; ++j)
+  {
+    k = j;
+    c_k1 = __ldg(cd + k + 1);
+    if (r1 < c_k1)
+      break;
+    k = j + 1;
+    c_k = c_k1;
+  }
+  const double E_l_k = __ldg(eo + k), p_l_k = __ldg(pd + k);
+  double E_out;
+  o.lin_lin = __ldg(L.tab_interp + first + l) != 1;
+  o.E_l_k1 = 0.0;
+  if (!o.lin_lin)
+  {
+    if (p_l_k > 0.0 && k >= n_discrete)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+    else
+      E_out = E_l_k;
+  }
+  else
+  {
+    const double E_l_k1 = __ldg(eo + k + 1), p_l_k1 = __ldg(pd + k + 1);
+    o.E_l_k1 = E_l_k1;
+    const double frac = (p_l_k1 - p_l_k) / (E_l_k1 - E_l_k);
+    if (frac == 0.0)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+    else
+      E_out = E_l_k + (sqrt(fmax(0.0, p_l_k * p_l_k + 2.0 * frac * (r1 - c_k))) - p_l_k) / frac;
+  }
+  o.E_unscaled = E_out; // the Kalbach-Mann parameters interpolate with this value (secondary_kalbach.cpp:206-209)
+  if (k >= n_discrete)
+  {
+    if (l == i)
+      E_out = E_1 + (E_out - E_i_1) * (E_K - E_1) / (E_i_K - E_i_1);
+    else
+      E_out = E_1 + (E_out - E_i1_1) * (E_K - E_1) / (E_i1_K - E_i1_1);
+  }
+  o.E_out = E_out;
+  o.r1 = r1, o.c_k = c_k, o.c_k1 = c_k1, o.E_l_k = E_l_k;
+  o.point = b - __ldg(L.tab_off + first) + k;
+  return o;
+}
+
+// The product distributions that give energy and cosine together (OMC reaction_product.cpp:70-79):
+// CorrelatedAngleEnergy::sample (secondary_correlated.cpp:156-262), KalbachMann::sample (secondary_kalbach.cpp:117-235),
+// NBodyPhaseSpace::sample (secondary_nbody.cpp:25-68).  Out of line: three rarely sampled laws.
+__device__ __noinline__ double2 mcw_product_sample(const McwLibraryDev* Lp, int i_nuc, double E_in, uint64_t* seed_io)
+{
+  const McwLibraryDev& L = *Lp;
+  const McwNucParams& nuc = L.nuc[i_nuc];
+  uint64_t seed = *seed_io;
+  double E_out, mu;
+  if (nuc.inel_law == MCW_LAW_NBODY)
+  {
+    mu = mcw_uniform(-1., 1., seed);
+    const double Ap = nuc.nbody_mass_ratio;
+    const double E_max = (Ap - 1.0) / Ap * (nuc.awr / (nuc.awr + 1.0) * E_in + nuc.nbody_q);
+    const double x = mcw_maxwell_spectrum(1.0, seed);
+    double y;
+    if (nuc.nbody_n == 3)
+      y = mcw_maxwell_spectrum(1.0, seed);
+    else if (nuc.nbody_n == 4)
+    {
+      const double r1 = mcw_prn(seed), r2 = mcw_prn(seed), r3 = mcw_prn(seed);
+      y = -mcw_log_c(r1 * r2 * r3);
+    }
+    else
+    {
+      const double r1 = mcw_prn(seed), r2 = mcw_prn(seed), r3 = mcw_prn(seed), r4 = mcw_prn(seed), r5 = mcw_prn(seed),
+                   r6 = mcw_prn(seed);
+      const double c = mcw_cos_c(MCW_PI / 2.0 * r6);
+      y = -mcw_log_c(r1 * r2 * r3 * r4) - mcw_log_c(r5) * (c * c);
+    }
+    const double v = x / (x + y);
+    E_out = E_max * v;
+  }
+  else
+  {
+    const McwEnergyPick o = mcw_correlated_energy_sample(L, nuc.inel_en_first, nuc.inel_en_n, E_in, seed);
+    E_out = o.E_out;
+    if (nuc.inel_law == MCW_LAW_CORRELATED)
+    {
+      // the angular distribution of the closer outgoing-energy point (:247-261)
+      if (o.r1 - o.c_k < o.c_k1 - o.r1 || !o.lin_lin)
+        mu = mcw_tabular_sample(L, nuc.law_first + o.point, seed);
+      else
+        mu = mcw_tabular_sample(L, nuc.law_first + o.point + 1, seed);
+    }
+    else
+    {
+      // Kalbach-Mann: precompound fraction r and slope a of the sampled point (:189-234)
+      const int b = __ldg(L.tab_off + nuc.law_first) + o.point;
+      const double r_k = __ldg(L.tab_x + b), a_k = __ldg(L.tab_p + b);
+      double km_r = r_k, km_a = a_k;
+      if (o.lin_lin)
+      {
+        const double t = (o.E_unscaled - o.E_l_k) / (o.E_l_k1 - o.E_l_k);
+        km_r = r_k + t * (__ldg(L.tab_x + b + 1) - r_k);
+        km_a = a_k + t * (__ldg(L.tab_p + b + 1) - a_k);
+      }
+      if (mcw_prn(seed) > km_r)
+      {
+        const double T = mcw_uniform(-1., 1., seed) * mcw_sinh(km_a);
+        mu = mcw_log_c(T + sqrt(T * T + 1.0)) / km_a;
+      }
+      else
+      {
+        const double r1 = mcw_prn(seed);
+        mu = mcw_log_c(r1 * mcw_exp(km_a) + (1.0 - r1) * mcw_exp(-km_a)) / km_a;
+      }
+    }
+  }
+  *seed_io = seed;
+  return make_double2(E_out, mu);
+}
+
 // OMC physics.cpp:1073-1120 inelastic_scatter over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68):
 // cosine from the reaction's tabular angle distribution or uniform, outgoing energy from LevelInelastic
 // (distribution_energy.cpp:48-51) or ContinuousTabular (:150-275), then CM -> LAB if the reaction scatters in CM
 MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p)
 {
   double E_in = p.E;
-  double mu;
-  if (MCW_RARE && nuc.inel_ang_n > 0)
-    mu = mcw_angle_sample(L, nuc.inel_ang_first, nuc.inel_ang_n, E_in, p.seed);
+  double mu, E;
+  if (MCW_RARE && nuc.inel_law >= MCW_LAW_CORRELATED)
+  {
+    const double2 em = mcw_product_sample(L.self_dev, (int)(&nuc - L.nuc), E_in, &p.seed);
+    E = em.x;
+    mu = em.y;
+  }
   else
-    mu = mcw_uniform(-1., 1., p.seed);
-  double E;
-  if (MCW_RARE && nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
-    E = mcw_continuous_tabular_sample(L, nuc.inel_en_first, nuc.inel_en_n, nuc.inel_en_hist != 0, E_in, p.seed);
-  else
-    E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  {
+    if (MCW_RARE && nuc.inel_ang_n > 0)
+      mu = mcw_angle_sample(L, nuc.inel_ang_first, nuc.inel_ang_n, E_in, p.seed);
+    else
+      mu = mcw_uniform(-1., 1., p.seed);
+    if (MCW_RARE && nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+      E = mcw_continuous_tabular_sample(L, nuc.inel_en_first, nuc.inel_en_n, nuc.inel_en_hist != 0, E_in, p.seed);
+    else
+      E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  }
   if (!MCW_RARE || nuc.inel_in_cm) // the level law always scatters in the centre of mass
   {
     double E_cm = E;

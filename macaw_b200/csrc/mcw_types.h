@@ -34,7 +34,7 @@ struct McwNucParams
   int32_t fissionable;
   int32_t n_inel, inel_thr;
   int32_t n_precursor;
-  int32_t inel_law;            // MCW_LAW_LEVEL / MCW_LAW_CONTINUOUS_TABULAR
+  int32_t inel_law;            // MCW_LAW_*
   // tabulated secondary distributions: first incoming energy in McwLibraryDev::tab_* and how many (0 = absent)
   int32_t el_ang_first, el_ang_n;
   int32_t inel_ang_first, inel_ang_n;
@@ -43,6 +43,11 @@ struct McwNucParams
   // unresolved-resonance probability tables (mcw_urr_desc): energies at McwLibraryDev::urr_pool[urr_first ..], then the
   // table [n_energy][6][n_band]; urr_n = 0: none
   int32_t urr_first, urr_n, urr_bands, urr_inel_flag, urr_multiply_smooth, urr_pad;
+  // product distributions that give energy and cosine together (inel_law >= MCW_LAW_CORRELATED): law_first is an entry
+  // of the tab_* pools -- correlated: the first of one angular distribution per point of the outgoing-energy table
+  // (point j of the table -> entry law_first + j); Kalbach-Mann: ONE entry whose tab_x / tab_p hold r / a per point
+  int32_t law_first, nbody_n;
+  double nbody_mass_ratio, nbody_q;
 };
 
 // One temperature of an S(alpha, beta) table (mcw_thermal_desc): offsets into McwLibraryDev::sab_pool (doubles) /

@@ -42,8 +42,13 @@ class Nuclide:
     # optional tabulated secondary distributions (Tabular2D below); None = isotropic in CM / level law
     elastic_angle: object = None
     inelastic_angle: object = None
-    inelastic_energy: object = None  # ContinuousTabular law of the inelastic reaction (then inelastic_in_cm as given)
+    inelastic_energy: object = None  # outgoing-energy table of the inelastic reaction (then inelastic_in_cm as given)
     inelastic_in_cm: bool = True
+    inelastic_law: int = -1          # -1: level, or continuous tabular when inelastic_energy is set; 2 correlated, 3 Kalbach-Mann, 4 N-body
+    corr_angle: object = None        # law 2: (offset, interpolation, mu, pdf, cdf): one angular Tabular per point of inelastic_energy
+    km_r: np.ndarray = None          # law 3: precompound fraction / slope per point of inelastic_energy
+    km_a: np.ndarray = None
+    nbody: tuple = None              # law 4: (n_particles, total_mass, q_value)
 
 
 @dataclass
@@ -107,6 +112,18 @@ def make_continuous_table(rng, e_thr, e_hi, n_energy=4, discrete=True) -> Tabula
         off.append(off[-1] + n_d + n_c)
     return Tabular2D(energy, np.array(off, np.int32), np.array(interp, np.int32), np.concatenate(xs), np.concatenate(ps),
                      np.concatenate(cs), np.array(nd, np.int32), False)
+
+
+def make_point_angles(rng, n_points):
+    """One angular Tabular per point of an outgoing-energy table (the "mu" dataset of a correlated distribution)."""
+    off, interp, xs, ps, cs = [0], [], [], [], []
+    for j in range(n_points):
+        n = int(rng.integers(3, 9))
+        mu = np.sort(np.concatenate([[-1.0, 1.0], rng.uniform(-1, 1, n - 2)]))
+        it = 1 if j % 3 == 0 else 2
+        p, c = _tabulated_pdf(rng, mu, it)
+        xs.append(mu); ps.append(p); cs.append(c); interp.append(it); off.append(off[-1] + n)
+    return (np.array(off, np.int32), np.array(interp, np.int32), np.concatenate(xs), np.concatenate(ps), np.concatenate(cs))
 
 
 @dataclass
@@ -388,6 +405,29 @@ def make_library(n_nuclides=9, G=2000, seed=1, n_log_bins=8000, tabular=False) -
                     n.inelastic_energy = make_continuous_table(trng, n.inel_threshold_energy, 1.9e7, discrete=k_inel % 4 == 0)
                     n.inelastic_in_cm = k_inel % 4 != 0
                 k_inel += 1
+        # product distributions that give energy and cosine together (drawn after everything above, so the library
+        # without them is unchanged): the inelastic reactions WITHOUT a table so far cycle through correlated,
+        # Kalbach-Mann and N-body
+        k_law = 0
+        for n in nucs:
+            if not n.inelastic.size or n.inelastic_energy is not None:
+                continue
+            law = (2, 3, 4)[k_law % 3]
+            k_law += 1
+            n.inelastic_law = law
+            n.inelastic_angle = None
+            if law == 4:
+                n.nbody = (3 + (k_law // 3) % 3, float(trng.uniform(2.5, 4.0)), -0.5 * n.inel_threshold_energy)
+                n.inelastic_in_cm = True
+                continue
+            n.inelastic_energy = make_continuous_table(trng, n.inel_threshold_energy, 1.9e7, discrete=False)
+            n.inelastic_in_cm = k_law % 2 == 0
+            npts = int(n.inelastic_energy.offset[-1])
+            if law == 2:
+                n.corr_angle = make_point_angles(trng, npts)
+            else:
+                n.km_r = trng.uniform(0.0, 1.0, npts)
+                n.km_a = trng.uniform(0.3, 3.0, npts)
     mats = standard_materials(n_nuclides)
     return Library(nucs, mats, n_log_bins)
 
@@ -484,7 +524,10 @@ class NuclideDesc(C.Structure):
                 ("delayed_yield", C.c_double * MAX_DELAYED_GROUPS), ("delayed_theta", C.c_double * MAX_DELAYED_GROUPS),
                 ("watt_a", C.c_double), ("watt_b", C.c_double), ("q_fission", C.c_double),
                 ("elastic_angle", Tabular2DDesc), ("inelastic_angle", Tabular2DDesc), ("inelastic_law", C.c_int32),
-                ("inelastic_in_cm", C.c_int32), ("inelastic_energy", Tabular2DDesc)]
+                ("inelastic_in_cm", C.c_int32), ("inelastic_energy", Tabular2DDesc),
+                ("corr_offset", C.c_void_p), ("corr_interp", C.c_void_p), ("corr_mu", C.c_void_p), ("corr_pdf", C.c_void_p),
+                ("corr_cdf", C.c_void_p), ("km_r", C.c_void_p), ("km_a", C.c_void_p), ("nbody_n", C.c_int32),
+                ("reserved1", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double)]
 
 
 class ThermalDesc(C.Structure):
@@ -541,6 +584,26 @@ def pack_thermal(tables):
     return td, keep
 
 
+def pack_inelastic_law(d, n, keep):
+    """inelastic_law and the data of the product distributions that give energy and cosine together"""
+    law = getattr(n, "inelastic_law", -1)
+    d.inelastic_law = law if law >= 0 else (1 if getattr(n, "inelastic_energy", None) is not None else 0)
+    d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
+
+    def ptr(a, dt):
+        b = np.ascontiguousarray(a, dt)
+        keep.append(b)
+        return b.ctypes.data
+    if d.inelastic_law == 2:
+        off, interp, mu, pdf, cdf = n.corr_angle
+        d.corr_offset, d.corr_interp = ptr(off, np.int32), ptr(interp, np.int32)
+        d.corr_mu, d.corr_pdf, d.corr_cdf = ptr(mu, np.float64), ptr(pdf, np.float64), ptr(cdf, np.float64)
+    elif d.inelastic_law == 3:
+        d.km_r, d.km_a = ptr(n.km_r, np.float64), ptr(n.km_a, np.float64)
+    elif d.inelastic_law == 4:
+        d.nbody_n, d.nbody_mass_ratio, d.nbody_q = int(n.nbody[0]), float(n.nbody[1]), float(n.nbody[2])
+
+
 class MaterialDesc(C.Structure):
     _fields_ = [("n_nuclides", C.c_int32), ("reserved0", C.c_int32), ("nuclide", C.c_void_p),
                 ("atom_density", C.c_void_p), ("isotropic_in_lab", C.c_void_p)]
@@ -571,8 +634,7 @@ def pack_library(lib: Library):
         _pack_table(d.elastic_angle, getattr(n, "elastic_angle", None), keep)
         _pack_table(d.inelastic_angle, getattr(n, "inelastic_angle", None), keep)
         _pack_table(d.inelastic_energy, getattr(n, "inelastic_energy", None), keep)
-        d.inelastic_law = 1 if getattr(n, "inelastic_energy", None) is not None else 0
-        d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
+        pack_inelastic_law(d, n, keep)
     md = (MaterialDesc * len(lib.materials))()
     for d, m in zip(md, lib.materials):
         idx = np.ascontiguousarray(m.nuclides, np.int32)

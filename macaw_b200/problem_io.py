@@ -47,6 +47,19 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
                                                    t.offset, t.interpolation, nd]).astype(np.int32)
             r[f"nuc{k}.{key}.e"] = np.ascontiguousarray(t.energy, np.float64)
             r[f"nuc{k}.{key}.xpc"] = np.concatenate([t.x, t.pdf, t.cdf]).astype(np.float64)
+        # product distributions that give energy and cosine together (MCW_LAW_CORRELATED / KALBACH_MANN / NBODY)
+        law = getattr(n, "inelastic_law", -1)
+        if law >= 2:
+            li, lf = [law, int(n.inelastic_in_cm), 0], [0.0, 0.0]
+            if law == 4:
+                li[2], lf = int(n.nbody[0]), [float(n.nbody[1]), float(n.nbody[2])]
+            elif law == 2:
+                off, interp, mu, pdf, cdf = n.corr_angle
+                li, lf = np.concatenate([li, off, interp]), np.concatenate([lf, mu, pdf, cdf])
+            else:
+                lf = np.concatenate([lf, n.km_r, n.km_a])
+            r[f"nuc{k}.law.i"] = np.asarray(li, np.int32)
+            r[f"nuc{k}.law.f"] = np.asarray(lf, np.float64)
     for k, m in enumerate(lib.materials):
         r[f"mat{k}.nuclide"] = np.ascontiguousarray(m.nuclides, np.int32)
         r[f"mat{k}.density"] = np.ascontiguousarray(m.densities, np.float64)

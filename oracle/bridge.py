@@ -53,7 +53,9 @@ def _load(name):
     lib.orc_score_events.restype = C.c_int64
     lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
                                      f64p, f64p]
-    for f in ("orc_log", "orc_sin", "orc_cos"):
+    lib.orc_law_samples.argtypes = [C.POINTER(C.c_longlong)]
+    lib.orc_law_samples.restype = None
+    for f in ("orc_log", "orc_sin", "orc_cos", "orc_exp", "orc_sinh"):
         getattr(lib, f).restype = C.c_double
         getattr(lib, f).argtypes = [C.c_double]
     lib.orc_is_within_segment.argtypes = [f64p, f64p, f64p, C.c_double]
@@ -152,6 +154,8 @@ def ref_lib():
             r.ref_transport_histories.argtypes = [C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int64, f64p, C.c_double, f64p,
                                                   u64p, C.c_int64, f64p, f64p, C.c_int, f64p]
         r.ref_tracklength_kappa.argtypes = [C.c_int, C.c_int64, f64p, f64p, f64p, C.c_double, f64p]
+        if hasattr(r, "ref_stage_law"):
+            r.ref_stage_law.argtypes = [C.c_void_p]
         if hasattr(r, "ref_stage_urr"):
             r.ref_stage_urr.argtypes = [C.c_void_p]
         if hasattr(r, "ref_add_thermal_table"):
@@ -217,6 +221,11 @@ def ref_load_library(r, libr: nucdata.Library):
                 _nd._pack_table(d, getattr(n, a, None), keep)
                 descs.append(d)
             r.ref_stage_tables(C.addressof(descs[0]), C.addressof(descs[1]), C.addressof(descs[2]), int(n.inelastic_in_cm))
+        if getattr(n, "inelastic_law", -1) >= 2:
+            from macaw_b200 import nucdata as _nd
+            one = _nd.Library([n], [])
+            ndesc, _, keep_l = _nd.pack_library(one)
+            r.ref_stage_law(C.addressof(ndesc))
         urr = [t for t in (getattr(libr, "urr_tables", None) or []) if libr.nuclides[t.nuclide] is n]
         if urr:
             from macaw_b200 import nucdata as _nd

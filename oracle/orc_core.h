@@ -44,10 +44,14 @@ namespace orc
 inline double xlog(double x) { return std::log(x); }
 inline double xsin(double x) { return std::sin(x); }
 inline double xcos(double x) { return std::cos(x); }
+inline double xexp(double x) { return std::exp(x); }
+inline double xsinh(double x) { return std::sinh(x); }
 #else
 inline double xlog(double x) { return mcw_log(x); }
 inline double xsin(double x) { return mcw_sin(x); }
 inline double xcos(double x) { return mcw_cos(x); }
+inline double xexp(double x) { return mcw_exp(x); }
+inline double xsinh(double x) { return mcw_sinh(x); }
 #endif
 
 constexpr double PI = 3.1415926535897932384626433832795028841971693993751058209749445923078164062;
@@ -218,6 +222,12 @@ struct Nuclide
   Tabular2D el_angle, inel_angle, inel_energy; // optional tabulated secondary distributions
   int inel_law = MCW_LAW_LEVEL;
   bool inel_in_cm = true;
+  // product distributions that give energy and cosine together: correlated (one angular Tabular per point of inel_energy:
+  // Tabular2D with one "incoming energy" per point), Kalbach-Mann (r, a per point), N-body
+  Tabular2D corr_angle;
+  std::vector<double> km_r, km_a;
+  int nbody_n = 0;
+  double nbody_mass_ratio = 0, nbody_q = 0;
   // unresolved-resonance probability tables (mcw_urr_desc; OMC urr.cpp UrrData); urr_energy empty = none
   std::vector<double> urr_energy, urr_table; // table[n_energy][6][n_band]
   int urr_bands = 0, urr_inel_flag = -1, urr_multiply_smooth = 0;

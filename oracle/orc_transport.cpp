@@ -518,22 +518,199 @@ static void elastic_scatter(const Nuclide& nuc, double kT, Hist& p, bool use_pta
   p.u = v_n / vel;
 }
 
+// The outgoing-energy part CorrelatedAngleEnergy::sample (OMC secondary_correlated.cpp:156-245) and KalbachMann::sample
+// (secondary_kalbach.cpp:117-222) share: like ContinuousTabular but without the histogram-in-incoming-energy case and
+// without its E_l_k != E_l_k1 guard.  Returns what the angular parts need.
+struct EnergyPick
+{
+  double E_out, E_unscaled, r1, c_k, c_k1, E_l_k, E_l_k1;
+  int l, k;      // distribution, point within it
+  bool lin_lin;
+};
+static EnergyPick correlated_energy_sample(const Tabular2D& t, double E_in, uint64_t* seed)
+{
+  EnergyPick o;
+  const int n_energy_in = (int)t.energy.size();
+  int i;
+  double r;
+  if (E_in < t.energy[0])
+  {
+    i = 0;
+    r = 0.0;
+  }
+  else if (E_in > t.energy[n_energy_in - 1])
+  {
+    i = n_energy_in - 2;
+    r = 1.0;
+  }
+  else
+  {
+    i = lower_bound_index(t.energy, E_in);
+    r = (E_in - t.energy[i]) / (t.energy[i + 1] - t.energy[i]);
+  }
+  const int l = r > prn(seed) ? i + 1 : i;
+  const double E_i_1 = t.x[t.off[i] + t.ndisc[i]], E_i_K = t.x[t.off[i + 1] - 1];
+  const double E_i1_1 = t.x[t.off[i + 1] + t.ndisc[i + 1]], E_i1_K = t.x[t.off[i + 2] - 1];
+  const double E_1 = E_i_1 + r * (E_i1_1 - E_i_1);
+  const double E_K = E_i_K + r * (E_i1_K - E_i_K);
+  const int b = t.off[l], n_energy_out = t.off[l + 1] - b, n_discrete = t.ndisc[l];
+  const double* eo = &t.x[b];
+  const double* pd = &t.p[b];
+  const double* cd = &t.c[b];
+  const double r1 = prn(seed);
+  double c_k = cd[0];
+  int k = 0, end = n_energy_out - 2;
+  for (int j = 0; j < n_discrete; ++j)
+  {
+    k = j;
+    c_k = cd[k];
+    if (r1 < c_k)
+    {
+      end = j;
+      break;
+    }
+  }
+  double c_k1 = 0.0; // uninitialised in the reference when the continuous loop does not run; the data here always run it
+  for (int j = n_discrete; j < end; ++j)
+  {
+    k = j;
+    c_k1 = cd[k + 1];
+    if (r1 < c_k1)
+      break;
+    k = j + 1;
+    c_k = c_k1;
+  }
+  const double E_l_k = eo[k], p_l_k = pd[k];
+  double E_out;
+  o.lin_lin = t.interp[l] != 1;
+  o.E_l_k1 = 0.0;
+  if (!o.lin_lin)
+  {
+    if (p_l_k > 0.0 && k >= n_discrete)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+    else
+      E_out = E_l_k;
+  }
+  else
+  {
+    const double E_l_k1 = eo[k + 1], p_l_k1 = pd[k + 1];
+    o.E_l_k1 = E_l_k1;
+    const double frac = (p_l_k1 - p_l_k) / (E_l_k1 - E_l_k);
+    if (frac == 0.0)
+      E_out = E_l_k + (r1 - c_k) / p_l_k;
+    else
+      E_out = E_l_k + (std::sqrt(std::max(0.0, p_l_k * p_l_k + 2.0 * frac * (r1 - c_k))) - p_l_k) / frac;
+  }
+  const double E_unscaled = E_out; // the Kalbach-Mann parameters interpolate with this value (:206-209)
+  if (k >= n_discrete)
+  {
+    if (l == i)
+      E_out = E_1 + (E_out - E_i_1) * (E_K - E_1) / (E_i_K - E_i_1);
+    else
+      E_out = E_1 + (E_out - E_i1_1) * (E_K - E_1) / (E_i1_K - E_i1_1);
+  }
+  o.E_out = E_out, o.E_unscaled = E_unscaled, o.r1 = r1, o.c_k = c_k, o.c_k1 = c_k1, o.E_l_k = E_l_k, o.l = l, o.k = k;
+  return o;
+}
+
+// CorrelatedAngleEnergy::sample, the angular part (:247-261): the Tabular of the closer outgoing-energy point
+static void correlated_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  const EnergyPick o = correlated_energy_sample(nuc.inel_energy, E_in, seed);
+  E_out = o.E_out;
+  const int point = nuc.inel_energy.off[o.l] + o.k; // absolute point index = "incoming energy" index of corr_angle
+  if (o.r1 - o.c_k < o.c_k1 - o.r1 || !o.lin_lin)
+    mu = tabular_sample(nuc.corr_angle, point, seed);
+  else
+    mu = tabular_sample(nuc.corr_angle, point + 1, seed);
+}
+
+// KalbachMann::sample, the angular part (:189-234)
+static void kalbach_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  const EnergyPick o = correlated_energy_sample(nuc.inel_energy, E_in, seed);
+  E_out = o.E_out;
+  const int point = nuc.inel_energy.off[o.l] + o.k;
+  double km_r, km_a;
+  if (!o.lin_lin)
+  {
+    km_r = nuc.km_r[point];
+    km_a = nuc.km_a[point];
+  }
+  else
+  {
+    km_r = nuc.km_r[point] + (o.E_unscaled - o.E_l_k) / (o.E_l_k1 - o.E_l_k) * (nuc.km_r[point + 1] - nuc.km_r[point]);
+    km_a = nuc.km_a[point] + (o.E_unscaled - o.E_l_k) / (o.E_l_k1 - o.E_l_k) * (nuc.km_a[point + 1] - nuc.km_a[point]);
+  }
+  if (prn(seed) > km_r)
+  {
+    const double T = uniform_distribution(-1., 1., seed) * xsinh(km_a);
+    mu = xlog(T + std::sqrt(T * T + 1.0)) / km_a;
+  }
+  else
+  {
+    const double r1 = prn(seed);
+    mu = xlog(r1 * xexp(km_a) + (1.0 - r1) * xexp(-km_a)) / km_a;
+  }
+}
+
+// NBodyPhaseSpace::sample (OMC secondary_nbody.cpp:25-68)
+static void nbody_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+{
+  mu = uniform_distribution(-1., 1., seed);
+  const double Ap = nuc.nbody_mass_ratio;
+  const double E_max = (Ap - 1.0) / Ap * (nuc.awr / (nuc.awr + 1.0) * E_in + nuc.nbody_q);
+  const double x = maxwell_spectrum(1.0, seed);
+  double y;
+  if (nuc.nbody_n == 3)
+    y = maxwell_spectrum(1.0, seed);
+  else if (nuc.nbody_n == 4)
+  {
+    const double r1 = prn(seed), r2 = prn(seed), r3 = prn(seed);
+    y = -xlog(r1 * r2 * r3);
+  }
+  else
+  {
+    const double r1 = prn(seed), r2 = prn(seed), r3 = prn(seed), r4 = prn(seed), r5 = prn(seed), r6 = prn(seed);
+    const double c = xcos(PI / 2.0 * r6);
+    y = -xlog(r1 * r2 * r3 * r4) - xlog(r5) * (c * c); // std::pow(cos, 2) is the correctly rounded square
+  }
+  const double v = x / (x + y);
+  E_out = E_max * v;
+}
+
 // OMC physics.cpp:1073-1120 over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68): cosine from the
 // reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
 // (:150-275), CM -> LAB when scatter_in_cm_, yield 1
+static long long g_law_samples[5]; // how often each MCW_LAW_* was sampled (test coverage: orc_law_samples)
 static void inelastic_scatter(const Nuclide& nuc, Hist& p)
 {
   double E_in = p.E;
-  double mu;
-  if (!nuc.inel_angle.empty())
-    mu = angle_sample(nuc.inel_angle, E_in, &p.seeds[0]);
+  double mu, E;
+  if (nuc.inel_law >= 0 && nuc.inel_law < 5)
+  {
+#pragma omp atomic
+    g_law_samples[nuc.inel_law]++;
+  }
+  // ReactionProduct::sample -> the product's distribution: correlated, Kalbach-Mann and N-body give energy and cosine
+  // together (reaction_product.cpp:70-79); uncorrelated = angle table (or isotropic) + energy law
+  if (nuc.inel_law == MCW_LAW_CORRELATED)
+    correlated_sample(nuc, E_in, E, mu, &p.seeds[0]);
+  else if (nuc.inel_law == MCW_LAW_KALBACH_MANN)
+    kalbach_sample(nuc, E_in, E, mu, &p.seeds[0]);
+  else if (nuc.inel_law == MCW_LAW_NBODY)
+    nbody_sample(nuc, E_in, E, mu, &p.seeds[0]);
   else
-    mu = uniform_distribution(-1., 1., &p.seeds[0]);
-  double E;
-  if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
-    E = continuous_tabular_sample(nuc.inel_energy, E_in, &p.seeds[0]);
-  else
-    E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  {
+    if (!nuc.inel_angle.empty())
+      mu = angle_sample(nuc.inel_angle, E_in, &p.seeds[0]);
+    else
+      mu = uniform_distribution(-1., 1., &p.seeds[0]);
+    if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+      E = continuous_tabular_sample(nuc.inel_energy, E_in, &p.seeds[0]);
+    else
+      E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  }
   if (nuc.inel_in_cm)
   {
     double E_cm = E;
@@ -1057,8 +1234,19 @@ void orc_isotropic_direction(double* uvw, uint64_t* seed)
   uvw[1] = u.y;
   uvw[2] = u.z;
 }
+// samples of each inelastic law since the last call (so a test can assert that its problem really reaches every law)
+void orc_law_samples(long long* out5)
+{
+  for (int i = 0; i < 5; ++i)
+  {
+    out5[i] = g_law_samples[i];
+    g_law_samples[i] = 0;
+  }
+}
 double orc_log(double x) { return xlog(x); }
 double orc_sin(double x) { return xsin(x); }
+double orc_exp(double x) { return xexp(x); }
+double orc_sinh(double x) { return xsinh(x); }
 double orc_cos(double x) { return xcos(x); }
 int orc_is_within_segment(const double* s1, const double* s2, const double* p, double tol)
 {
@@ -1149,6 +1337,31 @@ int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
     N.inel_energy.take(d[i].inelastic_energy, true);
     N.inel_law = d[i].inelastic_law;
     N.inel_in_cm = N.inel_law == MCW_LAW_LEVEL ? true : d[i].inelastic_in_cm != 0;
+    if (N.inel_law == MCW_LAW_CORRELATED || N.inel_law == MCW_LAW_KALBACH_MANN)
+    {
+      const int np = N.inel_energy.off.back();
+      if (N.inel_law == MCW_LAW_CORRELATED)
+      {
+        // one "incoming energy" per point: reuse Tabular2D (energy unused)
+        Tabular2D& c = N.corr_angle;
+        c = Tabular2D();
+        c.energy.assign(np, 0.0);
+        c.off.assign(d[i].corr_offset, d[i].corr_offset + np + 1);
+        c.interp.assign(d[i].corr_interp, d[i].corr_interp + np);
+        c.ndisc.assign(np, 0);
+        c.x.assign(d[i].corr_mu, d[i].corr_mu + c.off[np]);
+        c.p.assign(d[i].corr_pdf, d[i].corr_pdf + c.off[np]);
+        c.c.assign(d[i].corr_cdf, d[i].corr_cdf + c.off[np]);
+      }
+      else
+      {
+        N.km_r.assign(d[i].km_r, d[i].km_r + np);
+        N.km_a.assign(d[i].km_a, d[i].km_a + np);
+      }
+    }
+    N.nbody_n = d[i].nbody_n;
+    N.nbody_mass_ratio = d[i].nbody_mass_ratio;
+    N.nbody_q = d[i].nbody_q;
     P.lib.nuclides.push_back(std::move(N));
   }
   P.lib.n_log_bins = n_log_bins;

@@ -40,6 +40,7 @@ std::unique_ptr<memh5::Node> g_root;
 const mcw_tabular2d *g_el_angle = nullptr, *g_inel_angle = nullptr, *g_inel_energy = nullptr;
 int g_inel_in_cm = 1;
 const mcw_urr_desc* g_urr = nullptr; // probability tables staged for the next ref_add_nuclide
+const mcw_nuclide_desc* g_law = nullptr; // product distribution (correlated / Kalbach-Mann / N-body) of the next nuclide's inelastic reaction
 
 // (3, N) dataset x / pdf / cdf with `offsets` and `interpolation` attributes: the layout of an angular distribution's `mu`
 // (OMC distribution_angle.cpp:26-33) and of a continuous law's `distribution` (distribution_energy.cpp:80-92)
@@ -144,6 +145,12 @@ REF_API void ref_stage_tables(const mcw_tabular2d* elastic_angle, const mcw_tabu
   g_inel_in_cm = inelastic_in_cm;
 }
 
+// Product distribution of the NEXT nuclide's inelastic reaction when it is one of those that give energy and cosine
+// together: written as the "correlated" / "kalbach-mann" / "nbody" group the reference's own CorrelatedAngleEnergy /
+// KalbachMann / NBodyPhaseSpace constructors read (secondary_correlated.cpp:22-150, secondary_kalbach.cpp:24-110,
+// secondary_nbody.cpp:16-23).  d = the product's own nuclide descriptor (inelastic_law >= MCW_LAW_CORRELATED).
+REF_API void ref_stage_law(const mcw_nuclide_desc* d) { g_law = d; }
+
 // Probability tables of the NEXT nuclide added: written as the `urr/<T>K` group UrrData's own constructor reads
 // (urr.cpp:7-33: attributes interpolation / inelastic / absorption / multiply_smooth, datasets energy and table)
 REF_API void ref_stage_urr(const mcw_urr_desc* urr) { g_urr = urr; }
@@ -176,8 +183,54 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
                                         0, "prompt", {1.0});
     if (g_inel_angle)
       angle_group(dist, *g_inel_angle);
+    if (g_law && g_law->inelastic_law >= MCW_LAW_CORRELATED)
+    {
+      const mcw_nuclide_desc& L = *g_law;
+      if (L.inelastic_law == MCW_LAW_NBODY)
+      {
+        dist->attr("type", "nbody");
+        dist->attr("n_particles", L.nbody_n);
+        dist->attr("total_mass", L.nbody_mass_ratio);
+        dist->attr("atomic_weight_ratio", awr);
+        dist->attr("q_value", L.nbody_q);
+      }
+      else
+      {
+        const mcw_tabular2d& t = L.inelastic_energy;
+        const int n = t.n_energy, np = t.offset[n];
+        memh5::Node* en = dist->dataset("energy", std::vector<double>(t.energy, t.energy + n));
+        en->attr("interpolation", std::vector<int>{n, 2}, {2, 1});
+        std::vector<double> eo(5 * (size_t)np);
+        for (int k = 0; k < np; ++k)
+        {
+          eo[k] = t.x[k], eo[np + k] = t.pdf[k], eo[2 * (size_t)np + k] = t.cdf[k];
+          if (L.inelastic_law == MCW_LAW_CORRELATED)
+            eo[3 * (size_t)np + k] = L.corr_interp[k], eo[4 * (size_t)np + k] = L.corr_offset[k];
+          else
+            eo[3 * (size_t)np + k] = L.km_r[k], eo[4 * (size_t)np + k] = L.km_a[k];
+        }
+        memh5::Node* d = dist->dataset(L.inelastic_law == MCW_LAW_CORRELATED ? "energy_out" : "distribution", eo,
+                                       {5, (unsigned long long)np});
+        d->attr("offsets", std::vector<int>(t.offset, t.offset + n));
+        d->attr("interpolation", std::vector<int>(t.interpolation, t.interpolation + n));
+        d->attr("n_discrete_lines", std::vector<int>(n, 0));
+        if (L.inelastic_law == MCW_LAW_CORRELATED)
+        {
+          dist->attr("type", "correlated");
+          const int nm = L.corr_offset[np];
+          std::vector<double> mu(3 * (size_t)nm);
+          for (int k = 0; k < nm; ++k)
+            mu[k] = L.corr_mu[k], mu[nm + k] = L.corr_pdf[k], mu[2 * (size_t)nm + k] = L.corr_cdf[k];
+          dist->dataset("mu", mu, {3, (unsigned long long)nm});
+        }
+        else
+          dist->attr("type", "kalbach-mann");
+      }
+    }
     memh5::Node* e = dist->group("energy");
-    if (g_inel_energy)
+    if (g_law && g_law->inelastic_law >= MCW_LAW_CORRELATED)
+      ; // the product distribution above replaces the uncorrelated angle + energy pair
+    else if (g_inel_energy)
     {
       // ContinuousTabular (OMC distribution_energy.cpp:56-148): `energy` with one incoming-energy interpolation region
       const mcw_tabular2d& t = *g_inel_energy;
@@ -198,6 +251,7 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     }
   }
   g_el_angle = g_inel_angle = g_inel_energy = nullptr;
+  g_law = nullptr;
   if (g_urr)
   {
     memh5::Node* u = g->group("urr")->group(temp);

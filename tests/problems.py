@@ -101,7 +101,19 @@ def pin_cell_tet_tabular(**kw):
     """Tabulated secondary distributions in the data: angular distributions of elastic / inelastic reactions,
     ContinuousTabular laws in the CM and the LAB system (OMC distribution_angle.cpp, distribution_energy.cpp)."""
     mesh, lib, bm, s = pin_cell_tet(**kw)
-    lib2 = nucdata.make_library(9, G=lib.nuclides[0].energy.size, tabular=True)
+    # 15 nuclides: enough inelastic reactions for every law (level-free here: continuous tabular in CM / LAB, correlated,
+    # Kalbach-Mann, N-body)
+    lib2 = nucdata.make_library(15, G=lib.nuclides[0].energy.size, tabular=True)
+    # the nuclides whose inelastic reaction is a correlated / Kalbach-Mann / N-body product get a density at which
+    # a few thousand histories sample each law; Pu239 (Kalbach-Mann in CM) joins the fuel
+    fuel = lib2.materials[0]
+    if 4 not in fuel.nuclides:
+        fuel.nuclides.append(4)
+        fuel.densities.append(1e-5)
+    for m in lib2.materials:
+        for j, i in enumerate(m.nuclides):
+            if lib2.nuclides[i].inelastic.size and lib2.nuclides[i].inelastic_law >= 2:
+                m.densities[j] = max(m.densities[j], 1e-2)
     return mesh, lib2, bm, s
 
 

@@ -53,6 +53,7 @@ def test_problem_files_carry_the_full_physics(tmp_path, name):
     r = problem_io.read_records(path)
     if name.endswith("tabular"):
         assert any(k.endswith("el_angle.xpc") for k in r) and any(k.endswith("inel_energy.e") for k in r)
+        assert any(k.endswith("law.i") for k in r) and any(k.endswith("law.f") for k in r)  # correlated, Kalbach-Mann, N-body
     if name.endswith("sab"):
         assert r["lib.n_thermal"][0] == 3 and "mat3.sab_i" in r and r["sab0.i_offset"].size > 2
     if name.endswith("urr"):

@@ -131,6 +131,12 @@ def test_detmath_within_one_ulp_of_glibc(oracle_bridge):
     ok = np.abs(np.cos(ph)) > 1e-3
     assert ulps(c[ok], np.cos(ph)[ok]).max() <= 1
     assert np.abs(s - np.sin(ph)).max() < 2e-16 and np.abs(c - np.cos(ph)).max() < 2e-16
+    # exp / sinh (Kalbach-Mann slope parameters: O(1) arguments)
+    a = rng.uniform(-30, 30, 20000)
+    assert ulps(np.array([L.orc_exp(v) for v in a]), np.exp(a)).max() <= 1
+    b = np.concatenate([rng.uniform(0.05, 8, 10000), -rng.uniform(0.05, 8, 10000)])
+    sh = np.array([L.orc_sinh(v) for v in b])
+    assert np.abs(sh / np.sinh(b) - 1).max() < 1e-14
 
 
 def test_is_within_segment_known_answers(oracle_bridge):
@@ -625,8 +631,14 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
     tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
     ContinuousTabular constructors from the in-memory nuclide file."""
     from macaw_b200 import nucdata
-    lib = nucdata.make_library(n_nuclides=9, G=G, seed=3, n_log_bins=n_log_bins, tabular=tabular)
+    # tabular: 15 nuclides, so that every secondary law occurs (continuous tabular CM / LAB, correlated, Kalbach-Mann, N-body)
+    lib = nucdata.make_library(n_nuclides=15 if tabular else 9, G=G, seed=3, n_log_bins=n_log_bins, tabular=tabular)
     lib.materials[3].isotropic = [1] + [0] * (len(lib.materials[3].nuclides) - 1)
+    if tabular:
+        # a fifth material holding every nuclide with an inelastic reaction at the same density, so that each secondary
+        # law (continuous tabular CM / LAB, correlated CM / LAB, Kalbach-Mann CM / LAB, N-body) is sampled thousands of times
+        inel = [i for i, n in enumerate(lib.nuclides) if n.inelastic.size]
+        lib.materials.append(nucdata.Material("laws", inel, [0.01] * len(inel)))
     if thermal:  # S(a,b) tables, read by the reference's own ThermalScattering / ThermalData constructors
         nucdata.add_thermal_scattering(lib)
         lib.materials[3].isotropic = None
