@@ -102,6 +102,40 @@ typedef struct mcw_tabular2d
 #define MCW_LAW_KALBACH_MANN 3       /* KalbachMann, OMC secondary_kalbach.cpp:117-235 */
 #define MCW_LAW_NBODY 4              /* NBodyPhaseSpace, OMC secondary_nbody.cpp:25-68 */
 
+/* A further scattering reaction of a nuclide besides elastic and the first inelastic one (which mcw_nuclide_desc
+ * describes inline): one entry of Nuclide::index_inelastic_scatter_ (OMC nuclide.cpp:216-219 -- every non-redundant
+ * reaction with is_inelastic_scatter(mt), endf.cpp:63-78: levels MT 51-91, (n,2n) MT 16 / 875-891, (n,3n), (n,n'alpha)
+ * ...).  scatter() walks the list in order, adding each reaction's cross section above its threshold until the sampled
+ * cutoff is passed (OMC physics.cpp:676-697), then inelastic_scatter samples that reaction's neutron product and
+ * applies its yield (physics.cpp:1073-1120).  Fields as for the inline reaction. */
+typedef struct mcw_reaction_desc
+{
+  int32_t mt;                   /* ENDF MT number (Particle::event_mt; informational) */
+  int32_t threshold;            /* grid index of the threshold (xs_.threshold) */
+  const double* xs;             /* [n_grid - threshold] */
+  double threshold_energy;      /* MCW_LAW_LEVEL: LevelInelastic threshold_ */
+  double mass_ratio;            /* MCW_LAW_LEVEL: LevelInelastic mass_ratio_ */
+  /* neutron multiplicity of the product, a constant (Polynomial of order 0).  Integral (1 for levels, 2 for (n,2n)):
+   * yield - 1 secondary neutrons, which MaCaw pops and drops (MC CollisionKernel.C:232-236), the history itself goes on
+   * unchanged.  Not integral: the weight is multiplied by it (OMC physics.cpp:1108-1118).  0 means 1. */
+  double yield;
+  int32_t law;                  /* MCW_LAW_* */
+  int32_t in_cm;                /* scatter_in_cm_ (level: always 1) */
+  mcw_tabular2d angle;          /* angular distribution (uncorrelated laws), n_energy = 0: isotropic */
+  mcw_tabular2d energy;         /* outgoing-energy table of CONTINUOUS_TABULAR, CORRELATED, KALBACH_MANN */
+  const int32_t* corr_offset;   /* MCW_LAW_CORRELATED, as mcw_nuclide_desc::corr_* */
+  const int32_t* corr_interp;
+  const double* corr_mu;
+  const double* corr_pdf;
+  const double* corr_cdf;
+  const double* km_r;           /* MCW_LAW_KALBACH_MANN */
+  const double* km_a;
+  int32_t nbody_n;              /* MCW_LAW_NBODY */
+  int32_t reserved0;
+  double nbody_mass_ratio;
+  double nbody_q;
+} mcw_reaction_desc;
+
 /* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
  * (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
  * col = total, absorption, fission, nu-fission, photon-production.  Reactions present: elastic
@@ -117,7 +151,7 @@ typedef struct mcw_nuclide_desc
   const double* energy;    /* [n_grid] strictly non-decreasing */
   const double* xs;        /* [n_grid][5] row-major */
   const double* elastic;   /* [n_grid] MT 2 */
-  int32_t n_inelastic;     /* 0 or 1 */
+  int32_t n_inelastic;     /* 0 or 1: the first inelastic reaction, described inline (further ones: more_reactions) */
   int32_t inel_threshold;  /* grid index of the reaction threshold (OMC reaction xs_.threshold) */
   const double* inelastic; /* [n_grid - inel_threshold] */
   double inel_threshold_energy; /* LevelInelastic threshold_ */
@@ -154,6 +188,12 @@ typedef struct mcw_nuclide_desc
   int32_t reserved1;
   double nbody_mass_ratio;
   double nbody_q;
+  /* Neutron multiplicity of the inline inelastic reaction (see mcw_reaction_desc::yield; 0 means 1), and the further
+   * scattering reactions that follow it in Nuclide::index_inelastic_scatter_ order (needs n_inelastic = 1). */
+  double inelastic_yield;
+  int32_t n_more_reactions;
+  int32_t reserved2;
+  const mcw_reaction_desc* more_reactions;
 } mcw_nuclide_desc;
 
 /* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab

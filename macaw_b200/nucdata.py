@@ -49,6 +49,27 @@ class Nuclide:
     km_r: np.ndarray = None          # law 3: precompound fraction / slope per point of inelastic_energy
     km_a: np.ndarray = None
     nbody: tuple = None              # law 4: (n_particles, total_mass, q_value)
+    inelastic_yield: float = 1.0     # neutron multiplicity of the inline inelastic reaction
+    more_reactions: list = None      # further scattering reactions (Reaction), index_inelastic_scatter_ order
+
+
+@dataclass
+class Reaction:
+    """A further scattering reaction of a nuclide (mcw_reaction_desc; one entry of OpenMC's index_inelastic_scatter_)."""
+    mt: int
+    threshold: int                   # grid index
+    xs: np.ndarray                   # (G - threshold,)
+    threshold_energy: float = 0.0    # level law
+    mass_ratio: float = 0.0
+    yield_: float = 1.0
+    law: int = 0                     # MCW_LAW_*
+    in_cm: bool = True
+    angle: object = None             # Tabular2D
+    energy: object = None            # Tabular2D
+    corr_angle: object = None
+    km_r: np.ndarray = None
+    km_a: np.ndarray = None
+    nbody: tuple = None
 
 
 @dataclass
@@ -462,6 +483,68 @@ def library_for_names(names, G=2000, seed=1, n_log_bins=8000) -> Library:
     return Library(nucs, [], n_log_bins)
 
 
+def add_reactions(lib: Library, seed=11) -> Library:
+    """Gives every nuclide that has an inelastic reaction a realistic LIST of scattering reactions after it (MT order, as
+    OpenMC's index_inelastic_scatter_ has them): two more levels MT 52 / 53 (level law; the second with an angular
+    distribution), the continuum MT 91 (continuous tabular in the LAB system, or Kalbach-Mann for every second nuclide,
+    with a NON-integral multiplicity 1.25 for every third nuclide: the weight changes) and (n,2n) as MT 875 (N-body for
+    every second nuclide, else correlated; multiplicity 2: the second neutron is what MaCaw drops).  The total cross
+    section grows by the new reactions, summed in the order Nuclide::create_derived adds them (MT 2, 18, 51, 52, 53, 91,
+    102, 875)."""
+    rng = np.random.Generator(np.random.PCG64([seed, 5]))
+    k = 0
+    for n in lib.nuclides:
+        if not n.inelastic.size:
+            continue
+        e, G, thr0 = n.energy, n.energy.size, n.inel_threshold
+        mr = (n.awr / (n.awr + 1.0)) ** 2
+
+        def xs_from(thr, height, width):
+            return height * (1.0 - np.exp(-(e[thr:] - e[thr]) / width))
+
+        def later(f):  # a threshold above the first level's
+            return int(min(max(np.searchsorted(e, e[thr0] * f), thr0 + 1), G - 3))
+        rxs = []
+        for mt, f, h in ((52, 1.6, 0.5), (53, 2.7, 0.35)):
+            t = later(f)
+            r = Reaction(mt, t, xs_from(t, h * float(rng.uniform(0.5, 1.5)), 2.0 * e[t]), float(e[t] * 0.999), mr)
+            if mt == 53:
+                r.angle = make_angle_table(rng, e[t], 1.9e7)
+            rxs.append(r)
+        t = later(4.0)
+        r91 = Reaction(91, t, xs_from(t, 0.8 * float(rng.uniform(0.5, 1.5)), 3.0 * e[t]), law=1, in_cm=False,
+                       yield_=1.25 if k % 3 == 0 else 1.0)
+        r91.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=k % 2 == 0)
+        if k % 2:
+            r91.law, r91.in_cm = 3, True
+            r91.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=False)
+            npts = int(r91.energy.offset[-1])
+            r91.km_r, r91.km_a = rng.uniform(0.0, 1.0, npts), rng.uniform(0.3, 3.0, npts)
+        rxs.append(r91)
+        t = later(9.0)
+        r2n = Reaction(875, t, xs_from(t, 0.6 * float(rng.uniform(0.5, 1.5)), 2.0 * e[t]), yield_=2.0)
+        if k % 2:
+            r2n.law, r2n.nbody = 4, (3 + (k // 2) % 3, float(rng.uniform(2.5, 4.0)), -0.5 * float(e[t]))
+        else:
+            r2n.law = 2
+            r2n.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=False)
+            r2n.corr_angle = make_point_angles(rng, int(r2n.energy.offset[-1]))
+        rxs.append(r2n)
+        n.more_reactions = rxs
+        # total in create_derived order; capture = absorption - fission (exact for the non-fissionable nuclides)
+        fission, capture = n.xs[:, 2].copy(), n.xs[:, 1] - n.xs[:, 2]
+        full = lambda thr, v: np.concatenate([np.zeros(thr), v])
+        total = n.elastic + fission + full(thr0, n.inelastic)
+        for r in rxs[:3]:
+            total = total + full(r.threshold, r.xs)
+        total = total + capture
+        total = total + full(r2n.threshold, r2n.xs)
+        n.xs = n.xs.copy()
+        n.xs[:, 0] = total
+        k += 1
+    return lib
+
+
 def standard_materials(n_nuclides) -> list:
     """Material 0 fuel (UO2 3.1 %), 1 gap (He), 2 clad (Zr + generic alloying nuclides), 3 borated water.
     Indices follow `_BASE`; nuclides beyond the named ones are spread over clad and fuel like the
@@ -527,7 +610,18 @@ class NuclideDesc(C.Structure):
                 ("inelastic_in_cm", C.c_int32), ("inelastic_energy", Tabular2DDesc),
                 ("corr_offset", C.c_void_p), ("corr_interp", C.c_void_p), ("corr_mu", C.c_void_p), ("corr_pdf", C.c_void_p),
                 ("corr_cdf", C.c_void_p), ("km_r", C.c_void_p), ("km_a", C.c_void_p), ("nbody_n", C.c_int32),
-                ("reserved1", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double)]
+                ("reserved1", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double),
+                ("inelastic_yield", C.c_double), ("n_more_reactions", C.c_int32), ("reserved2", C.c_int32),
+                ("more_reactions", C.c_void_p)]
+
+
+class ReactionDesc(C.Structure):
+    _fields_ = [("mt", C.c_int32), ("threshold", C.c_int32), ("xs", C.c_void_p), ("threshold_energy", C.c_double),
+                ("mass_ratio", C.c_double), ("yield_", C.c_double), ("law", C.c_int32), ("in_cm", C.c_int32),
+                ("angle", Tabular2DDesc), ("energy", Tabular2DDesc),
+                ("corr_offset", C.c_void_p), ("corr_interp", C.c_void_p), ("corr_mu", C.c_void_p), ("corr_pdf", C.c_void_p),
+                ("corr_cdf", C.c_void_p), ("km_r", C.c_void_p), ("km_a", C.c_void_p), ("nbody_n", C.c_int32),
+                ("reserved0", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double)]
 
 
 class ThermalDesc(C.Structure):
@@ -584,24 +678,43 @@ def pack_thermal(tables):
     return td, keep
 
 
-def pack_inelastic_law(d, n, keep):
-    """inelastic_law and the data of the product distributions that give energy and cosine together"""
-    law = getattr(n, "inelastic_law", -1)
-    d.inelastic_law = law if law >= 0 else (1 if getattr(n, "inelastic_energy", None) is not None else 0)
-    d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
-
+def _pack_product(d, law, n, keep):
+    """data of the product distributions that give energy and cosine together (same field names in both descriptors)"""
     def ptr(a, dt):
         b = np.ascontiguousarray(a, dt)
         keep.append(b)
         return b.ctypes.data
-    if d.inelastic_law == 2:
+    if law == 2:
         off, interp, mu, pdf, cdf = n.corr_angle
         d.corr_offset, d.corr_interp = ptr(off, np.int32), ptr(interp, np.int32)
         d.corr_mu, d.corr_pdf, d.corr_cdf = ptr(mu, np.float64), ptr(pdf, np.float64), ptr(cdf, np.float64)
-    elif d.inelastic_law == 3:
+    elif law == 3:
         d.km_r, d.km_a = ptr(n.km_r, np.float64), ptr(n.km_a, np.float64)
-    elif d.inelastic_law == 4:
+    elif law == 4:
         d.nbody_n, d.nbody_mass_ratio, d.nbody_q = int(n.nbody[0]), float(n.nbody[1]), float(n.nbody[2])
+
+
+def pack_inelastic_law(d, n, keep):
+    """inelastic_law of the inline reaction, its product distribution, its yield, and the further reactions"""
+    law = getattr(n, "inelastic_law", -1)
+    d.inelastic_law = law if law >= 0 else (1 if getattr(n, "inelastic_energy", None) is not None else 0)
+    d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
+    _pack_product(d, d.inelastic_law, n, keep)
+    d.inelastic_yield = float(getattr(n, "inelastic_yield", 1.0))
+    more = getattr(n, "more_reactions", None) or []
+    if more:
+        rd = (ReactionDesc * len(more))()
+        keep.append(rd)
+        for r, x in zip(rd, more):
+            xs = np.ascontiguousarray(x.xs, np.float64)
+            keep.append(xs)
+            r.mt, r.threshold, r.xs = x.mt, x.threshold, xs.ctypes.data
+            r.threshold_energy, r.mass_ratio, r.yield_ = x.threshold_energy, x.mass_ratio, x.yield_
+            r.law, r.in_cm = x.law, int(x.in_cm)
+            _pack_table(r.angle, x.angle, keep)
+            _pack_table(r.energy, x.energy, keep)
+            _pack_product(r, x.law, x, keep)
+        d.n_more_reactions, d.more_reactions = len(more), C.addressof(rd)
 
 
 class MaterialDesc(C.Structure):

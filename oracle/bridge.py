@@ -55,6 +55,8 @@ def _load(name):
                                      f64p, f64p]
     lib.orc_law_samples.argtypes = [C.POINTER(C.c_longlong)]
     lib.orc_law_samples.restype = None
+    lib.orc_reaction_samples.argtypes = [C.POINTER(C.c_longlong)]
+    lib.orc_reaction_samples.restype = None
     for f in ("orc_log", "orc_sin", "orc_cos", "orc_exp", "orc_sinh"):
         getattr(lib, f).restype = C.c_double
         getattr(lib, f).argtypes = [C.c_double]
@@ -221,7 +223,7 @@ def ref_load_library(r, libr: nucdata.Library):
                 _nd._pack_table(d, getattr(n, a, None), keep)
                 descs.append(d)
             r.ref_stage_tables(C.addressof(descs[0]), C.addressof(descs[1]), C.addressof(descs[2]), int(n.inelastic_in_cm))
-        if getattr(n, "inelastic_law", -1) >= 2:
+        if getattr(n, "inelastic_law", -1) >= 2 or getattr(n, "more_reactions", None) or getattr(n, "inelastic_yield", 1.0) != 1.0:
             from macaw_b200 import nucdata as _nd
             one = _nd.Library([n], [])
             ndesc, _, keep_l = _nd.pack_library(one)

@@ -206,20 +206,15 @@ struct Tabular2D
   }
 };
 
-struct Nuclide
+// One scattering reaction other than elastic (an entry of OMC Nuclide::index_inelastic_scatter_): threshold, the neutron
+// product's distribution and its multiplicity.  The nuclide's first one is the Nuclide itself (its base class: the
+// descriptor carries it inline), further ones are Nuclide::more.
+struct RxLaw
 {
-  int G = 0;
-  bool fissionable = false;
-  double awr = 1, kT = 0;
-  std::vector<double> energy, xs, elastic, inelastic;
-  int n_inel = 0, inel_thr = 0;
+  int mt = 51;
+  int inel_thr = 0;
   double inel_E = 0, inel_ratio = 0;
-  double nu_poly[2] = {0, 0};
-  int n_precursor = 0;
-  double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
-  double watt_a = 0, watt_b = 0, q = 0;
-  std::vector<int> grid_index;
-  Tabular2D el_angle, inel_angle, inel_energy; // optional tabulated secondary distributions
+  Tabular2D inel_angle, inel_energy; // optional tabulated secondary distributions
   int inel_law = MCW_LAW_LEVEL;
   bool inel_in_cm = true;
   // product distributions that give energy and cosine together: correlated (one angular Tabular per point of inel_energy:
@@ -228,6 +223,24 @@ struct Nuclide
   std::vector<double> km_r, km_a;
   int nbody_n = 0;
   double nbody_mass_ratio = 0, nbody_q = 0;
+  double yield = 1.0;         // constant multiplicity of the neutron product
+  std::vector<double> rx_xs;  // further reactions only: cross section from the threshold on
+};
+
+struct Nuclide : RxLaw
+{
+  int G = 0;
+  bool fissionable = false;
+  double awr = 1, kT = 0;
+  std::vector<double> energy, xs, elastic, inelastic;
+  int n_inel = 0;
+  std::vector<RxLaw> more; // the scattering reactions after the first
+  double nu_poly[2] = {0, 0};
+  int n_precursor = 0;
+  double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
+  double watt_a = 0, watt_b = 0, q = 0;
+  std::vector<int> grid_index;
+  Tabular2D el_angle;
   // unresolved-resonance probability tables (mcw_urr_desc; OMC urr.cpp UrrData); urr_energy empty = none
   std::vector<double> urr_energy, urr_table; // table[n_energy][6][n_band]
   int urr_bands = 0, urr_inel_flag = -1, urr_multiply_smooth = 0;

@@ -614,7 +614,7 @@ static EnergyPick correlated_energy_sample(const Tabular2D& t, double E_in, uint
 }
 
 // CorrelatedAngleEnergy::sample, the angular part (:247-261): the Tabular of the closer outgoing-energy point
-static void correlated_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+static void correlated_sample(const RxLaw& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
 {
   const EnergyPick o = correlated_energy_sample(nuc.inel_energy, E_in, seed);
   E_out = o.E_out;
@@ -626,7 +626,7 @@ static void correlated_sample(const Nuclide& nuc, double E_in, double& E_out, do
 }
 
 // KalbachMann::sample, the angular part (:189-234)
-static void kalbach_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+static void kalbach_sample(const RxLaw& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
 {
   const EnergyPick o = correlated_energy_sample(nuc.inel_energy, E_in, seed);
   E_out = o.E_out;
@@ -655,11 +655,11 @@ static void kalbach_sample(const Nuclide& nuc, double E_in, double& E_out, doubl
 }
 
 // NBodyPhaseSpace::sample (OMC secondary_nbody.cpp:25-68)
-static void nbody_sample(const Nuclide& nuc, double E_in, double& E_out, double& mu, uint64_t* seed)
+static void nbody_sample(const RxLaw& nuc, double awr, double E_in, double& E_out, double& mu, uint64_t* seed)
 {
   mu = uniform_distribution(-1., 1., seed);
   const double Ap = nuc.nbody_mass_ratio;
-  const double E_max = (Ap - 1.0) / Ap * (nuc.awr / (nuc.awr + 1.0) * E_in + nuc.nbody_q);
+  const double E_max = (Ap - 1.0) / Ap * (awr / (awr + 1.0) * E_in + nuc.nbody_q);
   const double x = maxwell_spectrum(1.0, seed);
   double y;
   if (nuc.nbody_n == 3)
@@ -683,7 +683,8 @@ static void nbody_sample(const Nuclide& nuc, double E_in, double& E_out, double&
 // reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
 // (:150-275), CM -> LAB when scatter_in_cm_, yield 1
 static long long g_law_samples[5]; // how often each MCW_LAW_* was sampled (test coverage: orc_law_samples)
-static void inelastic_scatter(const Nuclide& nuc, Hist& p)
+static long long g_rx_samples[8];  // ... and each position of the reaction list (orc_reaction_samples)
+static void inelastic_scatter(const RxLaw& nuc, double awr, Hist& p)
 {
   double E_in = p.E;
   double mu, E;
@@ -699,7 +700,7 @@ static void inelastic_scatter(const Nuclide& nuc, Hist& p)
   else if (nuc.inel_law == MCW_LAW_KALBACH_MANN)
     kalbach_sample(nuc, E_in, E, mu, &p.seeds[0]);
   else if (nuc.inel_law == MCW_LAW_NBODY)
-    nbody_sample(nuc, E_in, E, mu, &p.seeds[0]);
+    nbody_sample(nuc, awr, E_in, E, mu, &p.seeds[0]);
   else
   {
     if (!nuc.inel_angle.empty())
@@ -714,7 +715,7 @@ static void inelastic_scatter(const Nuclide& nuc, Hist& p)
   if (nuc.inel_in_cm)
   {
     double E_cm = E;
-    double A = nuc.awr;
+    double A = awr;
     E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
     mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
   }
@@ -722,6 +723,11 @@ static void inelastic_scatter(const Nuclide& nuc, Hist& p)
     mu = std::copysign(1.0, mu);
   p.E = E;
   p.u = rotate_angle(p.u, mu, nullptr, &p.seeds[0]);
+  // the product's yield (:1108-1118): an integral one makes yield - 1 secondary neutrons -- which MaCaw pops from the
+  // scratch particle's bank and drops (MC CollisionKernel.C:232-236) -- and leaves the history as it is; any other
+  // multiplies the weight
+  if (std::floor(nuc.yield) != nuc.yield)
+    p.wgt *= nuc.yield;
 }
 
 // OMC physics.cpp:1006-1071
@@ -869,13 +875,48 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
     int ig = mx.i_grid;
     // micro.elastic: corrected by calculate_sab_xs when a table applies, else evaluated now (physics.cpp:644-647)
     double elastic = (mx.i_sab >= 0 || mx.use_ptable) ? mx.elastic : (1.0 - f) * nuc.elastic[ig] + f * nuc.elastic[ig + 1];
-    bool can_inelastic = nuc.n_inel > 0 && ig >= nuc.inel_thr;
+    // the scattering reactions in index_inelastic_scatter_ order (:676-697): each one above its threshold adds its cross
+    // section until the cutoff is passed.  One reaction: it is the one sampled whatever its value (the loop ends there).
+    // Should rounding leave the cutoff above the sum, the last reaction above its threshold is taken (the reference would
+    // run off the list there: "Did not sample any reaction").
+    const RxLaw* rx = nullptr;
+    if (nuc.n_inel > 0)
+    {
+      if (nuc.more.empty())
+      {
+        if (ig >= nuc.inel_thr)
+          rx = &nuc;
+      }
+      else
+      {
+        double prob = elastic;
+        for (size_t j = 0; j <= nuc.more.size(); ++j)
+        {
+          const RxLaw& r = j == 0 ? (const RxLaw&)nuc : nuc.more[j - 1];
+          if (ig < r.inel_thr)
+            continue;
+          rx = &r;
+          const double* v = j == 0 ? &nuc.inelastic[ig] : &r.rx_xs[ig - r.inel_thr];
+          prob += (1.0 - f) * v[0] + f * v[1];
+          if (!(prob < cut))
+            break;
+        }
+      }
+    }
     if (elastic - mx.thermal > cut)
       elastic_scatter(nuc, nuc.kT, p, mx.use_ptable); // non-S(a,b) elastic (:649-661)
     else if (elastic > cut && mx.i_sab >= 0)
       sab_scatter(P.lib.thermal[mx.i_sab], mx, p); // :663-672
-    else if (can_inelastic)
-      inelastic_scatter(nuc, p);
+    else if (rx)
+    {
+      const int j = rx == (const RxLaw*)&nuc ? 0 : 1 + (int)(rx - nuc.more.data());
+      if (j < 8)
+      {
+#pragma omp atomic
+        g_rx_samples[j]++;
+      }
+      inelastic_scatter(*rx, nuc.awr, p);
+    }
     else
       elastic_scatter(nuc, nuc.kT, p, mx.use_ptable);
     // isotropic-in-lab override for nuclides of the material's <isotropic> list (OMC physics.cpp:706-718)
@@ -1243,6 +1284,14 @@ void orc_law_samples(long long* out5)
     g_law_samples[i] = 0;
   }
 }
+void orc_reaction_samples(long long* out8)
+{
+  for (int i = 0; i < 8; ++i)
+  {
+    out8[i] = g_rx_samples[i];
+    g_rx_samples[i] = 0;
+  }
+}
 double orc_log(double x) { return xlog(x); }
 double orc_sin(double x) { return xsin(x); }
 double orc_exp(double x) { return xexp(x); }
@@ -1296,6 +1345,46 @@ int orc_set_mesh(void* h, int elem_type, int64_t n_nodes, const double* xyz, int
   return 0;
 }
 
+// the law part of a reaction, from either descriptor
+static void take_law(RxLaw& N, int law, int in_cm, const mcw_tabular2d& angle, const mcw_tabular2d& energy,
+                     const int32_t* corr_offset, const int32_t* corr_interp, const double* corr_mu, const double* corr_pdf,
+                     const double* corr_cdf, const double* km_r, const double* km_a, int nbody_n, double nbody_mass_ratio,
+                     double nbody_q, double yield)
+{
+  N.inel_angle.take(angle, false);
+  N.inel_energy.take(energy, true);
+  N.inel_law = law;
+  N.inel_in_cm = law == MCW_LAW_LEVEL ? true : in_cm != 0;
+  if (law == MCW_LAW_CORRELATED || law == MCW_LAW_KALBACH_MANN)
+  {
+    const int np = N.inel_energy.off.back();
+    if (law == MCW_LAW_CORRELATED)
+    {
+      // one "incoming energy" per point: reuse Tabular2D (energy unused)
+      Tabular2D& c = N.corr_angle;
+      c = Tabular2D();
+      c.energy.assign(np, 0.0);
+      c.off.assign(corr_offset, corr_offset + np + 1);
+      c.interp.assign(corr_interp, corr_interp + np);
+      c.ndisc.assign(np, 0);
+      c.x.assign(corr_mu, corr_mu + c.off[np]);
+      c.p.assign(corr_pdf, corr_pdf + c.off[np]);
+      c.c.assign(corr_cdf, corr_cdf + c.off[np]);
+    }
+    else
+    {
+      N.km_r.assign(km_r, km_r + np);
+      N.km_a.assign(km_a, km_a + np);
+    }
+  }
+  if (law >= MCW_LAW_CORRELATED)
+    N.inel_angle = Tabular2D(); // the product distribution gives the cosine itself
+  N.nbody_n = nbody_n;
+  N.nbody_mass_ratio = nbody_mass_ratio;
+  N.nbody_q = nbody_q;
+  N.yield = yield == 0.0 ? 1.0 : yield;
+}
+
 int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
 {
   Problem& P = *(Problem*)h;
@@ -1333,35 +1422,22 @@ int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
     N.watt_b = d[i].watt_b;
     N.q = d[i].q_fission;
     N.el_angle.take(d[i].elastic_angle, false);
-    N.inel_angle.take(d[i].inelastic_angle, false);
-    N.inel_energy.take(d[i].inelastic_energy, true);
-    N.inel_law = d[i].inelastic_law;
-    N.inel_in_cm = N.inel_law == MCW_LAW_LEVEL ? true : d[i].inelastic_in_cm != 0;
-    if (N.inel_law == MCW_LAW_CORRELATED || N.inel_law == MCW_LAW_KALBACH_MANN)
+    take_law(N, d[i].inelastic_law, d[i].inelastic_in_cm, d[i].inelastic_angle, d[i].inelastic_energy, d[i].corr_offset,
+             d[i].corr_interp, d[i].corr_mu, d[i].corr_pdf, d[i].corr_cdf, d[i].km_r, d[i].km_a, d[i].nbody_n,
+             d[i].nbody_mass_ratio, d[i].nbody_q, d[i].inelastic_yield);
+    for (int j = 0; j < d[i].n_more_reactions && N.n_inel; ++j)
     {
-      const int np = N.inel_energy.off.back();
-      if (N.inel_law == MCW_LAW_CORRELATED)
-      {
-        // one "incoming energy" per point: reuse Tabular2D (energy unused)
-        Tabular2D& c = N.corr_angle;
-        c = Tabular2D();
-        c.energy.assign(np, 0.0);
-        c.off.assign(d[i].corr_offset, d[i].corr_offset + np + 1);
-        c.interp.assign(d[i].corr_interp, d[i].corr_interp + np);
-        c.ndisc.assign(np, 0);
-        c.x.assign(d[i].corr_mu, d[i].corr_mu + c.off[np]);
-        c.p.assign(d[i].corr_pdf, d[i].corr_pdf + c.off[np]);
-        c.c.assign(d[i].corr_cdf, d[i].corr_cdf + c.off[np]);
-      }
-      else
-      {
-        N.km_r.assign(d[i].km_r, d[i].km_r + np);
-        N.km_a.assign(d[i].km_a, d[i].km_a + np);
-      }
+      const mcw_reaction_desc& r = d[i].more_reactions[j];
+      RxLaw R;
+      R.mt = r.mt;
+      R.inel_thr = r.threshold;
+      R.inel_E = r.threshold_energy;
+      R.inel_ratio = r.mass_ratio;
+      R.rx_xs.assign(r.xs, r.xs + (N.G - r.threshold));
+      take_law(R, r.law, r.in_cm, r.angle, r.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r,
+               r.km_a, r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield);
+      N.more.push_back(std::move(R));
     }
-    N.nbody_n = d[i].nbody_n;
-    N.nbody_mass_ratio = d[i].nbody_mass_ratio;
-    N.nbody_q = d[i].nbody_q;
     P.lib.nuclides.push_back(std::move(N));
   }
   P.lib.n_log_bins = n_log_bins;
@@ -1589,7 +1665,7 @@ void orc_history_identity(void* h, int64_t i_local, int batch, int64_t* id, uint
 // Replays n independent collision events in material i_mat through the lookup + collision of the transport loop above
 // (Library::macro_xs, collide); exists so tests can hold them against the reference's own Material::calculate_xs and
 // Particle::event_collide (oracle/_ref ref_collide_events, same argument layout: macro4 = total, absorption, fission,
-// nu_fission; state8 = E, u, alive, k_collision, k_absorption, sampled nuclide; site7 = E, u, delayed_group, parent_id,
+// nu_fission; state8 = E, u, alive * weight, k_collision, k_absorption, sampled nuclide; site7 = E, u, delayed_group, parent_id,
 // progeny_id).  seeds are 4 per event like the reference's streams; the oracle keeps the first 3.
 int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const double* E, const double* u3, const uint64_t* seeds4,
                            const int64_t* id, double* macro4, double* state8, uint64_t* seeds_out, int32_t* n_sites,
@@ -1615,7 +1691,7 @@ int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const dou
     const size_t before = bank.size();
     const CollisionOut co = collide(P, p, i_mat, macro, micro.data(), 0, bank, bank_capacity);
     double* st = state8 + 8 * k;
-    st[0] = p.E, st[1] = p.u.x, st[2] = p.u.y, st[3] = p.u.z, st[4] = co.event == EV_ABSORB ? 0.0 : 1.0;
+    st[0] = p.E, st[1] = p.u.x, st[2] = p.u.y, st[3] = p.u.z, st[4] = co.event == EV_ABSORB ? 0.0 : p.wgt;
     st[5] = p.k_col, st[6] = p.k_abs, st[7] = co.nuclide;
     if (kappa)
     {

@@ -103,6 +103,85 @@ memh5::Node* neutron_product(memh5::Node* rx, int k, const char* mode, const std
   d->attr("type", "uncorrelated"); // no "angle" group: isotropic (secondary_uncorrelated.cpp:60-63)
   return d;
 }
+// What the distribution of a reaction's neutron product is made from (either descriptor)
+struct LawView
+{
+  int law;
+  const mcw_tabular2d *angle, *energy;
+  const int32_t *corr_offset, *corr_interp;
+  const double *corr_mu, *corr_pdf, *corr_cdf, *km_r, *km_a;
+  int nbody_n;
+  double nbody_mass_ratio, nbody_q, level_E, level_ratio;
+};
+// distribution_0 of a neutron product as the reference's constructors read it: "uncorrelated" (angle table or none +
+// level / continuous energy law: secondary_uncorrelated.cpp:17-52), "correlated" (secondary_correlated.cpp:22-150),
+// "kalbach-mann" (secondary_kalbach.cpp:24-110), "nbody" (secondary_nbody.cpp:16-23)
+void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
+{
+  if (L.law < MCW_LAW_CORRELATED && L.angle)
+    angle_group(dist, *L.angle);
+  if (L.law == MCW_LAW_NBODY)
+  {
+    dist->attr("type", "nbody");
+    dist->attr("n_particles", L.nbody_n);
+    dist->attr("total_mass", L.nbody_mass_ratio);
+    dist->attr("atomic_weight_ratio", awr);
+    dist->attr("q_value", L.nbody_q);
+  }
+  else if (L.law >= MCW_LAW_CORRELATED)
+  {
+    const mcw_tabular2d& t = *L.energy;
+    const int n = t.n_energy, np = t.offset[n];
+    memh5::Node* en = dist->dataset("energy", std::vector<double>(t.energy, t.energy + n));
+    en->attr("interpolation", std::vector<int>{n, 2}, {2, 1});
+    std::vector<double> eo(5 * (size_t)np);
+    for (int k = 0; k < np; ++k)
+    {
+      eo[k] = t.x[k], eo[np + k] = t.pdf[k], eo[2 * (size_t)np + k] = t.cdf[k];
+      if (L.law == MCW_LAW_CORRELATED)
+        eo[3 * (size_t)np + k] = L.corr_interp[k], eo[4 * (size_t)np + k] = L.corr_offset[k];
+      else
+        eo[3 * (size_t)np + k] = L.km_r[k], eo[4 * (size_t)np + k] = L.km_a[k];
+    }
+    memh5::Node* d = dist->dataset(L.law == MCW_LAW_CORRELATED ? "energy_out" : "distribution", eo, {5, (unsigned long long)np});
+    d->attr("offsets", std::vector<int>(t.offset, t.offset + n));
+    d->attr("interpolation", std::vector<int>(t.interpolation, t.interpolation + n));
+    d->attr("n_discrete_lines", std::vector<int>(n, 0));
+    if (L.law == MCW_LAW_CORRELATED)
+    {
+      dist->attr("type", "correlated");
+      const int nm = L.corr_offset[np];
+      std::vector<double> mu(3 * (size_t)nm);
+      for (int k = 0; k < nm; ++k)
+        mu[k] = L.corr_mu[k], mu[nm + k] = L.corr_pdf[k], mu[2 * (size_t)nm + k] = L.corr_cdf[k];
+      dist->dataset("mu", mu, {3, (unsigned long long)nm});
+    }
+    else
+      dist->attr("type", "kalbach-mann");
+  }
+  if (L.law >= MCW_LAW_CORRELATED)
+    return; // the product distribution above replaces the uncorrelated angle + energy pair
+  memh5::Node* e = dist->group("energy");
+  if (L.law == MCW_LAW_CONTINUOUS_TABULAR)
+  {
+    // ContinuousTabular (OMC distribution_energy.cpp:56-148): `energy` with one incoming-energy interpolation region
+    const mcw_tabular2d& t = *L.energy;
+    e->attr("type", "continuous");
+    memh5::Node* en = e->dataset("energy", std::vector<double>(t.energy, t.energy + t.n_energy));
+    en->attr("interpolation", std::vector<int>{t.n_energy, t.histogram_in_energy ? 1 : 2}, {2, 1});
+    memh5::Node* d = table_dataset(e, "distribution", t);
+    std::vector<int> nd(t.n_energy, 0);
+    if (t.n_discrete)
+      nd.assign(t.n_discrete, t.n_discrete + t.n_energy);
+    d->attr("n_discrete_lines", nd);
+  }
+  else
+  {
+    e->attr("type", "level");
+    e->attr("threshold", L.level_E);
+    e->attr("mass_ratio", L.level_ratio);
+  }
+}
 } // namespace
 
 extern "C" {
@@ -145,10 +224,11 @@ REF_API void ref_stage_tables(const mcw_tabular2d* elastic_angle, const mcw_tabu
   g_inel_in_cm = inelastic_in_cm;
 }
 
-// Product distribution of the NEXT nuclide's inelastic reaction when it is one of those that give energy and cosine
-// together: written as the "correlated" / "kalbach-mann" / "nbody" group the reference's own CorrelatedAngleEnergy /
-// KalbachMann / NBodyPhaseSpace constructors read (secondary_correlated.cpp:22-150, secondary_kalbach.cpp:24-110,
-// secondary_nbody.cpp:16-23).  d = the product's own nuclide descriptor (inelastic_law >= MCW_LAW_CORRELATED).
+// The NEXT nuclide's own descriptor, for what ref_add_nuclide's argument list does not carry: the product distribution of
+// its inelastic reaction when that gives energy and cosine together -- written as the "correlated" / "kalbach-mann" /
+// "nbody" group the reference's own CorrelatedAngleEnergy / KalbachMann / NBodyPhaseSpace constructors read
+// (secondary_correlated.cpp:22-150, secondary_kalbach.cpp:24-110, secondary_nbody.cpp:16-23) --, that reaction's yield,
+// and the scattering reactions after it (more_reactions: one reaction_<MT> group each).
 REF_API void ref_stage_law(const mcw_nuclide_desc* d) { g_law = d; }
 
 // Probability tables of the NEXT nuclide added: written as the `urr/<T>K` group UrrData's own constructor reads
@@ -179,75 +259,41 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     angle_group(del, *g_el_angle);
   if (n_inel > 0)
   {
-    memh5::Node* dist = neutron_product(reaction(rxs, 51, -inel_E, g_inel_energy ? g_inel_in_cm != 0 : true, temp, inel, n_inel, inel_thr),
-                                        0, "prompt", {1.0});
-    if (g_inel_angle)
-      angle_group(dist, *g_inel_angle);
-    if (g_law && g_law->inelastic_law >= MCW_LAW_CORRELATED)
+    const double y0 = g_law && g_law->inelastic_yield != 0.0 ? g_law->inelastic_yield : 1.0;
+    const bool cm0 = g_law ? (g_law->inelastic_law == MCW_LAW_LEVEL ? true : g_law->inelastic_in_cm != 0)
+                           : (g_inel_energy ? g_inel_in_cm != 0 : true);
+    memh5::Node* dist = neutron_product(reaction(rxs, 51, -inel_E, cm0, temp, inel, n_inel, inel_thr), 0, "prompt", {y0});
+    LawView v{};
+    v.law = g_law ? g_law->inelastic_law : (g_inel_energy ? MCW_LAW_CONTINUOUS_TABULAR : MCW_LAW_LEVEL);
+    v.angle = g_inel_angle, v.energy = g_inel_energy;
+    if (g_law)
     {
       const mcw_nuclide_desc& L = *g_law;
-      if (L.inelastic_law == MCW_LAW_NBODY)
-      {
-        dist->attr("type", "nbody");
-        dist->attr("n_particles", L.nbody_n);
-        dist->attr("total_mass", L.nbody_mass_ratio);
-        dist->attr("atomic_weight_ratio", awr);
-        dist->attr("q_value", L.nbody_q);
-      }
-      else
-      {
-        const mcw_tabular2d& t = L.inelastic_energy;
-        const int n = t.n_energy, np = t.offset[n];
-        memh5::Node* en = dist->dataset("energy", std::vector<double>(t.energy, t.energy + n));
-        en->attr("interpolation", std::vector<int>{n, 2}, {2, 1});
-        std::vector<double> eo(5 * (size_t)np);
-        for (int k = 0; k < np; ++k)
-        {
-          eo[k] = t.x[k], eo[np + k] = t.pdf[k], eo[2 * (size_t)np + k] = t.cdf[k];
-          if (L.inelastic_law == MCW_LAW_CORRELATED)
-            eo[3 * (size_t)np + k] = L.corr_interp[k], eo[4 * (size_t)np + k] = L.corr_offset[k];
-          else
-            eo[3 * (size_t)np + k] = L.km_r[k], eo[4 * (size_t)np + k] = L.km_a[k];
-        }
-        memh5::Node* d = dist->dataset(L.inelastic_law == MCW_LAW_CORRELATED ? "energy_out" : "distribution", eo,
-                                       {5, (unsigned long long)np});
-        d->attr("offsets", std::vector<int>(t.offset, t.offset + n));
-        d->attr("interpolation", std::vector<int>(t.interpolation, t.interpolation + n));
-        d->attr("n_discrete_lines", std::vector<int>(n, 0));
-        if (L.inelastic_law == MCW_LAW_CORRELATED)
-        {
-          dist->attr("type", "correlated");
-          const int nm = L.corr_offset[np];
-          std::vector<double> mu(3 * (size_t)nm);
-          for (int k = 0; k < nm; ++k)
-            mu[k] = L.corr_mu[k], mu[nm + k] = L.corr_pdf[k], mu[2 * (size_t)nm + k] = L.corr_cdf[k];
-          dist->dataset("mu", mu, {3, (unsigned long long)nm});
-        }
-        else
-          dist->attr("type", "kalbach-mann");
-      }
+      if (L.inelastic_energy.n_energy)
+        v.energy = &L.inelastic_energy;
+      if (L.inelastic_angle.n_energy)
+        v.angle = &L.inelastic_angle;
+      v.corr_offset = L.corr_offset, v.corr_interp = L.corr_interp, v.corr_mu = L.corr_mu, v.corr_pdf = L.corr_pdf;
+      v.corr_cdf = L.corr_cdf, v.km_r = L.km_r, v.km_a = L.km_a, v.nbody_n = L.nbody_n;
+      v.nbody_mass_ratio = L.nbody_mass_ratio, v.nbody_q = L.nbody_q;
     }
-    memh5::Node* e = dist->group("energy");
-    if (g_law && g_law->inelastic_law >= MCW_LAW_CORRELATED)
-      ; // the product distribution above replaces the uncorrelated angle + energy pair
-    else if (g_inel_energy)
+    v.level_E = inel_E, v.level_ratio = inel_ratio;
+    fill_distribution(dist, awr, v);
+    // the scattering reactions after the first (index_inelastic_scatter_ follows the MT order of the group names)
+    for (int j = 0; g_law && j < g_law->n_more_reactions; ++j)
     {
-      // ContinuousTabular (OMC distribution_energy.cpp:56-148): `energy` with one incoming-energy interpolation region
-      const mcw_tabular2d& t = *g_inel_energy;
-      e->attr("type", "continuous");
-      memh5::Node* en = e->dataset("energy", std::vector<double>(t.energy, t.energy + t.n_energy));
-      en->attr("interpolation", std::vector<int>{t.n_energy, t.histogram_in_energy ? 1 : 2}, {2, 1});
-      memh5::Node* d = table_dataset(e, "distribution", t);
-      std::vector<int> nd(t.n_energy, 0);
-      if (t.n_discrete)
-        nd.assign(t.n_discrete, t.n_discrete + t.n_energy);
-      d->attr("n_discrete_lines", nd);
-    }
-    else
-    {
-      e->attr("type", "level");
-      e->attr("threshold", inel_E);
-      e->attr("mass_ratio", inel_ratio);
+      const mcw_reaction_desc& r = g_law->more_reactions[j];
+      memh5::Node* dj = neutron_product(reaction(rxs, r.mt, -r.threshold_energy, r.law == MCW_LAW_LEVEL ? true : r.in_cm != 0, temp, r.xs,
+                                                 G - r.threshold, r.threshold),
+                                        0, "prompt", {r.yield == 0.0 ? 1.0 : r.yield});
+      LawView w{};
+      w.law = r.law;
+      w.angle = r.angle.n_energy ? &r.angle : nullptr, w.energy = r.energy.n_energy ? &r.energy : nullptr;
+      w.corr_offset = r.corr_offset, w.corr_interp = r.corr_interp, w.corr_mu = r.corr_mu, w.corr_pdf = r.corr_pdf;
+      w.corr_cdf = r.corr_cdf, w.km_r = r.km_r, w.km_a = r.km_a, w.nbody_n = r.nbody_n;
+      w.nbody_mass_ratio = r.nbody_mass_ratio, w.nbody_q = r.nbody_q;
+      w.level_E = r.threshold_energy, w.level_ratio = r.mass_ratio;
+      fill_distribution(dj, awr, w);
     }
   }
   g_el_angle = g_inel_angle = g_inel_energy = nullptr;
@@ -510,7 +556,7 @@ REF_API int64_t ref_collide_events(int i_mat, double keff, int64_t n, const doub
     if (tally)
       kappa[k] = tally->results_(0, 0, static_cast<int>(TallyResult::VALUE));
     double* st = state8 + 8 * k;
-    st[0] = p.E(), st[1] = p.u().x, st[2] = p.u().y, st[3] = p.u().z, st[4] = p.alive();
+    st[0] = p.E(), st[1] = p.u().x, st[2] = p.u().y, st[3] = p.u().z, st[4] = p.alive() ? p.wgt() : 0.0;
     st[5] = p.keff_tally_collision(), st[6] = p.keff_tally_absorption(), st[7] = p.event_nuclide();
     for (int s = 0; s < N_STREAMS; ++s)
       seeds_out[4 * k + s] = p.seeds(s);

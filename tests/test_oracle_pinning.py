@@ -625,7 +625,7 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
     assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
 
 
-def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False):
+def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False, reactions=False):
     """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
     tables, so both sides hold the same numbers.  One material is given <isotropic> flags.  tabular: the nuclides carry
     tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
@@ -634,6 +634,10 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
     # tabular: 15 nuclides, so that every secondary law occurs (continuous tabular CM / LAB, correlated, Kalbach-Mann, N-body)
     lib = nucdata.make_library(n_nuclides=15 if tabular else 9, G=G, seed=3, n_log_bins=n_log_bins, tabular=tabular)
     lib.materials[3].isotropic = [1] + [0] * (len(lib.materials[3].nuclides) - 1)
+    if reactions:
+        # a list of scattering reactions after the first on every nuclide that has one: further levels, the continuum with
+        # a non-integral multiplicity, (n,2n) -- read by the reference's own Reaction / ReactionProduct constructors
+        nucdata.add_reactions(lib)
     if tabular:
         # a fifth material holding every nuclide with an inelastic reaction at the same density, so that each secondary
         # law (continuous tabular CM / LAB, correlated CM / LAB, Kalbach-Mann CM / LAB, N-body) is sampled thousands of times
@@ -676,7 +680,7 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -704,7 +708,11 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     thermal, urr = tabular == "thermal", tabular == "urr"
     if urr and not hasattr(r, "ref_stage_urr"):
         pytest.skip("oracle/_ref built without the probability-table doorway")
-    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular is True, thermal=thermal, urr=urr)
+    reactions = tabular == "reactions"
+    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
+                                   reactions=reactions)
+    rx_seen = np.zeros(8, np.int64)
+    o_reset = np.zeros(8, np.int64)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
     o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
     f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
@@ -728,7 +736,10 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
                    sites.ctypes.data_as(f64p), kappa.ctypes.data_as(f64p))
             return macro, st, so, ns, sites[:nb], kappa
         ref = run(r.ref_collide_events, i_mat, keff, extra=(float(np.sqrt(lib.nuclides[0].kT)),))
+        o.L.orc_reaction_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
         mine = run(o.L.orc_collide_events, o.h, i_mat, keff)
+        o.L.orc_reaction_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
+        rx_seen += o_reset
         assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
         assert np.array_equal(mine[2], ref[2]) and np.array_equal(mine[3], ref[3])       # seeds, site counts
         assert mine[4].shape == ref[4].shape
@@ -747,9 +758,14 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
         seen["absorbed"] += int((st[:, 4] == 0).sum())
         seen["sites"] += len(sites)
         seen["delayed"] += int((sites[:, 4] > 0).sum())
-        seen["upscatter"] += int(((st[:, 0] > E) & (st[:, 4] == 1)).sum())
-        seen["inelastic"] += int(((st[:, 0] < 0.5 * E) & (E > 1e6) & (st[:, 4] == 1)).sum())
+        seen["upscatter"] += int(((st[:, 0] > E) & (st[:, 4] > 0)).sum())
+        seen["inelastic"] += int(((st[:, 0] < 0.5 * E) & (E > 1e6) & (st[:, 4] > 0)).sum())
+        if reactions:  # st[4] = alive * weight: the continuum reaction of every third nuclide multiplies the weight by 1.25
+            seen["weight"] = seen.get("weight", 0) + int((st[:, 4] == 1.25).sum())
+            assert set(np.unique(st[:, 4])) <= {0.0, 1.0, 1.25}
     assert all(v > 0 for v in seen.values()), seen
+    if reactions:  # every position of the reaction list was sampled: MT 51, 52, 53, 91, 875
+        assert (rx_seen[:5] >= 20).all() and rx_seen[5:].sum() == 0, rx_seen
 
 
 @pytest.mark.parametrize("libm", [True, False])
