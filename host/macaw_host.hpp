@@ -73,6 +73,29 @@ struct Tabular2D
     return t;
   }
 };
+// A scattering reaction after a nuclide's first (mcw_reaction_desc; OMC Nuclide::index_inelastic_scatter_ order)
+struct Reaction
+{
+  int mt = 0, threshold = 0, law = MCW_LAW_LEVEL, in_cm = 1, nbody_n = 0;
+  double threshold_energy = 0, mass_ratio = 0, yield = 1, nbody_mass_ratio = 0, nbody_q = 0;
+  std::vector<double> xs;
+  Tabular2D angle, energy;
+  std::vector<int32_t> corr_offset, corr_interp;
+  std::vector<double> corr_mu, corr_pdf, corr_cdf, km_r, km_a;
+  mcw_reaction_desc desc() const
+  {
+    mcw_reaction_desc r{};
+    r.mt = mt, r.threshold = threshold, r.xs = xs.data();
+    r.threshold_energy = threshold_energy, r.mass_ratio = mass_ratio, r.yield = yield;
+    r.law = law, r.in_cm = in_cm;
+    r.angle = angle.desc(), r.energy = energy.desc();
+    r.corr_offset = corr_offset.data(), r.corr_interp = corr_interp.data();
+    r.corr_mu = corr_mu.data(), r.corr_pdf = corr_pdf.data(), r.corr_cdf = corr_cdf.data();
+    r.km_r = km_r.data(), r.km_a = km_a.data();
+    r.nbody_n = nbody_n, r.nbody_mass_ratio = nbody_mass_ratio, r.nbody_q = nbody_q;
+    return r;
+  }
+};
 struct Nuclide
 {
   std::string name; // as in materials.xml (OMC data::nuclide_map); may be empty for generated libraries
@@ -85,6 +108,9 @@ struct Nuclide
   int inelastic_law = -1;
   std::vector<int32_t> corr_offset, corr_interp;
   std::vector<double> corr_mu, corr_pdf, corr_cdf, km_r, km_a;
+  double inelastic_yield = 1.0;
+  std::vector<Reaction> more_reactions;
+  mutable std::vector<mcw_reaction_desc> more_descs; // filled by Library::nuclideDescs(), which hands out pointers into it
   mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
 };
 struct Material
@@ -156,6 +182,12 @@ struct Library
       d.corr_offset = n.corr_offset.data(), d.corr_interp = n.corr_interp.data();
       d.corr_mu = n.corr_mu.data(), d.corr_pdf = n.corr_pdf.data(), d.corr_cdf = n.corr_cdf.data();
       d.km_r = n.km_r.data(), d.km_a = n.km_a.data();
+      d.inelastic_yield = n.inelastic_yield;
+      n.more_descs.clear();
+      for (const auto& r : n.more_reactions)
+        n.more_descs.push_back(r.desc());
+      d.n_more_reactions = (int32_t)n.more_descs.size();
+      d.more_reactions = n.more_descs.empty() ? nullptr : n.more_descs.data();
       out.push_back(d);
     }
     return out;

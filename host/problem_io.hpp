@@ -130,6 +130,47 @@ public:
       table("el_angle", n.elastic_angle);
       table("inel_angle", n.inelastic_angle);
       table("inel_energy", n.inelastic_energy);
+      if (has(p + "rx.head"))
+      {
+        // the scattering reactions after the first: rx<j>.i = mt, threshold, law, in_cm, n_particles; rx<j>.f =
+        // threshold_energy, mass_ratio, yield, total_mass, q_value; rx<j>.xs; tables rx<j>.ang / rx<j>.en like the
+        // nuclide's; rx<j>.corr.i / .f, rx<j>.km
+        const auto head = f64(p + "rx.head");
+        n.inelastic_yield = head[1];
+        const int keep_cm = n.inelastic_in_cm;
+        for (int j = 0; j < (int)head[0]; ++j)
+        {
+          const std::string q = "rx" + std::to_string(j) + ".";
+          Reaction R;
+          const auto ri = i32(p + q + "i");
+          const auto rf = f64(p + q + "f");
+          R.mt = ri[0], R.threshold = ri[1], R.law = ri[2], R.in_cm = ri[3], R.nbody_n = ri[4];
+          R.threshold_energy = rf[0], R.mass_ratio = rf[1], R.yield = rf[2], R.nbody_mass_ratio = rf[3], R.nbody_q = rf[4];
+          R.xs = f64(p + q + "xs");
+          table(q + "ang", R.angle);
+          table(q + "en", R.energy);
+          const size_t np = R.energy.offset.empty() ? 0 : (size_t)R.energy.offset.back();
+          if (R.law == MCW_LAW_CORRELATED)
+          {
+            const auto ci = i32(p + q + "corr.i");
+            const auto cf = f64(p + q + "corr.f");
+            R.corr_offset.assign(ci.begin(), ci.begin() + np + 1);
+            R.corr_interp.assign(ci.begin() + np + 1, ci.begin() + 2 * np + 1);
+            const size_t nm = (size_t)R.corr_offset.back();
+            R.corr_mu.assign(cf.begin(), cf.begin() + nm);
+            R.corr_pdf.assign(cf.begin() + nm, cf.begin() + 2 * nm);
+            R.corr_cdf.assign(cf.begin() + 2 * nm, cf.begin() + 3 * nm);
+          }
+          else if (R.law == MCW_LAW_KALBACH_MANN)
+          {
+            const auto km = f64(p + q + "km");
+            R.km_r.assign(km.begin(), km.begin() + np);
+            R.km_a.assign(km.begin() + np, km.begin() + 2 * np);
+          }
+          n.more_reactions.push_back(std::move(R));
+        }
+        n.inelastic_in_cm = keep_cm;
+      }
       if (has(p + "law.i"))
       {
         // law, in_cm, n_particles [, offsets[np + 1], interpolation[np]]; total_mass, q_value [, mu / pdf / cdf | r / a]

@@ -397,6 +397,13 @@ int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz
  * [OMC nuclide.cpp:50-302,446-476; simulation.cpp:553-619]. */
 int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
 
+/* The checks mcw_set_library makes, without a handle and without a device (host code only): grids sorted, tables complete,
+ * every law the library implements, reaction lists well formed.  Returns the code mcw_set_library would return and writes
+ * its message (what mcw_last_error would say) into `message`.  For adapters that want to refuse a nuclide they cannot
+ * express before any GPU work starts (OMC raises the matching fatal_error while reading the file, e.g.
+ * secondary_uncorrelated.cpp:47, distribution.cpp:201-205). */
+int mcw_validate_library(const mcw_nuclide_desc* nuclides, int n, char* message, int message_bytes);
+
 /* Materials and the block -> material map of CollisionKernel's `blocks` / `materials` parameters
  * [MC CollisionKernel.C:34-37,64-69,110]. */
 int mcw_set_materials(mcw_handle h, const mcw_material_desc* materials, int n,

@@ -52,14 +52,23 @@ struct HostUrr // one mcw_urr_desc, copied
   int n_band = 0, inel_flag = -1, multiply_smooth = 0;
 };
 
+struct HostRx // one scattering reaction after a nuclide's first (mcw_reaction_desc), copied
+{
+  McwRxParams prm;
+  std::vector<double> xs;
+  HostTable angle, energy, law;
+};
+
 struct HostNuclide
 {
+  std::vector<HostRx> more;
   HostUrr urr;
   McwNucParams prm;
   std::vector<double> energy, xs5, elastic, inelastic_full;
   std::vector<int32_t> grid_index;
   HostTable el_angle, inel_angle, inel_energy;
   HostTable law; // correlated: one angular distribution per point of inel_energy; Kalbach-Mann: one entry, x = r, p = a
+  double inel_yield = 1.0;
 };
 
 // copies and checks one table of the descriptor; returns an error text or nullptr
@@ -95,6 +104,52 @@ static const char* take_table(const mcw_tabular2d& t, HostTable& out, bool conti
   out.x.assign(t.x, t.x + total);
   out.p.assign(t.pdf, t.pdf + total);
   out.c.assign(t.cdf, t.cdf + total);
+  return nullptr;
+}
+
+// checks a reaction's law against its outgoing-energy table and copies what the product distributions that give energy and
+// cosine together need into `out` (correlated: one angular distribution per point of the energy table; Kalbach-Mann: one
+// entry, x = r, p = a); returns an error text or nullptr
+static const char* take_law(int law, const HostTable& energy, const int32_t* corr_offset, const int32_t* corr_interp,
+                            const double* corr_mu, const double* corr_pdf, const double* corr_cdf, const double* km_r,
+                            const double* km_a, int nbody_n, HostTable& out)
+{
+  out = HostTable();
+  if ((law == MCW_LAW_CONTINUOUS_TABULAR || law == MCW_LAW_CORRELATED || law == MCW_LAW_KALBACH_MANN) && energy.energy.empty())
+    return "tabulated inelastic law without its outgoing-energy table";
+  if (law == MCW_LAW_CORRELATED)
+  {
+    // one angular Tabular per point of the outgoing-energy table (OMC secondary_correlated.cpp:100-147)
+    const int np = energy.off.back();
+    if (!corr_offset || !corr_interp || !corr_mu || !corr_pdf || !corr_cdf)
+      return "correlated law without its angular distributions";
+    out.energy.assign(np, 0.0);
+    out.off.assign(corr_offset, corr_offset + np + 1);
+    out.interp.assign(corr_interp, corr_interp + np);
+    out.ndisc.assign(np, 0);
+    for (int k = 0; k < np; ++k)
+      if (out.off[k + 1] - out.off[k] < 2 || (out.interp[k] != 1 && out.interp[k] != 2))
+        return "correlated law: every angular distribution needs >= 2 points, histogram or lin-lin";
+    out.x.assign(corr_mu, corr_mu + out.off[np]);
+    out.p.assign(corr_pdf, corr_pdf + out.off[np]);
+    out.c.assign(corr_cdf, corr_cdf + out.off[np]);
+  }
+  if (law == MCW_LAW_KALBACH_MANN)
+  {
+    const int np = energy.off.back();
+    if (!km_r || !km_a)
+      return "Kalbach-Mann law without r / a";
+    out.energy.assign(1, 0.0);
+    out.off = {0, np};
+    out.interp.assign(1, 2);
+    out.ndisc.assign(1, 0);
+    out.x.assign(km_r, km_r + np);
+    out.p.assign(km_a, km_a + np);
+    out.c.assign(np, 0.0);
+  }
+  if (law == MCW_LAW_NBODY && (nbody_n < 3 || nbody_n > 5))
+    // OMC secondary_nbody.cpp:57 "N-body phase space with >5 bodies."
+    return "N-body phase space needs 3, 4 or 5 bodies";
   return nullptr;
 }
 
@@ -487,11 +542,17 @@ int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz
   return MCW_OK;
 }
 
-int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
+} // extern "C"
+
+// mcw_set_library's checks and copies, without a device: also behind mcw_validate_library
+static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNuclide>& nuclides, std::string& err)
 {
-  if (!h || !d || n <= 0)
-    return MCW_E_INVALID_ARGUMENT;
-  h->nuclides.clear();
+  auto fail = [&](void*, int code, const std::string& msg) {
+    err = msg;
+    return code;
+  };
+  void* h = nullptr;
+  nuclides.clear();
   int64_t off = 0;
   for (int i = 0; i < n; ++i)
   {
@@ -549,66 +610,87 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
     if (!bad)
       bad = take_table(d[i].inelastic_energy, N.inel_energy, true);
     const int law = N.prm.inel_law;
-    if (!bad && N.prm.n_inel && (law == MCW_LAW_CONTINUOUS_TABULAR || law == MCW_LAW_CORRELATED || law == MCW_LAW_KALBACH_MANN) &&
-        N.inel_energy.energy.empty())
-      bad = "tabulated inelastic law without its outgoing-energy table";
-    if (!bad && N.prm.n_inel && law == MCW_LAW_CORRELATED)
-    {
-      // one angular Tabular per point of the outgoing-energy table (OMC secondary_correlated.cpp:100-147)
-      const int np = N.inel_energy.off.back();
-      if (!d[i].corr_offset || !d[i].corr_interp || !d[i].corr_mu || !d[i].corr_pdf || !d[i].corr_cdf)
-        bad = "correlated law without its angular distributions";
-      else
-      {
-        HostTable& t = N.law;
-        t.energy.assign(np, 0.0);
-        t.off.assign(d[i].corr_offset, d[i].corr_offset + np + 1);
-        t.interp.assign(d[i].corr_interp, d[i].corr_interp + np);
-        t.ndisc.assign(np, 0);
-        for (int k = 0; k < np && !bad; ++k)
-          if (t.off[k + 1] - t.off[k] < 2 || (t.interp[k] != 1 && t.interp[k] != 2))
-            bad = "correlated law: every angular distribution needs >= 2 points, histogram or lin-lin";
-        if (!bad)
-        {
-          t.x.assign(d[i].corr_mu, d[i].corr_mu + t.off[np]);
-          t.p.assign(d[i].corr_pdf, d[i].corr_pdf + t.off[np]);
-          t.c.assign(d[i].corr_cdf, d[i].corr_cdf + t.off[np]);
-        }
-      }
-    }
-    if (!bad && N.prm.n_inel && law == MCW_LAW_KALBACH_MANN)
-    {
-      const int np = N.inel_energy.off.back();
-      if (!d[i].km_r || !d[i].km_a)
-        bad = "Kalbach-Mann law without r / a";
-      else
-      {
-        HostTable& t = N.law;
-        t.energy.assign(1, 0.0);
-        t.off = {0, np};
-        t.interp.assign(1, 2);
-        t.ndisc.assign(1, 0);
-        t.x.assign(d[i].km_r, d[i].km_r + np);
-        t.p.assign(d[i].km_a, d[i].km_a + np);
-        t.c.assign(np, 0.0);
-      }
-    }
-    if (!bad && N.prm.n_inel && law == MCW_LAW_NBODY && (d[i].nbody_n < 3 || d[i].nbody_n > 5))
-      // OMC secondary_nbody.cpp:57 "N-body phase space with >5 bodies."
-      bad = "N-body phase space needs 3, 4 or 5 bodies";
+    if (!bad && N.prm.n_inel)
+      bad = take_law(law, N.inel_energy, d[i].corr_offset, d[i].corr_interp, d[i].corr_mu, d[i].corr_pdf, d[i].corr_cdf, d[i].km_r,
+                     d[i].km_a, d[i].nbody_n, N.law);
     N.prm.nbody_n = d[i].nbody_n;
     N.prm.nbody_mass_ratio = d[i].nbody_mass_ratio;
     N.prm.nbody_q = d[i].nbody_q;
     if (law >= MCW_LAW_CORRELATED)
       N.inel_angle = HostTable(); // the product distribution gives the cosine itself
+    N.inel_yield = d[i].inelastic_yield == 0.0 ? 1.0 : d[i].inelastic_yield;
+    if (!bad && d[i].n_more_reactions > 0 && (!N.prm.n_inel || !d[i].more_reactions))
+      bad = "more_reactions needs the inline inelastic reaction (n_inelastic = 1) before them";
+    for (int j = 0; !bad && j < d[i].n_more_reactions; ++j)
+    {
+      const mcw_reaction_desc& r = d[i].more_reactions[j];
+      HostRx R;
+      memset(&R.prm, 0, sizeof(R.prm));
+      if (r.threshold < 0 || r.threshold >= G - 1 || !r.xs)
+        bad = "reaction threshold outside the grid, or its cross section missing";
+      else if (r.law < MCW_LAW_LEVEL || r.law > MCW_LAW_NBODY)
+        bad = "reaction law not implemented (level, continuous tabular, correlated, Kalbach-Mann, N-body)";
+      if (bad)
+        break;
+      R.xs.assign(r.xs, r.xs + (G - r.threshold));
+      R.prm.thr = r.threshold;
+      R.prm.law = r.law;
+      R.prm.in_cm = r.law == MCW_LAW_LEVEL ? 1 : (r.in_cm != 0);
+      R.prm.level_E = r.threshold_energy;
+      R.prm.level_ratio = r.mass_ratio;
+      R.prm.yield = r.yield == 0.0 ? 1.0 : r.yield;
+      R.prm.nbody_n = r.nbody_n;
+      R.prm.nbody_mass_ratio = r.nbody_mass_ratio;
+      R.prm.nbody_q = r.nbody_q;
+      bad = take_table(r.angle, R.angle, false);
+      if (!bad)
+        bad = take_table(r.energy, R.energy, true);
+      if (!bad)
+        bad = take_law(r.law, R.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r, r.km_a, r.nbody_n,
+                       R.law);
+      if (r.law >= MCW_LAW_CORRELATED)
+        R.angle = HostTable();
+      N.more.push_back(std::move(R));
+    }
     if (bad)
       return fail(h, MCW_E_INVALID_ARGUMENT, std::string("mcw_set_library: ") + bad);
-    h->nuclides.push_back(std::move(N));
+    nuclides.push_back(std::move(N));
+  }
+  return MCW_OK;
+}
+
+extern "C" {
+
+int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
+{
+  if (!h || !d || n <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  const int rc = parse_library(d, n, h->nuclides, h->err);
+  if (rc)
+  {
+    h->nuclides.clear();
+    return rc;
   }
   h->have_lib = true;
   h->prepared = false;
   return MCW_OK;
 }
+
+int mcw_validate_library(const mcw_nuclide_desc* d, int n, char* message, int message_bytes)
+{
+  if (!d || n <= 0)
+    return MCW_E_INVALID_ARGUMENT;
+  std::vector<HostNuclide> scratch;
+  std::string err;
+  const int rc = parse_library(d, n, scratch, err);
+  if (message && message_bytes > 0)
+  {
+    strncpy(message, err.c_str(), (size_t)message_bytes - 1);
+    message[message_bytes - 1] = 0;
+  }
+  return rc;
+}
+
 
 int mcw_set_materials(mcw_handle h, const mcw_material_desc* m, int n, const int32_t* block_ids,
                       const int32_t* block_material, int n_blocks)
@@ -884,7 +966,7 @@ static int prepare(mcw_handle h)
       rare |= !tl.nuclides.empty();
     for (const auto& n : h->nuclides)
       rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty() ||
-              (n.prm.n_inel && n.prm.inel_law >= MCW_LAW_CORRELATED);
+              (n.prm.n_inel && (n.prm.inel_law >= MCW_LAW_CORRELATED || !n.more.empty() || n.inel_yield != 1.0));
     h->rare = rare || h->force_rare > 0;
   }
 
@@ -918,6 +1000,8 @@ static int prepare(mcw_handle h)
     tab_p.insert(tab_p.end(), t.p.begin(), t.p.end());
     tab_c.insert(tab_c.end(), t.c.begin(), t.c.end());
   };
+  std::vector<McwRxParams> rx;
+  std::vector<double> rx_xs;
   std::vector<double> urr_pool;
   int n_urr = 0;
   for (auto& n : h->nuclides)
@@ -942,6 +1026,33 @@ static int prepare(mcw_handle h)
     {
       int32_t count;
       add_table(n.law, n.prm.law_first, count);
+    }
+    // the scattering reactions: the inline one again, then the further ones with their tables and cross sections
+    n.prm.rx_first = (int32_t)rx.size();
+    n.prm.n_rx_more = (int32_t)n.more.size();
+    if (n.prm.n_inel)
+    {
+      McwRxParams r0;
+      memset(&r0, 0, sizeof(r0));
+      r0.level_E = n.prm.inel_E, r0.level_ratio = n.prm.inel_ratio, r0.yield = n.inel_yield;
+      r0.nbody_mass_ratio = n.prm.nbody_mass_ratio, r0.nbody_q = n.prm.nbody_q, r0.nbody_n = n.prm.nbody_n;
+      r0.xs_off = -1;
+      r0.thr = n.prm.inel_thr, r0.law = n.prm.inel_law, r0.in_cm = n.prm.inel_in_cm;
+      r0.ang_first = n.prm.inel_ang_first, r0.ang_n = n.prm.inel_ang_n;
+      r0.en_first = n.prm.inel_en_first, r0.en_n = n.prm.inel_en_n, r0.en_hist = n.prm.inel_en_hist;
+      r0.law_first = n.prm.law_first;
+      rx.push_back(r0);
+      for (auto& m : n.more)
+      {
+        int32_t count;
+        add_table(m.angle, m.prm.ang_first, m.prm.ang_n);
+        add_table(m.energy, m.prm.en_first, m.prm.en_n);
+        m.prm.en_hist = m.energy.hist;
+        add_table(m.law, m.prm.law_first, count);
+        m.prm.xs_off = (int64_t)rx_xs.size();
+        rx_xs.insert(rx_xs.end(), m.xs.begin(), m.xs.end());
+        rx.push_back(m.prm);
+      }
     }
     const int G = n.prm.G;
     energy.insert(energy.end(), n.energy.begin(), n.energy.end());
@@ -1029,6 +1140,11 @@ static int prepare(mcw_handle h)
     CK(dev_upload(h, &d_td, tab_ndisc));
     P.lib.tab_energy = d_te, P.lib.tab_x = d_tx, P.lib.tab_p = d_tp, P.lib.tab_c = d_tc;
     P.lib.tab_off = d_to, P.lib.tab_end = d_tn, P.lib.tab_interp = d_ti, P.lib.tab_ndisc = d_td;
+    McwRxParams* d_rx;
+    double* d_rxx;
+    CK(dev_upload(h, &d_rx, rx));
+    CK(dev_upload(h, &d_rxx, rx_xs));
+    P.lib.rx = d_rx, P.lib.rx_xs = d_rxx;
   }
   {
     // thermal scattering: tables into one pool, per material entry its table and bound fraction
@@ -1625,6 +1741,9 @@ int mcw_transport_generation(mcw_handle h, int batch)
   CK(cudaMemsetAsync(h->d_reduce + h->n_tally_values, 0, 5 * sizeof(double), st));
   MCWK(mcwk_init_histories, P, h->d_source, n, h->d_q_fly[0], st);
   R.n_kernel_launches += 1;
+  // simulation::total_weight is the sum of the SOURCE weights (OMC simulation.cpp:466 in initialize_history): reduced now,
+  // before a reaction with a non-integral yield can change a history's weight
+  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.wgt, h->d_reduce + h->n_tally_values + 4, n, st);
   {
     unsigned long long nn = (unsigned long long)n;
     CK(cudaMemcpyAsync(&P.counters->n_fly[0], &nn, sizeof(nn), cudaMemcpyHostToDevice, st));
@@ -1749,7 +1868,6 @@ int mcw_transport_generation(mcw_handle h, int batch)
   MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_col, g + 0, n, st);
   MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_abs, g + 1, n, st);
   MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.k_trk, g + 2, n, st);
-  MCWK(mcwk_reduce_sum, h->d_temp, h->temp_bytes, P.p.wgt, g + 4, n, st);
   MCWK(mcwk_bank_sort, h->d_temp, h->temp_bytes, P.p, n, P.work_offset, h->d_bank, h->n_bank, h->d_i64_a, h->d_i64_b,
                  h->d_sorted, st);
   R.n_kernel_launches += 4 * 2 + 4;

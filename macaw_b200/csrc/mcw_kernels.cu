@@ -377,6 +377,15 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
       mcw_elastic_scatter(L, nuc, c, use_ptable); // non-S(a,b) elastic (OMC physics.cpp:649-661)
     else if (i_sab >= 0 && elastic > cut)
       mcw_sab_scatter(L.self_dev, i_sab, thermal, thermal_el, c); // :663-672
+    else if (MCW_RARE && nuc.n_rx_more > 0)
+    {
+      // a list of scattering reactions (:676-697)
+      const int j_rx = mcw_pick_reaction(L.self_dev, k_nuc, mx.i_grid, mx.f, elastic, r0.y, r1.y, cut);
+      if (j_rx >= 0)
+        mcw_inelastic_scatter(L, nuc, c, j_rx);
+      else
+        mcw_elastic_scatter(L, nuc, c, use_ptable);
+    }
     else if (can_inelastic)
       mcw_inelastic_scatter(L, nuc, c);
     else
@@ -421,6 +430,8 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
   p.n_progeny[i] = c.n_progeny;
   p.n_coll[i] += 1;
   p.E[i] = c.E;
+  if (MCW_RARE && c.wgt != wgt_last) // a reaction with a non-integral yield (OMC physics.cpp:1116-1118)
+    p.wgt[i] = c.wgt;
   atomicAdd(&P.counters->n_collisions, 1ull);
   if (absorbed)
   {

@@ -708,22 +708,22 @@ MCW_D McwEnergyPick mcw_correlated_energy_sample(const McwLibraryDev& L, int fir
 // The product distributions that give energy and cosine together (OMC reaction_product.cpp:70-79):
 // CorrelatedAngleEnergy::sample (secondary_correlated.cpp:156-262), KalbachMann::sample (secondary_kalbach.cpp:117-235),
 // NBodyPhaseSpace::sample (secondary_nbody.cpp:25-68).  Out of line: three rarely sampled laws.
-__device__ __noinline__ double2 mcw_product_sample(const McwLibraryDev* Lp, int i_nuc, double E_in, uint64_t* seed_io)
+__device__ __noinline__ double2 mcw_product_sample(const McwLibraryDev* Lp, int i_rx, double awr, double E_in, uint64_t* seed_io)
 {
   const McwLibraryDev& L = *Lp;
-  const McwNucParams& nuc = L.nuc[i_nuc];
+  const McwRxParams& rx = L.rx[i_rx];
   uint64_t seed = *seed_io;
   double E_out, mu;
-  if (nuc.inel_law == MCW_LAW_NBODY)
+  if (rx.law == MCW_LAW_NBODY)
   {
     mu = mcw_uniform(-1., 1., seed);
-    const double Ap = nuc.nbody_mass_ratio;
-    const double E_max = (Ap - 1.0) / Ap * (nuc.awr / (nuc.awr + 1.0) * E_in + nuc.nbody_q);
+    const double Ap = rx.nbody_mass_ratio;
+    const double E_max = (Ap - 1.0) / Ap * (awr / (awr + 1.0) * E_in + rx.nbody_q);
     const double x = mcw_maxwell_spectrum(1.0, seed);
     double y;
-    if (nuc.nbody_n == 3)
+    if (rx.nbody_n == 3)
       y = mcw_maxwell_spectrum(1.0, seed);
-    else if (nuc.nbody_n == 4)
+    else if (rx.nbody_n == 4)
     {
       const double r1 = mcw_prn(seed), r2 = mcw_prn(seed), r3 = mcw_prn(seed);
       y = -mcw_log_c(r1 * r2 * r3);
@@ -740,20 +740,20 @@ __device__ __noinline__ double2 mcw_product_sample(const McwLibraryDev* Lp, int 
   }
   else
   {
-    const McwEnergyPick o = mcw_correlated_energy_sample(L, nuc.inel_en_first, nuc.inel_en_n, E_in, seed);
+    const McwEnergyPick o = mcw_correlated_energy_sample(L, rx.en_first, rx.en_n, E_in, seed);
     E_out = o.E_out;
-    if (nuc.inel_law == MCW_LAW_CORRELATED)
+    if (rx.law == MCW_LAW_CORRELATED)
     {
       // the angular distribution of the closer outgoing-energy point (:247-261)
       if (o.r1 - o.c_k < o.c_k1 - o.r1 || !o.lin_lin)
-        mu = mcw_tabular_sample(L, nuc.law_first + o.point, seed);
+        mu = mcw_tabular_sample(L, rx.law_first + o.point, seed);
       else
-        mu = mcw_tabular_sample(L, nuc.law_first + o.point + 1, seed);
+        mu = mcw_tabular_sample(L, rx.law_first + o.point + 1, seed);
     }
     else
     {
       // Kalbach-Mann: precompound fraction r and slope a of the sampled point (:189-234)
-      const int b = __ldg(L.tab_off + nuc.law_first) + o.point;
+      const int b = __ldg(L.tab_off + rx.law_first) + o.point;
       const double r_k = __ldg(L.tab_x + b), a_k = __ldg(L.tab_p + b);
       double km_r = r_k, km_a = a_k;
       if (o.lin_lin)
@@ -781,28 +781,45 @@ __device__ __noinline__ double2 mcw_product_sample(const McwLibraryDev* Lp, int 
 // OMC physics.cpp:1073-1120 inelastic_scatter over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68):
 // cosine from the reaction's tabular angle distribution or uniform, outgoing energy from LevelInelastic
 // (distribution_energy.cpp:48-51) or ContinuousTabular (:150-275), then CM -> LAB if the reaction scatters in CM
-MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p)
+MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, ColState& p, int j_rx = 0)
 {
   double E_in = p.E;
   double mu, E;
-  if (MCW_RARE && nuc.inel_law >= MCW_LAW_CORRELATED)
+  bool in_cm = true;
+  if (!MCW_RARE)
   {
-    const double2 em = mcw_product_sample(L.self_dev, (int)(&nuc - L.nuc), E_in, &p.seed);
-    E = em.x;
-    mu = em.y;
+    // the common build: one level per nuclide, isotropic in the centre of mass, yield 1
+    mu = mcw_uniform(-1., 1., p.seed);
+    E = nuc.inel_ratio * (E_in - nuc.inel_E);
   }
   else
   {
-    if (MCW_RARE && nuc.inel_ang_n > 0)
-      mu = mcw_angle_sample(L, nuc.inel_ang_first, nuc.inel_ang_n, E_in, p.seed);
+    const int i_rx = nuc.rx_first + j_rx;
+    const McwRxParams& rx = L.rx[i_rx];
+    if (rx.law >= MCW_LAW_CORRELATED)
+    {
+      const double2 em = mcw_product_sample(L.self_dev, i_rx, nuc.awr, E_in, &p.seed);
+      E = em.x;
+      mu = em.y;
+    }
     else
-      mu = mcw_uniform(-1., 1., p.seed);
-    if (MCW_RARE && nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
-      E = mcw_continuous_tabular_sample(L, nuc.inel_en_first, nuc.inel_en_n, nuc.inel_en_hist != 0, E_in, p.seed);
-    else
-      E = nuc.inel_ratio * (E_in - nuc.inel_E);
+    {
+      if (rx.ang_n > 0)
+        mu = mcw_angle_sample(L, rx.ang_first, rx.ang_n, E_in, p.seed);
+      else
+        mu = mcw_uniform(-1., 1., p.seed);
+      if (rx.law == MCW_LAW_CONTINUOUS_TABULAR)
+        E = mcw_continuous_tabular_sample(L, rx.en_first, rx.en_n, rx.en_hist != 0, E_in, p.seed);
+      else
+        E = rx.level_ratio * (E_in - rx.level_E);
+    }
+    in_cm = rx.in_cm != 0; // the level law always scatters in the centre of mass
+    // the product's yield (OMC physics.cpp:1108-1118): integral = secondaries, which MaCaw drops (MC
+    // CollisionKernel.C:232-236); otherwise the weight is multiplied
+    if (floor(rx.yield) != rx.yield)
+      p.wgt *= rx.yield;
   }
-  if (!MCW_RARE || nuc.inel_in_cm) // the level law always scatters in the centre of mass
+  if (in_cm)
   {
     double E_cm = E;
     double A = nuc.awr;
@@ -813,6 +830,37 @@ MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc
     mu = copysign(1.0, mu);
   p.E = E;
   p.u = mcw_rotate_angle(p.u, mu, p.seed);
+}
+
+// Which of the nuclide's scattering reactions a non-elastic scatter is (OMC physics.cpp:676-697): in list order, every
+// reaction above its threshold adds its cross section at (i_grid, f) until the sum passes the cutoff.  inel0 / inel1 =
+// the first reaction's values at i_grid and i_grid + 1 (el_inel).  -1: none is above its threshold.  Should rounding
+// leave the cutoff above the sum the last eligible reaction is taken (the reference would run off its list there).
+__device__ __noinline__ int mcw_pick_reaction(const McwLibraryDev* Lp, int i_nuc, int i_grid, double f, double elastic, double inel0,
+                                              double inel1, double cut)
+{
+  const McwLibraryDev& L = *Lp;
+  const McwNucParams& nuc = L.nuc[i_nuc];
+  double prob = elastic;
+  int pick = -1;
+  for (int j = 0; j <= nuc.n_rx_more; ++j)
+  {
+    const McwRxParams& rx = L.rx[nuc.rx_first + j];
+    if (i_grid < rx.thr)
+      continue;
+    pick = j;
+    double v0 = inel0, v1 = inel1;
+    if (j > 0)
+    {
+      const double* v = L.rx_xs + rx.xs_off + (i_grid - rx.thr);
+      v0 = __ldg(v);
+      v1 = __ldg(v + 1);
+    }
+    prob += (1.0 - f) * v0 + f * v1;
+    if (!(prob < cut))
+      break;
+  }
+  return pick;
 }
 
 // OMC physics.cpp:1006-1071

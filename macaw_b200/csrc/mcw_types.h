@@ -48,6 +48,24 @@ struct McwNucParams
   // (point j of the table -> entry law_first + j); Kalbach-Mann: ONE entry whose tab_x / tab_p hold r / a per point
   int32_t law_first, nbody_n;
   double nbody_mass_ratio, nbody_q;
+  // the nuclide's scattering reactions other than elastic, in OMC index_inelastic_scatter_ order: McwLibraryDev::rx
+  // [rx_first, rx_first + 1 + n_rx_more); the first is the inline reaction above again (the common kernel build reads the
+  // inline fields only: level law, yield 1), the others exist only in problems that run on the full build
+  int32_t rx_first, n_rx_more;
+};
+
+// One scattering reaction (mcw_reaction_desc, or the nuclide's inline one): what inelastic_scatter needs
+struct McwRxParams
+{
+  double level_E, level_ratio; // MCW_LAW_LEVEL
+  double yield;                // constant multiplicity of the neutron product
+  double nbody_mass_ratio, nbody_q;
+  int64_t xs_off;              // McwLibraryDev::rx_xs[xs_off + (i_grid - thr)]; -1 for the inline reaction (el_inel holds it)
+  int32_t thr, law, in_cm;
+  int32_t ang_first, ang_n;    // tab_* entries as in McwNucParams
+  int32_t en_first, en_n, en_hist;
+  int32_t law_first, nbody_n;
+  int32_t pad[2];
 };
 
 // One temperature of an S(alpha, beta) table (mcw_thermal_desc): offsets into McwLibraryDev::sab_pool (doubles) /
@@ -82,6 +100,8 @@ struct McwLibraryDev
   const int32_t* tab_interp;
   const int32_t* tab_ndisc;
   const double *tab_x, *tab_p, *tab_c;
+  const McwRxParams* rx; // scattering reactions of all nuclides (McwNucParams::rx_first)
+  const double* rx_xs;   // cross sections of the reactions after each nuclide's first, from their thresholds on
   // thermal scattering: tables, their pools, and per material entry the table (-1 = none) and the bound fraction
   const McwSabDev* sab;
   const double* sab_pool;

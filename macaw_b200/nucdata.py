@@ -509,15 +509,16 @@ def add_reactions(lib: Library, seed=11) -> Library:
             t = later(f)
             r = Reaction(mt, t, xs_from(t, h * float(rng.uniform(0.5, 1.5)), 2.0 * e[t]), float(e[t] * 0.999), mr)
             if mt == 53:
-                r.angle = make_angle_table(rng, e[t], 1.9e7)
+                r.angle = make_angle_table(rng, e[t], max(1.9e7, 1.2 * e[t]))
             rxs.append(r)
         t = later(4.0)
         r91 = Reaction(91, t, xs_from(t, 0.8 * float(rng.uniform(0.5, 1.5)), 3.0 * e[t]), law=1, in_cm=False,
                        yield_=1.25 if k % 3 == 0 else 1.0)
-        r91.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=k % 2 == 0)
+        top = max(1.9e7, 1.2 * e[t])  # the tables reach from the threshold to above it, wherever the threshold lies
+        r91.energy = make_continuous_table(rng, e[t], top, discrete=k % 2 == 0)
         if k % 2:
             r91.law, r91.in_cm = 3, True
-            r91.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=False)
+            r91.energy = make_continuous_table(rng, e[t], top, discrete=False)
             npts = int(r91.energy.offset[-1])
             r91.km_r, r91.km_a = rng.uniform(0.0, 1.0, npts), rng.uniform(0.3, 3.0, npts)
         rxs.append(r91)
@@ -527,7 +528,7 @@ def add_reactions(lib: Library, seed=11) -> Library:
             r2n.law, r2n.nbody = 4, (3 + (k // 2) % 3, float(rng.uniform(2.5, 4.0)), -0.5 * float(e[t]))
         else:
             r2n.law = 2
-            r2n.energy = make_continuous_table(rng, e[t], 1.9e7, discrete=False)
+            r2n.energy = make_continuous_table(rng, e[t], max(1.9e7, 1.2 * e[t]), discrete=False)
             r2n.corr_angle = make_point_angles(rng, int(r2n.energy.offset[-1]))
         rxs.append(r2n)
         n.more_reactions = rxs
@@ -586,6 +587,10 @@ class Tabular2DDesc(C.Structure):
 def _pack_table(d: Tabular2DDesc, t, keep):
     if t is None:
         return
+    # what mcw_set_library checks (csrc/mcw_api.cu take_table), so that bad synthetic data fail where there is no GPU too
+    assert len(t.energy) >= 2 and np.all(np.diff(t.energy) > 0), "tabulated distribution: incoming energies must increase"
+    assert np.all(np.diff(t.offset) >= 2) and set(np.unique(t.interpolation)) <= {1, 2}
+    assert np.all(np.asarray(t.cdf)[np.asarray(t.offset[1:]) - 1] == 1.0), "tabulated distribution: the cdf must end at exactly 1"
     arrs = [np.ascontiguousarray(t.energy, np.float64), np.ascontiguousarray(t.offset, np.int32),
             np.ascontiguousarray(t.interpolation, np.int32), np.ascontiguousarray(t.x, np.float64),
             np.ascontiguousarray(t.pdf, np.float64), np.ascontiguousarray(t.cdf, np.float64)]

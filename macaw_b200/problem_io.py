@@ -60,6 +60,30 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
                 lf = np.concatenate([lf, n.km_r, n.km_a])
             r[f"nuc{k}.law.i"] = np.asarray(li, np.int32)
             r[f"nuc{k}.law.f"] = np.asarray(lf, np.float64)
+        # the scattering reactions after the first (mcw_reaction_desc) and the first one's yield
+        more = getattr(n, "more_reactions", None) or []
+        if more or getattr(n, "inelastic_yield", 1.0) != 1.0:
+            r[f"nuc{k}.rx.head"] = np.array([len(more), float(getattr(n, "inelastic_yield", 1.0))], np.float64)
+        for j, x in enumerate(more):
+            q = f"nuc{k}.rx{j}."
+            r[q + "i"] = np.array([x.mt, x.threshold, x.law, int(x.in_cm), 0 if x.nbody is None else int(x.nbody[0])], np.int32)
+            r[q + "f"] = np.array([x.threshold_energy, x.mass_ratio, x.yield_, 0.0 if x.nbody is None else x.nbody[1],
+                                   0.0 if x.nbody is None else x.nbody[2]], np.float64)
+            r[q + "xs"] = np.ascontiguousarray(x.xs, np.float64)
+            for key, t in (("ang", x.angle), ("en", x.energy)):
+                if t is None:
+                    continue
+                nd = t.n_discrete if t.n_discrete is not None else np.zeros(len(t.energy), np.int32)
+                r[q + key + ".i"] = np.concatenate([[int(t.histogram_in_energy), int(x.in_cm)], t.offset, t.interpolation,
+                                                    nd]).astype(np.int32)
+                r[q + key + ".e"] = np.ascontiguousarray(t.energy, np.float64)
+                r[q + key + ".xpc"] = np.concatenate([t.x, t.pdf, t.cdf]).astype(np.float64)
+            if x.law == 2:
+                off, interp, mu, pdf, cdf = x.corr_angle
+                r[q + "corr.i"] = np.concatenate([off, interp]).astype(np.int32)
+                r[q + "corr.f"] = np.concatenate([mu, pdf, cdf]).astype(np.float64)
+            elif x.law == 3:
+                r[q + "km"] = np.concatenate([x.km_r, x.km_a]).astype(np.float64)
     for k, m in enumerate(lib.materials):
         r[f"mat{k}.nuclide"] = np.ascontiguousarray(m.nuclides, np.int32)
         r[f"mat{k}.density"] = np.ascontiguousarray(m.densities, np.float64)

@@ -117,6 +117,14 @@ def pin_cell_tet_tabular(**kw):
     return mesh, lib2, bm, s
 
 
+def pin_cell_tet_reactions(**kw):
+    """Every nuclide with an inelastic reaction carries a LIST of scattering reactions (OMC index_inelastic_scatter_):
+    levels MT 51 / 52 / 53, the continuum MT 91 (for every third nuclide with multiplicity 1.25: the weight changes) and
+    (n,2n) MT 875 with multiplicity 2 -- on top of the tabulated distributions of pin_cell_tet_tabular."""
+    mesh, lib, bm, s = pin_cell_tet_tabular(**kw)
+    return mesh, nucdata.add_reactions(lib), bm, s
+
+
 def pin_cell_tet_sab(**kw):
     """S(alpha, beta) tables on hydrogen (continuous inelastic), on a second nuclide per material (coherent elastic +
     discrete inelastic, fraction 0.75) and a third (incoherent-discrete elastic + skewed discrete inelastic)."""
@@ -151,7 +159,7 @@ def infinite_medium_sab(**kw):
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
 
 
-PROBLEMS = {"pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+PROBLEMS = {"pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
             "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,

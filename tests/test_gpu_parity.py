@@ -185,6 +185,9 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     # tabulated secondary distributions (AngleDistribution, ContinuousTabular in CM and LAB)
     ("pin_cell_tet_tabular", {}, EVENT), ("pin_cell_tet_tabular", {}, FUSED), ("pin_cell_tet_tabular", {}, PUMP),
     ("pin_cell_tet_tabular", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # lists of scattering reactions with yields (further levels, continuum with a non-integral multiplicity, (n,2n))
+    ("pin_cell_tet_reactions", {}, EVENT), ("pin_cell_tet_reactions", {}, FUSED), ("pin_cell_tet_reactions", {}, PUMP),
+    ("pin_cell_tet_reactions", {"n_particles": 20000}, {"tail_threshold": 3000}),
     # thermal scattering S(a,b): bound cross sections below energy_max, sab_scatter (continuous / discrete inelastic,
     # coherent / incoherent-discrete elastic, partial binding)
     ("infinite_medium_sab", {}, EVENT), ("pin_cell_tet_sab", {}, EVENT), ("pin_cell_tet_sab", {}, FUSED),
@@ -204,9 +207,15 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
     g.sample_initial_source()
     laws = np.zeros(5, np.int64)
     o.L.orc_law_samples(laws.ctypes.data_as(C.POINTER(C.c_longlong)))  # reset
+    o.L.orc_reaction_samples(np.zeros(8, np.int64).ctypes.data_as(C.POINTER(C.c_longlong)))
     for batch in range(1, 4):
         ro = o.run_generation(batch)
         rg = g.run_generation(batch)
+        if name == "pin_cell_tet_reactions" and batch == 3:
+            # every position of the reaction lists was sampled (MT 51, 52, 53, 91, 875)
+            rxs = np.zeros(8, np.int64)
+            o.L.orc_reaction_samples(rxs.ctypes.data_as(C.POINTER(C.c_longlong)))
+            assert (rxs[:5] >= 30).all(), rxs
         if name == "pin_cell_tet_tabular" and batch == 3:
             # the problem reaches every inelastic law: continuous tabular, correlated, Kalbach-Mann, N-body
             o.L.orc_law_samples(laws.ctypes.data_as(C.POINTER(C.c_longlong)))

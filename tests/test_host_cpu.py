@@ -43,6 +43,52 @@ def test_c_abi_struct_sizes_match_ctypes_mirror():
     assert out[5] == cstructs.RECORD_DTYPE.itemsize
 
 
+def test_library_validation_without_a_device():
+    """mcw_validate_library runs mcw_set_library's own checks and copies on the host (no handle, no GPU): every library
+    the tests and the bench use is accepted -- including the nucleus descriptor size the ctypes mirror assumes --, and
+    malformed data are refused with the reference's kind of message instead of reaching a kernel."""
+    import copy
+    from macaw_b200 import lib, nucdata
+    from tests import problems
+    L = lib.load()
+    out = (C.c_int32 * 6)()
+    L.mcw_struct_sizes(out, 6)
+    assert out[1] == C.sizeof(nucdata.NuclideDesc)
+    msg = C.create_string_buffer(512)
+
+    def check(library):
+        nd, _, keep = nucdata.pack_library(library)
+        return L.mcw_validate_library(C.addressof(nd), len(library.nuclides), msg, 512), msg.value.decode()
+    for name, make in problems.PROBLEMS.items():
+        _, library, _, _ = make(n_particles=100)
+        rc, text = check(library)
+        assert rc == 0, (name, text)
+    base = nucdata.add_reactions(nucdata.make_library(15, G=300, tabular=True))
+    assert check(base)[0] == 0
+    # a reaction whose threshold lies outside the grid
+    bad = copy.deepcopy(base)
+    bad.nuclides[2].more_reactions[1].threshold = 299
+    bad.nuclides[2].more_reactions[1].xs = np.zeros(1)
+    rc, text = check(bad)
+    assert rc != 0 and "threshold" in text
+    # a law the library does not implement
+    bad = copy.deepcopy(base)
+    bad.nuclides[2].more_reactions[0].law = 9
+    rc, text = check(bad)
+    assert rc != 0 and "not implemented" in text
+    # N-body with six bodies (OMC secondary_nbody.cpp:57)
+    bad = copy.deepcopy(base)
+    r = [x for n in bad.nuclides for x in (n.more_reactions or []) if x.law == 4][0]
+    r.nbody = (6, r.nbody[1], r.nbody[2])
+    rc, text = check(bad)
+    assert rc != 0 and "N-body" in text
+    # an unsorted energy grid
+    bad = copy.deepcopy(base)
+    bad.nuclides[0].energy = bad.nuclides[0].energy[::-1].copy()
+    rc, text = check(bad)
+    assert rc != 0 and "not sorted" in text
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     """Without a CUDA device mcw_create must fail (MCW_E_CUDA); nothing routes to the CPU."""
     import torch
