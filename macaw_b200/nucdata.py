@@ -51,6 +51,7 @@ class Nuclide:
     nbody: tuple = None              # law 4: (n_particles, total_mass, q_value)
     inelastic_yield: float = 1.0     # neutron multiplicity of the inline inelastic reaction
     more_reactions: list = None      # further scattering reactions (Reaction), index_inelastic_scatter_ order
+    more_temperatures: list = None   # further data sets of this nuclide (Nuclide objects at other kT; OMC kTs_, grid_[t], xs_[t])
 
 
 @dataclass
@@ -303,6 +304,11 @@ class Library:
     def total_points(self):
         return int(sum(n.energy.size for n in self.nuclides))
 
+    def temperature_sets(self):
+        """[(nuclide index, data set)] of the further temperatures, in library-entry order: set k is entry
+        len(nuclides) + k (what mcw_add_temperature_set returns, and what an UrrTable of that set names)."""
+        return [(i, m) for i, n in enumerate(self.nuclides) for m in (getattr(n, "more_temperatures", None) or [])]
+
     def bytes(self):
         return int(sum(n.energy.nbytes + n.xs.nbytes + n.elastic.nbytes + n.inelastic.nbytes for n in self.nuclides))
 
@@ -546,6 +552,77 @@ def add_reactions(lib: Library, seed=11) -> Library:
     return lib
 
 
+def add_temperatures(lib: Library, temperatures=(600.0, 900.0), seed=21, skip_every=4) -> Library:
+    """Gives the nuclides further data sets at other temperatures (all but every `skip_every`-th, which stay
+    single-temperature): each set has its OWN energy grid (a thinned and jittered copy, as Doppler-broadened evaluations
+    have) and every reaction's cross section re-tabulated on it with a smooth temperature-dependent factor; thresholds
+    are re-indexed on the new grid, the secondary distributions are the nuclide's (they do not depend on temperature in
+    the data format).  Nuclides with probability tables get tables for every set (OpenMC reads `urr/<T>K` for each
+    temperature it loads); those are addressed by the library ENTRY of the set: entries [0, n) are the nuclides, further
+    sets follow in nuclide order (Library.entries())."""
+    import copy
+    rng = np.random.Generator(np.random.PCG64([seed, 31]))
+    n_nuc = len(lib.nuclides)
+    entry = n_nuc
+    urr_of = {t.nuclide: t for t in (getattr(lib, "urr_tables", None) or [])}
+    for i, n in enumerate(lib.nuclides):
+        if skip_every and i % skip_every == skip_every - 1:
+            continue
+        n.more_temperatures = []
+        e0, G = n.energy, n.energy.size
+        thr_e = e0[n.inel_threshold] if n.inelastic.size else 0.0
+        for T in temperatures:
+            kT = 8.617333262e-5 * float(T)
+            keep = np.sort(rng.choice(np.arange(1, G - 1), int(0.9 * (G - 2)), replace=False))
+            mid = e0[keep] * (1.0 + 1e-4 * rng.uniform(-1, 1, keep.size))
+            e = np.unique(np.concatenate([[e0[0] * 1.5], mid[(mid > e0[0] * 1.5) & (mid < e0[-1] * 0.97)], [e0[-1] * 0.97]]))
+            fac = 1.0 + 0.08 * (T / 293.6 - 1.0) * np.sin(np.log(e))
+
+            def on(x, thr):  # a reaction's values (from its threshold on) re-tabulated on the new grid
+                full = np.concatenate([np.zeros(thr), x])
+                return np.interp(e, e0, full) * fac
+            m = copy.copy(n)
+            m.more_temperatures, m.kT, m.energy = None, kT, e
+            m.elastic = on(n.elastic, 0)
+            fission = on(n.xs[:, 2], 0)
+            capture = on(n.xs[:, 1] - n.xs[:, 2], 0)
+            total = m.elastic + fission
+            if n.inelastic.size:
+                t = int(min(np.searchsorted(e, thr_e), e.size - 3))
+                m.inel_threshold = t
+                m.inelastic = on(n.inelastic, n.inel_threshold)[t:]
+                total = total + np.concatenate([np.zeros(t), m.inelastic])
+            if n.more_reactions:
+                m.more_reactions = []
+                for r in n.more_reactions:
+                    r2 = copy.copy(r)
+                    t = int(min(np.searchsorted(e, e0[r.threshold]), e.size - 3))
+                    r2.threshold, r2.xs = t, on(r.xs, r.threshold)[t:]
+                    m.more_reactions.append(r2)
+            # total in create_derived order: MT 2, 18, 51 ... 91, 102, then the reactions filed after capture (875)
+            for r2 in (m.more_reactions or []):
+                if r2.mt < 102:
+                    total = total + np.concatenate([np.zeros(r2.threshold), r2.xs])
+            total = total + capture
+            for r2 in (m.more_reactions or []):
+                if r2.mt > 102:
+                    total = total + np.concatenate([np.zeros(r2.threshold), r2.xs])
+            xs = np.zeros((e.size, 5))
+            xs[:, 0], xs[:, 1], xs[:, 2] = total, fission + capture, fission
+            xs[:, 3] = (n.nu_poly[1] * e + n.nu_poly[0]) * fission if n.fissionable else 0.0
+            m.xs = xs
+            n.more_temperatures.append(m)
+            if i in urr_of:
+                u = copy.copy(urr_of[i])
+                u.nuclide = entry
+                u.table = u.table.copy()
+                u.table[:, 2:5] *= 1.0 + 0.05 * (T / 293.6 - 1.0)
+                u.table[:, 1] = u.table[:, 2] + u.table[:, 3] + u.table[:, 4]
+                lib.urr_tables.append(u)
+            entry += 1
+    return lib
+
+
 def standard_materials(n_nuclides) -> list:
     """Material 0 fuel (UO2 3.1 %), 1 gap (He), 2 clad (Zr + generic alloying nuclides), 3 borated water.
     Indices follow `_BASE`; nuclides beyond the named ones are spread over clad and fuel like the
@@ -643,6 +720,16 @@ class UrrDesc(C.Structure):
     _fields_ = [("nuclide", C.c_int32), ("interpolation", C.c_int32), ("inelastic_flag", C.c_int32),
                 ("absorption_flag", C.c_int32), ("multiply_smooth", C.c_int32), ("n_energy", C.c_int32),
                 ("n_band", C.c_int32), ("reserved0", C.c_int32), ("energy", C.c_void_p), ("table", C.c_void_p)]
+
+
+def pack_temperature_sets(lib: Library):
+    """mcw_nuclide_desc of every further temperature set; returns ([(nuclide index, desc)], keepalive)."""
+    out, keep = [], []
+    for i, m in lib.temperature_sets():
+        nd, _, k = pack_library(Library([m], []))
+        keep += [nd, k]
+        out.append((i, nd))
+    return out, keep
 
 
 def pack_urr(tables):

@@ -53,6 +53,8 @@ def _load(name):
     lib.orc_score_events.restype = C.c_int64
     lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
                                      f64p, f64p]
+    lib.orc_add_temperature_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.orc_set_temperature.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.orc_law_samples.argtypes = [C.POINTER(C.c_longlong)]
     lib.orc_law_samples.restype = None
     lib.orc_reaction_samples.argtypes = [C.POINTER(C.c_longlong)]
@@ -160,6 +162,10 @@ def ref_lib():
             r.ref_stage_law.argtypes = [C.c_void_p]
         if hasattr(r, "ref_stage_urr"):
             r.ref_stage_urr.argtypes = [C.c_void_p]
+        if hasattr(r, "ref_stage_temperature_set"):
+            r.ref_stage_temperature_set.argtypes = [C.c_void_p, C.c_void_p]
+            r.ref_nuclide_temperatures.argtypes = [C.c_int, f64p]
+            r.ref_nuclide_tables_t.argtypes = [C.c_int, C.c_int, f64p, C.c_void_p]
         if hasattr(r, "ref_add_thermal_table"):
             r.ref_add_thermal_table.argtypes = [C.c_char_p, C.c_void_p, C.c_double]
             r.ref_set_material_thermal.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, f64p]
@@ -209,6 +215,7 @@ def ref_load_library(r, libr: nucdata.Library):
     def dp(a):
         return a.ctypes.data_as(f64p)
     r.ref_library_reset()
+    stash = []
     for n in libr.nuclides:
         e, el = np.ascontiguousarray(n.energy, np.float64), np.ascontiguousarray(n.elastic, np.float64)
         fis = np.ascontiguousarray(n.xs[:, 2])
@@ -228,7 +235,15 @@ def ref_load_library(r, libr: nucdata.Library):
             one = _nd.Library([n], [])
             ndesc, _, keep_l = _nd.pack_library(one)
             r.ref_stage_law(C.addressof(ndesc))
-        urr = [t for t in (getattr(libr, "urr_tables", None) or []) if libr.nuclides[t.nuclide] is n]
+        for m in (getattr(n, "more_temperatures", None) or []):  # further temperatures of this nuclide, with their URR tables
+            from macaw_b200 import nucdata as _nd
+            sd, _, keep_s = _nd.pack_library(_nd.Library([m], []))
+            entry = len(libr.nuclides) + [id(x) for _, x in libr.temperature_sets()].index(id(m))
+            su = [t for t in (getattr(libr, "urr_tables", None) or []) if t.nuclide == entry]
+            ud_s, keep_us = _nd.pack_urr(su) if su else (None, None)
+            stash.append((sd, keep_s, ud_s, keep_us))
+            r.ref_stage_temperature_set(C.addressof(sd), C.addressof(ud_s) if su else None)
+        urr = [t for t in (getattr(libr, "urr_tables", None) or []) if t.nuclide < len(libr.nuclides) and libr.nuclides[t.nuclide] is n]
         if urr:
             from macaw_b200 import nucdata as _nd
             ud, keep_u = _nd.pack_urr(urr)
@@ -243,6 +258,20 @@ def ref_load_library(r, libr: nucdata.Library):
         fz, npre = C.c_int32(), C.c_int32()
         r.ref_nuclide_tables(i, dp(xs5), C.byref(fz), C.byref(npre), gi.ctypes.data)
         out.append((xs5, bool(fz.value), npre.value, gi))
+        # further temperatures: the reference's derived tables xs_[t] and grid_[t].grid_index, by increasing kT; the set
+        # at position t of the sorted temperatures is the library's own entry or one of more_temperatures
+        more = getattr(n, "more_temperatures", None) or []
+        if more:
+            kts = np.zeros(len(more) + 1)
+            assert r.ref_nuclide_temperatures(i, dp(kts)) == len(more) + 1
+            by_kt = sorted([n] + list(more), key=lambda x: x.kT)
+            assert np.array_equal(kts, [x.kT for x in by_kt])
+            per_set = {}
+            for t, x in enumerate(by_kt):
+                xs_t, gi_t = np.zeros((x.energy.size, 5)), np.zeros(libr.n_log_bins + 1, np.int32)
+                r.ref_nuclide_tables_t(i, t, dp(xs_t), gi_t.ctypes.data)
+                per_set[id(x)] = (xs_t, gi_t)
+            out[-1] = out[-1] + (per_set,)
     for m in libr.materials:
         nn, dd = np.ascontiguousarray(m.nuclides, np.int32), np.ascontiguousarray(m.densities, np.float64)
         iso = np.ascontiguousarray(m.isotropic, np.int32) if m.isotropic is not None else None
@@ -293,6 +322,12 @@ class Oracle:
         nd, md, keep = nucdata.pack_library(libr)
         self._keep.append((nd, md, keep))
         self.L.orc_set_library(self.h, C.addressof(nd), len(libr.nuclides), libr.n_log_bins)
+        sets, keep_s = nucdata.pack_temperature_sets(libr)  # further temperatures: entries len(nuclides), ...
+        self._keep.append((sets, keep_s))
+        for k, (i, d) in enumerate(sets):
+            entry = C.c_int(-1)
+            if self.L.orc_add_temperature_set(self.h, i, C.addressof(d), C.byref(entry)) or entry.value != len(libr.nuclides) + k:
+                raise RuntimeError("orc_add_temperature_set failed")
         bm = np.ascontiguousarray(block_material, np.int32)
         self.L.orc_set_materials(self.h, C.addressof(md), len(libr.materials), _p(bm), bm.size)
         if getattr(libr, "urr_tables", None):
@@ -311,6 +346,10 @@ class Oracle:
                     fr = np.ascontiguousarray([a[2] for a in m.sab], np.float64)
                     if self.L.orc_set_material_thermal(self.h, im, pos.size, _p(pos), _p(tab), _p(fr)):
                         raise RuntimeError("orc_set_material_thermal failed")
+
+    def set_temperature(self, T):
+        T = np.ascontiguousarray(np.atleast_1d(T), np.float64)
+        self.L.orc_set_temperature(self.h, _p(T), T.size)
 
     def set_settings(self, s: Settings):
         self.settings = s

@@ -235,6 +235,12 @@ struct Nuclide : RxLaw
   std::vector<double> energy, xs, elastic, inelastic;
   int n_inel = 0;
   std::vector<RxLaw> more; // the scattering reactions after the first
+  // Several temperatures (OMC Nuclide::kTs_ / grid_[t] / xs_[t] / reactions_[r]->xs_[t] / urr_data_[t]): every data set is
+  // an entry of Library::nuclides; entries [0, n_identities) are the nuclides themselves (materials, tallies and the URR
+  // stream count those), further entries are additional data sets with `identity` naming their nuclide.  `sets` (on the
+  // nuclide's own entry) lists all of its data sets by increasing kT.
+  int identity = -1;
+  std::vector<int> sets;
   double nu_poly[2] = {0, 0};
   int n_precursor = 0;
   double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
@@ -278,6 +284,7 @@ struct Micro // subset of OMC particle_data.h:82-112 NuclideMicroXS
   double total, absorption, fission, nu_fission;
   int i_grid;
   double f;
+  int entry = -1; // the data set of the nuclide these values come from (micro.index_temp: Library::pick_set)
   // S(a,b) treatment (OMC nuclide.cpp:740-791): index_sab, thermal = sab_frac * (elastic + inelastic), thermal_elastic,
   // and the corrected micro.elastic; i_sab < 0 = free-atom scattering (elastic is then evaluated on demand)
   int i_sab = -1;
@@ -306,14 +313,18 @@ struct Library
   std::vector<ThermalTable> thermal;
   double E_min = 0, E_max = 0, log_spacing = 0;
   int n_log_bins = 8000;
+  int n_identities = 0; // nuclides (OMC data::nuclides.size()); entries beyond are further temperature sets.  0: all
+  int identities() const { return n_identities > 0 ? n_identities : (int)nuclides.size(); }
 
   // OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
   void finalize()
   {
     E_min = 0.0;
     E_max = INFINITY;
-    for (auto& n : nuclides)
+    // every nuclide's FIRST (lowest-temperature) grid bounds the energy range (simulation.cpp:558-566 grid_[0])
+    for (int i = 0; i < identities(); ++i)
     {
+      const Nuclide& n = nuclides[nuclides[i].sets.empty() ? i : nuclides[i].sets[0]];
       E_min = std::max(E_min, n.energy.front());
       E_max = std::min(E_max, n.energy.back());
     }
@@ -344,6 +355,33 @@ struct Library
         if (nuclides[i].fissionable)
           m.fissionable = true;
     }
+  }
+
+  // OMC nuclide.cpp:614-626 TemperatureMethod::NEAREST: the data set whose kT is closest to the particle's (the first of
+  // equally close ones; kTs_ is sorted).  kT = sqrtkT * sqrtkT with sqrtkT = sqrt(K_BOLTZMANN * T) as MaCaw sets it
+  // (MC CollisionKernel.C:109).
+  int pick_set(int i_nuc, double kT) const
+  {
+    const Nuclide& n = nuclides[i_nuc];
+    if (n.sets.size() <= 1)
+      return i_nuc;
+    int i_temp = -1;
+    double max_diff = INFINITY;
+    for (size_t t = 0; t < n.sets.size(); ++t)
+    {
+      const double diff = std::fabs(nuclides[n.sets[t]].kT - kT);
+      if (diff < max_diff)
+      {
+        i_temp = (int)t;
+        max_diff = diff;
+      }
+    }
+    return n.sets[i_temp];
+  }
+  static double kT_of(double T)
+  {
+    const double sqrtkT = std::sqrt(K_BOLTZMANN * T);
+    return sqrtkT * sqrtkT;
   }
 
   // OMC search.h:14-20
@@ -497,20 +535,23 @@ struct Library
 
   // OMC material.cpp:748-831.  seed_urr: the history's URR stream seed (null: no history, smooth cross sections)
   Macro macro_xs(int i_mat, double E, Micro* cache /* [materials[i_mat].nuc.size()] or null */,
-                 int64_t* n_nuclide_lookups = nullptr, const uint64_t* seed_urr = nullptr) const
+                 int64_t* n_nuclide_lookups = nullptr, const uint64_t* seed_urr = nullptr, double kT = 0.0) const
   {
     const Material& mat = materials[i_mat];
     Macro M;
     int i_log = log_bin(E);
     for (size_t i = 0; i < mat.nuc.size(); ++i)
     {
-      Micro m = micro_xs(mat.nuc[i], E, i_log);
+      const int entry = pick_set(mat.nuc[i], kT);
+      Micro m = micro_xs(entry, E, i_log);
+      m.entry = entry;
       // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)
       if (!mat.sab_table.empty() && mat.sab_table[i] >= 0 && !(E > thermal[mat.sab_table[i]].energy_max))
-        apply_sab(nuclides[mat.nuc[i]], mat.sab_table[i], mat.sab_frac[i], E, m);
+        apply_sab(nuclides[entry], mat.sab_table[i], mat.sab_frac[i], E, m);
       {
-        // probability tables, strictly inside their energy range (nuclide.cpp:753-759)
-        const Nuclide& n = nuclides[mat.nuc[i]];
+        // probability tables (those of the chosen data set, urr_data_[i_temp]), strictly inside their energy range
+        // (nuclide.cpp:753-759); the band is drawn with the NUCLIDE's index (index_, :809)
+        const Nuclide& n = nuclides[entry];
         if (seed_urr && !n.urr_energy.empty() && E > n.urr_energy.front() && E < n.urr_energy.back())
           apply_urr(n, mat.nuc[i], E, *seed_urr, m);
       }

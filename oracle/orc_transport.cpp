@@ -33,6 +33,8 @@ struct Problem
   std::vector<int32_t> block_material; // block index -> material index
   int n_blocks = 0;
   std::vector<double> temperature;
+  // kT of the first (or only) temperature value: what calls without an element use (stand-alone lookups, event replays)
+  double kT0() const { return temperature.empty() ? 0.0 : Library::kT_of(temperature[0]); }
   std::vector<Tally> tallies;
   int rank = 0, nranks = 1;
   std::vector<int64_t> work_index;
@@ -798,7 +800,7 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
     const double flux = p.wgt / macro.total;
     for (size_t i = 0; i < mat.nuc.size(); ++i)
     {
-      const Nuclide& n = P.lib.nuclides[mat.nuc[i]];
+      const Nuclide& n = P.lib.nuclides[micro[i].entry >= 0 ? micro[i].entry : mat.nuc[i]];
       if (n.fissionable)
         out.kappa_score += n.q * micro[i].fission * mat.dens[i] * flux;
     }
@@ -816,8 +818,9 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
       break;
     }
   }
-  const Nuclide& nuc = P.lib.nuclides[mat.nuc[k]];
   const Micro& mx = micro[k];
+  // the data set the cross sections came from (micro.index_temp): its reaction tables, its kT for the free-gas target
+  const Nuclide& nuc = P.lib.nuclides[mx.entry >= 0 ? mx.entry : mat.nuc[k]];
   out.nuclide = mat.nuc[k];
   const double E_last = p.E;
   if (nuc.fissionable)
@@ -925,7 +928,7 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
   }
   // URR stream advance when the energy changed (OMC physics.cpp:140-144)
   if (p.E != E_last)
-    p.seeds[STREAM_URR] = future_seed((uint64_t)P.lib.nuclides.size(), p.seeds[STREAM_URR]);
+    p.seeds[STREAM_URR] = future_seed((uint64_t)P.lib.identities(), p.seeds[STREAM_URR]);
   return out;
 }
 
@@ -991,7 +994,7 @@ static void score_tally_nuclides(const Problem& P, Tally& t, int64_t spatial, do
       continue;
     const Micro& m = micro[q];
     const double dens = mat.dens[q];
-    const Nuclide& nuc = P.lib.nuclides[in];
+    const Nuclide& nuc = P.lib.nuclides[m.entry >= 0 ? m.entry : in];
     for (size_t s = 0; s < ns; ++s)
     {
       double v;
@@ -1030,7 +1033,7 @@ static double tracklength_kappa(const Problem& P, const Material& mat, const Mic
 {
   double kappa = 0;
   for (size_t i = 0; i < mat.nuc.size(); ++i)
-    if (P.lib.nuclides[mat.nuc[i]].fissionable)
+    if (P.lib.nuclides[mat.nuc[i]].fissionable) // q and the flag are the nuclide's, whatever data set was picked
       kappa += P.lib.nuclides[mat.nuc[i]].q * micro[i].fission * mat.dens[i] * flux;
   return kappa;
 }
@@ -1140,7 +1143,9 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
     if (micro.size() < mat.nuc.size())
       micro.resize(mat.nuc.size());
     // event_calculate_xs: macro recomputed every segment
-    Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR]);
+    // p.sqrtkT from the coupled temperature of the element (MC CollisionKernel.C:109): picks each nuclide's data set
+    const double kT = P.temperature.empty() ? 0.0 : Library::kT_of(P.temperature[P.temperature.size() == 1 ? 0 : (size_t)c.elem]);
+    Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR], kT);
     ++p.n_xs;
     // distance to collision: 1 RN per segment (MC CollisionKernel.C:150)
     const double d = -xlog(prn(&p.seeds[0])) / macro.total;
@@ -1385,62 +1390,100 @@ static void take_law(RxLaw& N, int law, int in_cm, const mcw_tabular2d& angle, c
   N.yield = yield == 0.0 ? 1.0 : yield;
 }
 
+// one data set of the descriptor array as the oracle's Nuclide
+static Nuclide nuclide_from_desc(const mcw_nuclide_desc& d)
+{
+  Nuclide N;
+  N.G = d.n_grid;
+  N.fissionable = d.fissionable != 0;
+  N.awr = d.awr;
+  N.kT = d.kT;
+  N.energy.assign(d.energy, d.energy + N.G);
+  N.xs.assign(d.xs, d.xs + 5 * (size_t)N.G);
+  N.elastic.assign(d.elastic, d.elastic + N.G);
+  N.n_inel = d.n_inelastic;
+  N.inel_thr = d.inel_threshold;
+  if (N.n_inel)
+  {
+    // stored over the full grid with zeros below threshold so indexing matches i_grid
+    N.inelastic.assign(N.G, 0.0);
+    for (int k = N.inel_thr; k < N.G; ++k)
+      N.inelastic[k] = d.inelastic[k - N.inel_thr];
+  }
+  N.inel_E = d.inel_threshold_energy;
+  N.inel_ratio = d.inel_mass_ratio;
+  N.nu_poly[0] = d.nu_poly[0];
+  N.nu_poly[1] = d.nu_poly[1];
+  N.n_precursor = d.n_precursor;
+  for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
+  {
+    N.dyield[g] = d.delayed_yield[g];
+    N.dtheta[g] = d.delayed_theta[g];
+  }
+  N.watt_a = d.watt_a;
+  N.watt_b = d.watt_b;
+  N.q = d.q_fission;
+  N.el_angle.take(d.elastic_angle, false);
+  take_law(N, d.inelastic_law, d.inelastic_in_cm, d.inelastic_angle, d.inelastic_energy, d.corr_offset,
+           d.corr_interp, d.corr_mu, d.corr_pdf, d.corr_cdf, d.km_r, d.km_a, d.nbody_n,
+           d.nbody_mass_ratio, d.nbody_q, d.inelastic_yield);
+  for (int j = 0; j < d.n_more_reactions && N.n_inel; ++j)
+  {
+    const mcw_reaction_desc& r = d.more_reactions[j];
+    RxLaw R;
+    R.mt = r.mt;
+    R.inel_thr = r.threshold;
+    R.inel_E = r.threshold_energy;
+    R.inel_ratio = r.mass_ratio;
+    R.rx_xs.assign(r.xs, r.xs + (N.G - r.threshold));
+    take_law(R, r.law, r.in_cm, r.angle, r.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r,
+             r.km_a, r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield);
+    N.more.push_back(std::move(R));
+  }
+  return N;
+}
+
 int orc_set_library(void* h, const mcw_nuclide_desc* d, int n, int n_log_bins)
 {
   Problem& P = *(Problem*)h;
   P.lib.nuclides.clear();
   for (int i = 0; i < n; ++i)
   {
-    Nuclide N;
-    N.G = d[i].n_grid;
-    N.fissionable = d[i].fissionable != 0;
-    N.awr = d[i].awr;
-    N.kT = d[i].kT;
-    N.energy.assign(d[i].energy, d[i].energy + N.G);
-    N.xs.assign(d[i].xs, d[i].xs + 5 * (size_t)N.G);
-    N.elastic.assign(d[i].elastic, d[i].elastic + N.G);
-    N.n_inel = d[i].n_inelastic;
-    N.inel_thr = d[i].inel_threshold;
-    if (N.n_inel)
-    {
-      // stored over the full grid with zeros below threshold so indexing matches i_grid
-      N.inelastic.assign(N.G, 0.0);
-      for (int k = N.inel_thr; k < N.G; ++k)
-        N.inelastic[k] = d[i].inelastic[k - N.inel_thr];
-    }
-    N.inel_E = d[i].inel_threshold_energy;
-    N.inel_ratio = d[i].inel_mass_ratio;
-    N.nu_poly[0] = d[i].nu_poly[0];
-    N.nu_poly[1] = d[i].nu_poly[1];
-    N.n_precursor = d[i].n_precursor;
-    for (int g = 0; g < MCW_MAX_DELAYED_GROUPS; ++g)
-    {
-      N.dyield[g] = d[i].delayed_yield[g];
-      N.dtheta[g] = d[i].delayed_theta[g];
-    }
-    N.watt_a = d[i].watt_a;
-    N.watt_b = d[i].watt_b;
-    N.q = d[i].q_fission;
-    N.el_angle.take(d[i].elastic_angle, false);
-    take_law(N, d[i].inelastic_law, d[i].inelastic_in_cm, d[i].inelastic_angle, d[i].inelastic_energy, d[i].corr_offset,
-             d[i].corr_interp, d[i].corr_mu, d[i].corr_pdf, d[i].corr_cdf, d[i].km_r, d[i].km_a, d[i].nbody_n,
-             d[i].nbody_mass_ratio, d[i].nbody_q, d[i].inelastic_yield);
-    for (int j = 0; j < d[i].n_more_reactions && N.n_inel; ++j)
-    {
-      const mcw_reaction_desc& r = d[i].more_reactions[j];
-      RxLaw R;
-      R.mt = r.mt;
-      R.inel_thr = r.threshold;
-      R.inel_E = r.threshold_energy;
-      R.inel_ratio = r.mass_ratio;
-      R.rx_xs.assign(r.xs, r.xs + (N.G - r.threshold));
-      take_law(R, r.law, r.in_cm, r.angle, r.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r,
-               r.km_a, r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield);
-      N.more.push_back(std::move(R));
-    }
+    Nuclide N = nuclide_from_desc(d[i]);
+    N.identity = i;
+    N.sets.assign(1, i);
     P.lib.nuclides.push_back(std::move(N));
   }
+  P.lib.n_identities = n;
   P.lib.n_log_bins = n_log_bins;
+  return 0;
+}
+
+// A further data set of nuclide `nuclide` at the temperature d->kT (OMC Nuclide::kTs_[t], grid_[t], xs_[t], every
+// reaction's xs_[t]; nuclide.cpp:170-200).  It becomes library entry *entry (>= the number of nuclides), which
+// orc_set_urr_tables can address for that temperature's probability tables.
+int orc_add_temperature_set(void* h, int nuclide, const mcw_nuclide_desc* d, int* entry)
+{
+  Problem& P = *(Problem*)h;
+  if (nuclide < 0 || nuclide >= P.lib.identities())
+    return -1;
+  Nuclide N = nuclide_from_desc(*d);
+  N.identity = nuclide;
+  const int e = (int)P.lib.nuclides.size();
+  P.lib.nuclides.push_back(std::move(N));
+  std::vector<int>& sets = P.lib.nuclides[nuclide].sets;
+  sets.push_back(e);
+  std::stable_sort(sets.begin(), sets.end(), [&](int a, int b) { return P.lib.nuclides[a].kT < P.lib.nuclides[b].kT; });
+  if (entry)
+    *entry = e;
+  return 0;
+}
+
+// the coupled temperature variable of CollisionKernel: one value, or one per element (MC CollisionKernel.C:33,109)
+int orc_set_temperature(void* h, const double* T, int64_t n)
+{
+  Problem& P = *(Problem*)h;
+  P.temperature.assign(T, T + n);
   return 0;
 }
 
@@ -1617,7 +1660,7 @@ void orc_score_nuclide_bins(void* h, int i_mat, const int32_t* nuclides, int n_b
   for (int64_t k = 0; k < n; ++k)
   {
     int64_t n_nuc = 0;
-    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc);
+    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc, nullptr, P.kT0());
     double sc[MCW_N_SCORES];
     double flux;
     if (distance)
@@ -1647,7 +1690,7 @@ void orc_tracklength_kappa(void* h, int i_mat, int64_t n, const double* E, const
   for (int64_t k = 0; k < n; ++k)
   {
     int64_t n_nuc = 0;
-    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc);
+    const Macro macro = P.lib.macro_xs(i_mat, E[k], micro.data(), &n_nuc, nullptr, P.kT0());
     out[k] = macro.absorption == 0. ? 0.0 : tracklength_kappa(P, mat, micro.data(), wgt[k] * distance[k]);
   }
 }
@@ -1685,7 +1728,7 @@ int64_t orc_collide_events(void* h, int i_mat, double keff, int64_t n, const dou
     for (int s = 0; s < 3; ++s)
       p.seeds[s] = seeds4[4 * k + s];
     int64_t n_nuc = 0;
-    const Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR]);
+    const Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR], P.kT0());
     macro4[4 * k] = macro.total, macro4[4 * k + 1] = macro.absorption;
     macro4[4 * k + 2] = macro.fission, macro4[4 * k + 3] = macro.nu_fission;
     const size_t before = bank.size();
@@ -1769,7 +1812,7 @@ int orc_xs_lookup(void* h, int64_t n, const double* E, const int32_t* mat, doubl
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i)
   {
-    Macro M = P.lib.macro_xs(mat[i], E[i], nullptr);
+    Macro M = P.lib.macro_xs(mat[i], E[i], nullptr, nullptr, nullptr, P.kT0());
     out[4 * i + 0] = M.total;
     out[4 * i + 1] = M.absorption;
     out[4 * i + 2] = M.fission;

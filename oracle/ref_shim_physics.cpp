@@ -40,6 +40,7 @@ std::unique_ptr<memh5::Node> g_root;
 const mcw_tabular2d *g_el_angle = nullptr, *g_inel_angle = nullptr, *g_inel_energy = nullptr;
 int g_inel_in_cm = 1;
 const mcw_urr_desc* g_urr = nullptr; // probability tables staged for the next ref_add_nuclide
+std::vector<std::pair<const mcw_nuclide_desc*, const mcw_urr_desc*>> g_sets; // further temperatures of the next nuclide
 const mcw_nuclide_desc* g_law = nullptr; // product distribution (correlated / Kalbach-Mann / N-body) of the next nuclide's inelastic reaction
 
 // (3, N) dataset x / pdf / cdf with `offsets` and `interpolation` attributes: the layout of an angular distribution's `mu`
@@ -92,6 +93,14 @@ memh5::Node* reaction(memh5::Node* rxs, int mt, double q, bool cm, const std::st
   d->attr("threshold_idx", threshold);
   return r;
 }
+// the cross section of an existing reaction group at one more temperature (Reaction::Reaction reads `<T>K/xs` for every
+// temperature of the nuclide, reaction.cpp:25-50)
+void reaction_temperature(memh5::Node* r, const std::string& temp, const double* xs, int n, int threshold)
+{
+  memh5::Node* d = r->group(temp)->dataset("xs", std::vector<double>(xs, xs + n));
+  d->attr("threshold_idx", threshold);
+}
+std::string temperature_name(double kT) { return std::to_string((int)std::round(kT / openmc::K_BOLTZMANN)) + "K"; }
 memh5::Node* neutron_product(memh5::Node* rx, int k, const char* mode, const std::vector<double>& yield_coef)
 {
   memh5::Node* p = rx->group("product_" + std::to_string(k));
@@ -196,6 +205,7 @@ REF_API void ref_library_reset()
   data::thermal_scatt.clear();
   data::thermal_scatt_map.clear();
   g_root.reset(new memh5::Node);
+  g_sets.clear();
   settings::run_CE = true;
   settings::run_mode = RunMode::EIGENVALUE;
   settings::survival_biasing = false;
@@ -235,6 +245,11 @@ REF_API void ref_stage_law(const mcw_nuclide_desc* d) { g_law = d; }
 // (urr.cpp:7-33: attributes interpolation / inelastic / absorption / multiply_smooth, datasets energy and table)
 REF_API void ref_stage_urr(const mcw_urr_desc* urr) { g_urr = urr; }
 
+// One more temperature of the NEXT nuclide added (call once per further temperature): its own energy grid and every
+// reaction's cross section on it, written as the `<T>K` members the reference's Nuclide / Reaction / UrrData constructors
+// read for each temperature of `kTs` (nuclide.cpp:170-200, 225-237).  urr: that temperature's probability tables or null.
+REF_API void ref_stage_temperature_set(const mcw_nuclide_desc* set, const mcw_urr_desc* urr) { g_sets.push_back({set, urr}); }
+
 // One synthetic nuclide of macaw_b200/nucdata.py as a nuclide file: MT 2 elastic (isotropic in the centre of mass),
 // optionally MT 51 (one level, isotropic CM), MT 102 capture, optionally MT 18 fission with a polynomial total nu, a Watt
 // prompt spectrum and n_precursor Maxwell delayed groups of constant yield.  Returns the nuclide's index.
@@ -254,7 +269,10 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
   g->group("kTs")->dataset(temp, {kT}, {})->data.shape.clear();
   g->group("energy")->dataset(temp, std::vector<double>(energy, energy + G));
   memh5::Node* rxs = g->group("reactions");
-  memh5::Node* del = neutron_product(reaction(rxs, 2, 0.0, true, temp, elastic, G, 0), 0, "prompt", {1.0});
+  memh5::Node* r_el = reaction(rxs, 2, 0.0, true, temp, elastic, G, 0);
+  memh5::Node *r_inel = nullptr, *r_cap = nullptr, *r_fis = nullptr;
+  std::vector<memh5::Node*> r_more;
+  memh5::Node* del = neutron_product(r_el, 0, "prompt", {1.0});
   if (g_el_angle)
     angle_group(del, *g_el_angle);
   if (n_inel > 0)
@@ -262,7 +280,8 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     const double y0 = g_law && g_law->inelastic_yield != 0.0 ? g_law->inelastic_yield : 1.0;
     const bool cm0 = g_law ? (g_law->inelastic_law == MCW_LAW_LEVEL ? true : g_law->inelastic_in_cm != 0)
                            : (g_inel_energy ? g_inel_in_cm != 0 : true);
-    memh5::Node* dist = neutron_product(reaction(rxs, 51, -inel_E, cm0, temp, inel, n_inel, inel_thr), 0, "prompt", {y0});
+    r_inel = reaction(rxs, 51, -inel_E, cm0, temp, inel, n_inel, inel_thr);
+    memh5::Node* dist = neutron_product(r_inel, 0, "prompt", {y0});
     LawView v{};
     v.law = g_law ? g_law->inelastic_law : (g_inel_energy ? MCW_LAW_CONTINUOUS_TABULAR : MCW_LAW_LEVEL);
     v.angle = g_inel_angle, v.energy = g_inel_energy;
@@ -283,9 +302,9 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     for (int j = 0; g_law && j < g_law->n_more_reactions; ++j)
     {
       const mcw_reaction_desc& r = g_law->more_reactions[j];
-      memh5::Node* dj = neutron_product(reaction(rxs, r.mt, -r.threshold_energy, r.law == MCW_LAW_LEVEL ? true : r.in_cm != 0, temp, r.xs,
-                                                 G - r.threshold, r.threshold),
-                                        0, "prompt", {r.yield == 0.0 ? 1.0 : r.yield});
+      r_more.push_back(reaction(rxs, r.mt, -r.threshold_energy, r.law == MCW_LAW_LEVEL ? true : r.in_cm != 0, temp, r.xs, G - r.threshold,
+                                r.threshold));
+      memh5::Node* dj = neutron_product(r_more.back(), 0, "prompt", {r.yield == 0.0 ? 1.0 : r.yield});
       LawView w{};
       w.law = r.law;
       w.angle = r.angle.n_energy ? &r.angle : nullptr, w.energy = r.energy.n_energy ? &r.energy : nullptr;
@@ -310,10 +329,10 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     u->dataset("table", std::vector<double>(g_urr->table, g_urr->table + ne * 6 * nb), {ne, 6, nb});
     g_urr = nullptr;
   }
-  reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
+  r_cap = reaction(rxs, 102, 0.0, false, temp, capture, G, 0);
   if (fission)
   {
-    memh5::Node* f = reaction(rxs, 18, q_fission, false, temp, fission, G, 0);
+    memh5::Node* f = r_fis = reaction(rxs, 18, q_fission, false, temp, fission, G, 0);
     const double e0 = energy[0], e1 = energy[G - 1];
     double nu_d = 0.0;
     for (int k = 0; k < n_precursor; ++k)
@@ -335,7 +354,42 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
       f->children.at("product_" + std::to_string(k + 1))->attr("decay_rate", 1.0);
     polynomial(g->group("total_nu"), "yield", {nu_poly[0], nu_poly[1]});
   }
-  data::nuclides.push_back(std::make_unique<Nuclide>(memh5::id_of(g), std::vector<double>{(double)T}));
+  // further temperatures: kTs / energy / every reaction's xs (/ urr) under their own `<T>K`
+  std::vector<double> temps{(double)T};
+  for (const auto& su : g_sets)
+  {
+    const mcw_nuclide_desc& S = *su.first;
+    const std::string tn = temperature_name(S.kT);
+    temps.push_back(std::round(S.kT / K_BOLTZMANN));
+    const int Gs = S.n_grid;
+    g->children.at("kTs")->dataset(tn, {S.kT}, {})->data.shape.clear();
+    g->children.at("energy")->dataset(tn, std::vector<double>(S.energy, S.energy + Gs));
+    reaction_temperature(r_el, tn, S.elastic, Gs, 0);
+    if (r_inel)
+      reaction_temperature(r_inel, tn, S.inelastic, Gs - S.inel_threshold, S.inel_threshold);
+    for (size_t j = 0; j < r_more.size(); ++j)
+      reaction_temperature(r_more[j], tn, S.more_reactions[j].xs, Gs - S.more_reactions[j].threshold, S.more_reactions[j].threshold);
+    std::vector<double> cap(Gs), fis(Gs);
+    for (int k = 0; k < Gs; ++k)
+      fis[k] = S.xs[5 * (size_t)k + 2], cap[k] = S.xs[5 * (size_t)k + 1] - S.xs[5 * (size_t)k + 2];
+    reaction_temperature(r_cap, tn, cap.data(), Gs, 0);
+    if (r_fis)
+      reaction_temperature(r_fis, tn, fis.data(), Gs, 0);
+    if (su.second)
+    {
+      const mcw_urr_desc& U = *su.second;
+      memh5::Node* u = g->group("urr")->group(tn);
+      u->attr("interpolation", U.interpolation);
+      u->attr("inelastic", U.inelastic_flag);
+      u->attr("absorption", U.absorption_flag);
+      u->attr("multiply_smooth", U.multiply_smooth);
+      const unsigned long long ne = U.n_energy, nb = U.n_band;
+      u->dataset("energy", std::vector<double>(U.energy, U.energy + ne));
+      u->dataset("table", std::vector<double>(U.table, U.table + ne * 6 * nb), {ne, 6, nb});
+    }
+  }
+  g_sets.clear();
+  data::nuclides.push_back(std::make_unique<Nuclide>(memh5::id_of(g), temps));
   return (int)data::nuclides.size() - 1;
 }
 
@@ -461,6 +515,28 @@ REF_API void ref_finish_library(int n_log_bins)
 }
 
 // derived tables of nuclide i (create_derived, nuclide.cpp:317-390): xs_[0] as [G][5], and its flags
+// number of temperatures nuclide i was read with and kTs_[t]
+REF_API int ref_nuclide_temperatures(int i, double* kTs)
+{
+  const auto& nuc = *openmc::data::nuclides[i];
+  for (size_t t = 0; kTs && t < nuc.kTs_.size(); ++t)
+    kTs[t] = nuc.kTs_[t];
+  return (int)nuc.kTs_.size();
+}
+
+// ref_nuclide_tables for temperature index t (xs_[t], grid_[t].grid_index)
+REF_API void ref_nuclide_tables_t(int i, int t, double* xs5, int32_t* grid_index)
+{
+  const auto& nuc = *openmc::data::nuclides[i];
+  const auto& xs = nuc.xs_[t];
+  for (size_t k = 0; k < xs.shape()[0]; ++k)
+    for (int c = 0; c < 5; ++c)
+      xs5[5 * k + c] = xs(k, c);
+  if (grid_index)
+    for (size_t k = 0; k < nuc.grid_[t].grid_index.size(); ++k)
+      grid_index[k] = nuc.grid_[t].grid_index[k];
+}
+
 REF_API void ref_nuclide_tables(int i, double* xs5, int32_t* fissionable, int32_t* n_precursor, int32_t* grid_index)
 {
   const auto& nuc = *openmc::data::nuclides[i];

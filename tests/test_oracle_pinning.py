@@ -625,7 +625,8 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
     assert v[..., 2].sum() > 0 and v[..., 3].sum() > 0
 
 
-def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False, reactions=False):
+def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False, reactions=False,
+                       temperatures=False):
     """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
     tables, so both sides hold the same numbers.  One material is given <isotropic> flags.  tabular: the nuclides carry
     tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
@@ -648,11 +649,18 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
         lib.materials[3].isotropic = None
     if urr:      # probability tables, read by the reference's own UrrData constructor
         nucdata.add_urr_tables(lib)
+    if temperatures:  # data sets at 600 K and 900 K with their own grids (and probability tables), read by the reference's
+        nucdata.add_temperatures(lib)  # own Nuclide / Reaction / UrrData constructors for every temperature of `kTs`
     generator = [n.xs.copy() for n in lib.nuclides]
     tables = oracle_bridge.ref_load_library(r, lib)
-    for n, (xs5, fissionable, n_precursor, _) in zip(lib.nuclides, tables):
+    for n, tb in zip(lib.nuclides, tables):
+        xs5, fissionable, n_precursor = tb[0], tb[1], tb[2]
         assert fissionable == n.fissionable and n_precursor == n.n_precursor
         n.xs = xs5.copy()
+        if len(tb) > 4:  # the reference's derived tables of every temperature
+            for x in [n] + list(n.more_temperatures):
+                assert np.allclose(tb[4][id(x)][0][:, :4], x.xs[:, :4], rtol=1e-12, atol=0)
+                x.xs = tb[4][id(x)][0].copy()
     return lib, generator, tables
 
 
@@ -680,7 +688,7 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -708,9 +716,13 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     thermal, urr = tabular == "thermal", tabular == "urr"
     if urr and not hasattr(r, "ref_stage_urr"):
         pytest.skip("oracle/_ref built without the probability-table doorway")
-    reactions = tabular == "reactions"
-    lib, _, _ = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
-                                   reactions=reactions)
+    temperatures = tabular == "temperatures"
+    if temperatures and not hasattr(r, "ref_stage_temperature_set"):
+        pytest.skip("oracle/_ref built without the temperature-set doorway")
+    reactions = tabular == "reactions" or temperatures
+    urr = urr or temperatures
+    lib, _, tables = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
+                                        reactions=reactions, temperatures=temperatures)
     rx_seen = np.zeros(8, np.int64)
     o_reset = np.zeros(8, np.int64)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
@@ -735,12 +747,26 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
                    macro.ctypes.data_as(f64p), st.ctypes.data_as(f64p), so.ctypes.data_as(u64p), ns.ctypes.data, cap,
                    sites.ctypes.data_as(f64p), kappa.ctypes.data_as(f64p))
             return macro, st, so, ns, sites[:nb], kappa
-        ref = run(r.ref_collide_events, i_mat, keff, extra=(float(np.sqrt(lib.nuclides[0].kT)),))
+        sqrtkT = float(np.sqrt(lib.nuclides[0].kT))
+        if temperatures:
+            # the particle's temperature (MaCaw: the element's, MC CollisionKernel.C:109) picks every nuclide's data set
+            # (nuclide.cpp:614-626 NEAREST): 0 K and 293.6 K -> the 293.6 K sets, 446 K -> 293.6 K (152.4 < 154), 447.5 K and
+            # 700 K -> 600 K, 1200 K -> 900 K
+            T = [0.0, 446.0, 700.0, 1200.0, 447.5][i_mat % 5]
+            sqrtkT = float(np.sqrt(8.617333262e-5 * T))
+            o.set_temperature(T)
+        ref = run(r.ref_collide_events, i_mat, keff, extra=(sqrtkT,))
         o.L.orc_reaction_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
         mine = run(o.L.orc_collide_events, o.h, i_mat, keff)
         o.L.orc_reaction_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
         rx_seen += o_reset
         assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
+        if temperatures and T > 447:
+            # ... which really come from other data sets than at room temperature
+            o.set_temperature(293.6)
+            cold = run(o.L.orc_collide_events, o.h, i_mat, keff)
+            assert (cold[0][:, 0] != mine[0][:, 0]).mean() > 0.9
+            seen["hot sets"] = seen.get("hot sets", 0) + 1
         assert np.array_equal(mine[2], ref[2]) and np.array_equal(mine[3], ref[3])       # seeds, site counts
         assert mine[4].shape == ref[4].shape
         if libm:
