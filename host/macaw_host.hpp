@@ -157,15 +157,33 @@ struct UrrTable
 struct Library
 {
   std::vector<Nuclide> nuclides;
+  // further data sets of the nuclides at other temperatures (OMC Nuclide::kTs_ / grid_[t] / xs_[t]): (nuclide index, set);
+  // set k becomes library entry nuclides.size() + k (mcw_add_temperature_set), which an UrrTable of that set names
+  std::vector<std::pair<int, Nuclide>> temperature_sets;
   std::vector<Material> materials;
   std::vector<ThermalTable> thermal; // data::thermal_scatt
   std::vector<UrrTable> urr;         // urr_data_ of the nuclides that have it
   std::vector<mcw_nuclide_desc> nuclideDescs() const
   {
+    std::vector<const Nuclide*> all;
+    for (const auto& n : nuclides)
+      all.push_back(&n);
+    return descsOf(all);
+  }
+  std::vector<mcw_nuclide_desc> temperatureSetDescs() const
+  {
+    std::vector<const Nuclide*> all;
+    for (const auto& s : temperature_sets)
+      all.push_back(&s.second);
+    return descsOf(all);
+  }
+  static std::vector<mcw_nuclide_desc> descsOf(const std::vector<const Nuclide*>& list)
+  {
     std::vector<mcw_nuclide_desc> out;
     static const double zero = 0.0;
-    for (const auto& n : nuclides)
+    for (const Nuclide* np : list)
     {
+      const Nuclide& n = *np;
       mcw_nuclide_desc d = n.d;
       d.n_grid = (int32_t)n.energy.size();
       d.energy = n.energy.data();
@@ -426,6 +444,17 @@ public:
                           (int)mesh.bnd_kind.size(), mesh.bnd_kind.data()));
     auto nd = library.nuclideDescs();
     _h.check(mcw_set_library(_h.get(), nd.data(), (int)nd.size()));
+    {
+      // further temperatures of the nuclides (OMC kTs_): the study's coupled temperature picks the nearest per element
+      auto sd = library.temperatureSetDescs();
+      for (size_t k = 0; k < sd.size(); ++k)
+      {
+        int entry = -1;
+        _h.check(mcw_add_temperature_set(_h.get(), library.temperature_sets[k].first, &sd[k], &entry));
+        if (entry != (int)(nd.size() + k))
+          mooseError("temperature set became library entry " + std::to_string(entry) + ", expected " + std::to_string(nd.size() + k));
+      }
+    }
     auto md = library.materialDescs();
     auto bid = kernel.blockIds();
     auto bm = kernel.materialIndices();

@@ -91,7 +91,9 @@ public:
     P.mesh.side_bnd_id = i32("mesh.side_bnd_id");
     P.mesh.bnd_kind = i32("mesh.bnd_kind");
     const auto counts = i32("lib.counts");
-    for (int k = 0; k < counts[0]; ++k)
+    // further temperature sets of the nuclides follow them as nuc<n>, nuc<n + 1>, ...; lib.set_of names each one's nuclide
+    const std::vector<int32_t> set_of = has("lib.set_of") ? i32("lib.set_of") : std::vector<int32_t>();
+    for (int k = 0; k < counts[0] + (int)set_of.size(); ++k)
     {
       const std::string p = "nuc" + std::to_string(k) + ".";
       Nuclide n;
@@ -196,7 +198,10 @@ public:
           n.km_a.assign(lf.begin() + 2 + np, lf.begin() + 2 + 2 * np);
         }
       }
-      P.library.nuclides.push_back(std::move(n));
+      if (k < counts[0])
+        P.library.nuclides.push_back(std::move(n));
+      else
+        P.library.temperature_sets.push_back({set_of[k - counts[0]], std::move(n)});
     }
     for (int k = 0; k < counts[1]; ++k)
     {

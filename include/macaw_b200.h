@@ -397,6 +397,20 @@ int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz
  * [OMC nuclide.cpp:50-302,446-476; simulation.cpp:553-619]. */
 int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
 
+/* One more data set of nuclide `nuclide` (its index in mcw_set_library's array) at the temperature set->kT: OpenMC's
+ * Nuclide::kTs_[t] with grid_[t], xs_[t], every reaction's xs_[t] and threshold [OMC nuclide.cpp:170-200,
+ * reaction.cpp:25-50].  Everything temperature dependent is taken from `set` (energy, xs, elastic, the inelastic reactions'
+ * cross sections and threshold indices); it must hold the same reactions as the nuclide, whose secondary distributions
+ * apply at every temperature.  *entry receives the library entry of the set (>= the number of nuclides): the index
+ * mcw_urr_desc::nuclide uses for that temperature's probability tables.  Materials and tally nuclide bins keep naming
+ * nuclides.  At run time a history in an element of temperature T (mcw_set_temperature; MC CollisionKernel.C:109:
+ * sqrtkT = sqrt(K_BOLTZMANN T)) uses, for every nuclide, the data set whose kT is nearest to sqrtkT^2 -- the first of
+ * equally near ones by increasing kT -- [OMC nuclide.cpp:614-626, TemperatureMethod::NEAREST, the default]: its cross
+ * sections, its kT for the free-gas target [physics.cpp:649-652], its probability tables.  The energy range of the problem
+ * comes from every nuclide's lowest-temperature grid [simulation.cpp:558-566].  S(alpha, beta) tables stay
+ * single-temperature.  Call after mcw_set_library (which discards earlier sets) and before mcw_set_urr_tables. */
+int mcw_add_temperature_set(mcw_handle h, int nuclide, const mcw_nuclide_desc* set, int* entry);
+
 /* The checks mcw_set_library makes, without a handle and without a device (host code only): grids sorted, tables complete,
  * every law the library implements, reaction lists well formed.  Returns the code mcw_set_library would return and writes
  * its message (what mcw_last_error would say) into `message`.  For adapters that want to refuse a nuclide they cannot
@@ -422,8 +436,9 @@ int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* n
  * stream: they return the smooth cross sections. */
 int mcw_set_urr_tables(mcw_handle h, const mcw_urr_desc* tables, int n);
 
-/* Coupled temperature variable of CollisionKernel, one value per element or one scalar (n = 1)
- * [MC CollisionKernel.C:33,109]. */
+/* Coupled temperature variable of CollisionKernel in K, one value per element or one scalar (n = 1)
+ * [MC CollisionKernel.C:33,109]; not set: 0 K, as in MaCaw's own study test.  Picks each nuclide's data set
+ * (mcw_add_temperature_set); with one data set per nuclide it has no effect, like NEAREST in the reference. */
 int mcw_set_temperature(mcw_handle h, const double* T, int64_t n);
 
 int mcw_set_settings(mcw_handle h, const mcw_settings* s);

@@ -64,6 +64,12 @@ class Context:
         nd, md, keep = nucdata.pack_library(libr)
         self._keep.append((nd, md, keep))
         self._ck(self.L.mcw_set_library(self.h, C.addressof(nd), len(libr.nuclides)))
+        sets, keep_s = nucdata.pack_temperature_sets(libr)  # further temperatures of the nuclides: entries len(nuclides), ...
+        self._keep.append((sets, keep_s))
+        for k, (i, d) in enumerate(sets):
+            entry = C.c_int(-1)
+            self._ck(self.L.mcw_add_temperature_set(self.h, i, C.addressof(d), C.byref(entry)))
+            assert entry.value == len(libr.nuclides) + k
         ids = np.ascontiguousarray(self.mesh.block_ids_sorted() if block_ids is None else block_ids, np.int32)
         bm = np.ascontiguousarray(block_material, np.int32)
         assert ids.size == bm.size

@@ -61,6 +61,10 @@ struct HostRx // one scattering reaction after a nuclide's first (mcw_reaction_d
 
 struct HostNuclide
 {
+  // several temperatures: entries [0, n_identities) of Handle::nuclides are the nuclides, later ones further data sets of
+  // nuclide `identity`; `sets` (on the nuclide's own entry) = all its data sets by increasing kT
+  int identity = -1;
+  std::vector<int> sets;
   std::vector<HostRx> more;
   HostUrr urr;
   McwNucParams prm;
@@ -222,6 +226,7 @@ struct mcw_context
   std::vector<std::vector<int32_t>> mat_sab;       // per material, per nuclide position: table or -1 (empty = none)
   std::vector<std::vector<double>> mat_sab_frac;
   std::vector<int32_t> block_ids, block_material;
+  int n_identities = 0; // nuclides given to mcw_set_library; h->nuclides beyond are further temperature sets
   std::vector<double> temperature;
   std::vector<HostTally> tallies;
   mcw_settings set{};
@@ -669,9 +674,46 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* d, int n)
   if (rc)
   {
     h->nuclides.clear();
+    h->n_identities = 0;
     return rc;
   }
+  h->n_identities = n;
+  for (int i = 0; i < n; ++i)
+  {
+    h->nuclides[i].identity = i;
+    h->nuclides[i].sets.assign(1, i);
+  }
   h->have_lib = true;
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_add_temperature_set(mcw_handle h, int nuclide, const mcw_nuclide_desc* set, int* entry)
+{
+  if (!h || !set || !h->have_lib)
+    return MCW_E_INVALID_ARGUMENT;
+  if (nuclide < 0 || nuclide >= h->n_identities)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_add_temperature_set: no such nuclide");
+  std::vector<HostNuclide> one;
+  const int rc = parse_library(set, 1, one, h->err);
+  if (rc)
+    return rc;
+  const HostNuclide& base = h->nuclides[nuclide];
+  if ((one[0].prm.n_inel != 0) != (base.prm.n_inel != 0) || one[0].more.size() != base.more.size() ||
+      one[0].prm.fissionable != base.prm.fissionable)
+    // every reaction has a cross section at every temperature (OMC reaction.cpp:25-50)
+    return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_add_temperature_set: the data set must hold the same reactions as the nuclide");
+  for (int e : base.sets)
+    if (h->nuclides[e].prm.kT == one[0].prm.kT)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_add_temperature_set: the nuclide already has a data set at this temperature");
+  one[0].identity = nuclide;
+  const int e = (int)h->nuclides.size();
+  h->nuclides.push_back(std::move(one[0]));
+  std::vector<int>& sets = h->nuclides[nuclide].sets;
+  sets.push_back(e);
+  std::stable_sort(sets.begin(), sets.end(), [&](int a, int b) { return h->nuclides[a].prm.kT < h->nuclides[b].prm.kT; });
+  if (entry)
+    *entry = e;
   h->prepared = false;
   return MCW_OK;
 }
@@ -926,7 +968,7 @@ int mcw_set_tally_nuclides(mcw_handle h, int id, const int32_t* nuclides, int n)
     if (t.id == id)
     {
       for (int j = 0; j < n; ++j)
-        if (nuclides[j] < -2 || nuclides[j] >= (int)h->nuclides.size())
+        if (nuclides[j] < -2 || nuclides[j] >= (h->have_lib ? h->n_identities : (int)h->nuclides.size()))
           // OMC tally.cpp:552-554 "Could not find the nuclide ... specified in tally ... in any material"
           return fail(h, MCW_E_INVALID_ARGUMENT, "Could not find the nuclide with index " + std::to_string(nuclides[j]) +
                                                      " specified in tally " + std::to_string(id) + " in the library");
@@ -951,16 +993,116 @@ static int prepare(mcw_handle h)
   McwParams& P = h->P;
   memset(&P, 0, sizeof(P));
   TopoRT t = topo_of(h->elem_type);
-  const int n_nuc = (int)h->nuclides.size(), n_mat = (int)h->mat_nuc.size();
+  const int n_nuc = (int)h->nuclides.size(), n_id = h->n_identities;
   for (auto& mn : h->mat_nuc)
     for (int v : mn)
-      if (v < 0 || v >= n_nuc)
+      if (v < 0 || v >= n_id)
         return fail(h, MCW_E_INVALID_ARGUMENT, "material refers to a nuclide outside the library");
+  // ---- temperatures.  Every nuclide may have several data sets; the particle's temperature -- the coupled temperature of
+  // the element it is in (MC CollisionKernel.C:109: sqrtkT = sqrt(K_BOLTZMANN * T)) -- picks the nearest one per nuclide
+  // (OMC nuclide.cpp:614-626).  Elements whose temperature picks the same set for every nuclide form a class; a material
+  // in a class is an "effective material" whose entries name the picked data sets, and the kernels see nothing but
+  // effective materials: effective index = class * n_materials + material, class 0 = the class of the first temperature
+  // value (what the stand-alone lookups use).  One data set per nuclide: one class, the materials as given.
+  struct
+  {
+    std::vector<std::vector<int32_t>> nuc, iso, sab;
+    std::vector<std::vector<double>> dens, sab_frac;
+    std::vector<int32_t> elem_class; // per element, empty = all elements in class 0
+    int n_class = 1;
+  } EM;
+  {
+    const int n_mat0 = (int)h->mat_nuc.size();
+    bool multi = false;
+    for (int i = 0; i < n_id; ++i)
+      multi |= h->nuclides[i].sets.size() > 1;
+    const int64_t nT = (int64_t)h->temperature.size();
+    if (nT > 1 && nT != h->n_elem)
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_temperature: one value or one per element");
+    std::vector<std::vector<int>> class_sel; // per class, the picked entry of every nuclide
+    auto pick_all = [&](double T) {
+      const double sqrtkT = std::sqrt(8.617333262e-5 * T); // OMC constants.h:90 K_BOLTZMANN
+      const double kT = sqrtkT * sqrtkT;
+      std::vector<int> sel(n_id);
+      for (int i = 0; i < n_id; ++i)
+      {
+        const auto& sets = h->nuclides[i].sets;
+        int i_temp = 0;
+        double max_diff = INFINITY;
+        for (size_t t = 0; t < sets.size(); ++t)
+        {
+          const double diff = std::fabs(h->nuclides[sets[t]].prm.kT - kT);
+          if (diff < max_diff)
+          {
+            i_temp = (int)t;
+            max_diff = diff;
+          }
+        }
+        sel[i] = sets.empty() ? i : sets[i_temp];
+      }
+      return sel;
+    };
+    if (!multi)
+      class_sel.push_back(pick_all(0.0));
+    else
+    {
+      std::map<double, int> class_of_T;
+      std::map<std::vector<int>, int> class_of_sel;
+      auto class_for = [&](double T) {
+        auto it = class_of_T.find(T);
+        if (it != class_of_T.end())
+          return it->second;
+        std::vector<int> sel = pick_all(T);
+        auto js = class_of_sel.find(sel);
+        int c;
+        if (js == class_of_sel.end())
+        {
+          c = (int)class_sel.size();
+          class_of_sel[sel] = c;
+          class_sel.push_back(std::move(sel));
+        }
+        else
+          c = js->second;
+        class_of_T[T] = c;
+        return c;
+      };
+      if (nT <= 1)
+        class_for(nT == 1 ? h->temperature[0] : 0.0);
+      else
+      {
+        EM.elem_class.resize(h->n_elem);
+        for (int64_t e = 0; e < h->n_elem; ++e)
+          EM.elem_class[e] = class_for(h->temperature[e]);
+      }
+    }
+    EM.n_class = (int)class_sel.size();
+    for (int c = 0; c < EM.n_class; ++c)
+      for (int m = 0; m < n_mat0; ++m)
+      {
+        std::vector<int32_t> nuc(h->mat_nuc[m].size());
+        for (size_t q = 0; q < nuc.size(); ++q)
+          nuc[q] = class_sel[c][h->mat_nuc[m][q]];
+        EM.nuc.push_back(std::move(nuc));
+        EM.dens.push_back(h->mat_dens[m]);
+        EM.iso.push_back(h->mat_iso[m]);
+        EM.sab.push_back((size_t)m < h->mat_sab.size() ? h->mat_sab[m] : std::vector<int32_t>());
+        EM.sab_frac.push_back((size_t)m < h->mat_sab_frac.size() ? h->mat_sab_frac[m] : std::vector<double>());
+      }
+    // every data set starts at an even grid point of the concatenated grids (16-byte aligned windows, mcw_xs.cuh)
+    int64_t off = 0;
+    for (auto& n : h->nuclides)
+    {
+      n.prm.off = off;
+      off += n.prm.G + (n.prm.G & 1);
+    }
+  }
+  const int n_mat0 = (int)h->mat_nuc.size();
+  const int n_mat = (int)EM.nuc.size();
   {
     // which build of the kernels this problem needs (mcw_kernels.h)
     bool rare = h->set.record_traces == 2;
-    for (size_t m = 0; m < h->mat_sab.size(); ++m)
-      for (int32_t ts : h->mat_sab[m])
+    for (size_t m = 0; m < EM.sab.size(); ++m)
+      for (int32_t ts : EM.sab[m])
         rare |= ts >= 0;
     for (const auto& tl : h->tallies)
       rare |= !tl.nuclides.empty();
@@ -973,8 +1115,10 @@ static int prepare(mcw_handle h)
   // ---- library: OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
   const int M = h->set.n_log_bins;
   double E_min = 0.0, E_max = INFINITY;
-  for (auto& n : h->nuclides)
+  for (int i = 0; i < n_id; ++i)
   {
+    // every nuclide's FIRST (lowest-temperature) grid bounds the energy range (OMC simulation.cpp:558-566 grid_[0])
+    const HostNuclide& n = h->nuclides[h->nuclides[i].sets.empty() ? i : h->nuclides[i].sets[0]];
     E_min = std::max(E_min, n.energy.front());
     E_max = std::min(E_max, n.energy.back());
   }
@@ -1012,7 +1156,7 @@ static int prepare(mcw_handle h)
     n.prm.urr_bands = n.urr.n_band;
     n.prm.urr_inel_flag = n.urr.inel_flag;
     n.prm.urr_multiply_smooth = n.urr.multiply_smooth;
-    n.prm.urr_pad = 0;
+    n.prm.identity = n.identity;
     urr_pool.insert(urr_pool.end(), n.urr.energy.begin(), n.urr.energy.end());
     urr_pool.insert(urr_pool.end(), n.urr.table.begin(), n.urr.table.end());
     n_urr += n.prm.urr_n > 0;
@@ -1093,14 +1237,14 @@ static int prepare(mcw_handle h)
   for (int m = 0; m < n_mat; ++m)
   {
     bool fis = false;
-    for (size_t i = 0; i < h->mat_nuc[m].size(); ++i)
+    for (size_t i = 0; i < EM.nuc[m].size(); ++i)
     {
-      mat_nuc.push_back(h->mat_nuc[m][i]);
-      mat_dens.push_back(h->mat_dens[m][i]);
-      mat_iso.push_back(h->mat_iso[m][i] != 0);
-      mat_e0.push_back(h->nuclides[h->mat_nuc[m][i]].energy.front());
-      mat_e1.push_back(h->nuclides[h->mat_nuc[m][i]].energy.back());
-      fis |= h->nuclides[h->mat_nuc[m][i]].prm.fissionable != 0;
+      mat_nuc.push_back(EM.nuc[m][i]);
+      mat_dens.push_back(EM.dens[m][i]);
+      mat_iso.push_back(EM.iso[m][i] != 0);
+      mat_e0.push_back(h->nuclides[EM.nuc[m][i]].energy.front());
+      mat_e1.push_back(h->nuclides[EM.nuc[m][i]].energy.back());
+      fis |= h->nuclides[EM.nuc[m][i]].prm.fissionable != 0;
     }
     mat_off.push_back((int32_t)mat_nuc.size());
     mat_fis.push_back(fis);
@@ -1173,11 +1317,11 @@ static int prepare(mcw_handle h)
     }
     bool any = false;
     for (int m = 0; m < n_mat; ++m)
-      for (size_t i = 0; i < h->mat_nuc[m].size(); ++i)
+      for (size_t i = 0; i < EM.nuc[m].size(); ++i)
       {
-        const bool have = (size_t)m < h->mat_sab.size() && h->mat_sab[m].size() == h->mat_nuc[m].size();
-        mat_sab.push_back(have ? h->mat_sab[m][i] : -1);
-        mat_sab_frac.push_back(have ? h->mat_sab_frac[m][i] : 0.0);
+        const bool have = (size_t)m < EM.sab.size() && EM.sab[m].size() == EM.nuc[m].size();
+        mat_sab.push_back(have ? EM.sab[m][i] : -1);
+        mat_sab_frac.push_back(have ? EM.sab_frac[m][i] : 0.0);
         if (mat_sab.back() >= (int32_t)sab.size())
           return fail(h, MCW_E_INVALID_ARGUMENT, "a material names a thermal table that is not set");
         any |= mat_sab.back() >= 0;
@@ -1217,6 +1361,7 @@ static int prepare(mcw_handle h)
   P.lib.mat_dens = d_dens;
   P.lib.mat_fissionable = d_mfis;
   P.lib.n_nuc = n_nuc;
+  P.lib.n_identities = n_id;
   P.lib.n_mat = n_mat;
   P.lib.M = M;
   P.lib.E_min = E_min;
@@ -1253,6 +1398,8 @@ static int prepare(mcw_handle h)
       }
     block_hmax[eblock[e]] = std::max(block_hmax[eblock[e]], std::sqrt(h2));
   }
+  // the effective material of an element: its block's material in its temperature class
+  auto emat = [&](int64_t e) { return (EM.elem_class.empty() ? 0 : EM.elem_class[e]) * n_mat0 + h->block_material[eblock[e]]; };
   const int n_bnd = (int)h->bnd_kind.size();
   if (h->n_elem > MCW_MAX_ELEMS)
     return fail(h, MCW_E_UNSUPPORTED, "more than 2^28 elements: side codes hold neighbour << 3 | back side in 32 bits");
@@ -1261,7 +1408,7 @@ static int prepare(mcw_handle h)
   {
     std::vector<char> used(n_mat, 0);
     for (int64_t e = 0; e < h->n_elem; ++e)
-      used[h->block_material[eblock[e]]] = 1;
+      used[emat(e)] = 1;
     int ns = 0;
     for (int m = 0; m < n_mat; ++m)
       if (used[m])
@@ -1278,13 +1425,13 @@ static int prepare(mcw_handle h)
     for (int sl = 0; sl < ns; ++sl)
     {
       const int m = P.slot_mat[sl];
-      every_slot &= !h->mat_nuc[m].empty();
-      for (size_t q = 0; q < h->mat_nuc[m].size(); ++q)
+      every_slot &= !EM.nuc[m].empty();
+      for (size_t q = 0; q < EM.nuc[m].size(); ++q)
       {
-        const HostNuclide& N = h->nuclides[h->mat_nuc[m][q]];
-        pl_nuc.push_back(h->mat_nuc[m][q]);
+        const HostNuclide& N = h->nuclides[EM.nuc[m][q]];
+        pl_nuc.push_back(EM.nuc[m][q]);
         pl_slot.push_back(sl);
-        pl_dens.push_back(h->mat_dens[m][q]);
+        pl_dens.push_back(EM.dens[m][q]);
         pl_e0.push_back(N.energy.front());
         pl_e1.push_back(N.energy.back());
       }
@@ -1296,7 +1443,7 @@ static int prepare(mcw_handle h)
     {
       P.slot_plan_off[sl] = q;
       if (sl < ns)
-        q += (int)h->mat_nuc[P.slot_mat[sl]].size();
+        q += (int)EM.nuc[P.slot_mat[sl]].size();
     }
     int32_t *d_pn, *d_ps;
     double *d_pd, *d_p0, *d_p1;
@@ -1337,7 +1484,7 @@ static int prepare(mcw_handle h)
       }
     }
     *reinterpret_cast<double*>(r + t.nv * t.cpv * 8 + t.ns * 4) = block_hmax[eblock[e]];
-    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 8) = slot_of[h->block_material[eblock[e]]];
+    *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 8) = slot_of[emat(e)];
     *reinterpret_cast<int32_t*>(r + t.nv * t.cpv * 8 + t.ns * 4 + 12) = eblock[e];
   }
   // node -> elements CSR

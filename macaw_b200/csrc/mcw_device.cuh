@@ -352,7 +352,7 @@ __device__ __noinline__ void mcw_urr_apply_ool(const McwLibraryDev* Lg, int i_nu
   int i_energy = 0;
   while (E >= en[i_energy + 1])
     ++i_energy;
-  uint64_t fseed = mcw_future_seed((uint64_t)i_nuc, seed); // future_prn (OMC random_lcg.cpp:49-53)
+  uint64_t fseed = mcw_future_seed((uint64_t)n.identity, seed); // future_prn(index_, ...) (OMC nuclide.cpp:809, random_lcg.cpp:49-53)
   const double r = mcw_prn(fseed);
   const double* t0 = tab + (size_t)i_energy * 6 * nb;
   const double* t1 = t0 + 6 * nb;

@@ -393,7 +393,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     if (L.mat_iso[q_nuc]) // isotropic-in-lab override (OMC physics.cpp:706-718): phi, then mu
       c.u = mcw_isotropic_direction(c.seed);
     if (c.E != E_last) // OMC physics.cpp:140-144
-      seed_urr = mcw_future_seed((uint64_t)L.n_nuc, seed_urr);
+      seed_urr = mcw_future_seed((uint64_t)L.n_identities, seed_urr);
   }
   // collision-estimator tallies (OMC tally_scoring.cpp:2354-2420)
   if (P.tallies_active && P.any_collision_tally)

@@ -103,7 +103,7 @@ __device__ __noinline__ void mcw_score_tally_nuclides(const McwLibraryDev* Lg, c
     }
     int q = L.mat_off[i_mat];
     const int qe = L.mat_off[i_mat + 1];
-    while (q < qe && L.mat_nuc[q] != in)
+    while (q < qe && L.nuc[L.mat_nuc[q]].identity != in) // the material's entry may be any of the nuclide's data sets
       ++q;
     if (q == qe)
       continue; // mat_nuclide_index_ == C_NONE

@@ -42,7 +42,9 @@ struct McwNucParams
   int32_t inel_en_hist, inel_in_cm; // ContinuousTabular: histogram interpolation in incoming energy; scatter_in_cm_
   // unresolved-resonance probability tables (mcw_urr_desc): energies at McwLibraryDev::urr_pool[urr_first ..], then the
   // table [n_energy][6][n_band]; urr_n = 0: none
-  int32_t urr_first, urr_n, urr_bands, urr_inel_flag, urr_multiply_smooth, urr_pad;
+  int32_t urr_first, urr_n, urr_bands, urr_inel_flag, urr_multiply_smooth;
+  int32_t identity; // the nuclide this data set belongs to (its index among the nuclides, OMC Nuclide::index_): what the URR
+                    // band draw and the nuclide tally bins go by when a nuclide has data sets at several temperatures
   // product distributions that give energy and cosine together (inel_law >= MCW_LAW_CORRELATED): law_first is an entry
   // of the tab_* pools -- correlated: the first of one angular distribution per point of the outgoing-energy table
   // (point j of the table -> entry law_first + j); Kalbach-Mann: ONE entry whose tab_x / tab_p hold r / a per point
@@ -115,6 +117,7 @@ struct McwLibraryDev
   // local memory, so the rare out-of-line paths (S(a,b), nuclide tally bins) are handed this pointer instead.
   const McwLibraryDev* self_dev;
   int32_t n_nuc, n_mat, M;
+  int32_t n_identities; // nuclides (OMC data::nuclides.size(): the URR stream advance); n_nuc counts every data set
   double E_min, E_max, log_spacing;
 };
 

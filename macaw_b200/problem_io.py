@@ -26,7 +26,12 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
     r["mesh.side_bnd_id"] = np.ascontiguousarray(mesh.side_bnd_id, np.int32).ravel()
     r["mesh.bnd_kind"] = np.ascontiguousarray(mesh.bnd_kind, np.int32)
     r["lib.counts"] = np.array([len(lib.nuclides), len(lib.materials), lib.n_log_bins], np.int32)
-    for k, n in enumerate(lib.nuclides):
+    # further temperature sets of the nuclides follow them as records nuc<n>, nuc<n + 1>, ... (their library entries);
+    # lib.set_of names the nuclide of each
+    sets = lib.temperature_sets() if hasattr(lib, "temperature_sets") else []
+    if sets:
+        r["lib.set_of"] = np.array([i for i, _ in sets], np.int32)
+    for k, n in enumerate(list(lib.nuclides) + [m for _, m in sets]):
         r[f"nuc{k}.ints"] = np.array([n.energy.size, int(n.fissionable), int(n.inelastic.size > 0), n.inel_threshold,
                                       n.n_precursor], np.int32)
         r[f"nuc{k}.scalars"] = np.array([n.awr, n.kT, n.inel_threshold_energy, n.inel_mass_ratio, n.nu_poly[0],
@@ -115,6 +120,8 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
         r[f"urr{k}.table"] = np.ascontiguousarray(t.table, np.float64).ravel()
     r["kernel.blocks"] = np.ascontiguousarray(blocks, np.int32)
     r["kernel.materials"] = np.ascontiguousarray(materials, np.int32)  # OpenMC material ids, 1-based
+    if getattr(lib, "element_temperature", None) is not None:
+        temperature = lib.element_temperature
     r["kernel.temperature"] = np.atleast_1d(np.asarray(temperature, np.float64))
     s = settings
     r["settings.ints"] = np.array([s.n_particles, s.master_seed, s.n_inactive, s.n_log_bins, s.is_2d,

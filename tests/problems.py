@@ -20,6 +20,8 @@ def configure(obj, mesh, lib, block_material, settings, tallies=True, track_tall
     else:
         obj.set_mesh(mesh)
         obj.set_library(lib, block_material, block_ids)
+    if getattr(lib, "element_temperature", None) is not None:  # the coupled temperature of CollisionKernel, per element
+        obj.set_temperature(lib.element_temperature)
     obj.set_settings(settings)
     if tallies:
         obj.add_tally(1, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["cell"], ALL_SCORES, EBINS)
@@ -125,6 +127,20 @@ def pin_cell_tet_reactions(**kw):
     return mesh, nucdata.add_reactions(lib), bm, s
 
 
+def pin_cell_tet_temperatures(**kw):
+    """Several temperatures per nuclide (data sets at 293.6 / 600 / 900 K with their own grids, reaction lists and
+    probability tables; every fourth nuclide keeps one set) and a temperature FIELD on the mesh, hot in the middle of the
+    fuel (1100 K) and cold at the cell corner (100 K): fuel and water each span two temperature classes, each nuclide's
+    data set is the one nearest to the element's temperature (OMC nuclide.cpp:614-626, MC CollisionKernel.C:109)."""
+    urr = kw.pop("urr", True)  # False: no probability tables, so that the staged (tile) refresh kernels run as well
+    mesh, lib, bm, s = pin_cell_tet_reactions(**kw)
+    nucdata.add_temperatures(nucdata.add_urr_tables(lib) if urr else lib)
+    c = mesh.xyz[mesh.conn].mean(axis=1)
+    r = np.hypot(c[:, 0], c[:, 1])
+    lib.element_temperature = 1100.0 - 1000.0 * r / r.max()
+    return mesh, lib, bm, s
+
+
 def pin_cell_tet_sab(**kw):
     """S(alpha, beta) tables on hydrogen (continuous inelastic), on a second nuclide per material (coherent elastic +
     discrete inelastic, fraction 0.75) and a third (incoherent-discrete elastic + skewed discrete inelastic)."""
@@ -159,7 +175,7 @@ def infinite_medium_sab(**kw):
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
 
 
-PROBLEMS = {"pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+PROBLEMS = {"pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
             "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,

@@ -188,6 +188,12 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     # lists of scattering reactions with yields (further levels, continuum with a non-integral multiplicity, (n,2n))
     ("pin_cell_tet_reactions", {}, EVENT), ("pin_cell_tet_reactions", {}, FUSED), ("pin_cell_tet_reactions", {}, PUMP),
     ("pin_cell_tet_reactions", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # several temperatures per nuclide (own grids, reaction lists, probability tables) under a temperature field: every
+    # element's temperature picks each nuclide's nearest data set
+    ("pin_cell_tet_temperatures", {}, EVENT), ("pin_cell_tet_temperatures", {}, FUSED),
+    ("pin_cell_tet_temperatures", {"sort_xs_queue": 1}, SORTED), ("pin_cell_tet_temperatures", {"urr": False}, PUMP),
+    ("pin_cell_tet_temperatures", {"urr": False, "sort_xs_queue": 1}, SORTED),
+    ("pin_cell_tet_temperatures", {"n_particles": 20000}, {"tail_threshold": 3000}),
     # thermal scattering S(a,b): bound cross sections below energy_max, sab_scatter (continuous / discrete inelastic,
     # coherent / incoherent-discrete elastic, partial binding)
     ("infinite_medium_sab", {}, EVENT), ("pin_cell_tet_sab", {}, EVENT), ("pin_cell_tet_sab", {}, FUSED),
@@ -244,7 +250,7 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
 
 
 @pytest.mark.parametrize("name,opts", [("pin_cell_tet", MIXED), ("beavrs_assembly", EVENT), ("infinite_medium", FUSED),
-                                       ("assembly_quad", PUMP)])
+                                       ("assembly_quad", PUMP), ("pin_cell_tet_temperatures", MIXED)])
 def test_nuclide_bin_tallies(oracle_bridge, ctx_factory, name, opts):
     """Tallies with nuclide bins (mcw_set_tally_nuclides; MC OpenMCTally.C:188-204 `nuclides = all | list`) on both
     estimators against the oracle, whose per-bin scoring equals the reference's own score_all_nuclides / nuclide-bin loop

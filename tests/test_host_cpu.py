@@ -58,7 +58,11 @@ def test_library_validation_without_a_device():
 
     def check(library):
         nd, _, keep = nucdata.pack_library(library)
-        return L.mcw_validate_library(C.addressof(nd), len(library.nuclides), msg, 512), msg.value.decode()
+        rc = L.mcw_validate_library(C.addressof(nd), len(library.nuclides), msg, 512)
+        sets, keep_s = nucdata.pack_temperature_sets(library)  # further temperature sets: one descriptor each
+        for _, d in sets:
+            rc = rc or L.mcw_validate_library(C.addressof(d), 1, msg, 512)
+        return rc, msg.value.decode()
     for name, make in problems.PROBLEMS.items():
         _, library, _, _ = make(n_particles=100)
         rc, text = check(library)
