@@ -55,6 +55,7 @@ struct Problem
   double total_weight = 0;
   TraceStats stats;
   int64_t n_collisions = 0, n_xs = 0, n_nuc_lookups = 0;
+  int64_t n_bank_dropped = 0; // fission sites of the generation that did not fit into the bank (OMC physics.cpp:203-209)
 
   // point location grid
   int gx = 1, gy = 1, gz = 1;
@@ -857,6 +858,8 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
         // OMC physics.cpp:203-209: the site is not banked and no further ones are sampled.  The id it took is handed
         // back so that progeny_per_particle counts banked sites only and sort_fission_bank's offsets stay inside the bank.
         --p.n_progeny;
+#pragma omp atomic
+        P.n_bank_dropped += nu - i;
         break;
       }
     }
@@ -1990,6 +1993,7 @@ int orc_transport_generation(void* h, int batch, int n_threads)
   P.fission_bank.clear();
   P.traces.clear();
   P.fission_bank.reserve(3 * n);
+  P.n_bank_dropped = 0;
   P.records.assign(n, mcw_history_record{});
   P.total_weight = 0.0;
   const bool tallies_active = batch > P.set.n_inactive;
@@ -2161,6 +2165,7 @@ int orc_finalize_generation(void* h, int batch, const double* reduced5, mcw_gene
     out->n_xs_lookups = P.n_xs;
     out->n_nuclide_lookups = P.n_nuc_lookups;
     out->n_bank_sites = (int64_t)P.fission_bank.size();
+    out->n_bank_dropped = P.n_bank_dropped;
     out->n_vertex_edge_hits = P.stats.vertex_edge_hits;
     out->n_moved_through_neighbors = P.stats.moved_through_neighbors;
     out->n_failed_traces = P.stats.failed;

@@ -45,6 +45,18 @@ def infinite_medium(n_particles=2000, G=400, n_inactive=1, **kw):
     return mesh, lib, [0, 1], s
 
 
+def infinite_medium_supercritical(**kw):
+    """nu ten times as large: k is about 4, so the first generation (keff guess 1) makes more than the 3 n sites the
+    fission bank holds (OMC physics.cpp:203-209 "The shared fission bank is full")."""
+    mesh, lib, bm, s = infinite_medium(**kw)
+    for n in lib.nuclides:
+        if n.fissionable:
+            n.nu_poly = (10.0 * n.nu_poly[0], 10.0 * n.nu_poly[1])
+            n.xs = n.xs.copy()
+            n.xs[:, 3] = (n.nu_poly[1] * n.energy + n.nu_poly[0]) * n.xs[:, 2]
+    return mesh, lib, bm, s
+
+
 def pin_cell_tet(n_particles=2000, G=400, n_xy=8, n_z=3, n_inactive=1, **kw):
     mesh = meshgen.pin_cell_tet(n_xy, n_z)
     lib = nucdata.make_library(9, G=G)
@@ -173,6 +185,22 @@ def beavrs_assembly_full(**kw):
 def infinite_medium_sab(**kw):
     mesh, lib, bm, s = infinite_medium(**kw)
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
+
+
+def check_full_bank(r, rec, bank, n):
+    """What has to hold when the fission bank overflowed (OMC physics.cpp:203-209): the generation goes on with the sites
+    that fit, dropped sites are counted, and n_progeny counts BANKED sites only, so that sort_fission_bank's offsets
+    (exclusive scan of n_progeny, bank.cpp:60-104) stay inside the bank: the sorted bank has no holes."""
+    assert r.n_bank_dropped > 0 and r.n_bank_sites == 3 * n == len(bank)
+    assert int(rec["n_progeny"].sum()) == r.n_bank_sites
+    assert bank["parent_id"].min() >= 1 and bank["parent_id"].max() <= n
+    order = np.lexsort((bank["progeny_id"], bank["parent_id"]))
+    assert np.array_equal(order, np.arange(len(bank)))  # sorted by (parent, progeny)
+    counts = np.bincount(bank["parent_id"] - 1, minlength=n)
+    assert np.array_equal(counts, rec["n_progeny"])      # every parent's sites are there ...
+    first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    assert np.array_equal(bank["progeny_id"], np.arange(len(bank)) - np.repeat(first, counts))  # ... numbered 0, 1, 2, ...
+    assert np.isfinite(bank["E"]).all() and (bank["E"] > 0).all()
 
 
 PROBLEMS = {"pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,

@@ -384,6 +384,24 @@ def test_ragged_banks_bit_exact(oracle_bridge, ctx_factory, n):
         assert rg.k_generation == pytest.approx(ro.k_generation, rel=1e-12)
 
 
+def test_full_fission_bank(oracle_bridge, ctx_factory):
+    """k about 4 with the keff guess 1 of the first generation: more sites than the bank's 3 n.  Which sites are dropped
+    depends on the order histories reach the bank (thread / atomic order, in the reference too), so this is held by
+    properties, on the GPU and on the oracle alike: tests/problems.py check_full_bank.  The next generation (keff now
+    about 4) fits again and is an ordinary one."""
+    n = 3000
+    mesh, lib, bm, s = problems.infinite_medium_supercritical(n_particles=n, n_inactive=1)
+    for obj in (problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s), problems.configure(ctx_factory(), mesh, lib, bm, s)):
+        obj.sample_initial_source()
+        r = obj.run_generation(1)
+        problems.check_full_bank(r, obj.history_records(), obj.fission_bank(), n)
+        assert 3.0 < r.k_generation < 6.0
+        assert len(obj.source_bank()) == n
+        r2 = obj.run_generation(2)
+        assert r2.n_bank_dropped == 0 and 0.5 * n < r2.n_bank_sites < 2 * n and r2.n_failed_traces == 0
+    assert "fission bank is full" in obj.L.mcw_last_error(obj.h).decode()
+
+
 def test_empty_inputs(ctx_factory):
     """Zero-length calls are no-ops, not errors or crashes (the reference's containers are simply empty)."""
     import torch

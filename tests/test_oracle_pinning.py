@@ -1083,3 +1083,21 @@ def test_work_split_against_reference_simulation_cpp(oracle_bridge):
             assert L.mcw_calculate_work(n, P, mine.ctypes.data) == 0
             assert np.array_equal(mine, want) and np.array_equal(dist.calculate_work(n, P), want)
             assert per_rank == np.diff(want).tolist() and want[-1] == n
+
+
+def test_full_fission_bank_keeps_the_bank_consistent(oracle_bridge):
+    """More fission sites than the bank's 3 n (k about 4 under the first generation's keff guess 1): like
+    create_fission_sites (OMC physics.cpp:203-209) the site that does not fit is not counted in n_progeny and no further
+    ones are sampled for that collision, so sort_fission_bank's offsets stay inside the bank -- no holes, every parent's
+    sites numbered 0, 1, 2, ... -- and the next generation is an ordinary one (tests/problems.py check_full_bank; the same
+    properties are asserted of the GPU path in tests/test_gpu_parity.py::test_full_fission_bank)."""
+    from tests import problems
+    n = 3000
+    mesh, lib, bm, s = problems.infinite_medium_supercritical(n_particles=n, n_inactive=1)
+    o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s)
+    o.sample_initial_source()
+    r = o.run_generation(1)
+    problems.check_full_bank(r, o.history_records(), o.fission_bank(), n)
+    assert len(o.source_bank()) == n
+    r2 = o.run_generation(2)
+    assert r2.n_bank_dropped == 0 and 0.5 * n < r2.n_bank_sites < 2 * n
