@@ -101,6 +101,41 @@ typedef struct mcw_tabular2d
 #define MCW_LAW_CORRELATED 2         /* CorrelatedAngleEnergy, OMC secondary_correlated.cpp:156-262 */
 #define MCW_LAW_KALBACH_MANN 3       /* KalbachMann, OMC secondary_kalbach.cpp:117-235 */
 #define MCW_LAW_NBODY 4              /* NBodyPhaseSpace, OMC secondary_nbody.cpp:25-68 */
+/* energy laws of fission-neutron products (mcw_fission_product) */
+#define MCW_LAW_MAXWELL 5            /* MaxwellEnergy, OMC distribution_energy.cpp:279-291 */
+#define MCW_LAW_EVAPORATION 6        /* Evaporation, OMC distribution_energy.cpp:305-322 */
+#define MCW_LAW_WATT 7               /* WattEnergy, OMC distribution_energy.cpp:342-356 */
+
+/* A function of the incoming energy as nuclide files hold them (OMC endf.h Function1D): a Polynomial (coefficients in
+ * increasing powers, Horner; endf.cpp:112-121) or a Tabulated1D with one interpolation region, histogram or
+ * linear-linear, constant outside its range (endf.cpp:156-210).  kind 0 = absent. */
+#define MCW_FN_NONE 0
+#define MCW_FN_POLYNOMIAL 1
+#define MCW_FN_TABULATED 2
+typedef struct mcw_function1d
+{
+  int32_t kind;
+  int32_t n;             /* coefficients, or points */
+  int32_t interpolation; /* tabulated: 1 histogram, 2 linear-linear */
+  int32_t reserved0;
+  const double* x;       /* tabulated: abscissae (increasing); polynomial: unused */
+  const double* y;       /* tabulated: ordinates; polynomial: the coefficients */
+} mcw_function1d;
+
+/* One neutron product of the fission reaction (OMC ReactionProduct of fission_rx_[0]): the prompt neutrons (first) or one
+ * delayed group.  yield = neutrons per fission as a function of the incoming energy; the outgoing energy comes from a
+ * Watt spectrum with tabulated a(E), b(E), a Maxwell or an evaporation spectrum with tabulated theta(E) (in `a`) -- each
+ * with its restriction energy u: E_out <= E - u -- or a continuous tabular law; the cosine is isotropic
+ * (UncorrelatedAngleEnergy without an angle table, secondary_uncorrelated.cpp:54-68). */
+typedef struct mcw_fission_product
+{
+  mcw_function1d yield;
+  int32_t law; /* MCW_LAW_WATT, MCW_LAW_MAXWELL, MCW_LAW_EVAPORATION, MCW_LAW_CONTINUOUS_TABULAR */
+  int32_t reserved0;
+  double u;
+  mcw_function1d a, b;
+  mcw_tabular2d energy;
+} mcw_fission_product;
 
 /* A further scattering reaction of a nuclide besides elastic and the first inelastic one (which mcw_nuclide_desc
  * describes inline): one entry of Nuclide::index_inelastic_scatter_ (OMC nuclide.cpp:216-219 -- every non-redundant
@@ -194,6 +229,15 @@ typedef struct mcw_nuclide_desc
   int32_t n_more_reactions;
   int32_t reserved2;
   const mcw_reaction_desc* more_reactions;
+  /* Fission neutrons as a nuclide file has them, instead of the scalar description above (nu_poly, delayed_yield,
+   * delayed_theta, watt_a, watt_b): n_fission_products = 1 + n_precursor products (prompt, then the delayed groups) and the
+   * total nu (kind 0: the prompt yield stands in, OMC nuclide.cpp:510-516).  sample_fission_neutron (physics.cpp:1006-1071)
+   * evaluates beta = sum of the delayed yields / total nu, picks the group by the yields and samples the product's law,
+   * resampling energies >= the problem's maximum.  0 products: the scalar description. */
+  int32_t n_fission_products;
+  int32_t reserved3;
+  const mcw_fission_product* fission_products;
+  mcw_function1d total_nu;
 } mcw_nuclide_desc;
 
 /* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab

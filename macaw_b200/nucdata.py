@@ -52,6 +52,40 @@ class Nuclide:
     inelastic_yield: float = 1.0     # neutron multiplicity of the inline inelastic reaction
     more_reactions: list = None      # further scattering reactions (Reaction), index_inelastic_scatter_ order
     more_temperatures: list = None   # further data sets of this nuclide (Nuclide objects at other kT; OMC kTs_, grid_[t], xs_[t])
+    fission_products: list = None    # FissionProduct x (1 + n_precursor): prompt, delayed groups (replaces nu_poly / watt / ...)
+    total_nu: object = None          # Function1D or None (then the prompt yield stands in)
+
+
+@dataclass
+class Function1D:
+    """mcw_function1d: kind 1 polynomial (y = coefficients), kind 2 tabulated (x, y; interpolation 1 histogram, 2 lin-lin)."""
+    kind: int
+    y: np.ndarray
+    x: np.ndarray = None
+    interpolation: int = 2
+
+    def __call__(self, E):
+        E = np.asarray(E, np.float64)
+        if self.kind == 1:
+            out = np.zeros_like(E)
+            for c in self.y[::-1]:
+                out = out * E + c
+            return out
+        if self.interpolation == 1:
+            i = np.clip(np.searchsorted(self.x, E, side="right") - 1, 0, len(self.x) - 1)
+            return np.asarray(self.y)[i]
+        return np.interp(E, self.x, self.y)
+
+
+@dataclass
+class FissionProduct:
+    """mcw_fission_product"""
+    yield_: Function1D
+    law: int                 # 7 Watt, 5 Maxwell, 6 evaporation, 1 continuous tabular
+    u: float = -2.0e7
+    a: Function1D = None     # Watt a(E) or theta(E)
+    b: Function1D = None
+    energy: object = None    # Tabular2D
 
 
 @dataclass
@@ -623,6 +657,80 @@ def add_temperatures(lib: Library, temperatures=(600.0, 900.0), seed=21, skip_ev
     return lib
 
 
+def add_fission_data(lib: Library, seed=41) -> Library:
+    """Gives the fissionable nuclides fission-neutron data as evaluated files have them instead of the scalar description:
+    a tabulated total nu (lin-lin), a prompt yield (tabulated, or a polynomial for every second nuclide), six delayed
+    groups with energy-dependent yields (one of them a histogram table), and product spectra of every kind -- prompt: Watt
+    with tabulated a(E), b(E) or a continuous tabular law; delayed: Maxwell, evaporation and continuous tabular.  The
+    nu-fission column of the derived table becomes total_nu(E) * fission as Nuclide::create_derived forms it."""
+    rng = np.random.Generator(np.random.PCG64([seed, 8]))
+    k = 0
+    for n in lib.nuclides:
+        if not n.fissionable:
+            continue
+        eg = np.array([1.0e-5, 1.0, 1.0e3, 1.0e5, 1.0e6, 4.0e6, 1.0e7, 2.0e7])
+        nu_t = n.nu_poly[0] + n.nu_poly[1] * eg + 0.02 * np.sin(np.log(eg))
+        total = Function1D(2, nu_t, eg, 2)
+        frac = 0.06 * np.array([0.1, 0.2, 0.2, 0.25, 0.15, 0.1])  # 6 % delayed: every group and law is sampled often
+        prods = []
+        dsum = np.zeros_like(eg)
+        for g in range(6):
+            yg = frac[g] * nu_t[0] * (1.0 - 0.3 * eg / 2.0e7) * (1.0 + 0.1 * g * (eg > 1.0e5))
+            dsum += yg
+            y = Function1D(2, yg, eg, 1 if g == 3 else 2)
+            if g % 3 == 0:
+                p = FissionProduct(y, 5, -2.0e7, Function1D(2, (0.25e6 + 2.0e4 * g) * (1 + 0.1 * np.log10(eg / 1e-5) / 12), eg, 2))
+            elif g % 3 == 1:
+                p = FissionProduct(y, 6, -2.0e7, Function1D(2, (0.4e6 + 1.0e4 * g) * (1 + 0.05 * np.log10(eg / 1e-5) / 12), eg, 2))
+            else:
+                p = FissionProduct(y, 1, energy=make_continuous_table(rng, 1.0e-5, 1.9e7, n_energy=3, discrete=False))
+                p.energy.x = np.abs(p.energy.x) * 0.05 + 1.0e3  # delayed neutrons: a few hundred keV
+                p.energy = _renormalise(p.energy)
+            prods.append(p)
+        if k % 2 == 0:
+            prompt_y = Function1D(2, nu_t - dsum, eg, 2)
+            prompt = FissionProduct(prompt_y, 7, -2.0e7, Function1D(2, n.watt_a * (1 + 0.02 * np.log10(eg / 1e-5)), eg, 2),
+                                    Function1D(2, n.watt_b * (1 - 0.01 * np.log10(eg / 1e-5)), eg, 2))
+        else:
+            prompt_y = Function1D(1, np.array([n.nu_poly[0] - dsum[0], n.nu_poly[1], -1.0e-16]))
+            tab = make_continuous_table(rng, 1.0e-5, 1.9e7, n_energy=4, discrete=False)
+            tab.x = np.abs(tab.x) * 0.3 + 1.0e4
+            prompt = FissionProduct(prompt_y, 1, energy=_renormalise(tab))
+        n.fission_products = [prompt] + prods
+        n.total_nu = total if k % 3 != 2 else None   # every third nuclide: no total nu, the prompt yield stands in
+        n.n_precursor = 6
+        nu_at = (n.total_nu or prompt_y)(n.energy)
+        n.xs = n.xs.copy()
+        n.xs[:, 3] = nu_at * n.xs[:, 2]
+        for m in (getattr(n, "more_temperatures", None) or []):
+            m.fission_products, m.total_nu, m.n_precursor = n.fission_products, n.total_nu, 6
+            m.xs = m.xs.copy()
+            m.xs[:, 3] = (n.total_nu or prompt_y)(m.energy) * m.xs[:, 2]
+        k += 1
+    return lib
+
+
+def _renormalise(t: Tabular2D) -> Tabular2D:
+    """pdf / cdf of every distribution recomputed for (possibly rescaled, re-sorted) abscissae, cdf ending at exactly 1"""
+    x, p, c = t.x.copy(), t.pdf.copy(), t.cdf.copy()
+    for k in range(len(t.energy)):
+        a, b = int(t.offset[k]), int(t.offset[k + 1])
+        xs = np.sort(x[a:b])
+        for j in range(1, xs.size):  # strictly increasing
+            if xs[j] <= xs[j - 1]:
+                xs[j] = xs[j - 1] * (1 + 1e-9) + 1e-9
+        pp = np.abs(p[a:b]) + 1e-30
+        if t.interpolation[k] == 1:
+            cc = np.concatenate([[0.0], np.cumsum(pp[:-1] * np.diff(xs))])
+        else:
+            cc = np.concatenate([[0.0], np.cumsum(0.5 * (pp[:-1] + pp[1:]) * np.diff(xs))])
+        pp, cc = pp / cc[-1], cc / cc[-1]
+        cc[-1] = 1.0
+        x[a:b], p[a:b], c[a:b] = xs, pp, cc
+    nd = None if t.n_discrete is None else np.zeros_like(t.n_discrete)
+    return Tabular2D(t.energy, t.offset, t.interpolation, x, p, c, nd, t.histogram_in_energy)
+
+
 def standard_materials(n_nuclides) -> list:
     """Material 0 fuel (UO2 3.1 %), 1 gap (He), 2 clad (Zr + generic alloying nuclides), 3 borated water.
     Indices follow `_BASE`; nuclides beyond the named ones are spread over clad and fuel like the
@@ -680,6 +788,29 @@ def _pack_table(d: Tabular2DDesc, t, keep):
         d.n_discrete = nd.ctypes.data
 
 
+class Function1DDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("interpolation", C.c_int32), ("reserved0", C.c_int32),
+                ("x", C.c_void_p), ("y", C.c_void_p)]
+
+
+class FissionProductDesc(C.Structure):
+    _fields_ = [("yield_", Function1DDesc), ("law", C.c_int32), ("reserved0", C.c_int32), ("u", C.c_double),
+                ("a", Function1DDesc), ("b", Function1DDesc), ("energy", Tabular2DDesc)]
+
+
+def _pack_function(d, f, keep):
+    if f is None:
+        return
+    y = np.ascontiguousarray(f.y, np.float64)
+    keep.append(y)
+    d.kind, d.n, d.interpolation, d.y = f.kind, y.size, f.interpolation, y.ctypes.data
+    if f.kind == 2:
+        x = np.ascontiguousarray(f.x, np.float64)
+        assert x.size == y.size and np.all(np.diff(x) > 0)
+        keep.append(x)
+        d.x = x.ctypes.data
+
+
 class NuclideDesc(C.Structure):
     _fields_ = [("n_grid", C.c_int32), ("fissionable", C.c_int32), ("awr", C.c_double), ("kT", C.c_double),
                 ("energy", C.c_void_p), ("xs", C.c_void_p), ("elastic", C.c_void_p),
@@ -694,7 +825,9 @@ class NuclideDesc(C.Structure):
                 ("corr_cdf", C.c_void_p), ("km_r", C.c_void_p), ("km_a", C.c_void_p), ("nbody_n", C.c_int32),
                 ("reserved1", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double),
                 ("inelastic_yield", C.c_double), ("n_more_reactions", C.c_int32), ("reserved2", C.c_int32),
-                ("more_reactions", C.c_void_p)]
+                ("more_reactions", C.c_void_p),
+                ("n_fission_products", C.c_int32), ("reserved3", C.c_int32), ("fission_products", C.c_void_p),
+                ("total_nu", Function1DDesc)]
 
 
 class ReactionDesc(C.Structure):
@@ -807,6 +940,18 @@ def pack_inelastic_law(d, n, keep):
             _pack_table(r.energy, x.energy, keep)
             _pack_product(r, x.law, x, keep)
         d.n_more_reactions, d.more_reactions = len(more), C.addressof(rd)
+    prods = getattr(n, "fission_products", None) or []
+    if prods:  # fission neutrons as a nuclide file has them
+        fd = (FissionProductDesc * len(prods))()
+        keep.append(fd)
+        for f, x in zip(fd, prods):
+            _pack_function(f.yield_, x.yield_, keep)
+            f.law, f.u = x.law, x.u
+            _pack_function(f.a, x.a, keep)
+            _pack_function(f.b, x.b, keep)
+            _pack_table(f.energy, x.energy, keep)
+        d.n_fission_products, d.fission_products = len(prods), C.addressof(fd)
+        _pack_function(d.total_nu, getattr(n, "total_nu", None), keep)
 
 
 class MaterialDesc(C.Structure):

@@ -230,7 +230,8 @@ def ref_load_library(r, libr: nucdata.Library):
                 _nd._pack_table(d, getattr(n, a, None), keep)
                 descs.append(d)
             r.ref_stage_tables(C.addressof(descs[0]), C.addressof(descs[1]), C.addressof(descs[2]), int(n.inelastic_in_cm))
-        if getattr(n, "inelastic_law", -1) >= 2 or getattr(n, "more_reactions", None) or getattr(n, "inelastic_yield", 1.0) != 1.0:
+        if getattr(n, "inelastic_law", -1) >= 2 or getattr(n, "more_reactions", None) or getattr(n, "inelastic_yield", 1.0) != 1.0 \
+                or getattr(n, "fission_products", None):
             from macaw_b200 import nucdata as _nd
             one = _nd.Library([n], [])
             ndesc, _, keep_l = _nd.pack_library(one)

@@ -206,6 +206,57 @@ struct Tabular2D
   }
 };
 
+// mcw_function1d: OMC Polynomial (endf.cpp:112-121) or Tabulated1D with one region, histogram or lin-lin (:156-210)
+struct Fn
+{
+  int kind = MCW_FN_NONE, interp = 2;
+  std::vector<double> x, y;
+  void take(const mcw_function1d& f)
+  {
+    kind = f.kind;
+    interp = f.interpolation;
+    x.clear(), y.clear();
+    if (kind == MCW_FN_NONE)
+      return;
+    y.assign(f.y, f.y + f.n);
+    if (kind == MCW_FN_TABULATED)
+      x.assign(f.x, f.x + f.n);
+  }
+  double operator()(double v) const
+  {
+    if (kind == MCW_FN_POLYNOMIAL)
+    {
+      double r = 0.0;
+      for (size_t k = y.size(); k-- > 0;)
+        r = r * v + y[k];
+      return r;
+    }
+    const int n = (int)x.size();
+    if (v < x[0])
+      return y[0];
+    if (v > x[n - 1])
+      return y[n - 1];
+    int i;
+    if (x[0] == v)
+      i = 0;
+    else
+      i = (int)(std::lower_bound(x.begin(), x.end(), v) - x.begin()) - 1;
+    if (interp == 1)
+      return y[i];
+    const double r = (v - x[i]) / (x[i + 1] - x[i]);
+    return y[i] + r * (y[i + 1] - y[i]);
+  }
+};
+
+// mcw_fission_product: one neutron product of the fission reaction
+struct FisProduct
+{
+  Fn yield, a, b;
+  int law = MCW_LAW_WATT;
+  double u = 0;
+  Tabular2D energy;
+};
+
 // One scattering reaction other than elastic (an entry of OMC Nuclide::index_inelastic_scatter_): threshold, the neutron
 // product's distribution and its multiplicity.  The nuclide's first one is the Nuclide itself (its base class: the
 // descriptor carries it inline), further ones are Nuclide::more.
@@ -252,17 +303,29 @@ struct Nuclide : RxLaw
   int urr_bands = 0, urr_inel_flag = -1, urr_multiply_smooth = 0;
   double urr_prob(int i_energy, int param, int band) const { return urr_table[((size_t)i_energy * 6 + param) * urr_bands + band]; }
 
+  // fission neutrons as a nuclide file has them (mcw_fission_product x (1 + n_precursor), total nu); empty: the scalars
+  std::vector<FisProduct> fis;
+  Fn total_nu_fn;
+
   // OMC endf.cpp:112-121 Polynomial (Horner, increasing powers) on nu_poly; nuclide.cpp:478-517
   double nu_total(double E) const
   {
+    if (!fis.empty())
+      return total_nu_fn.kind != MCW_FN_NONE ? total_nu_fn(E) : fis[0].yield(E); // :510-516
     double y = 0.0;
     y = y * E + nu_poly[1];
     y = y * E + nu_poly[0];
     return y;
   }
-  double nu_delayed(double) const
+  double nu_delayed(double E) const
   {
     double nu = 0.0;
+    if (!fis.empty())
+    {
+      for (size_t i = 1; i < fis.size(); ++i) // :494-503
+        nu += fis[i].yield(E);
+      return nu;
+    }
     for (int g = 0; g < n_precursor; ++g)
       nu += dyield[g];
     return nu;

@@ -733,6 +733,43 @@ static void inelastic_scatter(const RxLaw& nuc, double awr, Hist& p)
     p.wgt *= nuc.yield;
 }
 
+// the energy law of a fission-neutron product: WattEnergy / MaxwellEnergy / Evaporation::sample with tabulated parameters
+// and the restriction energy u (OMC distribution_energy.cpp:342-356, 279-291, 305-322), or ContinuousTabular (:150-275)
+static double fission_product_energy(const FisProduct& f, double E, uint64_t* seed)
+{
+  if (f.law == MCW_LAW_CONTINUOUS_TABULAR)
+    return continuous_tabular_sample(f.energy, E, seed);
+  if (f.law == MCW_LAW_WATT)
+  {
+    const double a = f.a(E), b = f.b(E);
+    while (true)
+    {
+      const double E_out = watt_spectrum(a, b, seed);
+      if (E_out <= E - f.u)
+        return E_out;
+    }
+  }
+  const double theta = f.a(E);
+  if (f.law == MCW_LAW_MAXWELL)
+    while (true)
+    {
+      const double E_out = maxwell_spectrum(theta, seed);
+      if (E_out <= E - f.u)
+        return E_out;
+    }
+  const double y = (E - f.u) / theta;
+  const double v = 1.0 - xexp(-y);
+  double x;
+  while (true)
+  {
+    const double r1 = prn(seed), r2 = prn(seed);
+    x = -xlog((1.0 - v * r1) * (1.0 - v * r2));
+    if (x <= y)
+      break;
+  }
+  return x * theta;
+}
+
 // OMC physics.cpp:1006-1071
 static void sample_fission_neutron(const Nuclide& nuc, double E_in, double E_max,
                                    mcw_source_site* site, uint64_t* seed)
@@ -747,7 +784,7 @@ static void sample_fission_neutron(const Nuclide& nuc, double E_in, double E_max
     int group;
     for (group = 1; group < nuc.n_precursor; ++group)
     {
-      prob += nuc.dyield[group - 1];
+      prob += nuc.fis.empty() ? nuc.dyield[group - 1] : nuc.fis[group].yield(E_in);
       if (xi < prob)
         break;
     }
@@ -761,7 +798,9 @@ static void sample_fission_neutron(const Nuclide& nuc, double E_in, double E_max
   {
     // OMC reaction_product.cpp:85-105 (single law) -> secondary_uncorrelated.cpp:54-68
     mu = uniform_distribution(-1., 1., seed);
-    if (site->delayed_group == 0)
+    if (!nuc.fis.empty())
+      site->E = fission_product_energy(nuc.fis[site->delayed_group], E_in, seed);
+    else if (site->delayed_group == 0)
       site->E = watt_spectrum(nuc.watt_a, nuc.watt_b, seed); // distribution_energy.cpp:342-356
     else
       site->E = maxwell_spectrum(nuc.dtheta[site->delayed_group - 1], seed); // :279-291
@@ -1423,6 +1462,20 @@ static Nuclide nuclide_from_desc(const mcw_nuclide_desc& d)
     N.dyield[g] = d.delayed_yield[g];
     N.dtheta[g] = d.delayed_theta[g];
   }
+  for (int k = 0; k < d.n_fission_products; ++k)
+  {
+    const mcw_fission_product& f = d.fission_products[k];
+    FisProduct F;
+    F.yield.take(f.yield);
+    F.a.take(f.a);
+    F.b.take(f.b);
+    F.law = f.law;
+    F.u = f.u;
+    F.energy.take(f.energy, true);
+    N.fis.push_back(std::move(F));
+  }
+  if (d.n_fission_products)
+    N.total_nu_fn.take(d.total_nu);
   N.watt_a = d.watt_a;
   N.watt_b = d.watt_b;
   N.q = d.q_fission;

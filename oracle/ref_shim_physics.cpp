@@ -75,6 +75,23 @@ void constant_function(memh5::Node* parent, const char* name, double v, double e
   d->attr("breakpoints", std::vector<int>{2});
   d->attr("interpolation", std::vector<int>{2});
 }
+// a mcw_function1d as the dataset endf.cpp read_function reads: Polynomial (coefficients) or Tabulated1D ((2, n) x / y with
+// one interpolation region)
+void function_dataset(memh5::Node* parent, const char* name, const mcw_function1d& f)
+{
+  if (f.kind == MCW_FN_POLYNOMIAL)
+  {
+    memh5::Node* d = parent->dataset(name, std::vector<double>(f.y, f.y + f.n));
+    d->attr("type", "Polynomial");
+    return;
+  }
+  std::vector<double> xy(f.x, f.x + f.n);
+  xy.insert(xy.end(), f.y, f.y + f.n);
+  memh5::Node* d = parent->dataset(name, xy, {2, (unsigned long long)f.n});
+  d->attr("type", "Tabulated1D");
+  d->attr("breakpoints", std::vector<int>{f.n});
+  d->attr("interpolation", std::vector<int>{f.interpolation});
+}
 void polynomial(memh5::Node* parent, const char* name, const std::vector<double>& coef)
 {
   memh5::Node* d = parent->dataset(name, coef);
@@ -316,6 +333,7 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     }
   }
   g_el_angle = g_inel_angle = g_inel_energy = nullptr;
+  const mcw_nuclide_desc* g_fis = g_law; // the staged descriptor also carries the fission products
   g_law = nullptr;
   if (g_urr)
   {
@@ -333,6 +351,53 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
   if (fission)
   {
     memh5::Node* f = r_fis = reaction(rxs, 18, q_fission, false, temp, fission, G, 0);
+    if (g_fis && g_fis->n_fission_products > 0)
+    {
+      // fission neutrons as a nuclide file has them: every product with its yield function and its own energy law, read by
+      // the reference's ReactionProduct / WattEnergy / MaxwellEnergy / Evaporation / ContinuousTabular constructors
+      for (int k = 0; k < g_fis->n_fission_products; ++k)
+      {
+        const mcw_fission_product& P = g_fis->fission_products[k];
+        memh5::Node* p = f->group("product_" + std::to_string(k));
+        p->attr("particle", "neutron");
+        p->attr("emission_mode", k == 0 ? "prompt" : "delayed");
+        if (k > 0)
+          p->attr("decay_rate", 1.0);
+        p->attr("n_distribution", 1);
+        function_dataset(p, "yield", P.yield);
+        memh5::Node* d = p->group("distribution_0");
+        d->attr("type", "uncorrelated");
+        memh5::Node* en = d->group("energy");
+        if (P.law == MCW_LAW_CONTINUOUS_TABULAR)
+        {
+          const mcw_tabular2d& t = P.energy;
+          en->attr("type", "continuous");
+          memh5::Node* ee = en->dataset("energy", std::vector<double>(t.energy, t.energy + t.n_energy));
+          ee->attr("interpolation", std::vector<int>{t.n_energy, t.histogram_in_energy ? 1 : 2}, {2, 1});
+          memh5::Node* dd = table_dataset(en, "distribution", t);
+          std::vector<int> nd(t.n_energy, 0);
+          if (t.n_discrete)
+            nd.assign(t.n_discrete, t.n_discrete + t.n_energy);
+          dd->attr("n_discrete_lines", nd);
+        }
+        else
+        {
+          en->attr("type", P.law == MCW_LAW_WATT ? "watt" : (P.law == MCW_LAW_MAXWELL ? "maxwell" : "evaporation"));
+          en->attr("u", P.u);
+          if (P.law == MCW_LAW_WATT)
+          {
+            function_dataset(en, "a", P.a);
+            function_dataset(en, "b", P.b);
+          }
+          else
+            function_dataset(en, "theta", P.a);
+        }
+      }
+      if (g_fis->total_nu.kind != MCW_FN_NONE)
+        function_dataset(g->group("total_nu"), "yield", g_fis->total_nu);
+    }
+    else
+    {
     const double e0 = energy[0], e1 = energy[G - 1];
     double nu_d = 0.0;
     for (int k = 0; k < n_precursor; ++k)
@@ -353,6 +418,7 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
     for (int k = 0; k < n_precursor; ++k)
       f->children.at("product_" + std::to_string(k + 1))->attr("decay_rate", 1.0);
     polynomial(g->group("total_nu"), "yield", {nu_poly[0], nu_poly[1]});
+    }
   }
   // further temperatures: kTs / energy / every reaction's xs (/ urr) under their own `<T>K`
   std::vector<double> temps{(double)T};

@@ -626,7 +626,7 @@ def test_scoring_against_reference_tally_scoring_cpp(oracle_bridge, use_universe
 
 
 def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, thermal=False, urr=False, reactions=False,
-                       temperatures=False):
+                       temperatures=False, fission=False):
     """A 9-nuclide synthetic library loaded into the reference's own data objects; the oracle gets the reference's derived
     tables, so both sides hold the same numbers.  One material is given <isotropic> flags.  tabular: the nuclides carry
     tabulated angular distributions and ContinuousTabular laws, read by the reference's own AngleDistribution /
@@ -649,6 +649,11 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
         lib.materials[3].isotropic = None
     if urr:      # probability tables, read by the reference's own UrrData constructor
         nucdata.add_urr_tables(lib)
+    if fission:
+        # fission neutrons as evaluated files have them: tabulated total nu and yields, six delayed groups, Watt / Maxwell /
+        # evaporation spectra with tabulated parameters and continuous tabular spectra -- read by the reference's own
+        # ReactionProduct / Tabulated1D / WattEnergy / MaxwellEnergy / Evaporation / ContinuousTabular constructors
+        nucdata.add_fission_data(lib)
     if temperatures:  # data sets at 600 K and 900 K with their own grids (and probability tables), read by the reference's
         nucdata.add_temperatures(lib)  # own Nuclide / Reaction / UrrData constructors for every temperature of `kTs`
     generator = [n.xs.copy() for n in lib.nuclides]
@@ -688,7 +693,7 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures", "fission"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -719,10 +724,11 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     temperatures = tabular == "temperatures"
     if temperatures and not hasattr(r, "ref_stage_temperature_set"):
         pytest.skip("oracle/_ref built without the temperature-set doorway")
-    reactions = tabular == "reactions" or temperatures
-    urr = urr or temperatures
+    fission = tabular == "fission"
+    reactions = tabular == "reactions" or temperatures or fission
+    urr = urr or temperatures or fission
     lib, _, tables = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
-                                        reactions=reactions, temperatures=temperatures)
+                                        reactions=reactions, temperatures=temperatures, fission=fission)
     rx_seen = np.zeros(8, np.int64)
     o_reset = np.zeros(8, np.int64)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
@@ -784,6 +790,9 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
         seen["absorbed"] += int((st[:, 4] == 0).sum())
         seen["sites"] += len(sites)
         seen["delayed"] += int((sites[:, 4] > 0).sum())
+        if fission:
+            for g in range(7):  # prompt and every delayed group: Watt / continuous, Maxwell, evaporation, continuous, ...
+                seen[f"group {g}"] = seen.get(f"group {g}", 0) + int((sites[:, 4] == g).sum())
         seen["upscatter"] += int(((st[:, 0] > E) & (st[:, 4] > 0)).sum())
         seen["inelastic"] += int(((st[:, 0] < 0.5 * E) & (E > 1e6) & (st[:, 4] > 0)).sum())
         if reactions:  # st[4] = alive * weight: the continuum reaction of every third nuclide multiplies the weight by 1.25
