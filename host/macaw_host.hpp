@@ -73,6 +73,33 @@ struct Tabular2D
     return t;
   }
 };
+// mcw_function1d: a Polynomial or a one-region Tabulated1D (OMC endf.h Function1D)
+struct Function1D
+{
+  int kind = MCW_FN_NONE, interpolation = 2;
+  std::vector<double> x, y;
+  mcw_function1d desc() const
+  {
+    mcw_function1d f{};
+    f.kind = kind, f.n = (int32_t)y.size(), f.interpolation = interpolation;
+    f.x = x.empty() ? nullptr : x.data(), f.y = y.data();
+    return f;
+  }
+};
+// One neutron product of the fission reaction (mcw_fission_product): prompt, or a delayed group
+struct FissionProduct
+{
+  Function1D yield, a, b;
+  int law = MCW_LAW_WATT;
+  double u = 0;
+  Tabular2D energy;
+  mcw_fission_product desc() const
+  {
+    mcw_fission_product f{};
+    f.yield = yield.desc(), f.law = law, f.u = u, f.a = a.desc(), f.b = b.desc(), f.energy = energy.desc();
+    return f;
+  }
+};
 // A scattering reaction after a nuclide's first (mcw_reaction_desc; OMC Nuclide::index_inelastic_scatter_ order)
 struct Reaction
 {
@@ -111,6 +138,9 @@ struct Nuclide
   double inelastic_yield = 1.0;
   std::vector<Reaction> more_reactions;
   mutable std::vector<mcw_reaction_desc> more_descs; // filled by Library::nuclideDescs(), which hands out pointers into it
+  std::vector<FissionProduct> fission_products;      // fission neutrons as a nuclide file has them (empty: the scalars in d)
+  Function1D total_nu;
+  mutable std::vector<mcw_fission_product> fission_descs;
   mcw_nuclide_desc d{}; // scalar fields; the pointers are filled by Library::descs()
 };
 struct Material
@@ -206,6 +236,12 @@ struct Library
         n.more_descs.push_back(r.desc());
       d.n_more_reactions = (int32_t)n.more_descs.size();
       d.more_reactions = n.more_descs.empty() ? nullptr : n.more_descs.data();
+      n.fission_descs.clear();
+      for (const auto& f : n.fission_products)
+        n.fission_descs.push_back(f.desc());
+      d.n_fission_products = (int32_t)n.fission_descs.size();
+      d.fission_products = n.fission_descs.empty() ? nullptr : n.fission_descs.data();
+      d.total_nu = n.total_nu.desc();
       out.push_back(d);
     }
     return out;

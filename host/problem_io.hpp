@@ -132,6 +132,42 @@ public:
       table("el_angle", n.elastic_angle);
       table("inel_angle", n.inelastic_angle);
       table("inel_energy", n.inelastic_energy);
+      if (has(p + "fis.head"))
+      {
+        // fission neutrons as a nuclide file has them: fis.head = count, laws; fis.u; functions as [kind, interpolation] +
+        // x + y (fis.nu total nu, fis<j>.y yield, .a, .b); continuous tabular spectra fis<j>.en like the nuclide's tables
+        auto fn = [&](const std::string& key, Function1D& f) {
+          if (!has(p + key))
+            return;
+          const auto v = f64(p + key);
+          f.kind = (int)v[0], f.interpolation = (int)v[1];
+          const size_t m = v.size() - 2;
+          if (f.kind == MCW_FN_TABULATED)
+          {
+            f.x.assign(v.begin() + 2, v.begin() + 2 + m / 2);
+            f.y.assign(v.begin() + 2 + m / 2, v.end());
+          }
+          else
+            f.y.assign(v.begin() + 2, v.end());
+        };
+        const auto head = i32(p + "fis.head");
+        const auto us = f64(p + "fis.u");
+        fn("fis.nu", n.total_nu);
+        const int keep_cm = n.inelastic_in_cm;
+        for (int j = 0; j < head[0]; ++j)
+        {
+          const std::string q = "fis" + std::to_string(j) + ".";
+          FissionProduct F;
+          F.law = head[1 + j];
+          F.u = us[j];
+          fn(q + "y", F.yield);
+          fn(q + "a", F.a);
+          fn(q + "b", F.b);
+          table(q + "en", F.energy);
+          n.fission_products.push_back(std::move(F));
+        }
+        n.inelastic_in_cm = keep_cm;
+      }
       if (has(p + "rx.head"))
       {
         // the scattering reactions after the first: rx<j>.i = mt, threshold, law, in_cm, n_particles; rx<j>.f =

@@ -52,6 +52,20 @@ struct HostUrr // one mcw_urr_desc, copied
   int n_band = 0, inel_flag = -1, multiply_smooth = 0;
 };
 
+struct HostFn // mcw_function1d, copied
+{
+  int kind = MCW_FN_NONE, interp = 2;
+  std::vector<double> x, y;
+};
+
+struct HostFis // mcw_fission_product, copied
+{
+  HostFn yield, a, b;
+  int law = MCW_LAW_WATT;
+  double u = 0;
+  HostTable energy;
+};
+
 struct HostRx // one scattering reaction after a nuclide's first (mcw_reaction_desc), copied
 {
   McwRxParams prm;
@@ -73,6 +87,8 @@ struct HostNuclide
   HostTable el_angle, inel_angle, inel_energy;
   HostTable law; // correlated: one angular distribution per point of inel_energy; Kalbach-Mann: one entry, x = r, p = a
   double inel_yield = 1.0;
+  std::vector<HostFis> fis; // fission neutrons as a nuclide file has them (empty: the scalar description)
+  HostFn total_nu;
 };
 
 // copies and checks one table of the descriptor; returns an error text or nullptr
@@ -108,6 +124,32 @@ static const char* take_table(const mcw_tabular2d& t, HostTable& out, bool conti
   out.x.assign(t.x, t.x + total);
   out.p.assign(t.pdf, t.pdf + total);
   out.c.assign(t.cdf, t.cdf + total);
+  return nullptr;
+}
+
+// copies and checks one function; returns an error text or nullptr
+static const char* take_fn(const mcw_function1d& f, HostFn& out, bool required)
+{
+  out = HostFn();
+  if (f.kind == MCW_FN_NONE)
+    return required ? "fission product: a function it needs is missing" : nullptr;
+  if ((f.kind != MCW_FN_POLYNOMIAL && f.kind != MCW_FN_TABULATED) || f.n < 1 || !f.y)
+    return "function: polynomial or tabulated, with its values";
+  out.kind = f.kind;
+  out.y.assign(f.y, f.y + f.n);
+  if (f.kind == MCW_FN_TABULATED)
+  {
+    if (f.n < 2 || !f.x)
+      return "tabulated function: needs >= 2 points";
+    if (f.interpolation != 1 && f.interpolation != 2)
+      // OMC endf.cpp:190-205 also knows lin-log, log-lin and log-log
+      return "tabulated function: only histogram and linear-linear interpolation are carried";
+    out.interp = f.interpolation;
+    out.x.assign(f.x, f.x + f.n);
+    for (int k = 1; k < f.n; ++k)
+      if (!(out.x[k] > out.x[k - 1]))
+        return "tabulated function: abscissae must increase";
+  }
   return nullptr;
 }
 
@@ -657,6 +699,38 @@ static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNucli
         R.angle = HostTable();
       N.more.push_back(std::move(R));
     }
+    if (!bad && d[i].n_fission_products > 0)
+    {
+      // fission neutrons as a nuclide file has them: prompt + one product per delayed group
+      if (!N.prm.fissionable || !d[i].fission_products || d[i].n_fission_products != 1 + d[i].n_precursor)
+        bad = "fission products: needs a fissionable nuclide and 1 + n_precursor products";
+      for (int k = 0; !bad && k < d[i].n_fission_products; ++k)
+      {
+        const mcw_fission_product& f = d[i].fission_products[k];
+        HostFis F;
+        F.law = f.law;
+        F.u = f.u;
+        bad = take_fn(f.yield, F.yield, true);
+        if (!bad && f.law == MCW_LAW_CONTINUOUS_TABULAR)
+        {
+          bad = take_table(f.energy, F.energy, true);
+          if (!bad && F.energy.energy.empty())
+            bad = "fission product: continuous tabular law without its table";
+        }
+        else if (!bad && (f.law == MCW_LAW_WATT || f.law == MCW_LAW_MAXWELL || f.law == MCW_LAW_EVAPORATION))
+        {
+          bad = take_fn(f.a, F.a, true);
+          if (!bad && f.law == MCW_LAW_WATT)
+            bad = take_fn(f.b, F.b, true);
+        }
+        else if (!bad)
+          // OMC secondary_uncorrelated.cpp:47 "Energy distribution type '...' not implemented."
+          bad = "fission product: energy law not implemented (Watt, Maxwell, evaporation, continuous tabular)";
+        N.fis.push_back(std::move(F));
+      }
+      if (!bad)
+        bad = take_fn(d[i].total_nu, N.total_nu, false);
+    }
     if (bad)
       return fail(h, MCW_E_INVALID_ARGUMENT, std::string("mcw_set_library: ") + bad);
     nuclides.push_back(std::move(N));
@@ -700,7 +774,7 @@ int mcw_add_temperature_set(mcw_handle h, int nuclide, const mcw_nuclide_desc* s
     return rc;
   const HostNuclide& base = h->nuclides[nuclide];
   if ((one[0].prm.n_inel != 0) != (base.prm.n_inel != 0) || one[0].more.size() != base.more.size() ||
-      one[0].prm.fissionable != base.prm.fissionable)
+      one[0].prm.fissionable != base.prm.fissionable || one[0].fis.size() != base.fis.size())
     // every reaction has a cross section at every temperature (OMC reaction.cpp:25-50)
     return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_add_temperature_set: the data set must hold the same reactions as the nuclide");
   for (int e : base.sets)
@@ -1108,7 +1182,7 @@ static int prepare(mcw_handle h)
       rare |= !tl.nuclides.empty();
     for (const auto& n : h->nuclides)
       rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty() ||
-              (n.prm.n_inel && (n.prm.inel_law >= MCW_LAW_CORRELATED || !n.more.empty() || n.inel_yield != 1.0));
+              (n.prm.n_inel && (n.prm.inel_law >= MCW_LAW_CORRELATED || !n.more.empty() || n.inel_yield != 1.0)) || !n.fis.empty();
     h->rare = rare || h->force_rare > 0;
   }
 
@@ -1146,6 +1220,15 @@ static int prepare(mcw_handle h)
   };
   std::vector<McwRxParams> rx;
   std::vector<double> rx_xs;
+  std::vector<McwFisProduct> fis;
+  std::vector<double> fn_pool;
+  auto add_fn = [&](const HostFn& f) {
+    McwFn o;
+    o.kind = f.kind, o.n = (int32_t)f.y.size(), o.interp = f.interp, o.off = (int32_t)fn_pool.size();
+    fn_pool.insert(fn_pool.end(), f.x.begin(), f.x.end()); // tabulated: x[n] then y[n]; polynomial: y[n]
+    fn_pool.insert(fn_pool.end(), f.y.begin(), f.y.end());
+    return o;
+  };
   std::vector<double> urr_pool;
   int n_urr = 0;
   for (auto& n : h->nuclides)
@@ -1170,6 +1253,21 @@ static int prepare(mcw_handle h)
     {
       int32_t count;
       add_table(n.law, n.prm.law_first, count);
+    }
+    // fission neutrons as a nuclide file has them: functions into fn_pool, continuous tabular spectra into the tab_* pools
+    n.prm.fis_first = n.fis.empty() ? -1 : (int32_t)fis.size();
+    n.prm.fis_pad = 0;
+    n.prm.total_nu = add_fn(n.total_nu);
+    for (const HostFis& f : n.fis)
+    {
+      McwFisProduct F;
+      memset(&F, 0, sizeof(F));
+      F.yield = add_fn(f.yield), F.a = add_fn(f.a), F.b = add_fn(f.b);
+      F.u = f.u;
+      F.law = f.law;
+      add_table(f.energy, F.en_first, F.en_n);
+      F.en_hist = f.energy.hist;
+      fis.push_back(F);
     }
     // the scattering reactions: the inline one again, then the further ones with their tables and cross sections
     n.prm.rx_first = (int32_t)rx.size();
@@ -1289,6 +1387,11 @@ static int prepare(mcw_handle h)
     CK(dev_upload(h, &d_rx, rx));
     CK(dev_upload(h, &d_rxx, rx_xs));
     P.lib.rx = d_rx, P.lib.rx_xs = d_rxx;
+    McwFisProduct* d_fis;
+    double* d_fn;
+    CK(dev_upload(h, &d_fis, fis));
+    CK(dev_upload(h, &d_fn, fn_pool));
+    P.lib.fis = d_fis, P.lib.fn_pool = d_fn;
   }
   {
     // thermal scattering: tables into one pool, per material entry its table and bound fraction

@@ -326,6 +326,43 @@ MCW_D void mcw_sab_apply(const McwLibraryDev& L, int q, int i_sab, double E, Mic
 }
 
 // ---- unresolved-resonance probability tables (OMC nuclide.cpp:753-759, 795-924)
+// mcw_function1d: Polynomial (OMC endf.cpp:112-121, Horner over increasing powers) or Tabulated1D with one region,
+// histogram or lin-lin, constant outside its range (:156-210)
+MCW_D double mcw_fn_eval(const McwLibraryDev& L, const McwFn& f, double v)
+{
+  const double* __restrict__ p = L.fn_pool + f.off;
+  if (f.kind == MCW_FN_POLYNOMIAL)
+  {
+    double r = 0.0;
+    for (int k = f.n - 1; k >= 0; --k)
+      r = r * v + __ldg(p + k);
+    return r;
+  }
+  const double* __restrict__ y = p + f.n;
+  if (v < __ldg(p))
+    return __ldg(y);
+  if (v > __ldg(p + f.n - 1))
+    return __ldg(y + f.n - 1);
+  const int i = mcw_lower_bound_index(p, f.n, v);
+  if (f.interp == 1)
+    return __ldg(y + i);
+  const double x0 = __ldg(p + i), x1 = __ldg(p + i + 1), y0 = __ldg(y + i), y1 = __ldg(y + i + 1);
+  const double r = (v - x0) / (x1 - x0);
+  return y0 + r * (y1 - y0);
+}
+
+// Nuclide::nu(E, total) (OMC nuclide.cpp:510-516): the total-nu function, else the prompt yield; scalar description: the
+// polynomial nu_poly
+MCW_D double mcw_nu_total(const McwLibraryDev& L, const McwNucParams& n, double E)
+{
+  if (MCW_RARE && n.fis_first >= 0)
+    return mcw_fn_eval(L, n.total_nu.kind != MCW_FN_NONE ? n.total_nu : L.fis[n.fis_first].yield, E);
+  double nu = 0.0; // Polynomial (OMC endf.cpp:112-121): Horner, increasing powers
+  nu = nu * E + n.nu_poly[1];
+  nu = nu * E + n.nu_poly[0];
+  return nu;
+}
+
 // true when nuclide i_nuc has tables and E lies strictly inside their range
 MCW_D bool mcw_urr_in_range(const McwLibraryDev& L, int i_nuc, double E)
 {
@@ -386,10 +423,7 @@ __device__ __noinline__ void mcw_urr_apply_ool(const McwLibraryDev* Lg, int i_nu
   out5[0] = elastic + inelastic + capture + fission;
   out5[1] = capture + fission;
   out5[2] = fission;
-  double nu = 0.0; // Polynomial (OMC endf.cpp:112-121): Horner, increasing powers
-  nu = nu * E + n.nu_poly[1];
-  nu = nu * E + n.nu_poly[0];
-  out5[3] = nu * fission;
+  out5[3] = mcw_nu_total(L, n, E) * fission;
   out5[4] = elastic;
 }
 MCW_D void mcw_urr_apply(const McwLibraryDev& L, int i_nuc, double E, uint64_t seed, Micro& m, double& elastic)

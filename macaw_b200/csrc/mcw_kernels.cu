@@ -324,7 +324,7 @@ MCW_D bool mcw_collide_history(const McwParams& P, int i, bool valid)
     site.progeny_id = c.n_progeny++;
     site.surf_id = 0;
     site.elem = elem;
-    mcw_sample_fission_neutron(nuc, c.E, L.E_max, site, c.seed);
+    mcw_sample_fission_neutron(L, nuc, c.E, L.E_max, site, c.seed);
     const unsigned long long bank_slot = base + k;
     if ((int64_t)bank_slot < P.bank_capacity)
       P.bank[bank_slot] = site;

@@ -863,10 +863,97 @@ __device__ __noinline__ int mcw_pick_reaction(const McwLibraryDev* Lp, int i_nuc
   return pick;
 }
 
+// sample_fission_neutron (OMC physics.cpp:1006-1071) on fission data as a nuclide file has them (mcw_fission_product):
+// beta from the yield functions, the group by the delayed yields, the product's own energy law -- WattEnergy / MaxwellEnergy
+// / Evaporation::sample with tabulated parameters and restriction energy (distribution_energy.cpp:342-356, 279-291,
+// 305-322) or ContinuousTabular -- resampled while E >= E_max.  Returns (E, mu), the group in *group_out.  Out of line.
+__device__ __noinline__ double2 mcw_fission_neutron_general(const McwLibraryDev* Lp, int i_nuc, double E_in, int* group_out,
+                                                            uint64_t* seed_io)
+{
+  const McwLibraryDev& L = *Lp;
+  const McwNucParams& nuc = L.nuc[i_nuc];
+  const McwFisProduct* fp = L.fis + nuc.fis_first;
+  uint64_t seed = *seed_io;
+  const double nu_t = mcw_nu_total(L, nuc, E_in);
+  double nu_d = 0.0;
+  for (int g = 1; g <= nuc.n_precursor; ++g)
+    nu_d += mcw_fn_eval(L, fp[g].yield, E_in);
+  const double beta = nu_d / nu_t;
+  int group = 0;
+  if (mcw_prn(seed) < beta)
+  {
+    const double xi = mcw_prn(seed) * nu_d;
+    double prob = 0.0;
+    for (group = 1; group < nuc.n_precursor; ++group)
+    {
+      prob += mcw_fn_eval(L, fp[group].yield, E_in);
+      if (xi < prob)
+        break;
+    }
+    group = min(group, nuc.n_precursor);
+  }
+  const McwFisProduct& f = fp[group];
+  double pa = 0.0, pb = 0.0; // the law's parameters at E_in
+  if (f.law != MCW_LAW_CONTINUOUS_TABULAR)
+  {
+    pa = mcw_fn_eval(L, f.a, E_in);
+    if (f.law == MCW_LAW_WATT)
+      pb = mcw_fn_eval(L, f.b, E_in);
+  }
+  double mu, Eo;
+  while (true)
+  {
+    mu = mcw_uniform(-1., 1., seed); // secondary_uncorrelated.cpp:54-68
+    if (f.law == MCW_LAW_CONTINUOUS_TABULAR)
+      Eo = mcw_continuous_tabular_sample(L, f.en_first, f.en_n, f.en_hist != 0, E_in, seed);
+    else if (f.law == MCW_LAW_WATT)
+    {
+      do
+        Eo = mcw_watt_spectrum(pa, pb, seed);
+      while (!(Eo <= E_in - f.u));
+    }
+    else if (f.law == MCW_LAW_MAXWELL)
+    {
+      do
+        Eo = mcw_maxwell_spectrum(pa, seed);
+      while (!(Eo <= E_in - f.u));
+    }
+    else
+    {
+      const double y = (E_in - f.u) / pa;
+      const double v = 1.0 - mcw_exp(-y);
+      double x;
+      do
+      {
+        const double r1 = mcw_prn(seed), r2 = mcw_prn(seed);
+        x = -mcw_log_c((1.0 - v * r1) * (1.0 - v * r2));
+      } while (!(x <= y));
+      Eo = x * pa;
+    }
+    if (Eo < L.E_max)
+      break;
+  }
+  *seed_io = seed;
+  *group_out = group;
+  return make_double2(Eo, mu);
+}
+
 // OMC physics.cpp:1006-1071
-MCW_D void mcw_sample_fission_neutron(const McwNucParams& nuc, double E_in, double E_max,
+MCW_D void mcw_sample_fission_neutron(const McwLibraryDev& L, const McwNucParams& nuc, double E_in, double E_max,
                                       mcw_source_site& site, uint64_t& seed)
 {
+  if (MCW_RARE && nuc.fis_first >= 0)
+  {
+    int group;
+    const double2 em = mcw_fission_neutron_general(L.self_dev, (int)(&nuc - L.nuc), E_in, &group, &seed);
+    site.delayed_group = group;
+    site.E = em.x;
+    V3 u = mcw_rotate_angle(v3(1., 0., 0.), em.y, seed);
+    site.u[0] = u.x;
+    site.u[1] = u.y;
+    site.u[2] = u.z;
+    return;
+  }
   double nu_t = 0.0;
   nu_t = nu_t * E_in + nuc.nu_poly[1]; // OMC endf.cpp:112-121 Horner
   nu_t = nu_t * E_in + nuc.nu_poly[0];

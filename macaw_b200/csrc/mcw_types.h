@@ -21,6 +21,20 @@
 #define MCW_NBR_SHIFT 3       // side code = neighbour << 3 | back side
 #define MCW_MAX_ELEMS (1ll << 28)
 
+// mcw_function1d on the device: values in McwLibraryDev::fn_pool at `off` -- tabulated: x[n] then y[n]; polynomial: y[n]
+struct McwFn
+{
+  int32_t kind, n, interp, off;
+};
+
+// mcw_fission_product on the device; the continuous tabular law's table sits in the tab_* pools like every other
+struct McwFisProduct
+{
+  McwFn yield, a, b;
+  double u;
+  int32_t law, en_first, en_n, en_hist;
+};
+
 struct McwNucParams
 {
   double awr, kT;
@@ -54,6 +68,10 @@ struct McwNucParams
   // [rx_first, rx_first + 1 + n_rx_more); the first is the inline reaction above again (the common kernel build reads the
   // inline fields only: level law, yield 1), the others exist only in problems that run on the full build
   int32_t rx_first, n_rx_more;
+  // fission neutrons as a nuclide file has them: McwLibraryDev::fis[fis_first + 0] prompt, [+ g] delayed group g, and the
+  // total nu (kind 0: the prompt yield); fis_first < 0: the scalar description above.  Full kernel build only.
+  int32_t fis_first, fis_pad;
+  McwFn total_nu;
 };
 
 // One scattering reaction (mcw_reaction_desc, or the nuclide's inline one): what inelastic_scatter needs
@@ -102,6 +120,8 @@ struct McwLibraryDev
   const int32_t* tab_interp;
   const int32_t* tab_ndisc;
   const double *tab_x, *tab_p, *tab_c;
+  const McwFisProduct* fis; // fission-neutron products (McwNucParams::fis_first)
+  const double* fn_pool;    // values of every McwFn
   const McwRxParams* rx; // scattering reactions of all nuclides (McwNucParams::rx_first)
   const double* rx_xs;   // cross sections of the reactions after each nuclide's first, from their thresholds on
   // thermal scattering: tables, their pools, and per material entry the table (-1 = none) and the bound fraction

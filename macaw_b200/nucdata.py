@@ -643,7 +643,10 @@ def add_temperatures(lib: Library, temperatures=(600.0, 900.0), seed=21, skip_ev
                     total = total + np.concatenate([np.zeros(r2.threshold), r2.xs])
             xs = np.zeros((e.size, 5))
             xs[:, 0], xs[:, 1], xs[:, 2] = total, fission + capture, fission
-            xs[:, 3] = (n.nu_poly[1] * e + n.nu_poly[0]) * fission if n.fissionable else 0.0
+            if n.fissionable and getattr(n, "fission_products", None):  # create_derived: nu(E, total) * fission
+                xs[:, 3] = (n.total_nu or n.fission_products[0].yield_)(e) * fission
+            else:
+                xs[:, 3] = (n.nu_poly[1] * e + n.nu_poly[0]) * fission if n.fissionable else 0.0
             m.xs = xs
             n.more_temperatures.append(m)
             if i in urr_of:

@@ -65,6 +65,27 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
                 lf = np.concatenate([lf, n.km_r, n.km_a])
             r[f"nuc{k}.law.i"] = np.asarray(li, np.int32)
             r[f"nuc{k}.law.f"] = np.asarray(lf, np.float64)
+        # fission neutrons as a nuclide file has them: products (prompt, delayed groups) and the total nu
+        prods = getattr(n, "fission_products", None) or []
+
+        def fn(key, f):  # a mcw_function1d: [kind, interpolation] + x + y
+            if f is not None:
+                r[key] = np.concatenate([[f.kind, f.interpolation], [] if f.x is None else f.x, f.y]).astype(np.float64)
+        if prods:
+            r[f"nuc{k}.fis.head"] = np.array([len(prods)] + [p.law for p in prods], np.int32)
+            r[f"nuc{k}.fis.u"] = np.array([p.u for p in prods], np.float64)
+            fn(f"nuc{k}.fis.nu", getattr(n, "total_nu", None))
+            for j, pr in enumerate(prods):
+                q = f"nuc{k}.fis{j}."
+                fn(q + "y", pr.yield_)
+                fn(q + "a", pr.a)
+                fn(q + "b", pr.b)
+                t = pr.energy
+                if t is not None:
+                    nd = t.n_discrete if t.n_discrete is not None else np.zeros(len(t.energy), np.int32)
+                    r[q + "en.i"] = np.concatenate([[int(t.histogram_in_energy), 0], t.offset, t.interpolation, nd]).astype(np.int32)
+                    r[q + "en.e"] = np.ascontiguousarray(t.energy, np.float64)
+                    r[q + "en.xpc"] = np.concatenate([t.x, t.pdf, t.cdf]).astype(np.float64)
         # the scattering reactions after the first (mcw_reaction_desc) and the first one's yield
         more = getattr(n, "more_reactions", None) or []
         if more or getattr(n, "inelastic_yield", 1.0) != 1.0:

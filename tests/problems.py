@@ -139,6 +139,14 @@ def pin_cell_tet_reactions(**kw):
     return mesh, nucdata.add_reactions(lib), bm, s
 
 
+def pin_cell_tet_fission(**kw):
+    """Fission neutrons as evaluated files have them (tabulated total nu and yields, six delayed groups with Maxwell /
+    evaporation / continuous tabular spectra, prompt Watt with tabulated parameters or continuous tabular), on top of the
+    reaction lists and tabulated distributions."""
+    mesh, lib, bm, s = pin_cell_tet_reactions(**kw)
+    return mesh, nucdata.add_fission_data(lib), bm, s
+
+
 def pin_cell_tet_temperatures(**kw):
     """Several temperatures per nuclide (data sets at 293.6 / 600 / 900 K with their own grids, reaction lists and
     probability tables; every fourth nuclide keeps one set) and a temperature FIELD on the mesh, hot in the middle of the
@@ -146,6 +154,7 @@ def pin_cell_tet_temperatures(**kw):
     data set is the one nearest to the element's temperature (OMC nuclide.cpp:614-626, MC CollisionKernel.C:109)."""
     urr = kw.pop("urr", True)  # False: no probability tables, so that the staged (tile) refresh kernels run as well
     mesh, lib, bm, s = pin_cell_tet_reactions(**kw)
+    nucdata.add_fission_data(lib)  # before the temperature sets, which share the nuclide's fission data
     nucdata.add_temperatures(nucdata.add_urr_tables(lib) if urr else lib)
     c = mesh.xyz[mesh.conn].mean(axis=1)
     r = np.hypot(c[:, 0], c[:, 1])
@@ -203,7 +212,7 @@ def check_full_bank(r, rec, bank, n):
     assert np.isfinite(bank["E"]).all() and (bank["E"] > 0).all()
 
 
-PROBLEMS = {"pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+PROBLEMS = {"pin_cell_tet_fission": pin_cell_tet_fission, "pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
             "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,

@@ -188,6 +188,9 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     # lists of scattering reactions with yields (further levels, continuum with a non-integral multiplicity, (n,2n))
     ("pin_cell_tet_reactions", {}, EVENT), ("pin_cell_tet_reactions", {}, FUSED), ("pin_cell_tet_reactions", {}, PUMP),
     ("pin_cell_tet_reactions", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # fission neutrons as nuclide files have them (function yields, total nu, Watt / Maxwell / evaporation / tabular spectra)
+    ("pin_cell_tet_fission", {}, EVENT), ("pin_cell_tet_fission", {}, FUSED), ("pin_cell_tet_fission", {}, PUMP),
+    ("pin_cell_tet_fission", {"n_particles": 20000}, {"tail_threshold": 3000}),
     # several temperatures per nuclide (own grids, reaction lists, probability tables) under a temperature field: every
     # element's temperature picks each nuclide's nearest data set
     ("pin_cell_tet_temperatures", {}, EVENT), ("pin_cell_tet_temperatures", {}, FUSED),
