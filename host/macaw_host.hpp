@@ -109,9 +109,12 @@ struct Reaction
   Tabular2D angle, energy;
   std::vector<int32_t> corr_offset, corr_interp;
   std::vector<double> corr_mu, corr_pdf, corr_cdf, km_r, km_a;
+  Function1D yield_fn, a, b; // energy-dependent multiplicity; parameters of the Maxwell / evaporation / Watt laws
+  double u = 0;
   mcw_reaction_desc desc() const
   {
     mcw_reaction_desc r{};
+    r.yield_fn = yield_fn.desc(), r.u = u, r.a = a.desc(), r.b = b.desc();
     r.mt = mt, r.threshold = threshold, r.xs = xs.data();
     r.threshold_energy = threshold_energy, r.mass_ratio = mass_ratio, r.yield = yield;
     r.law = law, r.in_cm = in_cm;
@@ -136,6 +139,8 @@ struct Nuclide
   std::vector<int32_t> corr_offset, corr_interp;
   std::vector<double> corr_mu, corr_pdf, corr_cdf, km_r, km_a;
   double inelastic_yield = 1.0;
+  Function1D inelastic_yield_fn, inelastic_a, inelastic_b; // the inline reaction's Reaction::yield_fn, a, b, u
+  double inelastic_u = 0;
   std::vector<Reaction> more_reactions;
   mutable std::vector<mcw_reaction_desc> more_descs; // filled by Library::nuclideDescs(), which hands out pointers into it
   std::vector<FissionProduct> fission_products;      // fission neutrons as a nuclide file has them (empty: the scalars in d)
@@ -231,6 +236,8 @@ struct Library
       d.corr_mu = n.corr_mu.data(), d.corr_pdf = n.corr_pdf.data(), d.corr_cdf = n.corr_cdf.data();
       d.km_r = n.km_r.data(), d.km_a = n.km_a.data();
       d.inelastic_yield = n.inelastic_yield;
+      d.inelastic_yield_fn = n.inelastic_yield_fn.desc(), d.inelastic_u = n.inelastic_u;
+      d.inelastic_a = n.inelastic_a.desc(), d.inelastic_b = n.inelastic_b.desc();
       n.more_descs.clear();
       for (const auto& r : n.more_reactions)
         n.more_descs.push_back(r.desc());

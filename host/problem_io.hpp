@@ -132,11 +132,8 @@ public:
       table("el_angle", n.elastic_angle);
       table("inel_angle", n.inelastic_angle);
       table("inel_energy", n.inelastic_energy);
-      if (has(p + "fis.head"))
-      {
-        // fission neutrons as a nuclide file has them: fis.head = count, laws; fis.u; functions as [kind, interpolation] +
-        // x + y (fis.nu total nu, fis<j>.y yield, .a, .b); continuous tabular spectra fis<j>.en like the nuclide's tables
-        auto fn = [&](const std::string& key, Function1D& f) {
+      // a function record: [kind, interpolation] + x + y (tabulated) or + coefficients (polynomial)
+      auto fn = [&](const std::string& key, Function1D& f) {
           if (!has(p + key))
             return;
           const auto v = f64(p + key);
@@ -149,7 +146,11 @@ public:
           }
           else
             f.y.assign(v.begin() + 2, v.end());
-        };
+      };
+      if (has(p + "fis.head"))
+      {
+        // fission neutrons as a nuclide file has them: fis.head = count, laws; fis.u; functions fis.nu (total nu),
+        // fis<j>.y (yield), .a, .b; continuous tabular spectra fis<j>.en like the nuclide's tables
         const auto head = i32(p + "fis.head");
         const auto us = f64(p + "fis.u");
         fn("fis.nu", n.total_nu);
@@ -175,6 +176,10 @@ public:
         // nuclide's; rx<j>.corr.i / .f, rx<j>.km
         const auto head = f64(p + "rx.head");
         n.inelastic_yield = head[1];
+        n.inelastic_u = head.size() > 2 ? head[2] : 0.0;
+        fn("rx.y", n.inelastic_yield_fn);
+        fn("rx.a", n.inelastic_a);
+        fn("rx.b", n.inelastic_b);
         const int keep_cm = n.inelastic_in_cm;
         for (int j = 0; j < (int)head[0]; ++j)
         {
@@ -185,6 +190,10 @@ public:
           R.mt = ri[0], R.threshold = ri[1], R.law = ri[2], R.in_cm = ri[3], R.nbody_n = ri[4];
           R.threshold_energy = rf[0], R.mass_ratio = rf[1], R.yield = rf[2], R.nbody_mass_ratio = rf[3], R.nbody_q = rf[4];
           R.xs = f64(p + q + "xs");
+          R.u = has(p + q + "u") ? f64(p + q + "u")[0] : 0.0;
+          fn(q + "y", R.yield_fn);
+          fn(q + "a", R.a);
+          fn(q + "b", R.b);
           table(q + "ang", R.angle);
           table(q + "en", R.energy);
           const size_t np = R.energy.offset.empty() ? 0 : (size_t)R.energy.offset.back();

@@ -101,7 +101,7 @@ typedef struct mcw_tabular2d
 #define MCW_LAW_CORRELATED 2         /* CorrelatedAngleEnergy, OMC secondary_correlated.cpp:156-262 */
 #define MCW_LAW_KALBACH_MANN 3       /* KalbachMann, OMC secondary_kalbach.cpp:117-235 */
 #define MCW_LAW_NBODY 4              /* NBodyPhaseSpace, OMC secondary_nbody.cpp:25-68 */
-/* energy laws of fission-neutron products (mcw_fission_product) */
+/* evaporation-type energy laws: fission-neutron products (mcw_fission_product) and uncorrelated scattering products */
 #define MCW_LAW_MAXWELL 5            /* MaxwellEnergy, OMC distribution_energy.cpp:279-291 */
 #define MCW_LAW_EVAPORATION 6        /* Evaporation, OMC distribution_energy.cpp:305-322 */
 #define MCW_LAW_WATT 7               /* WattEnergy, OMC distribution_energy.cpp:342-356 */
@@ -154,7 +154,7 @@ typedef struct mcw_reaction_desc
    * yield - 1 secondary neutrons, which MaCaw pops and drops (MC CollisionKernel.C:232-236), the history itself goes on
    * unchanged.  Not integral: the weight is multiplied by it (OMC physics.cpp:1108-1118).  0 means 1. */
   double yield;
-  int32_t law;                  /* MCW_LAW_* */
+  int32_t law;                  /* MCW_LAW_* (0 ... 7) */
   int32_t in_cm;                /* scatter_in_cm_ (level: always 1) */
   mcw_tabular2d angle;          /* angular distribution (uncorrelated laws), n_energy = 0: isotropic */
   mcw_tabular2d energy;         /* outgoing-energy table of CONTINUOUS_TABULAR, CORRELATED, KALBACH_MANN */
@@ -169,6 +169,12 @@ typedef struct mcw_reaction_desc
   int32_t reserved0;
   double nbody_mass_ratio;
   double nbody_q;
+  /* An energy-dependent multiplicity (Polynomial / Tabulated1D yield_, OMC reaction_product.cpp:40-43) instead of the
+   * constant `yield` (kind 0: the constant), and the parameters of MCW_LAW_MAXWELL / _EVAPORATION / _WATT when the
+   * uncorrelated product's energy law is one of those (theta(E) in `a`; Watt a(E), b(E); restriction energy u). */
+  mcw_function1d yield_fn;
+  double u;
+  mcw_function1d a, b;
 } mcw_reaction_desc;
 
 /* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
@@ -238,6 +244,10 @@ typedef struct mcw_nuclide_desc
   int32_t reserved3;
   const mcw_fission_product* fission_products;
   mcw_function1d total_nu;
+  /* the inline inelastic reaction's mcw_reaction_desc::yield_fn, u, a, b */
+  mcw_function1d inelastic_yield_fn;
+  double inelastic_u;
+  mcw_function1d inelastic_a, inelastic_b;
 } mcw_nuclide_desc;
 
 /* One material (OMC src/material.cpp: nuclide_, atom_density_ in atom/b-cm).  isotropic_in_lab

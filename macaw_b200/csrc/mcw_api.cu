@@ -68,6 +68,8 @@ struct HostFis // mcw_fission_product, copied
 
 struct HostRx // one scattering reaction after a nuclide's first (mcw_reaction_desc), copied
 {
+  HostFn yield_fn, fa, fb; // energy-dependent multiplicity; parameters of the Maxwell / evaporation / Watt laws
+  double fu = 0;
   McwRxParams prm;
   std::vector<double> xs;
   HostTable angle, energy, law;
@@ -87,6 +89,8 @@ struct HostNuclide
   HostTable el_angle, inel_angle, inel_energy;
   HostTable law; // correlated: one angular distribution per point of inel_energy; Kalbach-Mann: one entry, x = r, p = a
   double inel_yield = 1.0;
+  HostFn inel_yield_fn, inel_fa, inel_fb; // the inline reaction's mcw_reaction_desc::yield_fn, a, b, u
+  double inel_fu = 0;
   std::vector<HostFis> fis; // fission neutrons as a nuclide file has them (empty: the scalar description)
   HostFn total_nu;
 };
@@ -151,6 +155,18 @@ static const char* take_fn(const mcw_function1d& f, HostFn& out, bool required)
         return "tabulated function: abscissae must increase";
   }
   return nullptr;
+}
+
+// a scattering reaction's optional yield function and the parameter functions of the Maxwell / evaporation / Watt laws
+static const char* take_law_functions(int law, const mcw_function1d& yield_fn, const mcw_function1d& a, const mcw_function1d& b,
+                                      HostFn& out_yield, HostFn& out_a, HostFn& out_b)
+{
+  const char* bad = take_fn(yield_fn, out_yield, false);
+  if (!bad && law >= MCW_LAW_MAXWELL)
+    bad = take_fn(a, out_a, true);
+  if (!bad && law == MCW_LAW_WATT)
+    bad = take_fn(b, out_b, true);
+  return bad;
 }
 
 // checks a reaction's law against its outgoing-energy table and copies what the product distributions that give energy and
@@ -647,10 +663,10 @@ static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNucli
     }
     N.prm.inel_law = d[i].inelastic_law;
     N.prm.inel_in_cm = N.prm.inel_law == MCW_LAW_LEVEL ? 1 : (d[i].inelastic_in_cm != 0);
-    if (N.prm.inel_law < MCW_LAW_LEVEL || N.prm.inel_law > MCW_LAW_NBODY)
+    if (N.prm.inel_law < MCW_LAW_LEVEL || N.prm.inel_law > MCW_LAW_WATT)
       // OMC secondary_uncorrelated.cpp:47 "Energy distribution type '...' not implemented."
       return fail(h, MCW_E_UNSUPPORTED, "mcw_set_library: inelastic law not implemented (level, continuous tabular, "
-                                        "correlated, Kalbach-Mann, N-body)");
+                                        "correlated, Kalbach-Mann, N-body, Maxwell, evaporation, Watt)");
     const char* bad = take_table(d[i].elastic_angle, N.el_angle, false);
     if (!bad)
       bad = take_table(d[i].inelastic_angle, N.inel_angle, false);
@@ -663,9 +679,12 @@ static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNucli
     N.prm.nbody_n = d[i].nbody_n;
     N.prm.nbody_mass_ratio = d[i].nbody_mass_ratio;
     N.prm.nbody_q = d[i].nbody_q;
-    if (law >= MCW_LAW_CORRELATED)
+    if (law >= MCW_LAW_CORRELATED && law <= MCW_LAW_NBODY)
       N.inel_angle = HostTable(); // the product distribution gives the cosine itself
     N.inel_yield = d[i].inelastic_yield == 0.0 ? 1.0 : d[i].inelastic_yield;
+    if (!bad && N.prm.n_inel)
+      bad = take_law_functions(law, d[i].inelastic_yield_fn, d[i].inelastic_a, d[i].inelastic_b, N.inel_yield_fn, N.inel_fa, N.inel_fb);
+    N.inel_fu = d[i].inelastic_u;
     if (!bad && d[i].n_more_reactions > 0 && (!N.prm.n_inel || !d[i].more_reactions))
       bad = "more_reactions needs the inline inelastic reaction (n_inelastic = 1) before them";
     for (int j = 0; !bad && j < d[i].n_more_reactions; ++j)
@@ -675,8 +694,8 @@ static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNucli
       memset(&R.prm, 0, sizeof(R.prm));
       if (r.threshold < 0 || r.threshold >= G - 1 || !r.xs)
         bad = "reaction threshold outside the grid, or its cross section missing";
-      else if (r.law < MCW_LAW_LEVEL || r.law > MCW_LAW_NBODY)
-        bad = "reaction law not implemented (level, continuous tabular, correlated, Kalbach-Mann, N-body)";
+      else if (r.law < MCW_LAW_LEVEL || r.law > MCW_LAW_WATT)
+        bad = "reaction law not implemented (level, continuous tabular, correlated, Kalbach-Mann, N-body, Maxwell, evaporation, Watt)";
       if (bad)
         break;
       R.xs.assign(r.xs, r.xs + (G - r.threshold));
@@ -695,8 +714,11 @@ static int parse_library(const mcw_nuclide_desc* d, int n, std::vector<HostNucli
       if (!bad)
         bad = take_law(r.law, R.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r, r.km_a, r.nbody_n,
                        R.law);
-      if (r.law >= MCW_LAW_CORRELATED)
+      if (r.law >= MCW_LAW_CORRELATED && r.law <= MCW_LAW_NBODY)
         R.angle = HostTable();
+      if (!bad)
+        bad = take_law_functions(r.law, r.yield_fn, r.a, r.b, R.yield_fn, R.fa, R.fb);
+      R.fu = r.u;
       N.more.push_back(std::move(R));
     }
     if (!bad && d[i].n_fission_products > 0)
@@ -1182,7 +1204,9 @@ static int prepare(mcw_handle h)
       rare |= !tl.nuclides.empty();
     for (const auto& n : h->nuclides)
       rare |= !n.el_angle.energy.empty() || !n.inel_angle.energy.empty() || !n.inel_energy.energy.empty() || !n.urr.energy.empty() ||
-              (n.prm.n_inel && (n.prm.inel_law >= MCW_LAW_CORRELATED || !n.more.empty() || n.inel_yield != 1.0)) || !n.fis.empty();
+              (n.prm.n_inel && (n.prm.inel_law >= MCW_LAW_CORRELATED || !n.more.empty() || n.inel_yield != 1.0 ||
+                                n.inel_yield_fn.kind != MCW_FN_NONE)) ||
+              !n.fis.empty();
     h->rare = rare || h->force_rare > 0;
   }
 
@@ -1283,6 +1307,7 @@ static int prepare(mcw_handle h)
       r0.ang_first = n.prm.inel_ang_first, r0.ang_n = n.prm.inel_ang_n;
       r0.en_first = n.prm.inel_en_first, r0.en_n = n.prm.inel_en_n, r0.en_hist = n.prm.inel_en_hist;
       r0.law_first = n.prm.law_first;
+      r0.yield_fn = add_fn(n.inel_yield_fn), r0.a = add_fn(n.inel_fa), r0.b = add_fn(n.inel_fb), r0.u = n.inel_fu;
       rx.push_back(r0);
       for (auto& m : n.more)
       {
@@ -1291,6 +1316,7 @@ static int prepare(mcw_handle h)
         add_table(m.energy, m.prm.en_first, m.prm.en_n);
         m.prm.en_hist = m.energy.hist;
         add_table(m.law, m.prm.law_first, count);
+        m.prm.yield_fn = add_fn(m.yield_fn), m.prm.a = add_fn(m.fa), m.prm.b = add_fn(m.fb), m.prm.u = m.fu;
         m.prm.xs_off = (int64_t)rx_xs.size();
         rx_xs.insert(rx_xs.end(), m.xs.begin(), m.xs.end());
         rx.push_back(m.prm);

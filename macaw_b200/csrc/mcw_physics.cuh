@@ -605,6 +605,41 @@ MCW_D void mcw_elastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc, 
   p.u = v_n / vel;
 }
 
+// WattEnergy / MaxwellEnergy / Evaporation::sample (OMC distribution_energy.cpp:342-356, 279-291, 305-322) with the
+// parameters pa (theta, or Watt's a) and pb (Watt's b) already evaluated at E_in and the restriction energy u: fission
+// products and uncorrelated scattering products.  Out of line.
+__device__ __noinline__ double mcw_evaporation_type_sample(int law, double pa, double pb, double u, double E_in, uint64_t* seed_io)
+{
+  uint64_t seed = *seed_io;
+  double Eo;
+  if (law == MCW_LAW_WATT)
+  {
+    do
+      Eo = mcw_watt_spectrum(pa, pb, seed);
+    while (!(Eo <= E_in - u));
+  }
+  else if (law == MCW_LAW_MAXWELL)
+  {
+    do
+      Eo = mcw_maxwell_spectrum(pa, seed);
+    while (!(Eo <= E_in - u));
+  }
+  else
+  {
+    const double y = (E_in - u) / pa;
+    const double v = 1.0 - mcw_exp(-y);
+    double x;
+    do
+    {
+      const double r1 = mcw_prn(seed), r2 = mcw_prn(seed);
+      x = -mcw_log_c((1.0 - v * r1) * (1.0 - v * r2));
+    } while (!(x <= y));
+    Eo = x * pa;
+  }
+  *seed_io = seed;
+  return Eo;
+}
+
 // The outgoing-energy part CorrelatedAngleEnergy::sample (OMC secondary_correlated.cpp:156-245) and KalbachMann::sample
 // (secondary_kalbach.cpp:117-222) share: ContinuousTabular without the histogram-in-incoming-energy case and without its
 // E_l_k != E_l_k1 guard.  Returns what the angular parts need.
@@ -796,7 +831,7 @@ MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc
   {
     const int i_rx = nuc.rx_first + j_rx;
     const McwRxParams& rx = L.rx[i_rx];
-    if (rx.law >= MCW_LAW_CORRELATED)
+    if (rx.law >= MCW_LAW_CORRELATED && rx.law <= MCW_LAW_NBODY)
     {
       const double2 em = mcw_product_sample(L.self_dev, i_rx, nuc.awr, E_in, &p.seed);
       E = em.x;
@@ -810,14 +845,21 @@ MCW_D void mcw_inelastic_scatter(const McwLibraryDev& L, const McwNucParams& nuc
         mu = mcw_uniform(-1., 1., p.seed);
       if (rx.law == MCW_LAW_CONTINUOUS_TABULAR)
         E = mcw_continuous_tabular_sample(L, rx.en_first, rx.en_n, rx.en_hist != 0, E_in, p.seed);
+      else if (rx.law >= MCW_LAW_MAXWELL)
+      {
+        const double pa = mcw_fn_eval(L, rx.a, E_in);
+        const double pb = rx.law == MCW_LAW_WATT ? mcw_fn_eval(L, rx.b, E_in) : 0.0;
+        E = mcw_evaporation_type_sample(rx.law, pa, pb, rx.u, E_in, &p.seed);
+      }
       else
         E = rx.level_ratio * (E_in - rx.level_E);
     }
     in_cm = rx.in_cm != 0; // the level law always scatters in the centre of mass
     // the product's yield (OMC physics.cpp:1108-1118): integral = secondaries, which MaCaw drops (MC
     // CollisionKernel.C:232-236); otherwise the weight is multiplied
-    if (floor(rx.yield) != rx.yield)
-      p.wgt *= rx.yield;
+    const double yield = rx.yield_fn.kind != MCW_FN_NONE ? mcw_fn_eval(L, rx.yield_fn, E_in) : rx.yield;
+    if (floor(yield) != yield)
+      p.wgt *= yield;
   }
   if (in_cm)
   {
@@ -906,30 +948,8 @@ __device__ __noinline__ double2 mcw_fission_neutron_general(const McwLibraryDev*
     mu = mcw_uniform(-1., 1., seed); // secondary_uncorrelated.cpp:54-68
     if (f.law == MCW_LAW_CONTINUOUS_TABULAR)
       Eo = mcw_continuous_tabular_sample(L, f.en_first, f.en_n, f.en_hist != 0, E_in, seed);
-    else if (f.law == MCW_LAW_WATT)
-    {
-      do
-        Eo = mcw_watt_spectrum(pa, pb, seed);
-      while (!(Eo <= E_in - f.u));
-    }
-    else if (f.law == MCW_LAW_MAXWELL)
-    {
-      do
-        Eo = mcw_maxwell_spectrum(pa, seed);
-      while (!(Eo <= E_in - f.u));
-    }
     else
-    {
-      const double y = (E_in - f.u) / pa;
-      const double v = 1.0 - mcw_exp(-y);
-      double x;
-      do
-      {
-        const double r1 = mcw_prn(seed), r2 = mcw_prn(seed);
-        x = -mcw_log_c((1.0 - v * r1) * (1.0 - v * r2));
-      } while (!(x <= y));
-      Eo = x * pa;
-    }
+      Eo = mcw_evaporation_type_sample(f.law, pa, pb, f.u, E_in, &seed);
     if (Eo < L.E_max)
       break;
   }

@@ -86,6 +86,9 @@ struct McwRxParams
   int32_t en_first, en_n, en_hist;
   int32_t law_first, nbody_n;
   int32_t pad[2];
+  McwFn yield_fn;              // energy-dependent multiplicity (kind 0: the constant `yield`)
+  McwFn a, b;                  // MCW_LAW_MAXWELL / _EVAPORATION / _WATT: theta(E) or a(E), b(E) ...
+  double u;                    // ... and the restriction energy
 };
 
 // One temperature of an S(alpha, beta) table (mcw_thermal_desc): offsets into McwLibraryDev::sab_pool (doubles) /

@@ -50,6 +50,10 @@ class Nuclide:
     km_a: np.ndarray = None
     nbody: tuple = None              # law 4: (n_particles, total_mass, q_value)
     inelastic_yield: float = 1.0     # neutron multiplicity of the inline inelastic reaction
+    inelastic_yield_fn: object = None  # ... as a Function1D of the incoming energy
+    inelastic_u: float = 0.0         # inline reaction with law 5 / 6 / 7: restriction energy and parameters
+    inelastic_a: object = None
+    inelastic_b: object = None
     more_reactions: list = None      # further scattering reactions (Reaction), index_inelastic_scatter_ order
     more_temperatures: list = None   # further data sets of this nuclide (Nuclide objects at other kT; OMC kTs_, grid_[t], xs_[t])
     fission_products: list = None    # FissionProduct x (1 + n_precursor): prompt, delayed groups (replaces nu_poly / watt / ...)
@@ -105,6 +109,10 @@ class Reaction:
     km_r: np.ndarray = None
     km_a: np.ndarray = None
     nbody: tuple = None
+    yield_fn: object = None          # Function1D: energy-dependent multiplicity (else the constant yield_)
+    u: float = 0.0                   # laws 5 / 6 / 7 (Maxwell / evaporation / Watt): restriction energy and parameters
+    a: object = None
+    b: object = None
 
 
 @dataclass
@@ -660,6 +668,41 @@ def add_temperatures(lib: Library, temperatures=(600.0, 900.0), seed=21, skip_ev
     return lib
 
 
+def add_evaporation_laws(lib: Library) -> Library:
+    """After add_reactions: evaporation-type energy laws and energy-dependent yields on scattering reactions.  Of every
+    nuclide with a reaction list, MT 53 becomes an evaporation spectrum (keeping its angular distribution), the continuum
+    MT 91 of every second one a Maxwell spectrum with a tabulated multiplicity rising from 1 to 1.6 (not integral: the
+    weight follows it), (n,2n) MT 875 of the others a Watt spectrum; the first reaction (inline, MT 51) of every third
+    nuclide whose law is level or continuous tabular becomes an evaporation spectrum in the LAB system with a polynomial
+    multiplicity.  Spectrum parameters grow with the incoming energy (tabulated, lin-lin), restriction energies lie below
+    the thresholds."""
+    k = 0
+    for n in lib.nuclides:
+        if not n.more_reactions:
+            continue
+        e = n.energy
+        def theta(t, f):
+            lo = float(e[t])
+            return Function1D(2, np.array([f * lo, f * 2.0e7]), np.array([lo, 2.0e7]), 2)
+        r52, r53, r91, r2n = n.more_reactions
+        r53.law, r53.in_cm, r53.u, r53.a = 6, True, 0.5 * float(e[r53.threshold]), theta(r53.threshold, 0.2)
+        if k % 2 == 0:
+            t = r91.threshold
+            r91.law, r91.in_cm, r91.energy, r91.u, r91.a = 5, False, None, 0.4 * float(e[t]), theta(t, 0.15)
+            r91.yield_fn = Function1D(2, np.array([1.0, 1.3, 1.6]), np.array([float(e[t]), 0.5 * (float(e[t]) + 2.0e7), 2.0e7]), 2)
+        else:
+            t = r2n.threshold
+            r2n.law, r2n.in_cm, r2n.nbody, r2n.u = 7, True, None, -2.0e7
+            r2n.a, r2n.b = theta(t, 0.05), Function1D(2, np.array([2.0e-6, 3.0e-6]), np.array([float(e[t]), 2.0e7]), 2)
+        if k % 3 == 0 and n.inelastic_law == -1:
+            t = n.inel_threshold
+            n.inelastic_law, n.inelastic_in_cm, n.inelastic_angle, n.inelastic_energy = 6, False, None, None
+            n.inelastic_u, n.inelastic_a = 0.5 * float(e[t]), theta(t, 0.25)
+            n.inelastic_yield_fn = Function1D(1, np.array([1.0, 2.0e-9]))
+        k += 1
+    return lib
+
+
 def add_fission_data(lib: Library, seed=41) -> Library:
     """Gives the fissionable nuclides fission-neutron data as evaluated files have them instead of the scalar description:
     a tabulated total nu (lin-lin), a prompt yield (tabulated, or a polynomial for every second nuclide), six delayed
@@ -830,7 +873,9 @@ class NuclideDesc(C.Structure):
                 ("inelastic_yield", C.c_double), ("n_more_reactions", C.c_int32), ("reserved2", C.c_int32),
                 ("more_reactions", C.c_void_p),
                 ("n_fission_products", C.c_int32), ("reserved3", C.c_int32), ("fission_products", C.c_void_p),
-                ("total_nu", Function1DDesc)]
+                ("total_nu", Function1DDesc),
+                ("inelastic_yield_fn", Function1DDesc), ("inelastic_u", C.c_double), ("inelastic_a", Function1DDesc),
+                ("inelastic_b", Function1DDesc)]
 
 
 class ReactionDesc(C.Structure):
@@ -839,7 +884,8 @@ class ReactionDesc(C.Structure):
                 ("angle", Tabular2DDesc), ("energy", Tabular2DDesc),
                 ("corr_offset", C.c_void_p), ("corr_interp", C.c_void_p), ("corr_mu", C.c_void_p), ("corr_pdf", C.c_void_p),
                 ("corr_cdf", C.c_void_p), ("km_r", C.c_void_p), ("km_a", C.c_void_p), ("nbody_n", C.c_int32),
-                ("reserved0", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double)]
+                ("reserved0", C.c_int32), ("nbody_mass_ratio", C.c_double), ("nbody_q", C.c_double),
+                ("yield_fn", Function1DDesc), ("u", C.c_double), ("a", Function1DDesc), ("b", Function1DDesc)]
 
 
 class ThermalDesc(C.Structure):
@@ -929,6 +975,10 @@ def pack_inelastic_law(d, n, keep):
     d.inelastic_in_cm = int(getattr(n, "inelastic_in_cm", True))
     _pack_product(d, d.inelastic_law, n, keep)
     d.inelastic_yield = float(getattr(n, "inelastic_yield", 1.0))
+    _pack_function(d.inelastic_yield_fn, getattr(n, "inelastic_yield_fn", None), keep)
+    d.inelastic_u = float(getattr(n, "inelastic_u", 0.0))
+    _pack_function(d.inelastic_a, getattr(n, "inelastic_a", None), keep)
+    _pack_function(d.inelastic_b, getattr(n, "inelastic_b", None), keep)
     more = getattr(n, "more_reactions", None) or []
     if more:
         rd = (ReactionDesc * len(more))()
@@ -942,6 +992,10 @@ def pack_inelastic_law(d, n, keep):
             _pack_table(r.angle, x.angle, keep)
             _pack_table(r.energy, x.energy, keep)
             _pack_product(r, x.law, x, keep)
+            _pack_function(r.yield_fn, x.yield_fn, keep)
+            r.u = float(x.u)
+            _pack_function(r.a, x.a, keep)
+            _pack_function(r.b, x.b, keep)
         d.n_more_reactions, d.more_reactions = len(more), C.addressof(rd)
     prods = getattr(n, "fission_products", None) or []
     if prods:  # fission neutrons as a nuclide file has them

@@ -61,9 +61,9 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
             elif law == 2:
                 off, interp, mu, pdf, cdf = n.corr_angle
                 li, lf = np.concatenate([li, off, interp]), np.concatenate([lf, mu, pdf, cdf])
-            else:
+            elif law == 3:
                 lf = np.concatenate([lf, n.km_r, n.km_a])
-            r[f"nuc{k}.law.i"] = np.asarray(li, np.int32)
+            r[f"nuc{k}.law.i"] = np.asarray(li, np.int32)  # laws 5 / 6 / 7: law and in_cm only (parameters: rx.a / rx.b)
             r[f"nuc{k}.law.f"] = np.asarray(lf, np.float64)
         # fission neutrons as a nuclide file has them: products (prompt, delayed groups) and the total nu
         prods = getattr(n, "fission_products", None) or []
@@ -88,14 +88,23 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
                     r[q + "en.xpc"] = np.concatenate([t.x, t.pdf, t.cdf]).astype(np.float64)
         # the scattering reactions after the first (mcw_reaction_desc) and the first one's yield
         more = getattr(n, "more_reactions", None) or []
-        if more or getattr(n, "inelastic_yield", 1.0) != 1.0:
-            r[f"nuc{k}.rx.head"] = np.array([len(more), float(getattr(n, "inelastic_yield", 1.0))], np.float64)
+        law0 = getattr(n, "inelastic_law", -1)
+        if more or getattr(n, "inelastic_yield", 1.0) != 1.0 or law0 >= 5 or getattr(n, "inelastic_yield_fn", None) is not None:
+            r[f"nuc{k}.rx.head"] = np.array([len(more), float(getattr(n, "inelastic_yield", 1.0)),
+                                             float(getattr(n, "inelastic_u", 0.0))], np.float64)
+            fn(f"nuc{k}.rx.y", getattr(n, "inelastic_yield_fn", None))
+            fn(f"nuc{k}.rx.a", getattr(n, "inelastic_a", None))
+            fn(f"nuc{k}.rx.b", getattr(n, "inelastic_b", None))
         for j, x in enumerate(more):
             q = f"nuc{k}.rx{j}."
             r[q + "i"] = np.array([x.mt, x.threshold, x.law, int(x.in_cm), 0 if x.nbody is None else int(x.nbody[0])], np.int32)
             r[q + "f"] = np.array([x.threshold_energy, x.mass_ratio, x.yield_, 0.0 if x.nbody is None else x.nbody[1],
                                    0.0 if x.nbody is None else x.nbody[2]], np.float64)
             r[q + "xs"] = np.ascontiguousarray(x.xs, np.float64)
+            r[q + "u"] = np.array([float(x.u)], np.float64)
+            fn(q + "y", x.yield_fn)
+            fn(q + "a", x.a)
+            fn(q + "b", x.b)
             for key, t in (("ang", x.angle), ("en", x.energy)):
                 if t is None:
                     continue

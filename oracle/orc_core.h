@@ -274,7 +274,10 @@ struct RxLaw
   std::vector<double> km_r, km_a;
   int nbody_n = 0;
   double nbody_mass_ratio = 0, nbody_q = 0;
-  double yield = 1.0;         // constant multiplicity of the neutron product
+  double yield = 1.0;         // constant multiplicity of the neutron product ...
+  Fn yield_fn;                // ... or a function of the incoming energy (kind 0: the constant)
+  double law_u = 0;           // MCW_LAW_MAXWELL / _EVAPORATION / _WATT: restriction energy, theta(E) or a(E), b(E)
+  Fn law_a, law_b;
   std::vector<double> rx_xs;  // further reactions only: cross section from the threshold on
 };
 

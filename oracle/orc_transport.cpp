@@ -682,63 +682,16 @@ static void nbody_sample(const RxLaw& nuc, double awr, double E_in, double& E_ou
   E_out = E_max * v;
 }
 
-// OMC physics.cpp:1073-1120 over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68): cosine from the
-// reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
-// (:150-275), CM -> LAB when scatter_in_cm_, yield 1
-static long long g_law_samples[5]; // how often each MCW_LAW_* was sampled (test coverage: orc_law_samples)
-static long long g_rx_samples[8];  // ... and each position of the reaction list (orc_reaction_samples)
-static void inelastic_scatter(const RxLaw& nuc, double awr, Hist& p)
+// WattEnergy / MaxwellEnergy / Evaporation::sample with tabulated parameters and the restriction energy u (OMC
+// distribution_energy.cpp:342-356, 279-291, 305-322): fission-neutron products and uncorrelated scattering products
+static double evaporation_type_energy(int law, const Fn& fa, const Fn& fb, double u, double E, uint64_t* seed)
 {
-  double E_in = p.E;
-  double mu, E;
-  if (nuc.inel_law >= 0 && nuc.inel_law < 5)
+  struct
   {
-#pragma omp atomic
-    g_law_samples[nuc.inel_law]++;
-  }
-  // ReactionProduct::sample -> the product's distribution: correlated, Kalbach-Mann and N-body give energy and cosine
-  // together (reaction_product.cpp:70-79); uncorrelated = angle table (or isotropic) + energy law
-  if (nuc.inel_law == MCW_LAW_CORRELATED)
-    correlated_sample(nuc, E_in, E, mu, &p.seeds[0]);
-  else if (nuc.inel_law == MCW_LAW_KALBACH_MANN)
-    kalbach_sample(nuc, E_in, E, mu, &p.seeds[0]);
-  else if (nuc.inel_law == MCW_LAW_NBODY)
-    nbody_sample(nuc, awr, E_in, E, mu, &p.seeds[0]);
-  else
-  {
-    if (!nuc.inel_angle.empty())
-      mu = angle_sample(nuc.inel_angle, E_in, &p.seeds[0]);
-    else
-      mu = uniform_distribution(-1., 1., &p.seeds[0]);
-    if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
-      E = continuous_tabular_sample(nuc.inel_energy, E_in, &p.seeds[0]);
-    else
-      E = nuc.inel_ratio * (E_in - nuc.inel_E);
-  }
-  if (nuc.inel_in_cm)
-  {
-    double E_cm = E;
-    double A = awr;
-    E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
-    mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
-  }
-  if (std::fabs(mu) > 1.0)
-    mu = std::copysign(1.0, mu);
-  p.E = E;
-  p.u = rotate_angle(p.u, mu, nullptr, &p.seeds[0]);
-  // the product's yield (:1108-1118): an integral one makes yield - 1 secondary neutrons -- which MaCaw pops from the
-  // scratch particle's bank and drops (MC CollisionKernel.C:232-236) -- and leaves the history as it is; any other
-  // multiplies the weight
-  if (std::floor(nuc.yield) != nuc.yield)
-    p.wgt *= nuc.yield;
-}
-
-// the energy law of a fission-neutron product: WattEnergy / MaxwellEnergy / Evaporation::sample with tabulated parameters
-// and the restriction energy u (OMC distribution_energy.cpp:342-356, 279-291, 305-322), or ContinuousTabular (:150-275)
-static double fission_product_energy(const FisProduct& f, double E, uint64_t* seed)
-{
-  if (f.law == MCW_LAW_CONTINUOUS_TABULAR)
-    return continuous_tabular_sample(f.energy, E, seed);
+    int law;
+    const Fn &a, &b;
+    double u;
+  } f{law, fa, fb, u};
   if (f.law == MCW_LAW_WATT)
   {
     const double a = f.a(E), b = f.b(E);
@@ -768,6 +721,68 @@ static double fission_product_energy(const FisProduct& f, double E, uint64_t* se
       break;
   }
   return x * theta;
+}
+
+// the energy law of a fission-neutron product: one of the above, or ContinuousTabular (:150-275)
+static double fission_product_energy(const FisProduct& f, double E, uint64_t* seed)
+{
+  if (f.law == MCW_LAW_CONTINUOUS_TABULAR)
+    return continuous_tabular_sample(f.energy, E, seed);
+  return evaporation_type_energy(f.law, f.a, f.b, f.u, E, seed);
+}
+
+// OMC physics.cpp:1073-1120 over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68): cosine from the
+// reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
+// (:150-275), CM -> LAB when scatter_in_cm_, yield 1
+static long long g_law_samples[8]; // how often each MCW_LAW_* was sampled (test coverage: orc_law_samples)
+static long long g_rx_samples[8];  // ... and each position of the reaction list (orc_reaction_samples)
+static void inelastic_scatter(const RxLaw& nuc, double awr, Hist& p)
+{
+  double E_in = p.E;
+  double mu, E;
+  if (nuc.inel_law >= 0 && nuc.inel_law < 8)
+  {
+#pragma omp atomic
+    g_law_samples[nuc.inel_law]++;
+  }
+  // ReactionProduct::sample -> the product's distribution: correlated, Kalbach-Mann and N-body give energy and cosine
+  // together (reaction_product.cpp:70-79); uncorrelated = angle table (or isotropic) + energy law
+  if (nuc.inel_law == MCW_LAW_CORRELATED)
+    correlated_sample(nuc, E_in, E, mu, &p.seeds[0]);
+  else if (nuc.inel_law == MCW_LAW_KALBACH_MANN)
+    kalbach_sample(nuc, E_in, E, mu, &p.seeds[0]);
+  else if (nuc.inel_law == MCW_LAW_NBODY)
+    nbody_sample(nuc, awr, E_in, E, mu, &p.seeds[0]);
+  else
+  {
+    if (!nuc.inel_angle.empty())
+      mu = angle_sample(nuc.inel_angle, E_in, &p.seeds[0]);
+    else
+      mu = uniform_distribution(-1., 1., &p.seeds[0]);
+    if (nuc.inel_law == MCW_LAW_CONTINUOUS_TABULAR)
+      E = continuous_tabular_sample(nuc.inel_energy, E_in, &p.seeds[0]);
+    else if (nuc.inel_law >= MCW_LAW_MAXWELL)
+      E = evaporation_type_energy(nuc.inel_law, nuc.law_a, nuc.law_b, nuc.law_u, E_in, &p.seeds[0]);
+    else
+      E = nuc.inel_ratio * (E_in - nuc.inel_E);
+  }
+  if (nuc.inel_in_cm)
+  {
+    double E_cm = E;
+    double A = awr;
+    E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * std::sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
+    mu = mu * std::sqrt(E_cm / E) + 1.0 / (A + 1.0) * std::sqrt(E_in / E);
+  }
+  if (std::fabs(mu) > 1.0)
+    mu = std::copysign(1.0, mu);
+  p.E = E;
+  p.u = rotate_angle(p.u, mu, nullptr, &p.seeds[0]);
+  // the product's yield (:1108-1118): an integral one makes yield - 1 secondary neutrons -- which MaCaw pops from the
+  // scratch particle's bank and drops (MC CollisionKernel.C:232-236) -- and leaves the history as it is; any other
+  // multiplies the weight
+  const double yield = nuc.yield_fn.kind != MCW_FN_NONE ? nuc.yield_fn(E_in) : nuc.yield;
+  if (std::floor(yield) != yield)
+    p.wgt *= yield;
 }
 
 // OMC physics.cpp:1006-1071
@@ -1323,11 +1338,11 @@ void orc_isotropic_direction(double* uvw, uint64_t* seed)
   uvw[2] = u.z;
 }
 // samples of each inelastic law since the last call (so a test can assert that its problem really reaches every law)
-void orc_law_samples(long long* out5)
+void orc_law_samples(long long* out8)
 {
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 8; ++i)
   {
-    out5[i] = g_law_samples[i];
+    out8[i] = g_law_samples[i];
     g_law_samples[i] = 0;
   }
 }
@@ -1396,8 +1411,13 @@ int orc_set_mesh(void* h, int elem_type, int64_t n_nodes, const double* xyz, int
 static void take_law(RxLaw& N, int law, int in_cm, const mcw_tabular2d& angle, const mcw_tabular2d& energy,
                      const int32_t* corr_offset, const int32_t* corr_interp, const double* corr_mu, const double* corr_pdf,
                      const double* corr_cdf, const double* km_r, const double* km_a, int nbody_n, double nbody_mass_ratio,
-                     double nbody_q, double yield)
+                     double nbody_q, double yield, const mcw_function1d& yield_fn, double u, const mcw_function1d& a,
+                     const mcw_function1d& b)
 {
+  N.yield_fn.take(yield_fn);
+  N.law_u = u;
+  N.law_a.take(a);
+  N.law_b.take(b);
   N.inel_angle.take(angle, false);
   N.inel_energy.take(energy, true);
   N.inel_law = law;
@@ -1424,7 +1444,7 @@ static void take_law(RxLaw& N, int law, int in_cm, const mcw_tabular2d& angle, c
       N.km_a.assign(km_a, km_a + np);
     }
   }
-  if (law >= MCW_LAW_CORRELATED)
+  if (law >= MCW_LAW_CORRELATED && law <= MCW_LAW_NBODY)
     N.inel_angle = Tabular2D(); // the product distribution gives the cosine itself
   N.nbody_n = nbody_n;
   N.nbody_mass_ratio = nbody_mass_ratio;
@@ -1482,7 +1502,7 @@ static Nuclide nuclide_from_desc(const mcw_nuclide_desc& d)
   N.el_angle.take(d.elastic_angle, false);
   take_law(N, d.inelastic_law, d.inelastic_in_cm, d.inelastic_angle, d.inelastic_energy, d.corr_offset,
            d.corr_interp, d.corr_mu, d.corr_pdf, d.corr_cdf, d.km_r, d.km_a, d.nbody_n,
-           d.nbody_mass_ratio, d.nbody_q, d.inelastic_yield);
+           d.nbody_mass_ratio, d.nbody_q, d.inelastic_yield, d.inelastic_yield_fn, d.inelastic_u, d.inelastic_a, d.inelastic_b);
   for (int j = 0; j < d.n_more_reactions && N.n_inel; ++j)
   {
     const mcw_reaction_desc& r = d.more_reactions[j];
@@ -1493,7 +1513,7 @@ static Nuclide nuclide_from_desc(const mcw_nuclide_desc& d)
     R.inel_ratio = r.mass_ratio;
     R.rx_xs.assign(r.xs, r.xs + (N.G - r.threshold));
     take_law(R, r.law, r.in_cm, r.angle, r.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r,
-             r.km_a, r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield);
+             r.km_a, r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield, r.yield_fn, r.u, r.a, r.b);
     N.more.push_back(std::move(R));
   }
   return N;

@@ -138,13 +138,16 @@ struct LawView
   const double *corr_mu, *corr_pdf, *corr_cdf, *km_r, *km_a;
   int nbody_n;
   double nbody_mass_ratio, nbody_q, level_E, level_ratio;
+  double u;
+  const mcw_function1d *a, *b;
 };
 // distribution_0 of a neutron product as the reference's constructors read it: "uncorrelated" (angle table or none +
 // level / continuous energy law: secondary_uncorrelated.cpp:17-52), "correlated" (secondary_correlated.cpp:22-150),
 // "kalbach-mann" (secondary_kalbach.cpp:24-110), "nbody" (secondary_nbody.cpp:16-23)
 void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
 {
-  if (L.law < MCW_LAW_CORRELATED && L.angle)
+  const bool together = L.law >= MCW_LAW_CORRELATED && L.law <= MCW_LAW_NBODY; // energy and cosine from one distribution
+  if (!together && L.angle)
     angle_group(dist, *L.angle);
   if (L.law == MCW_LAW_NBODY)
   {
@@ -154,7 +157,7 @@ void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
     dist->attr("atomic_weight_ratio", awr);
     dist->attr("q_value", L.nbody_q);
   }
-  else if (L.law >= MCW_LAW_CORRELATED)
+  else if (together)
   {
     const mcw_tabular2d& t = *L.energy;
     const int n = t.n_energy, np = t.offset[n];
@@ -185,7 +188,7 @@ void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
     else
       dist->attr("type", "kalbach-mann");
   }
-  if (L.law >= MCW_LAW_CORRELATED)
+  if (together)
     return; // the product distribution above replaces the uncorrelated angle + energy pair
   memh5::Node* e = dist->group("energy");
   if (L.law == MCW_LAW_CONTINUOUS_TABULAR)
@@ -200,6 +203,19 @@ void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
     if (t.n_discrete)
       nd.assign(t.n_discrete, t.n_discrete + t.n_energy);
     d->attr("n_discrete_lines", nd);
+  }
+  else if (L.law >= MCW_LAW_MAXWELL)
+  {
+    // MaxwellEnergy / Evaporation / WattEnergy of a scattering product (distribution_energy.cpp:265-356)
+    e->attr("type", L.law == MCW_LAW_WATT ? "watt" : (L.law == MCW_LAW_MAXWELL ? "maxwell" : "evaporation"));
+    e->attr("u", L.u);
+    if (L.law == MCW_LAW_WATT)
+    {
+      function_dataset(e, "a", *L.a);
+      function_dataset(e, "b", *L.b);
+    }
+    else
+      function_dataset(e, "theta", *L.a);
   }
   else
   {
@@ -314,7 +330,14 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
       v.nbody_mass_ratio = L.nbody_mass_ratio, v.nbody_q = L.nbody_q;
     }
     v.level_E = inel_E, v.level_ratio = inel_ratio;
+    if (g_law)
+      v.u = g_law->inelastic_u, v.a = &g_law->inelastic_a, v.b = &g_law->inelastic_b;
     fill_distribution(dist, awr, v);
+    if (g_law && g_law->inelastic_yield_fn.kind != MCW_FN_NONE) // an energy-dependent multiplicity replaces the constant
+    {
+      r_inel->children.at("product_0")->children.erase("yield");
+      function_dataset(r_inel->children.at("product_0").get(), "yield", g_law->inelastic_yield_fn);
+    }
     // the scattering reactions after the first (index_inelastic_scatter_ follows the MT order of the group names)
     for (int j = 0; g_law && j < g_law->n_more_reactions; ++j)
     {
@@ -329,7 +352,13 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
       w.corr_cdf = r.corr_cdf, w.km_r = r.km_r, w.km_a = r.km_a, w.nbody_n = r.nbody_n;
       w.nbody_mass_ratio = r.nbody_mass_ratio, w.nbody_q = r.nbody_q;
       w.level_E = r.threshold_energy, w.level_ratio = r.mass_ratio;
+      w.u = r.u, w.a = &r.a, w.b = &r.b;
       fill_distribution(dj, awr, w);
+      if (r.yield_fn.kind != MCW_FN_NONE)
+      {
+        r_more.back()->children.at("product_0")->children.erase("yield");
+        function_dataset(r_more.back()->children.at("product_0").get(), "yield", r.yield_fn);
+      }
     }
   }
   g_el_angle = g_inel_angle = g_inel_energy = nullptr;

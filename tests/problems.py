@@ -139,6 +139,13 @@ def pin_cell_tet_reactions(**kw):
     return mesh, nucdata.add_reactions(lib), bm, s
 
 
+def pin_cell_tet_evaporation(**kw):
+    """Reaction lists with Maxwell / evaporation / Watt spectra and energy-dependent multiplicities on scattering reactions
+    (nucdata.add_evaporation_laws), incl. the first (inline) reaction of some nuclides."""
+    mesh, lib, bm, s = pin_cell_tet_reactions(**kw)
+    return mesh, nucdata.add_evaporation_laws(lib), bm, s
+
+
 def pin_cell_tet_fission(**kw):
     """Fission neutrons as evaluated files have them (tabulated total nu and yields, six delayed groups with Maxwell /
     evaporation / continuous tabular spectra, prompt Watt with tabulated parameters or continuous tabular), on top of the
@@ -212,7 +219,7 @@ def check_full_bank(r, rec, bank, n):
     assert np.isfinite(bank["E"]).all() and (bank["E"] > 0).all()
 
 
-PROBLEMS = {"pin_cell_tet_fission": pin_cell_tet_fission, "pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+PROBLEMS = {"pin_cell_tet_evaporation": pin_cell_tet_evaporation, "pin_cell_tet_fission": pin_cell_tet_fission, "pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
             "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,

@@ -42,8 +42,8 @@ def test_problem_file_round_trip(tmp_path):
     assert r["settings.ints"][0] == 100 and r["kernel.materials"].tolist() == [1, 2, 3, 4]
 
 
-@pytest.mark.parametrize("name", ["pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_fission", "pin_cell_tet_temperatures",
-                                  "pin_cell_tet_sab", "pin_cell_tet_urr"])
+@pytest.mark.parametrize("name", ["pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_evaporation", "pin_cell_tet_fission",
+                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_urr"])
 def test_problem_files_carry_the_full_physics(tmp_path, name):
     """Tabulated distributions, thermal-scattering tables with their material assignments and probability tables travel
     through the problem file: the records are there, and the C++ reader gets as far as creating the device handle
@@ -57,6 +57,8 @@ def test_problem_files_carry_the_full_physics(tmp_path, name):
         assert any(k.endswith("law.i") for k in r) and any(k.endswith("law.f") for k in r)  # correlated, Kalbach-Mann, N-body
     if name.endswith("reactions"):
         assert r["nuc1.rx.head"][0] == 4 and r["nuc1.rx3.i"][0] == 875 and any(k.endswith("corr.f") for k in r)
+    if name.endswith("evaporation"):
+        assert "nuc1.rx.a" in r and "nuc1.rx2.y" in r and r["nuc1.law.i"][0] == 6 and r["nuc1.rx1.i"][2] == 6
     if name.endswith("fission") or name.endswith("temperatures"):
         assert r["nuc2.fis.head"][0] == 7 and "nuc2.fis0.y" in r and any(k.endswith("en.xpc") and ".fis" in k for k in r)
     if name.endswith("temperatures"):
@@ -89,8 +91,8 @@ def test_cpp_host_builds_and_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.parametrize("name", ["infinite_medium", "pin_cell_tet", "assembly_quad", "pin_cell_tet_iso",
                                   # tabulated distributions, S(a,b) and probability tables through the problem file and
                                   # host/macaw_host.hpp's Library (mcw_set_thermal_tables / _material_thermal / _urr_tables)
-                                  "pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_fission", "pin_cell_tet_temperatures",
-                                  "pin_cell_tet_sab", "pin_cell_tet_urr"])
+                                  "pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_evaporation", "pin_cell_tet_fission",
+                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_urr"])
 def test_cpp_host_matches_oracle(oracle_bridge, tmp_path, name):
     exe = _build()
     path, (mesh, lib, bm, s) = _write(tmp_path, name, n_particles=3000)

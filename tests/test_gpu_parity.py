@@ -188,6 +188,9 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     # lists of scattering reactions with yields (further levels, continuum with a non-integral multiplicity, (n,2n))
     ("pin_cell_tet_reactions", {}, EVENT), ("pin_cell_tet_reactions", {}, FUSED), ("pin_cell_tet_reactions", {}, PUMP),
     ("pin_cell_tet_reactions", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # Maxwell / evaporation / Watt spectra and energy-dependent multiplicities on scattering reactions
+    ("pin_cell_tet_evaporation", {}, EVENT), ("pin_cell_tet_evaporation", {}, FUSED), ("pin_cell_tet_evaporation", {}, PUMP),
+    ("pin_cell_tet_evaporation", {"n_particles": 20000}, {"tail_threshold": 3000}),
     # fission neutrons as nuclide files have them (function yields, total nu, Watt / Maxwell / evaporation / tabular spectra)
     ("pin_cell_tet_fission", {}, EVENT), ("pin_cell_tet_fission", {}, FUSED), ("pin_cell_tet_fission", {}, PUMP),
     ("pin_cell_tet_fission", {"n_particles": 20000}, {"tail_threshold": 3000}),
@@ -214,7 +217,7 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
         g.set_option(k, v)
     o.sample_initial_source()
     g.sample_initial_source()
-    laws = np.zeros(5, np.int64)
+    laws = np.zeros(8, np.int64)
     o.L.orc_law_samples(laws.ctypes.data_as(C.POINTER(C.c_longlong)))  # reset
     o.L.orc_reaction_samples(np.zeros(8, np.int64).ctypes.data_as(C.POINTER(C.c_longlong)))
     for batch in range(1, 4):
@@ -228,7 +231,11 @@ def test_generations_bit_exact(oracle_bridge, ctx_factory, name, kw, opts):
         if name == "pin_cell_tet_tabular" and batch == 3:
             # the problem reaches every inelastic law: continuous tabular, correlated, Kalbach-Mann, N-body
             o.L.orc_law_samples(laws.ctypes.data_as(C.POINTER(C.c_longlong)))
-            assert laws[0] == 0 and (laws[1:] >= 50).all(), laws
+            assert laws[0] == 0 and (laws[1:5] >= 50).all(), laws
+        if name == "pin_cell_tet_evaporation" and batch == 3:
+            # ... and the Maxwell, evaporation and Watt spectra
+            o.L.orc_law_samples(laws.ctypes.data_as(C.POINTER(C.c_longlong)))
+            assert (laws[5:] >= 30).all(), laws
         a, b = o.history_records(), g.history_records()
         for f in ("seed_tracking", "seed_source", "seed_urr", "n_segments", "n_collisions", "n_progeny",
                   "last_elem", "fate", "trace_hash"):

@@ -639,6 +639,10 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
         # a list of scattering reactions after the first on every nuclide that has one: further levels, the continuum with
         # a non-integral multiplicity, (n,2n) -- read by the reference's own Reaction / ReactionProduct constructors
         nucdata.add_reactions(lib)
+    if reactions == "evaporation":
+        # ... some of them with Maxwell / evaporation / Watt spectra and energy-dependent multiplicities (Tabulated1D /
+        # Polynomial yield_), read by the reference's MaxwellEnergy / Evaporation / WattEnergy constructors
+        nucdata.add_evaporation_laws(lib)
     if tabular:
         # a fifth material holding every nuclide with an inelastic reaction at the same density, so that each secondary
         # law (continuous tabular CM / LAB, correlated CM / LAB, Kalbach-Mann CM / LAB, N-body) is sampled thousands of times
@@ -693,7 +697,7 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures", "fission"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures", "fission", "evaporation"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -725,10 +729,13 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     if temperatures and not hasattr(r, "ref_stage_temperature_set"):
         pytest.skip("oracle/_ref built without the temperature-set doorway")
     fission = tabular == "fission"
-    reactions = tabular == "reactions" or temperatures or fission
+    evaporation = tabular == "evaporation"
+    reactions = tabular == "reactions" or temperatures or fission or evaporation
     urr = urr or temperatures or fission
     lib, _, tables = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
-                                        reactions=reactions, temperatures=temperatures, fission=fission)
+                                        reactions="evaporation" if evaporation else reactions, temperatures=temperatures,
+                                        fission=fission)
+    law_seen = np.zeros(8, np.int64)
     rx_seen = np.zeros(8, np.int64)
     o_reset = np.zeros(8, np.int64)
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
@@ -766,6 +773,8 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
         mine = run(o.L.orc_collide_events, o.h, i_mat, keff)
         o.L.orc_reaction_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
         rx_seen += o_reset
+        o.L.orc_law_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
+        law_seen += o_reset
         assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
         if temperatures and T > 447:
             # ... which really come from other data sets than at room temperature
@@ -795,10 +804,14 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
                 seen[f"group {g}"] = seen.get(f"group {g}", 0) + int((sites[:, 4] == g).sum())
         seen["upscatter"] += int(((st[:, 0] > E) & (st[:, 4] > 0)).sum())
         seen["inelastic"] += int(((st[:, 0] < 0.5 * E) & (E > 1e6) & (st[:, 4] > 0)).sum())
-        if reactions:  # st[4] = alive * weight: the continuum reaction of every third nuclide multiplies the weight by 1.25
+        if evaporation:  # tabulated multiplicities between 1 and 1.6, a polynomial one just above 1
+            seen["weight"] = seen.get("weight", 0) + int(((st[:, 4] > 1.0) & (st[:, 4] <= 1.6)).sum())
+        elif reactions:  # st[4] = alive * weight: the continuum reaction of every third nuclide multiplies the weight by 1.25
             seen["weight"] = seen.get("weight", 0) + int((st[:, 4] == 1.25).sum())
             assert set(np.unique(st[:, 4])) <= {0.0, 1.0, 1.25}
     assert all(v > 0 for v in seen.values()), seen
+    if evaporation:  # Maxwell (5), evaporation (6) and Watt (7) spectra were sampled, next to the other laws
+        assert (law_seen[5:] >= 20).all(), law_seen
     if reactions:  # every position of the reaction list was sampled: MT 51, 52, 53, 91, 875
         assert (rx_seen[:5] >= 20).all() and rx_seen[5:].sum() == 0, rx_seen
 
