@@ -281,12 +281,21 @@ struct RxLaw
   std::vector<double> rx_xs;  // further reactions only: cross section from the threshold on
 };
 
-struct Nuclide : RxLaw
+// What every cross-section lookup touches, kept together at the start of Nuclide (two cache lines): the lookup walks up
+// to 35 nuclides per material and the CPU baseline is timed on it
+struct NuclideHot
 {
   int G = 0;
   bool fissionable = false;
   double awr = 1, kT = 0;
-  std::vector<double> energy, xs, elastic, inelastic;
+  std::vector<double> energy, xs;
+  std::vector<int> grid_index;
+  std::vector<double> urr_energy; // unresolved-resonance probability tables: energies (empty = none)
+};
+
+struct Nuclide : NuclideHot, RxLaw
+{
+  std::vector<double> elastic, inelastic;
   int n_inel = 0;
   std::vector<RxLaw> more; // the scattering reactions after the first
   // Several temperatures (OMC Nuclide::kTs_ / grid_[t] / xs_[t] / reactions_[r]->xs_[t] / urr_data_[t]): every data set is
@@ -299,10 +308,9 @@ struct Nuclide : RxLaw
   int n_precursor = 0;
   double dyield[MCW_MAX_DELAYED_GROUPS], dtheta[MCW_MAX_DELAYED_GROUPS];
   double watt_a = 0, watt_b = 0, q = 0;
-  std::vector<int> grid_index;
   Tabular2D el_angle;
   // unresolved-resonance probability tables (mcw_urr_desc; OMC urr.cpp UrrData); urr_energy empty = none
-  std::vector<double> urr_energy, urr_table; // table[n_energy][6][n_band]
+  std::vector<double> urr_table; // table[n_energy][6][n_band]
   int urr_bands = 0, urr_inel_flag = -1, urr_multiply_smooth = 0;
   double urr_prob(int i_energy, int param, int band) const { return urr_table[((size_t)i_energy * 6 + param) * urr_bands + band]; }
 
@@ -380,6 +388,7 @@ struct Library
   double E_min = 0, E_max = 0, log_spacing = 0;
   int n_log_bins = 8000;
   int n_identities = 0; // nuclides (OMC data::nuclides.size()); entries beyond are further temperature sets.  0: all
+  bool multi_temperature() const { return n_identities > 0 && (size_t)n_identities < nuclides.size(); }
   int identities() const { return n_identities > 0 ? n_identities : (int)nuclides.size(); }
 
   // OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
@@ -606,9 +615,10 @@ struct Library
     const Material& mat = materials[i_mat];
     Macro M;
     int i_log = log_bin(E);
+    const bool pick = multi_temperature();
     for (size_t i = 0; i < mat.nuc.size(); ++i)
     {
-      const int entry = pick_set(mat.nuc[i], kT);
+      const int entry = pick ? pick_set(mat.nuc[i], kT) : mat.nuc[i];
       Micro m = micro_xs(entry, E, i_log);
       m.entry = entry;
       // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)

@@ -734,13 +734,14 @@ static double fission_product_energy(const FisProduct& f, double E, uint64_t* se
 // OMC physics.cpp:1073-1120 over UncorrelatedAngleEnergy::sample (secondary_uncorrelated.cpp:54-68): cosine from the
 // reaction's angle table or uniform, energy from LevelInelastic (distribution_energy.cpp:48-51) or ContinuousTabular
 // (:150-275), CM -> LAB when scatter_in_cm_, yield 1
+static bool g_count_samples = false; // the counters below are shared by all threads: off unless a test reads them
 static long long g_law_samples[8]; // how often each MCW_LAW_* was sampled (test coverage: orc_law_samples)
 static long long g_rx_samples[8];  // ... and each position of the reaction list (orc_reaction_samples)
 static void inelastic_scatter(const RxLaw& nuc, double awr, Hist& p)
 {
   double E_in = p.E;
   double mu, E;
-  if (nuc.inel_law >= 0 && nuc.inel_law < 8)
+  if (g_count_samples && nuc.inel_law >= 0 && nuc.inel_law < 8)
   {
 #pragma omp atomic
     g_law_samples[nuc.inel_law]++;
@@ -970,7 +971,7 @@ static CollisionOut collide(Problem& P, Hist& p, int i_mat, const Macro& macro, 
     else if (rx)
     {
       const int j = rx == (const RxLaw*)&nuc ? 0 : 1 + (int)(rx - nuc.more.data());
-      if (j < 8)
+      if (g_count_samples && j < 8)
       {
 #pragma omp atomic
         g_rx_samples[j]++;
@@ -1201,7 +1202,9 @@ static void run_history(Problem& P, int64_t i_local, int batch, bool tallies_act
       micro.resize(mat.nuc.size());
     // event_calculate_xs: macro recomputed every segment
     // p.sqrtkT from the coupled temperature of the element (MC CollisionKernel.C:109): picks each nuclide's data set
-    const double kT = P.temperature.empty() ? 0.0 : Library::kT_of(P.temperature[P.temperature.size() == 1 ? 0 : (size_t)c.elem]);
+    const double kT = (P.temperature.empty() || !P.lib.multi_temperature())
+                          ? 0.0
+                          : Library::kT_of(P.temperature[P.temperature.size() == 1 ? 0 : (size_t)c.elem]);
     Macro macro = P.lib.macro_xs(i_mat, p.E, micro.data(), &n_nuc, &p.seeds[STREAM_URR], kT);
     ++p.n_xs;
     // distance to collision: 1 RN per segment (MC CollisionKernel.C:150)
@@ -1340,6 +1343,7 @@ void orc_isotropic_direction(double* uvw, uint64_t* seed)
 // samples of each inelastic law since the last call (so a test can assert that its problem really reaches every law)
 void orc_law_samples(long long* out8)
 {
+  g_count_samples = true; // counting starts with the first read (tests read once to reset)
   for (int i = 0; i < 8; ++i)
   {
     out8[i] = g_law_samples[i];
@@ -1348,6 +1352,7 @@ void orc_law_samples(long long* out8)
 }
 void orc_reaction_samples(long long* out8)
 {
+  g_count_samples = true;
   for (int i = 0; i < 8; ++i)
   {
     out8[i] = g_rx_samples[i];
