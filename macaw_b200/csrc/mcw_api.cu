@@ -998,9 +998,15 @@ int mcw_set_temperature(mcw_handle h, const double* T, int64_t n)
 {
   if (!h || !T || n <= 0)
     return MCW_E_INVALID_ARGUMENT;
-  // Single-temperature libraries: the coupled temperature only selects the (only) data set
-  // (OMC nuclide.cpp:614-626 NEAREST); kept so the CollisionKernel parameter has somewhere to go.
-  h->temperature.assign(T, T + n);
+  // The coupled temperature picks every nuclide's nearest data set (OMC nuclide.cpp:614-626 NEAREST); with one data set
+  // per nuclide it selects that one whatever it is.  The pick is made in prepare() (temperature classes, effective
+  // materials), so a change of the field after prepare() prepares again.
+  if (h->temperature.size() != (size_t)n || memcmp(h->temperature.data(), T, sizeof(double) * (size_t)n) != 0)
+  {
+    h->temperature.assign(T, T + n);
+    if ((int)h->nuclides.size() > h->n_identities)
+      h->prepared = false;
+  }
   return MCW_OK;
 }
 

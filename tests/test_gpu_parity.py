@@ -551,6 +551,39 @@ def test_xs_lookup_against_reference_objects_fixture(ctx_factory, golden_dir):
         assert np.array_equal(g.grid_index(i, lib.n_log_bins), ref[f"grid_index_{i}"]), i
 
 
+def test_xs_lookup_at_temperatures_against_reference_fixture(ctx_factory, golden_dir):
+    """GPU against the REFERENCE's own outputs on a library with data sets at 293.6 / 600 / 900 K (own grids) and reaction
+    lists: tests/golden/ref_collisions_full.npz holds what the reference's Material::calculate_xs gave at particle
+    temperatures of 0, 446, 700, 1200 and 447.5 K, i.e. after Nuclide::calculate_xs picked each nuclide's nearest data set
+    (OMC nuclide.cpp:614-626).  mcw_xs_lookup under mcw_set_temperature(T) returns the same macroscopic cross sections bit
+    for bit, and every data set's logarithmic grid index equals Nuclide::init_grid's on its own grid."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_ref_collisions_full", os.path.join(golden_dir, "make_ref_collisions_full.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ref = np.load(os.path.join(golden_dir, "ref_collisions_full.npz"))
+    lib = gen.library()
+    for key, x in gen.data_sets(lib):
+        if f"xs_{key}" in ref:
+            x.xs = ref[f"xs_{key}"].copy()
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100, n_log_bins=lib.n_log_bins)
+    g = problems.configure(ctx_factory(), mesh, lib, bm, s, False)
+    differ = 0
+    for i_mat in range(len(lib.materials)):
+        E, _, _, _ = gen.events(i_mat, lib)
+        g.set_temperature(gen.TEMPERATURES[i_mat])
+        got = g.xs_lookup(E, np.full(E.size, i_mat, np.int32))
+        assert np.array_equal(got.view(np.uint64), ref[f"m{i_mat}_macro"].view(np.uint64)), i_mat
+        g.set_temperature(293.6)
+        differ += int((g.xs_lookup(E, np.full(E.size, i_mat, np.int32))[:, 0] != got[:, 0]).sum())
+    assert differ > 2000  # the 600 K and 900 K sets really are other numbers
+    entries = [str(i) for i in range(len(lib.nuclides))] + [f"{i}_{k}" for i, n in enumerate(lib.nuclides)
+                                                           for k in range(len(n.more_temperatures or []))]
+    for e, key in enumerate(entries):
+        assert np.array_equal(g.grid_index(e, lib.n_log_bins), ref[f"grid_index_{key}"]), key
+
+
 @pytest.mark.parametrize("name,world", [("pin_cell_tet", 2), ("beavrs_assembly", 2)])
 def test_two_gpus_equal_one_gpu(ctx_factory, tmp_path, name, world):
     """Rank-count invariance ON THE GPUS over NCCL (OMC eigenvalue.cpp:71-311 synchronize_bank): the next source

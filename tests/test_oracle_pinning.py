@@ -1123,3 +1123,62 @@ def test_full_fission_bank_keeps_the_bank_consistent(oracle_bridge):
     assert len(o.source_bank()) == n
     r2 = o.run_generation(2)
     assert r2.n_bank_dropped == 0 and 0.5 * n < r2.n_bank_sites < 2 * n
+
+
+def _full_fixture():
+    """tests/golden/ref_collisions_full.npz + its generator module + the library with the reference's derived tables"""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(here, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    gen, base = load("make_ref_collisions_full"), load("make_ref_collisions")
+    g = np.load(os.path.join(here, "ref_collisions_full.npz"))
+    lib = gen.library()
+    for key, x in gen.data_sets(lib):
+        if f"xs_{key}" in g:
+            x.xs = g[f"xs_{key}"].copy()
+    return gen, base, g, lib
+
+
+@pytest.mark.parametrize("libm", [True, False])
+def test_full_physics_fixture_from_reference_objects(oracle_bridge, libm):
+    """tests/golden/ref_collisions_full.npz (tests/golden/make_ref_collisions_full.py, made where the reference tree
+    exists): 5 x 1000 collisions through the reference's own Material::calculate_xs + Particle::event_collide on a
+    library with reaction lists, every secondary law, energy-dependent multiplicities, fission products with function
+    yields and tabulated spectra, and data sets at three temperatures, at particle temperatures that pick each set.  Needs
+    neither /root/reference nor oracle/_ref: the oracle reproduces the reference's outputs bit for bit on glibc math --
+    cross sections, outgoing energy / direction / weight, all seeds, fission sites -- and to 1e-12 with identical seeds /
+    counts / fates on its deterministic math; every data set's logarithmic grid index equals Nuclide::init_grid's."""
+    from tests import problems
+    gen, base, g, lib = _full_fixture()
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    o = problems.configure(oracle_bridge.Oracle(libm=libm), mesh, lib, bm, s, tallies=False)
+    entries = [str(i) for i in range(len(lib.nuclides))] + [f"{i}_{k}" for i, n in enumerate(lib.nuclides)
+                                                           for k in range(len(n.more_temperatures or []))]
+    for e, key in enumerate(entries):  # library entries: the nuclides, then the further sets in nuclide order
+        assert np.array_equal(o.grid_index(e, lib.n_log_bins), g[f"grid_index_{key}"]), key
+    weights = set()
+    for i_mat in range(len(lib.materials)):
+        E, u, seeds, ids = gen.events(i_mat, lib)
+        o.set_temperature(gen.TEMPERATURES[i_mat])
+        mine = base.run_events(o.L.orc_collide_events, (o.h, i_mat, gen.KEFF), E, u, seeds, ids)
+        ref = {k: g[f"m{i_mat}_{k}"] for k in mine}
+        assert np.array_equal(mine["macro"].view(np.uint64), ref["macro"].view(np.uint64))
+        assert np.array_equal(mine["seeds_out"], ref["seeds_out"]) and np.array_equal(mine["n_sites"], ref["n_sites"])
+        assert mine["sites"].shape == ref["sites"].shape
+        if libm:
+            assert np.array_equal(mine["state"].view(np.uint64), ref["state"].view(np.uint64))
+            assert np.array_equal(mine["sites"].view(np.uint64), ref["sites"].view(np.uint64))
+        else:
+            assert np.array_equal(mine["state"][:, 7], ref["state"][:, 7]) and np.array_equal(mine["sites"][:, 4:], ref["sites"][:, 4:])
+            assert np.allclose(mine["state"], ref["state"], rtol=1e-12, atol=1e-14)
+            assert np.allclose(mine["sites"], ref["sites"], rtol=1e-12, atol=1e-14)
+        assert np.array_equal(mine["kappa"].view(np.uint64), ref["kappa"].view(np.uint64))
+        weights |= set(np.unique(ref["state"][:, 4]).tolist())
+    assert len(weights) > 10 and max(weights) <= 1.6  # energy-dependent multiplicities moved the weight
+    assert set(np.unique(np.concatenate([g[f"m{m}_sites"][:, 4] for m in range(5)])).tolist()) == set(range(7))  # all groups
