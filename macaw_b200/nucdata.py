@@ -75,10 +75,17 @@ class Function1D:
             for c in self.y[::-1]:
                 out = out * E + c
             return out
+        # Tabulated1D::operator() (OMC endf.cpp:156-210) operation for operation, so that tables derived with it (nu-fission)
+        # equal the reference's bit for bit: constant outside the range, i = lower_bound_index, r = (x - x0) / (x1 - x0)
+        x, y = np.asarray(self.x, np.float64), np.asarray(self.y, np.float64)
+        i = np.clip(np.searchsorted(x, E, side="left") - 1, 0, x.size - 2)
+        i = np.where(E == x[0], 0, i)
         if self.interpolation == 1:
-            i = np.clip(np.searchsorted(self.x, E, side="right") - 1, 0, len(self.x) - 1)
-            return np.asarray(self.y)[i]
-        return np.interp(E, self.x, self.y)
+            out = y[i]
+        else:
+            r = (E - x[i]) / (x[i + 1] - x[i])
+            out = y[i] + r * (y[i + 1] - y[i])
+        return np.where(E < x[0], y[0], np.where(E > x[-1], y[-1], out))
 
 
 @dataclass

@@ -162,6 +162,9 @@ def ref_lib():
             r.ref_stage_law.argtypes = [C.c_void_p]
         if hasattr(r, "ref_stage_urr"):
             r.ref_stage_urr.argtypes = [C.c_void_p]
+        if hasattr(r, "ref_dump_tree"):
+            r.ref_dump_tree.restype = C.c_int64
+            r.ref_dump_tree.argtypes = [C.c_void_p, C.c_int64]
         if hasattr(r, "ref_stage_temperature_set"):
             r.ref_stage_temperature_set.argtypes = [C.c_void_p, C.c_void_p]
             r.ref_nuclide_temperatures.argtypes = [C.c_int, f64p]
@@ -204,6 +207,15 @@ def ref_lib():
 
 def _p(a):
     return a.ctypes.data if a is not None else None
+
+
+def ref_nuclide_file_image(r) -> bytes:
+    """The in-memory nuclide-file image the reference's constructors read in the last ref_load_library, as bytes
+    (macaw_b200.openmc_hdf5.read_image parses them)."""
+    n = r.ref_dump_tree(None, 0)
+    buf = (C.c_ubyte * n)()
+    assert r.ref_dump_tree(C.addressof(buf), n) == n
+    return bytes(buf)
 
 
 def ref_load_library(r, libr: nucdata.Library):

@@ -610,6 +610,72 @@ REF_API void ref_finish_library(int n_log_bins)
 }
 
 // derived tables of nuclide i (create_derived, nuclide.cpp:317-390): xs_[0] as [G][5], and its flags
+// The in-memory nuclide file image as a byte stream (so that macaw_b200/openmc_hdf5.py, the converter from OpenMC's
+// nuclide-file layout to the library's descriptors, can be run on exactly what the reference's constructors just read):
+//   node  = 'G' | 'D', name, n_attrs, {name, array}, [array if 'D'], n_children, {node}
+//   array = kind (0 real, 1 int, 2 text), n_dims, dims (u64), payload (f64 / i64 / bytes)
+// strings are u32 length + bytes; everything little endian.
+namespace
+{
+void put_u32(std::vector<unsigned char>& o, uint32_t v) { o.insert(o.end(), (unsigned char*)&v, (unsigned char*)&v + 4); }
+void put_str(std::vector<unsigned char>& o, const std::string& s)
+{
+  put_u32(o, (uint32_t)s.size());
+  o.insert(o.end(), s.begin(), s.end());
+}
+void put_array(std::vector<unsigned char>& o, const memh5::Array& a)
+{
+  o.push_back((unsigned char)a.kind);
+  put_u32(o, (uint32_t)a.shape.size());
+  for (unsigned long long d : a.shape)
+    o.insert(o.end(), (unsigned char*)&d, (unsigned char*)&d + 8);
+  if (a.kind == memh5::Array::REAL)
+  {
+    put_u32(o, (uint32_t)a.real.size());
+    o.insert(o.end(), (const unsigned char*)a.real.data(), (const unsigned char*)(a.real.data() + a.real.size()));
+  }
+  else if (a.kind == memh5::Array::INT)
+  {
+    put_u32(o, (uint32_t)a.integer.size());
+    o.insert(o.end(), (const unsigned char*)a.integer.data(), (const unsigned char*)(a.integer.data() + a.integer.size()));
+  }
+  else
+    put_str(o, a.text);
+}
+void put_node(std::vector<unsigned char>& o, const memh5::Node& n)
+{
+  o.push_back(n.is_dataset ? 'D' : 'G');
+  put_str(o, n.name);
+  put_u32(o, (uint32_t)n.attrs.size());
+  for (const auto& kv : n.attrs)
+  {
+    put_str(o, kv.first);
+    put_array(o, kv.second);
+  }
+  if (n.is_dataset)
+    put_array(o, n.data);
+  put_u32(o, (uint32_t)n.children.size());
+  for (const auto& kv : n.children)
+    put_node(o, *kv.second);
+}
+std::vector<unsigned char> g_dump;
+} // namespace
+
+// serialises the tree; returns the byte count, copies min(count, capacity) bytes into out (call with capacity 0 first)
+REF_API int64_t ref_dump_tree(unsigned char* out, int64_t capacity)
+{
+  if (capacity <= 0)
+  {
+    g_dump.clear();
+    if (g_root)
+      put_node(g_dump, *g_root);
+    return (int64_t)g_dump.size();
+  }
+  const int64_t n = std::min<int64_t>(capacity, (int64_t)g_dump.size());
+  memcpy(out, g_dump.data(), (size_t)n);
+  return n;
+}
+
 // number of temperatures nuclide i was read with and kTs_[t]
 REF_API int ref_nuclide_temperatures(int i, double* kTs)
 {

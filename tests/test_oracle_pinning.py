@@ -1182,3 +1182,169 @@ def test_full_physics_fixture_from_reference_objects(oracle_bridge, libm):
         weights |= set(np.unique(ref["state"][:, 4]).tolist())
     assert len(weights) > 10 and max(weights) <= 1.6  # energy-dependent multiplicities moved the weight
     assert set(np.unique(np.concatenate([g[f"m{m}_sites"][:, 4] for m in range(5)])).tolist()) == set(range(7))  # all groups
+
+
+def _same(a, b, path=""):
+    """deep equality of what nucdata objects hold: arrays bit for bit, None == None, dataclasses field by field"""
+    import dataclasses
+    if path.endswith("n_discrete") and (a is None or b is None):
+        assert (a is None or not np.any(a)) and (b is None or not np.any(b)), path  # no discrete lines, said either way
+    elif a is None or b is None:
+        assert a is None and b is None, path
+    elif dataclasses.is_dataclass(a):
+        for f in dataclasses.fields(a):
+            _same(getattr(a, f.name), getattr(b, f.name), f"{path}.{f.name}")
+    elif isinstance(a, (tuple, list)):
+        assert len(a) == len(b), path
+        for k, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, f"{path}[{k}]")
+    elif isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape, (path, a.shape, b.shape)
+        if a.dtype.kind == "f" or b.dtype.kind == "f":
+            assert np.array_equal(a.astype(np.float64).view(np.uint64), b.astype(np.float64).view(np.uint64)), path
+        else:
+            assert np.array_equal(a, b), path
+    else:
+        assert a == b, (path, a, b)
+
+
+def _everything_library(nucdata, G=600):
+    lib = nucdata.make_library(n_nuclides=15, G=G, seed=3, n_log_bins=500, tabular=True)
+    nucdata.add_evaporation_laws(nucdata.add_reactions(lib))
+    nucdata.add_fission_data(lib)
+    nucdata.add_urr_tables(lib)
+    nucdata.add_temperatures(lib)
+    return lib
+
+
+def _check_converted(lib, conv):
+    """the converted library equals the one the image was written from, field by field"""
+    from macaw_b200 import nucdata
+    assert len(conv.nuclides) == len(lib.nuclides)
+    for n, c in zip(lib.nuclides, conv.nuclides):
+        for x, y in zip([n] + list(n.more_temperatures or []), [c] + list(c.more_temperatures or [])):
+            p = f"{n.name}@{x.kT:.4f}"
+            assert y.kT == x.kT and y.awr == x.awr and y.fissionable == x.fissionable and y.n_precursor == x.n_precursor, p
+            for f in ("energy", "elastic", "inelastic"):
+                _same(getattr(x, f), getattr(y, f), f"{p}.{f}")
+            assert np.array_equal(y.xs[:, :4].view(np.uint64), x.xs[:, :4].view(np.uint64)), p  # create_derived's tables
+            assert y.inel_threshold == x.inel_threshold
+            if x.inelastic.size:
+                law = lambda z: z.inelastic_law if z.inelastic_law >= 0 else (1 if z.inelastic_energy is not None else 0)
+                assert law(x) == law(y), p
+                if law(x) == 0:
+                    assert (y.inel_threshold_energy, y.inel_mass_ratio) == (x.inel_threshold_energy, x.inel_mass_ratio), p
+                if law(x) != 0:
+                    assert bool(y.inelastic_in_cm) == bool(x.inelastic_in_cm), p
+                for f in ("inelastic_energy", "corr_angle", "km_r", "km_a", "nbody", "inelastic_yield_fn", "inelastic_a",
+                          "inelastic_b"):
+                    _same(getattr(x, f), getattr(y, f), f"{p}.{f}")
+                if law(x) < 2 or law(x) >= 5:
+                    _same(x.inelastic_angle, y.inelastic_angle, p + ".inelastic_angle")
+                assert (x.inelastic_yield_fn is not None or y.inelastic_yield == x.inelastic_yield) and \
+                    (law(x) < 5 or y.inelastic_u == x.inelastic_u), p
+            _same(x.elastic_angle, y.elastic_angle, p + ".elastic_angle")
+            assert len(x.more_reactions or []) == len(y.more_reactions or []), p
+            for rx, ry in zip(x.more_reactions or [], y.more_reactions or []):
+                q = f"{p}.MT{rx.mt}"
+                assert (ry.mt, ry.threshold, ry.law) == (rx.mt, rx.threshold, rx.law), q
+                assert rx.yield_fn is not None or ry.yield_ == rx.yield_, q  # a yield function stands in for the constant
+                assert ry.law == 0 or bool(ry.in_cm) == bool(rx.in_cm), q
+                if rx.law == 0:
+                    assert (ry.threshold_energy, ry.mass_ratio) == (rx.threshold_energy, rx.mass_ratio), q
+                if rx.law >= 5:
+                    assert ry.u == rx.u, q
+                for f in ("xs", "energy", "corr_angle", "km_r", "km_a", "nbody", "yield_fn", "a", "b"):
+                    _same(getattr(rx, f), getattr(ry, f), f"{q}.{f}")
+                if rx.law < 2 or rx.law >= 5:
+                    _same(rx.angle, ry.angle, q + ".angle")
+            if x.fissionable:
+                assert y.q_fission == x.q_fission, p
+                _same(x.total_nu, y.total_nu, p + ".total_nu")
+                assert len(y.fission_products) == len(x.fission_products) == 7, p
+                for k, (fx, fy) in enumerate(zip(x.fission_products, y.fission_products)):
+                    assert fy.law == fx.law and (fx.law == 1 or fy.u == fx.u), (p, k)
+                    for f in ("yield_", "a", "b", "energy"):
+                        _same(getattr(fx, f), getattr(fy, f), f"{p}.fis{k}.{f}")
+    ux = sorted(lib.urr_tables, key=lambda t: t.nuclide)
+    uy = sorted(conv.urr_tables, key=lambda t: t.nuclide)
+    assert [t.nuclide for t in ux] == [t.nuclide for t in uy]
+    for a, b in zip(ux, uy):
+        assert (a.inelastic_flag, a.absorption_flag, bool(a.multiply_smooth)) == (b.inelastic_flag, b.absorption_flag, bool(b.multiply_smooth))
+        _same(a.energy, b.energy, "urr.energy")
+        _same(a.table, b.table, "urr.table")
+
+
+def test_nuclide_file_converter_against_reference_nuclide_cpp(oracle_bridge):
+    """macaw_b200/openmc_hdf5.py, the converter from OpenMC's nuclide-file layout to the library's descriptors, on exactly the
+    image the REFERENCE's own constructors read: a library with everything (reaction lists, every law, function yields,
+    fission products, probability tables, three temperatures) is written as a nuclide-file image by oracle/_ref, read by
+    the reference's Nuclide / Reaction / ReactionProduct / UrrData constructors -- and, through ref_dump_tree, by the
+    converter.  The converter's derived total / absorption / fission / nu-fission tables equal the reference's own
+    Nuclide::create_derived bit for bit at every temperature, its reaction lists, laws, tables, yields, fission products
+    and probability tables equal what was written, and the converted library collides exactly like the original."""
+    from macaw_b200 import nucdata, openmc_hdf5
+    from tests import problems
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_dump_tree"):
+        pytest.skip("oracle/_ref not built with the image dump (no /root/reference on this box)")
+    lib = _everything_library(nucdata)
+    tables = oracle_bridge.ref_load_library(r, lib)
+    for n, tb in zip(lib.nuclides, tables):  # the reference's derived tables, every temperature
+        n.xs = tb[0].copy()
+        if len(tb) > 4:
+            for x in [n] + list(n.more_temperatures):
+                x.xs = tb[4][id(x)][0].copy()
+    root = openmc_hdf5.read_image(oracle_bridge.ref_nuclide_file_image(r))
+    conv = openmc_hdf5.library_from_groups([(n.name, root[n.name]) for n in lib.nuclides], lib.materials, lib.n_log_bins)
+    _check_converted(lib, conv)
+    # the converted library through the oracle: same collisions as the original, bit for bit
+    mesh, _, bm, s = problems.infinite_medium(n_particles=100)
+    rng = np.random.default_rng(9)
+    n_ev = 3000
+    E = np.exp(rng.uniform(np.log(1.2e-5), np.log(1.9e7), n_ev))
+    u = rng.normal(size=(n_ev, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    seeds = rng.integers(1, 2 ** 63, (n_ev, 4), dtype=np.uint64)
+    ids = np.arange(1, n_ev + 1, dtype=np.int64)
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_ref_collisions", os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                                       "golden", "make_ref_collisions.py"))
+    base = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(base)
+    outs = []
+    for L in (lib, conv):
+        o = problems.configure(oracle_bridge.Oracle(), mesh, L, bm, s, tallies=False)
+        o.set_temperature(700.0)
+        outs.append(base.run_events(o.L.orc_collide_events, (o.h, 0, 1.02), E, u, seeds, ids))
+    for k in outs[0]:
+        assert outs[0][k].tobytes() == outs[1][k].tobytes(), k
+    # what the library does not carry is refused, not dropped
+    bad = root["U235"]["reactions"]["reaction_018"]
+    bad.attrs["mt"] = np.int64(19)
+    with pytest.raises(openmc_hdf5.Refused):
+        openmc_hdf5.nuclide_from_group(root["U235"], "U235")
+
+
+def test_nuclide_file_converter_fixture():
+    """tests/golden/nuclide_file_image.npz (tests/golden/make_nuclide_file_image.py, made where the reference tree exists):
+    the bytes of a nuclide-file image the reference's own constructors read, and the tables its Nuclide::create_derived
+    made of them.  Needs neither /root/reference nor oracle/_ref: macaw_b200/openmc_hdf5.py turns the image into a library
+    whose derived tables equal the reference's bit for bit at every temperature and whose reactions, laws, yields, fission
+    products and probability tables equal the library the image was written from."""
+    import importlib.util
+    import os
+    from macaw_b200 import openmc_hdf5
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_nuclide_file_image", os.path.join(here, "make_nuclide_file_image.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "nuclide_file_image.npz"))
+    lib = gen.library()
+    for key, x in gen.data_sets(lib):
+        x.xs = g[f"xs_{key}"].copy()
+    root = openmc_hdf5.read_image(g["image"].tobytes())
+    conv = openmc_hdf5.library_from_groups([(n.name, root[n.name]) for n in lib.nuclides], lib.materials, lib.n_log_bins)
+    _check_converted(lib, conv)
