@@ -177,12 +177,14 @@ typedef struct mcw_reaction_desc
   mcw_function1d a, b;
 } mcw_reaction_desc;
 
-/* One continuous-energy nuclide, single temperature.  Field meaning follows openmc::Nuclide
- * (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
- * col = total, absorption, fission, nu-fission, photon-production.  Reactions present: elastic
- * (MT 2, isotropic in CM, free-gas below 400 kT), optionally one level-inelastic (LevelInelastic,
- * OMC distribution_energy.cpp:48-51, scatter in CM), radiative capture, optionally fission with
- * polynomial total nu, constant delayed yields, Watt prompt spectrum and Maxwell delayed spectra. */
+/* One continuous-energy nuclide at one temperature (further temperatures: mcw_add_temperature_set).  Field meaning
+ * follows openmc::Nuclide (OMC src/nuclide.cpp:50-302, 309-444): `xs` is the derived 5-column table xs_[t](i, col) with
+ * col = total, absorption, fission, nu-fission, photon-production, as Nuclide::create_derived sums it.  Reactions:
+ * elastic (MT 2; isotropic in CM or a tabulated angular distribution; free-gas target below 400 kT), a list of further
+ * scattering reactions -- the first one inline, the others as mcw_reaction_desc -- each with its law (MCW_LAW_*), system,
+ * and multiplicity; radiative capture and the other disappearance reactions (in `xs` only); fission, described either by
+ * scalars (polynomial total nu, constant delayed yields, Watt prompt and Maxwell delayed spectra) or by
+ * mcw_fission_product entries as a nuclide file has them. */
 typedef struct mcw_nuclide_desc
 {
   int32_t n_grid;

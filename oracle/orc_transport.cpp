@@ -686,31 +686,26 @@ static void nbody_sample(const RxLaw& nuc, double awr, double E_in, double& E_ou
 // distribution_energy.cpp:342-356, 279-291, 305-322): fission-neutron products and uncorrelated scattering products
 static double evaporation_type_energy(int law, const Fn& fa, const Fn& fb, double u, double E, uint64_t* seed)
 {
-  struct
+  if (law == MCW_LAW_WATT)
   {
-    int law;
-    const Fn &a, &b;
-    double u;
-  } f{law, fa, fb, u};
-  if (f.law == MCW_LAW_WATT)
-  {
-    const double a = f.a(E), b = f.b(E);
+    const double a = fa(E), b = fb(E);
     while (true)
     {
       const double E_out = watt_spectrum(a, b, seed);
-      if (E_out <= E - f.u)
+      if (E_out <= E - u)
         return E_out;
     }
   }
-  const double theta = f.a(E);
-  if (f.law == MCW_LAW_MAXWELL)
+  const double theta = fa(E);
+  if (law == MCW_LAW_MAXWELL)
     while (true)
     {
       const double E_out = maxwell_spectrum(theta, seed);
-      if (E_out <= E - f.u)
+      if (E_out <= E - u)
         return E_out;
     }
-  const double y = (E - f.u) / theta;
+  // Evaporation (:305-322); the two random numbers of the product commute
+  const double y = (E - u) / theta;
   const double v = 1.0 - xexp(-y);
   double x;
   while (true)
