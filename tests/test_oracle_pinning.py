@@ -1348,3 +1348,46 @@ def test_nuclide_file_converter_fixture():
     root = openmc_hdf5.read_image(g["image"].tobytes())
     conv = openmc_hdf5.library_from_groups([(n.name, root[n.name]) for n in lib.nuclides], lib.materials, lib.n_log_bins)
     _check_converted(lib, conv)
+
+
+def test_nuclide_file_converter_refuses_what_the_library_lacks():
+    """The converter never drops what the library cannot express: partial fission reactions, products with several
+    distributions, Tabulated1D functions with logarithmic interpolation or several regions, log-log probability tables and
+    unknown energy laws raise openmc_hdf5.Refused with the reason (image: tests/golden/nuclide_file_image.npz)."""
+    import os
+    from macaw_b200 import openmc_hdf5
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    image = np.load(os.path.join(here, "nuclide_file_image.npz"))["image"].tobytes()
+
+    def refused(change, nuclide="U235"):
+        root = openmc_hdf5.read_image(image)
+        change(root[nuclide])
+        with pytest.raises(openmc_hdf5.Refused) as e:
+            openmc_hdf5.nuclide_from_group(root[nuclide], nuclide)
+        return str(e.value)
+    assert openmc_hdf5.nuclide_from_group(openmc_hdf5.read_image(image)["U235"], "U235")[0].fissionable  # unchanged: accepted
+
+    def partial(g):
+        g["reactions/reaction_018"].attrs["mt"] = np.int64(19)
+    assert "partial fission" in refused(partial)
+
+    def two_distributions(g):
+        g["reactions/reaction_052/product_0"].attrs["n_distribution"] = np.int64(2)
+    assert "several distributions" in refused(two_distributions)
+
+    def log_interpolation(g):
+        g["total_nu/yield"].attrs["interpolation"] = np.array([5])
+    assert "logarithmic" in refused(log_interpolation)
+
+    def two_regions(g):
+        g["total_nu/yield"].attrs["interpolation"] = np.array([2, 2])
+        g["total_nu/yield"].attrs["breakpoints"] = np.array([3, 8])
+    assert "several regions" in refused(two_regions)
+
+    def loglog_urr(g):
+        g["urr/294K"].attrs["interpolation"] = np.int64(5)
+    assert "log-log" in refused(loglog_urr)
+
+    def unknown_law(g):
+        g["reactions/reaction_052/product_0/distribution_0/energy"].attrs["type"] = "madland-nix"
+    assert "madland-nix" in refused(unknown_law)
