@@ -228,6 +228,8 @@ class ThermalTable:
     elastic_x: np.ndarray = None
     elastic_y: np.ndarray = None
     elastic_mu: np.ndarray = None  # (n_elastic, n_elastic_mu)
+    kT: float = KT_ROOM            # the temperature of this set
+    more_temperatures: list = None  # further temperatures of the table (ThermalTable objects; OMC ThermalScattering::data_[t])
 
 
 def make_thermal_table(rng, name, kind="continuous", elastic="none", energy_max=4.0, n_mu=8) -> ThermalTable:
@@ -342,6 +344,23 @@ def add_thermal_scattering(lib: "Library", seed=5):
     return lib
 
 
+def add_thermal_temperatures(lib: "Library", temperatures=(400.0, 600.0), seed=17) -> "Library":
+    """Gives every S(a,b) table further temperatures (tables of the same kinds drawn anew, same energy_max): the history's
+    temperature picks the closer of the two that bound it (OMC thermal.cpp:149-171)."""
+    rng = np.random.Generator(np.random.PCG64([seed, 77]))
+    kinds = {(0, 0): ("continuous", "none"), (1, 1): ("discrete", "coherent"), (1, 2): ("discrete_skewed", "incoherent_discrete")}
+    for t in lib.thermal_tables:
+        t.more_temperatures = []
+        kind, el = kinds[(t.inelastic_type, t.elastic_type)]
+        if t.inelastic_type == 1 and not t.skewed:
+            kind = "discrete"
+        for T in temperatures:
+            m = make_thermal_table(rng, t.name, kind, el, t.energy_max, t.n_mu)
+            m.kT = 8.617333262e-5 * float(T)
+            t.more_temperatures.append(m)
+    return lib
+
+
 @dataclass
 class Library:
     nuclides: list
@@ -352,6 +371,18 @@ class Library:
 
     def total_points(self):
         return int(sum(n.energy.size for n in self.nuclides))
+
+    def thermal_entries(self):
+        """(tables, same_table_as, kT): every temperature of every S(a,b) table as one entry -- the tables themselves
+        first (what materials name), then their further temperatures in table order."""
+        tables = list(self.thermal_tables or [])
+        same, kT = list(range(len(tables))), [t.kT for t in tables]
+        for k, t in enumerate(self.thermal_tables or []):
+            for m in (getattr(t, "more_temperatures", None) or []):
+                tables.append(m)
+                same.append(k)
+                kT.append(m.kT)
+        return tables, np.array(same, np.int32), np.array(kT, np.float64)
 
     def temperature_sets(self):
         """[(nuclide index, data set)] of the further temperatures, in library-entry order: set k is entry

@@ -53,6 +53,7 @@ def _load(name):
     lib.orc_score_events.restype = C.c_int64
     lib.orc_score_events.argtypes = [C.c_int64, f64p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p, f64p,
                                      f64p, f64p]
+    lib.orc_set_thermal_temperatures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.orc_add_temperature_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     lib.orc_set_temperature.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.orc_law_samples.argtypes = [C.POINTER(C.c_longlong)]
@@ -171,6 +172,8 @@ def ref_lib():
             r.ref_nuclide_tables_t.argtypes = [C.c_int, C.c_int, f64p, C.c_void_p]
         if hasattr(r, "ref_add_thermal_table"):
             r.ref_add_thermal_table.argtypes = [C.c_char_p, C.c_void_p, C.c_double]
+            if hasattr(r, "ref_stage_thermal_temperature"):
+                r.ref_stage_thermal_temperature.argtypes = [C.c_void_p, C.c_double]
             r.ref_set_material_thermal.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, f64p]
         if hasattr(r, "ref_score_nuclide_bins"):
             r.ref_score_nuclide_bins.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int64,
@@ -293,7 +296,13 @@ def ref_load_library(r, libr: nucdata.Library):
         from macaw_b200 import nucdata as _nd
         td, keep = _nd.pack_thermal(libr.thermal_tables)
         for k, t in enumerate(libr.thermal_tables):
-            r.ref_add_thermal_table(t.name.encode(), C.addressof(td[k]), libr.nuclides[0].kT)
+            more = getattr(t, "more_temperatures", None) or []
+            if more:  # further temperatures of the table: one `<T>K` group each
+                md, keep_m = _nd.pack_thermal(more)
+                stash.append((md, keep_m))
+                for j, m in enumerate(more):
+                    r.ref_stage_thermal_temperature(C.addressof(md[j]), m.kT)
+            r.ref_add_thermal_table(t.name.encode(), C.addressof(td[k]), getattr(t, "kT", libr.nuclides[0].kT))
         for im, m in enumerate(libr.materials):
             if getattr(m, "sab", None):
                 pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)
@@ -349,9 +358,12 @@ class Oracle:
             if self.L.orc_set_urr_tables(self.h, C.addressof(ud), len(libr.urr_tables)):
                 raise RuntimeError("orc_set_urr_tables failed")
         if getattr(libr, "thermal_tables", None):
-            td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
+            tables, same, kT = libr.thermal_entries()  # every temperature of every table as one entry
+            td, keep2 = nucdata.pack_thermal(tables)
             self._keep.append((td, keep2))
-            self.L.orc_set_thermal_tables(self.h, C.addressof(td), len(libr.thermal_tables))
+            self.L.orc_set_thermal_tables(self.h, C.addressof(td), len(tables))
+            if len(tables) > len(libr.thermal_tables) and self.L.orc_set_thermal_temperatures(self.h, _p(same), _p(kT), len(tables)):
+                raise RuntimeError("orc_set_thermal_temperatures failed")
             for im, m in enumerate(libr.materials):
                 if getattr(m, "sab", None):
                     pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)

@@ -385,10 +385,29 @@ struct Library
   std::vector<Nuclide> nuclides;
   std::vector<Material> materials;
   std::vector<ThermalTable> thermal;
+  // Several temperatures of an S(a,b) table (OMC ThermalScattering::kTs_ / data_[t]): every temperature is an entry of
+  // `thermal`; thermal_sets[t] (for the entry t that materials name) lists all entries of that table by increasing kT,
+  // thermal_kT[k] is entry k's kT.  Empty: every table has one temperature.
+  std::vector<std::vector<int>> thermal_sets;
+  std::vector<double> thermal_kT;
+  // ThermalScattering::calculate_xs (OMC thermal.cpp:149-171), nearest temperature: the closer of the two bounding ones
+  int pick_thermal(int t, double kT) const
+  {
+    if (thermal_sets.empty() || thermal_sets[t].size() <= 1)
+      return t;
+    const std::vector<int>& s = thermal_sets[t];
+    const size_t n = s.size();
+    size_t i = 0;
+    while (thermal_kT[s[i + 1]] < kT && i + 1 < n - 1)
+      ++i;
+    if (kT - thermal_kT[s[i]] > thermal_kT[s[i + 1]] - kT)
+      ++i;
+    return s[i];
+  }
   double E_min = 0, E_max = 0, log_spacing = 0;
   int n_log_bins = 8000;
   int n_identities = 0; // nuclides (OMC data::nuclides.size()); entries beyond are further temperature sets.  0: all
-  bool multi_temperature() const { return n_identities > 0 && (size_t)n_identities < nuclides.size(); }
+  bool multi_temperature() const { return (n_identities > 0 && (size_t)n_identities < nuclides.size()) || !thermal_sets.empty(); }
   int identities() const { return n_identities > 0 ? n_identities : (int)nuclides.size(); }
 
   // OMC simulation.cpp:553-619 initialize_data + nuclide.cpp:446-476 init_grid
@@ -623,7 +642,7 @@ struct Library
       m.entry = entry;
       // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)
       if (!mat.sab_table.empty() && mat.sab_table[i] >= 0 && !(E > thermal[mat.sab_table[i]].energy_max))
-        apply_sab(nuclides[entry], mat.sab_table[i], mat.sab_frac[i], E, m);
+        apply_sab(nuclides[entry], pick_thermal(mat.sab_table[i], kT), mat.sab_frac[i], E, m);
       {
         // probability tables (those of the chosen data set, urr_data_[i_temp]), strictly inside their energy range
         // (nuclide.cpp:753-759); the band is drawn with the NUCLIDE's index (index_, :809)

@@ -1587,6 +1587,8 @@ int orc_set_thermal_tables(void* h, const mcw_thermal_desc* d, int n)
 {
   Problem& P = *(Problem*)h;
   P.lib.thermal.clear();
+  P.lib.thermal_sets.clear();
+  P.lib.thermal_kT.clear();
   for (int k = 0; k < n; ++k)
   {
     const mcw_thermal_desc& s = d[k];
@@ -1625,6 +1627,26 @@ int orc_set_thermal_tables(void* h, const mcw_thermal_desc* d, int n)
     }
     P.lib.thermal.push_back(std::move(t));
   }
+  return 0;
+}
+
+// Several temperatures of S(a,b) tables: entry k of orc_set_thermal_tables is a temperature (kT[k]) of the table whose
+// first entry is same_table_as[k] (k itself for a table's first or only temperature); materials name first entries.
+int orc_set_thermal_temperatures(void* h, const int32_t* same_table_as, const double* kT, int n)
+{
+  Problem& P = *(Problem*)h;
+  if (n != (int)P.lib.thermal.size())
+    return -1;
+  P.lib.thermal_sets.assign(n, {});
+  P.lib.thermal_kT.assign(kT, kT + n);
+  for (int k = 0; k < n; ++k)
+  {
+    if (same_table_as[k] < 0 || same_table_as[k] > k)
+      return -1;
+    P.lib.thermal_sets[same_table_as[k]].push_back(k);
+  }
+  for (auto& s : P.lib.thermal_sets)
+    std::stable_sort(s.begin(), s.end(), [&](int a, int b) { return P.lib.thermal_kT[a] < P.lib.thermal_kT[b]; });
   return 0;
 }
 

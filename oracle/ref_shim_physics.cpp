@@ -41,6 +41,7 @@ const mcw_tabular2d *g_el_angle = nullptr, *g_inel_angle = nullptr, *g_inel_ener
 int g_inel_in_cm = 1;
 const mcw_urr_desc* g_urr = nullptr; // probability tables staged for the next ref_add_nuclide
 std::vector<std::pair<const mcw_nuclide_desc*, const mcw_urr_desc*>> g_sets; // further temperatures of the next nuclide
+std::vector<std::pair<const mcw_thermal_desc*, double>> g_thermal_sets; // further temperatures of the next thermal table
 const mcw_nuclide_desc* g_law = nullptr; // product distribution (correlated / Kalbach-Mann / N-body) of the next nuclide's inelastic reaction
 
 // (3, N) dataset x / pdf / cdf with `offsets` and `interpolation` attributes: the layout of an angular distribution's `mu`
@@ -239,6 +240,7 @@ REF_API void ref_library_reset()
   data::thermal_scatt_map.clear();
   g_root.reset(new memh5::Node);
   g_sets.clear();
+  g_thermal_sets.clear();
   settings::run_CE = true;
   settings::run_mode = RunMode::EIGENVALUE;
   settings::survival_biasing = false;
@@ -492,7 +494,10 @@ REF_API int ref_add_nuclide(const char* name, double awr, double kT, int G, cons
 // ThermalScattering / ThermalData constructors (thermal.cpp:38-227) -- and through them Tabulated1D, CoherentElasticXS,
 // CorrelatedAngleEnergy -> IncoherentInelasticAE, IncoherentInelasticAEDiscrete, CoherentElasticAE,
 // IncoherentElasticAEDiscrete.  Returns its index in data::thermal_scatt.
-REF_API int ref_add_thermal_table(const char* name, const mcw_thermal_desc* t, double kT)
+// One more temperature of the NEXT thermal table added (ThermalScattering reads every `<T>K` group of `kTs`)
+REF_API void ref_stage_thermal_temperature(const mcw_thermal_desc* t, double kT) { g_thermal_sets.push_back({t, kT}); }
+
+REF_API int ref_add_thermal_table(const char* name, const mcw_thermal_desc* t0, double kT0)
 {
   using namespace openmc;
   auto tabulated = [](memh5::Node* parent, const double* x, const double* y, int n) {
@@ -507,9 +512,18 @@ REF_API int ref_add_thermal_table(const char* name, const mcw_thermal_desc* t, d
   };
   memh5::Node* g = g_root->group(name);
   g->attr("atomic_weight_ratio", 0.999167);
-  g->attr("energy_max", t->energy_max);
+  g->attr("energy_max", t0->energy_max);
   g->attrs["nuclides"] = memh5::Array{memh5::Array::TEXT, {1}, {}, {}, "H1"};
+  std::vector<std::pair<const mcw_thermal_desc*, double>> all{{t0, kT0}};
+  all.insert(all.end(), g_thermal_sets.begin(), g_thermal_sets.end());
+  g_thermal_sets.clear();
+  std::vector<double> temps;
+  for (const auto& tk : all)
+  {
+  const mcw_thermal_desc* t = tk.first;
+  const double kT = tk.second;
   const int T = (int)std::round(kT / K_BOLTZMANN);
+  temps.push_back((double)T);
   const std::string temp = std::to_string(T) + "K";
   g->group("kTs")->dataset(temp, {kT}, {})->data.shape.clear();
   memh5::Node* tg = g->group(temp);
@@ -577,7 +591,8 @@ REF_API int ref_add_thermal_table(const char* name, const mcw_thermal_desc* t, d
                   {(unsigned long long)n, (unsigned long long)t->n_elastic_mu});
     }
   }
-  data::thermal_scatt.push_back(std::make_unique<ThermalScattering>(memh5::id_of(g), std::vector<double>{(double)T}));
+  } // every temperature
+  data::thermal_scatt.push_back(std::make_unique<ThermalScattering>(memh5::id_of(g), temps));
   return (int)data::thermal_scatt.size() - 1;
 }
 

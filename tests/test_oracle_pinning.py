@@ -651,6 +651,8 @@ def _reference_library(oracle_bridge, r, n_log_bins=500, G=600, tabular=False, t
     if thermal:  # S(a,b) tables, read by the reference's own ThermalScattering / ThermalData constructors
         nucdata.add_thermal_scattering(lib)
         lib.materials[3].isotropic = None
+    if thermal == "temperatures":  # ... at 293.6 / 400 / 600 K each (ThermalScattering::kTs_, data_[t])
+        nucdata.add_thermal_temperatures(lib)
     if urr:      # probability tables, read by the reference's own UrrData constructor
         nucdata.add_urr_tables(lib)
     if fission:
@@ -697,7 +699,8 @@ def test_library_tables_and_grid_index_against_reference_nuclide_cpp(oracle_brid
     assert n_exact >= 5
 
 
-@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures", "fission", "evaporation"])
+@pytest.mark.parametrize("tabular", [False, True, "thermal", "urr", "reactions", "temperatures", "fission", "evaporation",
+                                     "thermal temperatures"])
 @pytest.mark.parametrize("libm", [True, False])
 def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm, tabular):
     """The chain MaCaw's CollisionKernel.C:143,185 runs, on the reference's own compiled code and data objects:
@@ -722,9 +725,12 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     if r is None or not hasattr(r, "ref_collide_events") or (tabular and not hasattr(r, "ref_stage_tables")) or \
             (tabular == "thermal" and not hasattr(r, "ref_add_thermal_table")):
         pytest.skip("oracle/_ref not built with physics.cpp + particle.cpp (no /root/reference on this box)")
-    thermal, urr = tabular == "thermal", tabular == "urr"
+    thermal, urr = tabular in ("thermal", "thermal temperatures"), tabular == "urr"
     if urr and not hasattr(r, "ref_stage_urr"):
         pytest.skip("oracle/_ref built without the probability-table doorway")
+    thermal_T = tabular == "thermal temperatures"
+    if thermal_T and not hasattr(r, "ref_stage_thermal_temperature"):
+        pytest.skip("oracle/_ref built without the thermal-temperature doorway")
     temperatures = tabular == "temperatures"
     if temperatures and not hasattr(r, "ref_stage_temperature_set"):
         pytest.skip("oracle/_ref built without the temperature-set doorway")
@@ -732,7 +738,8 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
     evaporation = tabular == "evaporation"
     reactions = tabular == "reactions" or temperatures or fission or evaporation
     urr = urr or temperatures or fission
-    lib, _, tables = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions, thermal=thermal, urr=urr,
+    lib, _, tables = _reference_library(oracle_bridge, r, tabular=tabular is True or reactions,
+                                        thermal="temperatures" if thermal_T else thermal, urr=urr,
                                         reactions="evaporation" if evaporation else reactions, temperatures=temperatures,
                                         fission=fission)
     law_seen = np.zeros(8, np.int64)
@@ -761,6 +768,12 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
                    sites.ctypes.data_as(f64p), kappa.ctypes.data_as(f64p))
             return macro, st, so, ns, sites[:nb], kappa
         sqrtkT = float(np.sqrt(lib.nuclides[0].kT))
+        if thermal_T:
+            # ThermalScattering::calculate_xs (thermal.cpp:149-171): the closer of the two temperatures that bound the
+            # particle's: 0 K and 340 K -> 293.6 K, 347 K -> 400 K (midpoint 346.8), 501 K -> 600 K, 2000 K -> 600 K
+            T = [0.0, 340.0, 347.0, 501.0, 2000.0][i_mat % 5]
+            sqrtkT = float(np.sqrt(8.617333262e-5 * T))
+            o.set_temperature(T)
         if temperatures:
             # the particle's temperature (MaCaw: the element's, MC CollisionKernel.C:109) picks every nuclide's data set
             # (nuclide.cpp:614-626 NEAREST): 0 K and 293.6 K -> the 293.6 K sets, 446 K -> 293.6 K (152.4 < 154), 447.5 K and
@@ -776,6 +789,12 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
         o.L.orc_law_samples(o_reset.ctypes.data_as(C.POINTER(C.c_longlong)))
         law_seen += o_reset
         assert np.array_equal(mine[0].view(np.uint64), ref[0].view(np.uint64))          # macroscopic cross sections
+        if thermal_T and T > 346.8 and getattr(m, "sab", None):
+            # ... the bound cross sections below energy_max really come from the hotter tables
+            o.set_temperature(293.6)
+            cold = run(o.L.orc_collide_events, o.h, i_mat, keff)
+            assert (cold[0][:, 0] != mine[0][:, 0]).mean() > 0.2
+            seen["hot tables"] = seen.get("hot tables", 0) + 1
         if temperatures and T > 447:
             # ... which really come from other data sets than at room temperature
             o.set_temperature(293.6)
@@ -810,6 +829,7 @@ def test_lookup_and_collision_against_reference_physics_cpp(oracle_bridge, libm,
             seen["weight"] = seen.get("weight", 0) + int((st[:, 4] == 1.25).sum())
             assert set(np.unique(st[:, 4])) <= {0.0, 1.0, 1.25}
     assert all(v > 0 for v in seen.values()), seen
+    assert not thermal_T or seen.get("hot tables", 0) >= 2
     if evaporation:  # Maxwell (5), evaporation (6) and Watt (7) spectra were sampled, next to the other laws
         assert (law_seen[5:] >= 20).all(), law_seen
     if reactions:  # every position of the reaction list was sampled: MT 51, 52, 53, 91, 875
