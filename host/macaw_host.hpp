@@ -196,7 +196,11 @@ struct Library
   // set k becomes library entry nuclides.size() + k (mcw_add_temperature_set), which an UrrTable of that set names
   std::vector<std::pair<int, Nuclide>> temperature_sets;
   std::vector<Material> materials;
-  std::vector<ThermalTable> thermal; // data::thermal_scatt
+  std::vector<ThermalTable> thermal; // data::thermal_scatt: every temperature of every table as one entry
+  // several temperatures per table (mcw_set_thermal_temperatures): per entry the first entry of its table, and its kT;
+  // empty = one temperature per table
+  std::vector<int32_t> thermal_same;
+  std::vector<double> thermal_kT;
   std::vector<UrrTable> urr;         // urr_data_ of the nuclides that have it
   std::vector<mcw_nuclide_desc> nuclideDescs() const
   {
@@ -515,6 +519,8 @@ public:
       for (const auto& t : library.thermal)
         td.push_back(t.desc());
       _h.check(mcw_set_thermal_tables(_h.get(), td.data(), (int)td.size()));
+      if (!library.thermal_same.empty())
+        _h.check(mcw_set_thermal_temperatures(_h.get(), library.thermal_same.data(), library.thermal_kT.data(), (int)td.size()));
       for (size_t m = 0; m < library.materials.size(); ++m)
       {
         const Material& M = library.materials[m];

@@ -275,6 +275,8 @@ public:
       t.i_offset = i32(p + "i_offset");
       P.library.thermal.push_back(std::move(t));
     }
+    if (has("lib.sab_same"))  // several temperatures per table: the first entry of each entry's table, and the kTs
+      P.library.thermal_same = i32("lib.sab_same"), P.library.thermal_kT = f64("lib.sab_kT");
     const int n_urr = has("lib.n_urr") ? i32("lib.n_urr")[0] : 0;
     for (int k = 0; k < n_urr; ++k)
     {

@@ -463,8 +463,8 @@ int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
  * sqrtkT = sqrt(K_BOLTZMANN T)) uses, for every nuclide, the data set whose kT is nearest to sqrtkT^2 -- the first of
  * equally near ones by increasing kT -- [OMC nuclide.cpp:614-626, TemperatureMethod::NEAREST, the default]: its cross
  * sections, its kT for the free-gas target [physics.cpp:649-652], its probability tables.  The energy range of the problem
- * comes from every nuclide's lowest-temperature grid [simulation.cpp:558-566].  S(alpha, beta) tables stay
- * single-temperature.  Call after mcw_set_library (which discards earlier sets) and before mcw_set_urr_tables. */
+ * comes from every nuclide's lowest-temperature grid [simulation.cpp:558-566].  S(alpha, beta) tables have their own
+ * temperatures: mcw_set_thermal_temperatures.  Call after mcw_set_library (which discards earlier sets) and before mcw_set_urr_tables. */
 int mcw_add_temperature_set(mcw_handle h, int nuclide, const mcw_nuclide_desc* set, int* entry);
 
 /* The checks mcw_set_library makes, without a handle and without a device (host code only): grids sorted, tables complete,
@@ -486,6 +486,14 @@ int mcw_set_materials(mcw_handle h, const mcw_material_desc* materials, int n,
 int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* tables, int n);
 int mcw_set_material_thermal(mcw_handle h, int material, int n, const int32_t* nuclide_position, const int32_t* table,
                              const double* fraction);
+
+/* Several temperatures of S(alpha, beta) tables (openmc::ThermalScattering::kTs_ / data_[t], OMC thermal.cpp:38-147):
+ * entry k of mcw_set_thermal_tables is the temperature kT[k] of the table whose FIRST entry is same_table_as[k] (k itself
+ * for a table's first or only temperature); n = the number of entries.  Materials (mcw_set_material_thermal) name first
+ * entries.  A history in an element of temperature T uses, for every table, the closer of the two temperatures that bound
+ * K_BOLTZMANN T -- ThermalScattering::calculate_xs with the nearest-temperature method [thermal.cpp:149-171] -- for the
+ * bound cross sections and for sab_scatter.  Call after mcw_set_thermal_tables (which discards it). */
+int mcw_set_thermal_temperatures(mcw_handle h, const int32_t* same_table_as, const double* kT, int n);
 
 /* Probability tables of the nuclides that have them (`urr/<T>K` of a nuclide file, OMC nuclide.cpp:225-270).  Call after
  * mcw_set_library.  The stand-alone lookups mcw_xs_lookup / mcw_xs_lookup_device have no history and therefore no URR

@@ -79,9 +79,12 @@ class Context:
             self._keep.append((ud, keep3))
             self._ck(self.L.mcw_set_urr_tables(self.h, C.addressof(ud), len(libr.urr_tables)))
         if getattr(libr, "thermal_tables", None):  # S(a,b): data::thermal_scatt + the materials' <sab> entries
-            td, keep2 = nucdata.pack_thermal(libr.thermal_tables)
+            tables, same, kT = libr.thermal_entries()  # every temperature of every table as one entry
+            td, keep2 = nucdata.pack_thermal(tables)
             self._keep.append((td, keep2))
-            self._ck(self.L.mcw_set_thermal_tables(self.h, C.addressof(td), len(libr.thermal_tables)))
+            self._ck(self.L.mcw_set_thermal_tables(self.h, C.addressof(td), len(tables)))
+            if len(tables) > len(libr.thermal_tables):
+                self._ck(self.L.mcw_set_thermal_temperatures(self.h, _p(same), _p(kT), len(tables)))
             for im, m in enumerate(libr.materials):
                 if getattr(m, "sab", None):
                     pos = np.ascontiguousarray([a[0] for a in m.sab], np.int32)

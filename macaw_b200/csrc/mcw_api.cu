@@ -285,6 +285,10 @@ struct mcw_context
   std::vector<std::vector<double>> mat_sab_frac;
   std::vector<int32_t> block_ids, block_material;
   int n_identities = 0; // nuclides given to mcw_set_library; h->nuclides beyond are further temperature sets
+  // several temperatures of S(a,b) tables (mcw_set_thermal_temperatures): per thermal entry the first entry of its table
+  // and its kT; empty = one temperature per table
+  std::vector<int32_t> thermal_same;
+  std::vector<double> thermal_kT;
   std::vector<double> temperature;
   std::vector<HostTally> tallies;
   mcw_settings set{};
@@ -933,6 +937,21 @@ int mcw_set_thermal_tables(mcw_handle h, const mcw_thermal_desc* d, int n)
     out.push_back(std::move(t));
   }
   h->thermal = std::move(out);
+  h->thermal_same.clear();
+  h->thermal_kT.clear();
+  h->prepared = false;
+  return MCW_OK;
+}
+
+int mcw_set_thermal_temperatures(mcw_handle h, const int32_t* same_table_as, const double* kT, int n)
+{
+  if (!h || !same_table_as || !kT || n != (int)h->thermal.size())
+    return MCW_E_INVALID_ARGUMENT;
+  for (int k = 0; k < n; ++k)
+    if (same_table_as[k] < 0 || same_table_as[k] > k || same_table_as[same_table_as[k]] != same_table_as[k])
+      return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_thermal_temperatures: same_table_as must name a table's first entry");
+  h->thermal_same.assign(same_table_as, same_table_as + n);
+  h->thermal_kT.assign(kT, kT + n);
   h->prepared = false;
   return MCW_OK;
 }
@@ -1004,7 +1023,7 @@ int mcw_set_temperature(mcw_handle h, const double* T, int64_t n)
   if (h->temperature.size() != (size_t)n || memcmp(h->temperature.data(), T, sizeof(double) * (size_t)n) != 0)
   {
     h->temperature.assign(T, T + n);
-    if ((int)h->nuclides.size() > h->n_identities)
+    if ((int)h->nuclides.size() > h->n_identities || !h->thermal_same.empty())
       h->prepared = false;
   }
   return MCW_OK;
@@ -1118,6 +1137,16 @@ static int prepare(mcw_handle h)
     bool multi = false;
     for (int i = 0; i < n_id; ++i)
       multi |= h->nuclides[i].sets.size() > 1;
+    // temperatures of the S(a,b) tables: the entries of every table (named by its first entry) by increasing kT
+    const int n_th = (int)h->thermal.size();
+    std::vector<std::vector<int>> th_sets(n_th);
+    for (int k = 0; k < (int)h->thermal_same.size(); ++k)
+      th_sets[h->thermal_same[k]].push_back(k);
+    for (auto& ts : th_sets)
+    {
+      std::stable_sort(ts.begin(), ts.end(), [&](int a, int b) { return h->thermal_kT[a] < h->thermal_kT[b]; });
+      multi |= ts.size() > 1;
+    }
     const int64_t nT = (int64_t)h->temperature.size();
     if (nT > 1 && nT != h->n_elem)
       return fail(h, MCW_E_INVALID_ARGUMENT, "mcw_set_temperature: one value or one per element");
@@ -1125,7 +1154,21 @@ static int prepare(mcw_handle h)
     auto pick_all = [&](double T) {
       const double sqrtkT = std::sqrt(8.617333262e-5 * T); // OMC constants.h:90 K_BOLTZMANN
       const double kT = sqrtkT * sqrtkT;
-      std::vector<int> sel(n_id);
+      std::vector<int> sel(n_id + n_th);
+      for (int t = 0; t < n_th; ++t)
+      {
+        // ThermalScattering::calculate_xs (OMC thermal.cpp:149-171): the closer of the two temperatures that bound kT
+        const std::vector<int>& ts = th_sets[t];
+        size_t i = 0;
+        if (ts.size() > 1)
+        {
+          while (h->thermal_kT[ts[i + 1]] < kT && i + 1 < ts.size() - 1)
+            ++i;
+          if (kT - h->thermal_kT[ts[i]] > h->thermal_kT[ts[i + 1]] - kT)
+            ++i;
+        }
+        sel[n_id + t] = ts.empty() ? t : ts[i];
+      }
       for (int i = 0; i < n_id; ++i)
       {
         const auto& sets = h->nuclides[i].sets;
@@ -1187,7 +1230,11 @@ static int prepare(mcw_handle h)
         EM.nuc.push_back(std::move(nuc));
         EM.dens.push_back(h->mat_dens[m]);
         EM.iso.push_back(h->mat_iso[m]);
-        EM.sab.push_back((size_t)m < h->mat_sab.size() ? h->mat_sab[m] : std::vector<int32_t>());
+        std::vector<int32_t> sab = (size_t)m < h->mat_sab.size() ? h->mat_sab[m] : std::vector<int32_t>();
+        for (int32_t& ts : sab) // the table's temperature for this class
+          if (ts >= 0 && ts < n_th)
+            ts = class_sel[c][n_id + ts];
+        EM.sab.push_back(std::move(sab));
         EM.sab_frac.push_back((size_t)m < h->mat_sab_frac.size() ? h->mat_sab_frac[m] : std::vector<double>());
       }
     // every data set starts at an even grid point of the concatenated grids (16-byte aligned windows, mcw_xs.cuh)

@@ -129,6 +129,10 @@ def _records(mesh, lib, blocks, materials, settings, tallies, temperature):
             r[f"mat{k}.sab_f"] = np.array([a[2] for a in m.sab], np.float64)
     # thermal scattering tables (mcw_thermal_desc) and probability tables (mcw_urr_desc)
     th = getattr(lib, "thermal_tables", None) or []
+    if th and any(getattr(t, "more_temperatures", None) for t in th):
+        # every temperature of every table as one entry; lib.sab_same names the first entry of each entry's table
+        th, same, kT = lib.thermal_entries()
+        r["lib.sab_same"], r["lib.sab_kT"] = same, kT
     r["lib.n_thermal"] = np.array([len(th)], np.int32)
     for k, t in enumerate(th):
         zero = np.zeros(0)

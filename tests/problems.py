@@ -176,6 +176,18 @@ def pin_cell_tet_sab(**kw):
     return mesh, nucdata.add_thermal_scattering(lib), bm, s
 
 
+def pin_cell_tet_sab_temperatures(**kw):
+    """S(a,b) tables at 293.6 / 400 / 600 K under a temperature field (1100 K in the middle of the fuel, 100 K at the cell
+    corner): the water spans all three table temperatures (OMC thermal.cpp:149-171: the closer of the two that bound the
+    element's temperature)."""
+    mesh, lib, bm, s = pin_cell_tet_sab(**kw)
+    nucdata.add_thermal_temperatures(lib)
+    c = mesh.xyz[mesh.conn].mean(axis=1)
+    r = np.hypot(c[:, 0], c[:, 1])
+    lib.element_temperature = 1100.0 - 1000.0 * r / r.max()
+    return mesh, lib, bm, s
+
+
 def beavrs_assembly_sab(**kw):
     """The BEAVRS assembly with bound hydrogen in the water, as its materials.xml has it (<sab name="c_H_in_H2O"/>)."""
     mesh, lib, bm, s = beavrs_assembly(**kw)
@@ -219,7 +231,7 @@ def check_full_bank(r, rec, bank, n):
     assert np.isfinite(bank["E"]).all() and (bank["E"] > 0).all()
 
 
-PROBLEMS = {"pin_cell_tet_evaporation": pin_cell_tet_evaporation, "pin_cell_tet_fission": pin_cell_tet_fission, "pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
+PROBLEMS = {"pin_cell_tet_sab_temperatures": pin_cell_tet_sab_temperatures, "pin_cell_tet_evaporation": pin_cell_tet_evaporation, "pin_cell_tet_fission": pin_cell_tet_fission, "pin_cell_tet_temperatures": pin_cell_tet_temperatures, "pin_cell_tet_reactions": pin_cell_tet_reactions, "pin_cell_tet_urr": pin_cell_tet_urr, "beavrs_assembly_full": beavrs_assembly_full,
             "pin_cell_tet_tabular": pin_cell_tet_tabular, "pin_cell_tet_sab": pin_cell_tet_sab,
             "beavrs_assembly_sab": beavrs_assembly_sab, "infinite_medium_sab": infinite_medium_sab,
             "beavrs_assembly": beavrs_assembly, "infinite_medium_iso": infinite_medium_iso, "pin_cell_tet_iso": pin_cell_tet_iso,

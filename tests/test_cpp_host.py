@@ -43,7 +43,7 @@ def test_problem_file_round_trip(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_evaporation", "pin_cell_tet_fission",
-                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_urr"])
+                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_sab_temperatures", "pin_cell_tet_urr"])
 def test_problem_files_carry_the_full_physics(tmp_path, name):
     """Tabulated distributions, thermal-scattering tables with their material assignments and probability tables travel
     through the problem file: the records are there, and the C++ reader gets as far as creating the device handle
@@ -59,12 +59,14 @@ def test_problem_files_carry_the_full_physics(tmp_path, name):
         assert r["nuc1.rx.head"][0] == 4 and r["nuc1.rx3.i"][0] == 875 and any(k.endswith("corr.f") for k in r)
     if name.endswith("evaporation"):
         assert "nuc1.rx.a" in r and "nuc1.rx2.y" in r and r["nuc1.law.i"][0] == 6 and r["nuc1.rx1.i"][2] == 6
-    if name.endswith("fission") or name.endswith("temperatures"):
+    if name.endswith("fission") or name == "pin_cell_tet_temperatures":
         assert r["nuc2.fis.head"][0] == 7 and "nuc2.fis0.y" in r and any(k.endswith("en.xpc") and ".fis" in k for k in r)
-    if name.endswith("temperatures"):
+    if name == "pin_cell_tet_temperatures":
         n = len(lib.nuclides)
         assert r["lib.set_of"].size == len(lib.temperature_sets()) > 10 and f"nuc{n}.energy" in r
         assert r["kernel.temperature"].size == mesh.n_elem
+    if name.endswith("sab_temperatures"):
+        assert r["lib.n_thermal"][0] == 9 and r["lib.sab_same"].tolist() == [0, 1, 2, 0, 0, 1, 1, 2, 2] and r["lib.sab_kT"].size == 9
     if name.endswith("sab"):
         assert r["lib.n_thermal"][0] == 3 and "mat3.sab_i" in r and r["sab0.i_offset"].size > 2
     if name.endswith("urr"):
@@ -92,7 +94,7 @@ def test_cpp_host_builds_and_fails_loudly_without_gpu(tmp_path):
                                   # tabulated distributions, S(a,b) and probability tables through the problem file and
                                   # host/macaw_host.hpp's Library (mcw_set_thermal_tables / _material_thermal / _urr_tables)
                                   "pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_evaporation", "pin_cell_tet_fission",
-                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_urr"])
+                                  "pin_cell_tet_temperatures", "pin_cell_tet_sab", "pin_cell_tet_sab_temperatures", "pin_cell_tet_urr"])
 def test_cpp_host_matches_oracle(oracle_bridge, tmp_path, name):
     exe = _build()
     path, (mesh, lib, bm, s) = _write(tmp_path, name, n_particles=3000)

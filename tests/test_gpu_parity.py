@@ -205,6 +205,9 @@ PUMP_TAIL = {"pump_threshold": 700, "tail_threshold": 0}
     ("infinite_medium_sab", {}, EVENT), ("pin_cell_tet_sab", {}, EVENT), ("pin_cell_tet_sab", {}, FUSED),
     ("pin_cell_tet_sab", {"sort_xs_queue": 1}, SORTED), ("pin_cell_tet_sab", {}, PUMP),
     ("beavrs_assembly_sab", {"sort_xs_queue": 1}, MIXED), ("pin_cell_tet_sab", {"n_particles": 20000}, {"tail_threshold": 3000}),
+    # ... with tables at three temperatures under a temperature field
+    ("pin_cell_tet_sab_temperatures", {}, EVENT), ("pin_cell_tet_sab_temperatures", {}, FUSED),
+    ("pin_cell_tet_sab_temperatures", {"n_particles": 20000}, {"tail_threshold": 3000}),
     # unresolved-resonance probability tables: cross sections that depend on the history's URR stream, targets at rest
     ("pin_cell_tet_urr", {}, EVENT), ("pin_cell_tet_urr", {}, FUSED), ("pin_cell_tet_urr", {"sort_xs_queue": 1}, SORTED),
     ("pin_cell_tet_urr", {}, PUMP), ("pin_cell_tet_urr", {"n_particles": 20000}, {"tail_threshold": 3000}),
