@@ -627,22 +627,30 @@ struct Library
       m.nu_fission = n.nu_total(E) * m.fission;
   }
 
-  // OMC material.cpp:748-831.  seed_urr: the history's URR stream seed (null: no history, smooth cross sections)
+  // OMC material.cpp:748-831.  seed_urr: the history's URR stream seed (null: no history, smooth cross sections).  kT: the
+  // particle's temperature, which picks the data sets of libraries with several temperatures; the loop without the picks
+  // is a separate instantiation (timed on a quiet host the picks cost the baseline 3 percent even when never taken:
+  // profiles/oracle_ab_r02y.txt).
   Macro macro_xs(int i_mat, double E, Micro* cache /* [materials[i_mat].nuc.size()] or null */,
                  int64_t* n_nuclide_lookups = nullptr, const uint64_t* seed_urr = nullptr, double kT = 0.0) const
+  {
+    return multi_temperature() ? macro_xs_impl<true>(i_mat, E, cache, n_nuclide_lookups, seed_urr, kT)
+                               : macro_xs_impl<false>(i_mat, E, cache, n_nuclide_lookups, seed_urr, kT);
+  }
+  template <bool PICK>
+  Macro macro_xs_impl(int i_mat, double E, Micro* cache, int64_t* n_nuclide_lookups, const uint64_t* seed_urr, double kT) const
   {
     const Material& mat = materials[i_mat];
     Macro M;
     int i_log = log_bin(E);
-    const bool pick = multi_temperature();
     for (size_t i = 0; i < mat.nuc.size(); ++i)
     {
-      const int entry = pick ? pick_set(mat.nuc[i], kT) : mat.nuc[i];
+      const int entry = PICK ? pick_set(mat.nuc[i], kT) : mat.nuc[i];
       Micro m = micro_xs(entry, E, i_log);
       m.entry = entry;
       // S(a,b) table of this nuclide in this material, unless the energy is above the table (material.cpp:778-806)
       if (!mat.sab_table.empty() && mat.sab_table[i] >= 0 && !(E > thermal[mat.sab_table[i]].energy_max))
-        apply_sab(nuclides[entry], pick_thermal(mat.sab_table[i], kT), mat.sab_frac[i], E, m);
+        apply_sab(nuclides[entry], PICK ? pick_thermal(mat.sab_table[i], kT) : mat.sab_table[i], mat.sab_frac[i], E, m);
       {
         // probability tables (those of the chosen data set, urr_data_[i_temp]), strictly inside their energy range
         // (nuclide.cpp:753-759); the band is drawn with the NUCLIDE's index (index_, :809)
