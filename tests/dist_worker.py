@@ -2,7 +2,7 @@
 macaw_b200.dist.synchronize_banks (the same host code the GPU study runs over NCCL) and writes what
 rank r ended up with to <out>.<r>.npz.
 
-  python tests/dist_worker.py <rank> <world> <port> <out> <n_particles> <n_batches>
+  python tests/dist_worker.py <rank> <world> <port> <out> <n_particles> <n_batches> [problem]
 """
 import os
 import sys
@@ -74,7 +74,8 @@ def main():
     from tests import problems
     td.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     dist.warm_up(None, "cpu")  # the channel warm-up the GPU study does at construction
-    mesh, lib, bm, s = problems.pin_cell_tet(n_particles=n_particles)
+    name = sys.argv[7] if len(sys.argv) > 7 else "pin_cell_tet"
+    mesh, lib, bm, s = problems.PROBLEMS[name](n_particles=n_particles)
     o = problems.configure(bridge.Oracle(rank=rank, nranks=world), mesh, lib, bm, s, True, False)
     wi = dist.calculate_work(n_particles, world)
     o.sample_initial_source()

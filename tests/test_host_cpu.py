@@ -143,8 +143,11 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_bank_synchronisation_world_size_n_equals_single_rank(oracle_bridge, tmp_path, world):
+@pytest.mark.parametrize("world,name", [(2, "pin_cell_tet"), (3, "pin_cell_tet"),
+                                        # temperature field + data sets at several temperatures, fission products, and
+                                        # multiplicities that move the weights: the shards still add up to the one-rank run
+                                        (2, "pin_cell_tet_temperatures"), (3, "pin_cell_tet_evaporation")])
+def test_bank_synchronisation_world_size_n_equals_single_rank(oracle_bridge, tmp_path, world, name):
     """OpenMC's synchronize_bank is rank-count invariant: the next source bank and k_generation of an
     N-rank run equal the 1-rank run's (OMC eigenvalue.cpp:71-311).  Runs N gloo processes."""
     from tests import problems
@@ -152,12 +155,12 @@ def test_bank_synchronisation_world_size_n_equals_single_rank(oracle_bridge, tmp
     port = _free_port()
     out = str(tmp_path / "w")
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world),
-                               str(port), out, str(n_particles), str(n_batches)], cwd=ROOT,
+                               str(port), out, str(n_particles), str(n_batches), name], cwd=ROOT,
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     logs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
 
-    mesh, lib, bm, s = problems.pin_cell_tet(n_particles=n_particles)
+    mesh, lib, bm, s = problems.PROBLEMS[name](n_particles=n_particles)
     o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, True, False)
     o.sample_initial_source()
     ks = []
