@@ -86,6 +86,27 @@ def test_library_validation_without_a_device():
     r.nbody = (6, r.nbody[1], r.nbody[2])
     rc, text = check(bad)
     assert rc != 0 and "N-body" in text
+    # fission products: a tabulated function with logarithmic interpolation, a product missing, an unknown spectrum
+    full = nucdata.add_fission_data(nucdata.add_evaporation_laws(copy.deepcopy(base)))
+    assert check(full)[0] == 0
+    bad = copy.deepcopy(full)
+    bad.nuclides[2].total_nu.interpolation = 5
+    rc, text = check(bad)
+    assert rc != 0 and "histogram and linear-linear" in text
+    bad = copy.deepcopy(full)
+    bad.nuclides[2].fission_products = bad.nuclides[2].fission_products[:-1]
+    rc, text = check(bad)
+    assert rc != 0 and "1 + n_precursor" in text
+    bad = copy.deepcopy(full)
+    bad.nuclides[2].fission_products[1].law = 4
+    rc, text = check(bad)
+    assert rc != 0 and "energy law not implemented" in text
+    # an evaporation spectrum on a scattering reaction without its theta(E)
+    bad = copy.deepcopy(full)
+    r = [x for n in bad.nuclides for x in (n.more_reactions or []) if x.law == 6][0]
+    r.a = None
+    rc, text = check(bad)
+    assert rc != 0 and "function it needs is missing" in text
     # an unsorted energy grid
     bad = copy.deepcopy(base)
     bad.nuclides[0].energy = bad.nuclides[0].energy[::-1].copy()
