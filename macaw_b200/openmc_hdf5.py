@@ -380,3 +380,60 @@ def library_from_files(paths, materials=(), n_log_bins=8000) -> nucdata.Library:
         name = [k for k in f.keys()][0]
         groups.append((name, f[name]))
     return library_from_groups(groups, materials, n_log_bins)
+
+
+def thermal_from_group(g, name=None) -> nucdata.ThermalTable:
+    """One table group of a thermal-scattering file (OMC ThermalScattering thermal.cpp:38-147, ThermalData :177-227) ->
+    nucdata.ThermalTable with its further temperatures in more_temperatures.  Inelastic: incoherent_inelastic (continuous
+    outgoing energies, equiprobable discrete cosines per outgoing energy) or incoherent_inelastic_discrete; elastic: none,
+    coherent_elastic (Bragg edges) or incoherent_elastic_discrete.  The Debye-Waller form is refused."""
+    name = name or getattr(g, "name", "table").strip("/")
+    energy_max = float(np.asarray(g.attrs["energy_max"]))
+    temps = sorted(g["kTs"].keys(), key=lambda t: float(np.asarray(_data(g["kTs"][t]))))
+    sets = []
+    for T in temps:
+        tg = g[T]
+        inel = tg["inelastic"]
+        xs = read_function(inel["xs"])
+        if xs.kind != 2 or xs.interpolation != 2:
+            raise Refused("thermal inelastic cross section that is not a lin-lin table")
+        d = inel["distribution"]
+        kind = _s(d.attrs["type"])
+        if kind == "incoherent_inelastic":
+            _one_region(d["energy"], "thermal inelastic distribution")
+            eo, mu = _data(d["energy_out"]), _data(d["mu"])
+            off = _a(d["energy_out"].attrs["offsets"]).astype(np.int64)
+            n_pts = eo.shape[1]
+            if np.any(eo[3] != 0) or n_pts == 0 or mu.shape[1] % n_pts:
+                raise Refused("thermal inelastic distribution whose cosines are not equiprobable discrete ones")
+            n_mu = mu.shape[1] // n_pts
+            if np.any(eo[4] != np.arange(n_pts) * n_mu):
+                raise Refused("thermal inelastic distribution with a varying number of cosines")
+            t = nucdata.ThermalTable(name, energy_max, 0, xs.x, xs.y, n_mu)
+            t.inelastic_energy = np.asarray(_data(d["energy"]), np.float64)
+            t.inelastic_offset = np.concatenate([off, [n_pts]]).astype(np.int32)
+            t.inelastic_e_out, t.inelastic_pdf, t.inelastic_cdf = eo[0].copy(), eo[1].copy(), eo[2].copy()
+            t.inelastic_mu = mu[0].reshape(n_pts, n_mu).copy()
+        elif kind == "incoherent_inelastic_discrete":
+            e_out, mu_out = _data(d["energy_out"]), _data(d["mu_out"])
+            t = nucdata.ThermalTable(name, energy_max, 1, xs.x, xs.y, int(mu_out.shape[2]))
+            t.n_e_out, t.skewed = int(e_out.shape[1]), bool(np.asarray(_data(d["skewed"])))
+            t.inelastic_e_out, t.inelastic_mu = e_out.copy(), mu_out.copy()
+        else:
+            raise Refused(f"thermal inelastic distribution type '{kind}'")
+        if "elastic" in tg:
+            el = tg["elastic"]
+            ekind = _s(el["distribution"].attrs["type"])
+            if ekind == "coherent_elastic":
+                v = _data(el["xs"])
+                t.elastic_type, t.elastic_x, t.elastic_y = 1, v[0].copy(), v[1].copy()
+            elif ekind == "incoherent_elastic_discrete":
+                f = read_function(el["xs"])
+                t.elastic_type, t.elastic_x, t.elastic_y = 2, f.x, f.y
+                t.elastic_mu = _data(el["distribution"]["mu_out"]).copy()
+            else:
+                raise Refused(f"thermal elastic distribution type '{ekind}' (the Debye-Waller form is not carried)")
+        t.kT = float(np.asarray(_data(g["kTs"][T])))
+        sets.append(t)
+    sets[0].more_temperatures = sets[1:] or None
+    return sets[0]

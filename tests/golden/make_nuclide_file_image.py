@@ -1,6 +1,6 @@
 """Regenerates tests/golden/nuclide_file_image.npz: the nuclide-file image oracle/_ref writes for a synthetic library
 with everything (reaction lists, every secondary law, function yields, fission products, probability tables, three
-temperatures; 15 nuclides x 200 grid points) -- the bytes the REFERENCE's own Nuclide constructors read -- together
+temperatures, S(a,b) tables at three temperatures; 15 nuclides x 200 grid points) -- the bytes the REFERENCE's own Nuclide constructors read -- together
 with the tables Nuclide::create_derived made of it at every temperature.  Run in the build container, where
 /root/reference exists; tests/test_oracle_pinning.py::test_nuclide_file_converter_fixture then holds
 macaw_b200/openmc_hdf5.py against it anywhere."""
@@ -21,6 +21,7 @@ def library():
     nucdata.add_fission_data(lib)
     nucdata.add_urr_tables(lib)
     nucdata.add_temperatures(lib)
+    nucdata.add_thermal_temperatures(nucdata.add_thermal_scattering(lib))  # three S(a,b) tables x three temperatures
     return lib
 
 

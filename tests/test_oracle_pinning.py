@@ -1368,6 +1368,12 @@ def test_nuclide_file_converter_fixture():
     root = openmc_hdf5.read_image(g["image"].tobytes())
     conv = openmc_hdf5.library_from_groups([(n.name, root[n.name]) for n in lib.nuclides], lib.materials, lib.n_log_bins)
     _check_converted(lib, conv)
+    for t in lib.thermal_tables:  # the thermal-scattering tables of the image, every temperature
+        c = openmc_hdf5.thermal_from_group(root[t.name], t.name)
+        for x, y in zip([t] + list(t.more_temperatures), [c] + list(c.more_temperatures)):
+            assert (y.kT, y.energy_max, y.inelastic_type, y.elastic_type) == (x.kT, x.energy_max, x.inelastic_type, x.elastic_type)
+            for f in ("inelastic_xs", "inelastic_e_out", "inelastic_mu", "elastic_x", "elastic_y", "elastic_mu"):
+                _same(getattr(x, f), getattr(y, f), f"{t.name}.{f}")
 
 
 def test_nuclide_file_converter_refuses_what_the_library_lacks():
@@ -1411,3 +1417,30 @@ def test_nuclide_file_converter_refuses_what_the_library_lacks():
     def unknown_law(g):
         g["reactions/reaction_052/product_0/distribution_0/energy"].attrs["type"] = "madland-nix"
     assert "madland-nix" in refused(unknown_law)
+
+
+def test_thermal_file_converter_against_reference_thermal_cpp(oracle_bridge):
+    """openmc_hdf5.thermal_from_group on the thermal-scattering file image the REFERENCE's own ThermalScattering /
+    ThermalData constructors read in oracle/_ref: the three kinds of tables (continuous inelastic; discrete inelastic +
+    coherent elastic; skewed discrete inelastic + incoherent-discrete elastic) at three temperatures each come back as the
+    tables the image was written from, array for array."""
+    from macaw_b200 import nucdata, openmc_hdf5
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_dump_tree") or not hasattr(r, "ref_stage_thermal_temperature"):
+        pytest.skip("oracle/_ref not built with the image dump (no /root/reference on this box)")
+    lib = nucdata.make_library(n_nuclides=9, G=300, seed=3, n_log_bins=500)
+    nucdata.add_thermal_temperatures(nucdata.add_thermal_scattering(lib))
+    oracle_bridge.ref_load_library(r, lib)
+    root = openmc_hdf5.read_image(oracle_bridge.ref_nuclide_file_image(r))
+    for t in lib.thermal_tables:
+        c = openmc_hdf5.thermal_from_group(root[t.name], t.name)
+        for x, y in zip([t] + list(t.more_temperatures), [c] + list(c.more_temperatures)):
+            assert (y.kT, y.energy_max, y.inelastic_type, y.elastic_type, y.n_mu, y.n_e_out, bool(y.skewed)) == \
+                (x.kT, x.energy_max, x.inelastic_type, x.elastic_type, x.n_mu, x.n_e_out, bool(x.skewed)), t.name
+            for f in ("inelastic_xs_energy", "inelastic_xs", "inelastic_energy", "inelastic_offset", "inelastic_e_out",
+                      "inelastic_pdf", "inelastic_cdf", "inelastic_mu", "elastic_x", "elastic_y", "elastic_mu"):
+                _same(getattr(x, f), getattr(y, f), f"{t.name}.{f}")
+    bad = root[lib.thermal_tables[1].name]
+    bad[sorted(bad["kTs"].keys())[0]]["elastic"]["distribution"].attrs["type"] = "incoherent_elastic"
+    with pytest.raises(openmc_hdf5.Refused):
+        openmc_hdf5.thermal_from_group(bad)
