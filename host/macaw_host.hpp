@@ -545,6 +545,19 @@ public:
     _h.check(mcw_sample_initial_source(_h.get())); // openmc_simulation_init -> initialize_source (:147)
   }
 
+  // The coupled temperature changed (a new time step of the multiphysics solve, MC CollisionKernel.C:109 reads it every
+  // segment).  With several temperatures in the library the new field re-prepares the problem, which starts the run
+  // over: the source bank of this rank is carried across; k statistics and tally sums restart with the new field.
+  void setTemperature(const std::vector<double>& T)
+  {
+    int64_t n = 0;
+    std::vector<mcw_source_site> bank((size_t)std::max<int64_t>(_settings.n_particles, 1));
+    _h.check(mcw_get_source_bank(_h.get(), bank.data(), (int64_t)bank.size(), &n));
+    _h.check(mcw_set_temperature(_h.get(), T.data(), (int64_t)T.size()));
+    if (n > 0)
+      _h.check(mcw_set_source_bank(_h.get(), bank.data(), n));
+  }
+
   // One batch.  Returns the generation result; prints the reference's line when verbose (:399-401).
   mcw_generation_result execute()
   {

@@ -502,7 +502,12 @@ int mcw_set_urr_tables(mcw_handle h, const mcw_urr_desc* tables, int n);
 
 /* Coupled temperature variable of CollisionKernel in K, one value per element or one scalar (n = 1)
  * [MC CollisionKernel.C:33,109]; not set: 0 K, as in MaCaw's own study test.  Picks each nuclide's data set
- * (mcw_add_temperature_set); with one data set per nuclide it has no effect, like NEAREST in the reference. */
+ * (mcw_add_temperature_set) and each S(alpha, beta) table's temperature (mcw_set_thermal_temperatures); with one data set
+ * everywhere it has no effect, like NEAREST in the reference.  The picks are part of the prepared problem: a field that
+ * differs from the current one, on a library with several temperatures, prepares the problem again on the next call
+ * that needs it -- which, like every change of the problem, starts the run over (source bank, k statistics, tally sums).
+ * A coupled run that updates the field between time steps carries its source bank across with mcw_get_source_bank /
+ * mcw_set_source_bank (host/macaw_host.hpp OpenMCStudy::setTemperature does). */
 int mcw_set_temperature(mcw_handle h, const double* T, int64_t n);
 
 int mcw_set_settings(mcw_handle h, const mcw_settings* s);

@@ -116,6 +116,15 @@ class OpenMCStudy:
             import torch
             dist.warm_up(group, torch.device("cuda", torch.cuda.current_device()))
 
+    def set_temperature(self, T):
+        """The coupled temperature changed (a new time step of the multiphysics solve).  With several temperatures in the
+        library the new field re-prepares the problem, which starts the run over: this rank's source bank is carried
+        across; k statistics and tally sums restart with the new field (include/macaw_b200.h mcw_set_temperature)."""
+        bank = self.ctx.source_bank()
+        self.ctx.set_temperature(T)
+        if len(bank):
+            self.ctx.set_source_bank(bank)
+
     # -- one Transient time step (OpenMCStudy.C:366-402)
     def execute(self):
         self.batch += 1
