@@ -876,9 +876,10 @@ def test_collision_fixture_from_reference_objects(oracle_bridge, libm):
         assert np.array_equal(mine["kappa"].view(np.uint64), ref["kappa"].view(np.uint64))  # per-nuclide summation order
 
 
+@pytest.mark.parametrize("physics", ["base", "full"])
 @pytest.mark.parametrize("renormalise,libm", [(0, True), (1, True), (1, False)])
 @pytest.mark.parametrize("i_mat", [0, 3])
-def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, renormalise, libm):
+def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, renormalise, libm, physics):
     """Whole histories, all carried state: the reference's own initialize_history + transport_history_based_single_particle
     (OMC simulation.cpp:451,662-677: event_calculate_xs, event_advance, event_collide, event_revive_from_secondary,
     event_death) in a one-cell, no-surface geometry of one material, against the oracle's PRODUCTION history loop
@@ -894,13 +895,41 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     relative; k scores 1e-10), while seeds, collision and progeny counts, bank size and ids stay identical.  libm=False:
     the deterministic-math build, i.e. exactly the configuration the GPU is bit-compared with -- LCG streams, counts and
     bank ids of whole histories still identical to the reference's (the north star's stream-parity bar, by transitivity
-    GPU == oracle == OpenMC)."""
+    GPU == oracle == OpenMC).
+    physics="full": the same on a library with everything a real evaluation brings -- reaction lists with every secondary
+    law and energy-dependent multiplicities (the weight changes along the history and with it every k score, the
+    fission-site numbers and the tallies), fission products with function yields and tabulated spectra, probability
+    tables, data sets at three temperatures -- at a particle temperature of 700 K (the 600 K sets).  Only (n,2n)'s
+    integral multiplicity is set to 1 there: the reference's loop would go on to transport the second neutron, which
+    MaCaw drops (MC CollisionKernel.C:232-236)."""
     from macaw_b200 import cstructs, meshgen
     from tests import problems
     r = oracle_bridge.ref_lib()
     if r is None or not hasattr(r, "ref_transport_histories"):
         pytest.skip("oracle/_ref not built with the history loop (no /root/reference on this box)")
-    lib, _, _ = _reference_library(oracle_bridge, r)
+    T = 0.0
+    if physics == "full":
+        if not hasattr(r, "ref_stage_temperature_set"):
+            pytest.skip("oracle/_ref built without the temperature-set doorway")
+        from macaw_b200 import nucdata
+        _orig = nucdata.add_reactions
+
+        def one_neutron(lib_, *a, **k):  # (n,2n) with multiplicity 1: no secondaries for the reference's loop to transport
+            _orig(lib_, *a, **k)
+            for nn in lib_.nuclides:
+                for rx in (nn.more_reactions or []):
+                    if rx.yield_ == 2.0:
+                        rx.yield_ = 1.0
+            return lib_
+        nucdata.add_reactions = one_neutron
+        try:
+            lib, _, _ = _reference_library(oracle_bridge, r, tabular=True, reactions="evaporation", fission=True, urr=True,
+                                           temperatures=True)
+        finally:
+            nucdata.add_reactions = _orig
+        T = 700.0
+    else:
+        lib, _, _ = _reference_library(oracle_bridge, r)
     n, batch, keff, master_seed, L = 1500, 3, 0.97, 11, 1.0e9
     mesh = meshgen.hex_grid(1, 1, 1, (-L, -L, -L), (L, L, L), meshgen.BC_REFLECT, None, "one_element")
     s = cstructs.make_settings(n, n_inactive=0, source_box=(-1, -1, -1, 1, 1, 1), seed=master_seed,
@@ -916,6 +945,8 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     sites["u"] = u / np.linalg.norm(u, axis=1)[:, None]
     sites["E"] = np.exp(rng.uniform(np.log(1e-2), np.log(1.0e7), n))
     sites["wgt"], sites["elem"] = 1.0, -1
+    if physics == "full":
+        o.set_temperature(T)
     o.set_source_bank(sites)
     o.L.orc_set_keff(o.h, keff)
     o.L.orc_set_renormalise_direction(o.h, renormalise)
@@ -927,7 +958,8 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     state, seeds, cap = np.zeros((n, 8)), np.zeros((n, 4), np.uint64), 4 * n
     site7, ref_tallies = np.zeros((cap, 7)), np.zeros((2, edges.size - 1, 4))
     nb = r.ref_transport_histories(i_mat, keff, master_seed, batch, n, site8.ctypes.data_as(f64p),
-                                   float(np.sqrt(lib.nuclides[0].kT)), state.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p),
+                                   float(np.sqrt(8.617333262e-5 * T)) if physics == "full" else float(np.sqrt(lib.nuclides[0].kT)),
+                                   state.ctypes.data_as(f64p), seeds.ctypes.data_as(u64p),
                                    cap, site7.ctypes.data_as(f64p), edges.ctypes.data_as(f64p), edges.size,
                                    ref_tallies.ctypes.data_as(f64p))
     r.ref_set_master_seed(1)
