@@ -1064,22 +1064,32 @@ def test_tracklength_kappa_fission_against_reference_objects(oracle_bridge):
     assert n_pos >= n   # the fuel material scores on every segment, the others never
 
 
+@pytest.mark.parametrize("temperatures", [False, True])
 @pytest.mark.parametrize("estimator", ["collision", "tracklength"])
 @pytest.mark.parametrize("mode", ["all", "list"])
-def test_nuclide_bins_against_reference_tally_objects(oracle_bridge, estimator, mode):
+def test_nuclide_bins_against_reference_tally_objects(oracle_bridge, estimator, mode, temperatures):
     """Tallies with nuclide bins (MC OpenMCTally.C:188-204 `nuclides = all | list`): the reference's own Tally built the way
     OpenMCTally::initialize builds it (nuclides_ + all_nuclides_, or the list followed by total), scored by its own
     score_collision_tally / score_tracklength_tally -> score_all_nuclides / the nuclide-bin loop -> score_general_ce
     (OMC tally_scoring.cpp:2142-2175, :2381-2407, :516-1260) on its own Material / Nuclide objects, against the oracle's
     score_tally_nuclides: every (nuclide bin, score) VALUE of every event BIT FOR BIT -- flux, total, fission, nu-fission
-    and kappa-fission; bins whose nuclide is not in the material stay zero on both sides."""
+    and kappa-fission; bins whose nuclide is not in the material stay zero on both sides.  temperatures=True: nuclides
+    with data sets at three temperatures (and fission products with a tabulated nu), particles at 700 K: the bins are the
+    NUCLIDES' whatever data set the temperature picked, on both sides."""
     from tests import problems
     r = oracle_bridge.ref_lib()
     if r is None or not hasattr(r, "ref_score_nuclide_bins"):
         pytest.skip("oracle/_ref not built with the nuclide-bin doorway (no /root/reference on this box)")
-    lib, _, _ = _reference_library(oracle_bridge, r)
+    if temperatures and not hasattr(r, "ref_stage_temperature_set"):
+        pytest.skip("oracle/_ref built without the temperature-set doorway")
+    lib, _, _ = _reference_library(oracle_bridge, r, tabular=temperatures, reactions=temperatures, fission=temperatures,
+                                   temperatures=temperatures)
+    T = 700.0 if temperatures else None
     mesh, _, bm, s = problems.infinite_medium(n_particles=100)
     o = problems.configure(oracle_bridge.Oracle(), mesh, lib, bm, s, tallies=False)
+    if temperatures:
+        o.set_temperature(T)
+    sqrtkT = float(np.sqrt(8.617333262e-5 * T)) if temperatures else float(np.sqrt(lib.nuclides[0].kT))
     f64p = C.POINTER(C.c_double)
     names = [b"flux", b"total", b"fission", b"nu-fission", b"kappa-fission"]
     scores = np.arange(5, dtype=np.int32)
@@ -1095,8 +1105,7 @@ def test_nuclide_bins_against_reference_tally_objects(oracle_bridge, estimator, 
         dp = d.ctypes.data_as(f64p) if estimator == "tracklength" else None
         ref, mine = np.zeros((n, nb.size, 5)), np.zeros((n, nb.size, 5))
         r.ref_score_nuclide_bins(i_mat, int(mode == "all"), nb.ctypes.data, nb.size, (C.c_char_p * 5)(*names), 5, n,
-                                 E.ctypes.data_as(f64p), w.ctypes.data_as(f64p), dp, float(np.sqrt(lib.nuclides[0].kT)),
-                                 ref.ctypes.data_as(f64p))
+                                 E.ctypes.data_as(f64p), w.ctypes.data_as(f64p), dp, sqrtkT, ref.ctypes.data_as(f64p))
         o.L.orc_score_nuclide_bins(o.h, i_mat, nb.ctypes.data, nb.size, scores.ctypes.data, 5, n, E.ctypes.data_as(f64p),
                                    w.ctypes.data_as(f64p), dp, mine.ctypes.data_as(f64p))
         assert np.array_equal(mine.view(np.uint64), ref.view(np.uint64))
