@@ -2,7 +2,7 @@
 // does for the hot path (Transient executioner, one OpenMCStudy::execute per time step;
 // MC OpenMCStudy.C:366-402), on a problem file instead of a MOOSE input + Exodus mesh.
 //
-//   mcw_run problem.bin [--batches N] [--device D] [--nccl-id FILE] [--quiet]
+//   mcw_run problem.bin [--batches N] [--device D] [--nccl-id FILE] [--quiet] [--digest]
 //   mcw_run --input run.i --tables lib.bin [--xml-dir DIR] [...]     the reference's input-file surface:
 //            a MOOSE input (Mesh / RayKernels / RayBCs / UserObjects / AuxKernels / Executioner blocks) next
 //            to OpenMC's settings.xml and materials.xml (host/input_file.hpp)
@@ -38,6 +38,7 @@ int main(int argc, char** argv)
   }
   int batches = -1, device = -1;
   bool quiet = false, check = false; // --check: parse the inputs, print what was understood, touch no GPU
+  bool digest = false;               // --digest: validate the library and print mcw_digest of its descriptors, touch no GPU
   std::string id_file = "/tmp/mcw_nccl_id", problem_path, input_path, xml_dir, tables_path;
   for (int a = 1; a < argc; ++a)
   {
@@ -59,6 +60,8 @@ int main(int argc, char** argv)
       quiet = true;
     else if (!std::strcmp(argv[a], "--check"))
       check = true;
+    else if (!std::strcmp(argv[a], "--digest"))
+      digest = true;
   }
   const int rank = env_int("RANK", 0), nranks = env_int("WORLD_SIZE", 1);
   if (device < 0)
@@ -85,6 +88,33 @@ int main(int argc, char** argv)
     if (batches < 0)
       batches = 5;
     const Problem P = input_path.empty() ? ProblemFile(problem_path).problem() : in.problem;
+    if (digest)
+    {
+      // what this host would hand to the library, as the library's own digest of it (host code only): equal to the digest
+      // of the Python host's descriptors when both read the same problem (tests/test_cpp_host.py)
+      const auto nd = P.library.nuclideDescs();
+      const auto sd = P.library.temperatureSetDescs();
+      std::vector<mcw_thermal_desc> td;
+      for (const auto& t : P.library.thermal)
+        td.push_back(t.desc());
+      std::vector<mcw_urr_desc> ud;
+      for (const auto& u : P.library.urr)
+        ud.push_back(u.desc());
+      char msg[512] = "";
+      if (mcw_validate_library(nd.data(), (int)nd.size(), msg, sizeof(msg)))
+        mooseError(std::string("library refused: ") + msg);
+      for (const auto& d : sd)
+        if (mcw_validate_library(&d, 1, msg, sizeof(msg)))
+          mooseError(std::string("temperature set refused: ") + msg);
+      uint64_t h[4] = {0, 0, 0, 0};
+      mcw_digest(0, nd.data(), (int)nd.size(), &h[0]);
+      mcw_digest(0, sd.data(), (int)sd.size(), &h[1]);
+      mcw_digest(1, td.data(), (int)td.size(), &h[2]);
+      mcw_digest(2, ud.data(), (int)ud.size(), &h[3]);
+      std::printf("{\"nuclides\": \"%016llx\", \"temperature_sets\": \"%016llx\", \"thermal\": \"%016llx\", \"urr\": \"%016llx\"}\n",
+                  (unsigned long long)h[0], (unsigned long long)h[1], (unsigned long long)h[2], (unsigned long long)h[3]);
+      return 0;
+    }
     if (check)
     {
       std::printf("{\"elem_type\": %d, \"n_elem\": %lld, \"n_nodes\": %lld, \"batches\": %d, \"n_particles\": %lld, \"n_inactive\": %d, "

@@ -453,6 +453,12 @@ int mcw_set_mesh(mcw_handle h, int elem_type, int64_t n_nodes, const double* xyz
  * [OMC nuclide.cpp:50-302,446-476; simulation.cpp:553-619]. */
 int mcw_set_library(mcw_handle h, const mcw_nuclide_desc* nuclides, int n);
 
+/* A 64-bit digest (FNV-1a) of everything an array of descriptors says -- scalars and every array they point to, in
+ * declaration order, what the library would copy -- so that two hosts (an adapter and a reference run, the C++ and the
+ * Python host of this repository) can check that they hand over the same data.  kind 0: mcw_nuclide_desc, 1:
+ * mcw_thermal_desc, 2: mcw_urr_desc.  Host code only, no handle, no device. */
+int mcw_digest(int kind, const void* descriptors, int n, uint64_t* out);
+
 /* One more data set of nuclide `nuclide` (its index in mcw_set_library's array) at the temperature set->kT: OpenMC's
  * Nuclide::kTs_[t] with grid_[t], xs_[t], every reaction's xs_[t] and threshold [OMC nuclide.cpp:170-200,
  * reaction.cpp:25-50].  Everything temperature dependent is taken from `set` (energy, xs, elastic, the inelastic reactions'

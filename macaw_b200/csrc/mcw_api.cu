@@ -818,6 +818,185 @@ int mcw_add_temperature_set(mcw_handle h, int nuclide, const mcw_nuclide_desc* s
   return MCW_OK;
 }
 
+} // extern "C"
+
+// ---- mcw_digest: FNV-1a over everything a descriptor array says, arrays included, in declaration order (host only)
+namespace
+{
+struct Fnv
+{
+  uint64_t h = 1469598103934665603ull;
+  void bytes(const void* p, size_t n)
+  {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i)
+      h = (h ^ b[i]) * 1099511628211ull;
+  }
+  template <typename T>
+  void val(T v) { bytes(&v, sizeof(v)); }
+  template <typename T>
+  void arr(const T* p, size_t n)
+  {
+    val((uint64_t)(p ? n : 0));
+    if (p && n)
+      bytes(p, n * sizeof(T));
+  }
+  void table(const mcw_tabular2d& t)
+  {
+    val(t.n_energy);
+    if (t.n_energy <= 0)
+      return;
+    val(t.histogram_in_energy);
+    const size_t n = (size_t)t.n_energy, np = (size_t)t.offset[n];
+    arr(t.energy, n), arr(t.offset, n + 1), arr(t.interpolation, n);
+    for (size_t k = 0; k < n; ++k) // an absent n_discrete means zeros
+      val((int32_t)(t.n_discrete ? t.n_discrete[k] : 0));
+    arr(t.x, np), arr(t.pdf, np), arr(t.cdf, np);
+  }
+  void fn(const mcw_function1d& f)
+  {
+    val(f.kind);
+    if (f.kind == MCW_FN_NONE)
+      return;
+    val(f.n);
+    if (f.kind == MCW_FN_TABULATED)
+      val(f.interpolation), arr(f.x, (size_t)f.n);
+    arr(f.y, (size_t)f.n);
+  }
+  // the law part shared by the inline reaction and mcw_reaction_desc
+  void law(int law, int in_cm, const mcw_tabular2d& angle, const mcw_tabular2d& energy, const int32_t* co, const int32_t* ci,
+           const double* cm, const double* cp, const double* cc, const double* kr, const double* ka, int nbody_n,
+           double nbody_mass, double nbody_q, double yield, const mcw_function1d& yfn, double u, const mcw_function1d& a,
+           const mcw_function1d& b)
+  {
+    val(law), val((int32_t)(law == MCW_LAW_LEVEL ? 1 : (in_cm != 0)));
+    const bool together = law >= MCW_LAW_CORRELATED && law <= MCW_LAW_NBODY;
+    if (!together)
+      table(angle);
+    if (law == MCW_LAW_CONTINUOUS_TABULAR || law == MCW_LAW_CORRELATED || law == MCW_LAW_KALBACH_MANN)
+      table(energy);
+    const size_t np = energy.n_energy > 0 ? (size_t)energy.offset[energy.n_energy] : 0;
+    if (law == MCW_LAW_CORRELATED)
+      arr(co, np + 1), arr(ci, np), arr(cm, (size_t)co[np]), arr(cp, (size_t)co[np]), arr(cc, (size_t)co[np]);
+    if (law == MCW_LAW_KALBACH_MANN)
+      arr(kr, np), arr(ka, np);
+    if (law == MCW_LAW_NBODY)
+      val(nbody_n), val(nbody_mass), val(nbody_q);
+    if (yfn.kind != MCW_FN_NONE)
+      fn(yfn);
+    else
+      val(yield == 0.0 ? 1.0 : yield);
+    if (law >= MCW_LAW_MAXWELL)
+    {
+      val(u), fn(a);
+      if (law == MCW_LAW_WATT)
+        fn(b);
+    }
+  }
+};
+} // namespace
+
+extern "C" {
+
+int mcw_digest(int kind, const void* descriptors, int n, uint64_t* out)
+{
+  if ((!descriptors && n > 0) || n < 0 || !out || kind < 0 || kind > 2)
+    return MCW_E_INVALID_ARGUMENT;
+  Fnv f;
+  f.val((int32_t)kind), f.val((int32_t)n);
+  for (int i = 0; i < n; ++i)
+  {
+    if (kind == 0)
+    {
+      const mcw_nuclide_desc& d = ((const mcw_nuclide_desc*)descriptors)[i];
+      const size_t G = (size_t)d.n_grid;
+      f.val(d.n_grid), f.val((int32_t)(d.fissionable != 0)), f.val(d.awr), f.val(d.kT);
+      f.arr(d.energy, G), f.arr(d.xs, 5 * G), f.arr(d.elastic, G);
+      f.table(d.elastic_angle);
+      f.val((int32_t)(d.n_inelastic != 0));
+      if (d.n_inelastic)
+      {
+        f.val(d.inel_threshold), f.arr(d.inelastic, G - (size_t)d.inel_threshold);
+        if (d.inelastic_law == MCW_LAW_LEVEL)
+          f.val(d.inel_threshold_energy), f.val(d.inel_mass_ratio);
+        f.law(d.inelastic_law, d.inelastic_in_cm, d.inelastic_angle, d.inelastic_energy, d.corr_offset, d.corr_interp, d.corr_mu,
+              d.corr_pdf, d.corr_cdf, d.km_r, d.km_a, d.nbody_n, d.nbody_mass_ratio, d.nbody_q, d.inelastic_yield,
+              d.inelastic_yield_fn, d.inelastic_u, d.inelastic_a, d.inelastic_b);
+        f.val(d.n_more_reactions);
+        for (int j = 0; j < d.n_more_reactions; ++j)
+        {
+          const mcw_reaction_desc& r = d.more_reactions[j];
+          f.val(r.mt), f.val(r.threshold), f.arr(r.xs, G - (size_t)r.threshold);
+          if (r.law == MCW_LAW_LEVEL)
+            f.val(r.threshold_energy), f.val(r.mass_ratio);
+          f.law(r.law, r.in_cm, r.angle, r.energy, r.corr_offset, r.corr_interp, r.corr_mu, r.corr_pdf, r.corr_cdf, r.km_r, r.km_a,
+                r.nbody_n, r.nbody_mass_ratio, r.nbody_q, r.yield, r.yield_fn, r.u, r.a, r.b);
+        }
+      }
+      if (d.fissionable)
+      {
+        f.val(d.q_fission), f.val(d.n_precursor), f.val(d.n_fission_products);
+        if (d.n_fission_products > 0)
+        {
+          f.fn(d.total_nu);
+          for (int k = 0; k < d.n_fission_products; ++k)
+          {
+            const mcw_fission_product& p = d.fission_products[k];
+            f.fn(p.yield), f.val(p.law);
+            if (p.law == MCW_LAW_CONTINUOUS_TABULAR)
+              f.table(p.energy);
+            else
+            {
+              f.val(p.u), f.fn(p.a);
+              if (p.law == MCW_LAW_WATT)
+                f.fn(p.b);
+            }
+          }
+        }
+        else
+        {
+          f.val(d.nu_poly[0]), f.val(d.nu_poly[1]), f.val(d.watt_a), f.val(d.watt_b);
+          for (int g = 0; g < d.n_precursor; ++g)
+            f.val(d.delayed_yield[g]), f.val(d.delayed_theta[g]);
+        }
+      }
+    }
+    else if (kind == 1)
+    {
+      const mcw_thermal_desc& t = ((const mcw_thermal_desc*)descriptors)[i];
+      f.val(t.energy_max), f.val(t.inelastic_type), f.val(t.elastic_type), f.val(t.n_mu);
+      f.arr(t.inelastic_xs_energy, (size_t)t.n_inelastic_xs), f.arr(t.inelastic_xs, (size_t)t.n_inelastic_xs);
+      if (t.inelastic_type == MCW_SAB_INELASTIC_CONTINUOUS)
+      {
+        const size_t ne = (size_t)t.n_inelastic_energy, np = (size_t)t.inelastic_offset[ne];
+        f.arr(t.inelastic_energy, ne), f.arr(t.inelastic_offset, ne + 1);
+        f.arr(t.inelastic_e_out, np), f.arr(t.inelastic_pdf, np), f.arr(t.inelastic_cdf, np), f.arr(t.inelastic_mu, np * (size_t)t.n_mu);
+      }
+      else
+      {
+        const size_t np = (size_t)t.n_inelastic_xs * (size_t)t.n_e_out;
+        f.val(t.n_e_out), f.val((int32_t)(t.skewed != 0));
+        f.arr(t.inelastic_e_out, np), f.arr(t.inelastic_mu, np * (size_t)t.n_mu);
+      }
+      if (t.elastic_type != MCW_SAB_ELASTIC_NONE)
+      {
+        f.arr(t.elastic_x, (size_t)t.n_elastic), f.arr(t.elastic_y, (size_t)t.n_elastic);
+        if (t.elastic_type == MCW_SAB_ELASTIC_INCOHERENT_DISCRETE)
+          f.val(t.n_elastic_mu), f.arr(t.elastic_mu, (size_t)t.n_elastic * (size_t)t.n_elastic_mu);
+      }
+    }
+    else
+    {
+      const mcw_urr_desc& u = ((const mcw_urr_desc*)descriptors)[i];
+      f.val(u.nuclide), f.val(u.interpolation), f.val(u.inelastic_flag), f.val(u.absorption_flag), f.val((int32_t)(u.multiply_smooth != 0));
+      f.val(u.n_energy), f.val(u.n_band);
+      f.arr(u.energy, (size_t)u.n_energy), f.arr(u.table, (size_t)u.n_energy * 6 * (size_t)u.n_band);
+    }
+  }
+  *out = f.h;
+  return MCW_OK;
+}
+
 int mcw_validate_library(const mcw_nuclide_desc* d, int n, char* message, int message_bytes)
 {
   if (!d || n <= 0)

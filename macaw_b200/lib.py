@@ -38,6 +38,7 @@ def load():
         "mcw_set_mesh": [vp, C.c_int, i64, vp, i64, vp, vp, vp, vp, C.c_int, vp],
         "mcw_set_library": [vp, vp, C.c_int],
         "mcw_validate_library": [vp, C.c_int, C.c_char_p, C.c_int],
+        "mcw_digest": [C.c_int, vp, C.c_int, P(C.c_uint64)],
         "mcw_add_temperature_set": [vp, C.c_int, vp, P(C.c_int)],
         "mcw_set_materials": [vp, vp, C.c_int, vp, vp, C.c_int],
         "mcw_set_thermal_tables": [vp, vp, C.c_int],
@@ -98,7 +99,7 @@ def loaded_path():
 
 
 EXPORTS = ["mcw_create", "mcw_destroy", "mcw_last_error", "mcw_version", "mcw_set_option", "mcw_prepare", "mcw_stream",
-           "mcw_struct_sizes", "mcw_set_mesh", "mcw_set_library", "mcw_validate_library", "mcw_add_temperature_set", "mcw_set_materials", "mcw_set_thermal_tables", "mcw_set_material_thermal", "mcw_set_urr_tables", "mcw_set_thermal_temperatures", "mcw_set_temperature",
+           "mcw_struct_sizes", "mcw_set_mesh", "mcw_set_library", "mcw_validate_library", "mcw_digest", "mcw_add_temperature_set", "mcw_set_materials", "mcw_set_thermal_tables", "mcw_set_material_thermal", "mcw_set_urr_tables", "mcw_set_thermal_temperatures", "mcw_set_temperature",
            "mcw_set_settings", "mcw_add_tally", "mcw_set_tally_nuclides", "mcw_tally_nuclide_bins",
            "mcw_sample_initial_source", "mcw_set_source_bank",
            "mcw_get_source_bank", "mcw_transport_generation", "mcw_finalize_generation", "mcw_run_generation",

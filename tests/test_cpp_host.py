@@ -2,6 +2,7 @@
 C ABI + the mcw_run driver).  CPU: it builds, reads the problem file the Python side wrote, rejects
 bad parameters with the reference's messages and fails loudly without a GPU.  GPU: its k per batch
 and its tally read-back equal the oracle's on the same problem file."""
+import ctypes as C
 import json
 import os
 import subprocess
@@ -431,3 +432,43 @@ def test_python_and_cpp_hosts_agree_on_a_deck(tmp_path):
     got = np.array([a for a in lines if "aux" in a][0]["aux"][0]["values"])
     assert nr == 3 and np.allclose(got, t[:, 0, 0], rtol=1e-10, atol=1e-300)
     study.ctx.close()
+
+
+@pytest.mark.parametrize("name", ["pin_cell_tet", "pin_cell_tet_tabular", "pin_cell_tet_reactions", "pin_cell_tet_evaporation",
+                                  "pin_cell_tet_fission", "pin_cell_tet_temperatures", "pin_cell_tet_sab_temperatures",
+                                  "pin_cell_tet_urr", "beavrs_assembly_full"])
+def test_cpp_host_hands_over_the_same_library_as_the_python_host(tmp_path, name):
+    """No GPU needed: `mcw_run problem.bin --digest` reads the problem file with host/problem_io.hpp, builds the descriptors
+    with host/macaw_host.hpp, has the library check them (mcw_validate_library) and prints the library's own digest of
+    them (mcw_digest: every scalar and every array the descriptors point to).  The Python host's descriptors of the same
+    problem (macaw_b200/nucdata.py pack_*) give the same four digests: nuclides, further temperature sets, S(a,b) tables,
+    probability tables -- so both hosts hand the library the same data, bit for bit, for every kind of physics."""
+    from macaw_b200 import lib as mlib, nucdata
+    exe = _build()
+    path, (mesh, lib, bm, s) = _write(tmp_path, name, n_particles=100)
+    out = subprocess.run([exe, path, "--digest"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout)
+    L = mlib.load()
+
+    def digest(kind, addr, n):
+        h = C.c_uint64()
+        assert L.mcw_digest(kind, addr, n, C.byref(h)) == 0
+        return f"{h.value:016x}"
+    nd, _, keep = nucdata.pack_library(lib)
+    assert got["nuclides"] == digest(0, C.addressof(nd), len(lib.nuclides))
+    sets, keep_s = nucdata.pack_temperature_sets(lib)
+    if sets:
+        arr = (nucdata.NuclideDesc * len(sets))()
+        for k, (_, d) in enumerate(sets):
+            C.memmove(C.addressof(arr[k]), C.addressof(d), C.sizeof(nucdata.NuclideDesc))
+        assert got["temperature_sets"] == digest(0, C.addressof(arr), len(sets))
+    else:
+        assert got["temperature_sets"] == digest(0, C.addressof(nd), 0)
+    if getattr(lib, "thermal_tables", None):
+        tables, _, _ = lib.thermal_entries()
+        td, keep_t = nucdata.pack_thermal(tables)
+        assert got["thermal"] == digest(1, C.addressof(td), len(tables))
+    if getattr(lib, "urr_tables", None):
+        ud, keep_u = nucdata.pack_urr(lib.urr_tables)
+        assert got["urr"] == digest(2, C.addressof(ud), len(lib.urr_tables))
