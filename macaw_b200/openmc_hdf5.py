@@ -156,8 +156,10 @@ def read_function(d) -> nucdata.Function1D:
     if kind != "Tabulated1D":
         raise Refused(f"function type '{kind}'")
     interp, nbt = _a(d.attrs["interpolation"]), _a(d.attrs["breakpoints"])
-    if interp.size != 1 or int(nbt[-1]) != v.shape[1] or int(interp[0]) not in (1, 2):
-        raise Refused("Tabulated1D with several regions or logarithmic interpolation")
+    # several regions that all interpolate the same way are one region (Tabulated1D::operator() only looks the code up,
+    # endf.cpp:172-184)
+    if np.any(interp != interp[0]) or int(nbt[-1]) != v.shape[1] or int(interp[0]) not in (1, 2):
+        raise Refused("Tabulated1D with several regions of different interpolation, or logarithmic interpolation")
     return nucdata.Function1D(2, np.asarray(v[1], np.float64), np.asarray(v[0], np.float64), int(interp[0]))
 
 

@@ -1447,9 +1447,16 @@ def test_nuclide_file_converter_refuses_what_the_library_lacks():
     assert "logarithmic" in refused(log_interpolation)
 
     def two_regions(g):
-        g["total_nu/yield"].attrs["interpolation"] = np.array([2, 2])
+        g["total_nu/yield"].attrs["interpolation"] = np.array([2, 1])
         g["total_nu/yield"].attrs["breakpoints"] = np.array([3, 8])
     assert "several regions" in refused(two_regions)
+    # ... but regions that all interpolate the same way are one region
+    root = openmc_hdf5.read_image(image)
+    root["U235"]["total_nu/yield"].attrs["interpolation"] = np.array([2, 2])
+    root["U235"]["total_nu/yield"].attrs["breakpoints"] = np.array([3, 8])
+    same, _ = openmc_hdf5.nuclide_from_group(root["U235"], "U235")
+    plain, _ = openmc_hdf5.nuclide_from_group(openmc_hdf5.read_image(image)["U235"], "U235")
+    assert same.total_nu.interpolation == 2 and np.array_equal(same.xs, plain.xs)
 
     def loglog_urr(g):
         g["urr/294K"].attrs["interpolation"] = np.int64(5)
