@@ -438,4 +438,8 @@ def thermal_from_group(g, name=None) -> nucdata.ThermalTable:
         t.kT = float(np.asarray(_data(g["kTs"][T])))
         sets.append(t)
     sets[0].more_temperatures = sets[1:] or None
+    # the nuclides the table binds (ThermalScattering::nuclides_, thermal.cpp:49; Material assigns tables by them,
+    # material.cpp:317-360): kept on the returned object for the host that builds Material.sab
+    who = g.attrs["nuclides"]
+    sets[0].applies_to = [_s(w) for w in (who if isinstance(who, (list, tuple, np.ndarray)) and np.ndim(who) else [who])]
     return sets[0]

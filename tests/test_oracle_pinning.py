@@ -1482,6 +1482,7 @@ def test_thermal_file_converter_against_reference_thermal_cpp(oracle_bridge):
     root = openmc_hdf5.read_image(oracle_bridge.ref_nuclide_file_image(r))
     for t in lib.thermal_tables:
         c = openmc_hdf5.thermal_from_group(root[t.name], t.name)
+        assert c.applies_to == ["H1"]
         for x, y in zip([t] + list(t.more_temperatures), [c] + list(c.more_temperatures)):
             assert (y.kT, y.energy_max, y.inelastic_type, y.elastic_type, y.n_mu, y.n_e_out, bool(y.skewed)) == \
                 (x.kT, x.energy_max, x.inelastic_type, x.elastic_type, x.n_mu, x.n_e_out, bool(x.skewed)), t.name
