@@ -227,6 +227,9 @@ void fill_distribution(memh5::Node* dist, double awr, const LawView& L)
 }
 } // namespace
 
+// the image's root for oracle/ref_gather.cpp (host/openmc_nuclide_reader.hpp reads the same image)
+memh5::Node* ref_image_root() { return g_root.get(); }
+
 extern "C" {
 #define REF_API __attribute__((visibility("default")))
 

@@ -1493,3 +1493,42 @@ def test_thermal_file_converter_against_reference_thermal_cpp(oracle_bridge):
     bad[sorted(bad["kTs"].keys())[0]]["elastic"]["distribution"].attrs["type"] = "incoherent_elastic"
     with pytest.raises(openmc_hdf5.Refused):
         openmc_hdf5.thermal_from_group(bad)
+
+
+def test_cpp_nuclide_reader_against_reference_nuclide_cpp(oracle_bridge):
+    """host/openmc_nuclide_reader.hpp -- the MaCaw-side gatherLibrary() of INTEGRATION.md, written against OpenMC's own
+    hdf5_interface.h -- on the nuclide-file image the REFERENCE's own constructors just read (oracle/_ref links the header's
+    functions to an in-memory tree instead of libhdf5): the library's digest (mcw_digest: every scalar and every array of
+    the descriptors) of what the C++ reader gathered equals the digest of the library the image was written from with the
+    reference's own Nuclide::create_derived tables in it -- nuclides, further temperature sets and probability tables.
+    So the adapter code a maintainer would add derives the same tables as OpenMC, bit for bit, and hands over every
+    reaction list, law, yield and fission product unchanged."""
+    from macaw_b200 import lib as mlib, nucdata
+    r = oracle_bridge.ref_lib()
+    if r is None or not hasattr(r, "ref_gather_digest"):
+        pytest.skip("oracle/_ref not built with the C++ reader doorway (no /root/reference on this box)")
+    lib = _everything_library(nucdata)
+    tables = oracle_bridge.ref_load_library(r, lib)
+    for n, tb in zip(lib.nuclides, tables):  # the reference's derived tables, every temperature
+        n.xs = tb[0].copy()
+        if len(tb) > 4:
+            for x in [n] + list(n.more_temperatures):
+                x.xs = tb[4][id(x)][0].copy()
+    L = mlib.load()
+    got, msg = (C.c_uint64 * 3)(), C.create_string_buffer(512)
+    rc = r.ref_gather_digest(C.cast(L.mcw_digest, C.c_void_p), got, msg, 512)
+    assert rc == 0, msg.value.decode()
+
+    def digest(kind, addr, n):
+        h = C.c_uint64()
+        assert L.mcw_digest(kind, addr, n, C.byref(h)) == 0
+        return h.value
+    nd, _, keep = nucdata.pack_library(lib)
+    assert got[0] == digest(0, C.addressof(nd), len(lib.nuclides))
+    sets, keep_s = nucdata.pack_temperature_sets(lib)
+    arr = (nucdata.NuclideDesc * len(sets))()
+    for k, (_, d) in enumerate(sets):
+        C.memmove(C.addressof(arr[k]), C.addressof(d), C.sizeof(nucdata.NuclideDesc))
+    assert len(sets) > 20 and got[1] == digest(0, C.addressof(arr), len(sets))
+    ud, keep_u = nucdata.pack_urr(lib.urr_tables)
+    assert got[2] == digest(2, C.addressof(ud), len(lib.urr_tables))
