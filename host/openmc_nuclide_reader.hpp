@@ -474,6 +474,128 @@ inline GatheredNuclide readNuclide(hid_t g, const std::string& name)
   return out;
 }
 
+// One table group of a thermal-scattering file (OMC ThermalScattering thermal.cpp:38-147, ThermalData :177-227): every
+// temperature as one ThermalTable, by increasing kT, with the kTs.  Inelastic: incoherent_inelastic (continuous outgoing
+// energies with equiprobable discrete cosines) or incoherent_inelastic_discrete; elastic: none, coherent_elastic (Bragg
+// edges) or incoherent_elastic_discrete; the Debye-Waller form is refused.
+inline std::vector<std::pair<double, ThermalTable>> readThermalTable(hid_t g)
+{
+  std::vector<std::pair<double, ThermalTable>> out;
+  double energy_max = 0;
+  openmc::read_attribute(g, "energy_max", energy_max);
+  hid_t kts = openmc::open_group(g, "kTs");
+  std::vector<std::pair<double, std::string>> temps;
+  for (const std::string& t : openmc::dataset_names(kts))
+  {
+    double kT = 0;
+    openmc::read_dataset(kts, t.c_str(), kT);
+    temps.push_back({kT, t});
+  }
+  openmc::close_group(kts);
+  std::sort(temps.begin(), temps.end());
+  for (const auto& kt : temps)
+  {
+    ThermalTable t;
+    t.energy_max = energy_max;
+    hid_t tg = openmc::open_group(g, kt.second.c_str());
+    hid_t in = openmc::open_group(tg, "inelastic");
+    const Function1D xs = readFunction(in, "xs");
+    if (xs.kind != MCW_FN_TABULATED || xs.interpolation != 2)
+      refuse("thermal inelastic cross section that is not a lin-lin table");
+    t.i_xs_energy = xs.x, t.i_xs = xs.y;
+    hid_t d = openmc::open_group(in, "distribution");
+    std::string type;
+    openmc::read_attribute(d, "type", type);
+    if (type == "incoherent_inelastic")
+    {
+      t.inelastic_type = MCW_SAB_INELASTIC_CONTINUOUS;
+      oneRegionIsHistogram(d, "thermal inelastic distribution");
+      openmc::read_dataset(d, "energy", t.i_energy);
+      const Tabular2D eo = readTable(d, "energy_out", t.i_energy, true);
+      const xt::xarray<double> raw = array2d(d, "energy_out"), mu = array2d(d, "mu");
+      const size_t np = raw.shape()[1];
+      if (np == 0 || mu.shape()[1] % np)
+        refuse("thermal inelastic distribution whose cosines are not equiprobable discrete ones");
+      t.n_mu = (int)(mu.shape()[1] / np);
+      for (size_t k = 0; k < np; ++k)
+        if (raw(3, k) != 0.0 || raw(4, k) != (double)(k * (size_t)t.n_mu))
+          refuse("thermal inelastic distribution with tabulated cosines or a varying number of them");
+      t.i_offset = eo.offset, t.i_e_out = eo.x, t.i_pdf = eo.pdf, t.i_cdf = eo.cdf;
+      t.i_mu.assign(mu.data(), mu.data() + mu.shape()[1]);
+    }
+    else if (type == "incoherent_inelastic_discrete")
+    {
+      t.inelastic_type = MCW_SAB_INELASTIC_DISCRETE;
+      const xt::xarray<double> eo = array2d(d, "energy_out"), mu = array2d(d, "mu_out");
+      t.n_e_out = (int)eo.shape()[1], t.n_mu = (int)mu.shape()[2];
+      double skewed = 0;
+      openmc::read_dataset(d, "skewed", skewed);
+      t.skewed = skewed != 0;
+      t.i_e_out.assign(eo.data(), eo.data() + eo.size());
+      t.i_mu.assign(mu.data(), mu.data() + mu.size());
+    }
+    else
+      refuse("thermal inelastic distribution type '" + type + "'");
+    openmc::close_group(d);
+    openmc::close_group(in);
+    if (openmc::object_exists(tg, "elastic"))
+    {
+      hid_t el = openmc::open_group(tg, "elastic");
+      hid_t ed = openmc::open_group(el, "distribution");
+      std::string etype;
+      openmc::read_attribute(ed, "type", etype);
+      if (etype == "coherent_elastic")
+      {
+        t.elastic_type = MCW_SAB_ELASTIC_COHERENT;
+        const xt::xarray<double> v = array2d(el, "xs");
+        const size_t n = v.shape()[1];
+        t.e_x.assign(v.data(), v.data() + n), t.e_y.assign(v.data() + n, v.data() + 2 * n);
+      }
+      else if (etype == "incoherent_elastic_discrete")
+      {
+        t.elastic_type = MCW_SAB_ELASTIC_INCOHERENT_DISCRETE;
+        const Function1D f = readFunction(el, "xs");
+        t.e_x = f.x, t.e_y = f.y;
+        const xt::xarray<double> mu = array2d(ed, "mu_out");
+        t.n_elastic_mu = (int)mu.shape()[1];
+        t.e_mu.assign(mu.data(), mu.data() + mu.size());
+      }
+      else
+        refuse("thermal elastic distribution type '" + etype + "' (the Debye-Waller form is not carried)");
+      openmc::close_group(ed);
+      openmc::close_group(el);
+    }
+    openmc::close_group(tg);
+    out.push_back({kt.first, std::move(t)});
+  }
+  return out;
+}
+
+// Thermal tables in the order of openmc::data::thermal_scatt: fills Library::thermal (every table's lowest temperature
+// first -- what materials name --, then the further temperatures in table order), thermal_same and thermal_kT
+inline void readThermalTables(const std::vector<hid_t>& groups, Library& lib)
+{
+  std::vector<std::vector<std::pair<double, ThermalTable>>> all;
+  for (hid_t g : groups)
+    all.push_back(readThermalTable(g));
+  bool several = false;
+  for (const auto& t : all)
+    several |= t.size() > 1;
+  for (size_t k = 0; k < all.size(); ++k)
+  {
+    lib.thermal.push_back(all[k][0].second);
+    lib.thermal_same.push_back((int32_t)k), lib.thermal_kT.push_back(all[k][0].first);
+  }
+  for (size_t k = 0; k < all.size(); ++k)
+    for (size_t j = 1; j < all[k].size(); ++j)
+    {
+      lib.thermal.push_back(all[k][j].second);
+      lib.thermal_same.push_back((int32_t)k), lib.thermal_kT.push_back(all[k][j].first);
+    }
+  if (!several)
+    lib.thermal_same.clear(), lib.thermal_kT.clear();
+}
+
 // groups: the nuclide groups in the order of openmc::data::nuclides (the order materials refer to)
 inline Library readLibrary(const std::vector<std::pair<std::string, hid_t>>& groups)
 {

@@ -164,7 +164,8 @@ def ref_lib():
         if hasattr(r, "ref_stage_urr"):
             r.ref_stage_urr.argtypes = [C.c_void_p]
         if hasattr(r, "ref_gather_digest"):
-            r.ref_gather_digest.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+            r.ref_gather_digest.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_int, C.POINTER(C.c_uint64),
+                                            C.c_void_p, C.c_void_p, C.c_int]
         if hasattr(r, "ref_dump_tree"):
             r.ref_dump_tree.restype = C.c_int64
             r.ref_dump_tree.argtypes = [C.c_void_p, C.c_int64]

@@ -1516,7 +1516,7 @@ def test_cpp_nuclide_reader_against_reference_nuclide_cpp(oracle_bridge):
                 x.xs = tb[4][id(x)][0].copy()
     L = mlib.load()
     got, msg = (C.c_uint64 * 3)(), C.create_string_buffer(512)
-    rc = r.ref_gather_digest(C.cast(L.mcw_digest, C.c_void_p), got, msg, 512)
+    rc = r.ref_gather_digest(C.cast(L.mcw_digest, C.c_void_p), got, msg, 512, None, None, None, 0)
     assert rc == 0, msg.value.decode()
 
     def digest(kind, addr, n):
@@ -1532,3 +1532,14 @@ def test_cpp_nuclide_reader_against_reference_nuclide_cpp(oracle_bridge):
     assert len(sets) > 20 and got[1] == digest(0, C.addressof(arr), len(sets))
     ud, keep_u = nucdata.pack_urr(lib.urr_tables)
     assert got[2] == digest(2, C.addressof(ud), len(lib.urr_tables))
+    # thermal-scattering files: three kinds of tables at three temperatures each, read by the reference's ThermalScattering
+    lib2 = nucdata.make_library(n_nuclides=9, G=300, seed=3, n_log_bins=500)
+    nucdata.add_thermal_temperatures(nucdata.add_thermal_scattering(lib2))
+    oracle_bridge.ref_load_library(r, lib2)
+    th, same, kT = (C.c_uint64 * 1)(), np.zeros(16, np.int32), np.zeros(16)
+    rc = r.ref_gather_digest(C.cast(L.mcw_digest, C.c_void_p), got, msg, 512, th, same.ctypes.data, kT.ctypes.data, 16)
+    assert rc == 0, msg.value.decode()
+    tables, same_py, kT_py = lib2.thermal_entries()
+    td, keep_t = nucdata.pack_thermal(tables)
+    assert th[0] == digest(1, C.addressof(td), len(tables))
+    assert np.array_equal(same[:len(tables)], same_py) and np.array_equal(kT[:len(tables)], kT_py)
