@@ -899,7 +899,8 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
     physics="full": the same on a library with everything a real evaluation brings -- reaction lists with every secondary
     law and energy-dependent multiplicities (the weight changes along the history and with it every k score, the
     fission-site numbers and the tallies), fission products with function yields and tabulated spectra, probability
-    tables, data sets at three temperatures -- at a particle temperature of 700 K (the 600 K sets).  Only (n,2n)'s
+    tables, data sets at three temperatures, S(a,b) tables at three temperatures -- at a particle temperature of 700 K
+    (the 600 K sets and tables).  Only (n,2n)'s
     integral multiplicity is set to 1 there: the reference's loop would go on to transport the second neutron, which
     MaCaw drops (MC CollisionKernel.C:232-236)."""
     from macaw_b200 import cstructs, meshgen
@@ -924,7 +925,7 @@ def test_whole_histories_against_reference_history_loop(oracle_bridge, i_mat, re
         nucdata.add_reactions = one_neutron
         try:
             lib, _, _ = _reference_library(oracle_bridge, r, tabular=True, reactions="evaporation", fission=True, urr=True,
-                                           temperatures=True)
+                                           temperatures=True, thermal="temperatures")
         finally:
             nucdata.add_reactions = _orig
         T = 700.0
