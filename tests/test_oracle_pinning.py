@@ -1544,3 +1544,55 @@ def test_cpp_nuclide_reader_against_reference_nuclide_cpp(oracle_bridge):
     td, keep_t = nucdata.pack_thermal(tables)
     assert th[0] == digest(1, C.addressof(td), len(tables))
     assert np.array_equal(same[:len(tables)], same_py) and np.array_equal(kT[:len(tables)], kT_py)
+
+
+@pytest.mark.parametrize("i_mat", [0, 3])
+def test_whole_history_full_fixture_from_reference_loop(oracle_bridge, i_mat):
+    """tests/golden/ref_histories_full.npz (tests/golden/make_ref_histories_full.py): 400 whole histories per material through
+    the reference's own history loop on the library with everything at once (reaction lists and every law, multiplicities
+    that move the weight, fission products, probability tables, nuclide and S(a,b) data at three temperatures), particles
+    at 700 K.  Needs neither /root/reference nor oracle/_ref: the oracle's production loop (glibc math, direction
+    re-normalisation off) on one huge element reproduces final energies, stream seeds, collision and progeny counts, k
+    scores, the fission bank and both tallies bit for bit."""
+    import importlib.util
+    import os
+    from macaw_b200 import cstructs, meshgen
+    from tests import problems
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_ref_histories_full", os.path.join(here, "make_ref_histories_full.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "ref_histories_full.npz"))
+    lib, L = gen.library(), gen.HALF
+    for key, x in gen.data_sets(lib):
+        if f"xs_{key}" in g:
+            x.xs = g[f"xs_{key}"].copy()
+    mesh = meshgen.hex_grid(1, 1, 1, (-L, -L, -L), (L, L, L), meshgen.BC_REFLECT, None, "one_element")
+    s = cstructs.make_settings(gen.N, n_inactive=0, source_box=(-1, -1, -1, 1, 1, 1), seed=gen.MASTER_SEED,
+                               n_log_bins=lib.n_log_bins, seed_through_double=False)
+    o = problems.configure(oracle_bridge.Oracle(libm=True), mesh, lib, [i_mat], s, tallies=False)
+    o.add_tally(1, cstructs.ESTIMATOR["collision"], cstructs.GRANULARITY["cell"], [0, 1, 2, 3], gen.EDGES)
+    o.add_tally(2, cstructs.ESTIMATOR["tracklength"], cstructs.GRANULARITY["cell"], [0, 1, 2, 3], gen.EDGES)
+    o.set_temperature(gen.TEMPERATURE)
+    o.set_source_bank(gen.sites(i_mat))
+    o.L.orc_set_keff(o.h, gen.KEFF)
+    o.L.orc_set_renormalise_direction(o.h, 0)
+    o.transport_generation(gen.BATCH, 1)
+    rec, bank = o.history_records(), o.fission_bank()
+    state, seeds, sites, tallies = (g[f"m{i_mat}_{k}"] for k in ("state", "seeds", "sites", "tallies"))
+
+    def bits(a):
+        return np.ascontiguousarray(a, np.float64).view(np.uint64)
+    assert np.array_equal(bits(state[:, 0]), bits(rec["E"]))
+    assert np.array_equal(state[:, 1].astype(np.int64), rec["n_collisions"]) and np.array_equal(state[:, 2].astype(np.int64), rec["n_progeny"])
+    for col, f in ((0, "seed_tracking"), (1, "seed_source"), (2, "seed_urr")):
+        assert np.array_equal(seeds[:, col], rec[f]), f
+    for col, f in ((3, "k_collision"), (4, "k_absorption"), (5, "k_tracklength")):
+        assert np.array_equal(bits(state[:, col]), bits(rec[f])), f
+    assert len(sites) == bank.size
+    assert np.array_equal(sites[:, 5].astype(np.int64), bank["parent_id"]) and np.array_equal(sites[:, 6].astype(np.int64), bank["progeny_id"])
+    assert np.array_equal(bits(sites[:, 0]), bits(bank["E"])) and np.array_equal(bits(sites[:, 1:4]), bits(bank["u"]))
+    assert np.array_equal(sites[:, 4].astype(np.int32), bank["delayed_group"])
+    for t, tid in enumerate((1, 2)):
+        v, _, _, _ = o.get_tally(tid)
+        assert np.array_equal(bits(v), bits(tallies[t].ravel())), tid
